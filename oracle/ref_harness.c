@@ -1,0 +1,222 @@
+/* TEST INFRASTRUCTURE ONLY (oracle/): drives the UNMODIFIED reference implementation of the
+ * hot path (compiled from /root/reference by oracle/Makefile into oracle/_ref/) so that the
+ * CPU restatement in oracle/cmc_oracle.c and the CUDA path can be checked against the real thing.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may use it.
+ *
+ * The reference keeps all state in process globals (include/cmc/cmc_vars.h); this file allocates
+ * and fills them the way the reference's own start-up does:
+ *   star/binary calloc           cmc_io.c:2099-2101
+ *   star_r/star_m/star_phi       cmc_io.c:3431-3437
+ *   sentinels star_r[0]=ZERO     cmc_fits.c:128-136
+ *   madhoc = 1/N_STAR            cmc_utils.c:1183
+ *   rng                          cmc_utils.c:2364-2375 (set_rng_states)
+ *   q_root (Brent solver)        cmc_io.c:3398
+ * and then calls the reference's own entry points
+ *   new_orbits_calculate (cmc_utils.c:2194), qsorts_new (:2232), post_sort_comm (:2259),
+ *   calc_potential_new (:2006).
+ * Every uniform draw the orbit step consumes is recorded (taus113's rng_t113_dbl_new is
+ * renamed at compile time with -D and wrapped here) so the same draws can be fed to the
+ * oracle port and to the CUDA kernel. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include "cmc.h"
+#include "cmc_vars.h"
+
+#define EXPORT __attribute__((visibility("default")))
+
+/* the real generator, renamed by -Drng_t113_dbl_new=ref_real_rng_t113_dbl_new when
+ * taus113-v2.c is compiled; every other TU calls the wrapper below */
+double ref_real_rng_t113_dbl_new(struct rng_t113_state *state);
+
+static double *draw_log = NULL;
+static long draw_cap = 0, draw_cnt = 0;
+static int draw_replay = 0;      /* 1: serve draws from draw_log instead of the generator */
+static long draw_pos = 0;
+
+double rng_t113_dbl_new(struct rng_t113_state *state)
+{
+	if (draw_replay) {
+		if (draw_pos >= draw_cnt) { fprintf(stderr, "ref_harness: replay ran out of draws\n"); exit(7); }
+		return draw_log[draw_pos++];
+	}
+	double u = ref_real_rng_t113_dbl_new(state);
+	if (draw_log) {
+		if (draw_cnt == draw_cap) {
+			draw_cap = draw_cap ? 2 * draw_cap : (1 << 20);
+			draw_log = realloc(draw_log, draw_cap * sizeof(double));
+		}
+		draw_log[draw_cnt++] = u;
+	}
+	return u;
+}
+
+EXPORT long ref_sizeof_star(void) { return (long) sizeof(star_t); }
+EXPORT long ref_sizeof_binary(void) { return (long) sizeof(binary_t); }
+EXPORT long ref_sizeof_orbit_rs(void) { return (long) sizeof(orbit_rs_t); }
+
+/* offsets of the star_t / binary_t fields the path touches (include/cmc/cmc.h:409-601, :231-390) */
+EXPORT long ref_star_offset(const char *f)
+{
+#define O(n) if (!strcmp(f, #n)) return (long) offsetof(star_t, n)
+	O(r); O(vr); O(vt); O(m); O(E); O(J); O(EI); O(Eint); O(rnew); O(vrnew); O(vtnew); O(rOld); O(X); O(Y);
+	O(r_peri); O(r_apo); O(phi); O(interacted); O(binind); O(id); O(rad); O(Uoldrold); O(Uoldrnew); O(vtold); O(vrold);
+	O(se_k);
+#undef O
+	return -1;
+}
+EXPORT long ref_binary_offset(const char *f)
+{
+#define O(n) if (!strcmp(f, #n)) return (long) offsetof(binary_t, n)
+	O(id1); O(id2); O(rad1); O(rad2); O(m1); O(m2); O(Eint1); O(Eint2); O(a); O(e); O(inuse);
+#undef O
+	return -1;
+}
+
+EXPORT int ref_init(long n_star, long n_star_dim, long n_bin_dim, long min_chunk, int samplesize, long idum, double orbit_r_in)
+{
+	MPI_Comm_size(MPI_COMM_WORLD, &procs);
+	MPI_Comm_rank(MPI_COMM_WORLD, &myid);
+	debug = 0; quiet = 1;
+	N_STAR_DIM = N_STAR_DIM_OPT = n_star_dim;
+	N_BIN_DIM = N_BIN_DIM_OPT = n_bin_dim;
+	star = calloc(n_star_dim, sizeof(star_t));
+	binary = calloc(n_bin_dim, sizeof(binary_t));
+	star_r = malloc(n_star_dim * sizeof(double));
+	star_m = malloc(n_star_dim * sizeof(double));
+	star_phi = malloc(n_star_dim * sizeof(double));
+	if (!star || !binary || !star_r || !star_m || !star_phi) return -1;
+	memset(star_r, 0, n_star_dim * sizeof(double));
+	memset(star_m, 0, n_star_dim * sizeof(double));
+	memset(star_phi, 0, n_star_dim * sizeof(double));
+	Start = calloc(procs, sizeof(int)); End = calloc(procs, sizeof(int));
+	mpiDisp = calloc(procs, sizeof(int)); mpiLen = calloc(procs, sizeof(int));
+	clus.N_STAR = clus.N_STAR_NEW = clus.N_MAX = n_star;
+	clus.N_BINARY = 0;
+	madhoc = 1.0 / (double) clus.N_STAR;
+	MIN_CHUNK_SIZE = min_chunk;
+	SAMPLESIZE = samplesize;
+	SEARCH_GRID = 0;
+	IDUM = idum;
+	orbit_r = orbit_r_in;
+	APSIDES_PRECISION = 1.0e-11; APSIDES_MAX_ITER = 100; APSIDES_CONVERGENCE = 5.e-13;   /* cmc_io.c:1752-1754 */
+	q_root = gsl_root_fsolver_alloc(gsl_root_fsolver_brent);
+	units.t = units.m = units.l = units.E = units.mstar = 1.0;
+	cenma.m = cenma.m_new = cenma.E = cenma.E_new = 0.0;
+	tcount = 1; TotalTime = 0.0;
+	mpi_escfile_buf = malloc(STR_BUF_LEN);
+	mpi_escfile_wrbuf = malloc(1 << 26);
+	mpi_escfile_wrbuf[0] = 0; mpi_escfile_len = 0;
+	set_rng_states();
+	findLimits(clus.N_MAX, MIN_CHUNK_SIZE);
+	mpiFindIndicesCustom(clus.N_MAX, MIN_CHUNK_SIZE, myid, &mpiBegin, &mpiEnd);
+	clus.N_MAX_NEW = mpiEnd - mpiBegin + 1;
+	star_r[0] = ZERO; star_m[0] = 0.0;
+	star[0].r = ZERO; star[0].m = 0.0;
+	return 0;
+}
+
+EXPORT void ref_free(void)
+{
+	free(star); free(binary); free(star_r); free(star_m); free(star_phi);
+	free(Start); free(End); free(mpiDisp); free(mpiLen); free(curr_st);
+	free(mpi_escfile_buf); free(mpi_escfile_wrbuf); free(draw_log);
+	gsl_root_fsolver_free(q_root);
+	star = NULL; binary = NULL; star_r = star_m = star_phi = NULL; draw_log = NULL; draw_cap = draw_cnt = 0;
+}
+
+EXPORT void *ref_star(void) { return star; }
+EXPORT void *ref_binary(void) { return binary; }
+EXPORT double *ref_star_r(void) { return star_r; }
+EXPORT double *ref_star_m(void) { return star_m; }
+EXPORT double *ref_star_phi(void) { return star_phi; }
+EXPORT int *ref_Start(void) { return Start; }
+EXPORT int *ref_End(void) { return End; }
+EXPORT int ref_procs(void) { return procs; }
+EXPORT int ref_myid(void) { return myid; }
+
+EXPORT void ref_set_scalars(long N_MAX, long N_MAX_NEW, long N_BINARY, double cenma_m, double cenma_m_new, double Rtidal_in, double Mtotal_in)
+{
+	clus.N_MAX = N_MAX; clus.N_MAX_NEW = N_MAX_NEW; clus.N_BINARY = N_BINARY; N_b_local = N_BINARY;
+	cenma.m = cenma_m; cenma.m_new = cenma_m_new; Rtidal = Rtidal_in; Mtotal = Mtotal_in;
+}
+
+/* out[0..15]: N_MAX, N_MAX_NEW, Mtotal, Rtidal, cenma.m, max_r, TidalMassLoss, Eescaped, Jescaped,
+ * Eintescaped, Ebescaped, Etidal, mpiBegin, mpiEnd, N_b_local, escfile bytes */
+EXPORT void ref_get_scalars(double *out)
+{
+	out[0] = clus.N_MAX; out[1] = clus.N_MAX_NEW; out[2] = Mtotal; out[3] = Rtidal; out[4] = cenma.m;
+	out[5] = max_r; out[6] = TidalMassLoss; out[7] = Eescaped; out[8] = Jescaped; out[9] = Eintescaped;
+	out[10] = Ebescaped; out[11] = Etidal; out[12] = mpiBegin; out[13] = mpiEnd; out[14] = N_b_local;
+	out[15] = (double) mpi_escfile_len;
+}
+
+EXPORT void ref_find_limits(long N, int blk) { findLimits(N, blk); }
+EXPORT void ref_find_indices_custom(long N, int blk, int i, int *b, int *e) { mpiFindIndicesCustom(N, blk, i, b, e); }
+
+EXPORT void ref_calc_potential_new(void) { calc_potential_new(); }
+EXPORT void ref_qsorts_new(void) { qsorts_new(); }
+EXPORT void ref_post_sort_comm(void) { post_sort_comm(); }
+
+/* draw recording: mode 0 = off, 1 = record from taus113, 2 = replay the recorded log */
+EXPORT void ref_draw_mode(int mode)
+{
+	if (mode == 1) {
+		if (!draw_log) { draw_cap = 1 << 20; draw_log = malloc(draw_cap * sizeof(double)); }
+		draw_cnt = 0; draw_replay = 0;
+	} else if (mode == 2) { draw_replay = 1; draw_pos = 0; }
+	else { draw_replay = 0; }
+}
+EXPORT long ref_draw_count(void) { return draw_cnt; }
+EXPORT const double *ref_draw_log(void) { return draw_log; }
+EXPORT void ref_set_draws(const double *d, long n)
+{
+	if (n > draw_cap) { draw_cap = n; draw_log = realloc(draw_log, n * sizeof(double)); }
+	memcpy(draw_log, d, n * sizeof(double)); draw_cnt = n;
+}
+
+EXPORT void ref_new_orbits_calculate(void)
+{
+	mpi_escfile_wrbuf[0] = 0; mpi_escfile_len = 0;
+	new_orbits_calculate();
+}
+
+/* single-orbit probes for unit-level parity */
+EXPORT double ref_potential(double r) { return potential(r); }
+EXPORT long ref_find_zero_Q(long j, long kmin, long kmax, double E, double J) { return find_zero_Q(j, kmin, kmax, E, J); }
+EXPORT double ref_function_q(long j, double r, double pot, double E, double J) { return function_q(j, r, pot, E, J); }
+EXPORT void ref_calc_orbit_new(long index, double E, double J, double *out)
+{
+	orbit_rs_t o = calc_orbit_new(index, E, J);
+	out[0] = o.rp; out[1] = o.ra; out[2] = o.dQdrp; out[3] = o.dQdra; out[4] = o.kmax; out[5] = o.kmin; out[6] = o.circular_flag;
+}
+EXPORT double ref_find_root_vr(long index, long k, double E, double J) { return find_root_vr(index, k, E, J); }
+
+/* taus113 known-answer access (src/libs/taus113-v2.c:166-216, 253-270) */
+EXPORT void ref_rng_reset(unsigned long seed, unsigned int *z) { struct rng_t113_state s; reset_rng_t113_new(seed, &s); z[0] = s.z[0]; z[1] = s.z[1]; z[2] = s.z[2]; z[3] = s.z[3]; }
+EXPORT void ref_rng_jump80(unsigned int *z) { struct rng_t113_state s; memcpy(s.z, z, 16); s = rng_t113_jump(s, JPoly_2_80); memcpy(z, s.z, 16); }
+EXPORT double ref_rng_next(unsigned int *z) { struct rng_t113_state s; memcpy(s.z, z, 16); double u = ref_real_rng_t113_dbl_new(&s); memcpy(z, s.z, 16); return u; }
+
+/* timing leg for bench.py: one pass of orbit step -> (caller refreshes r) -> sort -> post_sort_comm -> potential.
+ * Brackets follow timeStartSimple/timeEndSimple (cmc_utils.c:1681-1707): barrier, wall clock. */
+EXPORT void ref_time_step(double *t_orb, double *t_sort, double *t_comm, double *t_pot)
+{
+	double t0;
+	long i;
+	MPI_Barrier(MPI_COMM_WORLD); t0 = MPI_Wtime();
+	ref_new_orbits_calculate();
+	MPI_Barrier(MPI_COMM_WORLD); *t_orb = MPI_Wtime() - t0;
+	/* what ComputeIntermediateEnergy does to create the sort key (cmc_utils.c:368-391): r <- rnew, m <- star_m */
+	for (i = 1; i <= clus.N_MAX_NEW; i++) {
+		star[i].rOld = star_r[get_global_idx(i)]; star[i].r = star[i].rnew; star[i].vr = star[i].vrnew; star[i].vt = star[i].vtnew;
+		star[i].m = star_m[get_global_idx(i)];
+	}
+	MPI_Barrier(MPI_COMM_WORLD); t0 = MPI_Wtime();
+	qsorts_new();
+	MPI_Barrier(MPI_COMM_WORLD); *t_sort = MPI_Wtime() - t0; t0 = MPI_Wtime();
+	post_sort_comm();
+	MPI_Barrier(MPI_COMM_WORLD); *t_comm = MPI_Wtime() - t0; t0 = MPI_Wtime();
+	calc_potential_new();
+	MPI_Barrier(MPI_COMM_WORLD); *t_pot = MPI_Wtime() - t0;
+}

@@ -1,0 +1,141 @@
+"""ctypes binding to oracle/_ref/libcmc_ref.so -- the UNMODIFIED reference hot path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, bench.py's reference/cpu_baseline legs and
+__graft_entry__.smoke(); never by the product package.  The library is built by
+oracle/Makefile from the sources under /root/reference (container) and travels to the GPU box prebuilt.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "..", "oracle", "_ref", "libcmc_ref.so")
+
+SF_INFINITY = 1.0e10
+ZERO = 1.0e-20
+
+
+def available():
+    return os.path.exists(REF_SO)
+
+
+class Ref:
+    """One in-process rank of the reference (procs == 1)."""
+
+    def __init__(self):
+        L = C.CDLL(REF_SO)
+        self.L = L
+        L.ref_sizeof_star.restype = C.c_long
+        L.ref_sizeof_binary.restype = C.c_long
+        L.ref_star_offset.restype = C.c_long
+        L.ref_star_offset.argtypes = [C.c_char_p]
+        L.ref_binary_offset.restype = C.c_long
+        L.ref_binary_offset.argtypes = [C.c_char_p]
+        L.ref_init.argtypes = [C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_long, C.c_double]
+        for f in ("ref_star", "ref_binary", "ref_star_r", "ref_star_m", "ref_star_phi", "ref_draw_log", "ref_Start", "ref_End"):
+            getattr(L, f).restype = C.c_void_p
+        L.ref_set_scalars.argtypes = [C.c_long, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.ref_get_scalars.argtypes = [C.c_void_p]
+        L.ref_draw_count.restype = C.c_long
+        L.ref_set_draws.argtypes = [C.c_void_p, C.c_long]
+        L.ref_potential.restype = C.c_double
+        L.ref_potential.argtypes = [C.c_double]
+        L.ref_find_zero_Q.restype = C.c_long
+        L.ref_find_zero_Q.argtypes = [C.c_long, C.c_long, C.c_long, C.c_double, C.c_double]
+        L.ref_function_q.restype = C.c_double
+        L.ref_function_q.argtypes = [C.c_long, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.ref_calc_orbit_new.argtypes = [C.c_long, C.c_double, C.c_double, C.c_void_p]
+        L.ref_find_root_vr.restype = C.c_double
+        L.ref_find_root_vr.argtypes = [C.c_long, C.c_long, C.c_double, C.c_double]
+        L.ref_find_limits.argtypes = [C.c_long, C.c_int]
+        L.ref_rng_reset.argtypes = [C.c_ulong, C.c_void_p]
+        L.ref_rng_jump80.argtypes = [C.c_void_p]
+        L.ref_rng_next.restype = C.c_double
+        L.ref_rng_next.argtypes = [C.c_void_p]
+        L.ref_time_step.argtypes = [C.c_void_p] * 4
+        self.sizeof_star = L.ref_sizeof_star()
+        self.sizeof_binary = L.ref_sizeof_binary()
+        self.n_star_dim = 0
+
+    def star_offset(self, name):
+        return self.L.ref_star_offset(name.encode())
+
+    def binary_offset(self, name):
+        return self.L.ref_binary_offset(name.encode())
+
+    def init(self, n_star, n_star_dim=None, n_bin_dim=None, min_chunk=40, samplesize=1024, idum=1234, orbit_r=1e6):
+        n_star_dim = n_star_dim or int(1.5 * (n_star + 2)) + 16
+        n_bin_dim = n_bin_dim or 16
+        rc = self.L.ref_init(n_star, n_star_dim, n_bin_dim, min_chunk, samplesize, idum, orbit_r)
+        assert rc == 0
+        self.n_star = n_star
+        self.n_star_dim = n_star_dim
+        self.n_bin_dim = n_bin_dim
+
+    def free(self):
+        self.L.ref_free()
+
+    # --- views onto the reference's own arrays (no copies) ---
+    def _view(self, ptr, nbytes, dtype):
+        buf = (C.c_char * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype)
+
+    def star_bytes(self):
+        return self._view(self.L.ref_star(), self.n_star_dim * self.sizeof_star, np.uint8).reshape(self.n_star_dim, self.sizeof_star)
+
+    def binary_bytes(self):
+        return self._view(self.L.ref_binary(), self.n_bin_dim * self.sizeof_binary, np.uint8).reshape(self.n_bin_dim, self.sizeof_binary)
+
+    def star_field(self, name, dtype=np.float64):
+        off = self.star_offset(name)
+        assert off >= 0, name
+        raw = self._view(self.L.ref_star(), self.n_star_dim * self.sizeof_star, np.uint8)
+        return np.lib.stride_tricks.as_strided(raw[off:off + 8].view(dtype), shape=(self.n_star_dim,), strides=(self.sizeof_star,))
+
+    def star_r(self):
+        return self._view(self.L.ref_star_r(), self.n_star_dim * 8, np.float64)
+
+    def star_m(self):
+        return self._view(self.L.ref_star_m(), self.n_star_dim * 8, np.float64)
+
+    def star_phi(self):
+        return self._view(self.L.ref_star_phi(), self.n_star_dim * 8, np.float64)
+
+    def scalars(self):
+        out = np.zeros(16)
+        self.L.ref_get_scalars(out.ctypes.data)
+        keys = ["N_MAX", "N_MAX_NEW", "Mtotal", "Rtidal", "cenma_m", "max_r", "TidalMassLoss", "Eescaped", "Jescaped",
+                "Eintescaped", "Ebescaped", "Etidal", "mpiBegin", "mpiEnd", "N_b_local", "esc_bytes"]
+        return dict(zip(keys, out))
+
+    def set_scalars(self, N_MAX, N_MAX_NEW, N_BINARY=0, cenma_m=0.0, cenma_m_new=0.0, Rtidal=1e6, Mtotal=1.0):
+        self.L.ref_set_scalars(N_MAX, N_MAX_NEW, N_BINARY, cenma_m, cenma_m_new, Rtidal, Mtotal)
+
+    def draws(self):
+        n = self.L.ref_draw_count()
+        return self._view(self.L.ref_draw_log(), n * 8, np.float64).copy()
+
+    # --- convenience: load a sorted cluster the way the reference's start-up does ---
+    def load_cluster(self, r, vr, vt, m_star_units, binind=None, ids=None):
+        """r sorted ascending (N,), m in star_m units (obj_m * N_STAR)."""
+        n = len(r)
+        assert n == self.n_star
+        sr, sm = self.star_r(), self.star_m()
+        sr[0] = ZERO; sm[0] = 0.0
+        sr[1:n + 1] = r; sm[1:n + 1] = m_star_units
+        sr[n + 1] = SF_INFINITY; sm[n + 1] = 0.0
+        for name, val in (("r", r), ("vr", vr), ("vt", vt), ("m", m_star_units)):
+            self.star_field(name)[1:n + 1] = val
+        self.star_field("r")[0] = ZERO
+        self.star_field("r")[n + 1] = SF_INFINITY
+        self.star_field("id", np.int64)[1:n + 1] = np.arange(1, n + 1) if ids is None else ids
+        if binind is not None:
+            self.star_field("binind", np.int64)[1:n + 1] = binind
+
+    def compute_energy(self):
+        """E, J exactly as ComputeEnergy (reference cmc_utils.c:614-615), single rank."""
+        n = int(self.scalars()["N_MAX"])
+        phi, r = self.star_phi(), self.star_r()
+        vr, vt = self.star_field("vr"), self.star_field("vt")
+        self.star_field("E")[1:n + 1] = phi[1:n + 1] + 0.5 * (vr[1:n + 1] * vr[1:n + 1] + vt[1:n + 1] * vt[1:n + 1])
+        self.star_field("J")[1:n + 1] = r[1:n + 1] * vt[1:n + 1]
