@@ -1,0 +1,442 @@
+/* TEST INFRASTRUCTURE ONLY -- see cmc_oracle.h.  CPU restatement of the reference's
+ * sort / potential / new-orbit path with explicit arguments.  Compiled with -ffp-contract=off:
+ * the reference is built for baseline x86-64 (no FMA), so every double operation rounds once,
+ * and `long double` is the x87 80-bit format exactly as in the reference build. */
+#include "cmc_oracle.h"
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ partition ---- */
+
+/* cmc_utils.c:2299-2311 (findIndices): N blocks of blkSize over procs ranks, 1-based inclusive */
+static void orc_find_indices(long nblocks, int blk, int procs, int i, int *begin, int *end)
+{
+	long chunk = (nblocks / procs) * blk;
+	long extra = nblocks % procs;
+	if (i < extra) {
+		*begin = (int) (i * chunk + (long) i * blk + 1);
+		*end = (int) (*begin + chunk + blk - 1);
+	} else {
+		*begin = (int) (i * chunk + extra * blk + 1);
+		*end = (int) (*begin + chunk - 1);
+	}
+}
+
+/* cmc_utils.c:2319-2333 (findLimits): remainder N % blk goes to the last rank */
+void orc_find_limits(long N, int blk, int procs, int *Start, int *End)
+{
+	int nblocks = (int) (N / blk), rem = (int) (N % blk);
+	for (int i = 0; i < procs; i++)
+		orc_find_indices(nblocks, blk, procs, i, &Start[i], &End[i]);
+	End[procs - 1] += rem;
+}
+
+/* ------------------------------------------------------------------ potential ---- */
+
+/* cmc_utils.c:675-736 */
+long orc_potential_calculate(double *star_r, const double *star_m, double *star_phi, long N_MAX_in, long N_STAR,
+			     double *cenma_m, double *cenma_m_new, double madhoc, double orbit_r, double *Mtotal, double *Rtidal)
+{
+	long k = 1;
+	double mprev = 0.0;
+	while (star_r[k] < ORC_SF_INFINITY && k <= N_MAX_in) { /* :685-693 forward sequential sum */
+		mprev += star_m[k];
+		k++;
+	}
+	long N_MAX = k - 1;                                     /* :696 */
+	*cenma_m += *cenma_m_new;                               /* :699-700 */
+	*cenma_m_new = 0.0;
+	*Mtotal = mprev * madhoc + *cenma_m * madhoc;           /* :703 */
+	*Rtidal = orbit_r * pow(*Mtotal, 1.0 / 3.0);            /* :707 */
+	star_r[N_MAX + 1] = ORC_SF_INFINITY;                    /* :713-714 */
+	star_phi[N_MAX + 1] = 0.0;
+	mprev = *Mtotal;
+	for (k = N_MAX; k >= 1; k--) {                          /* :717-727 backward sequential recurrence */
+		star_phi[k] = star_phi[k + 1] - mprev * (1.0 / star_r[k] - 1.0 / star_r[k + 1]);
+		mprev -= star_m[k] / N_STAR;
+	}
+	star_phi[0] = star_phi[1] + *cenma_m * madhoc / star_r[1]; /* :729 */
+	return N_MAX;
+}
+
+/* ------------------------------------------------------------------ lookups ---- */
+
+/* cmc_nr.c:62-82: largest k in [kmin,kmax] with star_r[k] < r, probing ktry=(kmin+kmax+1)/2 */
+long orc_FindZero_r(const double *star_r, long kmin, long kmax, double r)
+{
+	do {
+		long ktry = (kmin + kmax + 1) / 2;
+		if (star_r[ktry] < r) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
+}
+
+/* cmc_utils.c:112-165 with SEARCH_GRID=0 (cmc_io.c:1738 default; grid init is commented out, cmc_io.c:3390-3396) */
+double orc_potential(const orc_tables_t *t, double r)
+{
+	const double *sr = t->r, *sp = t->phi;
+	if (r == 0.0) return sp[0];                                              /* :117-119 */
+	if (r < sr[1]) return sp[0] - (sp[0] - sp[1]) * sr[1] / r;               /* :121-123 */
+	long kmax = t->N_MAX + 1, kmin = 1, i;
+	i = (kmin == kmax - 1) ? kmin : orc_FindZero_r(sr, kmin, kmax, r);       /* :133-140 */
+	if (sr[i] > r || sr[i + 1] < r) {                                        /* :144-152 fatal in the reference */
+		fprintf(stderr, "orc_potential: bracket failed i=%ld r=%g\n", i, r);
+		return NAN;
+	}
+	if (i == 0) return sp[1];
+	return sp[i] + (sp[i + 1] - sp[i]) * (1.0 / sr[i] - 1.0 / r) / (1.0 / sr[i] - 1.0 / sr[i + 1]); /* :158-161 */
+}
+
+/* MPI_PHI_S, include/cmc/cmc.h:2175, for a double radius */
+static double phi_s(const orc_tables_t *t, double rad, long j)
+{
+	return (rad >= t->r[j] ? t->m[j] / rad : t->m[j] / t->r[j]) * (1.0 / t->N_STAR);
+}
+
+static inline double sqr_d(double a) { return a * a; } /* SQR under GCC: include/cmc/cmc.h:2026-2028 */
+
+/* cmc_utils.c:1654-1662.  x87 long double; SQR() takes and returns double, so (J/r) is rounded to
+ * double before squaring; the self term is long double only when r >= star_r[j] (the division has a
+ * long double operand) and plain double otherwise; the result is rounded to double. */
+double orc_function_q(const orc_tables_t *t, long j, long double r, long double pot, long double E, long double J)
+{
+	long double Jr = sqr_d((double) (J / r));
+	long double phis = (r >= t->r[j] ? t->m[j] / r : (long double) (t->m[j] / t->r[j])) * (1.0 / t->N_STAR);
+	double res = (double) (2.0 * (E - (pot + phis)) - Jr);
+	return res;
+}
+
+/* cmc_nr.c:316-383 */
+long orc_find_zero_Q(const orc_tables_t *t, long j, long kmin, long kmax, long double E, long double J)
+{
+	long double qmin = orc_function_q(t, j, t->r[kmin], t->phi[kmin], E, J);
+	long double qmax = orc_function_q(t, j, t->r[kmax], t->phi[kmax], E, J);
+	int increasing = qmin < qmax;                                            /* :342 */
+	do {
+		long ktry = (kmin + kmax + 1) / 2;
+		long double q = orc_function_q(t, j, t->r[ktry], t->phi[ktry], E, J);
+		int go_up = increasing ? (q < 0.e0) : (q > 0.e0);                /* :349 / :362 */
+		if (go_up) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
+}
+
+/* cmc_orbit.c:722-740 */
+static void set_a_b(const orc_tables_t *t, long index, long k, double *a, double *b)
+{
+	if (k == 0) {
+		*a = -t->cenma_m * t->madhoc;
+		*b = t->phi[1] + t->cenma_m * t->madhoc / t->r[1] + t->m[index] * t->madhoc / t->r[index];
+	} else {
+		double rk = t->r[k], rk1 = t->r[k + 1];
+		double Uk = t->phi[k] + phi_s(t, rk, index);
+		double Uk1 = t->phi[k + 1] + phi_s(t, rk1, index);
+		*a = (Uk1 - Uk) / (1. / rk1 - 1. / rk);
+		*b = (Uk / rk1 - Uk1 / rk) / (1. / rk1 - 1. / rk);
+	}
+}
+
+/* cmc_nr.c:279-302 (calc_pot_within_interval) + :393-405 (calc_vr_within_interval) */
+static double vr2_within_interval(const orc_tables_t *t, long index, long k, double E, double J, double r)
+{
+	double pot;
+	if (fabs(r - t->r[k]) < DBL_EPSILON) pot = t->phi[k];
+	else if (fabs(r - t->r[k + 1]) < DBL_EPSILON) pot = t->phi[k + 1];
+	else if (r < t->r[1]) pot = t->phi[0] - t->cenma_m * t->madhoc / r;
+	else pot = t->phi[k] + (t->phi[k + 1] - t->phi[k]) * (1.0 / t->r[k] - 1.0 / r) / (1.0 / t->r[k] - 1.0 / t->r[k + 1]);
+	return orc_function_q(t, index, r, pot, E, J);
+}
+
+/* cmc_nr.c:500-603: Brent-Dekker on [r_k, r_k+1] (GSL gsl_root_fsolver_brent, un-vendored dependency, version
+ * unpinned -- PARITY UNPINNED for this branch), stop on |hi-lo| < eps + eps*min(|lo|,|hi|) with
+ * eps = APSIDES_PRECISION = 1e-11 (cmc_io.c:1752), at most APSIDES_MAX_ITER = 100 iterations; in the last 10 the
+ * APSIDES_CONVERGENCE = 5e-13 delta test also applies (:556-569); then pick the end with vr^2 >= 0 (:590-597). */
+double orc_find_root_vr(const orc_tables_t *t, long index, long k, double E, double J)
+{
+	const double PREC = 1.0e-11, CONV = 5.e-13;
+	long iter = 100;
+	double a = t->r[k], b = t->r[k + 1], c = b;
+	double fa = vr2_within_interval(t, index, k, E, J, a), fb = vr2_within_interval(t, index, k, E, J, b), fc = fb;
+	double d = b - a, e = b - a, root = 0.5 * (a + b), lo = a, hi = b, prev_apsis = -1.0;
+	int not_converged = 1;
+	while (not_converged && iter) {
+		int ac_equal = 0;
+		double tol, m;
+		if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) { ac_equal = 1; c = a; fc = fa; d = b - a; e = b - a; }
+		if (fabs(fc) < fabs(fb)) { ac_equal = 1; a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+		tol = 0.5 * DBL_EPSILON * fabs(b);
+		m = 0.5 * (c - b);
+		if (fb == 0) { root = lo = hi = b; }
+		else if (fabs(m) <= tol) { root = b; if (b < c) { lo = b; hi = c; } else { lo = c; hi = b; } }
+		else {
+			if (fabs(e) < tol || fabs(fa) <= fabs(fb)) { d = m; e = m; }
+			else {
+				double p, q, r, s = fb / fa;
+				if (ac_equal) { p = 2 * m * s; q = 1 - s; }
+				else { q = fa / fc; r = fb / fc; p = s * (2 * m * q * (q - r) - (b - a) * (r - 1)); q = (q - 1) * (r - 1) * (s - 1); }
+				if (p > 0) q = -q; else p = -p;
+				double lim1 = 3 * m * q - fabs(tol * q), lim2 = fabs(e * q);
+				if (2 * p < (lim1 < lim2 ? lim1 : lim2)) { e = d; d = p / q; } else { d = m; e = m; }
+			}
+			a = b; fa = fb;
+			if (fabs(d) > tol) b += d; else b += (m > 0 ? +tol : -tol);
+			fb = vr2_within_interval(t, index, k, E, J, b);
+			root = b;
+			if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) c = a;
+			if (b < c) { lo = b; hi = c; } else { lo = c; hi = b; }
+		}
+		{
+			double al = fabs(lo), ah = fabs(hi);
+			double min_abs = ((lo > 0.0 && hi > 0.0) || (lo < 0.0 && hi < 0.0)) ? (al < ah ? al : ah) : 0;
+			not_converged = !(fabs(hi - lo) < PREC + PREC * min_abs);
+		}
+		iter--;
+		if (iter < 10) {
+			if (prev_apsis < 0.) prev_apsis = root;
+			else {
+				int delta_continue = !(fabs(root - prev_apsis) < CONV + CONV * fabs(root) || root == prev_apsis);
+				not_converged = not_converged && delta_continue;
+				prev_apsis = root;
+			}
+		}
+	}
+	double apsis = root;
+	if (vr2_within_interval(t, index, k, E, J, apsis) < 0.) {
+		if (vr2_within_interval(t, index, k, E, J, lo) < 0.) apsis = hi;
+		if (vr2_within_interval(t, index, k, E, J, hi) < 0.) apsis = lo;
+	}
+	return apsis;
+}
+
+/* cmc_orbit.c:30-59 */
+static long get_positive_Q_index(const orc_tables_t *t, long g_si, int is_new, double rnew, double E, double J)
+{
+	long ktemp = g_si;
+	if (is_new) ktemp = orc_FindZero_r(t->r, 0, t->N_MAX, rnew) + 1;         /* :39-41 */
+	double Q = orc_function_q(t, g_si, t->r[ktemp], t->phi[ktemp], E, J);
+	if (Q <= 0.0) {                                                           /* :46-57 linear scan from 0 */
+		ktemp = -1;
+		do {
+			ktemp++;
+			Q = orc_function_q(t, g_si, t->r[ktemp], t->phi[ktemp], E, J);
+		} while (Q <= 0.0 && ktemp <= t->N_MAX);
+		if (ktemp >= t->N_MAX) return -1;
+	}
+	return ktemp;
+}
+
+/* cmc_orbit.c:413-540 */
+void orc_calc_orbit_new(const orc_tables_t *t, long g_si, int is_new, double rnew_of_new, double E, double J, orc_orbit_t *o)
+{
+	o->used_brent = 0;
+	long ktemp = get_positive_Q_index(t, g_si, is_new, rnew_of_new, E, J);
+	int circular = 0;
+	double rmin = 0, rmax = 0, dQdr_min = 0, dQdr_max = 0, a, b;
+	long kmin = 0, kmax = 0;
+	if (ktemp <= -1) {
+		circular = 1;                                                     /* :424-438 */
+	} else {
+		kmin = orc_find_zero_Q(t, g_si, 0, ktemp, E, J);                  /* :441 */
+		kmax = orc_find_zero_Q(t, g_si, ktemp, t->N_MAX + 1, E, J);       /* :444 */
+		double rkmin = t->r[kmin], rk1min = t->r[kmin + 1], rkmax = t->r[kmax], rk1max = t->r[kmax + 1];
+		set_a_b(t, g_si, kmin, &a, &b);                                   /* :456 */
+		double inside = a * a - 2.0 * J * J * (b - E);
+		if (inside < 0.0) {                                               /* :459-474 */
+			rmin = -1.0 * J * J / a;
+			if (rmin < rkmin || rmin > rk1min) { rmin = orc_find_root_vr(t, g_si, kmin, E, J); o->used_brent++; }
+		} else {
+			rmin = J * J / (-a + sqrt(inside));                       /* :476 */
+		}
+		dQdr_min = 2.0 * J * J / (rmin * rmin * rmin) + 2.0 * a / (rmin * rmin); /* :479 */
+		set_a_b(t, g_si, kmax, &a, &b);                                   /* :482 */
+		inside = a * a - 2.0 * J * J * (b - E);
+		if (inside < 0.0) {                                               /* :485-500 */
+			rmax = -a / (2.0 * (b - E));
+			if (rmax < rkmax || rmax > rk1max) { rmax = orc_find_root_vr(t, g_si, kmax, E, J); o->used_brent++; }
+		} else {
+			rmax = (-a + sqrt(inside)) / (2.0 * (b - E));             /* :502 */
+		}
+		dQdr_max = 2.0 * J * J / (rmax * rmax * rmax) + 2.0 * a / (rmax * rmax); /* :505 */
+		if (rmin > rmax || dQdr_min <= 0. || dQdr_max >= 0.) circular = 1; /* :510 */
+	}
+	if (circular) {                                                           /* :520-528 */
+		o->rp = o->ra = t->r[g_si];
+		o->kmin = o->kmax = g_si;
+		o->dQdrp = o->dQdra = 0.0;
+		o->circular_flag = 1;
+	} else {
+		o->rp = rmin; o->ra = rmax; o->kmin = kmin; o->kmax = kmax;
+		o->dQdrp = dQdr_min; o->dQdra = dQdr_max; o->circular_flag = 0;
+	}
+}
+
+/* ------------------------------------------------------------------ orbit step ---- */
+
+/* cmc_evolution_thr.c:784-937 */
+double orc_get_positions(const orc_tables_t *t, long n_local, const long *g_idx, const unsigned char *is_new,
+			 const double *E_in, const double *J_in, const double *vr_in, const double *vt_in, const double *rnew_in,
+			 double Rtidal, const double *draws, long n_draws, const long *csr_off_in, long *draw_off_out,
+			 int *status, double *rnew, double *vrnew, double *vtnew, double *X_out, double *r_peri, double *r_apo,
+			 long *kmin_out, long *kmax_out, long *n_brent)
+{
+	double max_rad = 0.0;
+	long pos = 0, brent = 0;
+	for (long j = 0; j < n_local; j++) {
+		long g_j = g_idx[j];
+		if (csr_off_in) pos = csr_off_in[j];
+		if (draw_off_out) draw_off_out[j] = pos;
+		double E = E_in[j] + phi_s(t, t->r[g_j], g_j);                    /* :806 */
+		double J = J_in[j];
+		if (kmin_out) kmin_out[j] = -1;
+		if (kmax_out) kmax_out[j] = -1;
+		X_out[j] = r_peri[j] = r_apo[j] = NAN;                            /* "not written" marker for the caller */
+		if (t->m[g_j] < ORC_ZERO) {                                       /* :816-820 */
+			status[j] = ORC_ST_MASSLESS;
+			rnew[j] = ORC_SF_INFINITY; vrnew[j] = 0.0; vtnew[j] = 0.0;  /* remove_star_center :760-765 */
+			continue;
+		}
+		if (E >= 0.0) {                                                   /* :823-829 */
+			status[j] = ORC_ST_UNBOUND;
+			rnew[j] = ORC_SF_INFINITY; vrnew[j] = 0.0; vtnew[j] = 0.0;  /* remove_star :662-664 */
+			continue;
+		}
+		orc_orbit_t o;
+		orc_calc_orbit_new(t, g_j, is_new ? is_new[j] : 0, rnew_in ? rnew_in[j] : 0.0, E, J, &o); /* :832 */
+		brent += o.used_brent;
+		if (kmin_out) kmin_out[j] = o.kmin;
+		if (kmax_out) kmax_out[j] = o.kmax;
+		if (o.circular_flag == 1) {                                       /* :835-839 */
+			status[j] = ORC_ST_CIRCULAR;
+			rnew[j] = t->r[g_j]; vrnew[j] = vr_in[j]; vtnew[j] = vt_in[j];
+			continue;
+		}
+		double rmin = o.rp, rmax = o.ra, dQdr_min = o.dQdrp, dQdr_max = o.dQdra;
+		if (rmax >= Rtidal) {                                             /* :848-855 */
+			status[j] = ORC_ST_TIDAL;
+			r_apo[j] = rmax; r_peri[j] = rmin;
+			rnew[j] = ORC_SF_INFINITY; vrnew[j] = 0.0; vtnew[j] = 0.0;
+			continue;
+		}
+		double g1 = sqrt(3.0 * (rmax - rmin) / dQdr_min);                 /* :857-860 */
+		double g2 = sqrt(-3.0 * (rmax - rmin) / dQdr_max);
+		double F = 1.2 * (g1 >= g2 ? g1 : g2);
+		double r = 0.0, vr = 0.0, X = 0.0;
+		long k;
+		for (k = 1; k <= ORC_N_TRY; k++) {                                /* :862-888 */
+			if (pos + 2 > (csr_off_in ? csr_off_in[j + 1] : n_draws)) { fprintf(stderr, "orc_get_positions: out of draws at star %ld\n", j); status[j] = ORC_ST_NTRY; break; }
+			X = draws[pos++];
+			double s0 = 2.0 * X - 1.0;
+			double g0 = F * draws[pos++];
+			r = 0.5 * (rmin + rmax) + 0.25 * (rmax - rmin) * (3.0 * s0 - s0 * s0 * s0);
+			double pot = orc_potential(t, r) + phi_s(t, r, g_j);
+			double drds = 0.25 * (rmax - rmin) * (3.0 - 3.0 * s0 * s0);
+			double Q = 2.0 * E - 2.0 * pot - J * J / r / r;
+			if (Q >= 0.0) vr = sqrt(Q); else vr = 0;
+			if (g0 < 1.0 / vr * drds) break;
+		}
+		if (k == ORC_N_TRY + 1 || status[j] == ORC_ST_NTRY) { status[j] = ORC_ST_NTRY; rnew[j] = NAN; vrnew[j] = vtnew[j] = NAN; continue; }
+		X_out[j] = X; r_peri[j] = rmin; r_apo[j] = rmax;                  /* :918-920 */
+		if (draws[pos++] < 0.5) vr = -vr;                                 /* :923-924 */
+		status[j] = ORC_ST_OK;
+		rnew[j] = r; vrnew[j] = vr; vtnew[j] = J / r;                     /* :926-931 */
+		if (r > max_rad) max_rad = r;
+	}
+	if (draw_off_out) draw_off_out[n_local] = pos;
+	if (n_brent) *n_brent = brent;
+	return max_rad;
+}
+
+/* ------------------------------------------------------------------ sort ---- */
+
+typedef struct { double key; long idx; } keyidx_t;
+static int cmp_keyidx(const void *a, const void *b)
+{
+	const keyidx_t *x = a, *y = b;
+	if (x->key < y->key) return -1;       /* compare_type, cmc_sort.c:245-250 */
+	if (x->key > y->key) return 1;
+	return (x->idx > y->idx) - (x->idx < y->idx); /* ties: original order (libc qsort leaves this unspecified; cmc_utils.c:670 assumes none) */
+}
+
+long orc_sort_stars(unsigned char *star1, long n, long sizeof_star, long key_off, long binind_off,
+		    unsigned char *binary1, long n_bin_dim, long sizeof_binary, long *n_bin_out, long *perm_out)
+{
+	keyidx_t *ki = malloc((n > 0 ? n : 1) * sizeof(*ki));
+	for (long i = 0; i < n; i++) { memcpy(&ki[i].key, star1 + i * sizeof_star + key_off, 8); ki[i].idx = i; }
+	qsort(ki, n, sizeof(*ki), cmp_keyidx);                                    /* cmc_sort.c:407 */
+	unsigned char *tmp = malloc((n > 0 ? n : 1) * sizeof_star);
+	for (long i = 0; i < n; i++) memcpy(tmp + i * sizeof_star, star1 + ki[i].idx * sizeof_star, sizeof_star);
+	long n_new = n;
+	while (n_new > 0 && ki[n_new - 1].key == ORC_SF_INFINITY) n_new--;       /* remove_stripped_stars, :343-354 */
+	/* binaries follow their star: packed in star order (:521-538, 716-729), numbered from 1 (:571-579, 757-766),
+	 * the rest of binary[1..n_bin_dim-1] zeroed (:541) */
+	long nb = 0;
+	if (binary1) {
+		unsigned char *btmp = malloc((size_t) (n_bin_dim > 0 ? n_bin_dim : 1) * sizeof_binary);
+		for (long i = 0; i < n_new; i++) {
+			long bi; memcpy(&bi, tmp + i * sizeof_star + binind_off, 8);
+			if (bi > 0) {
+				memcpy(btmp + nb * sizeof_binary, binary1 + (bi - 1) * sizeof_binary, sizeof_binary);
+				nb++;
+				memcpy(tmp + i * sizeof_star + binind_off, &nb, 8);
+			}
+		}
+		memset(binary1, 0, (size_t) (n_bin_dim - 1) * sizeof_binary);
+		memcpy(binary1, btmp, (size_t) nb * sizeof_binary);
+		free(btmp);
+	}
+	memcpy(star1, tmp, (size_t) n * sizeof_star);
+	if (perm_out) for (long i = 0; i < n; i++) perm_out[i] = ki[i].idx;
+	if (n_bin_out) *n_bin_out = nb;
+	free(tmp); free(ki);
+	return n_new;
+}
+
+/* ------------------------------------------------------------------ taus113 ---- */
+
+const unsigned int orc_JPoly_2_20[4] = {0x0c382e31, 0x1b040425, 0x0b49a509, 0x0173f6b0}; /* taus113-v2.c:70 */
+const unsigned int orc_JPoly_2_80[4] = {0x487cf69c, 0x00be6310, 0x04bfe2bb, 0x000824f9}; /* taus113-v2.c:74 */
+
+/* one step of the four Tausworthe components (L'Ecuyer 1999 taus113; taus113-v2.c:166-181):
+ * component c: b = ((z << q) ^ z) >> (k - s);  z = ((z & mask) << s) ^ b */
+static void t113_step(unsigned int z[4])
+{
+	static const int q[4] = {6, 2, 13, 3}, rs[4] = {13, 27, 21, 12}, s[4] = {18, 2, 7, 13};
+	static const unsigned int mask[4] = {4294967294u, 4294967288u, 4294967280u, 4294967168u};
+	for (int c = 0; c < 4; c++) {
+		unsigned int b = ((z[c] << q[c]) ^ z[c]) >> rs[c];
+		z[c] = ((z[c] & mask[c]) << s[c]) ^ b;
+	}
+}
+
+double orc_t113_dbl(unsigned int z[4])
+{
+	t113_step(z);
+	return (double) (z[0] ^ z[1] ^ z[2] ^ z[3]) / 4294967296.0;              /* :191-193 */
+}
+
+void orc_t113_seed(unsigned long s, unsigned int z[4])                        /* :197-216 */
+{
+	static const unsigned int lo[4] = {2, 8, 16, 128};
+	if (s == 0) s = 1;
+	unsigned long v = s;
+	for (int c = 0; c < 4; c++) {
+		v = (69069UL * v) & 0xffffffffUL;
+		if (v < lo[c]) v += lo[c];
+		z[c] = (unsigned int) v;
+	}
+	for (int i = 0; i < 10; i++) t113_step(z);
+}
+
+void orc_t113_jump(unsigned int z[4], const unsigned int jpoly[4])            /* :253-270 */
+{
+	unsigned int acc[4] = {0, 0, 0, 0}, st[4] = {z[0], z[1], z[2], z[3]};
+	for (int bit = 0; bit < 32; bit++) {
+		for (int c = 0; c < 4; c++)
+			if (jpoly[c] & (1u << bit)) acc[c] ^= st[c];
+		t113_step(st);
+	}
+	memcpy(z, acc, sizeof(acc));
+}

@@ -1,0 +1,95 @@
+/* TEST INFRASTRUCTURE ONLY.  CPU restatement ("port") of the reference's per-timestep
+ * data-parallel core: radius sort, potential rebuild, new-orbit step.  Explicit arguments
+ * instead of the reference's process globals; every function cites the reference file:line
+ * it follows (paths relative to the reference root).
+ *
+ * Pinning: the reference's own tests hold no golden vector for this path, so this
+ * port is pinned against the reference ITSELF, compiled unmodified into oracle/_ref/libcmc_ref.so and
+ * run on identical inputs (tests/test_oracle_vs_ref.py), and against fixtures that run generated
+ * (tests/golden/, tests/golden/make_golden.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it. */
+#ifndef CMC_ORACLE_H
+#define CMC_ORACLE_H
+
+#define ORC_SF_INFINITY 1.0e10 /* include/cmc/cmc.h:58 */
+#define ORC_ZERO 1.0e-20       /* include/cmc/cmc.h:60 */
+#define ORC_N_TRY 50000        /* include/cmc/cmc.h:64 */
+
+/* per-star outcome of the orbit step (the branches of get_positions_loop, cmc_evolution_thr.c:802-933) */
+enum {
+	ORC_ST_OK = 0,        /* new radius sampled                               :857-933 */
+	ORC_ST_MASSLESS = 1,  /* star_m < ZERO -> destroy_obj                     :816-820 */
+	ORC_ST_UNBOUND = 2,   /* E >= 0 -> remove_star                            :823-829 */
+	ORC_ST_CIRCULAR = 3,  /* circular_flag -> keeps r, vr, vt                 :835-839 */
+	ORC_ST_TIDAL = 4,     /* rmax >= Rtidal -> remove_star                    :848-855 */
+	ORC_ST_NTRY = 5       /* N_TRY exceeded (fatal in the reference)          :890-893 */
+};
+
+/* the replicated tables every function on the path reads (include/cmc/cmc_vars.h:218-226) */
+typedef struct {
+	const double *r, *m, *phi; /* star_r, star_m, star_phi: [0] sentinel, [1..N_MAX], [N_MAX+1] = SF_INFINITY/0 */
+	long N_MAX;
+	long N_STAR;               /* clus.N_STAR: the 1/N_STAR in MPI_PHI_S */
+	double cenma_m;            /* cenma.m */
+	double madhoc;             /* 1/N_STAR (cmc_utils.c:1183) */
+} orc_tables_t;
+
+typedef struct { /* orbit_rs_t, include/cmc/cmc.h:1621-1650 */
+	double rp, ra, dQdrp, dQdra;
+	long kmax, kmin;
+	int circular_flag;
+	int used_brent; /* not in the reference: counts find_root_vr fallbacks */
+} orc_orbit_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* partition arithmetic: findLimits/findIndices cmc_utils.c:2299-2333 (== mpiFindIndicesCustom cmc_mpi.c:77-114) */
+void orc_find_limits(long N, int blk, int procs, int *Start, int *End);
+
+/* potential_calculate, cmc_utils.c:675-736.  star_r[N_MAX+1], star_phi[0..N_MAX+1] are written.  Returns new N_MAX. */
+long orc_potential_calculate(double *star_r, const double *star_m, double *star_phi, long N_MAX_in, long N_STAR,
+			     double *cenma_m, double *cenma_m_new, double madhoc, double orbit_r, double *Mtotal, double *Rtidal);
+
+long orc_FindZero_r(const double *star_r, long kmin, long kmax, double r);          /* cmc_nr.c:62-82 */
+double orc_potential(const orc_tables_t *t, double r);                               /* cmc_utils.c:112-165 */
+double orc_function_q(const orc_tables_t *t, long j, long double r, long double pot, long double E, long double J); /* cmc_utils.c:1654-1662 */
+long orc_find_zero_Q(const orc_tables_t *t, long j, long kmin, long kmax, long double E, long double J);           /* cmc_nr.c:316-383 */
+/* calc_orbit_new, cmc_orbit.c:413-540.  g_si = global index of the star; is_new/rnew: star created this step (cmc_orbit.c:39-41) */
+void orc_calc_orbit_new(const orc_tables_t *t, long g_si, int is_new, double rnew_of_new, double E, double J, orc_orbit_t *o);
+double orc_find_root_vr(const orc_tables_t *t, long index, long k, double E, double J); /* cmc_nr.c:500-603 */
+
+/* get_positions_loop, cmc_evolution_thr.c:784-937, for n_local stars whose global indices are g_idx[0..n_local).
+ * E_in is star[j].E (WITHOUT the self term; the loop adds it, :806).
+ * draws: the uniform stream the loop consumes, in order.  draw_off[j] (out, n_local+1 entries) = index of the first
+ * draw star j consumed; draw_off[n_local] = total consumed.  If draws_per_star_off != NULL it is used as INPUT
+ * (CSR offsets; star j reads draws[off[j]..off[j+1])) instead of the single sequential stream.
+ * Outputs are per-star arrays; stars whose status is not ORC_ST_OK/CIRCULAR get rnew = SF_INFINITY, vrnew = vtnew = 0
+ * like remove_star/destroy_obj do (cmc_evolution_thr.c:662-664, 760-765).
+ * Returns max_rad. */
+double orc_get_positions(const orc_tables_t *t, long n_local, const long *g_idx, const unsigned char *is_new,
+			 const double *E_in, const double *J_in, const double *vr_in, const double *vt_in, const double *rnew_in,
+			 double Rtidal, const double *draws, long n_draws, const long *csr_off_in, long *draw_off_out,
+			 int *status, double *rnew, double *vrnew, double *vtnew, double *X, double *r_peri, double *r_apo,
+			 long *kmin_out, long *kmax_out, long *n_brent);
+
+/* Radius sort of a local star array + binary re-pack, single rank or the global result of the P-rank
+ * sample sort (cmc_sort.c:375-629 + load_balance :634-791): ascending by the double at key_off, trailing
+ * keys == SF_INFINITY trimmed (:343-354), binaries compacted in star order with binind = 1,2,... (:571-579, 757-766),
+ * binary[nb+1..n_bin_dim-1] zeroed (:541).  star/binary point at element 1 (the reference passes star+1, binary+1).
+ * perm_out[i] = original 0-based position of the record now at i.  Returns the trimmed count. */
+long orc_sort_stars(unsigned char *star1, long n, long sizeof_star, long key_off, long binind_off,
+		    unsigned char *binary1, long n_bin_dim, long sizeof_binary, long *n_bin_out, long *perm_out);
+
+/* taus113 (src/libs/taus113-v2.c:166-216 seeding, :218-251 generator, :253-270 jump) */
+void orc_t113_seed(unsigned long s, unsigned int z[4]);
+double orc_t113_dbl(unsigned int z[4]);
+void orc_t113_jump(unsigned int z[4], const unsigned int jpoly[4]);
+extern const unsigned int orc_JPoly_2_20[4], orc_JPoly_2_80[4];
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -194,9 +194,10 @@ EXPORT void ref_calc_orbit_new(long index, double E, double J, double *out)
 EXPORT double ref_find_root_vr(long index, long k, double E, double J) { return find_root_vr(index, k, E, J); }
 
 /* taus113 known-answer access (src/libs/taus113-v2.c:166-216, 253-270) */
-EXPORT void ref_rng_reset(unsigned long seed, unsigned int *z) { struct rng_t113_state s; reset_rng_t113_new(seed, &s); z[0] = s.z[0]; z[1] = s.z[1]; z[2] = s.z[2]; z[3] = s.z[3]; }
-EXPORT void ref_rng_jump80(unsigned int *z) { struct rng_t113_state s; memcpy(s.z, z, 16); s = rng_t113_jump(s, JPoly_2_80); memcpy(z, s.z, 16); }
-EXPORT double ref_rng_next(unsigned int *z) { struct rng_t113_state s; memcpy(s.z, z, 16); double u = ref_real_rng_t113_dbl_new(&s); memcpy(z, s.z, 16); return u; }
+EXPORT void ref_rng_reset(unsigned long seed, unsigned int *z) { struct rng_t113_state s; int i; reset_rng_t113_new(seed, &s); for (i = 0; i < 4; i++) z[i] = (unsigned int) s.z[i]; }
+EXPORT void ref_rng_jump80(unsigned int *z) { struct rng_t113_state s; int i; for (i = 0; i < 4; i++) s.z[i] = z[i]; s = rng_t113_jump(s, JPoly_2_80); for (i = 0; i < 4; i++) z[i] = (unsigned int) s.z[i]; }
+EXPORT void ref_rng_jump20(unsigned int *z) { struct rng_t113_state s; int i; for (i = 0; i < 4; i++) s.z[i] = z[i]; s = rng_t113_jump(s, JPoly_2_20); for (i = 0; i < 4; i++) z[i] = (unsigned int) s.z[i]; }
+EXPORT double ref_rng_next(unsigned int *z) { struct rng_t113_state s; int i; double u; for (i = 0; i < 4; i++) s.z[i] = z[i]; u = ref_real_rng_t113_dbl_new(&s); for (i = 0; i < 4; i++) z[i] = (unsigned int) s.z[i]; return u; }
 
 /* timing leg for bench.py: one pass of orbit step -> (caller refreshes r) -> sort -> post_sort_comm -> potential.
  * Brackets follow timeStartSimple/timeEndSimple (cmc_utils.c:1681-1707): barrier, wall clock. */

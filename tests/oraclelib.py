@@ -1,0 +1,130 @@
+"""ctypes binding to oracle/libcmc_oracle.so (the CPU restatement).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(_HERE, "..", "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libcmc_oracle.so")
+
+SF_INFINITY = 1.0e10
+ZERO = 1.0e-20
+ST_OK, ST_MASSLESS, ST_UNBOUND, ST_CIRCULAR, ST_TIDAL, ST_NTRY = range(6)
+
+
+class Tables(C.Structure):
+    _fields_ = [("r", C.c_void_p), ("m", C.c_void_p), ("phi", C.c_void_p), ("N_MAX", C.c_long), ("N_STAR", C.c_long),
+                ("cenma_m", C.c_double), ("madhoc", C.c_double)]
+
+
+class Orbit(C.Structure):
+    _fields_ = [("rp", C.c_double), ("ra", C.c_double), ("dQdrp", C.c_double), ("dQdra", C.c_double),
+                ("kmax", C.c_long), ("kmin", C.c_long), ("circular_flag", C.c_int), ("used_brent", C.c_int)]
+
+
+def _build():
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "cmc_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libcmc_oracle.so"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _build()
+        L = C.CDLL(ORACLE_SO)
+        L.orc_find_limits.argtypes = [C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_potential_calculate.restype = C.c_long
+        L.orc_potential_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p,
+                                              C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_FindZero_r.restype = C.c_long
+        L.orc_FindZero_r.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_double]
+        L.orc_potential.restype = C.c_double
+        L.orc_potential.argtypes = [C.POINTER(Tables), C.c_double]
+        L.orc_calc_orbit_new.argtypes = [C.POINTER(Tables), C.c_long, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(Orbit)]
+        L.orc_find_root_vr.restype = C.c_double
+        L.orc_find_root_vr.argtypes = [C.POINTER(Tables), C.c_long, C.c_long, C.c_double, C.c_double]
+        L.orc_get_positions.restype = C.c_double
+        L.orc_get_positions.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 7 + [C.c_double, C.c_void_p, C.c_long] + [C.c_void_p] * 12
+        L.orc_sort_stars.restype = C.c_long
+        L.orc_sort_stars.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p]
+        L.orc_t113_seed.argtypes = [C.c_ulong, C.c_void_p]
+        L.orc_t113_dbl.restype = C.c_double
+        L.orc_t113_dbl.argtypes = [C.c_void_p]
+        L.orc_t113_jump.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def find_limits(N, blk, procs):
+    S = np.zeros(procs, np.int32); E = np.zeros(procs, np.int32)
+    lib().orc_find_limits(N, blk, procs, _p(S), _p(E))
+    return S, E
+
+
+def potential_calculate(star_r, star_m, N_MAX_in, N_STAR, cenma_m=0.0, cenma_m_new=0.0, orbit_r=1e6):
+    """star_r/star_m: full tables with sentinel at [0]; star_r is modified at [N_MAX+1] like the reference does."""
+    phi = np.zeros_like(star_r)
+    cm = C.c_double(cenma_m); cmn = C.c_double(cenma_m_new); Mt = C.c_double(); Rt = C.c_double()
+    nmax = lib().orc_potential_calculate(_p(star_r), _p(star_m), _p(phi), N_MAX_in, N_STAR, C.addressof(cm), C.addressof(cmn),
+                                         1.0 / N_STAR, orbit_r, C.addressof(Mt), C.addressof(Rt))
+    return dict(N_MAX=nmax, phi=phi, Mtotal=Mt.value, Rtidal=Rt.value, cenma_m=cm.value)
+
+
+def tables(star_r, star_m, star_phi, N_MAX, N_STAR, cenma_m=0.0):
+    t = Tables(_p(star_r), _p(star_m), _p(star_phi), N_MAX, N_STAR, cenma_m, 1.0 / N_STAR)
+    t._keep = (star_r, star_m, star_phi)
+    return t
+
+
+def get_positions(t, g_idx, E, J, vr, vt, Rtidal, draws, csr_off=None, is_new=None, rnew_in=None):
+    n = len(g_idx)
+    g_idx = np.ascontiguousarray(g_idx, np.int64)
+    out = dict(draw_off=np.zeros(n + 1, np.int64), status=np.zeros(n, np.int32), rnew=np.zeros(n), vrnew=np.zeros(n), vtnew=np.zeros(n),
+               X=np.zeros(n), r_peri=np.zeros(n), r_apo=np.zeros(n), kmin=np.zeros(n, np.int64), kmax=np.zeros(n, np.int64))
+    nb = C.c_long(0)
+    draws = np.ascontiguousarray(draws, np.float64)
+    if csr_off is not None:
+        csr_off = np.ascontiguousarray(csr_off, np.int64)
+    out["max_rad"] = lib().orc_get_positions(
+        C.byref(t), n, _p(g_idx), _p(is_new), _p(np.ascontiguousarray(E)), _p(np.ascontiguousarray(J)), _p(np.ascontiguousarray(vr)),
+        _p(np.ascontiguousarray(vt)), _p(rnew_in), Rtidal, _p(draws), len(draws), _p(csr_off), _p(out["draw_off"]),
+        _p(out["status"]), _p(out["rnew"]), _p(out["vrnew"]), _p(out["vtnew"]), _p(out["X"]), _p(out["r_peri"]), _p(out["r_apo"]),
+        _p(out["kmin"]), _p(out["kmax"]), C.addressof(nb))
+    out["n_brent"] = nb.value
+    return out
+
+
+def sort_stars(star1, n, sizeof_star, key_off, binind_off, binary1=None, n_bin_dim=0, sizeof_binary=464):
+    """star1: uint8 array (>= n*sizeof_star) starting at element 1; sorted in place.  Returns (n_new, n_bin, perm)."""
+    perm = np.zeros(n, np.int64)
+    nb = C.c_long(0)
+    n_new = lib().orc_sort_stars(_p(star1), n, sizeof_star, key_off, binind_off, _p(binary1), n_bin_dim, sizeof_binary, C.addressof(nb), _p(perm))
+    return n_new, nb.value, perm
+
+
+class Taus113:
+    JPOLY_2_80 = np.array([0x487cf69c, 0x00be6310, 0x04bfe2bb, 0x000824f9], np.uint32)
+    JPOLY_2_20 = np.array([0x0c382e31, 0x1b040425, 0x0b49a509, 0x0173f6b0], np.uint32)
+
+    def __init__(self, seed, rank=0):
+        self.z = np.zeros(4, np.uint32)
+        lib().orc_t113_seed(seed, _p(self.z))
+        for _ in range(rank):
+            self.jump(self.JPOLY_2_80)
+
+    def jump(self, poly):
+        lib().orc_t113_jump(_p(self.z), _p(poly))
+
+    def dbl(self):
+        return lib().orc_t113_dbl(_p(self.z))
+
+    def draws(self, n):
+        return np.array([self.dbl() for _ in range(n)])
