@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's interface for the sort / potential / new-orbit path.
+
+The reference exposes this path as four ``void f(void)`` functions working on process globals
+(reference src/cmc/cmc.c:311,335,339,344; globals in include/cmc/cmc_vars.h).  :class:`Cluster` holds those globals as
+attributes with the reference's names (``star``, ``binary``, ``star_r``, ``star_m``, ``star_phi``, ``clus``, ``cenma``,
+``Mtotal``, ``Rtidal``, ``max_r`` ...) and offers the four functions under their own names.  Each of them forwards to
+the C ABI of ``libcmcb200.so`` -- the same entry points the C shim in INTEGRATION.md binds.
+
+Two ways to run:
+  * host-buffer form (``new_orbits_calculate`` / ``qsorts_new`` / ``post_sort_comm`` / ``calc_potential_new``): the drop-in
+    behaviour, every call copies its inputs to the GPU and its outputs back;
+  * resident form (``upload`` once, then ``dev_*`` / ``dev_step``): the arrays stay in HBM across timesteps.
+"""
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import lib as _lib
+from .layout import (BINARY_DTYPE_SIZE, SF_INFINITY, STAR_DTYPE_SIZE, ZERO, binary_field, star_field)
+
+
+def _host_array(shape, dtype, pinned):
+    if pinned:
+        import torch
+        t = torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        a = t.numpy()
+        a._keep = t
+        return a
+    return np.zeros(shape, dtype)
+
+
+class Cluster:
+    def __init__(self, n_star, n_star_dim=None, n_bin_dim=None, device=0, min_chunk=40, orbit_r=1.0e6, pinned=False, stream=None):
+        L = _lib.load()
+        self.L = L
+        # N_STAR_DIM_OPT = 1.5 * (1 + N/P + 2 N_bin/P), reference src/cmc/cmc_io.c:2092-2099
+        self.N_STAR_DIM = int(n_star_dim or int(1.5 * (n_star + 2)) + 16)
+        self.N_BIN_DIM = int(n_bin_dim or 16)
+        self.MIN_CHUNK_SIZE = min_chunk
+        self.star = _host_array((self.N_STAR_DIM, STAR_DTYPE_SIZE), np.uint8, pinned)
+        self.binary = _host_array((self.N_BIN_DIM, BINARY_DTYPE_SIZE), np.uint8, pinned)
+        self.star_r = _host_array((self.N_STAR_DIM,), np.float64, pinned)
+        self.star_m = _host_array((self.N_STAR_DIM,), np.float64, pinned)
+        self.star_phi = _host_array((self.N_STAR_DIM,), np.float64, pinned)
+        self.clus = SimpleNamespace(N_STAR=n_star, N_STAR_NEW=n_star, N_MAX=n_star, N_MAX_NEW=n_star, N_BINARY=0)
+        self.cenma = SimpleNamespace(m=0.0, m_new=0.0, E=0.0, E_new=0.0)
+        self.madhoc = 1.0 / float(n_star)           # reference src/cmc/cmc_utils.c:1183
+        self.orbit_r = orbit_r
+        self.Mtotal = 1.0
+        self.Rtidal = orbit_r
+        self.max_r = 0.0
+        self.N_b_local = 0
+        self.myid, self.procs = 0, 1
+        self.Start, self.End = np.array([1], np.int32), np.array([n_star], np.int32)
+        self.mpiBegin, self.mpiEnd = 1, n_star
+        self.tcount = 1
+        self.last_orbit = None
+        self.last_status = None
+        ctx = C.c_void_p()
+        _lib.check(L.cmcb200_create(C.byref(ctx), device, self.N_STAR_DIM, self.N_BIN_DIM), "cmcb200_create")
+        self.ctx = ctx
+        if stream is not None:
+            _lib.check(L.cmcb200_set_stream(ctx, C.c_void_p(stream)), "cmcb200_set_stream")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.cmcb200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- field views -------------------------------------------------------------------------------------------
+    def field(self, name):
+        return star_field(self.star, name)
+
+    def bfield(self, name):
+        return binary_field(self.binary, name)
+
+    def load(self, r, vr, vt, m_star_units, binind=None, ids=None):
+        """Fill the arrays from a radius-sorted cluster the way the reference's start-up does
+        (sentinels: src/cmc/cmc_fits.c:128-136).  m_star_units = obj_m * N_STAR."""
+        n = len(r)
+        assert n == self.clus.N_STAR and n + 2 <= self.N_STAR_DIM
+        self.star_r[0], self.star_m[0] = ZERO, 0.0
+        self.star_r[1:n + 1], self.star_m[1:n + 1] = r, m_star_units
+        self.star_r[n + 1], self.star_m[n + 1] = SF_INFINITY, 0.0
+        for name, val in (("r", r), ("vr", vr), ("vt", vt), ("m", m_star_units)):
+            self.field(name)[1:n + 1] = val
+        self.field("r")[0] = ZERO
+        self.field("r")[n + 1] = SF_INFINITY
+        self.field("id")[1:n + 1] = np.arange(1, n + 1) if ids is None else ids
+        if binind is not None:
+            self.field("binind")[1:n + 1] = binind
+            self.N_b_local = self.clus.N_BINARY = int((np.asarray(binind) > 0).sum())
+
+    # ---- the reference's four entry points, host-buffer form ------------------------------------------------------
+    def calc_potential_new(self):
+        """calc_potential_new -> potential_calculate (reference src/cmc/cmc_utils.c:2006-2012, 675-736)."""
+        nmax = C.c_long(self.clus.N_MAX)
+        cm, cmn, Mt, Rt = C.c_double(self.cenma.m), C.c_double(self.cenma.m_new), C.c_double(), C.c_double()
+        _lib.check(self.L.cmcb200_calc_potential_new(self.ctx, self.star_r.ctypes.data, self.star_m.ctypes.data, self.star_phi.ctypes.data,
+                                                     C.byref(nmax), self.clus.N_STAR, C.byref(cm), C.byref(cmn), self.orbit_r,
+                                                     C.byref(Mt), C.byref(Rt)), "calc_potential_new")
+        self.clus.N_MAX = nmax.value
+        self.cenma.m, self.cenma.m_new = cm.value, cmn.value
+        self.Mtotal, self.Rtidal = Mt.value, Rt.value
+        S, E = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        self.L.cmcb200_find_limits(self.clus.N_MAX, self.MIN_CHUNK_SIZE, 1, S.ctypes.data, E.ctypes.data)  # mpiFindIndicesCustom, :2011
+        self.mpiBegin, self.mpiEnd = int(S[0]), int(E[0])
+        return self.clus.N_MAX
+
+    def qsorts_new(self):
+        """qsorts_new -> sample_sort (reference src/cmc/cmc_utils.c:2232-2254) fused with post_sort_comm's r/m extraction."""
+        n = C.c_long(self.clus.N_MAX_NEW)
+        nb = C.c_long(self._n_bin_in_use())
+        _lib.check(self.L.cmcb200_qsorts_new(self.ctx, self.star[1:].ctypes.data, C.byref(n), self.binary[1:].ctypes.data, self.N_BIN_DIM,
+                                             C.byref(nb), self.star_r.ctypes.data, self.star_m.ctypes.data), "qsorts_new")
+        self.clus.N_MAX = self.clus.N_MAX_NEW = n.value
+        self.N_b_local = nb.value
+        self.Start[0], self.End[0] = 1, n.value    # findLimits inside sample_sort (cmc_sort.c:421)
+
+    def post_sort_comm(self):
+        """post_sort_comm (reference src/cmc/cmc_utils.c:2259-2288): on one rank star_r/star_m were already written by qsorts_new;
+        the cenma reductions are identities."""
+        return None
+
+    def _n_bin_in_use(self):
+        b = self.field("binind")[1:self.clus.N_MAX_NEW + 1]
+        return int(b.max()) if b.size and b.max() > 0 else 0
+
+    def orbit_params(self, draws=None, draw_off=None, seed=0):
+        n_old = int(self.End[0] - self.Start[0] + 1)
+        n_new_stars = max(0, self.clus.N_MAX_NEW - n_old)
+        p = _lib.OrbitParams(self.clus.N_MAX_NEW, n_old, int(self.Start[0]), self.clus.N_MAX, self.clus.N_STAR,
+                             self.clus.N_MAX + 2 + n_new_stars, self.cenma.m, self.Rtidal, None, None, seed, self.tcount)
+        if draws is not None:
+            self._draws = np.ascontiguousarray(draws, np.float64)
+            self._draw_off = np.ascontiguousarray(draw_off, np.int64)
+            p.draws, p.draw_off = self._draws.ctypes.data, self._draw_off.ctypes.data
+        return p
+
+    def new_orbits_calculate(self, draws=None, draw_off=None, seed=0, want_status=True):
+        """new_orbits_calculate -> get_positions (reference src/cmc/cmc_utils.c:2194-2211).  Returns the per-star status codes;
+        the host-side side effects of removed stars (remove_star, destroy_obj) are the caller's, in star order."""
+        p = self.orbit_params(draws, draw_off, seed)
+        n = self.clus.N_MAX_NEW
+        res = _lib.OrbitResult()
+        status = np.zeros(n, np.int32) if want_status else None
+        kmin = np.zeros(n, np.int64) if want_status else None
+        kmax = np.zeros(n, np.int64) if want_status else None
+        _lib.check(self.L.cmcb200_new_orbits_calculate(self.ctx, self.star[1:].ctypes.data, self.star_r.ctypes.data, self.star_m.ctypes.data,
+                                                       self.star_phi.ctypes.data, C.byref(p),
+                                                       status.ctypes.data if want_status else None, kmin.ctypes.data if want_status else None,
+                                                       kmax.ctypes.data if want_status else None, C.byref(res)), "new_orbits_calculate")
+        self.max_r = res.max_r                       # MPI_Allreduce(max_r, MAX) is the identity on one rank
+        self.last_orbit = res
+        self.last_status, self.last_kmin, self.last_kmax = status, kmin, kmax
+        return status
+
+    def compute_energy(self):
+        """E, J as ComputeEnergy does (reference src/cmc/cmc_utils.c:612-616), host arrays."""
+        n = self.clus.N_MAX
+        vr, vt = self.field("vr")[1:n + 1], self.field("vt")[1:n + 1]
+        self.field("E")[1:n + 1] = self.star_phi[1:n + 1] + 0.5 * (vr * vr + vt * vt)
+        self.field("J")[1:n + 1] = self.star_r[1:n + 1] * vt
+
+    # ---- resident form ----------------------------------------------------------------------------------------------
+    def upload(self):
+        n, nb = self.clus.N_MAX_NEW, self._n_bin_in_use()
+        _lib.check(self.L.cmcb200_upload(self.ctx, self.star[1:].ctypes.data, n, self.binary[1:].ctypes.data, nb, self.star_r.ctypes.data,
+                                         self.star_m.ctypes.data, self.star_phi.ctypes.data, min(self.N_STAR_DIM, self.clus.N_MAX + 2)), "upload")
+        self.N_b_local = nb
+
+    def download(self):
+        n = self.clus.N_MAX_NEW
+        _lib.check(self.L.cmcb200_download(self.ctx, self.star[1:].ctypes.data, n, self.binary[1:].ctypes.data, self.N_b_local,
+                                           self.star_r.ctypes.data, self.star_m.ctypes.data, self.star_phi.ctypes.data,
+                                           min(self.N_STAR_DIM, self.clus.N_MAX + 2)), "download")
+
+    def dev_new_orbits(self, draws=None, draw_off=None, seed=0, want_status=False):
+        p = self.orbit_params(draws, draw_off, seed)
+        res = _lib.OrbitResult()
+        _lib.check(self.L.cmcb200_dev_new_orbits(self.ctx, C.byref(p), int(want_status), C.byref(res)), "dev_new_orbits")
+        self.max_r, self.last_orbit = res.max_r, res
+        return res
+
+    def dev_read_status(self):
+        n = self.clus.N_MAX_NEW
+        status, kmin, kmax = np.zeros(n, np.int32), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        _lib.check(self.L.cmcb200_dev_read_status(self.ctx, status.ctypes.data, kmin.ctypes.data, kmax.ctypes.data, n), "dev_read_status")
+        return status, kmin, kmax
+
+    def dev_transfer_new_positions(self):
+        n_old = int(self.End[0] - self.Start[0] + 1)
+        _lib.check(self.L.cmcb200_dev_transfer_new_positions(self.ctx, self.clus.N_MAX_NEW, n_old, int(self.Start[0]), self.clus.N_MAX), "dev_transfer")
+
+    def dev_qsorts_new(self):
+        n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
+        _lib.check(self.L.cmcb200_dev_qsorts_new(self.ctx, C.byref(n), max(self.N_b_local, 0), C.byref(nb)), "dev_qsorts_new")
+        self.clus.N_MAX = self.clus.N_MAX_NEW = n.value
+        self.N_b_local = nb.value
+        self.Start[0], self.End[0] = 1, n.value
+
+    def dev_calc_potential_new(self):
+        nmax = C.c_long(self.clus.N_MAX)
+        cm, cmn, Mt, Rt = C.c_double(self.cenma.m), C.c_double(self.cenma.m_new), C.c_double(), C.c_double()
+        _lib.check(self.L.cmcb200_dev_calc_potential_new(self.ctx, C.byref(nmax), self.clus.N_STAR, C.byref(cm), C.byref(cmn), self.orbit_r,
+                                                         C.byref(Mt), C.byref(Rt)), "dev_calc_potential_new")
+        self.clus.N_MAX = nmax.value
+        self.cenma.m, self.cenma.m_new = cm.value, cmn.value
+        self.Mtotal, self.Rtidal = Mt.value, Rt.value
+        self.mpiBegin, self.mpiEnd = 1, self.clus.N_MAX
+
+    def dev_compute_energy(self):
+        _lib.check(self.L.cmcb200_dev_compute_energy(self.ctx, self.clus.N_MAX, 1), "dev_compute_energy")
+
+    def dev_step(self, seed=0, draws=None, draw_off=None):
+        """One pass of the hot path on the resident arrays: orbit step -> r <- rnew -> sort -> potential -> E, J."""
+        res = self.dev_new_orbits(draws, draw_off, seed)
+        self.dev_transfer_new_positions()
+        self.dev_qsorts_new()
+        self.dev_calc_potential_new()
+        self.dev_compute_energy()
+        self.tcount += 1
+        return res
+
+    def sync(self):
+        _lib.check(self.L.cmcb200_sync(self.ctx), "sync")
+
+    # ---- instrumentation ------------------------------------------------------------------------------------------------
+    def profile(self, on=True):
+        self.L.cmcb200_profile(self.ctx, int(on))
+
+    def profile_read(self, reset=True):
+        ms, n = np.zeros(_lib.N_STAGES), np.zeros(_lib.N_STAGES, np.int64)
+        _lib.check(self.L.cmcb200_profile_read(self.ctx, ms.ctypes.data, n.ctypes.data, int(reset)), "profile_read")
+        return {k: (float(a), int(b)) for k, a, b in zip(_lib.STAGE_NAMES, ms, n)}
+
+    def potential_stats(self):
+        ev, fb = C.c_long(), C.c_long()
+        _lib.check(self.L.cmcb200_potential_stats(self.ctx, C.byref(ev), C.byref(fb)), "potential_stats")
+        return ev.value, fb.value

@@ -1,0 +1,560 @@
+// C ABI of libcmcb200.so (include/cmcb200.h): context, device-resident mirrors, host<->device staging.
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/cmcb200.h"
+#include "common.cuh"
+#include "orbit.cuh"
+#include "potential.cuh"
+#include "sort.cuh"
+#include "star_layout.h"
+
+namespace cmcb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+} // namespace cmcb
+
+using namespace cmcb;
+
+enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H };
+
+struct StageEvent {
+	int stage;
+	cudaEvent_t a, b;
+};
+
+struct cmcb200_ctx {
+	int device;
+	long n_star_dim, n_bin_dim;
+	cudaStream_t stream;
+	bool own_stream;
+	// resident arrays.  d_star[cur] holds the live star array: record 0 = sentinel (star[0]), star1 = base + 424.
+	char *d_star[2];
+	char *d_bin[2]; // record 0 = binary[0] (unused by the reference), binary1 = base + 464
+	int cur_star, cur_bin;
+	double *d_r, *d_m, *d_phi, *d_mprev;
+	// sort scratch
+	SortBuffers sbuf;
+	SortState *d_sort;
+	unsigned *d_tile_hist;
+	long tile_hist_words;
+	unsigned char *d_binflag;
+	unsigned *d_bin_block_cnt;
+	// potential scratch
+	PotScalars *d_pot;
+	void *d_seqwork;
+	SeqWork seqwork;
+	// orbit scratch
+	OrbitStats *d_ostats;
+	int *d_status;
+	long *d_kmin, *d_kmax;
+	double *d_draws;
+	long *d_draw_off;
+	long draws_cap, draw_off_cap;
+	// pinned scalars for read-back
+	void *h_pinned;
+	// profiling
+	bool profiling;
+	std::vector<StageEvent> events;
+	std::vector<cudaEvent_t> pool;
+	double acc_ms[CMCB200_N_STAGES];
+	long acc_n[CMCB200_N_STAGES];
+};
+
+static char *star1(cmcb200_ctx *c) { return c->d_star[c->cur_star] + CMCB_SIZEOF_STAR; }
+static char *bin1(cmcb200_ctx *c) { return c->d_bin[c->cur_bin] + CMCB_SIZEOF_BINARY; }
+
+namespace {
+
+struct StageTimer { // brackets a stage with events when profiling is on
+	cmcb200_ctx *c;
+	int idx;
+	StageTimer(cmcb200_ctx *ctx, int stage) : c(ctx), idx(-1)
+	{
+		if (!c->profiling) return;
+		StageEvent e;
+		e.stage = stage;
+		for (cudaEvent_t *p : {&e.a, &e.b}) {
+			if (!c->pool.empty()) { *p = c->pool.back(); c->pool.pop_back(); }
+			else cudaEventCreate(p);
+		}
+		cudaEventRecord(e.a, c->stream);
+		c->events.push_back(e);
+		idx = (int) c->events.size() - 1;
+	}
+	~StageTimer()
+	{
+		if (idx >= 0) cudaEventRecord(c->events[idx].b, c->stream);
+	}
+};
+
+int ensure(void **p, long *cap, long need, size_t elem)
+{
+	if (need <= *cap) return 0;
+	if (*p) cudaFree(*p);
+	*p = nullptr;
+	long ncap = need + need / 4 + 1024;
+	CMCB_CUDA_OK(cudaMalloc(p, (size_t) ncap * elem));
+	*cap = ncap;
+	return 0;
+}
+
+} // namespace
+
+extern "C" const char *cmcb200_last_error(void) { return get_error(); }
+
+extern "C" void cmcb200_layout(long out[16])
+{
+	const long v[16] = {CMCB_SIZEOF_STAR, CMCB_SIZEOF_BINARY, CMCB_OFF_R, CMCB_OFF_VR, CMCB_OFF_VT, CMCB_OFF_M, CMCB_OFF_E, CMCB_OFF_J,
+			    CMCB_OFF_RNEW, CMCB_OFF_VRNEW, CMCB_OFF_VTNEW, CMCB_OFF_ROLD, CMCB_OFF_X, CMCB_OFF_R_PERI, CMCB_OFF_R_APO, CMCB_OFF_BININD};
+	memcpy(out, v, sizeof(v));
+}
+
+// findIndices / findLimits, reference src/cmc/cmc_utils.c:2299-2333
+extern "C" void cmcb200_find_limits(long N, int blk, int procs, int *Start, int *End)
+{
+	const long blocks = N / blk, remain = N % blk;
+	const long chunk = (blocks / procs) * blk, extra = blocks % procs;
+	for (int i = 0; i < procs; i++) {
+		long b, e;
+		if (i < extra) { b = i * chunk + (long) i * blk + 1; e = b + chunk + blk - 1; }
+		else { b = i * chunk + extra * blk + 1; e = b + chunk - 1; }
+		Start[i] = (int) b;
+		End[i] = (int) e;
+	}
+	End[procs - 1] += (int) remain;
+}
+
+extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, long n_bin_dim)
+{
+	*out = nullptr;
+	if (n_star_dim < 4 || n_bin_dim < 2) { set_error("cmcb200_create: n_star_dim >= 4 and n_bin_dim >= 2 required"); return -1; }
+	if (n_star_dim >= (1L << 30)) { set_error("cmcb200_create: n_star_dim must be < 2^30 (30-bit look-back words)"); return -1; }
+	int ndev = 0;
+	CMCB_CUDA_OK(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) { set_error("cmcb200_create: no CUDA device %d (found %d)", device, ndev); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CMCB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) { set_error("cmcb200_create: built for sm_100a, device %d is sm_%d%d", device, prop.major, prop.minor); return -1; }
+	cmcb200_ctx *c = new cmcb200_ctx();
+	c->device = device;
+	c->n_star_dim = n_star_dim;
+	c->n_bin_dim = n_bin_dim;
+	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	c->own_stream = true;
+	const size_t sb = (size_t) n_star_dim * CMCB_SIZEOF_STAR + 64, bb = (size_t) n_bin_dim * CMCB_SIZEOF_BINARY + 64;
+	for (int i = 0; i < 2; i++) {
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_star[i], sb));
+		CMCB_CUDA_OK(cudaMemsetAsync(c->d_star[i], 0, sb, c->stream));
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_bin[i], bb));
+		CMCB_CUDA_OK(cudaMemsetAsync(c->d_bin[i], 0, bb, c->stream));
+	}
+	const size_t tb = (size_t) n_star_dim * sizeof(double);
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_r, tb));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_m, tb));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_phi, tb));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_mprev, tb));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r, 0, tb, c->stream));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_m, 0, tb, c->stream));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_phi, 0, tb, c->stream));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->sbuf.keys_a, (size_t) n_star_dim * 8));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->sbuf.keys_b, (size_t) n_star_dim * 8));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->sbuf.vals_a, (size_t) n_star_dim * 4));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->sbuf.vals_b, (size_t) n_star_dim * 4));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_sort, sizeof(SortState)));
+	const long ntiles = (n_star_dim + SORT_TILE - 1) / SORT_TILE;
+	c->tile_hist_words = ntiles * 256 * 8;
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_tile_hist, (size_t) c->tile_hist_words * 4));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_binflag, (size_t) n_star_dim));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_bin_block_cnt, (size_t) (n_star_dim / 2048 + 2) * 4));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pot, sizeof(PotScalars)));
+	const size_t wb = pot_work_bytes(n_star_dim);
+	CMCB_CUDA_OK(cudaMalloc(&c->d_seqwork, wb));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_seqwork, 0, wb, c->stream));
+	pot_work_bind(c->seqwork, c->d_seqwork, n_star_dim);
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_ostats, sizeof(OrbitStats)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_status, (size_t) n_star_dim * sizeof(int)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_kmin, (size_t) n_star_dim * sizeof(long)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_kmax, (size_t) n_star_dim * sizeof(long)));
+	CMCB_CUDA_OK(cudaMallocHost(&c->h_pinned, 4096));
+	if (sort_setup()) { set_error("cmcb200_create: cannot raise the dynamic shared memory limit of the sort kernel"); return -1; }
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*out = c;
+	return 0;
+}
+
+extern "C" void cmcb200_destroy(cmcb200_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (int i = 0; i < 2; i++) { cudaFree(c->d_star[i]); cudaFree(c->d_bin[i]); }
+	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev);
+	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
+	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
+	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
+	if (c->d_draws) cudaFree(c->d_draws);
+	if (c->d_draw_off) cudaFree(c->d_draw_off);
+	cudaFreeHost(c->h_pinned);
+	for (auto &e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+	for (auto &e : c->pool) cudaEventDestroy(e);
+	if (c->own_stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" int cmcb200_set_stream(cmcb200_ctx *c, void *s)
+{
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	if (c->own_stream) cudaStreamDestroy(c->stream);
+	c->stream = (cudaStream_t) s;
+	c->own_stream = false;
+	return 0;
+}
+
+extern "C" int cmcb200_sync(cmcb200_ctx *c)
+{
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" int cmcb200_profile(cmcb200_ctx *c, int on)
+{
+	c->profiling = on != 0;
+	return 0;
+}
+
+extern "C" int cmcb200_profile_read(cmcb200_ctx *c, double ms[CMCB200_N_STAGES], long launches[CMCB200_N_STAGES], int reset)
+{
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	for (auto &e : c->events) {
+		float t = 0.f;
+		if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) { c->acc_ms[e.stage] += t; c->acc_n[e.stage]++; }
+		c->pool.push_back(e.a);
+		c->pool.push_back(e.b);
+	}
+	c->events.clear();
+	for (int i = 0; i < CMCB200_N_STAGES; i++) { ms[i] = c->acc_ms[i]; launches[i] = c->acc_n[i]; }
+	if (reset) for (int i = 0; i < CMCB200_N_STAGES; i++) { c->acc_ms[i] = 0; c->acc_n[i] = 0; }
+	return 0;
+}
+
+extern "C" int cmcb200_potential_stats(cmcb200_ctx *c, long *n_events, long *n_fallbacks)
+{
+	long h[2];
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->seqwork.stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*n_events = h[0];
+	*n_fallbacks = h[1];
+	return 0;
+}
+
+// ---- potential ------------------------------------------------------------------------------------------------
+
+extern "C" int cmcb200_dev_calc_potential_new(cmcb200_ctx *c, long *N_MAX, long N_STAR, double *cenma_m, double *cenma_m_new, double orbit_r,
+					      double *Mtotal, double *Rtidal)
+{
+	if (*N_MAX + 2 > c->n_star_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds n_star_dim = %ld", *N_MAX + 2, c->n_star_dim); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	{
+		StageTimer t(c, ST_POTENTIAL);
+		CMCB_CUDA_OK(cudaMemsetAsync(c->seqwork.stats, 0, 2 * sizeof(long), c->stream));
+		PotArgs a;
+		a.r = c->d_r; a.m = c->d_m; a.phi = c->d_phi; a.mprev = c->d_mprev; a.sc = c->d_pot; a.work = c->seqwork;
+		a.n_max_in = *N_MAX; a.n_star = (double) N_STAR; a.madhoc = 1.0 / ((double) N_STAR);
+		a.cenma_m = *cenma_m; a.cenma_m_new = *cenma_m_new;
+		potential_calculate_device(a, c->stream);
+		CMCB_CUDA_OK(cudaGetLastError());
+	}
+	PotScalars *h = (PotScalars *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_pot, sizeof(PotScalars), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*N_MAX = h->n_max;
+	*cenma_m = h->cenma_m;
+	*cenma_m_new = h->cenma_m_new;
+	*Mtotal = h->Mtotal;
+	// libm pow on the host: the same correctly rounded glibc routine the reference calls (cmc_utils.c:707); CUDA's pow is not
+	*Rtidal = orbit_r * pow(h->Mtotal, 1.0 / 3.0);
+	return 0;
+}
+
+extern "C" int cmcb200_calc_potential_new(cmcb200_ctx *c, double *star_r, const double *star_m, double *star_phi, long *N_MAX, long N_STAR,
+					  double *cenma_m, double *cenma_m_new, double orbit_r, double *Mtotal, double *Rtidal)
+{
+	const long n_in = *N_MAX + 2;
+	if (n_in > c->n_star_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds n_star_dim = %ld", n_in, c->n_star_dim); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	{
+		StageTimer t(c, ST_H2D);
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	}
+	if (cmcb200_dev_calc_potential_new(c, N_MAX, N_STAR, cenma_m, cenma_m_new, orbit_r, Mtotal, Rtidal)) return -1;
+	{
+		StageTimer t(c, ST_D2H);
+		CMCB_CUDA_OK(cudaMemcpyAsync(star_phi, c->d_phi, (*N_MAX + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	}
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	star_r[*N_MAX + 1] = CMCB200_SF_INFINITY; // cmc_utils.c:713
+	return 0;
+}
+
+// ---- sort -------------------------------------------------------------------------------------------------------
+
+extern "C" int cmcb200_dev_qsorts_new(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_bin)
+{
+	const long n = *n_local;
+	if (n + 2 > c->n_star_dim) { set_error("qsorts_new: n_local + 2 = %ld exceeds n_star_dim = %ld", n + 2, c->n_star_dim); return -1; }
+	if (n_bin_clear > c->n_bin_dim - 1) n_bin_clear = c->n_bin_dim - 1;
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	SortArgs a;
+	a.star_in = star1(c);
+	a.star_out = c->d_star[c->cur_star ^ 1] + CMCB_SIZEOF_STAR;
+	a.n = n;
+	a.key_off = CMCB_OFF_R;
+	a.buf = c->sbuf;
+	a.st = c->d_sort;
+	a.tile_hist = c->d_tile_hist;
+	a.star_r = c->d_r;
+	a.star_m = c->d_m;
+	a.binflag = c->d_binflag;
+	a.bin_block_cnt = c->d_bin_block_cnt;
+	a.bin_in = bin1(c);
+	a.bin_out = c->d_bin[c->cur_bin ^ 1] + CMCB_SIZEOF_BINARY;
+	a.n_bin_clear = n_bin_clear;
+	{ StageTimer t(c, ST_KEYS); sort_stage_keys(a, c->stream); }
+	{ StageTimer t(c, ST_PASSES); sort_stage_passes(a, c->stream); }
+	{
+		StageTimer t(c, ST_GATHER);
+		// the sentinel record star[0] travels with the array
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_star[c->cur_star ^ 1], c->d_star[c->cur_star], CMCB_SIZEOF_STAR, cudaMemcpyDeviceToDevice, c->stream));
+		sort_stage_gather(a, c->stream);
+	}
+	{ StageTimer t(c, ST_BINARIES); sort_stage_binaries(a, c->stream); }
+	CMCB_CUDA_OK(cudaGetLastError());
+	c->cur_star ^= 1;
+	c->cur_bin ^= 1;
+	long *h = (long *) c->h_pinned; // n_eq_inf, n_gt_inf, n_total, n_new, n_bin
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, &c->d_sort->n_eq_inf, 5 * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*n_local = h[3];
+	*n_bin = h[4];
+	return 0;
+}
+
+extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, void *binary1_h, long n_bin_dim, long *n_bin,
+				  double *star_r, double *star_m)
+{
+	const long n = *n_local, nb_in = binary1_h ? *n_bin : 0;
+	if (n + 2 > c->n_star_dim) { set_error("qsorts_new: n_local + 2 = %ld exceeds n_star_dim = %ld", n + 2, c->n_star_dim); return -1; }
+	if (nb_in + 1 > c->n_bin_dim || n_bin_dim > c->n_bin_dim) { set_error("qsorts_new: binary capacity %ld exceeded", c->n_bin_dim); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	{
+		StageTimer t(c, ST_H2D);
+		CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) n * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
+		if (nb_in > 0) CMCB_CUDA_OK(cudaMemcpyAsync(bin1(c), binary1_h, (size_t) nb_in * CMCB_SIZEOF_BINARY, cudaMemcpyHostToDevice, c->stream));
+	}
+	long nb_out = 0;
+	// nothing to clear on the device: the host tail is zeroed below
+	if (cmcb200_dev_qsorts_new(c, n_local, 0, &nb_out)) return -1;
+	{
+		StageTimer t(c, ST_D2H);
+		CMCB_CUDA_OK(cudaMemcpyAsync(star1_h, star1(c), (size_t) n * CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
+		if (binary1_h && nb_out > 0) CMCB_CUDA_OK(cudaMemcpyAsync(binary1_h, bin1(c), (size_t) nb_out * CMCB_SIZEOF_BINARY, cudaMemcpyDeviceToHost, c->stream));
+		if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(star_r + 1, c->d_r + 1, (size_t) *n_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(star_m + 1, c->d_m + 1, (size_t) *n_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	}
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	// memset(b_buf, 0, (N_BIN_DIM_OPT-1)*sizeof(binary_t)) (cmc_sort.c:541): everything past the packed binaries is zero
+	if (binary1_h && n_bin_dim - 1 > nb_out)
+		memset((char *) binary1_h + (size_t) nb_out * CMCB_SIZEOF_BINARY, 0, (size_t) (n_bin_dim - 1 - nb_out) * CMCB_SIZEOF_BINARY);
+	if (n_bin) *n_bin = nb_out;
+	return 0;
+}
+
+// ---- orbit step ---------------------------------------------------------------------------------------------------
+
+static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res)
+{
+	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_star_dim) { set_error("new_orbits_calculate: size exceeds n_star_dim = %ld", c->n_star_dim); return -1; }
+	OrbitArgs a;
+	a.star1 = star1(c);
+	a.n_local = p->n_local;
+	a.n_old_local = p->n_old_local;
+	a.first_global = p->first_global;
+	a.t.r = c->d_r; a.t.m = c->d_m; a.t.phi = c->d_phi;
+	a.t.N_MAX = p->N_MAX;
+	a.t.invN = 1.0 / p->N_STAR;
+	a.t.madhoc = 1.0 / ((double) p->N_STAR);
+	a.t.cenma_m = p->cenma_m;
+	a.Rtidal = p->Rtidal;
+	a.draws = nullptr; a.draw_off = nullptr;
+	a.seed = p->seed; a.tcount = p->tcount;
+	if (p->draws) {
+		const long nd = p->draw_off[p->n_local];
+		if (ensure((void **) &c->d_draws, &c->draws_cap, nd + 1, sizeof(double))) return -1;
+		if (ensure((void **) &c->d_draw_off, &c->draw_off_cap, p->n_local + 1, sizeof(long))) return -1;
+		StageTimer t(c, ST_H2D);
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_draws, p->draws, (size_t) nd * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_draw_off, p->draw_off, (size_t) (p->n_local + 1) * sizeof(long), cudaMemcpyHostToDevice, c->stream));
+		a.draws = c->d_draws;
+		a.draw_off = c->d_draw_off;
+	}
+	a.status = want_status ? c->d_status : nullptr;
+	a.kmin = want_status ? c->d_kmin : nullptr;
+	a.kmax = want_status ? c->d_kmax : nullptr;
+	a.n_draws = nullptr;
+	a.stats = c->d_ostats;
+	{
+		StageTimer t(c, ST_ORBIT);
+		orbit_step_device(a, c->stream);
+		CMCB_CUDA_OK(cudaGetLastError());
+	}
+	OrbitStats *h = (OrbitStats *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	if (res) {
+		memcpy(&res->max_r, &h->max_rad_bits, 8);
+		res->n_draws = h->n_draws; res->n_exact = h->n_exact; res->n_brent = h->n_brent;
+		unsigned long long other = 0;
+		for (int i = 1; i < 6; i++) { res->n_status[i] = h->n_status[i]; other += h->n_status[i]; }
+		res->n_status[0] = (unsigned long long) p->n_local - other;
+	}
+	return 0;
+}
+
+extern "C" int cmcb200_dev_new_orbits(cmcb200_ctx *c, const cmcb200_orbit_params *p, int want_status, cmcb200_orbit_result *res)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	return orbit_common(c, p, want_status != 0, res);
+}
+
+extern "C" int cmcb200_dev_read_status(cmcb200_ctx *c, int *status, long *kmin, long *kmax, long n_local)
+{
+	StageTimer t(c, ST_D2H);
+	if (status) CMCB_CUDA_OK(cudaMemcpyAsync(status, c->d_status, (size_t) n_local * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	if (kmin) CMCB_CUDA_OK(cudaMemcpyAsync(kmin, c->d_kmin, (size_t) n_local * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	if (kmax) CMCB_CUDA_OK(cudaMemcpyAsync(kmax, c->d_kmax, (size_t) n_local * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const double *star_r, const double *star_m, const double *star_phi,
+					    const cmcb200_orbit_params *p, int *status, long *kmin, long *kmax, cmcb200_orbit_result *res)
+{
+	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_star_dim) { set_error("new_orbits_calculate: size exceeds n_star_dim = %ld", c->n_star_dim); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	{
+		StageTimer t(c, ST_H2D);
+		CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_phi, star_phi, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	}
+	const bool want = status || kmin || kmax;
+	if (orbit_common(c, p, want, res)) return -1;
+	{
+		StageTimer t(c, ST_D2H);
+		CMCB_CUDA_OK(cudaMemcpyAsync(star1_h, star1(c), (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
+	}
+	if (want) return cmcb200_dev_read_status(c, status, kmin, kmax, p->n_local);
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+// ---- resident-array plumbing ----------------------------------------------------------------------------------------
+
+extern "C" int cmcb200_upload(cmcb200_ctx *c, const void *star1_h, long n_local, const void *binary1_h, long n_bin,
+			      const double *star_r, const double *star_m, const double *star_phi, long n_table)
+{
+	if (n_local + 2 > c->n_star_dim || n_table > c->n_star_dim || n_bin + 1 > c->n_bin_dim) { set_error("upload: sizes exceed the context capacity"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	StageTimer t(c, ST_H2D);
+	if (star1_h) CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) n_local * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
+	if (binary1_h && n_bin > 0) CMCB_CUDA_OK(cudaMemcpyAsync(bin1(c), binary1_h, (size_t) n_bin * CMCB_SIZEOF_BINARY, cudaMemcpyHostToDevice, c->stream));
+	if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	if (star_phi) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_phi, star_phi, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	return 0;
+}
+
+extern "C" int cmcb200_download(cmcb200_ctx *c, void *star1_h, long n_local, void *binary1_h, long n_bin,
+				double *star_r, double *star_m, double *star_phi, long n_table)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	{
+		StageTimer t(c, ST_D2H);
+		if (star1_h) CMCB_CUDA_OK(cudaMemcpyAsync(star1_h, star1(c), (size_t) n_local * CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
+		if (binary1_h && n_bin > 0) CMCB_CUDA_OK(cudaMemcpyAsync(binary1_h, bin1(c), (size_t) n_bin * CMCB_SIZEOF_BINARY, cudaMemcpyDeviceToHost, c->stream));
+		if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(star_r, c->d_r, (size_t) n_table * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(star_m, c->d_m, (size_t) n_table * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		if (star_phi) CMCB_CUDA_OK(cudaMemcpyAsync(star_phi, c->d_phi, (size_t) n_table * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	}
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+// ---- the two per-star elementwise steps that chain the pipeline on the device -----------------------------------------
+
+namespace cmcb {
+
+// ComputeIntermediateEnergy's transfer loop (reference src/cmc/cmc_utils.c:380-390)
+__global__ void transfer_new_positions_kernel(char *star1, long n_local, long n_old_local, long first_global, long N_MAX,
+					      const double *__restrict__ star_r, const double *__restrict__ star_m)
+{
+	long j0 = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	if (j0 >= n_local) return;
+	long j = j0 + 1;
+	long g = j > n_old_local ? 1 + N_MAX + (j - n_old_local) : first_global + j - 1;
+	char *rec = star1 + j0 * CMCB_SIZEOF_STAR;
+	*(double *) (rec + CMCB_OFF_ROLD) = star_r[g];
+	*(double *) (rec + CMCB_OFF_R) = *(const double *) (rec + CMCB_OFF_RNEW);
+	*(double *) (rec + CMCB_OFF_M) = star_m[g];
+	*(double *) (rec + CMCB_OFF_VR) = *(const double *) (rec + CMCB_OFF_VRNEW);
+	*(double *) (rec + CMCB_OFF_VT) = *(const double *) (rec + CMCB_OFF_VTNEW);
+}
+
+// first loop of ComputeEnergy (reference src/cmc/cmc_utils.c:612-616)
+__global__ void compute_energy_kernel(char *star1, long n_local, long first_global, const double *__restrict__ star_r, const double *__restrict__ star_phi)
+{
+	long j0 = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	if (j0 >= n_local) return;
+	long g = first_global + j0;
+	char *rec = star1 + j0 * CMCB_SIZEOF_STAR;
+	double vr = *(const double *) (rec + CMCB_OFF_VR), vt = *(const double *) (rec + CMCB_OFF_VT);
+	*(double *) (rec + CMCB_OFF_E) = dadd(star_phi[g], dmul(0.5, dadd(dmul(vr, vr), dmul(vt, vt))));
+	*(double *) (rec + CMCB_OFF_J) = dmul(star_r[g], vt);
+}
+
+} // namespace cmcb
+
+extern "C" int cmcb200_dev_transfer_new_positions(cmcb200_ctx *c, long n_local, long n_old_local, long first_global, long N_MAX)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	StageTimer t(c, ST_TRANSFER);
+	if (n_local > 0)
+		transfer_new_positions_kernel<<<(unsigned) ((n_local + 255) / 256), 256, 0, c->stream>>>(star1(c), n_local, n_old_local, first_global, N_MAX, c->d_r, c->d_m);
+	CMCB_CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cmcb200_dev_compute_energy(cmcb200_ctx *c, long n_local, long first_global)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	StageTimer t(c, ST_ENERGY);
+	if (n_local > 0)
+		compute_energy_kernel<<<(unsigned) ((n_local + 255) / 256), 256, 0, c->stream>>>(star1(c), n_local, first_global, c->d_r, c->d_phi);
+	CMCB_CUDA_OK(cudaGetLastError());
+	return 0;
+}

@@ -1,0 +1,36 @@
+#pragma once
+#include "common.cuh"
+#include "orbit_core.h"
+#include "star_layout.h"
+
+namespace cmcb {
+
+struct OrbitStats { // device-resident, zeroed per launch
+	unsigned long long max_rad_bits; // max over ORBIT_OK stars of rnew (positive doubles order like their bit patterns)
+	unsigned long long n_draws, n_exact, n_brent;
+	unsigned long long n_status[6];
+};
+
+struct OrbitArgs {
+	char *star1;        // &star[1] on the device (AoS, reference layout)
+	long n_local;       // clus.N_MAX_NEW: local stars, including stars created this step
+	long n_old_local;   // End[myid]-Start[myid]+1: stars beyond are new (get_global_idx, cmc_utils.c:2384-2407)
+	long first_global;  // Start[myid]
+	OrbitTables t;      // device tables
+	double Rtidal;
+	// draws: either a recorded stream in CSR form (parity mode) ...
+	const double *draws;
+	const long *draw_off; // [n_local + 1]
+	// ... or a counter-based generator keyed by (seed, tcount, global star index) (production mode, draws == nullptr)
+	unsigned long long seed;
+	unsigned long long tcount;
+	// optional per-star diagnostics (may be null)
+	int *status;
+	long *kmin, *kmax;
+	int *n_draws;
+	OrbitStats *stats;
+};
+
+void orbit_step_device(const OrbitArgs &a, cudaStream_t s);
+
+} // namespace cmcb

@@ -1,0 +1,370 @@
+// Per-star new-orbit step, shared by the CUDA kernel (orbit.cu) and the host-side emulation used by the CPU tests.
+//
+// Follows the reference's get_positions_loop (src/cmc/cmc_evolution_thr.c:802-933) and what it calls:
+//   calc_orbit_new / get_positive_Q_index / set_a_b   src/cmc/cmc_orbit.c:413-540, 30-59, 722-740
+//   find_zero_Q, FindZero_r, find_root_vr             src/cmc/cmc_nr.c:316-383, 62-82, 500-603
+//   function_q, potential                             src/cmc/cmc_utils.c:1654-1662, 112-165
+//   MPI_PHI_S                                         include/cmc/cmc.h:2175
+// Every FP64 operation is issued through fp64_exact.h in the reference's evaluation order (single rounding, no
+// FMA contraction), so given the same r/m/Phi tables and the same uniform draws the outputs are bit-identical to
+// the reference's.  The reference's `long double` evaluation of Q is handled by sign_Q(): FP64 plus a rigorous
+// error bound on the fast path, exact x87 replay (x87emu.h) when the sign is within the bound.
+#pragma once
+#include "fp64_exact.h"
+#include "x87emu.h"
+
+namespace cmcb {
+
+#define CMCB_SF_INFINITY 1.0e10 /* reference include/cmc/cmc.h:58 */
+#define CMCB_ZERO 1.0e-20       /* :60 */
+#define CMCB_N_TRY 50000        /* :64 */
+
+enum OrbitStatus {
+	ORBIT_OK = 0,       // new radius sampled                      cmc_evolution_thr.c:857-933
+	ORBIT_MASSLESS = 1, // star_m < ZERO -> destroy_obj            :816-820
+	ORBIT_UNBOUND = 2,  // E >= 0 -> remove_star                   :823-829
+	ORBIT_CIRCULAR = 3, // circular_flag: keeps r, vr, vt          :835-839
+	ORBIT_TIDAL = 4,    // rmax >= Rtidal -> remove_star           :848-855
+	ORBIT_NTRY = 5      // N_TRY exceeded (fatal in the reference) :890-893
+};
+
+struct OrbitTables {
+	const double *r, *m, *phi; // star_r, star_m, star_phi: [0] sentinel, [1..N_MAX], [N_MAX+1] = SF_INFINITY / 0
+	long N_MAX;
+	double invN;    // 1.0 / clus.N_STAR evaluated in double (the factor in MPI_PHI_S)
+	double madhoc;  // 1.0 / (double) clus.N_STAR (cmc_utils.c:1183) -- same value, kept separate like the reference
+	double cenma_m; // cenma.m
+};
+
+struct OrbitOut {
+	double rnew, vrnew, vtnew, X, r_peri, r_apo;
+	long kmin, kmax;
+	int status;
+	int n_draws; // uniforms consumed
+	int n_exact; // Q evaluations that needed the exact x87 replay
+	int n_brent; // find_root_vr fallbacks
+};
+
+// ---- table lookups -------------------------------------------------------------------------------------------
+
+CMCB_HD double tbl_ld(const double *p, long k)
+{
+#if defined(__CUDA_ARCH__)
+	return __ldg(p + k);
+#else
+	return p[k];
+#endif
+}
+
+// MPI_PHI_S(rad, j) with the star's own r_j, m_j already in registers
+CMCB_HD double phi_self(double rad, double r_j, double m_j, double invN)
+{
+	return dmul(rad >= r_j ? ddiv(m_j, rad) : ddiv(m_j, r_j), invN);
+}
+
+// FindZero_r (cmc_nr.c:62-82)
+CMCB_HD long find_zero_r(const double *star_r, long kmin, long kmax, double r)
+{
+	do {
+		long ktry = (kmin + kmax + 1) / 2;
+		if (tbl_ld(star_r, ktry) < r) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
+}
+
+// potential(r) (cmc_utils.c:112-165, SEARCH_GRID = 0).  *fail is set when the bracket check (:144-152) would abort.
+CMCB_HD double potential_at(const OrbitTables &t, double r, int *fail)
+{
+	double phi0 = tbl_ld(t.phi, 0);
+	if (r == 0.0) return phi0;
+	double r1 = tbl_ld(t.r, 1);
+	if (r < r1) return dsub(phi0, ddiv(dmul(dsub(phi0, tbl_ld(t.phi, 1)), r1), r));
+	long kmax = t.N_MAX + 1, kmin = 1;
+	long i = (kmin == kmax - 1) ? kmin : find_zero_r(t.r, kmin, kmax, r);
+	double ri = tbl_ld(t.r, i), ri1 = tbl_ld(t.r, i + 1);
+	if (ri > r || ri1 < r) { *fail = 1; return 0.0; }
+	double pi = tbl_ld(t.phi, i), pi1 = tbl_ld(t.phi, i + 1);
+	double inv_i = ddiv(1.0, ri);
+	return dadd(pi, ddiv(dmul(dsub(pi1, pi), dsub(inv_i, ddiv(1.0, r))), dsub(inv_i, ddiv(1.0, ri1))));
+}
+
+// ---- Q(r): sign with the reference's long-double semantics ---------------------------------------------------
+
+struct StarConst {
+	double E, J;     // energy including the self term (cmc_evolution_thr.c:806), angular momentum
+	double r_j, m_j; // star_r[g_j], star_m[g_j]
+	long g_j;
+};
+
+// FP64 evaluation of function_q and a bound B with |Qd - (x87 result before its final rounding)| <= B.
+// Roundings: ratio, phis, pot+phis, E-(..), J/r (one ulp more for the x87 double rounding), its square, the final
+// subtraction -- each <= 2^-52 relative to a term no larger than |E|+|pot|+|phis|+Jr; 2^-48 covers them with slack.
+CMCB_HD double q_fp64(const OrbitTables &t, const StarConst &s, double r, double pot, double *B)
+{
+	double phis = phi_self(r, s.r_j, s.m_j, t.invN);
+	double jr = ddiv(s.J, r);
+	double Jr = dmul(jr, jr);
+	double Q = dsub(dmul(2.0, dsub(s.E, dadd(pot, phis))), Jr);
+	*B = dmul(3.552713678800501e-15 /* 2^-48 */, dadd(dadd(dabs(s.E), dabs(pot)), dadd(dabs(phis), Jr)));
+	return Q;
+}
+
+// value the reference's function_q returns (a double), exact
+CMCB_HD double q_exact(const OrbitTables &t, const StarConst &s, double r, double pot)
+{
+	return x87_function_q(r, pot, s.E, s.J, s.m_j, s.r_j, t.invN);
+}
+
+// sign of function_q(j, star_r[k], star_phi[k], E, J): -1, 0, +1
+CMCB_HD int sign_Q(const OrbitTables &t, const StarConst &s, long k, int *n_exact)
+{
+	double r = tbl_ld(t.r, k), pot = tbl_ld(t.phi, k), B;
+	double Q = q_fp64(t, s, r, pot, &B);
+	if (Q > B) return 1;
+	if (Q < -B) return -1;
+	(*n_exact)++;
+	double q = q_exact(t, s, r, pot);
+	return q > 0.0 ? 1 : (q < 0.0 ? -1 : 0);
+}
+
+// find_zero_Q (cmc_nr.c:316-383): the same probe sequence ktry = (kmin+kmax+1)/2
+CMCB_HD long find_zero_Q(const OrbitTables &t, const StarConst &s, long kmin, long kmax, int *n_exact)
+{
+	double Bmin, Bmax;
+	double rmin = tbl_ld(t.r, kmin), pmin = tbl_ld(t.phi, kmin), rmax = tbl_ld(t.r, kmax), pmax = tbl_ld(t.phi, kmax);
+	double qmin = q_fp64(t, s, rmin, pmin, &Bmin), qmax = q_fp64(t, s, rmax, pmax, &Bmax);
+	bool increasing;
+	// 2^-52 |q| covers the final rounding to double of each value
+	double slack = dadd(dadd(Bmin, Bmax), dmul(2.220446049250313e-16, dadd(dabs(qmin), dabs(qmax))));
+	if (dabs(dsub(qmin, qmax)) > slack) increasing = qmin < qmax;
+	else { (*n_exact) += 2; increasing = q_exact(t, s, rmin, pmin) < q_exact(t, s, rmax, pmax); } // :342
+	do {
+		long ktry = (kmin + kmax + 1) / 2;
+		int sg = sign_Q(t, s, ktry, n_exact);
+		bool up = increasing ? (sg < 0) : (sg > 0); // :349 / :362
+		if (up) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
+}
+
+// set_a_b (cmc_orbit.c:722-740)
+CMCB_HD void set_a_b(const OrbitTables &t, const StarConst &s, long k, double *a, double *b)
+{
+	if (k == 0) {
+		*a = dmul(-t.cenma_m, t.madhoc);
+		*b = dadd(dadd(tbl_ld(t.phi, 1), ddiv(dmul(t.cenma_m, t.madhoc), tbl_ld(t.r, 1))), ddiv(dmul(s.m_j, t.madhoc), s.r_j));
+	} else {
+		double rk = tbl_ld(t.r, k), rk1 = tbl_ld(t.r, k + 1);
+		double Uk = dadd(tbl_ld(t.phi, k), phi_self(rk, s.r_j, s.m_j, t.invN));
+		double Uk1 = dadd(tbl_ld(t.phi, k + 1), phi_self(rk1, s.r_j, s.m_j, t.invN));
+		double den = dsub(ddiv(1., rk1), ddiv(1., rk));
+		*a = ddiv(dsub(Uk1, Uk), den);
+		*b = ddiv(dsub(ddiv(Uk, rk1), ddiv(Uk1, rk)), den);
+	}
+}
+
+// calc_vr_within_interval (cmc_nr.c:393-405 + 279-302): vr^2 inside [r_k, r_k+1]; Brent needs the VALUE, so this is
+// always the exact x87 replay (rare path)
+CMCB_HD double vr2_within_interval(const OrbitTables &t, const StarConst &s, long k, double r)
+{
+	const double EPS = 2.220446049250313e-16; // DBL_EPSILON
+	double rk = tbl_ld(t.r, k), rk1 = tbl_ld(t.r, k + 1), pot;
+	if (dabs(dsub(r, rk)) < EPS) pot = tbl_ld(t.phi, k);
+	else if (dabs(dsub(r, rk1)) < EPS) pot = tbl_ld(t.phi, k + 1);
+	else if (r < tbl_ld(t.r, 1)) pot = dsub(tbl_ld(t.phi, 0), ddiv(dmul(t.cenma_m, t.madhoc), r));
+	else {
+		double pk = tbl_ld(t.phi, k), inv_k = ddiv(1.0, rk);
+		pot = dadd(pk, ddiv(dmul(dsub(tbl_ld(t.phi, k + 1), pk), dsub(inv_k, ddiv(1.0, r))), dsub(inv_k, ddiv(1.0, rk1))));
+	}
+	return q_exact(t, s, r, pot);
+}
+
+// find_root_vr (cmc_nr.c:500-603): Brent-Dekker as GSL's gsl_root_fsolver_brent iterates it (un-vendored
+// dependency of the reference, version unpinned -> this branch is "parity unpinned"), APSIDES_PRECISION = 1e-11,
+// APSIDES_MAX_ITER = 100, APSIDES_CONVERGENCE = 5e-13 (cmc_io.c:1752-1754).
+CMCB_HD double find_root_vr(const OrbitTables &t, const StarConst &s, long k)
+{
+	const double PREC = 1.0e-11, CONV = 5.e-13, EPS = 2.220446049250313e-16;
+	long iter = 100;
+	double a = tbl_ld(t.r, k), b = tbl_ld(t.r, k + 1), c = b;
+	double fa = vr2_within_interval(t, s, k, a), fb = vr2_within_interval(t, s, k, b), fc = fb;
+	double d = dsub(b, a), e = d, root = dmul(0.5, dadd(a, b)), lo = a, hi = b, prev_apsis = -1.0;
+	bool not_converged = true;
+	while (not_converged && iter) {
+		bool ac_equal = false;
+		if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) { ac_equal = true; c = a; fc = fa; d = dsub(b, a); e = d; }
+		if (dabs(fc) < dabs(fb)) { ac_equal = true; a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+		double tol = dmul(dmul(0.5, EPS), dabs(b));
+		double m = dmul(0.5, dsub(c, b));
+		if (fb == 0) { root = lo = hi = b; }
+		else if (dabs(m) <= tol) { root = b; if (b < c) { lo = b; hi = c; } else { lo = c; hi = b; } }
+		else {
+			if (dabs(e) < tol || dabs(fa) <= dabs(fb)) { d = m; e = m; }
+			else {
+				double p, q, r, sf = ddiv(fb, fa);
+				if (ac_equal) { p = dmul(dmul(2, m), sf); q = dsub(1, sf); }
+				else {
+					q = ddiv(fa, fc); r = ddiv(fb, fc);
+					p = dmul(sf, dsub(dmul(dmul(dmul(2, m), q), dsub(q, r)), dmul(dsub(b, a), dsub(r, 1))));
+					q = dmul(dmul(dsub(q, 1), dsub(r, 1)), dsub(sf, 1));
+				}
+				if (p > 0) q = -q; else p = -p;
+				double lim1 = dsub(dmul(dmul(3, m), q), dabs(dmul(tol, q))), lim2 = dabs(dmul(e, q));
+				if (dmul(2, p) < (lim1 < lim2 ? lim1 : lim2)) { e = d; d = ddiv(p, q); } else { d = m; e = m; }
+			}
+			a = b; fa = fb;
+			if (dabs(d) > tol) b = dadd(b, d); else b = dadd(b, (m > 0 ? tol : -tol));
+			fb = vr2_within_interval(t, s, k, b);
+			root = b;
+			if ((fb < 0 && fc < 0) || (fb > 0 && fc > 0)) c = a;
+			if (b < c) { lo = b; hi = c; } else { lo = c; hi = b; }
+		}
+		{
+			double al = dabs(lo), ah = dabs(hi);
+			double min_abs = ((lo > 0.0 && hi > 0.0) || (lo < 0.0 && hi < 0.0)) ? (al < ah ? al : ah) : 0;
+			not_converged = !(dabs(dsub(hi, lo)) < dadd(PREC, dmul(PREC, min_abs)));
+		}
+		iter--;
+		if (iter < 10) {
+			if (prev_apsis < 0.) prev_apsis = root;
+			else {
+				bool delta_continue = !(dabs(dsub(root, prev_apsis)) < dadd(CONV, dmul(CONV, dabs(root))) || root == prev_apsis);
+				not_converged = not_converged && delta_continue;
+				prev_apsis = root;
+			}
+		}
+	}
+	double apsis = root;
+	if (vr2_within_interval(t, s, k, apsis) < 0.) {
+		if (vr2_within_interval(t, s, k, lo) < 0.) apsis = hi;
+		if (vr2_within_interval(t, s, k, hi) < 0.) apsis = lo;
+	}
+	return apsis;
+}
+
+struct OrbitRS { // orbit_rs_t, reference include/cmc/cmc.h:1621-1650
+	double rp, ra, dQdrp, dQdra;
+	long kmin, kmax;
+	int circular;
+};
+
+// calc_orbit_new (cmc_orbit.c:413-540) incl. get_positive_Q_index (:30-59)
+CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is_new, double rnew_of_new, int *n_exact, int *n_brent)
+{
+	OrbitRS o;
+	long ktemp = s.g_j;
+	if (is_new) ktemp = find_zero_r(t.r, 0, t.N_MAX, rnew_of_new) + 1; // cmc_orbit.c:39-41
+	if (sign_Q(t, s, ktemp, n_exact) <= 0) {                            // :46-57 linear scan from 0
+		ktemp = -1;
+		int sg;
+		do {
+			ktemp++;
+			sg = sign_Q(t, s, ktemp, n_exact);
+		} while (sg <= 0 && ktemp <= t.N_MAX);
+		if (ktemp >= t.N_MAX) ktemp = -1;
+	}
+	bool circular = ktemp <= -1;
+	double rmin = 0, rmax = 0, dQdr_min = 0, dQdr_max = 0;
+	long kmin = 0, kmax = 0;
+	if (!circular) {
+		kmin = find_zero_Q(t, s, 0, ktemp, n_exact);               // :441
+		kmax = find_zero_Q(t, s, ktemp, t.N_MAX + 1, n_exact);     // :444
+		double a, b;
+		const double J = s.J, E = s.E;
+		double JJ2 = dmul(dmul(2.0, J), J);
+		set_a_b(t, s, kmin, &a, &b);                               // :456
+		double inside = dsub(dmul(a, a), dmul(JJ2, dsub(b, E)));
+		if (inside < 0.0) {                                        // :459-474
+			rmin = ddiv(dmul(dmul(-1.0, J), J), a);
+			if (rmin < tbl_ld(t.r, kmin) || rmin > tbl_ld(t.r, kmin + 1)) { rmin = find_root_vr(t, s, kmin); (*n_brent)++; }
+		} else {
+			rmin = ddiv(dmul(J, J), dadd(-a, dsqrt(inside)));      // :476
+		}
+		dQdr_min = dadd(ddiv(JJ2, dmul(dmul(rmin, rmin), rmin)), ddiv(dmul(2.0, a), dmul(rmin, rmin))); // :479
+		set_a_b(t, s, kmax, &a, &b);                               // :482
+		inside = dsub(dmul(a, a), dmul(JJ2, dsub(b, E)));
+		if (inside < 0.0) {                                        // :485-500
+			rmax = ddiv(-a, dmul(2.0, dsub(b, E)));
+			if (rmax < tbl_ld(t.r, kmax) || rmax > tbl_ld(t.r, kmax + 1)) { rmax = find_root_vr(t, s, kmax); (*n_brent)++; }
+		} else {
+			rmax = ddiv(dadd(-a, dsqrt(inside)), dmul(2.0, dsub(b, E))); // :502
+		}
+		dQdr_max = dadd(ddiv(JJ2, dmul(dmul(rmax, rmax), rmax)), ddiv(dmul(2.0, a), dmul(rmax, rmax))); // :505
+		if (rmin > rmax || dQdr_min <= 0. || dQdr_max >= 0.) circular = true; // :510
+	}
+	if (circular) { // :520-528
+		o.rp = o.ra = s.r_j; o.kmin = o.kmax = s.g_j; o.dQdrp = o.dQdra = 0.0; o.circular = 1;
+	} else {
+		o.rp = rmin; o.ra = rmax; o.kmin = kmin; o.kmax = kmax; o.dQdrp = dQdr_min; o.dQdra = dQdr_max; o.circular = 0;
+	}
+	return o;
+}
+
+// One iteration of the loop body of get_positions_loop (cmc_evolution_thr.c:802-933).
+// E_star is star[j].E (without the self term), Draws provides `double next()` and `bool has(int n)`.
+template <class Draws>
+CMCB_HD void orbit_step_star(const OrbitTables &t, long g_j, bool is_new, double rnew_of_new, double E_star, double J,
+			     double vr_in, double vt_in, double Rtidal, Draws &draws, OrbitOut &out)
+{
+	StarConst s;
+	s.g_j = g_j;
+	s.r_j = tbl_ld(t.r, g_j);
+	s.m_j = tbl_ld(t.m, g_j);
+	s.J = J;
+	s.E = dadd(E_star, phi_self(s.r_j, s.r_j, s.m_j, t.invN)); // :806
+	out.n_draws = 0; out.n_exact = 0; out.n_brent = 0;
+	out.kmin = out.kmax = -1;
+	out.X = out.r_peri = out.r_apo = 0.0;
+	if (s.m_j < CMCB_ZERO) {               // :816-820 (destroy_obj: rnew = SF_INFINITY, vrnew = vtnew = 0, :760-765)
+		out.status = ORBIT_MASSLESS; out.rnew = CMCB_SF_INFINITY; out.vrnew = 0.0; out.vtnew = 0.0;
+		return;
+	}
+	if (s.E >= 0.0) {                      // :823-829 (remove_star :662-664)
+		out.status = ORBIT_UNBOUND; out.rnew = CMCB_SF_INFINITY; out.vrnew = 0.0; out.vtnew = 0.0;
+		return;
+	}
+	OrbitRS o = calc_orbit_new(t, s, is_new, rnew_of_new, &out.n_exact, &out.n_brent); // :832
+	out.kmin = o.kmin; out.kmax = o.kmax;
+	if (o.circular) {                      // :835-839
+		out.status = ORBIT_CIRCULAR; out.rnew = s.r_j; out.vrnew = vr_in; out.vtnew = vt_in;
+		return;
+	}
+	double rmin = o.rp, rmax = o.ra;
+	if (rmax >= Rtidal) {                  // :848-855
+		out.status = ORBIT_TIDAL; out.r_apo = rmax; out.r_peri = rmin;
+		out.rnew = CMCB_SF_INFINITY; out.vrnew = 0.0; out.vtnew = 0.0;
+		return;
+	}
+	double span = dsub(rmax, rmin);
+	double g1 = dsqrt(ddiv(dmul(3.0, span), o.dQdrp));   // :857
+	double g2 = dsqrt(ddiv(dmul(-3.0, span), o.dQdra));  // :858
+	double F = dmul(1.2, (g1 >= g2 ? g1 : g2));          // :860
+	double mid = dmul(0.5, dadd(rmin, rmax)), quarter = dmul(0.25, span), twoE = dmul(2.0, s.E), JJ = dmul(J, J);
+	double r = 0.0, vr = 0.0, X = 0.0;
+	long k;
+	int fail = 0;
+	for (k = 1; k <= CMCB_N_TRY; k++) {    // :862-888
+		if (!draws.has(2)) { fail = 1; break; }
+		X = draws.next();
+		double s0 = dsub(dmul(2.0, X), 1.0);
+		double g0 = dmul(F, draws.next());
+		out.n_draws += 2;
+		r = dadd(mid, dmul(quarter, dsub(dmul(3.0, s0), dmul(dmul(s0, s0), s0))));
+		double pot = dadd(potential_at(t, r, &fail), phi_self(r, s.r_j, s.m_j, t.invN));
+		double drds = dmul(quarter, dsub(3.0, dmul(dmul(3.0, s0), s0)));
+		double Q = dsub(dsub(twoE, dmul(2.0, pot)), ddiv(ddiv(JJ, r), r));
+		vr = (Q >= 0.0) ? dsqrt(Q) : 0.0;
+		if (g0 < dmul(ddiv(1.0, vr), drds)) break;
+	}
+	if (k == CMCB_N_TRY + 1 || fail || !draws.has(1)) {
+		out.status = ORBIT_NTRY; out.rnew = s.r_j; out.vrnew = vr_in; out.vtnew = vt_in;
+		return;
+	}
+	out.X = X; out.r_peri = rmin; out.r_apo = rmax;          // :918-920
+	if (draws.next() < 0.5) vr = -vr;                        // :923-924
+	out.n_draws += 1;
+	out.status = ORBIT_OK;
+	out.rnew = r; out.vrnew = vr; out.vtnew = ddiv(J, r);    // :926-931
+}
+
+} // namespace cmcb

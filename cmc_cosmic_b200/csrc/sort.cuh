@@ -1,0 +1,53 @@
+#pragma once
+#include "common.cuh"
+#include "star_layout.h"
+
+namespace cmcb {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 (key, index) pairs per CTA iteration
+
+struct SortState { // device-resident bookkeeping of one sort
+	unsigned hist[8][256];    // digit histograms of the 8 LSD passes
+	unsigned base[8][256];    // exclusive scans of them
+	int skip[8];              // pass is the identity (all keys share the digit)
+	int src_buf[8];           // buffer (0 = A, 1 = B) the pass reads
+	int final_buf;            // buffer holding the sorted permutation
+	unsigned tile_counter[8]; // dynamic tile ids
+	long n_eq_inf, n_gt_inf;  // keys == / > SF_INFINITY
+	long n_total;             // records sorted
+	long n_new;               // records kept after trimming stripped stars
+	long n_bin;               // binaries after compaction
+};
+
+struct SortBuffers {
+	uint64_t *keys_a, *keys_b;
+	unsigned *vals_a, *vals_b;
+};
+
+struct SortArgs {
+	const char *star_in; // &star[1] (device), n records
+	char *star_out;      // &star_sorted[1]
+	long n;
+	long key_off;        // byte offset of the sort key inside star_t (r)
+	SortBuffers buf;
+	SortState *st;
+	unsigned *tile_hist; // [8][ntiles][256] look-back words
+	double *star_r, *star_m; // SoA tables (index 0 = sentinel), written at [1..n_new]
+	unsigned char *binflag;  // [n]
+	unsigned *bin_block_cnt; // [ceil(n/2048)]
+	const char *bin_in;  // &binary[1] before the sort (may be null)
+	char *bin_out;       // &binary[1] after
+	long n_bin_clear;    // zero bin_out records [n_bin, n_bin_clear)
+};
+
+int sort_setup();
+size_t sort_smem_bytes();
+void sort_stage_keys(const SortArgs &a, cudaStream_t s);
+void sort_stage_passes(const SortArgs &a, cudaStream_t s);
+void sort_stage_gather(const SortArgs &a, cudaStream_t s);
+void sort_stage_binaries(const SortArgs &a, cudaStream_t s);
+
+} // namespace cmcb

@@ -1,0 +1,31 @@
+"""Record layout of the reference's star_t / binary_t (reference include/cmc/cmc.h:409-601, :231-390).
+
+The arrays are kept byte for byte; the fields this path touches are exposed as numpy views.
+"""
+import numpy as np
+
+SF_INFINITY = 1.0e10   # include/cmc/cmc.h:58
+ZERO = 1.0e-20         # include/cmc/cmc.h:60
+STAR_DTYPE_SIZE = 424
+BINARY_DTYPE_SIZE = 464
+
+STAR_OFFSETS = dict(r=0, vr=8, vt=16, m=24, E=32, J=40, EI=48, Eint=56, rnew=64, vrnew=72, vtnew=80, rOld=88, X=96, Y=104,
+                    r_peri=112, r_apo=120, phi=128, binind=152, id=160)
+STAR_INT_FIELDS = ("binind", "id")
+BINARY_OFFSETS = dict(id1=0, id2=8, rad1=16, rad2=24, m1=32, m2=40, Eint1=48, Eint2=56, a=64, e=72, inuse=80)
+
+
+def star_field(buf, name):
+    """View of one star_t field over a (n, 424) uint8 array."""
+    off = STAR_OFFSETS[name]
+    dt = np.int64 if name in STAR_INT_FIELDS else np.float64
+    flat = buf.reshape(-1)
+    return np.lib.stride_tricks.as_strided(flat[off:off + 8].view(dt), shape=(buf.shape[0],), strides=(STAR_DTYPE_SIZE,))
+
+
+def binary_field(buf, name, dtype=None):
+    off = BINARY_OFFSETS[name]
+    dt = dtype or (np.int64 if name in ("id1", "id2") else (np.int32 if name == "inuse" else np.float64))
+    flat = buf.reshape(-1)
+    sz = np.dtype(dt).itemsize
+    return np.lib.stride_tricks.as_strided(flat[off:off + sz].view(dt), shape=(buf.shape[0],), strides=(BINARY_DTYPE_SIZE,))

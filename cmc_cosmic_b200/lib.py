@@ -1,0 +1,77 @@
+"""ctypes binding of libcmcb200.so (include/cmcb200.h).  Fails loudly when the CUDA library is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcmcb200.so")
+N_STAGES = 10
+STAGE_NAMES = ["keys_hist", "radix_passes", "record_gather", "binaries", "potential", "orbit", "transfer", "energy", "h2d", "d2h"]
+
+
+class OrbitParams(C.Structure):
+    _fields_ = [("n_local", C.c_long), ("n_old_local", C.c_long), ("first_global", C.c_long), ("N_MAX", C.c_long), ("N_STAR", C.c_long),
+                ("n_table", C.c_long), ("cenma_m", C.c_double), ("Rtidal", C.c_double), ("draws", C.c_void_p), ("draw_off", C.c_void_p),
+                ("seed", C.c_ulonglong), ("tcount", C.c_ulonglong)]
+
+
+class OrbitResult(C.Structure):
+    _fields_ = [("max_r", C.c_double), ("n_draws", C.c_ulonglong), ("n_exact", C.c_ulonglong), ("n_brent", C.c_ulonglong),
+                ("n_status", C.c_ulonglong * 6)]
+
+
+class CmcB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = [
+    "cmcb200_create", "cmcb200_destroy", "cmcb200_last_error", "cmcb200_set_stream", "cmcb200_layout", "cmcb200_find_limits",
+    "cmcb200_calc_potential_new", "cmcb200_qsorts_new", "cmcb200_new_orbits_calculate", "cmcb200_upload", "cmcb200_download",
+    "cmcb200_dev_new_orbits", "cmcb200_dev_transfer_new_positions", "cmcb200_dev_qsorts_new", "cmcb200_dev_calc_potential_new",
+    "cmcb200_dev_compute_energy", "cmcb200_dev_read_status", "cmcb200_sync", "cmcb200_profile", "cmcb200_profile_read",
+    "cmcb200_potential_stats",
+]
+
+
+def load():
+    """dlopen the library and declare the prototypes.  No GPU is needed for this (cudart initialises lazily)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CmcB200Error(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, lg, dbl, pl = C.c_void_p, C.c_long, C.c_double, C.POINTER(C.c_long)
+    L.cmcb200_create.argtypes = [C.POINTER(vp), C.c_int, lg, lg]
+    L.cmcb200_destroy.argtypes = [vp]
+    L.cmcb200_destroy.restype = None
+    L.cmcb200_last_error.restype = C.c_char_p
+    L.cmcb200_set_stream.argtypes = [vp, vp]
+    L.cmcb200_layout.argtypes = [vp]
+    L.cmcb200_layout.restype = None
+    L.cmcb200_find_limits.argtypes = [lg, C.c_int, C.c_int, vp, vp]
+    L.cmcb200_find_limits.restype = None
+    L.cmcb200_calc_potential_new.argtypes = [vp, vp, vp, vp, pl, lg, C.POINTER(dbl), C.POINTER(dbl), dbl, C.POINTER(dbl), C.POINTER(dbl)]
+    L.cmcb200_qsorts_new.argtypes = [vp, vp, pl, vp, lg, pl, vp, vp]
+    L.cmcb200_new_orbits_calculate.argtypes = [vp, vp, vp, vp, vp, C.POINTER(OrbitParams), vp, vp, vp, C.POINTER(OrbitResult)]
+    L.cmcb200_upload.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg]
+    L.cmcb200_download.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg]
+    L.cmcb200_dev_new_orbits.argtypes = [vp, C.POINTER(OrbitParams), C.c_int, C.POINTER(OrbitResult)]
+    L.cmcb200_dev_transfer_new_positions.argtypes = [vp, lg, lg, lg, lg]
+    L.cmcb200_dev_qsorts_new.argtypes = [vp, pl, lg, pl]
+    L.cmcb200_dev_calc_potential_new.argtypes = [vp, pl, lg, C.POINTER(dbl), C.POINTER(dbl), dbl, C.POINTER(dbl), C.POINTER(dbl)]
+    L.cmcb200_dev_compute_energy.argtypes = [vp, lg, lg]
+    L.cmcb200_dev_read_status.argtypes = [vp, vp, vp, vp, lg]
+    L.cmcb200_sync.argtypes = [vp]
+    L.cmcb200_profile.argtypes = [vp, C.c_int]
+    L.cmcb200_profile_read.argtypes = [vp, vp, vp, C.c_int]
+    L.cmcb200_potential_stats.argtypes = [vp, pl, pl]
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise CmcB200Error(f"{what}: {load().cmcb200_last_error().decode()}")

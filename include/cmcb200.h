@@ -1,0 +1,162 @@
+/* cmcb200 -- B200-native drop-in for the per-timestep data-parallel core of ClusterMonteCarlo/CMC-COSMIC:
+ * radius sort, potential rebuild, per-star new-orbit step.
+ *
+ * C ABI: plain pointers and sizes, no C++/torch types.  Paths cite the reference tree (ClusterMonteCarlo/CMC-COSMIC).
+ *
+ * The reference has no plugin API: the boundary is four `void f(void)` functions that main() calls on process
+ * globals (src/cmc/cmc.c:311,335,339,344):
+ *     void new_orbits_calculate(void)   include/cmc/cmc.h:1801   -> cmcb200_new_orbits_calculate
+ *     void qsorts_new(void)             include/cmc/cmc.h:1922   -> cmcb200_qsorts_new
+ *     void post_sort_comm(void)         include/cmc/cmc.h:1805   -> (fused into cmcb200_qsorts_new: star_r / star_m out)
+ *     void calc_potential_new(void)     include/cmc/cmc.h:1791   -> cmcb200_calc_potential_new
+ * Each entry point below takes what the corresponding function reads from include/cmc/cmc_vars.h as explicit
+ * arguments and returns what it writes.  INTEGRATION.md shows the shim that defines the four functions on the
+ * reference's globals and forwards here.
+ *
+ * Conventions
+ *  - All functions return 0 on success, non-zero on failure; cmcb200_last_error() describes the failure.  The
+ *    reference's convention (eprintf + exit_cleanly -> MPI_Abort, src/cmc/cmc_utils.c:208-220) is applied by the shim.
+ *  - "host" pointers are ordinary host memory owned by the caller (pinned memory makes the copies faster but is not
+ *    required).  The *_dev entry points work on the context's device-resident mirrors and move no bulk data.
+ *  - star_t / binary_t keep the reference's layout byte for byte (include/cmc/cmc.h:409-601, :231-390;
+ *    sizeof = 424 / 464); cmcb200_layout() reports the constants the kernels were built with.
+ *  - Index conventions are the reference's: star[0] / star_r[0] is the sentinel, live stars are 1..N.
+ *  - One context drives one GPU from one host thread (the reference runs one thread per MPI rank).
+ */
+#ifndef CMCB200_H
+#define CMCB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmcb200_ctx cmcb200_ctx;
+
+#define CMCB200_SF_INFINITY 1.0e10 /* include/cmc/cmc.h:58 */
+#define CMCB200_ZERO 1.0e-20       /* include/cmc/cmc.h:60 */
+
+/* per-star outcome of the orbit step: the branches of get_positions_loop (src/cmc/cmc_evolution_thr.c:802-933) */
+enum {
+	CMCB200_ORBIT_OK = 0,       /* new radius sampled */
+	CMCB200_ORBIT_MASSLESS = 1, /* star_m < ZERO: the shim must call destroy_obj(j)                              :816-820 */
+	CMCB200_ORBIT_UNBOUND = 2,  /* E >= 0: the shim must call count_esc_bhs(j); remove_star(j, ...)              :823-829 */
+	CMCB200_ORBIT_CIRCULAR = 3, /* circular_flag: rnew/vrnew/vtnew = r/vr/vt                                     :835-839 */
+	CMCB200_ORBIT_TIDAL = 4,    /* rmax >= Rtidal: r_peri/r_apo set; the shim must call remove_star(j, ...)      :848-855 */
+	CMCB200_ORBIT_NTRY = 5      /* N_TRY exceeded: fatal in the reference (exit_cleanly)                         :890-893 */
+};
+
+/* ---- life cycle -------------------------------------------------------------------------------------------- */
+
+/* device: CUDA ordinal.  n_star_dim / n_bin_dim: capacity in records of star[] / binary[] (N_STAR_DIM_OPT, N_BIN_DIM_OPT,
+ * src/cmc/cmc_io.c:2092-2101) -- also the capacity of star_r / star_m / star_phi (src/cmc/cmc_io.c:3431-3437). */
+int cmcb200_create(cmcb200_ctx **ctx, int device, long n_star_dim, long n_bin_dim);
+void cmcb200_destroy(cmcb200_ctx *ctx);
+const char *cmcb200_last_error(void);
+/* run the context's kernels on an existing CUDA stream (cudaStream_t passed as void*); default: a private stream */
+int cmcb200_set_stream(cmcb200_ctx *ctx, void *cuda_stream);
+/* sizeof(star_t), sizeof(binary_t) and the byte offsets of r, vr, vt, m, E, J, rnew, vrnew, vtnew, rOld, X, r_peri, r_apo,
+ * binind the library was built for (out[0..15]); the shim static-asserts them against the reference headers */
+void cmcb200_layout(long out[16]);
+
+/* ---- partition arithmetic (integer, bit-exact) --------------------------------------------------------------- */
+
+/* findLimits (src/cmc/cmc_utils.c:2319-2333) == mpiFindIndicesCustom per rank (src/cmc/cmc_mpi.c:100-114):
+ * Start[i], End[i] (1-based, inclusive) of rank i when N stars are dealt in blocks of blk to procs ranks. */
+void cmcb200_find_limits(long N, int blk, int procs, int *Start, int *End);
+
+/* ---- calc_potential_new -> potential_calculate (src/cmc/cmc_utils.c:2006-2012, 675-736) ----------------------- */
+
+/* Host-buffer form.  star_r, star_m: the replicated tables ([0] sentinel .. [*N_MAX + 1]); star_phi is written at
+ * [0 .. new N_MAX + 1]; star_r[new N_MAX + 1] = SF_INFINITY like the reference (:713).
+ * *N_MAX: clus.N_MAX in/out.  N_STAR: clus.N_STAR.  cenma_m / cenma_m_new: cenma.m, cenma.m_new in/out (:699-700).
+ * orbit_r -> *Rtidal = orbit_r * Mtotal^(1/3) (:707).  Results carry the reference's sequential FP64 roundings bit for bit. */
+int cmcb200_calc_potential_new(cmcb200_ctx *ctx, double *star_r, const double *star_m, double *star_phi, long *N_MAX, long N_STAR,
+			       double *cenma_m, double *cenma_m_new, double orbit_r, double *Mtotal, double *Rtidal);
+
+/* ---- qsorts_new + post_sort_comm (src/cmc/cmc_utils.c:2232-2288; src/cmc/cmc_sort.c:375-791), one rank ------------ */
+
+/* Host-buffer form.  star1 = &star[1], binary1 = &binary[1] (what the reference passes to sample_sort).
+ * *n_local: clus.N_MAX_NEW in; out = stars kept (trailing r == SF_INFINITY trimmed, cmc_sort.c:343-354) = new clus.N_MAX
+ * and clus.N_MAX_NEW on one rank.  Records [0, n_in) are permuted into ascending r (ties keep input order); binaries are
+ * re-packed in star order, binind renumbered 1,2,.. and binary1[*n_bin .. n_bin_dim-2] zeroed (cmc_sort.c:541,571-579).
+ * star_r / star_m (may be NULL): receive star[i].r / star[i].m at [1 .. *n_local] (post_sort_comm). */
+int cmcb200_qsorts_new(cmcb200_ctx *ctx, void *star1, long *n_local, void *binary1, long n_bin_dim, long *n_bin,
+		       double *star_r, double *star_m);
+
+/* ---- new_orbits_calculate -> get_positions (src/cmc/cmc_utils.c:2194-2211; src/cmc/cmc_evolution_thr.c:784-1023) --- */
+
+typedef struct {
+	long n_local;       /* clus.N_MAX_NEW */
+	long n_old_local;   /* End[myid] - Start[myid] + 1; local stars beyond it were created this step (get_global_idx) */
+	long first_global;  /* Start[myid] */
+	long N_MAX;         /* clus.N_MAX */
+	long N_STAR;        /* clus.N_STAR */
+	long n_table;       /* entries of star_r/star_m/star_phi to make visible (>= N_MAX + 2 + number of new stars) */
+	double cenma_m;     /* cenma.m */
+	double Rtidal;
+	/* uniform draws.  draws != NULL: a recorded stream in CSR form -- star j (0-based local) consumes
+	 * draws[draw_off[j] .. draw_off[j+1]) in order (X, then the g0 draw, per try; one more for the sign of vr):
+	 * "the same uniform random draws fed in as an input array".  draws == NULL: a counter-based Philox4x32-10 stream per
+	 * star keyed by (seed, tcount, global index); statistically equivalent to the reference's per-rank taus113 stream. */
+	const double *draws;
+	const long *draw_off;
+	unsigned long long seed, tcount;
+} cmcb200_orbit_params;
+
+typedef struct {
+	double max_r;                 /* max over sampled stars of the new radius (get_positions' return value) */
+	unsigned long long n_draws;   /* uniforms consumed */
+	unsigned long long n_exact;   /* Q evaluations that needed the exact 80-bit replay */
+	unsigned long long n_brent;   /* find_root_vr fallbacks */
+	unsigned long long n_status[6];
+} cmcb200_orbit_result;
+
+/* Host-buffer form.  star1 = &star[1]: reads .E .J .vr .vt (.rnew for new stars); writes .rnew .vrnew .vtnew .X .r_peri
+ * .r_apo exactly where the reference's loop body does.  status (may be NULL) receives one CMCB200_ORBIT_* per star; the
+ * shim replays the host-side side effects (remove_star / destroy_obj / count_esc_bhs, esc log) for the flagged stars in
+ * star order.  kmin / kmax (may be NULL): the bracket indices of calc_orbit_new, for parity tests. */
+int cmcb200_new_orbits_calculate(cmcb200_ctx *ctx, void *star1, const double *star_r, const double *star_m, const double *star_phi,
+				 const cmcb200_orbit_params *p, int *status, long *kmin, long *kmax, cmcb200_orbit_result *res);
+
+/* ---- device-resident pipeline ------------------------------------------------------------------------------------ */
+/* The star array lives in HBM across timesteps; the host touches O(encounters) records through the get/put calls. */
+
+int cmcb200_upload(cmcb200_ctx *ctx, const void *star1, long n_local, const void *binary1, long n_bin,
+		   const double *star_r, const double *star_m, const double *star_phi, long n_table);
+int cmcb200_download(cmcb200_ctx *ctx, void *star1, long n_local, void *binary1, long n_bin,
+		     double *star_r, double *star_m, double *star_phi, long n_table);
+
+/* orbit step on the resident arrays (same semantics as cmcb200_new_orbits_calculate; star_r/m/phi = resident tables) */
+int cmcb200_dev_new_orbits(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int want_status, cmcb200_orbit_result *res);
+/* the transfer half of ComputeIntermediateEnergy (src/cmc/cmc_utils.c:380-390): rOld <- star_r, r <- rnew, m <- star_m,
+ * vr <- vrnew, vt <- vtnew for local stars 1..n_local -- this is what creates the sort key */
+int cmcb200_dev_transfer_new_positions(cmcb200_ctx *ctx, long n_local, long n_old_local, long first_global, long N_MAX);
+/* qsorts_new + post_sort_comm on the resident arrays; *n_local in/out, *n_bin out */
+int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, long *n_bin);
+/* calc_potential_new on the resident tables */
+int cmcb200_dev_calc_potential_new(cmcb200_ctx *ctx, long *N_MAX, long N_STAR, double *cenma_m, double *cenma_m_new, double orbit_r,
+				   double *Mtotal, double *Rtidal);
+/* E, J of every star from the new potential: the first loop of ComputeEnergy (src/cmc/cmc_utils.c:612-616) */
+int cmcb200_dev_compute_energy(cmcb200_ctx *ctx, long n_local, long first_global);
+/* per-star outputs of the last dev orbit step (status needs want_status) */
+int cmcb200_dev_read_status(cmcb200_ctx *ctx, int *status, long *kmin, long *kmax, long n_local);
+/* wait for everything queued on the context's stream */
+int cmcb200_sync(cmcb200_ctx *ctx);
+
+/* ---- instrumentation --------------------------------------------------------------------------------------------- */
+
+/* With profiling on, every stage is bracketed by CUDA events on the launching stream.  cmcb200_profile_read returns the
+ * accumulated milliseconds and launch counts since the last reset for: 0 keys+histogram, 1 radix passes, 2 record
+ * gather, 3 binaries, 4 potential, 5 orbit step, 6 transfer, 7 energy, 8 h2d, 9 d2h. */
+#define CMCB200_N_STAGES 10
+int cmcb200_profile(cmcb200_ctx *ctx, int on);
+int cmcb200_profile_read(cmcb200_ctx *ctx, double ms[CMCB200_N_STAGES], long launches[CMCB200_N_STAGES], int reset);
+/* exact-sum diagnostics of the last potential rebuild: events resolved sequentially, full sequential fallbacks */
+int cmcb200_potential_stats(cmcb200_ctx *ctx, long *n_events, long *n_fallbacks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

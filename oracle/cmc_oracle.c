@@ -440,3 +440,9 @@ void orc_t113_jump(unsigned int z[4], const unsigned int jpoly[4])            /*
 	}
 	memcpy(z, acc, sizeof(acc));
 }
+
+/* n consecutive rng_t113_dbl_new() values (convenience for the tests) */
+void orc_t113_fill(unsigned int z[4], double *out, long n)
+{
+	for (long i = 0; i < n; i++) out[i] = orc_t113_dbl(z);
+}

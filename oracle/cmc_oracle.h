@@ -87,6 +87,7 @@ long orc_sort_stars(unsigned char *star1, long n, long sizeof_star, long key_off
 void orc_t113_seed(unsigned long s, unsigned int z[4]);
 double orc_t113_dbl(unsigned int z[4]);
 void orc_t113_jump(unsigned int z[4], const unsigned int jpoly[4]);
+void orc_t113_fill(unsigned int z[4], double *out, long n);
 extern const unsigned int orc_JPoly_2_20[4], orc_JPoly_2_80[4];
 
 #ifdef __cplusplus

@@ -24,7 +24,7 @@ class Orbit(C.Structure):
 
 
 def _build():
-    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "cmc_oracle.c")):
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("cmc_oracle.c", "cmc_oracle.h")):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libcmc_oracle.so"])
 
 
@@ -55,6 +55,7 @@ def lib():
         L.orc_t113_dbl.restype = C.c_double
         L.orc_t113_dbl.argtypes = [C.c_void_p]
         L.orc_t113_jump.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_t113_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
         _lib = L
     return _lib
 
@@ -127,4 +128,6 @@ class Taus113:
         return lib().orc_t113_dbl(_p(self.z))
 
     def draws(self, n):
-        return np.array([self.dbl() for _ in range(n)])
+        out = np.empty(n)
+        lib().orc_t113_fill(_p(self.z), _p(out), n)
+        return out

@@ -1,0 +1,169 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on identical inputs.
+
+Bars (BASELINE.json north_star): sort permutation / integer indices bit-exact; Phi rel. err <= 1e-12; r_min, r_max and the
+new r rel. err <= 1e-10 given the same draws.  The implementation aims higher -- every FP64 output is compared BIT FOR BIT.
+"""
+import numpy as np
+import pytest
+
+import common as cm
+import oraclelib as ol
+from cmc_cosmic_b200.cluster import Cluster
+from cmc_cosmic_b200.layout import star_field, binary_field, STAR_DTYPE_SIZE, BINARY_DTYPE_SIZE
+
+pytestmark = pytest.mark.gpu
+
+
+def _potential_case(r, star_m, N_STAR=None, cenma_m=0.0, cenma_m_new=0.0, N_MAX_in=None):
+    n = len(r)
+    want = cm.oracle_potential(r, star_m, N_STAR, cenma_m, cenma_m_new, N_MAX_in=N_MAX_in)
+    c = Cluster(N_STAR or n, n_star_dim=n + 64)
+    c.star_r[:n + 2], c.star_m[:n + 2] = cm.make_tables(r, star_m)
+    c.clus.N_MAX = n if N_MAX_in is None else N_MAX_in
+    c.cenma.m, c.cenma.m_new = cenma_m, cenma_m_new
+    c.calc_potential_new()
+    nm = want["N_MAX"]
+    assert c.clus.N_MAX == nm
+    assert c.Mtotal == want["Mtotal"] and c.Rtidal == want["Rtidal"] and c.cenma.m == want["cenma_m"]
+    cm.assert_bits_equal(c.star_phi[:nm + 2], want["phi"][:nm + 2], "star_phi")
+    assert c.star_r[nm + 1] == cm.SF_INFINITY
+    ev, fb = c.potential_stats()
+    c.close()
+    return ev, fb
+
+
+@pytest.mark.parametrize("kind,N,masses", [("plummer", 1000, "equal"), ("plummer", 100000, "equal"), ("king", 300000, "equal"),
+                                           ("plummer", 100000, "imf"), ("plummer", 1 << 20, "equal"), ("plummer", 2049, "imf")])
+def test_potential_bit_exact(kind, N, masses):
+    r, vr, vt, sm = cm.cluster_state(kind, N, masses=masses)
+    ev, fb = _potential_case(r, sm)
+    assert fb == 0 and 0 < ev < 2000
+
+
+def test_potential_edge_cases():
+    rng = np.random.default_rng(5)
+    # central mass, pending central mass, N_STAR != N, stripped stars at the end (N_MAX shrinks)
+    r = np.sort(rng.uniform(0.01, 50.0, 5000)); sm = rng.uniform(0.2, 3.0, 5000)
+    _potential_case(r, sm, N_STAR=6000, cenma_m=12.5, cenma_m_new=0.75)
+    r2 = r.copy(); r2[-37:] = cm.SF_INFINITY
+    _potential_case(r2, sm, N_STAR=6000)
+    # tiny systems
+    _potential_case(np.array([0.5]), np.array([1.0]))
+    _potential_case(np.array([0.5, 0.7, 3.0]), np.array([1.0, 1.0, 1.0]))
+    # N_MAX_in smaller than the table
+    _potential_case(r, sm, N_MAX_in=4000)
+    # adversarial for the exact-sum machinery: many exact ties -> many events, possibly the sequential fallback
+    sm3 = np.where(rng.uniform(size=5000) < 0.5, 2.0 ** -20, 1.0 + 2.0 ** -30)
+    _potential_case(r, sm3)
+
+
+def _sort_case(n, n_bin, n_stripped, seed, ties=False):
+    rng = np.random.default_rng(seed)
+    nbd = n_bin + 8
+    c = Cluster(n, n_star_dim=n + 64, n_bin_dim=nbd)
+    c.star[:] = rng.integers(0, 256, c.star.shape, dtype=np.uint8)        # every byte of the record must travel
+    c.binary[:] = rng.integers(0, 256, c.binary.shape, dtype=np.uint8)
+    r = rng.uniform(1e-3, 1e2, n) if not ties else rng.integers(1, 50, n).astype(np.float64)
+    strip = rng.choice(n, n_stripped, replace=False)
+    r[strip] = cm.SF_INFINITY
+    c.field("r")[1:n + 1] = r
+    c.field("m")[1:n + 1] = rng.uniform(0.1, 2.0, n)
+    binind = np.zeros(n, np.int64)
+    live = np.setdiff1d(np.arange(n), strip)
+    who = rng.choice(live, min(n_bin, live.size), replace=False)
+    binind[who] = rng.permutation(np.arange(1, who.size + 1))
+    c.field("binind")[1:n + 1] = binind
+    c.clus.N_MAX_NEW = n
+    ref_star = c.star[1:n + 1].copy(); ref_bin = c.binary[1:].copy()
+    n_new, nb, perm = ol.sort_stars(ref_star, n, STAR_DTYPE_SIZE, 0, 152, ref_bin, nbd, BINARY_DTYPE_SIZE)
+    c.qsorts_new()
+    assert c.clus.N_MAX == n_new and c.clus.N_MAX_NEW == n_new and c.N_b_local == nb
+    assert np.array_equal(c.star[1:n_new + 1], ref_star[:n_new]), "sorted star records differ"
+    assert np.array_equal(c.binary[1:], ref_bin), "binary array differs"
+    assert np.array_equal(c.star_r[1:n_new + 1], star_field(ref_star, "r")[:n_new])
+    assert np.array_equal(c.star_m[1:n_new + 1], star_field(ref_star, "m")[:n_new])
+    c.close()
+
+
+@pytest.mark.parametrize("n,n_bin,n_stripped", [(1, 0, 0), (2, 1, 1), (4095, 100, 3), (4097, 0, 0), (100000, 9000, 41), (1000003, 50000, 1000)])
+def test_sort_bit_exact(n, n_bin, n_stripped):
+    _sort_case(n, n_bin, n_stripped, seed=n)
+
+
+def test_sort_ties_and_all_stripped():
+    _sort_case(50000, 100, 10, seed=3, ties=True)     # massive ties: stable order == the oracle's tie rule
+    _sort_case(100, 0, 100, seed=4)                   # everything stripped
+
+
+def _orbit_case(kind, N, masses="equal", seed=1234, tidal=None):
+    r, vr, vt, sm = cm.cluster_state(kind, N, masses=masses, seed=seed)
+    pot = cm.oracle_potential(r, sm)
+    phi, sr, smt = pot["phi"], pot["star_r"], pot["star_m"]
+    E, J = cm.energies(phi[1:N + 1], r, vr, vt)
+    Rtidal = tidal if tidal is not None else pot["Rtidal"]
+    want = cm.oracle_orbits(sr, smt, phi, N, N, E, J, vr, vt, Rtidal, seed=seed)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.star_phi[:N + 2] = phi[:N + 2]
+    c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+    c.Rtidal = Rtidal
+    status = c.new_orbits_calculate(draws=want["draws"], draw_off=want["draw_off"])
+    assert np.array_equal(status, want["status"])
+    ok = want["status"] == ol.ST_OK
+    has_orbit = (want["status"] != ol.ST_MASSLESS) & (want["status"] != ol.ST_UNBOUND)
+    assert np.array_equal(c.last_kmin[has_orbit], want["kmin"][has_orbit]) and np.array_equal(c.last_kmax[has_orbit], want["kmax"][has_orbit])
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(c.field(f)[1:N + 1], want[f], f)
+    for f in ("X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(c.field(f)[1:N + 1][ok], want[f][ok], f)
+    tid = want["status"] == ol.ST_TIDAL
+    cm.assert_bits_equal(c.field("r_apo")[1:N + 1][tid], want["r_apo"][tid], "r_apo(tidal)")
+    assert c.max_r == want["max_rad"]
+    assert c.last_orbit.n_draws == len(want["draws"])
+    res = c.last_orbit
+    c.close()
+    return want, res
+
+
+@pytest.mark.parametrize("kind,N,masses", [("plummer", 2000, "equal"), ("plummer", 100000, "equal"), ("king", 200000, "equal"), ("plummer", 50000, "imf")])
+def test_orbit_step_bit_exact(kind, N, masses):
+    _orbit_case(kind, N, masses)
+
+
+def test_orbit_step_branches():
+    # a small tidal radius exercises the TIDAL branch; unbound / massless / circular stars are planted by hand
+    want, res = _orbit_case("plummer", 20000, tidal=3.0)
+    assert (want["status"] == ol.ST_TIDAL).sum() > 10
+
+
+def test_resident_pipeline_matches_host_buffer_form():
+    """orbit -> transfer -> sort -> potential on resident arrays == the same through host buffers and the oracle."""
+    N = 60000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=77)
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, pot["Rtidal"], seed=9)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.calc_potential_new()
+    c.compute_energy()
+    c.upload()
+    c.dev_new_orbits(draws=want["draws"], draw_off=want["draw_off"])
+    c.dev_transfer_new_positions()
+    c.dev_qsorts_new()
+    c.dev_calc_potential_new()
+    c.dev_compute_energy()
+    c.download()
+    # oracle: same chain on the host
+    rnew, vrn, vtn = want["rnew"], want["vrnew"], want["vtnew"]
+    order = np.argsort(rnew, kind="stable")
+    n_new = int((rnew < cm.SF_INFINITY).sum())
+    assert c.clus.N_MAX == n_new
+    cm.assert_bits_equal(c.star_r[1:n_new + 1], rnew[order][:n_new], "sorted r")
+    pot2 = cm.oracle_potential(rnew[order][:n_new], sm[order][:n_new], N_STAR=N)
+    cm.assert_bits_equal(c.star_phi[:n_new + 2], pot2["phi"][:n_new + 2], "phi after the step")
+    E2, J2 = cm.energies(pot2["phi"][1:n_new + 1], rnew[order][:n_new], vrn[order][:n_new], vtn[order][:n_new])
+    cm.assert_bits_equal(c.field("E")[1:n_new + 1], E2, "E")
+    cm.assert_bits_equal(c.field("J")[1:n_new + 1], J2, "J")
+    cm.assert_bits_equal(c.field("rOld")[1:n_new + 1], r[order][:n_new], "rOld")
+    c.close()
