@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Throughput of the sort + potential + new-orbit path: stars*timesteps/s (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
+    python bench.py --impl reference --gpus N ...            the reference's own CPU implementation of the path on all host cores
+
+One "step" is one pass of the hot path over one cluster state: new-orbit step for every star -> r <- rnew ->
+radius sort (keys, 424-byte record gather, binaries) -> potential rebuild -> E, J from the new potential.
+`value` times it with the arrays resident in HBM (CUDA events on the launching stream); `e2e` times the same work
+through the host-buffer C-ABI entry points (what the reference-side shim calls) including every host<->device copy.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "stars*timesteps/s (radius sort + potential rebuild + new-orbit step)"
+UNIT = "stars*steps/s"
+# algorithmic HBM bytes per star and step (SURVEY.md 8d / DESIGN.md): the dominant kernel is the record gather
+BYTES_GATHER = 848.0
+BYTES_STEP = 996.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if there is one"""
+    p = os.path.join(ROOT, "profiles", "gather_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_star")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, smax = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def workload(N, seed=1234):
+    from cmc_cosmic_b200 import models
+    r, vr, vt, m = models.plummer(N, seed=seed)
+    return r, vr, vt, np.ones(N)          # equal masses: star_m = obj_m * N_STAR = 1
+
+
+# ---------------------------------------------------------------------------------------------- reference / CPU legs
+
+
+def run_reference_cpu(N, steps, warmup, procs):
+    """The reference's own sources (oracle/_ref) as `procs` forked ranks over the mini-MPI shim; TIMER-style brackets
+    (barrier, wall clock) around new_orbits_calculate, qsorts_new, post_sort_comm, calc_potential_new.
+    Returns (stars*steps/s, per-phase seconds) on rank 0; other ranks never return."""
+    import refharness as rh
+    r, vr, vt, sm = workload(N)
+    R = rh.Ref()
+    win = int(3.0 * (N / procs + 4096) * 424) + (1 << 22)
+    if R.L.ref_spawn(procs, win) != 0:
+        raise RuntimeError("mini-MPI spawn failed")
+    rank = R.L.ref_rank()
+    R.init(N, n_star_dim=int(2.5 * (N // procs + 4096)) if procs > 1 else N + 4096, n_table_dim=N + 4096, min_chunk=40)
+    S = np.ctypeslib.as_array((C.c_int * procs).from_address(R.L.ref_Start()))
+    E = np.ctypeslib.as_array((C.c_int * procs).from_address(R.L.ref_End()))
+    lo, hi = int(S[rank]), int(E[rank])
+    nl = hi - lo + 1
+    sr, smm = R.star_r(), R.star_m()
+    sr[0] = 1e-20; sr[1:N + 1] = r; sr[N + 1] = 1e10; smm[1:N + 1] = sm
+    for name, val in (("r", r), ("vr", vr), ("vt", vt), ("m", sm)):
+        R.star_field(name)[1:nl + 1] = val[lo - 1:hi]
+    R.star_field("id", np.int64)[1:nl + 1] = np.arange(lo, hi + 1)
+    R.set_scalars(N, nl)
+    R.L.ref_calc_potential_new()
+    R.L.ref_compute_energy()
+    t = [C.c_double() for _ in range(4)]
+    tot, phases, stars = 0.0, np.zeros(4), 0
+    for step in range(warmup + steps):
+        n_now = int(R.scalars()["N_MAX"])
+        R.L.ref_time_step(*[C.byref(x) for x in t])
+        R.L.ref_compute_energy()
+        if step >= warmup:
+            ph = np.array([x.value for x in t])
+            phases += ph; tot += ph.sum(); stars += n_now
+    if R.L.ref_join() != 0 and rank == 0:
+        raise RuntimeError("a reference rank failed")
+    return stars / tot, phases / max(steps, 1)
+
+
+def cpu_baseline_leg(N_sample, kind_pref="reference"):
+    """bounded single-core sample for the `cpu_baseline` object of the GPU arm (in-process, no fork: CUDA is live)"""
+    import refharness as rh
+    if kind_pref == "reference" and rh.available():
+        r, vr, vt, sm = workload(N_sample, seed=99)
+        R = rh.Ref()
+        R.init(N_sample, n_star_dim=N_sample + 4096)
+        R.load_cluster(r, vr, vt, sm)
+        R.L.ref_calc_potential_new()
+        R.L.ref_compute_energy()
+        t = [C.c_double() for _ in range(4)]
+        best = None
+        for _ in range(2):
+            R.L.ref_time_step(*[C.byref(x) for x in t])
+            R.L.ref_compute_energy()
+            tot = sum(x.value for x in t)
+            best = tot if best is None else min(best, tot)
+        R.free()
+        return {"value": N_sample / best, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"plummer N={N_sample}, 1 rank of the compiled reference (oracle/_ref), best of 2 steps, TIMER-style brackets"}
+    # fall back to the restatement
+    import common as cm
+    r, vr, vt, sm = cm.cluster_state("plummer", N_sample, seed=99)
+    t0 = time.perf_counter()
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N_sample + 1], r, vr, vt)
+    out = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N_sample, N_sample, E, J, vr, vt, pot["Rtidal"])
+    order = np.argsort(out["rnew"], kind="stable")
+    cm.oracle_potential(out["rnew"][order], sm[order])
+    dt = time.perf_counter() - t0
+    return {"value": N_sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"plummer N={N_sample}, oracle restatement (keys-only sort), 1 step"}
+
+
+# ---------------------------------------------------------------------------------------------- the CUDA arm
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from cmc_cosmic_b200.cluster import Cluster
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    N = args.n_stars
+    if world > 1:
+        # round 1: the radius-sharded multi-GPU path (sample sort over NCCL all-to-all + Phi allgather) is not built yet.
+        # The path does shard, so replicas would be a made-up number: report that plainly.
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world, "unavailable": "multi-GPU radius-sharded path not implemented in round 1"}))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
+    stream = torch.cuda.Stream()
+    r, vr, vt, sm = workload(N)
+    with torch.cuda.stream(stream):
+        c = Cluster(N, n_star_dim=N + 4096, device=local_rank, pinned=True, stream=stream.cuda_stream)
+        c.load(r, vr, vt, sm)
+        c.calc_potential_new()
+        c.compute_energy()
+        c.upload()
+        c.sync()
+        # ---- resident arm: `value` ----
+        for _ in range(args.warmup):
+            c.dev_step(seed=args.seed)
+        c.sync()
+        c.profile(True)
+        c.profile_read(reset=True)
+        l0 = c.launch_count()
+        clocks = ClockSampler(local_rank)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        stars = 0
+        e0.record(stream)
+        for _ in range(args.steps):
+            stars += c.clus.N_MAX_NEW
+            c.dev_step(seed=args.seed)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop()
+        launches = c.launch_count() - l0
+        prof = c.profile_read(reset=True)
+        c.profile(False)
+        value = stars / (ms * 1e-3)
+        n_now = c.clus.N_MAX_NEW
+
+        # ---- e2e arm: the host-buffer C-ABI calls, copies included ----
+        c.download()
+        c.sync()
+        e2e_t, e2e_stars = 0.0, 0
+        h2d = d2h = 0
+        for it in range(max(1, min(args.steps, 3)) + 1):
+            n = c.clus.N_MAX_NEW
+            t0 = time.perf_counter()
+            c.new_orbits_calculate(seed=args.seed + it, want_status=False)
+            t1 = time.perf_counter()
+            # host code of the caller between the two calls (ComputeIntermediateEnergy's transfer, reference cmc_utils.c:380-390): untimed
+            for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
+                c.field(dst)[1:n + 1] = c.field(src)[1:n + 1]
+            t2 = time.perf_counter()
+            c.qsorts_new()
+            c.post_sort_comm()
+            c.calc_potential_new()
+            t3 = time.perf_counter()
+            c.compute_energy()
+            if it > 0:  # first pass is warm-up (page faults, pinning)
+                e2e_t += (t1 - t0) + (t3 - t2)
+                e2e_stars += n
+                nt = n + 2
+                h2d = n * 424 + 3 * 8 * nt + n * 424 + 2 * 8 * nt
+                d2h = n * 424 + n * 424 + 2 * 8 * n + 8 * nt
+        e2e = {"value": e2e_stars / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "note": "new_orbits_calculate + qsorts_new + post_sort_comm + calc_potential_new through the host-buffer C ABI, pinned host arrays, "
+                       "wall clock; the caller's r<-rnew transfer between the calls is host code of the reference and is not timed"}
+        c.close()
+
+    peak, peak_src = measured_peak()
+    g_ms, g_n = prof["record_gather"]
+    gather_avg_ms = g_ms / max(g_n, 1)
+    achieved = BYTES_GATHER * n_now / (gather_avg_ms * 1e-3) / 1e9 if gather_avg_ms > 0 else None
+    traffic = profile_traffic()
+    stage_ms = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items()}
+    cpu = cpu_baseline_leg(args.cpu_sample)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (Plummer sphere, equal masses, Henon units; numpy generator in cmc_cosmic_b200/models.py)",
+        "config": {"workload": f"plummer_n{N:.0e}".replace("+0", "").replace("+", ""), "n_stars": N, "record_bytes": 424,
+                   "rng": "philox4x32-10 per star (production mode)", "l2": "inputs larger than L2 (star array %.2f GB)" % (N * 424 / 1e9),
+                   "step": "orbit step -> r<-rnew -> radix sort + 424 B record gather -> potential (exact sequential rounding) -> E,J"},
+        "clocks": clk,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "sort_gather_records", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": (traffic * n_now if traffic else None),
+                     "peak_source": peak_src, "algorithmic_bytes_per_star": BYTES_GATHER,
+                     "step_bytes_per_star": BYTES_STEP, "step_achieved_gbs": BYTES_STEP * n_now / (ms / args.steps * 1e-3) / 1e9},
+        "stage_ms_per_step": stage_ms,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import refharness as rh
+    if not rh.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcmc_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    cores = len(os.sched_getaffinity(0))
+    procs = min(cores, 64)
+    # bounded sample: the whole workload if ~10 s per step suffices (2.5e5 stars/s/core measured), else proportionally fewer stars
+    N = args.ref_sample or int(min(args.n_stars, 2.5e5 * procs * 0.5 * 10.0))
+    val, phases = run_reference_cpu(N, args.steps, min(args.warmup, 1), procs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": float(phases.sum() * 1e3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (same Plummer generator as the CUDA arm)",
+        "config": {"workload": f"plummer_n{args.n_stars:.0e}".replace("+0", "").replace("+", ""), "sample_n_stars": N,
+                   "phases_s": {"t_orb": phases[0], "t_sort": phases[1], "t_postsort_comm": phases[2], "t_pot_cal": phases[3]}},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "reference",
+                         "sample": f"plummer N={N} per step (bounded sample of the N={args.n_stars} workload), {procs} forked ranks of the compiled "
+                                   "reference over a shared-memory mini-MPI, TIMER-style brackets"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--n-stars", type=int, default=10_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--ref-sample", type=int, default=0, help="stars per step of the reference arm (0: derive from the core count)")
+    ap.add_argument("--seed", type=int, default=1234)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -241,6 +241,9 @@ class Cluster:
         _lib.check(self.L.cmcb200_profile_read(self.ctx, ms.ctypes.data, n.ctypes.data, int(reset)), "profile_read")
         return {k: (float(a), int(b)) for k, a, b in zip(_lib.STAGE_NAMES, ms, n)}
 
+    def launch_count(self):
+        return int(self.L.cmcb200_launch_count(self.ctx))
+
     def potential_stats(self):
         ev, fb = C.c_long(), C.c_long()
         _lib.check(self.L.cmcb200_potential_stats(self.ctx, C.byref(ev), C.byref(fb)), "potential_stats")

@@ -70,6 +70,7 @@ struct cmcb200_ctx {
 	std::vector<cudaEvent_t> pool;
 	double acc_ms[CMCB200_N_STAGES];
 	long acc_n[CMCB200_N_STAGES];
+	long launches; // kernels launched since creation
 };
 
 static char *star1(cmcb200_ctx *c) { return c->d_star[c->cur_star] + CMCB_SIZEOF_STAR; }
@@ -250,6 +251,8 @@ extern "C" int cmcb200_profile_read(cmcb200_ctx *c, double ms[CMCB200_N_STAGES],
 	return 0;
 }
 
+extern "C" long cmcb200_launch_count(cmcb200_ctx *c) { return c->launches; }
+
 extern "C" int cmcb200_potential_stats(cmcb200_ctx *c, long *n_events, long *n_fallbacks)
 {
 	long h[2];
@@ -274,7 +277,7 @@ extern "C" int cmcb200_dev_calc_potential_new(cmcb200_ctx *c, long *N_MAX, long 
 		a.r = c->d_r; a.m = c->d_m; a.phi = c->d_phi; a.mprev = c->d_mprev; a.sc = c->d_pot; a.work = c->seqwork;
 		a.n_max_in = *N_MAX; a.n_star = (double) N_STAR; a.madhoc = 1.0 / ((double) N_STAR);
 		a.cenma_m = *cenma_m; a.cenma_m_new = *cenma_m_new;
-		potential_calculate_device(a, c->stream);
+		c->launches += potential_calculate_device(a, c->stream);
 		CMCB_CUDA_OK(cudaGetLastError());
 	}
 	PotScalars *h = (PotScalars *) c->h_pinned;
@@ -333,15 +336,15 @@ extern "C" int cmcb200_dev_qsorts_new(cmcb200_ctx *c, long *n_local, long n_bin_
 	a.bin_in = bin1(c);
 	a.bin_out = c->d_bin[c->cur_bin ^ 1] + CMCB_SIZEOF_BINARY;
 	a.n_bin_clear = n_bin_clear;
-	{ StageTimer t(c, ST_KEYS); sort_stage_keys(a, c->stream); }
-	{ StageTimer t(c, ST_PASSES); sort_stage_passes(a, c->stream); }
+	{ StageTimer t(c, ST_KEYS); c->launches += sort_stage_keys(a, c->stream); }
+	{ StageTimer t(c, ST_PASSES); c->launches += sort_stage_passes(a, c->stream); }
 	{
 		StageTimer t(c, ST_GATHER);
 		// the sentinel record star[0] travels with the array
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_star[c->cur_star ^ 1], c->d_star[c->cur_star], CMCB_SIZEOF_STAR, cudaMemcpyDeviceToDevice, c->stream));
-		sort_stage_gather(a, c->stream);
+		c->launches += sort_stage_gather(a, c->stream);
 	}
-	{ StageTimer t(c, ST_BINARIES); sort_stage_binaries(a, c->stream); }
+	{ StageTimer t(c, ST_BINARIES); c->launches += sort_stage_binaries(a, c->stream); }
 	CMCB_CUDA_OK(cudaGetLastError());
 	c->cur_star ^= 1;
 	c->cur_bin ^= 1;
@@ -418,7 +421,7 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 	a.stats = c->d_ostats;
 	{
 		StageTimer t(c, ST_ORBIT);
-		orbit_step_device(a, c->stream);
+		c->launches += orbit_step_device(a, c->stream);
 		CMCB_CUDA_OK(cudaGetLastError());
 	}
 	OrbitStats *h = (OrbitStats *) c->h_pinned;
@@ -544,7 +547,10 @@ extern "C" int cmcb200_dev_transfer_new_positions(cmcb200_ctx *c, long n_local, 
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	StageTimer t(c, ST_TRANSFER);
 	if (n_local > 0)
+	{
 		transfer_new_positions_kernel<<<(unsigned) ((n_local + 255) / 256), 256, 0, c->stream>>>(star1(c), n_local, n_old_local, first_global, N_MAX, c->d_r, c->d_m);
+		c->launches++;
+	}
 	CMCB_CUDA_OK(cudaGetLastError());
 	return 0;
 }
@@ -554,7 +560,10 @@ extern "C" int cmcb200_dev_compute_energy(cmcb200_ctx *c, long n_local, long fir
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	StageTimer t(c, ST_ENERGY);
 	if (n_local > 0)
+	{
 		compute_energy_kernel<<<(unsigned) ((n_local + 255) / 256), 256, 0, c->stream>>>(star1(c), n_local, first_global, c->d_r, c->d_phi);
+		c->launches++;
+	}
 	CMCB_CUDA_OK(cudaGetLastError());
 	return 0;
 }

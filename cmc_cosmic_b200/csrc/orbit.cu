@@ -129,13 +129,14 @@ __global__ void orbit_stats_reset(OrbitStats *s)
 	for (int i = 0; i < 6; i++) s->n_status[i] = 0;
 }
 
-void orbit_step_device(const OrbitArgs &a, cudaStream_t s)
+int orbit_step_device(const OrbitArgs &a, cudaStream_t s)
 {
 	orbit_stats_reset<<<1, 1, 0, s>>>(a.stats);
-	if (a.n_local <= 0) return;
+	if (a.n_local <= 0) return 1;
 	unsigned blocks = (unsigned) ((a.n_local + 127) / 128);
 	if (a.draws) orbit_step_kernel<true><<<blocks, 128, 0, s>>>(a);
 	else orbit_step_kernel<false><<<blocks, 128, 0, s>>>(a);
+	return 2;
 }
 
 } // namespace cmcb

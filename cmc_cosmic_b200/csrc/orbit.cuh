@@ -31,6 +31,6 @@ struct OrbitArgs {
 	OrbitStats *stats;
 };
 
-void orbit_step_device(const OrbitArgs &a, cudaStream_t s);
+int orbit_step_device(const OrbitArgs &a, cudaStream_t s);
 
 } // namespace cmcb

@@ -135,7 +135,7 @@ void pot_work_bind(SeqWork &w, void *base, long n_dim)
 	w.max_tiles = ntiles;
 }
 
-void potential_calculate_device(const PotArgs &a, cudaStream_t st)
+int potential_calculate_device(const PotArgs &a, cudaStream_t st)
 {
 	const int grid_persist = NUM_SMS_B200 * 4;
 	pot_init_scalars<<<1, 1, 0, st>>>(a.sc, a.n_max_in, a.cenma_m, a.cenma_m_new);
@@ -153,6 +153,7 @@ void potential_calculate_device(const PotArgs &a, cudaStream_t st)
 	ChainPhi cp{a.r, a.mprev, a.phi, a.sc};
 	seq_scan_launch(cp, a.work, a.n_max_in, &a.sc->phi_sum, grid_persist, grid_persist, st);
 	pot_phi0<<<1, 1, 0, st>>>(a.sc, a.r, a.phi, a.madhoc);
+	return (a.n_max_in > 0 ? 5 : 4) + 3 * 4; // scalars, find, set, totals, phi0 + 3 chains x (reset, classify, resolve, finalize)
 }
 
 } // namespace cmcb

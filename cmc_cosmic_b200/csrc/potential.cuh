@@ -29,6 +29,6 @@ struct PotArgs {
 
 size_t pot_work_bytes(long n_dim);
 void pot_work_bind(SeqWork &w, void *base, long n_dim);
-void potential_calculate_device(const PotArgs &a, cudaStream_t st);
+int potential_calculate_device(const PotArgs &a, cudaStream_t st);
 
 } // namespace cmcb

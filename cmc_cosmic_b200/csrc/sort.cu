@@ -386,7 +386,7 @@ __global__ void sort_iota_if_skipped(SortBuffers b, const SortState *st, long n)
 }
 
 // stage 0: keys + digit histograms + plan
-void sort_stage_keys(const SortArgs &a, cudaStream_t s)
+int sort_stage_keys(const SortArgs &a, cudaStream_t s)
 {
 	const long n = a.n;
 	const long ntiles = (n + SORT_TILE - 1) / SORT_TILE;
@@ -395,13 +395,14 @@ void sort_stage_keys(const SortArgs &a, cudaStream_t s)
 	if (n > 0) sort_histogram<<<NUM_SMS_B200 * 2, 512, 0, s>>>(a.buf.keys_a, n, a.st);
 	sort_scan_hist<<<8, 256, 0, s>>>(a.st, n);
 	sort_plan<<<1, 1, 0, s>>>(a.st, n);
+	return n > 0 ? 5 : 3;
 }
 
 // stage 1: the LSD passes (pass 0 generates the indices itself; when it is skipped they come from sort_iota_if_skipped)
-void sort_stage_passes(const SortArgs &a, cudaStream_t s)
+int sort_stage_passes(const SortArgs &a, cudaStream_t s)
 {
 	const long n = a.n;
-	if (n <= 0) return;
+	if (n <= 0) return 0;
 	const long ntiles = (n + SORT_TILE - 1) / SORT_TILE;
 	sort_iota_if_skipped<<<NUM_SMS_B200 * 2, 256, 0, s>>>(a.buf, a.st, n);
 	const int grid = (int) (ntiles < NUM_SMS_B200 * 2 ? ntiles : NUM_SMS_B200 * 2);
@@ -412,24 +413,29 @@ void sort_stage_passes(const SortArgs &a, cudaStream_t s)
 		else if (p == 7) sort_onesweep_pass<false, true><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
 		else sort_onesweep_pass<false, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
 	}
+	return 9;
 }
 
 // stage 2: move the 424-byte records, emit star_r / star_m / binary flags
-void sort_stage_gather(const SortArgs &a, cudaStream_t s)
+int sort_stage_gather(const SortArgs &a, cudaStream_t s)
 {
 	if (a.n > 0) sort_gather_records<<<NUM_SMS_B200 * 8, 256, 0, s>>>(a.star_in, a.star_out, a.buf, a.st, a.star_r, a.star_m, a.binflag);
+	return a.n > 0 ? 1 : 0;
 }
 
 // stage 3: binaries follow their star
-void sort_stage_binaries(const SortArgs &a, cudaStream_t s)
+int sort_stage_binaries(const SortArgs &a, cudaStream_t s)
 {
+	int launches = 0;
 	if (a.n > 0) {
+		launches += a.bin_in ? 3 : 2;
 		const long nbt = (a.n + BIN_TILE - 1) / BIN_TILE;
 		sort_binary_count<<<(unsigned) nbt, 256, 0, s>>>(a.binflag, a.st, a.bin_block_cnt);
 		sort_binary_scan<<<1, 1024, 0, s>>>(a.bin_block_cnt, nbt, a.st);
 		if (a.bin_in) sort_binary_move<<<(unsigned) nbt, 256, 0, s>>>(a.star_out, a.binflag, a.bin_block_cnt, a.st, a.bin_in, a.bin_out);
 	}
-	if (a.bin_out && a.n_bin_clear > 0) sort_binary_clear<<<NUM_SMS_B200 * 2, 256, 0, s>>>(a.bin_out, a.st, a.n_bin_clear);
+	if (a.bin_out && a.n_bin_clear > 0) { sort_binary_clear<<<NUM_SMS_B200 * 2, 256, 0, s>>>(a.bin_out, a.st, a.n_bin_clear); launches++; }
+	return launches;
 }
 
 } // namespace cmcb

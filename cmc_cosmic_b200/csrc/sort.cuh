@@ -45,9 +45,9 @@ struct SortArgs {
 
 int sort_setup();
 size_t sort_smem_bytes();
-void sort_stage_keys(const SortArgs &a, cudaStream_t s);
-void sort_stage_passes(const SortArgs &a, cudaStream_t s);
-void sort_stage_gather(const SortArgs &a, cudaStream_t s);
-void sort_stage_binaries(const SortArgs &a, cudaStream_t s);
+int sort_stage_keys(const SortArgs &a, cudaStream_t s);
+int sort_stage_passes(const SortArgs &a, cudaStream_t s);
+int sort_stage_gather(const SortArgs &a, cudaStream_t s);
+int sort_stage_binaries(const SortArgs &a, cudaStream_t s);
 
 } // namespace cmcb

@@ -153,6 +153,8 @@ int cmcb200_sync(cmcb200_ctx *ctx);
 #define CMCB200_N_STAGES 10
 int cmcb200_profile(cmcb200_ctx *ctx, int on);
 int cmcb200_profile_read(cmcb200_ctx *ctx, double ms[CMCB200_N_STAGES], long launches[CMCB200_N_STAGES], int reset);
+/* kernels launched by this context since it was created */
+long cmcb200_launch_count(cmcb200_ctx *ctx);
 /* exact-sum diagnostics of the last potential rebuild: events resolved sequentially, full sequential fallbacks */
 int cmcb200_potential_stats(cmcb200_ctx *ctx, long *n_events, long *n_fallbacks);
 

@@ -74,7 +74,7 @@ EXPORT long ref_binary_offset(const char *f)
 	return -1;
 }
 
-EXPORT int ref_init(long n_star, long n_star_dim, long n_bin_dim, long min_chunk, int samplesize, long idum, double orbit_r_in)
+EXPORT int ref_init(long n_star, long n_star_dim, long n_table_dim, long n_bin_dim, long min_chunk, int samplesize, long idum, double orbit_r_in)
 {
 	MPI_Comm_size(MPI_COMM_WORLD, &procs);
 	MPI_Comm_rank(MPI_COMM_WORLD, &myid);
@@ -83,13 +83,11 @@ EXPORT int ref_init(long n_star, long n_star_dim, long n_bin_dim, long min_chunk
 	N_BIN_DIM = N_BIN_DIM_OPT = n_bin_dim;
 	star = calloc(n_star_dim, sizeof(star_t));
 	binary = calloc(n_bin_dim, sizeof(binary_t));
-	star_r = malloc(n_star_dim * sizeof(double));
-	star_m = malloc(n_star_dim * sizeof(double));
-	star_phi = malloc(n_star_dim * sizeof(double));
+	/* the replicated tables are sized for the whole cluster, the star array for this rank's share (cmc_io.c:2092-2099, 3431-3437) */
+	star_r = calloc(n_table_dim, sizeof(double));
+	star_m = calloc(n_table_dim, sizeof(double));
+	star_phi = calloc(n_table_dim, sizeof(double));
 	if (!star || !binary || !star_r || !star_m || !star_phi) return -1;
-	memset(star_r, 0, n_star_dim * sizeof(double));
-	memset(star_m, 0, n_star_dim * sizeof(double));
-	memset(star_phi, 0, n_star_dim * sizeof(double));
 	Start = calloc(procs, sizeof(int)); End = calloc(procs, sizeof(int));
 	mpiDisp = calloc(procs, sizeof(int)); mpiLen = calloc(procs, sizeof(int));
 	clus.N_STAR = clus.N_STAR_NEW = clus.N_MAX = n_star;
@@ -198,6 +196,15 @@ EXPORT void ref_rng_reset(unsigned long seed, unsigned int *z) { struct rng_t113
 EXPORT void ref_rng_jump80(unsigned int *z) { struct rng_t113_state s; int i; for (i = 0; i < 4; i++) s.z[i] = z[i]; s = rng_t113_jump(s, JPoly_2_80); for (i = 0; i < 4; i++) z[i] = (unsigned int) s.z[i]; }
 EXPORT void ref_rng_jump20(unsigned int *z) { struct rng_t113_state s; int i; for (i = 0; i < 4; i++) s.z[i] = z[i]; s = rng_t113_jump(s, JPoly_2_20); for (i = 0; i < 4; i++) z[i] = (unsigned int) s.z[i]; }
 EXPORT double ref_rng_next(unsigned int *z) { struct rng_t113_state s; int i; double u; for (i = 0; i < 4; i++) s.z[i] = z[i]; u = ref_real_rng_t113_dbl_new(&s); for (i = 0; i < 4; i++) z[i] = (unsigned int) s.z[i]; return u; }
+
+/* multi-rank runs: fork nprocs-1 copies of the calling process (mini_mpi.c).  Every copy returns from this call with
+ * its own rank; call BEFORE ref_init.  ref_join(): children exit, rank 0 waits for them. */
+EXPORT int ref_spawn(int nprocs, size_t window_bytes) { return mini_mpi_spawn(nprocs, window_bytes); }
+EXPORT int ref_join(void) { return mini_mpi_join(); }
+EXPORT int ref_rank(void) { int r; MPI_Comm_rank(MPI_COMM_WORLD, &r); return r; }
+EXPORT void ref_barrier(void) { MPI_Barrier(MPI_COMM_WORLD); }
+/* the reference's own ComputeEnergy (cmc_utils.c:604-656): E, J of the local stars from the new potential */
+EXPORT void ref_compute_energy(void) { ComputeEnergy(); }
 
 /* timing leg for bench.py: one pass of orbit step -> (caller refreshes r) -> sort -> post_sort_comm -> potential.
  * Brackets follow timeStartSimple/timeEndSimple (cmc_utils.c:1681-1707): barrier, wall clock. */

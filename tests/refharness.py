@@ -31,7 +31,7 @@ class Ref:
         L.ref_star_offset.argtypes = [C.c_char_p]
         L.ref_binary_offset.restype = C.c_long
         L.ref_binary_offset.argtypes = [C.c_char_p]
-        L.ref_init.argtypes = [C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_long, C.c_double]
+        L.ref_init.argtypes = [C.c_long, C.c_long, C.c_long, C.c_long, C.c_long, C.c_int, C.c_long, C.c_double]
         for f in ("ref_star", "ref_binary", "ref_star_r", "ref_star_m", "ref_star_phi", "ref_draw_log", "ref_Start", "ref_End"):
             getattr(L, f).restype = C.c_void_p
         L.ref_set_scalars.argtypes = [C.c_long, C.c_long, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double]
@@ -53,6 +53,7 @@ class Ref:
         L.ref_rng_next.restype = C.c_double
         L.ref_rng_next.argtypes = [C.c_void_p]
         L.ref_time_step.argtypes = [C.c_void_p] * 4
+        L.ref_spawn.argtypes = [C.c_int, C.c_size_t]
         self.sizeof_star = L.ref_sizeof_star()
         self.sizeof_binary = L.ref_sizeof_binary()
         self.n_star_dim = 0
@@ -63,13 +64,15 @@ class Ref:
     def binary_offset(self, name):
         return self.L.ref_binary_offset(name.encode())
 
-    def init(self, n_star, n_star_dim=None, n_bin_dim=None, min_chunk=40, samplesize=1024, idum=1234, orbit_r=1e6):
+    def init(self, n_star, n_star_dim=None, n_bin_dim=None, min_chunk=40, samplesize=1024, idum=1234, orbit_r=1e6, n_table_dim=None):
         n_star_dim = n_star_dim or int(1.5 * (n_star + 2)) + 16
+        n_table_dim = n_table_dim or max(n_star_dim, n_star + 16)
         n_bin_dim = n_bin_dim or 16
-        rc = self.L.ref_init(n_star, n_star_dim, n_bin_dim, min_chunk, samplesize, idum, orbit_r)
+        rc = self.L.ref_init(n_star, n_star_dim, n_table_dim, n_bin_dim, min_chunk, samplesize, idum, orbit_r)
         assert rc == 0
         self.n_star = n_star
         self.n_star_dim = n_star_dim
+        self.n_table_dim = n_table_dim
         self.n_bin_dim = n_bin_dim
 
     def free(self):
@@ -93,13 +96,13 @@ class Ref:
         return np.lib.stride_tricks.as_strided(raw[off:off + 8].view(dtype), shape=(self.n_star_dim,), strides=(self.sizeof_star,))
 
     def star_r(self):
-        return self._view(self.L.ref_star_r(), self.n_star_dim * 8, np.float64)
+        return self._view(self.L.ref_star_r(), self.n_table_dim * 8, np.float64)
 
     def star_m(self):
-        return self._view(self.L.ref_star_m(), self.n_star_dim * 8, np.float64)
+        return self._view(self.L.ref_star_m(), self.n_table_dim * 8, np.float64)
 
     def star_phi(self):
-        return self._view(self.L.ref_star_phi(), self.n_star_dim * 8, np.float64)
+        return self._view(self.L.ref_star_phi(), self.n_table_dim * 8, np.float64)
 
     def scalars(self):
         out = np.zeros(16)
