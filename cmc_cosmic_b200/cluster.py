@@ -24,9 +24,7 @@ def _host_array(shape, dtype, pinned):
     if pinned:
         import torch
         t = torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-        a = t.numpy()
-        a._keep = t
-        return a
+        return t.numpy()    # the view keeps the pinned tensor alive
     return np.zeros(shape, dtype)
 
 

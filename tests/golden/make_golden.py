@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference (compiled by oracle/Makefile into
+oracle/_ref/libcmc_ref.so) on inputs produced by the reference's OWN generators / input file.
+
+    python tests/golden/make_golden.py          (needs /root/reference; run in the build container)
+
+The reference has no golden vector for the sort / potential / new-orbit path, so these files are what pins
+the oracle restatement (oracle/cmc_oracle.c) and the CUDA path on machines where /root/reference does not exist.
+Cases
+  plummer_n4000   COSMIC sample/cmc/elson.py draw_r_vr_vt(N, r_max=100, gamma=4), np.random.seed(1234), m = 1/N
+                  (examples/PlummerSphere.ini, BASELINE.json configs[1] at small N)
+  king_w5_n3000   COSMIC sample/cmc/king.py draw_r_vr_vt(N, w_0=5), np.random.seed(12345), m = 1/N (examples/KingProfile.ini)
+  king_w7_imf_bin king.py w_0=7, N=3000, power-law masses, 10 % of the stars carry a binary_t (configs[4] at small N)
+  ci_input        ci/input.hdf5 as it is (N = 10 000, Kroupa masses, 1 967 binaries; BASELINE.json configs[0]); the
+                  CLUS_OBJ_DATA table is read straight from the file bytes (no HDF5 library in this image)
+  cosmic_plummer_n100 / cosmic_king_n100   the N=100 vectors of COSMIC's own unit tests (tests/data/cmc_*_test.npz)
+Every case records ONE full pass of the path by the reference:
+  calc_potential_new -> ComputeEnergy -> new_orbits_calculate (taus113 draws recorded) -> r <- rnew (ComputeIntermediateEnergy's
+  transfer) -> qsorts_new -> post_sort_comm -> calc_potential_new
+with all inputs and all outputs.  A second set of arrays holds a tidally truncated run (small Rtidal) to reach the
+TIDAL / UNBOUND branches.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import refharness as rh  # noqa: E402
+
+REF = os.environ.get("CMC_REFERENCE", "/root/reference")
+SAMPLE = os.path.join(REF, "src/bse_wrap/bse/COSMIC/src/cosmic/sample/cmc")
+STAR_FIELDS_F = ("r", "vr", "vt", "m", "E", "J", "rnew", "vrnew", "vtnew", "rOld", "X", "r_peri", "r_apo")
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(SAMPLE, name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def read_ci_input():
+    """CLUS_OBJ_DATA/block0_values of ci/input.hdf5: contiguous little-endian float64[10002][8] (columns id, k, m, Reff, r, vr, vt,
+    binind; src/libs/fitslib.c:381-390), located by its id column pattern."""
+    raw = open(os.path.join(REF, "ci/input.hdf5"), "rb").read()
+    pat = np.array([1.0, 2.0, 3.0]).tobytes()
+    off = None
+    for cand in range(0, len(raw) - 200, 8):
+        if raw[cand:cand + 8] == pat[:8] and raw[cand + 64:cand + 72] == pat[8:16] and raw[cand + 128:cand + 136] == pat[16:24]:
+            off = cand - 64
+            break
+    assert off is not None
+    a = np.frombuffer(raw, dtype="<f8", count=10002 * 8, offset=off).reshape(10002, 8)
+    assert a[0, 4] == np.finfo(float).tiny and a[-1, 4] == 1e40 and abs(a[:, 2].sum() - 1.0) < 1e-12 and np.all(np.diff(a[1:-1, 4]) > 0)
+    return a
+
+
+def run_case(R, name, r, vr, vt, obj_m, binind=None, seed=1234, min_chunk=40, rtidal_override=None, cenma_m=0.0, samplesize=1024):
+    n = len(r)
+    n_bin = int((binind > 0).sum()) if binind is not None else 0
+    R.init(n, n_star_dim=n + 64, n_bin_dim=n_bin + 8, min_chunk=min_chunk, idum=seed, samplesize=samplesize)
+    sm = obj_m * n                                         # star_m = obj_m * N_STAR ... see cmc_fits.c:123-136 (units.mstar = 1)
+    R.load_cluster(r, vr, vt, sm, binind=binind)
+    if n_bin:
+        bb = R.binary_bytes()
+        # recognisable, compressible content: 8-byte word w of binary[i] holds i * 64 + w
+        words = (np.arange(1, n_bin + 1, dtype=np.int64)[:, None] * 64 + np.arange(R.sizeof_binary // 8, dtype=np.int64)[None, :])
+        bb[1:n_bin + 1] = words.view(np.uint8).reshape(n_bin, R.sizeof_binary)
+    R.set_scalars(n, n, N_BINARY=n_bin, cenma_m=cenma_m)
+    R.L.ref_calc_potential_new()
+    R.compute_energy()
+    sc0 = R.scalars()
+    out = dict(r=r.copy(), vr=vr.copy(), vt=vt.copy(), star_m=sm.copy(), N_STAR=n, min_chunk=min_chunk, seed=seed, cenma_m=cenma_m,
+               phi0=R.star_phi()[:n + 2].copy(), Mtotal0=sc0["Mtotal"], Rtidal0=sc0["Rtidal"],
+               E=R.star_field("E")[1:n + 1].copy(), J=R.star_field("J")[1:n + 1].copy())
+    if binind is not None:
+        out["binind"] = binind.astype(np.int64)
+        out["binary_in"] = R.binary_bytes()[1:n_bin + 1].copy()
+    if rtidal_override is not None:
+        R.set_scalars(n, n, N_BINARY=n_bin, cenma_m=cenma_m, Rtidal=rtidal_override, Mtotal=sc0["Mtotal"])
+    out["Rtidal_used"] = R.scalars()["Rtidal"]
+    R.L.ref_draw_mode(1)
+    R.L.ref_new_orbits_calculate()
+    R.L.ref_draw_mode(0)
+    out["draws"] = R.draws()
+    for f in ("rnew", "vrnew", "vtnew", "X", "r_peri", "r_apo"):
+        out[f] = R.star_field(f)[1:n + 1].copy()
+    sc1 = R.scalars()
+    out["max_r"] = sc1["max_r"]
+    out["TidalMassLoss"] = sc1["TidalMassLoss"]
+    # the transfer that creates the sort key (ComputeIntermediateEnergy, cmc_utils.c:380-390)
+    srr, smm = R.star_r(), R.star_m()
+    for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
+        R.star_field(dst)[1:n + 1] = R.star_field(src)[1:n + 1]
+    R.star_field("rOld")[1:n + 1] = srr[1:n + 1]
+    R.star_field("m")[1:n + 1] = smm[1:n + 1]
+    R.L.ref_qsorts_new()
+    R.L.ref_post_sort_comm()
+    R.L.ref_calc_potential_new()
+    sc2 = R.scalars()
+    n2 = int(sc2["N_MAX"])
+    out["N_MAX_after"] = n2
+    out["sorted_id"] = R.star_field("id", np.int64)[1:n2 + 1].copy()
+    out["sorted_binind"] = R.star_field("binind", np.int64)[1:n2 + 1].copy()
+    out["star_r_after"] = R.star_r()[:n2 + 2].copy()
+    out["star_m_after"] = R.star_m()[:n2 + 2].copy()
+    out["phi_after"] = R.star_phi()[:n2 + 2].copy()
+    out["Mtotal_after"], out["Rtidal_after"] = sc2["Mtotal"], sc2["Rtidal"]
+    out["N_b_local_after"] = int(sc2["N_b_local"])
+    if n_bin:
+        out["binary_after"] = R.binary_bytes()[1:n_bin + 1].copy()
+    R.free()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    st_ok = np.isfinite(out["rnew"]) & (out["rnew"] < 1e10)
+    print(f"{name}: N={n} draws={len(out['draws'])} ({(len(out['draws']) / n - 1) / 2:.2f} tries/star) removed={n - int(st_ok.sum())} "
+          f"N_MAX_after={n2} n_bin={n_bin}->{out['N_b_local_after']}")
+
+
+def main():
+    assert rh.available(), "build oracle/_ref first (make -C oracle)"
+    el, kg = _load("elson"), _load("king")
+    R = rh.Ref()
+    np.random.seed(1234)
+    r, vr, vt = el.draw_r_vr_vt(N=4000, r_max=100, gamma=4)
+    o = np.argsort(r, kind="stable")
+    run_case(R, "plummer_n4000", r[o], vr[o], vt[o], np.full(4000, 1.0 / 4000), seed=1234)
+    run_case(R, "plummer_n4000_tidal", r[o], vr[o], vt[o], np.full(4000, 1.0 / 4000), seed=77, rtidal_override=4.0)
+    np.random.seed(12345)
+    r, vr, vt = kg.draw_r_vr_vt(N=3000, w_0=5)
+    o = np.argsort(r, kind="stable")
+    run_case(R, "king_w5_n3000", r[o], vr[o], vt[o], np.full(3000, 1.0 / 3000), seed=12345)
+    np.random.seed(7)
+    r, vr, vt = kg.draw_r_vr_vt(N=3000, w_0=7)
+    o = np.argsort(r, kind="stable")
+    rng = np.random.default_rng(7)
+    m = (0.08 ** -1.3 + rng.uniform(size=3000) * (150.0 ** -1.3 - 0.08 ** -1.3)) ** (-1 / 1.3)
+    m /= m.sum()
+    binind = np.zeros(3000, np.int64)
+    who = rng.choice(3000, 300, replace=False)
+    binind[who] = rng.permutation(np.arange(1, 301))
+    run_case(R, "king_w7_imf_bin", r[o], vr[o], vt[o], m, binind=binind, seed=7, cenma_m=0.0)
+    a = read_ci_input()
+    run_case(R, "ci_input", a[1:-1, 4].copy(), a[1:-1, 5].copy(), a[1:-1, 6].copy(), a[1:-1, 2].copy(), binind=a[1:-1, 7].astype(np.int64), seed=1729217,
+             min_chunk=40)    # ci/Params.ini:524,536
+    for kind in ("plummer", "king"):
+        g = np.load(os.path.join(REF, f"src/bse_wrap/bse/COSMIC/src/cosmic/tests/data/cmc_{kind}_test.npz"))
+        r, vr, vt = g["arr_0"], g["arr_1"], g["arr_2"]
+        o = np.argsort(r, kind="stable")
+        run_case(R, f"cosmic_{kind}_n100", r[o], vr[o], vt[o], np.full(100, 0.01), seed=2, min_chunk=20, samplesize=16)
+
+
+if __name__ == "__main__":
+    main()

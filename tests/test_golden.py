@@ -1,0 +1,178 @@
+"""Golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py from runs of the UNMODIFIED reference) against
+
+  * the oracle restatement (oracle/cmc_oracle.c)               -- CPU, pins the oracle where /root/reference does not exist
+  * the host build of the kernel's per-star code (orbit_core.h) -- CPU
+  * the CUDA path through the C ABI                             -- `-m gpu`
+
+Everything is compared bit for bit (the north_star bars are: indices bit-exact, Phi <= 1e-12, r_min/r_max/r <= 1e-10).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common as cm
+import oraclelib as ol
+
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(cm.GOLDEN, "*.npz")))
+SF = cm.SF_INFINITY
+
+
+def load(case):
+    g = np.load(os.path.join(cm.GOLDEN, case + ".npz"))
+    return {k: (g[k] if g[k].ndim else g[k].item()) for k in g.files}
+
+
+def test_fixture_inventory():
+    assert {"plummer_n4000", "plummer_n4000_tidal", "king_w5_n3000", "king_w7_imf_bin", "ci_input", "cosmic_plummer_n100", "cosmic_king_n100"} <= set(CASES)
+
+
+def expected_status(g):
+    """per-star branch of get_positions_loop recovered from the reference's outputs.  remove_star ends in destroy_obj -> zero_star
+    (cmc_evolution_thr.c:712, cmc_dynamics_helper.c:131-153), so a removed star's record holds no trace of WHY it was removed: unbound
+    stars are recognised by E + phi_s >= 0 (:806,823) in the arithmetic of the reference, the other removed ones were tidally stripped."""
+    n = g["N_STAR"]
+    st = np.full(n, ol.ST_OK, np.int32)
+    removed = g["rnew"] == SF
+    E_tot = g["E"] + (g["star_m"] / g["r"]) * (1.0 / n)
+    st[removed & (E_tot >= 0.0)] = ol.ST_UNBOUND
+    st[removed & (E_tot < 0.0)] = ol.ST_TIDAL
+    st[removed & (g["star_m"] < cm.ZERO)] = ol.ST_MASSLESS
+    circ = ~removed & (g["rnew"] == g["r"]) & (g["X"] == 0.0)
+    st[circ] = ol.ST_CIRCULAR
+    return st
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_potential_matches_reference(case):
+    g = load(case)
+    n = g["N_STAR"]
+    want = cm.oracle_potential(g["r"], g["star_m"], n, cenma_m=g["cenma_m"])
+    cm.assert_bits_equal(want["phi"][:n + 2], g["phi0"], "phi0")
+    assert want["Mtotal"] == g["Mtotal0"] and want["Rtidal"] == g["Rtidal0"] and want["N_MAX"] == n
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_orbit_step_matches_reference(case):
+    g = load(case)
+    n = g["N_STAR"]
+    sr, sm = cm.make_tables(g["r"], g["star_m"])
+    t = ol.tables(sr, sm, g["phi0"].copy(), n, n, g["cenma_m"])
+    out = ol.get_positions(t, np.arange(1, n + 1), g["E"], g["J"], g["vr"], g["vt"], g["Rtidal_used"], g["draws"])
+    assert int(out["draw_off"][-1]) == len(g["draws"]), "the oracle consumed a different number of draws than the reference"
+    st = expected_status(g)
+    assert np.array_equal(out["status"], st)
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(out[f], g[f], f)
+    ok = st == ol.ST_OK
+    for f in ("X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(out[f][ok], g[f][ok], f)
+    assert out["max_rad"] == g["max_r"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_sort_and_second_potential_match_reference(case):
+    g = load(case)
+    n, n2 = g["N_STAR"], g["N_MAX_after"]
+    star = np.zeros((n, 424), np.uint8)
+    from cmc_cosmic_b200.layout import star_field
+    star_field(star, "r")[:] = g["rnew"]
+    star_field(star, "m")[:] = g["star_m"]
+    star_field(star, "id")[:] = np.arange(1, n + 1)
+    binary = None
+    nbd = 0
+    if "binind" in g:
+        star_field(star, "binind")[:] = g["binind"]
+        nb = len(g["binary_in"])
+        nbd = nb + 8
+        binary = np.zeros((nbd - 1, 464), np.uint8)
+        binary[:nb] = g["binary_in"]
+    n_new, nb_out, perm = ol.sort_stars(star, n, 424, 0, 152, binary, nbd, 464)
+    assert n_new == n2
+    assert np.array_equal(star_field(star, "id")[:n2], g["sorted_id"])
+    if binary is not None:
+        assert nb_out == g["N_b_local_after"]
+        assert np.array_equal(star_field(star, "binind")[:n2], g["sorted_binind"])
+        assert np.array_equal(binary[:nb_out], g["binary_after"][:nb_out])
+    cm.assert_bits_equal(star_field(star, "r")[:n2].copy(), g["star_r_after"][1:n2 + 1], "sorted r")
+    want = cm.oracle_potential(star_field(star, "r")[:n2].copy(), star_field(star, "m")[:n2].copy(), n, cenma_m=g["cenma_m"])
+    cm.assert_bits_equal(want["phi"][:n2 + 2], g["phi_after"], "phi after the step")
+    assert want["Mtotal"] == g["Mtotal_after"] and want["Rtidal"] == g["Rtidal_after"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_kernel_core_on_host_matches_reference(case):
+    """orbit_core.h (the code the CUDA kernel runs per star, incl. the FP64+bound / x87 replay of function_q) built for the host"""
+    import hostemul
+    g = load(case)
+    n = g["N_STAR"]
+    sr, sm = cm.make_tables(g["r"], g["star_m"])
+    out = hostemul.get_positions(sr, sm, g["phi0"].copy(), n, n, g["cenma_m"], np.arange(1, n + 1), g["E"], g["J"], g["vr"], g["vt"],
+                                 g["Rtidal_used"], g["draws"])
+    assert out["n_draws"] == len(g["draws"])
+    st = expected_status(g)
+    assert np.array_equal(out["status"], st)
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(out[f], g[f], f)
+    ok = st == ol.ST_OK
+    for f in ("X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(out[f][ok], g[f][ok], f)
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_full_step_matches_reference(case):
+    """One pass of the path through the C ABI (host-buffer entry points, the ones the reference-side shim binds) on the reference's
+    own inputs and its recorded taus113 draws: every output bit-identical to what the reference produced."""
+    from cmc_cosmic_b200.cluster import Cluster
+    g = load(case)
+    n, n2 = g["N_STAR"], g["N_MAX_after"]
+    has_bin = "binind" in g
+    nb = len(g["binary_in"]) if has_bin else 0
+    c = Cluster(n, n_star_dim=n + 64, n_bin_dim=nb + 8, min_chunk=g["min_chunk"])
+    c.load(g["r"], g["vr"], g["vt"], g["star_m"], binind=g["binind"] if has_bin else None)
+    if has_bin:
+        c.binary[1:nb + 1] = g["binary_in"]
+    c.cenma.m = g["cenma_m"]
+    c.calc_potential_new()
+    cm.assert_bits_equal(c.star_phi[:n + 2], g["phi0"], "phi0")
+    assert c.Mtotal == g["Mtotal0"] and c.Rtidal == g["Rtidal0"]
+    c.compute_energy()
+    cm.assert_bits_equal(c.field("E")[1:n + 1], g["E"], "E")
+    cm.assert_bits_equal(c.field("J")[1:n + 1], g["J"], "J")
+    c.Rtidal = g["Rtidal_used"]
+    # CSR offsets of the sequential stream: from the oracle (already pinned against the same fixture above)
+    sr, sm = cm.make_tables(g["r"], g["star_m"])
+    t = ol.tables(sr, sm, g["phi0"].copy(), n, n, g["cenma_m"])
+    off = ol.get_positions(t, np.arange(1, n + 1), g["E"], g["J"], g["vr"], g["vt"], g["Rtidal_used"], g["draws"])["draw_off"]
+    status = c.new_orbits_calculate(draws=g["draws"], draw_off=off)
+    st = expected_status(g)
+    assert np.array_equal(status, st)
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(c.field(f)[1:n + 1], g[f], f)
+    ok = st == ol.ST_OK
+    for f in ("X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(c.field(f)[1:n + 1][ok], g[f][ok], f)
+    assert c.max_r == g["max_r"]
+    # the caller's transfer (ComputeIntermediateEnergy), then sort + potential
+    for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
+        c.field(dst)[1:n + 1] = c.field(src)[1:n + 1]
+    c.field("m")[1:n + 1] = c.star_m[1:n + 1]
+    c.qsorts_new()
+    c.post_sort_comm()
+    c.calc_potential_new()
+    assert c.clus.N_MAX == n2
+    assert np.array_equal(c.field("id")[1:n2 + 1], g["sorted_id"])
+    cm.assert_bits_equal(c.star_r[:n2 + 2], g["star_r_after"], "star_r after")
+    cm.assert_bits_equal(c.star_m[1:n2 + 1], g["star_m_after"][1:n2 + 1], "star_m after")
+    cm.assert_bits_equal(c.star_phi[:n2 + 2], g["phi_after"], "phi after")
+    assert c.Mtotal == g["Mtotal_after"] and c.Rtidal == g["Rtidal_after"]
+    if has_bin:
+        assert c.N_b_local == g["N_b_local_after"]
+        assert np.array_equal(c.field("binind")[1:n2 + 1], g["sorted_binind"])
+        assert np.array_equal(c.binary[1:nb + 1], g["binary_after"])
+    c.close()

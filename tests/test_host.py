@@ -1,0 +1,102 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/cmcb200.h declares, partition arithmetic, the exact-sum and x87
+machinery (host builds of the headers the kernels are made of), and the multi-rank reference harness."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import common as cm
+import oraclelib as ol
+import refharness as rh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_EMUL = os.path.join(ROOT, "tests", "host_emul")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from cmc_cosmic_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "cmcb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cmcb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    L = lib.load()
+    for sym in declared:
+        assert hasattr(L, sym), f"libcmcb200.so does not export {sym}"
+    assert set(declared) == set(lib.EXPORTS), "lib.EXPORTS and include/cmcb200.h disagree"
+
+
+def test_no_cpu_fallback_when_library_is_missing(monkeypatch):
+    from cmc_cosmic_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libcmcb200.so")
+    with pytest.raises(lib.CmcB200Error):
+        lib.load()
+
+
+def test_product_package_never_touches_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "cmc_cosmic_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"oraclelib|refharness|cmc_oracle|libcmc_ref|hostemul", txt):
+                    bad.append(f)
+    assert not bad, f"product files reference the oracle: {bad}"
+
+
+@pytest.mark.parametrize("N,blk,procs", [(10000, 20, 1), (10000, 20, 2), (100000, 40, 8), (99999, 40, 7), (1000003, 40, 16), (39, 40, 4), (0, 40, 3),
+                                         (10 ** 7, 40, 8), (2 * 10 ** 6 + 17, 40, 5)])
+def test_find_limits_matches_oracle(N, blk, procs):
+    from cmc_cosmic_b200.partition import find_limits
+    S, E = find_limits(N, blk, procs)
+    S0, E0 = ol.find_limits(N, blk, procs)
+    assert np.array_equal(S, S0) and np.array_equal(E, E0)
+    # the partition tiles 1..N with multiples of blk on every rank but the last
+    assert S[0] == 1 and E[-1] == N and np.all(S[1:] == E[:-1] + 1) and np.all((E[:-1] - S[:-1] + 1) % blk == 0)
+
+
+def _run(exe, *args):
+    subprocess.check_call(["make", "-s", "-C", HOST_EMUL])
+    p = subprocess.run([os.path.join(HOST_EMUL, "_build", exe), *args], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "PASS" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_exact_sequential_sum_classification_is_bit_exact():
+    """exactsum.h: the parallel evaluation of y_i = fl(y_{i-1} +- a_i) (run sums + sequentially resolved events) reproduces the
+    sequential roundings on equal-mass / IMF / adversarial chains (tests/host_emul/test_exactsum.cpp)"""
+    _run("test_exactsum")
+
+
+def test_x87_emulation_matches_hardware_long_double():
+    """x87emu.h against the host's real 80-bit long double, incl. function_q right at its sign changes (tests/host_emul/test_x87emu.cpp)"""
+    _run("test_x87emu", "300000")
+
+
+@pytest.mark.parametrize("kind,N,masses", [("plummer", 20000, "equal"), ("king", 20000, "equal"), ("plummer", 10000, "imf")])
+def test_kernel_core_on_host_matches_oracle(kind, N, masses):
+    import hostemul
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 3, masses=masses)
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, 3.5 if masses == "imf" else pot["Rtidal"], seed=5)
+    out = hostemul.get_positions(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0, np.arange(1, N + 1), E, J, vr, vt,
+                                 3.5 if masses == "imf" else pot["Rtidal"], want["draws"], csr_off=want["draw_off"])
+    assert np.array_equal(out["status"], want["status"])
+    has = (want["status"] != ol.ST_MASSLESS) & (want["status"] != ol.ST_UNBOUND)
+    assert np.array_equal(out["kmin"][has], want["kmin"][has]) and np.array_equal(out["kmax"][has], want["kmax"][has])
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(out[f], want[f], f)
+    ok = want["status"] == ol.ST_OK
+    for f in ("X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(out[f][ok], want[f][ok], f)
+
+
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref/libcmc_ref.so not built")
+@pytest.mark.parametrize("procs,N", [(2, 10000), (4, 50000), (3, 10007)])
+def test_multirank_reference_equals_single_rank_oracle(procs, N):
+    """P forked ranks of the compiled reference (sample sort + load balance + allgather + replicated potential) give the global result
+    the oracle computes in one piece -- this is the contract the radius-sharded GPU path has to meet"""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_multirank_check.py"), str(procs), str(N)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "MULTIRANK OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

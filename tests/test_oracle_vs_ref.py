@@ -1,0 +1,190 @@
+"""The oracle restatement (oracle/cmc_oracle.c) against the UNMODIFIED reference compiled into oracle/_ref/libcmc_ref.so, on seeded
+inputs larger and more varied than the committed fixtures.  Skipped where the compiled reference is absent (it is built from
+/root/reference by oracle/Makefile and travels to the GPU box prebuilt)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common as cm
+import oraclelib as ol
+import refharness as rh
+from cmc_cosmic_b200 import layout
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="oracle/_ref/libcmc_ref.so not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def R():
+    return rh.Ref()
+
+
+def test_layout_constants_match_reference_headers(R):
+    """sizeof/offsetof of star_t / binary_t in the compiled reference (include/cmc/cmc.h:409-601, :231-390) == the frozen layout the
+    kernels address (csrc/star_layout.h, reported by cmcb200_layout) == the numpy views (layout.py)."""
+    from cmc_cosmic_b200 import lib
+    out = (C.c_long * 16)()
+    lib.load().cmcb200_layout(out)
+    names = ["r", "vr", "vt", "m", "E", "J", "rnew", "vrnew", "vtnew", "rOld", "X", "r_peri", "r_apo", "binind"]
+    assert out[0] == R.sizeof_star == layout.STAR_DTYPE_SIZE == 424
+    assert out[1] == R.sizeof_binary == layout.BINARY_DTYPE_SIZE == 464
+    for i, f in enumerate(names):
+        assert out[2 + i] == R.star_offset(f) == layout.STAR_OFFSETS[f], f
+    for f in ("EI", "Eint", "Y", "phi", "id"):
+        assert R.star_offset(f) == layout.STAR_OFFSETS[f], f
+    for f, off in layout.BINARY_OFFSETS.items():
+        assert R.binary_offset(f) == off, f
+
+
+@pytest.mark.parametrize("kind,N,masses,cenma", [("plummer", 30000, "equal", 0.0), ("king", 20000, "equal", 0.0), ("plummer", 20000, "imf", 0.0),
+                                                 ("plummer", 5000, "imf", 37.5)])
+def test_full_step(R, kind, N, masses, cenma):
+    """potential -> E,J -> orbit step (taus113 draws recorded) -> transfer -> sort -> potential, reference vs oracle, bit for bit"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 1, masses=masses)
+    R.init(N, n_star_dim=N + 64, idum=4321)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N, cenma_m=cenma)
+    R.L.ref_calc_potential_new()
+    R.compute_energy()
+    sc = R.scalars()
+    want = cm.oracle_potential(r, sm, N, cenma_m=cenma)
+    cm.assert_bits_equal(want["phi"][:N + 2], R.star_phi()[:N + 2], "phi")
+    assert want["Mtotal"] == sc["Mtotal"] and want["Rtidal"] == sc["Rtidal"]
+    E, J = R.star_field("E")[1:N + 1].copy(), R.star_field("J")[1:N + 1].copy()
+    E2, J2 = cm.energies(want["phi"][1:N + 1], r, vr, vt)
+    cm.assert_bits_equal(E2, E, "E")
+    cm.assert_bits_equal(J2, J, "J")
+    R.L.ref_draw_mode(1)
+    R.L.ref_new_orbits_calculate()
+    R.L.ref_draw_mode(0)
+    draws = R.draws()
+    t = ol.tables(want["star_r"], want["star_m"], want["phi"], N, N, cenma)
+    out = ol.get_positions(t, np.arange(1, N + 1), E, J, vr, vt, sc["Rtidal"], draws)
+    assert int(out["draw_off"][-1]) == len(draws)
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(out[f], R.star_field(f)[1:N + 1], f)
+    ok = out["status"] == ol.ST_OK
+    for f in ("X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(out[f][ok], R.star_field(f)[1:N + 1][ok], f)
+    assert out["max_rad"] == R.scalars()["max_r"]
+    # sort + second potential
+    for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
+        R.star_field(dst)[1:N + 1] = R.star_field(src)[1:N + 1]
+    R.star_field("m")[1:N + 1] = R.star_m()[1:N + 1]
+    R.L.ref_qsorts_new()
+    R.L.ref_post_sort_comm()
+    R.L.ref_calc_potential_new()
+    n2 = int(R.scalars()["N_MAX"])
+    order = np.argsort(out["rnew"], kind="stable")
+    assert n2 == int((out["rnew"] < cm.SF_INFINITY).sum())
+    assert np.array_equal(R.star_field("id", np.int64)[1:n2 + 1], order[:n2] + 1)
+    want2 = cm.oracle_potential(out["rnew"][order][:n2], sm[order][:n2], N, cenma_m=cenma)
+    cm.assert_bits_equal(want2["phi"][:n2 + 2], R.star_phi()[:n2 + 2], "phi after")
+    R.free()
+
+
+def test_sort_with_binaries_and_stripped_stars(R):
+    n, nb, n_strip = 20000, 1500, 23
+    rng = np.random.default_rng(8)
+    R.init(n, n_star_dim=n + 64, n_bin_dim=nb + 8)
+    sb, bb = R.star_bytes(), R.binary_bytes()
+    sb[1:n + 1] = rng.integers(0, 256, (n, R.sizeof_star), dtype=np.uint8)
+    bb[1:nb + 1] = rng.integers(0, 256, (nb, R.sizeof_binary), dtype=np.uint8)
+    r = rng.uniform(1e-3, 1e2, n)
+    r[rng.choice(n, n_strip, replace=False)] = cm.SF_INFINITY
+    R.star_field("r")[1:n + 1] = r
+    R.star_field("m")[1:n + 1] = rng.uniform(0.1, 2.0, n)
+    binind = np.zeros(n, np.int64)
+    live = np.nonzero(r < cm.SF_INFINITY)[0]
+    who = rng.choice(live, nb, replace=False)
+    binind[who] = rng.permutation(np.arange(1, nb + 1))
+    R.star_field("binind", np.int64)[1:n + 1] = binind
+    R.set_scalars(n, n, N_BINARY=nb)
+    mine = sb[1:n + 1].copy()
+    mine_b = bb[1:].copy()
+    n_new, nb_out, perm = ol.sort_stars(mine, n, R.sizeof_star, 0, R.star_offset("binind"), mine_b, nb + 8, R.sizeof_binary)
+    R.L.ref_qsorts_new()
+    sc = R.scalars()
+    assert int(sc["N_MAX"]) == n_new == n - n_strip and int(sc["N_b_local"]) == nb_out == nb
+    assert np.array_equal(sb[1:n_new + 1], mine[:n_new])
+    assert np.array_equal(bb[1:], mine_b)
+    R.free()
+
+
+def test_potential_lookup_and_orbit_probes(R):
+    """potential(r), find_zero_Q, function_q, calc_orbit_new as standalone functions on random arguments"""
+    N = 5000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=3, masses="imf")
+    R.init(N, n_star_dim=N + 64)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N)
+    R.L.ref_calc_potential_new()
+    R.compute_energy()
+    sr, smt, phi = R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy()
+    t = ol.tables(sr, smt, phi, N, N)
+    rng = np.random.default_rng(0)
+    L = ol.lib()
+    for rad in np.concatenate([rng.uniform(0.0, r[-1], 300), r[:50], [0.0, r[0] * 0.5, r[-1]]]):
+        a, b = R.L.ref_potential(float(rad)), L.orc_potential(C.byref(t), float(rad))
+        assert a == b or (np.isnan(a) and np.isnan(b))
+    E, J = R.star_field("E")[1:N + 1].copy(), R.star_field("J")[1:N + 1].copy()
+    o = ol.Orbit()
+    buf = np.zeros(7)
+    for j in rng.integers(1, N + 1, 400):
+        Ej = E[j - 1] + (smt[j] / sr[j]) * (1.0 / N)
+        R.L.ref_calc_orbit_new(int(j), Ej, J[j - 1], buf.ctypes.data)
+        L.orc_calc_orbit_new(C.byref(t), int(j), 0, 0.0, Ej, J[j - 1], C.byref(o))
+        assert (buf[0], buf[1], buf[2], buf[3], buf[4], buf[5], buf[6]) == (o.rp, o.ra, o.dQdrp, o.dQdra, o.kmax, o.kmin, o.circular_flag)
+    R.free()
+
+
+def test_find_root_vr_brent_shim_agrees(R):
+    """find_root_vr (cmc_nr.c:500-603) iterates GSL's Brent solver, an un-vendored dependency: the compiled reference runs on
+    oracle/ref_shim/gsl_shim.c, the oracle on its own restatement -- two independent restatements of the published algorithm must
+    agree bit for bit (this branch stays 'parity unpinned' against a real GSL)."""
+    N = 4000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=5)
+    R.init(N, n_star_dim=N + 64)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N)
+    R.L.ref_calc_potential_new()
+    R.compute_energy()
+    sr, smt, phi = R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy()
+    t = ol.tables(sr, smt, phi, N, N)
+    E, J = R.star_field("E")[1:N + 1].copy(), R.star_field("J")[1:N + 1].copy()
+    buf = np.zeros(7)
+    L = ol.lib()
+    rng = np.random.default_rng(1)
+    n_checked = 0
+    for j in rng.integers(1, N + 1, 300):
+        Ej = E[j - 1] + (smt[j] / sr[j]) * (1.0 / N)
+        R.L.ref_calc_orbit_new(int(j), Ej, J[j - 1], buf.ctypes.data)
+        if buf[6]:
+            continue
+        for k in (int(buf[5]), int(buf[4])):
+            if k < 1:
+                continue
+            a, b = R.L.ref_find_root_vr(int(j), k, Ej, J[j - 1]), L.orc_find_root_vr(C.byref(t), int(j), k, Ej, J[j - 1])
+            assert a == b
+            n_checked += 1
+    assert n_checked > 100
+    R.free()
+
+
+def test_taus113_known_answers(R):
+    """seeding, stepping and the 2^80 jump of the reference's generator (src/libs/taus113-v2.c) vs the oracle's restatement; includes the
+    reference's own self-check: 2^20 steps == one JPoly_2_20 jump (testjumping(), taus113-v2.c:272-292)"""
+    for seed in (1, 1234, 1729217, 0):
+        z = np.zeros(4, np.uint32)
+        R.L.ref_rng_reset(seed, z.ctypes.data)
+        mine = ol.Taus113(seed)
+        assert np.array_equal(z, mine.z)
+        a = np.array([R.L.ref_rng_next(z.ctypes.data) for _ in range(100)])
+        assert np.array_equal(a, mine.draws(100))
+        R.L.ref_rng_jump80(z.ctypes.data)
+        mine.jump(ol.Taus113.JPOLY_2_80)
+        assert np.array_equal(z, mine.z)
+    g1, g2 = ol.Taus113(99), ol.Taus113(99)
+    g1.draws(1 << 20)
+    g2.jump(ol.Taus113.JPOLY_2_20)
+    assert np.array_equal(g1.z, g2.z)
