@@ -1,0 +1,141 @@
+/* Reference-side binding of libcmcb200.so: defines CMC's four hot-path entry points
+ *     void new_orbits_calculate(void)   src/cmc/cmc_utils.c:2194-2211   (get_positions: src/cmc/cmc_evolution_thr.c:944-1023)
+ *     void qsorts_new(void)             src/cmc/cmc_utils.c:2232-2254   (sample_sort:   src/cmc/cmc_sort.c:375-629)
+ *     void post_sort_comm(void)         src/cmc/cmc_utils.c:2259-2288
+ *     void calc_potential_new(void)     src/cmc/cmc_utils.c:2006-2012   (potential_calculate: :675-736)
+ * on the reference's own process globals (include/cmc/cmc_vars.h) and forwards to the C ABI in include/cmcb200.h.
+ * This file is compiled against the reference's headers and linked INSTEAD of those four definitions
+ * (-Wl,--wrap=..., objcopy --weaken-symbol, or an #ifndef around them); everything else in CMC --
+ * relaxation, stellar evolution, fewbody, I/O -- is untouched and keeps calling these names.
+ *
+ * Host-side side effects of the orbit step (remove_star / destroy_obj / count_esc_bhs: escaper accumulators, the esc
+ * log, zeroed records; src/cmc/cmc_evolution_thr.c:655-771, src/cmc/cmc_dynamics_helper.c:131-153) are replayed here,
+ * in star order, by the reference's own functions from the per-star status codes the kernel returns -- so the
+ * accumulators see the same additions in the same order as in get_positions_loop.
+ *
+ * Single rank per GPU.  procs > 1 goes through the radius-sharded entry points (cmcb200_shard_*). */
+#include <stdio.h>
+#include <stdlib.h>
+#include "cmc.h"
+#include "cmc_vars.h"
+#include "cmcb200.h"
+
+#ifdef CMCB200_SHIM_WRAP /* linked with -Wl,--wrap=new_orbits_calculate,--wrap=qsorts_new,... */
+#define SHIM(f) __wrap_##f
+#else
+#define SHIM(f) f
+#endif
+
+static cmcb200_ctx *ctx = NULL;
+static int *status_buf = NULL;
+static long status_cap = 0;
+/* parity mode: a recorded uniform stream in CSR form (NULL = production mode, counter-based Philox on the device) */
+static const double *shim_draws = NULL;
+static const long *shim_draw_off = NULL;
+static cmcb200_orbit_result last_orbit;
+
+static void shim_fail(const char *where)
+{
+	/* the reference's error convention: eprintf + exit_cleanly (src/cmc/cmc_utils.c:208-220) */
+	eprintf("%s: %s\n", where, cmcb200_last_error());
+	exit_cleanly(-1, where);
+}
+
+static void shim_init(void)
+{
+	long lay[16];
+	int dev = 0;
+	const char *e = getenv("CMCB200_DEVICE");
+	if (ctx) return;
+	if (procs != 1) {
+		eprintf("cmcb200 shim: this binding drives one GPU from one rank; use the sharded entry points for procs=%d\n", procs);
+		exit_cleanly(-1, __FUNCTION__);
+	}
+	cmcb200_layout(lay);
+	if (lay[0] != (long) sizeof(star_t) || lay[1] != (long) sizeof(binary_t) || lay[2] != (long) offsetof(star_t, r) ||
+	    lay[6] != (long) offsetof(star_t, E) || lay[7] != (long) offsetof(star_t, J) || lay[8] != (long) offsetof(star_t, rnew) ||
+	    lay[12] != (long) offsetof(star_t, X) || lay[13] != (long) offsetof(star_t, r_peri) || lay[15] != (long) offsetof(star_t, binind)) {
+		eprintf("cmcb200 shim: libcmcb200.so was built for a different star_t/binary_t layout\n");
+		exit_cleanly(-1, __FUNCTION__);
+	}
+	if (e) dev = atoi(e);
+	if (cmcb200_create(&ctx, dev, N_STAR_DIM_OPT, N_BIN_DIM_OPT)) shim_fail("cmcb200_create");
+}
+
+#define SHIM_EXPORT __attribute__((visibility("default")))
+SHIM_EXPORT void cmcb200_shim_set_draws(const double *draws, const long *draw_off) { shim_draws = draws; shim_draw_off = draw_off; }
+SHIM_EXPORT const cmcb200_orbit_result *cmcb200_shim_last_orbit(void) { return &last_orbit; }
+SHIM_EXPORT void cmcb200_shim_shutdown(void) { if (ctx) cmcb200_destroy(ctx); ctx = NULL; free(status_buf); status_buf = NULL; status_cap = 0; }
+
+/* src/cmc/cmc_utils.c:2194-2211 */
+void SHIM(new_orbits_calculate)(void)
+{
+	cmcb200_orbit_params p;
+	double phi_rtidal, phi_zero;
+	long j, n = clus.N_MAX_NEW, n_old = End[myid] - Start[myid] + 1;
+	shim_init();
+	OldTidalMassLoss = TidalMassLoss_old;
+	phi_rtidal = potential(Rtidal);                  /* get_positions, cmc_evolution_thr.c:963-964 */
+	phi_zero = potential(0.0);
+	if (n > status_cap) { status_cap = n + n / 4 + 64; status_buf = realloc(status_buf, status_cap * sizeof(int)); }
+	p.n_local = n;
+	p.n_old_local = n_old;
+	p.first_global = Start[myid];
+	p.N_MAX = clus.N_MAX;
+	p.N_STAR = clus.N_STAR;
+	p.n_table = clus.N_MAX + 2 + (n > n_old ? n - n_old : 0);
+	p.cenma_m = cenma.m;
+	p.Rtidal = Rtidal;
+	p.draws = shim_draws;
+	p.draw_off = shim_draw_off;
+	p.seed = (unsigned long long) IDUM;
+	p.tcount = (unsigned long long) tcount;
+	if (cmcb200_new_orbits_calculate(ctx, star + 1, star_r, star_m, star_phi, &p, status_buf, NULL, NULL, &last_orbit)) shim_fail("new_orbits_calculate");
+	for (j = 1; j <= n; j++) {                       /* the branches of get_positions_loop that touch host state, in star order */
+		switch (status_buf[j - 1]) {
+		case CMCB200_ORBIT_MASSLESS: destroy_obj(j); break;                                           /* :816-820 */
+		case CMCB200_ORBIT_UNBOUND: count_esc_bhs(j); remove_star(j, phi_rtidal, phi_zero); break;    /* :823-829 */
+		case CMCB200_ORBIT_TIDAL: remove_star(j, phi_rtidal, phi_zero); break;                        /* :848-855 */
+		case CMCB200_ORBIT_NTRY:                                                                      /* :890-893 */
+			eprintf("N_TRY exceeded\n");
+			exit_cleanly(-1, __FUNCTION__);
+		default: break;
+		}
+	}
+	max_r = last_orbit.max_r;
+	MPI_Allreduce(MPI_IN_PLACE, &max_r, 1, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
+	MPI_Allreduce(MPI_IN_PLACE, &TidalMassLoss, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+	TidalMassLoss += TidalMassLoss_old;
+}
+
+/* src/cmc/cmc_utils.c:2232-2254; the r/m extraction of post_sort_comm (:2269-2280) is fused into the same device pass */
+void SHIM(qsorts_new)(void)
+{
+	long n = clus.N_MAX_NEW, nb = N_b_local, i;
+	shim_init();
+	/* binaries referenced by the stars being sorted occupy binary[1..max binind]; N_b_local is only refreshed by load_balance */
+	for (i = 1; i <= n; i++) if (star[i].binind > nb) nb = star[i].binind;
+	if (cmcb200_qsorts_new(ctx, star + 1, &n, binary + 1, N_BIN_DIM_OPT, &nb, star_r, star_m)) shim_fail("qsorts_new");
+	clus.N_MAX = n;                                  /* sample_sort's return value: global count after trimming (cmc_sort.c:628) */
+	clus.N_MAX_NEW = n;
+	N_b_local = nb;                                  /* cmc_sort.c:741 */
+	findLimits(clus.N_MAX, MIN_CHUNK_SIZE);          /* find_expected_count (cmc_sort.c:421, :260-273) leaves Start/End for the new N_MAX */
+}
+
+/* src/cmc/cmc_utils.c:2259-2288: star_r / star_m were already written by qsorts_new; on one rank the reductions are identities */
+void SHIM(post_sort_comm)(void)
+{
+	MPI_Allreduce(MPI_IN_PLACE, &cenma.m_new, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+	MPI_Allreduce(MPI_IN_PLACE, &cenma.E_new, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+}
+
+/* src/cmc/cmc_utils.c:2006-2012 -> potential_calculate :675-736 */
+void SHIM(calc_potential_new)(void)
+{
+	long nmax = clus.N_MAX;
+	shim_init();
+	if (cmcb200_calc_potential_new(ctx, star_r, star_m, star_phi, &nmax, clus.N_STAR, &cenma.m, &cenma.m_new, orbit_r, &Mtotal, &Rtidal))
+		shim_fail("calc_potential_new");
+	clus.N_MAX = nmax;
+	mpiFindIndicesCustom(clus.N_MAX, MIN_CHUNK_SIZE, myid, &mpiBegin, &mpiEnd);
+}

@@ -10,6 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "..", "oracle", "_ref", "libcmc_ref.so")
+# the same reference objects + harness with the four hot-path entry points re-bound to cmc_cosmic_b200/shim/cmcb200_shim.c (ld --wrap)
+REF_B200_SO = os.path.join(_HERE, "..", "oracle", "_ref", "libcmc_ref_b200.so")
 
 SF_INFINITY = 1.0e10
 ZERO = 1.0e-20
@@ -22,8 +24,8 @@ def available():
 class Ref:
     """One in-process rank of the reference (procs == 1)."""
 
-    def __init__(self):
-        L = C.CDLL(REF_SO)
+    def __init__(self, so=REF_SO):
+        L = C.CDLL(so)
         self.L = L
         L.ref_sizeof_star.restype = C.c_long
         L.ref_sizeof_binary.restype = C.c_long
