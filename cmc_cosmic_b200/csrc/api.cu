@@ -44,6 +44,9 @@ struct cmcb200_ctx {
 	char *d_bin[2]; // record 0 = binary[0] (unused by the reference), binary1 = base + 464
 	int cur_star, cur_bin;
 	double *d_r, *d_m, *d_phi, *d_mprev;
+	RPhi *d_rp;       // packed (r, phi) lookup table of the orbit step
+	long *d_defer_star, *d_defer_found;
+	int orbit_min_blocks;
 	// sort scratch
 	SortBuffers sbuf;
 	SortState *d_sort;
@@ -153,6 +156,8 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 	c->device = device;
 	c->n_star_dim = n_star_dim;
 	c->n_bin_dim = n_bin_dim;
+	c->orbit_min_blocks = 8;
+	if (const char *e = getenv("CMCB200_ORBIT_MINB")) c->orbit_min_blocks = atoi(e); // tuning knob: 4 / 6 / 8
 	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->own_stream = true;
 	const size_t sb = (size_t) n_star_dim * CMCB_SIZEOF_STAR + 64, bb = (size_t) n_bin_dim * CMCB_SIZEOF_BINARY + 64;
@@ -167,6 +172,9 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_m, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_phi, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_mprev, tb));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rp, (size_t) n_star_dim * sizeof(RPhi)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_star, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_m, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_phi, 0, tb, c->stream));
@@ -203,6 +211,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaStreamSynchronize(c->stream);
 	for (int i = 0; i < 2; i++) { cudaFree(c->d_star[i]); cudaFree(c->d_bin[i]); }
 	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev);
+	cudaFree(c->d_rp); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
 	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
@@ -396,7 +405,9 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 	a.n_local = p->n_local;
 	a.n_old_local = p->n_old_local;
 	a.first_global = p->first_global;
-	a.t.r = c->d_r; a.t.m = c->d_m; a.t.phi = c->d_phi;
+	a.t.rp = c->d_rp; a.t.m = c->d_m;
+	a.defer_star = c->d_defer_star; a.defer_found = c->d_defer_found;
+	a.min_blocks = c->orbit_min_blocks;
 	a.t.N_MAX = p->N_MAX;
 	a.t.invN = 1.0 / p->N_STAR;
 	a.t.madhoc = 1.0 / ((double) p->N_STAR);
@@ -421,6 +432,7 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 	a.stats = c->d_ostats;
 	{
 		StageTimer t(c, ST_ORBIT);
+		c->launches += orbit_pack_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, c->stream);
 		c->launches += orbit_step_device(a, c->stream);
 		CMCB_CUDA_OK(cudaGetLastError());
 	}
@@ -433,6 +445,7 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 		unsigned long long other = 0;
 		for (int i = 1; i < 6; i++) { res->n_status[i] = h->n_status[i]; other += h->n_status[i]; }
 		res->n_status[0] = (unsigned long long) p->n_local - other;
+		res->n_deferred = h->n_defer;
 	}
 	return 0;
 }

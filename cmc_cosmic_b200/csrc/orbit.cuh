@@ -5,10 +5,18 @@
 
 namespace cmcb {
 
+constexpr int ORBIT_THREADS = 128;
+constexpr int ORBIT_SCAN_THREADS = 256;
+constexpr int ORBIT_SCAN_CHUNK = 4096;      // table entries per work item of the cooperative linear scan
+constexpr int ORBIT_DEFER_CAP = 65536;      // queued scans per launch (beyond it a star scans in its own thread)
+constexpr long ORBIT_NOT_FOUND = 0x7fffffffffffffffL;
+
 struct OrbitStats { // device-resident, zeroed per launch
 	unsigned long long max_rad_bits; // max over ORBIT_OK stars of rnew (positive doubles order like their bit patterns)
 	unsigned long long n_draws, n_exact, n_brent;
 	unsigned long long n_status[6];
+	unsigned n_defer;     // stars queued for the cooperative linear scan
+	unsigned scan_ticket; // work-item counter of orbit_scan_kernel
 };
 
 struct OrbitArgs {
@@ -29,8 +37,12 @@ struct OrbitArgs {
 	long *kmin, *kmax;
 	int *n_draws;
 	OrbitStats *stats;
+	int min_blocks;    // register cap variant of orbit_step_kernel: 4, 6 or 8 resident CTAs per SM
+	long *defer_star;  // [ORBIT_DEFER_CAP] local 0-based index of each queued star
+	long *defer_found; // [ORBIT_DEFER_CAP] first k with Q > 0 (ORBIT_NOT_FOUND: none)
 };
 
+int orbit_pack_tables_device(const double *r, const double *phi, RPhi *rp, long n, cudaStream_t s);
 int orbit_step_device(const OrbitArgs &a, cudaStream_t s);
 
 } // namespace cmcb

@@ -28,8 +28,13 @@ enum OrbitStatus {
 	ORBIT_NTRY = 5      // N_TRY exceeded (fatal in the reference) :890-893
 };
 
+struct RPhi { // one entry of the packed lookup table: every probe of the bisections needs r_k AND Phi_k -> one 16-byte load
+	double r, phi;
+};
+
 struct OrbitTables {
-	const double *r, *m, *phi; // star_r, star_m, star_phi: [0] sentinel, [1..N_MAX], [N_MAX+1] = SF_INFINITY / 0
+	const RPhi *rp;  // (star_r[k], star_phi[k]) interleaved: [0] sentinel, [1..N_MAX], [N_MAX+1] = (SF_INFINITY, 0)
+	const double *m; // star_m
 	long N_MAX;
 	double invN;    // 1.0 / clus.N_STAR evaluated in double (the factor in MPI_PHI_S)
 	double madhoc;  // 1.0 / (double) clus.N_STAR (cmc_utils.c:1183) -- same value, kept separate like the reference
@@ -55,6 +60,26 @@ CMCB_HD double tbl_ld(const double *p, long k)
 	return p[k];
 #endif
 }
+CMCB_HD RPhi tbl_rp(const OrbitTables &t, long k)
+{
+#if defined(__CUDA_ARCH__)
+	const double2 v = __ldg(reinterpret_cast<const double2 *>(t.rp + k));
+	RPhi o;
+	o.r = v.x;
+	o.phi = v.y;
+	return o;
+#else
+	return t.rp[k];
+#endif
+}
+CMCB_HD double tbl_r(const OrbitTables &t, long k) { return tbl_ld(&t.rp[k].r, 0); }
+CMCB_HD double tbl_phi(const OrbitTables &t, long k) { return tbl_ld(&t.rp[k].phi, 0); }
+
+#if defined(__CUDA_ARCH__)
+#define CMCB_COLD __device__ __noinline__
+#else
+#define CMCB_COLD inline
+#endif
 
 // MPI_PHI_S(rad, j) with the star's own r_j, m_j already in registers
 CMCB_HD double phi_self(double rad, double r_j, double m_j, double invN)
@@ -63,11 +88,11 @@ CMCB_HD double phi_self(double rad, double r_j, double m_j, double invN)
 }
 
 // FindZero_r (cmc_nr.c:62-82)
-CMCB_HD long find_zero_r(const double *star_r, long kmin, long kmax, double r)
+CMCB_HD long find_zero_r(const OrbitTables &t, long kmin, long kmax, double r)
 {
 	do {
 		long ktry = (kmin + kmax + 1) / 2;
-		if (tbl_ld(star_r, ktry) < r) kmin = ktry; else kmax = ktry - 1;
+		if (tbl_r(t, ktry) < r) kmin = ktry; else kmax = ktry - 1;
 	} while (kmax != kmin);
 	return kmin;
 }
@@ -75,17 +100,16 @@ CMCB_HD long find_zero_r(const double *star_r, long kmin, long kmax, double r)
 // potential(r) (cmc_utils.c:112-165, SEARCH_GRID = 0).  *fail is set when the bracket check (:144-152) would abort.
 CMCB_HD double potential_at(const OrbitTables &t, double r, int *fail)
 {
-	double phi0 = tbl_ld(t.phi, 0);
+	double phi0 = tbl_phi(t, 0);
 	if (r == 0.0) return phi0;
-	double r1 = tbl_ld(t.r, 1);
-	if (r < r1) return dsub(phi0, ddiv(dmul(dsub(phi0, tbl_ld(t.phi, 1)), r1), r));
+	const RPhi p1 = tbl_rp(t, 1);
+	if (r < p1.r) return dsub(phi0, ddiv(dmul(dsub(phi0, p1.phi), p1.r), r));
 	long kmax = t.N_MAX + 1, kmin = 1;
-	long i = (kmin == kmax - 1) ? kmin : find_zero_r(t.r, kmin, kmax, r);
-	double ri = tbl_ld(t.r, i), ri1 = tbl_ld(t.r, i + 1);
-	if (ri > r || ri1 < r) { *fail = 1; return 0.0; }
-	double pi = tbl_ld(t.phi, i), pi1 = tbl_ld(t.phi, i + 1);
-	double inv_i = ddiv(1.0, ri);
-	return dadd(pi, ddiv(dmul(dsub(pi1, pi), dsub(inv_i, ddiv(1.0, r))), dsub(inv_i, ddiv(1.0, ri1))));
+	long i = (kmin == kmax - 1) ? kmin : find_zero_r(t, kmin, kmax, r);
+	const RPhi a = tbl_rp(t, i), b = tbl_rp(t, i + 1);
+	if (a.r > r || b.r < r) { *fail = 1; return 0.0; }
+	double inv_i = ddiv(1.0, a.r);
+	return dadd(a.phi, ddiv(dmul(dsub(b.phi, a.phi), dsub(inv_i, ddiv(1.0, r))), dsub(inv_i, ddiv(1.0, b.r))));
 }
 
 // ---- Q(r): sign with the reference's long-double semantics ---------------------------------------------------
@@ -94,11 +118,25 @@ struct StarConst {
 	double E, J;     // energy including the self term (cmc_evolution_thr.c:806), angular momentum
 	double r_j, m_j; // star_r[g_j], star_m[g_j]
 	long g_j;
+	// derived once per star for the division-free sign test
+	double JJ;       // fl(J*J)
+	double mi;       // fl(m_j * invN):            phis * r^2 = mi * r        for r >= r_j
+	double c_in;     // fl(fl(m_j / r_j) * invN):  phis       = c_in          for r <  r_j
+	double absE;
 };
+
+CMCB_HD void star_const_derive(const OrbitTables &t, StarConst &s)
+{
+	s.JJ = dmul(s.J, s.J);
+	s.mi = dmul(s.m_j, t.invN);
+	s.c_in = dmul(ddiv(s.m_j, s.r_j), t.invN);
+	s.absE = dabs(s.E);
+}
 
 // FP64 evaluation of function_q and a bound B with |Qd - (x87 result before its final rounding)| <= B.
 // Roundings: ratio, phis, pot+phis, E-(..), J/r (one ulp more for the x87 double rounding), its square, the final
 // subtraction -- each <= 2^-52 relative to a term no larger than |E|+|pot|+|phis|+Jr; 2^-48 covers them with slack.
+// Used where the VALUE matters (the qmin < qmax direction test of find_zero_Q); the bisection probes use sign_Q.
 CMCB_HD double q_fp64(const OrbitTables &t, const StarConst &s, double r, double pot, double *B)
 {
 	double phis = phi_self(r, s.r_j, s.m_j, t.invN);
@@ -109,35 +147,55 @@ CMCB_HD double q_fp64(const OrbitTables &t, const StarConst &s, double r, double
 	return Q;
 }
 
-// value the reference's function_q returns (a double), exact
-CMCB_HD double q_exact(const OrbitTables &t, const StarConst &s, double r, double pot)
+// value the reference's function_q returns (a double), exact.  Cold: reached when a sign is within the error bound.
+CMCB_COLD double q_exact(const OrbitTables &t, const StarConst &s, double r, double pot)
 {
 	return x87_function_q(r, pot, s.E, s.J, s.m_j, s.r_j, t.invN);
 }
 
-// sign of function_q(j, star_r[k], star_phi[k], E, J): -1, 0, +1
-CMCB_HD int sign_Q(const OrbitTables &t, const StarConst &s, long k, int *n_exact)
+// Sign of function_q(j, r, pot, E, J) -- what every bisection probe and the linear scan consume -- WITHOUT a division:
+//      Q r^2 = 2 (E - pot) r^2 - 2 phis r^2 - J^2,     phis r^2 = (m_j invN) r  if r >= r_j,  (m_j / r_j invN) r^2  otherwise
+// evaluated in FP64 as S with a rigorous bound.  Error budget in units of 2^-53 (first order):
+//   a = E - pot: 1 (of |a|);  r2: 1;  t1 = a r2: 1  -> 3 |t1|;   t2: <= 4 |t2|;   JJ: 1;   d = t1 - t2: 1 (|t1| + |t2|);
+//   S = 2 d - JJ: 1 (2|d| + JJ)   =>  |S - S*| <= (10 |t1| + 12 |t2| + 2 JJ) 2^-53
+// and the reference's own deviation from the real-number Q, scaled by r^2: SQR(J/r) is a double square of a double-rounded
+// quotient, <= 3.1 * 2^-53 JJ; its 80-bit operations <= 2^-62 (|E| + |pot| + |phis|) r^2.
+// B = 2^-48 (|t1| + |t2| + JJ) + 2^-58 (|E| + |pot|) r^2 covers all of it with a factor >= 2 to spare (32 > 12, 10, 5.1).
+// Inside the bound the x87 arithmetic is replayed exactly (q_exact), so the returned sign is ALWAYS the reference's.
+CMCB_HD int sign_Q_at(const OrbitTables &t, const StarConst &s, const RPhi p, int *n_exact)
 {
-	double r = tbl_ld(t.r, k), pot = tbl_ld(t.phi, k), B;
-	double Q = q_fp64(t, s, r, pot, &B);
-	if (Q > B) return 1;
-	if (Q < -B) return -1;
+	const double a = dsub(s.E, p.phi);
+	const double r2 = dmul(p.r, p.r);
+	const double t1 = dmul(a, r2);
+	const double t2 = (p.r >= s.r_j) ? dmul(s.mi, p.r) : dmul(s.c_in, r2);
+	const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
+	const double B = dadd(dmul(3.552713678800501e-15 /* 2^-48 */, dadd(dadd(dabs(t1), dabs(t2)), s.JJ)),
+			      dmul(dmul(3.469446951953614e-18 /* 2^-58 */, dadd(s.absE, dabs(p.phi))), r2));
+	if (S > B) return 1;
+	if (S < -B) return -1;
 	(*n_exact)++;
-	double q = q_exact(t, s, r, pot);
+	const double q = q_exact(t, s, p.r, p.phi);
 	return q > 0.0 ? 1 : (q < 0.0 ? -1 : 0);
+}
+CMCB_HD int sign_Q(const OrbitTables &t, const StarConst &s, long k, int *n_exact) { return sign_Q_at(t, s, tbl_rp(t, k), n_exact); }
+
+// the direction test of find_zero_Q (cmc_nr.c:342): function_q(kmin) < function_q(kmax) on the VALUES
+CMCB_HD bool q_increasing(const OrbitTables &t, const StarConst &s, long kmin, long kmax, int *n_exact)
+{
+	double Bmin, Bmax;
+	const RPhi lo = tbl_rp(t, kmin), hi = tbl_rp(t, kmax);
+	double qmin = q_fp64(t, s, lo.r, lo.phi, &Bmin), qmax = q_fp64(t, s, hi.r, hi.phi, &Bmax);
+	// 2^-52 |q| covers the final rounding to double of each value
+	double slack = dadd(dadd(Bmin, Bmax), dmul(2.220446049250313e-16, dadd(dabs(qmin), dabs(qmax))));
+	if (dabs(dsub(qmin, qmax)) > slack) return qmin < qmax;
+	(*n_exact) += 2;
+	return q_exact(t, s, lo.r, lo.phi) < q_exact(t, s, hi.r, hi.phi);
 }
 
 // find_zero_Q (cmc_nr.c:316-383): the same probe sequence ktry = (kmin+kmax+1)/2
 CMCB_HD long find_zero_Q(const OrbitTables &t, const StarConst &s, long kmin, long kmax, int *n_exact)
 {
-	double Bmin, Bmax;
-	double rmin = tbl_ld(t.r, kmin), pmin = tbl_ld(t.phi, kmin), rmax = tbl_ld(t.r, kmax), pmax = tbl_ld(t.phi, kmax);
-	double qmin = q_fp64(t, s, rmin, pmin, &Bmin), qmax = q_fp64(t, s, rmax, pmax, &Bmax);
-	bool increasing;
-	// 2^-52 |q| covers the final rounding to double of each value
-	double slack = dadd(dadd(Bmin, Bmax), dmul(2.220446049250313e-16, dadd(dabs(qmin), dabs(qmax))));
-	if (dabs(dsub(qmin, qmax)) > slack) increasing = qmin < qmax;
-	else { (*n_exact) += 2; increasing = q_exact(t, s, rmin, pmin) < q_exact(t, s, rmax, pmax); } // :342
+	const bool increasing = q_increasing(t, s, kmin, kmax, n_exact);
 	do {
 		long ktry = (kmin + kmax + 1) / 2;
 		int sg = sign_Q(t, s, ktry, n_exact);
@@ -147,16 +205,30 @@ CMCB_HD long find_zero_Q(const OrbitTables &t, const StarConst &s, long kmin, lo
 	return kmin;
 }
 
+// the linear scan of get_positive_Q_index (cmc_orbit.c:46-57): first k from 0 with Q > 0; -1 if there is none below N_MAX.
+// Sequential form (host emulation, and the device's last resort); the CUDA path runs it as a grid-wide find-first.
+CMCB_HD long scan_positive_Q(const OrbitTables &t, const StarConst &s, int *n_exact)
+{
+	long ktemp = -1;
+	int sg;
+	do {
+		ktemp++;
+		sg = sign_Q(t, s, ktemp, n_exact);
+	} while (sg <= 0 && ktemp <= t.N_MAX);
+	return ktemp >= t.N_MAX ? -1 : ktemp;
+}
+
 // set_a_b (cmc_orbit.c:722-740)
 CMCB_HD void set_a_b(const OrbitTables &t, const StarConst &s, long k, double *a, double *b)
 {
 	if (k == 0) {
 		*a = dmul(-t.cenma_m, t.madhoc);
-		*b = dadd(dadd(tbl_ld(t.phi, 1), ddiv(dmul(t.cenma_m, t.madhoc), tbl_ld(t.r, 1))), ddiv(dmul(s.m_j, t.madhoc), s.r_j));
+		*b = dadd(dadd(tbl_phi(t, 1), ddiv(dmul(t.cenma_m, t.madhoc), tbl_r(t, 1))), ddiv(dmul(s.m_j, t.madhoc), s.r_j));
 	} else {
-		double rk = tbl_ld(t.r, k), rk1 = tbl_ld(t.r, k + 1);
-		double Uk = dadd(tbl_ld(t.phi, k), phi_self(rk, s.r_j, s.m_j, t.invN));
-		double Uk1 = dadd(tbl_ld(t.phi, k + 1), phi_self(rk1, s.r_j, s.m_j, t.invN));
+		const RPhi pk = tbl_rp(t, k), pk1 = tbl_rp(t, k + 1);
+		double rk = pk.r, rk1 = pk1.r;
+		double Uk = dadd(pk.phi, phi_self(rk, s.r_j, s.m_j, t.invN));
+		double Uk1 = dadd(pk1.phi, phi_self(rk1, s.r_j, s.m_j, t.invN));
 		double den = dsub(ddiv(1., rk1), ddiv(1., rk));
 		*a = ddiv(dsub(Uk1, Uk), den);
 		*b = ddiv(dsub(ddiv(Uk, rk1), ddiv(Uk1, rk)), den);
@@ -165,16 +237,16 @@ CMCB_HD void set_a_b(const OrbitTables &t, const StarConst &s, long k, double *a
 
 // calc_vr_within_interval (cmc_nr.c:393-405 + 279-302): vr^2 inside [r_k, r_k+1]; Brent needs the VALUE, so this is
 // always the exact x87 replay (rare path)
-CMCB_HD double vr2_within_interval(const OrbitTables &t, const StarConst &s, long k, double r)
+CMCB_COLD double vr2_within_interval(const OrbitTables &t, const StarConst &s, long k, double r)
 {
 	const double EPS = 2.220446049250313e-16; // DBL_EPSILON
-	double rk = tbl_ld(t.r, k), rk1 = tbl_ld(t.r, k + 1), pot;
-	if (dabs(dsub(r, rk)) < EPS) pot = tbl_ld(t.phi, k);
-	else if (dabs(dsub(r, rk1)) < EPS) pot = tbl_ld(t.phi, k + 1);
-	else if (r < tbl_ld(t.r, 1)) pot = dsub(tbl_ld(t.phi, 0), ddiv(dmul(t.cenma_m, t.madhoc), r));
+	double rk = tbl_r(t, k), rk1 = tbl_r(t, k + 1), pot;
+	if (dabs(dsub(r, rk)) < EPS) pot = tbl_phi(t, k);
+	else if (dabs(dsub(r, rk1)) < EPS) pot = tbl_phi(t, k + 1);
+	else if (r < tbl_r(t, 1)) pot = dsub(tbl_phi(t, 0), ddiv(dmul(t.cenma_m, t.madhoc), r));
 	else {
-		double pk = tbl_ld(t.phi, k), inv_k = ddiv(1.0, rk);
-		pot = dadd(pk, ddiv(dmul(dsub(tbl_ld(t.phi, k + 1), pk), dsub(inv_k, ddiv(1.0, r))), dsub(inv_k, ddiv(1.0, rk1))));
+		double pk = tbl_phi(t, k), inv_k = ddiv(1.0, rk);
+		pot = dadd(pk, ddiv(dmul(dsub(tbl_phi(t, k + 1), pk), dsub(inv_k, ddiv(1.0, r))), dsub(inv_k, ddiv(1.0, rk1))));
 	}
 	return q_exact(t, s, r, pot);
 }
@@ -182,11 +254,11 @@ CMCB_HD double vr2_within_interval(const OrbitTables &t, const StarConst &s, lon
 // find_root_vr (cmc_nr.c:500-603): Brent-Dekker as GSL's gsl_root_fsolver_brent iterates it (un-vendored
 // dependency of the reference, version unpinned -> this branch is "parity unpinned"), APSIDES_PRECISION = 1e-11,
 // APSIDES_MAX_ITER = 100, APSIDES_CONVERGENCE = 5e-13 (cmc_io.c:1752-1754).
-CMCB_HD double find_root_vr(const OrbitTables &t, const StarConst &s, long k)
+CMCB_COLD double find_root_vr(const OrbitTables &t, const StarConst &s, long k)
 {
 	const double PREC = 1.0e-11, CONV = 5.e-13, EPS = 2.220446049250313e-16;
 	long iter = 100;
-	double a = tbl_ld(t.r, k), b = tbl_ld(t.r, k + 1), c = b;
+	double a = tbl_r(t, k), b = tbl_r(t, k + 1), c = b;
 	double fa = vr2_within_interval(t, s, k, a), fb = vr2_within_interval(t, s, k, b), fc = fb;
 	double d = dsub(b, a), e = d, root = dmul(0.5, dadd(a, b)), lo = a, hi = b, prev_apsis = -1.0;
 	bool not_converged = true;
@@ -249,19 +321,25 @@ struct OrbitRS { // orbit_rs_t, reference include/cmc/cmc.h:1621-1650
 };
 
 // calc_orbit_new (cmc_orbit.c:413-540) incl. get_positive_Q_index (:30-59)
-CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is_new, double rnew_of_new, int *n_exact, int *n_brent)
+// ktemp_in: KTEMP_COMPUTE, or the result of the linear scan found elsewhere (>= -1).  need_scan != nullptr: instead of running the
+// O(N) scan in this thread, set *need_scan and return (the caller queues the star for the cooperative scan).
+constexpr long KTEMP_COMPUTE = -2;
+CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is_new, double rnew_of_new, int *n_exact, int *n_brent,
+			       long ktemp_in = KTEMP_COMPUTE, bool *need_scan = nullptr)
 {
 	OrbitRS o;
-	long ktemp = s.g_j;
-	if (is_new) ktemp = find_zero_r(t.r, 0, t.N_MAX, rnew_of_new) + 1; // cmc_orbit.c:39-41
-	if (sign_Q(t, s, ktemp, n_exact) <= 0) {                            // :46-57 linear scan from 0
-		ktemp = -1;
-		int sg;
-		do {
-			ktemp++;
-			sg = sign_Q(t, s, ktemp, n_exact);
-		} while (sg <= 0 && ktemp <= t.N_MAX);
-		if (ktemp >= t.N_MAX) ktemp = -1;
+	long ktemp = ktemp_in;
+	if (ktemp_in == KTEMP_COMPUTE) {
+		ktemp = s.g_j;
+		if (is_new) ktemp = find_zero_r(t, 0, t.N_MAX, rnew_of_new) + 1; // cmc_orbit.c:39-41
+		if (sign_Q(t, s, ktemp, n_exact) <= 0) {                          // :46-57 linear scan from 0
+			if (need_scan) {
+				*need_scan = true;
+				o.rp = o.ra = o.dQdrp = o.dQdra = 0.0; o.kmin = o.kmax = -1; o.circular = 0;
+				return o;
+			}
+			ktemp = scan_positive_Q(t, s, n_exact);
+		}
 	}
 	bool circular = ktemp <= -1;
 	double rmin = 0, rmax = 0, dQdr_min = 0, dQdr_max = 0;
@@ -276,7 +354,7 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 		double inside = dsub(dmul(a, a), dmul(JJ2, dsub(b, E)));
 		if (inside < 0.0) {                                        // :459-474
 			rmin = ddiv(dmul(dmul(-1.0, J), J), a);
-			if (rmin < tbl_ld(t.r, kmin) || rmin > tbl_ld(t.r, kmin + 1)) { rmin = find_root_vr(t, s, kmin); (*n_brent)++; }
+			if (rmin < tbl_r(t, kmin) || rmin > tbl_r(t, kmin + 1)) { rmin = find_root_vr(t, s, kmin); (*n_brent)++; }
 		} else {
 			rmin = ddiv(dmul(J, J), dadd(-a, dsqrt(inside)));      // :476
 		}
@@ -285,7 +363,7 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 		inside = dsub(dmul(a, a), dmul(JJ2, dsub(b, E)));
 		if (inside < 0.0) {                                        // :485-500
 			rmax = ddiv(-a, dmul(2.0, dsub(b, E)));
-			if (rmax < tbl_ld(t.r, kmax) || rmax > tbl_ld(t.r, kmax + 1)) { rmax = find_root_vr(t, s, kmax); (*n_brent)++; }
+			if (rmax < tbl_r(t, kmax) || rmax > tbl_r(t, kmax + 1)) { rmax = find_root_vr(t, s, kmax); (*n_brent)++; }
 		} else {
 			rmax = ddiv(dadd(-a, dsqrt(inside)), dmul(2.0, dsub(b, E))); // :502
 		}
@@ -302,16 +380,27 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 
 // One iteration of the loop body of get_positions_loop (cmc_evolution_thr.c:802-933).
 // E_star is star[j].E (without the self term), Draws provides `double next()` and `bool has(int n)`.
-template <class Draws>
-CMCB_HD void orbit_step_star(const OrbitTables &t, long g_j, bool is_new, double rnew_of_new, double E_star, double J,
-			     double vr_in, double vt_in, double Rtidal, Draws &draws, OrbitOut &out)
+// the star's constants as the loop body sets them up (:803-807)
+CMCB_HD StarConst star_const(const OrbitTables &t, long g_j, double E_star, double J)
 {
 	StarConst s;
 	s.g_j = g_j;
-	s.r_j = tbl_ld(t.r, g_j);
+	s.r_j = tbl_r(t, g_j);
 	s.m_j = tbl_ld(t.m, g_j);
 	s.J = J;
 	s.E = dadd(E_star, phi_self(s.r_j, s.r_j, s.m_j, t.invN)); // :806
+	star_const_derive(t, s);
+	return s;
+}
+
+constexpr int ORBIT_DEFERRED = 6; // internal to the CUDA path: the star waits for the cooperative linear scan; never leaves the library
+
+template <class Draws>
+CMCB_HD void orbit_step_star(const OrbitTables &t, long g_j, bool is_new, double rnew_of_new, double E_star, double J,
+			     double vr_in, double vt_in, double Rtidal, Draws &draws, OrbitOut &out,
+			     long ktemp_in = KTEMP_COMPUTE, bool allow_defer = false)
+{
+	const StarConst s = star_const(t, g_j, E_star, J);
 	out.n_draws = 0; out.n_exact = 0; out.n_brent = 0;
 	out.kmin = out.kmax = -1;
 	out.X = out.r_peri = out.r_apo = 0.0;
@@ -323,7 +412,9 @@ CMCB_HD void orbit_step_star(const OrbitTables &t, long g_j, bool is_new, double
 		out.status = ORBIT_UNBOUND; out.rnew = CMCB_SF_INFINITY; out.vrnew = 0.0; out.vtnew = 0.0;
 		return;
 	}
-	OrbitRS o = calc_orbit_new(t, s, is_new, rnew_of_new, &out.n_exact, &out.n_brent); // :832
+	bool need_scan = false;
+	OrbitRS o = calc_orbit_new(t, s, is_new, rnew_of_new, &out.n_exact, &out.n_brent, ktemp_in, allow_defer ? &need_scan : nullptr); // :832
+	if (need_scan) { out.status = ORBIT_DEFERRED; out.rnew = out.vrnew = out.vtnew = 0.0; return; }
 	out.kmin = o.kmin; out.kmax = o.kmax;
 	if (o.circular) {                      // :835-839
 		out.status = ORBIT_CIRCULAR; out.rnew = s.r_j; out.vrnew = vr_in; out.vtnew = vt_in;

@@ -16,7 +16,7 @@ class OrbitParams(C.Structure):
 
 class OrbitResult(C.Structure):
     _fields_ = [("max_r", C.c_double), ("n_draws", C.c_ulonglong), ("n_exact", C.c_ulonglong), ("n_brent", C.c_ulonglong),
-                ("n_status", C.c_ulonglong * 6)]
+                ("n_status", C.c_ulonglong * 6), ("n_deferred", C.c_ulonglong)]
 
 
 class CmcB200Error(RuntimeError):

@@ -27,6 +27,7 @@
 #endif
 
 static cmcb200_ctx *ctx = NULL;
+static long ctx_star_dim = 0, ctx_bin_dim = 0;
 static int *status_buf = NULL;
 static long status_cap = 0;
 /* parity mode: a recorded uniform stream in CSR form (NULL = production mode, counter-based Philox on the device) */
@@ -46,7 +47,8 @@ static void shim_init(void)
 	long lay[16];
 	int dev = 0;
 	const char *e = getenv("CMCB200_DEVICE");
-	if (ctx) return;
+	if (ctx && ctx_star_dim == N_STAR_DIM_OPT && ctx_bin_dim == N_BIN_DIM_OPT) return;
+	if (ctx) { cmcb200_destroy(ctx); ctx = NULL; } /* the arrays were re-dimensioned (a new run in the same process) */
 	if (procs != 1) {
 		eprintf("cmcb200 shim: this binding drives one GPU from one rank; use the sharded entry points for procs=%d\n", procs);
 		exit_cleanly(-1, __FUNCTION__);
@@ -60,6 +62,8 @@ static void shim_init(void)
 	}
 	if (e) dev = atoi(e);
 	if (cmcb200_create(&ctx, dev, N_STAR_DIM_OPT, N_BIN_DIM_OPT)) shim_fail("cmcb200_create");
+	ctx_star_dim = N_STAR_DIM_OPT;
+	ctx_bin_dim = N_BIN_DIM_OPT;
 }
 
 #define SHIM_EXPORT __attribute__((visibility("default")))

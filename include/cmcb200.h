@@ -111,6 +111,7 @@ typedef struct {
 	unsigned long long n_exact;   /* Q evaluations that needed the exact 80-bit replay */
 	unsigned long long n_brent;   /* find_root_vr fallbacks */
 	unsigned long long n_status[6];
+	unsigned long long n_deferred; /* stars whose own Q was <= 0: their O(N) linear scan (src/cmc/cmc_orbit.c:46-57) ran as a grid-wide find-first */
 } cmcb200_orbit_result;
 
 /* Host-buffer form.  star1 = &star[1]: reads .E .J .vr .vt (.rnew for new stars); writes .rnew .vrnew .vtnew .X .r_peri

@@ -1,8 +1,17 @@
 // Host build of cmc_cosmic_b200/csrc/orbit_core.h (the exact per-star code the CUDA kernel runs), so the CPU test
 // suite can check it bit-for-bit against the oracle / the compiled reference without a GPU.
 // TEST-ONLY: the product library never runs this on the host.  Build: g++ -O2 -ffp-contract=off -shared -fPIC.
+#include <vector>
 #include "../../cmc_cosmic_b200/csrc/orbit_core.h"
 using namespace cmcb;
+
+// the packed (r, phi) table the kernels read (built on the device by pack_tables_kernel in the product)
+static std::vector<RPhi> pack(const double *star_r, const double *star_phi, long n)
+{
+	std::vector<RPhi> v(n);
+	for (long i = 0; i < n; i++) { v[i].r = star_r[i]; v[i].phi = star_phi[i]; }
+	return v;
+}
 
 struct ArrayDraws {
 	const double *d; long pos, end;
@@ -18,7 +27,10 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 				     long *kmin, long *kmax, long *counters /* [0]=draws used, [1]=exact Q evals, [2]=brent */)
 {
 	OrbitTables t;
-	t.r = star_r; t.m = star_m; t.phi = star_phi; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = cenma_m;
+	long n_tab = N_MAX + 2;
+	for (long j = 0; j < n_local; j++) if (g_idx[j] + 1 > n_tab) n_tab = g_idx[j] + 1;
+	std::vector<RPhi> rp = pack(star_r, star_phi, n_tab);
+	t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = cenma_m;
 	(void) force_exact;
 	double max_rad = 0.0;
 	long pos = 0;
@@ -42,8 +54,10 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, const double *star_phi, long N_MAX, long N_STAR, long g_j,
 				 double E, double J, long kmin, long kmax, long *n_exact)
 {
-	OrbitTables t; t.r = star_r; t.m = star_m; t.phi = star_phi; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
+	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
+	OrbitTables t; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
 	StarConst s; s.g_j = g_j; s.r_j = star_r[g_j]; s.m_j = star_m[g_j]; s.E = E; s.J = J;
+	star_const_derive(t, s);
 	int ne = 0;
 	long k = find_zero_Q(t, s, kmin, kmax, &ne);
 	*n_exact = ne;

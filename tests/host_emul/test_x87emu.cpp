@@ -5,6 +5,7 @@
 #include <cfloat>
 #include <random>
 #include "../../cmc_cosmic_b200/csrc/x87emu.h"
+#include "../../cmc_cosmic_b200/csrc/orbit_core.h"
 using namespace cmcb;
 
 static_assert(LDBL_MANT_DIG == 64, "needs x87 long double");
@@ -74,6 +75,37 @@ int main(int argc, char **argv)
 		if ((qd < 0) != (q0 < 0) || (qd > 0) != (q0 > 0)) sign_only_diff++;
 	}
 	printf("function_q: %ld/%ld mismatches (plain-FP64 evaluation had the wrong sign in %ld of them)\n", badq, iters, sign_only_diff);
-	printf("%s\n", (bad || badq) ? "FAIL" : "PASS");
-	return (bad || badq) != 0;
+	// the division-free sign test of the bisection probes (orbit_core.h sign_Q_at): whenever its FP64 fast path decides, the sign
+	// must be the sign of the reference's function_q.  E is placed at the root and moved away in steps of 2^s ulps so that the
+	// decision straddles the error bound; radial (J = 0) and r < r_j / r >= r_j cases included.
+	long bads = 0, fast = 0, slow = 0;
+	for (long it = 0; it < iters; it++) {
+		long N = 1000 + rng() % 10000000;
+		double r = exp(-9 + 18 * U(rng)), m_j = 0.1 + 5 * U(rng);
+		double r_j = (it % 3 == 0) ? r : exp(-9 + 18 * U(rng));
+		double pot = -(0.05 + 2 * U(rng)) * ((it & 15) == 7 ? 1e-6 : 1.0);
+		double J = ((it & 7) == 5) ? 0.0 : U(rng) * r * sqrt(2 * fabs(pot));
+		if ((it & 31) == 9) r = 1e-20;
+		long double Jr = SQRd((double) ((long double) J / r));
+		long double ph = ((long double) r >= r_j ? m_j / (long double) r : (long double) (m_j / r_j)) * (1.0 / N);
+		double E0 = (double) ((long double) pot + ph + Jr / 2);
+		int sh = (int) (rng() % 12);
+		long k = (long) (rng() % 9) - 4;
+		double E = E0 * (1 + (double) (k << sh) * 0x1p-52);
+		if (!(E < 0) || !std::isfinite(E)) continue;
+		RPhi tab[1];
+		tab[0].r = r; tab[0].phi = pot;
+		OrbitTables t; t.rp = tab; t.m = nullptr; t.N_MAX = 0; t.invN = 1.0 / N; t.madhoc = t.invN; t.cenma_m = 0;
+		StarConst sc; sc.g_j = 0; sc.r_j = r_j; sc.m_j = m_j; sc.E = E; sc.J = J;
+		star_const_derive(t, sc);
+		int ne = 0;
+		int sg = sign_Q_at(t, sc, tab[0], &ne);
+		double q0 = ref_function_q(r, pot, E, J, m_j, r_j, N);
+		int want = q0 > 0 ? 1 : (q0 < 0 ? -1 : 0);
+		if (ne) slow++; else fast++;
+		if (sg != want) { if (bads++ < 5) printf("sign mismatch: got %d want %d (q=%a, exact path %d)\n", sg, want, q0, ne); }
+	}
+	printf("sign_Q_at: %ld mismatches; fast path decided %ld, exact replay %ld\n", bads, fast, slow);
+	printf("%s\n", (bad || badq || bads) ? "FAIL" : "PASS");
+	return (bad || badq || bads) != 0;
 }

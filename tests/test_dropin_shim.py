@@ -62,6 +62,8 @@ def _run(R, N, r, vr, vt, sm, binind, nb, rtidal, draws=None, draw_off=None, is_
     S = np.ctypeslib.as_array((C.c_int * 1).from_address(R.L.ref_Start())).copy()
     E = np.ctypeslib.as_array((C.c_int * 1).from_address(R.L.ref_End())).copy()
     snap["limits"] = (int(S[0]), int(E[0]))
+    if is_shim:
+        R.L.cmcb200_shim_shutdown()
     R.free()
     return snap
 

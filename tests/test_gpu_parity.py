@@ -167,3 +167,66 @@ def test_resident_pipeline_matches_host_buffer_form():
     cm.assert_bits_equal(c.field("J")[1:n_new + 1], J2, "J")
     cm.assert_bits_equal(c.field("rOld")[1:n_new + 1], r[order][:n_new], "rOld")
     c.close()
+
+
+def test_orbit_step_linear_scan_is_deferred_and_bit_exact():
+    """Stars with v_r == 0 sit exactly on a turning point: Q at their own index is 0 up to rounding, and where it is <= 0 the reference
+    runs get_positive_Q_index's linear scan from k = 0 (cmc_orbit.c:46-57).  The CUDA path queues those stars and runs the scans as a
+    grid-wide find-first; the result must be the reference's, bit for bit."""
+    N = 60000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=31)
+    rng = np.random.default_rng(2)
+    vr[rng.choice(N, 400, replace=False)] = 0.0
+    pot = cm.oracle_potential(r, sm)
+    phi, sr, smt = pot["phi"], pot["star_r"], pot["star_m"]
+    E, J = cm.energies(phi[1:N + 1], r, vr, vt)
+    want = cm.oracle_orbits(sr, smt, phi, N, N, E, J, vr, vt, pot["Rtidal"], seed=5)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.star_phi[:N + 2] = phi[:N + 2]
+    c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+    c.Rtidal = pot["Rtidal"]
+    status = c.new_orbits_calculate(draws=want["draws"], draw_off=want["draw_off"])
+    assert c.last_orbit.n_deferred > 20, "the test no longer reaches the deferred path"
+    assert np.array_equal(status, want["status"])
+    assert np.array_equal(c.last_kmin, want["kmin"]) and np.array_equal(c.last_kmax, want["kmax"])
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(c.field(f)[1:N + 1], want[f], f)
+    assert c.max_r == want["max_rad"] and c.last_orbit.n_draws == len(want["draws"])
+    c.close()
+
+
+def test_orbit_step_philox_mode():
+    """Production mode (no recorded draws): a counter-based Philox stream per star keyed by (seed, tcount, global index).  Deterministic,
+    independent of launch geometry, distinct per seed/step, and statistically the same orbit sampling as the reference's taus113 run:
+    every new radius inside its [r_peri, r_apo], mean number of rejection tries ~ 1.9, same radial distribution (KS distance)."""
+    N = 200000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=8)
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, pot["Rtidal"], seed=5)
+    outs = []
+    for seed, tcount in ((7, 1), (7, 1), (7, 2), (8, 1)):
+        c = Cluster(N, n_star_dim=N + 64)
+        c.load(r, vr, vt, sm)
+        c.star_phi[:N + 2] = pot["phi"][:N + 2]
+        c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+        c.Rtidal = pot["Rtidal"]
+        c.tcount = tcount
+        status = c.new_orbits_calculate(seed=seed)
+        outs.append((c.field("rnew")[1:N + 1].copy(), c.field("r_peri")[1:N + 1].copy(), c.field("r_apo")[1:N + 1].copy(), status.copy(), c.last_orbit.n_draws))
+        c.close()
+    a, b, c2, d = outs
+    assert np.array_equal(a[0], b[0]), "same (seed, tcount) must reproduce"
+    assert not np.array_equal(a[0], c2[0]) and not np.array_equal(a[0], d[0])
+    rn, rp, ra, st, nd = a
+    assert np.array_equal(st, want["status"])                       # the branch taken does not depend on the draws here (no tidal cut)
+    ok = st == ol.ST_OK
+    cm.assert_bits_equal(rp[ok], want["r_peri"][ok], "r_peri")     # the orbit itself is deterministic
+    cm.assert_bits_equal(ra[ok], want["r_apo"][ok], "r_apo")
+    assert np.all((rn[ok] >= rp[ok] * (1 - 1e-12)) & (rn[ok] <= ra[ok] * (1 + 1e-12)))
+    tries = (nd / ok.sum() - 1) / 2
+    assert abs(tries - (len(want["draws"]) / ok.sum() - 1) / 2) < 0.02, tries
+    xs, ys = np.sort(rn[ok]), np.sort(want["rnew"][ok])
+    ks = np.max(np.abs(np.searchsorted(xs, ys, side="right") / xs.size - np.arange(1, ys.size + 1) / ys.size))
+    assert ks < 1.36 * np.sqrt(2.0 / ok.sum()) * 1.5, ks          # two-sample KS at ~5 % with slack

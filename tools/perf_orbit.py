@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Times the orbit-step kernels alone (CUDA events through the library's stage profiler): first step from a fresh Plummer state and
+the steps after it (where stars with v_r == 0 exist and the linear scans are queued).  Usage: perf_orbit.py N [steps]"""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from cmc_cosmic_b200 import models
+from cmc_cosmic_b200.cluster import Cluster
+
+N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1000000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+r, vr, vt, m = models.plummer(N, seed=1234)
+c = Cluster(N, n_star_dim=N + 4096)
+c.load(r, vr, vt, np.ones(N))
+c.calc_potential_new()
+c.compute_energy()
+c.upload()
+c.profile(True)
+for s in range(steps):
+    c.profile_read(reset=True)
+    res = c.dev_step(seed=1)
+    p = c.profile_read(reset=True)
+    print(f"N={N} minb={os.environ.get('CMCB200_ORBIT_MINB', 'default')} step {s}: orbit {p['orbit'][0]:.3f} ms  deferred={res.n_deferred} exact={res.n_exact} "
+          f"brent={res.n_brent} status={list(res.n_status)} tries={(res.n_draws / max(res.n_status[0], 1) - 1) / 2:.3f} | "
+          + " ".join(f"{k}={v[0]:.3f}" for k, v in p.items() if k != 'orbit' and v[0] > 0), flush=True)
+c.close()
