@@ -26,9 +26,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "stars*timesteps/s (radius sort + potential rebuild + new-orbit step)"
 UNIT = "stars*steps/s"
-# algorithmic HBM bytes per star and step (SURVEY.md 8d / DESIGN.md): the dominant kernel is the record gather
-BYTES_GATHER = 848.0
-BYTES_STEP = 996.0
+# Algorithmic HBM bytes per star (restated in DESIGN.md "Kernels and their rooflines").
+BYTES_GATHER = 848.0          # sort_gather_records: 424 B read + 424 B written
+BYTES_STEP = 996.0            # whole step
+# orbit_prepare_kernel (the dominant kernel): the streaming share of 8d's 96 B/star that stage A moves (E, J read; star_r, star_m of the
+# star itself read; r_peri, r_apo and the envelope written) -- the bisection probes are NOT streaming traffic and are not counted here;
+# they show up in `traffic` (32-byte sectors fetched by ~2 x 24 dependent probes per star once the 16 B/star table exceeds L2).
+BYTES_ORBIT_PREPARE = 56.0
 
 
 def measured_peak():
@@ -38,12 +42,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profile_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if there is one"""
-    p = os.path.join(ROOT, "profiles", "gather_traffic.json")
+def profile_traffic(kernel):
+    """dram bytes per star of a kernel from the committed ncu capture (profiles/traffic_r01.json), if there is one"""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_star")
+            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_star")
         except Exception:
             return None
     return None
@@ -257,10 +261,17 @@ def run_cuda(args):
         c.close()
 
     peak, peak_src = measured_peak()
-    g_ms, g_n = prof["record_gather"]
-    gather_avg_ms = g_ms / max(g_n, 1)
-    achieved = BYTES_GATHER * n_now / (gather_avg_ms * 1e-3) / 1e9 if gather_avg_ms > 0 else None
-    traffic = profile_traffic()
+
+    def roof(stage, kernel, bytes_per_star, extra=None):
+        t_ms, n_l = prof[stage]
+        avg = t_ms / max(n_l, 1)
+        ach = bytes_per_star * n_now / (avg * 1e-3) / 1e9 if avg > 0 else None
+        tr = profile_traffic(kernel)
+        d = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+             "traffic": (tr * n_now if tr else None), "peak_source": peak_src, "algorithmic_bytes_per_star": bytes_per_star, "avg_launch_ms": avg}
+        d.update(extra or {})
+        return d
+
     stage_ms = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items()}
     cpu = cpu_baseline_leg(args.cpu_sample)
     line = {
@@ -268,15 +279,19 @@ def run_cuda(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (Plummer sphere, equal masses, Henon units; numpy generator in cmc_cosmic_b200/models.py)",
         "config": {"workload": f"plummer_n{N:.0e}".replace("+0", "").replace("+", ""), "n_stars": N, "record_bytes": 424,
-                   "rng": "philox4x32-10 per star (production mode)", "l2": "inputs larger than L2 (star array %.2f GB)" % (N * 424 / 1e9),
-                   "step": "orbit step -> r<-rnew -> radix sort + 424 B record gather -> potential (exact sequential rounding) -> E,J"},
+                   "rng": "philox4x32-10 per star (production mode)", "l2": "inputs larger than L2 (star array %.2f GB, r/Phi table %.0f MB)" % (N * 424 / 1e9, N * 16 / 1e6),
+                   "step": "E,J from Phi + orbits (index bisections) -> rejection rounds -> radix sort on rnew + 424 B record gather with r<-rnew -> "
+                           "potential (exact sequential rounding)"},
         "clocks": clk,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "sort_gather_records", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": (traffic * n_now if traffic else None),
-                     "peak_source": peak_src, "algorithmic_bytes_per_star": BYTES_GATHER,
-                     "step_bytes_per_star": BYTES_STEP, "step_achieved_gbs": BYTES_STEP * n_now / (ms / args.steps * 1e-3) / 1e9},
+        # the dominant kernel by time.  Its probes are random 32-byte sector reads, so the streaming-bytes fraction is tiny by construction;
+        # `traffic` and `dram_pct_of_peak_ncu` (profiles/) show what actually bounds it.
+        "roofline": roof("orbit_prepare", "orbit_prepare_kernel", BYTES_ORBIT_PREPARE,
+                         {"note": "latency/sector-bound index bisections: ncu shows DRAM at ~51 % of peak with 32-B random sectors (profiles/orbit_r01.md)"}),
+        # the dominant HBM-streaming kernel
+        "roofline_streaming": roof("record_gather", "sort_gather_records", BYTES_GATHER),
+        "step_bytes_per_star": BYTES_STEP, "step_achieved_gbs": BYTES_STEP * n_now / (ms / args.steps * 1e-3) / 1e9,
         "stage_ms_per_step": stage_ms,
         "cpu_baseline": cpu,
     }

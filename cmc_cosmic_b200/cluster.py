@@ -131,11 +131,11 @@ class Cluster:
         b = self.field("binind")[1:self.clus.N_MAX_NEW + 1]
         return int(b.max()) if b.size and b.max() > 0 else 0
 
-    def orbit_params(self, draws=None, draw_off=None, seed=0):
+    def orbit_params(self, draws=None, draw_off=None, seed=0, fuse_energy=False):
         n_old = int(self.End[0] - self.Start[0] + 1)
         n_new_stars = max(0, self.clus.N_MAX_NEW - n_old)
         p = _lib.OrbitParams(self.clus.N_MAX_NEW, n_old, int(self.Start[0]), self.clus.N_MAX, self.clus.N_STAR,
-                             self.clus.N_MAX + 2 + n_new_stars, self.cenma.m, self.Rtidal, None, None, seed, self.tcount)
+                             self.clus.N_MAX + 2 + n_new_stars, self.cenma.m, self.Rtidal, None, None, seed, self.tcount, int(fuse_energy))
         if draws is not None:
             self._draws = np.ascontiguousarray(draws, np.float64)
             self._draw_off = np.ascontiguousarray(draw_off, np.int64)
@@ -180,8 +180,8 @@ class Cluster:
                                            self.star_r.ctypes.data, self.star_m.ctypes.data, self.star_phi.ctypes.data,
                                            min(self.N_STAR_DIM, self.clus.N_MAX + 2)), "download")
 
-    def dev_new_orbits(self, draws=None, draw_off=None, seed=0, want_status=False):
-        p = self.orbit_params(draws, draw_off, seed)
+    def dev_new_orbits(self, draws=None, draw_off=None, seed=0, want_status=False, fuse_energy=False):
+        p = self.orbit_params(draws, draw_off, seed, fuse_energy)
         res = _lib.OrbitResult()
         _lib.check(self.L.cmcb200_dev_new_orbits(self.ctx, C.byref(p), int(want_status), C.byref(res)), "dev_new_orbits")
         self.max_r, self.last_orbit = res.max_r, res
@@ -204,6 +204,16 @@ class Cluster:
         self.N_b_local = nb.value
         self.Start[0], self.End[0] = 1, n.value
 
+    def dev_transfer_and_sort(self):
+        """dev_transfer_new_positions + dev_qsorts_new in one pass over the records"""
+        n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
+        n_old = int(self.End[0] - self.Start[0] + 1)
+        _lib.check(self.L.cmcb200_dev_transfer_and_sort(self.ctx, C.byref(n), n_old, int(self.Start[0]), self.clus.N_MAX, max(self.N_b_local, 0),
+                                                        C.byref(nb)), "dev_transfer_and_sort")
+        self.clus.N_MAX = self.clus.N_MAX_NEW = n.value
+        self.N_b_local = nb.value
+        self.Start[0], self.End[0] = 1, n.value
+
     def dev_calc_potential_new(self):
         nmax = C.c_long(self.clus.N_MAX)
         cm, cmn, Mt, Rt = C.c_double(self.cenma.m), C.c_double(self.cenma.m_new), C.c_double(), C.c_double()
@@ -217,13 +227,20 @@ class Cluster:
     def dev_compute_energy(self):
         _lib.check(self.L.cmcb200_dev_compute_energy(self.ctx, self.clus.N_MAX, 1), "dev_compute_energy")
 
-    def dev_step(self, seed=0, draws=None, draw_off=None):
-        """One pass of the hot path on the resident arrays: orbit step -> r <- rnew -> sort -> potential -> E, J."""
-        res = self.dev_new_orbits(draws, draw_off, seed)
-        self.dev_transfer_new_positions()
-        self.dev_qsorts_new()
-        self.dev_calc_potential_new()
-        self.dev_compute_energy()
+    def dev_step(self, seed=0, draws=None, draw_off=None, fused=True):
+        """One pass of the hot path on the resident arrays: (E, J from the potential ->) orbit step -> r <- rnew -> sort -> potential.
+        fused: the r <- rnew transfer rides on the sort's record gather and E, J are computed inside the orbit step; the unfused form
+        runs them as passes of their own (same results, bit for bit)."""
+        if fused:
+            res = self.dev_new_orbits(draws, draw_off, seed, fuse_energy=True)
+            self.dev_transfer_and_sort()
+            self.dev_calc_potential_new()
+        else:
+            self.dev_compute_energy()
+            res = self.dev_new_orbits(draws, draw_off, seed)
+            self.dev_transfer_new_positions()
+            self.dev_qsorts_new()
+            self.dev_calc_potential_new()
         self.tcount += 1
         return res
 

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 #include "../../include/cmcb200.h"
 #include "common.cuh"
@@ -27,7 +28,7 @@ const char *get_error() { return g_err; }
 
 using namespace cmcb;
 
-enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H };
+enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES };
 
 struct StageEvent {
 	int stage;
@@ -44,9 +45,14 @@ struct cmcb200_ctx {
 	char *d_bin[2]; // record 0 = binary[0] (unused by the reference), binary1 = base + 464
 	int cur_star, cur_bin;
 	double *d_r, *d_m, *d_phi, *d_mprev;
+	double *d_r_alt, *d_m_alt; // second copy of star_r / star_m: the fused transfer+sort reads the old tables while it writes the new ones
 	RPhi *d_rp;       // packed (r, phi) lookup table of the orbit step
 	long *d_defer_star, *d_defer_found;
-	int orbit_min_blocks;
+	uint2 *d_scan_list;
+	double *d_ridx_lvl;
+	unsigned char *d_oflag;
+	int *d_pend[2];
+	int orbit_min_blocks, orbit_use_index;
 	// sort scratch
 	SortBuffers sbuf;
 	SortState *d_sort;
@@ -158,6 +164,8 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 	c->n_bin_dim = n_bin_dim;
 	c->orbit_min_blocks = 8;
 	if (const char *e = getenv("CMCB200_ORBIT_MINB")) c->orbit_min_blocks = atoi(e); // tuning knob: 4 / 6 / 8
+	c->orbit_use_index = 0; // 16-ary index for potential(): measured neutral at N = 1e7 (-20 % DRAM bytes, same time) and 12 % slower at 1e6
+	if (const char *e = getenv("CMCB200_ORBIT_INDEX")) c->orbit_use_index = atoi(e);
 	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->own_stream = true;
 	const size_t sb = (size_t) n_star_dim * CMCB_SIZEOF_STAR + 64, bb = (size_t) n_bin_dim * CMCB_SIZEOF_BINARY + 64;
@@ -167,14 +175,28 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_bin[i], bb));
 		CMCB_CUDA_OK(cudaMemsetAsync(c->d_bin[i], 0, bb, c->stream));
 	}
-	const size_t tb = (size_t) n_star_dim * sizeof(double);
+	const size_t tb = (size_t) n_star_dim * sizeof(double) + 256; // readable a line past the end (16-ary index windows)
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_r, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_m, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_phi, tb));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_r_alt, tb));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_m_alt, tb));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r_alt, 0, tb, c->stream));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_m_alt, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_mprev, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rp, (size_t) n_star_dim * sizeof(RPhi)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_star, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_oflag, (size_t) n_star_dim));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_scan_list, (size_t) ORBIT_SCAN_LIST_CAP * sizeof(uint2)));
+	{
+		int off[RIDX_MAX_LEVELS + 1], H;
+		long total;
+		ridx_plan((kint) n_star_dim, off, &H, &total);
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_ridx_lvl, (size_t) (total + 64) * sizeof(double)));
+	}
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[0], (size_t) n_star_dim * sizeof(int)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[1], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_m, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_phi, 0, tb, c->stream));
@@ -210,8 +232,10 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	for (int i = 0; i < 2; i++) { cudaFree(c->d_star[i]); cudaFree(c->d_bin[i]); }
-	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev);
+	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev); cudaFree(c->d_r_alt); cudaFree(c->d_m_alt);
 	cudaFree(c->d_rp); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
+	cudaFree(c->d_scan_list); cudaFree(c->d_ridx_lvl);
+	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
 	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
@@ -324,7 +348,9 @@ extern "C" int cmcb200_calc_potential_new(cmcb200_ctx *c, double *star_r, const 
 
 // ---- sort -------------------------------------------------------------------------------------------------------
 
-extern "C" int cmcb200_dev_qsorts_new(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_bin)
+// fuse: the ComputeIntermediateEnergy transfer (r <- rnew ...) happens while the records move; n_old_local / first_global / N_MAX
+// are those of the orbit step that produced rnew
+static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_bin, bool fuse, long n_old_local, long first_global, long N_MAX)
 {
 	const long n = *n_local;
 	if (n + 2 > c->n_star_dim) { set_error("qsorts_new: n_local + 2 = %ld exceeds n_star_dim = %ld", n + 2, c->n_star_dim); return -1; }
@@ -334,12 +360,16 @@ extern "C" int cmcb200_dev_qsorts_new(cmcb200_ctx *c, long *n_local, long n_bin_
 	a.star_in = star1(c);
 	a.star_out = c->d_star[c->cur_star ^ 1] + CMCB_SIZEOF_STAR;
 	a.n = n;
-	a.key_off = CMCB_OFF_R;
+	a.key_off = fuse ? CMCB_OFF_RNEW : CMCB_OFF_R;
 	a.buf = c->sbuf;
 	a.st = c->d_sort;
 	a.tile_hist = c->d_tile_hist;
-	a.star_r = c->d_r;
-	a.star_m = c->d_m;
+	a.fuse_transfer = fuse;
+	a.old_r = c->d_r; a.old_m = c->d_m;
+	a.n_old_local = n_old_local; a.first_global = first_global; a.N_MAX = N_MAX;
+	// the fused form reads the old tables while the new ones are written: ping-pong
+	a.star_r = fuse ? c->d_r_alt : c->d_r;
+	a.star_m = fuse ? c->d_m_alt : c->d_m;
 	a.binflag = c->d_binflag;
 	a.bin_block_cnt = c->d_bin_block_cnt;
 	a.bin_in = bin1(c);
@@ -351,18 +381,33 @@ extern "C" int cmcb200_dev_qsorts_new(cmcb200_ctx *c, long *n_local, long n_bin_
 		StageTimer t(c, ST_GATHER);
 		// the sentinel record star[0] travels with the array
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_star[c->cur_star ^ 1], c->d_star[c->cur_star], CMCB_SIZEOF_STAR, cudaMemcpyDeviceToDevice, c->stream));
+		if (fuse) { // so does the table sentinel [0]
+			CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r_alt, c->d_r, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+			CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m_alt, c->d_m, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+		}
 		c->launches += sort_stage_gather(a, c->stream);
 	}
 	{ StageTimer t(c, ST_BINARIES); c->launches += sort_stage_binaries(a, c->stream); }
 	CMCB_CUDA_OK(cudaGetLastError());
 	c->cur_star ^= 1;
 	c->cur_bin ^= 1;
+	if (fuse) { std::swap(c->d_r, c->d_r_alt); std::swap(c->d_m, c->d_m_alt); }
 	long *h = (long *) c->h_pinned; // n_eq_inf, n_gt_inf, n_total, n_new, n_bin
 	CMCB_CUDA_OK(cudaMemcpyAsync(h, &c->d_sort->n_eq_inf, 5 * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	*n_local = h[3];
 	*n_bin = h[4];
 	return 0;
+}
+
+extern "C" int cmcb200_dev_qsorts_new(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_bin)
+{
+	return sort_common(c, n_local, n_bin_clear, n_bin, false, 0, 0, 0);
+}
+
+extern "C" int cmcb200_dev_transfer_and_sort(cmcb200_ctx *c, long *n_local, long n_old_local, long first_global, long N_MAX, long n_bin_clear, long *n_bin)
+{
+	return sort_common(c, n_local, n_bin_clear, n_bin, true, n_old_local, first_global, N_MAX);
 }
 
 extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, void *binary1_h, long n_bin_dim, long *n_bin,
@@ -408,6 +453,10 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 	a.t.rp = c->d_rp; a.t.m = c->d_m;
 	a.defer_star = c->d_defer_star; a.defer_found = c->d_defer_found;
 	a.min_blocks = c->orbit_min_blocks;
+	a.fuse_energy = p->fuse_compute_energy != 0;
+	a.use_index = c->orbit_use_index != 0;
+	a.scan_list = c->d_scan_list;
+	a.flag = c->d_oflag; a.pend_list[0] = c->d_pend[0]; a.pend_list[1] = c->d_pend[1];
 	a.t.N_MAX = p->N_MAX;
 	a.t.invN = 1.0 / p->N_STAR;
 	a.t.madhoc = 1.0 / ((double) p->N_STAR);
@@ -431,11 +480,15 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 	a.n_draws = nullptr;
 	a.stats = c->d_ostats;
 	{
-		StageTimer t(c, ST_ORBIT);
+		StageTimer t(c, ST_ORBIT_TABLES);
 		c->launches += orbit_pack_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, c->stream);
-		c->launches += orbit_step_device(a, c->stream);
-		CMCB_CUDA_OK(cudaGetLastError());
+		a.t.ridx.r = nullptr;
+		if (a.use_index) c->launches += orbit_build_index_device(a.t.ridx, c->d_r, c->d_ridx_lvl, (kint) (p->N_MAX + 1), c->stream);
 	}
+	{ StageTimer t(c, ST_ORBIT); c->launches += orbit_stage_prepare(a, c->stream); }
+	{ StageTimer t(c, ST_ORBIT_SCAN); c->launches += orbit_stage_scan(a, c->stream); }
+	{ StageTimer t(c, ST_ORBIT_TRIES); c->launches += orbit_stage_tries(a, c->stream); }
+	CMCB_CUDA_OK(cudaGetLastError());
 	OrbitStats *h = (OrbitStats *) c->h_pinned;
 	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));

@@ -77,10 +77,22 @@ __global__ void orbit_pack_tables(const double *__restrict__ r, const double *__
 	}
 }
 
+// the sampled levels of the 16-ary index over star_r (RIndex, orbit_core.h): ~N/15 strided reads
+__global__ void orbit_build_index(RIndex x, long total)
+{
+	long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	const long stride = (long) gridDim.x * blockDim.x;
+	for (; i < total; i += stride) {
+		int h = 1;
+		while (h < x.H && i >= x.off[h + 1]) h++;
+		const_cast<double *>(x.lvl)[i] = x.H >= 1 ? ridx_sample(x.r, x.M, h, i - x.off[h]) : __builtin_huge_val();
+	}
+}
+
 struct StarIn {
-	long g;
+	kint g;
 	bool is_new;
-	double E, J, vr, vt, rnew_of_new;
+	double E, J, rnew_of_new;
 };
 
 __device__ __forceinline__ StarIn load_star(const OrbitArgs &a, long j0)
@@ -88,10 +100,9 @@ __device__ __forceinline__ StarIn load_star(const OrbitArgs &a, long j0)
 	StarIn in;
 	const long j = j0 + 1; // the reference's 1-based local index
 	in.is_new = j > a.n_old_local;
-	in.g = in.is_new ? 1 + a.t.N_MAX + (j - a.n_old_local) : a.first_global + j - 1; // get_global_idx, cmc_utils.c:2384-2407
+	in.g = (kint) (in.is_new ? 1 + a.t.N_MAX + (j - a.n_old_local) : a.first_global + j - 1); // get_global_idx, cmc_utils.c:2384-2407
 	const char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
 	in.E = ld_field(rec, CMCB_OFF_E); in.J = ld_field(rec, CMCB_OFF_J);
-	in.vr = ld_field(rec, CMCB_OFF_VR); in.vt = ld_field(rec, CMCB_OFF_VT);
 	in.rnew_of_new = in.is_new ? ld_field(rec, CMCB_OFF_RNEW) : 0.0;
 	return in;
 }
@@ -100,7 +111,11 @@ __device__ __forceinline__ StarIn load_star(const OrbitArgs &a, long j0)
 __device__ __forceinline__ void store_star(const OrbitArgs &a, long j0, const OrbitOut &o)
 {
 	char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
-	if (o.status != ORBIT_NTRY) {
+	if (o.status == ORBIT_CIRCULAR) { // rnew / vrnew / vtnew = r / vr / vt (:836-838)
+		st_field(rec, CMCB_OFF_RNEW, o.rnew);
+		st_field(rec, CMCB_OFF_VRNEW, ld_field(rec, CMCB_OFF_VR));
+		st_field(rec, CMCB_OFF_VTNEW, ld_field(rec, CMCB_OFF_VT));
+	} else if (o.status != ORBIT_NTRY) {
 		st_field(rec, CMCB_OFF_RNEW, o.rnew);
 		st_field(rec, CMCB_OFF_VRNEW, o.vrnew);
 		st_field(rec, CMCB_OFF_VTNEW, o.vtnew);
@@ -116,25 +131,13 @@ __device__ __forceinline__ void store_star(const OrbitArgs &a, long j0, const Or
 	if (a.n_draws) a.n_draws[j0] = o.n_draws;
 }
 
-template <bool RECORDED>
-__device__ __forceinline__ void run_star(const OrbitArgs &a, long j0, const StarIn &in, long ktemp_in, bool allow_defer, OrbitOut &o)
-{
-	if (RECORDED) {
-		CsrDraws dr;
-		dr.d = a.draws; dr.pos = a.draw_off[j0]; dr.end = a.draw_off[j0 + 1];
-		orbit_step_star(a.t, in.g, in.is_new, in.rnew_of_new, in.E, in.J, in.vr, in.vt, a.Rtidal, dr, o, ktemp_in, allow_defer);
-	} else {
-		PhiloxDraws dr;
-		dr.init(a.seed, a.tcount, (unsigned long long) in.g);
-		orbit_step_star(a.t, in.g, in.is_new, in.rnew_of_new, in.E, in.J, in.vr, in.vt, a.Rtidal, dr, o, ktemp_in, allow_defer);
-	}
-}
+// ---- stage A: the orbit of every star (index bisections, r_min / r_max, envelope) ------------------------------------------
 
-// block-level accumulation of the per-launch statistics: one atomic per warp / block and counter
-__device__ __forceinline__ void accumulate_stats(OrbitStats *st, const OrbitOut &o, bool valid)
+// block-level accumulation of the per-launch statistics: one atomic per warp and counter
+__device__ __forceinline__ void accumulate_stats(OrbitStats *st, int status, double rnew, int n_draws, int n_exact, int n_brent, bool valid)
 {
-	unsigned long long my_max = (valid && o.status == ORBIT_OK) ? dbits(o.rnew) : 0ull; // positive doubles order like their bit patterns
-	unsigned long long my_draws = valid ? o.n_draws : 0, my_exact = valid ? o.n_exact : 0, my_brent = valid ? o.n_brent : 0;
+	unsigned long long my_max = (valid && status == ORBIT_OK) ? dbits(rnew) : 0ull; // positive doubles order like their bit patterns
+	unsigned my_draws = valid ? n_draws : 0, my_exact = valid ? n_exact : 0, my_brent = valid ? n_brent : 0;
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1) {
 		unsigned long long m = __shfl_xor_sync(0xffffffffu, my_max, d);
@@ -145,79 +148,133 @@ __device__ __forceinline__ void accumulate_stats(OrbitStats *st, const OrbitOut 
 	}
 	if (lane_id() == 0) {
 		if (my_max) atomicMax(&st->max_rad_bits, my_max);
-		if (my_draws) atomicAdd(&st->n_draws, my_draws);
-		if (my_exact) atomicAdd(&st->n_exact, my_exact);
-		if (my_brent) atomicAdd(&st->n_brent, my_brent);
+		if (my_draws) atomicAdd(&st->n_draws, (unsigned long long) my_draws);
+		if (my_exact) atomicAdd(&st->n_exact, (unsigned long long) my_exact);
+		if (my_brent) atomicAdd(&st->n_brent, (unsigned long long) my_brent);
 	}
-	if (valid && o.status > 0 && o.status < 6) atomicAdd(&st->n_status[o.status], 1ull); // the rare outcomes; OK count = n - sum
+	if (valid && status > 0 && status < 6) atomicAdd(&st->n_status[status], 1ull); // the rare outcomes; OK count = n - sum
 }
 
-// MINB = resident CTAs per SM the register allocation is capped for (4: 128 registers .. 8: 64 registers, with spills)
-template <bool RECORDED, int MINB>
-__global__ void __launch_bounds__(ORBIT_THREADS, MINB) orbit_step_kernel(OrbitArgs a)
+// A star whose orbit is known but whose new radius is not drawn yet parks its job in its own record: r_peri / r_apo hold
+// r_min / r_max (their final values, :919-920) and X holds the envelope F until the accepted X replaces it (:918).
+__device__ __forceinline__ void store_prepared(const OrbitArgs &a, long j0, const OrbitOut &o, const OrbitJob &job)
+{
+	if (o.status == ORBIT_PENDING) {
+		char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
+		st_field(rec, CMCB_OFF_X, job.F);
+		st_field(rec, CMCB_OFF_R_PERI, job.rmin);
+		st_field(rec, CMCB_OFF_R_APO, job.rmax);
+		a.flag[j0] = 1;
+		if (a.kmin) a.kmin[j0] = o.kmin;
+		if (a.kmax) a.kmax[j0] = o.kmax;
+	} else {
+		a.flag[j0] = 0;
+		store_star(a, j0, o);
+	}
+}
+
+// MINB = resident CTAs per SM the register allocation is capped for
+template <int MINB>
+__global__ void __launch_bounds__(ORBIT_THREADS, MINB) orbit_prepare_kernel(OrbitArgs a)
 {
 	const long j0 = blockIdx.x * (long) blockDim.x + threadIdx.x;
 	const bool valid = j0 < a.n_local;
 	OrbitOut o;
 	o.status = -1; o.rnew = 0.0; o.n_draws = o.n_exact = o.n_brent = 0;
 	if (valid) {
-		const StarIn in = load_star(a, j0);
-		run_star<RECORDED>(a, j0, in, KTEMP_COMPUTE, true, o);
+		StarIn in = load_star(a, j0);
+		if (a.fuse_energy && !in.is_new) { // ComputeEnergy's first loop (reference src/cmc/cmc_utils.c:612-616) for this star, then stored
+			char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
+			const RPhi own = tbl_rp(a.t, in.g);
+			const double vr = ld_field(rec, CMCB_OFF_VR), vt = ld_field(rec, CMCB_OFF_VT);
+			in.E = dadd(own.phi, dmul(0.5, dadd(dmul(vr, vr), dmul(vt, vt))));
+			in.J = dmul(own.r, vt);
+			st_field(rec, CMCB_OFF_E, in.E);
+			st_field(rec, CMCB_OFF_J, in.J);
+		}
+		const StarConst s = star_const(a.t, in.g, in.E, in.J);
+		OrbitJob job;
+		orbit_prepare(a.t, s, in.is_new, in.rnew_of_new, a.Rtidal, KTEMP_COMPUTE, true, o, job);
 		if (o.status == ORBIT_DEFERRED) {
 			const unsigned slot = atomicAdd(&a.stats->n_defer, 1u);
 			if (slot < ORBIT_DEFER_CAP) {
 				a.defer_star[slot] = j0;
 				a.defer_found[slot] = ORBIT_NOT_FOUND;
-			} else { // queue full (never seen: ~4e-6 of the stars defer): last resort, the scan in this thread
-				run_star<RECORDED>(a, j0, in, KTEMP_COMPUTE, false, o);
+			} else { // queue full (never seen: ~1e-5 of the stars defer): last resort, the scan in this thread
+				orbit_prepare(a.t, s, in.is_new, in.rnew_of_new, a.Rtidal, KTEMP_COMPUTE, false, o, job);
 			}
 		}
-		if (o.status != ORBIT_DEFERRED) store_star(a, j0, o);
+		if (o.status != ORBIT_DEFERRED) store_prepared(a, j0, o, job);
 	}
-	accumulate_stats(a.stats, o, valid && o.status != ORBIT_DEFERRED);
+	const bool counted = valid && o.status != ORBIT_DEFERRED;
+	accumulate_stats(a.stats, o.status, 0.0, 0, o.n_exact, o.n_brent, counted);
 }
 
 // ---- the queued linear scans ------------------------------------------------------------------------------------------
-
+//
 // first k in [0, N_MAX) with function_q(k) > 0 for every queued star (get_positive_Q_index, cmc_orbit.c:46-57: the loop runs
-// k = 0, 1, .. while Q <= 0 and k <= N_MAX, and a result >= N_MAX means "none")
-__global__ void __launch_bounds__(ORBIT_SCAN_THREADS) orbit_scan_kernel(OrbitArgs a)
+// k = 0, 1, .. while Q <= 0 and k <= N_MAX, and a result >= N_MAX means "none").
+//   orbit_scan_filter   one thread per (queued star, chunk of 4096 table entries): a two-load bound (q_maybe_positive_on) proves
+//                       Q <= 0 on the whole chunk for all but the one or two chunks next to the sign change; the others go
+//                       to a work list
+//   orbit_scan_chunks   one CTA per listed chunk evaluates every entry's sign exactly as the reference would and keeps the
+//                       smallest index with Q > 0
+// Every chunk is either proven all-non-positive or scanned, so the minimum is the reference's answer.
+
+__device__ __forceinline__ StarConst deferred_const(const OrbitArgs &a, unsigned slot)
 {
-	__shared__ unsigned s_item;
-	__shared__ long s_best;
+	const long j0 = a.defer_star[slot];
+	const StarIn in = load_star(a, j0);
+	return star_const(a.t, in.g, in.E, in.J);
+}
+
+__global__ void __launch_bounds__(256) orbit_scan_filter(OrbitArgs a)
+{
 	const unsigned n_defer = min(a.stats->n_defer, (unsigned) ORBIT_DEFER_CAP);
 	if (n_defer == 0) return;
 	const long n_scan = a.t.N_MAX; // candidates 0 .. N_MAX-1
 	const long n_chunks = (n_scan + ORBIT_SCAN_CHUNK - 1) / ORBIT_SCAN_CHUNK;
 	const unsigned long long n_items = (unsigned long long) n_chunks * n_defer;
-	for (;;) {
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			// One thread draws tickets until it holds an item that still matters: a chunk lying entirely above a hit that already
-			// exists for its star cannot contribute (hits only ever decrease), and deciding that here keeps the block convergent.
-			unsigned long long it;
-			do {
-				it = atomicAdd(&a.stats->scan_ticket, 1u);
-			} while (it < n_items && *(volatile long *) &a.defer_found[it % n_defer] < (long) (it / n_defer) * ORBIT_SCAN_CHUNK);
-			s_item = it < n_items ? (unsigned) it : 0xffffffffu;
-			s_best = ORBIT_NOT_FOUND;
-		}
-		__syncthreads();
-		if (s_item == 0xffffffffu) return;
-		const unsigned long long item = s_item;
-		const long chunk = (long) (item / n_defer);
-		const unsigned slot = (unsigned) (item % n_defer);
+	// consecutive threads = consecutive chunks of one star: the star's constants are fetched from cache, the bound loads coalesce
+	for (unsigned long long item = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; item < n_items; item += (unsigned long long) gridDim.x * blockDim.x) {
+		const unsigned slot = (unsigned) (item / n_chunks);
+		const long chunk = (long) (item % n_chunks);
 		const long k0 = chunk * ORBIT_SCAN_CHUNK;
-		const long j0 = a.defer_star[slot];
-		const StarIn in = load_star(a, j0);
-		const StarConst s = star_const(a.t, in.g, in.E, in.J);
+		const long k1 = min(k0 + (long) ORBIT_SCAN_CHUNK, n_scan) - 1;
+		const StarConst s = deferred_const(a, slot);
+		if (q_maybe_positive_on(s, tbl_rp(a.t, (kint) k0), tbl_rp(a.t, (kint) k1))) {
+			const unsigned w = atomicAdd(&a.stats->scan_items, 1u);
+			if (w < ORBIT_SCAN_LIST_CAP) a.scan_list[w] = make_uint2(slot, (unsigned) chunk);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(ORBIT_SCAN_THREADS) orbit_scan_chunks(OrbitArgs a)
+{
+	const unsigned n_defer = min(a.stats->n_defer, (unsigned) ORBIT_DEFER_CAP);
+	if (n_defer == 0) return;
+	const long n_scan = a.t.N_MAX;
+	const long n_chunks = (n_scan + ORBIT_SCAN_CHUNK - 1) / ORBIT_SCAN_CHUNK;
+	const unsigned listed = a.stats->scan_items;
+	// the list overflowed (the bound failed to dismiss most chunks -- not seen on any cluster): scan everything
+	const bool everything = listed > ORBIT_SCAN_LIST_CAP;
+	const unsigned long long n_items = everything ? (unsigned long long) n_chunks * n_defer : listed;
+	for (unsigned long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+		unsigned slot;
+		long chunk;
+		if (everything) { slot = (unsigned) (item % n_defer); chunk = (long) (item / n_defer); } // chunk-major: low chunks first
+		else { const uint2 w = a.scan_list[item]; slot = w.x; chunk = w.y; }
+		const long k0 = chunk * ORBIT_SCAN_CHUNK;
+		if (*(volatile long *) &a.defer_found[slot] < k0) continue; // a smaller hit exists (block-uniform enough: hits only decrease,
+		                                                             // and a thread that still scans only adds a larger candidate)
+		const StarConst s = deferred_const(a, slot);
 		long best = ORBIT_NOT_FOUND;
 		int n_exact = 0;
 #pragma unroll 4
 		for (int i = 0; i < ORBIT_SCAN_CHUNK / ORBIT_SCAN_THREADS; i++) {
 			const long k = k0 + i * ORBIT_SCAN_THREADS + threadIdx.x;
 			if (k < n_scan && k < best) {
-				if (sign_Q(a.t, s, k, &n_exact) > 0) best = k;
+				if (sign_Q(a.t, s, (kint) k, &n_exact) > 0) best = k;
 			}
 		}
 #pragma unroll
@@ -227,15 +284,12 @@ __global__ void __launch_bounds__(ORBIT_SCAN_THREADS) orbit_scan_kernel(OrbitArg
 			n_exact += __shfl_xor_sync(0xffffffffu, n_exact, d);
 		}
 		if (lane_id() == 0) {
-			if (best != ORBIT_NOT_FOUND) atomicMin((long long *) &s_best, (long long) best);
+			if (best != ORBIT_NOT_FOUND) atomicMin((long long *) &a.defer_found[slot], (long long) best);
 			if (n_exact) atomicAdd(&a.stats->n_exact, (unsigned long long) n_exact);
 		}
-		__syncthreads();
-		if (threadIdx.x == 0 && s_best != ORBIT_NOT_FOUND) atomicMin((long long *) &a.defer_found[slot], (long long) s_best);
 	}
 }
 
-template <bool RECORDED>
 __global__ void __launch_bounds__(ORBIT_THREADS) orbit_deferred_kernel(OrbitArgs a)
 {
 	const unsigned n_defer = min(a.stats->n_defer, (unsigned) ORBIT_DEFER_CAP);
@@ -248,10 +302,146 @@ __global__ void __launch_bounds__(ORBIT_THREADS) orbit_deferred_kernel(OrbitArgs
 			const long j0 = a.defer_star[slot];
 			const long found = a.defer_found[slot];
 			const StarIn in = load_star(a, j0);
-			run_star<RECORDED>(a, j0, in, found == ORBIT_NOT_FOUND ? -1 : found, false, o);
-			store_star(a, j0, o);
+			const StarConst s = star_const(a.t, in.g, in.E, in.J);
+			OrbitJob job;
+			orbit_prepare(a.t, s, in.is_new, in.rnew_of_new, a.Rtidal, found == ORBIT_NOT_FOUND ? -1 : (kint) found, false, o, job);
+			store_prepared(a, j0, o, job);
 		}
-		accumulate_stats(a.stats, o, valid);
+		accumulate_stats(a.stats, o.status, 0.0, 0, o.n_exact, o.n_brent, valid);
+	}
+}
+
+// ---- stage B: rejection sampling of the new radius, one ROUND of tries per launch -----------------------------------------
+//
+// Try number t of a star consumes uniforms 2t and 2t+1 of that star's stream and, when accepted, 2t+2 for the sign of v_r
+// (:863,867,923) -- so tries are independent of each other, and "the first accepted try in order" can be found round by round
+// instead of by one thread looping: every launch works on a COMPACTED list of the stars still pending, each lane evaluates one
+// try (a full-depth FindZero_r bisection), accepted stars are finished, the others are appended to the next round's list.
+// No lane waits for a neighbour's longer rejection streak (the old per-thread loop ran at 60 % lane utilisation).
+// Late rounds hold few stars and are latency-bound, so they evaluate W consecutive tries of each star at once (W lanes per
+// star, first accepted in order wins: identical result, fewer dependent rounds).
+
+struct TryDraws { // random access into a star's uniform stream
+	double X, u;
+};
+
+template <bool RECORDED>
+__device__ __forceinline__ bool draws_for_try(const OrbitArgs &a, long j0, kint g, unsigned t, TryDraws &d)
+{
+	if (RECORDED) {
+		const long pos = a.draw_off[j0] + 2l * t;
+		if (pos + 3 > a.draw_off[j0 + 1]) return false; // try + sign draw must exist
+		d.X = a.draws[pos];
+		d.u = a.draws[pos + 1];
+		return true;
+	} else {
+		PhiloxDraws p;
+		p.init(a.seed, a.tcount, (unsigned long long) g);
+		p.c3 = t >> 1; // uniforms 4b .. 4b+3 live in block b
+		p.refill();
+		d.X = (double) ((t & 1) ? p.o2 : p.o0) / 4294967296.0; // same 2^-32 grid as taus113's rng_t113_dbl_new (taus113-v2.c:191-193)
+		d.u = (double) ((t & 1) ? p.o3 : p.o1) / 4294967296.0;
+		return true;
+	}
+}
+
+template <bool RECORDED>
+__device__ __forceinline__ double sign_draw_for_try(const OrbitArgs &a, long j0, kint g, unsigned t)
+{
+	if (RECORDED) return a.draws[a.draw_off[j0] + 2l * t + 2];
+	PhiloxDraws p;
+	p.init(a.seed, a.tcount, (unsigned long long) g);
+	p.c3 = (2 * t + 2) >> 2;
+	p.refill();
+	return (double) ((t & 1) ? p.o0 : p.o2) / 4294967296.0;
+}
+
+// W lanes per star evaluate tries t0 .. t0+W-1.  FIRST: the work list is "every star whose flag is set" (round 0, no list yet).
+// LOOP: keep going (t0 += W) until the star is accepted or N_TRY is exceeded (the last round).
+template <bool RECORDED, int W, bool FIRST, bool LOOP>
+__global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitArgs a, int round, unsigned t0_base)
+{
+	const unsigned n_work = FIRST ? (unsigned) a.n_local : a.stats->round_count[round];
+	const int *__restrict__ list_in = a.pend_list[round & 1];
+	int *__restrict__ list_out = a.pend_list[(round + 1) & 1];
+	const unsigned sub = threadIdx.x % W;
+	const unsigned groups_per_block = ORBIT_TRY_THREADS / W;
+	const unsigned n_iter = (n_work + groups_per_block * gridDim.x - 1) / (groups_per_block * gridDim.x); // grid-uniform trip count
+	for (unsigned it = 0; it < n_iter; it++) {
+		const unsigned w = (it * gridDim.x + blockIdx.x) * groups_per_block + threadIdx.x / W;
+		bool have = w < n_work;
+		long j0 = 0;
+		if (have) {
+			j0 = FIRST ? (long) w : (long) list_in[w];
+			if (FIRST) have = a.flag[j0] != 0;
+		}
+		int status = -1, n_draws = 0;
+		double rnew = 0.0;
+		bool requeue = false;
+		if (have) {
+			const StarIn in = load_star(a, j0);
+			StarConst s;
+			s.g_j = in.g; s.r_j = tbl_r(a.t, in.g); s.m_j = tbl_ld(a.t.m, in.g); s.J = in.J;
+			s.E = dadd(in.E, phi_self(s.r_j, s.r_j, s.m_j, a.t.invN)); // :806
+			s.JJ = dmul(s.J, s.J);
+			const char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
+			OrbitJob job;
+			job.F = ld_field(rec, CMCB_OFF_X); job.rmin = ld_field(rec, CMCB_OFF_R_PERI); job.rmax = ld_field(rec, CMCB_OFF_R_APO);
+			unsigned t0 = t0_base;
+			for (;;) {
+				const unsigned t = t0 + sub;
+				TryDraws d;
+				int rc = -1; // -1: fatal (out of draws / bracket failure / beyond N_TRY), 0: rejected, 1: accepted
+				double r = 0.0, vr = 0.0;
+				if (t < CMCB_N_TRY && draws_for_try<RECORDED>(a, j0, in.g, t, d)) rc = orbit_try(a.t, s, job, d.X, d.u, &r, &vr);
+				// first lane of the group (lowest try index) that did not reject decides
+				int first_rc = rc;
+				unsigned first_sub = rc != 0 ? sub : W;
+				if (W > 1) {
+					const unsigned gmask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << (lane_id() & ~(W - 1)));
+					const unsigned decided = __ballot_sync(gmask, rc != 0) & gmask;
+					if (decided) {
+						const int src = __ffs(decided) - 1;
+						first_rc = __shfl_sync(gmask, rc, src);
+						first_sub = (unsigned) src - (lane_id() & ~(W - 1));
+					} else { first_rc = 0; first_sub = W; }
+				}
+				if (first_rc == 0) { // all W tries rejected
+					if (LOOP) { t0 += W; continue; }
+					requeue = sub == 0;
+					break;
+				}
+				if (sub == first_sub) {
+					OrbitOut o;
+					o.kmin = o.kmax = -1; o.n_exact = o.n_brent = 0;
+					if (first_rc > 0) orbit_finish(s, job, d.X, r, vr, sign_draw_for_try<RECORDED>(a, j0, in.g, t), (int) t + 1, o);
+					else { // :890-893, fatal in the reference
+						o.status = ORBIT_NTRY; o.rnew = s.r_j; o.vrnew = o.vtnew = 0.0; o.X = o.r_peri = o.r_apo = 0.0;
+						o.n_draws = 2 * (int) (t < CMCB_N_TRY ? t + 1 : CMCB_N_TRY);
+					}
+					char *wrec = a.star1 + j0 * CMCB_SIZEOF_STAR;
+					if (o.status == ORBIT_OK) {
+						st_field(wrec, CMCB_OFF_RNEW, o.rnew); st_field(wrec, CMCB_OFF_VRNEW, o.vrnew); st_field(wrec, CMCB_OFF_VTNEW, o.vtnew);
+						st_field(wrec, CMCB_OFF_X, o.X);
+					} else st_field(wrec, CMCB_OFF_X, 0.0); // the parked envelope must not survive in a field the reference leaves alone
+					if (a.status) a.status[j0] = o.status;
+					if (a.n_draws) a.n_draws[j0] = o.n_draws;
+					status = o.status; n_draws = o.n_draws; rnew = o.rnew;
+				}
+				break;
+			}
+		}
+		// compact the rejected stars into the next round's list: one atomic per warp
+		if (!LOOP) {
+			const unsigned m = __ballot_sync(0xffffffffu, requeue);
+			if (m) {
+				unsigned base = 0;
+				if (lane_id() == 0) base = atomicAdd(&a.stats->round_count[round + 1], (unsigned) __popc(m));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (requeue) list_out[base + __popc(m & ((1u << lane_id()) - 1u))] = (int) j0;
+			}
+		}
+		accumulate_stats(a.stats, status, rnew, n_draws, 0, 0, status >= 0);
 	}
 }
 
@@ -259,7 +449,8 @@ __global__ void orbit_stats_reset(OrbitStats *s)
 {
 	s->max_rad_bits = 0; s->n_draws = 0; s->n_exact = 0; s->n_brent = 0;
 	for (int i = 0; i < 6; i++) s->n_status[i] = 0;
-	s->n_defer = 0; s->scan_ticket = 0;
+	s->n_defer = 0; s->scan_items = 0;
+	for (int i = 0; i < ORBIT_MAX_ROUNDS + 2; i++) s->round_count[i] = 0;
 }
 
 int orbit_pack_tables_device(const double *r, const double *phi, RPhi *rp, long n, cudaStream_t s)
@@ -271,20 +462,67 @@ int orbit_pack_tables_device(const double *r, const double *phi, RPhi *rp, long 
 	return 1;
 }
 
-int orbit_step_device(const OrbitArgs &a, cudaStream_t s)
+template <bool RECORDED>
+static int launch_try_rounds(const OrbitArgs &a, cudaStream_t s)
+{
+	// Rounds 0..4: one try per pending star (about 100, 48, 23, 11, 5.3 % of the stars); round 5: four tries at once for the
+	// ~2.5 % left; round 6: a warp per star, 32 tries at a time until accepted.  The grids only bound the parallelism (the
+	// kernels run grid-stride over the device-side count), sized for the expected survivors with a wide margin.
+	const long n = a.n_local;
+	auto grid_for = [&](double frac, int w) {
+		long g = (long) (n * frac * w / ORBIT_TRY_THREADS) + 1;
+		const long cap = (long) NUM_SMS_B200 * 64;
+		if (g > (n * (long) w + ORBIT_TRY_THREADS - 1) / ORBIT_TRY_THREADS) g = (n * (long) w + ORBIT_TRY_THREADS - 1) / ORBIT_TRY_THREADS;
+		return (unsigned) (g < 1 ? 1 : (g > cap && frac < 1.0 ? cap : g));
+	};
+	orbit_try_kernel<RECORDED, 1, true, false><<<grid_for(1.0, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 0, 0u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.60, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 1, 1u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.35, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 2, 2u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.20, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 3, 3u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.12, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 4, 4u);
+	orbit_try_kernel<RECORDED, 4, false, false><<<grid_for(0.07, 4), ORBIT_TRY_THREADS, 0, s>>>(a, 5, 5u);
+	orbit_try_kernel<RECORDED, 32, false, true><<<grid_for(0.01, 32), ORBIT_TRY_THREADS, 0, s>>>(a, 6, 9u);
+	return 7;
+}
+
+int orbit_build_index_device(RIndex &x, const double *star_r, double *lvl, kint M, cudaStream_t s)
+{
+	long total;
+	x.r = star_r; x.lvl = lvl; x.M = M;
+	ridx_plan(M, x.off, &x.H, &total);
+	long blocks = (total + 255) / 256;
+	if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
+	orbit_build_index<<<(unsigned) blocks, 256, 0, s>>>(x, total);
+	return 1;
+}
+
+// stage A: reset + the orbit of every star
+int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s)
 {
 	orbit_stats_reset<<<1, 1, 0, s>>>(a.stats);
 	if (a.n_local <= 0) return 1;
 	const unsigned blocks = (unsigned) ((a.n_local + ORBIT_THREADS - 1) / ORBIT_THREADS);
-	const int minb = a.min_blocks >= 8 ? 8 : (a.min_blocks >= 6 ? 6 : 4);
-#define CMCB_LAUNCH_STEP(REC, MB) orbit_step_kernel<REC, MB><<<blocks, ORBIT_THREADS, 0, s>>>(a)
-	if (a.draws) { if (minb == 8) CMCB_LAUNCH_STEP(true, 8); else if (minb == 6) CMCB_LAUNCH_STEP(true, 6); else CMCB_LAUNCH_STEP(true, 4); }
-	else { if (minb == 8) CMCB_LAUNCH_STEP(false, 8); else if (minb == 6) CMCB_LAUNCH_STEP(false, 6); else CMCB_LAUNCH_STEP(false, 4); }
-#undef CMCB_LAUNCH_STEP
-	orbit_scan_kernel<<<NUM_SMS_B200 * 4, ORBIT_SCAN_THREADS, 0, s>>>(a);
-	if (a.draws) orbit_deferred_kernel<true><<<NUM_SMS_B200, ORBIT_THREADS, 0, s>>>(a);
-	else orbit_deferred_kernel<false><<<NUM_SMS_B200, ORBIT_THREADS, 0, s>>>(a);
-	return 4;
+	if (a.min_blocks >= 8) orbit_prepare_kernel<8><<<blocks, ORBIT_THREADS, 0, s>>>(a);
+	else if (a.min_blocks >= 6) orbit_prepare_kernel<6><<<blocks, ORBIT_THREADS, 0, s>>>(a);
+	else orbit_prepare_kernel<4><<<blocks, ORBIT_THREADS, 0, s>>>(a);
+	return 2;
+}
+
+// the queued linear scans and the stars that waited for them
+int orbit_stage_scan(const OrbitArgs &a, cudaStream_t s)
+{
+	if (a.n_local <= 0) return 0;
+	orbit_scan_filter<<<NUM_SMS_B200 * 4, 256, 0, s>>>(a);
+	orbit_scan_chunks<<<NUM_SMS_B200 * 4, ORBIT_SCAN_THREADS, 0, s>>>(a);
+	orbit_deferred_kernel<<<NUM_SMS_B200, ORBIT_THREADS, 0, s>>>(a);
+	return 3;
+}
+
+// stage B: the rejection rounds
+int orbit_stage_tries(const OrbitArgs &a, cudaStream_t s)
+{
+	if (a.n_local <= 0) return 0;
+	return a.draws ? launch_try_rounds<true>(a, s) : launch_try_rounds<false>(a, s);
 }
 
 } // namespace cmcb

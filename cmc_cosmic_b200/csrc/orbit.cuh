@@ -10,13 +10,17 @@ constexpr int ORBIT_SCAN_THREADS = 256;
 constexpr int ORBIT_SCAN_CHUNK = 4096;      // table entries per work item of the cooperative linear scan
 constexpr int ORBIT_DEFER_CAP = 65536;      // queued scans per launch (beyond it a star scans in its own thread)
 constexpr long ORBIT_NOT_FOUND = 0x7fffffffffffffffL;
+constexpr unsigned ORBIT_SCAN_LIST_CAP = 1u << 20;
+constexpr int ORBIT_TRY_THREADS = 256;
+constexpr int ORBIT_MAX_ROUNDS = 8;         // launches of the rejection-sampling stage
 
 struct OrbitStats { // device-resident, zeroed per launch
 	unsigned long long max_rad_bits; // max over ORBIT_OK stars of rnew (positive doubles order like their bit patterns)
 	unsigned long long n_draws, n_exact, n_brent;
 	unsigned long long n_status[6];
 	unsigned n_defer;     // stars queued for the cooperative linear scan
-	unsigned scan_ticket; // work-item counter of orbit_scan_kernel
+	unsigned scan_items;  // (star, chunk) pairs the bound could not dismiss
+	unsigned round_count[ORBIT_MAX_ROUNDS + 2]; // stars pending at the start of each rejection round
 };
 
 struct OrbitArgs {
@@ -37,12 +41,20 @@ struct OrbitArgs {
 	long *kmin, *kmax;
 	int *n_draws;
 	OrbitStats *stats;
+	unsigned char *flag; // [n_local] 1: orbit known, new radius still to be drawn
+	int *pend_list[2]; // [n_local] each: compacted lists of pending stars, ping-pong between rounds
+	bool fuse_energy;  // E, J of every star are computed from the table and (vr, vt) on the fly and stored (ComputeEnergy's first loop)
+	bool use_index;    // potential() through the 16-ary index instead of the plain bisection
 	int min_blocks;    // register cap variant of orbit_step_kernel: 4, 6 or 8 resident CTAs per SM
 	long *defer_star;  // [ORBIT_DEFER_CAP] local 0-based index of each queued star
+	uint2 *scan_list;  // [ORBIT_SCAN_LIST_CAP] (slot, chunk) pairs to scan entry by entry
 	long *defer_found; // [ORBIT_DEFER_CAP] first k with Q > 0 (ORBIT_NOT_FOUND: none)
 };
 
 int orbit_pack_tables_device(const double *r, const double *phi, RPhi *rp, long n, cudaStream_t s);
-int orbit_step_device(const OrbitArgs &a, cudaStream_t s);
+int orbit_build_index_device(RIndex &x, const double *star_r, double *lvl, kint M, cudaStream_t s);
+int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s);
+int orbit_stage_scan(const OrbitArgs &a, cudaStream_t s);
+int orbit_stage_tries(const OrbitArgs &a, cudaStream_t s);
 
 } // namespace cmcb

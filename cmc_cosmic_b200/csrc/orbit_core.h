@@ -28,14 +28,59 @@ enum OrbitStatus {
 	ORBIT_NTRY = 5      // N_TRY exceeded (fatal in the reference) :890-893
 };
 
+// Table indices: the library caps n_star_dim below 2^30 (cmcb200_create), so 32 bits hold every index and every
+// kmin + kmax + 1 of the bisections -- half the registers of `long` in the hot loops.
+typedef int kint;
+
 struct RPhi { // one entry of the packed lookup table: every probe of the bisections needs r_k AND Phi_k -> one 16-byte load
 	double r, phi;
 };
 
+// Sampled 16-ary index over the sorted radii star_r[0 .. M], M = N_MAX + 1, for potential()'s "largest k with r_k < r"
+// (FindZero_r, cmc_nr.c:62-82).  The answer of that bisection is a pure function of the sorted array -- the number of entries
+// below r -- so ANY search returns the same index; this one needs ceil(log16 N) dependent steps of one 128-byte line each
+// instead of ceil(log2 N) dependent 8-byte probes, and only its last step leaves the L2-resident part of the structure.
+//   level h (1..H): A_h[i] = star_r[(i + 1) 16^h - 1], the last entry of every complete block of 16^h entries, padded with +inf
+//   to a multiple of 16; level 0 is star_r itself.
+constexpr int RIDX_MAX_LEVELS = 8;
+struct RIndex {
+	const double *r;   // star_r (SoA, 128-byte aligned, readable up to index M + 15)
+	const double *lvl; // the sampled levels, level h at lvl + off[h]
+	int off[RIDX_MAX_LEVELS + 1];
+	int H;             // sampled levels (0: the leaf window covers everything)
+	kint M;            // last valid index of star_r
+};
+
+// layout of the sampled levels for a table with last index M: off[1..H], H, total doubles
+CMCB_HD void ridx_plan(kint M, int off[RIDX_MAX_LEVELS + 1], int *H, long *total)
+{
+	long n = (long) M + 1, pos = 0;
+	int h = 0;
+	off[0] = 0;
+	while (n > 16 && h < RIDX_MAX_LEVELS) {
+		n /= 16;                          // complete blocks of 16^(h+1) entries
+		h++;
+		off[h] = (int) pos;
+		pos += ((n + 15) / 16) * 16 + 16; // padded; one spare line so that a window starting at the padding is readable
+	}
+	*H = h;
+	*total = pos > 0 ? pos : 16;
+}
+
+// value of sample i of level h (what the builder stores)
+CMCB_HD double ridx_sample(const double *star_r, kint M, int h, long i)
+{
+	long stride = 1;
+	for (int q = 0; q < h; q++) stride *= 16;
+	const long idx = (i + 1) * stride - 1;
+	return idx <= (long) M ? star_r[idx] : __builtin_huge_val();
+}
+
 struct OrbitTables {
 	const RPhi *rp;  // (star_r[k], star_phi[k]) interleaved: [0] sentinel, [1..N_MAX], [N_MAX+1] = (SF_INFINITY, 0)
 	const double *m; // star_m
-	long N_MAX;
+	RIndex ridx;     // 16-ary index over star_r for potential(); ridx.r == nullptr: plain bisection on rp
+	kint N_MAX;
 	double invN;    // 1.0 / clus.N_STAR evaluated in double (the factor in MPI_PHI_S)
 	double madhoc;  // 1.0 / (double) clus.N_STAR (cmc_utils.c:1183) -- same value, kept separate like the reference
 	double cenma_m; // cenma.m
@@ -43,7 +88,7 @@ struct OrbitTables {
 
 struct OrbitOut {
 	double rnew, vrnew, vtnew, X, r_peri, r_apo;
-	long kmin, kmax;
+	kint kmin, kmax;
 	int status;
 	int n_draws; // uniforms consumed
 	int n_exact; // Q evaluations that needed the exact x87 replay
@@ -52,7 +97,7 @@ struct OrbitOut {
 
 // ---- table lookups -------------------------------------------------------------------------------------------
 
-CMCB_HD double tbl_ld(const double *p, long k)
+CMCB_HD double tbl_ld(const double *p, kint k)
 {
 #if defined(__CUDA_ARCH__)
 	return __ldg(p + k);
@@ -60,7 +105,7 @@ CMCB_HD double tbl_ld(const double *p, long k)
 	return p[k];
 #endif
 }
-CMCB_HD RPhi tbl_rp(const OrbitTables &t, long k)
+CMCB_HD RPhi tbl_rp(const OrbitTables &t, kint k)
 {
 #if defined(__CUDA_ARCH__)
 	const double2 v = __ldg(reinterpret_cast<const double2 *>(t.rp + k));
@@ -72,8 +117,8 @@ CMCB_HD RPhi tbl_rp(const OrbitTables &t, long k)
 	return t.rp[k];
 #endif
 }
-CMCB_HD double tbl_r(const OrbitTables &t, long k) { return tbl_ld(&t.rp[k].r, 0); }
-CMCB_HD double tbl_phi(const OrbitTables &t, long k) { return tbl_ld(&t.rp[k].phi, 0); }
+CMCB_HD double tbl_r(const OrbitTables &t, kint k) { return tbl_ld(&t.rp[k].r, 0); }
+CMCB_HD double tbl_phi(const OrbitTables &t, kint k) { return tbl_ld(&t.rp[k].phi, 0); }
 
 #if defined(__CUDA_ARCH__)
 #define CMCB_COLD __device__ __noinline__
@@ -88,13 +133,51 @@ CMCB_HD double phi_self(double rad, double r_j, double m_j, double invN)
 }
 
 // FindZero_r (cmc_nr.c:62-82)
-CMCB_HD long find_zero_r(const OrbitTables &t, long kmin, long kmax, double r)
+CMCB_HD kint find_zero_r(const OrbitTables &t, kint kmin, kint kmax, double r)
 {
 	do {
-		long ktry = (kmin + kmax + 1) / 2;
+		kint ktry = (kmin + kmax + 1) / 2;
 		if (tbl_r(t, ktry) < r) kmin = ktry; else kmax = ktry - 1;
 	} while (kmax != kmin);
 	return kmin;
+}
+
+// number of entries among 16 consecutive doubles (one 128-byte line) that are < r
+CMCB_HD int ridx_count16(const double *line, double r)
+{
+	int c = 0;
+#if defined(__CUDA_ARCH__)
+	const double2 *q = reinterpret_cast<const double2 *>(line);
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const double2 v = __ldg(q + i);
+		c += (v.x < r) + (v.y < r);
+	}
+#else
+	for (int i = 0; i < 16; i++) c += line[i] < r;
+#endif
+	return c;
+}
+
+// FindZero_r(1, N_MAX + 1, r) through the index: largest k in [1, N_MAX+1] with star_r[k] < r, 1 if there is none
+CMCB_HD kint find_zero_r_indexed(const RIndex &x, double r)
+{
+	long nb = 0; // complete blocks of the current level that lie entirely below r
+	for (int h = x.H; h >= 1; h--) nb = 16 * nb + ridx_count16(x.lvl + x.off[h] + 16 * nb, r);
+	const long base = 16 * nb;
+	int c = 0;
+#if defined(__CUDA_ARCH__)
+	const double2 *q = reinterpret_cast<const double2 *>(x.r + base);
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const double2 v = __ldg(q + i);
+		c += (base + 2 * i <= (long) x.M && v.x < r) + (base + 2 * i + 1 <= (long) x.M && v.y < r);
+	}
+#else
+	for (int i = 0; i < 16; i++) c += (base + i <= (long) x.M) && x.r[base + i] < r;
+#endif
+	const long below = base + c; // entries of star_r[0 .. M] that are < r; star_r[0] = ZERO is one of them
+	return below >= 2 ? (kint) (below - 1) : 1;
 }
 
 // potential(r) (cmc_utils.c:112-165, SEARCH_GRID = 0).  *fail is set when the bracket check (:144-152) would abort.
@@ -104,8 +187,8 @@ CMCB_HD double potential_at(const OrbitTables &t, double r, int *fail)
 	if (r == 0.0) return phi0;
 	const RPhi p1 = tbl_rp(t, 1);
 	if (r < p1.r) return dsub(phi0, ddiv(dmul(dsub(phi0, p1.phi), p1.r), r));
-	long kmax = t.N_MAX + 1, kmin = 1;
-	long i = (kmin == kmax - 1) ? kmin : find_zero_r(t, kmin, kmax, r);
+	kint kmax = t.N_MAX + 1, kmin = 1;
+	kint i = (kmin == kmax - 1) ? kmin : (t.ridx.r ? find_zero_r_indexed(t.ridx, r) : find_zero_r(t, kmin, kmax, r));
 	const RPhi a = tbl_rp(t, i), b = tbl_rp(t, i + 1);
 	if (a.r > r || b.r < r) { *fail = 1; return 0.0; }
 	double inv_i = ddiv(1.0, a.r);
@@ -117,7 +200,7 @@ CMCB_HD double potential_at(const OrbitTables &t, double r, int *fail)
 struct StarConst {
 	double E, J;     // energy including the self term (cmc_evolution_thr.c:806), angular momentum
 	double r_j, m_j; // star_r[g_j], star_m[g_j]
-	long g_j;
+	kint g_j;
 	// derived once per star for the division-free sign test
 	double JJ;       // fl(J*J)
 	double mi;       // fl(m_j * invN):            phis * r^2 = mi * r        for r >= r_j
@@ -148,9 +231,14 @@ CMCB_HD double q_fp64(const OrbitTables &t, const StarConst &s, double r, double
 }
 
 // value the reference's function_q returns (a double), exact.  Cold: reached when a sign is within the error bound.
-CMCB_COLD double q_exact(const OrbitTables &t, const StarConst &s, double r, double pot)
+// (scalars by value: a by-reference struct argument of a non-inlined function would pin the caller's copy in local memory)
+CMCB_COLD double q_exact_cold(double r, double pot, double E, double J, double m_j, double r_j, double invN)
 {
-	return x87_function_q(r, pot, s.E, s.J, s.m_j, s.r_j, t.invN);
+	return x87_function_q(r, pot, E, J, m_j, r_j, invN);
+}
+CMCB_HD double q_exact(const OrbitTables &t, const StarConst &s, double r, double pot)
+{
+	return q_exact_cold(r, pot, s.E, s.J, s.m_j, s.r_j, t.invN);
 }
 
 // Sign of function_q(j, r, pot, E, J) -- what every bisection probe and the linear scan consume -- WITHOUT a division:
@@ -177,10 +265,10 @@ CMCB_HD int sign_Q_at(const OrbitTables &t, const StarConst &s, const RPhi p, in
 	const double q = q_exact(t, s, p.r, p.phi);
 	return q > 0.0 ? 1 : (q < 0.0 ? -1 : 0);
 }
-CMCB_HD int sign_Q(const OrbitTables &t, const StarConst &s, long k, int *n_exact) { return sign_Q_at(t, s, tbl_rp(t, k), n_exact); }
+CMCB_HD int sign_Q(const OrbitTables &t, const StarConst &s, kint k, int *n_exact) { return sign_Q_at(t, s, tbl_rp(t, k), n_exact); }
 
 // the direction test of find_zero_Q (cmc_nr.c:342): function_q(kmin) < function_q(kmax) on the VALUES
-CMCB_HD bool q_increasing(const OrbitTables &t, const StarConst &s, long kmin, long kmax, int *n_exact)
+CMCB_HD bool q_increasing(const OrbitTables &t, const StarConst &s, kint kmin, kint kmax, int *n_exact)
 {
 	double Bmin, Bmax;
 	const RPhi lo = tbl_rp(t, kmin), hi = tbl_rp(t, kmax);
@@ -193,11 +281,11 @@ CMCB_HD bool q_increasing(const OrbitTables &t, const StarConst &s, long kmin, l
 }
 
 // find_zero_Q (cmc_nr.c:316-383): the same probe sequence ktry = (kmin+kmax+1)/2
-CMCB_HD long find_zero_Q(const OrbitTables &t, const StarConst &s, long kmin, long kmax, int *n_exact)
+CMCB_HD kint find_zero_Q(const OrbitTables &t, const StarConst &s, kint kmin, kint kmax, int *n_exact)
 {
 	const bool increasing = q_increasing(t, s, kmin, kmax, n_exact);
 	do {
-		long ktry = (kmin + kmax + 1) / 2;
+		kint ktry = (kmin + kmax + 1) / 2;
 		int sg = sign_Q(t, s, ktry, n_exact);
 		bool up = increasing ? (sg < 0) : (sg > 0); // :349 / :362
 		if (up) kmin = ktry; else kmax = ktry - 1;
@@ -205,11 +293,28 @@ CMCB_HD long find_zero_Q(const OrbitTables &t, const StarConst &s, long kmin, lo
 	return kmin;
 }
 
+// Can function_q be > 0 (or undecided) anywhere on table entries [k_lo, k_hi]?  false = PROVEN <= 0 on the whole range:
+//   Phi is non-decreasing in k (each phi_k = fl(phi_{k+1} - (a non-negative term)), cmc_utils.c:719), r is sorted, and the self
+//   term is non-increasing in r, so for every k in the range  Q(k) <= U := 2 (E - Phi_lo - phis(r_hi)) - J^2 / r_hi^2,
+//   and |Q(k)| >= |U| + (J^2/r_k^2 - J^2/r_hi^2) keeps the reference's computed sign on the side of the real-number sign
+//   (its noise is a 2^-51 multiple of |E| + |Phi_k| + phis + J^2/r_k^2).  U is evaluated in the division-free form of sign_Q_at
+//   with a 64x wider margin (2^-44): the test only has to dismiss ranges that are nowhere near a sign change.
+CMCB_HD bool q_maybe_positive_on(const StarConst &s, const RPhi lo, const RPhi hi)
+{
+	const double a = dsub(s.E, lo.phi);
+	const double r2 = dmul(hi.r, hi.r);
+	const double t1 = dmul(a, r2);
+	const double t2 = (hi.r >= s.r_j) ? dmul(s.mi, hi.r) : dmul(s.c_in, r2);
+	const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
+	const double mag = dadd(dadd(dmul(dadd(dadd(s.absE, dabs(lo.phi)), s.c_in), r2), s.JJ), dadd(dabs(t1), dabs(t2)));
+	return !(S < -dmul(5.684341886080802e-14 /* 2^-44 */, mag));
+}
+
 // the linear scan of get_positive_Q_index (cmc_orbit.c:46-57): first k from 0 with Q > 0; -1 if there is none below N_MAX.
 // Sequential form (host emulation, and the device's last resort); the CUDA path runs it as a grid-wide find-first.
-CMCB_HD long scan_positive_Q(const OrbitTables &t, const StarConst &s, int *n_exact)
+CMCB_HD kint scan_positive_Q(const OrbitTables &t, const StarConst &s, int *n_exact)
 {
-	long ktemp = -1;
+	kint ktemp = -1;
 	int sg;
 	do {
 		ktemp++;
@@ -219,7 +324,7 @@ CMCB_HD long scan_positive_Q(const OrbitTables &t, const StarConst &s, int *n_ex
 }
 
 // set_a_b (cmc_orbit.c:722-740)
-CMCB_HD void set_a_b(const OrbitTables &t, const StarConst &s, long k, double *a, double *b)
+CMCB_HD void set_a_b(const OrbitTables &t, const StarConst &s, kint k, double *a, double *b)
 {
 	if (k == 0) {
 		*a = dmul(-t.cenma_m, t.madhoc);
@@ -237,7 +342,7 @@ CMCB_HD void set_a_b(const OrbitTables &t, const StarConst &s, long k, double *a
 
 // calc_vr_within_interval (cmc_nr.c:393-405 + 279-302): vr^2 inside [r_k, r_k+1]; Brent needs the VALUE, so this is
 // always the exact x87 replay (rare path)
-CMCB_COLD double vr2_within_interval(const OrbitTables &t, const StarConst &s, long k, double r)
+CMCB_HD double vr2_within_interval(const OrbitTables &t, const StarConst &s, kint k, double r)
 {
 	const double EPS = 2.220446049250313e-16; // DBL_EPSILON
 	double rk = tbl_r(t, k), rk1 = tbl_r(t, k + 1), pot;
@@ -254,10 +359,10 @@ CMCB_COLD double vr2_within_interval(const OrbitTables &t, const StarConst &s, l
 // find_root_vr (cmc_nr.c:500-603): Brent-Dekker as GSL's gsl_root_fsolver_brent iterates it (un-vendored
 // dependency of the reference, version unpinned -> this branch is "parity unpinned"), APSIDES_PRECISION = 1e-11,
 // APSIDES_MAX_ITER = 100, APSIDES_CONVERGENCE = 5e-13 (cmc_io.c:1752-1754).
-CMCB_COLD double find_root_vr(const OrbitTables &t, const StarConst &s, long k)
+CMCB_COLD double find_root_vr(const OrbitTables t, const StarConst s, kint k) // by value: see q_exact_cold
 {
 	const double PREC = 1.0e-11, CONV = 5.e-13, EPS = 2.220446049250313e-16;
-	long iter = 100;
+	int iter = 100;
 	double a = tbl_r(t, k), b = tbl_r(t, k + 1), c = b;
 	double fa = vr2_within_interval(t, s, k, a), fb = vr2_within_interval(t, s, k, b), fc = fb;
 	double d = dsub(b, a), e = d, root = dmul(0.5, dadd(a, b)), lo = a, hi = b, prev_apsis = -1.0;
@@ -316,19 +421,19 @@ CMCB_COLD double find_root_vr(const OrbitTables &t, const StarConst &s, long k)
 
 struct OrbitRS { // orbit_rs_t, reference include/cmc/cmc.h:1621-1650
 	double rp, ra, dQdrp, dQdra;
-	long kmin, kmax;
+	kint kmin, kmax;
 	int circular;
 };
 
 // calc_orbit_new (cmc_orbit.c:413-540) incl. get_positive_Q_index (:30-59)
 // ktemp_in: KTEMP_COMPUTE, or the result of the linear scan found elsewhere (>= -1).  need_scan != nullptr: instead of running the
 // O(N) scan in this thread, set *need_scan and return (the caller queues the star for the cooperative scan).
-constexpr long KTEMP_COMPUTE = -2;
+constexpr kint KTEMP_COMPUTE = -2;
 CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is_new, double rnew_of_new, int *n_exact, int *n_brent,
-			       long ktemp_in = KTEMP_COMPUTE, bool *need_scan = nullptr)
+			       kint ktemp_in = KTEMP_COMPUTE, bool *need_scan = nullptr)
 {
 	OrbitRS o;
-	long ktemp = ktemp_in;
+	kint ktemp = ktemp_in;
 	if (ktemp_in == KTEMP_COMPUTE) {
 		ktemp = s.g_j;
 		if (is_new) ktemp = find_zero_r(t, 0, t.N_MAX, rnew_of_new) + 1; // cmc_orbit.c:39-41
@@ -343,7 +448,7 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 	}
 	bool circular = ktemp <= -1;
 	double rmin = 0, rmax = 0, dQdr_min = 0, dQdr_max = 0;
-	long kmin = 0, kmax = 0;
+	kint kmin = 0, kmax = 0;
 	if (!circular) {
 		kmin = find_zero_Q(t, s, 0, ktemp, n_exact);               // :441
 		kmax = find_zero_Q(t, s, ktemp, t.N_MAX + 1, n_exact);     // :444
@@ -381,7 +486,7 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 // One iteration of the loop body of get_positions_loop (cmc_evolution_thr.c:802-933).
 // E_star is star[j].E (without the self term), Draws provides `double next()` and `bool has(int n)`.
 // the star's constants as the loop body sets them up (:803-807)
-CMCB_HD StarConst star_const(const OrbitTables &t, long g_j, double E_star, double J)
+CMCB_HD StarConst star_const(const OrbitTables &t, kint g_j, double E_star, double J)
 {
 	StarConst s;
 	s.g_j = g_j;
@@ -394,13 +499,19 @@ CMCB_HD StarConst star_const(const OrbitTables &t, long g_j, double E_star, doub
 }
 
 constexpr int ORBIT_DEFERRED = 6; // internal to the CUDA path: the star waits for the cooperative linear scan; never leaves the library
+constexpr int ORBIT_PENDING = 7;  // internal: the orbit is known (job), the rejection sampling of the new radius is still to do
 
-template <class Draws>
-CMCB_HD void orbit_step_star(const OrbitTables &t, long g_j, bool is_new, double rnew_of_new, double E_star, double J,
-			     double vr_in, double vt_in, double Rtidal, Draws &draws, OrbitOut &out,
-			     long ktemp_in = KTEMP_COMPUTE, bool allow_defer = false)
+// What the rejection loop (:862-888) needs besides the star's constants: the orbit's turning points and the envelope F.
+struct OrbitJob {
+	double rmin, rmax, F;
+};
+
+// Everything of one loop iteration of get_positions_loop BEFORE the rejection sampling (:803-860): the early exits (massless,
+// unbound, circular, tidally stripped) are final and fill `out`; otherwise the status is ORBIT_PENDING and `job` is set.
+// (for ORBIT_CIRCULAR the caller fills vrnew / vtnew with the star's current vr / vt, :837-838)
+CMCB_HD void orbit_prepare(const OrbitTables &t, const StarConst &s, bool is_new, double rnew_of_new, double Rtidal,
+			   kint ktemp_in, bool allow_defer, OrbitOut &out, OrbitJob &job)
 {
-	const StarConst s = star_const(t, g_j, E_star, J);
 	out.n_draws = 0; out.n_exact = 0; out.n_brent = 0;
 	out.kmin = out.kmax = -1;
 	out.X = out.r_peri = out.r_apo = 0.0;
@@ -417,45 +528,82 @@ CMCB_HD void orbit_step_star(const OrbitTables &t, long g_j, bool is_new, double
 	if (need_scan) { out.status = ORBIT_DEFERRED; out.rnew = out.vrnew = out.vtnew = 0.0; return; }
 	out.kmin = o.kmin; out.kmax = o.kmax;
 	if (o.circular) {                      // :835-839
-		out.status = ORBIT_CIRCULAR; out.rnew = s.r_j; out.vrnew = vr_in; out.vtnew = vt_in;
+		out.status = ORBIT_CIRCULAR; out.rnew = s.r_j; out.vrnew = 0.0; out.vtnew = 0.0;
 		return;
 	}
-	double rmin = o.rp, rmax = o.ra;
+	const double rmin = o.rp, rmax = o.ra;
 	if (rmax >= Rtidal) {                  // :848-855
 		out.status = ORBIT_TIDAL; out.r_apo = rmax; out.r_peri = rmin;
 		out.rnew = CMCB_SF_INFINITY; out.vrnew = 0.0; out.vtnew = 0.0;
 		return;
 	}
-	double span = dsub(rmax, rmin);
-	double g1 = dsqrt(ddiv(dmul(3.0, span), o.dQdrp));   // :857
-	double g2 = dsqrt(ddiv(dmul(-3.0, span), o.dQdra));  // :858
-	double F = dmul(1.2, (g1 >= g2 ? g1 : g2));          // :860
-	double mid = dmul(0.5, dadd(rmin, rmax)), quarter = dmul(0.25, span), twoE = dmul(2.0, s.E), JJ = dmul(J, J);
-	double r = 0.0, vr = 0.0, X = 0.0;
-	long k;
+	const double span = dsub(rmax, rmin);
+	const double g1 = dsqrt(ddiv(dmul(3.0, span), o.dQdrp));   // :857
+	const double g2 = dsqrt(ddiv(dmul(-3.0, span), o.dQdra));  // :858
+	job.F = dmul(1.2, (g1 >= g2 ? g1 : g2));                   // :860
+	job.rmin = rmin; job.rmax = rmax;
+	out.r_peri = rmin; out.r_apo = rmax;                       // what :919-920 will store once a radius is accepted
+	out.status = ORBIT_PENDING;
+}
+
+// One pass of the rejection loop body (:863-887) with the two uniforms X, u of that try.  1: accepted (r, vr set), 0: rejected,
+// -1: the bracket check inside potential() failed (fatal in the reference, cmc_utils.c:144-152).
+CMCB_HD int orbit_try(const OrbitTables &t, const StarConst &s, const OrbitJob &job, double X, double u, double *r_out, double *vr_out)
+{
+	const double span = dsub(job.rmax, job.rmin);
+	const double mid = dmul(0.5, dadd(job.rmin, job.rmax)), quarter = dmul(0.25, span), twoE = dmul(2.0, s.E);
+	const double s0 = dsub(dmul(2.0, X), 1.0);
+	const double g0 = dmul(job.F, u);
+	const double r = dadd(mid, dmul(quarter, dsub(dmul(3.0, s0), dmul(dmul(s0, s0), s0))));
 	int fail = 0;
+	const double pot = dadd(potential_at(t, r, &fail), phi_self(r, s.r_j, s.m_j, t.invN));
+	const double drds = dmul(quarter, dsub(3.0, dmul(dmul(3.0, s0), s0)));
+	const double Q = dsub(dsub(twoE, dmul(2.0, pot)), ddiv(ddiv(s.JJ, r), r));
+	const double vr = (Q >= 0.0) ? dsqrt(Q) : 0.0;
+	*r_out = r;
+	*vr_out = vr;
+	if (fail) return -1;
+	return g0 < dmul(ddiv(1.0, vr), drds) ? 1 : 0;
+}
+
+// :918-931 once try number `tries` (1-based) was accepted with (X, r, vr); usign = the next uniform of the stream
+CMCB_HD void orbit_finish(const StarConst &s, const OrbitJob &job, double X, double r, double vr, double usign, int tries, OrbitOut &out)
+{
+	out.X = X; out.r_peri = job.rmin; out.r_apo = job.rmax;  // :918-920
+	if (usign < 0.5) vr = -vr;                               // :923-924
+	out.n_draws = 2 * tries + 1;
+	out.status = ORBIT_OK;
+	out.rnew = r; out.vrnew = vr; out.vtnew = ddiv(s.J, r);  // :926-931
+}
+
+// One iteration of the loop body of get_positions_loop (cmc_evolution_thr.c:802-933), start to end, on a sequential stream.
+// E_star is star[j].E (without the self term), Draws provides `double next()` and `bool has(int n)`.
+template <class Draws>
+CMCB_HD void orbit_step_star(const OrbitTables &t, kint g_j, bool is_new, double rnew_of_new, double E_star, double J,
+			     double vr_in, double vt_in, double Rtidal, Draws &draws, OrbitOut &out,
+			     kint ktemp_in = KTEMP_COMPUTE, bool allow_defer = false)
+{
+	const StarConst s = star_const(t, g_j, E_star, J);
+	OrbitJob job;
+	orbit_prepare(t, s, is_new, rnew_of_new, Rtidal, ktemp_in, allow_defer, out, job);
+	if (out.status == ORBIT_CIRCULAR) { out.vrnew = vr_in; out.vtnew = vt_in; }
+	if (out.status != ORBIT_PENDING) return;
+	double r = 0.0, vr = 0.0, X = 0.0;
+	int k, rc = 0;
 	for (k = 1; k <= CMCB_N_TRY; k++) {    // :862-888
-		if (!draws.has(2)) { fail = 1; break; }
+		if (!draws.has(2)) { rc = -1; break; }
 		X = draws.next();
-		double s0 = dsub(dmul(2.0, X), 1.0);
-		double g0 = dmul(F, draws.next());
-		out.n_draws += 2;
-		r = dadd(mid, dmul(quarter, dsub(dmul(3.0, s0), dmul(dmul(s0, s0), s0))));
-		double pot = dadd(potential_at(t, r, &fail), phi_self(r, s.r_j, s.m_j, t.invN));
-		double drds = dmul(quarter, dsub(3.0, dmul(dmul(3.0, s0), s0)));
-		double Q = dsub(dsub(twoE, dmul(2.0, pot)), ddiv(ddiv(JJ, r), r));
-		vr = (Q >= 0.0) ? dsqrt(Q) : 0.0;
-		if (g0 < dmul(ddiv(1.0, vr), drds)) break;
+		const double u = draws.next();
+		rc = orbit_try(t, s, job, X, u, &r, &vr);
+		if (rc != 0) break;
 	}
-	if (k == CMCB_N_TRY + 1 || fail || !draws.has(1)) {
+	if (k == CMCB_N_TRY + 1 || rc < 0 || !draws.has(1)) { // :890-893
 		out.status = ORBIT_NTRY; out.rnew = s.r_j; out.vrnew = vr_in; out.vtnew = vt_in;
+		out.X = out.r_peri = out.r_apo = 0.0;
+		out.n_draws = 2 * (k > CMCB_N_TRY ? CMCB_N_TRY : k);
 		return;
 	}
-	out.X = X; out.r_peri = rmin; out.r_apo = rmax;          // :918-920
-	if (draws.next() < 0.5) vr = -vr;                        // :923-924
-	out.n_draws += 1;
-	out.status = ORBIT_OK;
-	out.rnew = r; out.vrnew = vr; out.vtnew = ddiv(J, r);    // :926-931
+	orbit_finish(s, job, X, r, vr, draws.next(), k, out);
 }
 
 } // namespace cmcb

@@ -239,8 +239,14 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_pass(SortBuffers b
 // star_out[i] = star_in[perm[i]]; also star_r[1+i], star_m[1+i] (post_sort_comm) and flag[i] = binind > 0 for i < n_new.
 // One warp per record and iteration, 4 records in flight per warp; 8-byte words (424 = 53 * 8).
 constexpr int GATHER_UNROLL = 4;
+struct GatherFuse { // see SortArgs::fuse_transfer
+	const double *old_r, *old_m;
+	long n_old_local, first_global, N_MAX;
+};
+
+template <bool FUSE>
 __global__ void __launch_bounds__(256) sort_gather_records(const char *__restrict__ in, char *__restrict__ out, SortBuffers b, const SortState *st,
-						       double *__restrict__ star_r, double *__restrict__ star_m, unsigned char *__restrict__ binflag)
+						       double *__restrict__ star_r, double *__restrict__ star_m, unsigned char *__restrict__ binflag, GatherFuse f)
 {
 	const unsigned *__restrict__ perm = st->final_buf ? b.vals_b : b.vals_a;
 	const long n = st->n_total, n_new = st->n_new;
@@ -248,14 +254,34 @@ __global__ void __launch_bounds__(256) sort_gather_records(const char *__restric
 	long warp_global = (blockIdx.x * (long) blockDim.x + threadIdx.x) >> 5;
 	long nwarps = ((long) gridDim.x * blockDim.x) >> 5;
 	for (long i0 = warp_global * GATHER_UNROLL; i0 < n; i0 += nwarps * GATHER_UNROLL) {
-		unsigned long long w0[GATHER_UNROLL], w1[GATHER_UNROLL];
+		unsigned long long w0[GATHER_UNROLL], w1[GATHER_UNROLL], tab[GATHER_UNROLL];
+		// all loads of the GATHER_UNROLL records first (independent, in flight together) ...
 #pragma unroll
 		for (int u = 0; u < GATHER_UNROLL; u++) {
 			long i = i0 + u;
 			if (i < n) {
-				const unsigned long long *src = (const unsigned long long *) (in + (long) perm[i] * CMCB_SIZEOF_STAR);
+				const long p = perm[i];
+				const unsigned long long *src = (const unsigned long long *) (in + p * CMCB_SIZEOF_STAR);
 				w0[u] = __ldg(src + lane);
 				w1[u] = lane < CMCB_STAR_WORDS - 32 ? __ldg(src + 32 + lane) : 0ull;
+				if (FUSE) { // the record's global index BEFORE the sort: get_global_idx (cmc_utils.c:2384-2407)
+					const long j = p + 1;
+					const long g = j > f.n_old_local ? 1 + f.N_MAX + (j - f.n_old_local) : f.first_global + j - 1;
+					tab[u] = 0ull;
+					if (lane == CMCB_OFF_M / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(f.old_m + g));
+					else if (lane == CMCB_OFF_ROLD / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(f.old_r + g));
+				}
+			}
+		}
+		// ... then the transfer: words r 0, vr 1, vt 2 <- rnew 8, vrnew 9, vtnew 10; m 3 <- star_m[g]; rOld 11 <- star_r[g]
+		if (FUSE) {
+#pragma unroll
+			for (int u = 0; u < GATHER_UNROLL; u++) {
+				if (i0 + u < n) {
+					const unsigned long long moved = __shfl_sync(0xffffffffu, w0[u], (lane + 8) & 31);
+					if (lane < 3) w0[u] = moved;
+					else if (lane == CMCB_OFF_M / 8 || lane == CMCB_OFF_ROLD / 8) w0[u] = tab[u];
+				}
 			}
 		}
 #pragma unroll
@@ -419,7 +445,11 @@ int sort_stage_passes(const SortArgs &a, cudaStream_t s)
 // stage 2: move the 424-byte records, emit star_r / star_m / binary flags
 int sort_stage_gather(const SortArgs &a, cudaStream_t s)
 {
-	if (a.n > 0) sort_gather_records<<<NUM_SMS_B200 * 8, 256, 0, s>>>(a.star_in, a.star_out, a.buf, a.st, a.star_r, a.star_m, a.binflag);
+	GatherFuse f{a.old_r, a.old_m, a.n_old_local, a.first_global, a.N_MAX};
+	if (a.n > 0) {
+		if (a.fuse_transfer) sort_gather_records<true><<<NUM_SMS_B200 * 8, 256, 0, s>>>(a.star_in, a.star_out, a.buf, a.st, a.star_r, a.star_m, a.binflag, f);
+		else sort_gather_records<false><<<NUM_SMS_B200 * 8, 256, 0, s>>>(a.star_in, a.star_out, a.buf, a.st, a.star_r, a.star_m, a.binflag, f);
+	}
 	return a.n > 0 ? 1 : 0;
 }
 

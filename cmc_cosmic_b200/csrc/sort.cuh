@@ -41,6 +41,11 @@ struct SortArgs {
 	const char *bin_in;  // &binary[1] before the sort (may be null)
 	char *bin_out;       // &binary[1] after
 	long n_bin_clear;    // zero bin_out records [n_bin, n_bin_clear)
+	// fused ComputeIntermediateEnergy transfer (reference src/cmc/cmc_utils.c:380-390): the key is rnew, and while a record moves
+	// r <- rnew, vr <- vrnew, vt <- vtnew, m <- star_m[g], rOld <- star_r[g] (g = the record's global index BEFORE the sort)
+	bool fuse_transfer;
+	const double *old_r, *old_m; // the tables the transfer reads (must not alias star_r / star_m, which the gather writes)
+	long n_old_local, first_global, N_MAX;
 };
 
 int sort_setup();

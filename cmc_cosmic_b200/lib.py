@@ -4,14 +4,15 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmcb200.so")
-N_STAGES = 10
-STAGE_NAMES = ["keys_hist", "radix_passes", "record_gather", "binaries", "potential", "orbit", "transfer", "energy", "h2d", "d2h"]
+N_STAGES = 13
+STAGE_NAMES = ["keys_hist", "radix_passes", "record_gather", "binaries", "potential", "orbit_prepare", "transfer", "energy", "h2d", "d2h",
+               "orbit_scan", "orbit_tries", "orbit_tables"]
 
 
 class OrbitParams(C.Structure):
     _fields_ = [("n_local", C.c_long), ("n_old_local", C.c_long), ("first_global", C.c_long), ("N_MAX", C.c_long), ("N_STAR", C.c_long),
                 ("n_table", C.c_long), ("cenma_m", C.c_double), ("Rtidal", C.c_double), ("draws", C.c_void_p), ("draw_off", C.c_void_p),
-                ("seed", C.c_ulonglong), ("tcount", C.c_ulonglong)]
+                ("seed", C.c_ulonglong), ("tcount", C.c_ulonglong), ("fuse_compute_energy", C.c_int)]
 
 
 class OrbitResult(C.Structure):
@@ -28,7 +29,7 @@ _lib = None
 EXPORTS = [
     "cmcb200_create", "cmcb200_destroy", "cmcb200_last_error", "cmcb200_set_stream", "cmcb200_layout", "cmcb200_find_limits",
     "cmcb200_calc_potential_new", "cmcb200_qsorts_new", "cmcb200_new_orbits_calculate", "cmcb200_upload", "cmcb200_download",
-    "cmcb200_dev_new_orbits", "cmcb200_dev_transfer_new_positions", "cmcb200_dev_qsorts_new", "cmcb200_dev_calc_potential_new",
+    "cmcb200_dev_new_orbits", "cmcb200_dev_transfer_new_positions", "cmcb200_dev_qsorts_new", "cmcb200_dev_transfer_and_sort", "cmcb200_dev_calc_potential_new",
     "cmcb200_dev_compute_energy", "cmcb200_dev_read_status", "cmcb200_sync", "cmcb200_profile", "cmcb200_profile_read",
     "cmcb200_potential_stats", "cmcb200_launch_count",
 ]
@@ -61,6 +62,7 @@ def load():
     L.cmcb200_dev_new_orbits.argtypes = [vp, C.POINTER(OrbitParams), C.c_int, C.POINTER(OrbitResult)]
     L.cmcb200_dev_transfer_new_positions.argtypes = [vp, lg, lg, lg, lg]
     L.cmcb200_dev_qsorts_new.argtypes = [vp, pl, lg, pl]
+    L.cmcb200_dev_transfer_and_sort.argtypes = [vp, pl, lg, lg, lg, lg, pl]
     L.cmcb200_dev_calc_potential_new.argtypes = [vp, pl, lg, C.POINTER(dbl), C.POINTER(dbl), dbl, C.POINTER(dbl), C.POINTER(dbl)]
     L.cmcb200_dev_compute_energy.argtypes = [vp, lg, lg]
     L.cmcb200_dev_read_status.argtypes = [vp, vp, vp, vp, lg]

@@ -103,6 +103,9 @@ typedef struct {
 	const double *draws;
 	const long *draw_off;
 	unsigned long long seed, tcount;
+	/* resident pipeline only: != 0 computes E = star_phi[g] + (vr^2 + vt^2)/2, J = star_r[g] vt of every star on the fly and stores them
+	 * -- the first loop of ComputeEnergy (src/cmc/cmc_utils.c:612-616) fused into the orbit step instead of a pass of its own */
+	int fuse_compute_energy;
 } cmcb200_orbit_params;
 
 typedef struct {
@@ -136,6 +139,9 @@ int cmcb200_dev_new_orbits(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int 
 int cmcb200_dev_transfer_new_positions(cmcb200_ctx *ctx, long n_local, long n_old_local, long first_global, long N_MAX);
 /* qsorts_new + post_sort_comm on the resident arrays; *n_local in/out, *n_bin out */
 int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, long *n_bin);
+/* cmcb200_dev_transfer_new_positions + cmcb200_dev_qsorts_new in one pass over the records: the sort key is rnew and the transfer is
+ * applied to each 424-byte record while the gather moves it (n_old_local / first_global / N_MAX: those of the orbit step) */
+int cmcb200_dev_transfer_and_sort(cmcb200_ctx *ctx, long *n_local, long n_old_local, long first_global, long N_MAX, long n_bin_clear, long *n_bin);
 /* calc_potential_new on the resident tables */
 int cmcb200_dev_calc_potential_new(cmcb200_ctx *ctx, long *N_MAX, long N_STAR, double *cenma_m, double *cenma_m_new, double orbit_r,
 				   double *Mtotal, double *Rtidal);
@@ -150,8 +156,9 @@ int cmcb200_sync(cmcb200_ctx *ctx);
 
 /* With profiling on, every stage is bracketed by CUDA events on the launching stream.  cmcb200_profile_read returns the
  * accumulated milliseconds and launch counts since the last reset for: 0 keys+histogram, 1 radix passes, 2 record
- * gather, 3 binaries, 4 potential, 5 orbit step, 6 transfer, 7 energy, 8 h2d, 9 d2h. */
-#define CMCB200_N_STAGES 10
+ * gather, 3 binaries, 4 potential, 5 orbit stage A (orbits of all stars), 6 transfer, 7 energy, 8 h2d, 9 d2h, 10 orbit linear scans,
+ * 11 orbit stage B (rejection rounds), 12 orbit lookup tables. */
+#define CMCB200_N_STAGES 13
 int cmcb200_profile(cmcb200_ctx *ctx, int on);
 int cmcb200_profile_read(cmcb200_ctx *ctx, double ms[CMCB200_N_STAGES], long launches[CMCB200_N_STAGES], int reset);
 /* kernels launched by this context since it was created */

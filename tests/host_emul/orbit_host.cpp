@@ -19,6 +19,25 @@ struct ArrayDraws {
 	double next() { return d[pos++]; }
 };
 
+// the 16-ary index over star_r (built on the device by orbit_build_index in the product)
+struct HostIndex {
+	std::vector<double> r, lvl;
+	RIndex x;
+	HostIndex(const double *star_r, kint M)
+	{
+		r.assign(star_r, star_r + M + 1);
+		r.resize(M + 1 + 32, 0.0); // readable past M; the values there must not matter (the leaf step masks them)
+		long total;
+		ridx_plan(M, x.off, &x.H, &total);
+		lvl.assign(total, __builtin_huge_val());
+		for (int h = 1; h <= x.H; h++) {
+			long n = (h < x.H ? x.off[h + 1] : total) - x.off[h];
+			for (long i = 0; i < n; i++) lvl[x.off[h] + i] = ridx_sample(star_r, M, h, i);
+		}
+		x.r = r.data(); x.lvl = lvl.data(); x.M = M;
+	}
+};
+
 extern "C" double emul_get_positions(const double *star_r, const double *star_m, const double *star_phi, long N_MAX, long N_STAR,
 				     double cenma_m, long n_local, const long *g_idx, const unsigned char *is_new,
 				     const double *E_in, const double *J_in, const double *vr_in, const double *vt_in, const double *rnew_in,
@@ -31,7 +50,9 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 	for (long j = 0; j < n_local; j++) if (g_idx[j] + 1 > n_tab) n_tab = g_idx[j] + 1;
 	std::vector<RPhi> rp = pack(star_r, star_phi, n_tab);
 	t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = cenma_m;
-	(void) force_exact;
+	HostIndex hx(star_r, (kint) (N_MAX + 1));
+	t.ridx = hx.x;
+	if (force_exact) t.ridx.r = nullptr; // force_exact = 1: plain bisection instead of the 16-ary index
 	double max_rad = 0.0;
 	long pos = 0;
 	counters[0] = counters[1] = counters[2] = 0;
@@ -56,10 +77,23 @@ extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, con
 {
 	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
 	OrbitTables t; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
+	t.ridx.r = nullptr;
 	StarConst s; s.g_j = g_j; s.r_j = star_r[g_j]; s.m_j = star_m[g_j]; s.E = E; s.J = J;
 	star_const_derive(t, s);
 	int ne = 0;
 	long k = find_zero_Q(t, s, kmin, kmax, &ne);
 	*n_exact = ne;
 	return k;
+}
+
+// FindZero_r(1, N_MAX + 1, r): the reference's bisection and the 16-ary index, side by side
+extern "C" void emul_find_zero_r_both(const double *star_r, long N_MAX, const double *radii, long n, long *k_bisect, long *k_indexed)
+{
+	std::vector<RPhi> rp = pack(star_r, star_r, N_MAX + 2);
+	OrbitTables t; t.rp = rp.data(); t.m = nullptr; t.N_MAX = N_MAX; t.invN = 0; t.madhoc = 0; t.cenma_m = 0;
+	HostIndex hx(star_r, (kint) (N_MAX + 1));
+	for (long i = 0; i < n; i++) {
+		k_bisect[i] = find_zero_r(t, 1, (kint) (N_MAX + 1), radii[i]);
+		k_indexed[i] = find_zero_r_indexed(hx.x, radii[i]);
+	}
 }

@@ -25,6 +25,7 @@ def lib():
         L.emul_get_positions.argtypes = [vp, vp, vp, lg, lg, db, lg, vp, vp, vp, vp, vp, vp, vp, db, vp, lg, vp, C.c_int] + [vp] * 10
         L.emul_find_zero_Q.restype = lg
         L.emul_find_zero_Q.argtypes = [vp, vp, vp, lg, lg, lg, db, db, lg, lg, vp]
+        L.emul_find_zero_r_both.argtypes = [vp, lg, vp, lg, vp, vp]
         _lib = L
     return _lib
 
@@ -49,3 +50,11 @@ def get_positions(sr, sm, phi, N_MAX, N_STAR, cenma_m, g_idx, E, J, vr, vt, Rtid
                                               _p(out["r_peri"]), _p(out["r_apo"]), _p(out["kmin"]), _p(out["kmax"]), _p(cnt))
     out["n_draws"], out["n_exact"], out["n_brent"] = int(cnt[0]), int(cnt[1]), int(cnt[2])
     return out
+
+
+def find_zero_r_both(star_r, N_MAX, radii):
+    """(FindZero_r by the reference's bisection, by the 16-ary index) for each radius"""
+    radii = np.ascontiguousarray(radii, np.float64)
+    a, b = np.zeros(len(radii), np.int64), np.zeros(len(radii), np.int64)
+    lib().emul_find_zero_r_both(_p(np.ascontiguousarray(star_r)), N_MAX, _p(radii), len(radii), _p(a), _p(b))
+    return a, b

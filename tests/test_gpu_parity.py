@@ -230,3 +230,35 @@ def test_orbit_step_philox_mode():
     xs, ys = np.sort(rn[ok]), np.sort(want["rnew"][ok])
     ks = np.max(np.abs(np.searchsorted(xs, ys, side="right") / xs.size - np.arange(1, ys.size + 1) / ys.size))
     assert ks < 1.36 * np.sqrt(2.0 / ok.sum()) * 1.5, ks          # two-sample KS at ~5 % with slack
+
+
+def test_fused_step_equals_unfused_step():
+    """dev_step(fused=True) -- E, J computed inside the orbit step, r <- rnew applied while the sort's gather moves the records -- against
+    the same step made of separate passes: every byte of star[], binary[] and the tables after three steps (Philox draws, binaries)."""
+    N, nb = 150000, 9000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=41, masses="imf")
+    rng = np.random.default_rng(6)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    outs = []
+    for fused in (True, False):
+        c = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8)
+        c.star[:] = np.random.default_rng(1).integers(0, 256, c.star.shape, dtype=np.uint8)
+        c.binary[:] = np.random.default_rng(2).integers(0, 256, c.binary.shape, dtype=np.uint8)
+        c.field("rnew")[:] = 0.0
+        c.load(r, vr, vt, sm, binind=binind)
+        c.calc_potential_new()
+        c.upload()
+        for _ in range(3):
+            c.dev_step(seed=5, fused=fused)
+        c.dev_compute_energy()          # bring E, J of the fused run up to date for the comparison
+        c.download()
+        n = c.clus.N_MAX
+        outs.append((n, c.star[:n + 1].copy(), c.binary.copy(), c.star_r[:n + 2].copy(), c.star_m[:n + 2].copy(), c.star_phi[:n + 2].copy(), c.N_b_local))
+        c.close()
+    a, b = outs
+    assert a[0] == b[0] and a[6] == b[6]
+    assert np.array_equal(a[1], b[1]), "star[]"
+    assert np.array_equal(a[2], b[2]), "binary[]"
+    for x, y, name in zip(a[3:6], b[3:6], ("star_r", "star_m", "star_phi")):
+        cm.assert_bits_equal(x, y, name)

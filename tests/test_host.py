@@ -100,3 +100,26 @@ def test_multirank_reference_equals_single_rank_oracle(procs, N):
     the oracle computes in one piece -- this is the contract the radius-sharded GPU path has to meet"""
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_multirank_check.py"), str(procs), str(N)], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "MULTIRANK OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("N", [1, 2, 13, 14, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 65535, 65536, 70001, 1048575, 1048577])
+def test_indexed_find_zero_r_equals_reference_bisection(N):
+    """the 16-ary sampled index used by potential() on the device returns FindZero_r's index for every radius: between, on and
+    beyond the table entries, with ties, at every level boundary of the index"""
+    import hostemul
+    rng = np.random.default_rng(N)
+    r = np.sort(rng.uniform(1e-3, 50.0, N))
+    if N > 20:
+        r[N // 3:N // 3 + 5] = r[N // 3]                      # ties
+    sr = np.zeros(N + 2)
+    sr[0], sr[1:N + 1], sr[N + 1] = cm.ZERO, r, cm.SF_INFINITY
+    probes = np.concatenate([rng.uniform(r[0], r[-1] * 1.01, 4000), r[rng.integers(0, N, min(N, 2000))], r[:40], r[-40:],
+                             np.nextafter(r[:40], 0), np.nextafter(r[-40:], 1e9), [r[-1] * 2, 1e9, r[0]]])
+    edges = np.arange(16, N + 2, 16)
+    for d in (-1, 0, 1):                                       # radii right at the block boundaries of every level
+        idx = np.clip(edges + d, 1, N)
+        probes = np.concatenate([probes, sr[idx][:3000], np.nextafter(sr[idx][:3000], 1e9)])
+    probes = probes[probes >= r[0]]                            # potential() handles r < star_r[1] before the search
+    a, b = hostemul.find_zero_r_both(sr, N, probes)
+    bad = np.nonzero(a != b)[0]
+    assert bad.size == 0, (bad[:5], probes[bad[:5]], a[bad[:5]], b[bad[:5]])

@@ -22,7 +22,7 @@ for s in range(steps):
     c.profile_read(reset=True)
     res = c.dev_step(seed=1)
     p = c.profile_read(reset=True)
-    print(f"N={N} minb={os.environ.get('CMCB200_ORBIT_MINB', 'default')} step {s}: orbit {p['orbit'][0]:.3f} ms  deferred={res.n_deferred} exact={res.n_exact} "
+    print(f"N={N} minb={os.environ.get('CMCB200_ORBIT_MINB', 'default')} step {s}: orbit {p['orbit_prepare'][0] + p['orbit_scan'][0] + p['orbit_tries'][0] + p['orbit_tables'][0]:.3f} ms  deferred={res.n_deferred} exact={res.n_exact} "
           f"brent={res.n_brent} status={list(res.n_status)} tries={(res.n_draws / max(res.n_status[0], 1) - 1) / 2:.3f} | "
-          + " ".join(f"{k}={v[0]:.3f}" for k, v in p.items() if k != 'orbit' and v[0] > 0), flush=True)
+          + " ".join(f"{k}={v[0]:.3f}" for k, v in p.items() if v[0] > 0), flush=True)
 c.close()
