@@ -179,32 +179,42 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     from cmc_cosmic_b200.cluster import Cluster
+    from cmc_cosmic_b200.sharded import ShardedCluster
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
     N = args.n_stars
-    if world > 1:
-        # round 1: the radius-sharded multi-GPU path (sample sort over NCCL all-to-all + Phi allgather) is not built yet.
-        # The path does shard, so replicas would be a made-up number: report that plainly.
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": world, "unavailable": "multi-GPU radius-sharded path not implemented in round 1"}))
-        dist.barrier()
-        dist.destroy_process_group()
-        return
+    dev = f"cuda:{local_rank}"
+
+    def barrier_sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     stream = torch.cuda.Stream()
-    r, vr, vt, sm = workload(N)
+    r, vr, vt, sm = workload(N)           # every rank builds the same cluster (same seed) and keeps its radius shard
     with torch.cuda.stream(stream):
-        c = Cluster(N, n_star_dim=N + 4096, device=local_rank, pinned=True, stream=stream.cuda_stream)
-        c.load(r, vr, vt, sm)
+        if world == 1:
+            c = Cluster(N, n_star_dim=N + 4096, device=local_rank, pinned=True, stream=stream.cuda_stream)
+            c.load(r, vr, vt, sm)
+        else:
+            c = ShardedCluster(N, dist, device=local_rank, pinned=True, stream=stream)
+            c.load_global(r, vr, vt, sm)
         c.calc_potential_new()
-        c.compute_energy()
         c.upload()
         c.sync()
+        clocks = ClockSampler(local_rank) if rank == 0 else None     # sampled under load: warm-up and timed steps
         # ---- resident arm: `value` ----
         for _ in range(args.warmup):
             c.dev_step(seed=args.seed)
@@ -212,89 +222,117 @@ def run_cuda(args):
         c.profile(True)
         c.profile_read(reset=True)
         l0 = c.launch_count()
-        clocks = ClockSampler(local_rank)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
+        barrier_sync()
         stars = 0
         e0.record(stream)
         for _ in range(args.steps):
-            stars += c.clus.N_MAX_NEW
+            stars += c.clus.N_MAX                     # the whole cluster advances one step (all ranks together)
             c.dev_step(seed=args.seed)
         e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        clk = clocks.stop()
+        barrier_sync()
+        ms = max_over_ranks(e0.elapsed_time(e1))
         launches = c.launch_count() - l0
         prof = c.profile_read(reset=True)
         c.profile(False)
         value = stars / (ms * 1e-3)
-        n_now = c.clus.N_MAX_NEW
+        n_now, n_shard = c.clus.N_MAX, c.clus.N_MAX_NEW
 
-        # ---- e2e arm: the host-buffer C-ABI calls, copies included ----
+        # ---- e2e arm: the same step through the public API with HOST buffers, copies included ----
         c.download()
         c.sync()
-        e2e_t, e2e_stars = 0.0, 0
-        h2d = d2h = 0
-        for it in range(max(1, min(args.steps, 3)) + 1):
-            n = c.clus.N_MAX_NEW
-            t0 = time.perf_counter()
-            c.new_orbits_calculate(seed=args.seed + it, want_status=False)
-            t1 = time.perf_counter()
-            # host code of the caller between the two calls (ComputeIntermediateEnergy's transfer, reference cmc_utils.c:380-390): untimed
-            for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
-                c.field(dst)[1:n + 1] = c.field(src)[1:n + 1]
-            t2 = time.perf_counter()
-            c.qsorts_new()
-            c.post_sort_comm()
-            c.calc_potential_new()
-            t3 = time.perf_counter()
-            c.compute_energy()
-            if it > 0:  # first pass is warm-up (page faults, pinning)
-                e2e_t += (t1 - t0) + (t3 - t2)
-                e2e_stars += n
-                nt = n + 2
-                h2d = n * 424 + 3 * 8 * nt + n * 424 + 2 * 8 * nt
-                d2h = n * 424 + n * 424 + 2 * 8 * n + 8 * nt
-        e2e = {"value": e2e_stars / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "note": "new_orbits_calculate + qsorts_new + post_sort_comm + calc_potential_new through the host-buffer C ABI, pinned host arrays, "
-                       "wall clock; the caller's r<-rnew transfer between the calls is host code of the reference and is not timed"}
+        e2e_t, e2e_stars, h2d, d2h = 0.0, 0, 0, 0
+        if world == 1:
+            # the drop-in form: the four host-buffer C-ABI entry points the reference-side shim binds
+            for it in range(max(1, min(args.steps, 3)) + 1):
+                n = c.clus.N_MAX_NEW
+                c.compute_energy()
+                t0 = time.perf_counter()
+                c.new_orbits_calculate(seed=args.seed + it, want_status=False)
+                t1 = time.perf_counter()
+                # host code of the caller between the calls (ComputeIntermediateEnergy's transfer, reference cmc_utils.c:380-390): untimed
+                for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
+                    c.field(dst)[1:n + 1] = c.field(src)[1:n + 1]
+                t2 = time.perf_counter()
+                c.qsorts_new()
+                c.post_sort_comm()
+                c.calc_potential_new()
+                t3 = time.perf_counter()
+                if it > 0:  # the first pass is warm-up (page faults, pinning)
+                    e2e_t += (t1 - t0) + (t3 - t2)
+                    e2e_stars += n
+                    nt = n + 2
+                    h2d = n * 424 + 3 * 8 * nt + n * 424 + 2 * 8 * nt
+                    d2h = n * 424 + n * 424 + 2 * 8 * n + 8 * nt
+            note = ("new_orbits_calculate + qsorts_new + post_sort_comm + calc_potential_new through the host-buffer C ABI, pinned host arrays, "
+                    "wall clock; the caller's r<-rnew transfer between the calls is host code of the reference and is not timed")
+        else:
+            # sharded: every rank uploads its shard and the tables from pinned host memory, steps, and downloads them again
+            for it in range(max(1, min(args.steps, 3)) + 1):
+                barrier_sync()
+                t0 = time.perf_counter()
+                c.upload()
+                c.dev_step(seed=args.seed + it)
+                c.download()
+                c.sync()
+                barrier_sync()
+                dt = max_over_ranks(time.perf_counter() - t0)
+                if it > 0:
+                    e2e_t += dt
+                    e2e_stars += c.clus.N_MAX
+                    nt = c.clus.N_MAX + 2
+                    h2d = d2h = c.clus.N_MAX_NEW * 424 + 3 * 8 * nt
+            note = "per rank: upload(shard of star[] + tables) -> dev_step -> download, pinned host arrays, wall clock, max over ranks; bytes are per rank"
+        e2e = {"value": e2e_stars / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": note}
+        clk = clocks.stop() if clocks else None
         c.close()
 
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     peak, peak_src = measured_peak()
 
-    def roof(stage, kernel, bytes_per_star, extra=None):
+    def roof(stage, kernel, bytes_per_star, n_units, extra=None):
         t_ms, n_l = prof[stage]
         avg = t_ms / max(n_l, 1)
-        ach = bytes_per_star * n_now / (avg * 1e-3) / 1e9 if avg > 0 else None
+        ach = bytes_per_star * n_units / (avg * 1e-3) / 1e9 if avg > 0 else None
         tr = profile_traffic(kernel)
         d = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-             "traffic": (tr * n_now if tr else None), "peak_source": peak_src, "algorithmic_bytes_per_star": bytes_per_star, "avg_launch_ms": avg}
+             "traffic": (tr * n_units if tr else None), "peak_source": peak_src, "algorithmic_bytes_per_star": bytes_per_star, "avg_launch_ms": avg}
         d.update(extra or {})
         return d
 
     stage_ms = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items()}
-    cpu = cpu_baseline_leg(args.cpu_sample)
+    cpu = cpu_baseline_leg(args.cpu_sample) if world == 1 else None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (Plummer sphere, equal masses, Henon units; numpy generator in cmc_cosmic_b200/models.py)",
         "config": {"workload": f"plummer_n{N:.0e}".replace("+0", "").replace("+", ""), "n_stars": N, "record_bytes": 424,
                    "rng": "philox4x32-10 per star (production mode)", "l2": "inputs larger than L2 (star array %.2f GB, r/Phi table %.0f MB)" % (N * 424 / 1e9, N * 16 / 1e6),
+                   "partition": "1 GPU" if world == 1 else f"radius-sharded over {world} GPUs (findLimits, MIN_CHUNK_SIZE=40); records exchanged by peer stores over NVLink, "
+                                                           "tables replicated, potential rebuilt on every rank",
                    "step": "E,J from Phi + orbits (index bisections) -> rejection rounds -> radix sort on rnew + 424 B record gather with r<-rnew -> "
                            "potential (exact sequential rounding)"},
         "clocks": clk,
         "e2e": e2e,
         "gpu_launches": int(launches),
         # the dominant kernel by time.  Its probes are random 32-byte sector reads, so the streaming-bytes fraction is tiny by construction;
-        # `traffic` and `dram_pct_of_peak_ncu` (profiles/) show what actually bounds it.
-        "roofline": roof("orbit_prepare", "orbit_prepare_kernel", BYTES_ORBIT_PREPARE,
-                         {"note": "latency/sector-bound index bisections: ncu shows DRAM at ~51 % of peak with 32-B random sectors (profiles/orbit_r01.md)"}),
+        # `traffic` and the ncu DRAM utilisation (profiles/) show what actually bounds it.
+        "roofline": roof("orbit_prepare", "orbit_prepare_kernel", BYTES_ORBIT_PREPARE, n_shard,
+                         {"note": "latency/sector-bound index bisections: ncu shows DRAM at ~51 % of peak with 32-B random sectors (profiles/)"}),
         # the dominant HBM-streaming kernel
-        "roofline_streaming": roof("record_gather", "sort_gather_records", BYTES_GATHER),
+        "roofline_streaming": roof("record_gather", "sort_gather_records" if world == 1 else "shard_push_records", BYTES_GATHER, n_shard),
         "step_bytes_per_star": BYTES_STEP, "step_achieved_gbs": BYTES_STEP * n_now / (ms / args.steps * 1e-3) / 1e9,
         "stage_ms_per_step": stage_ms,
         "cpu_baseline": cpu,
     }
+    if world > 1:
+        line["stage_ms_per_step_rank"] = 0
+        dist.destroy_process_group()
     print(json.dumps(line))
 
 

@@ -29,18 +29,20 @@ def _host_array(shape, dtype, pinned):
 
 
 class Cluster:
-    def __init__(self, n_star, n_star_dim=None, n_bin_dim=None, device=0, min_chunk=40, orbit_r=1.0e6, pinned=False, stream=None):
+    def __init__(self, n_star, n_star_dim=None, n_bin_dim=None, device=0, min_chunk=40, orbit_r=1.0e6, pinned=False, stream=None, n_table_dim=None):
         L = _lib.load()
         self.L = L
         # N_STAR_DIM_OPT = 1.5 * (1 + N/P + 2 N_bin/P), reference src/cmc/cmc_io.c:2092-2099
         self.N_STAR_DIM = int(n_star_dim or int(1.5 * (n_star + 2)) + 16)
         self.N_BIN_DIM = int(n_bin_dim or 16)
+        self.N_TABLE_DIM = int(n_table_dim or self.N_STAR_DIM)   # star_r / star_m / star_phi hold the whole cluster (N_STAR_DIM in the reference)
+        self.device = device
         self.MIN_CHUNK_SIZE = min_chunk
         self.star = _host_array((self.N_STAR_DIM, STAR_DTYPE_SIZE), np.uint8, pinned)
         self.binary = _host_array((self.N_BIN_DIM, BINARY_DTYPE_SIZE), np.uint8, pinned)
-        self.star_r = _host_array((self.N_STAR_DIM,), np.float64, pinned)
-        self.star_m = _host_array((self.N_STAR_DIM,), np.float64, pinned)
-        self.star_phi = _host_array((self.N_STAR_DIM,), np.float64, pinned)
+        self.star_r = _host_array((self.N_TABLE_DIM,), np.float64, pinned)
+        self.star_m = _host_array((self.N_TABLE_DIM,), np.float64, pinned)
+        self.star_phi = _host_array((self.N_TABLE_DIM,), np.float64, pinned)
         self.clus = SimpleNamespace(N_STAR=n_star, N_STAR_NEW=n_star, N_MAX=n_star, N_MAX_NEW=n_star, N_BINARY=0)
         self.cenma = SimpleNamespace(m=0.0, m_new=0.0, E=0.0, E_new=0.0)
         self.madhoc = 1.0 / float(n_star)           # reference src/cmc/cmc_utils.c:1183
@@ -56,7 +58,7 @@ class Cluster:
         self.last_orbit = None
         self.last_status = None
         ctx = C.c_void_p()
-        _lib.check(L.cmcb200_create(C.byref(ctx), device, self.N_STAR_DIM, self.N_BIN_DIM), "cmcb200_create")
+        _lib.check(L.cmcb200_create_sharded(C.byref(ctx), device, self.N_STAR_DIM, self.N_TABLE_DIM, self.N_BIN_DIM), "cmcb200_create")
         self.ctx = ctx
         if stream is not None:
             _lib.check(L.cmcb200_set_stream(ctx, C.c_void_p(stream)), "cmcb200_set_stream")
@@ -83,7 +85,7 @@ class Cluster:
         """Fill the arrays from a radius-sorted cluster the way the reference's start-up does
         (sentinels: src/cmc/cmc_fits.c:128-136).  m_star_units = obj_m * N_STAR."""
         n = len(r)
-        assert n == self.clus.N_STAR and n + 2 <= self.N_STAR_DIM
+        assert n == self.clus.N_STAR and n + 2 <= self.N_STAR_DIM and n + 2 <= self.N_TABLE_DIM
         self.star_r[0], self.star_m[0] = ZERO, 0.0
         self.star_r[1:n + 1], self.star_m[1:n + 1] = r, m_star_units
         self.star_r[n + 1], self.star_m[n + 1] = SF_INFINITY, 0.0
@@ -171,14 +173,14 @@ class Cluster:
     def upload(self):
         n, nb = self.clus.N_MAX_NEW, self._n_bin_in_use()
         _lib.check(self.L.cmcb200_upload(self.ctx, self.star[1:].ctypes.data, n, self.binary[1:].ctypes.data, nb, self.star_r.ctypes.data,
-                                         self.star_m.ctypes.data, self.star_phi.ctypes.data, min(self.N_STAR_DIM, self.clus.N_MAX + 2)), "upload")
+                                         self.star_m.ctypes.data, self.star_phi.ctypes.data, min(self.N_TABLE_DIM, self.clus.N_MAX + 2)), "upload")
         self.N_b_local = nb
 
     def download(self):
         n = self.clus.N_MAX_NEW
         _lib.check(self.L.cmcb200_download(self.ctx, self.star[1:].ctypes.data, n, self.binary[1:].ctypes.data, self.N_b_local,
                                            self.star_r.ctypes.data, self.star_m.ctypes.data, self.star_phi.ctypes.data,
-                                           min(self.N_STAR_DIM, self.clus.N_MAX + 2)), "download")
+                                           min(self.N_TABLE_DIM, self.clus.N_MAX + 2)), "download")
 
     def dev_new_orbits(self, draws=None, draw_off=None, seed=0, want_status=False, fuse_energy=False):
         p = self.orbit_params(draws, draw_off, seed, fuse_energy)

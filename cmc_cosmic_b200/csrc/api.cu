@@ -5,12 +5,7 @@
 #include <cstring>
 #include <utility>
 #include <vector>
-#include "../../include/cmcb200.h"
-#include "common.cuh"
-#include "orbit.cuh"
-#include "potential.cuh"
-#include "sort.cuh"
-#include "star_layout.h"
+#include "ctx.cuh"
 
 namespace cmcb {
 
@@ -25,102 +20,6 @@ void set_error(const char *fmt, ...)
 const char *get_error() { return g_err; }
 
 } // namespace cmcb
-
-using namespace cmcb;
-
-enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES };
-
-struct StageEvent {
-	int stage;
-	cudaEvent_t a, b;
-};
-
-struct cmcb200_ctx {
-	int device;
-	long n_star_dim, n_bin_dim;
-	cudaStream_t stream;
-	bool own_stream;
-	// resident arrays.  d_star[cur] holds the live star array: record 0 = sentinel (star[0]), star1 = base + 424.
-	char *d_star[2];
-	char *d_bin[2]; // record 0 = binary[0] (unused by the reference), binary1 = base + 464
-	int cur_star, cur_bin;
-	double *d_r, *d_m, *d_phi, *d_mprev;
-	double *d_r_alt, *d_m_alt; // second copy of star_r / star_m: the fused transfer+sort reads the old tables while it writes the new ones
-	RPhi *d_rp;       // packed (r, phi) lookup table of the orbit step
-	long *d_defer_star, *d_defer_found;
-	uint2 *d_scan_list;
-	double *d_ridx_lvl;
-	unsigned char *d_oflag;
-	int *d_pend[2];
-	int orbit_min_blocks, orbit_use_index;
-	// sort scratch
-	SortBuffers sbuf;
-	SortState *d_sort;
-	unsigned *d_tile_hist;
-	long tile_hist_words;
-	unsigned char *d_binflag;
-	unsigned *d_bin_block_cnt;
-	// potential scratch
-	PotScalars *d_pot;
-	void *d_seqwork;
-	SeqWork seqwork;
-	// orbit scratch
-	OrbitStats *d_ostats;
-	int *d_status;
-	long *d_kmin, *d_kmax;
-	double *d_draws;
-	long *d_draw_off;
-	long draws_cap, draw_off_cap;
-	// pinned scalars for read-back
-	void *h_pinned;
-	// profiling
-	bool profiling;
-	std::vector<StageEvent> events;
-	std::vector<cudaEvent_t> pool;
-	double acc_ms[CMCB200_N_STAGES];
-	long acc_n[CMCB200_N_STAGES];
-	long launches; // kernels launched since creation
-};
-
-static char *star1(cmcb200_ctx *c) { return c->d_star[c->cur_star] + CMCB_SIZEOF_STAR; }
-static char *bin1(cmcb200_ctx *c) { return c->d_bin[c->cur_bin] + CMCB_SIZEOF_BINARY; }
-
-namespace {
-
-struct StageTimer { // brackets a stage with events when profiling is on
-	cmcb200_ctx *c;
-	int idx;
-	StageTimer(cmcb200_ctx *ctx, int stage) : c(ctx), idx(-1)
-	{
-		if (!c->profiling) return;
-		StageEvent e;
-		e.stage = stage;
-		for (cudaEvent_t *p : {&e.a, &e.b}) {
-			if (!c->pool.empty()) { *p = c->pool.back(); c->pool.pop_back(); }
-			else cudaEventCreate(p);
-		}
-		cudaEventRecord(e.a, c->stream);
-		c->events.push_back(e);
-		idx = (int) c->events.size() - 1;
-	}
-	~StageTimer()
-	{
-		if (idx >= 0) cudaEventRecord(c->events[idx].b, c->stream);
-	}
-};
-
-int ensure(void **p, long *cap, long need, size_t elem)
-{
-	if (need <= *cap) return 0;
-	if (*p) cudaFree(*p);
-	*p = nullptr;
-	long ncap = need + need / 4 + 1024;
-	CMCB_CUDA_OK(cudaMalloc(p, (size_t) ncap * elem));
-	*cap = ncap;
-	return 0;
-}
-
-} // namespace
 
 extern "C" const char *cmcb200_last_error(void) { return get_error(); }
 
@@ -148,9 +47,15 @@ extern "C" void cmcb200_find_limits(long N, int blk, int procs, int *Start, int 
 
 extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, long n_bin_dim)
 {
+	return cmcb200_create_sharded(out, device, n_star_dim, n_star_dim, n_bin_dim);
+}
+
+extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star_dim, long n_table_dim, long n_bin_dim)
+{
 	*out = nullptr;
 	if (n_star_dim < 4 || n_bin_dim < 2) { set_error("cmcb200_create: n_star_dim >= 4 and n_bin_dim >= 2 required"); return -1; }
-	if (n_star_dim >= (1L << 30)) { set_error("cmcb200_create: n_star_dim must be < 2^30 (30-bit look-back words)"); return -1; }
+	if (n_table_dim < n_star_dim) n_table_dim = n_star_dim;
+	if (n_table_dim >= (1L << 30)) { set_error("cmcb200_create: dimensions must be < 2^30 (30-bit look-back words, 32-bit table indices)"); return -1; }
 	int ndev = 0;
 	CMCB_CUDA_OK(cudaGetDeviceCount(&ndev));
 	if (device < 0 || device >= ndev) { set_error("cmcb200_create: no CUDA device %d (found %d)", device, ndev); return -1; }
@@ -161,6 +66,8 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 	cmcb200_ctx *c = new cmcb200_ctx();
 	c->device = device;
 	c->n_star_dim = n_star_dim;
+	c->n_table_dim = n_table_dim;
+	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
 	c->orbit_min_blocks = 8;
 	if (const char *e = getenv("CMCB200_ORBIT_MINB")) c->orbit_min_blocks = atoi(e); // tuning knob: 4 / 6 / 8
@@ -175,7 +82,7 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_bin[i], bb));
 		CMCB_CUDA_OK(cudaMemsetAsync(c->d_bin[i], 0, bb, c->stream));
 	}
-	const size_t tb = (size_t) n_star_dim * sizeof(double) + 256; // readable a line past the end (16-ary index windows)
+	const size_t tb = (size_t) n_table_dim * sizeof(double) + 256; // readable a line past the end (16-ary index windows)
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_r, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_m, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_phi, tb));
@@ -184,7 +91,7 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r_alt, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_m_alt, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_mprev, tb));
-	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rp, (size_t) n_star_dim * sizeof(RPhi)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rp, (size_t) n_table_dim * sizeof(RPhi)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_star, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_oflag, (size_t) n_star_dim));
@@ -192,7 +99,7 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 	{
 		int off[RIDX_MAX_LEVELS + 1], H;
 		long total;
-		ridx_plan((kint) n_star_dim, off, &H, &total);
+		ridx_plan((kint) n_table_dim, off, &H, &total);
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_ridx_lvl, (size_t) (total + 64) * sizeof(double)));
 	}
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[0], (size_t) n_star_dim * sizeof(int)));
@@ -211,10 +118,10 @@ extern "C" int cmcb200_create(cmcb200_ctx **out, int device, long n_star_dim, lo
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_binflag, (size_t) n_star_dim));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_bin_block_cnt, (size_t) (n_star_dim / 2048 + 2) * 4));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pot, sizeof(PotScalars)));
-	const size_t wb = pot_work_bytes(n_star_dim);
+	const size_t wb = pot_work_bytes(n_table_dim);
 	CMCB_CUDA_OK(cudaMalloc(&c->d_seqwork, wb));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_seqwork, 0, wb, c->stream));
-	pot_work_bind(c->seqwork, c->d_seqwork, n_star_dim);
+	pot_work_bind(c->seqwork, c->d_seqwork, n_table_dim);
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_ostats, sizeof(OrbitStats)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_status, (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_kmin, (size_t) n_star_dim * sizeof(long)));
@@ -235,6 +142,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev); cudaFree(c->d_r_alt); cudaFree(c->d_m_alt);
 	cudaFree(c->d_rp); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
 	cudaFree(c->d_scan_list); cudaFree(c->d_ridx_lvl);
+	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); }
 	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
@@ -301,7 +209,7 @@ extern "C" int cmcb200_potential_stats(cmcb200_ctx *c, long *n_events, long *n_f
 extern "C" int cmcb200_dev_calc_potential_new(cmcb200_ctx *c, long *N_MAX, long N_STAR, double *cenma_m, double *cenma_m_new, double orbit_r,
 					      double *Mtotal, double *Rtidal)
 {
-	if (*N_MAX + 2 > c->n_star_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds n_star_dim = %ld", *N_MAX + 2, c->n_star_dim); return -1; }
+	if (*N_MAX + 2 > c->n_table_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds the table capacity %ld", *N_MAX + 2, c->n_table_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	{
 		StageTimer t(c, ST_POTENTIAL);
@@ -329,7 +237,7 @@ extern "C" int cmcb200_calc_potential_new(cmcb200_ctx *c, double *star_r, const 
 					  double *cenma_m, double *cenma_m_new, double orbit_r, double *Mtotal, double *Rtidal)
 {
 	const long n_in = *N_MAX + 2;
-	if (n_in > c->n_star_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds n_star_dim = %ld", n_in, c->n_star_dim); return -1; }
+	if (n_in > c->n_table_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds the table capacity %ld", n_in, c->n_table_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	{
 		StageTimer t(c, ST_H2D);
@@ -364,6 +272,7 @@ static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_
 	a.buf = c->sbuf;
 	a.st = c->d_sort;
 	a.tile_hist = c->d_tile_hist;
+	a.keep_keys = false;
 	a.fuse_transfer = fuse;
 	a.old_r = c->d_r; a.old_m = c->d_m;
 	a.n_old_local = n_old_local; a.first_global = first_global; a.N_MAX = N_MAX;
@@ -391,7 +300,7 @@ static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_
 	CMCB_CUDA_OK(cudaGetLastError());
 	c->cur_star ^= 1;
 	c->cur_bin ^= 1;
-	if (fuse) { std::swap(c->d_r, c->d_r_alt); std::swap(c->d_m, c->d_m_alt); }
+	if (fuse) { std::swap(c->d_r, c->d_r_alt); std::swap(c->d_m, c->d_m_alt); c->r_parity ^= 1; }
 	long *h = (long *) c->h_pinned; // n_eq_inf, n_gt_inf, n_total, n_new, n_bin
 	CMCB_CUDA_OK(cudaMemcpyAsync(h, &c->d_sort->n_eq_inf, 5 * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -444,7 +353,7 @@ extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, 
 
 static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res)
 {
-	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_star_dim) { set_error("new_orbits_calculate: size exceeds n_star_dim = %ld", c->n_star_dim); return -1; }
+	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
 	OrbitArgs a;
 	a.star1 = star1(c);
 	a.n_local = p->n_local;
@@ -522,7 +431,7 @@ extern "C" int cmcb200_dev_read_status(cmcb200_ctx *c, int *status, long *kmin, 
 extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const double *star_r, const double *star_m, const double *star_phi,
 					    const cmcb200_orbit_params *p, int *status, long *kmin, long *kmax, cmcb200_orbit_result *res)
 {
-	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_star_dim) { set_error("new_orbits_calculate: size exceeds n_star_dim = %ld", c->n_star_dim); return -1; }
+	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	{
 		StageTimer t(c, ST_H2D);
@@ -547,7 +456,7 @@ extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const
 extern "C" int cmcb200_upload(cmcb200_ctx *c, const void *star1_h, long n_local, const void *binary1_h, long n_bin,
 			      const double *star_r, const double *star_m, const double *star_phi, long n_table)
 {
-	if (n_local + 2 > c->n_star_dim || n_table > c->n_star_dim || n_bin + 1 > c->n_bin_dim) { set_error("upload: sizes exceed the context capacity"); return -1; }
+	if (n_local + 2 > c->n_star_dim || n_table > c->n_table_dim || n_bin + 1 > c->n_bin_dim) { set_error("upload: sizes exceed the context capacity"); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	StageTimer t(c, ST_H2D);
 	if (star1_h) CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) n_local * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));

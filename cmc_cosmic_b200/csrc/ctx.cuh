@@ -1,0 +1,121 @@
+// The context behind the C ABI (include/cmcb200.h): device-resident mirrors, scratch, stage profiling.  Shared by api.cu and shard.cu.
+#pragma once
+#include <vector>
+#include "../../include/cmcb200.h"
+#include "common.cuh"
+#include "orbit.cuh"
+#include "potential.cuh"
+#include "sort.cuh"
+#include "star_layout.h"
+
+using namespace cmcb;
+
+constexpr int SHARD_MAX_RANKS = 16;
+enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_N_BUFFERS }; // peer-visible buffers
+
+enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES };
+
+struct StageEvent {
+	int stage;
+	cudaEvent_t a, b;
+};
+
+struct cmcb200_ctx {
+	int device;
+	long n_star_dim, n_bin_dim;
+	long n_table_dim; // capacity of star_r / star_m / star_phi (the whole cluster; n_star_dim is this rank's share of the records)
+	cudaStream_t stream;
+	bool own_stream;
+	// resident arrays.  d_star[cur] holds the live star array: record 0 = sentinel (star[0]), star1 = base + 424.
+	char *d_star[2];
+	char *d_bin[2]; // record 0 = binary[0] (unused by the reference), binary1 = base + 464
+	int cur_star, cur_bin;
+	double *d_r, *d_m, *d_phi, *d_mprev;
+	double *d_r_alt, *d_m_alt; // second copy of star_r / star_m: the fused transfer+sort reads the old tables while it writes the new ones
+	RPhi *d_rp;       // packed (r, phi) lookup table of the orbit step
+	long *d_defer_star, *d_defer_found;
+	uint2 *d_scan_list;
+	double *d_ridx_lvl;
+	unsigned char *d_oflag;
+	int *d_pend[2];
+	int orbit_min_blocks, orbit_use_index;
+	// sort scratch
+	SortBuffers sbuf;
+	SortState *d_sort;
+	unsigned *d_tile_hist;
+	long tile_hist_words;
+	unsigned char *d_binflag;
+	unsigned *d_bin_block_cnt;
+	// potential scratch
+	PotScalars *d_pot;
+	void *d_seqwork;
+	SeqWork seqwork;
+	// orbit scratch
+	OrbitStats *d_ostats;
+	int *d_status;
+	long *d_kmin, *d_kmax;
+	double *d_draws;
+	long *d_draw_off;
+	long draws_cap, draw_off_cap;
+	// pinned scalars for read-back
+	void *h_pinned;
+	// profiling
+	bool profiling;
+	std::vector<StageEvent> events;
+	std::vector<cudaEvent_t> pool;
+	double acc_ms[CMCB200_N_STAGES];
+	long acc_n[CMCB200_N_STAGES];
+	long launches; // kernels launched since creation
+	// radius-sharded operation (shard.cu): this context is rank `rank` of `nranks` GPUs of one node
+	int rank, nranks;
+	void *own_buf[SH_N_BUFFERS];                    // this rank's peer-visible buffers, in the order of the SH_* enum
+	void *peer_buf[SHARD_MAX_RANKS][SH_N_BUFFERS];  // the same buffers of every rank, mapped with cudaIpcOpenMemHandle ([rank] = own pointers)
+	uint64_t *d_keys_all;                           // [nranks][keys_stride] sorted keys of every rank (pushed by their owners)
+	unsigned char *d_src_all;                       // [n_star_dim] rank each record of the new shard came from (written by the pushing ranks)
+	long keys_stride;
+	unsigned *d_dest_pos;                           // [n] final local position of each local sorted element on its destination rank
+	unsigned char *d_dest_rank;                     // [n] destination rank
+	long *d_shard_meta;                             // device copy of (n_keep[q], start0[q]) per rank
+	int r_parity;                                   // which of (d_r, d_r_alt) is the buffer SH_R (flips with every fused sort)
+};
+
+static inline char *star1(cmcb200_ctx *c) { return c->d_star[c->cur_star] + CMCB_SIZEOF_STAR; }
+static inline char *bin1(cmcb200_ctx *c) { return c->d_bin[c->cur_bin] + CMCB_SIZEOF_BINARY; }
+
+namespace {
+
+struct StageTimer { // brackets a stage with events when profiling is on
+	cmcb200_ctx *c;
+	int idx;
+	StageTimer(cmcb200_ctx *ctx, int stage) : c(ctx), idx(-1)
+	{
+		if (!c->profiling) return;
+		StageEvent e;
+		e.stage = stage;
+		for (cudaEvent_t *p : {&e.a, &e.b}) {
+			if (!c->pool.empty()) { *p = c->pool.back(); c->pool.pop_back(); }
+			else cudaEventCreate(p);
+		}
+		cudaEventRecord(e.a, c->stream);
+		c->events.push_back(e);
+		idx = (int) c->events.size() - 1;
+	}
+	~StageTimer()
+	{
+		if (idx >= 0) cudaEventRecord(c->events[idx].b, c->stream);
+	}
+};
+
+inline int ensure(void **p, long *cap, long need, size_t elem)
+{
+	if (need <= *cap) return 0;
+	if (*p) cudaFree(*p);
+	*p = nullptr;
+	long ncap = need + need / 4 + 1024;
+	CMCB_CUDA_OK(cudaMalloc(p, (size_t) ncap * elem));
+	*cap = ncap;
+	return 0;
+}
+
+} // namespace
+

@@ -1,0 +1,416 @@
+// Radius-sharded operation over the GPUs of one NVLink/NVSwitch node: one process, one context, one GPU per rank; rank g owns the
+// sorted stars Start[g]..End[g] of findLimits -- the reference's own MPI partition (src/cmc/cmc_utils.c:2299-2333) -- and every rank
+// holds the full star_r / star_m / star_phi tables, as in the reference (include/cmc/cmc_vars.h:216-226).
+//
+// What replaces sample_sort + load_balance + post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2259-2288):
+//   1. every rank radix-sorts its own (key = rnew, index) pairs                                   [sort.cu]
+//   2. shard_push_keys      the sorted keys go into every peer's key table by plain stores over NVLink (peer memory mapped with
+//                           CUDA IPC), 8 B per star per peer
+//   3. shard_rank_kernel    each local element computes its GLOBAL rank = own position + (number of smaller keys in every other rank's
+//                           run; ties go to the lower rank, then to the lower local index: the stable order of the concatenated shards),
+//                           hence its destination rank and its final position there -- the partition is realised exactly, so the
+//                           reference's second exchange (load_balance) has nothing left to do
+//   4. shard_push_records   the fused gather + all-to-all: each 424-byte record is read once from the local array and written once,
+//                           straight to its final slot in the destination GPU's array (r <- rnew .. applied on the way), 16-byte
+//                           stores over NVLink; no staging buffer, no receive-side merge, no NCCL call on the data path
+//   5. shard_publish_tables every rank writes the r / m of the shard it now holds into every peer's tables (the MPI_Allgatherv pair)
+// Between the steps the ranks meet at a barrier supplied by the HOST layer (torch.distributed / MPI): kernel completion makes the
+// peer stores visible, the barrier orders them against the next step's reads.  The potential is then rebuilt on every rank from the
+// full tables (replicated, like potential_calculate in the reference, cmc_utils.c:660,716).
+#include <cstring>
+#include <utility>
+#include "ctx.cuh"
+
+namespace cmcb {
+
+__global__ void shard_push_keys(const SortBuffers b, const SortState *st, uint64_t *const *peer_keys, int nranks, long slot_offset)
+{
+	const uint64_t *__restrict__ keys = st->final_buf ? b.keys_b : b.keys_a;
+	const long n = st->n_new;
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+		const uint64_t k = keys[i];
+		for (int q = 0; q < nranks; q++) peer_keys[q][slot_offset + i] = k;
+	}
+}
+
+struct ShardMeta { // per step, uploaded by the host
+	long n_keep[SHARD_MAX_RANKS]; // stars each rank contributes (stripped stars already trimmed)
+	long start0[SHARD_MAX_RANKS]; // 0-based global rank of the first star of each destination rank
+	long count[SHARD_MAX_RANKS];  // stars of each destination rank
+	int nranks, rank;
+};
+
+__device__ __forceinline__ long lower_bound_u64(const uint64_t *__restrict__ a, long n, uint64_t key) // #elements < key
+{
+	long lo = 0, hi = n;
+	while (lo < hi) {
+		const long mid = (lo + hi) >> 1;
+		if (a[mid] < key) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+__device__ __forceinline__ long upper_bound_u64(const uint64_t *__restrict__ a, long n, uint64_t key) // #elements <= key
+{
+	long lo = 0, hi = n;
+	while (lo < hi) {
+		const long mid = (lo + hi) >> 1;
+		if (a[mid] <= key) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) shard_rank_kernel(const uint64_t *__restrict__ keys_all, long stride, const ShardMeta *__restrict__ meta,
+							  unsigned char *__restrict__ dest_rank, unsigned *__restrict__ dest_pos)
+{
+	const int P = meta->nranks, g = meta->rank;
+	const long n = meta->n_keep[g];
+	const uint64_t *__restrict__ mine = keys_all + (long) g * stride;
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+		const uint64_t key = mine[i];
+		long rank = i;
+		for (int q = 0; q < P; q++) {
+			if (q == g) continue;
+			const uint64_t *run = keys_all + (long) q * stride;
+			rank += q < g ? upper_bound_u64(run, meta->n_keep[q], key) : lower_bound_u64(run, meta->n_keep[q], key);
+		}
+		int d = 0;
+		while (d + 1 < P && rank >= meta->start0[d + 1]) d++;
+		dest_rank[i] = (unsigned char) d;
+		dest_pos[i] = (unsigned) (rank - meta->start0[d]);
+	}
+}
+
+struct PushArgs {
+	const char *in;             // &star[1] of this rank before the sort
+	char *out[SHARD_MAX_RANKS]; // &star[1] of every rank's output array
+	unsigned char *src_out[SHARD_MAX_RANKS]; // every rank's "which rank did this record come from" array (binaries are pulled from there)
+	int rank;
+	const double *old_r, *old_m;
+	long n_old_local, first_global, N_MAX;
+};
+
+// star_out[dest][pos] = transfer(star_in[perm[i]]): one warp per record, 8-byte words (424 = 53 * 8), GATHER_UNROLL records in flight
+constexpr int PUSH_UNROLL = 4;
+__global__ void __launch_bounds__(256) shard_push_records(PushArgs a, SortBuffers b, const SortState *st, const unsigned char *__restrict__ dest_rank,
+							   const unsigned *__restrict__ dest_pos)
+{
+	const unsigned *__restrict__ perm = st->final_buf ? b.vals_b : b.vals_a;
+	const long n = st->n_new; // stripped stars (r == SF_INFINITY, the tail of the local order) are not sent anywhere
+	const unsigned lane = lane_id();
+	const long warp_global = (blockIdx.x * (long) blockDim.x + threadIdx.x) >> 5;
+	const long nwarps = ((long) gridDim.x * blockDim.x) >> 5;
+	for (long i0 = warp_global * PUSH_UNROLL; i0 < n; i0 += nwarps * PUSH_UNROLL) {
+		unsigned long long w0[PUSH_UNROLL], w1[PUSH_UNROLL], tab[PUSH_UNROLL];
+		unsigned long long *dst[PUSH_UNROLL];
+#pragma unroll
+		for (int u = 0; u < PUSH_UNROLL; u++) {
+			const long i = i0 + u;
+			if (i < n) {
+				const long p = perm[i];
+				const unsigned long long *src = (const unsigned long long *) (a.in + p * CMCB_SIZEOF_STAR);
+				w0[u] = __ldg(src + lane);
+				w1[u] = lane < CMCB_STAR_WORDS - 32 ? __ldg(src + 32 + lane) : 0ull;
+				const long j = p + 1; // get_global_idx (cmc_utils.c:2384-2407) of the record before the sort
+				const long g = j > a.n_old_local ? 1 + a.N_MAX + (j - a.n_old_local) : a.first_global + j - 1;
+				tab[u] = 0ull;
+				if (lane == CMCB_OFF_M / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(a.old_m + g));
+				else if (lane == CMCB_OFF_ROLD / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(a.old_r + g));
+				dst[u] = (unsigned long long *) (a.out[dest_rank[i]] + (long) dest_pos[i] * CMCB_SIZEOF_STAR);
+			}
+		}
+		// ComputeIntermediateEnergy's transfer (cmc_utils.c:380-390): r, vr, vt <- rnew, vrnew, vtnew; m <- star_m[g]; rOld <- star_r[g]
+#pragma unroll
+		for (int u = 0; u < PUSH_UNROLL; u++) {
+			if (i0 + u < n) {
+				const unsigned long long moved = __shfl_sync(0xffffffffu, w0[u], (lane + 8) & 31);
+				if (lane < 3) w0[u] = moved;
+				else if (lane == CMCB_OFF_M / 8 || lane == CMCB_OFF_ROLD / 8) w0[u] = tab[u];
+				dst[u][lane] = w0[u];
+				if (lane < CMCB_STAR_WORDS - 32) dst[u][32 + lane] = w1[u];
+				if (lane == 0) a.src_out[dest_rank[i0 + u]][dest_pos[i0 + u]] = (unsigned char) a.rank;
+			}
+		}
+	}
+}
+
+// the shard this rank holds after the exchange: r, m of its records into every rank's (alternate) tables; binary flags for the local re-pack
+__global__ void shard_publish_tables(const char *__restrict__ star1, long n_local, long start0, double *const *peer_r, double *const *peer_m, int nranks,
+				     unsigned char *__restrict__ binflag)
+{
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n_local; i += (long) gridDim.x * blockDim.x) {
+		const char *rec = star1 + i * CMCB_SIZEOF_STAR;
+		const double r = *(const double *) (rec + CMCB_OFF_R), m = *(const double *) (rec + CMCB_OFF_M);
+		binflag[i] = *(const long long *) (rec + CMCB_OFF_BININD) > 0;
+		for (int q = 0; q < nranks; q++) {
+			peer_r[q][1 + start0 + i] = r;
+			peer_m[q][1 + start0 + i] = m;
+		}
+	}
+}
+
+// Binaries follow their star (cmc_sort.c:512-587, 716-771): the records of this rank's new shard carry the index their binary had in the
+// SOURCE rank's binary array; in star order each binary_t is pulled from that rank's array over NVLink into the local array and binind
+// becomes 1, 2, ...  (block_off = exclusive scan of the per-2048-star binary counts, as in sort_binary_move).
+constexpr int SHARD_BIN_TILE = 2048;
+struct BinPull {
+	const char *bin_in[SHARD_MAX_RANKS]; // &binary[1] of every rank before the exchange
+};
+__global__ void __launch_bounds__(256) shard_binary_pull(char *__restrict__ star, const unsigned char *__restrict__ binflag, const unsigned char *__restrict__ src_rank,
+							  const unsigned *__restrict__ block_off, long n_local, BinPull bp, char *__restrict__ bin_out)
+{
+	__shared__ unsigned s_w[8];
+	__shared__ unsigned s_idx[SHARD_BIN_TILE];
+	const long tile0 = blockIdx.x * (long) SHARD_BIN_TILE;
+	if (tile0 >= n_local) return;
+	const long base = tile0 + threadIdx.x * 8;
+	unsigned f[8], c = 0;
+	for (int j = 0; j < 8; j++) { f[j] = (base + j < n_local) ? binflag[base + j] : 0; c += f[j]; }
+	unsigned inc = c;
+	for (int o = 1; o < 32; o <<= 1) { unsigned x = __shfl_up_sync(0xffffffffu, inc, o); if (lane_id() >= (unsigned) o) inc += x; }
+	if (lane_id() == 31) s_w[warp_id()] = inc;
+	__syncthreads();
+	unsigned pre = 0, tot = 0;
+	for (unsigned w = 0; w < 8; w++) { if (w < warp_id()) pre += s_w[w]; tot += s_w[w]; }
+	unsigned r = pre + inc - c;
+	for (int j = 0; j < 8; j++) if (f[j]) s_idx[r++] = threadIdx.x * 8 + j;
+	__syncthreads();
+	const unsigned off = block_off[blockIdx.x];
+	for (unsigned bidx = warp_id(); bidx < tot; bidx += 8) {
+		const long si = tile0 + s_idx[bidx];
+		long long *pb = (long long *) (star + si * CMCB_SIZEOF_STAR + CMCB_OFF_BININD);
+		const long long old = *pb; // 1-based index in the source rank's binary array
+		const long long nw = (long long) off + bidx + 1;
+		const unsigned long long *src = (const unsigned long long *) (bp.bin_in[src_rank[si]] + (old - 1) * CMCB_SIZEOF_BINARY);
+		unsigned long long *dst = (unsigned long long *) (bin_out + (nw - 1) * CMCB_SIZEOF_BINARY);
+		const unsigned long long x = src[lane_id()], y = lane_id() < CMCB_BINARY_WORDS - 32 ? src[32 + lane_id()] : 0ull;
+		dst[lane_id()] = x;
+		if (lane_id() < CMCB_BINARY_WORDS - 32) dst[32 + lane_id()] = y;
+		__syncwarp();
+		if (lane_id() == 0) *pb = nw;
+	}
+}
+
+} // namespace cmcb
+
+using namespace cmcb;
+
+static void *own_buffer(cmcb200_ctx *c, int which)
+{
+	switch (which) {
+	case SH_STAR0: return c->d_star[0];
+	case SH_STAR1: return c->d_star[1];
+	case SH_BIN0: return c->d_bin[0];
+	case SH_BIN1: return c->d_bin[1];
+	case SH_R: return c->r_parity ? (void *) c->d_r_alt : (void *) c->d_r;
+	case SH_M: return c->r_parity ? (void *) c->d_m_alt : (void *) c->d_m;
+	case SH_R_ALT: return c->r_parity ? (void *) c->d_r : (void *) c->d_r_alt;
+	case SH_M_ALT: return c->r_parity ? (void *) c->d_m : (void *) c->d_m_alt;
+	case SH_KEYS_ALL: return c->d_keys_all;
+	case SH_SRC_ALL: return c->d_src_all;
+	}
+	return nullptr;
+}
+
+extern "C" int cmcb200_shard_handle_bytes(void) { return SH_N_BUFFERS * (int) sizeof(cudaIpcMemHandle_t); }
+
+// Allocates the exchange buffers for `nranks` ranks and writes this rank's CUDA IPC handles (cmcb200_shard_handle_bytes() bytes) to
+// `handles`; the host layer allgathers them (MPI_Allgather / torch.distributed) and hands the concatenation to cmcb200_shard_attach.
+extern "C" int cmcb200_shard_export(cmcb200_ctx *c, int rank, int nranks, void *handles)
+{
+	if (nranks < 1 || nranks > SHARD_MAX_RANKS || rank < 0 || rank >= nranks) { set_error("shard_export: rank %d of %d (max %d ranks)", rank, nranks, SHARD_MAX_RANKS); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	c->rank = rank;
+	c->nranks = nranks;
+	c->keys_stride = c->n_star_dim;
+	if (!c->d_keys_all) {
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_keys_all, (size_t) nranks * c->keys_stride * sizeof(uint64_t)));
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_src_all, (size_t) c->n_star_dim));
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_dest_pos, (size_t) c->n_star_dim * sizeof(unsigned)));
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_dest_rank, (size_t) c->n_star_dim));
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_shard_meta, sizeof(ShardMeta) + 4 * SHARD_MAX_RANKS * sizeof(void *)));
+	}
+	cudaIpcMemHandle_t *h = (cudaIpcMemHandle_t *) handles;
+	for (int b = 0; b < SH_N_BUFFERS; b++) {
+		c->own_buf[b] = own_buffer(c, b);
+		CMCB_CUDA_OK(cudaIpcGetMemHandle(&h[b], c->own_buf[b]));
+	}
+	return 0;
+}
+
+extern "C" int cmcb200_shard_attach(cmcb200_ctx *c, const void *all_handles)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *) all_handles;
+	for (int q = 0; q < c->nranks; q++)
+		for (int b = 0; b < SH_N_BUFFERS; b++) {
+			if (q == c->rank) { c->peer_buf[q][b] = c->own_buf[b]; continue; }
+			CMCB_CUDA_OK(cudaIpcOpenMemHandle(&c->peer_buf[q][b], h[q * SH_N_BUFFERS + b], cudaIpcMemLazyEnablePeerAccess));
+		}
+	return 0;
+}
+
+extern "C" int cmcb200_shard_detach(cmcb200_ctx *c)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	for (int q = 0; q < c->nranks; q++)
+		for (int b = 0; b < SH_N_BUFFERS; b++)
+			if (q != c->rank && c->peer_buf[q][b]) { cudaIpcCloseMemHandle(c->peer_buf[q][b]); c->peer_buf[q][b] = nullptr; }
+	c->nranks = 1;
+	c->rank = 0;
+	return 0;
+}
+
+// the physical buffer of rank q that currently plays `role` (the r / m tables and the star arrays ping-pong in lock step on all ranks)
+static void *peer_role(cmcb200_ctx *c, int q, int role)
+{
+	switch (role) {
+	case SH_R: return c->peer_buf[q][c->r_parity ? SH_R_ALT : SH_R];
+	case SH_M: return c->peer_buf[q][c->r_parity ? SH_M_ALT : SH_M];
+	case SH_R_ALT: return c->peer_buf[q][c->r_parity ? SH_R : SH_R_ALT];
+	case SH_M_ALT: return c->peer_buf[q][c->r_parity ? SH_M : SH_M_ALT];
+	default: return c->peer_buf[q][role];
+	}
+}
+
+// Step 1 + 2: local radix sort on rnew (sorted keys kept), trailing stripped stars trimmed (*n_keep = stars this rank contributes),
+// then the sorted keys are stored into every rank's key table.  The host layer follows with a barrier.
+extern "C" int cmcb200_shard_sort_local(cmcb200_ctx *c, long n_local, long *n_keep)
+{
+	if (n_local + 2 > c->n_star_dim) { set_error("shard_sort_local: n_local + 2 = %ld exceeds n_star_dim = %ld", n_local + 2, c->n_star_dim); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	SortArgs a;
+	memset(&a, 0, sizeof(a));
+	a.star_in = star1(c);
+	a.n = n_local;
+	a.key_off = CMCB_OFF_RNEW;
+	a.buf = c->sbuf;
+	a.st = c->d_sort;
+	a.tile_hist = c->d_tile_hist;
+	a.keep_keys = true;
+	{ StageTimer t(c, ST_KEYS); c->launches += sort_stage_keys(a, c->stream); }
+	{ StageTimer t(c, ST_PASSES); c->launches += sort_stage_passes(a, c->stream); }
+	{
+		StageTimer t(c, ST_SHARD_KEYS);
+		uint64_t *peers[SHARD_MAX_RANKS];
+		for (int q = 0; q < c->nranks; q++) peers[q] = (uint64_t *) c->peer_buf[q][SH_KEYS_ALL];
+		uint64_t **d_peers = (uint64_t **) ((char *) c->d_shard_meta + sizeof(ShardMeta));
+		CMCB_CUDA_OK(cudaMemcpyAsync(d_peers, peers, c->nranks * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+		if (n_local > 0) {
+			shard_push_keys<<<NUM_SMS_B200 * 4, 256, 0, c->stream>>>(c->sbuf, c->d_sort, d_peers, c->nranks, (long) c->rank * c->keys_stride);
+			c->launches++;
+		}
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	long *h = (long *) c->h_pinned; // n_eq_inf, n_gt_inf, n_total, n_new, n_bin
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, &c->d_sort->n_eq_inf, 5 * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*n_keep = h[3];
+	return 0;
+}
+
+// Step 3 + 4 (after the barrier): global ranks, then every record goes to its final slot on its destination rank.
+//   n_keep_all[q]   what every rank's cmcb200_shard_sort_local returned
+//   Start / End     findLimits(sum n_keep_all, MIN_CHUNK_SIZE, nranks): the NEW partition (1-based, inclusive)
+//   n_old_local, first_global, N_MAX   the partition the orbit step ran on (for the fused r <- rnew transfer)
+// The host layer follows with a barrier, then calls cmcb200_shard_publish.
+extern "C" int cmcb200_shard_exchange(cmcb200_ctx *c, const long *n_keep_all, const int *Start, const int *End, long n_old_local, long first_global, long N_MAX)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	ShardMeta m;
+	memset(&m, 0, sizeof(m));
+	m.nranks = c->nranks;
+	m.rank = c->rank;
+	for (int q = 0; q < c->nranks; q++) {
+		m.n_keep[q] = n_keep_all[q];
+		m.start0[q] = Start[q] - 1;
+		m.count[q] = End[q] - Start[q] + 1;
+		if (m.count[q] + 2 > c->n_star_dim) { set_error("shard_exchange: rank %d would hold %ld stars, capacity %ld", q, m.count[q], c->n_star_dim); return -1; }
+	}
+	CMCB_CUDA_OK(cudaMemcpyAsync(c->d_shard_meta, &m, sizeof(m), cudaMemcpyHostToDevice, c->stream));
+	const long n = n_keep_all[c->rank];
+	{
+		StageTimer t(c, ST_SHARD_RANK);
+		if (n > 0) {
+			long blocks = (n + 255) / 256;
+			if (blocks > NUM_SMS_B200 * 16) blocks = NUM_SMS_B200 * 16;
+			shard_rank_kernel<<<(unsigned) blocks, 256, 0, c->stream>>>(c->d_keys_all, c->keys_stride, (const ShardMeta *) c->d_shard_meta, c->d_dest_rank, c->d_dest_pos);
+			c->launches++;
+		}
+	}
+	{
+		StageTimer t(c, ST_GATHER);
+		PushArgs a;
+		a.in = star1(c);
+		for (int q = 0; q < c->nranks; q++) {
+			a.out[q] = (char *) c->peer_buf[q][SH_STAR0 + (c->cur_star ^ 1)] + CMCB_SIZEOF_STAR;
+			a.src_out[q] = (unsigned char *) c->peer_buf[q][SH_SRC_ALL];
+		}
+		a.rank = c->rank;
+		a.old_r = c->d_r; a.old_m = c->d_m;
+		a.n_old_local = n_old_local; a.first_global = first_global; a.N_MAX = N_MAX;
+		// the sentinel record star[0] stays with its rank
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_star[c->cur_star ^ 1], c->d_star[c->cur_star], CMCB_SIZEOF_STAR, cudaMemcpyDeviceToDevice, c->stream));
+		if (n > 0) {
+			shard_push_records<<<NUM_SMS_B200 * 8, 256, 0, c->stream>>>(a, c->sbuf, c->d_sort, c->d_dest_rank, c->d_dest_pos);
+			c->launches++;
+		}
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+// Step 5 (after the barrier): this rank now holds `n_new_local` sorted stars starting at global index start_global (1-based); their
+// r, m go into every rank's alternate tables.  The host layer follows with a barrier, then calls cmcb200_shard_finish.
+extern "C" int cmcb200_shard_publish(cmcb200_ctx *c, long n_new_local, long start_global, long n_bin_clear, long *n_bin)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	c->cur_star ^= 1;
+	StageTimer t(c, ST_SHARD_TABLES);
+	void *ptrs[2 * SHARD_MAX_RANKS];
+	for (int q = 0; q < c->nranks; q++) { ptrs[q] = peer_role(c, q, SH_R_ALT); ptrs[SHARD_MAX_RANKS + q] = peer_role(c, q, SH_M_ALT); }
+	void **d_ptrs = (void **) ((char *) c->d_shard_meta + sizeof(ShardMeta) + SHARD_MAX_RANKS * sizeof(void *));
+	CMCB_CUDA_OK(cudaMemcpyAsync(d_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, c->stream));
+	// the table sentinel [0] stays
+	CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r_alt, c->d_r, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m_alt, c->d_m, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	if (n_new_local > 0) {
+		long blocks = (n_new_local + 255) / 256;
+		if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
+		shard_publish_tables<<<(unsigned) blocks, 256, 0, c->stream>>>(star1(c), n_new_local, start_global - 1, (double *const *) d_ptrs,
+									       (double *const *) (d_ptrs + SHARD_MAX_RANKS), c->nranks, c->d_binflag);
+		c->launches++;
+	}
+	// binaries: count / scan as on one GPU (sort.cu), then pull each record from the rank its star came from
+	*n_bin = 0;
+	{
+		StageTimer tb(c, ST_BINARIES);
+		if (n_bin_clear > c->n_bin_dim - 1) n_bin_clear = c->n_bin_dim - 1;
+		char *bin_out = c->d_bin[c->cur_bin ^ 1] + CMCB_SIZEOF_BINARY;
+		c->launches += sort_binary_count_scan(c->d_binflag, c->d_sort, c->d_bin_block_cnt, n_new_local, c->stream);
+		if (n_new_local > 0) {
+			BinPull bp;
+			for (int q = 0; q < c->nranks; q++) bp.bin_in[q] = (const char *) c->peer_buf[q][SH_BIN0 + c->cur_bin] + CMCB_SIZEOF_BINARY;
+			const long nbt = (n_new_local + SHARD_BIN_TILE - 1) / SHARD_BIN_TILE;
+			shard_binary_pull<<<(unsigned) nbt, 256, 0, c->stream>>>(star1(c), c->d_binflag, c->d_src_all, c->d_bin_block_cnt, n_new_local, bp, bin_out);
+			c->launches++;
+		}
+		c->launches += sort_binary_clear_device(bin_out, c->d_sort, n_bin_clear, c->stream);
+		c->cur_bin ^= 1;
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	long *h = (long *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, &c->d_sort->n_bin, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*n_bin = h[0];
+	return 0;
+}
+
+// after the last barrier: the alternate tables become THE tables (on all ranks in lock step)
+extern "C" int cmcb200_shard_finish(cmcb200_ctx *c)
+{
+	std::swap(c->d_r, c->d_r_alt);
+	std::swap(c->d_m, c->d_m_alt);
+	c->r_parity ^= 1;
+	return 0;
+}

@@ -436,7 +436,7 @@ int sort_stage_passes(const SortArgs &a, cudaStream_t s)
 	for (int p = 0; p < 8; p++) {
 		unsigned *th = a.tile_hist + (long) p * ntiles * 256;
 		if (p == 0) sort_onesweep_pass<true, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
-		else if (p == 7) sort_onesweep_pass<false, true><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+		else if (p == 7 && !a.keep_keys) sort_onesweep_pass<false, true><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
 		else sort_onesweep_pass<false, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
 	}
 	return 9;
@@ -451,6 +451,24 @@ int sort_stage_gather(const SortArgs &a, cudaStream_t s)
 		else sort_gather_records<false><<<NUM_SMS_B200 * 8, 256, 0, s>>>(a.star_in, a.star_out, a.buf, a.st, a.star_r, a.star_m, a.binflag, f);
 	}
 	return a.n > 0 ? 1 : 0;
+}
+
+// count + scan of the binary flags of `n` stars (used by the sharded path, whose shard size is not what the local sort left in st->n_new)
+__global__ void sort_set_n_new(SortState *st, long n) { st->n_new = n; st->n_total = n; st->n_bin = 0; }
+int sort_binary_count_scan(const unsigned char *binflag, SortState *st, unsigned *bin_block_cnt, long n, cudaStream_t s)
+{
+	sort_set_n_new<<<1, 1, 0, s>>>(st, n);
+	if (n <= 0) return 1;
+	const long nbt = (n + BIN_TILE - 1) / BIN_TILE;
+	sort_binary_count<<<(unsigned) nbt, 256, 0, s>>>(binflag, st, bin_block_cnt);
+	sort_binary_scan<<<1, 1024, 0, s>>>(bin_block_cnt, nbt, st);
+	return 3;
+}
+int sort_binary_clear_device(char *bin_out, const SortState *st, long n_clear, cudaStream_t s)
+{
+	if (!bin_out || n_clear <= 0) return 0;
+	sort_binary_clear<<<NUM_SMS_B200 * 2, 256, 0, s>>>(bin_out, st, n_clear);
+	return 1;
 }
 
 // stage 3: binaries follow their star

@@ -43,6 +43,7 @@ struct SortArgs {
 	long n_bin_clear;    // zero bin_out records [n_bin, n_bin_clear)
 	// fused ComputeIntermediateEnergy transfer (reference src/cmc/cmc_utils.c:380-390): the key is rnew, and while a record moves
 	// r <- rnew, vr <- vrnew, vt <- vtnew, m <- star_m[g], rOld <- star_r[g] (g = the record's global index BEFORE the sort)
+	bool keep_keys;      // materialise the sorted keys too (the sharded sort ranks them against the other ranks' keys)
 	bool fuse_transfer;
 	const double *old_r, *old_m; // the tables the transfer reads (must not alias star_r / star_m, which the gather writes)
 	long n_old_local, first_global, N_MAX;
@@ -54,5 +55,7 @@ int sort_stage_keys(const SortArgs &a, cudaStream_t s);
 int sort_stage_passes(const SortArgs &a, cudaStream_t s);
 int sort_stage_gather(const SortArgs &a, cudaStream_t s);
 int sort_stage_binaries(const SortArgs &a, cudaStream_t s);
+int sort_binary_count_scan(const unsigned char *binflag, SortState *st, unsigned *bin_block_cnt, long n, cudaStream_t s);
+int sort_binary_clear_device(char *bin_out, const SortState *st, long n_clear, cudaStream_t s);
 
 } // namespace cmcb

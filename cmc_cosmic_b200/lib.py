@@ -4,9 +4,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmcb200.so")
-N_STAGES = 13
+N_STAGES = 16
 STAGE_NAMES = ["keys_hist", "radix_passes", "record_gather", "binaries", "potential", "orbit_prepare", "transfer", "energy", "h2d", "d2h",
-               "orbit_scan", "orbit_tries", "orbit_tables"]
+               "orbit_scan", "orbit_tries", "orbit_tables", "shard_keys", "shard_rank", "shard_tables"]
 
 
 class OrbitParams(C.Structure):
@@ -27,7 +27,8 @@ class CmcB200Error(RuntimeError):
 _lib = None
 
 EXPORTS = [
-    "cmcb200_create", "cmcb200_destroy", "cmcb200_last_error", "cmcb200_set_stream", "cmcb200_layout", "cmcb200_find_limits",
+    "cmcb200_create", "cmcb200_create_sharded", "cmcb200_shard_handle_bytes", "cmcb200_shard_export", "cmcb200_shard_attach", "cmcb200_shard_detach",
+    "cmcb200_shard_sort_local", "cmcb200_shard_exchange", "cmcb200_shard_publish", "cmcb200_shard_finish", "cmcb200_destroy", "cmcb200_last_error", "cmcb200_set_stream", "cmcb200_layout", "cmcb200_find_limits",
     "cmcb200_calc_potential_new", "cmcb200_qsorts_new", "cmcb200_new_orbits_calculate", "cmcb200_upload", "cmcb200_download",
     "cmcb200_dev_new_orbits", "cmcb200_dev_transfer_new_positions", "cmcb200_dev_qsorts_new", "cmcb200_dev_transfer_and_sort", "cmcb200_dev_calc_potential_new",
     "cmcb200_dev_compute_energy", "cmcb200_dev_read_status", "cmcb200_sync", "cmcb200_profile", "cmcb200_profile_read",
@@ -46,6 +47,14 @@ def load():
     L = C.CDLL(LIB_PATH)
     vp, lg, dbl, pl = C.c_void_p, C.c_long, C.c_double, C.POINTER(C.c_long)
     L.cmcb200_create.argtypes = [C.POINTER(vp), C.c_int, lg, lg]
+    L.cmcb200_create_sharded.argtypes = [C.POINTER(vp), C.c_int, lg, lg, lg]
+    L.cmcb200_shard_export.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.cmcb200_shard_attach.argtypes = [vp, vp]
+    L.cmcb200_shard_detach.argtypes = [vp]
+    L.cmcb200_shard_sort_local.argtypes = [vp, lg, pl]
+    L.cmcb200_shard_exchange.argtypes = [vp, vp, vp, vp, lg, lg, lg]
+    L.cmcb200_shard_publish.argtypes = [vp, lg, lg, lg, pl]
+    L.cmcb200_shard_finish.argtypes = [vp]
     L.cmcb200_destroy.argtypes = [vp]
     L.cmcb200_destroy.restype = None
     L.cmcb200_last_error.restype = C.c_char_p

@@ -52,6 +52,9 @@ enum {
 /* device: CUDA ordinal.  n_star_dim / n_bin_dim: capacity in records of star[] / binary[] (N_STAR_DIM_OPT, N_BIN_DIM_OPT,
  * src/cmc/cmc_io.c:2092-2101) -- also the capacity of star_r / star_m / star_phi (src/cmc/cmc_io.c:3431-3437). */
 int cmcb200_create(cmcb200_ctx **ctx, int device, long n_star_dim, long n_bin_dim);
+/* the same with a separate capacity for the replicated tables: with the star array sharded over several ranks n_star_dim is this rank's
+ * share of star[] (N_STAR_DIM_OPT) while star_r / star_m / star_phi hold the whole cluster (N_STAR_DIM, src/cmc/cmc_io.c:3431-3437) */
+int cmcb200_create_sharded(cmcb200_ctx **ctx, int device, long n_star_dim, long n_table_dim, long n_bin_dim);
 void cmcb200_destroy(cmcb200_ctx *ctx);
 const char *cmcb200_last_error(void);
 /* run the context's kernels on an existing CUDA stream (cudaStream_t passed as void*); default: a private stream */
@@ -152,13 +155,35 @@ int cmcb200_dev_read_status(cmcb200_ctx *ctx, int *status, long *kmin, long *kma
 /* wait for everything queued on the context's stream */
 int cmcb200_sync(cmcb200_ctx *ctx);
 
+/* ---- radius-sharded operation: one rank per GPU of an NVLink node ---------------------------------------------------------------- */
+/* Replaces sample_sort + load_balance + post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2259-2288) for procs > 1.
+ * The star array is sharded by radius rank exactly like the reference's MPI partition (findLimits), every rank keeps the full
+ * star_r / star_m / star_phi tables.  Ranks exchange data by storing straight into each other's device memory (CUDA IPC + NVLink);
+ * the HOST layer only moves a few bytes of metadata and provides the barriers between the phases (MPI in CMC, torch.distributed in
+ * the Python mirror).  Per timestep, on every rank:
+ *     cmcb200_dev_new_orbits(... first_global = Start[rank] ...)
+ *     cmcb200_shard_sort_local(ctx, n_local, &n_keep)                   host: allgather n_keep -> findLimits -> Start/End;  BARRIER
+ *     cmcb200_shard_exchange(ctx, n_keep_all, Start, End, ...)           BARRIER
+ *     cmcb200_shard_publish(ctx, End[rank]-Start[rank]+1, Start[rank], ...)   BARRIER
+ *     cmcb200_shard_finish(ctx)
+ *     cmcb200_dev_calc_potential_new(...)                                 (replicated on every rank, like potential_calculate)
+ * Set-up, once: cmcb200_create_sharded; cmcb200_shard_export -> host allgathers the handle blobs -> cmcb200_shard_attach. */
+int cmcb200_shard_handle_bytes(void);
+int cmcb200_shard_export(cmcb200_ctx *ctx, int rank, int nranks, void *handles);
+int cmcb200_shard_attach(cmcb200_ctx *ctx, const void *all_handles);
+int cmcb200_shard_detach(cmcb200_ctx *ctx);
+int cmcb200_shard_sort_local(cmcb200_ctx *ctx, long n_local, long *n_keep);
+int cmcb200_shard_exchange(cmcb200_ctx *ctx, const long *n_keep_all, const int *Start, const int *End, long n_old_local, long first_global, long N_MAX);
+int cmcb200_shard_publish(cmcb200_ctx *ctx, long n_new_local, long start_global, long n_bin_clear, long *n_bin);
+int cmcb200_shard_finish(cmcb200_ctx *ctx);
+
 /* ---- instrumentation --------------------------------------------------------------------------------------------- */
 
 /* With profiling on, every stage is bracketed by CUDA events on the launching stream.  cmcb200_profile_read returns the
  * accumulated milliseconds and launch counts since the last reset for: 0 keys+histogram, 1 radix passes, 2 record
  * gather, 3 binaries, 4 potential, 5 orbit stage A (orbits of all stars), 6 transfer, 7 energy, 8 h2d, 9 d2h, 10 orbit linear scans,
- * 11 orbit stage B (rejection rounds), 12 orbit lookup tables. */
-#define CMCB200_N_STAGES 13
+ * 11 orbit stage B (rejection rounds), 12 orbit lookup tables, 13 sharded: key push, 14 sharded: global ranks, 15 sharded: table publish. */
+#define CMCB200_N_STAGES 16
 int cmcb200_profile(cmcb200_ctx *ctx, int on);
 int cmcb200_profile_read(cmcb200_ctx *ctx, double ms[CMCB200_N_STAGES], long launches[CMCB200_N_STAGES], int reset);
 /* kernels launched by this context since it was created */

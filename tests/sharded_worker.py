@@ -1,0 +1,89 @@
+"""Worker of tests/test_gpu_sharded.py and tools/: one rank of a radius-sharded run (one process per GPU, NCCL) checked against a
+single-GPU run of the same cluster on the same device.  Philox draws are keyed by the star's GLOBAL index, so the sharded run must
+reproduce the single-GPU run bit for bit: every record of the shard, the replicated tables, the binaries."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def run(rank, world, port, N, nb, steps, kind="plummer", masses="imf"):
+    import torch
+    import torch.distributed as dist
+    import common as cm
+    from cmc_cosmic_b200.cluster import Cluster
+    from cmc_cosmic_b200.sharded import ShardedCluster
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=17, masses=masses)
+    rng = np.random.default_rng(3)
+    binind = np.zeros(N, np.int64)
+    if nb:
+        binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    gbin = np.zeros((nb + 1, 464), np.uint8)
+    if nb:
+        gbin[1:] = (np.arange(1, nb + 1, dtype=np.int64)[:, None] * 64 + np.arange(58, dtype=np.int64)[None, :]).view(np.uint8).reshape(nb, 464)
+
+    # ---- sharded run
+    c = ShardedCluster(N, dist, device=rank, n_bin_dim=nb + 8)
+    c.load_global(r, vr, vt, sm, binind_global=binind if nb else None)
+    if nb:
+        src = c._shard_binary_source
+        c.binary[1:len(src) + 1] = gbin[src]
+    c.calc_potential_new()
+    c.upload()
+    for _ in range(steps):
+        c.dev_step(seed=5)
+    c.dev_compute_energy()
+    c.download()
+    c.sync()
+    lo, hi, nl = int(c.Start[rank]), int(c.End[rank]), c.clus.N_MAX_NEW
+    shard = c.star[1:nl + 1].copy()
+    sb = c.binary[1:c.N_b_local + 1].copy()
+    tabs = (c.star_r[:c.clus.N_MAX + 2].copy(), c.star_m[:c.clus.N_MAX + 2].copy(), c.star_phi[:c.clus.N_MAX + 2].copy())
+    nmax, nbl = c.clus.N_MAX, c.N_b_local
+
+    # ---- the same cluster on this GPU alone
+    s = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8, device=rank)
+    s.load(r, vr, vt, sm, binind=binind if nb else None)
+    s.binary[1:nb + 1] = gbin[1:]
+    s.calc_potential_new()
+    s.upload()
+    for _ in range(steps):
+        s.dev_step(seed=5)
+    s.dev_compute_energy()
+    s.download()
+    assert nmax == s.clus.N_MAX, (nmax, s.clus.N_MAX)
+    assert hi - lo + 1 == nl
+    for a, b, name in zip(tabs, (s.star_r, s.star_m, s.star_phi), ("star_r", "star_m", "star_phi")):
+        assert np.array_equal(a.view(np.uint64), b[:nmax + 2].view(np.uint64)), f"rank {rank}: {name} differs"
+    want = s.star[lo:hi + 1].copy()
+    from cmc_cosmic_b200.layout import star_field
+    gb, lb = star_field(want, "binind").copy(), star_field(shard, "binind").copy()
+    assert np.array_equal(gb > 0, lb > 0), f"rank {rank}: binary flags differ"
+    star_field(want, "binind")[:] = 0
+    star_field(shard, "binind")[:] = 0
+    bad = np.nonzero((want != shard).any(axis=1))[0]
+    assert bad.size == 0, f"rank {rank}: {bad.size} of {nl} records differ, first local {bad[0]}"
+    if nb:
+        assert nbl == int((lb > 0).sum())
+        assert np.array_equal(lb[lb > 0], np.arange(1, nbl + 1)), f"rank {rank}: binind not renumbered 1.. in star order"
+        assert np.array_equal(sb, s.binary[gb[gb > 0]]), f"rank {rank}: binary records differ"
+    c.close()
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank}/{world}: sharded == single GPU (N={N}, binaries={nb}, steps={steps}, shard {lo}..{hi})", flush=True)
+
+
+if __name__ == "__main__":
+    # torchrun entry: RANK / WORLD_SIZE / MASTER_PORT from the environment
+    run(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("MASTER_PORT", "29511")),
+        int(float(sys.argv[1])) if len(sys.argv) > 1 else 200000, int(sys.argv[2]) if len(sys.argv) > 2 else 5000, int(sys.argv[3]) if len(sys.argv) > 3 else 3)

@@ -1,0 +1,29 @@
+"""Radius-sharded path on 2+ GPUs (one process per GPU, NCCL for barriers and metadata, records over NVLink peer stores) against the
+single-GPU path: bit-identical shards, tables and binaries.  Needs >= 2 visible GPUs; `gpurun --gpus 2`."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world,N,nb,steps", [(2, 200000, 5000, 3), (2, 30011, 0, 2)])
+def test_sharded_equals_single_gpu(world, N, nb, steps):
+    import torch.multiprocessing as mp
+    import sharded_worker
+    world = min(world, _n_gpus())
+    mp.spawn(sharded_worker.run, args=(world, 29500 + (N % 97), N, nb, steps), nprocs=world, join=True)
+
+
+@pytest.mark.skipif(_n_gpus() < 4, reason="needs 4 GPUs")
+def test_sharded_equals_single_gpu_4_ranks():
+    import torch.multiprocessing as mp
+    import sharded_worker
+    mp.spawn(sharded_worker.run, args=(4, 29533, 400003, 9000, 3), nprocs=4, join=True)
