@@ -261,6 +261,12 @@ class Cluster:
     def launch_count(self):
         return int(self.L.cmcb200_launch_count(self.ctx))
 
+    def transfer_bytes(self, reset=False):
+        """(host->device, device->host) bytes the host-buffer entry points have moved"""
+        a, b = C.c_long(), C.c_long()
+        _lib.check(self.L.cmcb200_transfer_bytes(self.ctx, C.byref(a), C.byref(b), int(reset)), "transfer_bytes")
+        return a.value, b.value
+
     def potential_stats(self):
         ev, fb = C.c_long(), C.c_long()
         _lib.check(self.L.cmcb200_potential_stats(self.ctx, C.byref(ev), C.byref(fb)), "potential_stats")

@@ -69,10 +69,13 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->n_table_dim = n_table_dim;
 	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
-	c->orbit_min_blocks = 8;
-	if (const char *e = getenv("CMCB200_ORBIT_MINB")) c->orbit_min_blocks = atoi(e); // tuning knob: 4 / 6 / 8
-	c->orbit_use_index = 0; // 16-ary index for potential(): measured neutral at N = 1e7 (-20 % DRAM bytes, same time) and 12 % slower at 1e6
-	if (const char *e = getenv("CMCB200_ORBIT_INDEX")) c->orbit_use_index = atoi(e);
+	c->orbit_ladders = 1;
+	c->zero_copy = 1;
+	if (const char *e = getenv("CMCB200_ZERO_COPY")) c->zero_copy = atoi(e); // 0: always stage whole records with cudaMemcpy
+	c->bytes_h2d = c->bytes_d2h = 0;
+	c->orbit_ctas = 4;
+	if (const char *e = getenv("CMCB200_ORBIT_CTAS")) c->orbit_ctas = atoi(e);
+	if (const char *e = getenv("CMCB200_ORBIT_LADDERS")) c->orbit_ladders = atoi(e); // 0: A/B measurement of the plain bisections
 	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->own_stream = true;
 	const size_t sb = (size_t) n_star_dim * CMCB_SIZEOF_STAR + 64, bb = (size_t) n_bin_dim * CMCB_SIZEOF_BINARY + 64;
@@ -91,17 +94,17 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r_alt, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_m_alt, 0, tb, c->stream));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_mprev, tb));
-	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rp, (size_t) n_table_dim * sizeof(RPhi)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rp, (size_t) (n_table_dim + 16) * sizeof(RPhi))); // the r ladder's last step reads whole 8-entry lines
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_rp, 0, (size_t) (n_table_dim + 16) * sizeof(RPhi), c->stream));
+	c->lad.q_cap = ladder_q_capacity(n_table_dim);
+	c->lad.r_cap = ladder_r_capacity(n_table_dim);
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->lad.q, (size_t) c->lad.q_cap * sizeof(LBlock)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->lad.r, (size_t) c->lad.r_cap * sizeof(double)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->lad.unsorted, sizeof(int)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_star, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_oflag, (size_t) n_star_dim));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_scan_list, (size_t) ORBIT_SCAN_LIST_CAP * sizeof(uint2)));
-	{
-		int off[RIDX_MAX_LEVELS + 1], H;
-		long total;
-		ridx_plan((kint) n_table_dim, off, &H, &total);
-		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_ridx_lvl, (size_t) (total + 64) * sizeof(double)));
-	}
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[0], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[1], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r, 0, tb, c->stream));
@@ -141,7 +144,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	for (int i = 0; i < 2; i++) { cudaFree(c->d_star[i]); cudaFree(c->d_bin[i]); }
 	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev); cudaFree(c->d_r_alt); cudaFree(c->d_m_alt);
 	cudaFree(c->d_rp); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
-	cudaFree(c->d_scan_list); cudaFree(c->d_ridx_lvl);
+	cudaFree(c->d_scan_list); cudaFree(c->lad.q); cudaFree(c->lad.r); cudaFree(c->lad.unsorted);
 	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); }
 	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
@@ -243,11 +246,13 @@ extern "C" int cmcb200_calc_potential_new(cmcb200_ctx *c, double *star_r, const 
 		StageTimer t(c, ST_H2D);
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		c->bytes_h2d += 2 * n_in * (long) sizeof(double);
 	}
 	if (cmcb200_dev_calc_potential_new(c, N_MAX, N_STAR, cenma_m, cenma_m_new, orbit_r, Mtotal, Rtidal)) return -1;
 	{
 		StageTimer t(c, ST_D2H);
 		CMCB_CUDA_OK(cudaMemcpyAsync(star_phi, c->d_phi, (*N_MAX + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		c->bytes_d2h += (*N_MAX + 2) * (long) sizeof(double);
 	}
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	star_r[*N_MAX + 1] = CMCB200_SF_INFINITY; // cmc_utils.c:713
@@ -330,6 +335,7 @@ extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, 
 		StageTimer t(c, ST_H2D);
 		CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) n * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
 		if (nb_in > 0) CMCB_CUDA_OK(cudaMemcpyAsync(bin1(c), binary1_h, (size_t) nb_in * CMCB_SIZEOF_BINARY, cudaMemcpyHostToDevice, c->stream));
+		c->bytes_h2d += n * CMCB_SIZEOF_STAR + nb_in * CMCB_SIZEOF_BINARY;
 	}
 	long nb_out = 0;
 	// nothing to clear on the device: the host tail is zeroed below
@@ -340,6 +346,7 @@ extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, 
 		if (binary1_h && nb_out > 0) CMCB_CUDA_OK(cudaMemcpyAsync(binary1_h, bin1(c), (size_t) nb_out * CMCB_SIZEOF_BINARY, cudaMemcpyDeviceToHost, c->stream));
 		if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(star_r + 1, c->d_r + 1, (size_t) *n_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(star_m + 1, c->d_m + 1, (size_t) *n_local * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		c->bytes_d2h += n * CMCB_SIZEOF_STAR + nb_out * CMCB_SIZEOF_BINARY + ((star_r ? 1 : 0) + (star_m ? 1 : 0)) * *n_local * (long) sizeof(double);
 	}
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	// memset(b_buf, 0, (N_BIN_DIM_OPT-1)*sizeof(binary_t)) (cmc_sort.c:541): everything past the packed binaries is zero
@@ -351,7 +358,7 @@ extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, 
 
 // ---- orbit step ---------------------------------------------------------------------------------------------------
 
-static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res)
+static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res, bool need_status = false)
 {
 	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
 	OrbitArgs a;
@@ -361,9 +368,8 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 	a.first_global = p->first_global;
 	a.t.rp = c->d_rp; a.t.m = c->d_m;
 	a.defer_star = c->d_defer_star; a.defer_found = c->d_defer_found;
-	a.min_blocks = c->orbit_min_blocks;
 	a.fuse_energy = p->fuse_compute_energy != 0;
-	a.use_index = c->orbit_use_index != 0;
+	a.prepare_ctas = c->orbit_ctas;
 	a.scan_list = c->d_scan_list;
 	a.flag = c->d_oflag; a.pend_list[0] = c->d_pend[0]; a.pend_list[1] = c->d_pend[1];
 	a.t.N_MAX = p->N_MAX;
@@ -383,16 +389,16 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 		a.draws = c->d_draws;
 		a.draw_off = c->d_draw_off;
 	}
-	a.status = want_status ? c->d_status : nullptr;
+	a.status = (want_status || need_status) ? c->d_status : nullptr;
 	a.kmin = want_status ? c->d_kmin : nullptr;
 	a.kmax = want_status ? c->d_kmax : nullptr;
 	a.n_draws = nullptr;
 	a.stats = c->d_ostats;
 	{
 		StageTimer t(c, ST_ORBIT_TABLES);
-		c->launches += orbit_pack_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, c->stream);
-		a.t.ridx.r = nullptr;
-		if (a.use_index) c->launches += orbit_build_index_device(a.t.ridx, c->d_r, c->d_ridx_lvl, (kint) (p->N_MAX + 1), c->stream);
+		LadderBuffers lb = c->lad;
+		if (!c->orbit_ladders) { lb.q = nullptr; lb.r = nullptr; }
+		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, p->N_MAX + 1, lb, a, c->stream);
 	}
 	{ StageTimer t(c, ST_ORBIT); c->launches += orbit_stage_prepare(a, c->stream); }
 	{ StageTimer t(c, ST_ORBIT_SCAN); c->launches += orbit_stage_scan(a, c->stream); }
@@ -428,24 +434,110 @@ extern "C" int cmcb200_dev_read_status(cmcb200_ctx *c, int *status, long *kmin, 
 	return 0;
 }
 
+namespace cmcb {
+
+// Host-buffer form of the orbit step when the caller's star[] is pinned and mapped into the device address space (cudaHostAlloc /
+// cudaHostRegister -- cmcb200_host_register): the kernels below move only the fields the step reads or writes, straight over PCIe,
+// instead of the whole 424-byte records both ways.
+//   import: r, vr, vt, m, E, J (bytes 0..47 of every record) and rnew of the stars created this step (read by calc_orbit_new, cmc_orbit.c:39-41)
+//   export: exactly the stores of the reference's loop body (cmc_evolution_thr.c:835-839, 852-853, 918-931; remove_star :662-664),
+//           selected by the per-star status like store_star() does on the device record
+// 8 lanes per record, one double each.
+__global__ void orbit_import_fields(char *__restrict__ dev1, const char *__restrict__ host1, long n_local, long n_old_local)
+{
+	const long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	const long j0 = t >> 3;
+	const int w = (int) (t & 7);
+	if (j0 >= n_local) return;
+	int off = -1;
+	if (w < 6) off = 8 * w;
+	else if (w == 6 && j0 + 1 > n_old_local) off = CMCB_OFF_RNEW;
+	if (off >= 0) *(double *) (dev1 + j0 * CMCB_SIZEOF_STAR + off) = *(const double *) (host1 + j0 * CMCB_SIZEOF_STAR + off);
+}
+
+__global__ void orbit_export_fields(const char *__restrict__ dev1, char *__restrict__ host1, const int *__restrict__ status, long n_local)
+{
+	const long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	const long j0 = t >> 3;
+	const int w = (int) (t & 7);
+	if (j0 >= n_local) return;
+	const int st = status[j0];
+	int off = -1;
+	if (w < 3) { if (st != ORBIT_NTRY) off = CMCB_OFF_RNEW + 8 * w; }                 // rnew, vrnew, vtnew
+	else if (w == 3) { if (st == ORBIT_OK) off = CMCB_OFF_X; }
+	else if (w < 6) { if (st == ORBIT_OK || st == ORBIT_TIDAL) off = CMCB_OFF_R_PERI + 8 * (w - 4); } // r_peri, r_apo
+	if (off >= 0) *(double *) (host1 + j0 * CMCB_SIZEOF_STAR + off) = *(const double *) (dev1 + j0 * CMCB_SIZEOF_STAR + off);
+}
+
+// device alias of a host pointer when the range is pinned + mapped, nullptr otherwise
+static void *mapped_alias(const void *host)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+	return at.devicePointer;
+}
+
+} // namespace cmcb
+
+extern "C" int cmcb200_host_register(void *ptr, size_t bytes)
+{
+	cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+	if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+	CMCB_CUDA_OK(e);
+	return 0;
+}
+
+extern "C" int cmcb200_host_unregister(void *ptr)
+{
+	cudaError_t e = cudaHostUnregister(ptr);
+	if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return 0; }
+	CMCB_CUDA_OK(e);
+	return 0;
+}
+
+extern "C" int cmcb200_transfer_bytes(cmcb200_ctx *c, long *h2d, long *d2h, int reset)
+{
+	if (h2d) *h2d = c->bytes_h2d;
+	if (d2h) *d2h = c->bytes_d2h;
+	if (reset) c->bytes_h2d = c->bytes_d2h = 0;
+	return 0;
+}
+
 extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const double *star_r, const double *star_m, const double *star_phi,
 					    const cmcb200_orbit_params *p, int *status, long *kmin, long *kmax, cmcb200_orbit_result *res)
 {
 	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	char *alias = c->zero_copy ? (char *) mapped_alias(star1_h) : nullptr;
+	const unsigned field_blocks = (unsigned) ((p->n_local * 8 + 255) / 256);
 	{
 		StageTimer t(c, ST_H2D);
-		CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
+		if (alias) {
+			if (p->n_local > 0) { orbit_import_fields<<<field_blocks, 256, 0, c->stream>>>(star1(c), alias, p->n_local, p->n_old_local); c->launches++; }
+			c->bytes_h2d += p->n_local * 48;
+		} else {
+			CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
+			c->bytes_h2d += p->n_local * CMCB_SIZEOF_STAR;
+		}
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_phi, star_phi, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		c->bytes_h2d += 3 * p->n_table * (long) sizeof(double);
 	}
 	const bool want = status || kmin || kmax;
-	if (orbit_common(c, p, want, res)) return -1;
+	if (orbit_common(c, p, want, res, alias != nullptr)) return -1;
 	{
 		StageTimer t(c, ST_D2H);
-		CMCB_CUDA_OK(cudaMemcpyAsync(star1_h, star1(c), (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
+		if (alias) {
+			if (p->n_local > 0) { orbit_export_fields<<<field_blocks, 256, 0, c->stream>>>(star1(c), alias, c->d_status, p->n_local); c->launches++; }
+			c->bytes_d2h += p->n_local * 48;
+		} else {
+			CMCB_CUDA_OK(cudaMemcpyAsync(star1_h, star1(c), (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
+			c->bytes_d2h += p->n_local * CMCB_SIZEOF_STAR;
+		}
 	}
+	CMCB_CUDA_OK(cudaGetLastError());
 	if (want) return cmcb200_dev_read_status(c, status, kmin, kmax, p->n_local);
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	return 0;

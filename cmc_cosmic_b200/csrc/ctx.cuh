@@ -35,10 +35,11 @@ struct cmcb200_ctx {
 	RPhi *d_rp;       // packed (r, phi) lookup table of the orbit step
 	long *d_defer_star, *d_defer_found;
 	uint2 *d_scan_list;
-	double *d_ridx_lvl;
+	LadderBuffers lad; // coarse levels of the lookup tables (orbit_core.h "ladders")
 	unsigned char *d_oflag;
 	int *d_pend[2];
-	int orbit_min_blocks, orbit_use_index;
+	int orbit_ctas;    // tuning knob CMCB200_ORBIT_CTAS: resident CTAs per SM orbit_prepare_kernel is compiled for (4 or 3)
+	int orbit_ladders; // 1 (default): the orbit step searches through the ladders; 0: every probe reads the fine table (CMCB200_ORBIT_LADDERS)
 	// sort scratch
 	SortBuffers sbuf;
 	SortState *d_sort;
@@ -66,6 +67,8 @@ struct cmcb200_ctx {
 	double acc_ms[CMCB200_N_STAGES];
 	long acc_n[CMCB200_N_STAGES];
 	long launches; // kernels launched since creation
+	long bytes_h2d, bytes_d2h; // bytes the host-buffer entry points moved over PCIe (cmcb200_transfer_bytes)
+	int zero_copy;  // 1 (default): mapped host arrays are read / written field-wise by kernels instead of staging whole records
 	// radius-sharded operation (shard.cu): this context is rank `rank` of `nranks` GPUs of one node
 	int rank, nranks;
 	void *own_buf[SH_N_BUFFERS];                    // this rank's peer-visible buffers, in the order of the SH_* enum

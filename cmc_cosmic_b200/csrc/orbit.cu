@@ -3,18 +3,22 @@
 // host-side emulation the CPU tests run); this file is the data movement and the work distribution around it.
 //
 //   orbit_pack_tables       (r_k, Phi_k) -> one 16-byte entry: every bisection probe needs both, so a probe costs one
-//                           32-byte sector instead of two
-//   orbit_step_kernel       one thread per star, consecutive threads = consecutive stars in radius order (the first probes
-//                           of the index bisections of neighbours fall into the same sectors).  Probes are division-free
-//                           FP64 sign tests with a rigorous bound, exact x87 replay inside the bound (cold, not inlined).
+//                           32-byte sector instead of two; the same pass emits the finest level of the Q ladder and
+//                           verifies that star_r is sorted.  qlad_coarsen / rlad_build: the other ladder levels (orbit_core.h)
+//   orbit_prepare_kernel    persistent CTAs, the coarsest Q-ladder level staged in shared memory by one TMA bulk copy per CTA;
+//                           one thread per star, consecutive threads = consecutive stars in radius order.  Probes of the index
+//                           bisections are answered from the ladder where a block bound proves the sign, else by the
+//                           division-free FP64 sign test with a rigorous bound on the fine table, exact x87 replay inside
+//                           the bound (cold, not inlined).
 //                           A star whose own Q is <= 0 would run get_positive_Q_index's O(N) linear scan
 //                           (cmc_orbit.c:46-57) in ONE thread while the rest of the GPU waits: it is queued instead.
 //   orbit_scan_kernel       the queued linear scans as a grid-wide find-first: work items (chunk of 4096 table entries,
 //                           queued star) are handed out chunk-major so all SMs work on the lowest unresolved chunks; a hit
 //                           retires the later chunks of that star.
 //   orbit_deferred_kernel   finishes the queued stars with the index the scan found.
-// The r/Phi table is L2-resident up to N ~ 7e6 (16 B per star, 126 MB L2); beyond that the bottom levels of every bisection
-// are DRAM sector reads.  Bound: dependent-load latency x occupancy, then L2/DRAM sector bandwidth -- not HBM streaming.
+// The fine r/Phi table (16 B per star) leaves L2 beyond N ~ 4e6; the ladders keep all but the last ~6 probes of a bisection and
+// all but the last line of a potential() lookup off it.  Bound: dependent-load latency x occupancy, then DRAM sector
+// bandwidth -- not HBM streaming.
 #include "orbit.cuh"
 
 namespace cmcb {
@@ -65,28 +69,69 @@ struct CsrDraws {
 __device__ __forceinline__ double ld_field(const char *rec, int off) { return *(const double *) (rec + off); }
 __device__ __forceinline__ void st_field(char *rec, int off, double v) { *(double *) (rec + off) = v; }
 
-__global__ void orbit_pack_tables(const double *__restrict__ r, const double *__restrict__ phi, RPhi *__restrict__ rp, long n)
+static_assert(QLAD_MIN_SHIFT == 4, "orbit_pack_tables reduces the finest Q-ladder blocks over 16-lane groups");
+
+// rp[i] = (r[i], phi[i]) for i < n; with q_fine != nullptr also block b of the finest Q-ladder level (entries [16 b, min(16 b + 16, M)]) and
+// the sortedness check of r[0 .. M] (any violation, or a NaN in phi, raises *unsorted: the kernels then ignore the ladders)
+__global__ void __launch_bounds__(256) orbit_pack_tables(const double *__restrict__ r, const double *__restrict__ phi, RPhi *__restrict__ rp, long n, long M,
+							 LBlock *__restrict__ q_fine, int *unsorted)
 {
-	long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
-	const long stride = (long) gridDim.x * blockDim.x;
-	for (; i < n; i += stride) {
-		double2 v;
-		v.x = r[i];
-		v.y = phi[i];
-		*reinterpret_cast<double2 *>(rp + i) = v;
+	const long stride = (long) gridDim.x * blockDim.x; // a multiple of 32: the 16-lane groups stay aligned to the blocks
+	const long n_round = ((n > M + 1 ? n : M + 1) + 31) / 32 * 32;
+	bool bad = false;
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n_round; i += stride) {
+		double2 v = make_double2(0.0, 0.0);
+		if (i < n) {
+			v.x = r[i];
+			v.y = phi[i];
+			*reinterpret_cast<double2 *>(rp + i) = v;
+		}
+		if (q_fine) {
+			const bool in = i <= M;
+			if (i < M && !(v.x <= r[i + 1])) bad = true;
+			if (in && !(v.y == v.y)) bad = true;
+			double pmin = in ? v.y : __builtin_huge_val(), pmax = in ? v.y : -__builtin_huge_val();
+#pragma unroll
+			for (int d = 8; d > 0; d >>= 1) {
+				pmin = fmin(pmin, __shfl_xor_sync(0xffffffffu, pmin, d));
+				pmax = fmax(pmax, __shfl_xor_sync(0xffffffffu, pmax, d));
+			}
+			if ((lane_id() & 15) == 0 && in) {
+				const long k1 = i + 16 < M ? i + 16 : M; // the block's last entry is the next block's first
+				const double p1 = phi[k1];
+				LBlock B;
+				B.r_lo = v.x; B.r_hi = r[k1]; B.phi_min = fmin(pmin, p1); B.phi_max = fmax(pmax, p1);
+				double2 *o = reinterpret_cast<double2 *>(q_fine + (i >> 4));
+				o[0] = make_double2(B.r_lo, B.r_hi);
+				o[1] = make_double2(B.phi_min, B.phi_max);
+			}
+		}
 	}
+	if (bad) *unsorted = 1;
 }
 
-// the sampled levels of the 16-ary index over star_r (RIndex, orbit_core.h): ~N/15 strided reads
-__global__ void orbit_build_index(RIndex x, long total)
+// one coarser level of the Q ladder: block b = the summary of child blocks [8 b, 8 b + 8)
+__global__ void qlad_coarsen(const LBlock *__restrict__ child, long n_child, LBlock *__restrict__ parent, long n_parent)
 {
-	long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	const long b = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	if (b >= n_parent) return;
+	const long c0 = b << QLAD_STEP;
+	const long nc = n_child - c0 < (1 << QLAD_STEP) ? n_child - c0 : (1 << QLAD_STEP);
+	parent[b] = lblock_merge(child + c0, nc);
+}
+
+struct RLadderPlan {
+	double *lvl[LADDER_MAX_LEVELS];
+	int shift[LADDER_MAX_LEVELS];
+	long count[LADDER_MAX_LEVELS], alloc[LADDER_MAX_LEVELS];
+};
+// the r ladder: level blockIdx.y holds star_r[b << shift], +inf in the padding
+__global__ void rlad_build(const double *__restrict__ r, RLadderPlan p)
+{
+	const int l = blockIdx.y;
 	const long stride = (long) gridDim.x * blockDim.x;
-	for (; i < total; i += stride) {
-		int h = 1;
-		while (h < x.H && i >= x.off[h + 1]) h++;
-		const_cast<double *>(x.lvl)[i] = x.H >= 1 ? ridx_sample(x.r, x.M, h, i - x.off[h]) : __builtin_huge_val();
-	}
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < p.alloc[l]; i += stride)
+		p.lvl[l][i] = i < p.count[l] ? r[i << p.shift[l]] : __builtin_huge_val();
 }
 
 struct StarIn {
@@ -173,15 +218,32 @@ __device__ __forceinline__ void store_prepared(const OrbitArgs &a, long j0, cons
 	}
 }
 
-// MINB = resident CTAs per SM the register allocation is capped for
-template <int MINB>
-__global__ void __launch_bounds__(ORBIT_THREADS, MINB) orbit_prepare_kernel(OrbitArgs a)
+// Stages `bytes` of a ladder's coarsest level into this CTA's shared memory with one TMA bulk copy and returns the shared address
+// (nullptr when the ladder is off).  Called by all threads of the CTA, once.
+__device__ __forceinline__ const void *stage_top_level(const void *level, unsigned bytes, bool on, unsigned char *smem, unsigned long long *bar)
 {
-	const long j0 = blockIdx.x * (long) blockDim.x + threadIdx.x;
-	const bool valid = j0 < a.n_local;
-	OrbitOut o;
-	o.status = -1; o.rnew = 0.0; o.n_draws = o.n_exact = o.n_brent = 0;
-	if (valid) {
+	if (!on) return nullptr; // CTA-uniform
+	if (threadIdx.x == 0) mbar_init(bar, 1);
+	__syncthreads();
+	if (threadIdx.x == 0) bulk_copy_g2s(smem, level, bytes, bar);
+	mbar_wait(bar, 0);
+	return smem;
+}
+
+// CTAS = resident CTAs per SM the register allocation is capped for (4: 64 registers, 3: 80)
+template <int CTAS>
+__global__ void __launch_bounds__(ORBIT_THREADS, CTAS) orbit_prepare_kernel(OrbitArgs a)
+{
+	extern __shared__ __align__(128) unsigned char orbit_smem[];
+	__shared__ __align__(8) unsigned long long bar;
+	LadderTops top;
+	top.q = (const LBlock *) stage_top_level(a.t.qlad.blk[0], a.q_top_bytes, a.t.qlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
+	top.r = nullptr; // potential() is not called in this stage
+	int n_exact = 0, n_brent = 0;
+	for (long base = blockIdx.x * (long) ORBIT_THREADS; base < a.n_local; base += (long) gridDim.x * ORBIT_THREADS) {
+		const long j0 = base + threadIdx.x;
+		if (j0 >= a.n_local) break;
+		OrbitOut o;
 		StarIn in = load_star(a, j0);
 		if (a.fuse_energy && !in.is_new) { // ComputeEnergy's first loop (reference src/cmc/cmc_utils.c:612-616) for this star, then stored
 			char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
@@ -194,20 +256,23 @@ __global__ void __launch_bounds__(ORBIT_THREADS, MINB) orbit_prepare_kernel(Orbi
 		}
 		const StarConst s = star_const(a.t, in.g, in.E, in.J);
 		OrbitJob job;
-		orbit_prepare(a.t, s, in.is_new, in.rnew_of_new, a.Rtidal, KTEMP_COMPUTE, true, o, job);
+		orbit_prepare(a.t, top, s, in.is_new, in.rnew_of_new, a.Rtidal, KTEMP_COMPUTE, true, o, job);
 		if (o.status == ORBIT_DEFERRED) {
 			const unsigned slot = atomicAdd(&a.stats->n_defer, 1u);
 			if (slot < ORBIT_DEFER_CAP) {
 				a.defer_star[slot] = j0;
 				a.defer_found[slot] = ORBIT_NOT_FOUND;
 			} else { // queue full (never seen: ~1e-5 of the stars defer): last resort, the scan in this thread
-				orbit_prepare(a.t, s, in.is_new, in.rnew_of_new, a.Rtidal, KTEMP_COMPUTE, false, o, job);
+				orbit_prepare(a.t, top, s, in.is_new, in.rnew_of_new, a.Rtidal, KTEMP_COMPUTE, false, o, job);
 			}
 		}
-		if (o.status != ORBIT_DEFERRED) store_prepared(a, j0, o, job);
+		if (o.status != ORBIT_DEFERRED) {
+			store_prepared(a, j0, o, job);
+			n_exact += o.n_exact; n_brent += o.n_brent;
+			if (o.status > 0 && o.status < 6) atomicAdd(&a.stats->n_status[o.status], 1ull); // the rare outcomes; OK count = n - sum
+		}
 	}
-	const bool counted = valid && o.status != ORBIT_DEFERRED;
-	accumulate_stats(a.stats, o.status, 0.0, 0, o.n_exact, o.n_brent, counted);
+	accumulate_stats(a.stats, -1, 0.0, 0, n_exact, n_brent, true); // one atomic per warp and counter, once per persistent CTA
 }
 
 // ---- the queued linear scans ------------------------------------------------------------------------------------------
@@ -304,7 +369,9 @@ __global__ void __launch_bounds__(ORBIT_THREADS) orbit_deferred_kernel(OrbitArgs
 			const StarIn in = load_star(a, j0);
 			const StarConst s = star_const(a.t, in.g, in.E, in.J);
 			OrbitJob job;
-			orbit_prepare(a.t, s, in.is_new, in.rnew_of_new, a.Rtidal, found == ORBIT_NOT_FOUND ? -1 : (kint) found, false, o, job);
+			LadderTops top; // the few queued stars bisect on the fine table
+			top.q = nullptr; top.r = nullptr;
+			orbit_prepare(a.t, top, s, in.is_new, in.rnew_of_new, a.Rtidal, found == ORBIT_NOT_FOUND ? -1 : (kint) found, false, o, job);
 			store_prepared(a, j0, o, job);
 		}
 		accumulate_stats(a.stats, o.status, 0.0, 0, o.n_exact, o.n_brent, valid);
@@ -361,7 +428,13 @@ __device__ __forceinline__ double sign_draw_for_try(const OrbitArgs &a, long j0,
 template <bool RECORDED, int W, bool FIRST, bool LOOP>
 __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitArgs a, int round, unsigned t0_base)
 {
+	extern __shared__ __align__(128) unsigned char orbit_smem[];
+	__shared__ __align__(8) unsigned long long bar;
 	const unsigned n_work = FIRST ? (unsigned) a.n_local : a.stats->round_count[round];
+	if ((unsigned long long) blockIdx.x * (ORBIT_TRY_THREADS / W) >= n_work) return; // nothing for this CTA: skip the staging too
+	LadderTops top;
+	top.q = nullptr;
+	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
 	const int *__restrict__ list_in = a.pend_list[round & 1];
 	int *__restrict__ list_out = a.pend_list[(round + 1) & 1];
 	const unsigned sub = threadIdx.x % W;
@@ -393,7 +466,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 				TryDraws d;
 				int rc = -1; // -1: fatal (out of draws / bracket failure / beyond N_TRY), 0: rejected, 1: accepted
 				double r = 0.0, vr = 0.0;
-				if (t < CMCB_N_TRY && draws_for_try<RECORDED>(a, j0, in.g, t, d)) rc = orbit_try(a.t, s, job, d.X, d.u, &r, &vr);
+				if (t < CMCB_N_TRY && draws_for_try<RECORDED>(a, j0, in.g, t, d)) rc = orbit_try(a.t, top, s, job, d.X, d.u, &r, &vr);
 				// first lane of the group (lowest try index) that did not reject decides
 				int first_rc = rc;
 				unsigned first_sub = rc != 0 ? sub : W;
@@ -453,13 +526,68 @@ __global__ void orbit_stats_reset(OrbitStats *s)
 	for (int i = 0; i < ORBIT_MAX_ROUNDS + 2; i++) s->round_count[i] = 0;
 }
 
-int orbit_pack_tables_device(const double *r, const double *phi, RPhi *rp, long n, cudaStream_t s)
+long ladder_q_capacity(long n_table_dim)
 {
+	int sh[LADDER_MAX_LEVELS];
+	long cnt[LADDER_MAX_LEVELS], total = 0;
+	const int n = qlad_plan(n_table_dim, sh, cnt);
+	for (int l = 0; l < n; l++) total += cnt[l] + 8;
+	return total + 8;
+}
+long ladder_r_capacity(long n_table_dim)
+{
+	int sh[LADDER_MAX_LEVELS];
+	long cnt[LADDER_MAX_LEVELS], al[LADDER_MAX_LEVELS], total = 0;
+	const int n = rlad_plan(n_table_dim, sh, cnt, al);
+	for (int l = 0; l < n; l++) total += al[l] + 16;
+	return total + 16;
+}
+
+int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long n, long M, const LadderBuffers &lb, OrbitArgs &a, cudaStream_t s)
+{
+	a.t.qlad.n_levels = 0; a.t.rlad.n_levels = 0; a.t.rlad.n_top = 0;
+	a.q_top_bytes = a.r_top_bytes = 0;
+	a.lad_unsorted = lb.unsorted;
 	if (n <= 0) return 0;
-	long blocks = (n + 255) / 256;
+	int launches = 0;
+	long qcnt[LADDER_MAX_LEVELS], rcnt[LADDER_MAX_LEVELS], ral[LADDER_MAX_LEVELS];
+	int nq = lb.q ? qlad_plan(M, a.t.qlad.shift, qcnt) : 0;
+	int nr = lb.r ? rlad_plan(M, a.t.rlad.shift, rcnt, ral) : 0;
+	// levels are stored finest first, each on a 128-byte boundary
+	LBlock *qlvl[LADDER_MAX_LEVELS];
+	{
+		long off = 0;
+		for (int l = nq - 1; l >= 0; l--) { qlvl[l] = lb.q + off; off += (qcnt[l] + 3) / 4 * 4; }
+		if (off > lb.q_cap) nq = 0; // cannot happen: the capacity was planned for the largest table
+	}
+	RLadderPlan rplan;
+	{
+		long off = 0;
+		for (int l = nr - 1; l >= 0; l--) { rplan.lvl[l] = lb.r + off; rplan.shift[l] = a.t.rlad.shift[l]; rplan.count[l] = rcnt[l]; rplan.alloc[l] = ral[l]; off += ral[l]; }
+		if (off > lb.r_cap) nr = 0;
+	}
+	cudaMemsetAsync(lb.unsorted, 0, sizeof(int), s);
+	long blocks = ((n > M + 1 ? n : M + 1) + 255) / 256;
 	if (blocks > NUM_SMS_B200 * 16) blocks = NUM_SMS_B200 * 16;
-	orbit_pack_tables<<<(unsigned) blocks, 256, 0, s>>>(r, phi, rp, n);
-	return 1;
+	orbit_pack_tables<<<(unsigned) blocks, 256, 0, s>>>(r, phi, rp, n, M, nq ? qlvl[nq - 1] : nullptr, lb.unsorted);
+	launches++;
+	for (int l = nq - 2; l >= 0; l--) {
+		qlad_coarsen<<<(unsigned) ((qcnt[l] + 255) / 256), 256, 0, s>>>(qlvl[l + 1], qcnt[l + 1], qlvl[l], qcnt[l]);
+		launches++;
+	}
+	if (nr) {
+		long rb = (ral[nr - 1] + 255) / 256;
+		if (rb > NUM_SMS_B200 * 8) rb = NUM_SMS_B200 * 8;
+		rlad_build<<<dim3((unsigned) rb, (unsigned) nr), 256, 0, s>>>(r, rplan);
+		launches++;
+	}
+	a.t.qlad.n_levels = nq;
+	for (int l = 0; l < nq; l++) a.t.qlad.blk[l] = qlvl[l];
+	if (nq) a.q_top_bytes = (unsigned) (qcnt[0] * sizeof(LBlock));
+	a.t.rlad.n_levels = nr;
+	for (int l = 0; l < nr; l++) a.t.rlad.lvl[l] = rplan.lvl[l];
+	if (nr) { a.t.rlad.n_top = (int) rcnt[0]; a.r_top_bytes = (unsigned) ((rcnt[0] + 1) / 2 * 2 * sizeof(double)); }
+	return launches;
 }
 
 template <bool RECORDED>
@@ -469,31 +597,20 @@ static int launch_try_rounds(const OrbitArgs &a, cudaStream_t s)
 	// ~2.5 % left; round 6: a warp per star, 32 tries at a time until accepted.  The grids only bound the parallelism (the
 	// kernels run grid-stride over the device-side count), sized for the expected survivors with a wide margin.
 	const long n = a.n_local;
-	auto grid_for = [&](double frac, int w) {
+	const unsigned smem = a.r_top_bytes;
+	auto grid_for = [&](double frac, int w) { // persistent CTAs: never more than fit on the device at once
 		long g = (long) (n * frac * w / ORBIT_TRY_THREADS) + 1;
-		const long cap = (long) NUM_SMS_B200 * 64;
-		if (g > (n * (long) w + ORBIT_TRY_THREADS - 1) / ORBIT_TRY_THREADS) g = (n * (long) w + ORBIT_TRY_THREADS - 1) / ORBIT_TRY_THREADS;
-		return (unsigned) (g < 1 ? 1 : (g > cap && frac < 1.0 ? cap : g));
+		const long cap = (long) NUM_SMS_B200 * ORBIT_CTAS_PER_SM;
+		return (unsigned) (g < 1 ? 1 : (g > cap ? cap : g));
 	};
-	orbit_try_kernel<RECORDED, 1, true, false><<<grid_for(1.0, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 0, 0u);
-	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.60, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 1, 1u);
-	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.35, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 2, 2u);
-	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.20, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 3, 3u);
-	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.12, 1), ORBIT_TRY_THREADS, 0, s>>>(a, 4, 4u);
-	orbit_try_kernel<RECORDED, 4, false, false><<<grid_for(0.07, 4), ORBIT_TRY_THREADS, 0, s>>>(a, 5, 5u);
-	orbit_try_kernel<RECORDED, 32, false, true><<<grid_for(0.01, 32), ORBIT_TRY_THREADS, 0, s>>>(a, 6, 9u);
+	orbit_try_kernel<RECORDED, 1, true, false><<<grid_for(1.0, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 0, 0u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.60, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 1, 1u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.35, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 2, 2u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.20, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 3, 3u);
+	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.12, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 4, 4u);
+	orbit_try_kernel<RECORDED, 4, false, false><<<grid_for(0.07, 4), ORBIT_TRY_THREADS, smem, s>>>(a, 5, 5u);
+	orbit_try_kernel<RECORDED, 32, false, true><<<grid_for(0.01, 32), ORBIT_TRY_THREADS, smem, s>>>(a, 6, 9u);
 	return 7;
-}
-
-int orbit_build_index_device(RIndex &x, const double *star_r, double *lvl, kint M, cudaStream_t s)
-{
-	long total;
-	x.r = star_r; x.lvl = lvl; x.M = M;
-	ridx_plan(M, x.off, &x.H, &total);
-	long blocks = (total + 255) / 256;
-	if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
-	orbit_build_index<<<(unsigned) blocks, 256, 0, s>>>(x, total);
-	return 1;
 }
 
 // stage A: reset + the orbit of every star
@@ -501,10 +618,11 @@ int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s)
 {
 	orbit_stats_reset<<<1, 1, 0, s>>>(a.stats);
 	if (a.n_local <= 0) return 1;
-	const unsigned blocks = (unsigned) ((a.n_local + ORBIT_THREADS - 1) / ORBIT_THREADS);
-	if (a.min_blocks >= 8) orbit_prepare_kernel<8><<<blocks, ORBIT_THREADS, 0, s>>>(a);
-	else if (a.min_blocks >= 6) orbit_prepare_kernel<6><<<blocks, ORBIT_THREADS, 0, s>>>(a);
-	else orbit_prepare_kernel<4><<<blocks, ORBIT_THREADS, 0, s>>>(a);
+	long blocks = (a.n_local + ORBIT_THREADS - 1) / ORBIT_THREADS;
+	const int ctas = a.prepare_ctas == 3 ? 3 : ORBIT_CTAS_PER_SM;
+	if (blocks > (long) NUM_SMS_B200 * ctas) blocks = (long) NUM_SMS_B200 * ctas;
+	if (ctas == 3) orbit_prepare_kernel<3><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
+	else orbit_prepare_kernel<ORBIT_CTAS_PER_SM><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
 	return 2;
 }
 

@@ -5,7 +5,8 @@
 
 namespace cmcb {
 
-constexpr int ORBIT_THREADS = 128;
+constexpr int ORBIT_THREADS = 256;          // persistent CTAs: each stages the coarsest ladder level in shared memory once
+constexpr int ORBIT_CTAS_PER_SM = 4;        // 1024 threads and <= 160 KB of staged tables per SM
 constexpr int ORBIT_SCAN_THREADS = 256;
 constexpr int ORBIT_SCAN_CHUNK = 4096;      // table entries per work item of the cooperative linear scan
 constexpr int ORBIT_DEFER_CAP = 65536;      // queued scans per launch (beyond it a star scans in its own thread)
@@ -44,15 +45,25 @@ struct OrbitArgs {
 	unsigned char *flag; // [n_local] 1: orbit known, new radius still to be drawn
 	int *pend_list[2]; // [n_local] each: compacted lists of pending stars, ping-pong between rounds
 	bool fuse_energy;  // E, J of every star are computed from the table and (vr, vt) on the fly and stored (ComputeEnergy's first loop)
-	bool use_index;    // potential() through the 16-ary index instead of the plain bisection
-	int min_blocks;    // register cap variant of orbit_step_kernel: 4, 6 or 8 resident CTAs per SM
+	const int *lad_unsorted; // device flag set by the table builder when star_r is not sorted (or Phi holds a NaN): ladders off
+	int prepare_ctas;  // register-cap variant of orbit_prepare_kernel: 4 (default) or 3 resident CTAs per SM (CMCB200_ORBIT_CTAS)
+	unsigned q_top_bytes, r_top_bytes; // size of the coarsest level of each ladder (what a CTA stages), multiples of 16
 	long *defer_star;  // [ORBIT_DEFER_CAP] local 0-based index of each queued star
 	uint2 *scan_list;  // [ORBIT_SCAN_LIST_CAP] (slot, chunk) pairs to scan entry by entry
 	long *defer_found; // [ORBIT_DEFER_CAP] first k with Q > 0 (ORBIT_NOT_FOUND: none)
 };
 
-int orbit_pack_tables_device(const double *r, const double *phi, RPhi *rp, long n, cudaStream_t s);
-int orbit_build_index_device(RIndex &x, const double *star_r, double *lvl, kint M, cudaStream_t s);
+// device storage of the ladders (sized for the table capacity at context creation)
+struct LadderBuffers {
+	LBlock *q;     // all levels of the Q ladder back to back, finest first
+	double *r;     // all levels of the r ladder back to back, finest first
+	long q_cap, r_cap; // capacity in blocks / doubles
+	int *unsorted; // device flag
+};
+long ladder_q_capacity(long n_table_dim);
+long ladder_r_capacity(long n_table_dim);
+// packs (r, Phi) of entries [0, n) and builds both ladders over [0, M]; fills t.rp-independent ladder descriptors of `a`
+int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long n, long M, const LadderBuffers &lb, OrbitArgs &a, cudaStream_t s);
 int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_scan(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_tries(const OrbitArgs &a, cudaStream_t s);

@@ -36,50 +36,119 @@ struct RPhi { // one entry of the packed lookup table: every probe of the bisect
 	double r, phi;
 };
 
-// Sampled 16-ary index over the sorted radii star_r[0 .. M], M = N_MAX + 1, for potential()'s "largest k with r_k < r"
-// (FindZero_r, cmc_nr.c:62-82).  The answer of that bisection is a pure function of the sorted array -- the number of entries
-// below r -- so ANY search returns the same index; this one needs ceil(log16 N) dependent steps of one 128-byte line each
-// instead of ceil(log2 N) dependent 8-byte probes, and only its last step leaves the L2-resident part of the structure.
-//   level h (1..H): A_h[i] = star_r[(i + 1) 16^h - 1], the last entry of every complete block of 16^h entries, padded with +inf
-//   to a multiple of 16; level 0 is star_r itself.
-constexpr int RIDX_MAX_LEVELS = 8;
-struct RIndex {
-	const double *r;   // star_r (SoA, 128-byte aligned, readable up to index M + 15)
-	const double *lvl; // the sampled levels, level h at lvl + off[h]
-	int off[RIDX_MAX_LEVELS + 1];
-	int H;             // sampled levels (0: the leaf window covers everything)
-	kint M;            // last valid index of star_r
+// ---- ladders: coarse summaries of the sorted tables -------------------------------------------------------------
+//
+// Both searches of the orbit step walk the 16 N-byte (r, Phi) table with ceil(log2 N) DEPENDENT probes; beyond N ~ 4e6 the
+// table does not fit in L2 and every probe of the lower levels is a DRAM sector.  The ladders answer most probes from small
+// summaries instead (the coarsest level is staged in shared memory by the kernels, the next ones stay L2-resident):
+//
+//  QLadder, for find_zero_Q (cmc_nr.c:316-383).  Block b of a level with shift s summarises table entries
+//      [b << s, min((b + 1) << s, M)] (both ends inclusive, M = N_MAX + 1) as (r_lo, r_hi, min Phi, max Phi) -- 32 bytes, one sector.
+//      r is sorted, the self term phi_s is non-increasing in r, so for EVERY k of the block
+//          2 (E - Phi_max - phi_s(r_lo)) - J^2 / r_lo^2  <=  Q(k)  <=  2 (E - Phi_min - phi_s(r_hi)) - J^2 / r_hi^2 .
+//      When the upper bound is below (the lower bound above) zero by more than a rigorous margin, the sign the reference
+//      computes at the probe index is PROVEN without touching the fine table (q_sign_on_block).  The bisection replays the
+//      reference's exact probe sequence ktry = (kmin + kmax + 1) / 2, so kmin / kmax are the reference's even where Q is
+//      not monotone; only the probes next to the sign change fall through to the fine table.
+//      (Phi is NOT assumed monotone: rounding makes the innermost Phi_k wiggle, and Phi_0 > Phi_1 with a central mass --
+//      the builder stores the true min / max.  Sortedness of r is verified by the builder; an unsorted table disables the ladders.)
+//
+//  RLadder, for potential()'s FindZero_r (cmc_nr.c:62-82): "largest k with star_r[k] < r" is a pure function of the sorted
+//      array, so any search returns the reference's index.  Level with shift s holds star_r[b << s]; the coarsest level is
+//      binary-searched (shared memory), every further level is ONE 128-byte line (16 samples), and the last step is one line of
+//      the fine table (8 entries), which also holds the two entries the interpolation needs.
+struct LBlock {
+	double r_lo, r_hi, phi_min, phi_max;
 };
 
-// layout of the sampled levels for a table with last index M: off[1..H], H, total doubles
-CMCB_HD void ridx_plan(kint M, int off[RIDX_MAX_LEVELS + 1], int *H, long *total)
+constexpr int LADDER_MAX_LEVELS = 8;
+#ifndef CMCB_QLAD_TOP_BLOCKS /* the CPU tests build a second copy with tiny top levels so that small tables get deep ladders */
+#define CMCB_QLAD_TOP_BLOCKS 1280
+#define CMCB_RLAD_TOP_ENTRIES 5120
+#endif
+constexpr int QLAD_MIN_SHIFT = 4, QLAD_STEP = 3, QLAD_TOP_BLOCKS = CMCB_QLAD_TOP_BLOCKS;   // coarsest level <= 40 KB
+constexpr int RLAD_MIN_SHIFT = 3, RLAD_STEP = 4, RLAD_TOP_ENTRIES = CMCB_RLAD_TOP_ENTRIES; // coarsest level <= 40 KB
+#ifndef CMCB_QLAD_WIDTH_FACTOR
+#define CMCB_QLAD_WIDTH_FACTOR 4
+#endif
+constexpr int QLAD_WIDTH_FACTOR = CMCB_QLAD_WIDTH_FACTOR; // a level is consulted while its blocks are at most 1/FACTOR of the bracket
+constexpr int LADDER_MIN_M = 64;                                          // smaller tables: plain bisection
+
+struct QLadder {
+	const LBlock *blk[LADDER_MAX_LEVELS]; // coarsest first
+	int shift[LADDER_MAX_LEVELS];
+	int n_levels; // 0: no ladder
+};
+
+struct RLadder {
+	const double *lvl[LADDER_MAX_LEVELS]; // coarsest first; every level padded with +inf to a multiple of 16 plus one spare line
+	int shift[LADDER_MAX_LEVELS];
+	int n_top;    // entries of the coarsest level
+	int n_levels; // 0: no ladder
+};
+
+// where the coarsest level of each ladder is to be read from: shared memory in the kernels (staged per CTA), the level itself on the host;
+// nullptr = that ladder is not used (table too small, or the builder found it unsorted)
+struct LadderTops {
+	const LBlock *q;
+	const double *r;
+};
+
+// shifts (coarsest first) and block counts of the Q ladder over a table with last index M; returns the number of levels
+CMCB_HD int qlad_plan(long M, int shift[LADDER_MAX_LEVELS], long count[LADDER_MAX_LEVELS])
 {
-	long n = (long) M + 1, pos = 0;
-	int h = 0;
-	off[0] = 0;
-	while (n > 16 && h < RIDX_MAX_LEVELS) {
-		n /= 16;                          // complete blocks of 16^(h+1) entries
-		h++;
-		off[h] = (int) pos;
-		pos += ((n + 15) / 16) * 16 + 16; // padded; one spare line so that a window starting at the padding is readable
-	}
-	*H = h;
-	*total = pos > 0 ? pos : 16;
+	if (M < LADDER_MIN_M) return 0;
+	int top = QLAD_MIN_SHIFT;
+	while ((M >> top) + 1 > QLAD_TOP_BLOCKS) top += QLAD_STEP;
+	int n = 0;
+	for (int s = top; s >= QLAD_MIN_SHIFT && n < LADDER_MAX_LEVELS; s -= QLAD_STEP) { shift[n] = s; count[n] = (M >> s) + 1; n++; }
+	return n;
 }
 
-// value of sample i of level h (what the builder stores)
-CMCB_HD double ridx_sample(const double *star_r, kint M, int h, long i)
+// the same for the r ladder; count = real samples, alloc = padded length in doubles
+CMCB_HD int rlad_plan(long M, int shift[LADDER_MAX_LEVELS], long count[LADDER_MAX_LEVELS], long alloc[LADDER_MAX_LEVELS])
 {
-	long stride = 1;
-	for (int q = 0; q < h; q++) stride *= 16;
-	const long idx = (i + 1) * stride - 1;
-	return idx <= (long) M ? star_r[idx] : __builtin_huge_val();
+	if (M < LADDER_MIN_M) return 0;
+	int top = RLAD_MIN_SHIFT;
+	while ((M >> top) + 1 > RLAD_TOP_ENTRIES) top += RLAD_STEP;
+	int n = 0;
+	for (int s = top; s >= RLAD_MIN_SHIFT && n < LADDER_MAX_LEVELS; s -= RLAD_STEP) {
+		shift[n] = s; count[n] = (M >> s) + 1; alloc[n] = ((count[n] + 15) / 16) * 16 + 16; n++;
+	}
+	return n;
+}
+
+// what the builders store: the summary of table entries [k0, k1] (inclusive); *unsorted is set when r decreases inside the range
+CMCB_HD LBlock lblock_of(const RPhi *rp, long k0, long k1, bool *unsorted)
+{
+	LBlock B;
+	B.r_lo = rp[k0].r; B.r_hi = rp[k1].r; B.phi_min = B.phi_max = rp[k0].phi;
+	for (long k = k0; k < k1; k++) {
+		if (!(rp[k].r <= rp[k + 1].r)) *unsorted = true;
+		const double p = rp[k + 1].phi;
+		if (p < B.phi_min) B.phi_min = p;
+		if (p > B.phi_max) B.phi_max = p;
+		if (!(p == p)) *unsorted = true; // a NaN would escape the min / max: no ladder then
+	}
+	return B;
+}
+// the summary of a run of consecutive child blocks (a coarser level from the next finer one)
+CMCB_HD LBlock lblock_merge(const LBlock *child, long n)
+{
+	LBlock B = child[0];
+	for (long i = 1; i < n; i++) {
+		B.r_hi = child[i].r_hi;
+		if (child[i].phi_min < B.phi_min) B.phi_min = child[i].phi_min;
+		if (child[i].phi_max > B.phi_max) B.phi_max = child[i].phi_max;
+	}
+	return B;
 }
 
 struct OrbitTables {
 	const RPhi *rp;  // (star_r[k], star_phi[k]) interleaved: [0] sentinel, [1..N_MAX], [N_MAX+1] = (SF_INFINITY, 0)
 	const double *m; // star_m
-	RIndex ridx;     // 16-ary index over star_r for potential(); ridx.r == nullptr: plain bisection on rp
+	QLadder qlad;    // coarse (r, Phi) summaries for find_zero_Q; n_levels == 0: every probe reads rp
+	RLadder rlad;    // coarse radii for potential(); n_levels == 0: plain bisection on rp
 	kint N_MAX;
 	double invN;    // 1.0 / clus.N_STAR evaluated in double (the factor in MPI_PHI_S)
 	double madhoc;  // 1.0 / (double) clus.N_STAR (cmc_utils.c:1183) -- same value, kept separate like the reference
@@ -143,7 +212,7 @@ CMCB_HD kint find_zero_r(const OrbitTables &t, kint kmin, kint kmax, double r)
 }
 
 // number of entries among 16 consecutive doubles (one 128-byte line) that are < r
-CMCB_HD int ridx_count16(const double *line, double r)
+CMCB_HD int count16_below(const double *line, double r)
 {
 	int c = 0;
 #if defined(__CUDA_ARCH__)
@@ -159,37 +228,80 @@ CMCB_HD int ridx_count16(const double *line, double r)
 	return c;
 }
 
-// FindZero_r(1, N_MAX + 1, r) through the index: largest k in [1, N_MAX+1] with star_r[k] < r, 1 if there is none
-CMCB_HD kint find_zero_r_indexed(const RIndex &x, double r)
+// the coarsest ladder levels live in shared memory on the device (the kernels substitute the pointer): generic loads, no __ldg
+CMCB_HD double top_ld(const double *p) { return *p; }
+CMCB_HD LBlock top_ld(const LBlock *p)
 {
-	long nb = 0; // complete blocks of the current level that lie entirely below r
-	for (int h = x.H; h >= 1; h--) nb = 16 * nb + ridx_count16(x.lvl + x.off[h] + 16 * nb, r);
-	const long base = 16 * nb;
-	int c = 0;
 #if defined(__CUDA_ARCH__)
-	const double2 *q = reinterpret_cast<const double2 *>(x.r + base);
+	const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+	LBlock o;
+	o.r_lo = a.x; o.r_hi = a.y; o.phi_min = b.x; o.phi_max = b.y;
+	return o;
+#else
+	return *p;
+#endif
+}
+CMCB_HD LBlock blk_ld(const LBlock *p)
+{
+#if defined(__CUDA_ARCH__)
+	const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+	LBlock o;
+	o.r_lo = a.x; o.r_hi = a.y; o.phi_min = b.x; o.phi_max = b.y;
+	return o;
+#else
+	return *p;
+#endif
+}
+
+// FindZero_r(1, N_MAX + 1, r) through the r ladder: largest k in [1, N_MAX+1] with star_r[k] < r, 1 if there is none.
+// *line_base / line[]: the fine-table line the last step read (entries line_base .. line_base + 7), for the caller's interpolation.
+CMCB_HD kint find_zero_r_ladder(const OrbitTables &t, const double *top, double r, kint *line_base, RPhi line[8])
+{
+	const RLadder &L = t.rlad;
+	int lo = 0, hi = L.n_top; // samples [0, lo) are < r, samples [hi, n_top) are >= r
+	while (lo < hi) {
+		const int mid = (lo + hi) >> 1;
+		if (top_ld(top + mid) < r) lo = mid + 1; else hi = mid;
+	}
+	long b = lo > 0 ? lo - 1 : 0; // last sample below r
+	for (int l = 1; l < L.n_levels; l++) {
+		const int c = count16_below(L.lvl[l] + 16 * b, r);
+		b = 16 * b + (c > 0 ? c - 1 : 0);
+	}
+	const kint base = (kint) (b << RLAD_MIN_SHIFT), M = t.N_MAX + 1;
+	int c = 0;
 #pragma unroll
 	for (int i = 0; i < 8; i++) {
-		const double2 v = __ldg(q + i);
-		c += (base + 2 * i <= (long) x.M && v.x < r) + (base + 2 * i + 1 <= (long) x.M && v.y < r);
+		line[i] = tbl_rp(t, base + i);
+		c += (base + i <= M && line[i].r < r);
 	}
-#else
-	for (int i = 0; i < 16; i++) c += (base + i <= (long) x.M) && x.r[base + i] < r;
-#endif
-	const long below = base + c; // entries of star_r[0 .. M] that are < r; star_r[0] = ZERO is one of them
-	return below >= 2 ? (kint) (below - 1) : 1;
+	*line_base = base;
+	const kint k = base + c - 1; // largest k in [0, M] with star_r[k] < r (-1: none)
+	return k >= 1 ? k : 1;
 }
 
 // potential(r) (cmc_utils.c:112-165, SEARCH_GRID = 0).  *fail is set when the bracket check (:144-152) would abort.
-CMCB_HD double potential_at(const OrbitTables &t, double r, int *fail)
+CMCB_HD double potential_at(const OrbitTables &t, const LadderTops &top, double r, int *fail)
 {
 	double phi0 = tbl_phi(t, 0);
 	if (r == 0.0) return phi0;
 	const RPhi p1 = tbl_rp(t, 1);
 	if (r < p1.r) return dsub(phi0, ddiv(dmul(dsub(phi0, p1.phi), p1.r), r));
 	kint kmax = t.N_MAX + 1, kmin = 1;
-	kint i = (kmin == kmax - 1) ? kmin : (t.ridx.r ? find_zero_r_indexed(t.ridx, r) : find_zero_r(t, kmin, kmax, r));
-	const RPhi a = tbl_rp(t, i), b = tbl_rp(t, i + 1);
+	RPhi a, b;
+	if (kmin != kmax - 1 && top.r) {
+		RPhi line[8];
+		kint base;
+		const kint i = find_zero_r_ladder(t, top.r, r, &base, line);
+		const int o = i - base; // 0 .. 7 (the k = 0 -> 1 clamp cannot happen here: r >= star_r[1])
+		a = line[0]; b = line[1];
+#pragma unroll
+		for (int q = 1; q < 7; q++) if (o == q) { a = line[q]; b = line[q + 1]; }
+		if (o == 7) { a = line[7]; b = tbl_rp(t, i + 1); }
+	} else {
+		const kint i = (kmin == kmax - 1) ? kmin : find_zero_r(t, kmin, kmax, r);
+		a = tbl_rp(t, i); b = tbl_rp(t, i + 1);
+	}
 	if (a.r > r || b.r < r) { *fail = 1; return 0.0; }
 	double inv_i = ddiv(1.0, a.r);
 	return dadd(a.phi, ddiv(dmul(dsub(b.phi, a.phi), dsub(inv_i, ddiv(1.0, r))), dsub(inv_i, ddiv(1.0, b.r))));
@@ -280,19 +392,6 @@ CMCB_HD bool q_increasing(const OrbitTables &t, const StarConst &s, kint kmin, k
 	return q_exact(t, s, lo.r, lo.phi) < q_exact(t, s, hi.r, hi.phi);
 }
 
-// find_zero_Q (cmc_nr.c:316-383): the same probe sequence ktry = (kmin+kmax+1)/2
-CMCB_HD kint find_zero_Q(const OrbitTables &t, const StarConst &s, kint kmin, kint kmax, int *n_exact)
-{
-	const bool increasing = q_increasing(t, s, kmin, kmax, n_exact);
-	do {
-		kint ktry = (kmin + kmax + 1) / 2;
-		int sg = sign_Q(t, s, ktry, n_exact);
-		bool up = increasing ? (sg < 0) : (sg > 0); // :349 / :362
-		if (up) kmin = ktry; else kmax = ktry - 1;
-	} while (kmax != kmin);
-	return kmin;
-}
-
 // Can function_q be > 0 (or undecided) anywhere on table entries [k_lo, k_hi]?  false = PROVEN <= 0 on the whole range:
 //   Phi is non-decreasing in k (each phi_k = fl(phi_{k+1} - (a non-negative term)), cmc_utils.c:719), r is sorted, and the self
 //   term is non-increasing in r, so for every k in the range  Q(k) <= U := 2 (E - Phi_lo - phis(r_hi)) - J^2 / r_hi^2,
@@ -308,6 +407,80 @@ CMCB_HD bool q_maybe_positive_on(const StarConst &s, const RPhi lo, const RPhi h
 	const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
 	const double mag = dadd(dadd(dmul(dadd(dadd(s.absE, dabs(lo.phi)), s.c_in), r2), s.JJ), dadd(dabs(t1), dabs(t2)));
 	return !(S < -dmul(5.684341886080802e-14 /* 2^-44 */, mag));
+}
+
+// The two-sided form on a ladder block (see "ladders" above): -1 = the reference's function_q is PROVEN < 0 at every table entry
+// of the block, +1 = proven > 0, 0 = undecided (the caller descends to a finer level).
+//   Upper side (the argument of q_maybe_positive_on with Phi_lo -> min Phi, |Phi| -> max |Phi| of the block):
+//     U r_hi^2 := 2 ((E - Phi_min) r_hi^2 - phis(r_hi) r_hi^2) - J^2 >= Q*(k) r_hi^2 + [(J^2/r_k^2 - J^2/r_hi^2) + 2 (phis(r_k) - phis(r_hi))] r_hi^2;
+//     the reference's noise at k is <= 2^-51 (J^2/r_k^2 + |E| + |Phi_k| + phis(r_k)), whose excess over the same expression at r_hi
+//     is 2^-51 times the bracket, so computed Q(k) < 0 whenever -U r_hi^2 > 2^-51 (J^2 + (|E| + max|Phi| + c_in) r_hi^2).
+//   Lower side:  L r_lo^2 := 2 ((E - Phi_max) r_lo^2 - phis(r_lo) r_lo^2) - J^2 <= Q*(k) r_lo^2 (Phi_k <= Phi_max, phis non-increasing,
+//     r_k >= r_lo), and the noise at k times r_lo^2 is <= 2^-51 (J^2 (r_lo/r_k)^2 + (|E| + |Phi_k| + phis(r_k)) r_lo^2)
+//     <= 2^-51 (J^2 + (|E| + max|Phi| + c_in) r_lo^2).
+//   Each side is evaluated in the division-free FP64 form of sign_Q_at, S = 2 (t1 - t2) - JJ with |S - exact| <= 2^-50 (|t1| + |t2| + JJ),
+//   against the margin 2^-44 mag, mag := (|E| + max|Phi| + c_in) r^2 + JJ  (>= (|t1| + |t2| + JJ) (1 - 2^-50) since |t1| <= (|E| + |Phi|) r^2
+//   and t2 <= c_in r^2): 40x the evaluation error and the reference's noise (2^-50 + 2^-51) mag together.
+CMCB_HD int q_sign_on_block(const StarConst &s, const LBlock B)
+{
+	const double pabs = dmax(dabs(B.phi_min), dabs(B.phi_max));
+	const double base = dadd(dadd(s.absE, pabs), s.c_in);
+	{
+		const double a = dsub(s.E, B.phi_min);
+		const double r2 = dmul(B.r_hi, B.r_hi);
+		const double t1 = dmul(a, r2);
+		const double t2 = (B.r_hi >= s.r_j) ? dmul(s.mi, B.r_hi) : dmul(s.c_in, r2);
+		const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
+		if (S < -dmul(5.684341886080802e-14 /* 2^-44 */, dadd(dmul(base, r2), s.JJ))) return -1;
+	}
+	{
+		const double a = dsub(s.E, B.phi_max);
+		const double r2 = dmul(B.r_lo, B.r_lo);
+		const double t1 = dmul(a, r2);
+		const double t2 = (B.r_lo >= s.r_j) ? dmul(s.mi, B.r_lo) : dmul(s.c_in, r2);
+		const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
+		if (S > dmul(5.684341886080802e-14 /* 2^-44 */, dadd(dmul(base, r2), s.JJ))) return 1;
+	}
+	return 0;
+}
+
+#ifdef CMCB_LADDER_STATS
+static long g_lad_stats[17]; // host-only instrumentation: [2l] proven at level l, [2l+1] undecided at level l, [16] fine probes
+#endif
+// sign of function_q at table index k during a bisection whose bracket is `width` = kmax - kmin entries wide: answered from the
+// coarsest ladder level whose blocks are at most an eighth of the bracket (the sign change sits somewhere in the bracket, the probe in
+// its middle: a block that small is rarely the one that straddles it), descending on "undecided", the fine table last.
+CMCB_HD int sign_Q_laddered(const OrbitTables &t, const LBlock *top, const StarConst &s, kint k, kint width, int *n_exact)
+{
+	const QLadder &L = t.qlad;
+	for (int l = 0; l < L.n_levels; l++) {
+		const int sh = L.shift[l];
+		if (((kint) QLAD_WIDTH_FACTOR << sh) > width) continue;
+		const LBlock B = (l == 0) ? top_ld(top + (k >> sh)) : blk_ld(L.blk[l] + (k >> sh));
+		const int sg = q_sign_on_block(s, B);
+#ifdef CMCB_LADDER_STATS
+		g_lad_stats[sg ? 2 * l : 2 * l + 1]++;
+#endif
+		if (sg) return sg;
+	}
+#ifdef CMCB_LADDER_STATS
+	g_lad_stats[16]++;
+#endif
+	return sign_Q(t, s, k, n_exact);
+}
+
+// find_zero_Q (cmc_nr.c:316-383): the same probe sequence ktry = (kmin+kmax+1)/2
+CMCB_HD kint find_zero_Q(const OrbitTables &t, const LadderTops &top, const StarConst &s, kint kmin, kint kmax, int *n_exact)
+{
+	const bool increasing = q_increasing(t, s, kmin, kmax, n_exact);
+	const bool laddered = top.q != nullptr;
+	do {
+		kint ktry = (kmin + kmax + 1) / 2;
+		int sg = laddered ? sign_Q_laddered(t, top.q, s, ktry, kmax - kmin, n_exact) : sign_Q(t, s, ktry, n_exact);
+		bool up = increasing ? (sg < 0) : (sg > 0); // :349 / :362
+		if (up) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
 }
 
 // the linear scan of get_positive_Q_index (cmc_orbit.c:46-57): first k from 0 with Q > 0; -1 if there is none below N_MAX.
@@ -359,8 +532,11 @@ CMCB_HD double vr2_within_interval(const OrbitTables &t, const StarConst &s, kin
 // find_root_vr (cmc_nr.c:500-603): Brent-Dekker as GSL's gsl_root_fsolver_brent iterates it (un-vendored
 // dependency of the reference, version unpinned -> this branch is "parity unpinned"), APSIDES_PRECISION = 1e-11,
 // APSIDES_MAX_ITER = 100, APSIDES_CONVERGENCE = 5e-13 (cmc_io.c:1752-1754).
-CMCB_COLD double find_root_vr(const OrbitTables t, const StarConst s, kint k) // by value: see q_exact_cold
+CMCB_COLD double find_root_vr(const RPhi *rp, double invN, double madhoc, double cenma_m, const StarConst s, kint k) // by value: see q_exact_cold
 {
+	OrbitTables t; // only what vr2_within_interval reads
+	t.rp = rp; t.m = nullptr; t.N_MAX = 0; t.invN = invN; t.madhoc = madhoc; t.cenma_m = cenma_m;
+	t.qlad.n_levels = 0; t.rlad.n_levels = 0;
 	const double PREC = 1.0e-11, CONV = 5.e-13, EPS = 2.220446049250313e-16;
 	int iter = 100;
 	double a = tbl_r(t, k), b = tbl_r(t, k + 1), c = b;
@@ -429,7 +605,7 @@ struct OrbitRS { // orbit_rs_t, reference include/cmc/cmc.h:1621-1650
 // ktemp_in: KTEMP_COMPUTE, or the result of the linear scan found elsewhere (>= -1).  need_scan != nullptr: instead of running the
 // O(N) scan in this thread, set *need_scan and return (the caller queues the star for the cooperative scan).
 constexpr kint KTEMP_COMPUTE = -2;
-CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is_new, double rnew_of_new, int *n_exact, int *n_brent,
+CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const LadderTops &top, const StarConst &s, bool is_new, double rnew_of_new, int *n_exact, int *n_brent,
 			       kint ktemp_in = KTEMP_COMPUTE, bool *need_scan = nullptr)
 {
 	OrbitRS o;
@@ -450,8 +626,8 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 	double rmin = 0, rmax = 0, dQdr_min = 0, dQdr_max = 0;
 	kint kmin = 0, kmax = 0;
 	if (!circular) {
-		kmin = find_zero_Q(t, s, 0, ktemp, n_exact);               // :441
-		kmax = find_zero_Q(t, s, ktemp, t.N_MAX + 1, n_exact);     // :444
+		kmin = find_zero_Q(t, top, s, 0, ktemp, n_exact);               // :441
+		kmax = find_zero_Q(t, top, s, ktemp, t.N_MAX + 1, n_exact);     // :444
 		double a, b;
 		const double J = s.J, E = s.E;
 		double JJ2 = dmul(dmul(2.0, J), J);
@@ -459,7 +635,7 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 		double inside = dsub(dmul(a, a), dmul(JJ2, dsub(b, E)));
 		if (inside < 0.0) {                                        // :459-474
 			rmin = ddiv(dmul(dmul(-1.0, J), J), a);
-			if (rmin < tbl_r(t, kmin) || rmin > tbl_r(t, kmin + 1)) { rmin = find_root_vr(t, s, kmin); (*n_brent)++; }
+			if (rmin < tbl_r(t, kmin) || rmin > tbl_r(t, kmin + 1)) { rmin = find_root_vr(t.rp, t.invN, t.madhoc, t.cenma_m, s, kmin); (*n_brent)++; }
 		} else {
 			rmin = ddiv(dmul(J, J), dadd(-a, dsqrt(inside)));      // :476
 		}
@@ -468,7 +644,7 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const StarConst &s, bool is
 		inside = dsub(dmul(a, a), dmul(JJ2, dsub(b, E)));
 		if (inside < 0.0) {                                        // :485-500
 			rmax = ddiv(-a, dmul(2.0, dsub(b, E)));
-			if (rmax < tbl_r(t, kmax) || rmax > tbl_r(t, kmax + 1)) { rmax = find_root_vr(t, s, kmax); (*n_brent)++; }
+			if (rmax < tbl_r(t, kmax) || rmax > tbl_r(t, kmax + 1)) { rmax = find_root_vr(t.rp, t.invN, t.madhoc, t.cenma_m, s, kmax); (*n_brent)++; }
 		} else {
 			rmax = ddiv(dadd(-a, dsqrt(inside)), dmul(2.0, dsub(b, E))); // :502
 		}
@@ -509,7 +685,7 @@ struct OrbitJob {
 // Everything of one loop iteration of get_positions_loop BEFORE the rejection sampling (:803-860): the early exits (massless,
 // unbound, circular, tidally stripped) are final and fill `out`; otherwise the status is ORBIT_PENDING and `job` is set.
 // (for ORBIT_CIRCULAR the caller fills vrnew / vtnew with the star's current vr / vt, :837-838)
-CMCB_HD void orbit_prepare(const OrbitTables &t, const StarConst &s, bool is_new, double rnew_of_new, double Rtidal,
+CMCB_HD void orbit_prepare(const OrbitTables &t, const LadderTops &top, const StarConst &s, bool is_new, double rnew_of_new, double Rtidal,
 			   kint ktemp_in, bool allow_defer, OrbitOut &out, OrbitJob &job)
 {
 	out.n_draws = 0; out.n_exact = 0; out.n_brent = 0;
@@ -524,7 +700,7 @@ CMCB_HD void orbit_prepare(const OrbitTables &t, const StarConst &s, bool is_new
 		return;
 	}
 	bool need_scan = false;
-	OrbitRS o = calc_orbit_new(t, s, is_new, rnew_of_new, &out.n_exact, &out.n_brent, ktemp_in, allow_defer ? &need_scan : nullptr); // :832
+	OrbitRS o = calc_orbit_new(t, top, s, is_new, rnew_of_new, &out.n_exact, &out.n_brent, ktemp_in, allow_defer ? &need_scan : nullptr); // :832
 	if (need_scan) { out.status = ORBIT_DEFERRED; out.rnew = out.vrnew = out.vtnew = 0.0; return; }
 	out.kmin = o.kmin; out.kmax = o.kmax;
 	if (o.circular) {                      // :835-839
@@ -548,7 +724,7 @@ CMCB_HD void orbit_prepare(const OrbitTables &t, const StarConst &s, bool is_new
 
 // One pass of the rejection loop body (:863-887) with the two uniforms X, u of that try.  1: accepted (r, vr set), 0: rejected,
 // -1: the bracket check inside potential() failed (fatal in the reference, cmc_utils.c:144-152).
-CMCB_HD int orbit_try(const OrbitTables &t, const StarConst &s, const OrbitJob &job, double X, double u, double *r_out, double *vr_out)
+CMCB_HD int orbit_try(const OrbitTables &t, const LadderTops &top, const StarConst &s, const OrbitJob &job, double X, double u, double *r_out, double *vr_out)
 {
 	const double span = dsub(job.rmax, job.rmin);
 	const double mid = dmul(0.5, dadd(job.rmin, job.rmax)), quarter = dmul(0.25, span), twoE = dmul(2.0, s.E);
@@ -556,7 +732,7 @@ CMCB_HD int orbit_try(const OrbitTables &t, const StarConst &s, const OrbitJob &
 	const double g0 = dmul(job.F, u);
 	const double r = dadd(mid, dmul(quarter, dsub(dmul(3.0, s0), dmul(dmul(s0, s0), s0))));
 	int fail = 0;
-	const double pot = dadd(potential_at(t, r, &fail), phi_self(r, s.r_j, s.m_j, t.invN));
+	const double pot = dadd(potential_at(t, top, r, &fail), phi_self(r, s.r_j, s.m_j, t.invN));
 	const double drds = dmul(quarter, dsub(3.0, dmul(dmul(3.0, s0), s0)));
 	const double Q = dsub(dsub(twoE, dmul(2.0, pot)), ddiv(ddiv(s.JJ, r), r));
 	const double vr = (Q >= 0.0) ? dsqrt(Q) : 0.0;
@@ -584,8 +760,10 @@ CMCB_HD void orbit_step_star(const OrbitTables &t, kint g_j, bool is_new, double
 			     kint ktemp_in = KTEMP_COMPUTE, bool allow_defer = false)
 {
 	const StarConst s = star_const(t, g_j, E_star, J);
+	LadderTops top;
+	top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
 	OrbitJob job;
-	orbit_prepare(t, s, is_new, rnew_of_new, Rtidal, ktemp_in, allow_defer, out, job);
+	orbit_prepare(t, top, s, is_new, rnew_of_new, Rtidal, ktemp_in, allow_defer, out, job);
 	if (out.status == ORBIT_CIRCULAR) { out.vrnew = vr_in; out.vtnew = vt_in; }
 	if (out.status != ORBIT_PENDING) return;
 	double r = 0.0, vr = 0.0, X = 0.0;
@@ -594,7 +772,7 @@ CMCB_HD void orbit_step_star(const OrbitTables &t, kint g_j, bool is_new, double
 		if (!draws.has(2)) { rc = -1; break; }
 		X = draws.next();
 		const double u = draws.next();
-		rc = orbit_try(t, s, job, X, u, &r, &vr);
+		rc = orbit_try(t, top, s, job, X, u, &r, &vr);
 		if (rc != 0) break;
 	}
 	if (k == CMCB_N_TRY + 1 || rc < 0 || !draws.has(1)) { // :890-893

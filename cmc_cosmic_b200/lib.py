@@ -32,7 +32,7 @@ EXPORTS = [
     "cmcb200_calc_potential_new", "cmcb200_qsorts_new", "cmcb200_new_orbits_calculate", "cmcb200_upload", "cmcb200_download",
     "cmcb200_dev_new_orbits", "cmcb200_dev_transfer_new_positions", "cmcb200_dev_qsorts_new", "cmcb200_dev_transfer_and_sort", "cmcb200_dev_calc_potential_new",
     "cmcb200_dev_compute_energy", "cmcb200_dev_read_status", "cmcb200_sync", "cmcb200_profile", "cmcb200_profile_read",
-    "cmcb200_potential_stats", "cmcb200_launch_count",
+    "cmcb200_potential_stats", "cmcb200_launch_count", "cmcb200_host_register", "cmcb200_host_unregister", "cmcb200_transfer_bytes",
 ]
 
 
@@ -81,6 +81,9 @@ def load():
     L.cmcb200_potential_stats.argtypes = [vp, pl, pl]
     L.cmcb200_launch_count.argtypes = [vp]
     L.cmcb200_launch_count.restype = lg
+    L.cmcb200_host_register.argtypes = [vp, C.c_size_t]
+    L.cmcb200_host_unregister.argtypes = [vp]
+    L.cmcb200_transfer_bytes.argtypes = [vp, pl, pl, C.c_int]
     _lib = L
     return L
 

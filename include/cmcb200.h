@@ -127,6 +127,17 @@ typedef struct {
 int cmcb200_new_orbits_calculate(cmcb200_ctx *ctx, void *star1, const double *star_r, const double *star_m, const double *star_phi,
 				 const cmcb200_orbit_params *p, int *status, long *kmin, long *kmax, cmcb200_orbit_result *res);
 
+/* ---- host memory ---------------------------------------------------------------------------------------------------- */
+
+/* Pin and map a host array the host-buffer entry points are called with (star[], binary[], star_r/m/phi: the reference callocs /
+ * mallocs them once, src/cmc/cmc_io.c:2099-2101, 3434-3436, so the shim registers them once at start-up).  Optional: pageable
+ * memory works, but (a) pinned memory copies at PCIe rate and (b) for a pinned + mapped star[] cmcb200_new_orbits_calculate moves
+ * only the fields the orbit step reads and writes (48 + <=48 bytes per star) instead of the 424-byte records both ways. */
+int cmcb200_host_register(void *ptr, size_t bytes);
+int cmcb200_host_unregister(void *ptr);
+/* bytes the host-buffer entry points have moved host->device / device->host since creation (or the last reset) */
+int cmcb200_transfer_bytes(cmcb200_ctx *ctx, long *h2d, long *d2h, int reset);
+
 /* ---- device-resident pipeline ------------------------------------------------------------------------------------ */
 /* The star array lives in HBM across timesteps; the host touches O(encounters) records through the get/put calls. */
 

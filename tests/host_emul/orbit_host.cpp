@@ -8,8 +8,9 @@ using namespace cmcb;
 // the packed (r, phi) table the kernels read (built on the device by pack_tables_kernel in the product)
 static std::vector<RPhi> pack(const double *star_r, const double *star_phi, long n)
 {
-	std::vector<RPhi> v(n);
+	std::vector<RPhi> v(n + 16); // the last step of the r ladder reads a whole 8-entry line (masked beyond the table)
 	for (long i = 0; i < n; i++) { v[i].r = star_r[i]; v[i].phi = star_phi[i]; }
+	for (long i = n; i < n + 16; i++) { v[i].r = 0.0; v[i].phi = 0.0; }
 	return v;
 }
 
@@ -19,22 +20,37 @@ struct ArrayDraws {
 	double next() { return d[pos++]; }
 };
 
-// the 16-ary index over star_r (built on the device by orbit_build_index in the product)
-struct HostIndex {
-	std::vector<double> r, lvl;
-	RIndex x;
-	HostIndex(const double *star_r, kint M)
+// the ladders (built on the device by orbit_build_ladders in the product): every level straight from the fine table,
+// independently of the device builder's level-by-level merge
+struct HostLadders {
+	std::vector<std::vector<LBlock>> qb;
+	std::vector<std::vector<double>> rl;
+	QLadder q;
+	RLadder r;
+	bool unsorted = false;
+	HostLadders(const std::vector<RPhi> &rp, kint M)
 	{
-		r.assign(star_r, star_r + M + 1);
-		r.resize(M + 1 + 32, 0.0); // readable past M; the values there must not matter (the leaf step masks them)
-		long total;
-		ridx_plan(M, x.off, &x.H, &total);
-		lvl.assign(total, __builtin_huge_val());
-		for (int h = 1; h <= x.H; h++) {
-			long n = (h < x.H ? x.off[h + 1] : total) - x.off[h];
-			for (long i = 0; i < n; i++) lvl[x.off[h] + i] = ridx_sample(star_r, M, h, i);
+		long cnt[LADDER_MAX_LEVELS], alloc[LADDER_MAX_LEVELS];
+		q.n_levels = qlad_plan(M, q.shift, cnt);
+		qb.resize(q.n_levels);
+		for (int l = 0; l < q.n_levels; l++) {
+			qb[l].resize(cnt[l]);
+			for (long b = 0; b < cnt[l]; b++) {
+				long k0 = b << q.shift[l], k1 = (b + 1) << q.shift[l];
+				if (k1 > M) k1 = M;
+				qb[l][b] = lblock_of(rp.data(), k0, k1, &unsorted);
+			}
+			q.blk[l] = qb[l].data();
 		}
-		x.r = r.data(); x.lvl = lvl.data(); x.M = M;
+		r.n_levels = rlad_plan(M, r.shift, cnt, alloc);
+		rl.resize(r.n_levels);
+		for (int l = 0; l < r.n_levels; l++) {
+			rl[l].assign(alloc[l], __builtin_huge_val());
+			for (long b = 0; b < cnt[l]; b++) rl[l][b] = rp[b << r.shift[l]].r;
+			r.lvl[l] = rl[l].data();
+		}
+		r.n_top = r.n_levels ? (int) cnt[0] : 0;
+		if (unsorted) { q.n_levels = 0; r.n_levels = 0; }
 	}
 };
 
@@ -43,16 +59,17 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 				     const double *E_in, const double *J_in, const double *vr_in, const double *vt_in, const double *rnew_in,
 				     double Rtidal, const double *draws, long n_draws, const long *csr_off, int force_exact,
 				     int *status, double *rnew, double *vrnew, double *vtnew, double *X, double *r_peri, double *r_apo,
-				     long *kmin, long *kmax, long *counters /* [0]=draws used, [1]=exact Q evals, [2]=brent */)
+				     long *kmin, long *kmax, long *counters /* [0]=draws used, [1]=exact Q evals, [2]=brent, [3]/[4]=ladder levels in use (Q / r) */)
 {
 	OrbitTables t;
 	long n_tab = N_MAX + 2;
 	for (long j = 0; j < n_local; j++) if (g_idx[j] + 1 > n_tab) n_tab = g_idx[j] + 1;
 	std::vector<RPhi> rp = pack(star_r, star_phi, n_tab);
 	t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = cenma_m;
-	HostIndex hx(star_r, (kint) (N_MAX + 1));
-	t.ridx = hx.x;
-	if (force_exact) t.ridx.r = nullptr; // force_exact = 1: plain bisection instead of the 16-ary index
+	HostLadders lad(rp, (kint) (N_MAX + 1));
+	t.qlad = lad.q; t.rlad = lad.r;
+	if (force_exact) { t.qlad.n_levels = 0; t.rlad.n_levels = 0; } // force_exact = 1: every probe reads the fine table
+	counters[3] = t.qlad.n_levels; counters[4] = t.rlad.n_levels;
 	double max_rad = 0.0;
 	long pos = 0;
 	counters[0] = counters[1] = counters[2] = 0;
@@ -71,29 +88,42 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 	return max_rad;
 }
 
-// unit access for targeted tests
+// unit access for targeted tests: find_zero_Q with (use_ladder = 1) and without the ladder
 extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, const double *star_phi, long N_MAX, long N_STAR, long g_j,
-				 double E, double J, long kmin, long kmax, long *n_exact)
+				 double E, double J, long kmin, long kmax, long *n_exact, int use_ladder)
 {
 	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
 	OrbitTables t; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
-	t.ridx.r = nullptr;
+	HostLadders lad(rp, (kint) (N_MAX + 1));
+	t.qlad = lad.q; t.rlad = lad.r;
+	if (!use_ladder) { t.qlad.n_levels = 0; t.rlad.n_levels = 0; }
 	StarConst s; s.g_j = g_j; s.r_j = star_r[g_j]; s.m_j = star_m[g_j]; s.E = E; s.J = J;
 	star_const_derive(t, s);
 	int ne = 0;
-	long k = find_zero_Q(t, s, kmin, kmax, &ne);
+	LadderTops top; top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
+	long k = find_zero_Q(t, top, s, kmin, kmax, &ne);
 	*n_exact = ne;
 	return k;
 }
 
-// FindZero_r(1, N_MAX + 1, r): the reference's bisection and the 16-ary index, side by side
-extern "C" void emul_find_zero_r_both(const double *star_r, long N_MAX, const double *radii, long n, long *k_bisect, long *k_indexed)
+// FindZero_r(1, N_MAX + 1, r): the reference's bisection and the r ladder, side by side
+extern "C" void emul_find_zero_r_both(const double *star_r, long N_MAX, const double *radii, long n, long *k_bisect, long *k_ladder)
 {
 	std::vector<RPhi> rp = pack(star_r, star_r, N_MAX + 2);
 	OrbitTables t; t.rp = rp.data(); t.m = nullptr; t.N_MAX = N_MAX; t.invN = 0; t.madhoc = 0; t.cenma_m = 0;
-	HostIndex hx(star_r, (kint) (N_MAX + 1));
+	HostLadders lad(rp, (kint) (N_MAX + 1));
+	t.qlad = lad.q; t.rlad = lad.r;
 	for (long i = 0; i < n; i++) {
 		k_bisect[i] = find_zero_r(t, 1, (kint) (N_MAX + 1), radii[i]);
-		k_indexed[i] = find_zero_r_indexed(hx.x, radii[i]);
+		RPhi line[8];
+		kint base;
+		k_ladder[i] = t.rlad.n_levels ? find_zero_r_ladder(t, t.rlad.lvl[0], radii[i], &base, line) : -1;
 	}
+}
+
+// the ladder plans (levels, shifts, sizes), for the tests of the layout arithmetic
+extern "C" int emul_ladder_plan(long M, int *qshift, long *qcount, int *rshift, long *rcount, long *ralloc, int *n_r)
+{
+	*n_r = rlad_plan(M, rshift, rcount, ralloc);
+	return qlad_plan(M, qshift, qcount);
 }

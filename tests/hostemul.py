@@ -8,7 +8,16 @@ import numpy as np
 
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
 _SO = os.path.join(_DIR, "_build", "libemul.so")
+_SO_DEEP = os.path.join(_DIR, "_build", "libemul_deep.so")  # tiny top levels: deep ladders on small tables
 _lib = None
+_deep = False
+
+
+def use_deep_ladders(on):
+    """switch to the build whose ladders have 6-block / 10-sample top levels"""
+    global _lib, _deep
+    if on != _deep:
+        _lib, _deep = None, on
 
 
 def build():
@@ -19,12 +28,14 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_SO)
+        L = C.CDLL(_SO_DEEP if _deep else _SO)
         vp, lg, db = C.c_void_p, C.c_long, C.c_double
         L.emul_get_positions.restype = db
         L.emul_get_positions.argtypes = [vp, vp, vp, lg, lg, db, lg, vp, vp, vp, vp, vp, vp, vp, db, vp, lg, vp, C.c_int] + [vp] * 10
         L.emul_find_zero_Q.restype = lg
-        L.emul_find_zero_Q.argtypes = [vp, vp, vp, lg, lg, lg, db, db, lg, lg, vp]
+        L.emul_find_zero_Q.argtypes = [vp, vp, vp, lg, lg, lg, db, db, lg, lg, vp, C.c_int]
+        L.emul_ladder_plan.restype = C.c_int
+        L.emul_ladder_plan.argtypes = [lg] + [vp] * 6
         L.emul_find_zero_r_both.argtypes = [vp, lg, vp, lg, vp, vp]
         _lib = L
     return _lib
@@ -34,7 +45,7 @@ def _p(a):
     return None if a is None else a.ctypes.data
 
 
-def get_positions(sr, sm, phi, N_MAX, N_STAR, cenma_m, g_idx, E, J, vr, vt, Rtidal, draws, csr_off=None, is_new=None, rnew_in=None):
+def get_positions(sr, sm, phi, N_MAX, N_STAR, cenma_m, g_idx, E, J, vr, vt, Rtidal, draws, csr_off=None, is_new=None, rnew_in=None, no_ladders=False):
     n = len(g_idx)
     g_idx = np.ascontiguousarray(g_idx, np.int64)
     arrs = [np.ascontiguousarray(x, np.float64) for x in (E, J, vr, vt)]
@@ -43,18 +54,33 @@ def get_positions(sr, sm, phi, N_MAX, N_STAR, cenma_m, g_idx, E, J, vr, vt, Rtid
         csr_off = np.ascontiguousarray(csr_off, np.int64)
     out = dict(status=np.zeros(n, np.int32), rnew=np.zeros(n), vrnew=np.zeros(n), vtnew=np.zeros(n), X=np.zeros(n), r_peri=np.zeros(n),
                r_apo=np.zeros(n), kmin=np.zeros(n, np.int64), kmax=np.zeros(n, np.int64))
-    cnt = np.zeros(3, np.int64)
+    cnt = np.zeros(5, np.int64)
     out["max_rad"] = lib().emul_get_positions(_p(sr), _p(sm), _p(phi), N_MAX, N_STAR, cenma_m, n, _p(g_idx), _p(is_new), _p(arrs[0]), _p(arrs[1]),
-                                              _p(arrs[2]), _p(arrs[3]), _p(rnew_in), Rtidal, _p(draws), len(draws), _p(csr_off), 0,
+                                              _p(arrs[2]), _p(arrs[3]), _p(rnew_in), Rtidal, _p(draws), len(draws), _p(csr_off), 1 if no_ladders else 0,
                                               _p(out["status"]), _p(out["rnew"]), _p(out["vrnew"]), _p(out["vtnew"]), _p(out["X"]),
                                               _p(out["r_peri"]), _p(out["r_apo"]), _p(out["kmin"]), _p(out["kmax"]), _p(cnt))
     out["n_draws"], out["n_exact"], out["n_brent"] = int(cnt[0]), int(cnt[1]), int(cnt[2])
+    out["q_levels"], out["r_levels"] = int(cnt[3]), int(cnt[4])
     return out
 
 
 def find_zero_r_both(star_r, N_MAX, radii):
-    """(FindZero_r by the reference's bisection, by the 16-ary index) for each radius"""
+    """(FindZero_r by the reference's bisection, by the r ladder [-1: table too small for a ladder]) for each radius"""
     radii = np.ascontiguousarray(radii, np.float64)
     a, b = np.zeros(len(radii), np.int64), np.zeros(len(radii), np.int64)
     lib().emul_find_zero_r_both(_p(np.ascontiguousarray(star_r)), N_MAX, _p(radii), len(radii), _p(a), _p(b))
     return a, b
+
+
+def find_zero_Q(sr, sm, phi, N_MAX, N_STAR, g_j, E, J, kmin, kmax, use_ladder=True):
+    ne = np.zeros(1, np.int64)
+    k = lib().emul_find_zero_Q(_p(sr), _p(sm), _p(phi), N_MAX, N_STAR, g_j, E, J, kmin, kmax, _p(ne), 1 if use_ladder else 0)
+    return int(k), int(ne[0])
+
+
+def ladder_plan(M):
+    qs, rs = np.zeros(8, np.int32), np.zeros(8, np.int32)
+    qc, rc, ra = np.zeros(8, np.int64), np.zeros(8, np.int64), np.zeros(8, np.int64)
+    nr = np.zeros(1, np.int32)
+    nq = lib().emul_ladder_plan(M, _p(qs), _p(qc), _p(rs), _p(rc), _p(ra), _p(nr))
+    return dict(q_shift=qs[:nq], q_count=qc[:nq], r_shift=rs[:nr[0]], r_count=rc[:nr[0]], r_alloc=ra[:nr[0]])

@@ -95,18 +95,19 @@ def test_sort_ties_and_all_stripped():
     _sort_case(100, 0, 100, seed=4)                   # everything stripped
 
 
-def _orbit_case(kind, N, masses="equal", seed=1234, tidal=None):
+def _orbit_case(kind, N, masses="equal", seed=1234, tidal=None, cenma_m=0.0):
     r, vr, vt, sm = cm.cluster_state(kind, N, masses=masses, seed=seed)
-    pot = cm.oracle_potential(r, sm)
+    pot = cm.oracle_potential(r, sm, cenma_m=cenma_m)
     phi, sr, smt = pot["phi"], pot["star_r"], pot["star_m"]
     E, J = cm.energies(phi[1:N + 1], r, vr, vt)
     Rtidal = tidal if tidal is not None else pot["Rtidal"]
-    want = cm.oracle_orbits(sr, smt, phi, N, N, E, J, vr, vt, Rtidal, seed=seed)
+    want = cm.oracle_orbits(sr, smt, phi, N, N, E, J, vr, vt, Rtidal, seed=seed, cenma_m=cenma_m)
     c = Cluster(N, n_star_dim=N + 64)
     c.load(r, vr, vt, sm)
     c.star_phi[:N + 2] = phi[:N + 2]
     c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
     c.Rtidal = Rtidal
+    c.cenma.m = cenma_m
     status = c.new_orbits_calculate(draws=want["draws"], draw_off=want["draw_off"])
     assert np.array_equal(status, want["status"])
     ok = want["status"] == ol.ST_OK
@@ -128,6 +129,54 @@ def _orbit_case(kind, N, masses="equal", seed=1234, tidal=None):
 @pytest.mark.parametrize("kind,N,masses", [("plummer", 2000, "equal"), ("plummer", 100000, "equal"), ("king", 200000, "equal"), ("plummer", 50000, "imf")])
 def test_orbit_step_bit_exact(kind, N, masses):
     _orbit_case(kind, N, masses)
+
+
+def test_orbit_step_deep_ladders_bit_exact():
+    """N = 700000: three levels in both ladders (Q: shifts 10/7/4, r: 11/7/3), every probe of the index bisections answered from the
+    coarsest level that proves its sign -- kmin / kmax / r_peri / r_apo / rnew still the reference's bit for bit"""
+    _orbit_case("plummer", 700000, seed=99)
+
+
+def test_orbit_step_with_central_mass():
+    """cenma.m > 0 makes star_phi[0] > star_phi[1] (cmc_utils.c:727): the Q-ladder blocks carry the true min / max of Phi, not its ends"""
+    _orbit_case("king", 120000, seed=17, cenma_m=0.02 * 120000)
+
+
+@pytest.mark.parametrize("knob,value", [("CMCB200_ORBIT_LADDERS", "0"), ("CMCB200_ORBIT_CTAS", "3")])
+def test_orbit_step_tuning_knobs_do_not_change_results(knob, value, monkeypatch):
+    """the plain-bisection path (ladders off) and the 3-CTA register variant of the orbit kernel stay bit-exact"""
+    monkeypatch.setenv(knob, value)
+    _orbit_case("plummer", 100000, seed=5)
+
+
+def test_new_orbits_zero_copy_equals_staged_records():
+    """host-buffer orbit step on a pinned + mapped star[] (kernels move the 48 input / <= 48 output bytes per star over PCIe) against the
+    pageable path (whole 424-byte records staged both ways): every byte of star[] afterwards, including the fields the step must not touch,
+    with tidal strippings and planted unbound / massless stars so every status-dependent store is exercised"""
+    N = 80000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=61)
+    rng = np.random.default_rng(3)
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    E[rng.choice(N, 50, replace=False)] = 0.5             # unbound
+    outs = []
+    for pinned in (True, False):
+        c = Cluster(N, n_star_dim=N + 64, pinned=pinned)
+        c.star[:] = np.random.default_rng(1).integers(0, 256, c.star.shape, dtype=np.uint8)
+        c.load(r, vr, vt, sm)
+        c.star_m[1 + 777] = 0.0                             # massless
+        c.star_phi[:N + 2] = pot["phi"][:N + 2]
+        c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+        c.Rtidal = 4.0
+        status = c.new_orbits_calculate(seed=11)
+        h2d, d2h = c.transfer_bytes()
+        outs.append((status.copy(), c.star.copy(), c.max_r, h2d, d2h))
+        c.close()
+    (sa, stara, ma, ha, da), (sb, starb, mb, hb, db) = outs
+    assert np.array_equal(sa, sb) and ma == mb
+    assert set(np.unique(sa)) >= {ol.ST_OK, ol.ST_UNBOUND, ol.ST_TIDAL}
+    assert np.array_equal(stara, starb), "star[] differs between the zero-copy and the staged path"
+    assert ha < hb / 3 and da < db / 3, (ha, hb, da, db)   # the zero-copy path moved a fraction of the bytes
 
 
 def test_orbit_step_branches():

@@ -74,23 +74,36 @@ def test_x87_emulation_matches_hardware_long_double():
     _run("test_x87emu", "300000")
 
 
-@pytest.mark.parametrize("kind,N,masses", [("plummer", 20000, "equal"), ("king", 20000, "equal"), ("plummer", 10000, "imf")])
-def test_kernel_core_on_host_matches_oracle(kind, N, masses):
+@pytest.mark.parametrize("kind,N,masses,deep", [("plummer", 20000, "equal", False), ("king", 20000, "equal", True), ("plummer", 10000, "imf", True),
+                                               ("plummer", 200000, "equal", False)])
+def test_kernel_core_on_host_matches_oracle(kind, N, masses, deep):
+    """orbit_core.h compiled for the host, with the ladders the kernels use (deep = the build with tiny top levels, so these small tables get
+    3- and 4-level ladders; N = 200000 gets a 3-level Q ladder with the production constants) and without them"""
     import hostemul
-    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 3, masses=masses)
-    pot = cm.oracle_potential(r, sm)
-    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
-    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, 3.5 if masses == "imf" else pot["Rtidal"], seed=5)
-    out = hostemul.get_positions(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0, np.arange(1, N + 1), E, J, vr, vt,
-                                 3.5 if masses == "imf" else pot["Rtidal"], want["draws"], csr_off=want["draw_off"])
-    assert np.array_equal(out["status"], want["status"])
-    has = (want["status"] != ol.ST_MASSLESS) & (want["status"] != ol.ST_UNBOUND)
-    assert np.array_equal(out["kmin"][has], want["kmin"][has]) and np.array_equal(out["kmax"][has], want["kmax"][has])
-    for f in ("rnew", "vrnew", "vtnew"):
-        cm.assert_bits_equal(out[f], want[f], f)
-    ok = want["status"] == ol.ST_OK
-    for f in ("X", "r_peri", "r_apo"):
-        cm.assert_bits_equal(out[f][ok], want[f][ok], f)
+    hostemul.use_deep_ladders(deep)
+    try:
+        r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 3, masses=masses)
+        pot = cm.oracle_potential(r, sm)
+        E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+        Rt = 3.5 if masses == "imf" else pot["Rtidal"]
+        want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, Rt, seed=5)
+        for no_ladders in (False, True):
+            out = hostemul.get_positions(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0, np.arange(1, N + 1), E, J, vr, vt,
+                                         Rt, want["draws"], csr_off=want["draw_off"], no_ladders=no_ladders)
+            if no_ladders:
+                assert out["q_levels"] == 0 and out["r_levels"] == 0
+            else:
+                assert out["q_levels"] >= (3 if deep or N >= 200000 else 1) and out["r_levels"] >= (3 if deep else 1), (out["q_levels"], out["r_levels"])
+            assert np.array_equal(out["status"], want["status"])
+            has = (want["status"] != ol.ST_MASSLESS) & (want["status"] != ol.ST_UNBOUND)
+            assert np.array_equal(out["kmin"][has], want["kmin"][has]) and np.array_equal(out["kmax"][has], want["kmax"][has])
+            for f in ("rnew", "vrnew", "vtnew"):
+                cm.assert_bits_equal(out[f], want[f], f)
+            ok = want["status"] == ol.ST_OK
+            for f in ("X", "r_peri", "r_apo"):
+                cm.assert_bits_equal(out[f][ok], want[f][ok], f)
+    finally:
+        hostemul.use_deep_ladders(False)
 
 
 @pytest.mark.skipif(not rh.available(), reason="oracle/_ref/libcmc_ref.so not built")
@@ -102,24 +115,60 @@ def test_multirank_reference_equals_single_rank_oracle(procs, N):
     assert p.returncode == 0 and "MULTIRANK OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
 
-@pytest.mark.parametrize("N", [1, 2, 13, 14, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 65535, 65536, 70001, 1048575, 1048577])
-def test_indexed_find_zero_r_equals_reference_bisection(N):
-    """the 16-ary sampled index used by potential() on the device returns FindZero_r's index for every radius: between, on and
-    beyond the table entries, with ties, at every level boundary of the index"""
+@pytest.mark.parametrize("deep", [False, True])
+@pytest.mark.parametrize("N", [1, 2, 13, 61, 62, 63, 64, 255, 256, 257, 4095, 4096, 4097, 40951, 40959, 40960, 65535, 65536, 70001, 655359, 655361, 1048577])
+def test_ladder_find_zero_r_equals_reference_bisection(N, deep):
+    """the r ladder used by potential() on the device returns FindZero_r's index for every radius: between, on and beyond the table
+    entries, with ties, at every block boundary of every level (deep: the build with a 10-sample top level -> up to 5 levels)"""
     import hostemul
-    rng = np.random.default_rng(N)
-    r = np.sort(rng.uniform(1e-3, 50.0, N))
-    if N > 20:
-        r[N // 3:N // 3 + 5] = r[N // 3]                      # ties
-    sr = np.zeros(N + 2)
-    sr[0], sr[1:N + 1], sr[N + 1] = cm.ZERO, r, cm.SF_INFINITY
-    probes = np.concatenate([rng.uniform(r[0], r[-1] * 1.01, 4000), r[rng.integers(0, N, min(N, 2000))], r[:40], r[-40:],
-                             np.nextafter(r[:40], 0), np.nextafter(r[-40:], 1e9), [r[-1] * 2, 1e9, r[0]]])
-    edges = np.arange(16, N + 2, 16)
-    for d in (-1, 0, 1):                                       # radii right at the block boundaries of every level
-        idx = np.clip(edges + d, 1, N)
-        probes = np.concatenate([probes, sr[idx][:3000], np.nextafter(sr[idx][:3000], 1e9)])
-    probes = probes[probes >= r[0]]                            # potential() handles r < star_r[1] before the search
-    a, b = hostemul.find_zero_r_both(sr, N, probes)
-    bad = np.nonzero(a != b)[0]
-    assert bad.size == 0, (bad[:5], probes[bad[:5]], a[bad[:5]], b[bad[:5]])
+    hostemul.use_deep_ladders(deep)
+    try:
+        rng = np.random.default_rng(N)
+        r = np.sort(rng.uniform(1e-3, 50.0, N))
+        if N > 20:
+            r[N // 3:N // 3 + 5] = r[N // 3]                      # ties
+        sr = np.zeros(N + 2)
+        sr[0], sr[1:N + 1], sr[N + 1] = cm.ZERO, r, cm.SF_INFINITY
+        probes = np.concatenate([rng.uniform(r[0], r[-1] * 1.01, 4000), r[rng.integers(0, N, min(N, 2000))], r[:40], r[-40:],
+                                 np.nextafter(r[:40], 0), np.nextafter(r[-40:], 1e9), [r[-1] * 2, 1e9, r[0]]])
+        edges = np.arange(8, N + 2, 8)
+        for d in (-1, 0, 1):                                       # radii right at the block boundaries of every level
+            idx = np.clip(edges + d, 1, N)
+            probes = np.concatenate([probes, sr[idx][:3000], sr[idx][-3000:], np.nextafter(sr[idx][:3000], 1e9)])
+        probes = probes[probes >= r[0]]                            # potential() handles r < star_r[1] before the search
+        a, b = hostemul.find_zero_r_both(sr, N, probes)
+        plan = hostemul.ladder_plan(N + 1)
+        if N + 1 < 64:
+            assert len(plan["r_shift"]) == 0 and np.all(b == -1)   # small tables keep the plain bisection
+            return
+        assert plan["r_shift"][-1] == 3 and np.all(np.diff(plan["r_shift"]) == -4) and plan["r_count"][0] <= (10 if deep else 5120)
+        bad = np.nonzero(a != b)[0]
+        assert bad.size == 0, (bad[:5], probes[bad[:5]], a[bad[:5]], b[bad[:5]])
+    finally:
+        hostemul.use_deep_ladders(False)
+
+
+@pytest.mark.parametrize("kind,N", [("plummer", 30000), ("king", 30000)])
+def test_laddered_find_zero_Q_replays_the_reference_bisection(kind, N):
+    """find_zero_Q answered from the Q ladder (block bounds prove the sign of most probes) returns the index of the plain bisection for random
+    (E, J) -- bound, unbound, nearly circular, radial -- on both brackets, and with a central mass that makes Phi_0 > Phi_1"""
+    import hostemul
+    hostemul.use_deep_ladders(True)
+    try:
+        rng = np.random.default_rng(N)
+        r, vr, vt, sm = cm.cluster_state(kind, N, seed=N)
+        for cenma in (0.0, 0.05 * N):
+            pot = cm.oracle_potential(r, sm, cenma_m=cenma)
+            phi = pot["phi"]
+            for _ in range(1500):
+                g = int(rng.integers(1, N + 1))
+                scale = rng.choice([1.0, 0.3, 1e-3, 3.0])
+                v2 = scale * rng.uniform(0, 2.0) * abs(phi[g])
+                E = phi[g] + 0.5 * v2 * rng.uniform(0, 1)
+                J = pot["star_r"][g] * np.sqrt(v2) * rng.uniform(0, 1)
+                for (k0, k1) in ((0, g), (g, N + 1)):
+                    ka, _ = hostemul.find_zero_Q(pot["star_r"], pot["star_m"], phi, N, N, g, E, J, k0, k1, use_ladder=True)
+                    kb, _ = hostemul.find_zero_Q(pot["star_r"], pot["star_m"], phi, N, N, g, E, J, k0, k1, use_ladder=False)
+                    assert ka == kb, (g, E, J, k0, k1, ka, kb)
+    finally:
+        hostemul.use_deep_ladders(False)
