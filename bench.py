@@ -307,6 +307,12 @@ def run_cuda(args):
         d.update(extra or {})
         return d
 
+    roofs = {
+        "orbit_prepare": roof("orbit_prepare", "orbit_prepare_kernel", BYTES_ORBIT_PREPARE, n_shard,
+                              {"note": "index bisections answered from the Q ladder (shared memory / L2), the last ~6 probes per bisection are DRAM sectors"}),
+        "record_gather": roof("record_gather", "sort_gather_records" if world == 1 else "shard_push_records", BYTES_GATHER, n_shard),
+    }
+    dominant = max(roofs, key=lambda k: roofs[k]["avg_launch_ms"])
     stage_ms = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items()}
     cpu = cpu_baseline_leg(args.cpu_sample) if world == 1 else None
     line = {
@@ -322,12 +328,12 @@ def run_cuda(args):
         "clocks": clk,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        # the dominant kernel by time.  Its probes are random 32-byte sector reads, so the streaming-bytes fraction is tiny by construction;
-        # `traffic` and the ncu DRAM utilisation (profiles/) show what actually bounds it.
-        "roofline": roof("orbit_prepare", "orbit_prepare_kernel", BYTES_ORBIT_PREPARE, n_shard,
-                         {"note": "latency/sector-bound index bisections: ncu shows DRAM at ~51 % of peak with 32-B random sectors (profiles/)"}),
-        # the dominant HBM-streaming kernel
-        "roofline_streaming": roof("record_gather", "sort_gather_records" if world == 1 else "shard_push_records", BYTES_GATHER, n_shard),
+        # the dominant kernel by time (largest average launch among the single-kernel stages) ...
+        "roofline": roofs[dominant],
+        # ... and both candidates: the 424-byte record gather (HBM streaming) and stage A of the orbit step (index bisections: its probes are
+        # 32-byte sector reads, so its streaming-bytes fraction is small by construction; `traffic` (ncu, profiles/) shows what bounds it)
+        "roofline_streaming": roofs["record_gather"],
+        "roofline_orbit": roofs["orbit_prepare"],
         "step_bytes_per_star": BYTES_STEP, "step_achieved_gbs": BYTES_STEP * n_now / (ms / args.steps * 1e-3) / 1e9,
         "stage_ms_per_step": stage_ms,
         "cpu_baseline": cpu,
