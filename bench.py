@@ -242,6 +242,7 @@ def run_cuda(args):
         c.download()
         c.sync()
         e2e_t, e2e_stars, h2d, d2h = 0.0, 0, 0, 0
+        e2e_calls = {}
         if world == 1:
             # the drop-in form: the four host-buffer C-ABI entry points the reference-side shim binds
             for it in range(max(1, min(args.steps, 3)) + 1):
@@ -249,6 +250,8 @@ def run_cuda(args):
                 c.compute_energy()
                 if it == 1:
                     c.transfer_bytes(reset=True)      # the library counts what its host-buffer entry points move
+                    c.profile(True)                   # stage timers (CUDA events) split the calls into copies and kernels
+                    c.profile_read(reset=True)
                 t0 = time.perf_counter()
                 c.new_orbits_calculate(seed=args.seed + it, want_status=False)
                 t1 = time.perf_counter()
@@ -258,13 +261,18 @@ def run_cuda(args):
                 t2 = time.perf_counter()
                 c.qsorts_new()
                 c.post_sort_comm()
+                t2b = time.perf_counter()
                 c.calc_potential_new()
                 t3 = time.perf_counter()
                 if it > 0:  # the first pass is warm-up (page faults, pinning)
                     e2e_t += (t1 - t0) + (t3 - t2)
                     e2e_stars += n
                     n_e2e = it
+                    for k, v in (("new_orbits_calculate", t1 - t0), ("qsorts_new+post_sort_comm", t2b - t2), ("calc_potential_new", t3 - t2b)):
+                        e2e_calls[k] = e2e_calls.get(k, 0.0) + v
             h2d, d2h = (x / n_e2e for x in c.transfer_bytes())
+            e2e_stage = {k: round(v[0] / n_e2e, 2) for k, v in c.profile_read(reset=True).items() if v[0] > 0}
+            c.profile(False)
             note = ("new_orbits_calculate + qsorts_new + post_sort_comm + calc_potential_new through the host-buffer C ABI, pinned + mapped host arrays "
                     "(orbit step: field-wise zero-copy kernels, 48 B in / <= 48 B out per star; sort: whole 424 B records both ways), "
                     "wall clock; the caller's r<-rnew transfer between the calls is host code of the reference and is not timed")
@@ -286,6 +294,9 @@ def run_cuda(args):
                     h2d = d2h = c.clus.N_MAX_NEW * 424 + 3 * 8 * nt
             note = "per rank: upload(shard of star[] + tables) -> dev_step -> download, pinned host arrays, wall clock, max over ranks; bytes are per rank"
         e2e = {"value": e2e_stars / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": note}
+        if e2e_calls:
+            e2e["ms_per_call"] = {k: round(1e3 * v / n_e2e, 2) for k, v in e2e_calls.items()}
+            e2e["device_ms_per_step"] = e2e_stage
         clk = clocks.stop() if clocks else None
         c.close()
 

@@ -51,6 +51,7 @@ class Cluster:
         self.Rtidal = orbit_r
         self.max_r = 0.0
         self.N_b_local = 0
+        self.bin_slots_in_use = None    # None: unknown, derived from star[].binind at the next call that needs it
         self.myid, self.procs = 0, 1
         self.Start, self.End = np.array([1], np.int32), np.array([n_star], np.int32)
         self.mpiBegin, self.mpiEnd = 1, n_star
@@ -97,6 +98,7 @@ class Cluster:
         if binind is not None:
             self.field("binind")[1:n + 1] = binind
             self.N_b_local = self.clus.N_BINARY = int((np.asarray(binind) > 0).sum())
+            self.bin_slots_in_use = int(np.max(binind)) if len(binind) else 0
 
     # ---- the reference's four entry points, host-buffer form ------------------------------------------------------
     def calc_potential_new(self):
@@ -121,7 +123,7 @@ class Cluster:
         _lib.check(self.L.cmcb200_qsorts_new(self.ctx, self.star[1:].ctypes.data, C.byref(n), self.binary[1:].ctypes.data, self.N_BIN_DIM,
                                              C.byref(nb), self.star_r.ctypes.data, self.star_m.ctypes.data), "qsorts_new")
         self.clus.N_MAX = self.clus.N_MAX_NEW = n.value
-        self.N_b_local = nb.value
+        self.N_b_local = self.bin_slots_in_use = nb.value      # packed 1 .. nb after the sort
         self.Start[0], self.End[0] = 1, n.value    # findLimits inside sample_sort (cmc_sort.c:421)
 
     def post_sort_comm(self):
@@ -130,8 +132,13 @@ class Cluster:
         return None
 
     def _n_bin_in_use(self):
-        b = self.field("binind")[1:self.clus.N_MAX_NEW + 1]
-        return int(b.max()) if b.size and b.max() > 0 else 0
+        """highest binary[] slot a star points at.  The reference carries this as global state (N_b_local / N_BIN_DIM_OPT loops in
+        src/cmc/cmc_sort.c:512-587); here it is known after load(binind=...) and after every sort, and re-derived from star[].binind
+        (a strided scan of the host array) only when the caller filled the field by hand."""
+        if self.bin_slots_in_use is None:
+            b = self.field("binind")[1:self.clus.N_MAX_NEW + 1]
+            self.bin_slots_in_use = int(b.max()) if b.size and b.max() > 0 else 0
+        return self.bin_slots_in_use
 
     def orbit_params(self, draws=None, draw_off=None, seed=0, fuse_energy=False):
         n_old = int(self.End[0] - self.Start[0] + 1)
@@ -203,7 +210,7 @@ class Cluster:
         n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
         _lib.check(self.L.cmcb200_dev_qsorts_new(self.ctx, C.byref(n), max(self.N_b_local, 0), C.byref(nb)), "dev_qsorts_new")
         self.clus.N_MAX = self.clus.N_MAX_NEW = n.value
-        self.N_b_local = nb.value
+        self.N_b_local = self.bin_slots_in_use = nb.value
         self.Start[0], self.End[0] = 1, n.value
 
     def dev_transfer_and_sort(self):
@@ -213,7 +220,7 @@ class Cluster:
         _lib.check(self.L.cmcb200_dev_transfer_and_sort(self.ctx, C.byref(n), n_old, int(self.Start[0]), self.clus.N_MAX, max(self.N_b_local, 0),
                                                         C.byref(nb)), "dev_transfer_and_sort")
         self.clus.N_MAX = self.clus.N_MAX_NEW = n.value
-        self.N_b_local = nb.value
+        self.N_b_local = self.bin_slots_in_use = nb.value
         self.Start[0], self.End[0] = 1, n.value
 
     def dev_calc_potential_new(self):

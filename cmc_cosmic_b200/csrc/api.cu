@@ -69,7 +69,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->n_table_dim = n_table_dim;
 	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
-	c->orbit_ladders = 1;
+	c->orbit_ladders = 1; // bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A)
 	c->zero_copy = 1;
 	if (const char *e = getenv("CMCB200_ZERO_COPY")) c->zero_copy = atoi(e); // 0: always stage whole records with cudaMemcpy
 	c->bytes_h2d = c->bytes_d2h = 0;
@@ -101,6 +101,10 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->lad.q, (size_t) c->lad.q_cap * sizeof(LBlock)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->lad.r, (size_t) c->lad.r_cap * sizeof(double)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->lad.unsorted, sizeof(int)));
+	c->lad.q_max_shift = 64; c->lad.q_max_width_log2 = 31; c->lad.q_factor_log2 = QLAD_FACTOR_LOG2;
+	if (const char *e = getenv("CMCB200_QLAD_MAX_SHIFT")) c->lad.q_max_shift = atoi(e);
+	if (const char *e = getenv("CMCB200_QLAD_MAX_WIDTH_LOG2")) c->lad.q_max_width_log2 = atoi(e);
+	if (const char *e = getenv("CMCB200_QLAD_FACTOR_LOG2")) c->lad.q_factor_log2 = atoi(e);
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_star, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_oflag, (size_t) n_star_dim));
@@ -397,7 +401,8 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 	{
 		StageTimer t(c, ST_ORBIT_TABLES);
 		LadderBuffers lb = c->lad;
-		if (!c->orbit_ladders) { lb.q = nullptr; lb.r = nullptr; }
+		if (!(c->orbit_ladders & 1)) lb.r = nullptr;
+		if (!(c->orbit_ladders & 2)) lb.q = nullptr;
 		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, p->N_MAX + 1, lb, a, c->stream);
 	}
 	{ StageTimer t(c, ST_ORBIT); c->launches += orbit_stage_prepare(a, c->stream); }

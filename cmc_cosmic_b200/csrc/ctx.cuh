@@ -39,7 +39,8 @@ struct cmcb200_ctx {
 	unsigned char *d_oflag;
 	int *d_pend[2];
 	int orbit_ctas;    // tuning knob CMCB200_ORBIT_CTAS: resident CTAs per SM orbit_prepare_kernel is compiled for (4 or 3)
-	int orbit_ladders; // 1 (default): the orbit step searches through the ladders; 0: every probe reads the fine table (CMCB200_ORBIT_LADDERS)
+	int orbit_ladders; // CMCB200_ORBIT_LADDERS: bit 0 = r ladder for potential() (default on), bit 1 = Q ladder for find_zero_Q (default off:
+	                   // measured slower than the plain bisection on B200); 0 = every probe reads the fine table
 	// sort scratch
 	SortBuffers sbuf;
 	SortState *d_sort;

@@ -236,9 +236,14 @@ __global__ void __launch_bounds__(ORBIT_THREADS, CTAS) orbit_prepare_kernel(Orbi
 {
 	extern __shared__ __align__(128) unsigned char orbit_smem[];
 	__shared__ __align__(8) unsigned long long bar;
-	LadderTops top;
-	top.q = (const LBlock *) stage_top_level(a.t.qlad.blk[0], a.q_top_bytes, a.t.qlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
+	__shared__ QLadder s_qlad; // the level table, indexed dynamically by the bisections
+	if (threadIdx.x == 0) s_qlad = a.t.qlad;
+	LadderTops top; // (stage_top_level's barrier also publishes s_qlad; without a ladder nobody reads it)
+	const bool lad_on = a.t.qlad.n_levels > 0 && *a.lad_unsorted == 0;
+	top.q = (const LBlock *) stage_top_level(a.t.qlad.blk[0], a.q_top_bytes, lad_on && a.q_top_bytes > 0, orbit_smem, &bar);
+	if (lad_on && a.q_top_bytes == 0) { top.q = a.t.qlad.blk[0]; __syncthreads(); } // coarsest level too large to stage (tuning knobs): read in place
 	top.r = nullptr; // potential() is not called in this stage
+	top.qdesc = &s_qlad;
 	int n_exact = 0, n_brent = 0;
 	for (long base = blockIdx.x * (long) ORBIT_THREADS; base < a.n_local; base += (long) gridDim.x * ORBIT_THREADS) {
 		const long j0 = base + threadIdx.x;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(ORBIT_THREADS) orbit_deferred_kernel(OrbitArgs
 			const StarConst s = star_const(a.t, in.g, in.E, in.J);
 			OrbitJob job;
 			LadderTops top; // the few queued stars bisect on the fine table
-			top.q = nullptr; top.r = nullptr;
+			top.q = nullptr; top.r = nullptr; top.qdesc = nullptr;
 			orbit_prepare(a.t, top, s, in.is_new, in.rnew_of_new, a.Rtidal, found == ORBIT_NOT_FOUND ? -1 : (kint) found, false, o, job);
 			store_prepared(a, j0, o, job);
 		}
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 	const unsigned n_work = FIRST ? (unsigned) a.n_local : a.stats->round_count[round];
 	if ((unsigned long long) blockIdx.x * (ORBIT_TRY_THREADS / W) >= n_work) return; // nothing for this CTA: skip the staging too
 	LadderTops top;
-	top.q = nullptr;
+	top.q = nullptr; top.qdesc = nullptr;
 	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
 	const int *__restrict__ list_in = a.pend_list[round & 1];
 	int *__restrict__ list_out = a.pend_list[(round + 1) & 1];
@@ -552,6 +557,14 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long
 	int launches = 0;
 	long qcnt[LADDER_MAX_LEVELS], rcnt[LADDER_MAX_LEVELS], ral[LADDER_MAX_LEVELS];
 	int nq = lb.q ? qlad_plan(M, a.t.qlad.shift, qcnt) : 0;
+	{ // tuning knob: drop the levels coarser than q_max_shift (brackets that wide then probe the fine table, see QLadder::max_width)
+		int drop = 0;
+		while (drop < nq && a.t.qlad.shift[drop] > lb.q_max_shift) drop++;
+		for (int l = drop; l < nq; l++) { a.t.qlad.shift[l - drop] = a.t.qlad.shift[l]; qcnt[l - drop] = qcnt[l]; }
+		nq -= drop;
+	}
+	a.t.qlad.factor_log2 = lb.q_factor_log2;
+	a.t.qlad.max_width = lb.q_max_width_log2 >= 31 ? 0x7fffffff : (1 << lb.q_max_width_log2);
 	int nr = lb.r ? rlad_plan(M, a.t.rlad.shift, rcnt, ral) : 0;
 	// levels are stored finest first, each on a 128-byte boundary
 	LBlock *qlvl[LADDER_MAX_LEVELS];
@@ -583,7 +596,7 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long
 	}
 	a.t.qlad.n_levels = nq;
 	for (int l = 0; l < nq; l++) a.t.qlad.blk[l] = qlvl[l];
-	if (nq) a.q_top_bytes = (unsigned) (qcnt[0] * sizeof(LBlock));
+	if (nq && qcnt[0] <= QLAD_TOP_BLOCKS) a.q_top_bytes = (unsigned) (qcnt[0] * sizeof(LBlock));
 	a.t.rlad.n_levels = nr;
 	for (int l = 0; l < nr; l++) a.t.rlad.lvl[l] = rplan.lvl[l];
 	if (nr) { a.t.rlad.n_top = (int) rcnt[0]; a.r_top_bytes = (unsigned) ((rcnt[0] + 1) / 2 * 2 * sizeof(double)); }
@@ -619,9 +632,12 @@ int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s)
 	orbit_stats_reset<<<1, 1, 0, s>>>(a.stats);
 	if (a.n_local <= 0) return 1;
 	long blocks = (a.n_local + ORBIT_THREADS - 1) / ORBIT_THREADS;
-	const int ctas = a.prepare_ctas == 3 ? 3 : ORBIT_CTAS_PER_SM;
+	int ctas = a.prepare_ctas >= 3 && a.prepare_ctas <= 6 ? a.prepare_ctas : ORBIT_CTAS_PER_SM;
+	while (ctas > 4 && (long) ctas * (a.q_top_bytes + 1024) > 227 * 1024) ctas--; // the staged levels of all resident CTAs must fit
 	if (blocks > (long) NUM_SMS_B200 * ctas) blocks = (long) NUM_SMS_B200 * ctas;
 	if (ctas == 3) orbit_prepare_kernel<3><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
+	else if (ctas == 5) orbit_prepare_kernel<5><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
+	else if (ctas == 6) orbit_prepare_kernel<6><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
 	else orbit_prepare_kernel<ORBIT_CTAS_PER_SM><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
 	return 2;
 }

@@ -59,6 +59,7 @@ struct LadderBuffers {
 	double *r;     // all levels of the r ladder back to back, finest first
 	long q_cap, r_cap; // capacity in blocks / doubles
 	int *unsorted; // device flag
+	int q_max_shift, q_max_width_log2, q_factor_log2; // tuning knobs of the Q ladder (CMCB200_QLAD_MAX_SHIFT / _MAX_WIDTH_LOG2 / _FACTOR_LOG2)
 };
 long ladder_q_capacity(long n_table_dim);
 long ladder_r_capacity(long n_table_dim);

@@ -68,16 +68,18 @@ constexpr int LADDER_MAX_LEVELS = 8;
 #endif
 constexpr int QLAD_MIN_SHIFT = 4, QLAD_STEP = 3, QLAD_TOP_BLOCKS = CMCB_QLAD_TOP_BLOCKS;   // coarsest level <= 40 KB
 constexpr int RLAD_MIN_SHIFT = 3, RLAD_STEP = 4, RLAD_TOP_ENTRIES = CMCB_RLAD_TOP_ENTRIES; // coarsest level <= 40 KB
-#ifndef CMCB_QLAD_WIDTH_FACTOR
-#define CMCB_QLAD_WIDTH_FACTOR 4
+#ifndef CMCB_QLAD_FACTOR_LOG2
+#define CMCB_QLAD_FACTOR_LOG2 2
 #endif
-constexpr int QLAD_WIDTH_FACTOR = CMCB_QLAD_WIDTH_FACTOR; // a level is consulted while its blocks are at most 1/FACTOR of the bracket
+constexpr int QLAD_FACTOR_LOG2 = CMCB_QLAD_FACTOR_LOG2; // default for QLadder::factor_log2
 constexpr int LADDER_MIN_M = 64;                                          // smaller tables: plain bisection
 
 struct QLadder {
 	const LBlock *blk[LADDER_MAX_LEVELS]; // coarsest first
 	int shift[LADDER_MAX_LEVELS];
-	int n_levels; // 0: no ladder
+	int n_levels;     // 0: no ladder
+	int factor_log2;  // a level is consulted while its blocks are at most 2^-factor_log2 of the bracket (default 2)
+	int max_width;    // brackets at least this wide probe the fine table directly (default: never) -- tuning knob, see orbit.cu
 };
 
 struct RLadder {
@@ -92,6 +94,7 @@ struct RLadder {
 struct LadderTops {
 	const LBlock *q;
 	const double *r;
+	const QLadder *qdesc; // the Q ladder's level table: a shared-memory copy in the kernels (dynamic indexing), &t.qlad on the host
 };
 
 // shifts (coarsest first) and block counts of the Q ladder over a table with last index M; returns the number of levels
@@ -211,20 +214,31 @@ CMCB_HD kint find_zero_r(const OrbitTables &t, kint kmin, kint kmax, double r)
 	return kmin;
 }
 
+// four consecutive doubles (one 32-byte sector, 32-byte aligned) with ONE load: sm_100's 256-bit LDG.  The rejection rounds are bound by
+// the L1's sector throughput (every lane reads its own lines), so a 128-byte line costs 4 sector accesses instead of 8 with 128-bit loads.
+struct Quad {
+	double a, b, c, d;
+};
+CMCB_HD Quad ld_quad(const double *p)
+{
+	Quad q;
+#if defined(__CUDA_ARCH__)
+	asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q.a), "=d"(q.b), "=d"(q.c), "=d"(q.d) : "l"(p));
+#else
+	q.a = p[0]; q.b = p[1]; q.c = p[2]; q.d = p[3];
+#endif
+	return q;
+}
+
 // number of entries among 16 consecutive doubles (one 128-byte line) that are < r
 CMCB_HD int count16_below(const double *line, double r)
 {
 	int c = 0;
-#if defined(__CUDA_ARCH__)
-	const double2 *q = reinterpret_cast<const double2 *>(line);
 #pragma unroll
-	for (int i = 0; i < 8; i++) {
-		const double2 v = __ldg(q + i);
-		c += (v.x < r) + (v.y < r);
+	for (int i = 0; i < 4; i++) {
+		const Quad v = ld_quad(line + 4 * i);
+		c += (v.a < r) + (v.b < r) + (v.c < r) + (v.d < r);
 	}
-#else
-	for (int i = 0; i < 16; i++) c += line[i] < r;
-#endif
 	return c;
 }
 
@@ -244,9 +258,8 @@ CMCB_HD LBlock top_ld(const LBlock *p)
 CMCB_HD LBlock blk_ld(const LBlock *p)
 {
 #if defined(__CUDA_ARCH__)
-	const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-	LBlock o;
-	o.r_lo = a.x; o.r_hi = a.y; o.phi_min = b.x; o.phi_max = b.y;
+	LBlock o; // one 256-bit load (sm_100): the block is exactly one 32-byte sector
+	asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o.r_lo), "=d"(o.r_hi), "=d"(o.phi_min), "=d"(o.phi_max) : "l"(p));
 	return o;
 #else
 	return *p;
@@ -271,10 +284,12 @@ CMCB_HD kint find_zero_r_ladder(const OrbitTables &t, const double *top, double 
 	const kint base = (kint) (b << RLAD_MIN_SHIFT), M = t.N_MAX + 1;
 	int c = 0;
 #pragma unroll
-	for (int i = 0; i < 8; i++) {
-		line[i] = tbl_rp(t, base + i);
-		c += (base + i <= M && line[i].r < r);
+	for (int i = 0; i < 4; i++) { // base is a multiple of 8: the line is 128-byte aligned, two entries per 256-bit load
+		const Quad v = ld_quad(&t.rp[base + 2 * i].r);
+		line[2 * i].r = v.a; line[2 * i].phi = v.b; line[2 * i + 1].r = v.c; line[2 * i + 1].phi = v.d;
 	}
+#pragma unroll
+	for (int i = 0; i < 8; i++) c += (base + i <= M && line[i].r < r);
 	*line_base = base;
 	const kint k = base + c - 1; // largest k in [0, M] with star_r[k] < r (-1: none)
 	return k >= 1 ? k : 1;
@@ -450,18 +465,30 @@ static long g_lad_stats[17]; // host-only instrumentation: [2l] proven at level 
 // sign of function_q at table index k during a bisection whose bracket is `width` = kmax - kmin entries wide: answered from the
 // coarsest ladder level whose blocks are at most an eighth of the bracket (the sign change sits somewhere in the bracket, the probe in
 // its middle: a block that small is rarely the one that straddles it), descending on "undecided", the fine table last.
-CMCB_HD int sign_Q_laddered(const OrbitTables &t, const LBlock *top, const StarConst &s, kint k, kint width, int *n_exact)
+CMCB_HD int floor_log2(unsigned v) // v >= 1
 {
-	const QLadder &L = t.qlad;
-	for (int l = 0; l < L.n_levels; l++) {
-		const int sh = L.shift[l];
-		if (((kint) QLAD_WIDTH_FACTOR << sh) > width) continue;
-		const LBlock B = (l == 0) ? top_ld(top + (k >> sh)) : blk_ld(L.blk[l] + (k >> sh));
-		const int sg = q_sign_on_block(s, B);
-#ifdef CMCB_LADDER_STATS
-		g_lad_stats[sg ? 2 * l : 2 * l + 1]++;
+#if defined(__CUDA_ARCH__)
+	return 31 - __clz((int) v);
+#else
+	return 31 - __builtin_clz(v);
 #endif
-		if (sg) return sg;
+}
+
+CMCB_HD int sign_Q_laddered(const OrbitTables &t, const QLadder &L, const LBlock *top, const StarConst &s, kint k, kint width, int *n_exact)
+{
+	if (width < L.max_width) {
+		// first level with (1 << (shift + factor_log2)) <= width: shifts go top, top - STEP, ...
+		const int want = floor_log2((unsigned) width) - L.factor_log2; // largest usable shift
+		int l = want >= L.shift[0] ? 0 : (L.shift[0] - want + QLAD_STEP - 1) / QLAD_STEP;
+		for (; l < L.n_levels; l++) {
+			const int sh = L.shift[l];
+			const LBlock B = (l == 0) ? top_ld(top + (k >> sh)) : blk_ld(L.blk[l] + (k >> sh));
+			const int sg = q_sign_on_block(s, B);
+#ifdef CMCB_LADDER_STATS
+			g_lad_stats[sg ? 2 * l : 2 * l + 1]++;
+#endif
+			if (sg) return sg;
+		}
 	}
 #ifdef CMCB_LADDER_STATS
 	g_lad_stats[16]++;
@@ -476,7 +503,7 @@ CMCB_HD kint find_zero_Q(const OrbitTables &t, const LadderTops &top, const Star
 	const bool laddered = top.q != nullptr;
 	do {
 		kint ktry = (kmin + kmax + 1) / 2;
-		int sg = laddered ? sign_Q_laddered(t, top.q, s, ktry, kmax - kmin, n_exact) : sign_Q(t, s, ktry, n_exact);
+		int sg = laddered ? sign_Q_laddered(t, *top.qdesc, top.q, s, ktry, kmax - kmin, n_exact) : sign_Q(t, s, ktry, n_exact);
 		bool up = increasing ? (sg < 0) : (sg > 0); // :349 / :362
 		if (up) kmin = ktry; else kmax = ktry - 1;
 	} while (kmax != kmin);
@@ -761,7 +788,7 @@ CMCB_HD void orbit_step_star(const OrbitTables &t, kint g_j, bool is_new, double
 {
 	const StarConst s = star_const(t, g_j, E_star, J);
 	LadderTops top;
-	top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
+	top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr; top.qdesc = &t.qlad;
 	OrbitJob job;
 	orbit_prepare(t, top, s, is_new, rnew_of_new, Rtidal, ktemp_in, allow_defer, out, job);
 	if (out.status == ORBIT_CIRCULAR) { out.vrnew = vr_in; out.vtnew = vt_in; }

@@ -32,6 +32,7 @@ struct HostLadders {
 	{
 		long cnt[LADDER_MAX_LEVELS], alloc[LADDER_MAX_LEVELS];
 		q.n_levels = qlad_plan(M, q.shift, cnt);
+		q.factor_log2 = QLAD_FACTOR_LOG2; q.max_width = 0x7fffffff;
 		qb.resize(q.n_levels);
 		for (int l = 0; l < q.n_levels; l++) {
 			qb[l].resize(cnt[l]);
@@ -100,7 +101,7 @@ extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, con
 	StarConst s; s.g_j = g_j; s.r_j = star_r[g_j]; s.m_j = star_m[g_j]; s.E = E; s.J = J;
 	star_const_derive(t, s);
 	int ne = 0;
-	LadderTops top; top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
+	LadderTops top; top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr; top.qdesc = &t.qlad;
 	long k = find_zero_Q(t, top, s, kmin, kmax, &ne);
 	*n_exact = ne;
 	return k;

@@ -131,22 +131,28 @@ def test_orbit_step_bit_exact(kind, N, masses):
     _orbit_case(kind, N, masses)
 
 
-def test_orbit_step_deep_ladders_bit_exact():
+def test_orbit_step_deep_ladders_bit_exact(monkeypatch):
     """N = 700000: three levels in both ladders (Q: shifts 10/7/4, r: 11/7/3), every probe of the index bisections answered from the
     coarsest level that proves its sign -- kmin / kmax / r_peri / r_apo / rnew still the reference's bit for bit"""
+    monkeypatch.setenv("CMCB200_ORBIT_LADDERS", "3")
     _orbit_case("plummer", 700000, seed=99)
 
 
-def test_orbit_step_with_central_mass():
+def test_orbit_step_with_central_mass(monkeypatch):
     """cenma.m > 0 makes star_phi[0] > star_phi[1] (cmc_utils.c:727): the Q-ladder blocks carry the true min / max of Phi, not its ends"""
+    _orbit_case("king", 120000, seed=17, cenma_m=0.02 * 120000)
+    monkeypatch.setenv("CMCB200_ORBIT_LADDERS", "3")
     _orbit_case("king", 120000, seed=17, cenma_m=0.02 * 120000)
 
 
-@pytest.mark.parametrize("knob,value", [("CMCB200_ORBIT_LADDERS", "0"), ("CMCB200_ORBIT_CTAS", "3")])
-def test_orbit_step_tuning_knobs_do_not_change_results(knob, value, monkeypatch):
-    """the plain-bisection path (ladders off) and the 3-CTA register variant of the orbit kernel stay bit-exact"""
-    monkeypatch.setenv(knob, value)
-    _orbit_case("plummer", 100000, seed=5)
+@pytest.mark.parametrize("knobs", [{"CMCB200_ORBIT_LADDERS": "0"}, {"CMCB200_ORBIT_LADDERS": "3"}, {"CMCB200_ORBIT_LADDERS": "2", "CMCB200_ORBIT_CTAS": "3"},
+                                   {"CMCB200_ORBIT_LADDERS": "3", "CMCB200_QLAD_MAX_SHIFT": "7", "CMCB200_QLAD_MAX_WIDTH_LOG2": "11"}])
+def test_orbit_step_tuning_knobs_do_not_change_results(knobs, monkeypatch):
+    """every combination of the search structures (no ladders / r ladder [default] / Q ladder / both, partial Q ladders read in place) and
+    the register variants of the orbit kernel is bit-exact"""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    _orbit_case("plummer", 300000, seed=5)
 
 
 def test_new_orbits_zero_copy_equals_staged_records():

@@ -18,7 +18,7 @@ configs = sys.argv[3:] or [""]
 r, vr, vt, m = models.plummer(N, seed=1234)
 for cfg in configs:
     knobs = dict(kv.split("=") for kv in cfg.split(",") if kv)
-    for k in ("CMCB200_ORBIT_LADDERS", "CMCB200_ORBIT_CTAS", "CMCB200_ZERO_COPY"):
+    for k in [k for k in os.environ if k.startswith("CMCB200_")]:
         os.environ.pop(k, None)
     os.environ.update(knobs)
     c = Cluster(N, n_star_dim=N + 4096)
