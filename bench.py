@@ -273,8 +273,8 @@ def run_cuda(args):
             h2d, d2h = (x / n_e2e for x in c.transfer_bytes())
             e2e_stage = {k: round(v[0] / n_e2e, 2) for k, v in c.profile_read(reset=True).items() if v[0] > 0}
             c.profile(False)
-            note = ("new_orbits_calculate + qsorts_new + post_sort_comm + calc_potential_new through the host-buffer C ABI, pinned + mapped host arrays "
-                    "(orbit step: field-wise zero-copy kernels, 48 B in / <= 48 B out per star; sort: whole 424 B records both ways), "
+            note = ("new_orbits_calculate + qsorts_new + post_sort_comm + calc_potential_new through the host-buffer C ABI, pinned host arrays "
+                    "(orbit step: 128 B in / 64 B out per star as strided DMA pipelined with the kernels; sort: whole 424 B records both ways), "
                     "wall clock; the caller's r<-rnew transfer between the calls is host code of the reference and is not timed")
         else:
             # sharded: every rank uploads its shard and the tables from pinned host memory, steps, and downloads them again

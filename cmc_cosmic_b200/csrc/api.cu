@@ -7,6 +7,8 @@
 #include <vector>
 #include "ctx.cuh"
 
+constexpr int ORBIT_MAX_CHUNKS = 16; // pipeline chunks of the host-buffer orbit step (their statistics live in the 4 KB pinned scratch)
+
 namespace cmcb {
 
 static thread_local char g_err[512] = "";
@@ -70,10 +72,10 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
 	c->orbit_ladders = 1; // bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A)
-	c->zero_copy = 1;
-	if (const char *e = getenv("CMCB200_ZERO_COPY")) c->zero_copy = atoi(e); // 0: always stage whole records with cudaMemcpy
 	c->bytes_h2d = c->bytes_d2h = 0;
 	c->orbit_ctas = 4;
+	c->orbit_max_chunks = 8;
+	if (const char *e = getenv("CMCB200_ORBIT_CHUNKS")) c->orbit_max_chunks = atoi(e) < 1 ? 1 : (atoi(e) > ORBIT_MAX_CHUNKS ? ORBIT_MAX_CHUNKS : atoi(e));
 	if (const char *e = getenv("CMCB200_ORBIT_CTAS")) c->orbit_ctas = atoi(e);
 	if (const char *e = getenv("CMCB200_ORBIT_LADDERS")) c->orbit_ladders = atoi(e); // 0: A/B measurement of the plain bisections
 	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -159,6 +161,10 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFreeHost(c->h_pinned);
 	for (auto &e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 	for (auto &e : c->pool) cudaEventDestroy(e);
+	if (c->s_in) {
+		cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
+		for (int k = 0; k < 16; k++) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_done[k]); }
+	}
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -362,10 +368,14 @@ extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, 
 
 // ---- orbit step ---------------------------------------------------------------------------------------------------
 
-static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res, bool need_status = false)
+// The orbit step in three parts so that the host-buffer form can pipeline it over chunks of the star range:
+//   orbit_begin   arguments, recorded draws, lookup tables (packed table + ladders) -- once per call
+//   orbit_range   the three stages on local stars [off, off + len): every star is independent of the others (its draws are keyed by its
+//                 global index or come from its own CSR slice), so the result does not depend on the chunking
+//   orbit_end     combines the per-chunk statistics
+static int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a)
 {
 	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
-	OrbitArgs a;
 	a.star1 = star1(c);
 	a.n_local = p->n_local;
 	a.n_old_local = p->n_old_local;
@@ -405,21 +415,53 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 		if (!(c->orbit_ladders & 2)) lb.q = nullptr;
 		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, p->N_MAX + 1, lb, a, c->stream);
 	}
+	return 0;
+}
+
+
+static int orbit_range(cmcb200_ctx *c, const OrbitArgs &whole, long off, long len, int chunk)
+{
+	OrbitArgs a = whole;
+	a.star1 += off * CMCB_SIZEOF_STAR;
+	a.n_local = len;
+	a.n_old_local = whole.n_old_local - off; // may be <= 0: every star of the chunk was created this step (get_global_idx, cmc_utils.c:2384-2407)
+	a.first_global = whole.first_global + off;
+	a.flag += off;
+	if (a.draw_off) a.draw_off += off;
+	if (a.status) a.status += off;
+	if (a.kmin) { a.kmin += off; a.kmax += off; }
 	{ StageTimer t(c, ST_ORBIT); c->launches += orbit_stage_prepare(a, c->stream); }
 	{ StageTimer t(c, ST_ORBIT_SCAN); c->launches += orbit_stage_scan(a, c->stream); }
 	{ StageTimer t(c, ST_ORBIT_TRIES); c->launches += orbit_stage_tries(a, c->stream); }
 	CMCB_CUDA_OK(cudaGetLastError());
-	OrbitStats *h = (OrbitStats *) c->h_pinned;
-	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
-	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
-	if (res) {
-		memcpy(&res->max_r, &h->max_rad_bits, 8);
-		res->n_draws = h->n_draws; res->n_exact = h->n_exact; res->n_brent = h->n_brent;
-		unsigned long long other = 0;
-		for (int i = 1; i < 6; i++) { res->n_status[i] = h->n_status[i]; other += h->n_status[i]; }
-		res->n_status[0] = (unsigned long long) p->n_local - other;
-		res->n_deferred = h->n_defer;
+	CMCB_CUDA_OK(cudaMemcpyAsync((OrbitStats *) c->h_pinned + chunk, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
+	return 0;
+}
+
+// after the stream has been synchronised
+static void orbit_end(cmcb200_ctx *c, const cmcb200_orbit_params *p, int n_chunks, cmcb200_orbit_result *res)
+{
+	if (!res) return;
+	const OrbitStats *h = (const OrbitStats *) c->h_pinned;
+	unsigned long long max_bits = 0, other = 0;
+	memset(res, 0, sizeof(*res));
+	for (int k = 0; k < n_chunks; k++) {
+		if (h[k].max_rad_bits > max_bits) max_bits = h[k].max_rad_bits; // positive doubles order like their bit patterns
+		res->n_draws += h[k].n_draws; res->n_exact += h[k].n_exact; res->n_brent += h[k].n_brent;
+		for (int i = 1; i < 6; i++) { res->n_status[i] += h[k].n_status[i]; other += h[k].n_status[i]; }
+		res->n_deferred += h[k].n_defer;
 	}
+	memcpy(&res->max_r, &max_bits, 8);
+	res->n_status[0] = (unsigned long long) p->n_local - other;
+}
+
+static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res)
+{
+	OrbitArgs a;
+	if (orbit_begin(c, p, want_status, false, a)) return -1;
+	if (orbit_range(c, a, 0, p->n_local, 0)) return -1;
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	orbit_end(c, p, 1, res);
 	return 0;
 }
 
@@ -438,52 +480,6 @@ extern "C" int cmcb200_dev_read_status(cmcb200_ctx *c, int *status, long *kmin, 
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	return 0;
 }
-
-namespace cmcb {
-
-// Host-buffer form of the orbit step when the caller's star[] is pinned and mapped into the device address space (cudaHostAlloc /
-// cudaHostRegister -- cmcb200_host_register): the kernels below move only the fields the step reads or writes, straight over PCIe,
-// instead of the whole 424-byte records both ways.
-//   import: r, vr, vt, m, E, J (bytes 0..47 of every record) and rnew of the stars created this step (read by calc_orbit_new, cmc_orbit.c:39-41)
-//   export: exactly the stores of the reference's loop body (cmc_evolution_thr.c:835-839, 852-853, 918-931; remove_star :662-664),
-//           selected by the per-star status like store_star() does on the device record
-// 8 lanes per record, one double each.
-__global__ void orbit_import_fields(char *__restrict__ dev1, const char *__restrict__ host1, long n_local, long n_old_local)
-{
-	const long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
-	const long j0 = t >> 3;
-	const int w = (int) (t & 7);
-	if (j0 >= n_local) return;
-	int off = -1;
-	if (w < 6) off = 8 * w;
-	else if (w == 6 && j0 + 1 > n_old_local) off = CMCB_OFF_RNEW;
-	if (off >= 0) *(double *) (dev1 + j0 * CMCB_SIZEOF_STAR + off) = *(const double *) (host1 + j0 * CMCB_SIZEOF_STAR + off);
-}
-
-__global__ void orbit_export_fields(const char *__restrict__ dev1, char *__restrict__ host1, const int *__restrict__ status, long n_local)
-{
-	const long t = blockIdx.x * (long) blockDim.x + threadIdx.x;
-	const long j0 = t >> 3;
-	const int w = (int) (t & 7);
-	if (j0 >= n_local) return;
-	const int st = status[j0];
-	int off = -1;
-	if (w < 3) { if (st != ORBIT_NTRY) off = CMCB_OFF_RNEW + 8 * w; }                 // rnew, vrnew, vtnew
-	else if (w == 3) { if (st == ORBIT_OK) off = CMCB_OFF_X; }
-	else if (w < 6) { if (st == ORBIT_OK || st == ORBIT_TIDAL) off = CMCB_OFF_R_PERI + 8 * (w - 4); } // r_peri, r_apo
-	if (off >= 0) *(double *) (host1 + j0 * CMCB_SIZEOF_STAR + off) = *(const double *) (dev1 + j0 * CMCB_SIZEOF_STAR + off);
-}
-
-// device alias of a host pointer when the range is pinned + mapped, nullptr otherwise
-static void *mapped_alias(const void *host)
-{
-	cudaPointerAttributes at;
-	if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-	if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
-	return at.devicePointer;
-}
-
-} // namespace cmcb
 
 extern "C" int cmcb200_host_register(void *ptr, size_t bytes)
 {
@@ -509,42 +505,61 @@ extern "C" int cmcb200_transfer_bytes(cmcb200_ctx *c, long *h2d, long *d2h, int 
 	return 0;
 }
 
+// Host-buffer form.  Of each 424-byte record the step reads bytes 0..47 (r, vr, vt, m, E, J; rnew at 64 for stars created this step) and
+// writes inside bytes 64..127 (rnew, vrnew, vtnew, X, r_peri, r_apo -- which of them depends on the star's outcome; rOld and Y in between
+// are not touched).  So only the first 128 bytes of every record travel to the device and bytes 64..127 travel back, as strided (2-D) DMA
+// copies: the device copy of bytes 64..127 starts as the host's, the kernels store exactly where the reference's loop body stores, and the
+// unconditional copy back therefore changes nothing else.  The star range is cut into chunks that flow through three streams
+// (copy in -> kernels -> copy out), so the two copy directions and the kernels overlap.
 extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const double *star_r, const double *star_m, const double *star_phi,
 					    const cmcb200_orbit_params *p, int *status, long *kmin, long *kmax, cmcb200_orbit_result *res)
 {
-	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
-	char *alias = c->zero_copy ? (char *) mapped_alias(star1_h) : nullptr;
-	const unsigned field_blocks = (unsigned) ((p->n_local * 8 + 255) / 256);
+	if (!c->s_in) {
+		CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+		CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+		for (int k = 0; k < ORBIT_MAX_CHUNKS; k++) {
+			CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+			CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+		}
+	}
+	const bool want = status || kmin || kmax;
+	const long n = p->n_local;
+	int n_chunks = (int) ((n + (1L << 19) - 1) >> 19); // >= 512 K stars per chunk: the kernels of a chunk still fill the GPU
+	if (n_chunks > c->orbit_max_chunks) n_chunks = c->orbit_max_chunks;
+	if (n_chunks < 1) n_chunks = 1;
+	const long per = (n + n_chunks - 1) / n_chunks;
+	const size_t pitch = CMCB_SIZEOF_STAR;
+	char *dev1 = star1(c);
+	// copies in: queued up front on their own stream (the device records are free: every call ends synchronised)
+	for (int k = 0; k < n_chunks; k++) {
+		const long off = k * per, len = n - off < per ? n - off : per;
+		if (len > 0) CMCB_CUDA_OK(cudaMemcpy2DAsync(dev1 + off * pitch, pitch, (const char *) star1_h + off * pitch, pitch, 128, (size_t) len, cudaMemcpyHostToDevice, c->s_in));
+		CMCB_CUDA_OK(cudaEventRecord(c->ev_in[k], c->s_in));
+	}
+	c->bytes_h2d += n * 128;
 	{
 		StageTimer t(c, ST_H2D);
-		if (alias) {
-			if (p->n_local > 0) { orbit_import_fields<<<field_blocks, 256, 0, c->stream>>>(star1(c), alias, p->n_local, p->n_old_local); c->launches++; }
-			c->bytes_h2d += p->n_local * 48;
-		} else {
-			CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
-			c->bytes_h2d += p->n_local * CMCB_SIZEOF_STAR;
-		}
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_phi, star_phi, (size_t) p->n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		c->bytes_h2d += 3 * p->n_table * (long) sizeof(double);
 	}
-	const bool want = status || kmin || kmax;
-	if (orbit_common(c, p, want, res, alias != nullptr)) return -1;
-	{
-		StageTimer t(c, ST_D2H);
-		if (alias) {
-			if (p->n_local > 0) { orbit_export_fields<<<field_blocks, 256, 0, c->stream>>>(star1(c), alias, c->d_status, p->n_local); c->launches++; }
-			c->bytes_d2h += p->n_local * 48;
-		} else {
-			CMCB_CUDA_OK(cudaMemcpyAsync(star1_h, star1(c), (size_t) p->n_local * CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
-			c->bytes_d2h += p->n_local * CMCB_SIZEOF_STAR;
-		}
+	OrbitArgs a;
+	if (orbit_begin(c, p, want, false, a)) return -1;
+	for (int k = 0; k < n_chunks; k++) {
+		const long off = k * per, len = n - off < per ? n - off : per;
+		CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+		if (orbit_range(c, a, off, len > 0 ? len : 0, k)) return -1;
+		CMCB_CUDA_OK(cudaEventRecord(c->ev_done[k], c->stream));
+		CMCB_CUDA_OK(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
+		if (len > 0) CMCB_CUDA_OK(cudaMemcpy2DAsync((char *) star1_h + off * pitch + 64, pitch, dev1 + off * pitch + 64, pitch, 64, (size_t) len, cudaMemcpyDeviceToHost, c->s_out));
 	}
-	CMCB_CUDA_OK(cudaGetLastError());
-	if (want) return cmcb200_dev_read_status(c, status, kmin, kmax, p->n_local);
+	c->bytes_d2h += n * 64;
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->s_out));
+	orbit_end(c, p, n_chunks, res);
+	if (want) return cmcb200_dev_read_status(c, status, kmin, kmax, p->n_local);
 	return 0;
 }
 

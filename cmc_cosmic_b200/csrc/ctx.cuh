@@ -38,6 +38,7 @@ struct cmcb200_ctx {
 	LadderBuffers lad; // coarse levels of the lookup tables (orbit_core.h "ladders")
 	unsigned char *d_oflag;
 	int *d_pend[2];
+	int orbit_max_chunks; // host-buffer orbit step: at most this many pipeline chunks (CMCB200_ORBIT_CHUNKS, default 8)
 	int orbit_ctas;    // tuning knob CMCB200_ORBIT_CTAS: resident CTAs per SM orbit_prepare_kernel is compiled for (4 or 3)
 	int orbit_ladders; // CMCB200_ORBIT_LADDERS: bit 0 = r ladder for potential() (default on), bit 1 = Q ladder for find_zero_Q (default off:
 	                   // measured slower than the plain bisection on B200); 0 = every probe reads the fine table
@@ -69,7 +70,9 @@ struct cmcb200_ctx {
 	long acc_n[CMCB200_N_STAGES];
 	long launches; // kernels launched since creation
 	long bytes_h2d, bytes_d2h; // bytes the host-buffer entry points moved over PCIe (cmcb200_transfer_bytes)
-	int zero_copy;  // 1 (default): mapped host arrays are read / written field-wise by kernels instead of staging whole records
+	// host-buffer orbit step: copy-in and copy-out streams and per-chunk events of the pipeline (created on first use)
+	cudaStream_t s_in, s_out;
+	cudaEvent_t ev_in[16], ev_done[16];
 	// radius-sharded operation (shard.cu): this context is rank `rank` of `nranks` GPUs of one node
 	int rank, nranks;
 	void *own_buf[SH_N_BUFFERS];                    // this rank's peer-visible buffers, in the order of the SH_* enum

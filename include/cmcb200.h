@@ -121,7 +121,8 @@ typedef struct {
 } cmcb200_orbit_result;
 
 /* Host-buffer form.  star1 = &star[1]: reads .E .J .vr .vt (.rnew for new stars); writes .rnew .vrnew .vtnew .X .r_peri
- * .r_apo exactly where the reference's loop body does.  status (may be NULL) receives one CMCB200_ORBIT_* per star; the
+ * .r_apo exactly where the reference's loop body does.  Only bytes 0..127 of each record are copied in and bytes 64..127 copied
+ * back (strided DMA, pipelined over chunks of the star range with the kernels).  status (may be NULL) receives one CMCB200_ORBIT_* per star; the
  * shim replays the host-side side effects (remove_star / destroy_obj / count_esc_bhs, esc log) for the flagged stars in
  * star order.  kmin / kmax (may be NULL): the bracket indices of calc_orbit_new, for parity tests. */
 int cmcb200_new_orbits_calculate(cmcb200_ctx *ctx, void *star1, const double *star_r, const double *star_m, const double *star_phi,
@@ -129,10 +130,10 @@ int cmcb200_new_orbits_calculate(cmcb200_ctx *ctx, void *star1, const double *st
 
 /* ---- host memory ---------------------------------------------------------------------------------------------------- */
 
-/* Pin and map a host array the host-buffer entry points are called with (star[], binary[], star_r/m/phi: the reference callocs /
- * mallocs them once, src/cmc/cmc_io.c:2099-2101, 3434-3436, so the shim registers them once at start-up).  Optional: pageable
- * memory works, but (a) pinned memory copies at PCIe rate and (b) for a pinned + mapped star[] cmcb200_new_orbits_calculate moves
- * only the fields the orbit step reads and writes (48 + <=48 bytes per star) instead of the 424-byte records both ways. */
+/* Pin a host array the host-buffer entry points are called with (star[], binary[], star_r/m/phi: the reference callocs / mallocs them
+ * once, src/cmc/cmc_io.c:2099-2101, 3434-3436, so the shim registers them once at start-up).  Optional: pageable memory works, but only
+ * pinned memory is copied by DMA at PCIe rate and asynchronously, which is what lets cmcb200_new_orbits_calculate overlap its copy-in,
+ * kernels and copy-out. */
 int cmcb200_host_register(void *ptr, size_t bytes);
 int cmcb200_host_unregister(void *ptr);
 /* bytes the host-buffer entry points have moved host->device / device->host since creation (or the last reset) */

@@ -155,34 +155,45 @@ def test_orbit_step_tuning_knobs_do_not_change_results(knobs, monkeypatch):
     _orbit_case("plummer", 300000, seed=5)
 
 
-def test_new_orbits_zero_copy_equals_staged_records():
-    """host-buffer orbit step on a pinned + mapped star[] (kernels move the 48 input / <= 48 output bytes per star over PCIe) against the
-    pageable path (whole 424-byte records staged both ways): every byte of star[] afterwards, including the fields the step must not touch,
-    with tidal strippings and planted unbound / massless stars so every status-dependent store is exercised"""
-    N = 80000
+def test_host_buffer_orbit_step_is_chunk_pipelined_and_touches_only_its_fields():
+    """cmcb200_new_orbits_calculate moves the first 128 bytes of every record in and bytes 64..127 out as strided DMA copies, pipelined over
+    chunks of the star range: against the resident form (whole records uploaded, one range) every byte of star[] must agree -- including the
+    fields the step must not touch (star[] starts as random bytes) and every status-dependent store (tidal strippings, planted unbound and
+    massless stars); N is large enough for three chunks, pinned and pageable host arrays"""
+    N = 1200000
     r, vr, vt, sm = cm.cluster_state("plummer", N, seed=61)
     rng = np.random.default_rng(3)
     pot = cm.oracle_potential(r, sm)
     E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
     E[rng.choice(N, 50, replace=False)] = 0.5             # unbound
     outs = []
-    for pinned in (True, False):
-        c = Cluster(N, n_star_dim=N + 64, pinned=pinned)
+    for mode in ("pinned", "pageable", "resident"):
+        c = Cluster(N, n_star_dim=N + 64, pinned=(mode == "pinned"))
         c.star[:] = np.random.default_rng(1).integers(0, 256, c.star.shape, dtype=np.uint8)
+        c.field("binind")[:] = 0
         c.load(r, vr, vt, sm)
         c.star_m[1 + 777] = 0.0                             # massless
         c.star_phi[:N + 2] = pot["phi"][:N + 2]
         c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
         c.Rtidal = 4.0
-        status = c.new_orbits_calculate(seed=11)
-        h2d, d2h = c.transfer_bytes()
-        outs.append((status.copy(), c.star.copy(), c.max_r, h2d, d2h))
+        if mode == "resident":
+            c.upload()
+            res = c.dev_new_orbits(seed=11, want_status=True)
+            status = c.dev_read_status()[0]
+            c.download()
+            h2d = d2h = 0
+        else:
+            status = c.new_orbits_calculate(seed=11)
+            res = c.last_orbit
+            h2d, d2h = c.transfer_bytes()
+        outs.append((status.copy(), c.star[:N + 1].copy(), res.max_r, res.n_draws, h2d, d2h))
         c.close()
-    (sa, stara, ma, ha, da), (sb, starb, mb, hb, db) = outs
-    assert np.array_equal(sa, sb) and ma == mb
-    assert set(np.unique(sa)) >= {ol.ST_OK, ol.ST_UNBOUND, ol.ST_TIDAL}
-    assert np.array_equal(stara, starb), "star[] differs between the zero-copy and the staged path"
-    assert ha < hb / 3 and da < db / 3, (ha, hb, da, db)   # the zero-copy path moved a fraction of the bytes
+    a, b, ref = outs
+    assert set(np.unique(ref[0])) >= {ol.ST_OK, ol.ST_MASSLESS, ol.ST_UNBOUND, ol.ST_TIDAL}
+    for x, name in ((a, "pinned"), (b, "pageable")):
+        assert np.array_equal(x[0], ref[0]) and x[2] == ref[2] and x[3] == ref[3], name
+        assert np.array_equal(x[1], ref[1]), f"star[] differs between the {name} host-buffer form and the resident form"
+        assert x[4] == N * 128 + 3 * 8 * (N + 2) and x[5] == N * 64, (name, x[4], x[5])
 
 
 def test_orbit_step_branches():
