@@ -110,7 +110,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_star, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_oflag, (size_t) n_star_dim));
-	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_scan_list, (size_t) ORBIT_SCAN_LIST_CAP * sizeof(uint2)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_first, (size_t) ORBIT_DEFER_CAP * sizeof(unsigned)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[0], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[1], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r, 0, tb, c->stream));
@@ -150,7 +150,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	for (int i = 0; i < 2; i++) { cudaFree(c->d_star[i]); cudaFree(c->d_bin[i]); }
 	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev); cudaFree(c->d_r_alt); cudaFree(c->d_m_alt);
 	cudaFree(c->d_rp); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
-	cudaFree(c->d_scan_list); cudaFree(c->lad.q); cudaFree(c->lad.r); cudaFree(c->lad.unsorted);
+	cudaFree(c->d_defer_first); cudaFree(c->lad.q); cudaFree(c->lad.r); cudaFree(c->lad.unsorted);
 	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); }
 	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
@@ -384,7 +384,7 @@ static int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_
 	a.defer_star = c->d_defer_star; a.defer_found = c->d_defer_found;
 	a.fuse_energy = p->fuse_compute_energy != 0;
 	a.prepare_ctas = c->orbit_ctas;
-	a.scan_list = c->d_scan_list;
+	a.defer_first = c->d_defer_first;
 	a.flag = c->d_oflag; a.pend_list[0] = c->d_pend[0]; a.pend_list[1] = c->d_pend[1];
 	a.t.N_MAX = p->N_MAX;
 	a.t.invN = 1.0 / p->N_STAR;

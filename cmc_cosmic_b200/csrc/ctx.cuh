@@ -34,7 +34,7 @@ struct cmcb200_ctx {
 	double *d_r_alt, *d_m_alt; // second copy of star_r / star_m: the fused transfer+sort reads the old tables while it writes the new ones
 	RPhi *d_rp;       // packed (r, phi) lookup table of the orbit step
 	long *d_defer_star, *d_defer_found;
-	uint2 *d_scan_list;
+	unsigned *d_defer_first;
 	LadderBuffers lad; // coarse levels of the lookup tables (orbit_core.h "ladders")
 	unsigned char *d_oflag;
 	int *d_pend[2];

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(ORBIT_THREADS, CTAS) orbit_prepare_kernel(Orbi
 			if (slot < ORBIT_DEFER_CAP) {
 				a.defer_star[slot] = j0;
 				a.defer_found[slot] = ORBIT_NOT_FOUND;
+				a.defer_first[slot] = 0xffffffffu;
 			} else { // queue full (never seen: ~1e-5 of the stars defer): last resort, the scan in this thread
 				orbit_prepare(a.t, top, s, in.is_new, in.rnew_of_new, a.Rtidal, KTEMP_COMPUTE, false, o, job);
 			}
@@ -285,11 +286,13 @@ __global__ void __launch_bounds__(ORBIT_THREADS, CTAS) orbit_prepare_kernel(Orbi
 // first k in [0, N_MAX) with function_q(k) > 0 for every queued star (get_positive_Q_index, cmc_orbit.c:46-57: the loop runs
 // k = 0, 1, .. while Q <= 0 and k <= N_MAX, and a result >= N_MAX means "none").
 //   orbit_scan_filter   one thread per (queued star, chunk of 4096 table entries): a two-load bound (q_maybe_positive_on) proves
-//                       Q <= 0 on the whole chunk for all but the one or two chunks next to the sign change; the others go
-//                       to a work list
-//   orbit_scan_chunks   one CTA per listed chunk evaluates every entry's sign exactly as the reference would and keeps the
-//                       smallest index with Q > 0
-// Every chunk is either proven all-non-positive or scanned, so the minimum is the reference's answer.
+//                       Q <= 0 on the whole chunk for every chunk well below the sign change; a chunk it cannot dismiss is tested again in
+//                       16 sub-chunks of 256 entries, and the lowest sub-chunk that still cannot be dismissed is kept per star
+//   orbit_scan_chunks   one CTA per queued star walks the sub-chunks from that one upwards, one table entry per thread, evaluating every
+//                       sign exactly as the reference would, until a sub-chunk holds an index with Q > 0 (almost always within a few steps)
+// Every entry below the answer is either in a range proven all-non-positive or evaluated, so the answer is the reference's.
+constexpr int ORBIT_SCAN_SUB = ORBIT_SCAN_THREADS;                    // 256 entries
+constexpr int ORBIT_SCAN_SUBS = ORBIT_SCAN_CHUNK / ORBIT_SCAN_SUB;     // 16 sub-chunks per chunk
 
 __device__ __forceinline__ StarConst deferred_const(const OrbitArgs &a, unsigned slot)
 {
@@ -309,54 +312,52 @@ __global__ void __launch_bounds__(256) orbit_scan_filter(OrbitArgs a)
 	for (unsigned long long item = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; item < n_items; item += (unsigned long long) gridDim.x * blockDim.x) {
 		const unsigned slot = (unsigned) (item / n_chunks);
 		const long chunk = (long) (item % n_chunks);
+		if ((unsigned) (chunk * ORBIT_SCAN_SUBS) >= *(volatile unsigned *) &a.defer_first[slot]) continue; // a lower candidate is already known
 		const long k0 = chunk * ORBIT_SCAN_CHUNK;
 		const long k1 = min(k0 + (long) ORBIT_SCAN_CHUNK, n_scan) - 1;
 		const StarConst s = deferred_const(a, slot);
-		if (q_maybe_positive_on(s, tbl_rp(a.t, (kint) k0), tbl_rp(a.t, (kint) k1))) {
-			const unsigned w = atomicAdd(&a.stats->scan_items, 1u);
-			if (w < ORBIT_SCAN_LIST_CAP) a.scan_list[w] = make_uint2(slot, (unsigned) chunk);
+		if (!q_maybe_positive_on(s, tbl_rp(a.t, (kint) k0), tbl_rp(a.t, (kint) k1))) continue;
+		for (int sub = 0; sub < ORBIT_SCAN_SUBS; sub++) {
+			const long s0 = k0 + (long) sub * ORBIT_SCAN_SUB;
+			if (s0 > k1) break;
+			const long s1 = min(s0 + (long) ORBIT_SCAN_SUB - 1, k1);
+			if (q_maybe_positive_on(s, tbl_rp(a.t, (kint) s0), tbl_rp(a.t, (kint) s1))) {
+				atomicMin(&a.defer_first[slot], (unsigned) (chunk * ORBIT_SCAN_SUBS + sub));
+				break;
+			}
 		}
 	}
 }
 
 __global__ void __launch_bounds__(ORBIT_SCAN_THREADS) orbit_scan_chunks(OrbitArgs a)
 {
+	__shared__ long s_best[ORBIT_SCAN_THREADS / 32];
 	const unsigned n_defer = min(a.stats->n_defer, (unsigned) ORBIT_DEFER_CAP);
-	if (n_defer == 0) return;
 	const long n_scan = a.t.N_MAX;
-	const long n_chunks = (n_scan + ORBIT_SCAN_CHUNK - 1) / ORBIT_SCAN_CHUNK;
-	const unsigned listed = a.stats->scan_items;
-	// the list overflowed (the bound failed to dismiss most chunks -- not seen on any cluster): scan everything
-	const bool everything = listed > ORBIT_SCAN_LIST_CAP;
-	const unsigned long long n_items = everything ? (unsigned long long) n_chunks * n_defer : listed;
-	for (unsigned long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-		unsigned slot;
-		long chunk;
-		if (everything) { slot = (unsigned) (item % n_defer); chunk = (long) (item / n_defer); } // chunk-major: low chunks first
-		else { const uint2 w = a.scan_list[item]; slot = w.x; chunk = w.y; }
-		const long k0 = chunk * ORBIT_SCAN_CHUNK;
-		if (*(volatile long *) &a.defer_found[slot] < k0) continue; // a smaller hit exists (block-uniform enough: hits only decrease,
-		                                                             // and a thread that still scans only adds a larger candidate)
+	const long n_subs = (n_scan + ORBIT_SCAN_SUB - 1) / ORBIT_SCAN_SUB;
+	for (unsigned slot = blockIdx.x; slot < n_defer; slot += gridDim.x) {
 		const StarConst s = deferred_const(a, slot);
-		long best = ORBIT_NOT_FOUND;
 		int n_exact = 0;
-#pragma unroll 4
-		for (int i = 0; i < ORBIT_SCAN_CHUNK / ORBIT_SCAN_THREADS; i++) {
-			const long k = k0 + i * ORBIT_SCAN_THREADS + threadIdx.x;
-			if (k < n_scan && k < best) {
-				if (sign_Q(a.t, s, (kint) k, &n_exact) > 0) best = k;
+		long found = ORBIT_NOT_FOUND;
+		for (long sub = a.defer_first[slot]; sub < n_subs && found == ORBIT_NOT_FOUND; sub++) { // 0xffffffff: no candidate at all
+			const long k = sub * ORBIT_SCAN_SUB + threadIdx.x;
+			long best = ORBIT_NOT_FOUND;
+			if (k < n_scan && sign_Q(a.t, s, (kint) k, &n_exact) > 0) best = k;
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) {
+				const long o = __shfl_xor_sync(0xffffffffu, best, d);
+				best = o < best ? o : best;
 			}
+			if (lane_id() == 0) s_best[warp_id()] = best;
+			__syncthreads();
+#pragma unroll
+			for (int w = 0; w < ORBIT_SCAN_THREADS / 32; w++) found = s_best[w] < found ? s_best[w] : found;
+			__syncthreads();
 		}
 #pragma unroll
-		for (int d = 16; d > 0; d >>= 1) {
-			long o = __shfl_xor_sync(0xffffffffu, best, d);
-			best = o < best ? o : best;
-			n_exact += __shfl_xor_sync(0xffffffffu, n_exact, d);
-		}
-		if (lane_id() == 0) {
-			if (best != ORBIT_NOT_FOUND) atomicMin((long long *) &a.defer_found[slot], (long long) best);
-			if (n_exact) atomicAdd(&a.stats->n_exact, (unsigned long long) n_exact);
-		}
+		for (int d = 16; d > 0; d >>= 1) n_exact += __shfl_xor_sync(0xffffffffu, n_exact, d);
+		if (lane_id() == 0 && n_exact) atomicAdd(&a.stats->n_exact, (unsigned long long) n_exact);
+		if (threadIdx.x == 0) a.defer_found[slot] = found;
 	}
 }
 
@@ -527,7 +528,7 @@ __global__ void orbit_stats_reset(OrbitStats *s)
 {
 	s->max_rad_bits = 0; s->n_draws = 0; s->n_exact = 0; s->n_brent = 0;
 	for (int i = 0; i < 6; i++) s->n_status[i] = 0;
-	s->n_defer = 0; s->scan_items = 0;
+	s->n_defer = 0;
 	for (int i = 0; i < ORBIT_MAX_ROUNDS + 2; i++) s->round_count[i] = 0;
 }
 
@@ -647,7 +648,7 @@ int orbit_stage_scan(const OrbitArgs &a, cudaStream_t s)
 {
 	if (a.n_local <= 0) return 0;
 	orbit_scan_filter<<<NUM_SMS_B200 * 4, 256, 0, s>>>(a);
-	orbit_scan_chunks<<<NUM_SMS_B200 * 4, ORBIT_SCAN_THREADS, 0, s>>>(a);
+	orbit_scan_chunks<<<NUM_SMS_B200 * 2, ORBIT_SCAN_THREADS, 0, s>>>(a);
 	orbit_deferred_kernel<<<NUM_SMS_B200, ORBIT_THREADS, 0, s>>>(a);
 	return 3;
 }

@@ -11,7 +11,6 @@ constexpr int ORBIT_SCAN_THREADS = 256;
 constexpr int ORBIT_SCAN_CHUNK = 4096;      // table entries per work item of the cooperative linear scan
 constexpr int ORBIT_DEFER_CAP = 65536;      // queued scans per launch (beyond it a star scans in its own thread)
 constexpr long ORBIT_NOT_FOUND = 0x7fffffffffffffffL;
-constexpr unsigned ORBIT_SCAN_LIST_CAP = 1u << 20;
 constexpr int ORBIT_TRY_THREADS = 256;
 constexpr int ORBIT_MAX_ROUNDS = 8;         // launches of the rejection-sampling stage
 
@@ -20,7 +19,6 @@ struct OrbitStats { // device-resident, zeroed per launch
 	unsigned long long n_draws, n_exact, n_brent;
 	unsigned long long n_status[6];
 	unsigned n_defer;     // stars queued for the cooperative linear scan
-	unsigned scan_items;  // (star, chunk) pairs the bound could not dismiss
 	unsigned round_count[ORBIT_MAX_ROUNDS + 2]; // stars pending at the start of each rejection round
 };
 
@@ -49,7 +47,7 @@ struct OrbitArgs {
 	int prepare_ctas;  // register-cap variant of orbit_prepare_kernel: 4 (default) or 3 resident CTAs per SM (CMCB200_ORBIT_CTAS)
 	unsigned q_top_bytes, r_top_bytes; // size of the coarsest level of each ladder (what a CTA stages), multiples of 16
 	long *defer_star;  // [ORBIT_DEFER_CAP] local 0-based index of each queued star
-	uint2 *scan_list;  // [ORBIT_SCAN_LIST_CAP] (slot, chunk) pairs to scan entry by entry
+	unsigned *defer_first; // [ORBIT_DEFER_CAP] lowest 256-entry sub-chunk of the table the bound could not prove free of Q > 0 (0xffffffff: none)
 	long *defer_found; // [ORBIT_DEFER_CAP] first k with Q > 0 (ORBIT_NOT_FOUND: none)
 };
 
