@@ -320,7 +320,8 @@ def run_cuda(args):
 
     roofs = {
         "orbit_prepare": roof("orbit_prepare", "orbit_prepare_kernel", BYTES_ORBIT_PREPARE, n_shard,
-                              {"note": "index bisections answered from the Q ladder (shared memory / L2), the last ~6 probes per bisection are DRAM sectors"}),
+                              {"note": "2 x log2(N) dependent probes of the 16 N-byte (r, Phi) table per star: bound by DRAM sector traffic (`traffic`, ncu: ~49 % of "
+                                       "peak DRAM throughput in 32-byte random sectors, L2 hit rate 38 %), not by the 56 B/star it streams"}),
         "record_gather": roof("record_gather", "sort_gather_records" if world == 1 else "shard_push_records", BYTES_GATHER, n_shard),
     }
     dominant = max(roofs, key=lambda k: roofs[k]["avg_launch_ms"])

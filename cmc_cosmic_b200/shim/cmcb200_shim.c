@@ -64,6 +64,15 @@ static void shim_init(void)
 	if (cmcb200_create(&ctx, dev, N_STAR_DIM_OPT, N_BIN_DIM_OPT)) shim_fail("cmcb200_create");
 	ctx_star_dim = N_STAR_DIM_OPT;
 	ctx_bin_dim = N_BIN_DIM_OPT;
+	/* the arrays are allocated once (src/cmc/cmc_io.c:2099-2101, 3434-3436): pin them so that every copy is DMA at link rate.  A failure
+	 * (locked-memory limit) is not fatal -- pageable memory only copies slower. */
+	if (!getenv("CMCB200_NO_PIN")) {
+		cmcb200_host_register(star, (size_t) N_STAR_DIM_OPT * sizeof(star_t));
+		cmcb200_host_register(binary, (size_t) N_BIN_DIM_OPT * sizeof(binary_t));
+		cmcb200_host_register(star_r, (size_t) N_STAR_DIM * sizeof(double));
+		cmcb200_host_register(star_m, (size_t) N_STAR_DIM * sizeof(double));
+		cmcb200_host_register(star_phi, (size_t) N_STAR_DIM * sizeof(double));
+	}
 }
 
 #define SHIM_EXPORT __attribute__((visibility("default")))
