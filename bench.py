@@ -186,6 +186,7 @@ def run_cuda(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL's version banner goes to stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N = args.n_stars
     dev = f"cuda:{local_rank}"

@@ -265,6 +265,25 @@ class Cluster:
         _lib.check(self.L.cmcb200_profile_read(self.ctx, ms.ctypes.data, n.ctypes.data, int(reset)), "profile_read")
         return {k: (float(a), int(b)) for k, a, b in zip(_lib.STAGE_NAMES, ms, n)}
 
+    MASS_PC_FIELDS = ("mass_r", "ave_mass_r", "no_star_r", "densities_r", "ke_rad_r", "ke_tan_r", "v2_rad_r", "v2_tan_r")
+
+    def dev_comp_mass_percent(self, mass_pc, bh_include=False, minimum_r=0.0, initial_total_mass=1.0):
+        """comp_mass_percent (reference src/cmc/cmc_utils.c:872-985) on the resident arrays: the Lagrange radii mass_r[], the star counts,
+        mean masses, densities and the cumulative kinetic sums at them, under the reference's names.  Entries the loop never reaches
+        keep their previous values (-1 on first use)."""
+        pc = np.ascontiguousarray(mass_pc, np.float64)
+        n = len(pc)
+        for f in self.MASS_PC_FIELDS:
+            if getattr(self, f, None) is None or len(getattr(self, f)) != n:
+                setattr(self, f, np.full(n, -1.0))
+        owner = np.zeros(n, np.int32)
+        p = _lib.MassPcParams(n, pc.ctypes.data, int(bh_include), minimum_r, initial_total_mass, self.Mtotal, self.cenma.m, self.clus.N_MAX,
+                              self.clus.N_STAR, self.clus.N_MAX_NEW, int(self.Start[self.myid]))
+        res = _lib.MassPcResult(*[getattr(self, f).ctypes.data for f in self.MASS_PC_FIELDS], owner.ctypes.data)
+        _lib.check(self.L.cmcb200_dev_comp_mass_percent(self.ctx, C.byref(p), C.byref(res)), "dev_comp_mass_percent")
+        self.mass_pc, self.mass_pc_owner, self.mass_pc_totals = pc, owner, np.array(list(res.totals))
+        return int(res.filled)
+
     def launch_count(self):
         return int(self.L.cmcb200_launch_count(self.ctx))
 

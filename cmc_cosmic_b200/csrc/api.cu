@@ -156,6 +156,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
 	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
+	if (c->d_lagrange) cudaFree(c->d_lagrange);
 	if (c->d_draws) cudaFree(c->d_draws);
 	if (c->d_draw_off) cudaFree(c->d_draw_off);
 	cudaFreeHost(c->h_pinned);

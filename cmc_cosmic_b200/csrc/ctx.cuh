@@ -13,7 +13,7 @@ using namespace cmcb;
 constexpr int SHARD_MAX_RANKS = 16;
 enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_N_BUFFERS }; // peer-visible buffers
 
-enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES };
+enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES, ST_LAGRANGE };
 
 struct StageEvent {
 	int stage;
@@ -55,6 +55,7 @@ struct cmcb200_ctx {
 	SeqWork seqwork;
 	// orbit scratch
 	OrbitStats *d_ostats;
+	void *d_lagrange; // device result block of comp_mass_percent (lagrange.cu), allocated on first use
 	int *d_status;
 	long *d_kmin, *d_kmax;
 	double *d_draws;

@@ -1,0 +1,159 @@
+// Lagrange radii on the resident arrays: comp_mass_percent (reference src/cmc/cmc_utils.c:872-985) -- SURVEY.md 8f N2, the first
+// consumer of the freshly sorted tables after calc_potential_new and the observable of the "statistically agree" check.
+//
+//   mprev_k    = mprev_0 + sum_{j<=k} star_m[j]/N_STAR, sequentially from k = 1 (:934)               chain E (+), replicated tables
+//   ke_rad_l   = sum_{j<=l} 0.5 star_m[g_j] madhoc vr_j^2, rank-local, sequentially from l = 1 (:907-913) and the same for
+//   ke_tan, v2_rad, v2_tan                                                                            chains K0..K3 (+), local records
+//   entry mcount is recorded at the first k (one threshold per k) with mprev_k > mass_pc[mcount] Mtotal (:936-977)
+// All five recurrences carry the reference's sequential roundings (seqscan.cuh), so the radii, star counts and sums are the
+// reference's bit for bit.  The sums are returned rank-local; the caller adds the MPI_Exscan prefix for indices a rank other than 0
+// owns, exactly like the reference (:945-951).  pow() for the densities runs on the host (glibc, as in the reference).
+#include <cmath>
+#include "ctx.cuh"
+#include "seqscan.cuh"
+
+namespace cmcb {
+
+constexpr int MASS_PC_MAX = 256;
+
+struct LagrangeDev { // device-resident result of one call
+	long n_filled;
+	long k[MASS_PC_MAX];
+	double mprev[MASS_PC_MAX], r[MASS_PC_MAX];
+	double sums[4][MASS_PC_MAX];
+	int owner[MASS_PC_MAX];
+	double totals[4];
+	double thr[MASS_PC_MAX]; // mass_pc (in)
+	double last;             // seq_scan_resolve's slot for a chain's final value (not used here)
+};
+
+struct ChainEnclosed { // y_i = y_{i-1} + star_m[i+1] / N_STAR, i = 0..N_MAX-1; stored at mcum[i+1]
+	static constexpr int SIGN = +1;
+	const double *m;
+	double *mcum;
+	long n;
+	double n_star, start;
+	__device__ long length() const { return n; }
+	__device__ double y0() const { return start; }
+	__device__ double term(long i) const { return ddiv(m[i + 1], n_star); }
+	__device__ void store(long i, double y) const { mcum[i + 1] = y; }
+};
+
+// WHICH: 0 ke_rad, 1 ke_tan, 2 v2_rad, 3 v2_tan.  Element i <-> local star i + 1 (record i of star1)
+template <int WHICH>
+struct ChainKinetic {
+	static constexpr int SIGN = +1;
+	const char *star1;
+	const double *m;
+	double *acc; // acc[l] = sum over local stars 1..l
+	long n, first_global;
+	double madhoc;
+	__device__ long length() const { return n; }
+	__device__ double y0() const { return 0.0; }
+	__device__ double term(long i) const
+	{
+		const double v = *(const double *) (star1 + i * CMCB_SIZEOF_STAR + ((WHICH & 1) ? CMCB_OFF_VT : CMCB_OFF_VR));
+		if (WHICH >= 2) return dmul(v, v);
+		return dmul(dmul(dmul(dmul(0.5, m[first_global + i]), madhoc), v), v); // 0.5 * star_m[g_k] * madhoc * v * v, left to right
+	}
+	__device__ void store(long i, double y) const { acc[i + 1] = y; }
+};
+
+// one thread: the threshold loop (:933-977) on the finished mprev array
+__global__ void lagrange_select(const double *__restrict__ mcum, const double *__restrict__ star_r, long N_MAX, long count, long mcount0, double Mtotal,
+				LagrangeDev *out)
+{
+	long mcount = mcount0, kprev = 0;
+	for (; mcount < count; mcount++) {
+		const double thr = dmul(out->thr[mcount], Mtotal);
+		// mcum is non-decreasing (sequentially rounded sums of non-negative terms): first k in (kprev, N_MAX] with mcum[k] > thr
+		long lo = kprev + 1, hi = N_MAX + 1;
+		while (lo < hi) {
+			const long mid = (lo + hi) >> 1;
+			if (mcum[mid] > thr) hi = mid; else lo = mid + 1;
+		}
+		if (lo > N_MAX) break;
+		out->k[mcount] = lo; out->mprev[mcount] = mcum[lo]; out->r[mcount] = star_r[lo];
+		out->owner[mcount] = 0;
+		kprev = lo;
+	}
+	out->n_filled = mcount;
+}
+
+// the cumulative sum `which` at the recorded indices this rank owns, and the rank's total
+__global__ void lagrange_pick(const double *__restrict__ acc, long n_local, long first_global, long mcount0, int which, LagrangeDev *out)
+{
+	const long i = mcount0 + threadIdx.x;
+	if (i < out->n_filled) {
+		const long k = out->k[i];
+		if (k >= first_global && k < first_global + n_local) {
+			out->sums[which][i] = acc[k - first_global + 1];
+			out->owner[i] = 1;
+		}
+	}
+	if (threadIdx.x == 0) out->totals[which] = n_local > 0 ? acc[n_local] : 0.0;
+}
+
+} // namespace cmcb
+
+extern "C" int cmcb200_dev_comp_mass_percent(cmcb200_ctx *c, const cmcb200_mass_pc_params *p, cmcb200_mass_pc_result *res)
+{
+	if (p->count < 0 || p->count > MASS_PC_MAX) { set_error("comp_mass_percent: MASS_PC_COUNT = %ld exceeds %d", p->count, MASS_PC_MAX); return -1; }
+	if (p->N_MAX + 2 > c->n_table_dim || p->n_local + 2 > c->n_star_dim) { set_error("comp_mass_percent: sizes exceed the context capacity"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
+	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
+	const double madhoc = 1.0 / ((double) p->N_STAR);
+	// :876-895 the thresholds the central mass alone exceeds
+	double mprev0 = 0.0;
+	long mcount0 = 0;
+	if (p->bh_include) {
+		mprev0 = p->cenma_m * madhoc;
+		for (mcount0 = 0; mcount0 < p->count; mcount0++) {
+			if (mprev0 / p->Mtotal > p->mass_pc[mcount0]) {
+				res->mass_r[mcount0] = p->minimum_r; res->ave_mass_r[mcount0] = 0.0; res->no_star_r[mcount0] = 0; res->densities_r[mcount0] = 0.0;
+				res->ke_rad_r[mcount0] = 0.0; res->ke_tan_r[mcount0] = 0.0; res->v2_rad_r[mcount0] = 0.0; res->v2_tan_r[mcount0] = 0.0;
+				if (res->owner) res->owner[mcount0] = 0;
+			} else break;
+		}
+	}
+	CMCB_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(LagrangeDev), c->stream));
+	if (p->count > 0) CMCB_CUDA_OK(cudaMemcpyAsync(d->thr, p->mass_pc, (size_t) p->count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	const int grid = NUM_SMS_B200 * 4;
+	double *mcum = c->d_mprev;                 // scratch of the potential rebuild, free between its calls
+	double *acc = (double *) c->sbuf.keys_a;   // scratch of the sort, free between its calls (n_star_dim doubles)
+	double *dummy = &d->last;                  // seq_scan_launch wants a slot for the chain's last value
+	{
+		StageTimer t(c, ST_LAGRANGE);
+		ChainEnclosed ce{c->d_m, mcum, p->N_MAX, (double) p->N_STAR, mprev0};
+		seq_scan_launch(ce, c->seqwork, p->N_MAX, dummy, grid, grid, c->stream);
+		lagrange_select<<<1, 1, 0, c->stream>>>(mcum, c->d_r, p->N_MAX, p->count, mcount0, p->Mtotal, d);
+		c->launches += 5;
+		const char *s1 = star1(c);
+		auto run = [&](auto chain, int which) {
+			seq_scan_launch(chain, c->seqwork, p->n_local, dummy, grid, grid, c->stream);
+			lagrange_pick<<<1, MASS_PC_MAX, 0, c->stream>>>(acc, p->n_local, p->first_global, mcount0, which, d);
+			c->launches += 5;
+		};
+		run(ChainKinetic<0>{s1, c->d_m, acc, p->n_local, p->first_global, madhoc}, 0);
+		run(ChainKinetic<1>{s1, c->d_m, acc, p->n_local, p->first_global, madhoc}, 1);
+		run(ChainKinetic<2>{s1, c->d_m, acc, p->n_local, p->first_global, madhoc}, 2);
+		run(ChainKinetic<3>{s1, c->d_m, acc, p->n_local, p->first_global, madhoc}, 3);
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	static thread_local LagrangeDev h;
+	CMCB_CUDA_OK(cudaMemcpyAsync(&h, d, sizeof(LagrangeDev), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	for (long i = mcount0; i < h.n_filled; i++) { // :937-940, with the host's libm like the reference
+		const long k = h.k[i];
+		res->mass_r[i] = h.r[i];
+		res->ave_mass_r[i] = h.mprev[i] / p->Mtotal / k * p->initial_total_mass;
+		res->no_star_r[i] = (double) k;
+		res->densities_r[i] = h.mprev[i] / (4.0 / 3.0 * 3.14159265358979323 /* PI, include/cmc/cmc.h:62 */ * pow(h.r[i], 3));
+		if (h.owner[i]) { res->ke_rad_r[i] = h.sums[0][i]; res->ke_tan_r[i] = h.sums[1][i]; res->v2_rad_r[i] = h.sums[2][i]; res->v2_tan_r[i] = h.sums[3][i]; }
+		if (res->owner) res->owner[i] = h.owner[i];
+	}
+	for (int q = 0; q < 4; q++) res->totals[q] = h.totals[q];
+	res->filled = h.n_filled;
+	return 0;
+}

@@ -4,9 +4,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmcb200.so")
-N_STAGES = 16
+N_STAGES = 17
 STAGE_NAMES = ["keys_hist", "radix_passes", "record_gather", "binaries", "potential", "orbit_prepare", "transfer", "energy", "h2d", "d2h",
-               "orbit_scan", "orbit_tries", "orbit_tables", "shard_keys", "shard_rank", "shard_tables"]
+               "orbit_scan", "orbit_tries", "orbit_tables", "shard_keys", "shard_rank", "shard_tables", "lagrange"]
 
 
 class OrbitParams(C.Structure):
@@ -18,6 +18,16 @@ class OrbitParams(C.Structure):
 class OrbitResult(C.Structure):
     _fields_ = [("max_r", C.c_double), ("n_draws", C.c_ulonglong), ("n_exact", C.c_ulonglong), ("n_brent", C.c_ulonglong),
                 ("n_status", C.c_ulonglong * 6), ("n_deferred", C.c_ulonglong)]
+
+
+class MassPcParams(C.Structure):
+    _fields_ = [("count", C.c_long), ("mass_pc", C.c_void_p), ("bh_include", C.c_int), ("minimum_r", C.c_double), ("initial_total_mass", C.c_double),
+                ("Mtotal", C.c_double), ("cenma_m", C.c_double), ("N_MAX", C.c_long), ("N_STAR", C.c_long), ("n_local", C.c_long), ("first_global", C.c_long)]
+
+
+class MassPcResult(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in ("mass_r", "ave_mass_r", "no_star_r", "densities_r", "ke_rad_r", "ke_tan_r", "v2_rad_r", "v2_tan_r", "owner")] + \
+               [("totals", C.c_double * 4), ("filled", C.c_long)]
 
 
 class CmcB200Error(RuntimeError):
@@ -33,6 +43,7 @@ EXPORTS = [
     "cmcb200_dev_new_orbits", "cmcb200_dev_transfer_new_positions", "cmcb200_dev_qsorts_new", "cmcb200_dev_transfer_and_sort", "cmcb200_dev_calc_potential_new",
     "cmcb200_dev_compute_energy", "cmcb200_dev_read_status", "cmcb200_sync", "cmcb200_profile", "cmcb200_profile_read",
     "cmcb200_potential_stats", "cmcb200_launch_count", "cmcb200_host_register", "cmcb200_host_unregister", "cmcb200_transfer_bytes",
+    "cmcb200_dev_comp_mass_percent",
 ]
 
 
@@ -84,6 +95,7 @@ def load():
     L.cmcb200_host_register.argtypes = [vp, C.c_size_t]
     L.cmcb200_host_unregister.argtypes = [vp]
     L.cmcb200_transfer_bytes.argtypes = [vp, pl, pl, C.c_int]
+    L.cmcb200_dev_comp_mass_percent.argtypes = [vp, C.POINTER(MassPcParams), C.POINTER(MassPcResult)]
     _lib = L
     return L
 

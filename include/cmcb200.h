@@ -167,6 +167,33 @@ int cmcb200_dev_read_status(cmcb200_ctx *ctx, int *status, long *kmin, long *kma
 /* wait for everything queued on the context's stream */
 int cmcb200_sync(cmcb200_ctx *ctx);
 
+/* ---- comp_mass_percent (src/cmc/cmc_utils.c:872-985): Lagrange radii on the resident arrays -------------------------------------- */
+
+typedef struct {
+	long count;                /* MASS_PC_COUNT (<= 256) */
+	const double *mass_pc;     /* [count] mass fractions, as in the reference's mass_pc[] */
+	int bh_include;            /* MASS_PC_BH_INCLUDE */
+	double minimum_r;          /* MINIMUM_R */
+	double initial_total_mass, Mtotal, cenma_m;
+	long N_MAX, N_STAR;        /* clus.N_MAX, clus.N_STAR */
+	long n_local, first_global; /* clus.N_MAX_NEW, Start[myid]: the local stars whose vr / vt enter the cumulative sums */
+} cmcb200_mass_pc_params;
+
+typedef struct {
+	/* caller's arrays [count], the reference's globals of the same names (include/cmc/cmc_vars.h:195-196); entries the loop never reaches
+	 * are left untouched, like the reference leaves them */
+	double *mass_r, *ave_mass_r, *no_star_r, *densities_r, *ke_rad_r, *ke_tan_r, *v2_rad_r, *v2_tan_r;
+	int *owner;                /* (may be NULL) 1 where this rank owns the recorded index, i.e. where the four sums were written */
+	double totals[4];          /* the rank's sums over all its local stars: its contribution to the MPI_Exscan (:915-931) */
+	long filled;               /* mcount at exit */
+} cmcb200_mass_pc_result;
+
+/* The enclosed-mass recurrence runs on the replicated tables, the four cumulative kinetic sums on this rank's resident records, all
+ * with the reference's sequential roundings.  The sums are RANK-LOCAL: for an index owned by a rank other than 0 the reference
+ * reports prefix + local (prefix = MPI_Exscan of the totals, :945-951) -- one addition the caller performs.  On one rank the
+ * results are the reference's as they are. */
+int cmcb200_dev_comp_mass_percent(cmcb200_ctx *ctx, const cmcb200_mass_pc_params *p, cmcb200_mass_pc_result *res);
+
 /* ---- radius-sharded operation: one rank per GPU of an NVLink node ---------------------------------------------------------------- */
 /* Replaces sample_sort + load_balance + post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2259-2288) for procs > 1.
  * The star array is sharded by radius rank exactly like the reference's MPI partition (findLimits), every rank keeps the full
@@ -195,7 +222,7 @@ int cmcb200_shard_finish(cmcb200_ctx *ctx);
  * accumulated milliseconds and launch counts since the last reset for: 0 keys+histogram, 1 radix passes, 2 record
  * gather, 3 binaries, 4 potential, 5 orbit stage A (orbits of all stars), 6 transfer, 7 energy, 8 h2d, 9 d2h, 10 orbit linear scans,
  * 11 orbit stage B (rejection rounds), 12 orbit lookup tables, 13 sharded: key push, 14 sharded: global ranks, 15 sharded: table publish. */
-#define CMCB200_N_STAGES 16
+#define CMCB200_N_STAGES 17
 int cmcb200_profile(cmcb200_ctx *ctx, int on);
 int cmcb200_profile_read(cmcb200_ctx *ctx, double ms[CMCB200_N_STAGES], long launches[CMCB200_N_STAGES], int reset);
 /* kernels launched by this context since it was created */

@@ -446,3 +446,67 @@ void orc_t113_fill(unsigned int z[4], double *out, long n)
 {
 	for (long i = 0; i < n; i++) out[i] = orc_t113_dbl(z);
 }
+
+/* ---- comp_mass_percent, src/cmc/cmc_utils.c:872-985 ------------------------------------------------------------------------------ */
+
+#define ORC_PI 3.14159265358979323 /* include/cmc/cmc.h:62 */
+
+long orc_comp_mass_percent(const double *star_r, const double *star_m, long N_MAX, long N_STAR, const double *vr, const double *vt, long n_local,
+			   long first_global, const double prefix[4], int is_rank0, double cenma_m, double madhoc, double Mtotal,
+			   double initial_total_mass, int bh_include, double minimum_r, const double *mass_pc, long count, double *mass_r,
+			   double *ave_mass_r, double *no_star_r, double *densities_r, double *ke_rad_r, double *ke_tan_r, double *v2_rad_r,
+			   double *v2_tan_r, int *owner, double totals[4])
+{
+	double mprev;
+	long k, mcount = 0;
+	/* :876-895 */
+	if (bh_include) {
+		mprev = cenma_m * madhoc;
+		for (mcount = 0; mcount < count; mcount++) {
+			if (mprev / Mtotal > mass_pc[mcount]) {
+				mass_r[mcount] = minimum_r; ave_mass_r[mcount] = 0.0; no_star_r[mcount] = 0; densities_r[mcount] = 0.0;
+				ke_rad_r[mcount] = 0.0; ke_tan_r[mcount] = 0.0; v2_rad_r[mcount] = 0.0; v2_tan_r[mcount] = 0.0;
+			} else break;
+		}
+	} else {
+		mprev = 0.;
+		mcount = 0;
+	}
+	if (owner) for (k = 0; k < count; k++) owner[k] = 0;
+	/* :899-913 the rank-local cumulative sums, every intermediate value kept */
+	double *a0 = (double *) calloc((size_t) n_local + 1, sizeof(double)), *a1 = (double *) calloc((size_t) n_local + 1, sizeof(double));
+	double *a2 = (double *) calloc((size_t) n_local + 1, sizeof(double)), *a3 = (double *) calloc((size_t) n_local + 1, sizeof(double));
+	for (k = 1; k <= n_local; k++) {
+		long g_k = first_global + k - 1;
+		a0[k] = a0[k - 1] + 0.5 * star_m[g_k] * madhoc * vr[k - 1] * vr[k - 1];
+		a1[k] = a1[k - 1] + 0.5 * star_m[g_k] * madhoc * vt[k - 1] * vt[k - 1];
+		a2[k] = a2[k - 1] + vr[k - 1] * vr[k - 1];
+		a3[k] = a3[k - 1] + vt[k - 1] * vt[k - 1];
+	}
+	totals[0] = a0[n_local]; totals[1] = a1[n_local]; totals[2] = a2[n_local]; totals[3] = a3[n_local];
+	/* :933-977 */
+	if (mcount < count) {
+		for (k = 1; k <= N_MAX; k++) {
+			mprev += star_m[k] / N_STAR;
+			if (mprev > mass_pc[mcount] * Mtotal) {
+				mass_r[mcount] = star_r[k];
+				ave_mass_r[mcount] = mprev / Mtotal / k * initial_total_mass;
+				no_star_r[mcount] = k;
+				densities_r[mcount] = mprev / (4.0 / 3.0 * ORC_PI * pow(star_r[k], 3));
+				if (k >= first_global && k < first_global + n_local) { /* this rank owns k (findProcForIndex) */
+					long l = k - first_global + 1;                       /* get_local_idx */
+					if (is_rank0) { ke_rad_r[mcount] = a0[l]; ke_tan_r[mcount] = a1[l]; v2_rad_r[mcount] = a2[l]; v2_tan_r[mcount] = a3[l]; }
+					else {
+						ke_rad_r[mcount] = prefix[0] + a0[l]; ke_tan_r[mcount] = prefix[1] + a1[l];
+						v2_rad_r[mcount] = prefix[2] + a2[l]; v2_tan_r[mcount] = prefix[3] + a3[l];
+					}
+					if (owner) owner[mcount] = 1;
+				}
+				mcount++;
+				if (mcount == count) break;
+			}
+		}
+	}
+	free(a0); free(a1); free(a2); free(a3);
+	return mcount;
+}

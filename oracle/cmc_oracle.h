@@ -83,6 +83,23 @@ double orc_get_positions(const orc_tables_t *t, long n_local, const long *g_idx,
 long orc_sort_stars(unsigned char *star1, long n, long sizeof_star, long key_off, long binind_off,
 		    unsigned char *binary1, long n_bin_dim, long sizeof_binary, long *n_bin_out, long *perm_out);
 
+/* comp_mass_percent, src/cmc/cmc_utils.c:872-985: Lagrange radii and the cumulative kinetic sums at them, as ONE rank of P sees it.
+ *   star_r, star_m: the replicated tables; vr, vt: star[k].vr / .vt of this rank's local stars k = 1..n_local at vr[k-1], vt[k-1];
+ *   first_global = Start[myid] (global index of local star 1; the function is called after the sort, so there are no new stars).
+ *   mprev starts at cenma.m*madhoc when MASS_PC_BH_INCLUDE (:878-892) and the leading thresholds it already exceeds get
+ *   mass_r = MINIMUM_R and zeros; then for k = 1..N_MAX: mprev += star_m[k]/N_STAR, and when mprev > mass_pc[mcount]*Mtotal the entry
+ *   mcount is recorded at THIS k and mcount advances by one (:930-977) -- one threshold per k.
+ *   The four cumulative sums (:907-913) are rank-local sequential sums from zero; for an index owned by a rank other than 0 the value is
+ *   prefix[i] + local[i] (prefix = MPI_Exscan of the ranks' totals, :925-931,945-951); rank 0 copies its local value (:962-968).
+ *   Outputs [count]: mass_r, ave_mass_r, no_star_r, densities_r on every rank (replicated loop); ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r only
+ *   at the entries whose index this rank owns (others are left untouched; owner[] (may be NULL) receives 1 there, 0 elsewhere).
+ *   totals[4] = the rank's local sums over all its stars (what it contributes to the Exscan).  Returns mcount: entries filled. */
+long orc_comp_mass_percent(const double *star_r, const double *star_m, long N_MAX, long N_STAR, const double *vr, const double *vt, long n_local,
+			   long first_global, const double prefix[4], int is_rank0, double cenma_m, double madhoc, double Mtotal,
+			   double initial_total_mass, int bh_include, double minimum_r, const double *mass_pc, long count, double *mass_r,
+			   double *ave_mass_r, double *no_star_r, double *densities_r, double *ke_rad_r, double *ke_tan_r, double *v2_rad_r,
+			   double *v2_tan_r, int *owner, double totals[4]);
+
 /* taus113 (src/libs/taus113-v2.c:166-216 seeding, :218-251 generator, :253-270 jump) */
 void orc_t113_seed(unsigned long s, unsigned int z[4]);
 double orc_t113_dbl(unsigned int z[4]);

@@ -206,6 +206,25 @@ EXPORT void ref_barrier(void) { MPI_Barrier(MPI_COMM_WORLD); }
 /* the reference's own ComputeEnergy (cmc_utils.c:604-656): E, J of the local stars from the new potential */
 EXPORT void ref_compute_energy(void) { ComputeEnergy(); }
 
+/* comp_mass_percent (src/cmc/cmc_utils.c:872-985) on the harness's cluster state: thresholds in, the eight result arrays out
+ * (out[8][count], in the order mass_r, ave_mass_r, no_star_r, densities_r, ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r; on ranks other than 0
+ * the last four hold what that rank computed, i.e. nothing meaningful -- the reference prints from rank 0 only). */
+EXPORT void ref_comp_mass_percent(const double *pc, long count, int bh_include, double minimum_r, double initial_total_mass_in, double *out)
+{
+	long i;
+	double **arr[8] = {&mass_r, &ave_mass_r, &no_star_r, &densities_r, &ke_rad_r, &ke_tan_r, &v2_rad_r, &v2_tan_r};
+	MASS_PC_COUNT = count;
+	MASS_PC_BH_INCLUDE = bh_include;
+	MINIMUM_R = minimum_r;
+	initial_total_mass = initial_total_mass_in;
+	mass_pc = (double *) malloc(count * sizeof(double));
+	for (i = 0; i < count; i++) mass_pc[i] = pc[i];
+	for (i = 0; i < 8; i++) { long j; *arr[i] = (double *) malloc(count * sizeof(double)); for (j = 0; j < count; j++) (*arr[i])[j] = -1.0; }
+	comp_mass_percent();
+	for (i = 0; i < 8; i++) { memcpy(out + i * count, *arr[i], count * sizeof(double)); free(*arr[i]); *arr[i] = NULL; }
+	free(mass_pc); mass_pc = NULL;
+}
+
 /* timing leg for bench.py: one pass of orbit step -> (caller refreshes r) -> sort -> post_sort_comm -> potential.
  * Brackets follow timeStartSimple/timeEndSimple (cmc_utils.c:1681-1707): barrier, wall clock. */
 EXPORT void ref_time_step(double *t_orb, double *t_sort, double *t_comm, double *t_pot)

@@ -29,6 +29,9 @@ typedef struct {
 	int counts[MM_MAX_RANKS][MM_MAX_RANKS];
 	int displs[MM_MAX_RANKS][MM_MAX_RANKS];
 	size_t nbytes[MM_MAX_RANKS];
+	/* point-to-point: one small mailbox per (destination, source) pair -- comp_mass_percent sends 4 doubles to rank 0 */
+	volatile int mail_full[MM_MAX_RANKS][MM_MAX_RANKS];
+	char mail[MM_MAX_RANKS][MM_MAX_RANKS][64];
 } mm_ctrl_t;
 
 static mm_ctrl_t *mm = NULL;
@@ -229,4 +232,49 @@ int MPI_Alltoall(const void *s, int sn, MPI_Datatype st, void *r, int rn, MPI_Da
 	int scnt[MM_MAX_RANKS], sdsp[MM_MAX_RANKS], rcnt[MM_MAX_RANKS], rdsp[MM_MAX_RANKS];
 	for (int q = 0; q < mm_size; q++) { scnt[q] = sn; sdsp[q] = q * sn; rcnt[q] = rn; rdsp[q] = q * rn; }
 	return MPI_Alltoallv(s, scnt, sdsp, st, r, rcnt, rdsp, rt, c);
+}
+
+/* MPI_Exscan (reference src/cmc/cmc_utils.c:925): rank i receives op(send_0, .., send_{i-1}), combined in rank order; rank 0's
+ * receive buffer is left untouched (undefined in MPI).  Only MPI_SUM over doubles is reached. */
+int MPI_Exscan(const void *s, void *r, int n, MPI_Datatype t, MPI_Op op, MPI_Comm c)
+{
+	(void) c; (void) op;
+	if (mm_size == 1) return 0;
+	size_t bytes = (size_t) n * MINI_MPI_SIZE(t);
+	mm_need(bytes, "MPI_Exscan");
+	memcpy(win(mm_rank), s, bytes);
+	mm_barrier();
+	if (mm_rank > 0) {
+		double *out = (double *) r;
+		for (int i = 0; i < n; i++) out[i] = ((const double *) win(0))[i];
+		for (int q = 1; q < mm_rank; q++)
+			for (int i = 0; i < n; i++) out[i] += ((const double *) win(q))[i];
+	}
+	mm_barrier();
+	return 0;
+}
+
+int MPI_Send(const void *b, int n, MPI_Datatype t, int dst, int tag, MPI_Comm c)
+{
+	(void) tag; (void) c;
+	size_t bytes = (size_t) n * MINI_MPI_SIZE(t);
+	if (mm_size == 1 || bytes > sizeof(mm->mail[0][0])) { fprintf(stderr, "mini_mpi: MPI_Send of %zu bytes not supported\n", bytes); _exit(5); }
+	while (mm->mail_full[dst][mm_rank]) { if (mm->abort_flag) _exit(3); sched_yield(); }
+	memcpy(mm->mail[dst][mm_rank], b, bytes);
+	__sync_synchronize();
+	mm->mail_full[dst][mm_rank] = 1;
+	return 0;
+}
+
+int MPI_Recv(void *b, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Status *st)
+{
+	(void) tag; (void) c; (void) st;
+	size_t bytes = (size_t) n * MINI_MPI_SIZE(t);
+	if (mm_size == 1 || bytes > sizeof(mm->mail[0][0])) { fprintf(stderr, "mini_mpi: MPI_Recv of %zu bytes not supported\n", bytes); _exit(5); }
+	while (!mm->mail_full[mm_rank][src]) { if (mm->abort_flag) _exit(3); sched_yield(); }
+	__sync_synchronize();
+	memcpy(b, mm->mail[mm_rank][src], bytes);
+	__sync_synchronize();
+	mm->mail_full[mm_rank][src] = 0;
+	return 0;
 }

@@ -14,6 +14,7 @@ Cases
   ci_input        ci/input.hdf5 as it is (N = 10 000, Kroupa masses, 1 967 binaries; BASELINE.json configs[0]); the
                   CLUS_OBJ_DATA table is read straight from the file bytes (no HDF5 library in this image)
   cosmic_plummer_n100 / cosmic_king_n100   the N=100 vectors of COSMIC's own unit tests (tests/data/cmc_*_test.npz)
+  lagrange_<case> comp_mass_percent (the Lagrange radii) on the initial state of <case>, `make_golden.py lagrange`
 Every case records ONE full pass of the path by the reference:
   calc_potential_new -> ComputeEnergy -> new_orbits_calculate (taus113 draws recorded) -> r <- rnew (ComputeIntermediateEnergy's
   transfer) -> qsorts_new -> post_sort_comm -> calc_potential_new
@@ -120,8 +121,31 @@ def run_case(R, name, r, vr, vt, obj_m, binind=None, seed=1234, min_chunk=40, rt
           f"N_MAX_after={n2} n_bin={n_bin}->{out['N_b_local_after']}")
 
 
+LAGRANGE_PCS = np.array([1e-4, 0.001, 0.005, 0.01, 0.03, 0.05, 0.07, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 0.99, 1.1])  # examples' MASS_PC + edges
+
+
+def lagrange_cases(R):
+    """lagrange_<case>.npz: comp_mass_percent (reference src/cmc/cmc_utils.c:872-985) run by the reference on the initial state of an existing
+    fixture (after calc_potential_new), without and with MASS_PC_BH_INCLUDE + a central mass.  Inputs are those of <case>.npz."""
+    for case, cenma, bh in (("plummer_n4000", 0.0, 0), ("king_w7_imf_bin", 0.0, 0), ("ci_input", 0.0, 0), ("king_w5_n3000", 0.003, 1)):
+        g = np.load(os.path.join(HERE, case + ".npz"))
+        n = int(g["N_STAR"])
+        R.init(n, n_star_dim=n + 64, n_bin_dim=8, min_chunk=int(g["min_chunk"]), idum=int(g["seed"]))
+        R.load_cluster(g["r"], g["vr"], g["vt"], g["star_m"])
+        R.set_scalars(n, n, cenma_m=cenma * n)
+        R.L.ref_calc_potential_new()
+        out = R.comp_mass_percent(LAGRANGE_PCS, bh_include=bh, minimum_r=1e-6, initial_total_mass=0.98)
+        out.update(mass_pc=LAGRANGE_PCS, cenma_m=cenma * n, bh_include=bh, minimum_r=1e-6, initial_total_mass=0.98, Mtotal=R.scalars()["Mtotal"], case=case)
+        R.free()
+        np.savez_compressed(os.path.join(HERE, f"lagrange_{case}.npz"), **out)
+        print(f"lagrange_{case}: mass_r = {out['mass_r'][[0, 7, 11, 15]]} no_star_r = {out['no_star_r'][[0, 7, 11, 15]]}")
+
+
 def main():
     assert rh.available(), "build oracle/_ref first (make -C oracle)"
+    if len(sys.argv) > 1 and sys.argv[1] == "lagrange":   # only the comp_mass_percent fixtures (the others are their inputs)
+        lagrange_cases(rh.Ref())
+        return
     el, kg = _load("elson"), _load("king")
     R = rh.Ref()
     np.random.seed(1234)

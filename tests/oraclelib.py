@@ -51,6 +51,9 @@ def lib():
         L.orc_get_positions.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 7 + [C.c_double, C.c_void_p, C.c_long] + [C.c_void_p] * 12
         L.orc_sort_stars.restype = C.c_long
         L.orc_sort_stars.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p]
+        L.orc_comp_mass_percent.restype = C.c_long
+        L.orc_comp_mass_percent.argtypes = ([C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_int]
+                                            + [C.c_double] * 4 + [C.c_int, C.c_double, C.c_void_p, C.c_long] + [C.c_void_p] * 10)
         L.orc_t113_seed.argtypes = [C.c_ulong, C.c_void_p]
         L.orc_t113_dbl.restype = C.c_double
         L.orc_t113_dbl.argtypes = [C.c_void_p]
@@ -131,3 +134,23 @@ class Taus113:
         out = np.empty(n)
         lib().orc_t113_fill(_p(self.z), _p(out), n)
         return out
+
+
+MASS_PC_FIELDS = ("mass_r", "ave_mass_r", "no_star_r", "densities_r", "ke_rad_r", "ke_tan_r", "v2_rad_r", "v2_tan_r")
+
+
+def comp_mass_percent(star_r, star_m, N_MAX, N_STAR, vr, vt, mass_pc, Mtotal, first_global=1, prefix=None, is_rank0=True, cenma_m=0.0,
+                      initial_total_mass=1.0, bh_include=False, minimum_r=0.0):
+    """comp_mass_percent as one rank sees it (vr, vt: this rank's local stars).  Returns the eight arrays (entries never reached stay -1),
+    `owner`, `totals` (the rank's contribution to the Exscan) and `filled`."""
+    vr, vt = np.ascontiguousarray(vr, np.float64), np.ascontiguousarray(vt, np.float64)
+    pc = np.ascontiguousarray(mass_pc, np.float64)
+    n = len(pc)
+    out = {f: np.full(n, -1.0) for f in MASS_PC_FIELDS}
+    owner, totals = np.zeros(n, np.int32), np.zeros(4)
+    pre = np.zeros(4) if prefix is None else np.ascontiguousarray(prefix, np.float64)
+    filled = lib().orc_comp_mass_percent(_p(star_r), _p(star_m), N_MAX, N_STAR, _p(vr), _p(vt), len(vr), first_global, _p(pre), int(is_rank0),
+                                         cenma_m, 1.0 / N_STAR, Mtotal, initial_total_mass, int(bh_include), minimum_r, _p(pc), n,
+                                         *[_p(out[f]) for f in MASS_PC_FIELDS], _p(owner), _p(totals))
+    out.update(owner=owner, totals=totals, filled=int(filled))
+    return out

@@ -43,6 +43,30 @@ def main(procs, N):
     ok = ok and np.array_equal(R.star_field("id", np.int64)[1:hi - lo + 2], order[lo - 1:hi] + 1)
     want = cm.oracle_potential(rnew[order], sm[order], N)
     ok = ok and np.array_equal(R.star_r()[1:N + 1], rnew[order]) and np.array_equal(R.star_phi()[:N + 2].view(np.uint64), want["phi"][:N + 2].view(np.uint64))
+    # comp_mass_percent (reference cmc_utils.c:872-985): rank-local cumulative sums + Exscan + the owner's values sent to rank 0
+    vrs, vts = vr[order], vt[order]
+    R.star_field("vr")[1:hi - lo + 2] = vrs[lo - 1:hi]
+    R.star_field("vt")[1:hi - lo + 2] = vts[lo - 1:hi]
+    pcs = np.array([1e-4, 0.001, 0.01, 0.1, 0.3, 0.5, 0.5000001, 0.9, 0.99, 0.999999, 1.5])
+    Mtot = R.scalars()["Mtotal"]
+    got = R.comp_mass_percent(pcs, initial_total_mass=0.97)
+    if rank == 0:
+        sr, smt = R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy()
+        parts, prefix = [], np.zeros(4)
+        for q in range(procs):   # the oracle as every rank in turn; MPI_Exscan = running sum of the lower ranks' totals in rank order
+            o = ol.comp_mass_percent(sr, smt, N, N, vrs[S[q] - 1:E[q]], vts[S[q] - 1:E[q]], pcs, Mtot, first_global=int(S[q]), prefix=prefix.copy(),
+                                     is_rank0=(q == 0), initial_total_mass=0.97)
+            parts.append(o)
+            prefix = o["totals"].copy() if q == 0 else prefix + o["totals"]
+        for f in ol.MASS_PC_FIELDS[:4]:
+            ok = ok and np.array_equal(got[f].view(np.uint64), parts[0][f].view(np.uint64))
+        for f in ol.MASS_PC_FIELDS[4:]:
+            merged = np.full(len(pcs), -1.0)
+            for o in parts:
+                merged[o["owner"] == 1] = o[f][o["owner"] == 1]
+            ok = ok and np.array_equal(got[f].view(np.uint64), merged.view(np.uint64))
+        ok = ok and parts[0]["filled"] == len(pcs) - 1 and got["mass_r"][-1] == -1.0     # 150 % of the mass is never reached
+        ok = ok and len({int(np.argmax([o["owner"][i] for o in parts])) for i in range(len(pcs) - 1)}) >= min(procs, 2)  # several owners
     if not ok:
         print(f"rank {rank}: MISMATCH", flush=True)
         sys.exit(3)

@@ -137,6 +137,15 @@ class Ref:
         if binind is not None:
             self.star_field("binind", np.int64)[1:n + 1] = binind
 
+    def comp_mass_percent(self, mass_pc, bh_include=False, minimum_r=0.0, initial_total_mass=1.0):
+        """the reference's comp_mass_percent on the harness's state; entries it never reaches stay -1"""
+        pc = np.ascontiguousarray(mass_pc, np.float64)
+        out = np.zeros((8, len(pc)))
+        self.L.ref_comp_mass_percent.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        self.L.ref_comp_mass_percent(pc.ctypes.data, len(pc), int(bh_include), minimum_r, initial_total_mass, out.ctypes.data)
+        names = ("mass_r", "ave_mass_r", "no_star_r", "densities_r", "ke_rad_r", "ke_tan_r", "v2_rad_r", "v2_tan_r")
+        return {k: out[i].copy() for i, k in enumerate(names)}
+
     def compute_energy(self):
         """E, J exactly as ComputeEnergy (reference cmc_utils.c:614-615), single rank."""
         n = int(self.scalars()["N_MAX"])

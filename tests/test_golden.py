@@ -15,7 +15,9 @@ import pytest
 import common as cm
 import oraclelib as ol
 
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(cm.GOLDEN, "*.npz")))
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(cm.GOLDEN, "*.npz")))
+CASES = [c for c in ALL if not c.startswith("lagrange_")]
+LAGRANGE = [c for c in ALL if c.startswith("lagrange_")]
 SF = cm.SF_INFINITY
 
 
@@ -26,6 +28,43 @@ def load(case):
 
 def test_fixture_inventory():
     assert {"plummer_n4000", "plummer_n4000_tidal", "king_w5_n3000", "king_w7_imf_bin", "ci_input", "cosmic_plummer_n100", "cosmic_king_n100"} <= set(CASES)
+
+
+def _lagrange_inputs(case):
+    g, base = load(case), None
+    base = load(g["case"])
+    n = base["N_STAR"]
+    sr, sm = cm.make_tables(base["r"], base["star_m"])
+    return g, base, n, sr, sm
+
+
+@pytest.mark.parametrize("case", LAGRANGE)
+def test_oracle_lagrange_radii_match_reference(case):
+    """comp_mass_percent (reference cmc_utils.c:872-985) by the oracle against what the compiled reference produced"""
+    g, base, n, sr, sm = _lagrange_inputs(case)
+    assert len(LAGRANGE) >= 4
+    want = ol.comp_mass_percent(sr, sm, n, n, base["vr"], base["vt"], g["mass_pc"], g["Mtotal"], cenma_m=g["cenma_m"], initial_total_mass=g["initial_total_mass"],
+                                bh_include=bool(g["bh_include"]), minimum_r=g["minimum_r"])
+    for f in ol.MASS_PC_FIELDS:
+        cm.assert_bits_equal(want[f], g[f], f)
+    assert want["filled"] == len(g["mass_pc"]) - 1 and g["mass_r"][-1] == -1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", LAGRANGE)
+def test_cuda_lagrange_radii_match_reference(case):
+    from cmc_cosmic_b200.cluster import Cluster
+    g, base, n, sr, sm = _lagrange_inputs(case)
+    c = Cluster(n, n_star_dim=n + 64)
+    c.load(base["r"], base["vr"], base["vt"], base["star_m"])
+    c.cenma.m = g["cenma_m"]
+    c.calc_potential_new()
+    assert c.Mtotal == g["Mtotal"]
+    c.upload()
+    c.dev_comp_mass_percent(g["mass_pc"], bh_include=bool(g["bh_include"]), minimum_r=g["minimum_r"], initial_total_mass=g["initial_total_mass"])
+    for f in ol.MASS_PC_FIELDS:
+        cm.assert_bits_equal(getattr(c, f), g[f], f)
+    c.close()
 
 
 def expected_status(g):

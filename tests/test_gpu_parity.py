@@ -328,3 +328,34 @@ def test_fused_step_equals_unfused_step():
     assert np.array_equal(a[2], b[2]), "binary[]"
     for x, y, name in zip(a[3:6], b[3:6], ("star_r", "star_m", "star_phi")):
         cm.assert_bits_equal(x, y, name)
+
+
+@pytest.mark.parametrize("kind,N,masses,cenma,bh", [("plummer", 1000, "equal", 0.0, False), ("plummer", 300000, "imf", 0.0, False),
+                                                    ("king", 1000000, "equal", 0.0, False), ("plummer", 200000, "imf", 0.004, True)])
+def test_lagrange_radii_bit_exact(kind, N, masses, cenma, bh):
+    """comp_mass_percent on the resident arrays: enclosed-mass and the four cumulative kinetic sums carry the reference's
+    sequential roundings, so radii, star counts, mean masses, densities and sums equal the oracle's bit for bit -- before and after a step
+    of the resident pipeline; thresholds the cluster never reaches stay untouched; MASS_PC_BH_INCLUDE with a central mass"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 1, masses=masses)
+    pcs = np.array([1e-5, 1e-4, 0.001, 0.005, 0.01, 0.05, 0.1, 0.2, 0.3, 0.5, 0.5 + 1e-9, 0.7, 0.9, 0.99, 0.999999, 1.2])
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.cenma.m = cenma * N
+    c.calc_potential_new()
+    c.upload()
+    for step in range(2):
+        filled = c.dev_comp_mass_percent(pcs, bh_include=bh, minimum_r=1e-7, initial_total_mass=0.93)
+        c.download()
+        n = c.clus.N_MAX
+        want = ol.comp_mass_percent(c.star_r[:n + 2].copy(), c.star_m[:n + 2].copy(), n, N, c.field("vr")[1:n + 1].copy(), c.field("vt")[1:n + 1].copy(),
+                                    pcs, c.Mtotal, cenma_m=c.cenma.m, initial_total_mass=0.93, bh_include=bh, minimum_r=1e-7)
+        assert filled == want["filled"] == len(pcs) - 1
+        for f in ol.MASS_PC_FIELDS:
+            cm.assert_bits_equal(getattr(c, f), want[f], f"{f} (step {step})")
+        assert c.mass_r[-1] == -1.0 and np.all(np.diff(c.mass_r[:-1]) >= 0)
+        cm.assert_bits_equal(c.mass_pc_totals, want["totals"], "totals")
+        if bh:
+            assert c.mass_r[0] == 1e-7 and c.no_star_r[0] == 0     # the central mass alone exceeds the first thresholds
+        c.compute_energy(); c.upload()
+        c.dev_step(seed=3)
+    c.close()
