@@ -45,6 +45,17 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 {
 	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// relaxed device-scope accesses (L2, no L1 invalidate / fence): enough when the polled word carries the data itself
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+	unsigned v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v)
+{
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ double ld_relaxed_f64(const double *p)
 {
 	double v;

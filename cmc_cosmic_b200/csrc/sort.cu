@@ -117,7 +117,7 @@ __global__ void sort_reset(SortState *st, unsigned *tile_hist, long n_words)
 constexpr unsigned LB_AGG = 1u << 30, LB_INCL = 2u << 30, LB_MASK = (1u << 30) - 1;
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_pass(SortBuffers b, SortState *st, unsigned *tile_hist /*[ntiles][256]*/, long n, int pass)
+__global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS_PER_SM) sort_onesweep_pass(SortBuffers b, SortState *st, unsigned *tile_hist /*[ntiles][256]*/, long n, int pass)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint64_t *s_keys = (uint64_t *) smem_raw;                       // [TILE]
@@ -173,45 +173,52 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_pass(SortBuffers b
 			__syncwarp();
 		}
 		__syncthreads();
-		// per digit (thread d): turn the per-warp counts into warp offsets, get the tile count
-		const unsigned d = threadIdx.x; // SORT_THREADS == 256
-		unsigned tcount = 0;
+		// per digit (threads 0..255, thread d = digit d): turn the per-warp counts into warp offsets, get the tile count
+		const unsigned d = threadIdx.x;
+		const bool digit_thread = d < 256;
+		unsigned tcount = 0, inc = 0, pad = 0;
+		if (digit_thread) {
 #pragma unroll
-		for (int w = 0; w < SORT_WARPS; w++) {
-			unsigned c = s_cnt[w * 256 + d];
-			s_cnt[w * 256 + d] = tcount;
-			tcount += c;
-		}
-		if (d == 255) tcount -= (unsigned) (SORT_TILE - tile_n); // padding lives at the end of digit 255
-		// publish, then look back over earlier tiles for this digit
-		unsigned *my = tile_hist + tile * 256 + d;
-		unsigned excl = 0;
-		if (tile == 0) st_release_u32(my, LB_INCL | tcount);
-		else {
-			st_release_u32(my, LB_AGG | tcount);
-			for (long t = tile - 1; t >= 0; t--) {
-				unsigned v;
-				do { v = ld_acquire_u32(tile_hist + t * 256 + d); } while ((v >> 30) == 0);
-				excl += v & LB_MASK;
-				if (v & LB_INCL) break;
+			for (int w = 0; w < SORT_WARPS; w++) {
+				unsigned c = s_cnt[w * 256 + d];
+				s_cnt[w * 256 + d] = tcount;
+				tcount += c;
 			}
-			st_release_u32(my, LB_INCL | (excl + tcount));
-		}
-		s_glob[d] = st->base[pass][d] + excl;
-		// position of each digit inside the tile (exclusive scan of tcount over the 256 digits)
-		unsigned pad = (d == 255) ? (unsigned) (SORT_TILE - tile_n) : 0u;
-		unsigned inc = tcount + pad;
+			if (d == 255) tcount -= (unsigned) (SORT_TILE - tile_n); // padding lives at the end of digit 255
+			// publish, then look back over earlier tiles for this digit.  Each look-back word holds its state AND its count, so
+			// relaxed device-scope accesses are enough (ld.acquire compiles to a load + CCTL.IVALL + fence: the spin invalidated
+			// the SM's whole L1 ~10 times per tile and digit -- 12 % of the pass's stall samples in ncu).
+			unsigned *my = tile_hist + tile * 256 + d;
+			unsigned excl = 0;
+			if (tile == 0) st_relaxed_u32(my, LB_INCL | tcount);
+			else {
+				st_relaxed_u32(my, LB_AGG | tcount);
+				for (long t = tile - 1; t >= 0; t--) {
+					unsigned v;
+					do { v = ld_relaxed_u32(tile_hist + t * 256 + d); } while ((v >> 30) == 0);
+					excl += v & LB_MASK;
+					if (v & LB_INCL) break;
+				}
+				st_relaxed_u32(my, LB_INCL | (excl + tcount));
+			}
+			s_glob[d] = st->base[pass][d] + excl;
+			// position of each digit inside the tile (exclusive scan of tcount over the 256 digits)
+			pad = (d == 255) ? (unsigned) (SORT_TILE - tile_n) : 0u;
+			inc = tcount + pad;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= (unsigned) o) inc += v;
+			for (int o = 1; o < 32; o <<= 1) {
+				unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+				if (lane >= (unsigned) o) inc += v;
+			}
+			if (lane == 31) s_wsum[warp] = inc;
 		}
-		if (lane == 31) s_wsum[warp] = inc;
 		__syncthreads();
-		unsigned pre = 0;
+		if (digit_thread) {
+			unsigned pre = 0;
 #pragma unroll
-		for (int w = 0; w < SORT_WARPS; w++) pre += (w < (int) warp) ? s_wsum[w] : 0u;
-		s_local_base[d] = pre + inc - (tcount + pad);
+			for (int w = 0; w < 256 / 32; w++) pre += (w < (int) warp) ? s_wsum[w] : 0u;
+			s_local_base[d] = pre + inc - (tcount + pad);
+		}
 		__syncthreads();
 		// scatter into shared memory in sorted-by-digit order
 #pragma unroll
@@ -431,7 +438,7 @@ int sort_stage_passes(const SortArgs &a, cudaStream_t s)
 	if (n <= 0) return 0;
 	const long ntiles = (n + SORT_TILE - 1) / SORT_TILE;
 	sort_iota_if_skipped<<<NUM_SMS_B200 * 2, 256, 0, s>>>(a.buf, a.st, n);
-	const int grid = (int) (ntiles < NUM_SMS_B200 * 2 ? ntiles : NUM_SMS_B200 * 2);
+	const int grid = (int) (ntiles < NUM_SMS_B200 * SORT_CTAS_PER_SM ? ntiles : NUM_SMS_B200 * SORT_CTAS_PER_SM);
 	const size_t sm = sort_smem_bytes();
 	for (int p = 0; p < 8; p++) {
 		unsigned *th = a.tile_hist + (long) p * ntiles * 256;

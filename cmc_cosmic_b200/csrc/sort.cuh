@@ -4,10 +4,13 @@
 
 namespace cmcb {
 
+// 512 threads x 8 items: the same 4096-pair tile as 256 x 16, but the per-thread arrays fit in 64 registers, so two CTAs = 32 warps are
+// resident per SM instead of 16 (the pass is bound by the latency of its look-back and shared-memory phases, not by HBM)
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 (key, index) pairs per CTA iteration
+constexpr int SORT_CTAS_PER_SM = 2;
 
 struct SortState { // device-resident bookkeeping of one sort
 	unsigned hist[8][256];    // digit histograms of the 8 LSD passes
