@@ -206,6 +206,16 @@ class Cluster:
         n_old = int(self.End[0] - self.Start[0] + 1)
         _lib.check(self.L.cmcb200_dev_transfer_new_positions(self.ctx, self.clus.N_MAX_NEW, n_old, int(self.Start[0]), self.clus.N_MAX), "dev_transfer")
 
+    def dev_energy_conservation2(self):
+        """energy_conservation2 (reference src/cmc/cmc_utils.c:2217-2226) on the resident arrays: Uoldrnew of every local star"""
+        p = self.orbit_params()
+        _lib.check(self.L.cmcb200_dev_energy_conservation2(self.ctx, C.byref(p)), "dev_energy_conservation2")
+
+    def dev_compute_intermediate_energy(self):
+        """ComputeIntermediateEnergy (reference src/cmc/cmc_utils.c:368-391) on the resident arrays: EI, then r <- rnew etc."""
+        p = self.orbit_params()
+        _lib.check(self.L.cmcb200_dev_compute_intermediate_energy(self.ctx, C.byref(p)), "dev_compute_intermediate_energy")
+
     def dev_qsorts_new(self):
         n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
         _lib.check(self.L.cmcb200_dev_qsorts_new(self.ctx, C.byref(n), max(self.N_b_local, 0), C.byref(nb)), "dev_qsorts_new")

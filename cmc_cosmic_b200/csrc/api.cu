@@ -472,6 +472,35 @@ extern "C" int cmcb200_dev_new_orbits(cmcb200_ctx *c, const cmcb200_orbit_params
 	return orbit_common(c, p, want_status != 0, res);
 }
 
+// energy_conservation2 / ComputeIntermediateEnergy on the resident arrays (orbit.cu: energy_rnew_kernel)
+static int energy_rnew(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool uold, bool ei, const char *what)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	OrbitArgs a;
+	if (orbit_begin(c, p, false, false, a)) return -1;
+	{ StageTimer t(c, ST_ENERGY); c->launches += orbit_energy_rnew(a, uold, ei, c->stream); }
+	CMCB_CUDA_OK(cudaGetLastError());
+	OrbitStats *h = (OrbitStats *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	if (h->n_status[ORBIT_NTRY]) { // eprintf + exit_cleanly(-2) in the reference (cmc_utils.c:144-152)
+		set_error("%s: binary search (FindZero_r) failed for %llu stars", what, h->n_status[ORBIT_NTRY]);
+		return -2;
+	}
+	return 0;
+}
+
+extern "C" int cmcb200_dev_energy_conservation2(cmcb200_ctx *c, const cmcb200_orbit_params *p)
+{
+	return energy_rnew(c, p, true, false, "energy_conservation2");
+}
+
+extern "C" int cmcb200_dev_compute_intermediate_energy(cmcb200_ctx *c, const cmcb200_orbit_params *p)
+{
+	if (energy_rnew(c, p, false, true, "ComputeIntermediateEnergy")) return -1;
+	return cmcb200_dev_transfer_new_positions(c, p->n_local, p->n_old_local, p->first_global, p->N_MAX);
+}
+
 extern "C" int cmcb200_dev_read_status(cmcb200_ctx *c, int *status, long *kmin, long *kmax, long n_local)
 {
 	StageTimer t(c, ST_D2H);

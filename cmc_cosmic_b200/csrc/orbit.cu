@@ -524,6 +524,53 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 	}
 }
 
+__global__ void orbit_stats_reset(OrbitStats *s);
+
+// ---- the energy scheme's lookups at the new radii -----------------------------------------------------------------------
+//
+//   UOLD: energy_conservation2 (reference src/cmc/cmc_utils.c:2217-2226)   star[i].Uoldrnew = potential(rnew) + MPI_PHI_S(rnew, g_i), every star
+//   EI:   ComputeIntermediateEnergy's first loop (:371-378)                 star[j].EI = sqr(vr) + sqr(vt) + star_phi[g_j] - potential(rnew)
+//                                                                           for the stars with rnew < 1e6
+// One potential() lookup per star through the r ladder (as in the rejection rounds), persistent CTAs.  A lookup whose bracket check
+// (cmc_utils.c:144-152) fails is fatal in the reference: it is counted in stats->n_status[ORBIT_NTRY] and reported by the caller.
+template <bool UOLD, bool EI>
+__global__ void __launch_bounds__(ORBIT_TRY_THREADS, ORBIT_CTAS_PER_SM) energy_rnew_kernel(OrbitArgs a)
+{
+	extern __shared__ __align__(128) unsigned char orbit_smem[];
+	__shared__ __align__(8) unsigned long long bar;
+	LadderTops top;
+	top.q = nullptr; top.qdesc = nullptr;
+	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
+	for (long j0 = blockIdx.x * (long) ORBIT_TRY_THREADS + threadIdx.x; j0 < a.n_local; j0 += (long) gridDim.x * ORBIT_TRY_THREADS) {
+		const long j = j0 + 1;
+		const kint g = (kint) (j > a.n_old_local ? 1 + a.t.N_MAX + (j - a.n_old_local) : a.first_global + j - 1); // get_global_idx
+		char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
+		const double rn = ld_field(rec, CMCB_OFF_RNEW);
+		if (!UOLD && !(rn < 1.0e6)) continue;
+		int fail = 0;
+		const double pot = potential_at(a.t, top, rn, &fail);
+		if (fail) { atomicAdd(&a.stats->n_status[ORBIT_NTRY], 1ull); continue; }
+		const RPhi own = tbl_rp(a.t, g);
+		if (UOLD) st_field(rec, CMCB_OFF_UOLDRNEW, dadd(pot, phi_self(rn, own.r, tbl_ld(a.t.m, g), a.t.invN)));
+		if (EI && rn < 1.0e6) {
+			const double vr = ld_field(rec, CMCB_OFF_VR), vt = ld_field(rec, CMCB_OFF_VT);
+			st_field(rec, CMCB_OFF_EI, dsub(dadd(dadd(dmul(vr, vr), dmul(vt, vt)), own.phi), pot));
+		}
+	}
+}
+
+int orbit_energy_rnew(const OrbitArgs &a, bool uold, bool ei, cudaStream_t s)
+{
+	orbit_stats_reset<<<1, 1, 0, s>>>(a.stats);
+	if (a.n_local <= 0) return 1;
+	long blocks = (a.n_local + ORBIT_TRY_THREADS - 1) / ORBIT_TRY_THREADS;
+	if (blocks > (long) NUM_SMS_B200 * ORBIT_CTAS_PER_SM) blocks = (long) NUM_SMS_B200 * ORBIT_CTAS_PER_SM;
+	if (uold && ei) energy_rnew_kernel<true, true><<<(unsigned) blocks, ORBIT_TRY_THREADS, a.r_top_bytes, s>>>(a);
+	else if (uold) energy_rnew_kernel<true, false><<<(unsigned) blocks, ORBIT_TRY_THREADS, a.r_top_bytes, s>>>(a);
+	else energy_rnew_kernel<false, true><<<(unsigned) blocks, ORBIT_TRY_THREADS, a.r_top_bytes, s>>>(a);
+	return 2;
+}
+
 __global__ void orbit_stats_reset(OrbitStats *s)
 {
 	s->max_rad_bits = 0; s->n_draws = 0; s->n_exact = 0; s->n_brent = 0;

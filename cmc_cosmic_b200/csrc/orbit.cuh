@@ -66,5 +66,6 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long
 int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_scan(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_tries(const OrbitArgs &a, cudaStream_t s);
+int orbit_energy_rnew(const OrbitArgs &a, bool uold, bool ei, cudaStream_t s);
 
 } // namespace cmcb

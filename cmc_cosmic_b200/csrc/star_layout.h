@@ -28,3 +28,4 @@
 #define CMCB_OFF_PHI 128
 #define CMCB_OFF_BININD 152
 #define CMCB_OFF_ID 160
+#define CMCB_OFF_UOLDRNEW 184

@@ -152,6 +152,15 @@ int cmcb200_dev_new_orbits(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int 
 /* the transfer half of ComputeIntermediateEnergy (src/cmc/cmc_utils.c:380-390): rOld <- star_r, r <- rnew, m <- star_m,
  * vr <- vrnew, vt <- vtnew for local stars 1..n_local -- this is what creates the sort key */
 int cmcb200_dev_transfer_new_positions(cmcb200_ctx *ctx, long n_local, long n_old_local, long first_global, long N_MAX);
+/* The two loops of the energy scheme between the orbit step and the sort that look the potential up at the new radii (one
+ * potential() per star, src/cmc/cmc_utils.c:112-165, through the same coarse-to-fine search as the orbit step's rejection rounds).
+ * p: the partition and table fields of the orbit step (n_local, n_old_local, first_global, N_MAX, N_STAR, n_table, cenma_m).
+ *   energy_conservation2 (src/cmc/cmc_utils.c:2217-2226):  star[i].Uoldrnew = potential(star[i].rnew) + MPI_PHI_S(star[i].rnew, g_i)
+ *   ComputeIntermediateEnergy (:368-391):                   star[j].EI = sqr(vr) + sqr(vt) + star_phi[g_j] - potential(star[j].rnew) where
+ *                                                           rnew < 1e6, then the transfer (cmcb200_dev_transfer_new_positions)
+ * A lookup whose bracket check fails (fatal in the reference, :144-152) makes the call return non-zero. */
+int cmcb200_dev_energy_conservation2(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
+int cmcb200_dev_compute_intermediate_energy(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
 /* qsorts_new + post_sort_comm on the resident arrays; *n_local in/out, *n_bin out */
 int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, long *n_bin);
 /* cmcb200_dev_transfer_new_positions + cmcb200_dev_qsorts_new in one pass over the records: the sort key is rnew and the transfer is

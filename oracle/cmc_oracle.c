@@ -510,3 +510,21 @@ long orc_comp_mass_percent(const double *star_r, const double *star_m, long N_MA
 	free(a0); free(a1); free(a2); free(a3);
 	return mcount;
 }
+
+/* ---- energy_conservation2 / ComputeIntermediateEnergy, src/cmc/cmc_utils.c:2217-2226, 368-378 ---------------------------------- */
+
+static double orc_mpi_phi_s(const orc_tables_t *t, double rad, long j) /* MPI_PHI_S, include/cmc/cmc.h:2175 */
+{
+	return (rad >= t->r[j] ? t->m[j] / rad : t->m[j] / t->r[j]) * (1.0 / t->N_STAR);
+}
+
+void orc_energy_conservation2(const orc_tables_t *t, long n_local, const long *g_idx, const double *rnew, double *Uoldrnew)
+{
+	for (long i = 0; i < n_local; i++) Uoldrnew[i] = orc_potential(t, rnew[i]) + orc_mpi_phi_s(t, rnew[i], g_idx[i]);
+}
+
+void orc_intermediate_energy(const orc_tables_t *t, long n_local, const long *g_idx, const double *rnew, const double *vr, const double *vt, double *EI)
+{
+	for (long j = 0; j < n_local; j++)
+		if (rnew[j] < 1.0e6) EI[j] = vr[j] * vr[j] + vt[j] * vt[j] + t->phi[g_idx[j]] - orc_potential(t, rnew[j]);
+}

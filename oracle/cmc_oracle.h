@@ -83,6 +83,13 @@ double orc_get_positions(const orc_tables_t *t, long n_local, const long *g_idx,
 long orc_sort_stars(unsigned char *star1, long n, long sizeof_star, long key_off, long binind_off,
 		    unsigned char *binary1, long n_bin_dim, long sizeof_binary, long *n_bin_out, long *perm_out);
 
+/* The two loops of the energy scheme that look the potential up at the NEW radii, between the orbit step and the sort:
+ *   energy_conservation2, src/cmc/cmc_utils.c:2217-2226:  Uoldrnew[i] = potential(rnew[i]) + MPI_PHI_S(rnew[i], g_i)  for every local star
+ *   ComputeIntermediateEnergy's first loop, :371-378:       EI[i] = sqr(vr[i]) + sqr(vt[i]) + star_phi[g_i] - potential(rnew[i])  where rnew[i] < 1e6
+ * g_idx: global index of each local star.  EI entries of escaped stars are left untouched. */
+void orc_energy_conservation2(const orc_tables_t *t, long n_local, const long *g_idx, const double *rnew, double *Uoldrnew);
+void orc_intermediate_energy(const orc_tables_t *t, long n_local, const long *g_idx, const double *rnew, const double *vr, const double *vt, double *EI);
+
 /* comp_mass_percent, src/cmc/cmc_utils.c:872-985: Lagrange radii and the cumulative kinetic sums at them, as ONE rank of P sees it.
  *   star_r, star_m: the replicated tables; vr, vt: star[k].vr / .vt of this rank's local stars k = 1..n_local at vr[k-1], vt[k-1];
  *   first_global = Start[myid] (global index of local star 1; the function is called after the sort, so there are no new stars).

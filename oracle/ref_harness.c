@@ -205,6 +205,8 @@ EXPORT int ref_rank(void) { int r; MPI_Comm_rank(MPI_COMM_WORLD, &r); return r; 
 EXPORT void ref_barrier(void) { MPI_Barrier(MPI_COMM_WORLD); }
 /* the reference's own ComputeEnergy (cmc_utils.c:604-656): E, J of the local stars from the new potential */
 EXPORT void ref_compute_energy(void) { ComputeEnergy(); }
+EXPORT void ref_energy_conservation2(void) { energy_conservation2(); }
+EXPORT void ref_compute_intermediate_energy(void) { ComputeIntermediateEnergy(); }
 
 /* comp_mass_percent (src/cmc/cmc_utils.c:872-985) on the harness's cluster state: thresholds in, the eight result arrays out
  * (out[8][count], in the order mass_r, ave_mass_r, no_star_r, densities_r, ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r; on ranks other than 0

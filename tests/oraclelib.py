@@ -51,6 +51,8 @@ def lib():
         L.orc_get_positions.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 7 + [C.c_double, C.c_void_p, C.c_long] + [C.c_void_p] * 12
         L.orc_sort_stars.restype = C.c_long
         L.orc_sort_stars.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p]
+        L.orc_energy_conservation2.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 3
+        L.orc_intermediate_energy.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 5
         L.orc_comp_mass_percent.restype = C.c_long
         L.orc_comp_mass_percent.argtypes = ([C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_int]
                                             + [C.c_double] * 4 + [C.c_int, C.c_double, C.c_void_p, C.c_long] + [C.c_void_p] * 10)
@@ -153,4 +155,19 @@ def comp_mass_percent(star_r, star_m, N_MAX, N_STAR, vr, vt, mass_pc, Mtotal, fi
                                          cenma_m, 1.0 / N_STAR, Mtotal, initial_total_mass, int(bh_include), minimum_r, _p(pc), n,
                                          *[_p(out[f]) for f in MASS_PC_FIELDS], _p(owner), _p(totals))
     out.update(owner=owner, totals=totals, filled=int(filled))
+    return out
+
+
+def energy_conservation2(t, g_idx, rnew):
+    g_idx, rnew = np.ascontiguousarray(g_idx, np.int64), np.ascontiguousarray(rnew, np.float64)
+    out = np.zeros(len(rnew))
+    lib().orc_energy_conservation2(C.byref(t), len(rnew), _p(g_idx), _p(rnew), _p(out))
+    return out
+
+
+def intermediate_energy(t, g_idx, rnew, vr, vt, EI_in):
+    g_idx = np.ascontiguousarray(g_idx, np.int64)
+    rnew, vr, vt = (np.ascontiguousarray(x, np.float64) for x in (rnew, vr, vt))
+    out = np.array(EI_in, dtype=np.float64, copy=True)
+    lib().orc_intermediate_energy(C.byref(t), len(rnew), _p(g_idx), _p(rnew), _p(vr), _p(vt), _p(out))
     return out

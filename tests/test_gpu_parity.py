@@ -359,3 +359,38 @@ def test_lagrange_radii_bit_exact(kind, N, masses, cenma, bh):
         c.compute_energy(); c.upload()
         c.dev_step(seed=3)
     c.close()
+
+
+@pytest.mark.parametrize("kind,N,masses,tidal", [("plummer", 50000, "equal", None), ("king", 800000, "equal", None), ("plummer", 120000, "imf", 3.0)])
+def test_energy_scheme_lookups_at_new_radii_bit_exact(kind, N, masses, tidal):
+    """SURVEY 8f N1 on the resident arrays: energy_conservation2 (Uoldrnew = potential(rnew) + MPI_PHI_S) and ComputeIntermediateEnergy
+    (EI where rnew < 1e6, then the transfer) after an orbit step with recorded draws, against the oracle: every potential() lookup goes
+    through the r ladder (3 levels at N = 800000) and must return the reference's interpolation bit for bit; escaped stars (tidal cut) keep
+    their EI and get Uoldrnew = potential(SF_INFINITY) + self term"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 7, masses=masses)
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    Rt = tidal if tidal is not None else pot["Rtidal"]
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, Rt, seed=3)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    g = np.arange(1, N + 1)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+    c.field("EI")[1:N + 1] = -7.0
+    c.Rtidal = Rt
+    c.upload()
+    c.dev_new_orbits(draws=want["draws"], draw_off=want["draw_off"])
+    c.dev_energy_conservation2()
+    c.dev_compute_intermediate_energy()
+    c.download()
+    cm.assert_bits_equal(c.field("Uoldrnew")[1:N + 1], ol.energy_conservation2(t, g, want["rnew"]), "Uoldrnew")
+    cm.assert_bits_equal(c.field("EI")[1:N + 1], ol.intermediate_energy(t, g, want["rnew"], vr, vt, np.full(N, -7.0)), "EI")
+    if tidal is not None:
+        esc = want["rnew"] >= 1.0e6
+        assert esc.sum() > 10 and np.all(c.field("EI")[1:N + 1][esc] == -7.0)
+    cm.assert_bits_equal(c.field("r")[1:N + 1], want["rnew"], "r <- rnew")
+    cm.assert_bits_equal(c.field("rOld")[1:N + 1], r, "rOld")
+    cm.assert_bits_equal(c.field("vr")[1:N + 1], want["vrnew"], "vr <- vrnew")
+    c.close()

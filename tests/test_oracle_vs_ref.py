@@ -67,10 +67,14 @@ def test_full_step(R, kind, N, masses, cenma):
     for f in ("X", "r_peri", "r_apo"):
         cm.assert_bits_equal(out[f][ok], R.star_field(f)[1:N + 1][ok], f)
     assert out["max_rad"] == R.scalars()["max_r"]
-    # sort + second potential
-    for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
-        R.star_field(dst)[1:N + 1] = R.star_field(src)[1:N + 1]
-    R.star_field("m")[1:N + 1] = R.star_m()[1:N + 1]
+    # the energy scheme's potential lookups at the new radii: energy_conservation2, ComputeIntermediateEnergy (EI + the transfer)
+    R.star_field("EI")[1:N + 1] = -7.0
+    R.L.ref_energy_conservation2()
+    cm.assert_bits_equal(ol.energy_conservation2(t, np.arange(1, N + 1), out["rnew"]), R.star_field("Uoldrnew")[1:N + 1], "Uoldrnew")
+    R.L.ref_compute_intermediate_energy()
+    cm.assert_bits_equal(ol.intermediate_energy(t, np.arange(1, N + 1), out["rnew"], vr, vt, np.full(N, -7.0)), R.star_field("EI")[1:N + 1], "EI")
+    assert np.array_equal(R.star_field("r")[1:N + 1], out["rnew"]) and np.array_equal(R.star_field("rOld")[1:N + 1], want["star_r"][1:N + 1])
+    # sort + second potential (the transfer was ComputeIntermediateEnergy's)
     R.L.ref_qsorts_new()
     R.L.ref_post_sort_comm()
     R.L.ref_calc_potential_new()
