@@ -120,11 +120,9 @@ void pot_work_bind(SeqWork &w, void *base, long n_dim)
 	w.tile_counter = (unsigned *) take(sizeof(unsigned));
 	w.fallback = (int *) take(sizeof(int));
 	w.stats = (long *) take(2 * sizeof(long));
-	w.tile_status = (int *) take(ntiles * sizeof(int));
 	w.tile_evcount = (int *) take(ntiles * sizeof(int));
 	w.tile_evoff = (int *) take(ntiles * sizeof(int));
-	w.tile_agg = (double *) take(ntiles * sizeof(double));
-	w.tile_incl = (double *) take(ntiles * sizeof(double));
+	w.tile_desc = (double2 *) take(ntiles * sizeof(double2));
 	w.tile_prefix = (double *) take(ntiles * sizeof(double));
 	w.tile_tail = (double *) take(ntiles * sizeof(double));
 	w.tile_carry = (double *) take(ntiles * sizeof(double));

@@ -37,9 +37,10 @@ struct SeqEvent {
 // Scratch shared by the chains of one context (they run one after the other on one stream).
 struct SeqWork {
 	unsigned *tile_counter; // dynamic tile id
-	int *tile_status;       // 0 none, 1 aggregate, 2 inclusive
-	double *tile_agg;       // approximate aggregate
-	double *tile_incl;      // approximate inclusive prefix
+	// look-back descriptor of a tile: {value, state} in ONE 16-byte word (state 0 none, 1 value = approximate aggregate, 2 value =
+	// approximate inclusive prefix), written and polled with single 128-bit relaxed device-scope accesses -- the pair is consistent by
+	// construction, so the poll needs no acquire (ld.acquire costs an L1 invalidate + fence per poll) and the publish no fence
+	double2 *tile_desc;
 	double *tile_prefix;    // approximate exclusive prefix (saved for finalize)
 	int *tile_evcount;      // events in the tile
 	double *tile_tail;      // exact run sum after the tile's last event (whole tile if none)
@@ -52,6 +53,18 @@ struct SeqWork {
 	long *stats;            // [0] events, [1] fallbacks (accumulated)
 	long max_tiles;
 };
+
+__device__ __forceinline__ void desc_publish(double2 *d, double value, int state)
+{
+	asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(d), "l"(__double_as_longlong(value)), "l"((long long) state) : "memory");
+}
+__device__ __forceinline__ int desc_poll(const double2 *d, double *value)
+{
+	long long v, s;
+	asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(s) : "l"(d) : "memory");
+	*value = __longlong_as_double(v);
+	return (int) s;
+}
 
 // ---- block-wide scans (256 threads) ----------------------------------------------------------------------------
 
@@ -208,9 +221,8 @@ __global__ void __launch_bounds__(SEQ_THREADS) seq_scan_classify(Chain ch, SeqWo
 		double thread_excl = tile_load(ch, n, tile_start, td, smem_w, &agg);
 		// publish the aggregate, then look back for the exclusive prefix (warp 0)
 		if (threadIdx.x == 0) {
-			w.tile_agg[tile] = agg;
-			if (tile == 0) { w.tile_incl[0] = agg; __threadfence(); st_release(&w.tile_status[0], 2); s_prefix = 0.0; }
-			else { __threadfence(); st_release(&w.tile_status[tile], 1); }
+			if (tile == 0) { desc_publish(&w.tile_desc[0], agg, 2); s_prefix = 0.0; }
+			else desc_publish(&w.tile_desc[tile], agg, 1);
 		}
 		if (tile > 0 && warp_id() == 0) {
 			double prefix = 0.0;
@@ -220,8 +232,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) seq_scan_classify(Chain ch, SeqWo
 				int st = 0;
 				double val = 0.0;
 				if (t >= 0) {
-					do { st = ld_acquire(&w.tile_status[t]); } while (st == 0);
-					val = ld_relaxed_f64(st == 2 ? &w.tile_incl[t] : &w.tile_agg[t]);
+					do { st = desc_poll(&w.tile_desc[t], &val); } while (st == 0);
 				} else st = 2; // virtual predecessor with inclusive prefix 0
 				unsigned incl_mask = __ballot_sync(0xffffffffu, st == 2);
 				int first_incl = __ffs(incl_mask) - 1; // nearest predecessor holding an inclusive prefix
@@ -233,9 +244,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) seq_scan_classify(Chain ch, SeqWo
 				look -= 32;
 			}
 			if (lane_id() == 0) {
-				w.tile_incl[tile] = dadd(prefix, agg);
-				__threadfence();
-				st_release(&w.tile_status[tile], 2);
+				desc_publish(&w.tile_desc[tile], dadd(prefix, agg), 2);
 				s_prefix = prefix;
 			}
 		}
@@ -400,7 +409,7 @@ static __global__ void seq_scan_reset(SeqWork w, long ntiles)
 {
 	long i = blockIdx.x * (long) blockDim.x + threadIdx.x;
 	if (i == 0) { *w.tile_counter = 0; *w.fallback = 0; }
-	if (i < ntiles) w.tile_status[i] = 0;
+	if (i < ntiles) w.tile_desc[i] = make_double2(0.0, 0.0); // state 0 (the state travels as the bit pattern of the second double)
 }
 
 // Launch the three kernels for one chain.  n_upper bounds ch.length() (which lives on the device).
