@@ -42,13 +42,20 @@ static void shim_fail(const char *where)
 	exit_cleanly(-1, where);
 }
 
+static void *pinned[5]; /* the arrays shim_init registered; they must be unregistered before the caller frees them */
+static void shim_unpin(void)
+{
+	int i;
+	for (i = 0; i < 5; i++) { if (pinned[i]) cmcb200_host_unregister(pinned[i]); pinned[i] = NULL; }
+}
+
 static void shim_init(void)
 {
 	long lay[16];
 	int dev = 0;
 	const char *e = getenv("CMCB200_DEVICE");
 	if (ctx && ctx_star_dim == N_STAR_DIM_OPT && ctx_bin_dim == N_BIN_DIM_OPT) return;
-	if (ctx) { cmcb200_destroy(ctx); ctx = NULL; } /* the arrays were re-dimensioned (a new run in the same process) */
+	if (ctx) { shim_unpin(); cmcb200_destroy(ctx); ctx = NULL; } /* the arrays were re-dimensioned (a new run in the same process) */
 	if (procs != 1) {
 		eprintf("cmcb200 shim: this binding drives one GPU from one rank; use the sharded entry points for procs=%d\n", procs);
 		exit_cleanly(-1, __FUNCTION__);
@@ -67,18 +74,18 @@ static void shim_init(void)
 	/* the arrays are allocated once (src/cmc/cmc_io.c:2099-2101, 3434-3436): pin them so that every copy is DMA at link rate.  A failure
 	 * (locked-memory limit) is not fatal -- pageable memory only copies slower. */
 	if (!getenv("CMCB200_NO_PIN")) {
-		cmcb200_host_register(star, (size_t) N_STAR_DIM_OPT * sizeof(star_t));
-		cmcb200_host_register(binary, (size_t) N_BIN_DIM_OPT * sizeof(binary_t));
-		cmcb200_host_register(star_r, (size_t) N_STAR_DIM * sizeof(double));
-		cmcb200_host_register(star_m, (size_t) N_STAR_DIM * sizeof(double));
-		cmcb200_host_register(star_phi, (size_t) N_STAR_DIM * sizeof(double));
+		void *arr[5] = {star, binary, star_r, star_m, star_phi};
+		size_t bytes[5] = {(size_t) N_STAR_DIM_OPT * sizeof(star_t), (size_t) N_BIN_DIM_OPT * sizeof(binary_t), (size_t) N_STAR_DIM * sizeof(double),
+				   (size_t) N_STAR_DIM * sizeof(double), (size_t) N_STAR_DIM * sizeof(double)};
+		int i;
+		for (i = 0; i < 5; i++) pinned[i] = cmcb200_host_register(arr[i], bytes[i]) == 0 ? arr[i] : NULL;
 	}
 }
 
 #define SHIM_EXPORT __attribute__((visibility("default")))
 SHIM_EXPORT void cmcb200_shim_set_draws(const double *draws, const long *draw_off) { shim_draws = draws; shim_draw_off = draw_off; }
 SHIM_EXPORT const cmcb200_orbit_result *cmcb200_shim_last_orbit(void) { return &last_orbit; }
-SHIM_EXPORT void cmcb200_shim_shutdown(void) { if (ctx) cmcb200_destroy(ctx); ctx = NULL; free(status_buf); status_buf = NULL; status_cap = 0; }
+SHIM_EXPORT void cmcb200_shim_shutdown(void) { shim_unpin(); if (ctx) cmcb200_destroy(ctx); ctx = NULL; free(status_buf); status_buf = NULL; status_cap = 0; }
 
 /* src/cmc/cmc_utils.c:2194-2211 */
 void SHIM(new_orbits_calculate)(void)

@@ -13,3 +13,5 @@ timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv python tools/perf_orbit.py 1e7 2 > $OUT/ncu_launch_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"orbit_prepare_kernel|orbit_try_kernel|sort_gather_records|sort_onesweep_pass|seq_scan_classify|seq_scan_finalize" -c 24 -f -o $OUT/prof_$TAG python tools/perf_orbit.py 1e7 1 > $OUT/ncu_full_$TAG.log 2>&1
 tail -3 $OUT/pytest_gpu_$TAG.log; cat $OUT/perf_1e7_$TAG.log; cat $OUT/bench_$TAG.json
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -2 $OUT/smoke_$TAG.log
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference_$TAG.json 2> $OUT/bench_reference_$TAG.err; cat $OUT/bench_reference_$TAG.json | cut -c1-600
