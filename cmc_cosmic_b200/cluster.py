@@ -294,6 +294,13 @@ class Cluster:
         self.mass_pc, self.mass_pc_owner, self.mass_pc_totals = pc, owner, np.array(list(res.totals))
         return int(res.filled)
 
+    def dev_clusdyn_calculate(self):
+        """clusdyn_calculate (reference src/cmc/cmc_utils.c:1613-1624): clusdyn.rh, the half-mass radius, from the resident tables"""
+        rh = C.c_double()
+        _lib.check(self.L.cmcb200_dev_clusdyn_calculate(self.ctx, self.clus.N_MAX, self.clus.N_STAR, self.Mtotal, C.byref(rh)), "dev_clusdyn_calculate")
+        self.clusdyn_rh = rh.value
+        return rh.value
+
     def launch_count(self):
         return int(self.L.cmcb200_launch_count(self.ctx))
 

@@ -80,6 +80,19 @@ __global__ void lagrange_select(const double *__restrict__ mcum, const double *_
 	out->n_filled = mcount;
 }
 
+// clusdyn_calculate (:1613-1624): `while (m < 0.5 Mtotal) { m += star_m[k] / N_STAR; k++; }  rh = star_r[k]` on the finished sums
+__global__ void lagrange_half_mass(const double *__restrict__ mcum, const double *__restrict__ star_r, long N_MAX, double Mtotal, double *rh)
+{
+	const double half = dmul(0.5, Mtotal);
+	long lo = 1, hi = N_MAX + 1; // first k with !(mcum[k] < half); mcum is non-decreasing
+	if (!(0.0 < half)) { *rh = star_r[1]; return; } // the loop body never runs: k stays 1
+	while (lo < hi) {
+		const long mid = (lo + hi) >> 1;
+		if (mcum[mid] < half) lo = mid + 1; else hi = mid;
+	}
+	*rh = star_r[(lo <= N_MAX ? lo : N_MAX) + 1]; // k was incremented once more after the add that reached the half
+}
+
 // the cumulative sum `which` at the recorded indices this rank owns, and the rank's total
 __global__ void lagrange_pick(const double *__restrict__ acc, long n_local, long first_global, long mcount0, int which, LagrangeDev *out)
 {
@@ -95,6 +108,26 @@ __global__ void lagrange_pick(const double *__restrict__ acc, long n_local, long
 }
 
 } // namespace cmcb
+
+extern "C" int cmcb200_dev_clusdyn_calculate(cmcb200_ctx *c, long N_MAX, long N_STAR, double Mtotal, double *rh)
+{
+	if (N_MAX + 2 > c->n_table_dim) { set_error("clusdyn_calculate: N_MAX + 2 exceeds the table capacity"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
+	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
+	{
+		StageTimer t(c, ST_LAGRANGE);
+		ChainEnclosed ce{c->d_m, c->d_mprev, N_MAX, (double) N_STAR, 0.0};
+		seq_scan_launch(ce, c->seqwork, N_MAX, &d->last, NUM_SMS_B200 * 4, NUM_SMS_B200 * 4, c->stream);
+		lagrange_half_mass<<<1, 1, 0, c->stream>>>(c->d_mprev, c->d_r, N_MAX, Mtotal, &d->totals[0]);
+		c->launches += 5;
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	CMCB_CUDA_OK(cudaMemcpyAsync(c->h_pinned, &d->totals[0], sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*rh = *(double *) c->h_pinned;
+	return 0;
+}
 
 extern "C" int cmcb200_dev_comp_mass_percent(cmcb200_ctx *c, const cmcb200_mass_pc_params *p, cmcb200_mass_pc_result *res)
 {

@@ -202,6 +202,9 @@ typedef struct {
  * reports prefix + local (prefix = MPI_Exscan of the totals, :945-951) -- one addition the caller performs.  On one rank the
  * results are the reference's as they are. */
 int cmcb200_dev_comp_mass_percent(cmcb200_ctx *ctx, const cmcb200_mass_pc_params *p, cmcb200_mass_pc_result *res);
+/* clusdyn_calculate (src/cmc/cmc_utils.c:1613-1624) on the resident tables: *rh = clusdyn.rh, the half-mass radius, from the same
+ * sequentially rounded enclosed-mass sums */
+int cmcb200_dev_clusdyn_calculate(cmcb200_ctx *ctx, long N_MAX, long N_STAR, double Mtotal, double *rh);
 
 /* ---- radius-sharded operation: one rank per GPU of an NVLink node ---------------------------------------------------------------- */
 /* Replaces sample_sort + load_balance + post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2259-2288) for procs > 1.

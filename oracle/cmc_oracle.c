@@ -528,3 +528,15 @@ void orc_intermediate_energy(const orc_tables_t *t, long n_local, const long *g_
 	for (long j = 0; j < n_local; j++)
 		if (rnew[j] < 1.0e6) EI[j] = vr[j] * vr[j] + vt[j] * vt[j] + t->phi[g_idx[j]] - orc_potential(t, rnew[j]);
 }
+
+/* clusdyn_calculate, src/cmc/cmc_utils.c:1613-1624 */
+double orc_clusdyn_calculate(const double *star_r, const double *star_m, long N_STAR, double Mtotal)
+{
+	double m = 0.0;
+	long k = 1;
+	while (m < 0.5 * Mtotal) {
+		m += star_m[k] / N_STAR;
+		k++;
+	}
+	return star_r[k];
+}

@@ -107,6 +107,10 @@ long orc_comp_mass_percent(const double *star_r, const double *star_m, long N_MA
 			   double *ave_mass_r, double *no_star_r, double *densities_r, double *ke_rad_r, double *ke_tan_r, double *v2_rad_r,
 			   double *v2_tan_r, int *owner, double totals[4]);
 
+/* clusdyn_calculate, src/cmc/cmc_utils.c:1613-1624: the half-mass radius clusdyn.rh = star_r[k], k = one past the first index at which the
+ * sequentially summed star_m[k]/N_STAR reaches 0.5 Mtotal */
+double orc_clusdyn_calculate(const double *star_r, const double *star_m, long N_STAR, double Mtotal);
+
 /* taus113 (src/libs/taus113-v2.c:166-216 seeding, :218-251 generator, :253-270 jump) */
 void orc_t113_seed(unsigned long s, unsigned int z[4]);
 double orc_t113_dbl(unsigned int z[4]);

@@ -205,6 +205,7 @@ EXPORT int ref_rank(void) { int r; MPI_Comm_rank(MPI_COMM_WORLD, &r); return r; 
 EXPORT void ref_barrier(void) { MPI_Barrier(MPI_COMM_WORLD); }
 /* the reference's own ComputeEnergy (cmc_utils.c:604-656): E, J of the local stars from the new potential */
 EXPORT void ref_compute_energy(void) { ComputeEnergy(); }
+EXPORT double ref_clusdyn_rh(void) { clusdyn_calculate(); return clusdyn.rh; }
 EXPORT void ref_energy_conservation2(void) { energy_conservation2(); }
 EXPORT void ref_compute_intermediate_energy(void) { ComputeIntermediateEnergy(); }
 

@@ -135,6 +135,7 @@ def lagrange_cases(R):
         R.set_scalars(n, n, cenma_m=cenma * n)
         R.L.ref_calc_potential_new()
         out = R.comp_mass_percent(LAGRANGE_PCS, bh_include=bh, minimum_r=1e-6, initial_total_mass=0.98)
+        out["clusdyn_rh"] = R.clusdyn_rh()        # clusdyn_calculate (cmc_utils.c:1613-1624)
         out.update(mass_pc=LAGRANGE_PCS, cenma_m=cenma * n, bh_include=bh, minimum_r=1e-6, initial_total_mass=0.98, Mtotal=R.scalars()["Mtotal"], case=case)
         R.free()
         np.savez_compressed(os.path.join(HERE, f"lagrange_{case}.npz"), **out)

@@ -53,6 +53,8 @@ def lib():
         L.orc_sort_stars.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p]
         L.orc_energy_conservation2.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 3
         L.orc_intermediate_energy.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 5
+        L.orc_clusdyn_calculate.restype = C.c_double
+        L.orc_clusdyn_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double]
         L.orc_comp_mass_percent.restype = C.c_long
         L.orc_comp_mass_percent.argtypes = ([C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_int]
                                             + [C.c_double] * 4 + [C.c_int, C.c_double, C.c_void_p, C.c_long] + [C.c_void_p] * 10)
@@ -171,3 +173,8 @@ def intermediate_energy(t, g_idx, rnew, vr, vt, EI_in):
     out = np.array(EI_in, dtype=np.float64, copy=True)
     lib().orc_intermediate_energy(C.byref(t), len(rnew), _p(g_idx), _p(rnew), _p(vr), _p(vt), _p(out))
     return out
+
+
+def clusdyn_calculate(star_r, star_m, N_STAR, Mtotal):
+    """clusdyn.rh, the half-mass radius (reference cmc_utils.c:1613-1624)"""
+    return lib().orc_clusdyn_calculate(_p(star_r), _p(star_m), N_STAR, Mtotal)

@@ -137,6 +137,10 @@ class Ref:
         if binind is not None:
             self.star_field("binind", np.int64)[1:n + 1] = binind
 
+    def clusdyn_rh(self):
+        self.L.ref_clusdyn_rh.restype = C.c_double
+        return self.L.ref_clusdyn_rh()
+
     def comp_mass_percent(self, mass_pc, bh_include=False, minimum_r=0.0, initial_total_mass=1.0):
         """the reference's comp_mass_percent on the harness's state; entries it never reaches stay -1"""
         pc = np.ascontiguousarray(mass_pc, np.float64)

@@ -48,6 +48,7 @@ def test_oracle_lagrange_radii_match_reference(case):
     for f in ol.MASS_PC_FIELDS:
         cm.assert_bits_equal(want[f], g[f], f)
     assert want["filled"] == len(g["mass_pc"]) - 1 and g["mass_r"][-1] == -1.0
+    assert ol.clusdyn_calculate(sr, sm, n, g["Mtotal"]) == g["clusdyn_rh"]          # clusdyn_calculate, the half-mass radius
 
 
 @pytest.mark.gpu
@@ -64,6 +65,7 @@ def test_cuda_lagrange_radii_match_reference(case):
     c.dev_comp_mass_percent(g["mass_pc"], bh_include=bool(g["bh_include"]), minimum_r=g["minimum_r"], initial_total_mass=g["initial_total_mass"])
     for f in ol.MASS_PC_FIELDS:
         cm.assert_bits_equal(getattr(c, f), g[f], f)
+    assert c.dev_clusdyn_calculate() == g["clusdyn_rh"]
     c.close()
 
 
