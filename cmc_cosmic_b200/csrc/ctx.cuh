@@ -84,6 +84,7 @@ struct cmcb200_ctx {
 	unsigned *d_dest_pos;                           // [n] final local position of each local sorted element on its destination rank
 	unsigned char *d_dest_rank;                     // [n] destination rank
 	long *d_shard_meta;                             // device copy of (n_keep[q], start0[q]) per rank
+	int shard_unfused;                              // 1: the sharded sort keys on r and moves the records unchanged (cmcb200_shard_fuse_transfer)
 	int r_parity;                                   // which of (d_r, d_r_alt) is the buffer SH_R (flips with every fused sort)
 };
 

@@ -90,7 +90,10 @@ struct PushArgs {
 };
 
 // star_out[dest][pos] = transfer(star_in[perm[i]]): one warp per record, 8-byte words (424 = 53 * 8), GATHER_UNROLL records in flight
+// FUSE: the ComputeIntermediateEnergy transfer is applied while the record moves (the key was rnew); otherwise the record moves as it is
+// (the key was r: qsorts_new on records whose transfer the caller already made)
 constexpr int PUSH_UNROLL = 4;
+template <bool FUSE>
 __global__ void __launch_bounds__(256) shard_push_records(PushArgs a, SortBuffers b, const SortState *st, const unsigned char *__restrict__ dest_rank,
 							   const unsigned *__restrict__ dest_pos)
 {
@@ -110,11 +113,13 @@ __global__ void __launch_bounds__(256) shard_push_records(PushArgs a, SortBuffer
 				const unsigned long long *src = (const unsigned long long *) (a.in + p * CMCB_SIZEOF_STAR);
 				w0[u] = __ldg(src + lane);
 				w1[u] = lane < CMCB_STAR_WORDS - 32 ? __ldg(src + 32 + lane) : 0ull;
-				const long j = p + 1; // get_global_idx (cmc_utils.c:2384-2407) of the record before the sort
-				const long g = j > a.n_old_local ? 1 + a.N_MAX + (j - a.n_old_local) : a.first_global + j - 1;
 				tab[u] = 0ull;
-				if (lane == CMCB_OFF_M / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(a.old_m + g));
-				else if (lane == CMCB_OFF_ROLD / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(a.old_r + g));
+				if (FUSE) {
+					const long j = p + 1; // get_global_idx (cmc_utils.c:2384-2407) of the record before the sort
+					const long g = j > a.n_old_local ? 1 + a.N_MAX + (j - a.n_old_local) : a.first_global + j - 1;
+					if (lane == CMCB_OFF_M / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(a.old_m + g));
+					else if (lane == CMCB_OFF_ROLD / 8) tab[u] = (unsigned long long) __double_as_longlong(__ldg(a.old_r + g));
+				}
 				dst[u] = (unsigned long long *) (a.out[dest_rank[i]] + (long) dest_pos[i] * CMCB_SIZEOF_STAR);
 			}
 		}
@@ -122,9 +127,11 @@ __global__ void __launch_bounds__(256) shard_push_records(PushArgs a, SortBuffer
 #pragma unroll
 		for (int u = 0; u < PUSH_UNROLL; u++) {
 			if (i0 + u < n) {
-				const unsigned long long moved = __shfl_sync(0xffffffffu, w0[u], (lane + 8) & 31);
-				if (lane < 3) w0[u] = moved;
-				else if (lane == CMCB_OFF_M / 8 || lane == CMCB_OFF_ROLD / 8) w0[u] = tab[u];
+				if (FUSE) {
+					const unsigned long long moved = __shfl_sync(0xffffffffu, w0[u], (lane + 8) & 31);
+					if (lane < 3) w0[u] = moved;
+					else if (lane == CMCB_OFF_M / 8 || lane == CMCB_OFF_ROLD / 8) w0[u] = tab[u];
+				}
 				dst[u][lane] = w0[u];
 				if (lane < CMCB_STAR_WORDS - 32) dst[u][32 + lane] = w1[u];
 				if (lane == 0) a.src_out[dest_rank[i0 + u]][dest_pos[i0 + u]] = (unsigned char) a.rank;
@@ -273,6 +280,14 @@ static void *peer_role(cmcb200_ctx *c, int q, int role)
 	}
 }
 
+// fused = 1 (default): the sort key is rnew and the ComputeIntermediateEnergy transfer rides on the exchange (resident pipeline);
+// fused = 0: the key is r and the records move unchanged -- qsorts_new as the reference calls it, after its own transfer
+extern "C" int cmcb200_shard_fuse_transfer(cmcb200_ctx *c, int fused)
+{
+	c->shard_unfused = fused ? 0 : 1;
+	return 0;
+}
+
 // Step 1 + 2: local radix sort on rnew (sorted keys kept), trailing stripped stars trimmed (*n_keep = stars this rank contributes),
 // then the sorted keys are stored into every rank's key table.  The host layer follows with a barrier.
 extern "C" int cmcb200_shard_sort_local(cmcb200_ctx *c, long n_local, long *n_keep)
@@ -283,7 +298,7 @@ extern "C" int cmcb200_shard_sort_local(cmcb200_ctx *c, long n_local, long *n_ke
 	memset(&a, 0, sizeof(a));
 	a.star_in = star1(c);
 	a.n = n_local;
-	a.key_off = CMCB_OFF_RNEW;
+	a.key_off = c->shard_unfused ? CMCB_OFF_R : CMCB_OFF_RNEW;
 	a.buf = c->sbuf;
 	a.st = c->d_sort;
 	a.tile_hist = c->d_tile_hist;
@@ -352,7 +367,8 @@ extern "C" int cmcb200_shard_exchange(cmcb200_ctx *c, const long *n_keep_all, co
 		// the sentinel record star[0] stays with its rank
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_star[c->cur_star ^ 1], c->d_star[c->cur_star], CMCB_SIZEOF_STAR, cudaMemcpyDeviceToDevice, c->stream));
 		if (n > 0) {
-			shard_push_records<<<NUM_SMS_B200 * 8, 256, 0, c->stream>>>(a, c->sbuf, c->d_sort, c->d_dest_rank, c->d_dest_pos);
+			if (c->shard_unfused) shard_push_records<false><<<NUM_SMS_B200 * 8, 256, 0, c->stream>>>(a, c->sbuf, c->d_sort, c->d_dest_rank, c->d_dest_pos);
+			else shard_push_records<true><<<NUM_SMS_B200 * 8, 256, 0, c->stream>>>(a, c->sbuf, c->d_sort, c->d_dest_rank, c->d_dest_pos);
 			c->launches++;
 		}
 	}

@@ -38,7 +38,7 @@ _lib = None
 
 EXPORTS = [
     "cmcb200_create", "cmcb200_create_sharded", "cmcb200_shard_handle_bytes", "cmcb200_shard_export", "cmcb200_shard_attach", "cmcb200_shard_detach",
-    "cmcb200_shard_sort_local", "cmcb200_shard_exchange", "cmcb200_shard_publish", "cmcb200_shard_finish", "cmcb200_destroy", "cmcb200_last_error", "cmcb200_set_stream", "cmcb200_layout", "cmcb200_find_limits",
+    "cmcb200_shard_fuse_transfer", "cmcb200_shard_sort_local", "cmcb200_shard_exchange", "cmcb200_shard_publish", "cmcb200_shard_finish", "cmcb200_destroy", "cmcb200_last_error", "cmcb200_set_stream", "cmcb200_layout", "cmcb200_find_limits",
     "cmcb200_calc_potential_new", "cmcb200_qsorts_new", "cmcb200_new_orbits_calculate", "cmcb200_upload", "cmcb200_download",
     "cmcb200_dev_new_orbits", "cmcb200_dev_transfer_new_positions", "cmcb200_dev_qsorts_new", "cmcb200_dev_transfer_and_sort", "cmcb200_dev_calc_potential_new",
     "cmcb200_dev_compute_energy", "cmcb200_dev_read_status", "cmcb200_sync", "cmcb200_profile", "cmcb200_profile_read",
@@ -62,6 +62,7 @@ def load():
     L.cmcb200_shard_export.argtypes = [vp, C.c_int, C.c_int, vp]
     L.cmcb200_shard_attach.argtypes = [vp, vp]
     L.cmcb200_shard_detach.argtypes = [vp]
+    L.cmcb200_shard_fuse_transfer.argtypes = [vp, C.c_int]
     L.cmcb200_shard_sort_local.argtypes = [vp, lg, pl]
     L.cmcb200_shard_exchange.argtypes = [vp, vp, vp, vp, lg, lg, lg]
     L.cmcb200_shard_publish.argtypes = [vp, lg, lg, lg, pl]

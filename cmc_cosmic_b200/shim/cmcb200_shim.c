@@ -56,10 +56,6 @@ static void shim_init(void)
 	const char *e = getenv("CMCB200_DEVICE");
 	if (ctx && ctx_star_dim == N_STAR_DIM_OPT && ctx_bin_dim == N_BIN_DIM_OPT) return;
 	if (ctx) { shim_unpin(); cmcb200_destroy(ctx); ctx = NULL; } /* the arrays were re-dimensioned (a new run in the same process) */
-	if (procs != 1) {
-		eprintf("cmcb200 shim: this binding drives one GPU from one rank; use the sharded entry points for procs=%d\n", procs);
-		exit_cleanly(-1, __FUNCTION__);
-	}
 	cmcb200_layout(lay);
 	if (lay[0] != (long) sizeof(star_t) || lay[1] != (long) sizeof(binary_t) || lay[2] != (long) offsetof(star_t, r) ||
 	    lay[6] != (long) offsetof(star_t, E) || lay[7] != (long) offsetof(star_t, J) || lay[8] != (long) offsetof(star_t, rnew) ||
@@ -68,7 +64,21 @@ static void shim_init(void)
 		exit_cleanly(-1, __FUNCTION__);
 	}
 	if (e) dev = atoi(e);
-	if (cmcb200_create(&ctx, dev, N_STAR_DIM_OPT, N_BIN_DIM_OPT)) shim_fail("cmcb200_create");
+	else dev = myid; /* one GPU per rank of the node */
+	if (procs == 1) {
+		if (cmcb200_create(&ctx, dev, N_STAR_DIM_OPT, N_BIN_DIM_OPT)) shim_fail("cmcb200_create");
+	} else {
+		/* radius-sharded operation (include/cmcb200.h): this rank's share of star[] / binary[], the whole tables; the ranks map each other's
+		 * device buffers once (CUDA IPC handles exchanged with one MPI_Allgather) and later store records straight into them over NVLink */
+		const int hb = cmcb200_shard_handle_bytes();
+		char *mine = (char *) malloc(hb), *all = (char *) malloc((size_t) hb * procs);
+		if (cmcb200_create_sharded(&ctx, dev, N_STAR_DIM_OPT, N_STAR_DIM, N_BIN_DIM_OPT)) shim_fail("cmcb200_create_sharded");
+		if (cmcb200_shard_export(ctx, myid, procs, mine)) shim_fail("cmcb200_shard_export");
+		MPI_Allgather(mine, hb, MPI_BYTE, all, hb, MPI_BYTE, MPI_COMM_WORLD);
+		if (cmcb200_shard_attach(ctx, all)) shim_fail("cmcb200_shard_attach");
+		cmcb200_shard_fuse_transfer(ctx, 0); /* qsorts_new sorts on .r: the caller has made the r <- rnew transfer itself */
+		free(mine); free(all);
+	}
 	ctx_star_dim = N_STAR_DIM_OPT;
 	ctx_bin_dim = N_BIN_DIM_OPT;
 	/* the arrays are allocated once (src/cmc/cmc_io.c:2099-2101, 3434-3436): pin them so that every copy is DMA at link rate.  A failure
@@ -85,7 +95,13 @@ static void shim_init(void)
 #define SHIM_EXPORT __attribute__((visibility("default")))
 SHIM_EXPORT void cmcb200_shim_set_draws(const double *draws, const long *draw_off) { shim_draws = draws; shim_draw_off = draw_off; }
 SHIM_EXPORT const cmcb200_orbit_result *cmcb200_shim_last_orbit(void) { return &last_orbit; }
-SHIM_EXPORT void cmcb200_shim_shutdown(void) { shim_unpin(); if (ctx) cmcb200_destroy(ctx); ctx = NULL; free(status_buf); status_buf = NULL; status_cap = 0; }
+SHIM_EXPORT void cmcb200_shim_shutdown(void)
+{
+	shim_unpin();
+	if (ctx && procs > 1) { cmcb200_sync(ctx); MPI_Barrier(MPI_COMM_WORLD); cmcb200_shard_detach(ctx); MPI_Barrier(MPI_COMM_WORLD); } /* nobody unmaps a buffer a peer still uses */
+	if (ctx) cmcb200_destroy(ctx);
+	ctx = NULL; free(status_buf); status_buf = NULL; status_cap = 0;
+}
 
 /* src/cmc/cmc_utils.c:2194-2211 */
 void SHIM(new_orbits_calculate)(void)
@@ -128,6 +144,33 @@ void SHIM(new_orbits_calculate)(void)
 	TidalMassLoss += TidalMassLoss_old;
 }
 
+/* procs > 1: sample_sort + load_balance + the Allgatherv pair of post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2269-2280) as
+ * the radius-sharded sequence of include/cmcb200.h.  MPI supplies two small collectives and the barriers between the phases; the
+ * records travel GPU to GPU.  Every rank ends with its findLimits share of the globally sorted stars, the binaries that follow them
+ * (binind = 1, 2, ..) and the full star_r / star_m tables -- what the reference's code leaves, bit for bit. */
+static void shim_sharded_sort(long n, long nb)
+{
+	long keep = 0, total = 0, nl, nb_out = 0, *keep_all = (long *) malloc(procs * sizeof(long));
+	int q;
+	if (cmcb200_upload(ctx, star + 1, n, binary + 1, nb, star_r, star_m, NULL, 1)) shim_fail("upload");          /* [0]: the table sentinel */
+	if (cmcb200_shard_sort_local(ctx, n, &keep)) shim_fail("shard_sort_local");
+	MPI_Allgather(&keep, 1, MPI_LONG, keep_all, 1, MPI_LONG, MPI_COMM_WORLD);                                    /* also: every rank's keys have landed */
+	for (q = 0; q < procs; q++) total += keep_all[q];
+	findLimits(total, MIN_CHUNK_SIZE);               /* the partition the reference's load_balance realises (cmc_sort.c:421, 634-791) */
+	if (cmcb200_shard_exchange(ctx, keep_all, Start, End, 0, 0, 0) || cmcb200_sync(ctx)) shim_fail("shard_exchange");
+	MPI_Barrier(MPI_COMM_WORLD);
+	nl = End[myid] - Start[myid] + 1;
+	if (cmcb200_shard_publish(ctx, nl, Start[myid], N_BIN_DIM_OPT - 1, &nb_out)) shim_fail("shard_publish");
+	MPI_Barrier(MPI_COMM_WORLD);
+	cmcb200_shard_finish(ctx);
+	if (cmcb200_download(ctx, star + 1, nl, binary + 1, nb_out, star_r, star_m, NULL, total + 1)) shim_fail("download");
+	if (N_BIN_DIM_OPT - 1 > nb_out) memset(binary + 1 + nb_out, 0, (size_t) (N_BIN_DIM_OPT - 1 - nb_out) * sizeof(binary_t));    /* cmc_sort.c:541 */
+	clus.N_MAX = total;                              /* sample_sort's return value (cmc_sort.c:628) */
+	clus.N_MAX_NEW = nl;
+	N_b_local = nb_out;                              /* cmc_sort.c:741 */
+	free(keep_all);
+}
+
 /* src/cmc/cmc_utils.c:2232-2254; the r/m extraction of post_sort_comm (:2269-2280) is fused into the same device pass */
 void SHIM(qsorts_new)(void)
 {
@@ -135,6 +178,7 @@ void SHIM(qsorts_new)(void)
 	shim_init();
 	/* binaries referenced by the stars being sorted occupy binary[1..max binind]; N_b_local is only refreshed by load_balance */
 	for (i = 1; i <= n; i++) if (star[i].binind > nb) nb = star[i].binind;
+	if (procs > 1) { shim_sharded_sort(n, nb); return; }
 	if (cmcb200_qsorts_new(ctx, star + 1, &n, binary + 1, N_BIN_DIM_OPT, &nb, star_r, star_m)) shim_fail("qsorts_new");
 	clus.N_MAX = n;                                  /* sample_sort's return value: global count after trimming (cmc_sort.c:628) */
 	clus.N_MAX_NEW = n;

@@ -223,6 +223,9 @@ int cmcb200_shard_handle_bytes(void);
 int cmcb200_shard_export(cmcb200_ctx *ctx, int rank, int nranks, void *handles);
 int cmcb200_shard_attach(cmcb200_ctx *ctx, const void *all_handles);
 int cmcb200_shard_detach(cmcb200_ctx *ctx);
+/* fused != 0 (default): the sort key is rnew and the r <- rnew transfer rides on the exchange; 0: key r, records unchanged (what the reference's
+ * qsorts_new does after ComputeIntermediateEnergy; n_old_local / first_global / N_MAX of cmcb200_shard_exchange are then ignored) */
+int cmcb200_shard_fuse_transfer(cmcb200_ctx *ctx, int fused);
 int cmcb200_shard_sort_local(cmcb200_ctx *ctx, long n_local, long *n_keep);
 int cmcb200_shard_exchange(cmcb200_ctx *ctx, const long *n_keep_all, const int *Start, const int *End, long n_old_local, long first_global, long N_MAX);
 int cmcb200_shard_publish(cmcb200_ctx *ctx, long n_new_local, long start_global, long n_bin_clear, long *n_bin);

@@ -79,7 +79,8 @@ EXPORT int ref_init(long n_star, long n_star_dim, long n_table_dim, long n_bin_d
 	MPI_Comm_size(MPI_COMM_WORLD, &procs);
 	MPI_Comm_rank(MPI_COMM_WORLD, &myid);
 	debug = 0; quiet = 1;
-	N_STAR_DIM = N_STAR_DIM_OPT = n_star_dim;
+	N_STAR_DIM_OPT = n_star_dim;   /* star[]: this rank's share (cmc_io.c:2092-2099) */
+	N_STAR_DIM = n_table_dim;      /* star_r / star_m / star_phi: the whole cluster (cmc_io.c:3431-3437) */
 	N_BIN_DIM = N_BIN_DIM_OPT = n_bin_dim;
 	star = calloc(n_star_dim, sizeof(star_t));
 	binary = calloc(n_bin_dim, sizeof(binary_t));

@@ -95,3 +95,34 @@ def test_reference_with_cuda_shim_equals_reference(kind, N, masses, nb, rtidal):
     for x, y, name in zip(b["tables_final"], a["tables_final"], ("star_r", "star_m", "star_phi")):
         cm.assert_bits_equal(x, y, name)
     assert b["scalars_final"] == a["scalars_final"]
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("procs,N", [(2, 60000), (2, 200003)])
+def test_multirank_reference_with_cuda_shim_equals_multirank_reference(procs, N, tmp_path):
+    """P forked MPI ranks of the compiled reference, once unmodified (sample_sort + load_balance + Allgatherv + potential on the CPU) and once
+    with qsorts_new / post_sort_comm / calc_potential_new re-bound to the shim (rank i drives GPU i: radius-sharded sort, records stored
+    GPU to GPU over NVLink, MPI only for two small collectives and the barriers): every rank must end with the same bytes -- its shard of
+    star[], its binaries, the replicated tables, N_MAX, N_MAX_NEW, N_b_local, Start/End"""
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin_multirank_worker.py")
+    for mode in ("ref", "shim"):
+        p = subprocess.run([sys.executable, worker, mode, str(procs), str(N), str(tmp_path)], capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0 and "WORKER OK" in p.stdout, (mode, p.stdout[-3000:], p.stderr[-3000:])
+    for rank in range(procs):
+        a, b = np.load(tmp_path / f"ref_rank{rank}.npz"), np.load(tmp_path / f"shim_rank{rank}.npz")
+        assert np.array_equal(a["scal"], b["scal"]), (rank, a["scal"], b["scal"])
+        assert np.array_equal(a["S"], b["S"]) and np.array_equal(a["E"], b["E"])
+        assert np.array_equal(a["star"], b["star"]), f"rank {rank}: star[] shard differs"
+        assert np.array_equal(a["binary"], b["binary"]), f"rank {rank}: binary[] differs"
+        for f in ("star_r", "star_m", "star_phi"):
+            assert np.array_equal(a[f].view(np.uint64), b[f].view(np.uint64)), f"rank {rank}: {f}"
