@@ -126,3 +126,27 @@ def test_multirank_reference_with_cuda_shim_equals_multirank_reference(procs, N,
         assert np.array_equal(a["binary"], b["binary"]), f"rank {rank}: binary[] differs"
         for f in ("star_r", "star_m", "star_phi"):
             assert np.array_equal(a[f].view(np.uint64), b[f].view(np.uint64)), f"rank {rank}: {f}"
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_multirank_orbit_step_through_the_shim_is_independent_of_the_rank_count(tmp_path):
+    """new_orbits_calculate through the shim on P = 1 and P = 2 forked ranks (each with its GPU): with the production draws (Philox keyed by
+    the global star index) every star must get the same new position whichever rank owns it; max_r and TidalMassLoss are reduced over the
+    ranks like the reference does (cmc_utils.c:2206-2209)"""
+    import subprocess
+    import sys
+    N = 150000
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin_multirank_orbit_worker.py")
+    for procs in (1, 2):
+        p = subprocess.run([sys.executable, worker, str(procs), str(N), str(tmp_path)], capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0 and "WORKER OK" in p.stdout, (procs, p.stdout[-3000:], p.stderr[-3000:])
+    one = np.load(tmp_path / "orbit_p1_rank0.npz")
+    parts = [np.load(tmp_path / f"orbit_p2_rank{q}.npz") for q in range(2)]
+    assert int(parts[0]["lo"]) == 1 and int(parts[1]["hi"]) == N and int(parts[1]["lo"]) == int(parts[0]["hi"]) + 1
+    for f in ("E", "J", "rnew", "vrnew", "vtnew", "X", "r_peri", "r_apo"):
+        both = np.concatenate([q[f] for q in parts])
+        assert np.array_equal(both.view(np.uint64), one[f].view(np.uint64)), f
+    assert (one["rnew"] == cm.SF_INFINITY).sum() > 10                          # the tidal cut removed stars
+    for q in parts:
+        assert q["max_r"] == one["max_r"]
+        assert abs(q["tml"] - one["tml"]) <= 1e-12 * abs(one["tml"])             # a sum over ranks: same value up to the order of the additions
