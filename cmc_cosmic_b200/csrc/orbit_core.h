@@ -267,8 +267,9 @@ CMCB_HD LBlock blk_ld(const LBlock *p)
 }
 
 // FindZero_r(1, N_MAX + 1, r) through the r ladder: largest k in [1, N_MAX+1] with star_r[k] < r, 1 if there is none.
-// *line_base / line[]: the fine-table line the last step read (entries line_base .. line_base + 7), for the caller's interpolation.
-CMCB_HD kint find_zero_r_ladder(const OrbitTables &t, const double *top, double r, kint *line_base, RPhi line[8])
+// The last step reads the fine-table line that holds the answer (entries base .. base + 7, four 256-bit loads) and only counts; the
+// caller then re-reads the two entries it interpolates between -- L1 hits, and 30 registers fewer than carrying the line along.
+CMCB_HD kint find_zero_r_ladder(const OrbitTables &t, const double *top, double r)
 {
 	const RLadder &L = t.rlad;
 	int lo = 0, hi = L.n_top; // samples [0, lo) are < r, samples [hi, n_top) are >= r
@@ -286,11 +287,8 @@ CMCB_HD kint find_zero_r_ladder(const OrbitTables &t, const double *top, double 
 #pragma unroll
 	for (int i = 0; i < 4; i++) { // base is a multiple of 8: the line is 128-byte aligned, two entries per 256-bit load
 		const Quad v = ld_quad(&t.rp[base + 2 * i].r);
-		line[2 * i].r = v.a; line[2 * i].phi = v.b; line[2 * i + 1].r = v.c; line[2 * i + 1].phi = v.d;
+		c += (base + 2 * i <= M && v.a < r) + (base + 2 * i + 1 <= M && v.c < r);
 	}
-#pragma unroll
-	for (int i = 0; i < 8; i++) c += (base + i <= M && line[i].r < r);
-	*line_base = base;
 	const kint k = base + c - 1; // largest k in [0, M] with star_r[k] < r (-1: none)
 	return k >= 1 ? k : 1;
 }
@@ -303,20 +301,8 @@ CMCB_HD double potential_at(const OrbitTables &t, const LadderTops &top, double 
 	const RPhi p1 = tbl_rp(t, 1);
 	if (r < p1.r) return dsub(phi0, ddiv(dmul(dsub(phi0, p1.phi), p1.r), r));
 	kint kmax = t.N_MAX + 1, kmin = 1;
-	RPhi a, b;
-	if (kmin != kmax - 1 && top.r) {
-		RPhi line[8];
-		kint base;
-		const kint i = find_zero_r_ladder(t, top.r, r, &base, line);
-		const int o = i - base; // 0 .. 7 (the k = 0 -> 1 clamp cannot happen here: r >= star_r[1])
-		a = line[0]; b = line[1];
-#pragma unroll
-		for (int q = 1; q < 7; q++) if (o == q) { a = line[q]; b = line[q + 1]; }
-		if (o == 7) { a = line[7]; b = tbl_rp(t, i + 1); }
-	} else {
-		const kint i = (kmin == kmax - 1) ? kmin : find_zero_r(t, kmin, kmax, r);
-		a = tbl_rp(t, i); b = tbl_rp(t, i + 1);
-	}
+	const kint i = (kmin == kmax - 1) ? kmin : (top.r ? find_zero_r_ladder(t, top.r, r) : find_zero_r(t, kmin, kmax, r));
+	const RPhi a = tbl_rp(t, i), b = tbl_rp(t, i + 1);
 	if (a.r > r || b.r < r) { *fail = 1; return 0.0; }
 	double inv_i = ddiv(1.0, a.r);
 	return dadd(a.phi, ddiv(dmul(dsub(b.phi, a.phi), dsub(inv_i, ddiv(1.0, r))), dsub(inv_i, ddiv(1.0, b.r))));

@@ -116,9 +116,7 @@ extern "C" void emul_find_zero_r_both(const double *star_r, long N_MAX, const do
 	t.qlad = lad.q; t.rlad = lad.r;
 	for (long i = 0; i < n; i++) {
 		k_bisect[i] = find_zero_r(t, 1, (kint) (N_MAX + 1), radii[i]);
-		RPhi line[8];
-		kint base;
-		k_ladder[i] = t.rlad.n_levels ? find_zero_r_ladder(t, t.rlad.lvl[0], radii[i], &base, line) : -1;
+		k_ladder[i] = t.rlad.n_levels ? find_zero_r_ladder(t, t.rlad.lvl[0], radii[i]) : -1;
 	}
 }
 
