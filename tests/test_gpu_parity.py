@@ -394,3 +394,40 @@ def test_energy_scheme_lookups_at_new_radii_bit_exact(kind, N, masses, tidal):
     cm.assert_bits_equal(c.field("rOld")[1:N + 1], r, "rOld")
     cm.assert_bits_equal(c.field("vr")[1:N + 1], want["vrnew"], "vr <- vrnew")
     c.close()
+
+
+def test_lagrange_radii_of_a_run_agree_statistically_with_the_reference_run():
+    """north_star: "Lagrangian radii from a full run must statistically agree with the reference run".  Six timesteps of the path
+    (orbit step -> r <- rnew -> sort -> potential -> E, J) from the same Plummer state: the CUDA pipeline with its production draws
+    (Philox) against the oracle with the reference's taus113 stream.  Different random numbers, same physics: the Lagrange radii of the
+    two final states must agree within the sampling noise of N = 1e5 stars, and both stay on the Plummer profile."""
+    N, steps = 100000, 6
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=71)
+    pcs = np.array([0.05, 0.1, 0.25, 0.5, 0.75, 0.9])
+    # reference run (oracle)
+    ro, vro, vto = r.copy(), vr.copy(), vt.copy()
+    for s in range(steps):
+        pot = cm.oracle_potential(ro, sm)
+        E, J = cm.energies(pot["phi"][1:N + 1], ro, vro, vto)
+        w = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vro, vto, pot["Rtidal"], seed=1000 + s)
+        assert np.all(w["status"] <= ol.ST_CIRCULAR)          # nobody leaves: N stays fixed, the comparison is star for star in number
+        o = np.argsort(w["rnew"], kind="stable")
+        ro, vro, vto = w["rnew"][o], w["vrnew"][o], w["vtnew"][o]
+    pot = cm.oracle_potential(ro, sm)
+    want = ol.comp_mass_percent(pot["star_r"], pot["star_m"], N, N, vro, vto, pcs, pot["Mtotal"])
+    # CUDA run
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.calc_potential_new()
+    c.upload()
+    for s in range(steps):
+        c.dev_step(seed=5)
+    c.dev_comp_mass_percent(pcs)
+    assert c.clus.N_MAX == N
+    a = 3 * np.pi / 16
+    plummer = a / np.sqrt(pcs ** (-2.0 / 3.0) - 1.0)
+    # sampling noise of a Lagrange radius: dr/r ~ sqrt(f (1 - f) / N) / (f dln M / dln r); a flat 1.5 % covers 4 sigma at every fraction here
+    assert np.allclose(c.mass_r, want["mass_r"], rtol=0.015), (c.mass_r, want["mass_r"])
+    assert np.allclose(c.mass_r, plummer, rtol=0.03) and np.allclose(want["mass_r"], plummer, rtol=0.03)
+    assert np.allclose(c.ke_rad_r + c.ke_tan_r, want["ke_rad_r"] + want["ke_tan_r"], rtol=0.02)   # enclosed kinetic energy at the same fractions
+    c.close()
