@@ -48,3 +48,22 @@ for w in (48, 64, 128):
     print(f"2-D DMA D2H width {w:3d}   {N * w / 1e9 / t:6.1f} GB/s of payload ({t * 1e3:.1f} ms)")
 # packed fields: one contiguous 48 N byte copy (what a host-side pack would ship)
 t = timed(lambda: d[:48 * N].copy_(host[:48 * N], non_blocking=True)); print(f"contiguous 48N H2D    {48 * N / 1e9 / t:6.1f} GB/s ({t * 1e3:.1f} ms)")
+
+
+def both2d():
+    rt.cudaMemcpy2DAsync(d.data_ptr(), REC, host.data_ptr(), REC, 128, N, kindH2D, C.c_void_p(s1.cuda_stream))
+    rt.cudaMemcpy2DAsync(C.c_void_p(host2.data_ptr() + 64), REC, C.c_void_p(d2.data_ptr() + 64), REC, 64, N, kindD2H, C.c_void_p(s2.cuda_stream))
+
+
+t = timed(both2d); print(f"2-D DMA H2D width 128 + D2H width 64 concurrently: {t * 1e3:.1f} ms (alone: see above)")
+
+
+def both2d_chunked(k=8):
+    per = N // k
+    for i in range(k):
+        o = i * per * REC
+        rt.cudaMemcpy2DAsync(C.c_void_p(d.data_ptr() + o), REC, C.c_void_p(host.data_ptr() + o), REC, 128, per, kindH2D, C.c_void_p(s1.cuda_stream))
+        rt.cudaMemcpy2DAsync(C.c_void_p(host2.data_ptr() + o + 64), REC, C.c_void_p(d2.data_ptr() + o + 64), REC, 64, per, kindD2H, C.c_void_p(s2.cuda_stream))
+
+
+t = timed(both2d_chunked); print(f"the same in 8 chunks each: {t * 1e3:.1f} ms")
