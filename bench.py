@@ -315,7 +315,10 @@ def run_cuda(args):
         ach = bytes_per_star * n_units / (avg * 1e-3) / 1e9 if avg > 0 else None
         tr = profile_traffic(kernel)
         d = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-             "traffic": (tr * n_units if tr else None), "peak_source": peak_src, "algorithmic_bytes_per_star": bytes_per_star, "avg_launch_ms": avg}
+             "traffic": (tr * n_units if tr else None), "peak_source": peak_src, "algorithmic_bytes_per_star": bytes_per_star, "avg_launch_ms": avg,
+             # the DRAM bytes ncu counted for this kernel (profiles/traffic_r01.json) over the launch time measured here, against the same peak:
+             # how close the kernel is to the memory system's limit on the traffic it actually causes
+             "traffic_frac": (tr * n_units / (avg * 1e-3) / 1e9 / peak) if (tr and avg > 0) else None}
         d.update(extra or {})
         return d
 
