@@ -179,8 +179,11 @@ class Cluster:
     # ---- resident form ----------------------------------------------------------------------------------------------
     def upload(self):
         n, nb = self.clus.N_MAX_NEW, self._n_bin_in_use()
+        # the tables hold the sorted stars [0 .. N_MAX + 1] and, behind them, the stars created this step (reference cmc_utils.c:2392-2395)
+        n_new_stars = max(0, n - int(self.End[self.myid] - self.Start[self.myid] + 1))
         _lib.check(self.L.cmcb200_upload(self.ctx, self.star[1:].ctypes.data, n, self.binary[1:].ctypes.data, nb, self.star_r.ctypes.data,
-                                         self.star_m.ctypes.data, self.star_phi.ctypes.data, min(self.N_TABLE_DIM, self.clus.N_MAX + 2)), "upload")
+                                         self.star_m.ctypes.data, self.star_phi.ctypes.data,
+                                         min(self.N_TABLE_DIM, self.clus.N_MAX + 2 + n_new_stars)), "upload")
         self.N_b_local = nb
 
     def download(self):

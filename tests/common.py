@@ -67,3 +67,25 @@ def assert_bits_equal(a, b, what=""):
     av, bv = a.view(np.uint64) if a.dtype == np.float64 else a, b.view(np.uint64) if b.dtype == np.float64 else b
     bad = np.nonzero(av != bv)[0]
     assert bad.size == 0, f"{what}: {bad.size} of {a.size} differ, first at {bad[0]}: {a[bad[0]]!r} vs {b[bad[0]]!r}"
+
+
+def with_new_stars(r, vr, vt, sm, pot, n_new, seed=0):
+    """A cluster state plus `n_new` stars created this step (collision products / disrupted binaries in CMC): they sit behind the old
+    local stars in star[], their r / m are appended to the tables at N_MAX + 2 .. (get_global_idx, reference cmc_utils.c:2384-2407), their
+    position is star[].rnew and calc_orbit_new looks their index up with FindZero_r (cmc_orbit.c:39-41).
+    Returns tables (sr, sm_t, phi) sized N + 2 + n_new, per-star arrays E, J, vr, vt over all N + n_new stars, g_idx, is_new, rnew_in."""
+    N = len(r)
+    rng = np.random.default_rng(seed)
+    src = rng.choice(N, n_new, replace=False)
+    r_new = r[src] * rng.uniform(0.999, 1.001, n_new)
+    sr, smt, phi = (np.concatenate([pot[k][:N + 2], np.zeros(n_new)]) for k in ("star_r", "star_m", "phi"))
+    sr[N + 2:], smt[N + 2:] = r_new, sm[src] * rng.uniform(0.5, 2.0, n_new)
+    t = ol.tables(sr, smt, phi, N, N, 0.0)
+    phi_new = np.array([ol.lib().orc_potential(ol.C.byref(t), float(x)) for x in r_new])
+    vr_a, vt_a = np.concatenate([vr, vr[src]]), np.concatenate([vt, vt[src]])
+    E = np.concatenate([pot["phi"][1:N + 1] + 0.5 * (vr * vr + vt * vt), phi_new + 0.5 * (vr[src] ** 2 + vt[src] ** 2)])
+    J = np.concatenate([r * vt, r_new * vt[src]])
+    g_idx = np.concatenate([np.arange(1, N + 1), N + 2 + np.arange(n_new)]).astype(np.int64)
+    is_new = np.concatenate([np.zeros(N, np.uint8), np.ones(n_new, np.uint8)])
+    rnew_in = np.concatenate([np.zeros(N), r_new])
+    return sr, smt, phi, E, J, vr_a, vt_a, g_idx, is_new, rnew_in

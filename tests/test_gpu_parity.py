@@ -431,3 +431,64 @@ def test_lagrange_radii_of_a_run_agree_statistically_with_the_reference_run():
     assert np.allclose(c.mass_r, plummer, rtol=0.03) and np.allclose(want["mass_r"], plummer, rtol=0.03)
     assert np.allclose(c.ke_rad_r + c.ke_tan_r, want["ke_rad_r"] + want["ke_tan_r"], rtol=0.02)   # enclosed kinetic energy at the same fractions
     c.close()
+
+
+def _cluster_with_new_stars(N, M, seed, pinned=False):
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=seed)
+    pot = cm.oracle_potential(r, sm)
+    sr, smt, phi, E, J, vra, vta, g_idx, is_new, rnew_in = cm.with_new_stars(r, vr, vt, sm, pot, M, seed=seed + 1)
+    c = Cluster(N, n_star_dim=N + M + 64, pinned=pinned)
+    c.load(r, vr, vt, sm)
+    c.star_r[:N + 2 + M], c.star_m[:N + 2 + M], c.star_phi[:N + 2 + M] = sr, smt, phi
+    c.field("E")[1:N + M + 1], c.field("J")[1:N + M + 1] = E, J
+    c.field("vr")[1:N + M + 1], c.field("vt")[1:N + M + 1] = vra, vta
+    c.field("rnew")[1:N + M + 1] = rnew_in
+    c.field("id")[N + 1:N + M + 1] = N + 1 + np.arange(M)
+    c.clus.N_MAX_NEW = N + M                  # the new stars sit behind the old shard; N_MAX, Start / End still describe the old stars
+    c.Rtidal = pot["Rtidal"]
+    return c, (sr, smt, phi, E, J, vra, vta, g_idx, is_new, rnew_in), pot
+
+
+def test_orbit_step_with_stars_created_this_step_bit_exact():
+    """new stars (collision products in CMC): local index beyond End - Start + 1, global index N_MAX + 2 .. (get_global_idx), position given in
+    star[].rnew and located by FindZero_r (cmc_orbit.c:39-41) -- host-buffer and resident form against the oracle, incl. the energy lookups"""
+    N, M = 60000, 300
+    c, (sr, smt, phi, E, J, vra, vta, g_idx, is_new, rnew_in), pot = _cluster_with_new_stars(N, M, seed=21)
+    want = cm.oracle_orbits(sr, smt, phi, N, N, E, J, vra, vta, pot["Rtidal"], seed=8, g_idx=g_idx, is_new=is_new, rnew_in=rnew_in)
+    assert (want["status"][N:] == ol.ST_OK).sum() > M // 2
+    status = c.new_orbits_calculate(draws=want["draws"], draw_off=want["draw_off"])
+    assert np.array_equal(status, want["status"])
+    assert np.array_equal(c.last_kmin, want["kmin"]) and np.array_equal(c.last_kmax, want["kmax"])
+    for f in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(c.field(f)[1:N + M + 1], want[f], f)
+    host_form = c.star[:N + M + 1].copy()
+    c.field("rnew")[1:N + M + 1] = rnew_in
+    c.upload()
+    c.dev_new_orbits(draws=want["draws"], draw_off=want["draw_off"])
+    c.dev_energy_conservation2()
+    c.download()
+    for f in ("rnew", "vrnew", "vtnew", "X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(c.field(f)[1:N + M + 1], star_field(host_form, f)[1:N + M + 1], f"resident {f}")
+    t = ol.tables(sr, smt, phi, N, N, 0.0)
+    cm.assert_bits_equal(c.field("Uoldrnew")[1:N + M + 1], ol.energy_conservation2(t, g_idx, want["rnew"]), "Uoldrnew")
+    c.close()
+
+
+def test_pipelined_host_buffer_orbit_step_with_new_stars_in_the_last_chunk():
+    """three pipeline chunks, the last one holding old AND new stars (its n_old_local is smaller than its length): against the resident form"""
+    N, M = 1100000, 4000
+    outs = []
+    for mode in ("host", "resident"):
+        c, (sr, smt, phi, E, J, vra, vta, g_idx, is_new, rnew_in), pot = _cluster_with_new_stars(N, M, seed=31, pinned=(mode == "host"))
+        if mode == "host":
+            status = c.new_orbits_calculate(seed=3)
+        else:
+            c.upload()
+            c.dev_new_orbits(seed=3, want_status=True)
+            status = c.dev_read_status()[0]
+            c.download()
+        outs.append((status.copy(), c.star[:N + M + 1].copy(), c.last_orbit.n_draws, c.max_r))
+        c.close()
+    a, b = outs
+    assert np.array_equal(a[0], b[0]) and a[2] == b[2] and a[3] == b[3]
+    assert np.array_equal(a[1], b[1]), "star[] differs between the pipelined host-buffer form and the resident form"

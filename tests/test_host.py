@@ -172,3 +172,19 @@ def test_laddered_find_zero_Q_replays_the_reference_bisection(kind, N):
                     assert ka == kb, (g, E, J, k0, k1, ka, kb)
     finally:
         hostemul.use_deep_ladders(False)
+
+
+def test_kernel_core_on_host_handles_stars_created_this_step():
+    """new stars (local index beyond the old shard, global index N_MAX + 2 .., position in star[].rnew): orbit_core.h against the oracle"""
+    import hostemul
+    N, M = 20000, 150
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=12)
+    pot = cm.oracle_potential(r, sm)
+    sr, smt, phi, E, J, vra, vta, g_idx, is_new, rnew_in = cm.with_new_stars(r, vr, vt, sm, pot, M, seed=4)
+    want = cm.oracle_orbits(sr, smt, phi, N, N, E, J, vra, vta, pot["Rtidal"], seed=8, g_idx=g_idx, is_new=is_new, rnew_in=rnew_in)
+    out = hostemul.get_positions(sr, smt, phi, N, N, 0.0, g_idx, E, J, vra, vta, pot["Rtidal"], want["draws"], csr_off=want["draw_off"],
+                                 is_new=is_new, rnew_in=rnew_in)
+    assert np.array_equal(out["status"], want["status"]) and (want["status"][N:] == ol.ST_OK).sum() > M // 2
+    assert np.array_equal(out["kmin"], want["kmin"]) and np.array_equal(out["kmax"], want["kmax"])
+    for f in ("rnew", "vrnew", "vtnew", "r_peri", "r_apo"):
+        cm.assert_bits_equal(out[f], want[f], f)
