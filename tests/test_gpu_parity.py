@@ -492,3 +492,42 @@ def test_pipelined_host_buffer_orbit_step_with_new_stars_in_the_last_chunk():
     a, b = outs
     assert np.array_equal(a[0], b[0]) and a[2] == b[2] and a[3] == b[3]
     assert np.array_equal(a[1], b[1]), "star[] differs between the pipelined host-buffer form and the resident form"
+
+
+def test_empty_and_degenerate_inputs():
+    """nothing to do is a valid request for every entry point: no local stars, no thresholds, a one-star cluster"""
+    c = Cluster(8, n_star_dim=64)
+    r = np.array([0.1, 0.2, 0.3, 0.5, 0.8, 1.3, 2.1, 3.4]); v = np.full(8, 0.1)
+    c.load(r, v, v, np.ones(8))
+    c.calc_potential_new()
+    c.compute_energy()
+    c.upload()
+    assert c.dev_comp_mass_percent(np.array([])) == 0
+    # a rank that owns no stars this step
+    n_keep, c.clus.N_MAX_NEW = c.clus.N_MAX_NEW, 0
+    c.End[0] = 0
+    status = c.new_orbits_calculate(seed=1)
+    assert status.size == 0 and c.last_orbit.n_draws == 0 and c.max_r == 0.0
+    res = c.dev_new_orbits(seed=1)
+    assert res.n_draws == 0
+    c.dev_energy_conservation2()
+    c.bin_slots_in_use = 0
+    c.qsorts_new()
+    assert c.clus.N_MAX == 0
+    c.close()
+    # one star: every table has its sentinels only around a single entry (FindZero_r's kmin == kmax - 1 shortcut, cmc_utils.c:136-138)
+    c = Cluster(1, n_star_dim=16)
+    c.load(np.array([0.7]), np.array([0.05]), np.array([0.3]), np.array([1.0]))
+    c.calc_potential_new()
+    want = cm.oracle_potential(np.array([0.7]), np.array([1.0]))
+    cm.assert_bits_equal(c.star_phi[:3], want["phi"][:3], "phi of a one-star cluster")
+    assert c.dev_clusdyn_calculate() == c.star_r[2]           # the loop adds the only star and stops one index later (cmc_utils.c:1619-1623)
+    c.compute_energy()
+    E, J = c.field("E")[1:2].copy(), c.field("J")[1:2].copy()
+    w = cm.oracle_orbits(want["star_r"], want["star_m"], want["phi"], 1, 1, E, J, np.array([0.05]), np.array([0.3]), want["Rtidal"], seed=2)
+    assert w["status"][0] == ol.ST_UNBOUND                    # without its own potential (the self term, :806) a lone star is not bound
+    c.upload()
+    c.dev_step(seed=2)                                        # ... so the step removes it and the sort trims it
+    c.download()
+    assert c.clus.N_MAX == 0 and c.star_r[1] == cm.SF_INFINITY
+    c.close()
