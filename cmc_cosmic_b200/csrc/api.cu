@@ -561,7 +561,9 @@ extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const
 	const long per = (n + n_chunks - 1) / n_chunks;
 	const size_t pitch = CMCB_SIZEOF_STAR;
 	char *dev1 = star1(c);
-	// copies in: queued up front on their own stream (the device records are free: every call ends synchronised)
+	// copies in: queued up front on their own stream, behind whatever the context's stream still has in flight (cmcb200_upload is asynchronous)
+	CMCB_CUDA_OK(cudaEventRecord(c->ev_done[ORBIT_MAX_CHUNKS - 1], c->stream));
+	CMCB_CUDA_OK(cudaStreamWaitEvent(c->s_in, c->ev_done[ORBIT_MAX_CHUNKS - 1], 0));
 	for (int k = 0; k < n_chunks; k++) {
 		const long off = k * per, len = n - off < per ? n - off : per;
 		if (len > 0) CMCB_CUDA_OK(cudaMemcpy2DAsync(dev1 + off * pitch, pitch, (const char *) star1_h + off * pitch, pitch, 128, (size_t) len, cudaMemcpyHostToDevice, c->s_in));
