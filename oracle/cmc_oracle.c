@@ -529,6 +529,79 @@ void orc_intermediate_energy(const orc_tables_t *t, long n_local, const long *g_
 		if (rnew[j] < 1.0e6) EI[j] = vr[j] * vr[j] + vt[j] * vt[j] + t->phi[g_idx[j]] - orc_potential(t, rnew[j]);
 }
 
+/* ---- energy_conservation1 / set_velocities3 (energy_conservation3), src/cmc/cmc_utils.c:2153-2174, 254-352 -------------------------- */
+
+void orc_energy_conservation1(const orc_tables_t *t, long n_local, const long *g_idx, const double *vr, const double *vt, double *vrold,
+			      double *vtold, double *Uoldrold)
+{
+	for (long i = 0; i < n_local; i++) {
+		vtold[i] = vt[i];
+		vrold[i] = vr[i];
+		Uoldrold[i] = t->phi[g_idx[i]] + orc_mpi_phi_s(t, t->r[g_idx[i]], g_idx[i]); /* :2168 */
+	}
+}
+
+#define ORC_MIN(a, b) ((a) <= (b) ? (a) : (b)) /* include/cmc/cmc.h:2242 */
+
+double orc_set_velocities3_first(const orc_tables_t *t, long n_local, const long *g_idx, const long *interacted, const double *rOld,
+				 const double *vrold, const double *vtold, const double *Uoldrold, const double *Uoldrnew, double *vr, double *vt,
+				 double *vrnew, double *vtnew, char *vnew2_arr)
+{
+	const double q = 0.5, E_dump_factor = 0.8; /* :258, :264 */
+	double Eexcess = 0.0;
+	for (long i = 0; i < n_local; i++) {
+		const long g = g_idx[i];
+		const double m = t->m[g];
+		if (interacted[i] != 0) continue; /* :273 */
+		const double Unewrold = orc_potential(t, rOld[i]) + orc_mpi_phi_s(t, rOld[i], g);
+		const double Unewrnew = t->phi[g] + orc_mpi_phi_s(t, t->r[g], g);
+		const double vold2 = vtold[i] * vtold[i] + vrold[i] * vrold[i];
+		const double vnew2 = vold2 + 2.0 * (1.0 - q) * (Uoldrold[i] - Uoldrnew[i]) + 2.0 * q * (Unewrold - Unewrnew); /* :281-282 */
+		vnew2_arr[i] = (vnew2 > 0.0) ? 1 : 0;
+		if (vnew2 <= 0.0) {
+			Eexcess += 0.5 * (vr[i] * vr[i] + vt[i] * vt[i] - vnew2) * m; /* :288 */
+		} else {
+			const double alpha = sqrt(vnew2 / (vr[i] * vr[i] + vt[i] * vt[i])); /* :291 */
+			vr[i] *= alpha;
+			vt[i] *= alpha;
+			const double v2 = vr[i] * vr[i] + vt[i] * vt[i];
+			vrnew[i] = vr[i];
+			vtnew[i] = vt[i];
+			const double E_dump_capacity = E_dump_factor * 0.5 * m * v2; /* :300 */
+			const double E_dump = ORC_MIN(E_dump_capacity, Eexcess);
+			if (Eexcess > 0) {
+				const double exc_ratio = sqrt((v2 - 2 * E_dump / m) / v2);
+				vr[i] *= exc_ratio;
+				vt[i] *= exc_ratio;
+				Eexcess -= E_dump;
+			}
+		}
+	}
+	return Eexcess;
+}
+
+double orc_set_velocities3_second(const orc_tables_t *t, long n_local, const long *g_idx, const long *interacted, const char *vnew2_arr,
+				  double Eexcess, double *vr, double *vt, const double *vrnew, const double *vtnew)
+{
+	const double E_dump_factor = 0.8;
+	for (long i = 0; i < n_local; i++) {
+		const double m = t->m[g_idx[i]];
+		const double v2_new = vrnew[i] * vrnew[i] + vtnew[i] * vtnew[i];
+		const double v2 = vr[i] * vr[i] + vt[i] * vt[i];
+		if (interacted[i] == 0 && vnew2_arr[i] == 1) {
+			const double E_dump_capacity = v2 * m * 0.5 - E_dump_factor * 0.5 * m * v2_new; /* :333 */
+			const double E_dump = ORC_MIN(E_dump_capacity, Eexcess);
+			if (Eexcess > 0) {
+				const double exc_ratio = sqrt((v2 - 2 * E_dump / m) / v2);
+				vr[i] *= exc_ratio;
+				vt[i] *= exc_ratio;
+				Eexcess -= E_dump;
+			}
+		}
+	}
+	return Eexcess;
+}
+
 /* clusdyn_calculate, src/cmc/cmc_utils.c:1613-1624 */
 double orc_clusdyn_calculate(const double *star_r, const double *star_m, long N_STAR, double Mtotal)
 {

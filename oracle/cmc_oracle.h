@@ -90,6 +90,25 @@ long orc_sort_stars(unsigned char *star1, long n, long sizeof_star, long key_off
 void orc_energy_conservation2(const orc_tables_t *t, long n_local, const long *g_idx, const double *rnew, double *Uoldrnew);
 void orc_intermediate_energy(const orc_tables_t *t, long n_local, const long *g_idx, const double *rnew, const double *vr, const double *vt, double *EI);
 
+/* The energy scheme's velocity correction after the potential rebuild (the last of the four potential() loops):
+ *   energy_conservation1, src/cmc/cmc_utils.c:2153-2174: vrold, vtold <- vr, vt; Uoldrold = star_phi[g] + MPI_PHI_S(star_r[g], g)
+ *   set_velocities3, :254-352 (called through energy_conservation3, :360-363), as ONE rank sees it:
+ *     _first  = the loop :268-311 over the local stars with interacted == 0: the predicted squared speed vnew2 (one potential(rOld) each);
+ *               vnew2 <= 0 adds the star's kinetic-energy deficit to the running Eexcess, otherwise (vr, vt) are rescaled to vnew2,
+ *               copied to (vrnew, vtnew), and while Eexcess > 0 the star gives up MIN(0.8 * its kinetic energy, Eexcess).  The carry
+ *               runs serially from star to star.  vnew2_arr[i] = (vnew2 > 0).  Returns the rank's leftover Eexcess.
+ *     _second = the loop :323-343 of one pass of the do-while: starts from the Eexcess received from the previous rank (0 on rank 0)
+ *               and lets every star with vnew2_arr == 1 give up MIN(v2*m/2 - 0.8*m*v2_new/2, Eexcess) while Eexcess > 0.  Returns
+ *               what is left.  The caller carries the Send/Recv (rank i -> i+1), repeats while the all-reduced sum is > 0 (:345-347) and
+ *               finally Eoops += -Eexcess*madhoc (:351).  On a single rank the received value is 0: the first loop's leftover is dropped. */
+void orc_energy_conservation1(const orc_tables_t *t, long n_local, const long *g_idx, const double *vr, const double *vt, double *vrold,
+			      double *vtold, double *Uoldrold);
+double orc_set_velocities3_first(const orc_tables_t *t, long n_local, const long *g_idx, const long *interacted, const double *rOld,
+				 const double *vrold, const double *vtold, const double *Uoldrold, const double *Uoldrnew, double *vr, double *vt,
+				 double *vrnew, double *vtnew, char *vnew2_arr);
+double orc_set_velocities3_second(const orc_tables_t *t, long n_local, const long *g_idx, const long *interacted, const char *vnew2_arr,
+				  double Eexcess, double *vr, double *vt, const double *vrnew, const double *vtnew);
+
 /* comp_mass_percent, src/cmc/cmc_utils.c:872-985: Lagrange radii and the cumulative kinetic sums at them, as ONE rank of P sees it.
  *   star_r, star_m: the replicated tables; vr, vt: star[k].vr / .vt of this rank's local stars k = 1..n_local at vr[k-1], vt[k-1];
  *   first_global = Start[myid] (global index of local star 1; the function is called after the sort, so there are no new stars).

@@ -210,6 +210,12 @@ EXPORT double ref_clusdyn_rh(void) { clusdyn_calculate(); return clusdyn.rh; }
 EXPORT void ref_energy_conservation2(void) { energy_conservation2(); }
 EXPORT void ref_compute_intermediate_energy(void) { ComputeIntermediateEnergy(); }
 
+/* energy_conservation1 (cmc_utils.c:2153-2174) and energy_conservation3 -> set_velocities3 (:254-363) on the harness's cluster state */
+EXPORT void ref_energy_conservation1(void) { energy_conservation1(); }
+EXPORT void ref_energy_conservation3(void) { energy_conservation3(); }
+EXPORT double ref_get_Eoops(void) { return Eoops; }
+EXPORT void ref_set_Eoops(double v) { Eoops = v; }
+
 /* comp_mass_percent (src/cmc/cmc_utils.c:872-985) on the harness's cluster state: thresholds in, the eight result arrays out
  * (out[8][count], in the order mass_r, ave_mass_r, no_star_r, densities_r, ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r; on ranks other than 0
  * the last four hold what that rank computed, i.e. nothing meaningful -- the reference prints from rank 0 only). */

@@ -89,3 +89,31 @@ def with_new_stars(r, vr, vt, sm, pot, n_new, seed=0):
     is_new = np.concatenate([np.zeros(N, np.uint8), np.ones(n_new, np.uint8)])
     rnew_in = np.concatenate([np.zeros(N), r_new])
     return sr, smt, phi, E, J, vr_a, vt_a, g_idx, is_new, rnew_in
+
+
+def sv3_fields(r, vr, vt, phi, seed=0, src_frac=0.004, long_chains=True):
+    """Inputs of set_velocities3 (reference cmc_utils.c:254-352) for a sorted cluster with potential phi[1..N]: the fields the energy scheme
+    left in star[] (interacted, rOld, vrold, vtold, Uoldrold, Uoldrnew) plus the current (vr, vt, vrnew, vtnew).  Built so that every
+    branch fires: interacted stars, stars whose predicted speed is unphysical (vnew2 <= 0: they feed the excess-energy carry) alone, in
+    runs, with deficits large enough that the carry crosses thousands of stars, one of them right at the end (the rank keeps a
+    leftover), rOld below star_r[1] and beyond star_r[N]."""
+    N = len(r)
+    rng = np.random.default_rng(seed)
+    f = dict(interacted=(rng.uniform(size=N) < 0.03).astype(np.int64))
+    f["rOld"] = r * np.exp(rng.normal(0.0, 0.05, N))
+    f["rOld"][rng.choice(N, 3, replace=False)] = [r[0] * 0.5, r[-1] * 1.5, r[-1] * 40.0]
+    f["vrold"] = vr * rng.uniform(0.97, 1.03, N)
+    f["vtold"] = vt * rng.uniform(0.97, 1.03, N)
+    f["Uoldrold"] = phi * rng.uniform(0.999, 1.001, N)
+    f["Uoldrnew"] = phi * rng.uniform(0.999, 1.001, N)
+    src = rng.choice(N, max(3, int(src_frac * N)), replace=False)
+    src = np.concatenate([src, np.clip(src[:len(src) // 4] + 1, 0, N - 1), [N - 1]])   # some in runs of two, one at the very end
+    f["vrold"][src] *= 0.01
+    f["vtold"][src] *= 0.01
+    f["Uoldrold"][src] = f["Uoldrnew"][src] + phi[src] * rng.uniform(0.01, 0.5, len(src))  # phi < 0: the predicted v^2 turns negative
+    if long_chains:
+        big = src[:3]
+        f["Uoldrold"][big] = f["Uoldrnew"][big] + phi[big] * 2000.0
+    f["vr"], f["vt"] = vr.copy(), vt.copy()
+    f["vrnew"], f["vtnew"] = vr * 1.5, vt * 0.5           # overwritten for every corrected star, kept for the others
+    return f

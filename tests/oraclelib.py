@@ -53,6 +53,11 @@ def lib():
         L.orc_sort_stars.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p]
         L.orc_energy_conservation2.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 3
         L.orc_intermediate_energy.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 5
+        L.orc_energy_conservation1.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 6
+        L.orc_set_velocities3_first.restype = C.c_double
+        L.orc_set_velocities3_first.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 12
+        L.orc_set_velocities3_second.restype = C.c_double
+        L.orc_set_velocities3_second.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 4
         L.orc_clusdyn_calculate.restype = C.c_double
         L.orc_clusdyn_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double]
         L.orc_comp_mass_percent.restype = C.c_long
@@ -173,6 +178,57 @@ def intermediate_energy(t, g_idx, rnew, vr, vt, EI_in):
     out = np.array(EI_in, dtype=np.float64, copy=True)
     lib().orc_intermediate_energy(C.byref(t), len(rnew), _p(g_idx), _p(rnew), _p(vr), _p(vt), _p(out))
     return out
+
+
+def energy_conservation1(t, g_idx, vr, vt):
+    """(vrold, vtold, Uoldrold) of energy_conservation1 (reference cmc_utils.c:2153-2174)"""
+    g_idx = np.ascontiguousarray(g_idx, np.int64)
+    vr, vt = np.ascontiguousarray(vr, np.float64), np.ascontiguousarray(vt, np.float64)
+    out = [np.zeros(len(vr)) for _ in range(3)]
+    lib().orc_energy_conservation1(C.byref(t), len(vr), _p(g_idx), _p(vr), _p(vt), *[_p(o) for o in out])
+    return dict(vrold=out[0], vtold=out[1], Uoldrold=out[2])
+
+
+SV3_IN = ("interacted", "rOld", "vrold", "vtold", "Uoldrold", "Uoldrnew")
+SV3_IO = ("vr", "vt", "vrnew", "vtnew")
+
+
+def set_velocities3_first(t, g_idx, f):
+    """first loop of set_velocities3 (reference cmc_utils.c:268-311) on the fields of dict f (SV3_IN + SV3_IO, local star order);
+    returns (fields after, vnew2_arr, the rank's leftover Eexcess)"""
+    g_idx = np.ascontiguousarray(g_idx, np.int64)
+    n = len(g_idx)
+    inter = np.ascontiguousarray(f["interacted"], np.int64)
+    ins = [np.ascontiguousarray(f[k], np.float64) for k in SV3_IN[1:]]
+    io = {k: np.array(f[k], dtype=np.float64, copy=True) for k in SV3_IO}
+    flags = np.zeros(n, np.int8)
+    left = lib().orc_set_velocities3_first(C.byref(t), n, _p(g_idx), _p(inter), *[_p(a) for a in ins], *[_p(io[k]) for k in SV3_IO], _p(flags))
+    return io, flags, left
+
+
+def set_velocities3_second(t, g_idx, interacted, flags, Eexcess, io):
+    """one pass of the do-while loop of set_velocities3 (reference cmc_utils.c:323-343) starting from the received Eexcess; io is updated
+    in place (vr, vt); returns what is left"""
+    g_idx, inter = np.ascontiguousarray(g_idx, np.int64), np.ascontiguousarray(interacted, np.int64)
+    return lib().orc_set_velocities3_second(C.byref(t), len(g_idx), _p(g_idx), _p(inter), _p(flags), Eexcess, _p(io["vr"]), _p(io["vt"]),
+                                            _p(io["vrnew"]), _p(io["vtnew"]))
+
+
+def set_velocities3(t, shards, fields):
+    """set_velocities3 as P ranks run it (reference cmc_utils.c:254-352).  shards = [(first_global, n_local)] in rank order, fields = one
+    dict per rank.  Returns (per-rank fields after, per-rank -Eexcess*madhoc added to Eoops, passes of the do-while loop)."""
+    P = len(shards)
+    g = [np.arange(s, s + n) for s, n in shards]
+    first = [set_velocities3_first(t, g[q], fields[q]) for q in range(P)]
+    io, flags, E = [x[0] for x in first], [x[1] for x in first], [x[2] for x in first]
+    passes = 0
+    while True:
+        prev = [0.0] + E[:-1]                                     # rank i sends to i+1 (:317-320); rank 0 keeps Eexcess_prev = 0
+        E = [set_velocities3_second(t, g[q], fields[q]["interacted"], flags[q], prev[q], io[q]) for q in range(P)]
+        passes += 1
+        if not sum(E) > 0:                                        # MPI_Allreduce(SUM), :345-347
+            break
+    return io, [-e * t.madhoc for e in E], passes
 
 
 def clusdyn_calculate(star_r, star_m, N_STAR, Mtotal):

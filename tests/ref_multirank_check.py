@@ -67,6 +67,21 @@ def main(procs, N):
             ok = ok and np.array_equal(got[f].view(np.uint64), merged.view(np.uint64))
         ok = ok and parts[0]["filled"] == len(pcs) - 1 and got["mass_r"][-1] == -1.0     # 150 % of the mass is never reached
         ok = ok and len({int(np.argmax([o["owner"][i] for o in parts])) for i in range(len(pcs) - 1)}) >= min(procs, 2)  # several owners
+    # set_velocities3 (reference cmc_utils.c:254-352): the excess-energy carry runs through every rank's shard and on to the next rank
+    # (MPI_Send / MPI_Recv, repeated while the all-reduced leftover is > 0)
+    phi = R.star_phi()[:N + 2].copy()
+    f = cm.sv3_fields(rnew[order], vrs, vts, phi[1:N + 1], seed=N + procs)
+    nl = hi - lo + 1
+    for k, v in f.items():
+        R.star_field(k, np.int64 if k == "interacted" else np.float64)[1:nl + 1] = v[lo - 1:hi]
+    R.L.ref_set_Eoops(0.0)
+    R.L.ref_energy_conservation3()
+    t = ol.tables(R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), phi, N, N, 0.0)
+    shards = [(int(S[q]), int(E[q] - S[q] + 1)) for q in range(procs)]
+    io, eoops, passes = ol.set_velocities3(t, shards, [{k: v[S[q] - 1:E[q]] for k, v in f.items()} for q in range(procs)])
+    for k in ol.SV3_IO:
+        ok = ok and np.array_equal(io[rank][k].view(np.uint64), R.star_field(k)[1:nl + 1].view(np.uint64))
+    ok = ok and R.L.ref_get_Eoops() == eoops[rank] and passes >= (2 if procs > 2 else 1)
     if not ok:
         print(f"rank {rank}: MISMATCH", flush=True)
         sys.exit(3)

@@ -56,6 +56,8 @@ class Ref:
         L.ref_rng_next.argtypes = [C.c_void_p]
         L.ref_time_step.argtypes = [C.c_void_p] * 4
         L.ref_spawn.argtypes = [C.c_int, C.c_size_t]
+        L.ref_get_Eoops.restype = C.c_double
+        L.ref_set_Eoops.argtypes = [C.c_double]
         self.sizeof_star = L.ref_sizeof_star()
         self.sizeof_binary = L.ref_sizeof_binary()
         self.n_star_dim = 0

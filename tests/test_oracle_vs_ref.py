@@ -87,6 +87,40 @@ def test_full_step(R, kind, N, masses, cenma):
     R.free()
 
 
+@pytest.mark.parametrize("kind,N,masses", [("plummer", 40000, "imf"), ("king", 25000, "equal")])
+def test_energy_scheme_velocity_correction(R, kind, N, masses):
+    """energy_conservation1 and energy_conservation3 -> set_velocities3 (reference cmc_utils.c:2153-2174, 254-363) of the
+    compiled reference against the restatement, bit for bit, on fields that make every branch fire (cm.sv3_fields)"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 7, masses=masses)
+    R.init(N, n_star_dim=N + 64)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N)
+    R.L.ref_calc_potential_new()
+    sr, smt, phi = R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy()
+    t = ol.tables(sr, smt, phi, N, N, 0.0)
+    g = np.arange(1, N + 1)
+    R.L.ref_energy_conservation1()
+    for k, v in ol.energy_conservation1(t, g, vr, vt).items():
+        cm.assert_bits_equal(v, R.star_field(k)[1:N + 1], k)
+    f = cm.sv3_fields(r, vr, vt, phi[1:N + 1], seed=N)
+    for k, v in f.items():
+        R.star_field(k, np.int64 if k == "interacted" else np.float64)[1:N + 1] = v
+    R.L.ref_set_Eoops(0.125)
+    R.L.ref_energy_conservation3()
+    io, flags, left = ol.set_velocities3_first(t, g, f)
+    assert left > 0 and 0 < flags.sum() < N and (f["interacted"] == 0).sum() - flags.sum() > 10     # sources, sinks and a leftover
+    touched = sum(int((io[k] != f[k]).sum()) for k in ("vr", "vt"))
+    assert touched > 0.9 * N
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(io[k], R.star_field(k)[1:N + 1], k)
+    assert R.L.ref_get_Eoops() == 0.125                  # single rank: Eexcess <- Eexcess_prev = 0 before the second loop (:322)
+    io2, eoops, passes = ol.set_velocities3(t, [(1, N)], [f])
+    assert passes == 1 and eoops[0] == 0.0
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(io2[0][k], io[k], k + " (driver)")
+    R.free()
+
+
 def test_sort_with_binaries_and_stripped_stars(R):
     n, nb, n_strip = 20000, 1500, 23
     rng = np.random.default_rng(8)
