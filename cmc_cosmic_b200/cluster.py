@@ -56,6 +56,7 @@ class Cluster:
         self.Start, self.End = np.array([1], np.int32), np.array([n_star], np.int32)
         self.mpiBegin, self.mpiEnd = 1, n_star
         self.tcount = 1
+        self.Eoops = 0.0                  # energy lost to the scheme (reference include/cmc/cmc_vars.h:293)
         self.last_orbit = None
         self.last_status = None
         ctx = C.c_void_p()
@@ -218,6 +219,26 @@ class Cluster:
         """ComputeIntermediateEnergy (reference src/cmc/cmc_utils.c:368-391) on the resident arrays: EI, then r <- rnew etc."""
         p = self.orbit_params()
         _lib.check(self.L.cmcb200_dev_compute_intermediate_energy(self.ctx, C.byref(p)), "dev_compute_intermediate_energy")
+
+    def dev_energy_conservation1(self):
+        """energy_conservation1 (reference src/cmc/cmc_utils.c:2153-2174) on the resident arrays: vrold, vtold, Uoldrold of every local star"""
+        p = self.orbit_params()
+        _lib.check(self.L.cmcb200_dev_energy_conservation1(self.ctx, C.byref(p)), "dev_energy_conservation1")
+
+    def dev_energy_conservation3(self):
+        """energy_conservation3 -> set_velocities3 (reference src/cmc/cmc_utils.c:254-363) on the resident arrays, one rank: the first loop;
+        the received Eexcess of the second loop is 0 on rank 0, so it changes nothing and Eoops += -0 (:322, :351).  Returns the leftover
+        excess of the first loop (a diagnostic: the reference drops it)."""
+        p, left = self.orbit_params(), C.c_double()
+        _lib.check(self.L.cmcb200_dev_set_velocities3(self.ctx, C.byref(p), C.byref(left)), "dev_set_velocities3")
+        self.Eoops += -0.0 * (1.0 / self.clus.N_STAR)
+        return left.value
+
+    def dev_set_velocities3_pass(self, Eexcess):
+        """one pass of set_velocities3's second loop (:323-343) from the Eexcess received from the previous rank; returns what is left"""
+        p, left = self.orbit_params(), C.c_double()
+        _lib.check(self.L.cmcb200_dev_set_velocities3_pass(self.ctx, C.byref(p), Eexcess, C.byref(left)), "dev_set_velocities3_pass")
+        return left.value
 
     def dev_qsorts_new(self):
         n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)

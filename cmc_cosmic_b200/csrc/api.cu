@@ -157,6 +157,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
 	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
 	if (c->d_lagrange) cudaFree(c->d_lagrange);
+	if (c->d_sv3) cudaFree(c->d_sv3);
 	if (c->d_draws) cudaFree(c->d_draws);
 	if (c->d_draw_off) cudaFree(c->d_draw_off);
 	cudaFreeHost(c->h_pinned);
@@ -374,7 +375,7 @@ extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, 
 //   orbit_range   the three stages on local stars [off, off + len): every star is independent of the others (its draws are keyed by its
 //                 global index or come from its own CSR slice), so the result does not depend on the chunking
 //   orbit_end     combines the per-chunk statistics
-static int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a)
+int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a)
 {
 	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
 	a.star1 = star1(c);

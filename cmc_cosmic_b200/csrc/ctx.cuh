@@ -56,6 +56,7 @@ struct cmcb200_ctx {
 	// orbit scratch
 	OrbitStats *d_ostats;
 	void *d_lagrange; // device result block of comp_mass_percent (lagrange.cu), allocated on first use
+	void *d_sv3;      // scratch of set_velocities3 (velocities.cu), allocated on first use for n_star_dim stars
 	int *d_status;
 	long *d_kmin, *d_kmax;
 	double *d_draws;
@@ -87,6 +88,9 @@ struct cmcb200_ctx {
 	int shard_unfused;                              // 1: the sharded sort keys on r and moves the records unchanged (cmcb200_shard_fuse_transfer)
 	int r_parity;                                   // which of (d_r, d_r_alt) is the buffer SH_R (flips with every fused sort)
 };
+
+// fills the orbit-step argument block from the context and the caller's parameters and (re)builds the lookup tables (api.cu)
+int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a);
 
 static inline char *star1(cmcb200_ctx *c) { return c->d_star[c->cur_star] + CMCB_SIZEOF_STAR; }
 static inline char *bin1(cmcb200_ctx *c) { return c->d_bin[c->cur_bin] + CMCB_SIZEOF_BINARY; }

@@ -66,9 +66,6 @@ struct CsrDraws {
 	__device__ double next() { return d[pos++]; }
 };
 
-__device__ __forceinline__ double ld_field(const char *rec, int off) { return *(const double *) (rec + off); }
-__device__ __forceinline__ void st_field(char *rec, int off, double v) { *(double *) (rec + off) = v; }
-
 static_assert(QLAD_MIN_SHIFT == 4, "orbit_pack_tables reduces the finest Q-ladder blocks over 16-lane groups");
 
 // rp[i] = (r[i], phi[i]) for i < n; with q_fine != nullptr also block b of the finest Q-ladder level (entries [16 b, min(16 b + 16, M)]) and
@@ -216,18 +213,6 @@ __device__ __forceinline__ void store_prepared(const OrbitArgs &a, long j0, cons
 		a.flag[j0] = 0;
 		store_star(a, j0, o);
 	}
-}
-
-// Stages `bytes` of a ladder's coarsest level into this CTA's shared memory with one TMA bulk copy and returns the shared address
-// (nullptr when the ladder is off).  Called by all threads of the CTA, once.
-__device__ __forceinline__ const void *stage_top_level(const void *level, unsigned bytes, bool on, unsigned char *smem, unsigned long long *bar)
-{
-	if (!on) return nullptr; // CTA-uniform
-	if (threadIdx.x == 0) mbar_init(bar, 1);
-	__syncthreads();
-	if (threadIdx.x == 0) bulk_copy_g2s(smem, level, bytes, bar);
-	mbar_wait(bar, 0);
-	return smem;
 }
 
 // CTAS = resident CTAs per SM the register allocation is capped for (4: 64 registers, 3: 80)
@@ -569,6 +554,12 @@ int orbit_energy_rnew(const OrbitArgs &a, bool uold, bool ei, cudaStream_t s)
 	else if (uold) energy_rnew_kernel<true, false><<<(unsigned) blocks, ORBIT_TRY_THREADS, a.r_top_bytes, s>>>(a);
 	else energy_rnew_kernel<false, true><<<(unsigned) blocks, ORBIT_TRY_THREADS, a.r_top_bytes, s>>>(a);
 	return 2;
+}
+
+int orbit_reset_stats(const OrbitArgs &a, cudaStream_t s)
+{
+	orbit_stats_reset<<<1, 1, 0, s>>>(a.stats);
+	return 1;
 }
 
 __global__ void orbit_stats_reset(OrbitStats *s)

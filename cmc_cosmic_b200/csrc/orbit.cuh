@@ -67,5 +67,23 @@ int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_scan(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_tries(const OrbitArgs &a, cudaStream_t s);
 int orbit_energy_rnew(const OrbitArgs &a, bool uold, bool ei, cudaStream_t s);
+int orbit_reset_stats(const OrbitArgs &a, cudaStream_t s); // zeroes a.stats (one launch)
+
+// ---- device helpers shared by orbit.cu and velocities.cu ----------------------------------------------------------------
+__device__ __forceinline__ double ld_field(const char *rec, int off) { return *(const double *) (rec + off); }
+__device__ __forceinline__ void st_field(char *rec, int off, double v) { *(double *) (rec + off) = v; }
+
+// Stages `bytes` of a ladder's coarsest level into this CTA's shared memory with one TMA bulk copy and returns the shared address
+// (nullptr when the ladder is off).  Called by all threads of the CTA, once.
+__device__ __forceinline__ const void *stage_top_level(const void *level, unsigned bytes, bool on, unsigned char *smem, unsigned long long *bar)
+{
+	if (!on) return nullptr; // CTA-uniform
+	if (threadIdx.x == 0) mbar_init(bar, 1);
+	__syncthreads();
+	if (threadIdx.x == 0) bulk_copy_g2s(smem, level, bytes, bar);
+	mbar_wait(bar, 0);
+	return smem;
+}
+
 
 } // namespace cmcb

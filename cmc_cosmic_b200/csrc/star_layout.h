@@ -26,6 +26,10 @@
 #define CMCB_OFF_R_PERI 112
 #define CMCB_OFF_R_APO 120
 #define CMCB_OFF_PHI 128
+#define CMCB_OFF_INTERACTED 136
 #define CMCB_OFF_BININD 152
 #define CMCB_OFF_ID 160
+#define CMCB_OFF_UOLDROLD 176
 #define CMCB_OFF_UOLDRNEW 184
+#define CMCB_OFF_VTOLD 192
+#define CMCB_OFF_VROLD 200

@@ -10,8 +10,8 @@ STAR_DTYPE_SIZE = 424
 BINARY_DTYPE_SIZE = 464
 
 STAR_OFFSETS = dict(r=0, vr=8, vt=16, m=24, E=32, J=40, EI=48, Eint=56, rnew=64, vrnew=72, vtnew=80, rOld=88, X=96, Y=104,
-                    r_peri=112, r_apo=120, phi=128, binind=152, id=160, Uoldrold=176, Uoldrnew=184)
-STAR_INT_FIELDS = ("binind", "id")
+                    r_peri=112, r_apo=120, phi=128, interacted=136, binind=152, id=160, Uoldrold=176, Uoldrnew=184, vtold=192, vrold=200)
+STAR_INT_FIELDS = ("binind", "id", "interacted")
 BINARY_OFFSETS = dict(id1=0, id2=8, rad1=16, rad2=24, m1=32, m2=40, Eint1=48, Eint2=56, a=64, e=72, inuse=80)
 
 

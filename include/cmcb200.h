@@ -161,6 +161,21 @@ int cmcb200_dev_transfer_new_positions(cmcb200_ctx *ctx, long n_local, long n_ol
  * A lookup whose bracket check fails (fatal in the reference, :144-152) makes the call return non-zero. */
 int cmcb200_dev_energy_conservation2(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
 int cmcb200_dev_compute_intermediate_energy(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
+/* The rest of the energy scheme (Stodolkiewicz), on the resident arrays; p as above, the records are the sorted ones after the potential rebuild.
+ *   energy_conservation1 (src/cmc/cmc_utils.c:2153-2174):  star[i].vrold/.vtold <- .vr/.vt;  .Uoldrold = star_phi[g_i] + MPI_PHI_S(star_r[g_i], g_i)
+ *   set_velocities3 (:254-352, called through energy_conservation3 :360-363), first loop (:268-311): for every star with interacted == 0 the
+ *     predicted squared speed vnew2 (one potential(rOld) lookup); vnew2 > 0: (vr, vt) rescaled to it and copied to (vrnew, vtnew); vnew2 <= 0:
+ *     the star's deficit joins Eexcess, which the following stars absorb (at most 0.8 of their kinetic energy each) -- a carry the reference
+ *     runs serially from star to star, reproduced here in star order (csrc/velocities_core.h).  *Eexcess_left = what the rank is left with.
+ *   On ONE rank that is the whole function: the reference resets Eexcess to the value received from the previous rank, 0 (:322), before the
+ *   second loop, so the leftover is dropped and Eoops does not change.
+ *   On P ranks the caller carries the reference's message pattern (:315-347): repeat { send Eexcess to rank+1; Eexcess <- received (0 on rank 0);
+ *   cmcb200_dev_set_velocities3_pass(Eexcess) = one pass of the second loop (:323-343) over this rank's stars, in star order; all-reduce the
+ *   leftovers } while their sum > 0, then Eoops += -Eexcess * madhoc (:351).
+ * A potential() lookup whose bracket check fails (fatal in the reference, :144-152) makes the call return non-zero. */
+int cmcb200_dev_energy_conservation1(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
+int cmcb200_dev_set_velocities3(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, double *Eexcess_left);
+int cmcb200_dev_set_velocities3_pass(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, double Eexcess_in, double *Eexcess_left);
 /* qsorts_new + post_sort_comm on the resident arrays; *n_local in/out, *n_bin out */
 int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, long *n_bin);
 /* cmcb200_dev_transfer_new_positions + cmcb200_dev_qsorts_new in one pass over the records: the sort key is rnew and the transfer is

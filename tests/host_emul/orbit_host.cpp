@@ -1,6 +1,7 @@
 // Host build of cmc_cosmic_b200/csrc/orbit_core.h (the exact per-star code the CUDA kernel runs), so the CPU test
 // suite can check it bit-for-bit against the oracle / the compiled reference without a GPU.
 // TEST-ONLY: the product library never runs this on the host.  Build: g++ -O2 -ffp-contract=off -shared -fPIC.
+#include <algorithm>
 #include <vector>
 #include "../../cmc_cosmic_b200/csrc/orbit_core.h"
 using namespace cmcb;
@@ -125,4 +126,66 @@ extern "C" int emul_ladder_plan(long M, int *qshift, long *qcount, int *rshift, 
 {
 	*n_r = rlad_plan(M, rshift, rcount, ralloc);
 	return qlad_plan(M, qshift, qcount);
+}
+
+// set_velocities3's first loop (reference cmc_utils.c:268-311) the way velocities.cu runs it: prepare per star, per-block carries from 0,
+// the serial pass over the block results, the real walk of the blocks that need one -- here one after the other, with the block length
+// as a parameter so that small clusters have many blocks.  vr/vt/vrnew/vtnew in/out.  Returns the leftover Eexcess; counters[0] = blocks
+// replayed by the carry pass, [1] = blocks walked by apply, [2] = failed potential() brackets.
+#include "../../cmc_cosmic_b200/csrc/velocities_core.h"
+extern "C" double emul_set_velocities3(const double *star_r, const double *star_m, const double *star_phi, long N_MAX, long N_STAR, long n_local,
+				       long first_global, long blk, const long *interacted, const double *rOld, const double *vrold, const double *vtold,
+				       const double *Uoldrold, const double *Uoldrnew, double *vr, double *vt, double *vrnew, double *vtnew,
+				       unsigned char *kind, long *counters)
+{
+	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
+	OrbitTables t; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = 0;
+	HostLadders lad(rp, (kint) (N_MAX + 1));
+	t.qlad = lad.q; t.rlad = lad.r;
+	LadderTops top; top.q = nullptr; top.qdesc = nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
+	const Sv3Index gi{first_global, n_local, N_MAX};
+	std::vector<double> val(n_local);
+	counters[0] = counters[1] = counters[2] = 0;
+	for (long j = 0; j < n_local; j++) { // prepare
+		Sv3In s{interacted[j], rOld[j], vrold[j], vtold[j], Uoldrold[j], Uoldrnew[j], vr[j], vt[j]};
+		int fail = 0;
+		double a = vr[j], b = vt[j];
+		kind[j] = (unsigned char) sv3_prepare_star(t, top, gi(j), s, &a, &b, &val[j], &fail);
+		counters[2] += fail;
+		if ((kind[j] & SV3_ACTIVE) && !(kind[j] & SV3_SOURCE)) { vr[j] = vrnew[j] = a; vt[j] = vtnew[j] = b; }
+	}
+	const long nb = (n_local + blk - 1) / blk;
+	std::vector<double> eb(nb), ein(nb);
+	std::vector<char> has(nb);
+	auto none = [](long, double) {};
+	for (long b = 0; b < nb; b++) { // blocks
+		const long lo = b * blk, hi = std::min(lo + blk, n_local);
+		has[b] = 0;
+		for (long i = lo; i < hi; i++) if (kind[i] & SV3_SOURCE) has[b] = 1;
+		eb[b] = has[b] ? sv3_walk(kind, val.data(), star_m, gi, lo, hi, 0.0, none) : 0.0;
+	}
+	double E = 0.0;
+	for (long b = 0; b < nb; b++) { // carry
+		ein[b] = E;
+		if (E == 0.0) E = eb[b];
+		else { E = sv3_walk(kind, val.data(), star_m, gi, b * blk, std::min((b + 1) * blk, n_local), E, none); counters[0]++; }
+	}
+	for (long b = 0; b < nb; b++) { // apply
+		if (ein[b] == 0.0 && !has[b]) continue;
+		counters[1]++;
+		sv3_walk(kind, val.data(), star_m, gi, b * blk, std::min((b + 1) * blk, n_local), ein[b], [&](long i, double ratio) { vr[i] = dmul(vr[i], ratio); vt[i] = dmul(vt[i], ratio); });
+	}
+	return E;
+}
+
+// one pass of the second loop (:323-343) from the received Eexcess
+extern "C" double emul_set_velocities3_second(const double *star_m, long N_MAX, long n_local, long first_global, const unsigned char *kind, double E,
+					      double *vr, double *vt, const double *vrnew, const double *vtnew)
+{
+	const Sv3Index gi{first_global, n_local, N_MAX};
+	for (long i = 0; i < n_local; i++) {
+		double ratio;
+		if (sv3_second_step(kind[i], vr[i], vt[i], vrnew[i], vtnew[i], star_m[gi(i)], E, &ratio)) { vr[i] = dmul(vr[i], ratio); vt[i] = dmul(vt[i], ratio); }
+	}
+	return E;
 }

@@ -37,6 +37,10 @@ def lib():
         L.emul_ladder_plan.restype = C.c_int
         L.emul_ladder_plan.argtypes = [lg] + [vp] * 6
         L.emul_find_zero_r_both.argtypes = [vp, lg, vp, lg, vp, vp]
+        L.emul_set_velocities3.restype = db
+        L.emul_set_velocities3.argtypes = [vp, vp, vp, lg, lg, lg, lg, lg] + [vp] * 12
+        L.emul_set_velocities3_second.restype = db
+        L.emul_set_velocities3_second.argtypes = [vp, lg, lg, lg, vp, db, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -84,3 +88,20 @@ def ladder_plan(M):
     nr = np.zeros(1, np.int32)
     nq = lib().emul_ladder_plan(M, _p(qs), _p(qc), _p(rs), _p(rc), _p(ra), _p(nr))
     return dict(q_shift=qs[:nq], q_count=qc[:nq], r_shift=rs[:nr[0]], r_count=rc[:nr[0]], r_alloc=ra[:nr[0]])
+
+
+def set_velocities3(sr, sm, phi, N_MAX, N_STAR, first_global, f, blk=1024):
+    """first loop of set_velocities3 as the CUDA path decomposes it (velocities_core.h); f: the fields of cm.sv3_fields for the local stars.
+    Returns (vr, vt, vrnew, vtnew after, kind bytes, leftover Eexcess, counters)"""
+    n = len(f["vr"])
+    inter = np.ascontiguousarray(f["interacted"], np.int64)
+    ins = [np.ascontiguousarray(f[k], np.float64) for k in ("rOld", "vrold", "vtold", "Uoldrold", "Uoldrnew")]
+    io = {k: np.array(f[k], dtype=np.float64, copy=True) for k in ("vr", "vt", "vrnew", "vtnew")}
+    kind, cnt = np.zeros(n, np.uint8), np.zeros(3, np.int64)
+    left = lib().emul_set_velocities3(_p(sr), _p(sm), _p(phi), N_MAX, N_STAR, n, first_global, blk, _p(inter), *[_p(a) for a in ins],
+                                      *[_p(io[k]) for k in ("vr", "vt", "vrnew", "vtnew")], _p(kind), _p(cnt))
+    return io, kind, left, dict(replayed=int(cnt[0]), walked=int(cnt[1]), failed=int(cnt[2]))
+
+
+def set_velocities3_second(sm, N_MAX, first_global, kind, Eexcess, io):
+    return lib().emul_set_velocities3_second(_p(sm), N_MAX, len(kind), first_global, _p(kind), Eexcess, _p(io["vr"]), _p(io["vt"]), _p(io["vrnew"]), _p(io["vtnew"]))

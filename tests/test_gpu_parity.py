@@ -396,6 +396,108 @@ def test_energy_scheme_lookups_at_new_radii_bit_exact(kind, N, masses, tidal):
     c.close()
 
 
+def _sv3_cluster(kind, N, masses, first=1, nl=None, seed=0, **kw):
+    """a sorted cluster with its potential on the device, the local stars first .. first + nl - 1 carrying cm.sv3_fields"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 7, masses=masses)
+    pot = cm.oracle_potential(r, sm)
+    nl = nl or N
+    f = {k: v[first - 1:first - 1 + nl].copy() for k, v in cm.sv3_fields(r, vr, vt, pot["phi"][1:N + 1], seed=seed, **kw).items()}
+    if first + nl - 1 < N:                                   # a shard: its last star feeds the carry too, so the shard keeps a leftover
+        f["interacted"][-1], f["vrold"][-1], f["vtold"][-1] = 0, 0.0, 0.0
+        f["Uoldrold"][-1] = f["Uoldrnew"][-1] + pot["phi"][first + nl - 1] * 0.3
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    rng = np.random.default_rng(seed + 1)
+    c.star[1:nl + 1] = rng.integers(0, 256, (nl, c.star.shape[1]), dtype=np.uint8)     # every other byte of the records is noise
+    for k, v in f.items():
+        c.field(k)[1:nl + 1] = v
+    c.clus.N_MAX_NEW, c.Start[0], c.End[0] = nl, first, first + nl - 1
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    return c, t, f, np.arange(first, first + nl)
+
+
+def _only_these_fields_changed(before, c, nl, names):
+    """every byte of star[1..nl] outside the named 8-byte fields is what it was"""
+    from cmc_cosmic_b200 import layout
+    mask = np.ones(c.star.shape[1], bool)
+    for k in names:
+        mask[layout.STAR_OFFSETS[k]:layout.STAR_OFFSETS[k] + 8] = False
+    assert np.array_equal(before[1:nl + 1][:, mask], c.star[1:nl + 1][:, mask])
+
+
+@pytest.mark.parametrize("kind,N,masses,first,nl", [("plummer", 50000, "imf", 1, None), ("king", 800000, "equal", 1, None), ("plummer", 4096, "equal", 1, None),
+                                                    ("plummer", 3000, "imf", 1, None), ("plummer", 120000, "imf", 30001, 50001)])
+def test_energy_scheme_velocity_correction_bit_exact(kind, N, masses, first, nl):
+    """SURVEY 8f N1, the last potential() loop of the energy scheme, on the resident arrays: energy_conservation1 and
+    energy_conservation3 -> set_velocities3 (reference cmc_utils.c:2153-2174, 254-363).  The excess-energy carry the reference runs serially
+    from star to star is decomposed into per-star, per-block and one short serial pass (csrc/velocities_core.h) and must reproduce every
+    rounding of the serial loop: chains inside a 1024-star block, across many blocks, a leftover at the end of the shard, a shard that
+    starts in the middle of the cluster; then passes of the second loop from a received excess.  Nothing else in the records changes."""
+    c, t, f, g = _sv3_cluster(kind, N, masses, first, nl, seed=N)
+    nl = len(g)
+    c.upload()
+    before = c.star.copy()
+    c.dev_energy_conservation1()
+    c.download()
+    for k, v in ol.energy_conservation1(t, g, f["vr"], f["vt"]).items():
+        cm.assert_bits_equal(c.field(k)[1:nl + 1], v, k)
+    _only_these_fields_changed(before, c, nl, ("vrold", "vtold", "Uoldrold"))
+    for k, v in f.items():                                  # the scheme's inputs (energy_conservation1 just overwrote three of them)
+        c.field(k)[1:nl + 1] = v
+    c.upload()
+    before = c.star.copy()
+    left = c.dev_energy_conservation3()
+    c.download()
+    want, flags, left0 = ol.set_velocities3_first(t, g, f)
+    assert (flags == 0).sum() > 3 and left0 > 0
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(c.field(k)[1:nl + 1], want[k], k)
+    assert left == left0 and c.Eoops == 0.0
+    _only_these_fields_changed(before, c, nl, ol.SV3_IO)
+    for Ein in (left0 * 3.0 + 0.01, 0.0, 1e-9, float(np.sum(0.5 * t.madhoc * (want["vr"] ** 2 + want["vt"] ** 2)))):   # the last: more than the shard can absorb
+        e0 = ol.set_velocities3_second(t, g, f["interacted"], flags, Ein, want)
+        e1 = c.dev_set_velocities3_pass(Ein)
+        c.download()
+        assert e1 == e0
+        for k in ol.SV3_IO:
+            cm.assert_bits_equal(c.field(k)[1:nl + 1], want[k], k + f" after a pass from {Ein}")
+    c.close()
+
+
+def test_energy_scheme_velocity_correction_edge_cases():
+    """no star takes part; no source at all (nothing to carry); every star a source; a failed potential() bracket is reported"""
+    N = 5000
+    for case in ("none", "no_source", "all_sources"):
+        c, t, f, g = _sv3_cluster("plummer", N, "equal", seed=5, src_frac=0.0 if case == "no_source" else 0.004, long_chains=False)
+        if case == "none":
+            f["interacted"][:] = 1
+        elif case == "no_source":
+            f["vrold"], f["vtold"] = f["vr"] * 3.0, f["vt"] * 3.0            # plenty of kinetic energy: every vnew2 > 0
+        else:
+            f["vrold"], f["vtold"] = f["vr"] * 0.0, f["vt"] * 0.0
+            f["Uoldrold"] = f["Uoldrnew"] + t_phi(t, g) * 5.0
+        for k, v in f.items():
+            c.field(k)[1:N + 1] = v
+        c.upload()
+        left = c.dev_energy_conservation3()
+        c.download()
+        want, flags, left0 = ol.set_velocities3_first(t, g, f)
+        if case == "no_source":
+            assert left0 == 0.0 and flags.sum() == (f["interacted"] == 0).sum()
+        if case == "all_sources":
+            assert flags.sum() == 0 and left0 > 0
+        for k in ol.SV3_IO:
+            cm.assert_bits_equal(c.field(k)[1:N + 1], want[k], f"{case}: {k}")
+        assert left == left0
+        c.close()
+
+
+def t_phi(t, g):
+    import ctypes
+    return np.ctypeslib.as_array(ctypes.cast(t.phi, ctypes.POINTER(ctypes.c_double)), shape=(t.N_MAX + 2,))[g].copy()
+
+
 def test_lagrange_radii_of_a_run_agree_statistically_with_the_reference_run():
     """north_star: "Lagrangian radii from a full run must statistically agree with the reference run".  Six timesteps of the path
     (orbit step -> r <- rnew -> sort -> potential -> E, J) from the same Plummer state: the CUDA pipeline with its production draws

@@ -188,3 +188,37 @@ def test_kernel_core_on_host_handles_stars_created_this_step():
     assert np.array_equal(out["kmin"], want["kmin"]) and np.array_equal(out["kmax"], want["kmax"])
     for f in ("rnew", "vrnew", "vtnew", "r_peri", "r_apo"):
         cm.assert_bits_equal(out[f], want[f], f)
+
+
+@pytest.mark.parametrize("deep", [False, True])
+@pytest.mark.parametrize("N,blk,first,nl", [(30000, 1024, 1, None), (30000, 64, 1, None), (5000, 8, 1, None), (20000, 1024, 4001, 9000), (3000, 1, 1, None)])
+def test_set_velocities3_block_decomposition_equals_serial_loop(N, blk, first, nl, deep):
+    """velocities_core.h (prepare / per-block carries / serial pass over the blocks / apply) against the restatement of the reference's
+    serial loop (cmc_utils.c:268-311), bit for bit: chains inside a block, across blocks, a whole shard, a leftover at the end; then one
+    pass of the second loop (:323-343) from a received excess"""
+    import hostemul
+    hostemul.use_deep_ladders(deep)
+    try:
+        r, vr, vt, sm = cm.cluster_state("plummer", N, seed=N + blk, masses="imf")
+        pot = cm.oracle_potential(r, sm, N)
+        f = cm.sv3_fields(r, vr, vt, pot["phi"][1:N + 1], seed=blk)
+        nl = nl or N
+        f = {k: v[first - 1:first - 1 + nl] for k, v in f.items()}
+        t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+        g = np.arange(first, first + nl)
+        want, flags, left = ol.set_velocities3_first(t, g, f)
+        got, kind, left2, cnt = hostemul.set_velocities3(pot["star_r"], pot["star_m"], pot["phi"], N, N, first, f, blk=blk)
+        assert cnt["failed"] == 0 and cnt["walked"] > 0 and (cnt["replayed"] > 0 or blk >= nl or first > 1)
+        for k in ol.SV3_IO:
+            cm.assert_bits_equal(got[k], want[k], k)
+        assert left2 == left and np.array_equal((kind & 4) != 0, flags == 1) and np.array_equal((kind & 1) != 0, f["interacted"] == 0)
+        for Ein in (0.0, left * 3.0, 1e-9):
+            a = {k: v.copy() for k, v in want.items()}
+            b = {k: v.copy() for k, v in want.items()}
+            ea = ol.set_velocities3_second(t, g, f["interacted"], flags, Ein, a)
+            eb = hostemul.set_velocities3_second(pot["star_m"], N, first, kind, Ein, b)
+            assert ea == eb
+            for k in ("vr", "vt"):
+                cm.assert_bits_equal(b[k], a[k], k + " second loop")
+    finally:
+        hostemul.use_deep_ladders(False)

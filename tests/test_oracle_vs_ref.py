@@ -30,8 +30,16 @@ def test_layout_constants_match_reference_headers(R):
     assert out[1] == R.sizeof_binary == layout.BINARY_DTYPE_SIZE == 464
     for i, f in enumerate(names):
         assert out[2 + i] == R.star_offset(f) == layout.STAR_OFFSETS[f], f
-    for f in ("EI", "Eint", "Y", "phi", "id"):
+    for f in layout.STAR_OFFSETS:
         assert R.star_offset(f) == layout.STAR_OFFSETS[f], f
+    # every offset the kernels use (csrc/star_layout.h)
+    import os, re
+    hdr = open(os.path.join(os.path.dirname(lib.__file__), "csrc", "star_layout.h")).read()
+    by_upper = {k.upper(): k for k in layout.STAR_OFFSETS}
+    defs = re.findall(r"#define CMCB_OFF_(\w+) (\d+)", hdr)
+    assert len(defs) >= 24
+    for name, off in defs:
+        assert R.star_offset(by_upper[name]) == int(off), name
     for f, off in layout.BINARY_OFFSETS.items():
         assert R.binary_offset(f) == off, f
 
