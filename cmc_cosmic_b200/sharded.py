@@ -45,6 +45,27 @@ def destinations(rank, Start):
     return d, rank - start0[d]
 
 
+def carry_excess_between_ranks(dist, Eexcess, run_pass, device="cpu"):
+    """The do-while loop of set_velocities3 (reference src/cmc/cmc_utils.c:313-347) around `run_pass`, one rank's view.
+    Eexcess: this rank's leftover of the first loop.  Every round each rank hands its Eexcess to rank + 1 (MPI_Send / MPI_Recv in the
+    reference; an allgather of one double here), rank 0 receives 0, `run_pass(received)` runs the second loop over the local stars and
+    returns what is left, and the rounds go on while the sum of the leftovers over the ranks is > 0.  Returns (final Eexcess, rounds);
+    the caller books Eoops += -Eexcess * madhoc (:351)."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rounds = 0
+    while True:
+        parts = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+        dist.all_gather(parts, torch.tensor([Eexcess], dtype=torch.float64, device=device))
+        prev = float(parts[rank - 1]) if rank > 0 else 0.0
+        Eexcess = run_pass(prev)
+        rounds += 1
+        total = torch.tensor([Eexcess], dtype=torch.float64, device=device)
+        dist.all_reduce(total)
+        if not float(total[0]) > 0:
+            return Eexcess, rounds
+
+
 class ShardedCluster(Cluster):
     """One rank of a radius-sharded cluster.  `dist` is an initialised torch.distributed process group (nccl); rank r drives cuda:`device`."""
 
@@ -176,6 +197,17 @@ class ShardedCluster(Cluster):
 
     def dev_compute_energy(self):
         _lib.check(self.L.cmcb200_dev_compute_energy(self.ctx, self.clus.N_MAX_NEW, int(self.Start[self.myid])), "dev_compute_energy")
+
+    def dev_energy_conservation3(self):
+        """energy_conservation3 -> set_velocities3 on P ranks (reference src/cmc/cmc_utils.c:254-363): the first loop on every shard, then the
+        excess each shard could not absorb travels to the next rank until none is left.  Returns the number of rounds of the second loop."""
+        import torch
+        p, left = self.orbit_params(), C.c_double()
+        _lib.check(self.L.cmcb200_dev_set_velocities3(self.ctx, C.byref(p), C.byref(left)), "dev_set_velocities3")
+        with torch.cuda.stream(self._tstream):
+            E, rounds = carry_excess_between_ranks(self.dist, left.value, self.dev_set_velocities3_pass, device=f"cuda:{self.device}")
+        self.Eoops += -E * (1.0 / self.clus.N_STAR)
+        return rounds
 
     def orbit_params(self, draws=None, draw_off=None, seed=0, fuse_energy=False):
         n_old = int(self.End[self.myid] - self.Start[self.myid] + 1)

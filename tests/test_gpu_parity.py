@@ -413,6 +413,7 @@ def _sv3_cluster(kind, N, masses, first=1, nl=None, seed=0, **kw):
     for k, v in f.items():
         c.field(k)[1:nl + 1] = v
     c.clus.N_MAX_NEW, c.Start[0], c.End[0] = nl, first, first + nl - 1
+    c.bin_slots_in_use = 0                                   # binind is noise here; no binary record travels
     t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
     return c, t, f, np.arange(first, first + nl)
 
@@ -473,7 +474,8 @@ def test_energy_scheme_velocity_correction_edge_cases():
         if case == "none":
             f["interacted"][:] = 1
         elif case == "no_source":
-            f["vrold"], f["vtold"] = f["vr"] * 3.0, f["vt"] * 3.0            # plenty of kinetic energy: every vnew2 > 0
+            f["vrold"], f["vtold"], f["Uoldrold"] = f["vr"] * 3.0, f["vt"] * 3.0, f["Uoldrnew"].copy()   # plenty of kinetic energy: every vnew2 > 0
+            f["rOld"] = c.star_r[1:N + 1].copy()
         else:
             f["vrold"], f["vtold"] = f["vr"] * 0.0, f["vt"] * 0.0
             f["Uoldrold"] = f["Uoldrnew"] + t_phi(t, g) * 5.0

@@ -80,3 +80,40 @@ def test_global_rank_rule_is_a_stable_sort_of_the_concatenation():
         inv[np.argsort(allv, kind="stable")] = np.arange(len(allv))
         got = np.concatenate([host_global_ranks(runs, g) for g in range(P)]) if len(allv) else inv
         assert np.array_equal(got, inv)
+
+
+def _sv3_worker(rank, world, port, N):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import common as cm
+    import oraclelib as ol
+    from cmc_cosmic_b200.sharded import carry_excess_between_ranks
+    from cmc_cosmic_b200.partition import find_limits
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=5, masses="imf")
+    pot = cm.oracle_potential(r, sm, N)
+    f = cm.sv3_fields(r, vr, vt, pot["phi"][1:N + 1], seed=world)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    S, E = find_limits(N, 40, world)
+    shards = [(int(S[q]), int(E[q] - S[q] + 1)) for q in range(world)]
+    parts = [{k: v[S[q] - 1:E[q]] for k, v in f.items()} for q in range(world)]
+    want_io, want_eoops, want_rounds = ol.set_velocities3(t, shards, parts)           # the oracle as all ranks in turn
+    g = np.arange(shards[rank][0], shards[rank][0] + shards[rank][1])
+    io, flags, left = ol.set_velocities3_first(t, g, parts[rank])                       # this rank's first loop
+    Eex, rounds = carry_excess_between_ranks(dist, left, lambda e: ol.set_velocities3_second(t, g, parts[rank]["interacted"], flags, e, io))
+    assert rounds == want_rounds and -Eex * t.madhoc == want_eoops[rank]
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(io[k], want_io[rank][k], k)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N", [(2, 10000), (3, 10007), (4, 50000)])
+def test_excess_energy_carry_between_ranks_on_gloo(world, N):
+    """the message pattern of set_velocities3's do-while loop (reference cmc_utils.c:313-347) as the sharded host layer runs it, with the
+    oracle's loops standing in for the kernels: same rounds, same velocities, same Eoops as the ranks of the reference (which
+    tests/ref_multirank_check.py pins against the same oracle driver)"""
+    import torch.multiprocessing as mp
+    mp.spawn(_sv3_worker, args=(world, 29700 + world * 5 + (N % 40), N), nprocs=world, join=True)
