@@ -466,6 +466,63 @@ def test_energy_scheme_velocity_correction_bit_exact(kind, N, masses, first, nl)
     c.close()
 
 
+@pytest.mark.parametrize("kind,N,masses", [("plummer", 60000, "imf"), ("king", 300000, "equal")])
+def test_whole_timestep_with_energy_scheme_bit_exact(kind, N, masses):
+    """The hot path inside the reference's timestep order (src/cmc/cmc.c:302-353), everything on the resident arrays with no host round trip:
+    energy_conservation1 -> new_orbits_calculate -> energy_conservation2 -> ComputeIntermediateEnergy -> qsorts_new -> calc_potential_new
+    -> energy_conservation3 (set_velocities3) -> ComputeEnergy, against the oracle run in the same order, bit for bit."""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 3, masses=masses)
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    g = np.arange(1, N + 1)
+    o1 = ol.energy_conservation1(t, g, vr, vt)
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, pot["Rtidal"], seed=3)
+    Uoldrnew = ol.energy_conservation2(t, g, want["rnew"])
+    order = np.argsort(want["rnew"], kind="stable")
+    n2 = int((want["rnew"] < cm.SF_INFINITY).sum())
+    order = order[:n2]
+    pot2 = cm.oracle_potential(want["rnew"][order], sm[order], N_STAR=N)
+    t2 = ol.tables(pot2["star_r"], pot2["star_m"], pot2["phi"], n2, N, 0.0)
+    f = dict(interacted=np.zeros(n2, np.int64), rOld=r[order], vrold=o1["vrold"][order], vtold=o1["vtold"][order], Uoldrold=o1["Uoldrold"][order],
+             Uoldrnew=Uoldrnew[order], vr=want["vrnew"][order], vt=want["vtnew"][order], vrnew=want["vrnew"][order], vtnew=want["vtnew"][order])
+    io, flags, left0 = ol.set_velocities3_first(t2, np.arange(1, n2 + 1), f)
+    E2, J2 = cm.energies(pot2["phi"][1:n2 + 1], want["rnew"][order], io["vr"], io["vt"])
+
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+    c.Rtidal = pot["Rtidal"]
+    c.upload()
+    c.dev_energy_conservation1()
+    c.dev_new_orbits(draws=want["draws"], draw_off=want["draw_off"])
+    c.dev_energy_conservation2()
+    c.dev_compute_intermediate_energy()
+    c.dev_qsorts_new()
+    c.dev_calc_potential_new()
+    left = c.dev_energy_conservation3()
+    c.dev_compute_energy()
+    c.download()
+    assert c.clus.N_MAX == n2 and left == left0
+    cm.assert_bits_equal(c.star_phi[:n2 + 2], pot2["phi"][:n2 + 2], "phi")
+    assert np.array_equal(c.field("id")[1:n2 + 1], order + 1)
+    for k in ("rOld", "vrold", "vtold", "Uoldrold", "Uoldrnew"):
+        cm.assert_bits_equal(c.field(k)[1:n2 + 1], f[k], k)
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(c.field(k)[1:n2 + 1], io[k], k)
+    cm.assert_bits_equal(c.field("E")[1:n2 + 1], E2, "E")
+    cm.assert_bits_equal(c.field("J")[1:n2 + 1], J2, "J")
+    # the scheme does what it is for: the corrected speeds conserve the total energy of the step far better than the uncorrected ones
+    m2 = sm[order] / N
+    def etot(vr_, vt_):
+        return float(np.sum(m2 * (0.5 * (vr_ ** 2 + vt_ ** 2) + 0.5 * pot2["phi"][1:n2 + 1])))
+    m1 = sm / N
+    e_before = float(np.sum(m1 * (0.5 * (vr ** 2 + vt ** 2) + 0.5 * pot["phi"][1:N + 1]))) - float(np.sum((m1 * E)[want["rnew"] >= cm.SF_INFINITY]))
+    assert abs(etot(io["vr"], io["vt"]) - e_before) < abs(etot(f["vr"], f["vt"]) - e_before) + 1e-9
+    c.close()
+
+
 def test_energy_scheme_velocity_correction_edge_cases():
     """no star takes part; no source at all (nothing to carry); every star a source; a failed potential() bracket is reported"""
     N = 5000
