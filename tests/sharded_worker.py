@@ -83,6 +83,48 @@ def run(rank, world, port, N, nb, steps, kind="plummer", masses="imf"):
     print(f"rank {rank}/{world}: sharded == single GPU (N={N}, binaries={nb}, steps={steps}, shard {lo}..{hi})", flush=True)
 
 
+def run_sv3(rank, world, port, N):
+    """energy_conservation3 -> set_velocities3 on `world` GPUs (first loop per shard on the device, the excess carried rank to rank by the
+    host layer, second-loop passes on the device) against the oracle run as all ranks in turn -- which tests/ref_multirank_check.py pins
+    against the ranks of the compiled reference."""
+    import torch
+    import torch.distributed as dist
+    import common as cm
+    import oraclelib as ol
+    from cmc_cosmic_b200.sharded import ShardedCluster
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=23, masses="imf")
+    pot = cm.oracle_potential(r, sm, N)
+    f = cm.sv3_fields(r, vr, vt, pot["phi"][1:N + 1], seed=world)
+    c = ShardedCluster(N, dist, device=rank)
+    c.load_global(r, vr, vt, sm)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    S, E = c.Start.copy(), c.End.copy()
+    lo, hi = int(S[rank]), int(E[rank])
+    nl = hi - lo + 1
+    for k, v in f.items():
+        c.field(k)[1:nl + 1] = v[lo - 1:hi]
+    c.upload()
+    rounds = c.dev_energy_conservation3()
+    c.download()
+    c.sync()
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    shards = [(int(S[q]), int(E[q] - S[q] + 1)) for q in range(world)]
+    want, eoops, want_rounds = ol.set_velocities3(t, shards, [{k: v[S[q] - 1:E[q]] for k, v in f.items()} for q in range(world)])
+    assert rounds == want_rounds, (rounds, want_rounds)
+    assert c.Eoops == eoops[rank], (c.Eoops, eoops[rank])
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(c.field(k)[1:nl + 1], want[rank][k], f"rank {rank}: {k}")
+    c.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank}/{world}: set_velocities3 == oracle ranks (N={N}, rounds={rounds}, shard {lo}..{hi})", flush=True)
+
+
 if __name__ == "__main__":
     # torchrun entry: RANK / WORLD_SIZE / MASTER_PORT from the environment
     run(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("MASTER_PORT", "29511")),

@@ -27,3 +27,14 @@ def test_sharded_equals_single_gpu_4_ranks():
     import torch.multiprocessing as mp
     import sharded_worker
     mp.spawn(sharded_worker.run, args=(4, 29533, 400003, 9000, 3), nprocs=4, join=True)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world,N", [(2, 100000), (4, 200003)])
+def test_sharded_energy_scheme_velocity_correction(world, N):
+    """set_velocities3 across ranks (reference cmc_utils.c:254-352): the excess-energy carry leaves a shard and is absorbed by the next"""
+    import torch.multiprocessing as mp
+    import sharded_worker
+    if world > _n_gpus():
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(sharded_worker.run_sv3, args=(world, 29540 + world, N), nprocs=world, join=True)
