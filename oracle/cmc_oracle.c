@@ -602,6 +602,42 @@ double orc_set_velocities3_second(const orc_tables_t *t, long n_local, const lon
 	return Eexcess;
 }
 
+/* ---- calc_sigma_r, src/cmc/cmc_dynamics_helper.c:2821-2975 ----------------------------------------------------------------------- */
+
+void orc_calc_sigma_r(long p, long n_limit, long first_global, long N_MAX, int is_first_rank, const double *star_r, const double *star_m,
+		      double madhoc, const double *vr, const double *vt, const double *ghost_prev_vr, const double *ghost_prev_vt,
+		      const double *ghost_next_vr, const double *ghost_next_vt, int r_0_mave_1, double *sig_r_or_mave, double *sig_sigma)
+{
+	long siminlast = 1, simaxlast = is_first_rank ? 0 : -p; /* :2906-2910 */
+	double Mv2ave = 0.0, Mave = 0.0;
+	for (long si = 1; si <= n_limit; si++) {
+		const long g_si = first_global + si - 1;
+		long simin = si - p, simax = simin + (2 * p - 1);
+		const long g_simin = g_si - p, g_simax = g_simin + (2 * p - 1);
+		if (g_simin < 1) { simin = 1; simax = simin + (2 * p - 1); }                 /* :2923-2926 */
+		else if (g_simax > N_MAX) { simax = n_limit; simin = simax - (2 * p - 1); } /* :2927-2931 */
+		for (long k = siminlast; k < simin; k++) { /* the stars leaving the window, :2935-2949 */
+			const double a = k < 1 ? ghost_prev_vr[k + p - 1] : vr[k - 1], b = k < 1 ? ghost_prev_vt[k + p - 1] : vt[k - 1];
+			const long g_k = first_global + k - 1;
+			Mv2ave -= star_m[g_k] * madhoc * (a * a + b * b);
+			Mave -= star_m[g_k] * madhoc;
+		}
+		for (long k = simaxlast + 1; k <= simax; k++) { /* the stars entering it, :2951-2968 */
+			const long g_k = first_global + k - 1;
+			double a, b;
+			if (k > n_limit) { a = ghost_next_vr[k - n_limit - 1]; b = ghost_next_vt[k - n_limit - 1]; }
+			else if (k < 1) { a = ghost_prev_vr[k + p - 1]; b = ghost_prev_vt[k + p - 1]; }
+			else { a = vr[k - 1]; b = vt[k - 1]; }
+			Mv2ave += star_m[g_k] * madhoc * (a * a + b * b);
+			Mave += star_m[g_k] * madhoc;
+		}
+		sig_r_or_mave[si] = r_0_mave_1 == 0 ? star_r[g_si] : Mave / 2. / p; /* :2971-2974 */
+		sig_sigma[si] = sqrt(Mv2ave / Mave);                                 /* :2977 */
+		siminlast = simin;
+		simaxlast = simax;
+	}
+}
+
 /* clusdyn_calculate, src/cmc/cmc_utils.c:1613-1624 */
 double orc_clusdyn_calculate(const double *star_r, const double *star_m, long N_STAR, double Mtotal)
 {

@@ -109,6 +109,17 @@ double orc_set_velocities3_first(const orc_tables_t *t, long n_local, const long
 double orc_set_velocities3_second(const orc_tables_t *t, long n_local, const long *g_idx, const long *interacted, const char *vnew2_arr,
 				  double Eexcess, double *vr, double *vt, const double *vrnew, const double *vtnew);
 
+/* calc_sigma_r, src/cmc/cmc_dynamics_helper.c:2821-2975: the local 3-D velocity dispersion around every local star,
+ * sigma = sqrt(sum m v^2 / sum m) over a window of 2p stars (p before, p - 1 after), as ONE rank computes it: two running sums that every
+ * star updates by subtracting the stars that left the window and adding those that entered, in that order, each a separately rounded
+ * operation; the window stops sliding at both ends of the cluster (:2923-2931).  A rank other than the first starts from an empty window p
+ * stars before its first one.  vr, vt: the local stars 1..n_limit at [0..n_limit-1]; ghost_prev_* [p]: the last p stars of the previous
+ * rank, ghost_next_* [p]: the first p of the next (the reference exchanges them with MPI_Send/Recv, :2862-2900); first_global = Start[myid].
+ * Outputs [n_limit + 1], entry 0 unused: sig_r_or_mave = star_r[g] (r_0_mave_1 == 0) or the mean mass Mave / 2 / p; sig_sigma. */
+void orc_calc_sigma_r(long p, long n_limit, long first_global, long N_MAX, int is_first_rank, const double *star_r, const double *star_m,
+		      double madhoc, const double *vr, const double *vt, const double *ghost_prev_vr, const double *ghost_prev_vt,
+		      const double *ghost_next_vr, const double *ghost_next_vt, int r_0_mave_1, double *sig_r_or_mave, double *sig_sigma);
+
 /* comp_mass_percent, src/cmc/cmc_utils.c:872-985: Lagrange radii and the cumulative kinetic sums at them, as ONE rank of P sees it.
  *   star_r, star_m: the replicated tables; vr, vt: star[k].vr / .vt of this rank's local stars k = 1..n_local at vr[k-1], vt[k-1];
  *   first_global = Start[myid] (global index of local star 1; the function is called after the sort, so there are no new stars).

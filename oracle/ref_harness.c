@@ -216,6 +216,13 @@ EXPORT void ref_energy_conservation3(void) { energy_conservation3(); }
 EXPORT double ref_get_Eoops(void) { return Eoops; }
 EXPORT void ref_set_Eoops(double v) { Eoops = v; }
 
+/* calc_sigma_r (src/cmc/cmc_dynamics_helper.c:2821-2975) on the harness's cluster state: out_a / out_sigma [n_limit + 1], entry 0 unused */
+EXPORT void ref_calc_sigma_r(long p, long n_limit, int r_0_mave_1, double *out_a, double *out_sigma)
+{
+	long n = 0;
+	calc_sigma_r(p, n_limit, out_a, out_sigma, &n, r_0_mave_1);
+}
+
 /* comp_mass_percent (src/cmc/cmc_utils.c:872-985) on the harness's cluster state: thresholds in, the eight result arrays out
  * (out[8][count], in the order mass_r, ave_mass_r, no_star_r, densities_r, ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r; on ranks other than 0
  * the last four hold what that rank computed, i.e. nothing meaningful -- the reference prints from rank 0 only). */

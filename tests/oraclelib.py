@@ -58,6 +58,7 @@ def lib():
         L.orc_set_velocities3_first.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 12
         L.orc_set_velocities3_second.restype = C.c_double
         L.orc_set_velocities3_second.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 4
+        L.orc_calc_sigma_r.argtypes = [C.c_long] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
         L.orc_clusdyn_calculate.restype = C.c_double
         L.orc_clusdyn_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double]
         L.orc_comp_mass_percent.restype = C.c_long
@@ -229,6 +230,30 @@ def set_velocities3(t, shards, fields):
         if not sum(E) > 0:                                        # MPI_Allreduce(SUM), :345-347
             break
     return io, [-e * t.madhoc for e in E], passes
+
+
+def calc_sigma_r(p, star_r, star_m, N_MAX, N_STAR, vr_all, vt_all, first_global=1, n_local=None, mave=False):
+    """calc_sigma_r (reference cmc_dynamics_helper.c:2821-2975) as the rank owning global stars first_global .. first_global + n_local - 1
+    sees it.  vr_all, vt_all: the velocities of the WHOLE sorted cluster (star k at [k - 1]); the rank's own stars and the p ghost stars on
+    either side (what the reference exchanges with MPI_Send / MPI_Recv) are cut from them.  Returns (r or mean mass, sigma), each
+    [n_local + 1] with entry 0 unused."""
+    vr_all, vt_all = np.ascontiguousarray(vr_all, np.float64), np.ascontiguousarray(vt_all, np.float64)
+    lo = first_global - 1
+    n = len(vr_all) - lo if n_local is None else n_local
+
+    def cut(x, start):                                        # p values from x[start:], zero-padded where the cluster ends
+        g = np.zeros(p)
+        if start >= 0:
+            seg = x[start:start + p]
+            g[:len(seg)] = seg
+        return g
+    loc = [np.ascontiguousarray(x[lo:lo + n]) for x in (vr_all, vt_all)]
+    prev = [cut(x, lo - p) for x in (vr_all, vt_all)]
+    nxt = [cut(x, lo + n) for x in (vr_all, vt_all)]
+    a, sg = np.zeros(n + 1), np.zeros(n + 1)
+    lib().orc_calc_sigma_r(p, n, first_global, N_MAX, int(first_global == 1), _p(star_r), _p(star_m), 1.0 / N_STAR, _p(loc[0]), _p(loc[1]),
+                           _p(prev[0]), _p(prev[1]), _p(nxt[0]), _p(nxt[1]), int(mave), _p(a), _p(sg))
+    return a, sg
 
 
 def clusdyn_calculate(star_r, star_m, N_STAR, Mtotal):

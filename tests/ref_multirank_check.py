@@ -67,6 +67,12 @@ def main(procs, N):
             ok = ok and np.array_equal(got[f].view(np.uint64), merged.view(np.uint64))
         ok = ok and parts[0]["filled"] == len(pcs) - 1 and got["mass_r"][-1] == -1.0     # 150 % of the mass is never reached
         ok = ok and len({int(np.argmax([o["owner"][i] for o in parts])) for i in range(len(pcs) - 1)}) >= min(procs, 2)  # several owners
+    # calc_sigma_r (reference cmc_dynamics_helper.c:2821-2975): every rank starts its running window sums from the ghost stars its
+    # neighbours sent (ring of MPI_Send / MPI_Recv)
+    for mave in (False, True):
+        a, sg = R.calc_sigma_r(20, hi - lo + 1, mave)
+        a0, sg0 = ol.calc_sigma_r(20, R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), N, N, vrs, vts, first_global=lo, n_local=hi - lo + 1, mave=mave)
+        ok = ok and np.array_equal(a[1:].view(np.uint64), a0[1:].view(np.uint64)) and np.array_equal(sg[1:].view(np.uint64), sg0[1:].view(np.uint64))
     # set_velocities3 (reference cmc_utils.c:254-352): the excess-energy carry runs through every rank's shard and on to the next rank
     # (MPI_Send / MPI_Recv, repeated while the all-reduced leftover is > 0)
     phi = R.star_phi()[:N + 2].copy()

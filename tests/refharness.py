@@ -152,6 +152,13 @@ class Ref:
         names = ("mass_r", "ave_mass_r", "no_star_r", "densities_r", "ke_rad_r", "ke_tan_r", "v2_rad_r", "v2_tan_r")
         return {k: out[i].copy() for i, k in enumerate(names)}
 
+    def calc_sigma_r(self, p, n_limit, mave=False):
+        """the reference's calc_sigma_r (cmc_dynamics_helper.c:2821-2975) on the harness's state -> (r or mean mass, sigma), [n_limit + 1]"""
+        a, sg = np.zeros(n_limit + 1), np.zeros(n_limit + 1)
+        self.L.ref_calc_sigma_r.argtypes = [C.c_long, C.c_long, C.c_int, C.c_void_p, C.c_void_p]
+        self.L.ref_calc_sigma_r(p, n_limit, int(mave), a.ctypes.data, sg.ctypes.data)
+        return a, sg
+
     def compute_energy(self):
         """E, J exactly as ComputeEnergy (reference cmc_utils.c:614-615), single rank."""
         n = int(self.scalars()["N_MAX"])

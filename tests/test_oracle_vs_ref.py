@@ -129,6 +129,30 @@ def test_energy_scheme_velocity_correction(R, kind, N, masses):
     R.free()
 
 
+@pytest.mark.parametrize("kind,N,masses,p", [("plummer", 30000, "imf", 20), ("king", 20000, "equal", 20), ("plummer", 5000, "imf", 3), ("plummer", 200, "imf", 20)])
+def test_calc_sigma_r(R, kind, N, masses, p):
+    """calc_sigma_r (reference cmc_dynamics_helper.c:2821-2975) of the compiled reference against the restatement, both
+    output modes, bit for bit: the running window sums carry every rounding of the reference's subtract-then-add updates"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + p, masses=masses)
+    R.init(N, n_star_dim=N + 64)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N)
+    R.L.ref_calc_potential_new()
+    sr, smt = R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy()
+    for mave in (False, True):
+        a, sg = R.calc_sigma_r(p, N, mave)
+        a0, sg0 = ol.calc_sigma_r(p, sr, smt, N, N, vr, vt, mave=mave)
+        cm.assert_bits_equal(a[1:], a0[1:], "r" if not mave else "mean mass")
+        cm.assert_bits_equal(sg[1:], sg0[1:], "sigma")
+    assert np.all(np.isfinite(sg0[1:])) and np.all(sg0[1:] > 0)
+    # the drift the reference's running sums accumulate against a freshly summed window: why only an exact replay can match it
+    k = N // 2
+    w = slice(k - p - 1, k + p - 1)
+    fresh = np.sqrt(np.sum(smt[1:][w] / N * (vr[w] ** 2 + vt[w] ** 2)) / np.sum(smt[1:][w] / N))
+    assert abs(sg0[k] / fresh - 1) < 1e-9
+    R.free()
+
+
 def test_sort_with_binaries_and_stripped_stars(R):
     n, nb, n_strip = 20000, 1500, 23
     rng = np.random.default_rng(8)
