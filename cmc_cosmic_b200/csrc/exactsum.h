@@ -60,4 +60,33 @@ CMCB_HD SeqTerm seq_classify(double a, double y_before, double y_after, double y
 	return t;
 }
 
+// The same for a chain whose terms carry their own sign, y_i = fl(y_{i-1} + a_i) with a_i of either sign and y > 0 -- a sliding-window sum
+// kept up to date by subtracting the element that leaves and adding the one that enters (calc_sigma_r, reference
+// src/cmc/cmc_dynamics_helper.c:2935-2968).  fl(y - a) = y - R_e(a) by the same argument.  Such a chain is not monotone: it crosses a
+// binade boundary every time its noise carries it over one (every crossing is an event), and the accumulated rounding is bounded by the
+// largest value the chain has EVER had, which the neighbouring values do not reveal: the caller supplies y_max >= |y_j| for all j.
+CMCB_HD SeqTerm seq_classify_signed(double a, double y_before, double y_after, double y_max, long i)
+{
+	SeqTerm t;
+	t.v = 0.0;
+	t.event = 1;
+	double S = dmax(y_max, dmax(dabs(y_before), dabs(y_after)));
+	double delta = dmul(dmul((double) (i + 64), 4.440892098500626e-16 /* 2^-51 */), S);
+	double lo = dsub(dmin(y_before, y_after), delta);
+	double hi = dadd(dmax(y_before, y_after), delta);
+	double aa = dabs(a);
+	if (!dfinite(a) || !(lo > 0.0) || !dfinite(hi)) return t;
+	uint64_t elo = dbits(lo) >> 52, ehi = dbits(hi) >> 52;
+	if (elo != ehi || elo < 64) return t;
+	double C = dfrombits(elo << 52);
+	if (aa > C) return t;
+	double R = dsub(dadd(aa, C), C);
+	double rho = dsub(aa, R);
+	double half_u = dfrombits((elo - 53) << 52);
+	if (dabs(rho) == half_u) return t;
+	t.v = a < 0.0 ? -R : R;
+	t.event = 0;
+	return t;
+}
+
 } // namespace cmcb

@@ -52,6 +52,43 @@ static void srs_emulated(const std::vector<double> &a, double y0, int sgn, std::
 	}
 }
 
+// signed chain (terms carry their sign, y0 = 0), with the caller's bound on the largest chain value
+static int check_signed(const char *name, const std::vector<double> &a, double y_max)
+{
+	size_t n = a.size();
+	std::vector<double> S, y(n);
+	approx_prefix(a, S);
+	double base = 0.0, G = 0.0;
+	long events = 0;
+	for (size_t i = 0; i < n; i++) {
+		SeqTerm t = seq_classify_signed(a[i], i ? S[i - 1] : 0.0, S[i], y_max, (long) i + 1);
+		if (t.event) { base = (base + G) + a[i]; G = 0.0; y[i] = base; events++; }
+		else { G += t.v; y[i] = base + G; }
+	}
+	double s = 0.0;
+	size_t bad = 0, first = 0;
+	for (size_t i = 0; i < n; i++) { s = s + a[i]; if (memcmp(&s, &y[i], 8) != 0) { if (!bad) first = i; bad++; } }
+	printf("%-34s n=%-9zu events=%-6ld %s", name, n, events, bad ? "MISMATCH" : "bit-exact\n");
+	if (bad) printf(" (%zu, first at %zu)\n", bad, first);
+	return bad != 0;
+}
+
+// the op sequence of a window of 2p terms sliding over t: 2p adds, then (subtract the oldest, add the next) per step
+static std::vector<double> window_ops(const std::vector<double> &t, size_t p, double *y_max)
+{
+	std::vector<double> a;
+	double w = 0, wmax = 0;
+	for (size_t k = 0; k < 2 * p && k < t.size(); k++) { a.push_back(t[k]); w += t[k]; }
+	wmax = w;
+	for (size_t k = 2 * p; k < t.size(); k++) {
+		a.push_back(-t[k - 2 * p]); a.push_back(t[k]);
+		double d = 0; for (size_t q = k - 2 * p + 1; q <= k; q++) d += t[q]; // the window summed afresh
+		if (d > wmax) wmax = d;
+	}
+	*y_max = 1.01 * wmax;
+	return a;
+}
+
 static int check(const char *name, const std::vector<double> &a, double y0, int sgn)
 {
 	std::vector<double> y;
@@ -125,6 +162,20 @@ int main(int argc, char **argv)
 			s = y1; for (size_t i = 0; i < n; i++) { s -= a[i]; if (memcmp(&s, &y[i], 8)) { fails++; printf("random(-) rep %d mismatch at %zu\n", rep, i); break; } }
 		}
 		printf("random chains done\n");
+	}
+	{ // sliding-window sums (calc_sigma_r): m v^2 falling by orders of magnitude outwards with star-to-star noise, equal masses, IMF masses
+		for (size_t p : {size_t(20), size_t(3)}) {
+			std::vector<double> t(N / 4);
+			double ymax;
+			for (size_t i = 0; i < t.size(); i++) t[i] = (1.0 / t.size()) * U(rng) * 2.0 / pow(1.0 + 30.0 * (double) i / t.size(), 2.0);
+			{ std::vector<double> ops = window_ops(t, p, &ymax); fails += check_signed("window sum of m v^2 (+-)", ops, ymax); }
+			for (auto &x : t) x = 1.0 / (double) t.size();
+			{ std::vector<double> ops = window_ops(t, p, &ymax); fails += check_signed("window sum of equal masses (+-)", ops, ymax); }
+			for (auto &x : t) x = 1.0 / 39.5 / 1048576.0; // 39 c < 2^-20 < 40 c: every operation crosses a binade boundary
+			{ std::vector<double> ops = window_ops(t, 20, &ymax); fails += check_signed("window sum straddling 2^-20 (+-)", ops, ymax); }
+			for (auto &x : t) x = 0.08 * pow(1.0 - U(rng) * (1 - pow(0.08 / 150.0, 1.35)), -1.0 / 1.35) / t.size();
+			{ std::vector<double> ops = window_ops(t, p, &ymax); fails += check_signed("window sum of IMF masses (+-)", ops, ymax); }
+		}
 	}
 	printf("%s (%d failures)\n", fails ? "FAIL" : "PASS", fails);
 	return fails != 0;
