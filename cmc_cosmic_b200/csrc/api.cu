@@ -80,6 +80,11 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	if (const char *e = getenv("CMCB200_ORBIT_LADDERS")) c->orbit_ladders = atoi(e); // 0: A/B measurement of the plain bisections
 	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->own_stream = true;
+	c->l2_persist_pct = 0;
+	c->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
+	if (const char *e = getenv("CMCB200_L2_PERSIST")) c->l2_persist_pct = atoi(e);
+	if (c->l2_persist_pct > 0 && prop.persistingL2CacheMaxSize > 0) CMCB_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) prop.persistingL2CacheMaxSize));
+	else c->l2_persist_pct = 0;
 	const size_t sb = (size_t) n_star_dim * CMCB_SIZEOF_STAR + 64, bb = (size_t) n_bin_dim * CMCB_SIZEOF_BINARY + 64;
 	for (int i = 0; i < 2; i++) {
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_star[i], sb));
@@ -375,6 +380,21 @@ extern "C" int cmcb200_qsorts_new(cmcb200_ctx *c, void *star1_h, long *n_local, 
 //   orbit_range   the three stages on local stars [off, off + len): every star is independent of the others (its draws are keyed by its
 //                 global index or come from its own CSR slice), so the result does not depend on the chunking
 //   orbit_end     combines the per-chunk statistics
+// Experiment knob CMCB200_L2_PERSIST: while the orbit kernels run, a random `pct` percent of the (r, Phi) table's lines are kept in L2's
+// persisting carve-out (stream access-policy window), so that the 424-byte record stream cannot evict them.  bytes == 0 switches it off.
+static void orbit_l2_window(cmcb200_ctx *c, size_t bytes)
+{
+	if (c->l2_persist_pct <= 0) return;
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof(v));
+	v.accessPolicyWindow.base_ptr = (void *) c->d_rp;
+	v.accessPolicyWindow.num_bytes = bytes < c->l2_window_max ? bytes : c->l2_window_max;
+	v.accessPolicyWindow.hitRatio = bytes ? (float) c->l2_persist_pct / 100.0f : 0.0f;
+	v.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+	v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+	cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a)
 {
 	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
@@ -417,6 +437,7 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 		if (!(c->orbit_ladders & 2)) lb.q = nullptr;
 		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, p->N_MAX + 1, lb, a, c->stream);
 	}
+	orbit_l2_window(c, (size_t) p->n_table * sizeof(RPhi));
 	return 0;
 }
 
@@ -443,6 +464,7 @@ static int orbit_range(cmcb200_ctx *c, const OrbitArgs &whole, long off, long le
 // after the stream has been synchronised
 static void orbit_end(cmcb200_ctx *c, const cmcb200_orbit_params *p, int n_chunks, cmcb200_orbit_result *res)
 {
+	orbit_l2_window(c, 0);
 	if (!res) return;
 	const OrbitStats *h = (const OrbitStats *) c->h_pinned;
 	unsigned long long max_bits = 0, other = 0;

@@ -40,6 +40,8 @@ struct cmcb200_ctx {
 	int *d_pend[2];
 	int orbit_max_chunks; // host-buffer orbit step: at most this many pipeline chunks (CMCB200_ORBIT_CHUNKS, default 8)
 	int orbit_ctas;    // tuning knob CMCB200_ORBIT_CTAS: resident CTAs per SM orbit_prepare_kernel is compiled for (4 or 3)
+	int l2_persist_pct;    // CMCB200_L2_PERSIST: > 0 = fraction (percent) of the (r, Phi) table pinned in L2's persisting carve-out during the orbit step
+	size_t l2_window_max;  // cudaDeviceProp.accessPolicyMaxWindowSize
 	int orbit_ladders; // CMCB200_ORBIT_LADDERS: bit 0 = r ladder for potential() (default on), bit 1 = Q ladder for find_zero_Q (default off:
 	                   // measured slower than the plain bisection on B200); 0 = every probe reads the fine table
 	// sort scratch
