@@ -220,6 +220,27 @@ class Cluster:
         p = self.orbit_params()
         _lib.check(self.L.cmcb200_dev_compute_intermediate_energy(self.ctx, C.byref(p)), "dev_compute_intermediate_energy")
 
+    def dev_energy_new_radii(self):
+        """energy_conservation2 and the EI loop of ComputeIntermediateEnergy from one potential(rnew) lookup per star; the transfer is left to
+        dev_transfer_and_sort (reference src/cmc/cmc.c:317-335 with TIDALLY_STRIP_STARS == 0)"""
+        p = self.orbit_params()
+        _lib.check(self.L.cmcb200_dev_energy_new_radii(self.ctx, C.byref(p)), "dev_energy_new_radii")
+
+    def dev_timestep(self, seed=0, draws=None, draw_off=None):
+        """One timestep of the reference's main loop around the hot path (src/cmc/cmc.c:302-353, no interacting stars, TIDALLY_STRIP_STARS == 0)
+        on the resident arrays, passes fused where they read the same data: energy_conservation1 -> new_orbits_calculate ->
+        energy_conservation2 + ComputeIntermediateEnergy (one lookup) -> transfer + qsorts_new (one pass over the records) ->
+        calc_potential_new -> energy_conservation3 -> ComputeEnergy.  Bit-identical to the calls made one by one."""
+        self.dev_energy_conservation1()
+        res = self.dev_new_orbits(draws, draw_off, seed)
+        self.dev_energy_new_radii()
+        self.dev_transfer_and_sort()
+        self.dev_calc_potential_new()
+        self.dev_energy_conservation3()
+        self.dev_compute_energy()
+        self.tcount += 1
+        return res
+
     def dev_energy_conservation1(self):
         """energy_conservation1 (reference src/cmc/cmc_utils.c:2153-2174) on the resident arrays: vrold, vtold, Uoldrold of every local star"""
         p = self.orbit_params()

@@ -524,6 +524,11 @@ extern "C" int cmcb200_dev_compute_intermediate_energy(cmcb200_ctx *c, const cmc
 	return cmcb200_dev_transfer_new_positions(c, p->n_local, p->n_old_local, p->first_global, p->N_MAX);
 }
 
+extern "C" int cmcb200_dev_energy_new_radii(cmcb200_ctx *c, const cmcb200_orbit_params *p)
+{
+	return energy_rnew(c, p, true, true, "energy_conservation2 + ComputeIntermediateEnergy");
+}
+
 extern "C" int cmcb200_dev_read_status(cmcb200_ctx *c, int *status, long *kmin, long *kmax, long n_local)
 {
 	StageTimer t(c, ST_D2H);

@@ -44,7 +44,7 @@ EXPORTS = [
     "cmcb200_dev_compute_energy", "cmcb200_dev_read_status", "cmcb200_sync", "cmcb200_profile", "cmcb200_profile_read",
     "cmcb200_potential_stats", "cmcb200_launch_count", "cmcb200_host_register", "cmcb200_host_unregister", "cmcb200_transfer_bytes",
     "cmcb200_dev_comp_mass_percent", "cmcb200_dev_clusdyn_calculate", "cmcb200_dev_energy_conservation2", "cmcb200_dev_compute_intermediate_energy",
-    "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass",
+    "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass", "cmcb200_dev_energy_new_radii",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     L.cmcb200_dev_energy_conservation2.argtypes = [vp, C.POINTER(OrbitParams)]
     L.cmcb200_dev_compute_intermediate_energy.argtypes = [vp, C.POINTER(OrbitParams)]
     L.cmcb200_dev_energy_conservation1.argtypes = [vp, C.POINTER(OrbitParams)]
+    L.cmcb200_dev_energy_new_radii.argtypes = [vp, C.POINTER(OrbitParams)]
     L.cmcb200_dev_set_velocities3.argtypes = [vp, C.POINTER(OrbitParams), C.POINTER(dbl)]
     L.cmcb200_dev_set_velocities3_pass.argtypes = [vp, C.POINTER(OrbitParams), dbl, C.POINTER(dbl)]
     L.cmcb200_dev_clusdyn_calculate.argtypes = [vp, lg, lg, dbl, C.POINTER(dbl)]

@@ -161,6 +161,11 @@ int cmcb200_dev_transfer_new_positions(cmcb200_ctx *ctx, long n_local, long n_ol
  * A lookup whose bracket check fails (fatal in the reference, :144-152) makes the call return non-zero. */
 int cmcb200_dev_energy_conservation2(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
 int cmcb200_dev_compute_intermediate_energy(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
+/* Both of the above from ONE lookup per star (they look up the same potential(rnew)): Uoldrnew and EI, WITHOUT the transfer -- follow with
+ * cmcb200_dev_transfer_and_sort, which applies it while the sort moves the records.  Equivalent to the reference's sequence
+ * energy_conservation2(); ComputeIntermediateEnergy(); qsorts_new(); (src/cmc/cmc.c:317-335) when nothing in between touches the stars,
+ * i.e. TIDALLY_STRIP_STARS == 0 (:321-322). */
+int cmcb200_dev_energy_new_radii(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
 /* The rest of the energy scheme (Stodolkiewicz), on the resident arrays; p as above, the records are the sorted ones after the potential rebuild.
  *   energy_conservation1 (src/cmc/cmc_utils.c:2153-2174):  star[i].vrold/.vtold <- .vr/.vt;  .Uoldrold = star_phi[g_i] + MPI_PHI_S(star_r[g_i], g_i)
  *   set_velocities3 (:254-352, called through energy_conservation3 :360-363), first loop (:268-311): for every star with interacted == 0 the

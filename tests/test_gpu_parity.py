@@ -466,8 +466,9 @@ def test_energy_scheme_velocity_correction_bit_exact(kind, N, masses, first, nl)
     c.close()
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("kind,N,masses", [("plummer", 60000, "imf"), ("king", 300000, "equal")])
-def test_whole_timestep_with_energy_scheme_bit_exact(kind, N, masses):
+def test_whole_timestep_with_energy_scheme_bit_exact(kind, N, masses, fused):
     """The hot path inside the reference's timestep order (src/cmc/cmc.c:302-353), everything on the resident arrays with no host round trip:
     energy_conservation1 -> new_orbits_calculate -> energy_conservation2 -> ComputeIntermediateEnergy -> qsorts_new -> calc_potential_new
     -> energy_conservation3 (set_velocities3) -> ComputeEnergy, against the oracle run in the same order, bit for bit."""
@@ -495,20 +496,24 @@ def test_whole_timestep_with_energy_scheme_bit_exact(kind, N, masses):
     c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
     c.Rtidal = pot["Rtidal"]
     c.upload()
-    c.dev_energy_conservation1()
-    c.dev_new_orbits(draws=want["draws"], draw_off=want["draw_off"])
-    c.dev_energy_conservation2()
-    c.dev_compute_intermediate_energy()
-    c.dev_qsorts_new()
-    c.dev_calc_potential_new()
-    left = c.dev_energy_conservation3()
-    c.dev_compute_energy()
+    if fused:       # the same passes, those that read the same data merged (Cluster.dev_timestep)
+        c.dev_timestep(draws=want["draws"], draw_off=want["draw_off"])
+    else:
+        c.dev_energy_conservation1()
+        c.dev_new_orbits(draws=want["draws"], draw_off=want["draw_off"])
+        c.dev_energy_conservation2()
+        c.dev_compute_intermediate_energy()
+        c.dev_qsorts_new()
+        c.dev_calc_potential_new()
+        assert c.dev_energy_conservation3() == left0
+        c.dev_compute_energy()
     c.download()
-    assert c.clus.N_MAX == n2 and left == left0
+    assert c.clus.N_MAX == n2
     cm.assert_bits_equal(c.star_phi[:n2 + 2], pot2["phi"][:n2 + 2], "phi")
     assert np.array_equal(c.field("id")[1:n2 + 1], order + 1)
     for k in ("rOld", "vrold", "vtold", "Uoldrold", "Uoldrnew"):
         cm.assert_bits_equal(c.field(k)[1:n2 + 1], f[k], k)
+    cm.assert_bits_equal(c.field("EI")[1:n2 + 1], ol.intermediate_energy(t, g, want["rnew"], vr, vt, np.zeros(N))[order], "EI")
     for k in ol.SV3_IO:
         cm.assert_bits_equal(c.field(k)[1:n2 + 1], io[k], k)
     cm.assert_bits_equal(c.field("E")[1:n2 + 1], E2, "E")

@@ -43,4 +43,7 @@ for s in range(steps):
     c.tcount += 1
     print(f"N={N} step {s}: energy_conservation1 {t1:.3f} ms | orbit {to:.3f} | energy_conservation2 {t2:.3f} | ComputeIntermediateEnergy {ti:.3f} | "
           f"sort {ts:.3f} | potential {tp:.3f} | energy_conservation3 {t3:.3f} (leftover Eexcess {left:.3e}) | ComputeEnergy {te:.3f}", flush=True)
+for s in range(steps):
+    _, tt = timed(lambda: c.dev_timestep(seed=1))
+    print(f"N={N} fused timestep {s} (Cluster.dev_timestep: one lookup for energy_conservation2 + ComputeIntermediateEnergy, transfer inside the gather): {tt:.3f} ms", flush=True)
 c.close()
