@@ -124,27 +124,38 @@ __global__ void __launch_bounds__(256) sv3_block_kernel(OrbitArgs a, Sv3Buffers 
 
 __global__ void __launch_bounds__(32) sv3_carry_kernel(OrbitArgs a, Sv3Buffers b, long n_blocks)
 {
+	constexpr int AHEAD = 8; // block results of AHEAD steps are loaded together: the walk is a chain of dependent steps, the loads are not
 	const unsigned lane = lane_id();
 	const Sv3Index gi = sv3_index(a);
 	double E = 0.0; // warp-uniform
-	for (long b0 = 0; b0 < n_blocks; b0 += 32) {
-		const long blk = b0 + lane;
-		const double e = blk < n_blocks ? b.eb[blk] : 0.0;
-		if (E == 0.0 && __ballot_sync(0xffffffffu, e != 0.0) == 0) { // nothing in flight, nothing emitted in these 32 blocks
-			if (blk < n_blocks) b.ein[blk] = 0.0;
-			continue;
+	for (long c0 = 0; c0 < n_blocks; c0 += 32 * AHEAD) {
+		double ek[AHEAD];
+#pragma unroll
+		for (int k = 0; k < AHEAD; k++) {
+			const long blk = c0 + 32L * k + lane;
+			ek[k] = blk < n_blocks ? b.eb[blk] : 0.0;
 		}
-		for (int l = 0; l < 32 && b0 + l < n_blocks; l++) {
-			const double el = __shfl_sync(0xffffffffu, e, l);
-			if (lane == 0) b.ein[b0 + l] = E;
-			if (E == 0.0) E = el; // 0 enters: the block kernel's result stands
-			else {            // a chain crosses into this block: replay it from the carry
-				double En = 0.0;
-				if (lane == 0) {
-					const long lo = (b0 + l) * SV3_BLOCK, hi = lo + SV3_BLOCK < a.n_local ? lo + SV3_BLOCK : a.n_local;
-					En = sv3_walk(b.kind, b.val, a.t.m, gi, lo, hi, E, Sv3Noop());
+#pragma unroll
+		for (int k = 0; k < AHEAD; k++) {
+			const long b0 = c0 + 32L * k, blk = b0 + lane;
+			if (b0 >= n_blocks) break;
+			const double e = ek[k];
+			if (E == 0.0 && __ballot_sync(0xffffffffu, e != 0.0) == 0) { // nothing in flight, nothing emitted in these 32 blocks
+				if (blk < n_blocks) b.ein[blk] = 0.0;
+				continue;
+			}
+			for (int l = 0; l < 32 && b0 + l < n_blocks; l++) {
+				const double el = __shfl_sync(0xffffffffu, e, l);
+				if (lane == 0) b.ein[b0 + l] = E;
+				if (E == 0.0) E = el; // 0 enters: the block kernel's result stands
+				else {            // a chain crosses into this block: replay it from the carry
+					double En = 0.0;
+					if (lane == 0) {
+						const long lo = (b0 + l) * SV3_BLOCK, hi = lo + SV3_BLOCK < a.n_local ? lo + SV3_BLOCK : a.n_local;
+						En = sv3_walk(b.kind, b.val, a.t.m, gi, lo, hi, E, Sv3Noop());
+					}
+					E = __shfl_sync(0xffffffffu, En, 0);
 				}
-				E = __shfl_sync(0xffffffffu, En, 0);
 			}
 		}
 	}
