@@ -252,7 +252,7 @@ class Cluster:
         excess of the first loop (a diagnostic: the reference drops it)."""
         p, left = self.orbit_params(), C.c_double()
         _lib.check(self.L.cmcb200_dev_set_velocities3(self.ctx, C.byref(p), C.byref(left)), "dev_set_velocities3")
-        self.Eoops += -0.0 * (1.0 / self.clus.N_STAR)
+        # Eoops += -Eexcess * madhoc with Eexcess = the received 0.0: unchanged
         return left.value
 
     def dev_set_velocities3_pass(self, Eexcess):
