@@ -15,6 +15,8 @@ Cases
                   CLUS_OBJ_DATA table is read straight from the file bytes (no HDF5 library in this image)
   cosmic_plummer_n100 / cosmic_king_n100   the N=100 vectors of COSMIC's own unit tests (tests/data/cmc_*_test.npz)
   lagrange_<case> comp_mass_percent (the Lagrange radii) on the initial state of <case>, `make_golden.py lagrange`
+  energy_<case>   energy_conservation1, energy_conservation3 -> set_velocities3 and calc_sigma_r (8f N3) on the initial state
+                  of <case> with the scheme's inputs of tests/common.py:sv3_fields, `make_golden.py energy`
 Every case records ONE full pass of the path by the reference:
   calc_potential_new -> ComputeEnergy -> new_orbits_calculate (taus113 draws recorded) -> r <- rnew (ComputeIntermediateEnergy's
   transfer) -> qsorts_new -> post_sort_comm -> calc_potential_new
@@ -142,8 +144,46 @@ def lagrange_cases(R):
         print(f"lagrange_{case}: mass_r = {out['mass_r'][[0, 7, 11, 15]]} no_star_r = {out['no_star_r'][[0, 7, 11, 15]]}")
 
 
+def energy_cases(R):
+    """energy_<case>.npz: the reference's energy_conservation1 (cmc_utils.c:2153-2174), energy_conservation3 -> set_velocities3 (:254-363) and
+    calc_sigma_r (cmc_dynamics_helper.c:2821-2975; AVEKERNEL = 20 and BH_AVEKERNEL = 3, both output modes) on the initial state of an
+    existing fixture after calc_potential_new.  The scheme's inputs (what the previous timestep left in star[]) come from
+    tests/common.py:sv3_fields and are stored with the outputs."""
+    import common as cm
+    for case in ("plummer_n4000", "king_w7_imf_bin"):
+        g = np.load(os.path.join(HERE, case + ".npz"))
+        n = int(g["N_STAR"])
+        R.init(n, n_star_dim=n + 64, n_bin_dim=8, min_chunk=int(g["min_chunk"]), idum=int(g["seed"]))
+        R.load_cluster(g["r"], g["vr"], g["vt"], g["star_m"])
+        R.set_scalars(n, n)
+        R.L.ref_calc_potential_new()
+        phi = R.star_phi()[:n + 2].copy()
+        out = dict(case=case, phi=phi)
+        R.L.ref_energy_conservation1()
+        for k in ("vrold", "vtold", "Uoldrold"):
+            out["ec1_" + k] = R.star_field(k)[1:n + 1].copy()
+        for p_win, mave in ((20, 0), (20, 1), (3, 1)):
+            a, sg = R.calc_sigma_r(p_win, n, bool(mave))
+            out[f"sigma_p{p_win}_m{mave}_a"], out[f"sigma_p{p_win}_m{mave}_sigma"] = a[1:].copy(), sg[1:].copy()
+        f = cm.sv3_fields(g["r"], g["vr"], g["vt"], phi[1:n + 1], seed=n)
+        for k, v in f.items():
+            R.star_field(k, np.int64 if k == "interacted" else np.float64)[1:n + 1] = v
+            out["in_" + k] = v
+        R.L.ref_set_Eoops(0.0)
+        R.L.ref_energy_conservation3()
+        for k in ("vr", "vt", "vrnew", "vtnew"):
+            out["out_" + k] = R.star_field(k)[1:n + 1].copy()
+        out["Eoops"] = R.L.ref_get_Eoops()
+        R.free()
+        np.savez_compressed(os.path.join(HERE, f"energy_{case}.npz"), **out)
+        print(f"energy_{case}: {int((out['out_vr'] != f['vr']).sum())} of {n} velocities corrected, sigma[n/2] = {out['sigma_p20_m0_sigma'][n // 2]:.6f}")
+
+
 def main():
     assert rh.available(), "build oracle/_ref first (make -C oracle)"
+    if len(sys.argv) > 1 and sys.argv[1] == "energy":     # only the energy-scheme / sigma fixtures
+        energy_cases(rh.Ref())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "lagrange":   # only the comp_mass_percent fixtures (the others are their inputs)
         lagrange_cases(rh.Ref())
         return

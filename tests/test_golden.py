@@ -16,8 +16,9 @@ import common as cm
 import oraclelib as ol
 
 ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(cm.GOLDEN, "*.npz")))
-CASES = [c for c in ALL if not c.startswith("lagrange_")]
+CASES = [c for c in ALL if not c.startswith(("lagrange_", "energy_"))]
 LAGRANGE = [c for c in ALL if c.startswith("lagrange_")]
+ENERGY = [c for c in ALL if c.startswith("energy_")]
 SF = cm.SF_INFINITY
 
 
@@ -66,6 +67,59 @@ def test_cuda_lagrange_radii_match_reference(case):
     for f in ol.MASS_PC_FIELDS:
         cm.assert_bits_equal(getattr(c, f), g[f], f)
     assert c.dev_clusdyn_calculate() == g["clusdyn_rh"]
+    c.close()
+
+
+def _energy_inputs(case):
+    g = load(case)
+    base = load(g["case"])
+    n = base["N_STAR"]
+    sr, sm = cm.make_tables(base["r"], base["star_m"])
+    t = ol.tables(sr, sm, np.ascontiguousarray(g["phi"]), n, n, 0.0)
+    f = {k[3:]: g[k] for k in g if k.startswith("in_")}
+    return g, base, n, sr, sm, t, f
+
+
+@pytest.mark.parametrize("case", ENERGY)
+def test_oracle_energy_scheme_and_sigma_match_reference(case):
+    """energy_conservation1, set_velocities3 (reference cmc_utils.c:2153-2174, 254-352) and calc_sigma_r (cmc_dynamics_helper.c:2821-2975) by
+    the oracle against what the compiled reference produced"""
+    g, base, n, sr, sm, t, f = _energy_inputs(case)
+    assert len(ENERGY) >= 2
+    idx = np.arange(1, n + 1)
+    for k, v in ol.energy_conservation1(t, idx, base["vr"], base["vt"]).items():
+        cm.assert_bits_equal(v, g["ec1_" + k], k)
+    io, flags, left = ol.set_velocities3_first(t, idx, f)
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(io[k], g["out_" + k], k)
+    assert g["Eoops"] == 0.0 and left > 0
+    for p_win, mave in ((20, 0), (20, 1), (3, 1)):
+        a, sg = ol.calc_sigma_r(p_win, sr, sm, n, n, base["vr"], base["vt"], mave=bool(mave))
+        cm.assert_bits_equal(a[1:], g[f"sigma_p{p_win}_m{mave}_a"], "r / mean mass")
+        cm.assert_bits_equal(sg[1:], g[f"sigma_p{p_win}_m{mave}_sigma"], "sigma")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ENERGY)
+def test_cuda_energy_scheme_matches_reference(case):
+    from cmc_cosmic_b200.cluster import Cluster
+    g, base, n, sr, sm, t, f = _energy_inputs(case)
+    c = Cluster(n, n_star_dim=n + 64)
+    c.load(base["r"], base["vr"], base["vt"], base["star_m"])
+    c.calc_potential_new()
+    cm.assert_bits_equal(c.star_phi[:n + 2], g["phi"], "phi")
+    c.upload()
+    c.dev_energy_conservation1()
+    c.download()
+    for k in ("vrold", "vtold", "Uoldrold"):
+        cm.assert_bits_equal(c.field(k)[1:n + 1], g["ec1_" + k], k)
+    for k, v in f.items():
+        c.field(k)[1:n + 1] = v
+    c.upload()
+    c.dev_energy_conservation3()
+    c.download()
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(c.field(k)[1:n + 1], g["out_" + k], k)
     c.close()
 
 
