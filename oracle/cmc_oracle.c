@@ -638,6 +638,24 @@ void orc_calc_sigma_r(long p, long n_limit, long first_global, long N_MAX, int i
 	}
 }
 
+/* ---- tidally_strip_stars, src/cmc/cmc_evolution_thr.c:443-645: the per-star criterion of one pass of its loop ------------------------------ */
+
+long orc_tidally_strip_select(long n_local, int tidal_treatment, double threshold, const double *r_apo, const double *E, double *rnew,
+			      double *vrnew, double *vtnew, long *idx_out)
+{
+	long count = 0;
+	for (long i = 0; i < n_local; i++) {
+		/* :479 radial cut-off (r_apo > Rtidal), :555 Giersz (E > gierszalpha * phi_rtidal); both only for stars still in the cluster */
+		const int strip = tidal_treatment == 0 ? (r_apo[i] > threshold && rnew[i] < 1000000) : (tidal_treatment == 1 ? (E[i] > threshold && rnew[i] < 1000000) : 0);
+		if (!strip) continue;
+		rnew[i] = ORC_SF_INFINITY; /* :481-483 / :557-559 */
+		vrnew[i] = 0.0;
+		vtnew[i] = 0.0;
+		idx_out[count++] = i + 1;
+	}
+	return count;
+}
+
 /* clusdyn_calculate, src/cmc/cmc_utils.c:1613-1624 */
 double orc_clusdyn_calculate(const double *star_r, const double *star_m, long N_STAR, double Mtotal)
 {

@@ -120,6 +120,15 @@ void orc_calc_sigma_r(long p, long n_limit, long first_global, long N_MAX, int i
 		      double madhoc, const double *vr, const double *vt, const double *ghost_prev_vr, const double *ghost_prev_vt,
 		      const double *ghost_next_vr, const double *ghost_next_vt, int r_0_mave_1, double *sig_r_or_mave, double *sig_sigma);
 
+/* tidally_strip_stars, src/cmc/cmc_evolution_thr.c:443-645 (between energy_conservation2 and ComputeIntermediateEnergy, cmc.c:321-322): one
+ * pass of its do-while loop over the local stars.  A star still in the cluster (rnew < 1e6) is stripped when r_apo > threshold = Rtidal
+ * (TIDAL_TREATMENT 0, :479) or E > threshold = gierszalpha * phi_rtidal (TIDAL_TREATMENT 1, :555): rnew = SF_INFINITY, vrnew = vtnew = 0.
+ * idx_out receives the 1-based local indices in star order; returns their number.  The caller does what the reference does per stripped
+ * star in that order (the escaper sums, the log line, destroy_obj), recomputes Rtidal from the mass lost and repeats while a pass strips
+ * anything (:624): tests/oraclelib.py:tidally_strip_stars. */
+long orc_tidally_strip_select(long n_local, int tidal_treatment, double threshold, const double *r_apo, const double *E, double *rnew,
+			      double *vrnew, double *vtnew, long *idx_out);
+
 /* comp_mass_percent, src/cmc/cmc_utils.c:872-985: Lagrange radii and the cumulative kinetic sums at them, as ONE rank of P sees it.
  *   star_r, star_m: the replicated tables; vr, vt: star[k].vr / .vt of this rank's local stars k = 1..n_local at vr[k-1], vt[k-1];
  *   first_global = Start[myid] (global index of local star 1; the function is called after the sort, so there are no new stars).

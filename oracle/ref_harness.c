@@ -223,6 +223,18 @@ EXPORT void ref_calc_sigma_r(long p, long n_limit, int r_0_mave_1, double *out_a
 	calc_sigma_r(p, n_limit, out_a, out_sigma, &n, r_0_mave_1);
 }
 
+/* tidally_strip_stars (src/cmc/cmc_evolution_thr.c:443-645) on the harness's cluster state; out[0..2] = Rtidal, TidalMassLoss, DTidalMassLoss */
+EXPORT void ref_tidally_strip_stars(long treatment, double gamma, double *out)
+{
+	TIDAL_TREATMENT = treatment;
+	GAMMA = gamma;
+	if (!mpi_logfile_buf) { mpi_logfile_buf = malloc(STR_BUF_LEN); mpi_logfile_wrbuf = malloc(1 << 20); }
+	mpi_logfile_wrbuf[0] = 0; mpi_logfile_len = 0;
+	mpi_escfile_wrbuf[0] = 0; mpi_escfile_len = 0;
+	tidally_strip_stars();
+	out[0] = Rtidal; out[1] = TidalMassLoss; out[2] = DTidalMassLoss;
+}
+
 /* comp_mass_percent (src/cmc/cmc_utils.c:872-985) on the harness's cluster state: thresholds in, the eight result arrays out
  * (out[8][count], in the order mass_r, ave_mass_r, no_star_r, densities_r, ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r; on ranks other than 0
  * the last four hold what that rank computed, i.e. nothing meaningful -- the reference prints from rank 0 only). */

@@ -59,6 +59,8 @@ def lib():
         L.orc_set_velocities3_second.restype = C.c_double
         L.orc_set_velocities3_second.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 4
         L.orc_calc_sigma_r.argtypes = [C.c_long] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_tidally_strip_select.restype = C.c_long
+        L.orc_tidally_strip_select.argtypes = [C.c_long, C.c_int, C.c_double] + [C.c_void_p] * 6
         L.orc_clusdyn_calculate.restype = C.c_double
         L.orc_clusdyn_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double]
         L.orc_comp_mass_percent.restype = C.c_long
@@ -254,6 +256,53 @@ def calc_sigma_r(p, star_r, star_m, N_MAX, N_STAR, vr_all, vt_all, first_global=
     lib().orc_calc_sigma_r(p, n, first_global, N_MAX, int(first_global == 1), _p(star_r), _p(star_m), 1.0 / N_STAR, _p(loc[0]), _p(loc[1]),
                            _p(prev[0]), _p(prev[1]), _p(nxt[0]), _p(nxt[1]), int(mave), _p(a), _p(sg))
     return a, sg
+
+
+def tidally_strip_select(tidal_treatment, threshold, f):
+    """one pass of tidally_strip_stars' criterion over the local stars (reference cmc_evolution_thr.c:467-609); f["rnew"], ["vrnew"], ["vtnew"]
+    are updated in place; returns the 1-based local indices of the stripped stars in star order"""
+    n = len(f["rnew"])
+    idx = np.zeros(n, np.int64)
+    r_apo, E = np.ascontiguousarray(f["r_apo"], np.float64), np.ascontiguousarray(f["E"], np.float64)
+    c = lib().orc_tidally_strip_select(n, tidal_treatment, threshold, _p(r_apo), _p(E), _p(f["rnew"]), _p(f["vrnew"]), _p(f["vtnew"]), _p(idx))
+    return idx[:c].copy()
+
+
+def tidally_strip_loop(select, potential, star_m_of, star_fields_of, binary_of, s, N_STAR, orbit_r, tidal_treatment, GAMMA):
+    """The do-while loop of tidally_strip_stars (reference cmc_evolution_thr.c:443-645) around a per-pass selection, with the reference's
+    bookkeeping per stripped star in star order (:484-496 / :560-572).  select(threshold) -> 1-based local indices; potential(r) -> Phi(r);
+    star_m_of(i) -> star_m[g_i]; star_fields_of(i) -> dict(E, J, Eint, binind); binary_of(k) -> dict(m1, m2, a, Eint1, Eint2).
+    s: dict with Mtotal, TidalMassLoss, OldTidalMassLoss, Eescaped, Jescaped, Eintescaped, Ebescaped -- updated in place, plus Rtidal, Etidal,
+    DTidalMassLoss, passes, stripped."""
+    import math
+    s["Etidal"], s["passes"], s["stripped"] = 0.0, 0, []
+    N = float(N_STAR)
+    while True:
+        s["Rtidal"] = orbit_r * math.pow(s["Mtotal"] - (s["TidalMassLoss"] - s["OldTidalMassLoss"]), 1.0 / 3.0)
+        phi_rtidal = potential(s["Rtidal"])
+        if tidal_treatment == 0:
+            thr = s["Rtidal"]
+        else:
+            thr = (1.5 - 3.0 * math.pow(math.log(GAMMA * N) / N, 0.25)) * phi_rtidal
+        D = 0.0
+        for i in select(thr):
+            m, f = star_m_of(i), star_fields_of(i)
+            s["Eescaped"] += f["E"] * m / N
+            s["Jescaped"] += f["J"] * m / N
+            if f["binind"] == 0:
+                s["Eintescaped"] += f["Eint"]
+            else:
+                b = binary_of(f["binind"])
+                s["Ebescaped"] += -(b["m1"] / N) * (b["m2"] / N) / (2.0 * b["a"])
+                s["Eintescaped"] += b["Eint1"] + b["Eint2"]
+            D += m / N
+            s["Etidal"] += f["E"] * m / N
+            s["stripped"].append(int(i))
+        s["passes"] += 1
+        s["TidalMassLoss"] += D
+        s["DTidalMassLoss"] = D
+        if not D > 0:
+            return s
 
 
 def clusdyn_calculate(star_r, star_m, N_STAR, Mtotal):

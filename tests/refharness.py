@@ -159,6 +159,13 @@ class Ref:
         self.L.ref_calc_sigma_r(p, n_limit, int(mave), a.ctypes.data, sg.ctypes.data)
         return a, sg
 
+    def tidally_strip_stars(self, treatment, gamma=0.11):
+        """the reference's tidally_strip_stars (cmc_evolution_thr.c:443-645) on the harness's state -> (Rtidal, TidalMassLoss, DTidalMassLoss)"""
+        out = np.zeros(3)
+        self.L.ref_tidally_strip_stars.argtypes = [C.c_long, C.c_double, C.c_void_p]
+        self.L.ref_tidally_strip_stars(treatment, gamma, out.ctypes.data)
+        return tuple(out)
+
     def compute_energy(self):
         """E, J exactly as ComputeEnergy (reference cmc_utils.c:614-615), single rank."""
         n = int(self.scalars()["N_MAX"])

@@ -153,6 +153,53 @@ def test_calc_sigma_r(R, kind, N, masses, p):
     R.free()
 
 
+@pytest.mark.parametrize("treatment,orbit_r", [(1, 6.0), (0, 6.0), (1, 1.0e6)])
+def test_tidally_strip_stars(R, treatment, orbit_r):
+    """tidally_strip_stars (reference cmc_evolution_thr.c:443-645), the step between energy_conservation2 and ComputeIntermediateEnergy when
+    TIDALLY_STRIP_STARS is on (both example .ini files): after an orbit step of the compiled reference, its own loop against the restated
+    criterion + the host loop (Rtidal shrinking with the mass lost until a pass strips nothing), both tidal treatments, singles and binaries"""
+    N, nb = 20000, 900
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=31, masses="imf")
+    rng = np.random.default_rng(5)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    R.init(N, n_star_dim=N + 64, n_bin_dim=nb + 8, idum=99, orbit_r=orbit_r)
+    R.load_cluster(r, vr, vt, sm, binind=binind)
+    bb = R.binary_bytes()
+    bf = {k: layout.binary_field(bb, k) for k in ("m1", "m2", "a", "Eint1", "Eint2", "inuse")}
+    for k, lo, hi in (("m1", 0.1, 5.0), ("m2", 0.1, 5.0), ("a", 1e-6, 1e-3), ("Eint1", 0.0, 1e-7), ("Eint2", 0.0, 1e-7)):
+        bf[k][1:nb + 1] = rng.uniform(lo, hi, nb)
+    bf["inuse"][1:nb + 1] = 1
+    R.star_field("Eint")[1:N + 1] = rng.uniform(0.0, 1e-7, N)
+    R.set_scalars(N, N, N_BINARY=nb)
+    R.L.ref_calc_potential_new()
+    R.compute_energy()
+    R.L.ref_new_orbits_calculate()
+    sc0 = R.scalars()
+    f = {k: R.star_field(k)[1:N + 1].copy() for k in ("r_apo", "E", "J", "Eint", "rnew", "vrnew", "vtnew")}
+    bi = R.star_field("binind", np.int64)[1:N + 1].copy()
+    bcopy = {k: v[:nb + 1].copy() for k, v in bf.items()}
+    t = ol.tables(R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy(), N, N, 0.0)
+    smt = R.star_m()[:N + 2].copy()
+    Rt, TML, DT = R.tidally_strip_stars(treatment)
+    s = dict(Mtotal=sc0["Mtotal"], TidalMassLoss=sc0["TidalMassLoss"], OldTidalMassLoss=0.0, Eescaped=sc0["Eescaped"], Jescaped=sc0["Jescaped"],
+             Eintescaped=sc0["Eintescaped"], Ebescaped=sc0["Ebescaped"])
+    ol.tidally_strip_loop(lambda thr: ol.tidally_strip_select(treatment, thr, f), lambda x: ol.lib().orc_potential(C.byref(t), x),
+                          lambda i: smt[i], lambda i: dict(E=f["E"][i - 1], J=f["J"][i - 1], Eint=f["Eint"][i - 1], binind=int(bi[i - 1])),
+                          lambda k: {q: bcopy[q][k] for q in ("m1", "m2", "a", "Eint1", "Eint2")}, s, N, orbit_r, treatment, 0.11)
+    sc = R.scalars()
+    assert (Rt, TML, DT) == (s["Rtidal"], s["TidalMassLoss"], 0.0) and sc["Rtidal"] == s["Rtidal"]
+    for k in ("Eescaped", "Jescaped", "Eintescaped", "Ebescaped", "Etidal"):
+        assert sc[k] == s[k], k
+    for k in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(R.star_field(k)[1:N + 1], f[k], k)
+    if orbit_r < 100:
+        assert s["passes"] >= 3 and len(s["stripped"]) > 50 and (bi[np.array(s["stripped"]) - 1] > 0).sum() > 2
+    else:
+        assert s["passes"] == 1 and not s["stripped"]
+    R.free()
+
+
 def test_sort_with_binaries_and_stripped_stars(R):
     n, nb, n_strip = 20000, 1500, 23
     rng = np.random.default_rng(8)
