@@ -195,7 +195,7 @@ def test_tidally_strip_stars(R, treatment, orbit_r):
         cm.assert_bits_equal(R.star_field(k)[1:N + 1], f[k], k)
     if orbit_r < 100:
         assert s["passes"] >= 2 and len(s["stripped"]) > 5
-            assert treatment == 0 or (bi[np.array(s["stripped"]) - 1] > 0).sum() > 2       # the Giersz criterion strips hundreds, binaries among them
+        assert treatment == 0 or (bi[np.array(s["stripped"]) - 1] > 0).sum() > 2       # the Giersz criterion strips hundreds, binaries among them
     else:
         assert s["passes"] == 1 and not s["stripped"]
     R.free()
