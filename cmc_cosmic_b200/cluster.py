@@ -57,6 +57,9 @@ class Cluster:
         self.mpiBegin, self.mpiEnd = 1, n_star
         self.tcount = 1
         self.Eoops = 0.0                  # energy lost to the scheme (reference include/cmc/cmc_vars.h:293)
+        # escaper bookkeeping of remove_star / tidally_strip_stars (include/cmc/cmc_vars.h)
+        self.Eescaped = self.Jescaped = self.Eintescaped = self.Ebescaped = self.Etidal = 0.0
+        self.TidalMassLoss = self.OldTidalMassLoss = self.DTidalMassLoss = 0.0
         self.last_orbit = None
         self.last_status = None
         ctx = C.c_void_p()
@@ -220,21 +223,78 @@ class Cluster:
         p = self.orbit_params()
         _lib.check(self.L.cmcb200_dev_compute_intermediate_energy(self.ctx, C.byref(p)), "dev_compute_intermediate_energy")
 
+    def dev_potential(self, r):
+        """potential() (reference src/cmc/cmc_utils.c:112-165) at the radii r on the resident tables"""
+        r = np.ascontiguousarray(np.atleast_1d(r), np.float64)
+        out = np.zeros(len(r))
+        p = self.orbit_params()
+        _lib.check(self.L.cmcb200_dev_potential(self.ctx, C.byref(p), r.ctypes.data, len(r), out.ctypes.data), "dev_potential")
+        return out
+
+    def dev_tidally_strip_stars(self, tidal_treatment=1, GAMMA=0.11, cap=65536):
+        """tidally_strip_stars (reference src/cmc/cmc_evolution_thr.c:443-645) on the resident records, one rank.  The criterion runs on the
+        device (one pass per call of cmcb200_dev_tidally_strip_select); this is the reference's host loop around it: Rtidal from the mass
+        lost so far, the per-star sums in star order from the handful of stripped records the device hands back, repeated while a pass
+        strips anything.  Returns the 1-based local indices of all stripped stars."""
+        import math
+        N = float(self.clus.N_STAR)
+        idx, cnt = np.zeros(cap, np.int64), C.c_long(0)
+        recs = np.zeros((cap, STAR_DTYPE_SIZE), np.uint8)
+        bins = np.zeros((cap, BINARY_DTYPE_SIZE), np.uint8)
+        self.Etidal, stripped = 0.0, []
+        first = int(self.Start[self.myid])
+        while True:
+            self.Rtidal = self.orbit_r * math.pow(self.Mtotal - (self.TidalMassLoss - self.OldTidalMassLoss), 1.0 / 3.0)   # :461-462
+            phi_rtidal = float(self.dev_potential(self.Rtidal)[0])
+            thr = self.Rtidal if tidal_treatment == 0 else (1.5 - 3.0 * math.pow(math.log(GAMMA * N) / N, 0.25)) * phi_rtidal   # :479 / :553-555
+            p = self.orbit_params()
+            _lib.check(self.L.cmcb200_dev_tidally_strip_select(self.ctx, C.byref(p), tidal_treatment, thr, idx.ctypes.data, cap, C.byref(cnt),
+                                                               recs.ctypes.data, bins.ctypes.data), "dev_tidally_strip_select")
+            n = cnt.value
+            D = 0.0
+            if n:
+                E, J, Eint, binind = (star_field(recs[:n], k) for k in ("E", "J", "Eint", "binind"))
+                bf = {k: binary_field(bins[:n], k) for k in ("m1", "m2", "a", "Eint1", "Eint2")}
+                for k in range(n):                                    # :484-496, in star order
+                    m = float(self.star_m[first + int(idx[k]) - 1])
+                    self.Eescaped += float(E[k]) * m / N
+                    self.Jescaped += float(J[k]) * m / N
+                    if binind[k] == 0:
+                        self.Eintescaped += float(Eint[k])
+                    else:
+                        self.Ebescaped += -(float(bf["m1"][k]) / N) * (float(bf["m2"][k]) / N) / (2.0 * float(bf["a"][k]))
+                        self.Eintescaped += float(bf["Eint1"][k]) + float(bf["Eint2"][k])
+                    D += m / N
+                    self.Etidal += float(E[k]) * m / N
+                stripped.extend(int(i) for i in idx[:n])
+            self.TidalMassLoss += D                                   # :617
+            self.DTidalMassLoss = D
+            if not D > 0:                                             # :624
+                return stripped
+
     def dev_energy_new_radii(self):
         """energy_conservation2 and the EI loop of ComputeIntermediateEnergy from one potential(rnew) lookup per star; the transfer is left to
         dev_transfer_and_sort (reference src/cmc/cmc.c:317-335 with TIDALLY_STRIP_STARS == 0)"""
         p = self.orbit_params()
         _lib.check(self.L.cmcb200_dev_energy_new_radii(self.ctx, C.byref(p)), "dev_energy_new_radii")
 
-    def dev_timestep(self, seed=0, draws=None, draw_off=None):
-        """One timestep of the reference's main loop around the hot path (src/cmc/cmc.c:302-353, no interacting stars, TIDALLY_STRIP_STARS == 0)
-        on the resident arrays, passes fused where they read the same data: energy_conservation1 -> new_orbits_calculate ->
-        energy_conservation2 + ComputeIntermediateEnergy (one lookup) -> transfer + qsorts_new (one pass over the records) ->
-        calc_potential_new -> energy_conservation3 -> ComputeEnergy.  Bit-identical to the calls made one by one."""
+    def dev_timestep(self, seed=0, draws=None, draw_off=None, tidally_strip=None, GAMMA=0.11):
+        """One timestep of the reference's main loop around the hot path (src/cmc/cmc.c:302-353, no interacting stars) on the resident arrays:
+        energy_conservation1 -> new_orbits_calculate -> energy_conservation2 -> [tidally_strip_stars] -> ComputeIntermediateEnergy ->
+        qsorts_new -> calc_potential_new -> energy_conservation3 -> ComputeEnergy.  tidally_strip: None (TIDALLY_STRIP_STARS = 0) or the
+        TIDAL_TREATMENT (0 / 1).  Without stripping the passes that read the same data are merged (one lookup for energy_conservation2 +
+        ComputeIntermediateEnergy, the transfer inside the sort's gather); bit-identical to the calls made one by one either way."""
         self.dev_energy_conservation1()
+        self.OldTidalMassLoss = self.TidalMassLoss                    # new_orbits_calculate, cmc_utils.c:2197
         res = self.dev_new_orbits(draws, draw_off, seed)
-        self.dev_energy_new_radii()
-        self.dev_transfer_and_sort()
+        if tidally_strip is None:
+            self.dev_energy_new_radii()
+            self.dev_transfer_and_sort()
+        else:
+            self.dev_energy_conservation2()
+            self.dev_tidally_strip_stars(tidally_strip, GAMMA)
+            self.dev_compute_intermediate_energy()
+            self.dev_qsorts_new()
         self.dev_calc_potential_new()
         self.dev_energy_conservation3()
         self.dev_compute_energy()

@@ -216,6 +216,40 @@ __global__ void __launch_bounds__(32) sv3_second_kernel(OrbitArgs a, Sv3Buffers 
 	if (lane == 0) b.result[0] = E;
 }
 
+// ---- tidally_strip_stars (reference src/cmc/cmc_evolution_thr.c:443-645): the per-star criterion of one pass -------------------------------
+// A star still in the cluster (rnew < 1e6) is stripped when r_apo > Rtidal (TIDAL_TREATMENT 0, :479) or E > gierszalpha * phi_rtidal
+// (TIDAL_TREATMENT 1, :555): rnew = SF_INFINITY, vrnew = vtnew = 0 (:481-483).  The hits are rare; their local indices are queued and
+// sorted by the caller, which does the reference's per-star bookkeeping in star order on the host.
+__global__ void __launch_bounds__(256) tidal_select_kernel(OrbitArgs a, int treatment, double threshold, long *list, unsigned *count, unsigned cap)
+{
+	for (long j0 = blockIdx.x * 256L + threadIdx.x; j0 < a.n_local; j0 += gridDim.x * 256L) {
+		char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
+		if (!(ld_field(rec, CMCB_OFF_RNEW) < 1000000)) continue;
+		const double v = ld_field(rec, treatment == 0 ? CMCB_OFF_R_APO : CMCB_OFF_E);
+		if (!(v > threshold)) continue;
+		st_field(rec, CMCB_OFF_RNEW, CMCB_SF_INFINITY);
+		st_field(rec, CMCB_OFF_VRNEW, 0.0);
+		st_field(rec, CMCB_OFF_VTNEW, 0.0);
+		const unsigned pos = atomicAdd(count, 1u);
+		if (pos < cap) list[pos] = j0 + 1;
+	}
+}
+
+// potential() (reference src/cmc/cmc_utils.c:112-165) at n radii through the r ladder; a failed bracket check is counted
+__global__ void __launch_bounds__(ORBIT_TRY_THREADS) potential_at_kernel(OrbitArgs a, const double *__restrict__ r, long n, double *__restrict__ out)
+{
+	extern __shared__ __align__(128) unsigned char orbit_smem[];
+	__shared__ __align__(8) unsigned long long bar;
+	LadderTops top;
+	top.q = nullptr; top.qdesc = nullptr;
+	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
+	for (long i = blockIdx.x * (long) ORBIT_TRY_THREADS + threadIdx.x; i < n; i += (long) gridDim.x * ORBIT_TRY_THREADS) {
+		int fail = 0;
+		out[i] = potential_at(a.t, top, r[i], &fail);
+		if (fail) atomicAdd(&a.stats->n_status[ORBIT_NTRY], 1ull);
+	}
+}
+
 } // namespace cmcb
 
 static int sv3_buffers(cmcb200_ctx *c, Sv3Buffers &b)
@@ -305,4 +339,79 @@ extern "C" int cmcb200_dev_set_velocities3_pass(cmcb200_ctx *c, const cmcb200_or
 		c->launches += 1;
 	}
 	return sv3_finish(c, b, Eexcess_left, "set_velocities3");
+}
+
+#include <algorithm>
+
+extern "C" int cmcb200_dev_potential(cmcb200_ctx *c, const cmcb200_orbit_params *p, const double *r, long n, double *out)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (n <= 0) return 0;
+	OrbitArgs a;
+	if (orbit_begin(c, p, false, false, a)) return -1;
+	if (ensure((void **) &c->d_draws, &c->draws_cap, 2 * n, sizeof(double))) return -1;
+	double *d_in = c->d_draws, *d_out = c->d_draws + n;
+	CMCB_CUDA_OK(cudaMemcpyAsync(d_in, r, (size_t) n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	{
+		StageTimer t(c, ST_ENERGY);
+		c->launches += orbit_reset_stats(a, c->stream);
+		potential_at_kernel<<<(unsigned) persistent_blocks(n), ORBIT_TRY_THREADS, a.r_top_bytes, c->stream>>>(a, d_in, n, d_out);
+		c->launches += 1;
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	OrbitStats *h = (OrbitStats *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaMemcpyAsync(out, d_out, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	if (h->n_status[ORBIT_NTRY]) { set_error("potential: binary search (FindZero_r) failed for %llu radii", h->n_status[ORBIT_NTRY]); return -2; }
+	return 0;
+}
+
+extern "C" int cmcb200_dev_tidally_strip_select(cmcb200_ctx *c, const cmcb200_orbit_params *p, int tidal_treatment, double threshold, long *idx_out,
+						 long cap, long *count, void *star_out, void *binary_out)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	*count = 0;
+	if (tidal_treatment != 0 && tidal_treatment != 1) return 0; // the reference's loop body has no other branch (:476, :551)
+	if (p->n_local <= 0 || cap <= 0) return 0;
+	if (p->n_local + 2 > c->n_star_dim) { set_error("tidally_strip_stars: n_local exceeds the capacity"); return -1; }
+	OrbitArgs a;
+	memset(&a, 0, sizeof(a));
+	a.star1 = star1(c);
+	a.n_local = p->n_local;
+	// queue: the deferred-scan list (ORBIT_DEFER_CAP longs) is free between orbit steps
+	const long qcap = cap < ORBIT_DEFER_CAP ? cap : ORBIT_DEFER_CAP;
+	unsigned *d_count = c->d_defer_first;
+	CMCB_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(unsigned), c->stream));
+	{
+		StageTimer t(c, ST_ENERGY);
+		tidal_select_kernel<<<(unsigned) persistent_blocks(p->n_local), 256, 0, c->stream>>>(a, tidal_treatment, threshold, c->d_defer_star, d_count, (unsigned) qcap);
+		c->launches += 1;
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	unsigned *h_count = (unsigned *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h_count, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	const long n = *h_count;
+	if (n > qcap) { set_error("tidally_strip_stars: %ld stars stripped in one pass, the caller's list holds %ld", n, qcap); return -3; }
+	if (n == 0) return 0;
+	CMCB_CUDA_OK(cudaMemcpyAsync(idx_out, c->d_defer_star, (size_t) n * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	std::sort(idx_out, idx_out + n); // star order
+	*count = n;
+	if (star_out) {
+		StageTimer t(c, ST_D2H);
+		for (long k = 0; k < n; k++)
+			CMCB_CUDA_OK(cudaMemcpyAsync((char *) star_out + k * CMCB_SIZEOF_STAR, star1(c) + (idx_out[k] - 1) * CMCB_SIZEOF_STAR, CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
+		CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+		if (binary_out) {
+			for (long k = 0; k < n; k++) {
+				const long b = *(const long *) ((const char *) star_out + k * CMCB_SIZEOF_STAR + CMCB_OFF_BININD);
+				if (b > 0 && b < c->n_bin_dim)
+					CMCB_CUDA_OK(cudaMemcpyAsync((char *) binary_out + k * CMCB_SIZEOF_BINARY, bin1(c) + (b - 1) * CMCB_SIZEOF_BINARY, CMCB_SIZEOF_BINARY, cudaMemcpyDeviceToHost, c->stream));
+			}
+			CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+		}
+	}
+	return 0;
 }

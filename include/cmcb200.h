@@ -181,6 +181,18 @@ int cmcb200_dev_energy_new_radii(cmcb200_ctx *ctx, const cmcb200_orbit_params *p
 int cmcb200_dev_energy_conservation1(cmcb200_ctx *ctx, const cmcb200_orbit_params *p);
 int cmcb200_dev_set_velocities3(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, double *Eexcess_left);
 int cmcb200_dev_set_velocities3_pass(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, double Eexcess_in, double *Eexcess_left);
+/* potential() (src/cmc/cmc_utils.c:112-165) at n radii on the resident tables: out[i] = potential(r[i]), bit for bit (r, out: host arrays) */
+int cmcb200_dev_potential(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, const double *r, long n, double *out);
+/* One pass of the loop of tidally_strip_stars (src/cmc/cmc_evolution_thr.c:443-645; between energy_conservation2 and
+ * ComputeIntermediateEnergy when TIDALLY_STRIP_STARS > 0, src/cmc/cmc.c:321-322) over the resident records: a star with rnew < 1e6 is
+ * stripped when r_apo > threshold = Rtidal (tidal_treatment 0, :479) or E > threshold = gierszalpha * phi_rtidal (tidal_treatment 1, :555):
+ * rnew = SF_INFINITY, vrnew = vtnew = 0.  idx_out[cap] receives the 1-based local indices in star order, *count their number; star_out
+ * (may be NULL) the stripped stars' 424-byte records and binary_out (may be NULL) the 464-byte record of each one that is a binary, both
+ * at position k of the list -- what the caller needs for the reference's per-star bookkeeping (:484-496: Eescaped, Jescaped, Eintescaped,
+ * Ebescaped, DTidalMassLoss, Etidal, the esc log line), which it does in that order, recomputes Rtidal from the mass lost and calls again
+ * while a pass strips anything (:624).  More than cap hits in one pass: non-zero return, the records are already marked. */
+int cmcb200_dev_tidally_strip_select(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int tidal_treatment, double threshold, long *idx_out,
+				     long cap, long *count, void *star_out, void *binary_out);
 /* qsorts_new + post_sort_comm on the resident arrays; *n_local in/out, *n_bin out */
 int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, long *n_bin);
 /* cmcb200_dev_transfer_new_positions + cmcb200_dev_qsorts_new in one pass over the records: the sort key is rnew and the transfer is

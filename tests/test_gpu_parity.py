@@ -562,6 +562,61 @@ def t_phi(t, g):
     return np.ctypeslib.as_array(ctypes.cast(t.phi, ctypes.POINTER(ctypes.c_double)), shape=(t.N_MAX + 2,))[g].copy()
 
 
+@pytest.mark.parametrize("treatment,orbit_r", [(1, 6.0), (0, 6.0), (1, 1.0e6)])
+def test_tidally_strip_stars_bit_exact(treatment, orbit_r):
+    """tidally_strip_stars (reference cmc_evolution_thr.c:443-645) on the resident records after an orbit step: the criterion on the device,
+    the reference's loop and per-star sums in the host mirror, against the oracle's criterion + loop (pinned against the compiled
+    reference in test_oracle_vs_ref.py::test_tidally_strip_stars): the same stars in the same passes, the same sums bit for bit, and
+    potential() at arbitrary radii (cmcb200_dev_potential)"""
+    import ctypes
+    N, nb = 60000, 2500
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=41, masses="imf")
+    pot = cm.oracle_potential(r, sm, orbit_r=orbit_r)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, pot["Rtidal"], seed=3)
+    rng = np.random.default_rng(6)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    bvals = {k: np.concatenate([[0.0], rng.uniform(lo, hi, nb)]) for k, lo, hi in (("m1", 0.1, 5.0), ("m2", 0.1, 5.0), ("a", 1e-6, 1e-3),
+                                                                                   ("Eint1", 0.0, 1e-7), ("Eint2", 0.0, 1e-7))}
+    Eint = rng.uniform(0.0, 1e-7, N)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    f = dict(r_apo=want["r_apo"].copy(), E=E, J=J, Eint=Eint, rnew=want["rnew"].copy(), vrnew=want["vrnew"].copy(), vtnew=want["vtnew"].copy())
+    tml0 = float(np.sum((sm / N)[want["rnew"] >= cm.SF_INFINITY]))          # what the orbit step removed
+    s = dict(Mtotal=pot["Mtotal"], TidalMassLoss=tml0, OldTidalMassLoss=0.0, Eescaped=0.25, Jescaped=0.5, Eintescaped=0.0, Ebescaped=0.0)
+    ol.tidally_strip_loop(lambda thr: ol.tidally_strip_select(treatment, thr, f), lambda x: ol.lib().orc_potential(ctypes.byref(t), x),
+                          lambda i: pot["star_m"][i], lambda i: dict(E=E[i - 1], J=J[i - 1], Eint=Eint[i - 1], binind=int(binind[i - 1])),
+                          lambda k: {q: bvals[q][k] for q in bvals}, s, N, orbit_r, treatment, 0.11)
+
+    c = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8, orbit_r=orbit_r)
+    c.load(r, vr, vt, sm, binind=binind)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    for k in ("E", "J", "Eint"):
+        c.field(k)[1:N + 1] = f[k] if k != "E" else E
+    for k in ("r_apo", "rnew", "vrnew", "vtnew"):
+        c.field(k)[1:N + 1] = want[k]
+    for k, v in bvals.items():
+        c.bfield(k)[:nb + 1] = v
+    c.Mtotal, c.TidalMassLoss, c.OldTidalMassLoss, c.Eescaped, c.Jescaped = pot["Mtotal"], tml0, 0.0, 0.25, 0.5
+    c.upload()
+    probe = np.concatenate([rng.uniform(r[0] * 0.5, r[-1] * 2.0, 5000), r[:50], [0.0, 1e9]])
+    cm.assert_bits_equal(c.dev_potential(probe), np.array([ol.lib().orc_potential(ctypes.byref(t), float(x)) for x in probe]), "potential()")
+    before = c.star.copy()
+    stripped = c.dev_tidally_strip_stars(tidal_treatment=treatment, GAMMA=0.11)
+    c.download()
+    assert stripped == s["stripped"]
+    for k in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(c.field(k)[1:N + 1], f[k], k)
+    _only_these_fields_changed(before, c, N, ("rnew", "vrnew", "vtnew"))
+    for k in ("Rtidal", "TidalMassLoss", "DTidalMassLoss", "Eescaped", "Jescaped", "Eintescaped", "Ebescaped", "Etidal"):
+        assert getattr(c, k) == s[k], (k, getattr(c, k), s[k])
+    if orbit_r < 100:
+        assert s["passes"] >= 2 and len(stripped) > 5 and (treatment == 0 or (binind[np.array(stripped) - 1] > 0).sum() > 2)
+    else:
+        assert not stripped
+    c.close()
+
+
 def test_lagrange_radii_of_a_run_agree_statistically_with_the_reference_run():
     """north_star: "Lagrangian radii from a full run must statistically agree with the reference run".  Six timesteps of the path
     (orbit step -> r <- rnew -> sort -> potential -> E, J) from the same Plummer state: the CUDA pipeline with its production draws
