@@ -282,10 +282,10 @@ class Cluster:
         """One timestep of the reference's main loop around the hot path (src/cmc/cmc.c:302-353, no interacting stars) on the resident arrays:
         energy_conservation1 -> new_orbits_calculate -> energy_conservation2 -> [tidally_strip_stars] -> ComputeIntermediateEnergy ->
         qsorts_new -> calc_potential_new -> energy_conservation3 -> ComputeEnergy.  tidally_strip: None (TIDALLY_STRIP_STARS = 0) or the
-        TIDAL_TREATMENT (0 / 1).  Without stripping the passes that read the same data are merged (one lookup for energy_conservation2 +
+        TIDAL_TREATMENT (0 / 1); TidalMassLoss / OldTidalMassLoss are the caller's to maintain across the orbit step
+        (reference cmc_utils.c:2197-2210).  Without stripping the passes that read the same data are merged (one lookup for energy_conservation2 +
         ComputeIntermediateEnergy, the transfer inside the sort's gather); bit-identical to the calls made one by one either way."""
         self.dev_energy_conservation1()
-        self.OldTidalMassLoss = self.TidalMassLoss                    # new_orbits_calculate, cmc_utils.c:2197
         res = self.dev_new_orbits(draws, draw_off, seed)
         if tidally_strip is None:
             self.dev_energy_new_radii()
