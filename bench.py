@@ -239,6 +239,23 @@ def run_cuda(args):
         value = stars / (ms * 1e-3)
         n_now, n_shard = c.clus.N_MAX, c.clus.N_MAX_NEW
 
+        # ---- auxiliary: the same step inside the reference's timestep order WITH the energy-conservation scheme and the tidal stripping
+        # around it (Cluster.dev_timestep), resident, CUDA events.  Not the metric: reported next to it.
+        timestep_ms = None
+        if world == 1:
+            try:
+                c.dev_timestep(seed=args.seed, tidally_strip=1)
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c.sync()
+                t0.record(stream)
+                for _ in range(3):
+                    c.dev_timestep(seed=args.seed, tidally_strip=1)
+                t1.record(stream)
+                c.sync()
+                timestep_ms = t0.elapsed_time(t1) / 3
+            except Exception as exc:            # never lose the bench line over the auxiliary number
+                print(f"bench: auxiliary timestep measurement skipped: {exc}", file=sys.stderr)
+
         # ---- e2e arm: the same step through the public API with HOST buffers, copies included ----
         c.download()
         c.sync()
@@ -353,6 +370,7 @@ def run_cuda(args):
         "step_bytes_per_star": BYTES_STEP, "step_achieved_gbs": BYTES_STEP * n_now / (ms / args.steps * 1e-3) / 1e9,
         "stage_ms_per_step": stage_ms,
         "cpu_baseline": cpu,
+        "timestep_with_energy_scheme_ms": timestep_ms,
     }
     if world > 1:
         line["stage_ms_per_step_rank"] = 0

@@ -231,16 +231,16 @@ class Cluster:
         _lib.check(self.L.cmcb200_dev_potential(self.ctx, C.byref(p), r.ctypes.data, len(r), out.ctypes.data), "dev_potential")
         return out
 
-    def dev_tidally_strip_stars(self, tidal_treatment=1, GAMMA=0.11, cap=65536):
+    def dev_tidally_strip_stars(self, tidal_treatment=1, GAMMA=0.11, cap=8192):
         """tidally_strip_stars (reference src/cmc/cmc_evolution_thr.c:443-645) on the resident records, one rank.  The criterion runs on the
         device (one pass per call of cmcb200_dev_tidally_strip_select); this is the reference's host loop around it: Rtidal from the mass
         lost so far, the per-star sums in star order from the handful of stripped records the device hands back, repeated while a pass
         strips anything.  Returns the 1-based local indices of all stripped stars."""
         import math
         N = float(self.clus.N_STAR)
-        idx, cnt = np.zeros(cap, np.int64), C.c_long(0)
-        recs = np.zeros((cap, STAR_DTYPE_SIZE), np.uint8)
-        bins = np.zeros((cap, BINARY_DTYPE_SIZE), np.uint8)
+        if getattr(self, "_strip_buf", None) is None or len(self._strip_buf[0]) != cap:      # hand-back buffers, kept between calls
+            self._strip_buf = (np.zeros(cap, np.int64), np.zeros((cap, STAR_DTYPE_SIZE), np.uint8), np.zeros((cap, BINARY_DTYPE_SIZE), np.uint8))
+        (idx, recs, bins), cnt = self._strip_buf, C.c_long(0)
         self.Etidal, stripped = 0.0, []
         first = int(self.Start[self.myid])
         while True:

@@ -35,6 +35,10 @@ for s in range(steps):
     _, t1 = timed(c.dev_energy_conservation1)
     _, to = timed(lambda: c.dev_new_orbits(seed=1))
     _, t2 = timed(c.dev_energy_conservation2)
+    import time
+    w0 = time.perf_counter()
+    _, tt = timed(lambda: c.dev_tidally_strip_stars(1))
+    tw = (time.perf_counter() - w0) * 1e3
     _, ti = timed(c.dev_compute_intermediate_energy)
     _, ts = timed(c.dev_qsorts_new)
     _, tp = timed(c.dev_calc_potential_new)
@@ -42,7 +46,7 @@ for s in range(steps):
     _, te = timed(c.dev_compute_energy)
     c.tcount += 1
     print(f"N={N} step {s}: energy_conservation1 {t1:.3f} ms | orbit {to:.3f} | energy_conservation2 {t2:.3f} | ComputeIntermediateEnergy {ti:.3f} | "
-          f"sort {ts:.3f} | potential {tp:.3f} | energy_conservation3 {t3:.3f} (leftover Eexcess {left:.3e}) | ComputeEnergy {te:.3f}", flush=True)
+          f"tidally_strip_stars {tt:.3f} (wall {tw:.2f}) | sort {ts:.3f} | potential {tp:.3f} | energy_conservation3 {t3:.3f} (leftover Eexcess {left:.3e}) | ComputeEnergy {te:.3f}", flush=True)
 for s in range(steps):
     _, tt = timed(lambda: c.dev_timestep(seed=1))
     print(f"N={N} fused timestep {s} (Cluster.dev_timestep: one lookup for energy_conservation2 + ComputeIntermediateEnergy, transfer inside the gather): {tt:.3f} ms", flush=True)
