@@ -269,40 +269,62 @@ def tidally_strip_select(tidal_treatment, threshold, f):
 
 
 def tidally_strip_loop(select, potential, star_m_of, star_fields_of, binary_of, s, N_STAR, orbit_r, tidal_treatment, GAMMA):
-    """The do-while loop of tidally_strip_stars (reference cmc_evolution_thr.c:443-645) around a per-pass selection, with the reference's
-    bookkeeping per stripped star in star order (:484-496 / :560-572).  select(threshold) -> 1-based local indices; potential(r) -> Phi(r);
-    star_m_of(i) -> star_m[g_i]; star_fields_of(i) -> dict(E, J, Eint, binind); binary_of(k) -> dict(m1, m2, a, Eint1, Eint2).
-    s: dict with Mtotal, TidalMassLoss, OldTidalMassLoss, Eescaped, Jescaped, Eintescaped, Ebescaped -- updated in place, plus Rtidal, Etidal,
-    DTidalMassLoss, passes, stripped."""
+    """tidally_strip_stars on one rank: see tidally_strip_loop_ranks"""
+    return tidally_strip_loop_ranks([select], potential, [star_m_of], [star_fields_of], [binary_of], [s], N_STAR, orbit_r, tidal_treatment, GAMMA)[0]
+
+
+def tidally_strip_loop_ranks(selects, potential, star_m_ofs, star_fields_ofs, binary_ofs, states, N_STAR, orbit_r, tidal_treatment, GAMMA):
+    """The do-while loop of tidally_strip_stars (reference cmc_evolution_thr.c:443-645) around a per-pass selection, as P ranks run it, with the
+    reference's bookkeeping per stripped star in star order (:484-496 / :560-572).  Per rank q: selects[q](threshold) -> 1-based local
+    indices; star_m_ofs[q](i) -> star_m[g_i]; star_fields_ofs[q](i) -> dict(E, J, Eint, binind); binary_ofs[q](k) -> dict(m1, m2, a, Eint1,
+    Eint2); states[q]: dict with Mtotal, TidalMassLoss, OldTidalMassLoss (the same on every rank) and the rank's Eescaped, Jescaped,
+    Eintescaped, Ebescaped -- updated in place, plus Rtidal, Etidal, DTidalMassLoss, passes, stripped.  potential(r) -> Phi(r) (replicated
+    tables).  The mass stripped in a pass is summed over the ranks (:612-616, rank order) and the five escaper sums at the end (:626-644)."""
     import math
-    s["Etidal"], s["passes"], s["stripped"] = 0.0, 0, []
+    P = len(states)
+    for s in states:
+        s["Etidal"], s["passes"], s["stripped"] = 0.0, 0, []
     N = float(N_STAR)
     while True:
-        s["Rtidal"] = orbit_r * math.pow(s["Mtotal"] - (s["TidalMassLoss"] - s["OldTidalMassLoss"]), 1.0 / 3.0)
-        phi_rtidal = potential(s["Rtidal"])
-        if tidal_treatment == 0:
-            thr = s["Rtidal"]
-        else:
-            thr = (1.5 - 3.0 * math.pow(math.log(GAMMA * N) / N, 0.25)) * phi_rtidal
-        D = 0.0
-        for i in select(thr):
-            m, f = star_m_of(i), star_fields_of(i)
-            s["Eescaped"] += f["E"] * m / N
-            s["Jescaped"] += f["J"] * m / N
-            if f["binind"] == 0:
-                s["Eintescaped"] += f["Eint"]
-            else:
-                b = binary_of(f["binind"])
-                s["Ebescaped"] += -(b["m1"] / N) * (b["m2"] / N) / (2.0 * b["a"])
-                s["Eintescaped"] += b["Eint1"] + b["Eint2"]
-            D += m / N
-            s["Etidal"] += f["E"] * m / N
-            s["stripped"].append(int(i))
-        s["passes"] += 1
-        s["TidalMassLoss"] += D
-        s["DTidalMassLoss"] = D
-        if not D > 0:
-            return s
+        s0 = states[0]
+        Rt = orbit_r * math.pow(s0["Mtotal"] - (s0["TidalMassLoss"] - s0["OldTidalMassLoss"]), 1.0 / 3.0)
+        phi_rtidal = potential(Rt)
+        thr = Rt if tidal_treatment == 0 else (1.5 - 3.0 * math.pow(math.log(GAMMA * N) / N, 0.25)) * phi_rtidal
+        Ds = []
+        for q in range(P):
+            s = states[q]
+            s["Rtidal"] = Rt
+            D = 0.0
+            for i in selects[q](thr):
+                m, f = star_m_ofs[q](i), star_fields_ofs[q](i)
+                s["Eescaped"] += f["E"] * m / N
+                s["Jescaped"] += f["J"] * m / N
+                if f["binind"] == 0:
+                    s["Eintescaped"] += f["Eint"]
+                else:
+                    b = binary_ofs[q](f["binind"])
+                    s["Ebescaped"] += -(b["m1"] / N) * (b["m2"] / N) / (2.0 * b["a"])
+                    s["Eintescaped"] += b["Eint1"] + b["Eint2"]
+                D += m / N
+                s["Etidal"] += f["E"] * m / N
+                s["stripped"].append(int(i))
+            Ds.append(D)
+        Dtot = Ds[0]
+        for q in range(1, P):
+            Dtot = Dtot + Ds[q]
+        for s in states:
+            s["passes"] += 1
+            s["TidalMassLoss"] += Dtot
+            s["DTidalMassLoss"] = Dtot
+        if not Dtot > 0:
+            break
+    for k in ("Eescaped", "Jescaped", "Eintescaped", "Ebescaped", "Etidal"):
+        tot = states[0][k]
+        for q in range(1, P):
+            tot = tot + states[q][k]
+        for s in states:
+            s[k] = tot
+    return states
 
 
 def clusdyn_calculate(star_r, star_m, N_STAR, Mtotal):

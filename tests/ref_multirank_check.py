@@ -88,6 +88,32 @@ def main(procs, N):
     for k in ol.SV3_IO:
         ok = ok and np.array_equal(io[rank][k].view(np.uint64), R.star_field(k)[1:nl + 1].view(np.uint64))
     ok = ok and R.L.ref_get_Eoops() == eoops[rank] and passes >= (2 if procs > 2 else 1)
+    # tidally_strip_stars (reference cmc_evolution_thr.c:443-645): per-rank passes, the stripped mass all-reduced per pass, the escaper sums
+    # all-reduced at the end
+    rng2 = np.random.default_rng(77)
+    Eg = -rng2.uniform(0.05, 1.0, N)
+    Eg[rng2.choice(N, N // 100, replace=False)] = -rng2.uniform(0.0, 2.8e-6, N // 100)      # around alpha * Phi(Rtidal) ~ -1.4e-6
+    fg = dict(E=Eg, J=rng2.uniform(0.0, 1.0, N), Eint=rng2.uniform(0.0, 1e-7, N), r_apo=rnew[order] * 2.0, rnew=rnew[order].copy(),
+              vrnew=vrs.copy(), vtnew=vts.copy())
+    for k, v in fg.items():
+        R.star_field(k)[1:nl + 1] = v[lo - 1:hi]
+    R.star_field("binind", np.int64)[1:nl + 1] = 0
+    smt = R.star_m()[:N + 2].copy()            # before the call: destroy_obj sets star_m[g] = DBL_MIN for the stars THIS rank strips
+    Rt, TML, DT = R.tidally_strip_stars(1)
+    sc = R.scalars()
+    parts = [{k: v[S[q] - 1:E[q]].copy() for k, v in fg.items()} for q in range(procs)]
+    states = [dict(Mtotal=sc["Mtotal"], TidalMassLoss=0.0, OldTidalMassLoss=0.0, Eescaped=0.0, Jescaped=0.0, Eintescaped=0.0, Ebescaped=0.0) for _ in range(procs)]
+    ol.tidally_strip_loop_ranks([(lambda thr, q=q: ol.tidally_strip_select(1, thr, parts[q])) for q in range(procs)],
+                                lambda x: ol.lib().orc_potential(C.byref(t), x),
+                                [(lambda i, q=q: smt[S[q] + i - 1]) for q in range(procs)],
+                                [(lambda i, q=q: dict(E=parts[q]["E"][i - 1], J=parts[q]["J"][i - 1], Eint=parts[q]["Eint"][i - 1], binind=0)) for q in range(procs)],
+                                [None] * procs, states, N, 1.0e6, 1, 0.11)
+    me = states[rank]
+    ok = ok and (Rt, TML) == (me["Rtidal"], me["TidalMassLoss"]) and me["passes"] >= 2 and len(me["stripped"]) > 3
+    for k in ("Eescaped", "Jescaped", "Eintescaped", "Etidal"):
+        ok = ok and sc[k] == me[k]
+    for k in ("rnew", "vrnew", "vtnew"):
+        ok = ok and np.array_equal(R.star_field(k)[1:nl + 1].view(np.uint64), parts[rank][k].view(np.uint64))
     if not ok:
         print(f"rank {rank}: MISMATCH", flush=True)
         sys.exit(3)
