@@ -232,10 +232,11 @@ class Cluster:
         return out
 
     def dev_tidally_strip_stars(self, tidal_treatment=1, GAMMA=0.11, cap=8192):
-        """tidally_strip_stars (reference src/cmc/cmc_evolution_thr.c:443-645) on the resident records, one rank.  The criterion runs on the
+        """tidally_strip_stars (reference src/cmc/cmc_evolution_thr.c:443-645) on the resident records.  The criterion runs on the
         device (one pass per call of cmcb200_dev_tidally_strip_select); this is the reference's host loop around it: Rtidal from the mass
         lost so far, the per-star sums in star order from the handful of stripped records the device hands back, repeated while a pass
-        strips anything.  Returns the 1-based local indices of all stripped stars."""
+        strips anything.  On several ranks (ShardedCluster) the stripped mass is summed over the ranks every pass and the escaper sums at the
+        end, as in the reference.  Returns the 1-based local indices of all stripped stars."""
         import math
         N = float(self.clus.N_STAR)
         if getattr(self, "_strip_buf", None) is None or len(self._strip_buf[0]) != cap:      # hand-back buffers, kept between calls
@@ -267,10 +268,19 @@ class Cluster:
                     D += m / N
                     self.Etidal += float(E[k]) * m / N
                 stripped.extend(int(i) for i in idx[:n])
+            D = self._allreduce_sum([D])[0]                           # :612-616 (one rank: the identity)
             self.TidalMassLoss += D                                   # :617
             self.DTidalMassLoss = D
             if not D > 0:                                             # :624
-                return stripped
+                break
+        # :626-644: the ranks' escaper sums become their totals
+        self.Eescaped, self.Jescaped, self.Eintescaped, self.Ebescaped, self.Etidal = self._allreduce_sum(
+            [self.Eescaped, self.Jescaped, self.Eintescaped, self.Ebescaped, self.Etidal])
+        return stripped
+
+    def _allreduce_sum(self, values):
+        """MPI_Allreduce(MPI_SUM) over the ranks of the run; one rank here (ShardedCluster overrides it)"""
+        return list(values)
 
     def dev_energy_new_radii(self):
         """energy_conservation2 and the EI loop of ComputeIntermediateEnergy from one potential(rnew) lookup per star; the transfer is left to

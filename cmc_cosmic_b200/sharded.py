@@ -209,6 +209,13 @@ class ShardedCluster(Cluster):
         self.Eoops += -E * (1.0 / self.clus.N_STAR)
         return rounds
 
+    def _allreduce_sum(self, values):
+        import torch
+        with torch.cuda.stream(self._tstream):
+            t = torch.tensor(list(values), dtype=torch.float64, device=f"cuda:{self.device}")
+            self.dist.all_reduce(t)
+            return [float(x) for x in t.cpu()]
+
     def orbit_params(self, draws=None, draw_off=None, seed=0, fuse_energy=False):
         n_old = int(self.End[self.myid] - self.Start[self.myid] + 1)
         n_new_stars = max(0, self.clus.N_MAX_NEW - n_old)

@@ -125,6 +125,60 @@ def run_sv3(rank, world, port, N):
     print(f"rank {rank}/{world}: set_velocities3 == oracle ranks (N={N}, rounds={rounds}, shard {lo}..{hi})", flush=True)
 
 
+def run_tidal(rank, world, port, N):
+    """tidally_strip_stars on `world` GPUs (criterion per shard on the device, the reference's loop in the host layer, the stripped mass and
+    the escaper sums all-reduced) against the oracle run as all ranks -- pinned against the ranks of the compiled reference in
+    tests/ref_multirank_check.py."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import common as cm
+    import oraclelib as ol
+    from cmc_cosmic_b200.sharded import ShardedCluster
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    orbit_r = 6.0
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=29, masses="imf")
+    pot = cm.oracle_potential(r, sm, N, orbit_r=orbit_r)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    rng = np.random.default_rng(8)
+    fg = dict(E=E, J=J, Eint=rng.uniform(0.0, 1e-7, N), r_apo=r * rng.uniform(1.0, 3.0, N), rnew=r.copy(), vrnew=vr.copy(), vtnew=vt.copy())
+    c = ShardedCluster(N, dist, device=rank, orbit_r=orbit_r)
+    c.load_global(r, vr, vt, sm)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    S, En = c.Start.copy(), c.End.copy()
+    lo, hi = int(S[rank]), int(En[rank])
+    nl = hi - lo + 1
+    for k, v in fg.items():
+        c.field(k)[1:nl + 1] = v[lo - 1:hi]
+    c.Mtotal = pot["Mtotal"]
+    c.upload()
+    stripped = c.dev_tidally_strip_stars(tidal_treatment=1)
+    c.download()
+    c.sync()
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    parts = [{k: v[S[q] - 1:En[q]].copy() for k, v in fg.items()} for q in range(world)]
+    states = [dict(Mtotal=pot["Mtotal"], TidalMassLoss=0.0, OldTidalMassLoss=0.0, Eescaped=0.0, Jescaped=0.0, Eintescaped=0.0, Ebescaped=0.0) for _ in range(world)]
+    ol.tidally_strip_loop_ranks([(lambda thr, q=q: ol.tidally_strip_select(1, thr, parts[q])) for q in range(world)],
+                                lambda x: ol.lib().orc_potential(ctypes.byref(t), x),
+                                [(lambda i, q=q: pot["star_m"][S[q] + i - 1]) for q in range(world)],
+                                [(lambda i, q=q: dict(E=parts[q]["E"][i - 1], J=parts[q]["J"][i - 1], Eint=parts[q]["Eint"][i - 1], binind=0)) for q in range(world)],
+                                [None] * world, states, N, orbit_r, 1, 0.11)
+    me = states[rank]
+    assert stripped == me["stripped"] and me["passes"] >= 2 and sum(len(s["stripped"]) for s in states) > 20
+    for k in ("Rtidal", "TidalMassLoss", "Eescaped", "Jescaped", "Eintescaped", "Etidal"):
+        assert getattr(c, k) == me[k], (k, getattr(c, k), me[k])
+    for k in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(c.field(k)[1:nl + 1], parts[rank][k], f"rank {rank}: {k}")
+    c.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank}/{world}: tidally_strip_stars == oracle ranks (N={N}, {len(stripped)} stripped here, {me['passes']} passes)", flush=True)
+
+
 if __name__ == "__main__":
     # torchrun entry: RANK / WORLD_SIZE / MASTER_PORT from the environment
     run(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("MASTER_PORT", "29511")),

@@ -38,3 +38,11 @@ def test_sharded_energy_scheme_velocity_correction(world, N):
     if world > _n_gpus():
         pytest.skip(f"needs {world} GPUs")
     mp.spawn(sharded_worker.run_sv3, args=(world, 29540 + world, N), nprocs=world, join=True)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_sharded_tidally_strip_stars():
+    """tidally_strip_stars across ranks (reference cmc_evolution_thr.c:443-645): per-shard passes, all-reduced mass loss and escaper sums"""
+    import torch.multiprocessing as mp
+    import sharded_worker
+    mp.spawn(sharded_worker.run_tidal, args=(2, 29561, 100000), nprocs=2, join=True)
