@@ -656,6 +656,29 @@ long orc_tidally_strip_select(long n_local, int tidal_treatment, double threshol
 	return count;
 }
 
+/* ---- ComputeEnergy's second loop, src/cmc/cmc_utils.c:619-636: the rank's energy sums ----------------------------------------------------- */
+
+void orc_compute_energy_totals(const orc_tables_t *t, long n_local, long first_global, const double *vr, const double *vt, const double *Eint,
+			       const long *binind, const int *bin_inuse, const double *bin_m1, const double *bin_m2, const double *bin_a,
+			       const double *bin_Eint1, const double *bin_Eint2, double out[4])
+{
+	const double phi0 = t->phi[0];
+	double K = 0.0, P = 0.0, Ei = 0.0, Eb = 0.0;
+	for (long i = 1; i <= n_local; i++) {
+		const long j = first_global + i - 1;
+		K += 0.5 * (vr[i - 1] * vr[i - 1] + vt[i - 1] * vt[i - 1]) * t->m[j] * t->madhoc;
+		P += t->phi[j] * t->m[j] * t->madhoc;
+		P += phi0 * t->cenma_m * t->madhoc / t->N_MAX;
+		const long b = binind[i - 1];
+		if (b == 0) Ei += Eint[i - 1];
+		else if (bin_inuse[b]) {
+			Eb += -(bin_m1[b] * t->madhoc) * (bin_m2[b] * t->madhoc) / (2.0 * bin_a[b]);
+			Ei += bin_Eint1[b] + bin_Eint2[b];
+		}
+	}
+	out[0] = K; out[1] = P; out[2] = Ei; out[3] = Eb; /* the caller: P *= 0.5, tot = K + P + Eint + Eb, Allreduce, + cenma.E + escaped (:638-655) */
+}
+
 /* clusdyn_calculate, src/cmc/cmc_utils.c:1613-1624 */
 double orc_clusdyn_calculate(const double *star_r, const double *star_m, long N_STAR, double Mtotal)
 {

@@ -129,6 +129,14 @@ void orc_calc_sigma_r(long p, long n_limit, long first_global, long N_MAX, int i
 long orc_tidally_strip_select(long n_local, int tidal_treatment, double threshold, const double *r_apo, const double *E, double *rnew,
 			      double *vrnew, double *vtnew, long *idx_out);
 
+/* ComputeEnergy's second loop, src/cmc/cmc_utils.c:619-636: the four sequentially summed energies of one rank's stars -- out[0] kinetic
+ * (buf_reduce[1]), out[1] potential BEFORE the factor 0.5 (buf_reduce[2]: two additions per star, the star's own term and the central
+ * mass's share), out[2] internal (buf_reduce[3]), out[3] binary binding (buf_reduce[4]).  binind[i-1] of local star i; the bin_* arrays
+ * are indexed by binind (entry 0 unused). */
+void orc_compute_energy_totals(const orc_tables_t *t, long n_local, long first_global, const double *vr, const double *vt, const double *Eint,
+			       const long *binind, const int *bin_inuse, const double *bin_m1, const double *bin_m2, const double *bin_a,
+			       const double *bin_Eint1, const double *bin_Eint2, double out[4]);
+
 /* comp_mass_percent, src/cmc/cmc_utils.c:872-985: Lagrange radii and the cumulative kinetic sums at them, as ONE rank of P sees it.
  *   star_r, star_m: the replicated tables; vr, vt: star[k].vr / .vt of this rank's local stars k = 1..n_local at vr[k-1], vt[k-1];
  *   first_global = Start[myid] (global index of local star 1; the function is called after the sort, so there are no new stars).

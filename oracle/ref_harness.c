@@ -235,6 +235,9 @@ EXPORT void ref_tidally_strip_stars(long treatment, double gamma, double *out)
 	out[0] = Rtidal; out[1] = TidalMassLoss; out[2] = DTidalMassLoss;
 }
 
+/* Etotal after ComputeEnergy (src/cmc/cmc_utils.c:604-656): tot, K, P, Eint, Eb */
+EXPORT void ref_get_etotal(double *out) { out[0] = Etotal.tot; out[1] = Etotal.K; out[2] = Etotal.P; out[3] = Etotal.Eint; out[4] = Etotal.Eb; }
+
 /* comp_mass_percent (src/cmc/cmc_utils.c:872-985) on the harness's cluster state: thresholds in, the eight result arrays out
  * (out[8][count], in the order mass_r, ave_mass_r, no_star_r, densities_r, ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r; on ranks other than 0
  * the last four hold what that rank computed, i.e. nothing meaningful -- the reference prints from rank 0 only). */

@@ -61,6 +61,7 @@ def lib():
         L.orc_calc_sigma_r.argtypes = [C.c_long] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
         L.orc_tidally_strip_select.restype = C.c_long
         L.orc_tidally_strip_select.argtypes = [C.c_long, C.c_int, C.c_double] + [C.c_void_p] * 6
+        L.orc_compute_energy_totals.argtypes = [C.POINTER(Tables), C.c_long, C.c_long] + [C.c_void_p] * 11
         L.orc_clusdyn_calculate.restype = C.c_double
         L.orc_clusdyn_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double]
         L.orc_comp_mass_percent.restype = C.c_long
@@ -325,6 +326,18 @@ def tidally_strip_loop_ranks(selects, potential, star_m_ofs, star_fields_ofs, bi
         for s in states:
             s[k] = tot
     return states
+
+
+def compute_energy_totals(t, first_global, vr, vt, Eint, binind, bins):
+    """(K, P before the factor 0.5, Eint, Eb) of ComputeEnergy's second loop (reference cmc_utils.c:619-636) over one rank's stars;
+    bins: dict of arrays indexed by binind (inuse int32, m1, m2, a, Eint1, Eint2)"""
+    vr, vt, Eint = (np.ascontiguousarray(x, np.float64) for x in (vr, vt, Eint))
+    binind = np.ascontiguousarray(binind, np.int64)
+    b = {k: np.ascontiguousarray(bins[k], np.int32 if k == "inuse" else np.float64) for k in ("inuse", "m1", "m2", "a", "Eint1", "Eint2")}
+    out = np.zeros(4)
+    lib().orc_compute_energy_totals(C.byref(t), len(vr), first_global, _p(vr), _p(vt), _p(Eint), _p(binind), _p(b["inuse"]), _p(b["m1"]), _p(b["m2"]),
+                                    _p(b["a"]), _p(b["Eint1"]), _p(b["Eint2"]), _p(out))
+    return out
 
 
 def clusdyn_calculate(star_r, star_m, N_STAR, Mtotal):

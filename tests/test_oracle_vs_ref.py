@@ -201,6 +201,39 @@ def test_tidally_strip_stars(R, treatment, orbit_r):
     R.free()
 
 
+@pytest.mark.parametrize("cenma", [0.0, 25.0])
+def test_compute_energy_totals(R, cenma):
+    """ComputeEnergy's energy sums (reference cmc_utils.c:619-655) against the restatement: kinetic, potential (two additions per star),
+    internal and binary binding energy, singles, binaries in use and destroyed binaries"""
+    N, nb = 20000, 900
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=33, masses="imf")
+    rng = np.random.default_rng(9)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    R.init(N, n_star_dim=N + 64, n_bin_dim=nb + 8)
+    R.load_cluster(r, vr, vt, sm, binind=binind)
+    bb = R.binary_bytes()
+    bf = {k: layout.binary_field(bb, k) for k in ("m1", "m2", "a", "Eint1", "Eint2", "inuse")}
+    for k, lo, hi in (("m1", 0.1, 5.0), ("m2", 0.1, 5.0), ("a", 1e-6, 1e-3), ("Eint1", 0.0, 1e-7), ("Eint2", 0.0, 1e-7)):
+        bf[k][1:nb + 1] = rng.uniform(lo, hi, nb)
+    bf["inuse"][1:nb + 1] = (rng.uniform(size=nb) < 0.9).astype(np.int32)
+    Eint = rng.uniform(0.0, 1e-7, N)
+    R.star_field("Eint")[1:N + 1] = Eint
+    R.set_scalars(N, N, N_BINARY=nb, cenma_m=cenma)
+    R.L.ref_calc_potential_new()
+    R.L.ref_compute_energy()
+    et = np.zeros(5)
+    R.L.ref_get_etotal.argtypes = [C.c_void_p]
+    R.L.ref_get_etotal(et.ctypes.data)
+    t = ol.tables(R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy(), N, N, cenma)
+    K, P, Ei, Eb = ol.compute_energy_totals(t, 1, vr, vt, Eint, binind, {k: v[:nb + 1].copy() for k, v in bf.items()})
+    sc = R.scalars()
+    assert (K, 0.5 * P, Ei, Eb) == (et[1], et[2], et[3], et[4])
+    assert et[0] == (K + 0.5 * P + Ei + Eb) + (0.0 + sc["Eescaped"] + sc["Ebescaped"] + sc["Eintescaped"])      # cenma.E = 0 here
+    assert K > 0 and P < 0 and Ei > 0 and Eb < 0
+    R.free()
+
+
 def test_sort_with_binaries_and_stripped_stars(R):
     n, nb, n_strip = 20000, 1500, 23
     rng = np.random.default_rng(8)
