@@ -361,6 +361,20 @@ class Cluster:
     def dev_compute_energy(self):
         _lib.check(self.L.cmcb200_dev_compute_energy(self.ctx, self.clus.N_MAX, 1), "dev_compute_energy")
 
+    def dev_compute_energy_totals(self):
+        """The second loop of ComputeEnergy (reference src/cmc/cmc_utils.c:619-655) on the resident arrays: Etotal.K / .P / .Eint / .Eb / .tot
+        as a SimpleNamespace (one rank; cenma.E is the caller's)."""
+        out = np.zeros(4)
+        _lib.check(self.L.cmcb200_dev_compute_energy_totals(self.ctx, self.clus.N_MAX_NEW, int(self.Start[self.myid]), self.clus.N_MAX, self.clus.N_STAR,
+                                                            self.cenma.m, out.ctypes.data), "dev_compute_energy_totals")
+        K, P, Eint, Eb = (float(x) for x in self._allreduce_sum([out[0], 0.5 * out[1], out[2], out[3]]))
+        tot = K + P + Eint + Eb
+        if self.procs > 1:
+            tot = self._allreduce_sum([float(out[0]) + 0.5 * float(out[1]) + float(out[2]) + float(out[3])])[0]   # buf_reduce[0] is reduced on its own (:640)
+        tot += getattr(self.cenma, "E", 0.0) + self.Eescaped + self.Ebescaped + self.Eintescaped                    # :655
+        self.Etotal = SimpleNamespace(tot=tot, K=K, P=P, Eint=Eint, Eb=Eb)
+        return self.Etotal
+
     def dev_step(self, seed=0, draws=None, draw_off=None, fused=True):
         """One pass of the hot path on the resident arrays: (E, J from the potential ->) orbit step -> r <- rnew -> sort -> potential.
         fused: the r <- rnew transfer rides on the sort's record gather and E, J are computed inside the orbit step; the unfused form

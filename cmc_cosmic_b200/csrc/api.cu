@@ -163,6 +163,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
 	if (c->d_lagrange) cudaFree(c->d_lagrange);
 	if (c->d_sv3) cudaFree(c->d_sv3);
+	if (c->d_seqwork2) cudaFree(c->d_seqwork2);
 	if (c->d_draws) cudaFree(c->d_draws);
 	if (c->d_draw_off) cudaFree(c->d_draw_off);
 	cudaFreeHost(c->h_pinned);

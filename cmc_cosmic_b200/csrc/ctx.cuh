@@ -58,6 +58,7 @@ struct cmcb200_ctx {
 	// orbit scratch
 	OrbitStats *d_ostats;
 	void *d_lagrange; // device result block of comp_mass_percent (lagrange.cu), allocated on first use
+	void *d_seqwork2; // exact-scan scratch for chains of 2 n_star_dim elements (ComputeEnergy's potential sum), allocated on first use
 	void *d_sv3;      // scratch of set_velocities3 (velocities.cu), allocated on first use for n_star_dim stars
 	int *d_status;
 	long *d_kmin, *d_kmax;

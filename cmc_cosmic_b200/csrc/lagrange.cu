@@ -190,3 +190,88 @@ extern "C" int cmcb200_dev_comp_mass_percent(cmcb200_ctx *c, const cmcb200_mass_
 	res->filled = h.n_filled;
 	return 0;
 }
+
+// ---- ComputeEnergy's second loop (reference src/cmc/cmc_utils.c:619-636): the rank's energy sums ---------------------------------------------
+// Four sequentially summed scalars over the local stars: kinetic, potential (two additions per star), internal, binary binding.  Each is a
+// chain of same-signed terms, summed on its magnitudes (fl(-x - a) = -fl(x + a)) through the exact scan; an element of the other sign
+// is an event and takes the hardware rounding.  Only the final values are wanted: store() is empty.
+namespace cmcb {
+
+struct EtotArgs {
+	const char *star1, *bin1;
+	const double *m, *phi;
+	long n, first_global;
+	double madhoc, cenma_m, n_max;
+};
+// WHICH: 0 kinetic, 1 potential (2 elements per star), 2 internal, 3 binding, 4 potential without a central mass (its share of every star is
+// +-0: one element per star)
+template <int WHICH>
+struct ChainEtot {
+	static constexpr int SIGN = +1;
+	EtotArgs a;
+	__device__ long length() const { return WHICH == 1 ? 2 * a.n : a.n; }
+	__device__ double y0() const { return 0.0; }
+	__device__ void store(long, double) const {}
+	__device__ double term(long e) const
+	{
+		const long i = WHICH == 1 ? e >> 1 : e;
+		if (WHICH == 4) return -dmul(dmul(a.phi[a.first_global + i], a.m[a.first_global + i]), a.madhoc);                        // :622
+		const char *rec = a.star1 + i * CMCB_SIZEOF_STAR;
+		const long j = a.first_global + i;
+		if (WHICH == 0) {
+			const double vr = *(const double *) (rec + CMCB_OFF_VR), vt = *(const double *) (rec + CMCB_OFF_VT);
+			return dmul(dmul(dmul(0.5, dadd(dmul(vr, vr), dmul(vt, vt))), a.m[j]), a.madhoc);                 // :621
+		}
+		if (WHICH == 1) {
+			if (!(e & 1)) return -dmul(dmul(a.phi[j], a.m[j]), a.madhoc);                                     // :622
+			return -ddiv(dmul(dmul(a.phi[0], a.cenma_m), a.madhoc), a.n_max);                                  // :623
+		}
+		const long b = *(const long *) (rec + CMCB_OFF_BININD);
+		if (b == 0) return WHICH == 2 ? *(const double *) (rec + CMCB_OFF_EINT) : 0.0;                            // :625-626
+		const char *bin = a.bin1 + (b - 1) * CMCB_SIZEOF_BINARY;
+		if (!*(const int *) (bin + 80 /* inuse */)) return 0.0;                                                    // :627
+		if (WHICH == 2) return dadd(*(const double *) (bin + 48 /* Eint1 */), *(const double *) (bin + 56 /* Eint2 */)); // :630
+		return ddiv(dmul(dmul(*(const double *) (bin + 32 /* m1 */), a.madhoc), dmul(*(const double *) (bin + 40 /* m2 */), a.madhoc)),
+			    dmul(2.0, *(const double *) (bin + 64 /* a */)));                                               // -(:628-629)
+	}
+};
+
+} // namespace cmcb
+
+extern "C" int cmcb200_dev_compute_energy_totals(cmcb200_ctx *c, long n_local, long first_global, long N_MAX, long N_STAR, double cenma_m, double out[4])
+{
+	if (n_local + 2 > c->n_star_dim || first_global + n_local > c->n_table_dim) { set_error("ComputeEnergy: sizes exceed the context capacity"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
+	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
+	CMCB_CUDA_OK(cudaMemsetAsync(d->totals, 0, sizeof(d->totals), c->stream));
+	EtotArgs a{star1(c), bin1(c), c->d_m, c->d_phi, n_local, first_global, 1.0 / ((double) N_STAR), cenma_m, (double) N_MAX};
+	const int grid = NUM_SMS_B200 * 4;
+	if (n_local > 0) {
+		StageTimer t(c, ST_ENERGY);
+		seq_scan_launch(ChainEtot<0>{a}, c->seqwork, n_local, &d->totals[0], grid, grid, c->stream);
+		if (cenma_m == 0.0) seq_scan_launch(ChainEtot<4>{a}, c->seqwork, n_local, &d->totals[1], grid, grid, c->stream);
+		else { // two additions per star: a scan twice as long as the tables the shared scratch was sized for
+			if (!c->d_seqwork2) {
+				const size_t wb = pot_work_bytes(2 * c->n_star_dim);
+				CMCB_CUDA_OK(cudaMalloc(&c->d_seqwork2, wb));
+				CMCB_CUDA_OK(cudaMemsetAsync(c->d_seqwork2, 0, wb, c->stream));
+			}
+			SeqWork w2;
+			pot_work_bind(w2, c->d_seqwork2, 2 * c->n_star_dim);
+			seq_scan_launch(ChainEtot<1>{a}, w2, 2 * n_local, &d->totals[1], grid, grid, c->stream);
+		}
+		seq_scan_launch(ChainEtot<2>{a}, c->seqwork, n_local, &d->totals[2], grid, grid, c->stream);
+		seq_scan_launch(ChainEtot<3>{a}, c->seqwork, n_local, &d->totals[3], grid, grid, c->stream);
+		c->launches += 16;
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	double *h = (double *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, d->totals, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	out[0] = h[0];
+	out[1] = h[1] == 0.0 ? 0.0 : -h[1]; // the potential and binding sums were taken on their magnitudes
+	out[2] = h[2];
+	out[3] = h[3] == 0.0 ? 0.0 : -h[3];
+	return 0;
+}

@@ -45,7 +45,7 @@ EXPORTS = [
     "cmcb200_potential_stats", "cmcb200_launch_count", "cmcb200_host_register", "cmcb200_host_unregister", "cmcb200_transfer_bytes",
     "cmcb200_dev_comp_mass_percent", "cmcb200_dev_clusdyn_calculate", "cmcb200_dev_energy_conservation2", "cmcb200_dev_compute_intermediate_energy",
     "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass", "cmcb200_dev_energy_new_radii",
-    "cmcb200_dev_potential", "cmcb200_dev_tidally_strip_select",
+    "cmcb200_dev_potential", "cmcb200_dev_tidally_strip_select", "cmcb200_dev_compute_energy_totals",
 ]
 
 
@@ -102,6 +102,7 @@ def load():
     L.cmcb200_dev_compute_intermediate_energy.argtypes = [vp, C.POINTER(OrbitParams)]
     L.cmcb200_dev_energy_conservation1.argtypes = [vp, C.POINTER(OrbitParams)]
     L.cmcb200_dev_energy_new_radii.argtypes = [vp, C.POINTER(OrbitParams)]
+    L.cmcb200_dev_compute_energy_totals.argtypes = [vp, lg, lg, lg, lg, dbl, vp]
     L.cmcb200_dev_potential.argtypes = [vp, C.POINTER(OrbitParams), vp, lg, vp]
     L.cmcb200_dev_tidally_strip_select.argtypes = [vp, C.POINTER(OrbitParams), C.c_int, dbl, vp, lg, pl, vp, vp]
     L.cmcb200_dev_set_velocities3.argtypes = [vp, C.POINTER(OrbitParams), C.POINTER(dbl)]

@@ -203,6 +203,11 @@ int cmcb200_dev_calc_potential_new(cmcb200_ctx *ctx, long *N_MAX, long N_STAR, d
 				   double *Mtotal, double *Rtidal);
 /* E, J of every star from the new potential: the first loop of ComputeEnergy (src/cmc/cmc_utils.c:612-616) */
 int cmcb200_dev_compute_energy(cmcb200_ctx *ctx, long n_local, long first_global);
+/* The second loop of ComputeEnergy (:619-636): this rank's sequentially summed energies, bit for bit -- out[0] kinetic (buf_reduce[1]),
+ * out[1] potential before the factor 0.5 (buf_reduce[2]), out[2] internal (buf_reduce[3]), out[3] binary binding (buf_reduce[4]).  The
+ * caller finishes like the reference (:638-655): out[1] *= 0.5, tot = the four added in that order, MPI_Allreduce, + cenma.E + the
+ * escaped energies. */
+int cmcb200_dev_compute_energy_totals(cmcb200_ctx *ctx, long n_local, long first_global, long N_MAX, long N_STAR, double cenma_m, double out[4]);
 /* per-star outputs of the last dev orbit step (status needs want_status) */
 int cmcb200_dev_read_status(cmcb200_ctx *ctx, int *status, long *kmin, long *kmax, long n_local);
 /* wait for everything queued on the context's stream */

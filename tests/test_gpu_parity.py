@@ -617,6 +617,38 @@ def test_tidally_strip_stars_bit_exact(treatment, orbit_r):
     c.close()
 
 
+@pytest.mark.parametrize("cenma,N", [(0.0, 60000), (25.0, 60000), (0.0, 1500000)])
+def test_compute_energy_totals_bit_exact(cenma, N):
+    """The second loop of ComputeEnergy (reference cmc_utils.c:619-655) on the resident arrays: four sequentially summed energies through
+    the exact scan (the potential sum takes two additions per star when there is a central mass), singles, binaries in use and
+    destroyed binaries, against the oracle (pinned against the compiled reference in test_oracle_vs_ref.py::test_compute_energy_totals)"""
+    nb = N // 20
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=35, masses="imf")
+    rng = np.random.default_rng(10)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    bins = {k: np.concatenate([[0.0], rng.uniform(lo, hi, nb)]) for k, lo, hi in (("m1", 0.1, 5.0), ("m2", 0.1, 5.0), ("a", 1e-6, 1e-3),
+                                                                                  ("Eint1", 0.0, 1e-7), ("Eint2", 0.0, 1e-7))}
+    bins["inuse"] = np.concatenate([[0], (rng.uniform(size=nb) < 0.9)]).astype(np.int32)
+    Eint = rng.uniform(0.0, 1e-7, N)
+    c = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8)
+    c.load(r, vr, vt, sm, binind=binind)
+    c.field("Eint")[1:N + 1] = Eint
+    for k, v in bins.items():
+        c.bfield(k)[:nb + 1] = v
+    c.cenma.m = cenma
+    c.calc_potential_new()
+    c.upload()
+    c.Eescaped, c.Ebescaped, c.Eintescaped = -0.001, -0.002, 0.0005
+    et = c.dev_compute_energy_totals()
+    t = ol.tables(c.star_r[:N + 2].copy(), c.star_m[:N + 2].copy(), c.star_phi[:N + 2].copy(), N, N, c.cenma.m)
+    K, P, Ei, Eb = ol.compute_energy_totals(t, 1, vr, vt, Eint, binind, bins)
+    assert (et.K, et.P, et.Eint, et.Eb) == (K, 0.5 * P, Ei, Eb), ((et.K, et.P, et.Eint, et.Eb), (K, 0.5 * P, Ei, Eb))
+    assert et.tot == (K + 0.5 * P + Ei + Eb) + (0.0 + -0.001 + -0.002 + 0.0005)
+    assert K > 0 and P < 0 and Ei > 0 and Eb < 0
+    c.close()
+
+
 def test_lagrange_radii_of_a_run_agree_statistically_with_the_reference_run():
     """north_star: "Lagrangian radii from a full run must statistically agree with the reference run".  Six timesteps of the path
     (orbit step -> r <- rnew -> sort -> potential -> E, J) from the same Plummer state: the CUDA pipeline with its production draws
