@@ -679,6 +679,55 @@ void orc_compute_energy_totals(const orc_tables_t *t, long n_local, long first_g
 	out[0] = K; out[1] = P; out[2] = Ei; out[3] = Eb; /* the caller: P *= 0.5, tot = K + P + Eint + Eb, Allreduce, + cenma.E + escaped (:638-655) */
 }
 
+/* ---- comp_multi_mass_percent, src/cmc/cmc_utils.c:769-861 (+ find_stars_mass_bin :755-764, m_binsearch include/common/gensearch.h) ------- */
+
+static long orc_mass_bin(const double *mass_bins, long n_bins, double smass)
+{
+	if (smass < mass_bins[0] || smass > mass_bins[n_bins - 1]) return -1;
+	long lo = 0, hi = n_bins - 1; /* largest index with mass_bins[index] < smass (ascending bins) */
+	do {
+		const long k = (lo + hi + 1) / 2;
+		if (mass_bins[k] < smass) lo = k; else hi = k - 1;
+	} while (hi != lo);
+	return lo;
+}
+
+void orc_comp_multi_mass_percent(const double *star_r, const double *star_m, long N_MAX, const double *mass_bins, long n_bins, double solar_mass_dyn,
+				 const double *mass_pc, long count, double *multi_mass_r /* [n_bins][count] */)
+{
+	if (n_bins <= 1) return;
+	for (long b = 0; b < n_bins; b++) {
+		/* :787-793 the bin's total mass, star count and last radius, summed in star order */
+		double mtotal = 0.0, r_last = 0.0;
+		long number = 0;
+		for (long i = 1; i <= N_MAX; i++)
+			if (orc_mass_bin(mass_bins, n_bins, star_m[i] / solar_mass_dyn) == b) { mtotal += star_m[i]; number++; r_last = star_r[i]; }
+		if (number == 0) continue;
+		if (number == 1) { for (long c = 0; c < count; c++) multi_mass_r[b * count + c] = r_last; continue; } /* :836-839 */
+		/* :808-818 (rs, percents) with the (0, 0) point, then gsl_interp_linear of rs over percents at mass_pc (:840-844) */
+		for (long c = 0; c < count; c++) {
+			const double x = mass_pc[c];
+			double mcount = 0.0, x_lo = 0.0, y_lo = 0.0, val = 0.0;
+			int found = 0;
+			long seen = 0;
+			for (long i = 1; i <= N_MAX && !found; i++) {
+				if (orc_mass_bin(mass_bins, n_bins, star_m[i] / solar_mass_dyn) != b) continue;
+				mcount += star_m[i];
+				seen++;
+				const double x_hi = mcount / mtotal, y_hi = star_r[i];
+				/* gsl_interp_bsearch: the interval [x_lo, x_hi) holding x, the last one closed */
+				if (x < x_hi || seen == number) {
+					const double dx = x_hi - x_lo;
+					val = dx > 0.0 ? y_lo + (x - x_lo) / dx * (y_hi - y_lo) : 0.0;
+					found = 1;
+				}
+				x_lo = x_hi; y_lo = y_hi;
+			}
+			multi_mass_r[b * count + c] = (x < 0.0 || x > 1.0) ? NAN : val;
+		}
+	}
+}
+
 /* clusdyn_calculate, src/cmc/cmc_utils.c:1613-1624 */
 double orc_clusdyn_calculate(const double *star_r, const double *star_m, long N_STAR, double Mtotal)
 {

@@ -137,6 +137,14 @@ void orc_compute_energy_totals(const orc_tables_t *t, long n_local, long first_g
 			       const long *binind, const int *bin_inuse, const double *bin_m1, const double *bin_m2, const double *bin_a,
 			       const double *bin_Eint1, const double *bin_Eint2, double out[4]);
 
+/* comp_multi_mass_percent, src/cmc/cmc_utils.c:769-861: Lagrange radii per mass bin.  A star belongs to bin b when mass_bins[b] <
+ * star_m/SOLAR_MASS_DYN <= mass_bins[b+1] (find_stars_mass_bin: m_binsearch, stars outside [bins[0], bins[n-1]] belong to none); per bin the
+ * cumulative mass fraction in star order (sequential sums) against the radius, linearly interpolated at mass_pc (gsl_interp_linear of the
+ * un-vendored GSL, restated: PARITY UNPINNED for the interpolation step).  multi_mass_r[n_bins][count]: entries of empty bins are left
+ * untouched, a bin of one star gets that star's radius. */
+void orc_comp_multi_mass_percent(const double *star_r, const double *star_m, long N_MAX, const double *mass_bins, long n_bins, double solar_mass_dyn,
+				 const double *mass_pc, long count, double *multi_mass_r);
+
 /* comp_mass_percent, src/cmc/cmc_utils.c:872-985: Lagrange radii and the cumulative kinetic sums at them, as ONE rank of P sees it.
  *   star_r, star_m: the replicated tables; vr, vt: star[k].vr / .vt of this rank's local stars k = 1..n_local at vr[k-1], vt[k-1];
  *   first_global = Start[myid] (global index of local star 1; the function is called after the sort, so there are no new stars).

@@ -238,6 +238,23 @@ EXPORT void ref_tidally_strip_stars(long treatment, double gamma, double *out)
 /* Etotal after ComputeEnergy (src/cmc/cmc_utils.c:604-656): tot, K, P, Eint, Eb */
 EXPORT void ref_get_etotal(double *out) { out[0] = Etotal.tot; out[1] = Etotal.K; out[2] = Etotal.P; out[3] = Etotal.Eint; out[4] = Etotal.Eb; }
 
+/* comp_multi_mass_percent (src/cmc/cmc_utils.c:769-861) on the harness's tables: out[n_bins][count] (entries of empty bins stay -1) */
+EXPORT void ref_comp_multi_mass_percent(const double *bins, long n_bins, double solar_mass_dyn, const double *pc, long count, double *out)
+{
+	long i, j;
+	NO_MASS_BINS = n_bins; SOLAR_MASS_DYN = solar_mass_dyn; MASS_PC_COUNT = count;
+	mass_bins = (double *) malloc(n_bins * sizeof(double));
+	mass_pc = (double *) malloc(count * sizeof(double));
+	memcpy(mass_bins, bins, n_bins * sizeof(double));
+	memcpy(mass_pc, pc, count * sizeof(double));
+	multi_mass_r = (double **) malloc(n_bins * sizeof(double *));
+	for (i = 0; i < n_bins; i++) { multi_mass_r[i] = (double *) malloc(count * sizeof(double)); for (j = 0; j < count; j++) multi_mass_r[i][j] = -1.0; }
+	comp_multi_mass_percent();
+	for (i = 0; i < n_bins; i++) { memcpy(out + i * count, multi_mass_r[i], count * sizeof(double)); free(multi_mass_r[i]); }
+	free(multi_mass_r); free(mass_bins); free(mass_pc);
+	multi_mass_r = NULL; mass_bins = NULL; mass_pc = NULL;
+}
+
 /* comp_mass_percent (src/cmc/cmc_utils.c:872-985) on the harness's cluster state: thresholds in, the eight result arrays out
  * (out[8][count], in the order mass_r, ave_mass_r, no_star_r, densities_r, ke_rad_r, ke_tan_r, v2_rad_r, v2_tan_r; on ranks other than 0
  * the last four hold what that rank computed, i.e. nothing meaningful -- the reference prints from rank 0 only). */

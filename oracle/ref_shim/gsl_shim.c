@@ -110,3 +110,45 @@ int gsl_root_test_delta(double x1, double x0, double epsabs, double epsrel)
 double fb_sqr(double x) { return x * x; }
 /* reference cmc_io.c close_buffers(): flushes log files on abnormal exit; nothing is open here */
 void close_buffers(void) {}
+
+/* ---- gsl_spline with gsl_interp_linear, as comp_multi_mass_percent uses it (reference src/cmc/cmc_utils.c:820-848) -------------------------
+ * GSL is un-vendored and its version unpinned (CMakeLists.txt:62): this restates the published algorithm of interpolation/linear.c
+ * (linear_eval) and interpolation/bsearch.c (gsl_interp_bsearch: the index i with x[i] <= x < x[i+1], the last interval closed) -- "parity
+ * unpinned" for whatever goes through it. */
+#include <stdlib.h>
+#include <string.h>
+#include "gsl/gsl_spline.h"
+static const gsl_interp_type shim_linear = {"linear"}, shim_cspline = {"cspline"};
+const gsl_interp_type *gsl_interp_linear = &shim_linear;
+const gsl_interp_type *gsl_interp_cspline = &shim_cspline;
+gsl_interp_accel *gsl_interp_accel_alloc(void) { return calloc(1, sizeof(gsl_interp_accel)); }
+void gsl_interp_accel_free(gsl_interp_accel *a) { free(a); }
+gsl_spline *gsl_spline_alloc(const gsl_interp_type *T, size_t size)
+{
+	gsl_spline *s = calloc(1, sizeof(*s));
+	s->type = T; s->size = size;
+	s->x = malloc(size * sizeof(double)); s->y = malloc(size * sizeof(double));
+	return s;
+}
+int gsl_spline_init(gsl_spline *s, const double *x, const double *y, size_t size)
+{
+	memcpy(s->x, x, size * sizeof(double));
+	memcpy(s->y, y, size * sizeof(double));
+	return GSL_SUCCESS;
+}
+double gsl_spline_eval(const gsl_spline *s, double x, gsl_interp_accel *a)
+{
+	size_t ilo = 0, ihi = s->size - 1;
+	(void) a; /* the accelerator only caches the index the search below returns */
+	if (x < s->x[0] || x > s->x[s->size - 1]) return NAN; /* GSL_EDOM -> GSL_NAN */
+	while (ihi > ilo + 1) {
+		size_t i = (ihi + ilo) / 2;
+		if (s->x[i] > x) ihi = i; else ilo = i;
+	}
+	{
+		const double x_lo = s->x[ilo], x_hi = s->x[ilo + 1], y_lo = s->y[ilo], y_hi = s->y[ilo + 1], dx = x_hi - x_lo;
+		if (dx > 0.0) return y_lo + (x - x_lo) / dx * (y_hi - y_lo);
+		return 0.0; /* GSL_EINVAL */
+	}
+}
+void gsl_spline_free(gsl_spline *s) { free(s->x); free(s->y); free(s); }

@@ -62,6 +62,7 @@ def lib():
         L.orc_tidally_strip_select.restype = C.c_long
         L.orc_tidally_strip_select.argtypes = [C.c_long, C.c_int, C.c_double] + [C.c_void_p] * 6
         L.orc_compute_energy_totals.argtypes = [C.POINTER(Tables), C.c_long, C.c_long] + [C.c_void_p] * 11
+        L.orc_comp_multi_mass_percent.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_long, C.c_void_p]
         L.orc_clusdyn_calculate.restype = C.c_double
         L.orc_clusdyn_calculate.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double]
         L.orc_comp_mass_percent.restype = C.c_long
@@ -337,6 +338,14 @@ def compute_energy_totals(t, first_global, vr, vt, Eint, binind, bins):
     out = np.zeros(4)
     lib().orc_compute_energy_totals(C.byref(t), len(vr), first_global, _p(vr), _p(vt), _p(Eint), _p(binind), _p(b["inuse"]), _p(b["m1"]), _p(b["m2"]),
                                     _p(b["a"]), _p(b["Eint1"]), _p(b["Eint2"]), _p(out))
+    return out
+
+
+def comp_multi_mass_percent(star_r, star_m, N_MAX, mass_bins, solar_mass_dyn, mass_pc):
+    """Lagrange radii per mass bin (reference cmc_utils.c:769-861) -> [n_bins, count]; entries of empty bins stay -1"""
+    bins, pc = np.ascontiguousarray(mass_bins, np.float64), np.ascontiguousarray(mass_pc, np.float64)
+    out = np.full((len(bins), len(pc)), -1.0)
+    lib().orc_comp_multi_mass_percent(_p(star_r), _p(star_m), N_MAX, _p(bins), len(bins), solar_mass_dyn, _p(pc), len(pc), _p(out))
     return out
 
 

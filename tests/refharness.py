@@ -166,6 +166,14 @@ class Ref:
         self.L.ref_tidally_strip_stars(treatment, gamma, out.ctypes.data)
         return tuple(out)
 
+    def comp_multi_mass_percent(self, mass_bins, solar_mass_dyn, mass_pc):
+        """the reference's comp_multi_mass_percent (cmc_utils.c:769-861) on the harness's tables -> [n_bins, count]"""
+        bins, pc = np.ascontiguousarray(mass_bins, np.float64), np.ascontiguousarray(mass_pc, np.float64)
+        out = np.zeros((len(bins), len(pc)))
+        self.L.ref_comp_multi_mass_percent.argtypes = [C.c_void_p, C.c_long, C.c_double, C.c_void_p, C.c_long, C.c_void_p]
+        self.L.ref_comp_multi_mass_percent(bins.ctypes.data, len(bins), solar_mass_dyn, pc.ctypes.data, len(pc), out.ctypes.data)
+        return out
+
     def compute_energy(self):
         """E, J exactly as ComputeEnergy (reference cmc_utils.c:614-615), single rank."""
         n = int(self.scalars()["N_MAX"])

@@ -234,6 +234,29 @@ def test_compute_energy_totals(R, cenma):
     R.free()
 
 
+def test_comp_multi_mass_percent(R):
+    """comp_multi_mass_percent (reference cmc_utils.c:769-861): Lagrange radii per mass bin, restatement against the compiled
+    reference.  The interpolation is GSL's gsl_interp_linear, un-vendored: both sides run a restatement of its published algorithm
+    (oracle/ref_shim/gsl_shim.c), so the pin covers the binning, the sequential per-bin sums and the search, not GSL itself."""
+    N = 30000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=37, masses="imf")
+    R.init(N, n_star_dim=N + 64)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N)
+    R.L.ref_calc_potential_new()
+    sr, smt = R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy()
+    q = np.quantile(smt[1:N + 1], [0.0, 0.3, 0.6, 0.9, 0.99, 0.9999, 1.0])
+    bins = np.concatenate([q[:-1] * [0.999, 1, 1, 1, 1, 1], [q[-2] * 1.0000001, q[-1] * 1.5, q[-1] * 2.0]])   # a one-star bin and an empty one at the top
+    pcs = np.array([0.0, 0.001, 0.01, 0.1, 0.3, 0.5, 0.7, 0.9, 0.99, 1.0])
+    got = R.comp_multi_mass_percent(bins, 1.0, pcs)
+    want = ol.comp_multi_mass_percent(sr, smt, N, bins, 1.0, pcs)
+    cm.assert_bits_equal(got, want, "multi_mass_r")
+    assert (want[-1] == -1.0).all() and (want[:4, 1:] > 0).all() and (want[:4, 0] == 0).all() and np.all(np.diff(want[0][1:]) > 0)
+    counts = [(want[b] != -1).all() for b in range(len(bins))]
+    assert sum(counts) >= 6
+    R.free()
+
+
 def test_sort_with_binaries_and_stripped_stars(R):
     n, nb, n_strip = 20000, 1500, 23
     rng = np.random.default_rng(8)
