@@ -189,3 +189,54 @@ extern "C" double emul_set_velocities3_second(const double *star_m, long N_MAX, 
 	}
 	return E;
 }
+
+// calc_sigma_r through the operation list of sigma_core.h.  mode 0: the list applied in order (checks the mapping against the oracle);
+// mode 1: the list through the exact-scan decomposition (approximate prefix in a different order, seq_classify_signed with the largest
+// freshly summed window as the bound, events applied in order) -- what the device path will run.  vr / vt: local stars 1..n at [p .. p+n-1],
+// the ghost stars of the previous rank at [0 .. p-1], of the next rank at [p+n .. 2p+n-1].  Outputs [n + 1], entry 0 unused; counters[0] = events.
+#include "../../cmc_cosmic_b200/csrc/sigma_core.h"
+#include "../../cmc_cosmic_b200/csrc/exactsum.h"
+extern "C" int emul_calc_sigma_r(long p, long n, long first_global, long N_MAX, const double *star_r, const double *star_m, double madhoc,
+				 const double *vr, const double *vt, int r_0_mave_1, int mode, double *sig_a, double *sig_sigma, long *counters)
+{
+	SigmaWindow w{p, n, first_global, N_MAX, first_global == 1};
+	if (!w.valid()) return -1;
+	const long L = w.n_ops();
+	std::vector<double> t2(n + 2 * p), t1(n + 2 * p); // index k + p - 1 for local star k in [1 - p, n + p]
+	for (long k = 1 - p; k <= n + p; k++) {
+		const long g = first_global + k - 1;
+		const double m = (g >= 0 && g <= N_MAX + 1) ? star_m[g] : 0.0;
+		sigma_terms(m, madhoc, vr[k + p - 1], vt[k + p - 1], &t2[k + p - 1], &t1[k + p - 1]);
+	}
+	counters[0] = 0;
+	for (int which = 0; which < 2; which++) {
+		const std::vector<double> &t = which == 0 ? t2 : t1;
+		std::vector<double> a(L), y(L);
+		for (long j = 0; j < L; j++) { long k; int s; w.op(j, &k, &s); a[j] = s == 0 ? 0.0 : (s > 0 ? t[k + p - 1] : -t[k + p - 1]); }
+		if (mode == 0) { double acc = 0.0; for (long j = 0; j < L; j++) { acc = dadd(acc, a[j]); y[j] = acc; } }
+		else {
+			double ymax = 0.0; // the largest freshly summed window, with a margin
+			for (long si = 1; si <= n; si++) { double s = 0.0; const long lo = w.simin(si); for (long k = lo; k < lo + 2 * p; k++) s += t[k + p - 1]; if (s > ymax) ymax = s; }
+			ymax *= 1.01;
+			std::vector<double> S(L); // approximate prefix: blocks of 37, block sums accumulated separately
+			{ double base = 0.0; for (long b = 0; b < L; b += 37) { double s = 0.0; for (long j = b; j < L && j < b + 37; j++) { s += a[j]; S[j] = base + s; } base += s; } }
+			double base = 0.0, G = 0.0;
+			for (long j = 0; j < L; j++) {
+				SeqTerm c = seq_classify_signed(a[j], j ? S[j - 1] : 0.0, S[j], ymax, j + 1);
+				if (c.event) { base = dadd(dadd(base, G), a[j]); G = 0.0; y[j] = base; counters[0]++; }
+				else { G += c.v; y[j] = base + G; }
+			}
+		}
+		for (long j = 0; j < L; j++) {
+			const long si = w.star_of(j);
+			if (!si) continue;
+			if (which == 0) sig_sigma[si] = y[j];                   // Mv2ave, finished below
+			else {
+				const double Mave = y[j];
+				sig_sigma[si] = dsqrt(ddiv(sig_sigma[si], Mave));  // :2977
+				sig_a[si] = r_0_mave_1 == 0 ? star_r[first_global + si - 1] : ddiv(ddiv(Mave, 2.), (double) p); // :2971-2974
+			}
+		}
+	}
+	return 0;
+}

@@ -41,6 +41,8 @@ def lib():
         L.emul_set_velocities3.argtypes = [vp, vp, vp, lg, lg, lg, lg, lg] + [vp] * 12
         L.emul_set_velocities3_second.restype = db
         L.emul_set_velocities3_second.argtypes = [vp, lg, lg, lg, vp, db, vp, vp, vp, vp]
+        L.emul_calc_sigma_r.restype = C.c_int
+        L.emul_calc_sigma_r.argtypes = [lg, lg, lg, lg, vp, vp, db, vp, vp, C.c_int, C.c_int, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -105,3 +107,23 @@ def set_velocities3(sr, sm, phi, N_MAX, N_STAR, first_global, f, blk=1024):
 
 def set_velocities3_second(sm, N_MAX, first_global, kind, Eexcess, io):
     return lib().emul_set_velocities3_second(_p(sm), N_MAX, len(kind), first_global, _p(kind), Eexcess, _p(io["vr"]), _p(io["vt"]), _p(io["vrnew"]), _p(io["vtnew"]))
+
+
+def calc_sigma_r(p, star_r, star_m, N_MAX, N_STAR, vr_all, vt_all, first_global=1, n_local=None, mave=False, exact_scan=False):
+    """calc_sigma_r through the operation list of sigma_core.h (exact_scan: through the exact-scan decomposition the device path will use).
+    vr_all / vt_all: the whole sorted cluster; the ghost stars are cut from them.  Returns (r or mean mass, sigma, events)"""
+    vr_all, vt_all = np.ascontiguousarray(vr_all, np.float64), np.ascontiguousarray(vt_all, np.float64)
+    lo = first_global - 1
+    n = len(vr_all) - lo if n_local is None else n_local
+    def cut(x):
+        out = np.zeros(n + 2 * p)
+        a, b = lo - p, lo + n + p
+        src = x[max(a, 0):min(b, len(x))]
+        out[max(a, 0) - a:max(a, 0) - a + len(src)] = src
+        return out
+    vr, vt = cut(vr_all), cut(vt_all)
+    a, sg, cnt = np.zeros(n + 1), np.zeros(n + 1), np.zeros(1, np.int64)
+    rc = lib().emul_calc_sigma_r(p, n, first_global, N_MAX, _p(np.ascontiguousarray(star_r)), _p(np.ascontiguousarray(star_m)), 1.0 / N_STAR, _p(vr), _p(vt),
+                                 int(mave), int(exact_scan), _p(a), _p(sg), _p(cnt))
+    assert rc == 0
+    return a, sg, int(cnt[0])

@@ -222,3 +222,27 @@ def test_set_velocities3_block_decomposition_equals_serial_loop(N, blk, first, n
                 cm.assert_bits_equal(b[k], a[k], k + " second loop")
     finally:
         hostemul.use_deep_ladders(False)
+
+
+@pytest.mark.parametrize("N,p,first,nl,masses", [(30000, 20, 1, None, "imf"), (30000, 3, 1, None, "imf"), (20000, 20, 1, None, "equal"),
+                                                 (30000, 20, 8001, 9000, "imf"), (30000, 20, 21001, 9000, "imf"), (30000, 20, 1, 9000, "imf")])
+def test_calc_sigma_r_as_one_signed_chain(N, p, first, nl, masses):
+    """sigma_core.h: calc_sigma_r (reference cmc_dynamics_helper.c:2821-2975) written as one list of signed operations reproduces the
+    restatement of the reference's loop bit for bit -- applied in order, and through the exact-scan decomposition with signed terms
+    (exactsum.h: seq_classify_signed) the device path will use; whole cluster, first / middle / last shard, both output modes"""
+    import hostemul
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=N + p, masses=masses)
+    sr, smt = cm.make_tables(r, sm)
+    events = 0
+    for mave in (False, True):
+        a0, s0 = ol.calc_sigma_r(p, sr, smt, N, N, vr, vt, first_global=first, n_local=nl, mave=mave)
+        for exact_scan in (False, True):
+            a1, s1, ev = hostemul.calc_sigma_r(p, sr, smt, N, N, vr, vt, first_global=first, n_local=nl, mave=mave, exact_scan=exact_scan)
+            cm.assert_bits_equal(a1[1:], a0[1:], "r / mean mass")
+            cm.assert_bits_equal(s1[1:], s0[1:], "sigma")
+            events = max(events, ev)
+    # the first window fills from zero (2p events per chain); beyond that every operation that crosses a binade boundary is one -- all of
+    # them for the mean-mass chain of N = 20000 equal masses, whose window sum alternates between 39/N and 40/N around 2^-9
+    assert 2 * p <= events <= 2 * (2 * p + 2 * ((nl or N) - 1))
+    if masses == "equal":
+        assert events > 2 * N
