@@ -239,25 +239,33 @@ class Cluster:
         end, as in the reference.  Returns the 1-based local indices of all stripped stars."""
         import math
         N = float(self.clus.N_STAR)
-        if getattr(self, "_strip_buf", None) is None or len(self._strip_buf[0]) != cap:      # hand-back buffers, kept between calls
-            self._strip_buf = (np.zeros(cap, np.int64), np.zeros((cap, STAR_DTYPE_SIZE), np.uint8), np.zeros((cap, BINARY_DTYPE_SIZE), np.uint8))
-        (idx, recs, bins), cnt = self._strip_buf, C.c_long(0)
+        def buffers(cap):
+            return (np.zeros(cap, np.int64), np.zeros((cap, STAR_DTYPE_SIZE), np.uint8), np.zeros((cap, BINARY_DTYPE_SIZE), np.uint8), np.zeros(cap))
+        if getattr(self, "_strip_buf", None) is None or len(self._strip_buf[0]) < cap:      # hand-back buffers, kept between calls
+            self._strip_buf = buffers(cap)
+        cnt = C.c_long(0)
         self.Etidal, stripped = 0.0, []
-        first = int(self.Start[self.myid])
         while True:
             self.Rtidal = self.orbit_r * math.pow(self.Mtotal - (self.TidalMassLoss - self.OldTidalMassLoss), 1.0 / 3.0)   # :461-462
             phi_rtidal = float(self.dev_potential(self.Rtidal)[0])
             thr = self.Rtidal if tidal_treatment == 0 else (1.5 - 3.0 * math.pow(math.log(GAMMA * N) / N, 0.25)) * phi_rtidal   # :479 / :553-555
             p = self.orbit_params()
-            _lib.check(self.L.cmcb200_dev_tidally_strip_select(self.ctx, C.byref(p), tidal_treatment, thr, idx.ctypes.data, cap, C.byref(cnt),
-                                                               recs.ctypes.data, bins.ctypes.data), "dev_tidally_strip_select")
+            while True:
+                idx, recs, bins, mass = self._strip_buf
+                rc = self.L.cmcb200_dev_tidally_strip_select(self.ctx, C.byref(p), tidal_treatment, thr, idx.ctypes.data, len(idx), C.byref(cnt),
+                                                             recs.ctypes.data, bins.ctypes.data, mass.ctypes.data)
+                if rc == -3 and cnt.value > len(idx):      # more hits than the list holds: nothing was marked, come back with a longer one
+                    self._strip_buf = buffers(int(cnt.value) + 1024)
+                    continue
+                _lib.check(rc, "dev_tidally_strip_select")
+                break
             n = cnt.value
             D = 0.0
             if n:
                 E, J, Eint, binind = (star_field(recs[:n], k) for k in ("E", "J", "Eint", "binind"))
                 bf = {k: binary_field(bins[:n], k) for k in ("m1", "m2", "a", "Eint1", "Eint2")}
                 for k in range(n):                                    # :484-496, in star order
-                    m = float(self.star_m[first + int(idx[k]) - 1])
+                    m = float(mass[k])                                # star_m[g] from the resident table (:471)
                     self.Eescaped += float(E[k]) * m / N
                     self.Jescaped += float(J[k]) * m / N
                     if binind[k] == 0:

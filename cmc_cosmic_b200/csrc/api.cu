@@ -574,6 +574,8 @@ extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const
 					    const cmcb200_orbit_params *p, int *status, long *kmin, long *kmax, cmcb200_orbit_result *res)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	// E and J are the caller's here (the host records hold them; remove_star reads them afterwards): the fused ComputeEnergy belongs to the resident pipeline
+	if (p->fuse_compute_energy) { set_error("new_orbits_calculate: fuse_compute_energy is for the resident pipeline (cmcb200_dev_new_orbits) only"); return -1; }
 	if (!c->s_in) {
 		CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
 		CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));

@@ -40,6 +40,9 @@ CMCB_HD SeqTerm seq_classify(double a, double y_before, double y_after, double y
 	SeqTerm t;
 	t.v = 0.0;
 	t.event = 1;
+	// fl(y + 0) = y for every y: a zero term is regular whatever the chain's value is (a chain of zeros -- Eint of a cluster without stellar
+	// evolution, the binding energies of a cluster without binaries -- has no events at all)
+	if (a == 0.0) { t.event = 0; return t; }
 	// rigorous bound on |approximate - true sequential value|: the chain commits <= i roundings of <= 2^-53 * max|y|,
 	// the parallel prefix at most as many; (i + 64) * 2^-51 leaves a factor 2 of slack.
 	double S = dmax(y0_abs, dmax(dabs(y_before), dabs(y_after)));
@@ -70,6 +73,7 @@ CMCB_HD SeqTerm seq_classify_signed(double a, double y_before, double y_after, d
 	SeqTerm t;
 	t.v = 0.0;
 	t.event = 1;
+	if (a == 0.0) { t.event = 0; return t; } // fl(y + 0) = y
 	double S = dmax(y_max, dmax(dabs(y_before), dabs(y_after)));
 	double delta = dmul(dmul((double) (i + 64), 4.440892098500626e-16 /* 2^-51 */), S);
 	double lo = dsub(dmin(y_before, y_after), delta);

@@ -245,6 +245,7 @@ extern "C" int cmcb200_dev_compute_energy_totals(cmcb200_ctx *c, long n_local, l
 	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
 	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
 	CMCB_CUDA_OK(cudaMemsetAsync(d->totals, 0, sizeof(d->totals), c->stream));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->seqwork.stats, 0, 2 * sizeof(long), c->stream)); // cmcb200_potential_stats then reports this call's chains
 	EtotArgs a{star1(c), bin1(c), c->d_m, c->d_phi, n_local, first_global, 1.0 / ((double) N_STAR), cenma_m, (double) N_MAX};
 	const int grid = NUM_SMS_B200 * 4;
 	if (n_local > 0) {

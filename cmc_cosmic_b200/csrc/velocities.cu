@@ -222,17 +222,30 @@ __global__ void __launch_bounds__(32) sv3_second_kernel(OrbitArgs a, Sv3Buffers 
 // sorted by the caller, which does the reference's per-star bookkeeping in star order on the host.
 __global__ void __launch_bounds__(256) tidal_select_kernel(OrbitArgs a, int treatment, double threshold, long *list, unsigned *count, unsigned cap)
 {
+	// phase 1: the criterion only -- nothing is stored, so a list that does not fit can be retried with a larger one
 	for (long j0 = blockIdx.x * 256L + threadIdx.x; j0 < a.n_local; j0 += gridDim.x * 256L) {
-		char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
+		const char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
 		if (!(ld_field(rec, CMCB_OFF_RNEW) < 1000000)) continue;
 		const double v = ld_field(rec, treatment == 0 ? CMCB_OFF_R_APO : CMCB_OFF_E);
 		if (!(v > threshold)) continue;
-		st_field(rec, CMCB_OFF_RNEW, CMCB_SF_INFINITY);
-		st_field(rec, CMCB_OFF_VRNEW, 0.0);
-		st_field(rec, CMCB_OFF_VTNEW, 0.0);
 		const unsigned pos = atomicAdd(count, 1u);
 		if (pos < cap) list[pos] = j0 + 1;
 	}
+}
+
+// phase 2, once the list is known to fit: the stores of the reference's loop body (src/cmc/cmc_evolution_thr.c:497-499 / :573-575) for the
+// listed stars (1-based local indices, star order) and star_m[g] of each (:471), the mass the caller's sums use
+__global__ void tidal_apply_kernel(OrbitArgs a, const long *__restrict__ list, long n, long N_MAX, const double *__restrict__ star_m, double *__restrict__ m_out)
+{
+	const long k = blockIdx.x * (long) blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	const long j = list[k];
+	char *rec = a.star1 + (j - 1) * CMCB_SIZEOF_STAR;
+	st_field(rec, CMCB_OFF_RNEW, CMCB_SF_INFINITY);
+	st_field(rec, CMCB_OFF_VRNEW, 0.0);
+	st_field(rec, CMCB_OFF_VTNEW, 0.0);
+	const long g = j > a.n_old_local ? 1 + N_MAX + (j - a.n_old_local) : a.first_global + j - 1; // get_global_idx, src/cmc/cmc_utils.c:2384-2407
+	m_out[k] = star_m[g];
 }
 
 // potential() (reference src/cmc/cmc_utils.c:112-165) at n radii through the r ladder; a failed bracket check is counted
@@ -368,7 +381,7 @@ extern "C" int cmcb200_dev_potential(cmcb200_ctx *c, const cmcb200_orbit_params 
 }
 
 extern "C" int cmcb200_dev_tidally_strip_select(cmcb200_ctx *c, const cmcb200_orbit_params *p, int tidal_treatment, double threshold, long *idx_out,
-						 long cap, long *count, void *star_out, void *binary_out)
+						 long cap, long *count, void *star_out, void *binary_out, double *m_out)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	*count = 0;
@@ -379,7 +392,9 @@ extern "C" int cmcb200_dev_tidally_strip_select(cmcb200_ctx *c, const cmcb200_or
 	memset(&a, 0, sizeof(a));
 	a.star1 = star1(c);
 	a.n_local = p->n_local;
-	// queue: the deferred-scan list (ORBIT_DEFER_CAP longs) is free between orbit steps
+	a.n_old_local = p->n_old_local;
+	a.first_global = p->first_global;
+	// queue: the deferred-scan list (ORBIT_DEFER_CAP longs) is free between orbit steps; the masses go to the list of found indices next to it
 	const long qcap = cap < ORBIT_DEFER_CAP ? cap : ORBIT_DEFER_CAP;
 	unsigned *d_count = c->d_defer_first;
 	CMCB_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(unsigned), c->stream));
@@ -393,12 +408,22 @@ extern "C" int cmcb200_dev_tidally_strip_select(cmcb200_ctx *c, const cmcb200_or
 	CMCB_CUDA_OK(cudaMemcpyAsync(h_count, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	const long n = *h_count;
-	if (n > qcap) { set_error("tidally_strip_stars: %ld stars stripped in one pass, the caller's list holds %ld", n, qcap); return -3; }
+	// nothing has been stored yet: the caller may come back with a longer list
+	if (n > qcap) { set_error("tidally_strip_stars: %ld stars meet the criterion in one pass, the caller's list holds %ld (no record was changed)", n, qcap); *count = n; return -3; }
 	if (n == 0) return 0;
 	CMCB_CUDA_OK(cudaMemcpyAsync(idx_out, c->d_defer_star, (size_t) n * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	std::sort(idx_out, idx_out + n); // star order
 	*count = n;
+	double *d_mass = (double *) c->d_defer_found;
+	CMCB_CUDA_OK(cudaMemcpyAsync(c->d_defer_star, idx_out, (size_t) n * sizeof(long), cudaMemcpyHostToDevice, c->stream));
+	{
+		StageTimer t(c, ST_ENERGY);
+		tidal_apply_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(a, c->d_defer_star, n, p->N_MAX, c->d_m, d_mass);
+		c->launches += 1;
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	if (m_out) CMCB_CUDA_OK(cudaMemcpyAsync(m_out, d_mass, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	if (star_out) {
 		StageTimer t(c, ST_D2H);
 		for (long k = 0; k < n; k++)
@@ -410,8 +435,8 @@ extern "C" int cmcb200_dev_tidally_strip_select(cmcb200_ctx *c, const cmcb200_or
 				if (b > 0 && b < c->n_bin_dim)
 					CMCB_CUDA_OK(cudaMemcpyAsync((char *) binary_out + k * CMCB_SIZEOF_BINARY, bin1(c) + (b - 1) * CMCB_SIZEOF_BINARY, CMCB_SIZEOF_BINARY, cudaMemcpyDeviceToHost, c->stream));
 			}
-			CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 		}
 	}
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	return 0;
 }

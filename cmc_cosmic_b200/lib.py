@@ -104,7 +104,7 @@ def load():
     L.cmcb200_dev_energy_new_radii.argtypes = [vp, C.POINTER(OrbitParams)]
     L.cmcb200_dev_compute_energy_totals.argtypes = [vp, lg, lg, lg, lg, dbl, vp]
     L.cmcb200_dev_potential.argtypes = [vp, C.POINTER(OrbitParams), vp, lg, vp]
-    L.cmcb200_dev_tidally_strip_select.argtypes = [vp, C.POINTER(OrbitParams), C.c_int, dbl, vp, lg, pl, vp, vp]
+    L.cmcb200_dev_tidally_strip_select.argtypes = [vp, C.POINTER(OrbitParams), C.c_int, dbl, vp, lg, pl, vp, vp, vp]
     L.cmcb200_dev_set_velocities3.argtypes = [vp, C.POINTER(OrbitParams), C.POINTER(dbl)]
     L.cmcb200_dev_set_velocities3_pass.argtypes = [vp, C.POINTER(OrbitParams), dbl, C.POINTER(dbl)]
     L.cmcb200_dev_clusdyn_calculate.argtypes = [vp, lg, lg, dbl, C.POINTER(dbl)]

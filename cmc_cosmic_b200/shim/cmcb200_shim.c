@@ -16,6 +16,7 @@
  * Single rank per GPU.  procs > 1 goes through the radius-sharded entry points (cmcb200_shard_*). */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "cmc.h"
 #include "cmc_vars.h"
 #include "cmcb200.h"
@@ -110,6 +111,7 @@ void SHIM(new_orbits_calculate)(void)
 	double phi_rtidal, phi_zero;
 	long j, n = clus.N_MAX_NEW, n_old = End[myid] - Start[myid] + 1;
 	shim_init();
+	memset(&p, 0, sizeof p);                         /* every field the shim does not set (fuse_compute_energy: resident pipeline only) is 0 */
 	OldTidalMassLoss = TidalMassLoss_old;
 	phi_rtidal = potential(Rtidal);                  /* get_positions, cmc_evolution_thr.c:963-964 */
 	phi_zero = potential(0.0);

@@ -190,9 +190,12 @@ int cmcb200_dev_potential(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, const
  * (may be NULL) the stripped stars' 424-byte records and binary_out (may be NULL) the 464-byte record of each one that is a binary, both
  * at position k of the list -- what the caller needs for the reference's per-star bookkeeping (:484-496: Eescaped, Jescaped, Eintescaped,
  * Ebescaped, DTidalMassLoss, Etidal, the esc log line), which it does in that order, recomputes Rtidal from the mass lost and calls again
- * while a pass strips anything (:624).  More than cap hits in one pass: non-zero return, the records are already marked. */
+ * while a pass strips anything (:624).  m_out[cap] (may be NULL): star_m[g] of each listed star (:471) from the resident table -- the mass
+ * the sums use; the caller's host copy of star_m may predate the last sort.  The pass is two-phase: the criterion is evaluated first and the
+ * records are only marked once the list is known to fit.  More than cap hits in one pass: return -3 with *count = the number of hits and NO
+ * record changed, so the caller can come back with a longer list. */
 int cmcb200_dev_tidally_strip_select(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int tidal_treatment, double threshold, long *idx_out,
-				     long cap, long *count, void *star_out, void *binary_out);
+				     long cap, long *count, void *star_out, void *binary_out, double *m_out);
 /* qsorts_new + post_sort_comm on the resident arrays; *n_local in/out, *n_bin out */
 int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, long *n_bin);
 /* cmcb200_dev_transfer_new_positions + cmcb200_dev_qsorts_new in one pass over the records: the sort key is rnew and the transfer is

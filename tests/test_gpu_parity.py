@@ -649,6 +649,67 @@ def test_compute_energy_totals_bit_exact(cenma, N):
     c.close()
 
 
+def test_compute_energy_totals_chains_of_zeros_stay_parallel():
+    """A cluster without stellar evolution and without binaries: every term of the Eint and Eb chains is exactly 0.  fl(y + 0) = y, so those
+    elements are regular -- no event, and above all no fall-back to the single-thread chain (which at N = 1e7 would take seconds)."""
+    N = 400000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=36)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.calc_potential_new()
+    c.upload()
+    et = c.dev_compute_energy_totals()
+    ev, fb = c.potential_stats()
+    assert fb == 0, f"{fb} sequential fall-backs"
+    t = ol.tables(c.star_r[:N + 2].copy(), c.star_m[:N + 2].copy(), c.star_phi[:N + 2].copy(), N, N, 0.0)
+    z = np.zeros(N)
+    bins = {k: np.zeros(1) for k in ("m1", "m2", "a", "Eint1", "Eint2")}
+    bins["inuse"] = np.zeros(1, np.int32)
+    K, P, Ei, Eb = ol.compute_energy_totals(t, 1, vr, vt, z, np.zeros(N, np.int64), bins)
+    assert (et.K, et.P, et.Eint, et.Eb) == (K, 0.5 * P, Ei, Eb) and Ei == 0.0 and Eb == 0.0
+    c.close()
+
+
+def test_tidally_strip_stars_uses_the_resident_masses_after_a_sort():
+    """On the resident pipeline the host copy of star_m is not refreshed by the sort: the mass of a stripped star must come from the device
+    table.  Two resident timesteps with stripping of an IMF cluster; afterwards the escaper sums equal the ones recomputed from the
+    downloaded records of the stripped stars (their .m is star_m[g] at the time of the strip, stored by the transfer before the sort)."""
+    N = 30000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=91, masses="imf")
+    c = Cluster(N, n_star_dim=N + 64, orbit_r=6.0)
+    c.load(r, vr, vt, sm)
+    c.calc_potential_new()
+    c.compute_energy()
+    c.upload()
+    total = 0
+    for step in range(3):
+        c.OldTidalMassLoss = c.TidalMassLoss
+        c.dev_energy_conservation1()
+        c.dev_new_orbits(seed=7)
+        c.dev_energy_conservation2()
+        e0, d0 = c.Eescaped, c.TidalMassLoss
+        stripped = c.dev_tidally_strip_stars(tidal_treatment=1)
+        # the records of the stripped stars, straight from the device (host star_m is deliberately stale from step 1 on)
+        c.download()
+        idx = np.array(stripped, np.int64)
+        if len(idx):
+            m_dev, E = c.star_m[idx], c.field("E")[idx]
+            # one pass at a time is not recoverable from here; the sums over all passes are order-sensitive only at rounding level
+            assert np.isclose(c.Eescaped - e0, float(np.sum(E * m_dev / N)), rtol=1e-9, atol=1e-15)
+            assert np.isclose(c.TidalMassLoss - d0, float(np.sum(m_dev / N)), rtol=1e-9, atol=1e-15)
+            total += len(idx)
+        c.dev_compute_intermediate_energy()
+        c.dev_qsorts_new()
+        c.dev_calc_potential_new()
+        c.dev_energy_conservation3()
+        c.dev_compute_energy()
+        c.tcount += 1
+        # make the host table useless on purpose: the next strip must not read it
+        c.star_m[:] = -1.0e300
+    assert total > 5
+    c.close()
+
+
 def test_lagrange_radii_of_a_run_agree_statistically_with_the_reference_run():
     """north_star: "Lagrangian radii from a full run must statistically agree with the reference run".  Six timesteps of the path
     (orbit step -> r <- rnew -> sort -> potential -> E, J) from the same Plummer state: the CUDA pipeline with its production draws
