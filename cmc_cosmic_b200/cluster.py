@@ -196,6 +196,47 @@ class Cluster:
                                            self.star_r.ctypes.data, self.star_m.ctypes.data, self.star_phi.ctypes.data,
                                            min(self.N_TABLE_DIM, self.clus.N_MAX + 2)), "download")
 
+    ALL_WORDS = (1 << (STAR_DTYPE_SIZE // 8)) - 1
+
+    @staticmethod
+    def dirty_mask(*fields_or_ranges):
+        """bit mask over the 8-byte words of star_t for cmcb200_resident_begin: field names (layout.py) or (first byte, last byte + 1) ranges"""
+        from .layout import STAR_OFFSETS
+        m = 0
+        for f in fields_or_ranges:
+            lo, hi = (STAR_OFFSETS[f], STAR_OFFSETS[f] + 8) if isinstance(f, str) else f
+            for w in range(lo // 8, (hi + 7) // 8):
+                m |= 1 << w
+        return m
+
+    def resident_begin(self, dirty_words=None):
+        """Start the timestep's upload of the host arrays (cmcb200_resident_begin): returns at once, the dev_* calls that follow are ordered
+        behind it on the device and the orbit step runs chunk by chunk under it.  dirty_words: see include/cmcb200.h (None = everything)."""
+        n, nb = self.clus.N_MAX_NEW, self._n_bin_in_use()
+        n_new_stars = max(0, n - int(self.End[self.myid] - self.Start[self.myid] + 1))
+        _lib.check(self.L.cmcb200_resident_begin(self.ctx, self.star[1:].ctypes.data, n, self.binary[1:].ctypes.data, nb, self.star_r.ctypes.data,
+                                                 self.star_m.ctypes.data, self.star_phi.ctypes.data, min(self.N_TABLE_DIM, self.clus.N_MAX + 2 + n_new_stars),
+                                                 self.ALL_WORDS if dirty_words is None else dirty_words), "resident_begin")
+        self.N_b_local = nb
+
+    def resident_end(self):
+        """Download records, binaries and tables and wait: the host arrays are coherent with the device again (cmcb200_resident_end)."""
+        _lib.check(self.L.cmcb200_resident_end(self.ctx, self.star[1:].ctypes.data, self.clus.N_MAX_NEW, self.binary[1:].ctypes.data, self.N_b_local,
+                                               self.N_BIN_DIM, self.star_r.ctypes.data, self.star_m.ctypes.data, self.star_phi.ctypes.data,
+                                               min(self.N_TABLE_DIM, self.clus.N_MAX + 2)), "resident_end")
+
+    def host_step(self, seed=0, draws=None, draw_off=None, dirty_words=None):
+        """One pass of the hot path on HOST arrays with the records crossing the link once each way: upload (asynchronous) -> orbit step
+        behind the arriving chunks -> r <- rnew + sort -> potential -> download.  What the resident mode of the shim does between
+        new_orbits_calculate and calc_potential_new; E and J are the caller's, as in the reference."""
+        self.resident_begin(dirty_words)
+        res = self.dev_new_orbits(draws, draw_off, seed)
+        self.dev_transfer_and_sort()
+        self.dev_calc_potential_new()
+        self.resident_end()
+        self.tcount += 1
+        return res
+
     def dev_new_orbits(self, draws=None, draw_off=None, seed=0, want_status=False, fuse_energy=False):
         p = self.orbit_params(draws, draw_off, seed, fuse_energy)
         res = _lib.OrbitResult()

@@ -172,6 +172,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	if (c->s_in) {
 		cudaStreamDestroy(c->s_in); cudaStreamDestroy(c->s_out);
 		for (int k = 0; k < 16; k++) { cudaEventDestroy(c->ev_in[k]); cudaEventDestroy(c->ev_done[k]); }
+		cudaEventDestroy(c->ev_tab); cudaEventDestroy(c->ev_bin);
 	}
 	if (c->own_stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -232,6 +233,7 @@ extern "C" int cmcb200_dev_calc_potential_new(cmcb200_ctx *c, long *N_MAX, long 
 {
 	if (*N_MAX + 2 > c->n_table_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds the table capacity %ld", *N_MAX + 2, c->n_table_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	{
 		StageTimer t(c, ST_POTENTIAL);
 		CMCB_CUDA_OK(cudaMemsetAsync(c->seqwork.stats, 0, 2 * sizeof(long), c->stream));
@@ -287,6 +289,7 @@ static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_
 	if (n + 2 > c->n_star_dim) { set_error("qsorts_new: n_local + 2 = %ld exceeds n_star_dim = %ld", n + 2, c->n_star_dim); return -1; }
 	if (n_bin_clear > c->n_bin_dim - 1) n_bin_clear = c->n_bin_dim - 1;
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	SortArgs a;
 	a.star_in = star1(c);
 	a.star_out = c->d_star[c->cur_star ^ 1] + CMCB_SIZEOF_STAR;
@@ -396,8 +399,24 @@ static void orbit_l2_window(cmcb200_ctx *c, size_t bytes)
 	cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
 }
 
+// copy-in / copy-out streams and the per-chunk events of the pipelines (host-buffer orbit step, resident timestep): created on first use
+static int copy_streams(cmcb200_ctx *c)
+{
+	if (c->s_in) return 0;
+	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+	for (int k = 0; k < ORBIT_MAX_CHUNKS; k++) {
+		CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
+		CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+	}
+	CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_tab, cudaEventDisableTiming));
+	CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_bin, cudaEventDisableTiming));
+	return 0;
+}
+
 int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a)
 {
+	if (join_uploads(c)) return -1;
 	if (p->n_local + 2 > c->n_star_dim || p->n_table > c->n_table_dim) { set_error("new_orbits_calculate: size exceeds the capacity (%ld records, %ld table entries)", c->n_star_dim, c->n_table_dim); return -1; }
 	a.star1 = star1(c);
 	a.n_local = p->n_local;
@@ -483,10 +502,29 @@ static void orbit_end(cmcb200_ctx *c, const cmcb200_orbit_params *p, int n_chunk
 static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res)
 {
 	OrbitArgs a;
-	if (orbit_begin(c, p, want_status, false, a)) return -1;
-	if (orbit_range(c, a, 0, p->n_local, 0)) return -1;
+	int n_chunks = 1;
+	if (c->up_pending && p->n_local == c->up_n && c->up_chunks > 1) {
+		// cmcb200_resident_begin's upload is still in flight: the step runs chunk by chunk behind it (every star is independent of the
+		// others, so the result does not depend on the chunking); only the tables must be complete before the first kernel
+		CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_tab, 0));
+		c->up_defer_join = true;
+		const int rc = orbit_begin(c, p, want_status, false, a);
+		c->up_defer_join = false;
+		if (rc) return -1;
+		n_chunks = c->up_chunks;
+		for (int k = 0; k < n_chunks; k++) {
+			const long off = k * c->up_per, len = p->n_local - off < c->up_per ? p->n_local - off : c->up_per;
+			CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+			if (orbit_range(c, a, off, len > 0 ? len : 0, k)) return -1;
+		}
+		CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_bin, 0));
+		c->up_pending = false;
+	} else {
+		if (orbit_begin(c, p, want_status, false, a)) return -1;
+		if (orbit_range(c, a, 0, p->n_local, 0)) return -1;
+	}
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
-	orbit_end(c, p, 1, res);
+	orbit_end(c, p, n_chunks, res);
 	return 0;
 }
 
@@ -532,6 +570,7 @@ extern "C" int cmcb200_dev_energy_new_radii(cmcb200_ctx *c, const cmcb200_orbit_
 
 extern "C" int cmcb200_dev_read_status(cmcb200_ctx *c, int *status, long *kmin, long *kmax, long n_local)
 {
+	if (join_uploads(c)) return -1;
 	StageTimer t(c, ST_D2H);
 	if (status) CMCB_CUDA_OK(cudaMemcpyAsync(status, c->d_status, (size_t) n_local * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	if (kmin) CMCB_CUDA_OK(cudaMemcpyAsync(kmin, c->d_kmin, (size_t) n_local * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
@@ -576,14 +615,7 @@ extern "C" int cmcb200_new_orbits_calculate(cmcb200_ctx *c, void *star1_h, const
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	// E and J are the caller's here (the host records hold them; remove_star reads them afterwards): the fused ComputeEnergy belongs to the resident pipeline
 	if (p->fuse_compute_energy) { set_error("new_orbits_calculate: fuse_compute_energy is for the resident pipeline (cmcb200_dev_new_orbits) only"); return -1; }
-	if (!c->s_in) {
-		CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
-		CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
-		for (int k = 0; k < ORBIT_MAX_CHUNKS; k++) {
-			CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
-			CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
-		}
-	}
+	if (copy_streams(c) || join_uploads(c)) return -1;
 	const bool want = status || kmin || kmax;
 	const long n = p->n_local;
 	int n_chunks = (int) ((n + (1L << 19) - 1) >> 19); // >= 512 K stars per chunk: the kernels of a chunk still fill the GPU
@@ -633,7 +665,11 @@ extern "C" int cmcb200_upload(cmcb200_ctx *c, const void *star1_h, long n_local,
 {
 	if (n_local + 2 > c->n_star_dim || n_table > c->n_table_dim || n_bin + 1 > c->n_bin_dim) { set_error("upload: sizes exceed the context capacity"); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	c->resident_valid = false;
 	StageTimer t(c, ST_H2D);
+	c->bytes_h2d += (star1_h ? n_local * CMCB_SIZEOF_STAR : 0) + (binary1_h && n_bin > 0 ? n_bin * CMCB_SIZEOF_BINARY : 0)
+			+ ((star_r ? 1 : 0) + (star_m ? 1 : 0) + (star_phi ? 1 : 0)) * n_table * (long) sizeof(double);
 	if (star1_h) CMCB_CUDA_OK(cudaMemcpyAsync(star1(c), star1_h, (size_t) n_local * CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
 	if (binary1_h && n_bin > 0) CMCB_CUDA_OK(cudaMemcpyAsync(bin1(c), binary1_h, (size_t) n_bin * CMCB_SIZEOF_BINARY, cudaMemcpyHostToDevice, c->stream));
 	if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -646,6 +682,9 @@ extern "C" int cmcb200_download(cmcb200_ctx *c, void *star1_h, long n_local, voi
 				double *star_r, double *star_m, double *star_phi, long n_table)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	c->bytes_d2h += (star1_h ? n_local * CMCB_SIZEOF_STAR : 0) + (binary1_h && n_bin > 0 ? n_bin * CMCB_SIZEOF_BINARY : 0)
+			+ ((star_r ? 1 : 0) + (star_m ? 1 : 0) + (star_phi ? 1 : 0)) * n_table * (long) sizeof(double);
 	{
 		StageTimer t(c, ST_D2H);
 		if (star1_h) CMCB_CUDA_OK(cudaMemcpyAsync(star1_h, star1(c), (size_t) n_local * CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
@@ -654,6 +693,111 @@ extern "C" int cmcb200_download(cmcb200_ctx *c, void *star1_h, long n_local, voi
 		if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(star_m, c->d_m, (size_t) n_table * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 		if (star_phi) CMCB_CUDA_OK(cudaMemcpyAsync(star_phi, c->d_phi, (size_t) n_table * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	}
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+// ---- resident timestep on host arrays: the records cross the host link once each way ---------------------------------------------
+
+// Runs of consecutive dirty 8-byte words of a record (bit w of the mask = word w); returns the number of runs
+static int dirty_runs(unsigned long long mask, int lo[CMCB_STAR_WORDS], int len[CMCB_STAR_WORDS])
+{
+	int n = 0;
+	for (int w = 0; w < CMCB_STAR_WORDS;) {
+		if (!((mask >> w) & 1ull)) { w++; continue; }
+		int e = w;
+		while (e < CMCB_STAR_WORDS && ((mask >> e) & 1ull)) e++;
+		lo[n] = w; len[n] = e - w; n++;
+		w = e;
+	}
+	return n;
+}
+
+extern "C" int cmcb200_resident_begin(cmcb200_ctx *c, const void *star1_h, long n_local, const void *binary1_h, long n_bin,
+					      const double *star_r, const double *star_m, const double *star_phi, long n_table, unsigned long long dirty_words)
+{
+	if (n_local + 2 > c->n_star_dim || n_table > c->n_table_dim || n_bin + 1 > c->n_bin_dim) { set_error("resident_begin: sizes exceed the context capacity"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (copy_streams(c) || join_uploads(c)) return -1;
+	const unsigned long long all = (1ull << CMCB_STAR_WORDS) - 1ull;
+	dirty_words &= all;
+	// a partial upload patches the copy the last cmcb200_resident_end left behind: same records, same order
+	if (!(c->resident_valid && c->resident_n == n_local)) dirty_words = all;
+	c->resident_valid = false;
+	// the copies start behind whatever the context's stream still has in flight
+	CMCB_CUDA_OK(cudaEventRecord(c->ev_done[ORBIT_MAX_CHUNKS - 1], c->stream));
+	CMCB_CUDA_OK(cudaStreamWaitEvent(c->s_in, c->ev_done[ORBIT_MAX_CHUNKS - 1], 0));
+	if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+	if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+	if (star_phi) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_phi, star_phi, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+	c->bytes_h2d += ((star_r ? 1 : 0) + (star_m ? 1 : 0) + (star_phi ? 1 : 0)) * n_table * (long) sizeof(double);
+	CMCB_CUDA_OK(cudaEventRecord(c->ev_tab, c->s_in));
+	int n_chunks = (int) ((n_local + (1L << 19) - 1) >> 19); // >= 512 K stars per chunk: the kernels of a chunk still fill the GPU
+	if (n_chunks > c->orbit_max_chunks) n_chunks = c->orbit_max_chunks;
+	if (n_chunks < 1) n_chunks = 1;
+	const long per = (n_local + n_chunks - 1) / n_chunks;
+	int lo[CMCB_STAR_WORDS], len[CMCB_STAR_WORDS];
+	const int n_runs = dirty_words == all ? 0 : dirty_runs(dirty_words, lo, len);
+	char *dev1 = star1(c);
+	const size_t pitch = CMCB_SIZEOF_STAR;
+	for (int k = 0; k < n_chunks; k++) {
+		const long off = k * per, n = n_local - off < per ? n_local - off : per;
+		if (n > 0 && star1_h) {
+			if (dirty_words == all) {
+				CMCB_CUDA_OK(cudaMemcpyAsync(dev1 + off * pitch, (const char *) star1_h + off * pitch, (size_t) n * pitch, cudaMemcpyHostToDevice, c->s_in));
+				c->bytes_h2d += n * (long) pitch;
+			} else {
+				for (int r = 0; r < n_runs; r++) { // strided (2-D) DMA of each run of dirty words
+					CMCB_CUDA_OK(cudaMemcpy2DAsync(dev1 + off * pitch + lo[r] * 8, pitch, (const char *) star1_h + off * pitch + lo[r] * 8, pitch, (size_t) len[r] * 8,
+								       (size_t) n, cudaMemcpyHostToDevice, c->s_in));
+					c->bytes_h2d += n * (long) len[r] * 8;
+				}
+			}
+		}
+		CMCB_CUDA_OK(cudaEventRecord(c->ev_in[k], c->s_in));
+	}
+	if (binary1_h && n_bin > 0) {
+		CMCB_CUDA_OK(cudaMemcpyAsync(bin1(c), binary1_h, (size_t) n_bin * CMCB_SIZEOF_BINARY, cudaMemcpyHostToDevice, c->s_in));
+		c->bytes_h2d += n_bin * CMCB_SIZEOF_BINARY;
+	}
+	CMCB_CUDA_OK(cudaEventRecord(c->ev_bin, c->s_in));
+	c->up_pending = true;
+	c->up_chunks = n_chunks;
+	c->up_per = per;
+	c->up_n = n_local;
+	return 0;
+}
+
+extern "C" int cmcb200_resident_end(cmcb200_ctx *c, void *star1_h, long n_local, void *binary1_h, long n_bin, long n_bin_dim,
+					    double *star_r, double *star_m, double *star_phi, long n_table)
+{
+	if (cmcb200_download(c, star1_h, n_local, binary1_h, n_bin, star_r, star_m, star_phi, n_table)) return -1;
+	// memset(b_buf, 0, (N_BIN_DIM_OPT-1)*sizeof(binary_t)) (cmc_sort.c:541): everything past the packed binaries is zero
+	if (binary1_h && n_bin_dim - 1 > n_bin) memset((char *) binary1_h + (size_t) n_bin * CMCB_SIZEOF_BINARY, 0, (size_t) (n_bin_dim - 1 - n_bin) * CMCB_SIZEOF_BINARY);
+	c->resident_valid = star1_h != nullptr;
+	c->resident_n = n_local;
+	return 0;
+}
+
+extern "C" int cmcb200_dev_get(cmcb200_ctx *c, void *star_rec, long j, void *binary_rec, long b)
+{
+	if (j < 1 || j + 1 > c->n_star_dim || (binary_rec && (b < 1 || b >= c->n_bin_dim))) { set_error("dev_get: index out of range"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	if (star_rec) CMCB_CUDA_OK(cudaMemcpyAsync(star_rec, star1(c) + (j - 1) * CMCB_SIZEOF_STAR, CMCB_SIZEOF_STAR, cudaMemcpyDeviceToHost, c->stream));
+	if (binary_rec) CMCB_CUDA_OK(cudaMemcpyAsync(binary_rec, bin1(c) + (b - 1) * CMCB_SIZEOF_BINARY, CMCB_SIZEOF_BINARY, cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" int cmcb200_dev_put(cmcb200_ctx *c, const void *star_rec, long j, const void *binary_rec, long b, const double *star_m_g, long g)
+{
+	if (j < 1 || j + 1 > c->n_star_dim || (binary_rec && (b < 1 || b >= c->n_bin_dim)) || (star_m_g && (g < 0 || g >= c->n_table_dim))) { set_error("dev_put: index out of range"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	if (star_rec) CMCB_CUDA_OK(cudaMemcpyAsync(star1(c) + (j - 1) * CMCB_SIZEOF_STAR, star_rec, CMCB_SIZEOF_STAR, cudaMemcpyHostToDevice, c->stream));
+	if (binary_rec) CMCB_CUDA_OK(cudaMemcpyAsync(bin1(c) + (b - 1) * CMCB_SIZEOF_BINARY, binary_rec, CMCB_SIZEOF_BINARY, cudaMemcpyHostToDevice, c->stream));
+	if (star_m_g) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m + g, star_m_g, sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	return 0;
 }
@@ -695,6 +839,7 @@ __global__ void compute_energy_kernel(char *star1, long n_local, long first_glob
 extern "C" int cmcb200_dev_transfer_new_positions(cmcb200_ctx *c, long n_local, long n_old_local, long first_global, long N_MAX)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	StageTimer t(c, ST_TRANSFER);
 	if (n_local > 0)
 	{
@@ -708,6 +853,7 @@ extern "C" int cmcb200_dev_transfer_new_positions(cmcb200_ctx *c, long n_local, 
 extern "C" int cmcb200_dev_compute_energy(cmcb200_ctx *c, long n_local, long first_global)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	StageTimer t(c, ST_ENERGY);
 	if (n_local > 0)
 	{

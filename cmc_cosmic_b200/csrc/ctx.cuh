@@ -78,6 +78,14 @@ struct cmcb200_ctx {
 	// host-buffer orbit step: copy-in and copy-out streams and per-chunk events of the pipeline (created on first use)
 	cudaStream_t s_in, s_out;
 	cudaEvent_t ev_in[16], ev_done[16];
+	// resident timestep on host arrays (cmcb200_resident_begin / _end, api.cu): the upload runs in row chunks on s_in.  up_pending: the
+	// context's stream has not yet been ordered behind all of it (join_uploads); up_defer_join: the chunk-wise orbit step orders itself
+	bool up_pending, up_defer_join;
+	int up_chunks;
+	long up_per, up_n;
+	cudaEvent_t ev_tab, ev_bin;
+	bool resident_valid; // the device records mirror the host's records [1 .. resident_n] as of the last cmcb200_resident_end
+	long resident_n;
 	// radius-sharded operation (shard.cu): this context is rank `rank` of `nranks` GPUs of one node
 	int rank, nranks;
 	void *own_buf[SH_N_BUFFERS];                    // this rank's peer-visible buffers, in the order of the SH_* enum
@@ -94,6 +102,17 @@ struct cmcb200_ctx {
 
 // fills the orbit-step argument block from the context and the caller's parameters and (re)builds the lookup tables (api.cu)
 int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a);
+
+// every entry point that works on the resident arrays orders the context's stream behind an upload cmcb200_resident_begin left in flight
+static inline int join_uploads(cmcb200_ctx *c)
+{
+	if (!c->up_pending || c->up_defer_join) return 0;
+	CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_tab, 0));
+	for (int k = 0; k < c->up_chunks; k++) CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+	CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_bin, 0));
+	c->up_pending = false;
+	return 0;
+}
 
 static inline char *star1(cmcb200_ctx *c) { return c->d_star[c->cur_star] + CMCB_SIZEOF_STAR; }
 static inline char *bin1(cmcb200_ctx *c) { return c->d_bin[c->cur_bin] + CMCB_SIZEOF_BINARY; }

@@ -113,6 +113,7 @@ extern "C" int cmcb200_dev_clusdyn_calculate(cmcb200_ctx *c, long N_MAX, long N_
 {
 	if (N_MAX + 2 > c->n_table_dim) { set_error("clusdyn_calculate: N_MAX + 2 exceeds the table capacity"); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
 	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
 	{
@@ -134,6 +135,7 @@ extern "C" int cmcb200_dev_comp_mass_percent(cmcb200_ctx *c, const cmcb200_mass_
 	if (p->count < 0 || p->count > MASS_PC_MAX) { set_error("comp_mass_percent: MASS_PC_COUNT = %ld exceeds %d", p->count, MASS_PC_MAX); return -1; }
 	if (p->N_MAX + 2 > c->n_table_dim || p->n_local + 2 > c->n_star_dim) { set_error("comp_mass_percent: sizes exceed the context capacity"); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
 	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
 	const double madhoc = 1.0 / ((double) p->N_STAR);
@@ -242,6 +244,7 @@ extern "C" int cmcb200_dev_compute_energy_totals(cmcb200_ctx *c, long n_local, l
 {
 	if (n_local + 2 > c->n_star_dim || first_global + n_local > c->n_table_dim) { set_error("ComputeEnergy: sizes exceed the context capacity"); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
 	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
 	CMCB_CUDA_OK(cudaMemsetAsync(d->totals, 0, sizeof(d->totals), c->stream));

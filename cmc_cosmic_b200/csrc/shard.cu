@@ -226,6 +226,7 @@ extern "C" int cmcb200_shard_export(cmcb200_ctx *c, int rank, int nranks, void *
 {
 	if (nranks < 1 || nranks > SHARD_MAX_RANKS || rank < 0 || rank >= nranks) { set_error("shard_export: rank %d of %d (max %d ranks)", rank, nranks, SHARD_MAX_RANKS); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	c->rank = rank;
 	c->nranks = nranks;
 	c->keys_stride = c->n_star_dim;
@@ -247,6 +248,7 @@ extern "C" int cmcb200_shard_export(cmcb200_ctx *c, int rank, int nranks, void *
 extern "C" int cmcb200_shard_attach(cmcb200_ctx *c, const void *all_handles)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *) all_handles;
 	for (int q = 0; q < c->nranks; q++)
 		for (int b = 0; b < SH_N_BUFFERS; b++) {
@@ -259,6 +261,7 @@ extern "C" int cmcb200_shard_attach(cmcb200_ctx *c, const void *all_handles)
 extern "C" int cmcb200_shard_detach(cmcb200_ctx *c)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	for (int q = 0; q < c->nranks; q++)
 		for (int b = 0; b < SH_N_BUFFERS; b++)
@@ -294,6 +297,7 @@ extern "C" int cmcb200_shard_sort_local(cmcb200_ctx *c, long n_local, long *n_ke
 {
 	if (n_local + 2 > c->n_star_dim) { set_error("shard_sort_local: n_local + 2 = %ld exceeds n_star_dim = %ld", n_local + 2, c->n_star_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	SortArgs a;
 	memset(&a, 0, sizeof(a));
 	a.star_in = star1(c);
@@ -332,6 +336,7 @@ extern "C" int cmcb200_shard_sort_local(cmcb200_ctx *c, long n_local, long *n_ke
 extern "C" int cmcb200_shard_exchange(cmcb200_ctx *c, const long *n_keep_all, const int *Start, const int *End, long n_old_local, long first_global, long N_MAX)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	ShardMeta m;
 	memset(&m, 0, sizeof(m));
 	m.nranks = c->nranks;
@@ -381,6 +386,7 @@ extern "C" int cmcb200_shard_exchange(cmcb200_ctx *c, const long *n_keep_all, co
 extern "C" int cmcb200_shard_publish(cmcb200_ctx *c, long n_new_local, long start_global, long n_bin_clear, long *n_bin)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	c->cur_star ^= 1;
 	StageTimer t(c, ST_SHARD_TABLES);
 	void *ptrs[2 * SHARD_MAX_RANKS];

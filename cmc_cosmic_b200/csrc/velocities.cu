@@ -287,6 +287,7 @@ static long persistent_blocks(long n)
 extern "C" int cmcb200_dev_energy_conservation1(cmcb200_ctx *c, const cmcb200_orbit_params *p)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	OrbitArgs a;
 	if (orbit_begin(c, p, false, false, a)) return -1;
 	if (p->n_local > 0) {
@@ -318,6 +319,7 @@ static int sv3_finish(cmcb200_ctx *c, const Sv3Buffers &b, double *Eexcess_left,
 extern "C" int cmcb200_dev_set_velocities3(cmcb200_ctx *c, const cmcb200_orbit_params *p, double *Eexcess_left)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	OrbitArgs a;
 	if (orbit_begin(c, p, false, false, a)) return -1;
 	Sv3Buffers b;
@@ -340,6 +342,7 @@ extern "C" int cmcb200_dev_set_velocities3(cmcb200_ctx *c, const cmcb200_orbit_p
 extern "C" int cmcb200_dev_set_velocities3_pass(cmcb200_ctx *c, const cmcb200_orbit_params *p, double Eexcess_in, double *Eexcess_left)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	if (!c->d_sv3) { set_error("set_velocities3_pass: call cmcb200_dev_set_velocities3 first (it records which stars the second loop corrects)"); return -1; }
 	OrbitArgs a;
 	if (orbit_begin(c, p, false, false, a)) return -1;
@@ -359,6 +362,7 @@ extern "C" int cmcb200_dev_set_velocities3_pass(cmcb200_ctx *c, const cmcb200_or
 extern "C" int cmcb200_dev_potential(cmcb200_ctx *c, const cmcb200_orbit_params *p, const double *r, long n, double *out)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	if (n <= 0) return 0;
 	OrbitArgs a;
 	if (orbit_begin(c, p, false, false, a)) return -1;
@@ -384,6 +388,7 @@ extern "C" int cmcb200_dev_tidally_strip_select(cmcb200_ctx *c, const cmcb200_or
 						 long cap, long *count, void *star_out, void *binary_out, double *m_out)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
 	*count = 0;
 	if (tidal_treatment != 0 && tidal_treatment != 1) return 0; // the reference's loop body has no other branch (:476, :551)
 	if (p->n_local <= 0 || cap <= 0) return 0;

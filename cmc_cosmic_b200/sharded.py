@@ -227,6 +227,20 @@ class ShardedCluster(Cluster):
             p.draws, p.draw_off = self._draws.ctypes.data, self._draw_off.ctypes.data
         return p
 
+    def host_step(self, seed=0, draws=None, draw_off=None, dirty_words=None):
+        """Cluster.host_step on this rank's shard: its records and the tables cross this rank's host link once each way; max_r is reduced
+        over the ranks like new_orbits_calculate does (reference cmc_utils.c:2206)."""
+        res = super().host_step(seed, draws, draw_off, dirty_words)
+        self.max_r = self._allreduce_max(res.max_r)
+        return res
+
+    def _allreduce_max(self, x):
+        import torch
+        with torch.cuda.stream(self._tstream):
+            m = torch.tensor([x], dtype=torch.float64, device=f"cuda:{self.device}")
+            self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX)
+            return float(m.item())
+
     def dev_step(self, seed=0, draws=None, draw_off=None, fused=True):
         """orbit step on the local shard -> sharded sort (records to their final rank and slot over NVLink) -> replicated potential.
         max_r is reduced over the ranks like new_orbits_calculate does (reference cmc_utils.c:2206)."""

@@ -13,7 +13,19 @@
  * in star order, by the reference's own functions from the per-star status codes the kernel returns -- so the
  * accumulators see the same additions in the same order as in get_positions_loop.
  *
- * Single rank per GPU.  procs > 1 goes through the radius-sharded entry points (cmcb200_shard_*). */
+ * Single rank per GPU.  procs > 1 goes through the radius-sharded entry points (cmcb200_shard_*).
+ *
+ * RESIDENT MODE (-DCMCB200_SHIM_RESIDENT, linked with --wrap): the whole block of the main loop from energy_conservation1() to ComputeEnergy()
+ * (src/cmc/cmc.c:302-353) is bound to the device-resident pipeline, so the star records cross the host link ONCE each way per timestep:
+ *     energy_conservation1        opens the window: cmcb200_resident_begin starts the upload of star[] / binary[] / star_r / star_m / star_phi
+ *     new_orbits_calculate        the orbit step, chunk by chunk behind the arriving records; then energy_conservation1's pass; host side
+ *                                 effects (remove_star ...) replayed by the reference's own functions and mirrored to the device
+ *     energy_conservation2, tidally_strip_stars, ComputeIntermediateEnergy, qsorts_new, post_sort_comm, calc_potential_new (tables come
+ *     back here: potential() has host callers), energy_conservation3, comp_mass_percent
+ *     ComputeEnergy               E, J, the energy sums; closes the window: cmcb200_resident_end downloads records, binaries and tables
+ * Outside a window (start-up: src/cmc/cmc.c:133-167) the four hot-path functions take the host-buffer form and the others the reference's
+ * own code (__real_*).  Between the first and the last call of a window the host must not touch star[] / binary[]: true for the block above
+ * when STAR_AGING_SCHEME == 0 (toy_rejuvenation is then a no-op); with procs > 1 or STAR_AGING_SCHEME > 0 no window is opened. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -105,11 +117,22 @@ SHIM_EXPORT void cmcb200_shim_shutdown(void)
 }
 
 /* src/cmc/cmc_utils.c:2194-2211 */
+#ifdef CMCB200_SHIM_RESIDENT
+static void res_new_orbits_calculate(void);
+static void res_qsorts_new(void);
+static void res_calc_potential_new(void);
+static int win_open;
+#define RES_ROUTE(f) do { if (win_open) { f(); return; } } while (0)
+#else
+#define RES_ROUTE(f) do { } while (0)
+#endif
+
 void SHIM(new_orbits_calculate)(void)
 {
 	cmcb200_orbit_params p;
 	double phi_rtidal, phi_zero;
 	long j, n = clus.N_MAX_NEW, n_old = End[myid] - Start[myid] + 1;
+	RES_ROUTE(res_new_orbits_calculate);
 	shim_init();
 	memset(&p, 0, sizeof p);                         /* every field the shim does not set (fuse_compute_energy: resident pipeline only) is 0 */
 	OldTidalMassLoss = TidalMassLoss_old;
@@ -177,6 +200,7 @@ static void shim_sharded_sort(long n, long nb)
 void SHIM(qsorts_new)(void)
 {
 	long n = clus.N_MAX_NEW, nb = N_b_local, i;
+	RES_ROUTE(res_qsorts_new);
 	shim_init();
 	/* binaries referenced by the stars being sorted occupy binary[1..max binind]; N_b_local is only refreshed by load_balance */
 	for (i = 1; i <= n; i++) if (star[i].binind > nb) nb = star[i].binind;
@@ -199,9 +223,313 @@ void SHIM(post_sort_comm)(void)
 void SHIM(calc_potential_new)(void)
 {
 	long nmax = clus.N_MAX;
+	RES_ROUTE(res_calc_potential_new);
 	shim_init();
 	if (cmcb200_calc_potential_new(ctx, star_r, star_m, star_phi, &nmax, clus.N_STAR, &cenma.m, &cenma.m_new, orbit_r, &Mtotal, &Rtidal))
 		shim_fail("calc_potential_new");
 	clus.N_MAX = nmax;
 	mpiFindIndicesCustom(clus.N_MAX, MIN_CHUNK_SIZE, myid, &mpiBegin, &mpiEnd);
 }
+
+
+#ifdef CMCB200_SHIM_RESIDENT
+#ifndef CMCB200_SHIM_WRAP
+#error "the resident mode needs the --wrap build: outside a window it calls the reference's own functions as __real_*"
+#endif
+void __real_energy_conservation1(void);
+void __real_energy_conservation2(void);
+void __real_energy_conservation3(void);
+void __real_tidally_strip_stars(void);
+void __real_ComputeIntermediateEnergy(void);
+void __real_ComputeEnergy(void);
+void __real_comp_mass_percent(void);
+
+static int win_open = 0;      /* (declared above) the records live on the device; the host copy of star[] / binary[] is stale */
+static int ec1_pending = 0;   /* energy_conservation1's pass has been deferred behind the orbit step (same result: see new_orbits_calculate) */
+static unsigned long long dirty_words = ~0ull; /* what the host may have written since the last window (cmcb200_shim_set_dirty_words) */
+static long win_n_bin = 0;    /* binary slots uploaded */
+
+/* the caller's promise for cmcb200_resident_begin: bit w = word w of star_t may have changed since the last ComputeEnergy() */
+SHIM_EXPORT void cmcb200_shim_set_dirty_words(unsigned long long mask) { dirty_words = mask; }
+SHIM_EXPORT int cmcb200_shim_window_open(void) { return win_open; }
+
+static void res_params(cmcb200_orbit_params *p)
+{
+	long n = clus.N_MAX_NEW, n_old = End[myid] - Start[myid] + 1;
+	memset(p, 0, sizeof *p);
+	p->n_local = n;
+	p->n_old_local = n_old;
+	p->first_global = Start[myid];
+	p->N_MAX = clus.N_MAX;
+	p->N_STAR = clus.N_STAR;
+	p->n_table = clus.N_MAX + 2 + (n > n_old ? n - n_old : 0);
+	p->cenma_m = cenma.m;
+	p->Rtidal = Rtidal;
+	p->draws = shim_draws;
+	p->draw_off = shim_draw_off;
+	p->seed = (unsigned long long) IDUM;
+	p->tcount = (unsigned long long) tcount;
+}
+
+static int res_allowed(void) { return procs == 1 && STAR_AGING_SCHEME == 0 && !getenv("CMCB200_NO_RESIDENT"); }
+
+static void res_flush_ec1(void)
+{
+	cmcb200_orbit_params p;
+	if (!ec1_pending) return;
+	res_params(&p);
+	if (cmcb200_dev_energy_conservation1(ctx, &p)) shim_fail("energy_conservation1");
+	ec1_pending = 0;
+}
+
+/* one record / table entry / binary back to the device after the reference's host code rewrote it (remove_star, destroy_obj) */
+static void res_push_star(long j, long k)
+{
+	int g = get_global_idx(j);
+	if (cmcb200_dev_put(ctx, star + j, j, k > 0 ? binary + k : NULL, k, star_m + g, g)) shim_fail("dev_put");
+}
+
+/* src/cmc/cmc_utils.c:2153-2174.  Opens the window.  The pass itself reads vr, vt and the tables and writes vrold, vtold, Uoldrold; the orbit
+ * step that follows reads and writes none of these, so the pass is queued BEHIND it (new_orbits_calculate below) -- the orbit step can then
+ * start on the first uploaded chunk instead of waiting for the last one. */
+void SHIM(energy_conservation1)(void)
+{
+	long n_new;
+	if (!res_allowed()) { __real_energy_conservation1(); return; }
+	shim_init();
+	n_new = clus.N_MAX_NEW - (End[myid] - Start[myid] + 1);
+	win_n_bin = N_BIN_DIM_OPT - 1; /* a star may point at any slot (binaries are created in free slots between two sorts) */
+	if (cmcb200_resident_begin(ctx, star + 1, clus.N_MAX_NEW, binary + 1, win_n_bin, star_r, star_m, star_phi, clus.N_MAX + 2 + (n_new > 0 ? n_new : 0), dirty_words))
+		shim_fail("resident_begin");
+	win_open = 1;
+	ec1_pending = 1;
+}
+
+static void res_new_orbits_calculate(void)
+{
+	cmcb200_orbit_params p;
+	double phi_rtidal, phi_zero;
+	long j, n = clus.N_MAX_NEW;
+	unsigned long long flagged;
+	OldTidalMassLoss = TidalMassLoss_old;
+	phi_rtidal = potential(Rtidal);                  /* get_positions, cmc_evolution_thr.c:963-964: the host tables are the uploaded ones */
+	phi_zero = potential(0.0);
+	res_params(&p);
+	if (cmcb200_dev_new_orbits(ctx, &p, 1, &last_orbit)) shim_fail("new_orbits_calculate");
+	res_flush_ec1();                                 /* before the removed stars' records are rewritten below: like the reference, where it ran first */
+	flagged = last_orbit.n_status[CMCB200_ORBIT_MASSLESS] + last_orbit.n_status[CMCB200_ORBIT_UNBOUND] + last_orbit.n_status[CMCB200_ORBIT_TIDAL] +
+		  last_orbit.n_status[CMCB200_ORBIT_NTRY];
+	if (flagged) {                                   /* rare: a few stars per step */
+		if (n > status_cap) { status_cap = n + n / 4 + 64; status_buf = realloc(status_buf, status_cap * sizeof(int)); }
+		if (cmcb200_dev_read_status(ctx, status_buf, NULL, NULL, n)) shim_fail("dev_read_status");
+		for (j = 1; j <= n; j++) {
+			int st = status_buf[j - 1];
+			if (st == CMCB200_ORBIT_OK || st == CMCB200_ORBIT_CIRCULAR) continue;
+			/* the reference's functions read the star's record as the loop body left it (r_peri / r_apo of a tidally stripped star are logged) */
+			long k;
+			if (cmcb200_dev_get(ctx, star + j, j, NULL, 0)) shim_fail("dev_get");
+			k = star[j].binind;                      /* destroy_obj zeroes the record: remember which binary it destroys with it */
+			switch (st) {
+			case CMCB200_ORBIT_MASSLESS: destroy_obj(j); break;                                           /* :816-820 */
+			case CMCB200_ORBIT_UNBOUND: count_esc_bhs(j); remove_star(j, phi_rtidal, phi_zero); break;    /* :823-829 */
+			case CMCB200_ORBIT_TIDAL: remove_star(j, phi_rtidal, phi_zero); break;                        /* :848-855 */
+			default:                                                                                      /* :890-893 */
+				eprintf("N_TRY exceeded\n");
+				exit_cleanly(-1, __FUNCTION__);
+			}
+			res_push_star(j, k);
+		}
+	}
+	max_r = last_orbit.max_r;
+	MPI_Allreduce(MPI_IN_PLACE, &max_r, 1, MPI_DOUBLE, MPI_MAX, MPI_COMM_WORLD);
+	MPI_Allreduce(MPI_IN_PLACE, &TidalMassLoss, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+	TidalMassLoss += TidalMassLoss_old;
+}
+
+/* src/cmc/cmc_utils.c:2217-2226 */
+void SHIM(energy_conservation2)(void)
+{
+	cmcb200_orbit_params p;
+	if (!win_open) { __real_energy_conservation2(); return; }
+	res_flush_ec1();
+	res_params(&p);
+	if (cmcb200_dev_energy_conservation2(ctx, &p)) shim_fail("energy_conservation2");
+}
+
+/* src/cmc/cmc_evolution_thr.c:443-645: the criterion runs over the resident records (one device pass per iteration of the reference's
+ * do-while); the loop around it, and for every stripped star the sums, the esc log line and destroy_obj, are host code in the reference's
+ * order.  The body below restates :484-547 for one star (a maintainer would factor it out of the loop instead). */
+static void res_strip_one(long i, double phi_rtidal, double phi_zero)
+{
+	int g_i = get_global_idx(i);
+	double m = star_m[g_i], r = star_r[g_i];
+	long k;
+	star[i].rnew = SF_INFINITY;
+	star[i].vrnew = 0.0;
+	star[i].vtnew = 0.0;
+	Eescaped += star[i].E * m / clus.N_STAR;
+	Jescaped += star[i].J * m / clus.N_STAR;
+	if (star[i].binind == 0) {
+		Eintescaped += star[i].Eint;
+	} else {
+		Ebescaped += -(binary[star[i].binind].m1 / clus.N_STAR) * (binary[star[i].binind].m2 / clus.N_STAR) / (2.0 * binary[star[i].binind].a);
+		Eintescaped += binary[star[i].binind].Eint1 + binary[star[i].binind].Eint2;
+	}
+	DTidalMassLoss += m / clus.N_STAR;
+	Etidal += star[i].E * m / clus.N_STAR;
+	parafprintf(escfile, "%ld %.8g %.8g %.8g %.8g %.8g %.8g %.8g %.8g %.8g %.8g %.8g %.8g %ld ", tcount, TotalTime, m * (units.m / clus.N_STAR) / MSUN, r,
+		    star[i].vr, star[i].vt, star[i].r_peri, star[i].r_apo, Rtidal, phi_rtidal, phi_zero, star[i].E, star[i].J, star[i].id);
+	k = star[i].binind;
+	if (k) parafprintf(escfile, "1 %.8g %.8g %ld %ld %.8g %.8g ", binary[k].m1 * (units.m / clus.N_STAR) / MSUN, binary[k].m2 * (units.m / clus.N_STAR) / MSUN,
+			   binary[k].id1, binary[k].id2, binary[k].a * units.l / AU, binary[k].e);
+	else parafprintf(escfile, "0 0 0 0 0 0 0 ");
+	if (k == 0)
+		parafprintf(escfile, "%d na na na na na na na na na na na na na na na na na na na na na na na na na na na na na na na na na na na %g na na %g %g %g",
+			    star[i].se_k, star[i].se_bhspin, star[i].se_ospin, star[i].se_scm_B, star[i].se_scm_formation);
+	else
+		parafprintf(escfile, "na %d %d %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g na %g %g na na na",
+			    binary[k].bse_kw[0], binary[k].bse_kw[1], binary[k].bse_radius[0], binary[k].bse_radius[1], binary[k].bse_tb, binary[k].bse_lum[0],
+			    binary[k].bse_lum[1], binary[k].bse_massc[0], binary[k].bse_massc[1], binary[k].bse_radc[0], binary[k].bse_radc[1], binary[k].bse_menv[0],
+			    binary[k].bse_menv[1], binary[k].bse_renv[0], binary[k].bse_renv[1], binary[k].bse_tms[0], binary[k].bse_tms[1], binary[k].bse_bcm_dmdt[0],
+			    binary[k].bse_bcm_dmdt[1], binary[k].bse_bcm_radrol[0], binary[k].bse_bcm_radrol[1], binary[k].bse_ospin[0], binary[k].bse_ospin[1],
+			    binary[k].bse_bcm_B[0], binary[k].bse_bcm_B[1], binary[k].bse_bcm_formation[0], binary[k].bse_bcm_formation[1], binary[k].bse_bacc[0],
+			    binary[k].bse_bacc[1], binary[k].bse_tacc[0], binary[k].bse_tacc[1], binary[k].bse_mass0[0], binary[k].bse_mass0[1], binary[k].bse_epoch[0],
+			    binary[k].bse_epoch[1], binary[k].bse_bhspin[0], binary[k].bse_bhspin[1]);
+	parafprintf(escfile, "\n");
+	destroy_obj(i);
+}
+
+void SHIM(tidally_strip_stars)(void)
+{
+	static long *idx = NULL, cap = 0;
+	cmcb200_orbit_params p;
+	double phi_rtidal, phi_zero, thr;
+	long j = 0, n, q;
+	int rc;
+	if (!win_open) { __real_tidally_strip_stars(); return; }
+	res_flush_ec1();
+	if (!idx) { cap = 4096; idx = malloc(cap * sizeof(long)); }
+	Etidal = 0.0;
+	DTidalMassLoss = TidalMassLoss - OldTidalMassLoss;
+	rootgprintf("tidally_strip_stars(): iteration %ld: OldTidalMassLoss=%.6g DTidalMassLoss=%.6g\n", j, OldTidalMassLoss, DTidalMassLoss);
+	pararootfprintf(logfile, "tidally_strip_stars(): iteration %ld: OldTidalMassLoss=%.6g DTidalMassLoss=%.6g\n", j, OldTidalMassLoss, DTidalMassLoss);
+	do {
+		Rtidal = orbit_r * pow(Mtotal - (TidalMassLoss - OldTidalMassLoss), 1.0 / 3.0);
+		phi_rtidal = potential(Rtidal);
+		phi_zero = potential(0.0);
+		DTidalMassLoss = 0.0;
+		thr = TIDAL_TREATMENT == 0 ? Rtidal : (1.5 - 3.0 * pow(log(GAMMA * ((double) clus.N_STAR)) / ((double) clus.N_STAR), 0.25)) * phi_rtidal;
+		res_params(&p);
+		for (;;) { /* the criterion over all resident records; nothing is marked when the list does not fit */
+			rc = cmcb200_dev_tidally_strip_select(ctx, &p, (int) TIDAL_TREATMENT, thr, idx, cap, &n, NULL, NULL, NULL);
+			if (rc == -3 && n > cap) { cap = n + 1024; idx = realloc(idx, cap * sizeof(long)); continue; }
+			if (rc) shim_fail("tidally_strip_stars");
+			break;
+		}
+		for (q = 0; q < n; q++) { /* star order: the sums see the reference's additions in the reference's order */
+			long i = idx[q], k;
+			if (cmcb200_dev_get(ctx, star + i, i, NULL, 0)) shim_fail("dev_get");
+			k = star[i].binind;
+			res_strip_one(i, phi_rtidal, phi_zero);
+			res_push_star(i, k);
+		}
+		j++;
+		MPI_Allreduce(MPI_IN_PLACE, &DTidalMassLoss, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+		TidalMassLoss += DTidalMassLoss;
+		rootgprintf("tidally_strip_stars(): iteration %ld: TidalMassLoss=%.6g DTidalMassLoss=%.6g\n", j, TidalMassLoss, DTidalMassLoss);
+		pararootfprintf(logfile, "tidally_strip_stars(): iteration %ld: TidalMassLoss=%.6g DTidalMassLoss=%.6g\n", j, TidalMassLoss, DTidalMassLoss);
+	} while (DTidalMassLoss > 0);
+	{
+		double buf_reduce[5] = {Eescaped, Jescaped, Eintescaped, Ebescaped, Etidal};
+		MPI_Allreduce(MPI_IN_PLACE, buf_reduce, 5, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+		Eescaped = buf_reduce[0]; Jescaped = buf_reduce[1]; Eintescaped = buf_reduce[2]; Ebescaped = buf_reduce[3]; Etidal = buf_reduce[4];
+	}
+}
+
+/* src/cmc/cmc_utils.c:368-391 */
+void SHIM(ComputeIntermediateEnergy)(void)
+{
+	cmcb200_orbit_params p;
+	if (!win_open) { __real_ComputeIntermediateEnergy(); return; }
+	res_flush_ec1();
+	res_params(&p);
+	if (cmcb200_dev_compute_intermediate_energy(ctx, &p)) shim_fail("ComputeIntermediateEnergy");
+}
+
+static void res_qsorts_new(void)
+{
+	long n = clus.N_MAX_NEW, nb = 0;
+	res_flush_ec1();
+	if (cmcb200_dev_qsorts_new(ctx, &n, win_n_bin, &nb)) shim_fail("qsorts_new");
+	clus.N_MAX = n;
+	clus.N_MAX_NEW = n;
+	N_b_local = nb;
+	win_n_bin = nb;
+	findLimits(clus.N_MAX, MIN_CHUNK_SIZE);
+}
+
+static void res_calc_potential_new(void)
+{
+	long nmax = clus.N_MAX;
+	if (cmcb200_dev_calc_potential_new(ctx, &nmax, clus.N_STAR, &cenma.m, &cenma.m_new, orbit_r, &Mtotal, &Rtidal)) shim_fail("calc_potential_new");
+	clus.N_MAX = nmax;
+	/* potential() / calc_orbit_new() / FindZero_r() have host callers: the tables come back now, the records at the end of the window */
+	if (cmcb200_download(ctx, NULL, 0, NULL, 0, star_r, star_m, star_phi, clus.N_MAX + 2)) shim_fail("download(tables)");
+	mpiFindIndicesCustom(clus.N_MAX, MIN_CHUNK_SIZE, myid, &mpiBegin, &mpiEnd);
+}
+
+/* src/cmc/cmc_utils.c:254-363 */
+void SHIM(energy_conservation3)(void)
+{
+	cmcb200_orbit_params p;
+	double Eexcess = 0.0, Eexcess_prev = 0.0, Eexcess_check = 0.0;
+	MPI_Status stat;
+	if (!win_open) { __real_energy_conservation3(); return; }
+	res_params(&p);
+	if (cmcb200_dev_set_velocities3(ctx, &p, &Eexcess)) shim_fail("set_velocities3");
+	do { /* :315-347: what a rank could not absorb travels to the next one */
+		if (myid != procs - 1) MPI_Send(&Eexcess, 1, MPI_DOUBLE, myid + 1, 0, MPI_COMM_WORLD);
+		if (myid != 0) MPI_Recv(&Eexcess_prev, 1, MPI_DOUBLE, myid - 1, 0, MPI_COMM_WORLD, &stat);
+		Eexcess = Eexcess_prev;
+		if (Eexcess > 0 && cmcb200_dev_set_velocities3_pass(ctx, &p, Eexcess, &Eexcess)) shim_fail("set_velocities3 (second loop)");
+		MPI_Allreduce(&Eexcess, &Eexcess_check, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+	} while (Eexcess_check > 0);
+	Eoops += -Eexcess * madhoc;
+}
+
+/* src/cmc/cmc_utils.c:872-985 */
+void SHIM(comp_mass_percent)(void)
+{
+	cmcb200_mass_pc_params p;
+	cmcb200_mass_pc_result r;
+	if (!win_open) { __real_comp_mass_percent(); return; }
+	memset(&p, 0, sizeof p); memset(&r, 0, sizeof r);
+	p.count = MASS_PC_COUNT; p.mass_pc = mass_pc; p.bh_include = MASS_PC_BH_INCLUDE; p.minimum_r = MINIMUM_R;
+	p.initial_total_mass = initial_total_mass; p.Mtotal = Mtotal; p.cenma_m = cenma.m;
+	p.N_MAX = clus.N_MAX; p.N_STAR = clus.N_STAR; p.n_local = clus.N_MAX_NEW; p.first_global = Start[myid];
+	r.mass_r = mass_r; r.ave_mass_r = ave_mass_r; r.no_star_r = no_star_r; r.densities_r = densities_r;
+	r.ke_rad_r = ke_rad_r; r.ke_tan_r = ke_tan_r; r.v2_rad_r = v2_rad_r; r.v2_tan_r = v2_tan_r;
+	if (cmcb200_dev_comp_mass_percent(ctx, &p, &r)) shim_fail("comp_mass_percent");
+}
+
+/* src/cmc/cmc_utils.c:604-656.  Closes the window. */
+void SHIM(ComputeEnergy)(void)
+{
+	double buf_reduce[5], s[4];
+	long n = mpiEnd - mpiBegin + 1;
+	if (!win_open) { __real_ComputeEnergy(); return; }
+	if (cmcb200_dev_compute_energy(ctx, n, Start[myid])) shim_fail("ComputeEnergy");
+	if (cmcb200_dev_compute_energy_totals(ctx, n, Start[myid], clus.N_MAX, clus.N_STAR, cenma.m, s)) shim_fail("ComputeEnergy (sums)");
+	buf_reduce[1] = s[0]; buf_reduce[2] = s[1]; buf_reduce[3] = s[2]; buf_reduce[4] = s[3];
+	buf_reduce[2] *= 0.5;
+	buf_reduce[0] = buf_reduce[1] + buf_reduce[2] + buf_reduce[3] + buf_reduce[4];
+	MPI_Allreduce(MPI_IN_PLACE, buf_reduce, 5, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+	Etotal.tot = buf_reduce[0]; Etotal.K = buf_reduce[1]; Etotal.P = buf_reduce[2]; Etotal.Eint = buf_reduce[3]; Etotal.Eb = buf_reduce[4];
+	cenma.E += cenma.E_new;
+	cenma.E_new = 0.0;
+	Etotal.tot += cenma.E + Eescaped + Ebescaped + Eintescaped;
+	/* everything the host reads next (reset_interaction_flags, update_vars, the output routines, dynamics_apply of the next step) */
+	if (cmcb200_resident_end(ctx, star + 1, clus.N_MAX_NEW, binary + 1, win_n_bin, N_BIN_DIM_OPT, NULL, NULL, NULL, 0)) shim_fail("resident_end");
+	win_open = 0;
+}
+#endif /* CMCB200_SHIM_RESIDENT */

@@ -147,6 +147,33 @@ int cmcb200_upload(cmcb200_ctx *ctx, const void *star1, long n_local, const void
 int cmcb200_download(cmcb200_ctx *ctx, void *star1, long n_local, void *binary1, long n_bin,
 		     double *star_r, double *star_m, double *star_phi, long n_table);
 
+/* Resident timestep on HOST arrays (the residency protocol of the drop-in shim): the records cross the host link once each
+ * way per timestep instead of once per entry point.
+ *   cmcb200_resident_begin   starts the upload of the caller's arrays and returns at once: tables first, then the records in row chunks, then
+ *                            the binaries, on the context's copy stream.  The cmcb200_dev_* calls that follow are ordered behind it ON THE
+ *                            DEVICE; cmcb200_dev_new_orbits runs chunk by chunk behind the arriving records, so the orbit step hides under
+ *                            the upload.  The caller must not write the arrays until a call that returns results computed from all of them
+ *                            has returned (any cmcb200_dev_* call that synchronises: the orbit step, the sort, the potential).
+ *                            dirty_words: bit w set = the 8-byte word w of the records (0 <= w < 53) may differ from the copy the last
+ *                            cmcb200_resident_end left on the device; ~0ull = everything (always used when there is no such copy or n_local
+ *                            changed).  Clean words are not sent -- the caller's promise, e.g. a run without stellar evolution never
+ *                            writes the se_* words between two timesteps.  Runs of dirty words travel as strided (2-D) DMA copies.
+ *   cmcb200_resident_end     downloads records, binaries (the tail of binary1 up to n_bin_dim - 1 is zeroed like cmc_sort.c:541 does) and
+ *                            tables, and waits: the host arrays are coherent with the device again.
+ * Any pointer may be NULL (not moved). */
+int cmcb200_resident_begin(cmcb200_ctx *ctx, const void *star1, long n_local, const void *binary1, long n_bin,
+			   const double *star_r, const double *star_m, const double *star_phi, long n_table, unsigned long long dirty_words);
+int cmcb200_resident_end(cmcb200_ctx *ctx, void *star1, long n_local, void *binary1, long n_bin, long n_bin_dim,
+			 double *star_r, double *star_m, double *star_phi, long n_table);
+
+/* Single records between two bulk transfers -- what the reference's host code needs when it handles one star of a resident window
+ * (remove_star / destroy_obj for an escaper: reads the record, zeroes it, sets star_m[g] = DBL_MIN, destroys its binary).
+ *   cmcb200_dev_get   star_rec <- resident record j (1-based local index); binary_rec (may be NULL) <- resident binary slot b
+ *   cmcb200_dev_put   the other way; star_m_g (may be NULL): the new value of the resident table entry star_m[g]
+ * Both wait for the copy. */
+int cmcb200_dev_get(cmcb200_ctx *ctx, void *star_rec, long j, void *binary_rec, long b);
+int cmcb200_dev_put(cmcb200_ctx *ctx, const void *star_rec, long j, const void *binary_rec, long b, const double *star_m_g, long g);
+
 /* orbit step on the resident arrays (same semantics as cmcb200_new_orbits_calculate; star_r/m/phi = resident tables) */
 int cmcb200_dev_new_orbits(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int want_status, cmcb200_orbit_result *res);
 /* the transfer half of ComputeIntermediateEnergy (src/cmc/cmc_utils.c:380-390): rOld <- star_r, r <- rnew, m <- star_m,

@@ -1,0 +1,111 @@
+"""The resident timestep on HOST arrays (cmcb200_resident_begin / _end): the records cross the host link once each way per timestep.
+
+Checked against the four host-buffer entry points called one after the other -- which tests/test_gpu_parity.py and tests/test_dropin_shim.py
+check against the oracle and the compiled reference -- byte for byte over the whole star array, tables and scalars; the orbit step runs
+chunk by chunk behind the arriving upload here (N is large enough for several chunks), so this also pins that the chunked step equals the
+whole one."""
+import numpy as np
+import pytest
+
+import common as cm
+from cmc_cosmic_b200.cluster import Cluster
+
+pytestmark = pytest.mark.gpu
+
+
+def _cluster(N, r, vr, vt, sm, pinned, binind=None, nb=0, fill_seed=5):
+    c = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8, pinned=pinned)
+    c.load(r, vr, vt, sm, binind=binind)
+    # every byte of the records travels: fill what the path never looks at with noise
+    rng = np.random.default_rng(fill_seed)
+    c.star[1:N + 1, 208:] = rng.integers(0, 256, (N, 424 - 208), dtype=np.uint8)
+    if nb:
+        c.binary[1:nb + 1] = rng.integers(0, 256, (nb, 464), dtype=np.uint8)
+    c.calc_potential_new()
+    c.compute_energy()
+    return c
+
+
+def _four_calls(c, draws, draw_off, seed):
+    n = c.clus.N_MAX_NEW
+    c.new_orbits_calculate(draws=draws, draw_off=draw_off, seed=seed)
+    # ComputeIntermediateEnergy's transfer (reference cmc_utils.c:380-390), host code of the caller between the calls
+    c.field("rOld")[1:n + 1] = c.star_r[1:n + 1]
+    c.field("m")[1:n + 1] = c.star_m[1:n + 1]
+    for dst, src in (("r", "rnew"), ("vr", "vrnew"), ("vt", "vtnew")):
+        c.field(dst)[1:n + 1] = c.field(src)[1:n + 1]
+    c.qsorts_new()
+    c.post_sort_comm()
+    c.calc_potential_new()
+    c.tcount += 1
+
+
+def _same(a, b, what):
+    n = a.clus.N_MAX
+    assert (a.clus.N_MAX, a.clus.N_MAX_NEW, a.N_b_local) == (b.clus.N_MAX, b.clus.N_MAX_NEW, b.N_b_local), what
+    assert np.array_equal(a.star[:n + 1], b.star[:n + 1]), f"{what}: star[]"
+    assert np.array_equal(a.binary, b.binary), f"{what}: binary[]"
+    for f in ("star_r", "star_m", "star_phi"):
+        cm.assert_bits_equal(getattr(a, f)[:n + 2], getattr(b, f)[:n + 2], f"{what}: {f}")
+    assert (a.Mtotal, a.Rtidal, a.max_r) == (b.Mtotal, b.Rtidal, b.max_r), what
+
+
+@pytest.mark.parametrize("N,pinned,nb", [(1_300_000, True, 0), (700_000, False, 20000), (5000, True, 0)])
+def test_host_step_equals_the_four_host_buffer_calls(N, pinned, nb):
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=N % 1000, masses="imf" if nb else "equal")
+    binind = None
+    if nb:
+        binind = np.zeros(N, np.int64)
+        rng = np.random.default_rng(3)
+        binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    a, b = (_cluster(N, r, vr, vt, sm, pinned, binind, nb) for _ in range(2))
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E, J, vr, vt, pot["Rtidal"], seed=3)
+    # step 1: recorded draws (the oracle's), everything uploaded
+    _four_calls(a, want["draws"], want["draw_off"], 0)
+    res = b.host_step(draws=want["draws"], draw_off=want["draw_off"])
+    assert int(res.n_draws) == len(want["draws"])
+    _same(a, b, "step 1")
+    n = a.clus.N_MAX
+    o = np.argsort(want["rnew"], kind="stable")[:n]
+    cm.assert_bits_equal(b.field("r")[1:n + 1], want["rnew"][o], "sorted new radii vs the oracle")
+    h2d, d2h = b.transfer_bytes(reset=True)
+    nb_now = b.N_b_local
+    assert h2d >= N * 424 + 3 * 8 * (N + 2) and d2h >= n * 424 + 3 * 8 * (n + 2) + nb_now * 464
+    # step 2: production draws; the host has rewritten E and J only (ComputeEnergy) and says so: the clean words stay on the device
+    for c in (a, b):
+        c.compute_energy()
+    _four_calls(a, None, None, 77)
+    b.host_step(seed=77, dirty_words=Cluster.dirty_mask("E", "J"))
+    _same(a, b, "step 2 (dirty words: E, J)")
+    h2d, _ = b.transfer_bytes(reset=True)
+    assert h2d < n * 16 + 3 * 8 * (n + 2) + nb_now * 464 + 4096, "only the dirty words and the tables were sent"
+    # step 3: a dirty mask is ignored (everything sent) once the device copy is not the one resident_end left: here after an upload()
+    for c in (a, b):
+        c.compute_energy()
+    b.upload()
+    _four_calls(a, None, None, 78)
+    b.host_step(seed=78, dirty_words=Cluster.dirty_mask("E"))
+    _same(a, b, "step 3 (stale device copy: full upload)")
+    a.close(); b.close()
+
+
+def test_resident_calls_order_themselves_behind_the_upload():
+    """Every dev_* entry point may be the first call after resident_begin: it waits (on the device) for the whole upload.  Here the energy
+    scheme's first pass and the sort are called straight after resident_begin, with the host-side upload() form as the reference."""
+    N = 1_200_000
+    r, vr, vt, sm = cm.cluster_state("king", N, seed=8)
+    a, b = (_cluster(N, r, vr, vt, sm, True) for _ in range(2))
+    a.upload()
+    a.dev_energy_conservation1()
+    a.dev_qsorts_new()
+    a.dev_calc_potential_new()
+    a.download()
+    b.resident_begin()
+    b.dev_energy_conservation1()
+    b.dev_qsorts_new()
+    b.dev_calc_potential_new()
+    b.resident_end()
+    _same(a, b, "ec1 + sort + potential")
+    a.close(); b.close()
