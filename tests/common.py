@@ -117,3 +117,48 @@ def sv3_fields(r, vr, vt, phi, seed=0, src_frac=0.004, long_chains=True):
     f["vr"], f["vt"] = vr.copy(), vt.copy()
     f["vrnew"], f["vtnew"] = vr * 1.5, vt * 0.5           # overwritten for every corrected star, kept for the others
     return f
+
+
+def brent_cluster(N=20000, seed=5, stride=20):
+    """A cluster state in which find_root_vr (reference cmc_nr.c:500-603; cmc_orbit.c:459-474, 485-500) actually fires.  On an ordinary
+    cluster it never does: Henon's closed form needs inside_sqrt = a^2 - 2 J^2 (b - E) >= 0 on the bracketing interval, which holds whenever Q
+    changes sign across it -- except by rounding.  So every `stride`-th star j is given the (E, J) of the orbit that is CIRCULAR AT ITS OWN
+    RADIUS for the interpolation Phi = a/r + b of a neighbouring interval (J^2 = -a r_j, E = b + a / (2 r_j), nudged by -4 .. +4 ulps): the
+    quadratic has a double root at the grid point r_j, Q(r_j) is a few ulps from zero, inside_sqrt comes out negative about as often as not
+    and the vertex -J^2/a falls outside the interval by rounding -- the Brent fallback.  Returns r, vr, vt, star_m, pot, E (star[].E, i.e.
+    WITHOUT the self term get_positions_loop adds, cmc_evolution_thr.c:806), J, planted (bool mask)."""
+    r, vr, vt, sm = cluster_state("plummer", N, seed=seed, masses="imf")
+    pot = oracle_potential(r, sm)
+    sr, smt, phi = pot["star_r"], pot["star_m"], pot["phi"]
+    E, J = energies(phi[1:N + 1], r, vr, vt)
+    planted = np.zeros(N, bool)
+
+    def phi_s(rad, j):   # MPI_PHI_S, include/cmc/cmc.h:2175
+        return (smt[j] / rad if rad >= sr[j] else smt[j] / sr[j]) * (1.0 / N)
+
+    for n, j in enumerate(range(100, N - 100, stride)):
+        k = j - 1 if n % 2 == 0 else j          # the interval below the star (r_min bracket) or above it (r_max bracket)
+        rk, rk1 = sr[k], sr[k + 1]
+        Uk, Uk1 = phi[k] + phi_s(rk, j), phi[k + 1] + phi_s(rk1, j)
+        a = (Uk1 - Uk) / (1. / rk1 - 1. / rk)   # set_a_b, cmc_orbit.c:722-740
+        b = (Uk / rk1 - Uk1 / rk) / (1. / rk1 - 1. / rk)
+        Jj = np.sqrt(-a * sr[j])
+        Ej = b + a / (2 * sr[j])
+        d = (n // 2) % 9 - 4
+        for _ in range(abs(d)):
+            Ej = np.nextafter(Ej, np.inf if d > 0 else -np.inf)
+        E[j - 1], J[j - 1] = Ej - phi_s(sr[j], j), Jj
+        vr[j - 1], vt[j - 1] = 0.0, Jj / sr[j]
+        planted[j - 1] = True
+    # such an orbit can also be so thin that the rejection sampling never accepts (N_TRY exceeded: fatal in the reference,
+    # cmc_evolution_thr.c:890-893): those stars get their ordinary E, J back
+    E0, J0 = energies(phi[1:N + 1], r, vr, vt)
+    t = ol.tables(sr, smt, phi, N, N)
+    draws = ol.Taus113(17).draws(200 * N)
+    for _ in range(4):
+        st = ol.get_positions(t, np.arange(1, N + 1), E, J, vr, vt, pot["Rtidal"], draws)["status"]
+        bad = np.nonzero(st == 5)[0]
+        if not bad.size:
+            break
+        E[bad], J[bad], planted[bad] = E0[bad], J0[bad], False
+    return r, vr, vt, sm, pot, E, J, planted

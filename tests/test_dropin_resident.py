@@ -112,7 +112,7 @@ def _run(R, N, r, vr, vt, sm, binind, nb, orbit_r, treatment, ref_snap=None, dir
 @pytest.mark.parametrize("kind,N,masses,nb,orbit_r,treatment,dirty2", [
     ("plummer", 30000, "equal", 0, 1.0e6, 1, None),
     ("plummer", 24000, "imf", 2000, 5.0, 0, None),
-    ("king", 26000, "imf", 1500, 6.0, 1, 0),          # second window: the host wrote nothing in between and says so
+    ("king", 26000, "imf", 1500, 2.5, 1, 0),          # second window: the host wrote nothing in between and says so
 ])
 def test_reference_with_resident_shim_equals_reference(kind, N, masses, nb, orbit_r, treatment, dirty2):
     r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 3, masses=masses)
@@ -136,4 +136,4 @@ def test_reference_with_resident_shim_equals_reference(kind, N, masses, nb, orbi
         for k in a[f"lagrange{step}"]:
             cm.assert_bits_equal(b[f"lagrange{step}"][k], a[f"lagrange{step}"][k], f"step {step}: {k}")
     if orbit_r < 100:
-        assert a["after_strip1"]["esc_bytes"] > 0 and a["n1"] < N, "the case must remove and strip stars"
+        assert a["n1"] < N and (a["after_orbits1"]["esc_bytes"] > 0 or a["after_strip1"]["esc_bytes"] > 0), "the case must remove or strip stars"

@@ -649,6 +649,41 @@ def test_compute_energy_totals_bit_exact(cenma, N):
     c.close()
 
 
+def test_orbit_step_where_find_root_vr_fires_bit_exact():
+    """SURVEY 8a a20 / a21 on the device: calc_orbit_new's Brent fallback find_root_vr and the helpers under it, on a cluster in which it fires
+    hundreds of times (common.brent_cluster), host-buffer form and resident form, against the oracle (pinned against the compiled reference
+    on the same cluster in test_oracle_vs_ref.py::test_orbit_step_where_find_root_vr_fires)"""
+    N = 20000
+    r, vr, vt, sm, pot, E, J, planted = cm.brent_cluster(N)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N)
+    draws = ol.Taus113(3).draws(200 * N)
+    want = ol.get_positions(t, np.arange(1, N + 1), E, J, vr, vt, pot["Rtidal"], draws)
+    used = draws[:want["draw_off"][-1]]
+    ok = want["status"] == ol.ST_OK
+    assert want["n_brent"] > 150 and (ok & planted).sum() > 100
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.calc_potential_new()
+    cm.assert_bits_equal(c.star_phi[:N + 2], pot["phi"][:N + 2], "phi")
+    c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+    for form in ("host", "resident"):
+        if form == "host":
+            status = c.new_orbits_calculate(draws=used, draw_off=want["draw_off"])
+            kmin, kmax, res = c.last_kmin, c.last_kmax, c.last_orbit
+        else:
+            c.upload()
+            res = c.dev_new_orbits(draws=used, draw_off=want["draw_off"], want_status=True)
+            status, kmin, kmax = c.dev_read_status()
+            c.download()
+        assert int(res.n_brent) == want["n_brent"], (form, int(res.n_brent), want["n_brent"])
+        assert np.array_equal(status, want["status"]) and np.array_equal(kmin[ok], want["kmin"][ok]) and np.array_equal(kmax[ok], want["kmax"][ok]), form
+        for k in ("rnew", "vrnew", "vtnew"):
+            cm.assert_bits_equal(c.field(k)[1:N + 1], want[k], f"{form}: {k}")
+        for k in ("r_peri", "r_apo", "X"):
+            cm.assert_bits_equal(c.field(k)[1:N + 1][ok], want[k][ok], f"{form}: {k}")
+    c.close()
+
+
 def test_compute_energy_totals_chains_of_zeros_stay_parallel():
     """A cluster without stellar evolution and without binaries: every term of the Eint and Eb chains is exactly 0.  fl(y + 0) = y, so those
     elements are regular -- no event, and above all no fall-back to the single-thread chain (which at N = 1e7 would take seconds)."""

@@ -246,3 +246,29 @@ def test_calc_sigma_r_as_one_signed_chain(N, p, first, nl, masses):
     assert 2 * p <= events <= 2 * (2 * p + 2 * ((nl or N) - 1))
     if masses == "equal":
         assert events > 2 * N
+
+
+def test_find_root_vr_fires_in_the_device_core_and_matches_the_oracle():
+    """calc_orbit_new's Brent fallback (reference cmc_orbit.c:459-474, 485-500; cmc_nr.c:500-603) and the helpers it
+    reaches (calc_vr_within_interval ...) on a cluster built so that it fires hundreds of times (common.brent_cluster): the per-star
+    code the CUDA kernels run (csrc/orbit_core.h, compiled for the host) against the oracle, bit for bit."""
+    import hostemul as he
+    N = 20000
+    r, vr, vt, sm, pot, E, J, planted = cm.brent_cluster(N)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N)
+    draws = ol.Taus113(3).draws(200 * N)
+    want = ol.get_positions(t, np.arange(1, N + 1), E, J, vr, vt, pot["Rtidal"], draws)
+    assert want["n_brent"] > 150 and (want["status"] == ol.ST_NTRY).sum() == 0
+    ok = want["status"] == ol.ST_OK
+    assert (ok & planted).sum() > 100          # most of the fallbacks end in a regular (non-circular) orbit
+    used = draws[:want["draw_off"][-1]]
+    for no_ladders in (False, True):
+        got = he.get_positions(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0, np.arange(1, N + 1), E, J, vr, vt, pot["Rtidal"], used,
+                               csr_off=want["draw_off"], no_ladders=no_ladders)
+        assert got["n_brent"] == want["n_brent"]
+        for k in ("status", "kmin", "kmax"):
+            assert np.array_equal(got[k], want[k]), k
+        for k in ("rnew", "vrnew", "vtnew"):
+            cm.assert_bits_equal(got[k], want[k], k)
+        for k in ("r_peri", "r_apo", "X"):
+            cm.assert_bits_equal(got[k][ok], want[k][ok], k)

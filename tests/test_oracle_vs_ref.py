@@ -345,6 +345,36 @@ def test_find_root_vr_brent_shim_agrees(R):
     R.free()
 
 
+def test_orbit_step_where_find_root_vr_fires(R):
+    """The whole orbit step of the compiled reference on common.brent_cluster -- hundreds of stars take calc_orbit_new's Brent fallback
+    (cmc_orbit.c:459-474, 485-500) -- against the oracle, bit for bit.  (GSL itself stays un-vendored: both sides iterate a restatement of
+    gsl_root_fsolver_brent, so this pins everything around the solver: when the fallback is taken, the bracket, the function it
+    evaluates -- calc_vr_within_interval / calc_pot_within_interval / function_q --, the post-selection of the end with v_r^2 >= 0.)"""
+    N = 20000
+    r, vr, vt, sm, pot, E, J, planted = cm.brent_cluster(N)
+    R.init(N, n_star_dim=N + 64, idum=77)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N)
+    R.L.ref_calc_potential_new()
+    cm.assert_bits_equal(R.star_phi()[:N + 2], pot["phi"][:N + 2], "phi")
+    R.star_field("E")[1:N + 1], R.star_field("J")[1:N + 1] = E, J
+    before = {k: R.star_field(k)[1:N + 1].copy() for k in ("X", "r_peri", "r_apo")}
+    R.L.ref_draw_mode(1)
+    R.L.ref_new_orbits_calculate()
+    R.L.ref_draw_mode(0)
+    draws = R.draws()
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N)
+    want = ol.get_positions(t, np.arange(1, N + 1), E, J, vr, vt, R.scalars()["Rtidal"], draws)
+    assert want["draw_off"][-1] == len(draws) and want["n_brent"] > 150
+    ok = want["status"] == ol.ST_OK
+    for k in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(R.star_field(k)[1:N + 1], want[k], k)
+    for k in ("X", "r_peri", "r_apo"):
+        cm.assert_bits_equal(R.star_field(k)[1:N + 1][ok], want[k][ok], k)
+        cm.assert_bits_equal(R.star_field(k)[1:N + 1][~ok], before[k][~ok], k + " of the other stars is untouched")
+    R.free()
+
+
 def test_taus113_known_answers(R):
     """seeding, stepping and the 2^80 jump of the reference's generator (src/libs/taus113-v2.c) vs the oracle's restatement; includes the
     reference's own self-check: 2^20 steps == one JPoly_2_20 jump (testjumping(), taus113-v2.c:272-292)"""
