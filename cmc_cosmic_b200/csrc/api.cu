@@ -71,7 +71,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->n_table_dim = n_table_dim;
 	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
-	c->orbit_ladders = 1; // bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A)
+	c->orbit_ladders = 1; // bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A), bit 2: FP32 screening copy of the (r, Phi) table for the index bisections
 	c->bytes_h2d = c->bytes_d2h = 0;
 	c->orbit_ctas = 4;
 	c->orbit_max_chunks = 8;
@@ -103,6 +103,8 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_mprev, tb));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rp, (size_t) (n_table_dim + 16) * sizeof(RPhi))); // the r ladder's last step reads whole 8-entry lines
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_rp, 0, (size_t) (n_table_dim + 16) * sizeof(RPhi), c->stream));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rpf, (size_t) (n_table_dim + 16) * sizeof(RPhiF)));
+	CMCB_CUDA_OK(cudaMemsetAsync(c->d_rpf, 0, (size_t) (n_table_dim + 16) * sizeof(RPhiF), c->stream));
 	c->lad.q_cap = ladder_q_capacity(n_table_dim);
 	c->lad.r_cap = ladder_r_capacity(n_table_dim);
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->lad.q, (size_t) c->lad.q_cap * sizeof(LBlock)));
@@ -154,7 +156,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaStreamSynchronize(c->stream);
 	for (int i = 0; i < 2; i++) { cudaFree(c->d_star[i]); cudaFree(c->d_bin[i]); }
 	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev); cudaFree(c->d_r_alt); cudaFree(c->d_m_alt);
-	cudaFree(c->d_rp); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
+	cudaFree(c->d_rp); cudaFree(c->d_rpf); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
 	cudaFree(c->d_defer_first); cudaFree(c->lad.q); cudaFree(c->lad.r); cudaFree(c->lad.unsorted);
 	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); }
 	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
@@ -455,7 +457,7 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 		LadderBuffers lb = c->lad;
 		if (!(c->orbit_ladders & 1)) lb.r = nullptr;
 		if (!(c->orbit_ladders & 2)) lb.q = nullptr;
-		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, p->n_table, p->N_MAX + 1, lb, a, c->stream);
+		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, (c->orbit_ladders & 4) ? c->d_rpf : nullptr, p->n_table, p->N_MAX + 1, lb, a, c->stream);
 	}
 	orbit_l2_window(c, (size_t) p->n_table * sizeof(RPhi));
 	return 0;

@@ -33,6 +33,7 @@ struct cmcb200_ctx {
 	double *d_r, *d_m, *d_phi, *d_mprev;
 	double *d_r_alt, *d_m_alt; // second copy of star_r / star_m: the fused transfer+sort reads the old tables while it writes the new ones
 	RPhi *d_rp;       // packed (r, phi) lookup table of the orbit step
+	RPhiF *d_rpf;     // its FP32 screening copy (orbit_core.h: sign_Q_screened)
 	long *d_defer_star, *d_defer_found;
 	unsigned *d_defer_first;
 	LadderBuffers lad; // coarse levels of the lookup tables (orbit_core.h "ladders")
@@ -42,7 +43,7 @@ struct cmcb200_ctx {
 	int orbit_ctas;    // tuning knob CMCB200_ORBIT_CTAS: resident CTAs per SM orbit_prepare_kernel is compiled for (4 or 3)
 	int l2_persist_pct;    // CMCB200_L2_PERSIST: > 0 = fraction (percent) of the (r, Phi) table pinned in L2's persisting carve-out during the orbit step
 	size_t l2_window_max;  // cudaDeviceProp.accessPolicyMaxWindowSize
-	int orbit_ladders; // CMCB200_ORBIT_LADDERS: bit 0 = r ladder for potential() (default on), bit 1 = Q ladder for find_zero_Q (default off:
+	int orbit_ladders; // CMCB200_ORBIT_LADDERS: bit 0 = r ladder for potential() (default on), bit 2 = FP32 screening table for find_zero_Q (default off: measured no faster), bit 1 = Q ladder for find_zero_Q (default off:
 	                   // measured slower than the plain bisection on B200); 0 = every probe reads the fine table
 	// sort scratch
 	SortBuffers sbuf;

@@ -70,8 +70,8 @@ static_assert(QLAD_MIN_SHIFT == 4, "orbit_pack_tables reduces the finest Q-ladde
 
 // rp[i] = (r[i], phi[i]) for i < n; with q_fine != nullptr also block b of the finest Q-ladder level (entries [16 b, min(16 b + 16, M)]) and
 // the sortedness check of r[0 .. M] (any violation, or a NaN in phi, raises *unsorted: the kernels then ignore the ladders)
-__global__ void __launch_bounds__(256) orbit_pack_tables(const double *__restrict__ r, const double *__restrict__ phi, RPhi *__restrict__ rp, long n, long M,
-							 LBlock *__restrict__ q_fine, int *unsorted)
+__global__ void __launch_bounds__(256) orbit_pack_tables(const double *__restrict__ r, const double *__restrict__ phi, RPhi *__restrict__ rp, RPhiF *__restrict__ rpf,
+							 long n, long M, LBlock *__restrict__ q_fine, int *unsorted)
 {
 	const long stride = (long) gridDim.x * blockDim.x; // a multiple of 32: the 16-lane groups stay aligned to the blocks
 	const long n_round = ((n > M + 1 ? n : M + 1) + 31) / 32 * 32;
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256) orbit_pack_tables(const double *__restric
 			v.x = r[i];
 			v.y = phi[i];
 			*reinterpret_cast<double2 *>(rp + i) = v;
+			if (rpf) *reinterpret_cast<float2 *>(rpf + i) = make_float2(__double2float_rn(v.x), __double2float_rn(v.y)); // the screening copy (orbit_core.h: sign_Q_screened)
 		}
 		if (q_fine) {
 			const bool in = i <= M;
@@ -587,8 +588,9 @@ long ladder_r_capacity(long n_table_dim)
 	return total + 16;
 }
 
-int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long n, long M, const LadderBuffers &lb, OrbitArgs &a, cudaStream_t s)
+int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhiF *rpf, long n, long M, const LadderBuffers &lb, OrbitArgs &a, cudaStream_t s)
 {
+	a.t.rpf = rpf;
 	a.t.qlad.n_levels = 0; a.t.rlad.n_levels = 0; a.t.rlad.n_top = 0;
 	a.q_top_bytes = a.r_top_bytes = 0;
 	a.lad_unsorted = lb.unsorted;
@@ -621,7 +623,7 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long
 	cudaMemsetAsync(lb.unsorted, 0, sizeof(int), s);
 	long blocks = ((n > M + 1 ? n : M + 1) + 255) / 256;
 	if (blocks > NUM_SMS_B200 * 16) blocks = NUM_SMS_B200 * 16;
-	orbit_pack_tables<<<(unsigned) blocks, 256, 0, s>>>(r, phi, rp, n, M, nq ? qlvl[nq - 1] : nullptr, lb.unsorted);
+	orbit_pack_tables<<<(unsigned) blocks, 256, 0, s>>>(r, phi, rp, rpf, n, M, nq ? qlvl[nq - 1] : nullptr, lb.unsorted);
 	launches++;
 	for (int l = nq - 2; l >= 0; l--) {
 		qlad_coarsen<<<(unsigned) ((qcnt[l] + 255) / 256), 256, 0, s>>>(qlvl[l + 1], qcnt[l + 1], qlvl[l], qcnt[l]);

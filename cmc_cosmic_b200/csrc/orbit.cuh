@@ -62,7 +62,7 @@ struct LadderBuffers {
 long ladder_q_capacity(long n_table_dim);
 long ladder_r_capacity(long n_table_dim);
 // packs (r, Phi) of entries [0, n) and builds both ladders over [0, M]; fills t.rp-independent ladder descriptors of `a`
-int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, long n, long M, const LadderBuffers &lb, OrbitArgs &a, cudaStream_t s);
+int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhiF *rpf, long n, long M, const LadderBuffers &lb, OrbitArgs &a, cudaStream_t s);
 int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_scan(const OrbitArgs &a, cudaStream_t s);
 int orbit_stage_tries(const OrbitArgs &a, cudaStream_t s);

@@ -147,8 +147,11 @@ CMCB_HD LBlock lblock_merge(const LBlock *child, long n)
 	return B;
 }
 
+struct RPhiF { float r, phi; }; // the same table rounded to FP32: 8 bytes per entry, half the footprint -- the screening copy of find_zero_Q
+
 struct OrbitTables {
 	const RPhi *rp;  // (star_r[k], star_phi[k]) interleaved: [0] sentinel, [1..N_MAX], [N_MAX+1] = (SF_INFINITY, 0)
+	const RPhiF *rpf; // FP32 screening copy of rp (nullptr: every probe reads rp)
 	const double *m; // star_m
 	QLadder qlad;    // coarse (r, Phi) summaries for find_zero_Q; n_levels == 0: every probe reads rp
 	RLadder rlad;    // coarse radii for potential(); n_levels == 0: plain bisection on rp
@@ -380,6 +383,47 @@ CMCB_HD int sign_Q_at(const OrbitTables &t, const StarConst &s, const RPhi p, in
 }
 CMCB_HD int sign_Q(const OrbitTables &t, const StarConst &s, kint k, int *n_exact) { return sign_Q_at(t, s, tbl_rp(t, k), n_exact); }
 
+// The same sign decided, where possible, from the FP32 copy of the table entry (8 bytes instead of 16: the copy of a 1e7-star table is 80 MB
+// and largely stays in L2, the FP64 table does not).  With r^ = fl32(r), phi^ = fl32(phi): r = r^ (1 + dr), phi = phi^ (1 + dp), |dr|, |dp| <= 2^-24
+// (round to nearest, both inside FP32's normal range -- checked), so for the real-number value S*(r, phi) = 2 ((E - phi) r^2 - t2(r)) - J^2
+//   |S*(r, phi) - S*(r^, phi^)| <= 2 |phi - phi^| r^2 + 2 |E - phi^| |r^2 - r^^2| + 2 |t2(r) - t2(r^)|
+//                               <= 2^-22 (|phi^| r^^2 + |t1^| + |t2^|)          (2^-23 (1 + 2^-23) < 2^-22; t2 is continuous across its branch at r_j,
+//                                                                                so a branch taken on the wrong side of r_j costs <= 2^-23 |t2|)
+// S^ is evaluated in FP64 like sign_Q_at, whose bound B (evaluation error + the reference's own noise) is taken at the rounded entry and doubled.
+// |S^| > 2^-21 (|phi^| r^^2 + |t1^| + |t2^|) + 2 B therefore PROVES the sign the reference computes at the FP64 entry; otherwise the probe is
+// repeated on the FP64 table (sign_Q: the last levels of a bisection, next to the sign change).  Same probe sequence, same signs, same result.
+#ifdef CMCB_SCREEN_STATS
+static long g_screen_stats[2]; // host-only instrumentation: [0] probes decided on the FP32 copy, [1] repeated on the FP64 table
+#endif
+CMCB_HD int sign_Q_screened(const OrbitTables &t, const StarConst &s, kint k, int *n_exact)
+{
+	if (t.rpf) {
+#if defined(__CUDA_ARCH__)
+		const float2 f = __ldg(reinterpret_cast<const float2 *>(t.rpf + k));
+		const double r = (double) f.x, phi = (double) f.y;
+#else
+		const double r = (double) t.rpf[k].r, phi = (double) t.rpf[k].phi;
+#endif
+		const double aphi = dabs(phi);
+		if (r > 1.0e-30 && r < 1.0e30 && aphi > 1.0e-30 && aphi < 1.0e30) { // FP32 normal range with room: the relative rounding bound holds
+			const double a = dsub(s.E, phi);
+			const double r2 = dmul(r, r);
+			const double t1 = dmul(a, r2);
+			const double t2 = (r >= s.r_j) ? dmul(s.mi, r) : dmul(s.c_in, r2);
+			const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
+			const double B = dadd(dmul(3.552713678800501e-15 /* 2^-48 */, dadd(dadd(dabs(t1), dabs(t2)), s.JJ)),
+					      dmul(dmul(3.469446951953614e-18 /* 2^-58 */, dadd(s.absE, aphi)), r2));
+			const double Bf = dadd(dmul(4.76837158203125e-07 /* 2^-21 */, dadd(dadd(dmul(aphi, r2), dabs(t1)), dabs(t2))), dmul(2.0, B));
+#ifdef CMCB_SCREEN_STATS
+			g_screen_stats[(S > Bf || S < -Bf) ? 0 : 1]++;
+#endif
+			if (S > Bf) return 1;
+			if (S < -Bf) return -1;
+		}
+	}
+	return sign_Q(t, s, k, n_exact);
+}
+
 // the direction test of find_zero_Q (cmc_nr.c:342): function_q(kmin) < function_q(kmax) on the VALUES
 CMCB_HD bool q_increasing(const OrbitTables &t, const StarConst &s, kint kmin, kint kmax, int *n_exact)
 {
@@ -489,7 +533,7 @@ CMCB_HD kint find_zero_Q(const OrbitTables &t, const LadderTops &top, const Star
 	const bool laddered = top.q != nullptr;
 	do {
 		kint ktry = (kmin + kmax + 1) / 2;
-		int sg = laddered ? sign_Q_laddered(t, *top.qdesc, top.q, s, ktry, kmax - kmin, n_exact) : sign_Q(t, s, ktry, n_exact);
+		int sg = laddered ? sign_Q_laddered(t, *top.qdesc, top.q, s, ktry, kmax - kmin, n_exact) : sign_Q_screened(t, s, ktry, n_exact);
 		bool up = increasing ? (sg < 0) : (sg > 0); // :349 / :362
 		if (up) kmin = ktry; else kmax = ktry - 1;
 	} while (kmax != kmin);

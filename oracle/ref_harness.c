@@ -103,6 +103,11 @@ EXPORT int ref_init(long n_star, long n_star_dim, long n_table_dim, long n_bin_d
 	q_root = gsl_root_fsolver_alloc(gsl_root_fsolver_brent);
 	units.t = units.m = units.l = units.E = units.mstar = 1.0;
 	cenma.m = cenma.m_new = cenma.E = cenma.E_new = 0.0;
+	/* a fresh run: the accumulators are process globals and a test process initialises the library more than once */
+	Eescaped = Jescaped = Eintescaped = Ebescaped = TidalMassLoss = Etidal = 0.0;
+	Eescaped_old = Jescaped_old = Eintescaped_old = Ebescaped_old = TidalMassLoss_old = Etidal_old = 0.0;
+	OldTidalMassLoss = DTidalMassLoss = 0.0;
+	Eoops = 0.0; max_r = 0.0;
 	tcount = 1; TotalTime = 0.0;
 	mpi_escfile_buf = malloc(STR_BUF_LEN);
 	mpi_escfile_wrbuf = malloc(1 << 26);

@@ -68,9 +68,13 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 	for (long j = 0; j < n_local; j++) if (g_idx[j] + 1 > n_tab) n_tab = g_idx[j] + 1;
 	std::vector<RPhi> rp = pack(star_r, star_phi, n_tab);
 	t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = cenma_m;
+	std::vector<RPhiF> rpf(rp.size()); // the FP32 screening copy, as orbit_pack_tables rounds it
+	for (size_t i = 0; i < rp.size(); i++) { rpf[i].r = (float) rp[i].r; rpf[i].phi = (float) rp[i].phi; }
+	t.rpf = rpf.data();
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
-	if (force_exact) { t.qlad.n_levels = 0; t.rlad.n_levels = 0; } // force_exact = 1: every probe reads the fine table
+	if (force_exact == 1) { t.qlad.n_levels = 0; t.rlad.n_levels = 0; t.rpf = nullptr; } // 1: every probe reads the fine FP64 table
+	if (force_exact == 2) t.qlad.n_levels = 0; // 2: the device's default configuration -- r ladder + FP32 screening of the index bisections, no Q ladder
 	counters[3] = t.qlad.n_levels; counters[4] = t.rlad.n_levels;
 	double max_rad = 0.0;
 	long pos = 0;
@@ -95,7 +99,7 @@ extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, con
 				 double E, double J, long kmin, long kmax, long *n_exact, int use_ladder)
 {
 	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
-	OrbitTables t; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
+	OrbitTables t; t.rpf = nullptr; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
 	if (!use_ladder) { t.qlad.n_levels = 0; t.rlad.n_levels = 0; }
@@ -112,7 +116,7 @@ extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, con
 extern "C" void emul_find_zero_r_both(const double *star_r, long N_MAX, const double *radii, long n, long *k_bisect, long *k_ladder)
 {
 	std::vector<RPhi> rp = pack(star_r, star_r, N_MAX + 2);
-	OrbitTables t; t.rp = rp.data(); t.m = nullptr; t.N_MAX = N_MAX; t.invN = 0; t.madhoc = 0; t.cenma_m = 0;
+	OrbitTables t; t.rpf = nullptr; t.rp = rp.data(); t.m = nullptr; t.N_MAX = N_MAX; t.invN = 0; t.madhoc = 0; t.cenma_m = 0;
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
 	for (long i = 0; i < n; i++) {
@@ -139,7 +143,7 @@ extern "C" double emul_set_velocities3(const double *star_r, const double *star_
 				       unsigned char *kind, long *counters)
 {
 	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
-	OrbitTables t; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = 0;
+	OrbitTables t; t.rpf = nullptr; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = 0;
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
 	LadderTops top; top.q = nullptr; top.qdesc = nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
@@ -240,3 +244,7 @@ extern "C" int emul_calc_sigma_r(long p, long n, long first_global, long N_MAX, 
 	}
 	return 0;
 }
+
+#ifdef CMCB_SCREEN_STATS
+extern "C" void emul_screen_stats(long *out, int reset) { out[0] = g_screen_stats[0]; out[1] = g_screen_stats[1]; if (reset) g_screen_stats[0] = g_screen_stats[1] = 0; }
+#endif

@@ -19,6 +19,15 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (rh.available() and os.pat
 PCS = np.array([0.01, 0.1, 0.5, 0.9])
 
 
+def _bits(x):
+    """scalars compared by their bit patterns (a NaN equals itself)"""
+    if isinstance(x, dict):
+        return {k: _bits(v) for k, v in x.items()}
+    if isinstance(x, (tuple, list)):
+        return tuple(_bits(v) for v in x)
+    return np.float64(x).view(np.uint64)
+
+
 def _timestep(R, snap, step, treatment, draws=None, draw_off=None, is_shim=False):
     """cmc.c:302-353 in the reference's order, through the harness's entry points"""
     N = int(R.scalars()["N_MAX"])
@@ -112,7 +121,7 @@ def _run(R, N, r, vr, vt, sm, binind, nb, orbit_r, treatment, ref_snap=None, dir
 @pytest.mark.parametrize("kind,N,masses,nb,orbit_r,treatment,dirty2", [
     ("plummer", 30000, "equal", 0, 1.0e6, 1, None),
     ("plummer", 24000, "imf", 2000, 5.0, 0, None),
-    ("king", 26000, "imf", 1500, 2.5, 1, 0),          # second window: the host wrote nothing in between and says so
+    ("king", 26000, "imf", 1500, 4.0, 1, 0),          # second window: the host wrote nothing in between and says so
 ])
 def test_reference_with_resident_shim_equals_reference(kind, N, masses, nb, orbit_r, treatment, dirty2):
     r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 3, masses=masses)
@@ -123,14 +132,14 @@ def test_reference_with_resident_shim_equals_reference(kind, N, masses, nb, orbi
     a = _run(rh.Ref(), N, r, vr, vt, sm, binind, nb, orbit_r, treatment)
     b = _run(rh.Ref(REF_B200RES_SO), N, r, vr, vt, sm, binind, nb, orbit_r, treatment, ref_snap=a, dirty2=dirty2)
     for step in (1, 2):
-        assert b[f"after_orbits{step}"] == a[f"after_orbits{step}"], (step, a[f"after_orbits{step}"], b[f"after_orbits{step}"])
-        assert b[f"strip{step}"] == a[f"strip{step}"] and b[f"after_strip{step}"] == a[f"after_strip{step}"], (step, a[f"after_strip{step}"], b[f"after_strip{step}"])
+        assert _bits(b[f"after_orbits{step}"]) == _bits(a[f"after_orbits{step}"]), (step, a[f"after_orbits{step}"], b[f"after_orbits{step}"])
+        assert _bits(b[f"strip{step}"]) == _bits(a[f"strip{step}"]) and _bits(b[f"after_strip{step}"]) == _bits(a[f"after_strip{step}"]), (step, a[f"after_strip{step}"], b[f"after_strip{step}"])
         assert b[f"n{step}"] == a[f"n{step}"]
         assert np.array_equal(b[f"star{step}"], a[f"star{step}"]), f"step {step}: star[] after the timestep"
         assert np.array_equal(b[f"binary{step}"], a[f"binary{step}"]), f"step {step}: binary[]"
         for x, y, name in zip(b[f"tables_final{step}"], a[f"tables_final{step}"], ("star_r", "star_m", "star_phi")):
             cm.assert_bits_equal(x, y, f"step {step}: {name}")
-        assert b[f"scalars{step}"] == a[f"scalars{step}"], (step, a[f"scalars{step}"], b[f"scalars{step}"])
+        assert _bits(b[f"scalars{step}"]) == _bits(a[f"scalars{step}"]), (step, a[f"scalars{step}"], b[f"scalars{step}"])
         assert np.array_equal(b[f"Etotal{step}"], a[f"Etotal{step}"]), (step, a[f"Etotal{step}"], b[f"Etotal{step}"])
         assert b[f"Eoops{step}"] == a[f"Eoops{step}"]
         for k in a[f"lagrange{step}"]:
