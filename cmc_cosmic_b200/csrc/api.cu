@@ -71,7 +71,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->n_table_dim = n_table_dim;
 	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
-	c->orbit_ladders = 1; // bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A), bit 2: FP32 screening copy of the (r, Phi) table for the index bisections
+	c->orbit_ladders = 9; // bit 3: sample ladder for the index bisections of stage A (find_zero_Q_sampled); bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A), bit 2: FP32 screening copy of the (r, Phi) table for the index bisections
 	c->bytes_h2d = c->bytes_d2h = 0;
 	c->orbit_ctas = 4;
 	c->orbit_max_chunks = 8;
@@ -142,7 +142,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_status, (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_kmin, (size_t) n_star_dim * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_kmax, (size_t) n_star_dim * sizeof(long)));
-	CMCB_CUDA_OK(cudaMallocHost(&c->h_pinned, 4096));
+	CMCB_CUDA_OK(cudaMallocHost(&c->h_pinned, 8192)); // [0, 4096): scratch of whichever call reads scalars back; [4096, 8192): the orbit step's per-chunk statistics
 	if (sort_setup()) { set_error("cmcb200_create: cannot raise the dynamic shared memory limit of the sort kernel"); return -1; }
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	*out = c;
@@ -158,7 +158,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev); cudaFree(c->d_r_alt); cudaFree(c->d_m_alt);
 	cudaFree(c->d_rp); cudaFree(c->d_rpf); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
 	cudaFree(c->d_defer_first); cudaFree(c->lad.q); cudaFree(c->lad.r); cudaFree(c->lad.unsorted);
-	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); }
+	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); cudaFree(c->d_shard_sync); }
 	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
@@ -456,7 +456,8 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 		StageTimer t(c, ST_ORBIT_TABLES);
 		LadderBuffers lb = c->lad;
 		if (!(c->orbit_ladders & 1)) lb.r = nullptr;
-		if (!(c->orbit_ladders & 2)) lb.q = nullptr;
+		lb.sampled = (c->orbit_ladders & 8) && !(c->orbit_ladders & 2); // the sample ladder lives in the Q ladder's buffer
+		if (!(c->orbit_ladders & 2) && !lb.sampled) lb.q = nullptr;
 		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, (c->orbit_ladders & 4) ? c->d_rpf : nullptr, p->n_table, p->N_MAX + 1, lb, a, c->stream);
 	}
 	orbit_l2_window(c, (size_t) p->n_table * sizeof(RPhi));
@@ -479,7 +480,7 @@ static int orbit_range(cmcb200_ctx *c, const OrbitArgs &whole, long off, long le
 	{ StageTimer t(c, ST_ORBIT_SCAN); c->launches += orbit_stage_scan(a, c->stream); }
 	{ StageTimer t(c, ST_ORBIT_TRIES); c->launches += orbit_stage_tries(a, c->stream); }
 	CMCB_CUDA_OK(cudaGetLastError());
-	CMCB_CUDA_OK(cudaMemcpyAsync((OrbitStats *) c->h_pinned + chunk, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaMemcpyAsync((OrbitStats *) ((char *) c->h_pinned + 4096) + chunk, c->d_ostats, sizeof(OrbitStats), cudaMemcpyDeviceToHost, c->stream));
 	return 0;
 }
 
@@ -488,7 +489,7 @@ static void orbit_end(cmcb200_ctx *c, const cmcb200_orbit_params *p, int n_chunk
 {
 	orbit_l2_window(c, 0);
 	if (!res) return;
-	const OrbitStats *h = (const OrbitStats *) c->h_pinned;
+	const OrbitStats *h = (const OrbitStats *) ((const char *) c->h_pinned + 4096);
 	unsigned long long max_bits = 0, other = 0;
 	memset(res, 0, sizeof(*res));
 	for (int k = 0; k < n_chunks; k++) {
@@ -501,7 +502,7 @@ static void orbit_end(cmcb200_ctx *c, const cmcb200_orbit_params *p, int n_chunk
 	res->n_status[0] = (unsigned long long) p->n_local - other;
 }
 
-static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res)
+static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res, bool wait)
 {
 	OrbitArgs a;
 	int n_chunks = 1;
@@ -525,6 +526,8 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 		if (orbit_begin(c, p, want_status, false, a)) return -1;
 		if (orbit_range(c, a, 0, p->n_local, 0)) return -1;
 	}
+	c->last_orbit_chunks = n_chunks;
+	if (!wait) return 0;
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	orbit_end(c, p, n_chunks, res);
 	return 0;
@@ -533,7 +536,23 @@ static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want
 extern "C" int cmcb200_dev_new_orbits(cmcb200_ctx *c, const cmcb200_orbit_params *p, int want_status, cmcb200_orbit_result *res)
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
-	return orbit_common(c, p, want_status != 0, res);
+	return orbit_common(c, p, want_status != 0, res, true);
+}
+
+// the same without waiting: the kernels are queued, the statistics are fetched by cmcb200_dev_orbit_result once something else has
+// synchronised the stream (or by that call itself)
+extern "C" int cmcb200_dev_new_orbits_async(cmcb200_ctx *c, const cmcb200_orbit_params *p, int want_status)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	return orbit_common(c, p, want_status != 0, nullptr, false);
+}
+
+extern "C" int cmcb200_dev_orbit_result(cmcb200_ctx *c, const cmcb200_orbit_params *p, cmcb200_orbit_result *res)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	orbit_end(c, p, c->last_orbit_chunks > 0 ? c->last_orbit_chunks : 1, res);
+	return 0;
 }
 
 // energy_conservation2 / ComputeIntermediateEnergy on the resident arrays (orbit.cu: energy_rnew_kernel)

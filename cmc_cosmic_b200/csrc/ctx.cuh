@@ -11,7 +11,7 @@
 using namespace cmcb;
 
 constexpr int SHARD_MAX_RANKS = 16;
-enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_N_BUFFERS }; // peer-visible buffers
+enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_SYNC, SH_N_BUFFERS }; // peer-visible buffers
 
 enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES, ST_LAGRANGE };
 
@@ -43,7 +43,7 @@ struct cmcb200_ctx {
 	int orbit_ctas;    // tuning knob CMCB200_ORBIT_CTAS: resident CTAs per SM orbit_prepare_kernel is compiled for (4 or 3)
 	int l2_persist_pct;    // CMCB200_L2_PERSIST: > 0 = fraction (percent) of the (r, Phi) table pinned in L2's persisting carve-out during the orbit step
 	size_t l2_window_max;  // cudaDeviceProp.accessPolicyMaxWindowSize
-	int orbit_ladders; // CMCB200_ORBIT_LADDERS: bit 0 = r ladder for potential() (default on), bit 2 = FP32 screening table for find_zero_Q (default off: measured no faster), bit 1 = Q ladder for find_zero_Q (default off:
+	int orbit_ladders; // CMCB200_ORBIT_LADDERS: bit 3 = sample ladder for find_zero_Q (default on), bit 0 = r ladder for potential() (default on), bit 2 = FP32 screening table for find_zero_Q (default off: measured no faster), bit 1 = Q ladder for find_zero_Q (default off:
 	                   // measured slower than the plain bisection on B200); 0 = every probe reads the fine table
 	// sort scratch
 	SortBuffers sbuf;
@@ -75,6 +75,7 @@ struct cmcb200_ctx {
 	double acc_ms[CMCB200_N_STAGES];
 	long acc_n[CMCB200_N_STAGES];
 	long launches; // kernels launched since creation
+	int last_orbit_chunks; // chunks of the last orbit step (their statistics wait in the pinned block for cmcb200_dev_orbit_result)
 	long bytes_h2d, bytes_d2h; // bytes the host-buffer entry points moved over PCIe (cmcb200_transfer_bytes)
 	// host-buffer orbit step: copy-in and copy-out streams and per-chunk events of the pipeline (created on first use)
 	cudaStream_t s_in, s_out;
@@ -97,6 +98,8 @@ struct cmcb200_ctx {
 	unsigned *d_dest_pos;                           // [n] final local position of each local sorted element on its destination rank
 	unsigned char *d_dest_rank;                     // [n] destination rank
 	long *d_shard_meta;                             // device copy of (n_keep[q], start0[q]) per rank
+	void *d_shard_sync;                             // ShardSync (shard.cu): flags and posted counts the peers store into -- the device-side barriers
+	unsigned long long shard_epoch;                 // barrier generation, advanced identically on every rank
 	int shard_unfused;                              // 1: the sharded sort keys on r and moves the records unchanged (cmcb200_shard_fuse_transfer)
 	int r_parity;                                   // which of (d_r, d_r_alt) is the buffer SH_R (flips with every fused sort)
 };

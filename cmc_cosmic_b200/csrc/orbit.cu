@@ -132,6 +132,20 @@ __global__ void rlad_build(const double *__restrict__ r, RLadderPlan p)
 		p.lvl[l][i] = i < p.count[l] ? r[i << p.shift[l]] : __builtin_huge_val();
 }
 
+// the sample ladder: level blockIdx.y holds the table entries (r, Phi) at k = b << shift
+struct SLadderPlan {
+	RPhi *lvl[LADDER_MAX_LEVELS];
+	int shift[LADDER_MAX_LEVELS];
+	long count[LADDER_MAX_LEVELS];
+};
+__global__ void slad_build(const RPhi *__restrict__ rp, SLadderPlan p)
+{
+	const int l = blockIdx.y;
+	const long stride = (long) gridDim.x * blockDim.x;
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < p.count[l]; i += stride)
+		*reinterpret_cast<double2 *>(p.lvl[l] + i) = *reinterpret_cast<const double2 *>(rp + (i << p.shift[l]));
+}
+
 struct StarIn {
 	kint g;
 	bool is_new;
@@ -223,13 +237,23 @@ __global__ void __launch_bounds__(ORBIT_THREADS, CTAS) orbit_prepare_kernel(Orbi
 	extern __shared__ __align__(128) unsigned char orbit_smem[];
 	__shared__ __align__(8) unsigned long long bar;
 	__shared__ QLadder s_qlad; // the level table, indexed dynamically by the bisections
-	if (threadIdx.x == 0) s_qlad = a.t.qlad;
-	LadderTops top; // (stage_top_level's barrier also publishes s_qlad; without a ladder nobody reads it)
+	__shared__ SLadder s_slad;
+	if (threadIdx.x == 0) {
+		s_qlad = a.t.qlad;
+		s_slad = a.t.slad;
+		// max |Phi| of a sorted table sits at its innermost entries (Phi_0 is the central-mass slot)
+		s_slad.phi_abs_max = fmax(fabs(tbl_rp(a.t, 0).phi), fabs(tbl_rp(a.t, 1).phi));
+	}
+	LadderTops top; // (stage_top_level's barrier also publishes s_qlad / s_slad; without a ladder nobody reads them)
 	const bool lad_on = a.t.qlad.n_levels > 0 && *a.lad_unsorted == 0;
+	const bool slad_on = a.t.slad.n_levels > 0 && *a.lad_unsorted == 0; // (never both: the two ladders share one buffer)
 	top.q = (const LBlock *) stage_top_level(a.t.qlad.blk[0], a.q_top_bytes, lad_on && a.q_top_bytes > 0, orbit_smem, &bar);
 	if (lad_on && a.q_top_bytes == 0) { top.q = a.t.qlad.blk[0]; __syncthreads(); } // coarsest level too large to stage (tuning knobs): read in place
+	top.s = (const RPhi *) stage_top_level(a.t.slad.lvl[0], a.s_top_bytes, slad_on, orbit_smem, &bar);
+	if (!lad_on && !slad_on) __syncthreads();
 	top.r = nullptr; // potential() is not called in this stage
 	top.qdesc = &s_qlad;
+	top.sdesc = &s_slad;
 	int n_exact = 0, n_brent = 0;
 	for (long base = blockIdx.x * (long) ORBIT_THREADS; base < a.n_local; base += (long) gridDim.x * ORBIT_THREADS) {
 		const long j0 = base + threadIdx.x;
@@ -362,7 +386,7 @@ __global__ void __launch_bounds__(ORBIT_THREADS) orbit_deferred_kernel(OrbitArgs
 			const StarConst s = star_const(a.t, in.g, in.E, in.J);
 			OrbitJob job;
 			LadderTops top; // the few queued stars bisect on the fine table
-			top.q = nullptr; top.r = nullptr; top.qdesc = nullptr;
+			top.q = nullptr; top.r = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
 			orbit_prepare(a.t, top, s, in.is_new, in.rnew_of_new, a.Rtidal, found == ORBIT_NOT_FOUND ? -1 : (kint) found, false, o, job);
 			store_prepared(a, j0, o, job);
 		}
@@ -425,7 +449,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 	const unsigned n_work = FIRST ? (unsigned) a.n_local : a.stats->round_count[round];
 	if ((unsigned long long) blockIdx.x * (ORBIT_TRY_THREADS / W) >= n_work) return; // nothing for this CTA: skip the staging too
 	LadderTops top;
-	top.q = nullptr; top.qdesc = nullptr;
+	top.q = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
 	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
 	const int *__restrict__ list_in = a.pend_list[round & 1];
 	int *__restrict__ list_out = a.pend_list[(round + 1) & 1];
@@ -525,7 +549,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, ORBIT_CTAS_PER_SM) energy_r
 	extern __shared__ __align__(128) unsigned char orbit_smem[];
 	__shared__ __align__(8) unsigned long long bar;
 	LadderTops top;
-	top.q = nullptr; top.qdesc = nullptr;
+	top.q = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
 	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
 	for (long j0 = blockIdx.x * (long) ORBIT_TRY_THREADS + threadIdx.x; j0 < a.n_local; j0 += (long) gridDim.x * ORBIT_TRY_THREADS) {
 		const long j = j0 + 1;
@@ -591,13 +615,13 @@ long ladder_r_capacity(long n_table_dim)
 int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhiF *rpf, long n, long M, const LadderBuffers &lb, OrbitArgs &a, cudaStream_t s)
 {
 	a.t.rpf = rpf;
-	a.t.qlad.n_levels = 0; a.t.rlad.n_levels = 0; a.t.rlad.n_top = 0;
-	a.q_top_bytes = a.r_top_bytes = 0;
+	a.t.qlad.n_levels = 0; a.t.rlad.n_levels = 0; a.t.rlad.n_top = 0; a.t.slad.n_levels = 0;
+	a.q_top_bytes = a.r_top_bytes = a.s_top_bytes = 0;
 	a.lad_unsorted = lb.unsorted;
 	if (n <= 0) return 0;
 	int launches = 0;
 	long qcnt[LADDER_MAX_LEVELS], rcnt[LADDER_MAX_LEVELS], ral[LADDER_MAX_LEVELS];
-	int nq = lb.q ? qlad_plan(M, a.t.qlad.shift, qcnt) : 0;
+	int nq = (lb.q && !lb.sampled) ? qlad_plan(M, a.t.qlad.shift, qcnt) : 0;
 	{ // tuning knob: drop the levels coarser than q_max_shift (brackets that wide then probe the fine table, see QLadder::max_width)
 		int drop = 0;
 		while (drop < nq && a.t.qlad.shift[drop] > lb.q_max_shift) drop++;
@@ -634,6 +658,24 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhi
 		if (rb > NUM_SMS_B200 * 8) rb = NUM_SMS_B200 * 8;
 		rlad_build<<<dim3((unsigned) rb, (unsigned) nr), 256, 0, s>>>(r, rplan);
 		launches++;
+	}
+	if (lb.q && lb.sampled) { // the sample ladder of find_zero_Q_sampled (orbit_core.h), in the Q ladder's buffer: 16-byte entries, 32-byte blocks
+		long scnt[LADDER_MAX_LEVELS];
+		const int ns = slad_plan(M, a.t.slad.shift, scnt);
+		SLadderPlan sp;
+		long off = 0; // in RPhi entries; every level on a 128-byte boundary
+		for (int l = ns - 1; l >= 0; l--) { sp.lvl[l] = (RPhi *) lb.q + off; sp.shift[l] = a.t.slad.shift[l]; sp.count[l] = scnt[l]; off += (scnt[l] + 7) / 8 * 8; }
+		if (ns && off <= 2 * lb.q_cap) {
+			long sb = (scnt[ns - 1] + 255) / 256;
+			if (sb > NUM_SMS_B200 * 8) sb = NUM_SMS_B200 * 8;
+			slad_build<<<dim3((unsigned) sb, (unsigned) ns), 256, 0, s>>>(rp, sp);
+			launches++;
+			a.t.slad.n_levels = ns;
+			for (int l = 0; l < ns; l++) a.t.slad.lvl[l] = sp.lvl[l];
+			a.t.slad.margin = (double) M * 7.105427357601002e-15 /* 2^-47 */ + 9.094947017729282e-13 /* 2^-40 */;
+			a.t.slad.phi_abs_max = 0.0; // filled by the kernels from the innermost entries
+			a.s_top_bytes = (unsigned) (scnt[0] * sizeof(RPhi));
+		}
 	}
 	a.t.qlad.n_levels = nq;
 	for (int l = 0; l < nq; l++) a.t.qlad.blk[l] = qlvl[l];
@@ -674,12 +716,13 @@ int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s)
 	if (a.n_local <= 0) return 1;
 	long blocks = (a.n_local + ORBIT_THREADS - 1) / ORBIT_THREADS;
 	int ctas = a.prepare_ctas >= 3 && a.prepare_ctas <= 6 ? a.prepare_ctas : ORBIT_CTAS_PER_SM;
-	while (ctas > 4 && (long) ctas * (a.q_top_bytes + 1024) > 227 * 1024) ctas--; // the staged levels of all resident CTAs must fit
+	const unsigned top_bytes = a.q_top_bytes > a.s_top_bytes ? a.q_top_bytes : a.s_top_bytes;
+	while (ctas > 4 && (long) ctas * (top_bytes + 1024) > 227 * 1024) ctas--; // the staged levels of all resident CTAs must fit
 	if (blocks > (long) NUM_SMS_B200 * ctas) blocks = (long) NUM_SMS_B200 * ctas;
-	if (ctas == 3) orbit_prepare_kernel<3><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
-	else if (ctas == 5) orbit_prepare_kernel<5><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
-	else if (ctas == 6) orbit_prepare_kernel<6><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
-	else orbit_prepare_kernel<ORBIT_CTAS_PER_SM><<<(unsigned) blocks, ORBIT_THREADS, a.q_top_bytes, s>>>(a);
+	if (ctas == 3) orbit_prepare_kernel<3><<<(unsigned) blocks, ORBIT_THREADS, top_bytes, s>>>(a);
+	else if (ctas == 5) orbit_prepare_kernel<5><<<(unsigned) blocks, ORBIT_THREADS, top_bytes, s>>>(a);
+	else if (ctas == 6) orbit_prepare_kernel<6><<<(unsigned) blocks, ORBIT_THREADS, top_bytes, s>>>(a);
+	else orbit_prepare_kernel<ORBIT_CTAS_PER_SM><<<(unsigned) blocks, ORBIT_THREADS, top_bytes, s>>>(a);
 	return 2;
 }
 

@@ -46,6 +46,7 @@ struct OrbitArgs {
 	const int *lad_unsorted; // device flag set by the table builder when star_r is not sorted (or Phi holds a NaN): ladders off
 	int prepare_ctas;  // register-cap variant of orbit_prepare_kernel: 4 (default) or 3 resident CTAs per SM (CMCB200_ORBIT_CTAS)
 	unsigned q_top_bytes, r_top_bytes; // size of the coarsest level of each ladder (what a CTA stages), multiples of 16
+	unsigned s_top_bytes;              // the same for the sample ladder (it shares the Q ladder's buffer: one of the two is in use)
 	long *defer_star;  // [ORBIT_DEFER_CAP] local 0-based index of each queued star
 	unsigned *defer_first; // [ORBIT_DEFER_CAP] lowest 256-entry sub-chunk of the table the bound could not prove free of Q > 0 (0xffffffff: none)
 	long *defer_found; // [ORBIT_DEFER_CAP] first k with Q > 0 (ORBIT_NOT_FOUND: none)
@@ -57,6 +58,7 @@ struct LadderBuffers {
 	double *r;     // all levels of the r ladder back to back, finest first
 	long q_cap, r_cap; // capacity in blocks / doubles
 	int *unsorted; // device flag
+	bool sampled;  // build the sample ladder (in q's memory) instead of the Q ladder
 	int q_max_shift, q_max_width_log2, q_factor_log2; // tuning knobs of the Q ladder (CMCB200_QLAD_MAX_SHIFT / _MAX_WIDTH_LOG2 / _FACTOR_LOG2)
 };
 long ladder_q_capacity(long n_table_dim);

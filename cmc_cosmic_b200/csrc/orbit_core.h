@@ -89,12 +89,37 @@ struct RLadder {
 	int n_levels; // 0: no ladder
 };
 
+// The SAMPLE ladder of the index bisections: level l holds the table entries (r_k, Phi_k) themselves at k = b << shift[l] -- not summaries.
+// See find_zero_Q_sampled below for what it proves and why that is enough.
+#ifndef CMCB_SLAD_TOP_ENTRIES
+#define CMCB_SLAD_TOP_ENTRIES 2560
+#endif
+constexpr int SLAD_MIN_SHIFT = 4, SLAD_STEP = 4, SLAD_TOP_ENTRIES = CMCB_SLAD_TOP_ENTRIES; // coarsest level <= 40 KB of (r, Phi) pairs
+struct SLadder {
+	const RPhi *lvl[LADDER_MAX_LEVELS]; // coarsest first
+	int shift[LADDER_MAX_LEVELS];
+	int n_levels; // 0: no ladder
+	double margin; // relative margin of a proven sign (see side_Q_margin)
+	double phi_abs_max; // max |Phi_k| over the table (= |Phi| at the innermost entries)
+};
+CMCB_HD int slad_plan(long M, int shift[LADDER_MAX_LEVELS], long count[LADDER_MAX_LEVELS])
+{
+	if (M < LADDER_MIN_M) return 0;
+	int top = SLAD_MIN_SHIFT;
+	while ((M >> top) + 1 > SLAD_TOP_ENTRIES) top += SLAD_STEP;
+	int n = 0;
+	for (int s = top; s >= SLAD_MIN_SHIFT && n < LADDER_MAX_LEVELS; s -= SLAD_STEP) { shift[n] = s; count[n] = (M >> s) + 1; n++; }
+	return n;
+}
+
 // where the coarsest level of each ladder is to be read from: shared memory in the kernels (staged per CTA), the level itself on the host;
 // nullptr = that ladder is not used (table too small, or the builder found it unsorted)
 struct LadderTops {
 	const LBlock *q;
 	const double *r;
 	const QLadder *qdesc; // the Q ladder's level table: a shared-memory copy in the kernels (dynamic indexing), &t.qlad on the host
+	const RPhi *s;        // coarsest level of the sample ladder (nullptr: plain bisection)
+	const SLadder *sdesc;
 };
 
 // shifts (coarsest first) and block counts of the Q ladder over a table with last index M; returns the number of levels
@@ -154,6 +179,7 @@ struct OrbitTables {
 	const RPhiF *rpf; // FP32 screening copy of rp (nullptr: every probe reads rp)
 	const double *m; // star_m
 	QLadder qlad;    // coarse (r, Phi) summaries for find_zero_Q; n_levels == 0: every probe reads rp
+	SLadder slad;    // sampled (r, Phi) entries for find_zero_Q (the default); n_levels == 0: off
 	RLadder rlad;    // coarse radii for potential(); n_levels == 0: plain bisection on rp
 	kint N_MAX;
 	double invN;    // 1.0 / clus.N_STAR evaluated in double (the factor in MPI_PHI_S)
@@ -526,10 +552,134 @@ CMCB_HD int sign_Q_laddered(const OrbitTables &t, const QLadder &L, const LBlock
 	return sign_Q(t, s, k, n_exact);
 }
 
+// ---- find_zero_Q through the sample ladder ---------------------------------------------------------------------------------------------
+//
+// The reference's bisection (cmc_nr.c:316-383) probes ktry = (kmin + kmax + 1) / 2 about log2(N) times, every probe a dependent load from a
+// table that does not fit the cache.  Almost all of those probes are far from the sign change, and their signs follow from a handful of
+// entries:
+//
+//   U_k := Phi_k + phis(r_k) (the potential of all OTHER stars at r_k) is, as a function of x = 1 / r, convex over the entries 1 .. N_MAX + 1:
+//   potential_calculate builds Phi_k = Phi_{k+1} - M_k (x_k - x_{k+1}) with the enclosed mass M_k non-decreasing in k (cmc_utils.c:716-720), and
+//   the self term removes the star's own share of M_k.  Hence Q*(k) = 2 (E - U_k) - J^2 x_k^2 is CONCAVE over the entries: for k1 < k2 < k3,
+//   Q*(k2) >= min(Q*(k1), Q*(k3)), and left of an entry with larger Q* it is non-decreasing, right of one non-increasing.
+//
+// So with an entry p where Q > 0 (the bracket end that get_positive_Q_index found) and an entry a on the other side of the sign change with
+// Q(a) < -margin, EVERY entry beyond a (away from p) has Q < 0; and with an entry b between the sign change and p with Q(b) > +margin and
+// Q(p) > +margin, every entry between b and p has Q > 0.  The margin absorbs what separates the stored table and the reference's evaluation
+// from that idealisation:
+//   - the stored Phi_k are sequentially rounded: over a span of n entries they leave an exactly convex sequence by at most n 2^-49 max|Phi|
+//     (five roundings per step of the recurrence, each <= 2^-52 (|Phi| + M/r));
+//   - the reference's own evaluation noise at an entry k, 2^-51 (|E| + |U_k| + J^2 / r_k^2): by the argument in the note below it never
+//     exceeds the margin at a plus the gap Q*(a) - Q*(k);
+//   - the FP64 evaluation of the margin test itself (sign_Q_at's bound B).
+//   margin = (N_MAX 2^-47 + 2^-40) (|E| + max|Phi| + J^2 / r^2), times r^2 in the division-free form: 7e-8 relative at N = 1e7 -- the band of
+//   entries it leaves undecided is a fraction of an index wide.
+//   (Note: for k beyond a, -Q*(k) = -Q*(a) + G with G = [J^2 (x_k^2 - x_a^2) - 2 (U_a - U_k)] >= 0, and the reference's noise at k is
+//    2^-51 (|E| + |U_k| + J^2 x_a^2 + J^2 (x_k^2 - x_a^2)) <= 2^-51 (|E| + 3 max|Phi| + J^2 x_a^2) + 2^-51 G < margin(a) + G.)
+//
+// The search: from the coarsest level (in shared memory) down, a binary search over the level's entries inside the current window moves the
+// window's ends onto entries whose sign is proven with that margin; an entry inside the margin ends the descent.  Then the reference's
+// bisection is replayed: a probe outside the window takes the proven sign WITHOUT touching memory, a probe inside is evaluated exactly like
+// before (sign_Q: FP64 with a rigorous bound, the x87 arithmetic replayed inside it).  Same probe sequence, same signs, same k_min / k_max --
+// with about 3 dependent line fetches instead of 24.  Whatever the proof needs and cannot be established (a bracket end inside the margin:
+// a star at its turning point; an unsorted table) falls back to the plain bisection.
+CMCB_HD int side_Q_margin(const StarConst &s, const RPhi p, double margin, double phi_abs_max)
+{
+	const double a = dsub(s.E, p.phi);
+	const double r2 = dmul(p.r, p.r);
+	const double t1 = dmul(a, r2);
+	const double t2 = (p.r >= s.r_j) ? dmul(s.mi, p.r) : dmul(s.c_in, r2);
+	const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
+	const double Bm = dmul(margin, dadd(dadd(dmul(dadd(s.absE, phi_abs_max), r2), s.JJ), dadd(dabs(t1), dabs(t2))));
+	if (S > Bm) return 1;
+	if (S < -Bm) return -1;
+	return 0;
+}
+
+CMCB_HD RPhi slad_ld(const RPhi *p)
+{
+#if defined(__CUDA_ARCH__)
+	const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+	RPhi o; o.r = v.x; o.phi = v.y;
+	return o;
+#else
+	return *p;
+#endif
+}
+
+CMCB_HD RPhi slad_top_ld(const RPhi *p)
+{
+#if defined(__CUDA_ARCH__)
+	const double2 v = *reinterpret_cast<const double2 *>(p);
+	RPhi o; o.r = v.x; o.phi = v.y;
+	return o;
+#else
+	return *p;
+#endif
+}
+
+CMCB_HD kint find_zero_Q_plain(const OrbitTables &t, const StarConst &s, kint kmin, kint kmax, bool increasing, int *n_exact)
+{
+	do {
+		kint ktry = (kmin + kmax + 1) / 2;
+		int sg = sign_Q_screened(t, s, ktry, n_exact);
+		bool up = increasing ? (sg < 0) : (sg > 0); // :349 / :362
+		if (up) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
+}
+
+CMCB_HD kint find_zero_Q_sampled(const OrbitTables &t, const LadderTops &top, const StarConst &s, kint kmin, kint kmax, bool increasing, int *n_exact)
+{
+	const SLadder &L = *top.sdesc;
+	// the kmin side of the sign change has sign `low` (the probes there answer "up"), the kmax side -low
+	const int low = increasing ? -1 : 1;
+	// both bracket ends must carry their sign with the margin: the end where Q > 0 anchors the concavity argument.  Entry 0 (r = ZERO, the
+	// central-mass slot) is never probed by the bisection and lies outside the convex sequence: Q there is -J^2 / ZERO^2.
+	if (kmax - kmin < 2 * (1 << SLAD_MIN_SHIFT)) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
+	if (kmin > 0 && side_Q_margin(s, tbl_rp(t, kmin), L.margin, L.phi_abs_max) != low) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
+	if (kmin == 0 && !(increasing && s.JJ > 0.0)) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
+	if (side_Q_margin(s, tbl_rp(t, kmax), L.margin, L.phi_abs_max) != -low) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
+	kint lo = kmin, hi = kmax; // every entry in [kmin, lo] has the sign `low`, every entry in [hi, kmax] the sign -low
+	for (int l = 0; l < L.n_levels; l++) {
+		const int sh = L.shift[l];
+		const RPhi *lvl = (l == 0) ? top.s : L.lvl[l];
+		kint a = lo >> sh, b = ((hi - 1) >> sh) + 1; // level entries a+1 .. b-1 lie strictly inside (lo, hi)
+		const kint a0 = a, b0 = b;
+		bool undecided = false;
+		while (b - a > 1) {
+			const kint mid = (a + b) >> 1;
+			// the coarsest level sits in shared memory in the kernels (a generic load), the others are read through the read-only path
+			const RPhi smp = (l == 0) ? slad_top_ld(lvl + mid) : slad_ld(lvl + mid);
+			const int sd = side_Q_margin(s, smp, L.margin, L.phi_abs_max);
+			if (sd == low) a = mid;
+			else if (sd == -low) b = mid;
+			else { undecided = true; break; }
+		}
+		if (a > a0) lo = a << sh;
+		if (b < b0) hi = b << sh;
+		if (undecided) break;
+	}
+	// the reference's probe sequence; only the probes strictly inside (lo, hi) read the table
+	do {
+		kint ktry = (kmin + kmax + 1) / 2;
+		bool up;
+		if (ktry <= lo) up = true;
+		else if (ktry >= hi) up = false;
+		else {
+			const int sg = sign_Q(t, s, ktry, n_exact);
+			up = increasing ? (sg < 0) : (sg > 0);
+		}
+		if (up) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
+}
+
 // find_zero_Q (cmc_nr.c:316-383): the same probe sequence ktry = (kmin+kmax+1)/2
 CMCB_HD kint find_zero_Q(const OrbitTables &t, const LadderTops &top, const StarConst &s, kint kmin, kint kmax, int *n_exact)
 {
 	const bool increasing = q_increasing(t, s, kmin, kmax, n_exact);
+	if (top.s != nullptr) return find_zero_Q_sampled(t, top, s, kmin, kmax, increasing, n_exact);
 	const bool laddered = top.q != nullptr;
 	do {
 		kint ktry = (kmin + kmax + 1) / 2;
@@ -819,6 +969,7 @@ CMCB_HD void orbit_step_star(const OrbitTables &t, kint g_j, bool is_new, double
 	const StarConst s = star_const(t, g_j, E_star, J);
 	LadderTops top;
 	top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr; top.qdesc = &t.qlad;
+	top.s = t.slad.n_levels ? t.slad.lvl[0] : nullptr; top.sdesc = &t.slad;
 	OrbitJob job;
 	orbit_prepare(t, top, s, is_new, rnew_of_new, Rtidal, ktemp_in, allow_defer, out, job);
 	if (out.status == ORBIT_CIRCULAR) { out.vrnew = vr_in; out.vtnew = vt_in; }

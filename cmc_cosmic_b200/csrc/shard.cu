@@ -37,8 +37,92 @@ struct ShardMeta { // per step, uploaded by the host
 	long n_keep[SHARD_MAX_RANKS]; // stars each rank contributes (stripped stars already trimmed)
 	long start0[SHARD_MAX_RANKS]; // 0-based global rank of the first star of each destination rank
 	long count[SHARD_MAX_RANKS];  // stars of each destination rank
+	long n_total;                 // their sum: the new clus.N_MAX
 	int nranks, rank;
 };
+
+// ---- barriers between the ranks without the host ---------------------------------------------------------------------------------------
+// Every rank owns a ShardSync block that all ranks map (CUDA IPC).  "post": a one-thread kernel, queued behind the kernels whose peer stores
+// it publishes, writes this rank's values into every peer's block, fences at system scope and then raises its flag there to the current
+// epoch (st.release.sys).  "wait": a one-warp kernel spins (ld.acquire.sys) until every rank's flag in the OWN block has reached the epoch;
+// the kernels queued behind it then read what the peers stored.  Epochs only grow, so a flag is never reset.  A wait gives up after
+// SHARD_WAIT_TIMEOUT_NS (a peer died): it sets `error` and lets the stream drain -- the host sees the flag at its next synchronisation.
+struct ShardSync {
+	unsigned long long flag[SHARD_MAX_RANKS][4]; // [source rank][phase]: epoch of that rank's last post
+	long n_keep[SHARD_MAX_RANKS];                // stars each rank contributes to this step's exchange (posted in phase 0)
+	int error;
+};
+constexpr unsigned long long SHARD_WAIT_TIMEOUT_NS = 4000000000ull;
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+struct SyncPeers { ShardSync *p[SHARD_MAX_RANKS]; };
+
+__global__ void shard_post_kernel(SyncPeers peers, int nranks, int rank, int phase, unsigned long long epoch, const SortState *st)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (st) { const long n = st->n_new; for (int q = 0; q < nranks; q++) peers.p[q]->n_keep[rank] = n; }
+	__threadfence_system();
+	for (int q = 0; q < nranks; q++) st_release_sys_u64(&peers.p[q]->flag[rank][phase], epoch);
+}
+
+__global__ void shard_wait_kernel(ShardSync *mine, int nranks, int phase, unsigned long long epoch)
+{
+	const int q = threadIdx.x;
+	if (q < nranks) {
+		const unsigned long long t0 = globaltimer_ns();
+		while (ld_acquire_sys_u64(&mine->flag[q][phase]) < epoch) {
+			if (globaltimer_ns() - t0 > SHARD_WAIT_TIMEOUT_NS) { mine->error = 1 + phase; break; }
+			__nanosleep(200);
+		}
+	}
+}
+
+// after the phase-0 wait: every rank's count is here; the new partition is findLimits over their sum (cmc_sort.c:416-421), computed by
+// every rank for itself -- integer arithmetic, identical everywhere
+__global__ void shard_plan_kernel(const ShardSync *mine, ShardMeta *meta, int nranks, int rank, int blk)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	long total = 0;
+	for (int q = 0; q < nranks; q++) { meta->n_keep[q] = mine->n_keep[q]; total += mine->n_keep[q]; }
+	const long blocks = total / blk, remain = total % blk;
+	const long chunk = (blocks / nranks) * blk, extra = blocks % nranks;
+	for (int i = 0; i < nranks; i++) { // findIndices / findLimits, src/cmc/cmc_utils.c:2299-2333
+		long b, e;
+		if (i < extra) { b = i * chunk + (long) i * blk + 1; e = b + chunk + blk - 1; }
+		else { b = i * chunk + extra * blk + 1; e = b + chunk - 1; }
+		if (i == nranks - 1) e += remain;
+		meta->start0[i] = b - 1;
+		meta->count[i] = e - b + 1;
+	}
+	meta->nranks = nranks;
+	meta->rank = rank;
+	meta->n_total = total;
+}
+
+// the sort state describes the local sorted run until the records have left; from then on the shard this rank received
+__global__ void shard_adopt_shard_kernel(SortState *st, const ShardMeta *meta)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	st->n_new = meta->count[meta->rank];
+	st->n_total = st->n_new;
+	st->n_bin = 0;
+}
 
 __device__ __forceinline__ long lower_bound_u64(const uint64_t *__restrict__ a, long n, uint64_t key) // #elements < key
 {
@@ -155,6 +239,37 @@ __global__ void shard_publish_tables(const char *__restrict__ star1, long n_loca
 	}
 }
 
+// the same with the shard's extent taken from the device-side plan (asynchronous step: the host does not know it yet); one coalesced pass
+// per destination rank -- consecutive threads store consecutive table entries of ONE peer
+__global__ void __launch_bounds__(256) shard_publish_tables_planned(const char *__restrict__ star1, const ShardMeta *__restrict__ meta, double *const *peer_r,
+									    double *const *peer_m, unsigned char *__restrict__ binflag)
+{
+	__shared__ double s_r[256], s_m[256];
+	const int P = meta->nranks;
+	const long n_local = meta->count[meta->rank], start0 = meta->start0[meta->rank];
+	for (long base = blockIdx.x * 256L; base < n_local; base += gridDim.x * 256L) {
+		const long i = base + threadIdx.x;
+		if (i < n_local) {
+			const char *rec = star1 + i * CMCB_SIZEOF_STAR;
+			s_r[threadIdx.x] = *(const double *) (rec + CMCB_OFF_R);
+			s_m[threadIdx.x] = *(const double *) (rec + CMCB_OFF_M);
+			binflag[i] = *(const long long *) (rec + CMCB_OFF_BININD) > 0;
+		}
+		__syncthreads();
+		const long cnt = n_local - base < 256 ? n_local - base : 256;
+		// 2 P runs of `cnt` doubles: thread t stores element (t mod 256) of run (t / 256), so a warp writes 256 contiguous bytes of one peer
+		for (long t = threadIdx.x; t < 2L * P * 256; t += 256) {
+			const int run = (int) (t >> 8), e = (int) (t & 255);
+			if (e < cnt) {
+				const int q = run >> 1;
+				double *dst = (run & 1) ? peer_m[q] : peer_r[q];
+				dst[1 + start0 + base + e] = (run & 1) ? s_m[e] : s_r[e];
+			}
+		}
+		__syncthreads();
+	}
+}
+
 // Binaries follow their star (cmc_sort.c:512-587, 716-771): the records of this rank's new shard carry the index their binary had in the
 // SOURCE rank's binary array; in star order each binary_t is pulled from that rank's array over NVLink into the local array and binind
 // becomes 1, 2, ...  (block_off = exclusive scan of the per-2048-star binary counts, as in sort_binary_move).
@@ -163,10 +278,11 @@ struct BinPull {
 	const char *bin_in[SHARD_MAX_RANKS]; // &binary[1] of every rank before the exchange
 };
 __global__ void __launch_bounds__(256) shard_binary_pull(char *__restrict__ star, const unsigned char *__restrict__ binflag, const unsigned char *__restrict__ src_rank,
-							  const unsigned *__restrict__ block_off, long n_local, BinPull bp, char *__restrict__ bin_out)
+							  const unsigned *__restrict__ block_off, long n_local_in, const SortState *st, BinPull bp, char *__restrict__ bin_out)
 {
 	__shared__ unsigned s_w[8];
 	__shared__ unsigned s_idx[SHARD_BIN_TILE];
+	const long n_local = st ? st->n_new : n_local_in; // asynchronous step: the shard size lives on the device
 	const long tile0 = blockIdx.x * (long) SHARD_BIN_TILE;
 	if (tile0 >= n_local) return;
 	const long base = tile0 + threadIdx.x * 8;
@@ -214,6 +330,7 @@ static void *own_buffer(cmcb200_ctx *c, int which)
 	case SH_M_ALT: return c->r_parity ? (void *) c->d_m : (void *) c->d_m_alt;
 	case SH_KEYS_ALL: return c->d_keys_all;
 	case SH_SRC_ALL: return c->d_src_all;
+	case SH_SYNC: return c->d_shard_sync;
 	}
 	return nullptr;
 }
@@ -236,6 +353,9 @@ extern "C" int cmcb200_shard_export(cmcb200_ctx *c, int rank, int nranks, void *
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_dest_pos, (size_t) c->n_star_dim * sizeof(unsigned)));
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_dest_rank, (size_t) c->n_star_dim));
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_shard_meta, sizeof(ShardMeta) + 4 * SHARD_MAX_RANKS * sizeof(void *)));
+		CMCB_CUDA_OK(cudaMalloc(&c->d_shard_sync, 1 << 21)); // an allocation of its own (2 MB granule): its IPC handle maps nothing else
+		CMCB_CUDA_OK(cudaMemset(c->d_shard_sync, 0, sizeof(ShardSync)));
+		c->shard_epoch = 0;
 	}
 	cudaIpcMemHandle_t *h = (cudaIpcMemHandle_t *) handles;
 	for (int b = 0; b < SH_N_BUFFERS; b++) {
@@ -414,7 +534,7 @@ extern "C" int cmcb200_shard_publish(cmcb200_ctx *c, long n_new_local, long star
 			BinPull bp;
 			for (int q = 0; q < c->nranks; q++) bp.bin_in[q] = (const char *) c->peer_buf[q][SH_BIN0 + c->cur_bin] + CMCB_SIZEOF_BINARY;
 			const long nbt = (n_new_local + SHARD_BIN_TILE - 1) / SHARD_BIN_TILE;
-			shard_binary_pull<<<(unsigned) nbt, 256, 0, c->stream>>>(star1(c), c->d_binflag, c->d_src_all, c->d_bin_block_cnt, n_new_local, bp, bin_out);
+			shard_binary_pull<<<(unsigned) nbt, 256, 0, c->stream>>>(star1(c), c->d_binflag, c->d_src_all, c->d_bin_block_cnt, n_new_local, nullptr, bp, bin_out);
 			c->launches++;
 		}
 		c->launches += sort_binary_clear_device(bin_out, c->d_sort, n_bin_clear, c->stream);
@@ -434,5 +554,151 @@ extern "C" int cmcb200_shard_finish(cmcb200_ctx *c)
 	std::swap(c->d_r, c->d_r_alt);
 	std::swap(c->d_m, c->d_m_alt);
 	c->r_parity ^= 1;
+	return 0;
+}
+
+
+// ---- the whole sharded sort as ONE asynchronous sequence ---------------------------------------------------------------------------------
+// cmcb200_shard_sort_local + _exchange + _publish + _finish without a single host round trip: the ranks meet at three device-side barriers
+// (ShardSync above), the counts every rank contributes travel with the first one, the new partition is planned on every device, and the
+// kernels behind it take their extents from that plan.  The host only enqueues; cmcb200_shard_step_result waits and returns what the
+// reference's globals need (clus.N_MAX, Start / End, N_b_local).  One host synchronisation per sort instead of three plus an allgather.
+static int shard_post(cmcb200_ctx *c, int phase, const SortState *st)
+{
+	SyncPeers sp;
+	for (int q = 0; q < c->nranks; q++) sp.p[q] = (ShardSync *) c->peer_buf[q][SH_SYNC];
+	shard_post_kernel<<<1, 32, 0, c->stream>>>(sp, c->nranks, c->rank, phase, c->shard_epoch, st);
+	c->launches++;
+	return 0;
+}
+static int shard_wait(cmcb200_ctx *c, int phase)
+{
+	shard_wait_kernel<<<1, 32, 0, c->stream>>>((ShardSync *) c->d_shard_sync, c->nranks, phase, c->shard_epoch);
+	c->launches++;
+	return 0;
+}
+
+extern "C" int cmcb200_shard_step_async(cmcb200_ctx *c, long n_local, long n_old_local, long first_global, long N_MAX, int min_chunk, long n_bin_clear)
+{
+	if (n_local + 2 > c->n_star_dim) { set_error("shard_step: n_local + 2 = %ld exceeds n_star_dim = %ld", n_local + 2, c->n_star_dim); return -1; }
+	if (!c->d_shard_sync || c->nranks < 1) { set_error("shard_step: call cmcb200_shard_export / _attach first"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	c->shard_epoch++;
+	ShardMeta *d_meta = (ShardMeta *) c->d_shard_meta;
+	// 1. local sort, sorted keys into every rank's key table, this rank's count with the first barrier
+	SortArgs a;
+	memset(&a, 0, sizeof(a));
+	a.star_in = star1(c);
+	a.n = n_local;
+	a.key_off = c->shard_unfused ? CMCB_OFF_R : CMCB_OFF_RNEW;
+	a.buf = c->sbuf;
+	a.st = c->d_sort;
+	a.tile_hist = c->d_tile_hist;
+	a.keep_keys = true;
+	{ StageTimer t(c, ST_KEYS); c->launches += sort_stage_keys(a, c->stream); }
+	{ StageTimer t(c, ST_PASSES); c->launches += sort_stage_passes(a, c->stream); }
+	{
+		StageTimer t(c, ST_SHARD_KEYS);
+		uint64_t *peers[SHARD_MAX_RANKS];
+		for (int q = 0; q < c->nranks; q++) peers[q] = (uint64_t *) c->peer_buf[q][SH_KEYS_ALL];
+		uint64_t **d_peers = (uint64_t **) ((char *) c->d_shard_meta + sizeof(ShardMeta));
+		CMCB_CUDA_OK(cudaMemcpyAsync(d_peers, peers, c->nranks * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+		if (n_local > 0) {
+			shard_push_keys<<<NUM_SMS_B200 * 4, 256, 0, c->stream>>>(c->sbuf, c->d_sort, d_peers, c->nranks, (long) c->rank * c->keys_stride);
+			c->launches++;
+		}
+		shard_post(c, 0, c->d_sort);
+		shard_wait(c, 0);
+		shard_plan_kernel<<<1, 32, 0, c->stream>>>((const ShardSync *) c->d_shard_sync, d_meta, c->nranks, c->rank, min_chunk);
+		c->launches++;
+	}
+	// 2. global ranks, every record to its final slot on its destination rank
+	{
+		StageTimer t(c, ST_SHARD_RANK);
+		if (n_local > 0) {
+			long blocks = (n_local + 255) / 256;
+			if (blocks > NUM_SMS_B200 * 16) blocks = NUM_SMS_B200 * 16;
+			shard_rank_kernel<<<(unsigned) blocks, 256, 0, c->stream>>>(c->d_keys_all, c->keys_stride, d_meta, c->d_dest_rank, c->d_dest_pos);
+			c->launches++;
+		}
+	}
+	{
+		StageTimer t(c, ST_GATHER);
+		PushArgs pa;
+		pa.in = star1(c);
+		for (int q = 0; q < c->nranks; q++) {
+			pa.out[q] = (char *) c->peer_buf[q][SH_STAR0 + (c->cur_star ^ 1)] + CMCB_SIZEOF_STAR;
+			pa.src_out[q] = (unsigned char *) c->peer_buf[q][SH_SRC_ALL];
+		}
+		pa.rank = c->rank;
+		pa.old_r = c->d_r; pa.old_m = c->d_m;
+		pa.n_old_local = n_old_local; pa.first_global = first_global; pa.N_MAX = N_MAX;
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_star[c->cur_star ^ 1], c->d_star[c->cur_star], CMCB_SIZEOF_STAR, cudaMemcpyDeviceToDevice, c->stream));
+		if (n_local > 0) {
+			if (c->shard_unfused) shard_push_records<false><<<NUM_SMS_B200 * 8, 256, 0, c->stream>>>(pa, c->sbuf, c->d_sort, c->d_dest_rank, c->d_dest_pos);
+			else shard_push_records<true><<<NUM_SMS_B200 * 8, 256, 0, c->stream>>>(pa, c->sbuf, c->d_sort, c->d_dest_rank, c->d_dest_pos);
+			c->launches++;
+		}
+		shard_post(c, 1, nullptr);
+		shard_wait(c, 1);
+	}
+	// 3. the shard this rank now holds: its r, m into every rank's tables, its binaries pulled from the ranks their stars came from
+	c->cur_star ^= 1;
+	{
+		StageTimer t(c, ST_SHARD_TABLES);
+		void *ptrs[2 * SHARD_MAX_RANKS];
+		for (int q = 0; q < c->nranks; q++) { ptrs[q] = peer_role(c, q, SH_R_ALT); ptrs[SHARD_MAX_RANKS + q] = peer_role(c, q, SH_M_ALT); }
+		void **d_ptrs = (void **) ((char *) c->d_shard_meta + sizeof(ShardMeta) + SHARD_MAX_RANKS * sizeof(void *));
+		CMCB_CUDA_OK(cudaMemcpyAsync(d_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, c->stream));
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r_alt, c->d_r, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m_alt, c->d_m, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+		shard_publish_tables_planned<<<NUM_SMS_B200 * 4, 256, 0, c->stream>>>(star1(c), d_meta, (double *const *) d_ptrs, (double *const *) (d_ptrs + SHARD_MAX_RANKS), c->d_binflag);
+		c->launches++;
+	}
+	{
+		StageTimer tb(c, ST_BINARIES);
+		if (n_bin_clear > c->n_bin_dim - 1) n_bin_clear = c->n_bin_dim - 1;
+		char *bin_out = c->d_bin[c->cur_bin ^ 1] + CMCB_SIZEOF_BINARY;
+		shard_adopt_shard_kernel<<<1, 32, 0, c->stream>>>(c->d_sort, d_meta);
+		c->launches++;
+		const long n_upper = c->n_star_dim; // the shard may be larger than what this rank contributed: size the grids for the capacity
+		const long nbt = (n_upper + SHARD_BIN_TILE - 1) / SHARD_BIN_TILE;
+		c->launches += sort_binary_count_scan_planned(c->d_binflag, c->d_sort, c->d_bin_block_cnt, n_upper, c->stream);
+		BinPull bp;
+		for (int q = 0; q < c->nranks; q++) bp.bin_in[q] = (const char *) c->peer_buf[q][SH_BIN0 + c->cur_bin] + CMCB_SIZEOF_BINARY;
+		shard_binary_pull<<<(unsigned) nbt, 256, 0, c->stream>>>(star1(c), c->d_binflag, c->d_src_all, c->d_bin_block_cnt, 0, c->d_sort, bp, bin_out);
+		c->launches++;
+		c->launches += sort_binary_clear_device(bin_out, c->d_sort, n_bin_clear, c->stream);
+		c->cur_bin ^= 1;
+		shard_post(c, 2, nullptr);
+		shard_wait(c, 2);
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	// 4. the alternate tables become THE tables (on all ranks in lock step)
+	std::swap(c->d_r, c->d_r_alt);
+	std::swap(c->d_m, c->d_m_alt);
+	c->r_parity ^= 1;
+	return 0;
+}
+
+extern "C" int cmcb200_shard_step_result(cmcb200_ctx *c, long *n_keep_all, int *Start, int *End, long *n_bin)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	char *h = (char *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_shard_meta, sizeof(ShardMeta), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaMemcpyAsync(h + sizeof(ShardMeta), &c->d_sort->n_bin, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaMemcpyAsync(h + sizeof(ShardMeta) + 8, &((ShardSync *) c->d_shard_sync)->error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	const ShardMeta *m = (const ShardMeta *) h;
+	const int err = *(const int *) (h + sizeof(ShardMeta) + 8);
+	if (err) { set_error("shard_step: barrier %d timed out -- a peer rank did not arrive", err - 1); return -2; }
+	for (int q = 0; q < c->nranks; q++) {
+		if (n_keep_all) n_keep_all[q] = m->n_keep[q];
+		if (Start) Start[q] = (int) (m->start0[q] + 1);
+		if (End) End[q] = (int) (m->start0[q] + m->count[q]);
+		if (m->count[q] + 2 > c->n_star_dim) { set_error("shard_step: rank %d holds %ld stars, capacity %ld", q, m->count[q], c->n_star_dim); return -1; }
+	}
+	if (n_bin) *n_bin = *(const long *) (h + sizeof(ShardMeta));
 	return 0;
 }

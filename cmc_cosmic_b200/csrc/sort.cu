@@ -471,6 +471,15 @@ int sort_binary_count_scan(const unsigned char *binflag, SortState *st, unsigned
 	sort_binary_scan<<<1, 1024, 0, s>>>(bin_block_cnt, nbt, st);
 	return 3;
 }
+// the same when st->n_new already holds the shard size (set on the device) and the host only knows an upper bound for the grids
+int sort_binary_count_scan_planned(const unsigned char *binflag, SortState *st, unsigned *bin_block_cnt, long n_upper, cudaStream_t s)
+{
+	if (n_upper <= 0) return 0;
+	const long nbt = (n_upper + BIN_TILE - 1) / BIN_TILE;
+	sort_binary_count<<<(unsigned) nbt, 256, 0, s>>>(binflag, st, bin_block_cnt);
+	sort_binary_scan<<<1, 1024, 0, s>>>(bin_block_cnt, nbt, st);
+	return 2;
+}
 int sort_binary_clear_device(char *bin_out, const SortState *st, long n_clear, cudaStream_t s)
 {
 	if (!bin_out || n_clear <= 0) return 0;

@@ -59,6 +59,7 @@ int sort_stage_passes(const SortArgs &a, cudaStream_t s);
 int sort_stage_gather(const SortArgs &a, cudaStream_t s);
 int sort_stage_binaries(const SortArgs &a, cudaStream_t s);
 int sort_binary_count_scan(const unsigned char *binflag, SortState *st, unsigned *bin_block_cnt, long n, cudaStream_t s);
+int sort_binary_count_scan_planned(const unsigned char *binflag, SortState *st, unsigned *bin_block_cnt, long n_upper, cudaStream_t s);
 int sort_binary_clear_device(char *bin_out, const SortState *st, long n_clear, cudaStream_t s);
 
 } // namespace cmcb

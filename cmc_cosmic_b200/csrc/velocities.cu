@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, ORBIT_CTAS_PER_SM) sv3_prep
 	extern __shared__ __align__(128) unsigned char orbit_smem[];
 	__shared__ __align__(8) unsigned long long bar;
 	LadderTops top;
-	top.q = nullptr; top.qdesc = nullptr;
+	top.q = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
 	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
 	const Sv3Index gi = sv3_index(a);
 	for (long j0 = blockIdx.x * (long) ORBIT_TRY_THREADS + threadIdx.x; j0 < n_pad; j0 += (long) gridDim.x * ORBIT_TRY_THREADS) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS) potential_at_kernel(OrbitAr
 	extern __shared__ __align__(128) unsigned char orbit_smem[];
 	__shared__ __align__(8) unsigned long long bar;
 	LadderTops top;
-	top.q = nullptr; top.qdesc = nullptr;
+	top.q = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
 	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
 	for (long i = blockIdx.x * (long) ORBIT_TRY_THREADS + threadIdx.x; i < n; i += (long) gridDim.x * ORBIT_TRY_THREADS) {
 		int fail = 0;

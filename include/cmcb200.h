@@ -176,6 +176,9 @@ int cmcb200_dev_put(cmcb200_ctx *ctx, const void *star_rec, long j, const void *
 
 /* orbit step on the resident arrays (same semantics as cmcb200_new_orbits_calculate; star_r/m/phi = resident tables) */
 int cmcb200_dev_new_orbits(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int want_status, cmcb200_orbit_result *res);
+/* the orbit step queued without waiting for it; cmcb200_dev_orbit_result waits for the stream and returns its statistics */
+int cmcb200_dev_new_orbits_async(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, int want_status);
+int cmcb200_dev_orbit_result(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, cmcb200_orbit_result *res);
 /* the transfer half of ComputeIntermediateEnergy (src/cmc/cmc_utils.c:380-390): rOld <- star_r, r <- rnew, m <- star_m,
  * vr <- vrnew, vt <- vtnew for local stars 1..n_local -- this is what creates the sort key */
 int cmcb200_dev_transfer_new_positions(cmcb200_ctx *ctx, long n_local, long n_old_local, long first_global, long N_MAX);
@@ -297,6 +300,13 @@ int cmcb200_shard_sort_local(cmcb200_ctx *ctx, long n_local, long *n_keep);
 int cmcb200_shard_exchange(cmcb200_ctx *ctx, const long *n_keep_all, const int *Start, const int *End, long n_old_local, long first_global, long N_MAX);
 int cmcb200_shard_publish(cmcb200_ctx *ctx, long n_new_local, long start_global, long n_bin_clear, long *n_bin);
 int cmcb200_shard_finish(cmcb200_ctx *ctx);
+/* The same four calls as ONE asynchronous sequence: the ranks meet at three barriers made of flags in each other's device memory
+ * (st.release.sys / ld.acquire.sys over NVLink), the counts travel with the first barrier, every device plans the new partition itself
+ * (findLimits with blk = min_chunk) and the kernels behind take their extents from that plan.  The host only enqueues;
+ * cmcb200_shard_step_result waits for the stream and returns what the reference's globals need: n_keep_all[procs], Start / End [procs] of the new
+ * partition (clus.N_MAX = End[procs-1]), the local binary count.  A barrier that a peer never reaches times out (4 s) and the result call fails. */
+int cmcb200_shard_step_async(cmcb200_ctx *ctx, long n_local, long n_old_local, long first_global, long N_MAX, int min_chunk, long n_bin_clear);
+int cmcb200_shard_step_result(cmcb200_ctx *ctx, long *n_keep_all, int *Start, int *End, long *n_bin);
 
 /* ---- instrumentation --------------------------------------------------------------------------------------------- */
 

@@ -74,7 +74,24 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
 	if (force_exact == 1) { t.qlad.n_levels = 0; t.rlad.n_levels = 0; t.rpf = nullptr; } // 1: every probe reads the fine FP64 table
-	if (force_exact == 2) t.qlad.n_levels = 0; // 2: the device's default configuration -- r ladder + FP32 screening of the index bisections, no Q ladder
+	if (force_exact == 2) t.qlad.n_levels = 0; // 2: r ladder + FP32 screening of the index bisections, no Q ladder
+	// 3: the device's default configuration -- r ladder + sample ladder (find_zero_Q_sampled), no Q ladder, no screening
+	std::vector<std::vector<RPhi>> slv;
+	t.slad.n_levels = 0;
+	if (force_exact == 3 && lad.r.n_levels > 0) {
+		t.qlad.n_levels = 0; t.rpf = nullptr;
+		long scnt[LADDER_MAX_LEVELS];
+		const int ns = slad_plan(N_MAX + 1, t.slad.shift, scnt);
+		slv.resize(ns);
+		for (int l = 0; l < ns; l++) {
+			slv[l].resize(scnt[l]);
+			for (long b = 0; b < scnt[l]; b++) slv[l][b] = rp[b << t.slad.shift[l]];
+			t.slad.lvl[l] = slv[l].data();
+		}
+		t.slad.n_levels = ns;
+		t.slad.margin = (double) (N_MAX + 1) * 7.105427357601002e-15 + 9.094947017729282e-13;
+		t.slad.phi_abs_max = __builtin_fmax(__builtin_fabs(rp[0].phi), __builtin_fabs(rp[1].phi));
+	}
 	counters[3] = t.qlad.n_levels; counters[4] = t.rlad.n_levels;
 	double max_rad = 0.0;
 	long pos = 0;
@@ -99,14 +116,14 @@ extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, con
 				 double E, double J, long kmin, long kmax, long *n_exact, int use_ladder)
 {
 	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
-	OrbitTables t; t.rpf = nullptr; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
+	OrbitTables t; t.rpf = nullptr; t.slad.n_levels = 0; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = t.invN; t.cenma_m = 0;
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
 	if (!use_ladder) { t.qlad.n_levels = 0; t.rlad.n_levels = 0; }
 	StarConst s; s.g_j = g_j; s.r_j = star_r[g_j]; s.m_j = star_m[g_j]; s.E = E; s.J = J;
 	star_const_derive(t, s);
 	int ne = 0;
-	LadderTops top; top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr; top.qdesc = &t.qlad;
+	LadderTops top; top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr; top.qdesc = &t.qlad; top.s = nullptr; top.sdesc = nullptr;
 	long k = find_zero_Q(t, top, s, kmin, kmax, &ne);
 	*n_exact = ne;
 	return k;
@@ -116,7 +133,7 @@ extern "C" long emul_find_zero_Q(const double *star_r, const double *star_m, con
 extern "C" void emul_find_zero_r_both(const double *star_r, long N_MAX, const double *radii, long n, long *k_bisect, long *k_ladder)
 {
 	std::vector<RPhi> rp = pack(star_r, star_r, N_MAX + 2);
-	OrbitTables t; t.rpf = nullptr; t.rp = rp.data(); t.m = nullptr; t.N_MAX = N_MAX; t.invN = 0; t.madhoc = 0; t.cenma_m = 0;
+	OrbitTables t; t.rpf = nullptr; t.slad.n_levels = 0; t.rp = rp.data(); t.m = nullptr; t.N_MAX = N_MAX; t.invN = 0; t.madhoc = 0; t.cenma_m = 0;
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
 	for (long i = 0; i < n; i++) {
@@ -143,10 +160,10 @@ extern "C" double emul_set_velocities3(const double *star_r, const double *star_
 				       unsigned char *kind, long *counters)
 {
 	std::vector<RPhi> rp = pack(star_r, star_phi, N_MAX + 2);
-	OrbitTables t; t.rpf = nullptr; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = 0;
+	OrbitTables t; t.rpf = nullptr; t.slad.n_levels = 0; t.rp = rp.data(); t.m = star_m; t.N_MAX = N_MAX; t.invN = 1.0 / N_STAR; t.madhoc = 1.0 / ((double) N_STAR); t.cenma_m = 0;
 	HostLadders lad(rp, (kint) (N_MAX + 1));
 	t.qlad = lad.q; t.rlad = lad.r;
-	LadderTops top; top.q = nullptr; top.qdesc = nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
+	LadderTops top; top.q = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr;
 	const Sv3Index gi{first_global, n_local, N_MAX};
 	std::vector<double> val(n_local);
 	counters[0] = counters[1] = counters[2] = 0;

@@ -95,7 +95,7 @@ int main(int argc, char **argv)
 		if (!(E < 0) || !std::isfinite(E)) continue;
 		RPhi tab[1];
 		tab[0].r = r; tab[0].phi = pot;
-		OrbitTables t; t.rpf = nullptr; t.rp = tab; t.m = nullptr; t.N_MAX = 0; t.invN = 1.0 / N; t.madhoc = t.invN; t.cenma_m = 0;
+		OrbitTables t; t.rpf = nullptr; t.slad.n_levels = 0; t.rp = tab; t.m = nullptr; t.N_MAX = 0; t.invN = 1.0 / N; t.madhoc = t.invN; t.cenma_m = 0;
 		StarConst sc; sc.g_j = 0; sc.r_j = r_j; sc.m_j = m_j; sc.E = E; sc.J = J;
 		star_const_derive(t, sc);
 		int ne = 0;

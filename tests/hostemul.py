@@ -51,8 +51,8 @@ def _p(a):
     return None if a is None else a.ctypes.data
 
 
-def get_positions(sr, sm, phi, N_MAX, N_STAR, cenma_m, g_idx, E, J, vr, vt, Rtidal, draws, csr_off=None, is_new=None, rnew_in=None, no_ladders=False, screened=False):
-    """no_ladders: every probe on the fine FP64 table; screened: the device's default configuration (r ladder + FP32 screening copy, no Q ladder)"""
+def get_positions(sr, sm, phi, N_MAX, N_STAR, cenma_m, g_idx, E, J, vr, vt, Rtidal, draws, csr_off=None, is_new=None, rnew_in=None, no_ladders=False, screened=False, sampled=False):
+    """no_ladders: every probe on the fine FP64 table; screened: r ladder + FP32 screening copy, no Q ladder; sampled: the device's default configuration (r ladder + sample ladder for the index bisections)"""
     n = len(g_idx)
     g_idx = np.ascontiguousarray(g_idx, np.int64)
     arrs = [np.ascontiguousarray(x, np.float64) for x in (E, J, vr, vt)]
@@ -63,7 +63,7 @@ def get_positions(sr, sm, phi, N_MAX, N_STAR, cenma_m, g_idx, E, J, vr, vt, Rtid
                r_apo=np.zeros(n), kmin=np.zeros(n, np.int64), kmax=np.zeros(n, np.int64))
     cnt = np.zeros(5, np.int64)
     out["max_rad"] = lib().emul_get_positions(_p(sr), _p(sm), _p(phi), N_MAX, N_STAR, cenma_m, n, _p(g_idx), _p(is_new), _p(arrs[0]), _p(arrs[1]),
-                                              _p(arrs[2]), _p(arrs[3]), _p(rnew_in), Rtidal, _p(draws), len(draws), _p(csr_off), 1 if no_ladders else (2 if screened else 0),
+                                              _p(arrs[2]), _p(arrs[3]), _p(rnew_in), Rtidal, _p(draws), len(draws), _p(csr_off), 1 if no_ladders else (2 if screened else (3 if sampled else 0)),
                                               _p(out["status"]), _p(out["rnew"]), _p(out["vrnew"]), _p(out["vtnew"]), _p(out["X"]),
                                               _p(out["r_peri"]), _p(out["r_apo"]), _p(out["kmin"]), _p(out["kmax"]), _p(cnt))
     out["n_draws"], out["n_exact"], out["n_brent"] = int(cnt[0]), int(cnt[1]), int(cnt[2])

@@ -272,3 +272,55 @@ def test_find_root_vr_fires_in_the_device_core_and_matches_the_oracle():
             cm.assert_bits_equal(got[k], want[k], k)
         for k in ("r_peri", "r_apo", "X"):
             cm.assert_bits_equal(got[k][ok], want[k][ok], k)
+
+
+@pytest.mark.parametrize("kind,N,masses,cenma", [("plummer", 120000, "equal", 0.0), ("king", 40000, "imf", 0.0), ("plummer", 20000, "imf", 50.0), ("plummer", 3000, "equal", 0.0)])
+def test_sample_ladder_index_bisections_bit_exact(kind, N, masses, cenma):
+    """find_zero_Q through the sample ladder (csrc/orbit_core.h: find_zero_Q_sampled -- the device's default): the signs of all probes far from
+    the sign change are PROVEN from a few sampled table entries (concavity of Q over the entries + a rigorous margin), the probes next to it
+    are evaluated exactly, the reference's probe sequence is replayed.  k_min / k_max and everything computed from them must equal the
+    oracle's bit for bit -- on ordinary clusters, with a central mass, with stars at (and within rounding of) their turning points, where a
+    bracket end sits inside the margin and the search must fall back, and with ladders of 2 .. 4 levels (the 'deep' build)."""
+    import hostemul as he
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=3, masses=masses)
+    pot = cm.oracle_potential(r, sm, cenma_m=cenma)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, cenma)
+    for turning in (False, True):
+        v = vr.copy()
+        g = np.arange(1, N + 1)
+        if turning:
+            v[::3] = 0.0
+            v[1::3] *= 1e-7
+            g = np.arange(1, N + 1, max(1, N // 4000))        # their linear scans are O(N) each in the oracle
+        E, J = cm.energies(pot["phi"][1:N + 1], r, v, vt)
+        d = ol.Taus113(3).draws(200 * len(g))
+        want = ol.get_positions(t, g, E[g - 1], J[g - 1], v[g - 1], vt[g - 1], pot["Rtidal"], d)
+        used = d[:want["draw_off"][-1]]
+        ok = want["status"] == ol.ST_OK
+        for deep in (False, True):
+            he.use_deep_ladders(deep)
+            try:
+                got = he.get_positions(pot["star_r"], pot["star_m"], pot["phi"], N, N, cenma, g, E[g - 1], J[g - 1], v[g - 1], vt[g - 1], pot["Rtidal"], used,
+                                       csr_off=want["draw_off"], sampled=True)
+            finally:
+                he.use_deep_ladders(False)
+            assert np.array_equal(got["status"], want["status"])
+            assert np.array_equal(got["kmin"][ok], want["kmin"][ok]) and np.array_equal(got["kmax"][ok], want["kmax"][ok])
+            for k in ("rnew", "vrnew", "vtnew"):
+                cm.assert_bits_equal(got[k], want[k], k)
+
+
+def test_sample_ladder_where_find_root_vr_fires():
+    import hostemul as he
+    N = 20000
+    r, vr, vt, sm, pot, E, J, planted = cm.brent_cluster(N)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N)
+    d = ol.Taus113(3).draws(200 * N)
+    want = ol.get_positions(t, np.arange(1, N + 1), E, J, vr, vt, pot["Rtidal"], d)
+    got = he.get_positions(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0, np.arange(1, N + 1), E, J, vr, vt, pot["Rtidal"], d[:want["draw_off"][-1]],
+                           csr_off=want["draw_off"], sampled=True)
+    ok = want["status"] == ol.ST_OK
+    assert got["n_brent"] == want["n_brent"] > 150 and np.array_equal(got["status"], want["status"])
+    assert np.array_equal(got["kmin"][ok], want["kmin"][ok]) and np.array_equal(got["kmax"][ok], want["kmax"][ok])
+    for k in ("rnew", "vrnew", "vtnew"):
+        cm.assert_bits_equal(got[k], want[k], k)
