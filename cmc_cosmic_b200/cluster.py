@@ -472,6 +472,16 @@ class Cluster:
         self.mass_pc, self.mass_pc_owner, self.mass_pc_totals = pc, owner, np.array(list(res.totals))
         return int(res.filled)
 
+    def dev_comp_multi_mass_percent(self, mass_bins, solar_mass_dyn, mass_pc):
+        """comp_multi_mass_percent (reference src/cmc/cmc_utils.c:769-861) on the resident tables: multi_mass_r[NO_MASS_BINS][MASS_PC_COUNT], the
+        Lagrange radii per mass bin (rows of empty bins keep their previous values, -1 on first use)"""
+        bins, pc = np.ascontiguousarray(mass_bins, np.float64), np.ascontiguousarray(mass_pc, np.float64)
+        if getattr(self, "multi_mass_r", None) is None or self.multi_mass_r.shape != (len(bins), len(pc)):
+            self.multi_mass_r = np.full((len(bins), len(pc)), -1.0)
+        _lib.check(self.L.cmcb200_dev_comp_multi_mass_percent(self.ctx, self.clus.N_MAX, bins.ctypes.data, len(bins), solar_mass_dyn, pc.ctypes.data, len(pc),
+                                                              self.multi_mass_r.ctypes.data), "dev_comp_multi_mass_percent")
+        return self.multi_mass_r
+
     def dev_clusdyn_calculate(self):
         """clusdyn_calculate (reference src/cmc/cmc_utils.c:1613-1624): clusdyn.rh, the half-mass radius, from the resident tables"""
         rh = C.c_double()

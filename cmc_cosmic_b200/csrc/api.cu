@@ -164,6 +164,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
 	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
 	if (c->d_lagrange) cudaFree(c->d_lagrange);
+	if (c->d_multimass) cudaFree(c->d_multimass);
 	if (c->d_sv3) cudaFree(c->d_sv3);
 	if (c->d_seqwork2) cudaFree(c->d_seqwork2);
 	if (c->d_draws) cudaFree(c->d_draws);
@@ -734,8 +735,28 @@ static int dirty_runs(unsigned long long mask, int lo[CMCB_STAR_WORDS], int len[
 	return n;
 }
 
+static int resident_begin_impl(cmcb200_ctx *c, const void *star1_h, long n_local, const void *binary1_h, long n_bin, const double *star_r, const double *star_m,
+			       const double *star_phi, long n_table, unsigned long long dirty_words, long slice_first, long slice_n);
+
 extern "C" int cmcb200_resident_begin(cmcb200_ctx *c, const void *star1_h, long n_local, const void *binary1_h, long n_bin,
 					      const double *star_r, const double *star_m, const double *star_phi, long n_table, unsigned long long dirty_words)
+{
+	return resident_begin_impl(c, star1_h, n_local, binary1_h, n_bin, star_r, star_m, star_phi, n_table, dirty_words, 0, -1);
+}
+
+// Radius-sharded form: every rank holds the same replicated host tables, so each one sends only ITS slice [slice_first, slice_first + slice_n) of
+// star_r / star_m / star_phi (plus the sentinel [0] and everything behind the last rank's slice: N_MAX + 1 and the stars created this step)
+// over its host link and the ranks hand the slices to each other over NVLink (peer stores + a device-side barrier) -- (P - 1) / P of the
+// table upload leaves the host links.
+extern "C" int cmcb200_resident_begin_sharded(cmcb200_ctx *c, const void *star1_h, long n_local, const void *binary1_h, long n_bin, const double *star_r,
+						      const double *star_m, const double *star_phi, long n_table, unsigned long long dirty_words, long slice_first, long slice_n)
+{
+	if (c->nranks <= 1 || !star_r || !star_m || !star_phi) slice_n = -1;
+	return resident_begin_impl(c, star1_h, n_local, binary1_h, n_bin, star_r, star_m, star_phi, n_table, dirty_words, slice_first, slice_n);
+}
+
+static int resident_begin_impl(cmcb200_ctx *c, const void *star1_h, long n_local, const void *binary1_h, long n_bin, const double *star_r, const double *star_m,
+			       const double *star_phi, long n_table, unsigned long long dirty_words, long slice_first, long slice_n)
 {
 	if (n_local + 2 > c->n_star_dim || n_table > c->n_table_dim || n_bin + 1 > c->n_bin_dim) { set_error("resident_begin: sizes exceed the context capacity"); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
@@ -748,11 +769,28 @@ extern "C" int cmcb200_resident_begin(cmcb200_ctx *c, const void *star1_h, long 
 	// the copies start behind whatever the context's stream still has in flight
 	CMCB_CUDA_OK(cudaEventRecord(c->ev_done[ORBIT_MAX_CHUNKS - 1], c->stream));
 	CMCB_CUDA_OK(cudaStreamWaitEvent(c->s_in, c->ev_done[ORBIT_MAX_CHUNKS - 1], 0));
-	if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
-	if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
-	if (star_phi) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_phi, star_phi, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
-	c->bytes_h2d += ((star_r ? 1 : 0) + (star_m ? 1 : 0) + (star_phi ? 1 : 0)) * n_table * (long) sizeof(double);
+	if (slice_n >= 0) {
+		// this rank's slice and the sentinel [0]; the caller extends the LAST rank's slice to n_table - 1 (N_MAX + 1 and the stars created this
+		// step lie behind the last shard), so the slices of all ranks cover [1, n_table)
+		if (slice_first < 1 || slice_first + slice_n > n_table) { set_error("resident_begin_sharded: slice [%ld, %ld) outside the tables", slice_first, slice_first + slice_n); return -1; }
+		const double *src[3] = {star_r, star_m, star_phi};
+		double *dst[3] = {c->d_r, c->d_m, c->d_phi};
+		for (int t = 0; t < 3; t++) {
+			CMCB_CUDA_OK(cudaMemcpyAsync(dst[t], src[t], sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+			if (slice_n > 0) CMCB_CUDA_OK(cudaMemcpyAsync(dst[t] + slice_first, src[t] + slice_first, (size_t) slice_n * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+		}
+		c->bytes_h2d += 3 * (slice_n + 1) * (long) sizeof(double);
+	} else {
+		if (star_r) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r, star_r, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+		if (star_m) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m, star_m, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+		if (star_phi) CMCB_CUDA_OK(cudaMemcpyAsync(c->d_phi, star_phi, (size_t) n_table * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+		c->bytes_h2d += ((star_r ? 1 : 0) + (star_m ? 1 : 0) + (star_phi ? 1 : 0)) * n_table * (long) sizeof(double);
+	}
 	CMCB_CUDA_OK(cudaEventRecord(c->ev_tab, c->s_in));
+	if (slice_n >= 0) { // the slices travel on to the peers behind the upload, on the context's stream; the kernels queued later find complete tables
+		CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_tab, 0));
+		if (shard_share_table_slices(c, slice_first, slice_n)) return -1;
+	}
 	int n_chunks = (int) ((n_local + (1L << 19) - 1) >> 19); // >= 512 K stars per chunk: the kernels of a chunk still fill the GPU
 	if (n_chunks > c->orbit_max_chunks) n_chunks = c->orbit_max_chunks;
 	if (n_chunks < 1) n_chunks = 1;

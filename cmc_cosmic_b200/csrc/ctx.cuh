@@ -11,7 +11,7 @@
 using namespace cmcb;
 
 constexpr int SHARD_MAX_RANKS = 16;
-enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_SYNC, SH_N_BUFFERS }; // peer-visible buffers
+enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_SYNC, SH_PHI, SH_N_BUFFERS }; // peer-visible buffers
 
 enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES, ST_LAGRANGE };
 
@@ -59,6 +59,7 @@ struct cmcb200_ctx {
 	// orbit scratch
 	OrbitStats *d_ostats;
 	void *d_lagrange; // device result block of comp_mass_percent (lagrange.cu), allocated on first use
+	void *d_multimass; // argument / result block of comp_multi_mass_percent (lagrange.cu), allocated on first use
 	void *d_seqwork2; // exact-scan scratch for chains of 2 n_star_dim elements (ComputeEnergy's potential sum), allocated on first use
 	void *d_sv3;      // scratch of set_velocities3 (velocities.cu), allocated on first use for n_star_dim stars
 	int *d_status;
@@ -100,9 +101,14 @@ struct cmcb200_ctx {
 	long *d_shard_meta;                             // device copy of (n_keep[q], start0[q]) per rank
 	void *d_shard_sync;                             // ShardSync (shard.cu): flags and posted counts the peers store into -- the device-side barriers
 	unsigned long long shard_epoch;                 // barrier generation, advanced identically on every rank
+	unsigned long long table_epoch;                 // generation of the table-sharing barrier (phase 3) of cmcb200_resident_begin_sharded
 	int shard_unfused;                              // 1: the sharded sort keys on r and moves the records unchanged (cmcb200_shard_fuse_transfer)
 	int r_parity;                                   // which of (d_r, d_r_alt) is the buffer SH_R (flips with every fused sort)
 };
+
+// shard.cu: this rank's slice [first, first + n) of star_r / star_m / star_phi stored into every peer's tables, then a device-side barrier --
+// queued on the context's stream (cmcb200_resident_begin_sharded)
+int shard_share_table_slices(cmcb200_ctx *c, long first, long n);
 
 // fills the orbit-step argument block from the context and the caller's parameters and (re)builds the lookup tables (api.cu)
 int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a);

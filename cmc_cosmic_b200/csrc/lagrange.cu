@@ -9,6 +9,8 @@
 // reference's bit for bit.  The sums are returned rank-local; the caller adds the MPI_Exscan prefix for indices a rank other than 0
 // owns, exactly like the reference (:945-951).  pow() for the densities runs on the host (glibc, as in the reference).
 #include <cmath>
+#include <cstring>
+#include <vector>
 #include "ctx.cuh"
 #include "seqscan.cuh"
 
@@ -277,5 +279,130 @@ extern "C" int cmcb200_dev_compute_energy_totals(cmcb200_ctx *c, long n_local, l
 	out[1] = h[1] == 0.0 ? 0.0 : -h[1]; // the potential and binding sums were taken on their magnitudes
 	out[2] = h[2];
 	out[3] = h[3] == 0.0 ? 0.0 : -h[3];
+	return 0;
+}
+
+
+// ---- comp_multi_mass_percent (reference src/cmc/cmc_utils.c:769-861): Lagrange radii per mass bin -----------------------------------------
+// For every mass bin the reference sums the masses of the bin's stars in star order (twice: the total, then the running fraction), and
+// interpolates radius over mass fraction linearly (gsl_interp_linear: un-vendored GSL, restated like the oracle restates it).  Here: one exact
+// sequential-sum chain per bin over the whole table whose terms are star_m for the bin's stars and 0 for the others (a zero term is regular:
+// fl(y + 0) = y), then per threshold two binary searches on the finished running sums.
+namespace cmcb {
+
+constexpr int MASS_BINS_MAX = 64;
+struct MultiMassArgs {
+	double bins[MASS_BINS_MAX]; // mass_bins[], ascending
+	double thr[MASS_PC_MAX];    // mass_pc[]
+	long n_bins, count;
+	double solar_mass_dyn;
+};
+
+// find_stars_mass_bin (:756-764) -> m_binsearch (include/common/gensearch.h): largest index with mass_bins[index] < smass, -1 outside the bins
+__device__ __forceinline__ long mass_bin_of(const double *bins, long n_bins, double smass)
+{
+	if (smass < bins[0] || smass > bins[n_bins - 1]) return -1;
+	long lo = 0, hi = n_bins - 1;
+	do {
+		const long k = (lo + hi + 1) / 2;
+		if (bins[k] < smass) lo = k; else hi = k - 1;
+	} while (hi != lo);
+	return lo;
+}
+
+struct ChainBinMass { // y_i = y_{i-1} + (star i+1 in bin b ? star_m[i+1] : 0); stored at ysum[i+1]
+	static constexpr int SIGN = +1;
+	const double *m;
+	double *ysum;
+	const MultiMassArgs *a;
+	long n, b;
+	__device__ long length() const { return n; }
+	__device__ double y0() const { return 0.0; }
+	__device__ double term(long i) const
+	{
+		const double mi = m[i + 1];
+		return mass_bin_of(a->bins, a->n_bins, ddiv(mi, a->solar_mass_dyn)) == b ? mi : 0.0;
+	}
+	__device__ void store(long i, double y) const { ysum[i + 1] = y; }
+};
+
+// thread c: multi_mass_r[b][c] from the bin's running sums ysum[1..N_MAX] (non-decreasing; it steps exactly at the bin's stars)
+__global__ void multi_mass_eval(const double *__restrict__ ysum, const double *__restrict__ star_r, long N_MAX, const MultiMassArgs *a, long b, double *out, int *filled)
+{
+	const long c = threadIdx.x;
+	if (c >= a->count) return;
+	const double total = N_MAX > 0 ? ysum[N_MAX] : 0.0;
+	auto first_with = [&](auto pred) { // first k in [1, N_MAX] with pred(ysum[k]); N_MAX + 1 if none (pred is monotone along the sums)
+		long lo = 1, hi = N_MAX + 1;
+		while (lo < hi) {
+			const long mid = (lo + hi) >> 1;
+			if (pred(ysum[mid])) hi = mid; else lo = mid + 1;
+		}
+		return lo;
+	};
+	const long k_first = first_with([&](double y) { return y > 0.0; });
+	if (k_first > N_MAX) { if (c == 0) filled[b] = 0; return; } // number_inbin == 0: the row is left untouched (:845-846)
+	if (c == 0) filled[b] = 1;
+	const long k_last = first_with([&](double y) { return y >= total; });
+	if (k_first == k_last) { out[b * a->count + c] = star_r[k_last]; return; } // number_inbin == 1 (:847-850)
+	const double x = a->thr[c];
+	// gsl_interp_bsearch over percents[]: the first star of the bin whose fraction exceeds x closes the interval, the last one if none does
+	long k_hi = first_with([&](double y) { return ddiv(y, total) > x; });
+	if (k_hi > N_MAX) k_hi = k_last;
+	const double y_before = ysum[k_hi - 1]; // the running sum up to the previous star of the bin (ysum[0] = 0 is never written: guard below)
+	double x_lo = 0.0, r_lo = 0.0;
+	if (k_hi > k_first) {
+		const double yb = y_before;
+		const long k_lo = first_with([&](double y) { return y >= yb; }); // where the sum reached that value: the previous star of the bin
+		x_lo = ddiv(yb, total);
+		r_lo = star_r[k_lo];
+	}
+	const double x_hi = ddiv(ysum[k_hi], total), r_hi = star_r[k_hi];
+	const double dx = dsub(x_hi, x_lo);
+	double val = dx > 0.0 ? dadd(r_lo, dmul(ddiv(dsub(x, x_lo), dx), dsub(r_hi, r_lo))) : 0.0;
+	if (x < 0.0 || x > 1.0) val = __longlong_as_double(0x7ff8000000000000ll);
+	out[b * a->count + c] = val;
+}
+
+} // namespace cmcb
+
+extern "C" int cmcb200_dev_comp_multi_mass_percent(cmcb200_ctx *c, long N_MAX, const double *mass_bins, long n_bins, double solar_mass_dyn,
+						    const double *mass_pc, long count, double *multi_mass_r)
+{
+	if (n_bins <= 1) return 0; // :786
+	if (n_bins > MASS_BINS_MAX || count < 0 || count > MASS_PC_MAX) { set_error("comp_multi_mass_percent: at most %d bins and %d fractions", MASS_BINS_MAX, MASS_PC_MAX); return -1; }
+	if (N_MAX + 2 > c->n_table_dim) { set_error("comp_multi_mass_percent: N_MAX + 2 exceeds the table capacity"); return -1; }
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	if (!c->d_lagrange) CMCB_CUDA_OK(cudaMalloc(&c->d_lagrange, sizeof(LagrangeDev)));
+	if (!c->d_multimass) CMCB_CUDA_OK(cudaMalloc(&c->d_multimass, sizeof(MultiMassArgs) + (size_t) MASS_BINS_MAX * MASS_PC_MAX * sizeof(double) + MASS_BINS_MAX * sizeof(int)));
+	LagrangeDev *d = (LagrangeDev *) c->d_lagrange;
+	MultiMassArgs *d_a = (MultiMassArgs *) c->d_multimass;
+	double *d_out = (double *) ((char *) c->d_multimass + sizeof(MultiMassArgs));
+	int *d_filled = (int *) (d_out + (size_t) MASS_BINS_MAX * MASS_PC_MAX);
+	MultiMassArgs h;
+	memset(&h, 0, sizeof(h));
+	for (long i = 0; i < n_bins; i++) h.bins[i] = mass_bins[i];
+	for (long i = 0; i < count; i++) h.thr[i] = mass_pc[i];
+	h.n_bins = n_bins; h.count = count; h.solar_mass_dyn = solar_mass_dyn;
+	CMCB_CUDA_OK(cudaMemcpyAsync(d_a, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream)); // h lives on this stack frame
+	{
+		StageTimer t(c, ST_LAGRANGE);
+		for (long b = 0; b < n_bins; b++) {
+			ChainBinMass ch{c->d_m, c->d_mprev, d_a, N_MAX, b}; // d_mprev: the potential's scratch, free between two rebuilds
+			seq_scan_launch(ch, c->seqwork, N_MAX, &d->last, NUM_SMS_B200 * 4, NUM_SMS_B200 * 4, c->stream);
+			if (count > 0) multi_mass_eval<<<1, MASS_PC_MAX, 0, c->stream>>>(c->d_mprev, c->d_r, N_MAX, d_a, b, d_out, d_filled);
+			c->launches += 5;
+		}
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	std::vector<double> out((size_t) n_bins * count);
+	std::vector<int> filled(n_bins);
+	if (count > 0) CMCB_CUDA_OK(cudaMemcpyAsync(out.data(), d_out, out.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaMemcpyAsync(filled.data(), d_filled, n_bins * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	for (long b = 0; b < n_bins; b++)
+		if (filled[b]) for (long k = 0; k < count; k++) multi_mass_r[b * count + k] = out[b * count + k]; // rows of empty bins stay as they are
 	return 0;
 }

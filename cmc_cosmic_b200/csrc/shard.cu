@@ -11,11 +11,14 @@
 //                           hence its destination rank and its final position there -- the partition is realised exactly, so the
 //                           reference's second exchange (load_balance) has nothing left to do
 //   4. shard_push_records   the fused gather + all-to-all: each 424-byte record is read once from the local array and written once,
-//                           straight to its final slot in the destination GPU's array (r <- rnew .. applied on the way), 16-byte
-//                           stores over NVLink; no staging buffer, no receive-side merge, no NCCL call on the data path
+//                           straight to its final slot in the destination GPU's array (r <- rnew .. applied on the way): a warp
+//                           per record, 8-byte lanes (the records are only 8-byte aligned: 424 = 53 * 8), two contiguous runs of 256 + 168
+//                           bytes over NVLink; no staging buffer, no receive-side merge, no NCCL call on the data path
 //   5. shard_publish_tables every rank writes the r / m of the shard it now holds into every peer's tables (the MPI_Allgatherv pair)
-// Between the steps the ranks meet at a barrier supplied by the HOST layer (torch.distributed / MPI): kernel completion makes the
-// peer stores visible, the barrier orders them against the next step's reads.  The potential is then rebuilt on every rank from the
+// Between the steps the ranks meet at a barrier: in the asynchronous form (cmcb200_shard_step_async, the default of the host mirror) flags in
+// each other's device memory, posted and awaited by one-warp kernels on the same stream -- no host round trip; in the older form a barrier
+// supplied by the HOST layer (torch.distributed / MPI).  Kernel completion makes the peer stores visible, the barrier orders them against the
+// next step's reads.  The potential is then rebuilt on every rank from the
 // full tables (replicated, like potential_calculate in the reference, cmc_utils.c:660,716).
 #include <cstring>
 #include <utility>
@@ -146,21 +149,40 @@ __device__ __forceinline__ long upper_bound_u64(const uint64_t *__restrict__ a, 
 __global__ void __launch_bounds__(256) shard_rank_kernel(const uint64_t *__restrict__ keys_all, long stride, const ShardMeta *__restrict__ meta,
 							  unsigned char *__restrict__ dest_rank, unsigned *__restrict__ dest_pos)
 {
+	// A CTA ranks 256 CONSECUTIVE elements of the local sorted run: in every other rank's run their answers lie between the lower bound of the
+	// first key and the upper bound of the last one.  2 (P - 1) threads find those two positions with full-length searches; the per-element
+	// searches then run over the few hundred entries in between (cache-resident) instead of over the whole run.
+	__shared__ long s_lo[SHARD_MAX_RANKS], s_hi[SHARD_MAX_RANKS];
 	const int P = meta->nranks, g = meta->rank;
 	const long n = meta->n_keep[g];
 	const uint64_t *__restrict__ mine = keys_all + (long) g * stride;
-	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
-		const uint64_t key = mine[i];
-		long rank = i;
-		for (int q = 0; q < P; q++) {
-			if (q == g) continue;
-			const uint64_t *run = keys_all + (long) q * stride;
-			rank += q < g ? upper_bound_u64(run, meta->n_keep[q], key) : lower_bound_u64(run, meta->n_keep[q], key);
+	for (long base = blockIdx.x * 256L; base < n; base += gridDim.x * 256L) {
+		const long last = base + 255 < n ? base + 255 : n - 1;
+		if (threadIdx.x < 2 * P) {
+			const int q = threadIdx.x >> 1;
+			if (q != g) {
+				const uint64_t *run = keys_all + (long) q * stride;
+				if (threadIdx.x & 1) s_hi[q] = upper_bound_u64(run, meta->n_keep[q], mine[last]);
+				else s_lo[q] = lower_bound_u64(run, meta->n_keep[q], mine[base]);
+			}
 		}
-		int d = 0;
-		while (d + 1 < P && rank >= meta->start0[d + 1]) d++;
-		dest_rank[i] = (unsigned char) d;
-		dest_pos[i] = (unsigned) (rank - meta->start0[d]);
+		__syncthreads();
+		const long i = base + threadIdx.x;
+		if (i < n) {
+			const uint64_t key = mine[i];
+			long rank = i;
+			for (int q = 0; q < P; q++) {
+				if (q == g) continue;
+				const uint64_t *run = keys_all + (long) q * stride + s_lo[q];
+				const long len = s_hi[q] - s_lo[q];
+				rank += s_lo[q] + (q < g ? upper_bound_u64(run, len, key) : lower_bound_u64(run, len, key));
+			}
+			int d = 0;
+			while (d + 1 < P && rank >= meta->start0[d + 1]) d++;
+			dest_rank[i] = (unsigned char) d;
+			dest_pos[i] = (unsigned) (rank - meta->start0[d]);
+		}
+		__syncthreads();
 	}
 }
 
@@ -270,6 +292,21 @@ __global__ void __launch_bounds__(256) shard_publish_tables_planned(const char *
 	}
 }
 
+// entries [first, first + n) of this rank's r / m / phi tables into the same entries of every peer's tables (coalesced runs per peer)
+struct TablePeers { double *r[SHARD_MAX_RANKS], *m[SHARD_MAX_RANKS], *phi[SHARD_MAX_RANKS]; };
+__global__ void shard_share_tables_kernel(const double *__restrict__ r, const double *__restrict__ m, const double *__restrict__ phi, long first, long n,
+					  TablePeers tp, int nranks, int rank)
+{
+	const long stride = (long) gridDim.x * blockDim.x;
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += stride) {
+		const double a = r[first + i], b = m[first + i], c = phi[first + i];
+		for (int q = 0; q < nranks; q++) {
+			if (q == rank) continue;
+			tp.r[q][first + i] = a; tp.m[q][first + i] = b; tp.phi[q][first + i] = c;
+		}
+	}
+}
+
 // Binaries follow their star (cmc_sort.c:512-587, 716-771): the records of this rank's new shard carry the index their binary had in the
 // SOURCE rank's binary array; in star order each binary_t is pulled from that rank's array over NVLink into the local array and binind
 // becomes 1, 2, ...  (block_off = exclusive scan of the per-2048-star binary counts, as in sort_binary_move).
@@ -331,6 +368,7 @@ static void *own_buffer(cmcb200_ctx *c, int which)
 	case SH_KEYS_ALL: return c->d_keys_all;
 	case SH_SRC_ALL: return c->d_src_all;
 	case SH_SYNC: return c->d_shard_sync;
+	case SH_PHI: return c->d_phi;
 	}
 	return nullptr;
 }
@@ -700,5 +738,31 @@ extern "C" int cmcb200_shard_step_result(cmcb200_ctx *c, long *n_keep_all, int *
 		if (m->count[q] + 2 > c->n_star_dim) { set_error("shard_step: rank %d holds %ld stars, capacity %ld", q, m->count[q], c->n_star_dim); return -1; }
 	}
 	if (n_bin) *n_bin = *(const long *) (h + sizeof(ShardMeta));
+	return 0;
+}
+
+
+int shard_share_table_slices(cmcb200_ctx *c, long first, long n)
+{
+	if (c->nranks <= 1) return 0;
+	TablePeers tp;
+	for (int q = 0; q < c->nranks; q++) {
+		tp.r[q] = (double *) peer_role(c, q, SH_R);
+		tp.m[q] = (double *) peer_role(c, q, SH_M);
+		tp.phi[q] = (double *) c->peer_buf[q][SH_PHI];
+	}
+	if (n > 0) {
+		long blocks = (n + 255) / 256;
+		if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
+		shard_share_tables_kernel<<<(unsigned) blocks, 256, 0, c->stream>>>(c->d_r, c->d_m, c->d_phi, first, n, tp, c->nranks, c->rank);
+		c->launches++;
+	}
+	c->table_epoch++;
+	SyncPeers sp;
+	for (int q = 0; q < c->nranks; q++) sp.p[q] = (ShardSync *) c->peer_buf[q][SH_SYNC];
+	shard_post_kernel<<<1, 32, 0, c->stream>>>(sp, c->nranks, c->rank, 3, c->table_epoch, nullptr);
+	shard_wait_kernel<<<1, 32, 0, c->stream>>>((ShardSync *) c->d_shard_sync, c->nranks, 3, c->table_epoch);
+	c->launches += 2;
+	CMCB_CUDA_OK(cudaGetLastError());
 	return 0;
 }

@@ -46,7 +46,7 @@ EXPORTS = [
     "cmcb200_dev_comp_mass_percent", "cmcb200_dev_clusdyn_calculate", "cmcb200_dev_energy_conservation2", "cmcb200_dev_compute_intermediate_energy",
     "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass", "cmcb200_dev_energy_new_radii",
     "cmcb200_dev_potential", "cmcb200_dev_tidally_strip_select", "cmcb200_dev_compute_energy_totals",
-    "cmcb200_shard_step_async", "cmcb200_shard_step_result", "cmcb200_dev_new_orbits_async", "cmcb200_dev_orbit_result", "cmcb200_resident_begin", "cmcb200_resident_end", "cmcb200_dev_get", "cmcb200_dev_put",
+    "cmcb200_shard_step_async", "cmcb200_shard_step_result", "cmcb200_dev_new_orbits_async", "cmcb200_dev_orbit_result", "cmcb200_resident_begin", "cmcb200_resident_begin_sharded", "cmcb200_resident_end", "cmcb200_dev_get", "cmcb200_dev_put", "cmcb200_dev_comp_multi_mass_percent",
 ]
 
 
@@ -115,8 +115,10 @@ def load():
     L.cmcb200_shard_step_result.argtypes = [vp, vp, vp, vp, pl]
     L.cmcb200_dev_new_orbits_async.argtypes = [vp, C.POINTER(OrbitParams), C.c_int]
     L.cmcb200_dev_orbit_result.argtypes = [vp, C.POINTER(OrbitParams), C.POINTER(OrbitResult)]
+    L.cmcb200_dev_comp_multi_mass_percent.argtypes = [vp, lg, vp, lg, dbl, vp, lg, vp]
     L.cmcb200_dev_get.argtypes = [vp, vp, lg, vp, lg]
     L.cmcb200_dev_put.argtypes = [vp, vp, lg, vp, lg, vp, lg]
+    L.cmcb200_resident_begin_sharded.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg, C.c_ulonglong, lg, lg]
     L.cmcb200_resident_end.argtypes = [vp, vp, lg, vp, lg, lg, vp, vp, vp, lg]
     _lib = L
     return L

@@ -162,6 +162,24 @@ class ShardedCluster(Cluster):
 
     # ---- the sharded sort: qsorts_new + post_sort_comm for procs > 1 ---------------------------------------------------------------
     def dev_transfer_and_sort(self):
+        """The whole sharded sort as one asynchronous device sequence (cmcb200_shard_step_async): the ranks meet at barriers made of flags in
+        each other's device memory, no torch.distributed call and no host round trip before the single wait at the end.
+        CMCB200_SHARD_HOST_BARRIERS=1 selects the older form below (host-side barriers through torch.distributed)."""
+        import os
+        if os.environ.get("CMCB200_SHARD_HOST_BARRIERS"):
+            return self.dev_transfer_and_sort_host_barriers()
+        n_old = int(self.End[self.myid] - self.Start[self.myid] + 1)
+        _lib.check(self.L.cmcb200_shard_step_async(self.ctx, self.clus.N_MAX_NEW, n_old, int(self.Start[self.myid]), self.clus.N_MAX, self.MIN_CHUNK_SIZE,
+                                                   max(self.N_b_local, 0)), "shard_step_async")
+        keep = np.zeros(self.procs, np.int64)
+        S, E, nb = np.zeros(self.procs, np.int32), np.zeros(self.procs, np.int32), C.c_long(0)
+        _lib.check(self.L.cmcb200_shard_step_result(self.ctx, keep.ctypes.data, S.ctypes.data, E.ctypes.data, C.byref(nb)), "shard_step_result")
+        self.Start, self.End = S, E
+        self.clus.N_MAX = int(keep.sum())
+        self.clus.N_MAX_NEW = int(E[self.myid] - S[self.myid] + 1)
+        self.N_b_local = nb.value
+
+    def dev_transfer_and_sort_host_barriers(self):
         import torch
         n_old = int(self.End[self.myid] - self.Start[self.myid] + 1)
         first_global, N_MAX_old = int(self.Start[self.myid]), self.clus.N_MAX
@@ -227,6 +245,19 @@ class ShardedCluster(Cluster):
             p.draws, p.draw_off = self._draws.ctypes.data, self._draw_off.ctypes.data
         return p
 
+    def resident_begin(self, dirty_words=None):
+        """Cluster.resident_begin for a shard: the records of this rank, and of the replicated tables only this rank's slice -- the ranks hand
+        the slices to each other over NVLink (cmcb200_resident_begin_sharded)"""
+        n, nb = self.clus.N_MAX_NEW, self._n_bin_in_use()
+        n_new_stars = max(0, n - int(self.End[self.myid] - self.Start[self.myid] + 1))
+        n_table = min(self.N_TABLE_DIM, self.clus.N_MAX + 2 + n_new_stars)
+        first = int(self.Start[self.myid])
+        n_slice = (n_table - first) if self.myid == self.procs - 1 else int(self.End[self.myid]) - first + 1
+        _lib.check(self.L.cmcb200_resident_begin_sharded(self.ctx, self.star[1:].ctypes.data, n, self.binary[1:].ctypes.data, nb, self.star_r.ctypes.data,
+                                                         self.star_m.ctypes.data, self.star_phi.ctypes.data, n_table,
+                                                         self.ALL_WORDS if dirty_words is None else dirty_words, first, n_slice), "resident_begin_sharded")
+        self.N_b_local = nb
+
     def host_step(self, seed=0, draws=None, draw_off=None, dirty_words=None):
         """Cluster.host_step on this rank's shard: its records and the tables cross this rank's host link once each way; max_r is reduced
         over the ranks like new_orbits_calculate does (reference cmc_utils.c:2206)."""
@@ -244,9 +275,19 @@ class ShardedCluster(Cluster):
     def dev_step(self, seed=0, draws=None, draw_off=None, fused=True):
         """orbit step on the local shard -> sharded sort (records to their final rank and slot over NVLink) -> replicated potential.
         max_r is reduced over the ranks like new_orbits_calculate does (reference cmc_utils.c:2206)."""
+        import os
         import torch
-        res = self.dev_new_orbits(draws, draw_off, seed, fuse_energy=True)
-        self.dev_transfer_and_sort()
+        if os.environ.get("CMCB200_SHARD_HOST_BARRIERS"):
+            res = self.dev_new_orbits(draws, draw_off, seed, fuse_energy=True)
+            self.dev_transfer_and_sort()
+        else:
+            # the orbit step is only queued; its statistics are read once the sort's single wait has drained the stream
+            p = self.orbit_params(draws, draw_off, seed, fuse_energy=True)
+            _lib.check(self.L.cmcb200_dev_new_orbits_async(self.ctx, C.byref(p), 0), "dev_new_orbits_async")
+            self.dev_transfer_and_sort()
+            res = _lib.OrbitResult()
+            _lib.check(self.L.cmcb200_dev_orbit_result(self.ctx, C.byref(p), C.byref(res)), "dev_orbit_result")
+            self.max_r, self.last_orbit = res.max_r, res
         self.dev_calc_potential_new()
         with torch.cuda.stream(self._tstream):
             m = torch.tensor([res.max_r], dtype=torch.float64, device=f"cuda:{self.device}")

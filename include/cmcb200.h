@@ -163,6 +163,12 @@ int cmcb200_download(cmcb200_ctx *ctx, void *star1, long n_local, void *binary1,
  * Any pointer may be NULL (not moved). */
 int cmcb200_resident_begin(cmcb200_ctx *ctx, const void *star1, long n_local, const void *binary1, long n_bin,
 			   const double *star_r, const double *star_m, const double *star_phi, long n_table, unsigned long long dirty_words);
+/* The same for a radius-sharded context (cmcb200_shard_attach done).  The host tables are replicated on every rank, so each rank sends only its
+ * own slice [slice_first, slice_first + slice_n) of star_r / star_m / star_phi (and the sentinel [0]) over its host link and the ranks hand the
+ * slices to each other over NVLink (peer stores + a device-side barrier).  The caller gives rank q the slice Start[q] .. End[q] and extends
+ * the LAST rank's slice to n_table - 1, so that the slices cover [1, n_table). */
+int cmcb200_resident_begin_sharded(cmcb200_ctx *ctx, const void *star1, long n_local, const void *binary1, long n_bin, const double *star_r,
+				   const double *star_m, const double *star_phi, long n_table, unsigned long long dirty_words, long slice_first, long slice_n);
 int cmcb200_resident_end(cmcb200_ctx *ctx, void *star1, long n_local, void *binary1, long n_bin, long n_bin_dim,
 			 double *star_r, double *star_m, double *star_phi, long n_table);
 
@@ -275,6 +281,14 @@ int cmcb200_dev_comp_mass_percent(cmcb200_ctx *ctx, const cmcb200_mass_pc_params
 /* clusdyn_calculate (src/cmc/cmc_utils.c:1613-1624) on the resident tables: *rh = clusdyn.rh, the half-mass radius, from the same
  * sequentially rounded enclosed-mass sums */
 int cmcb200_dev_clusdyn_calculate(cmcb200_ctx *ctx, long N_MAX, long N_STAR, double Mtotal, double *rh);
+
+/* comp_multi_mass_percent (src/cmc/cmc_utils.c:769-861) on the resident tables: Lagrange radii per mass bin.  mass_bins[n_bins] ascending (the
+ * reference's mass_bins[], in solar masses; a star belongs to the bin find_stars_mass_bin(star_m / SOLAR_MASS_DYN) gives, :756-764, -1 = none),
+ * mass_pc[count]; multi_mass_r[n_bins][count] row-major receives the radii -- the row of a bin without stars is left untouched, a bin with one
+ * star gets that star's radius in every entry, like the reference (:845-850).  The per-bin mass sums carry the reference's sequential roundings;
+ * the interpolation is gsl_interp_linear restated (GSL is un-vendored: that one step is parity-unpinned, on both sides of the comparison). */
+int cmcb200_dev_comp_multi_mass_percent(cmcb200_ctx *ctx, long N_MAX, const double *mass_bins, long n_bins, double solar_mass_dyn,
+					const double *mass_pc, long count, double *multi_mass_r);
 
 /* ---- radius-sharded operation: one rank per GPU of an NVLink node ---------------------------------------------------------------- */
 /* Replaces sample_sort + load_balance + post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2259-2288) for procs > 1.

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def run(rank, world, port, N, nb, steps, kind="plummer", masses="imf"):
+def run(rank, world, port, N, nb, steps, kind="plummer", masses="imf", host_barriers=False):
     import torch
     import torch.distributed as dist
     import common as cm
@@ -20,6 +20,10 @@ def run(rank, world, port, N, nb, steps, kind="plummer", masses="imf"):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if host_barriers:       # the older form of the sharded sort: barriers and the count exchange through torch.distributed
+        os.environ["CMCB200_SHARD_HOST_BARRIERS"] = "1"
+    else:
+        os.environ.pop("CMCB200_SHARD_HOST_BARRIERS", None)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     r, vr, vt, sm = cm.cluster_state(kind, N, seed=17, masses=masses)
@@ -76,11 +80,26 @@ def run(rank, world, port, N, nb, steps, kind="plummer", masses="imf"):
         assert nbl == int((lb > 0).sum())
         assert np.array_equal(lb[lb > 0], np.arange(1, nbl + 1)), f"rank {rank}: binind not renumbered 1.. in star order"
         assert np.array_equal(sb, s.binary[gb[gb > 0]]), f"rank {rank}: binary records differ"
+    # ---- one more step on HOST arrays (resident_begin: this rank's records and ITS slice of the tables up, the slices handed on over NVLink;
+    # resident_end: records and tables down), against the same on the single GPU
+    for x in (c, s):
+        x.compute_energy()
+    c.host_step(seed=9)
+    s.host_step(seed=9)
+    lo, hi, nl = int(c.Start[rank]), int(c.End[rank]), c.clus.N_MAX_NEW
+    assert c.clus.N_MAX == s.clus.N_MAX and c.max_r == s.max_r
+    for name in ("star_r", "star_m", "star_phi"):
+        assert np.array_equal(getattr(c, name)[:c.clus.N_MAX + 2].view(np.uint64), getattr(s, name)[:c.clus.N_MAX + 2].view(np.uint64)), f"rank {rank}: {name} after host_step"
+    want, shard = s.star[lo:hi + 1].copy(), c.star[1:nl + 1].copy()
+    star_field(want, "binind")[:] = 0
+    star_field(shard, "binind")[:] = 0
+    bad = np.nonzero((want != shard).any(axis=1))[0]
+    assert bad.size == 0, f"rank {rank}: host_step: {bad.size} of {nl} records differ, first local {bad[0]}"
     c.close()
     s.close()
     dist.barrier()
     dist.destroy_process_group()
-    print(f"rank {rank}/{world}: sharded == single GPU (N={N}, binaries={nb}, steps={steps}, shard {lo}..{hi})", flush=True)
+    print(f"rank {rank}/{world}: sharded == single GPU (N={N}, binaries={nb}, steps={steps} + 1 on host arrays, shard {lo}..{hi})", flush=True)
 
 
 def run_sv3(rank, world, port, N):

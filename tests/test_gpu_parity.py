@@ -649,6 +649,32 @@ def test_compute_energy_totals_bit_exact(cenma, N):
     c.close()
 
 
+@pytest.mark.parametrize("N", [30000, 1200000])
+def test_comp_multi_mass_percent_bit_exact(N):
+    """comp_multi_mass_percent (reference cmc_utils.c:769-861) on the resident tables: one exact sequential-sum chain per mass bin
+    (zero terms for the stars of other bins), two binary searches per threshold, the linear interpolation restated -- against the oracle,
+    which is pinned against the compiled reference (test_oracle_vs_ref.py::test_comp_multi_mass_percent): a one-star bin, an empty bin (its row
+    stays untouched), fractions 0 and 1, no sequential fall-back of the exact scan."""
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=37, masses="imf")
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.calc_potential_new()
+    c.upload()
+    q = np.quantile(sm, [0.0, 0.3, 0.6, 0.9, 0.99, 0.9999, 1.0])
+    bins = np.concatenate([q[:-1] * [0.999, 1, 1, 1, 1, 1], [q[-2] * 1.0000001, q[-1] * 1.5, q[-1] * 2.0]])
+    pcs = np.array([0.0, 0.001, 0.01, 0.1, 0.3, 0.5, 0.7, 0.9, 0.99, 1.0])
+    got = c.dev_comp_multi_mass_percent(bins, 1.0, pcs)
+    assert c.potential_stats()[1] == 0, "sequential fall-back in a per-bin chain"
+    want = ol.comp_multi_mass_percent(c.star_r[:N + 2].copy(), c.star_m[:N + 2].copy(), N, bins, 1.0, pcs)
+    cm.assert_bits_equal(got, want, "multi_mass_r")
+    assert (want[-1] == -1.0).all() and (want[:4, 1:] > 0).all()
+    # a second call overwrites only the rows of bins that hold stars
+    got[:] = -7.0
+    got2 = c.dev_comp_multi_mass_percent(bins, 1.0, pcs)
+    assert (got2[-1] == -7.0).all() and np.array_equal(got2[:-1].view(np.uint64)[want[:-1] != -1.0], want[:-1].view(np.uint64)[want[:-1] != -1.0])
+    c.close()
+
+
 def test_orbit_step_where_find_root_vr_fires_bit_exact():
     """SURVEY 8a a20 / a21 on the device: calc_orbit_new's Brent fallback find_root_vr and the helpers under it, on a cluster in which it fires
     hundreds of times (common.brent_cluster), host-buffer form and resident form, against the oracle (pinned against the compiled reference

@@ -14,12 +14,14 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("world,N,nb,steps", [(2, 200000, 5000, 3), (2, 30011, 0, 2)])
-def test_sharded_equals_single_gpu(world, N, nb, steps):
+@pytest.mark.parametrize("world,N,nb,steps,host_barriers", [(2, 200000, 5000, 3, False), (2, 30011, 0, 2, False), (2, 1500000, 40000, 2, False), (2, 200000, 5000, 2, True)])
+def test_sharded_equals_single_gpu(world, N, nb, steps, host_barriers):
+    """default: the asynchronous sharded sort (device-side barriers: flags in peer memory); host_barriers: the older form with
+    torch.distributed barriers between the phases"""
     import torch.multiprocessing as mp
     import sharded_worker
     world = min(world, _n_gpus())
-    mp.spawn(sharded_worker.run, args=(world, 29500 + (N % 97), N, nb, steps), nprocs=world, join=True)
+    mp.spawn(sharded_worker.run, args=(world, 29500 + (N % 97) + int(host_barriers), N, nb, steps, "plummer", "imf", host_barriers), nprocs=world, join=True)
 
 
 @pytest.mark.skipif(_n_gpus() < 4, reason="needs 4 GPUs")
