@@ -158,7 +158,8 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->d_r); cudaFree(c->d_m); cudaFree(c->d_phi); cudaFree(c->d_mprev); cudaFree(c->d_r_alt); cudaFree(c->d_m_alt);
 	cudaFree(c->d_rp); cudaFree(c->d_rpf); cudaFree(c->d_defer_star); cudaFree(c->d_defer_found);
 	cudaFree(c->d_defer_first); cudaFree(c->lad.q); cudaFree(c->lad.r); cudaFree(c->lad.unsorted);
-	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); cudaFree(c->d_shard_sync); }
+	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); cudaFree(c->d_shard_sync); cudaFree(c->d_rank_all); cudaFree(c->d_m_all);
+		if (c->s_aux) { cudaStreamDestroy(c->s_aux); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); } }
 	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
@@ -231,22 +232,33 @@ extern "C" int cmcb200_potential_stats(cmcb200_ctx *c, long *n_events, long *n_f
 
 // ---- potential ------------------------------------------------------------------------------------------------
 
+// the rebuild queued on `stream` (the context's own, or the second stream of the asynchronous sharded step).  n_max_upper: N_MAX on entry -- the
+// new N_MAX is the number of leading stars with r < SF_INFINITY (cmc_utils.c:685-696), found on the device
+int potential_enqueue(cmcb200_ctx *c, long n_max_upper, long N_STAR, double cenma_m, double cenma_m_new, cudaStream_t stream)
+{
+	cudaStream_t keep = c->stream;
+	c->stream = stream; // the stage timer records on the stream the kernels run on
+	{
+		StageTimer t(c, ST_POTENTIAL);
+		cudaMemsetAsync(c->seqwork.stats, 0, 2 * sizeof(long), stream);
+		PotArgs a;
+		a.r = c->d_r; a.m = c->d_m; a.phi = c->d_phi; a.mprev = c->d_mprev; a.sc = c->d_pot; a.work = c->seqwork;
+		a.n_max_in = n_max_upper; a.n_star = (double) N_STAR; a.madhoc = 1.0 / ((double) N_STAR);
+		a.cenma_m = cenma_m; a.cenma_m_new = cenma_m_new;
+		c->launches += potential_calculate_device(a, stream);
+	}
+	c->stream = keep;
+	CMCB_CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
 extern "C" int cmcb200_dev_calc_potential_new(cmcb200_ctx *c, long *N_MAX, long N_STAR, double *cenma_m, double *cenma_m_new, double orbit_r,
-					      double *Mtotal, double *Rtidal)
+						      double *Mtotal, double *Rtidal)
 {
 	if (*N_MAX + 2 > c->n_table_dim) { set_error("calc_potential_new: N_MAX + 2 = %ld exceeds the table capacity %ld", *N_MAX + 2, c->n_table_dim); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	if (join_uploads(c)) return -1;
-	{
-		StageTimer t(c, ST_POTENTIAL);
-		CMCB_CUDA_OK(cudaMemsetAsync(c->seqwork.stats, 0, 2 * sizeof(long), c->stream));
-		PotArgs a;
-		a.r = c->d_r; a.m = c->d_m; a.phi = c->d_phi; a.mprev = c->d_mprev; a.sc = c->d_pot; a.work = c->seqwork;
-		a.n_max_in = *N_MAX; a.n_star = (double) N_STAR; a.madhoc = 1.0 / ((double) N_STAR);
-		a.cenma_m = *cenma_m; a.cenma_m_new = *cenma_m_new;
-		c->launches += potential_calculate_device(a, c->stream);
-		CMCB_CUDA_OK(cudaGetLastError());
-	}
+	if (potential_enqueue(c, *N_MAX, N_STAR, *cenma_m, *cenma_m_new, c->stream)) return -1;
 	PotScalars *h = (PotScalars *) c->h_pinned;
 	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_pot, sizeof(PotScalars), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));

@@ -11,7 +11,7 @@
 using namespace cmcb;
 
 constexpr int SHARD_MAX_RANKS = 16;
-enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_SYNC, SH_PHI, SH_N_BUFFERS }; // peer-visible buffers
+enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_SYNC, SH_PHI, SH_RANK_ALL, SH_M_ALL, SH_N_BUFFERS }; // peer-visible buffers
 
 enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES, ST_LAGRANGE };
 
@@ -99,6 +99,11 @@ struct cmcb200_ctx {
 	unsigned *d_dest_pos;                           // [n] final local position of each local sorted element on its destination rank
 	unsigned char *d_dest_rank;                     // [n] destination rank
 	long *d_shard_meta;                             // device copy of (n_keep[q], start0[q]) per rank
+	unsigned *d_rank_all;                           // [nranks][keys_stride] global rank of every element of every rank's sorted run (pushed by their owners)
+	double *d_m_all;                                // [nranks][keys_stride] star_m of the same elements
+	cudaStream_t s_aux;                             // second stream of the asynchronous sharded step: tables + potential while the records travel
+	cudaEvent_t ev_fork, ev_join;
+	bool pot_queued;                                // the last asynchronous step queued the potential rebuild behind its tables
 	void *d_shard_sync;                             // ShardSync (shard.cu): flags and posted counts the peers store into -- the device-side barriers
 	unsigned long long shard_epoch;                 // barrier generation, advanced identically on every rank
 	unsigned long long table_epoch;                 // generation of the table-sharing barrier (phase 3) of cmcb200_resident_begin_sharded
@@ -109,6 +114,8 @@ struct cmcb200_ctx {
 // shard.cu: this rank's slice [first, first + n) of star_r / star_m / star_phi stored into every peer's tables, then a device-side barrier --
 // queued on the context's stream (cmcb200_resident_begin_sharded)
 int shard_share_table_slices(cmcb200_ctx *c, long first, long n);
+// api.cu: the potential rebuild queued on `stream` (no wait, no read-back); n_max_upper bounds the new N_MAX
+int potential_enqueue(cmcb200_ctx *c, long n_max_upper, long N_STAR, double cenma_m, double cenma_m_new, cudaStream_t stream);
 
 // fills the orbit-step argument block from the context and the caller's parameters and (re)builds the lookup tables (api.cu)
 int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a);

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <utility>
 #include "ctx.cuh"
+#include "potential.cuh"
 
 namespace cmcb {
 
@@ -51,7 +52,7 @@ struct ShardMeta { // per step, uploaded by the host
 // the kernels queued behind it then read what the peers stored.  Epochs only grow, so a flag is never reset.  A wait gives up after
 // SHARD_WAIT_TIMEOUT_NS (a peer died): it sets `error` and lets the stream drain -- the host sees the flag at its next synchronisation.
 struct ShardSync {
-	unsigned long long flag[SHARD_MAX_RANKS][4]; // [source rank][phase]: epoch of that rank's last post
+	unsigned long long flag[SHARD_MAX_RANKS][8]; // [source rank][phase]: epoch of that rank's last post
 	long n_keep[SHARD_MAX_RANKS];                // stars each rank contributes to this step's exchange (posted in phase 0)
 	int error;
 };
@@ -292,6 +293,63 @@ __global__ void __launch_bounds__(256) shard_publish_tables_planned(const char *
 	}
 }
 
+// ---- the new tables straight from the sorted keys -----------------------------------------------------------------------------------------
+// After the global ranks are known every element of a rank's sorted run has its place in the new star_r / star_m tables: the run's owner sends
+// (global rank, star_m) of its elements -- two contiguous arrays -- to every rank, and every rank scatters (r from the key it already holds, m)
+// into its own tables locally.  Nothing of this needs the 424-byte records, so it runs on a second stream WHILE they travel, followed by the
+// potential rebuild: at 8 GPUs the table exchange and the (replicated) potential disappear behind the record push.
+struct RankPeers { unsigned *rank[SHARD_MAX_RANKS]; double *m[SHARD_MAX_RANKS]; };
+template <bool FUSE>
+__global__ void __launch_bounds__(256) shard_publish_ranks(PushArgs a, SortBuffers b, const SortState *st, const ShardMeta *__restrict__ meta,
+							    const unsigned char *__restrict__ dest_rank, const unsigned *__restrict__ dest_pos, RankPeers rp, long slot_offset)
+{
+	const unsigned *__restrict__ perm = st->final_buf ? b.vals_b : b.vals_a;
+	const long n = st->n_new;
+	const int P = meta->nranks;
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+		const unsigned grank = (unsigned) (meta->start0[dest_rank[i]] + dest_pos[i]);
+		const long p = perm[i];
+		double m;
+		if (FUSE) { // star_m[g] of the record before the sort (ComputeIntermediateEnergy's m <- star_m[g], cmc_utils.c:387)
+			const long j = p + 1;
+			const long g = j > a.n_old_local ? 1 + a.N_MAX + (j - a.n_old_local) : a.first_global + j - 1;
+			m = a.old_m[g];
+		} else {
+			m = *(const double *) (a.in + p * CMCB_SIZEOF_STAR + CMCB_OFF_M);
+		}
+		for (int q = 0; q < P; q++) { rp.rank[q][slot_offset + i] = grank; rp.m[q][slot_offset + i] = m; }
+	}
+}
+
+__global__ void __launch_bounds__(256) shard_scatter_tables(const uint64_t *__restrict__ keys_all, const unsigned *__restrict__ rank_all, const double *__restrict__ m_all,
+							     long stride, const ShardMeta *__restrict__ meta, double *__restrict__ star_r, double *__restrict__ star_m)
+{
+	const int q = blockIdx.y;
+	const long n = meta->n_keep[q];
+	const uint64_t *__restrict__ keys = keys_all + (long) q * stride;
+	const unsigned *__restrict__ rk = rank_all + (long) q * stride;
+	const double *__restrict__ mm = m_all + (long) q * stride;
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+		const uint64_t k = keys[i];
+		const uint64_t bits = (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k; // inverse of key_from_double (sort.cu)
+		const long pos = 1 + (long) rk[i];
+		star_r[pos] = __longlong_as_double((long long) bits);
+		star_m[pos] = mm[i];
+	}
+	if (q == 0 && blockIdx.x == 0 && threadIdx.x == 0) { // the entry behind the last star ends potential_calculate's count of N_MAX (cmc_utils.c:685)
+		star_r[1 + meta->n_total] = CMCB200_SF_INFINITY;
+		star_m[1 + meta->n_total] = 0.0;
+	}
+}
+
+// flag[i] = star i of the shard this rank received has a binary
+__global__ void shard_binflag_kernel(const char *__restrict__ star1, const ShardMeta *__restrict__ meta, unsigned char *__restrict__ binflag)
+{
+	const long n_local = meta->count[meta->rank];
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < n_local; i += (long) gridDim.x * blockDim.x)
+		binflag[i] = *(const long long *) (star1 + i * CMCB_SIZEOF_STAR + CMCB_OFF_BININD) > 0;
+}
+
 // entries [first, first + n) of this rank's r / m / phi tables into the same entries of every peer's tables (coalesced runs per peer)
 struct TablePeers { double *r[SHARD_MAX_RANKS], *m[SHARD_MAX_RANKS], *phi[SHARD_MAX_RANKS]; };
 __global__ void shard_share_tables_kernel(const double *__restrict__ r, const double *__restrict__ m, const double *__restrict__ phi, long first, long n,
@@ -369,6 +427,8 @@ static void *own_buffer(cmcb200_ctx *c, int which)
 	case SH_SRC_ALL: return c->d_src_all;
 	case SH_SYNC: return c->d_shard_sync;
 	case SH_PHI: return c->d_phi;
+	case SH_RANK_ALL: return c->d_rank_all;
+	case SH_M_ALL: return c->d_m_all;
 	}
 	return nullptr;
 }
@@ -391,6 +451,11 @@ extern "C" int cmcb200_shard_export(cmcb200_ctx *c, int rank, int nranks, void *
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_dest_pos, (size_t) c->n_star_dim * sizeof(unsigned)));
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_dest_rank, (size_t) c->n_star_dim));
 		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_shard_meta, sizeof(ShardMeta) + 4 * SHARD_MAX_RANKS * sizeof(void *)));
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_rank_all, (size_t) nranks * c->keys_stride * sizeof(unsigned)));
+		CMCB_CUDA_OK(cudaMalloc((void **) &c->d_m_all, (size_t) nranks * c->keys_stride * sizeof(double)));
+		CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+		CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		CMCB_CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 		CMCB_CUDA_OK(cudaMalloc(&c->d_shard_sync, 1 << 21)); // an allocation of its own (2 MB granule): its IPC handle maps nothing else
 		CMCB_CUDA_OK(cudaMemset(c->d_shard_sync, 0, sizeof(ShardSync)));
 		c->shard_epoch = 0;
@@ -616,10 +681,12 @@ static int shard_wait(cmcb200_ctx *c, int phase)
 	return 0;
 }
 
-extern "C" int cmcb200_shard_step_async(cmcb200_ctx *c, long n_local, long n_old_local, long first_global, long N_MAX, int min_chunk, long n_bin_clear)
+extern "C" int cmcb200_shard_step_async(cmcb200_ctx *c, long n_local, long n_old_local, long first_global, long N_MAX, int min_chunk, long n_bin_clear,
+					      long pot_N_STAR, double pot_cenma_m, double pot_cenma_m_new)
 {
 	if (n_local + 2 > c->n_star_dim) { set_error("shard_step: n_local + 2 = %ld exceeds n_star_dim = %ld", n_local + 2, c->n_star_dim); return -1; }
 	if (!c->d_shard_sync || c->nranks < 1) { set_error("shard_step: call cmcb200_shard_export / _attach first"); return -1; }
+	if (N_MAX + 2 > c->n_table_dim) { set_error("shard_step: N_MAX + 2 exceeds the table capacity"); return -1; }
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	if (join_uploads(c)) return -1;
 	c->shard_epoch++;
@@ -651,27 +718,59 @@ extern "C" int cmcb200_shard_step_async(cmcb200_ctx *c, long n_local, long n_old
 		shard_plan_kernel<<<1, 32, 0, c->stream>>>((const ShardSync *) c->d_shard_sync, d_meta, c->nranks, c->rank, min_chunk);
 		c->launches++;
 	}
-	// 2. global ranks, every record to its final slot on its destination rank
+	PushArgs pa;
+	pa.in = star1(c);
+	for (int q = 0; q < c->nranks; q++) {
+		pa.out[q] = (char *) c->peer_buf[q][SH_STAR0 + (c->cur_star ^ 1)] + CMCB_SIZEOF_STAR;
+		pa.src_out[q] = (unsigned char *) c->peer_buf[q][SH_SRC_ALL];
+	}
+	pa.rank = c->rank;
+	pa.old_r = c->d_r; pa.old_m = c->d_m;
+	pa.n_old_local = n_old_local; pa.first_global = first_global; pa.N_MAX = N_MAX;
+	// 2. global ranks; (global rank, star_m) of this run to every rank
 	{
 		StageTimer t(c, ST_SHARD_RANK);
 		if (n_local > 0) {
 			long blocks = (n_local + 255) / 256;
 			if (blocks > NUM_SMS_B200 * 16) blocks = NUM_SMS_B200 * 16;
 			shard_rank_kernel<<<(unsigned) blocks, 256, 0, c->stream>>>(c->d_keys_all, c->keys_stride, d_meta, c->d_dest_rank, c->d_dest_pos);
+			RankPeers rp;
+			for (int q = 0; q < c->nranks; q++) { rp.rank[q] = (unsigned *) c->peer_buf[q][SH_RANK_ALL]; rp.m[q] = (double *) c->peer_buf[q][SH_M_ALL]; }
+			if (c->shard_unfused) shard_publish_ranks<false><<<(unsigned) blocks, 256, 0, c->stream>>>(pa, c->sbuf, c->d_sort, d_meta, c->d_dest_rank, c->d_dest_pos, rp, (long) c->rank * c->keys_stride);
+			else shard_publish_ranks<true><<<(unsigned) blocks, 256, 0, c->stream>>>(pa, c->sbuf, c->d_sort, d_meta, c->d_dest_rank, c->d_dest_pos, rp, (long) c->rank * c->keys_stride);
+			c->launches += 2;
+		}
+		shard_post(c, 4, nullptr);
+	}
+	// 3. second stream: once every rank's (rank, m) arrays are here, the new tables are scattered locally and the potential is rebuilt --
+	//    while the main stream moves the records
+	CMCB_CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));
+	CMCB_CUDA_OK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+	{
+		cudaStream_t keep = c->stream;
+		c->stream = c->s_aux;
+		{
+			StageTimer t(c, ST_SHARD_TABLES);
+			shard_wait(c, 4);
+			CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r_alt, c->d_r, sizeof(double), cudaMemcpyDeviceToDevice, c->s_aux)); // the table sentinel [0] stays
+			CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m_alt, c->d_m, sizeof(double), cudaMemcpyDeviceToDevice, c->s_aux));
+			long blocks = (c->keys_stride + 255) / 256;
+			if (blocks > NUM_SMS_B200 * 2) blocks = NUM_SMS_B200 * 2;
+			shard_scatter_tables<<<dim3((unsigned) blocks, (unsigned) c->nranks), 256, 0, c->s_aux>>>(c->d_keys_all, c->d_rank_all, c->d_m_all, c->keys_stride, d_meta, c->d_r_alt, c->d_m_alt);
 			c->launches++;
 		}
+		c->stream = keep;
 	}
+	// the alternate tables become THE tables (on all ranks in lock step); the fused push below still reads the OLD ones (pa.old_r / old_m)
+	std::swap(c->d_r, c->d_r_alt);
+	std::swap(c->d_m, c->d_m_alt);
+	c->r_parity ^= 1;
+	c->pot_queued = pot_N_STAR > 0;
+	if (pot_N_STAR > 0 && potential_enqueue(c, N_MAX, pot_N_STAR, pot_cenma_m, pot_cenma_m_new, c->s_aux)) return -1;
+	CMCB_CUDA_OK(cudaEventRecord(c->ev_join, c->s_aux));
+	// 4. main stream: every record to its final slot on its destination rank
 	{
 		StageTimer t(c, ST_GATHER);
-		PushArgs pa;
-		pa.in = star1(c);
-		for (int q = 0; q < c->nranks; q++) {
-			pa.out[q] = (char *) c->peer_buf[q][SH_STAR0 + (c->cur_star ^ 1)] + CMCB_SIZEOF_STAR;
-			pa.src_out[q] = (unsigned char *) c->peer_buf[q][SH_SRC_ALL];
-		}
-		pa.rank = c->rank;
-		pa.old_r = c->d_r; pa.old_m = c->d_m;
-		pa.n_old_local = n_old_local; pa.first_global = first_global; pa.N_MAX = N_MAX;
 		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_star[c->cur_star ^ 1], c->d_star[c->cur_star], CMCB_SIZEOF_STAR, cudaMemcpyDeviceToDevice, c->stream));
 		if (n_local > 0) {
 			if (c->shard_unfused) shard_push_records<false><<<NUM_SMS_B200 * 8, 256, 0, c->stream>>>(pa, c->sbuf, c->d_sort, c->d_dest_rank, c->d_dest_pos);
@@ -681,25 +780,15 @@ extern "C" int cmcb200_shard_step_async(cmcb200_ctx *c, long n_local, long n_old
 		shard_post(c, 1, nullptr);
 		shard_wait(c, 1);
 	}
-	// 3. the shard this rank now holds: its r, m into every rank's tables, its binaries pulled from the ranks their stars came from
+	// 5. the shard this rank now holds: its binaries pulled from the ranks their stars came from
 	c->cur_star ^= 1;
-	{
-		StageTimer t(c, ST_SHARD_TABLES);
-		void *ptrs[2 * SHARD_MAX_RANKS];
-		for (int q = 0; q < c->nranks; q++) { ptrs[q] = peer_role(c, q, SH_R_ALT); ptrs[SHARD_MAX_RANKS + q] = peer_role(c, q, SH_M_ALT); }
-		void **d_ptrs = (void **) ((char *) c->d_shard_meta + sizeof(ShardMeta) + SHARD_MAX_RANKS * sizeof(void *));
-		CMCB_CUDA_OK(cudaMemcpyAsync(d_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, c->stream));
-		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_r_alt, c->d_r, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-		CMCB_CUDA_OK(cudaMemcpyAsync(c->d_m_alt, c->d_m, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-		shard_publish_tables_planned<<<NUM_SMS_B200 * 4, 256, 0, c->stream>>>(star1(c), d_meta, (double *const *) d_ptrs, (double *const *) (d_ptrs + SHARD_MAX_RANKS), c->d_binflag);
-		c->launches++;
-	}
 	{
 		StageTimer tb(c, ST_BINARIES);
 		if (n_bin_clear > c->n_bin_dim - 1) n_bin_clear = c->n_bin_dim - 1;
 		char *bin_out = c->d_bin[c->cur_bin ^ 1] + CMCB_SIZEOF_BINARY;
 		shard_adopt_shard_kernel<<<1, 32, 0, c->stream>>>(c->d_sort, d_meta);
-		c->launches++;
+		shard_binflag_kernel<<<NUM_SMS_B200 * 4, 256, 0, c->stream>>>(star1(c), d_meta, c->d_binflag);
+		c->launches += 2;
 		const long n_upper = c->n_star_dim; // the shard may be larger than what this rank contributed: size the grids for the capacity
 		const long nbt = (n_upper + SHARD_BIN_TILE - 1) / SHARD_BIN_TILE;
 		c->launches += sort_binary_count_scan_planned(c->d_binflag, c->d_sort, c->d_bin_block_cnt, n_upper, c->stream);
@@ -712,18 +801,17 @@ extern "C" int cmcb200_shard_step_async(cmcb200_ctx *c, long n_local, long n_old
 		shard_post(c, 2, nullptr);
 		shard_wait(c, 2);
 	}
+	// 6. join: whatever is queued next on the context's stream finds the new tables and the new potential
+	CMCB_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
 	CMCB_CUDA_OK(cudaGetLastError());
-	// 4. the alternate tables become THE tables (on all ranks in lock step)
-	std::swap(c->d_r, c->d_r_alt);
-	std::swap(c->d_m, c->d_m_alt);
-	c->r_parity ^= 1;
 	return 0;
 }
 
-extern "C" int cmcb200_shard_step_result(cmcb200_ctx *c, long *n_keep_all, int *Start, int *End, long *n_bin)
+extern "C" int cmcb200_shard_step_result(cmcb200_ctx *c, long *n_keep_all, int *Start, int *End, long *n_bin, double pot_out[4])
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	char *h = (char *) c->h_pinned;
+	if (c->pot_queued) CMCB_CUDA_OK(cudaMemcpyAsync(h + 2048, c->d_pot, sizeof(PotScalars), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_shard_meta, sizeof(ShardMeta), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaMemcpyAsync(h + sizeof(ShardMeta), &c->d_sort->n_bin, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
 	CMCB_CUDA_OK(cudaMemcpyAsync(h + sizeof(ShardMeta) + 8, &((ShardSync *) c->d_shard_sync)->error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -738,6 +826,10 @@ extern "C" int cmcb200_shard_step_result(cmcb200_ctx *c, long *n_keep_all, int *
 		if (m->count[q] + 2 > c->n_star_dim) { set_error("shard_step: rank %d holds %ld stars, capacity %ld", q, m->count[q], c->n_star_dim); return -1; }
 	}
 	if (n_bin) *n_bin = *(const long *) (h + sizeof(ShardMeta));
+	if (pot_out && c->pot_queued) { // N_MAX, cenma.m, cenma.m_new, Mtotal of the rebuild queued with the step (the caller: Rtidal = orbit_r Mtotal^(1/3), cmc_utils.c:707)
+		const PotScalars *ps = (const PotScalars *) (h + 2048);
+		pot_out[0] = (double) ps->n_max; pot_out[1] = ps->cenma_m; pot_out[2] = ps->cenma_m_new; pot_out[3] = ps->Mtotal;
+	}
 	return 0;
 }
 

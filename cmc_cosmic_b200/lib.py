@@ -111,8 +111,8 @@ def load():
     L.cmcb200_dev_clusdyn_calculate.argtypes = [vp, lg, lg, dbl, C.POINTER(dbl)]
     L.cmcb200_dev_comp_mass_percent.argtypes = [vp, C.POINTER(MassPcParams), C.POINTER(MassPcResult)]
     L.cmcb200_resident_begin.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg, C.c_ulonglong]
-    L.cmcb200_shard_step_async.argtypes = [vp, lg, lg, lg, lg, C.c_int, lg]
-    L.cmcb200_shard_step_result.argtypes = [vp, vp, vp, vp, pl]
+    L.cmcb200_shard_step_async.argtypes = [vp, lg, lg, lg, lg, C.c_int, lg, lg, dbl, dbl]
+    L.cmcb200_shard_step_result.argtypes = [vp, vp, vp, vp, pl, vp]
     L.cmcb200_dev_new_orbits_async.argtypes = [vp, C.POINTER(OrbitParams), C.c_int]
     L.cmcb200_dev_orbit_result.argtypes = [vp, C.POINTER(OrbitParams), C.POINTER(OrbitResult)]
     L.cmcb200_dev_comp_multi_mass_percent.argtypes = [vp, lg, vp, lg, dbl, vp, lg, vp]

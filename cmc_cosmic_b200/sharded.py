@@ -168,16 +168,29 @@ class ShardedCluster(Cluster):
         import os
         if os.environ.get("CMCB200_SHARD_HOST_BARRIERS"):
             return self.dev_transfer_and_sort_host_barriers()
+        self._shard_step(with_potential=False)
+
+    def _shard_step(self, with_potential):
+        """cmcb200_shard_step_async + _result: the sort (and, with_potential, the potential rebuild queued behind the new tables on the second
+        stream, overlapping the record exchange); one wait"""
+        import math
         n_old = int(self.End[self.myid] - self.Start[self.myid] + 1)
         _lib.check(self.L.cmcb200_shard_step_async(self.ctx, self.clus.N_MAX_NEW, n_old, int(self.Start[self.myid]), self.clus.N_MAX, self.MIN_CHUNK_SIZE,
-                                                   max(self.N_b_local, 0)), "shard_step_async")
+                                                   max(self.N_b_local, 0), self.clus.N_STAR if with_potential else 0, self.cenma.m, self.cenma.m_new),
+                   "shard_step_async")
         keep = np.zeros(self.procs, np.int64)
-        S, E, nb = np.zeros(self.procs, np.int32), np.zeros(self.procs, np.int32), C.c_long(0)
-        _lib.check(self.L.cmcb200_shard_step_result(self.ctx, keep.ctypes.data, S.ctypes.data, E.ctypes.data, C.byref(nb)), "shard_step_result")
+        S, E, nb, pot = np.zeros(self.procs, np.int32), np.zeros(self.procs, np.int32), C.c_long(0), np.zeros(4)
+        _lib.check(self.L.cmcb200_shard_step_result(self.ctx, keep.ctypes.data, S.ctypes.data, E.ctypes.data, C.byref(nb), pot.ctypes.data), "shard_step_result")
         self.Start, self.End = S, E
         self.clus.N_MAX = int(keep.sum())
         self.clus.N_MAX_NEW = int(E[self.myid] - S[self.myid] + 1)
-        self.N_b_local = nb.value
+        self.N_b_local = self.bin_slots_in_use = nb.value
+        if with_potential:      # what cmcb200_dev_calc_potential_new hands back (reference cmc_utils.c:696-707, 2011)
+            self.clus.N_MAX = int(pot[0])
+            self.cenma.m, self.cenma.m_new, self.Mtotal = float(pot[1]), float(pot[2]), float(pot[3])
+            self.Rtidal = self.orbit_r * math.pow(self.Mtotal, 1.0 / 3.0)
+            S2, E2 = find_limits(self.clus.N_MAX, self.MIN_CHUNK_SIZE, self.procs)
+            self.mpiBegin, self.mpiEnd = int(S2[self.myid]), int(E2[self.myid])
 
     def dev_transfer_and_sort_host_barriers(self):
         import torch
@@ -203,7 +216,7 @@ class ShardedCluster(Cluster):
         self.Start, self.End = S, E
         self.clus.N_MAX = int(n_keep_all.sum())
         self.clus.N_MAX_NEW = nl
-        self.N_b_local = nb.value
+        self.N_b_local = self.bin_slots_in_use = nb.value
 
     def dev_qsorts_new(self):
         raise NotImplementedError("the sharded path sorts on rnew with the transfer fused (dev_transfer_and_sort)")
@@ -261,7 +274,19 @@ class ShardedCluster(Cluster):
     def host_step(self, seed=0, draws=None, draw_off=None, dirty_words=None):
         """Cluster.host_step on this rank's shard: its records and the tables cross this rank's host link once each way; max_r is reduced
         over the ranks like new_orbits_calculate does (reference cmc_utils.c:2206)."""
-        res = super().host_step(seed, draws, draw_off, dirty_words)
+        import os
+        if os.environ.get("CMCB200_SHARD_HOST_BARRIERS"):
+            res = super().host_step(seed, draws, draw_off, dirty_words)
+        else:
+            self.resident_begin(dirty_words)
+            p = self.orbit_params(draws, draw_off, seed)
+            _lib.check(self.L.cmcb200_dev_new_orbits_async(self.ctx, C.byref(p), 0), "dev_new_orbits_async")
+            self._shard_step(with_potential=True)
+            res = _lib.OrbitResult()
+            _lib.check(self.L.cmcb200_dev_orbit_result(self.ctx, C.byref(p), C.byref(res)), "dev_orbit_result")
+            self.last_orbit = res
+            self.resident_end()
+            self.tcount += 1
         self.max_r = self._allreduce_max(res.max_r)
         return res
 
@@ -284,11 +309,12 @@ class ShardedCluster(Cluster):
             # the orbit step is only queued; its statistics are read once the sort's single wait has drained the stream
             p = self.orbit_params(draws, draw_off, seed, fuse_energy=True)
             _lib.check(self.L.cmcb200_dev_new_orbits_async(self.ctx, C.byref(p), 0), "dev_new_orbits_async")
-            self.dev_transfer_and_sort()
+            self._shard_step(with_potential=True)
             res = _lib.OrbitResult()
             _lib.check(self.L.cmcb200_dev_orbit_result(self.ctx, C.byref(p), C.byref(res)), "dev_orbit_result")
             self.max_r, self.last_orbit = res.max_r, res
-        self.dev_calc_potential_new()
+        if os.environ.get("CMCB200_SHARD_HOST_BARRIERS"):
+            self.dev_calc_potential_new()
         with torch.cuda.stream(self._tstream):
             m = torch.tensor([res.max_r], dtype=torch.float64, device=f"cuda:{self.device}")
             self.dist.all_reduce(m, op=self.dist.ReduceOp.MAX)

@@ -318,9 +318,14 @@ int cmcb200_shard_finish(cmcb200_ctx *ctx);
  * (st.release.sys / ld.acquire.sys over NVLink), the counts travel with the first barrier, every device plans the new partition itself
  * (findLimits with blk = min_chunk) and the kernels behind take their extents from that plan.  The host only enqueues;
  * cmcb200_shard_step_result waits for the stream and returns what the reference's globals need: n_keep_all[procs], Start / End [procs] of the new
- * partition (clus.N_MAX = End[procs-1]), the local binary count.  A barrier that a peer never reaches times out (4 s) and the result call fails. */
-int cmcb200_shard_step_async(cmcb200_ctx *ctx, long n_local, long n_old_local, long first_global, long N_MAX, int min_chunk, long n_bin_clear);
-int cmcb200_shard_step_result(cmcb200_ctx *ctx, long *n_keep_all, int *Start, int *End, long *n_bin);
+ * partition (clus.N_MAX = End[procs-1]), the local binary count.  A barrier that a peer never reaches times out (4 s) and the result call fails.
+ * The new star_r / star_m tables do not wait for the records: every rank sends (global rank, star_m) of its sorted run to all ranks, each scatters
+ * them (with the radii it already holds as keys) into its own tables on a second stream, and -- with pot_N_STAR > 0 -- the potential rebuild
+ * (cmcb200_dev_calc_potential_new's kernels, with cenma.m / cenma.m_new as given) is queued right behind, so that tables and potential
+ * overlap the record exchange.  pot_out[4] (may be NULL) then receives N_MAX, cenma.m, cenma.m_new, Mtotal. */
+int cmcb200_shard_step_async(cmcb200_ctx *ctx, long n_local, long n_old_local, long first_global, long N_MAX, int min_chunk, long n_bin_clear,
+			     long pot_N_STAR, double pot_cenma_m, double pot_cenma_m_new);
+int cmcb200_shard_step_result(cmcb200_ctx *ctx, long *n_keep_all, int *Start, int *End, long *n_bin, double pot_out[4]);
 
 /* ---- instrumentation --------------------------------------------------------------------------------------------- */
 
