@@ -118,6 +118,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_oflag, (size_t) n_star_dim));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_first, (size_t) ORBIT_DEFER_CAP * sizeof(unsigned)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_job, (size_t) 5 * n_star_dim * sizeof(double)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[0], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[1], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r, 0, tb, c->stream));
@@ -160,7 +161,7 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	cudaFree(c->d_defer_first); cudaFree(c->lad.q); cudaFree(c->lad.r); cudaFree(c->lad.unsorted);
 	if (c->d_keys_all) { cudaFree(c->d_keys_all); cudaFree(c->d_src_all); cudaFree(c->d_dest_pos); cudaFree(c->d_dest_rank); cudaFree(c->d_shard_meta); cudaFree(c->d_shard_sync); cudaFree(c->d_rank_all); cudaFree(c->d_m_all);
 		if (c->s_aux) { cudaStreamDestroy(c->s_aux); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); } }
-	cudaFree(c->d_oflag); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
+	cudaFree(c->d_oflag); cudaFree(c->d_job); cudaFree(c->d_pend[0]); cudaFree(c->d_pend[1]);
 	cudaFree(c->sbuf.keys_a); cudaFree(c->sbuf.keys_b); cudaFree(c->sbuf.vals_a); cudaFree(c->sbuf.vals_b);
 	cudaFree(c->d_sort); cudaFree(c->d_tile_hist); cudaFree(c->d_binflag); cudaFree(c->d_bin_block_cnt);
 	cudaFree(c->d_pot); cudaFree(c->d_seqwork); cudaFree(c->d_ostats); cudaFree(c->d_status); cudaFree(c->d_kmin); cudaFree(c->d_kmax);
@@ -443,6 +444,7 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 	a.prepare_ctas = c->orbit_ctas;
 	a.defer_first = c->d_defer_first;
 	a.flag = c->d_oflag; a.pend_list[0] = c->d_pend[0]; a.pend_list[1] = c->d_pend[1];
+	a.job = c->d_job; a.job_stride = c->n_star_dim;
 	a.t.N_MAX = p->N_MAX;
 	a.t.invN = 1.0 / p->N_STAR;
 	a.t.madhoc = 1.0 / ((double) p->N_STAR);
@@ -486,6 +488,7 @@ static int orbit_range(cmcb200_ctx *c, const OrbitArgs &whole, long off, long le
 	a.n_old_local = whole.n_old_local - off; // may be <= 0: every star of the chunk was created this step (get_global_idx, cmc_utils.c:2384-2407)
 	a.first_global = whole.first_global + off;
 	a.flag += off;
+	a.job += off;
 	if (a.draw_off) a.draw_off += off;
 	if (a.status) a.status += off;
 	if (a.kmin) { a.kmin += off; a.kmax += off; }

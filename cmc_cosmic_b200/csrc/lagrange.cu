@@ -255,8 +255,8 @@ extern "C" int cmcb200_dev_compute_energy_totals(cmcb200_ctx *c, long n_local, l
 	const int grid = NUM_SMS_B200 * 4;
 	if (n_local > 0) {
 		StageTimer t(c, ST_ENERGY);
-		seq_scan_launch(ChainEtot<0>{a}, c->seqwork, n_local, &d->totals[0], grid, grid, c->stream);
-		if (cenma_m == 0.0) seq_scan_launch(ChainEtot<4>{a}, c->seqwork, n_local, &d->totals[1], grid, grid, c->stream);
+		seq_scan_launch(ChainEtot<0>{a}, c->seqwork, n_local, &d->totals[0], grid, grid, c->stream, false);
+		if (cenma_m == 0.0) seq_scan_launch(ChainEtot<4>{a}, c->seqwork, n_local, &d->totals[1], grid, grid, c->stream, false);
 		else { // two additions per star: a scan twice as long as the tables the shared scratch was sized for
 			if (!c->d_seqwork2) {
 				const size_t wb = pot_work_bytes(2 * c->n_star_dim);
@@ -265,11 +265,11 @@ extern "C" int cmcb200_dev_compute_energy_totals(cmcb200_ctx *c, long n_local, l
 			}
 			SeqWork w2;
 			pot_work_bind(w2, c->d_seqwork2, 2 * c->n_star_dim);
-			seq_scan_launch(ChainEtot<1>{a}, w2, 2 * n_local, &d->totals[1], grid, grid, c->stream);
+			seq_scan_launch(ChainEtot<1>{a}, w2, 2 * n_local, &d->totals[1], grid, grid, c->stream, false);
 		}
-		seq_scan_launch(ChainEtot<2>{a}, c->seqwork, n_local, &d->totals[2], grid, grid, c->stream);
-		seq_scan_launch(ChainEtot<3>{a}, c->seqwork, n_local, &d->totals[3], grid, grid, c->stream);
-		c->launches += 16;
+		seq_scan_launch(ChainEtot<2>{a}, c->seqwork, n_local, &d->totals[2], grid, grid, c->stream, false);
+		seq_scan_launch(ChainEtot<3>{a}, c->seqwork, n_local, &d->totals[3], grid, grid, c->stream, false);
+		c->launches += 12; // only the sums are wanted: no second pass over the terms
 	}
 	CMCB_CUDA_OK(cudaGetLastError());
 	double *h = (double *) c->h_pinned;

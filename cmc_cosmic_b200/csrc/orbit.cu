@@ -212,15 +212,20 @@ __device__ __forceinline__ void accumulate_stats(OrbitStats *st, int status, dou
 	if (valid && status > 0 && status < 6) atomicAdd(&st->n_status[status], 1ull); // the rare outcomes; OK count = n - sum
 }
 
-// A star whose orbit is known but whose new radius is not drawn yet parks its job in its own record: r_peri / r_apo hold
-// r_min / r_max (their final values, :919-920) and X holds the envelope F until the accepted X replaces it (:918).
-__device__ __forceinline__ void store_prepared(const OrbitArgs &a, long j0, const OrbitOut &o, const OrbitJob &job)
+// A star whose orbit is known but whose new radius is not drawn yet parks its job -- the envelope F, r_min, r_max and its E, J -- in five
+// compact arrays (OrbitArgs::job); r_peri / r_apo of its record receive r_min / r_max at once (their final values, :919-920).
+__device__ __forceinline__ void store_prepared(const OrbitArgs &a, long j0, const OrbitOut &o, const OrbitJob &job, double E, double J)
 {
 	if (o.status == ORBIT_PENDING) {
 		char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
-		st_field(rec, CMCB_OFF_X, job.F);
+		// r_min / r_max are final (:919-920): into the record now.  The job itself goes to the compact arrays the rejection rounds read.
 		st_field(rec, CMCB_OFF_R_PERI, job.rmin);
 		st_field(rec, CMCB_OFF_R_APO, job.rmax);
+		a.job[0 * a.job_stride + j0] = job.F;
+		a.job[1 * a.job_stride + j0] = job.rmin;
+		a.job[2 * a.job_stride + j0] = job.rmax;
+		a.job[3 * a.job_stride + j0] = E;
+		a.job[4 * a.job_stride + j0] = J;
 		a.flag[j0] = 1;
 		if (a.kmin) a.kmin[j0] = o.kmin;
 		if (a.kmax) a.kmax[j0] = o.kmax;
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(ORBIT_THREADS, CTAS) orbit_prepare_kernel(Orbi
 			}
 		}
 		if (o.status != ORBIT_DEFERRED) {
-			store_prepared(a, j0, o, job);
+			store_prepared(a, j0, o, job, in.E, in.J);
 			n_exact += o.n_exact; n_brent += o.n_brent;
 			if (o.status > 0 && o.status < 6) atomicAdd(&a.stats->n_status[o.status], 1ull); // the rare outcomes; OK count = n - sum
 		}
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(ORBIT_THREADS) orbit_deferred_kernel(OrbitArgs
 			LadderTops top; // the few queued stars bisect on the fine table
 			top.q = nullptr; top.r = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
 			orbit_prepare(a.t, top, s, in.is_new, in.rnew_of_new, a.Rtidal, found == ORBIT_NOT_FOUND ? -1 : (kint) found, false, o, job);
-			store_prepared(a, j0, o, job);
+			store_prepared(a, j0, o, job, in.E, in.J);
 		}
 		accumulate_stats(a.stats, o.status, 0.0, 0, o.n_exact, o.n_brent, valid);
 	}
@@ -468,14 +473,17 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 		double rnew = 0.0;
 		bool requeue = false;
 		if (have) {
-			const StarIn in = load_star(a, j0);
+			// the star's global index (get_global_idx) and its job: nothing of the 424-byte record is read in the rounds
+			StarIn in;
+			in.is_new = j0 + 1 > a.n_old_local;
+			in.g = (kint) (in.is_new ? 1 + a.t.N_MAX + (j0 + 1 - a.n_old_local) : a.first_global + j0);
+			OrbitJob job;
+			job.F = __ldg(a.job + 0 * a.job_stride + j0); job.rmin = __ldg(a.job + 1 * a.job_stride + j0); job.rmax = __ldg(a.job + 2 * a.job_stride + j0);
+			in.E = __ldg(a.job + 3 * a.job_stride + j0); in.J = __ldg(a.job + 4 * a.job_stride + j0);
 			StarConst s;
 			s.g_j = in.g; s.r_j = tbl_r(a.t, in.g); s.m_j = tbl_ld(a.t.m, in.g); s.J = in.J;
 			s.E = dadd(in.E, phi_self(s.r_j, s.r_j, s.m_j, a.t.invN)); // :806
 			s.JJ = dmul(s.J, s.J);
-			const char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
-			OrbitJob job;
-			job.F = ld_field(rec, CMCB_OFF_X); job.rmin = ld_field(rec, CMCB_OFF_R_PERI); job.rmax = ld_field(rec, CMCB_OFF_R_APO);
 			unsigned t0 = t0_base;
 			for (;;) {
 				const unsigned t = t0 + sub;
@@ -512,7 +520,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 					if (o.status == ORBIT_OK) {
 						st_field(wrec, CMCB_OFF_RNEW, o.rnew); st_field(wrec, CMCB_OFF_VRNEW, o.vrnew); st_field(wrec, CMCB_OFF_VTNEW, o.vtnew);
 						st_field(wrec, CMCB_OFF_X, o.X);
-					} else st_field(wrec, CMCB_OFF_X, 0.0); // the parked envelope must not survive in a field the reference leaves alone
+					}
 					if (a.status) a.status[j0] = o.status;
 					if (a.n_draws) a.n_draws[j0] = o.n_draws;
 					status = o.status; n_draws = o.n_draws; rnew = o.rnew;

@@ -41,6 +41,10 @@ struct OrbitArgs {
 	int *n_draws;
 	OrbitStats *stats;
 	unsigned char *flag; // [n_local] 1: orbit known, new radius still to be drawn
+	// the pending stars' jobs as five compact arrays (component c of local star j0 at job[c * job_stride + j0]: envelope F, r_min, r_max, E, J) --
+	// stage A writes them coalesced and the rejection rounds read them coalesced instead of five scattered fields of the 424-byte records
+	double *job;
+	long job_stride;
 	int *pend_list[2]; // [n_local] each: compacted lists of pending stars, ping-pong between rounds
 	bool fuse_energy;  // E, J of every star are computed from the table and (vr, vt) on the fly and stored (ComputeEnergy's first loop)
 	const int *lad_unsorted; // device flag set by the table builder when star_r is not sorted (or Phi holds a NaN): ladders off

@@ -259,16 +259,22 @@ CMCB_HD Quad ld_quad(const double *p)
 	return q;
 }
 
-// number of entries among 16 consecutive doubles (one 128-byte line) that are < r
+// number of entries among 16 consecutive SORTED doubles (one 128-byte line, padded with +inf) that are < r.
+// The kernels that call this are bound by the L1's sector throughput (every lane reads its own line), so the line is not read whole: the
+// sector holding samples 4..7 first; it settles the count alone when s4 < r <= s7, otherwise ONE more sector below, or one or two above
+// (1 + 1/4 ... 3 sector reads, 2 on average, instead of 4) -- dependent loads, which a throughput-bound kernel can afford.
 CMCB_HD int count16_below(const double *line, double r)
 {
-	int c = 0;
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		const Quad v = ld_quad(line + 4 * i);
-		c += (v.a < r) + (v.b < r) + (v.c < r) + (v.d < r);
+	const Quad q1 = ld_quad(line + 4);
+	if (!(q1.d < r)) { // the answer is <= 7
+		if (q1.a < r) return 5 + (q1.b < r) + (q1.c < r);      // s4 < r <= s7
+		const Quad q0 = ld_quad(line);                          // r <= s4
+		return (q0.a < r) + (q0.b < r) + (q0.c < r) + (q0.d < r);
 	}
-	return c;
+	const Quad q2 = ld_quad(line + 8);                              // s7 < r
+	if (!(q2.d < r)) return 8 + (q2.a < r) + (q2.b < r) + (q2.c < r);
+	const Quad q3 = ld_quad(line + 12);                             // s11 < r
+	return 12 + (q3.a < r) + (q3.b < r) + (q3.c < r) + (q3.d < r);
 }
 
 // the coarsest ladder levels live in shared memory on the device (the kernels substitute the pointer): generic loads, no __ldg
@@ -312,11 +318,20 @@ CMCB_HD kint find_zero_r_ladder(const OrbitTables &t, const double *top, double 
 		b = 16 * b + (c > 0 ? c - 1 : 0);
 	}
 	const kint base = (kint) (b << RLAD_MIN_SHIFT), M = t.N_MAX + 1;
-	int c = 0;
-#pragma unroll
-	for (int i = 0; i < 4; i++) { // base is a multiple of 8: the line is 128-byte aligned, two entries per 256-bit load
-		const Quad v = ld_quad(&t.rp[base + 2 * i].r);
-		c += (base + 2 * i <= M && v.a < r) + (base + 2 * i + 1 <= M && v.c < r);
+	// the fine-table line that holds the answer: entries base .. base + 7 (base is a multiple of 8: 128-byte aligned, two (r, Phi) entries per
+	// 256-bit load), sorted; entries beyond M do not count.  Same sector-sparing order as count16_below: the sector with entries 2, 3 first.
+	int c;
+	{
+		auto below = [&](kint k, double rk) { return (int) (k <= M && rk < r); };
+		const Quad v1 = ld_quad(&t.rp[base + 2].r);
+		if (!below(base + 3, v1.c)) { // the answer is <= 3
+			if (below(base + 2, v1.a)) c = 3;
+			else { const Quad v0 = ld_quad(&t.rp[base].r); c = below(base, v0.a) + below(base + 1, v0.c); }
+		} else {
+			const Quad v2 = ld_quad(&t.rp[base + 4].r);
+			if (!below(base + 5, v2.c)) c = 4 + below(base + 4, v2.a);
+			else { const Quad v3 = ld_quad(&t.rp[base + 6].r); c = 6 + below(base + 6, v3.a) + below(base + 7, v3.c); }
+		}
 	}
 	const kint k = base + c - 1; // largest k in [0, M] with star_r[k] < r (-1: none)
 	return k >= 1 ? k : 1;

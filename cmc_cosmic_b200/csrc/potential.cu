@@ -144,14 +144,14 @@ int potential_calculate_device(const PotArgs &a, cudaStream_t st)
 	}
 	pot_set_nmax<<<1, 1, 0, st>>>(a.sc);
 	ChainMass cf{a.m, a.sc};
-	seq_scan_launch(cf, a.work, a.n_max_in, &a.sc->mass_sum, grid_persist, grid_persist, st);
+	seq_scan_launch(cf, a.work, a.n_max_in, &a.sc->mass_sum, grid_persist, grid_persist, st, false); // only the sum is used (Mtotal): no second pass
 	pot_totals<<<1, 1, 0, st>>>(a.sc, a.r, a.phi, a.mprev, a.madhoc);
 	ChainMprev cm{a.m, a.mprev, a.sc, a.n_star};
 	seq_scan_launch(cm, a.work, a.n_max_in, &a.sc->mprev_end, grid_persist, grid_persist, st);
 	ChainPhi cp{a.r, a.mprev, a.phi, a.sc};
 	seq_scan_launch(cp, a.work, a.n_max_in, &a.sc->phi_sum, grid_persist, grid_persist, st);
 	pot_phi0<<<1, 1, 0, st>>>(a.sc, a.r, a.phi, a.madhoc);
-	return (a.n_max_in > 0 ? 5 : 4) + 3 * 4; // scalars, find, set, totals, phi0 + 3 chains x (reset, classify, resolve, finalize)
+	return (a.n_max_in > 0 ? 5 : 4) + 3 * 4 - 1; // scalars, find, set, totals, phi0 + 3 chains x (reset, classify, resolve, finalize), the mass sum without its finalize
 }
 
 } // namespace cmcb

@@ -413,8 +413,9 @@ static __global__ void seq_scan_reset(SeqWork w, long ntiles)
 }
 
 // Launch the three kernels for one chain.  n_upper bounds ch.length() (which lives on the device).
+// need_values = false: only the chain's final value is wanted (d_result, written by seq_scan_resolve) -- the second pass over the terms is skipped
 template <class Chain>
-inline void seq_scan_launch(const Chain &ch, const SeqWork &w, long n_upper, double *d_result, int grid_classify, int grid_finalize, cudaStream_t st)
+inline void seq_scan_launch(const Chain &ch, const SeqWork &w, long n_upper, double *d_result, int grid_classify, int grid_finalize, cudaStream_t st, bool need_values = true)
 {
 	long ntiles = (n_upper + SEQ_TILE - 1) / SEQ_TILE;
 	if (ntiles < 1) ntiles = 1;
@@ -422,6 +423,7 @@ inline void seq_scan_launch(const Chain &ch, const SeqWork &w, long n_upper, dou
 	int g1 = (int) (ntiles < grid_classify ? ntiles : grid_classify);
 	seq_scan_classify<Chain><<<g1, SEQ_THREADS, 0, st>>>(ch, w);
 	seq_scan_resolve<Chain><<<1, SEQ_RESOLVE_THREADS, 0, st>>>(ch, w, d_result);
+	if (!need_values) return;
 	int g3 = (int) (ntiles < grid_finalize ? ntiles : grid_finalize);
 	seq_scan_finalize<Chain><<<g3, SEQ_THREADS, 0, st>>>(ch, w);
 }
