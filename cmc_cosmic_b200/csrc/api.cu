@@ -471,6 +471,7 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 		StageTimer t(c, ST_ORBIT_TABLES);
 		LadderBuffers lb = c->lad;
 		if (!(c->orbit_ladders & 1)) lb.r = nullptr;
+		lb.r_whole_lines = (c->orbit_ladders & 16) != 0;
 		lb.sampled = (c->orbit_ladders & 8) && !(c->orbit_ladders & 2); // the sample ladder lives in the Q ladder's buffer
 		if (!(c->orbit_ladders & 2) && !lb.sampled) lb.q = nullptr;
 		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, (c->orbit_ladders & 4) ? c->d_rpf : nullptr, p->n_table, p->N_MAX + 1, lb, a, c->stream);

@@ -689,6 +689,7 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhi
 	for (int l = 0; l < nq; l++) a.t.qlad.blk[l] = qlvl[l];
 	if (nq && qcnt[0] <= QLAD_TOP_BLOCKS) a.q_top_bytes = (unsigned) (qcnt[0] * sizeof(LBlock));
 	a.t.rlad.n_levels = nr;
+	a.t.rlad.whole_lines = lb.r_whole_lines ? 1 : 0;
 	for (int l = 0; l < nr; l++) a.t.rlad.lvl[l] = rplan.lvl[l];
 	if (nr) { a.t.rlad.n_top = (int) rcnt[0]; a.r_top_bytes = (unsigned) ((rcnt[0] + 1) / 2 * 2 * sizeof(double)); }
 	return launches;

@@ -62,6 +62,7 @@ struct LadderBuffers {
 	double *r;     // all levels of the r ladder back to back, finest first
 	long q_cap, r_cap; // capacity in blocks / doubles
 	int *unsorted; // device flag
+	bool r_whole_lines; // the r ladder's lines are read whole (tuning knob: CMCB200_ORBIT_LADDERS bit 4)
 	bool sampled;  // build the sample ladder (in q's memory) instead of the Q ladder
 	int q_max_shift, q_max_width_log2, q_factor_log2; // tuning knobs of the Q ladder (CMCB200_QLAD_MAX_SHIFT / _MAX_WIDTH_LOG2 / _FACTOR_LOG2)
 };

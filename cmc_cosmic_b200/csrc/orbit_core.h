@@ -87,6 +87,7 @@ struct RLadder {
 	int shift[LADDER_MAX_LEVELS];
 	int n_top;    // entries of the coarsest level
 	int n_levels; // 0: no ladder
+	int whole_lines; // != 0: read every ladder line whole (four independent sector loads) instead of sector by sector (count16_below)
 };
 
 // The SAMPLE ladder of the index bisections: level l holds the table entries (r_k, Phi_k) themselves at k = b << shift[l] -- not summaries.
@@ -263,6 +264,16 @@ CMCB_HD Quad ld_quad(const double *p)
 // The kernels that call this are bound by the L1's sector throughput (every lane reads its own line), so the line is not read whole: the
 // sector holding samples 4..7 first; it settles the count alone when s4 < r <= s7, otherwise ONE more sector below, or one or two above
 // (1 + 1/4 ... 3 sector reads, 2 on average, instead of 4) -- dependent loads, which a throughput-bound kernel can afford.
+CMCB_HD int count16_whole(const double *line, double r)
+{
+	int c = 0;
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const Quad v = ld_quad(line + 4 * i);
+		c += (v.a < r) + (v.b < r) + (v.c < r) + (v.d < r);
+	}
+	return c;
+}
 CMCB_HD int count16_below(const double *line, double r)
 {
 	const Quad q1 = ld_quad(line + 4);
@@ -314,14 +325,21 @@ CMCB_HD kint find_zero_r_ladder(const OrbitTables &t, const double *top, double 
 	}
 	long b = lo > 0 ? lo - 1 : 0; // last sample below r
 	for (int l = 1; l < L.n_levels; l++) {
-		const int c = count16_below(L.lvl[l] + 16 * b, r);
+		const int c = L.whole_lines ? count16_whole(L.lvl[l] + 16 * b, r) : count16_below(L.lvl[l] + 16 * b, r);
 		b = 16 * b + (c > 0 ? c - 1 : 0);
 	}
 	const kint base = (kint) (b << RLAD_MIN_SHIFT), M = t.N_MAX + 1;
 	// the fine-table line that holds the answer: entries base .. base + 7 (base is a multiple of 8: 128-byte aligned, two (r, Phi) entries per
 	// 256-bit load), sorted; entries beyond M do not count.  Same sector-sparing order as count16_below: the sector with entries 2, 3 first.
 	int c;
-	{
+	if (L.whole_lines) {
+		c = 0;
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const Quad v = ld_quad(&t.rp[base + 2 * i].r);
+			c += (base + 2 * i <= M && v.a < r) + (base + 2 * i + 1 <= M && v.c < r);
+		}
+	} else {
 		auto below = [&](kint k, double rk) { return (int) (k <= M && rk < r); };
 		const Quad v1 = ld_quad(&t.rp[base + 2].r);
 		if (!below(base + 3, v1.c)) { // the answer is <= 3

@@ -52,6 +52,7 @@ struct HostLadders {
 			r.lvl[l] = rl[l].data();
 		}
 		r.n_top = r.n_levels ? (int) cnt[0] : 0;
+		r.whole_lines = 0;
 		if (unsorted) { q.n_levels = 0; r.n_levels = 0; }
 	}
 };
