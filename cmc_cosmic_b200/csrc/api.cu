@@ -71,7 +71,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->n_table_dim = n_table_dim;
 	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
-	c->orbit_ladders = 9; // bit 3: sample ladder for the index bisections of stage A (find_zero_Q_sampled); bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A), bit 2: FP32 screening copy of the (r, Phi) table for the index bisections
+	c->orbit_ladders = 9; // bit 5: the rejection rounds as lookup + try kernels (off: measured slower), bit 4: r-ladder lines read whole (off); bit 3: sample ladder for the index bisections of stage A (find_zero_Q_sampled); bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A), bit 2: FP32 screening copy of the (r, Phi) table for the index bisections
 	c->bytes_h2d = c->bytes_d2h = 0;
 	c->orbit_ctas = 4;
 	c->orbit_max_chunks = 8;
@@ -118,7 +118,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_found, (size_t) ORBIT_DEFER_CAP * sizeof(long)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_oflag, (size_t) n_star_dim));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_defer_first, (size_t) ORBIT_DEFER_CAP * sizeof(unsigned)));
-	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_job, (size_t) 5 * n_star_dim * sizeof(double)));
+	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_job, (size_t) 6 * n_star_dim * sizeof(double)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[0], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMalloc((void **) &c->d_pend[1], (size_t) n_star_dim * sizeof(int)));
 	CMCB_CUDA_OK(cudaMemsetAsync(c->d_r, 0, tb, c->stream));
@@ -445,6 +445,7 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 	a.defer_first = c->d_defer_first;
 	a.flag = c->d_oflag; a.pend_list[0] = c->d_pend[0]; a.pend_list[1] = c->d_pend[1];
 	a.job = c->d_job; a.job_stride = c->n_star_dim;
+	a.split_lookup = (c->orbit_ladders & 32) != 0 && (c->orbit_ladders & 1);
 	a.t.N_MAX = p->N_MAX;
 	a.t.invN = 1.0 / p->N_STAR;
 	a.t.madhoc = 1.0 / ((double) p->N_STAR);

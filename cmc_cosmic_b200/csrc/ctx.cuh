@@ -38,7 +38,7 @@ struct cmcb200_ctx {
 	unsigned *d_defer_first;
 	LadderBuffers lad; // coarse levels of the lookup tables (orbit_core.h "ladders")
 	unsigned char *d_oflag;
-	double *d_job;     // [5][n_star_dim] jobs of the pending stars (orbit.cuh: OrbitArgs::job)
+	double *d_job;     // [6][n_star_dim] jobs of the pending stars (orbit.cuh: OrbitArgs::job)
 	int *d_pend[2];
 	int orbit_max_chunks; // host-buffer orbit step: at most this many pipeline chunks (CMCB200_ORBIT_CHUNKS, default 8)
 	int orbit_ctas;    // tuning knob CMCB200_ORBIT_CTAS: resident CTAs per SM orbit_prepare_kernel is compiled for (4 or 3)

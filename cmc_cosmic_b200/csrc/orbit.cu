@@ -444,9 +444,43 @@ __device__ __forceinline__ double sign_draw_for_try(const OrbitArgs &a, long j0,
 	return (double) ((t & 1) ? p.o0 : p.o2) / 4294967296.0;
 }
 
+// The rejection rounds are bound by the latency of potential()'s dependent loads (72 % of the try kernel's stall samples are long-scoreboard
+// waits) at the 32 resident warps per SM its 64 registers allow.  So the lookup is a kernel of its own: it needs the proposed radius and the
+// ladder search only, fits 42 registers, and runs with 48 resident warps per SM (512-thread CTAs, 3 per SM: the staged top level is 40 KB per
+// CTA); it leaves potential(r) of every pending star's try `t` in the job array's sixth component (NaN: the bracket check failed).  The try
+// kernel proper (POT_READY) then has no dependent random access left.
+constexpr int ORBIT_LOOKUP_THREADS = 512;
+template <bool RECORDED, bool FIRST>
+__global__ void __launch_bounds__(ORBIT_LOOKUP_THREADS, 3) orbit_lookup_kernel(OrbitArgs a, int round, unsigned t)
+{
+	extern __shared__ __align__(128) unsigned char orbit_smem[];
+	__shared__ __align__(8) unsigned long long bar;
+	const unsigned n_work = FIRST ? (unsigned) a.n_local : a.stats->round_count[round];
+	if ((unsigned long long) blockIdx.x * ORBIT_LOOKUP_THREADS >= n_work) return;
+	LadderTops top;
+	top.q = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
+	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
+	const int *__restrict__ list_in = a.pend_list[round & 1];
+	for (unsigned w = blockIdx.x * ORBIT_LOOKUP_THREADS + threadIdx.x; w < n_work; w += gridDim.x * ORBIT_LOOKUP_THREADS) {
+		const long j0 = FIRST ? (long) w : (long) list_in[w];
+		if (FIRST && a.flag[j0] == 0) continue;
+		const kint g = (kint) (j0 + 1 > a.n_old_local ? 1 + a.t.N_MAX + (j0 + 1 - a.n_old_local) : a.first_global + j0);
+		TryDraws d;
+		double pot = __longlong_as_double(0x7ff8000000000000ll);
+		if (t < CMCB_N_TRY && draws_for_try<RECORDED>(a, j0, g, t, d)) {
+			const double r = orbit_try_radius(__ldg(a.job + 1 * a.job_stride + j0), __ldg(a.job + 2 * a.job_stride + j0), d.X);
+			int fail = 0;
+			const double p = potential_at(a.t, top, r, &fail);
+			if (!fail) pot = p;
+		}
+		a.job[5 * a.job_stride + j0] = pot;
+	}
+}
+
 // W lanes per star evaluate tries t0 .. t0+W-1.  FIRST: the work list is "every star whose flag is set" (round 0, no list yet).
 // LOOP: keep going (t0 += W) until the star is accepted or N_TRY is exceeded (the last round).
-template <bool RECORDED, int W, bool FIRST, bool LOOP>
+// POT_READY (W == 1 only): potential(r) of this try was left in the job array by orbit_lookup_kernel.
+template <bool RECORDED, int W, bool FIRST, bool LOOP, bool POT_READY = false>
 __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitArgs a, int round, unsigned t0_base)
 {
 	extern __shared__ __align__(128) unsigned char orbit_smem[];
@@ -455,7 +489,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 	if ((unsigned long long) blockIdx.x * (ORBIT_TRY_THREADS / W) >= n_work) return; // nothing for this CTA: skip the staging too
 	LadderTops top;
 	top.q = nullptr; top.qdesc = nullptr; top.s = nullptr; top.sdesc = nullptr;
-	top.r = (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
+	top.r = POT_READY ? nullptr : (const double *) stage_top_level(a.t.rlad.lvl[0], a.r_top_bytes, a.t.rlad.n_levels > 0 && *a.lad_unsorted == 0, orbit_smem, &bar);
 	const int *__restrict__ list_in = a.pend_list[round & 1];
 	int *__restrict__ list_out = a.pend_list[(round + 1) & 1];
 	const unsigned sub = threadIdx.x % W;
@@ -490,7 +524,13 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 				TryDraws d;
 				int rc = -1; // -1: fatal (out of draws / bracket failure / beyond N_TRY), 0: rejected, 1: accepted
 				double r = 0.0, vr = 0.0;
-				if (t < CMCB_N_TRY && draws_for_try<RECORDED>(a, j0, in.g, t, d)) rc = orbit_try(a.t, top, s, job, d.X, d.u, &r, &vr);
+				if (t < CMCB_N_TRY && draws_for_try<RECORDED>(a, j0, in.g, t, d)) {
+					if (POT_READY) {
+						const double pot_raw = __ldg(a.job + 5 * a.job_stride + j0);
+						r = orbit_try_radius(job.rmin, job.rmax, d.X);
+						rc = orbit_try_finish(a.t, s, job, d.X, d.u, r, pot_raw, pot_raw != pot_raw, &vr);
+					} else rc = orbit_try(a.t, top, s, job, d.X, d.u, &r, &vr);
+				}
 				// first lane of the group (lowest try index) that did not reject decides
 				int first_rc = rc;
 				unsigned first_sub = rc != 0 ? sub : W;
@@ -708,14 +748,32 @@ static int launch_try_rounds(const OrbitArgs &a, cudaStream_t s)
 		const long cap = (long) NUM_SMS_B200 * ORBIT_CTAS_PER_SM;
 		return (unsigned) (g < 1 ? 1 : (g > cap ? cap : g));
 	};
+	if (a.split_lookup) { // rounds 0..4 as lookup + try: see orbit_lookup_kernel
+		auto lgrid = [&](double frac) {
+			long g = (long) (n * frac / ORBIT_LOOKUP_THREADS) + 1;
+			const long cap = (long) NUM_SMS_B200 * 3;
+			return (unsigned) (g < 1 ? 1 : (g > cap ? cap : g));
+		};
+		const double frac[5] = {1.0, 0.60, 0.35, 0.20, 0.12};
+		for (int rd = 0; rd < 5; rd++) {
+			if (rd == 0) {
+				orbit_lookup_kernel<RECORDED, true><<<lgrid(frac[rd]), ORBIT_LOOKUP_THREADS, smem, s>>>(a, rd, (unsigned) rd);
+				orbit_try_kernel<RECORDED, 1, true, false, true><<<grid_for(frac[rd], 1), ORBIT_TRY_THREADS, 0, s>>>(a, rd, (unsigned) rd);
+			} else {
+				orbit_lookup_kernel<RECORDED, false><<<lgrid(frac[rd]), ORBIT_LOOKUP_THREADS, smem, s>>>(a, rd, (unsigned) rd);
+				orbit_try_kernel<RECORDED, 1, false, false, true><<<grid_for(frac[rd], 1), ORBIT_TRY_THREADS, 0, s>>>(a, rd, (unsigned) rd);
+			}
+		}
+	} else {
 	orbit_try_kernel<RECORDED, 1, true, false><<<grid_for(1.0, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 0, 0u);
 	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.60, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 1, 1u);
 	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.35, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 2, 2u);
 	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.20, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 3, 3u);
 	orbit_try_kernel<RECORDED, 1, false, false><<<grid_for(0.12, 1), ORBIT_TRY_THREADS, smem, s>>>(a, 4, 4u);
+	}
 	orbit_try_kernel<RECORDED, 4, false, false><<<grid_for(0.07, 4), ORBIT_TRY_THREADS, smem, s>>>(a, 5, 5u);
 	orbit_try_kernel<RECORDED, 32, false, true><<<grid_for(0.01, 32), ORBIT_TRY_THREADS, smem, s>>>(a, 6, 9u);
-	return 7;
+	return a.split_lookup ? 12 : 7;
 }
 
 // stage A: reset + the orbit of every star

@@ -45,6 +45,7 @@ struct OrbitArgs {
 	// stage A writes them coalesced and the rejection rounds read them coalesced instead of five scattered fields of the 424-byte records
 	double *job;
 	long job_stride;
+	bool split_lookup; // the rejection rounds run as lookup kernel + try kernel (CMCB200_ORBIT_LADDERS bit 5, off: measured slower); a sixth job component holds potential(r)
 	int *pend_list[2]; // [n_local] each: compacted lists of pending stars, ping-pong between rounds
 	bool fuse_energy;  // E, J of every star are computed from the table and (vr, vt) on the fly and stored (ComputeEnergy's first loop)
 	const int *lad_unsorted; // device flag set by the table builder when star_r is not sorted (or Phi holds a NaN): ladders off

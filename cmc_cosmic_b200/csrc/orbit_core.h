@@ -964,22 +964,38 @@ CMCB_HD void orbit_prepare(const OrbitTables &t, const LadderTops &top, const St
 
 // One pass of the rejection loop body (:863-887) with the two uniforms X, u of that try.  1: accepted (r, vr set), 0: rejected,
 // -1: the bracket check inside potential() failed (fatal in the reference, cmc_utils.c:144-152).
-CMCB_HD int orbit_try(const OrbitTables &t, const LadderTops &top, const StarConst &s, const OrbitJob &job, double X, double u, double *r_out, double *vr_out)
+// the radius a try proposes (:864-867): a function of the orbit's turning points and the uniform X alone
+CMCB_HD double orbit_try_radius(double rmin, double rmax, double X)
+{
+	const double span = dsub(rmax, rmin);
+	const double mid = dmul(0.5, dadd(rmin, rmax)), quarter = dmul(0.25, span);
+	const double s0 = dsub(dmul(2.0, X), 1.0);
+	return dadd(mid, dmul(quarter, dsub(dmul(3.0, s0), dmul(dmul(s0, s0), s0))));
+}
+
+// the rest of the try once potential(r) is known (pot_raw; fail: its bracket check failed)
+CMCB_HD int orbit_try_finish(const OrbitTables &t, const StarConst &s, const OrbitJob &job, double X, double u, double r, double pot_raw, int fail, double *vr_out)
 {
 	const double span = dsub(job.rmax, job.rmin);
-	const double mid = dmul(0.5, dadd(job.rmin, job.rmax)), quarter = dmul(0.25, span), twoE = dmul(2.0, s.E);
+	const double quarter = dmul(0.25, span), twoE = dmul(2.0, s.E);
 	const double s0 = dsub(dmul(2.0, X), 1.0);
 	const double g0 = dmul(job.F, u);
-	const double r = dadd(mid, dmul(quarter, dsub(dmul(3.0, s0), dmul(dmul(s0, s0), s0))));
-	int fail = 0;
-	const double pot = dadd(potential_at(t, top, r, &fail), phi_self(r, s.r_j, s.m_j, t.invN));
+	const double pot = dadd(pot_raw, phi_self(r, s.r_j, s.m_j, t.invN));
 	const double drds = dmul(quarter, dsub(3.0, dmul(dmul(3.0, s0), s0)));
 	const double Q = dsub(dsub(twoE, dmul(2.0, pot)), ddiv(ddiv(s.JJ, r), r));
 	const double vr = (Q >= 0.0) ? dsqrt(Q) : 0.0;
-	*r_out = r;
 	*vr_out = vr;
 	if (fail) return -1;
 	return g0 < dmul(ddiv(1.0, vr), drds) ? 1 : 0;
+}
+
+CMCB_HD int orbit_try(const OrbitTables &t, const LadderTops &top, const StarConst &s, const OrbitJob &job, double X, double u, double *r_out, double *vr_out)
+{
+	const double r = orbit_try_radius(job.rmin, job.rmax, X);
+	int fail = 0;
+	const double pot_raw = potential_at(t, top, r, &fail);
+	*r_out = r;
+	return orbit_try_finish(t, s, job, X, u, r, pot_raw, fail, vr_out);
 }
 
 // :918-931 once try number `tries` (1-based) was accepted with (X, r, vr); usign = the next uniform of the stream
