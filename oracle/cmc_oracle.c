@@ -638,6 +638,142 @@ void orc_calc_sigma_r(long p, long n_limit, long first_global, long N_MAX, int i
 	}
 }
 
+/* ---- dynamics_apply, src/cmc/cmc_dynamics.c:206-500: the pair loop without the strong encounters ----------------------------------------------- */
+
+#define ORC_PI 3.14159265358979323      /* include/cmc/cmc.h:62 */
+#define ORC_FB_PI 3.141592653589793238462643 /* include/fewbody-0.24/fewbody.h:35 */
+#define ORC_MSUN 1.989e+33              /* include/cmc/cmc.h:66, fewbody.h:38 */
+#define ORC_XBS 2.0                     /* include/cmc/cmc.h:83 */
+#define ORC_XBB 2.0                     /* include/cmc/cmc.h:85 */
+static double orc_sqr(double x) { return x * x; }
+static double orc_cub(double x) { return x * x * x; }
+
+/* calc_n_local, cmc_dynamics_helper.c:768-786 */
+static double orc_calc_n_local(const double *star_r, long k, long p, long N_LIMIT)
+{
+	long kmin = k - p, kmax = k + p;
+	if (kmin < 0) { kmin = 0; kmax = 2 * p + 1; }
+	else if (kmax > N_LIMIT) { kmax = N_LIMIT; kmin = N_LIMIT - 2 * p - 1; }
+	return (2.0 * ((double) p)) * 3.0 / (4.0 * ORC_PI * (orc_cub(star_r[kmax]) - orc_cub(star_r[kmin])));
+}
+
+long orc_dynamics_apply_pairs(const orc_tables_t *t, long n_local, long first_global, double dt, const orc_dyn_params_t *dp, const double *draws,
+			      double *vr, double *vt, double *E, double *J, double *Y, const long *binind, const int *se_k, const double *rad,
+			      const double *bin_a, const long *threebb, long *pair_k, long *pair_kp, int *pair_status, double *pair_rperi,
+			      double *pair_W, double *pair_rcm, orc_relax_stats_t *stats)
+{
+	const double relbeta[4] = {ORC_PI / 2.0, ORC_PI / 4.0, ORC_PI / 8.0, ORC_PI / 16.0}; /* :28 */
+	const double madhoc = t->madhoc, N_STAR = (double) t->N_STAR;
+	const long N_LIMIT = t->N_MAX, p = dp->p;
+	long npairs = 0, si = 1;
+	memset(stats, 0, sizeof *stats);
+	while (si <= n_local - n_local % 2 - 1) { /* :216 */
+		long k, kp, j;
+		double v[4], vp[4], w[4], W, rcm, rperi = 0.0, S, n_local_dens, mass_k, mass_kp, P_enc;
+		while (threebb && threebb[si - 1] == 1) si += 1; /* :226-228 */
+		k = si;
+		si += 1;
+		while (threebb && threebb[si - 1] == 1) si += 1; /* :233-236 */
+		kp = si;
+		si += 1;
+		const long g_k = first_global + k - 1, g_kp = first_global + kp - 1; /* get_global_idx of a star that is not new */
+		/* calc_encounter_dyns(k, kp, ..., setY = 1), cmc_dynamics_helper.c:831-870 */
+		Y[k - 1] = draws[3 * npairs];
+		Y[kp - 1] = Y[k - 1];
+		const double phi = Y[k - 1] * 2.0 * ORC_PI;
+		v[1] = vt[k - 1]; v[2] = 0.0; v[3] = vr[k - 1];
+		vp[1] = vt[kp - 1] * cos(phi); vp[2] = vt[kp - 1] * sin(phi); vp[3] = vr[kp - 1];
+		for (j = 1; j <= 3; j++) w[j] = vp[j] - v[j];
+		W = sqrt(orc_sqr(w[1]) + orc_sqr(w[2]) + orc_sqr(w[3]));
+		rcm = (t->m[g_k] * t->r[g_k] + t->m[g_kp] * t->r[g_kp]) / (t->m[g_k] + t->m[g_kp]);
+		n_local_dens = orc_calc_n_local(t->r, g_k, p, N_LIMIT); /* :249 */
+		mass_k = t->m[g_k];
+		mass_kp = t->m[g_kp];
+		const long bk = binind[k - 1], bkp = binind[kp - 1];
+		if (bk > 0 && bkp > 0) { /* :254-262 */
+			rperi = ORC_XBB * (bin_a[bk] + bin_a[bkp]);
+			S = dp->binbin ? ORC_PI * orc_sqr(rperi) * (1.0 + 2.0 * madhoc * (mass_k + mass_kp) / (rperi * orc_sqr(W))) : 0.0;
+		} else if (bk > 0 || bkp > 0) { /* :263-280 */
+			rperi = ORC_XBS * bin_a[bk > 0 ? bk : bkp];
+			S = dp->binsingle ? ORC_PI * orc_sqr(rperi) * (1.0 + 2.0 * madhoc * (mass_k + mass_kp) / (rperi * orc_sqr(W))) : 0.0;
+		} else if (dp->ss_collision) { /* :282-428 */
+			const int kk = se_k[k - 1], kkp = se_k[kp - 1];
+			const double rk = rad[k - 1], rkp = rad[kp - 1];
+			double S_tmp = 0.0, collisions_multiple, S_coll;
+			/* :285-303 is overwritten by :305-313 whatever CO_TDE says: WD_TC > 0 and two white dwarfs -> WD_TC, everything else COLL_FACTOR */
+			if (dp->wd_tc > 0 && (kkp >= 10 && kkp <= 12) && (kk >= 10 && kk <= 12)) collisions_multiple = dp->wd_tc;
+			else collisions_multiple = dp->coll_factor;
+			if (dp->tidal_capture) { /* :360-374 (Lombardi et al. 2006) */
+				double S_lombardi;
+				if ((kk <= 1 || kk >= 10 || kk == 7) && (kkp >= 2 && kkp <= 9 && kkp != 7)) {
+					rperi = 1.3 * rkp;
+					S_lombardi = ORC_PI * orc_sqr(rperi) * (1.0 + 2.0 * madhoc * (mass_k + mass_kp) / (rperi * orc_sqr(W)));
+				} else if ((kkp <= 1 || kkp >= 10 || kkp == 7) && (kk >= 2 && kk <= 9 && kk != 7)) {
+					rperi = 1.3 * rk;
+					S_lombardi = ORC_PI * orc_sqr(rperi) * (1.0 + 2.0 * madhoc * (mass_k + mass_kp) / (rperi * orc_sqr(W)));
+				} else S_lombardi = 0.0;
+				S_tmp = S_tmp > S_lombardi ? S_tmp : S_lombardi;
+			}
+			if (dp->bh_capture && kk == 14 && kkp == 14) { /* :378-389 (Quinlan & Shapiro) */
+				const double clight10o7 = pow(2.9979e10 / (dp->units_l / dp->units_t), 1.428571);
+				rperi = 2.6789966 * madhoc * pow(mass_k * mass_kp, 0.28571428) * pow(mass_k + mass_kp, 0.42857143) / pow(W, 0.57142857) / clight10o7;
+				const double S_brem = ORC_PI * orc_sqr(rperi) * (1.0 + 2.0 * madhoc * (mass_k + mass_kp) / (rperi * orc_sqr(W)));
+				S_tmp = S_tmp > S_brem ? S_tmp : S_brem;
+			}
+			if (dp->tc_factor > 1 && (kk <= 1 || kk == 7 || kk >= 10) && (kkp <= 1 || kkp == 7 || kkp >= 10)) { /* :393-402 */
+				rperi = dp->tc_factor * (rk + rkp);
+				const double S_tc_simple = ORC_PI * orc_sqr(rperi) * (1.0 + 2.0 * madhoc * (mass_k + mass_kp) / (rperi * orc_sqr(W)));
+				S_tmp = S_tmp > S_tc_simple ? S_tmp : S_tc_simple;
+			}
+			rperi = collisions_multiple * (rk + rkp); /* :405-406 */
+			S_coll = ORC_PI * orc_sqr(rperi) * (1.0 + 2.0 * madhoc * (mass_k + mass_kp) / (rperi * orc_sqr(W)));
+			S = S_coll > S_tmp ? S_coll : S_tmp; /* :409-410 */
+			rperi = madhoc * (mass_k + mass_kp) / orc_sqr(W) * (-1.0 + sqrt(1.0 + S / ORC_FB_PI * orc_sqr(W * W / (madhoc * mass_k + madhoc * mass_kp))));
+		} else S = 0.0;
+		P_enc = n_local_dens * W * S * (dt * N_STAR / log(dp->gamma * N_STAR)); /* :436 */
+		pair_k[npairs] = k; pair_kp[npairs] = kp;
+		pair_rperi[npairs] = rperi; pair_W[npairs] = W; pair_rcm[npairs] = rcm;
+		if (draws[3 * npairs + 1] < P_enc) { /* :444-467 */
+			pair_status[npairs] = (bk > 0 || bkp > 0) ? 2 : 1;
+		} else if (dp->relaxation) { /* :468-540 */
+			double w1[4], w2[4], w_new[4], v_new[4], vp_new[4], wp, beta, psi;
+			const double Trel12 = (ORC_PI / 32.0) * orc_cub(W) / (N_STAR * n_local_dens * orc_sqr((mass_k + mass_kp) * madhoc));
+			beta = (ORC_PI / 2.0) * sqrt(dt / Trel12);
+			stats->Nrel++;
+			for (int i = 0; i < 4; i++) {
+				if (beta > relbeta[i]) {
+					stats->Nrelbeta[i]++;
+					stats->qaverelbeta[i] += (mass_k > mass_kp ? mass_k : mass_kp) / (mass_k < mass_kp ? mass_k : mass_kp);
+					stats->maverelbeta[i] += (mass_k + mass_kp) / 2.0 * dp->units_mstar / ORC_MSUN;
+					stats->raverelbeta[i] += rcm;
+				}
+			}
+			if (beta > ORC_PI / 2.0) beta = ORC_PI / 2.0;
+			wp = sqrt(orc_sqr(w[1]) + orc_sqr(w[2]));
+			w1[1] = -w[2] * W / wp; w1[2] = w[1] * W / wp; w1[3] = 0.0;
+			w2[1] = -w[1] * w[3] / wp; w2[2] = -w[2] * w[3] / wp; w2[3] = wp;
+			psi = draws[3 * npairs + 2] * 2 * ORC_PI;
+			for (j = 1; j <= 3; j++) w_new[j] = w[j] * cos(beta) + w1[j] * sin(beta) * cos(psi) + w2[j] * sin(beta) * sin(psi);
+			for (j = 1; j <= 3; j++) {
+				v_new[j] = v[j] - mass_kp / (mass_k + mass_kp) * (w_new[j] - w[j]);
+				vp_new[j] = vp[j] + mass_k / (mass_k + mass_kp) * (w_new[j] - w[j]);
+			}
+			vr[k - 1] = v_new[3];
+			vt[k - 1] = sqrt(orc_sqr(v_new[1]) + orc_sqr(v_new[2]));
+			vr[kp - 1] = vp_new[3];
+			vt[kp - 1] = sqrt(orc_sqr(vp_new[1]) + orc_sqr(vp_new[2]));
+			/* set_star_EJ, cmc_dynamics_helper.c:878-882 */
+			E[k - 1] = t->phi[g_k] + 0.5 * (orc_sqr(vr[k - 1]) + orc_sqr(vt[k - 1]));
+			J[k - 1] = t->r[g_k] * vt[k - 1];
+			E[kp - 1] = t->phi[g_kp] + 0.5 * (orc_sqr(vr[kp - 1]) + orc_sqr(vt[kp - 1]));
+			J[kp - 1] = t->r[g_kp] * vt[kp - 1];
+			pair_status[npairs] = 0;
+		} else pair_status[npairs] = 3;
+		npairs++;
+	}
+	return npairs;
+}
+
 /* ---- tidally_strip_stars, src/cmc/cmc_evolution_thr.c:443-645: the per-star criterion of one pass of its loop ------------------------------ */
 
 long orc_tidally_strip_select(long n_local, int tidal_treatment, double threshold, const double *r_apo, const double *E, double *rnew,

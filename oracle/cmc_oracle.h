@@ -120,6 +120,32 @@ void orc_calc_sigma_r(long p, long n_limit, long first_global, long N_MAX, int i
 		      double madhoc, const double *vr, const double *vt, const double *ghost_prev_vr, const double *ghost_prev_vt,
 		      const double *ghost_next_vr, const double *ghost_next_vt, int r_0_mave_1, double *sig_r_or_mave, double *sig_sigma);
 
+/* dynamics_apply, src/cmc/cmc_dynamics.c:17-542: the loop over neighbouring pairs (:216-500) for everything that does not need
+ * fewbody / collisions / BSE -- the pair's kinematics (calc_encounter_dyns, cmc_dynamics_helper.c:831-870), the local density (calc_n_local,
+ * :768-786), the cross section S of the pair's type (:250-432), the encounter probability (:436), the decision (:444) and the two-body
+ * relaxation branch (:468-500: Trel12, beta, the rotated relative velocity, new vr / vt, set_star_EJ) with its scattering-angle statistics
+ * (:473-482).  A pair whose draw falls below P_enc is an ENCOUNTER: it is reported (status, rperi, W, rcm) and left to the caller, which
+ * runs binint_do / sscollision_do on it like the reference does.
+ * Pairs are (1,2), (3,4), ... of the local stars, skipping stars with threebb_interacted == 1 (:226-240; threebb may be NULL).
+ * draws: three uniforms per pair in pair order -- Y (the angle between the tangential velocities, calc_encounter_dyns), the encounter draw,
+ * psi (consumed only by a relaxed pair; an encounter pair leaves its third draw unused).
+ * Star fields are the local stars 1..n_local at [0..n_local-1]; bin_a is indexed by binind (entry 0 unused; may be NULL without binaries).
+ * TC_POLYTROPE, BH_LOSS_CONE with a central mass and THREEBODYBINARIES' own loop (:60-204) are outside this restatement.
+ * pair_k / pair_kp [n_local / 2]: 1-based local indices of each pair's stars; pair_status: 0 relaxed, 1 single-single encounter, 2 encounter
+ * with a binary, 3 untouched (RELAXATION == 0).  Returns the number of pairs. */
+typedef struct {
+	long relaxation, ss_collision, binsingle, binbin, tidal_capture, co_tde, bh_capture, p /* AVEKERNEL */;
+	double gamma, coll_factor, tc_factor, wd_tc, units_mstar, units_l, units_t;
+} orc_dyn_params_t;
+typedef struct {
+	long Nrel, Nrelbeta[4];
+	double qaverelbeta[4], maverelbeta[4], raverelbeta[4];
+} orc_relax_stats_t;
+long orc_dynamics_apply_pairs(const orc_tables_t *t, long n_local, long first_global, double dt, const orc_dyn_params_t *dp, const double *draws,
+			      double *vr, double *vt, double *E, double *J, double *Y, const long *binind, const int *se_k, const double *rad,
+			      const double *bin_a, const long *threebb, long *pair_k, long *pair_kp, int *pair_status, double *pair_rperi,
+			      double *pair_W, double *pair_rcm, orc_relax_stats_t *stats);
+
 /* tidally_strip_stars, src/cmc/cmc_evolution_thr.c:443-645 (between energy_conservation2 and ComputeIntermediateEnergy, cmc.c:321-322): one
  * pass of its do-while loop over the local stars.  A star still in the cluster (rnew < 1e6) is stripped when r_apo > threshold = Rtidal
  * (TIDAL_TREATMENT 0, :479) or E > threshold = gierszalpha * phi_rtidal (TIDAL_TREATMENT 1, :555): rnew = SF_INFINITY, vrnew = vtnew = 0.

@@ -62,7 +62,7 @@ EXPORT long ref_star_offset(const char *f)
 #define O(n) if (!strcmp(f, #n)) return (long) offsetof(star_t, n)
 	O(r); O(vr); O(vt); O(m); O(E); O(J); O(EI); O(Eint); O(rnew); O(vrnew); O(vtnew); O(rOld); O(X); O(Y);
 	O(r_peri); O(r_apo); O(phi); O(interacted); O(binind); O(id); O(rad); O(Uoldrold); O(Uoldrnew); O(vtold); O(vrold);
-	O(se_k);
+	O(se_k); O(threebb_interacted);
 #undef O
 	return -1;
 }
@@ -278,6 +278,56 @@ EXPORT void ref_comp_mass_percent(const double *pc, long count, int bh_include, 
 	for (i = 0; i < 8; i++) { memcpy(out + i * count, *arr[i], count * sizeof(double)); free(*arr[i]); *arr[i] = NULL; }
 	free(mass_pc); mass_pc = NULL;
 }
+
+/* dynamics_apply (src/cmc/cmc_dynamics.c:17-542) on the harness's cluster state.  The strong-encounter routines it calls are re-bound at link
+ * time (ld --wrap, oracle/Makefile) to the recorders below: an encounter pair is logged (type 0 = single-single, 1 = with a binary; k, kp,
+ * then rperi, W, rcm as doubles) and left alone, so that everything else -- calc_encounter_dyns, calc_n_local, the cross sections, the
+ * encounter probability, the two-body relaxation branch and the relaxation statistics -- is the reference's own code.
+ * flags: RELAXATION, SS_COLLISION, BINSINGLE, BINBIN, TIDAL_CAPTURE, TC_POLYTROPE, CO_TDE, BH_CAPTURE, BH_LOSS_CONE, THREEBODYBINARIES, AVEKERNEL
+ * par:   GAMMA, COLL_FACTOR, TC_FACTOR, WD_TC, units.mstar, units.l, units.t */
+static long *enc_log_k = NULL; static double *enc_log_d = NULL; static long enc_log_cap = 0, enc_log_n = 0;
+static void enc_record(long type, long k, long kp, double rperi, double W, double rcm)
+{
+	if (enc_log_n < enc_log_cap) {
+		enc_log_k[3 * enc_log_n] = type; enc_log_k[3 * enc_log_n + 1] = k; enc_log_k[3 * enc_log_n + 2] = kp;
+		enc_log_d[3 * enc_log_n] = rperi; enc_log_d[3 * enc_log_n + 1] = W; enc_log_d[3 * enc_log_n + 2] = rcm;
+	}
+	enc_log_n++;
+}
+void __wrap_sscollision_do(long k, long kp, double rperi, double w[4], double W, double rcm, double vcm[4], gsl_rng *rng)
+{ (void) w; (void) vcm; (void) rng; enc_record(0, k, kp, rperi, W, rcm); }
+void __wrap_binint_do(long k, long kp, double rperi, double w[4], double W, double rcm, double vcm[4], gsl_rng *rng)
+{ (void) w; (void) vcm; (void) rng; enc_record(1, k, kp, rperi, W, rcm); }
+void __wrap_break_wide_binaries(struct rng_t113_state *rng_st) { (void) rng_st; }
+void __wrap_bh_rand_walk(long index, double v[4], double vcm[4], double beta, double dt)
+{ (void) index; (void) v; (void) vcm; (void) beta; (void) dt; fprintf(stderr, "ref_harness: bh_rand_walk is outside the harness\n"); exit(8); }
+void __wrap_make_threebodybinary(void) { fprintf(stderr, "ref_harness: make_threebodybinary is outside the harness\n"); exit(8); }
+double __wrap_sigma_tc_nd(double n, double m1, double r1, double m2, double vinf)
+{ (void) n; (void) m1; (void) r1; (void) m2; (void) vinf; fprintf(stderr, "ref_harness: TC_POLYTROPE is outside the harness\n"); exit(8); }
+double __wrap_sigma_tc_nn(double na, double ma, double ra, double nb, double mb, double rb, double vinf)
+{ (void) na; (void) ma; (void) ra; (void) nb; (void) mb; (void) rb; (void) vinf; fprintf(stderr, "ref_harness: TC_POLYTROPE is outside the harness\n"); exit(8); }
+
+EXPORT long ref_dynamics_apply(double dt, const long *flags, const double *par, long *log_k, double *log_d, long log_cap, char *relax_text, long relax_cap)
+{
+	RELAXATION = flags[0]; SS_COLLISION = flags[1]; BINSINGLE = (int) flags[2]; BINBIN = (int) flags[3]; TIDAL_CAPTURE = flags[4];
+	TC_POLYTROPE = flags[5]; CO_TDE = (int) flags[6]; BH_CAPTURE = flags[7]; BH_LOSS_CONE = flags[8]; THREEBODYBINARIES = (int) flags[9];
+	AVEKERNEL = flags[10];
+	GAMMA = par[0]; COLL_FACTOR = par[1]; TC_FACTOR = par[2]; WD_TC = par[3]; units.mstar = par[4]; units.l = par[5]; units.t = par[6];
+	if (!mpi_logfile_buf) { mpi_logfile_buf = malloc(STR_BUF_LEN); mpi_logfile_wrbuf = malloc(1 << 20); }
+	if (!mpi_relaxationfile_buf) { mpi_relaxationfile_buf = malloc(STR_BUF_LEN); mpi_relaxationfile_wrbuf = malloc(1 << 16); }
+	mpi_logfile_wrbuf[0] = 0; mpi_logfile_len = 0;
+	mpi_relaxationfile_wrbuf[0] = 0; mpi_relaxationfile_len = 0;
+	if (!sigma_array.r) {
+		sigma_array.n = 0;
+		sigma_array.r = (double *) calloc(N_STAR_DIM_OPT, sizeof(double));      /* cmc_io.c:2103-2104 */
+		sigma_array.sigma = (double *) calloc(N_STAR_DIM_OPT, sizeof(double));
+	}
+	enc_log_k = log_k; enc_log_d = log_d; enc_log_cap = log_cap; enc_log_n = 0;
+	dynamics_apply(dt, NULL);
+	if (relax_text && relax_cap > 0) { strncpy(relax_text, mpi_relaxationfile_wrbuf, relax_cap - 1); relax_text[relax_cap - 1] = 0; }
+	return enc_log_n;
+}
+EXPORT const double *ref_sigma_array(int which) { return which ? sigma_array.sigma : sigma_array.r; }
 
 /* timing leg for bench.py: one pass of orbit step -> (caller refreshes r) -> sort -> post_sort_comm -> potential.
  * Brackets follow timeStartSimple/timeEndSimple (cmc_utils.c:1681-1707): barrier, wall clock. */

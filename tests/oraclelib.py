@@ -23,6 +23,26 @@ class Orbit(C.Structure):
                 ("kmax", C.c_long), ("kmin", C.c_long), ("circular_flag", C.c_int), ("used_brent", C.c_int)]
 
 
+class DynParams(C.Structure):
+    _fields_ = [(k, C.c_long) for k in ("relaxation", "ss_collision", "binsingle", "binbin", "tidal_capture", "co_tde", "bh_capture", "p")] + \
+               [(k, C.c_double) for k in ("gamma", "coll_factor", "tc_factor", "wd_tc", "units_mstar", "units_l", "units_t")]
+
+
+class RelaxStats(C.Structure):
+    _fields_ = [("Nrel", C.c_long), ("Nrelbeta", C.c_long * 4), ("qaverelbeta", C.c_double * 4), ("maverelbeta", C.c_double * 4),
+                ("raverelbeta", C.c_double * 4)]
+
+
+DYN_DEFAULTS = dict(relaxation=1, ss_collision=0, binsingle=0, binbin=0, tidal_capture=0, co_tde=0, bh_capture=0, p=20, gamma=0.11,
+                    coll_factor=1.0, tc_factor=1.0, wd_tc=0.0, units_mstar=1.989e33, units_l=3.0e18, units_t=1.0e13)
+
+
+def dyn_params(**kw):
+    d = dict(DYN_DEFAULTS)
+    d.update(kw)
+    return DynParams(**d)
+
+
 def _build():
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("cmc_oracle.c", "cmc_oracle.h")):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libcmc_oracle.so"])
@@ -59,6 +79,8 @@ def lib():
         L.orc_set_velocities3_second.restype = C.c_double
         L.orc_set_velocities3_second.argtypes = [C.POINTER(Tables), C.c_long] + [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 4
         L.orc_calc_sigma_r.argtypes = [C.c_long] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_dynamics_apply_pairs.restype = C.c_long
+        L.orc_dynamics_apply_pairs.argtypes = [C.POINTER(Tables), C.c_long, C.c_long, C.c_double, C.POINTER(DynParams)] + [C.c_void_p] * 17 + [C.POINTER(RelaxStats)]
         L.orc_tidally_strip_select.restype = C.c_long
         L.orc_tidally_strip_select.argtypes = [C.c_long, C.c_int, C.c_double] + [C.c_void_p] * 6
         L.orc_compute_energy_totals.argtypes = [C.POINTER(Tables), C.c_long, C.c_long] + [C.c_void_p] * 11
@@ -258,6 +280,31 @@ def calc_sigma_r(p, star_r, star_m, N_MAX, N_STAR, vr_all, vt_all, first_global=
     lib().orc_calc_sigma_r(p, n, first_global, N_MAX, int(first_global == 1), _p(star_r), _p(star_m), 1.0 / N_STAR, _p(loc[0]), _p(loc[1]),
                            _p(prev[0]), _p(prev[1]), _p(nxt[0]), _p(nxt[1]), int(mave), _p(a), _p(sg))
     return a, sg
+
+
+def dynamics_apply_pairs(t, first_global, dt, dp, draws, f, bin_a=None):
+    """dynamics_apply's pair loop without the strong encounters (reference cmc_dynamics.c:206-500).  f: dict of the local stars' fields vr, vt,
+    E, J, Y (float64, modified in place), binind (int64), se_k (int32), rad, optionally threebb (int64).  draws: 3 per pair."""
+    n = len(f["vr"])
+    npmax = n // 2 + 1
+    out = dict(pair_k=np.zeros(npmax, np.int64), pair_kp=np.zeros(npmax, np.int64), status=np.zeros(npmax, np.int32), rperi=np.zeros(npmax),
+               W=np.zeros(npmax), rcm=np.zeros(npmax))
+    st = RelaxStats()
+    draws = np.ascontiguousarray(draws, np.float64)
+    if len(draws) < 3 * (n // 2):                     # fewer pairs than n / 2 when threebb-flagged stars are skipped
+        draws = np.concatenate([draws, np.zeros(3 * (n // 2) - len(draws))])
+    for k in ("vr", "vt", "E", "J", "Y", "rad"):
+        assert f[k].dtype == np.float64 and f[k].flags.c_contiguous, k
+    assert f["binind"].dtype == np.int64 and f["se_k"].dtype == np.int32
+    thr = f.get("threebb")
+    npairs = lib().orc_dynamics_apply_pairs(C.byref(t), n, first_global, dt, C.byref(dp), _p(draws), _p(f["vr"]), _p(f["vt"]), _p(f["E"]), _p(f["J"]),
+                                            _p(f["Y"]), _p(f["binind"]), _p(f["se_k"]), _p(f["rad"]), _p(bin_a), _p(thr), _p(out["pair_k"]),
+                                            _p(out["pair_kp"]), _p(out["status"]), _p(out["rperi"]), _p(out["W"]), _p(out["rcm"]), C.byref(st))
+    out = {k: v[:npairs] for k, v in out.items()}
+    out["Nrel"] = st.Nrel
+    out["Nrelbeta"] = np.array(st.Nrelbeta[:])
+    out["qave"], out["mave"], out["rave"] = np.array(st.qaverelbeta[:]), np.array(st.maverelbeta[:]), np.array(st.raverelbeta[:])
+    return out
 
 
 def tidally_strip_select(tidal_treatment, threshold, f):

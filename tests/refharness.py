@@ -159,6 +159,24 @@ class Ref:
         self.L.ref_calc_sigma_r(p, n_limit, int(mave), a.ctypes.data, sg.ctypes.data)
         return a, sg
 
+    DYN_FLAGS = ("relaxation", "ss_collision", "binsingle", "binbin", "tidal_capture", "tc_polytrope", "co_tde", "bh_capture", "bh_loss_cone",
+                 "threebodybinaries", "p")
+    DYN_PARS = ("gamma", "coll_factor", "tc_factor", "wd_tc", "units_mstar", "units_l", "units_t")
+
+    def dynamics_apply(self, dt, cfg, log_cap=1 << 16):
+        """the reference's dynamics_apply (cmc_dynamics.c:17-542) on the harness's state with the strong-encounter routines re-bound to
+        recorders (oracle/ref_harness.c).  cfg: dict with the keys of DYN_FLAGS / DYN_PARS.  Returns (encounter log [(type, k, kp)],
+        [(rperi, W, rcm)], the relaxation file's line)."""
+        flags = np.array([int(cfg.get(k, 0)) for k in self.DYN_FLAGS], np.int64)
+        par = np.array([float(cfg[k]) for k in self.DYN_PARS], np.float64)
+        lk, ld = np.zeros((log_cap, 3), np.int64), np.zeros((log_cap, 3))
+        txt = C.create_string_buffer(4096)
+        self.L.ref_dynamics_apply.restype = C.c_long
+        self.L.ref_dynamics_apply.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        n = self.L.ref_dynamics_apply(dt, flags.ctypes.data, par.ctypes.data, lk.ctypes.data, ld.ctypes.data, log_cap, txt, 4096)
+        assert n <= log_cap
+        return lk[:n], ld[:n], txt.value.decode()
+
     def tidally_strip_stars(self, treatment, gamma=0.11):
         """the reference's tidally_strip_stars (cmc_evolution_thr.c:443-645) on the harness's state -> (Rtidal, TidalMassLoss, DTidalMassLoss)"""
         out = np.zeros(3)

@@ -153,6 +153,118 @@ def test_calc_sigma_r(R, kind, N, masses, p):
     R.free()
 
 
+DYN_CASES = {
+    # the Plummer example's configuration (examples/PlummerSphere.ini): relaxation only, odd N (the last star stays unpaired)
+    "relax_only": dict(kind="plummer", N=20001, masses="imf", nb=0, dt=2e-3, cfg=dict(relaxation=1)),
+    # the King example's switches (examples/KingProfile.ini) with radii and a time step large enough for encounters of every type
+    "encounters": dict(kind="king", N=20000, masses="imf", nb=1500, dt=4e-3,
+                       cfg=dict(relaxation=1, ss_collision=1, binsingle=1, binbin=1, bh_capture=1, tidal_capture=1, tc_factor=3.0, wd_tc=2.5, co_tde=1)),
+    "no_relaxation": dict(kind="plummer", N=6000, masses="equal", nb=0, dt=1e-3, cfg=dict(relaxation=0, ss_collision=1)),
+    "threebb_skips": dict(kind="plummer", N=8000, masses="imf", nb=0, dt=2e-3, cfg=dict(relaxation=1), threebb=True),
+}
+
+
+def dyn_case_setup(R, case, seed=11):
+    """a cluster with stellar types, radii and binaries on the harness + the same state as plain arrays for the restatement"""
+    c = DYN_CASES[case]
+    N, nb = c["N"], c["nb"]
+    r, vr, vt, sm = cm.cluster_state(c["kind"], N, seed=N + seed, masses=c["masses"])
+    rng = np.random.default_rng(seed)
+    binind = np.zeros(N, np.int64)
+    if nb:
+        binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    R.init(N, n_star_dim=N + 64, n_bin_dim=nb + 8, idum=77)
+    R.load_cluster(r, vr, vt, sm, binind=binind)
+    R.set_scalars(N, N, N_BINARY=nb)
+    se_k = rng.choice(np.array([0, 1, 1, 1, 3, 7, 10, 11, 13, 14, 14], np.int32), N).astype(np.int32)
+    rad = rng.uniform(2e-4, 3e-3, N)
+    R.star_field("se_k", np.int32)[1:N + 1] = se_k
+    R.star_field("rad")[1:N + 1] = rad
+    bin_a = np.zeros(nb + 1)
+    if nb:
+        bin_a[1:] = rng.uniform(1e-4, 4e-3, nb)
+        layout.binary_field(R.binary_bytes(), "a")[1:nb + 1] = bin_a[1:]
+        layout.binary_field(R.binary_bytes(), "inuse")[1:nb + 1] = 1
+    threebb = None
+    if c.get("threebb"):
+        threebb = np.zeros(N, np.int64)
+        tri = rng.choice(N // 3 - 2, 40, replace=False) * 3
+        for k in range(3):
+            threebb[tri + k] = 1
+        threebb[N - 30:] = 0
+        R.star_field("threebb_interacted", np.int64)[1:N + 1] = threebb
+    R.L.ref_calc_potential_new()
+    R.compute_energy()
+    cfg = dict(ol.DYN_DEFAULTS)
+    cfg.update(c["cfg"])
+    f = dict(vr=vr.copy(), vt=vt.copy(), E=R.star_field("E")[1:N + 1].copy(), J=R.star_field("J")[1:N + 1].copy(), Y=np.zeros(N), binind=binind,
+             se_k=se_k, rad=rad)
+    if threebb is not None:
+        f["threebb"] = threebb
+    tabs = (R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy())
+    return c, cfg, f, bin_a, tabs
+
+
+def per_pair_draws(stream, n_pairs, enc_first_stars, pair_k, relaxation):
+    """the reference's sequential stream cut into three draws per pair: an encounter pair (or any pair without relaxation) consumed two"""
+    out, pos = np.zeros(3 * n_pairs), 0
+    for i in range(n_pairs):
+        take = 2 if (pair_k[i] in enc_first_stars or not relaxation) else 3
+        out[3 * i:3 * i + take] = stream[pos:pos + take]
+        pos += take
+    assert pos == len(stream)
+    return out
+
+
+@pytest.mark.parametrize("case", list(DYN_CASES))
+def test_dynamics_apply_pairs(R, case):
+    """dynamics_apply (reference cmc_dynamics.c:17-542) of the compiled reference, its strong-encounter routines re-bound to
+    recorders, against the restated pair loop: kinematics, local density, every cross section, the encounter decision, the relaxation branch
+    (new vr, vt, E, J, Y of every star, bit for bit) and the scattering-angle statistics as the reference prints them"""
+    c, cfg, f, bin_a, (sr, smt, phi) = dyn_case_setup(R, case)
+    N = c["N"]
+    R.L.ref_draw_mode(1)
+    lk, ld, txt = R.dynamics_apply(c["dt"], cfg)
+    stream = R.draws()
+    R.L.ref_draw_mode(0)
+    # pairing is independent of the draws: a dry run of the restatement gives each pair's first star
+    t = ol.tables(sr, smt, phi, N, N)
+    dp = ol.dyn_params(**{k: v for k, v in cfg.items() if k in dict(ol.DynParams._fields_)})
+    dry = ol.dynamics_apply_pairs(t, 1, c["dt"], dp, np.ones(3 * (N // 2)), {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in f.items()}, bin_a)
+    draws = per_pair_draws(stream, len(dry["pair_k"]), set(lk[:, 1].tolist()), dry["pair_k"], cfg["relaxation"])
+    got = ol.dynamics_apply_pairs(t, 1, c["dt"], dp, draws, f, bin_a)
+    for name in ("vr", "vt", "E", "J", "Y"):
+        cm.assert_bits_equal(R.star_field(name)[1:N + 1], f[name], name)
+    enc = got["status"] > 0
+    enc &= got["status"] < 3
+    assert np.array_equal(got["pair_k"][enc], lk[:, 1]) and np.array_equal(got["pair_kp"][enc], lk[:, 2])
+    assert np.array_equal(got["status"][enc] - 1, lk[:, 0])
+    cm.assert_bits_equal(got["rperi"][enc], ld[:, 0], "rperi")
+    cm.assert_bits_equal(got["W"][enc], ld[:, 1], "W")
+    cm.assert_bits_equal(got["rcm"][enc], ld[:, 2], "rcm")
+    if case == "encounters":
+        assert (lk[:, 0] == 0).sum() > 20 and (lk[:, 0] == 1).sum() > 20, lk[:, 0]
+    if case == "threebb_skips":
+        assert not np.any(np.isin(got["pair_k"], np.nonzero(f["threebb"])[0] + 1))
+    if cfg["relaxation"]:
+        assert got["Nrel"] == len(got["pair_k"]) - enc.sum() and got["Nrelbeta"][3] > 0
+        # the reference's own line in the relaxation file (cmc_dynamics.c:523-531)
+        want = "%g" % 0.0
+        with np.errstate(invalid="ignore", divide="ignore"):
+            for i in range(4):
+                nb_ = float(got["Nrelbeta"][i])
+                want += " %s %s %s %s" % tuple(_g(x) for x in (nb_ / got["Nrel"], got["qave"][i] / nb_, got["mave"][i] / nb_, got["rave"][i] / nb_))
+        assert txt.splitlines()[-1] == want
+    R.free()
+
+
+def _g(x):
+    """printf's %g of a double (nan prints as -nan / nan depending on the sign bit, like glibc)"""
+    if np.isnan(x):
+        return "-nan" if np.signbit(x) else "nan"
+    return "%g" % x
+
+
 @pytest.mark.parametrize("treatment,orbit_r", [(1, 6.0), (0, 6.0), (1, 1.0e6)])
 def test_tidally_strip_stars(R, treatment, orbit_r):
     """tidally_strip_stars (reference cmc_evolution_thr.c:443-645), the step between energy_conservation2 and ComputeIntermediateEnergy when
