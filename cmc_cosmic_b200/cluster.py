@@ -380,6 +380,37 @@ class Cluster:
         _lib.check(self.L.cmcb200_dev_set_velocities3_pass(self.ctx, C.byref(p), Eexcess, C.byref(left)), "dev_set_velocities3_pass")
         return left.value
 
+    # the reference's switches dynamics_apply reads (include/cmc/cmc_vars.h), with the defaults of examples/PlummerSphere.ini
+    DYNAMICS = dict(RELAXATION=1, SS_COLLISION=0, BINSINGLE=0, BINBIN=0, TIDAL_CAPTURE=0, TC_POLYTROPE=0, BH_CAPTURE=0, BH_LOSS_CONE=0,
+                    AVEKERNEL=20, THREEBODYBINARIES=0, GAMMA=0.11, COLL_FACTOR=1.0, TC_FACTOR=1.0, WD_TC=0.0,
+                    units_mstar=1.989e33, units_l=3.0e18, units_t=1.0e13)
+
+    def dev_dynamics_apply(self, dt, draws=None, seed=0, **switches):
+        """dynamics_apply (reference src/cmc/cmc_dynamics.c:17-542) on the resident arrays: every pair of neighbouring stars is either relaxed in
+        place (new vr, vt, E, J) or, when its encounter draw falls below P_enc, listed for the host code that runs the reference's
+        binint_do / sscollision_do.  switches: the reference's globals of that name (``DYNAMICS``).  Returns the result block with the
+        scattering-angle statistics and ``encounters`` = dict(k, kp, type, rperi, W, rcm) in pair order."""
+        cfg = dict(self.DYNAMICS)
+        cfg.update(switches)
+        n = int(self.End[self.myid] - self.Start[self.myid] + 1)    # mpiEnd - mpiBegin + 1
+        p = _lib.DynamicsParams(n, int(self.Start[self.myid]), self.clus.N_MAX, self.clus.N_STAR, dt, cfg["RELAXATION"], cfg["SS_COLLISION"],
+                                cfg["BINSINGLE"], cfg["BINBIN"], cfg["TIDAL_CAPTURE"], cfg["TC_POLYTROPE"], cfg["BH_CAPTURE"], cfg["BH_LOSS_CONE"],
+                                cfg["AVEKERNEL"], cfg["THREEBODYBINARIES"], self.cenma.m, cfg["GAMMA"], cfg["COLL_FACTOR"], cfg["TC_FACTOR"],
+                                cfg["WD_TC"], cfg["units_mstar"], cfg["units_l"], cfg["units_t"], None, seed, self.tcount)
+        if draws is not None:
+            self._dyn_draws = np.ascontiguousarray(draws, np.float64)
+            assert len(self._dyn_draws) >= 3 * (n // 2)
+            p.draws = self._dyn_draws.ctypes.data
+        res = _lib.DynamicsResult()
+        _lib.check(self.L.cmcb200_dev_dynamics_apply(self.ctx, C.byref(p), C.byref(res)), "dev_dynamics_apply")
+        ne = res.n_encounters
+        enc = dict(k=np.zeros(ne, np.int64), kp=np.zeros(ne, np.int64), type=np.zeros(ne, np.int32), rperi=np.zeros(ne), W=np.zeros(ne), rcm=np.zeros(ne))
+        cnt = C.c_long()
+        _lib.check(self.L.cmcb200_dev_dynamics_encounters(self.ctx, ne, *[enc[k].ctypes.data for k in ("k", "kp", "type", "rperi", "W", "rcm")],
+                                                          C.byref(cnt)), "dev_dynamics_encounters")
+        res.encounters = enc
+        return res
+
     def dev_qsorts_new(self):
         n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
         _lib.check(self.L.cmcb200_dev_qsorts_new(self.ctx, C.byref(n), max(self.N_b_local, 0), C.byref(nb)), "dev_qsorts_new")

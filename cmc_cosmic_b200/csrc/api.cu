@@ -168,6 +168,8 @@ extern "C" void cmcb200_destroy(cmcb200_ctx *c)
 	if (c->d_lagrange) cudaFree(c->d_lagrange);
 	if (c->d_multimass) cudaFree(c->d_multimass);
 	if (c->d_sv3) cudaFree(c->d_sv3);
+	dynamics_free(c);
+	sigma_free(c);
 	if (c->d_seqwork2) cudaFree(c->d_seqwork2);
 	if (c->d_draws) cudaFree(c->d_draws);
 	if (c->d_draw_off) cudaFree(c->d_draw_off);

@@ -13,7 +13,7 @@ using namespace cmcb;
 constexpr int SHARD_MAX_RANKS = 16;
 enum { SH_STAR0 = 0, SH_STAR1, SH_BIN0, SH_BIN1, SH_R, SH_M, SH_R_ALT, SH_M_ALT, SH_KEYS_ALL, SH_SRC_ALL, SH_SYNC, SH_PHI, SH_RANK_ALL, SH_M_ALL, SH_N_BUFFERS }; // peer-visible buffers
 
-enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES, ST_LAGRANGE };
+enum { ST_KEYS = 0, ST_PASSES, ST_GATHER, ST_BINARIES, ST_POTENTIAL, ST_ORBIT, ST_TRANSFER, ST_ENERGY, ST_H2D, ST_D2H, ST_ORBIT_SCAN, ST_ORBIT_TRIES, ST_ORBIT_TABLES, ST_SHARD_KEYS, ST_SHARD_RANK, ST_SHARD_TABLES, ST_LAGRANGE, ST_DYNAMICS, ST_SIGMA };
 
 struct StageEvent {
 	int stage;
@@ -62,6 +62,8 @@ struct cmcb200_ctx {
 	void *d_lagrange; // device result block of comp_mass_percent (lagrange.cu), allocated on first use
 	void *d_multimass; // argument / result block of comp_multi_mass_percent (lagrange.cu), allocated on first use
 	void *d_seqwork2; // exact-scan scratch for chains of 2 n_star_dim elements (ComputeEnergy's potential sum), allocated on first use
+	void *d_dynamics; // scratch of dynamics_apply's pair loop (dynamics.cu), a host struct holding device buffers, allocated on first use
+	void *d_sigma;    // scratch of calc_sigma_r (sigma.cu), likewise
 	void *d_sv3;      // scratch of set_velocities3 (velocities.cu), allocated on first use for n_star_dim stars
 	int *d_status;
 	long *d_kmin, *d_kmax;
@@ -117,6 +119,10 @@ struct cmcb200_ctx {
 int shard_share_table_slices(cmcb200_ctx *c, long first, long n);
 // api.cu: the potential rebuild queued on `stream` (no wait, no read-back); n_max_upper bounds the new N_MAX
 int potential_enqueue(cmcb200_ctx *c, long n_max_upper, long N_STAR, double cenma_m, double cenma_m_new, cudaStream_t stream);
+
+// dynamics.cu / sigma.cu: release the scratch behind d_dynamics / d_sigma
+void dynamics_free(cmcb200_ctx *c);
+void sigma_free(cmcb200_ctx *c);
 
 // fills the orbit-step argument block from the context and the caller's parameters and (re)builds the lookup tables (api.cu)
 int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, bool need_status, OrbitArgs &a);

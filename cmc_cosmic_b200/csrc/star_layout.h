@@ -33,3 +33,7 @@
 #define CMCB_OFF_UOLDRNEW 184
 #define CMCB_OFF_VTOLD 192
 #define CMCB_OFF_VROLD 200
+#define CMCB_OFF_THREEBB_INTERACTED 144
+#define CMCB_OFF_RAD 168
+#define CMCB_OFF_SE_K 224 /* int */
+#define CMCB_BIN_OFF_A 64

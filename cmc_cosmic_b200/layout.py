@@ -10,17 +10,18 @@ STAR_DTYPE_SIZE = 424
 BINARY_DTYPE_SIZE = 464
 
 STAR_OFFSETS = dict(r=0, vr=8, vt=16, m=24, E=32, J=40, EI=48, Eint=56, rnew=64, vrnew=72, vtnew=80, rOld=88, X=96, Y=104,
-                    r_peri=112, r_apo=120, phi=128, interacted=136, binind=152, id=160, Uoldrold=176, Uoldrnew=184, vtold=192, vrold=200)
-STAR_INT_FIELDS = ("binind", "id", "interacted")
+                    r_peri=112, r_apo=120, phi=128, interacted=136, threebb_interacted=144, binind=152, id=160, rad=168, Uoldrold=176, Uoldrnew=184, vtold=192, vrold=200, se_k=224)
+STAR_INT_FIELDS = ("binind", "id", "interacted", "threebb_interacted")
+STAR_INT32_FIELDS = ("se_k",)
 BINARY_OFFSETS = dict(id1=0, id2=8, rad1=16, rad2=24, m1=32, m2=40, Eint1=48, Eint2=56, a=64, e=72, inuse=80)
 
 
 def star_field(buf, name):
     """View of one star_t field over a (n, 424) uint8 array."""
     off = STAR_OFFSETS[name]
-    dt = np.int64 if name in STAR_INT_FIELDS else np.float64
+    dt = np.int64 if name in STAR_INT_FIELDS else (np.int32 if name in STAR_INT32_FIELDS else np.float64)
     flat = buf.reshape(-1)
-    return np.lib.stride_tricks.as_strided(flat[off:off + 8].view(dt), shape=(buf.shape[0],), strides=(STAR_DTYPE_SIZE,))
+    return np.lib.stride_tricks.as_strided(flat[off:off + np.dtype(dt).itemsize].view(dt), shape=(buf.shape[0],), strides=(STAR_DTYPE_SIZE,))
 
 
 def binary_field(buf, name, dtype=None):

@@ -4,9 +4,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmcb200.so")
-N_STAGES = 17
+N_STAGES = 19
 STAGE_NAMES = ["keys_hist", "radix_passes", "record_gather", "binaries", "potential", "orbit_prepare", "transfer", "energy", "h2d", "d2h",
-               "orbit_scan", "orbit_tries", "orbit_tables", "shard_keys", "shard_rank", "shard_tables", "lagrange"]
+               "orbit_scan", "orbit_tries", "orbit_tables", "shard_keys", "shard_rank", "shard_tables", "lagrange", "dynamics", "sigma"]
 
 
 class OrbitParams(C.Structure):
@@ -30,6 +30,19 @@ class MassPcResult(C.Structure):
                [("totals", C.c_double * 4), ("filled", C.c_long)]
 
 
+class DynamicsParams(C.Structure):
+    _fields_ = [(k, C.c_long) for k in ("n_local", "first_global", "N_MAX", "N_STAR")] + [("dt", C.c_double)] + \
+               [(k, C.c_long) for k in ("relaxation", "ss_collision", "binsingle", "binbin", "tidal_capture", "tc_polytrope", "bh_capture",
+                                        "bh_loss_cone", "avekernel", "honor_threebb")] + \
+               [(k, C.c_double) for k in ("cenma_m", "gamma", "coll_factor", "tc_factor", "wd_tc", "units_mstar", "units_l", "units_t")] + \
+               [("draws", C.c_void_p), ("seed", C.c_ulonglong), ("tcount", C.c_ulonglong)]
+
+
+class DynamicsResult(C.Structure):
+    _fields_ = [("n_pairs", C.c_long), ("n_encounters", C.c_long), ("Nrel", C.c_long), ("Nrelbeta", C.c_long * 4),
+                ("qaverelbeta", C.c_double * 4), ("maverelbeta", C.c_double * 4), ("raverelbeta", C.c_double * 4)]
+
+
 class CmcB200Error(RuntimeError):
     pass
 
@@ -47,6 +60,7 @@ EXPORTS = [
     "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass", "cmcb200_dev_energy_new_radii",
     "cmcb200_dev_potential", "cmcb200_dev_tidally_strip_select", "cmcb200_dev_compute_energy_totals",
     "cmcb200_shard_step_async", "cmcb200_shard_step_result", "cmcb200_dev_new_orbits_async", "cmcb200_dev_orbit_result", "cmcb200_resident_begin", "cmcb200_resident_begin_sharded", "cmcb200_resident_end", "cmcb200_dev_get", "cmcb200_dev_put", "cmcb200_dev_comp_multi_mass_percent",
+    "cmcb200_dev_dynamics_apply", "cmcb200_dev_dynamics_encounters",
 ]
 
 
@@ -116,6 +130,8 @@ def load():
     L.cmcb200_dev_new_orbits_async.argtypes = [vp, C.POINTER(OrbitParams), C.c_int]
     L.cmcb200_dev_orbit_result.argtypes = [vp, C.POINTER(OrbitParams), C.POINTER(OrbitResult)]
     L.cmcb200_dev_comp_multi_mass_percent.argtypes = [vp, lg, vp, lg, dbl, vp, lg, vp]
+    L.cmcb200_dev_dynamics_apply.argtypes = [vp, C.POINTER(DynamicsParams), C.POINTER(DynamicsResult)]
+    L.cmcb200_dev_dynamics_encounters.argtypes = [vp, lg, vp, vp, vp, vp, vp, vp, pl]
     L.cmcb200_dev_get.argtypes = [vp, vp, lg, vp, lg]
     L.cmcb200_dev_put.argtypes = [vp, vp, lg, vp, lg, vp, lg]
     L.cmcb200_resident_begin_sharded.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg, C.c_ulonglong, lg, lg]

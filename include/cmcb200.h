@@ -290,6 +290,45 @@ int cmcb200_dev_clusdyn_calculate(cmcb200_ctx *ctx, long N_MAX, long N_STAR, dou
 int cmcb200_dev_comp_multi_mass_percent(cmcb200_ctx *ctx, long N_MAX, const double *mass_bins, long n_bins, double solar_mass_dyn,
 					const double *mass_pc, long count, double *multi_mass_r);
 
+/* ---- dynamics_apply (src/cmc/cmc_dynamics.c:17-542): the loop over neighbouring pairs on the resident arrays ---------------- */
+/* Everything of the pair loop (:206-500) that is not a strong encounter: per pair (k, kp) = local stars (1,2), (3,4), ... the kinematics of
+ * calc_encounter_dyns (src/cmc/cmc_dynamics_helper.c:831-870; star[k].Y = star[kp].Y = the pair's first draw), calc_n_local (:768-786), the
+ * cross section of the pair's type (cmc_dynamics.c:250-432: binary-binary, binary-single, single-single with the sticky-sphere, Lombardi,
+ * Quinlan-Shapiro and TC_FACTOR terms), P_enc (:436) and the decision (:444).  A pair whose second draw is < P_enc is an ENCOUNTER: it is
+ * listed and left untouched for the caller, which runs the reference's binint_do / sscollision_do on it (cmcb200_dev_get / _put).  Every
+ * other pair is relaxed when RELAXATION != 0 (:468-540): Trel12, beta, the relative velocity rotated by (beta, psi = third draw), new
+ * star[].vr, .vt and set_star_EJ's .E, .J for both stars.  The scattering-angle statistics of :473-482 come back in the result (sums in a
+ * fixed, run-to-run reproducible order that is not the reference's serial order: they agree to rounding and are only printed with %g).
+ * sin / cos / log / pow are CUDA's double-precision routines (<= 2 ulp from glibc's), so vr, vt, E, J agree with the reference to ~1e-15
+ * relative, not bit for bit; the parity tests state 1e-12.
+ * Not handled here (the call fails): TC_POLYTROPE; BH_LOSS_CONE with a central mass (bh_rand_walk).  The three-body loop (:60-204) stays
+ * with the caller; with honor_threebb != 0 the stars it flagged (star[].threebb_interacted == 1) are skipped when pairs are formed (:226-240). */
+typedef struct {
+	long n_local;        /* mpiEnd - mpiBegin + 1 */
+	long first_global;   /* Start[myid] */
+	long N_MAX, N_STAR;  /* clus.N_MAX (N_LIMIT of calc_n_local), clus.N_STAR */
+	double dt;
+	long relaxation, ss_collision, binsingle, binbin, tidal_capture, tc_polytrope, bh_capture, bh_loss_cone; /* the reference's switches */
+	long avekernel;      /* AVEKERNEL */
+	long honor_threebb;
+	double cenma_m;
+	double gamma, coll_factor, tc_factor, wd_tc, units_mstar, units_l, units_t;
+	/* draws != NULL: three uniforms per pair in pair order (host array: Y, the encounter draw, psi) -- "the same uniform random draws fed in
+	 * as an input array"; NULL: Philox4x32-10 keyed by (seed, tcount, global index of the pair's first star) */
+	const double *draws;
+	unsigned long long seed, tcount;
+} cmcb200_dynamics_params;
+typedef struct {
+	long n_pairs;       /* pairs formed (without skipped stars: n_local / 2) */
+	long n_encounters;  /* pairs listed for the caller */
+	long Nrel, Nrelbeta[4];
+	double qaverelbeta[4], maverelbeta[4], raverelbeta[4];
+} cmcb200_dynamics_result;
+int cmcb200_dev_dynamics_apply(cmcb200_ctx *ctx, const cmcb200_dynamics_params *p, cmcb200_dynamics_result *res);
+/* the encounter pairs of the last cmcb200_dev_dynamics_apply in pair order: 1-based local indices of both stars, the type (1 single-single,
+ * 2 with a binary) and what the reference hands to sscollision_do / binint_do (rperi, W, rcm).  More than cap pairs: -3, *count set. */
+int cmcb200_dev_dynamics_encounters(cmcb200_ctx *ctx, long cap, long *k, long *kp, int *type, double *rperi, double *W, double *rcm, long *count);
+
 /* ---- radius-sharded operation: one rank per GPU of an NVLink node ---------------------------------------------------------------- */
 /* Replaces sample_sort + load_balance + post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2259-2288) for procs > 1.
  * The star array is sharded by radius rank exactly like the reference's MPI partition (findLimits), every rank keeps the full
@@ -332,8 +371,9 @@ int cmcb200_shard_step_result(cmcb200_ctx *ctx, long *n_keep_all, int *Start, in
 /* With profiling on, every stage is bracketed by CUDA events on the launching stream.  cmcb200_profile_read returns the
  * accumulated milliseconds and launch counts since the last reset for: 0 keys+histogram, 1 radix passes, 2 record
  * gather, 3 binaries, 4 potential, 5 orbit stage A (orbits of all stars), 6 transfer, 7 energy, 8 h2d, 9 d2h, 10 orbit linear scans,
- * 11 orbit stage B (rejection rounds), 12 orbit lookup tables, 13 sharded: key push, 14 sharded: global ranks, 15 sharded: table publish. */
-#define CMCB200_N_STAGES 17
+ * 11 orbit stage B (rejection rounds), 12 orbit lookup tables, 13 sharded: key push, 14 sharded: global ranks, 15 sharded: table publish,
+ * 16 Lagrange radii, 17 dynamics_apply's pair loop, 18 calc_sigma_r. */
+#define CMCB200_N_STAGES 19
 int cmcb200_profile(cmcb200_ctx *ctx, int on);
 int cmcb200_profile_read(cmcb200_ctx *ctx, double ms[CMCB200_N_STAGES], long launches[CMCB200_N_STAGES], int reset);
 /* kernels launched by this context since it was created */

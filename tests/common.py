@@ -162,3 +162,50 @@ def brent_cluster(N=20000, seed=5, stride=20):
             break
         E[bad], J[bad], planted[bad] = E0[bad], J0[bad], False
     return r, vr, vt, sm, pot, E, J, planted
+
+
+DYN_CASES = {
+    # examples/PlummerSphere.ini: relaxation only; odd N (the last star stays unpaired)
+    "relax_only": dict(kind="plummer", N=20001, masses="imf", nb=0, dt=2e-3, cfg=dict(relaxation=1)),
+    # the switches of examples/KingProfile.ini with radii and a time step large enough for encounters of every type
+    "encounters": dict(kind="king", N=20000, masses="imf", nb=1500, dt=4e-3,
+                       cfg=dict(relaxation=1, ss_collision=1, binsingle=1, binbin=1, bh_capture=1, tidal_capture=1, tc_factor=3.0, wd_tc=2.5)),
+    "no_relaxation": dict(kind="plummer", N=6000, masses="equal", nb=0, dt=1e-3, cfg=dict(relaxation=0, ss_collision=1)),
+    "threebb_skips": dict(kind="plummer", N=8000, masses="imf", nb=0, dt=2e-3, cfg=dict(relaxation=1), threebb=True),
+    "large": dict(kind="plummer", N=600000, masses="imf", nb=20000, dt=1e-3, cfg=dict(relaxation=1, ss_collision=1, binsingle=1, binbin=1)),
+}
+
+
+def dynamics_case(case, seed=11, first=1, nl=None):
+    """the state dynamics_apply's pair loop reads, for one of DYN_CASES: tables with the oracle's potential, the local stars' fields (a shard
+    first .. first + nl - 1 of the cluster when given), stellar types, radii, binaries, the switches, three draws per pair"""
+    c = DYN_CASES[case]
+    N, nb = c["N"], c["nb"]
+    r, vr, vt, sm = cluster_state(c["kind"], N, seed=N + seed, masses=c["masses"])
+    rng = np.random.default_rng(seed)
+    binind = np.zeros(N, np.int64)
+    if nb:
+        binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    se_k = rng.choice(np.array([0, 1, 1, 1, 3, 7, 10, 11, 13, 14, 14], np.int32), N).astype(np.int32)
+    rad = rng.uniform(2e-4, 3e-3, N)
+    bin_a = np.zeros(nb + 1)
+    bin_a[1:] = rng.uniform(1e-4, 4e-3, nb)
+    threebb = None
+    if c.get("threebb"):
+        threebb = np.zeros(N, np.int64)
+        tri = rng.choice(N // 3 - 2, 40, replace=False) * 3
+        for k in range(3):
+            threebb[tri + k] = 1
+        threebb[N - 30:] = 0
+    pot = oracle_potential(r, sm)
+    E, J = energies(pot["phi"][1:N + 1], r, vr, vt)
+    cfg = dict(ol.DYN_DEFAULTS)
+    cfg.update(c["cfg"])
+    nl = N - first + 1 if nl is None else nl
+    sl = slice(first - 1, first - 1 + nl)
+    f = dict(vr=vr[sl].copy(), vt=vt[sl].copy(), E=E[sl].copy(), J=J[sl].copy(), Y=np.zeros(nl), binind=binind[sl].copy(), se_k=se_k[sl].copy(),
+             rad=rad[sl].copy())
+    if threebb is not None:
+        f["threebb"] = threebb[sl].copy()
+    draws = np.random.default_rng(seed + 1).random(3 * (nl // 2))
+    return dict(N=N, nb=nb, dt=c["dt"], cfg=cfg, f=f, bin_a=bin_a, r=r, sm=sm, pot=pot, draws=draws, first=first, nl=nl)

@@ -43,6 +43,8 @@ def lib():
         L.emul_set_velocities3_second.argtypes = [vp, lg, lg, lg, vp, db, vp, vp, vp, vp]
         L.emul_calc_sigma_r.restype = C.c_int
         L.emul_calc_sigma_r.argtypes = [lg, lg, lg, lg, vp, vp, db, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        L.emul_dynamics_pairs.restype = lg
+        L.emul_dynamics_pairs.argtypes = [vp, vp, vp, lg, lg, lg, lg, db] + [vp] * 17
         _lib = L
     return _lib
 
@@ -128,3 +130,15 @@ def calc_sigma_r(p, star_r, star_m, N_MAX, N_STAR, vr_all, vt_all, first_global=
                                  int(mave), int(exact_scan), _p(a), _p(sg), _p(cnt))
     assert rc == 0
     return a, sg, int(cnt[0])
+
+
+def dynamics_pairs(sr, sm, phi, N_MAX, N_STAR, first_global, dt, cfg, draws, f, bin_a):
+    """the per-pair code of dynamics.cu (csrc/dynamics_core.h) in a host loop; f as oraclelib.dynamics_apply_pairs takes it (modified in place)"""
+    n = len(f["vr"])
+    sw = np.array([cfg[k] for k in ("relaxation", "ss_collision", "binsingle", "binbin", "tidal_capture", "bh_capture", "p")], np.int64)
+    par = np.array([cfg[k] for k in ("gamma", "coll_factor", "tc_factor", "wd_tc", "units_mstar", "units_l", "units_t")], np.float64)
+    out = dict(status=np.zeros(n // 2, np.int32), rperi=np.zeros(n // 2), W=np.zeros(n // 2), rcm=np.zeros(n // 2), beta=np.zeros(n // 2))
+    lib().emul_dynamics_pairs(_p(sr), _p(sm), _p(phi), N_MAX, N_STAR, n, first_global, dt, _p(sw), _p(par), _p(np.ascontiguousarray(draws)), _p(f["vr"]),
+                              _p(f["vt"]), _p(f["E"]), _p(f["J"]), _p(f["Y"]), _p(f["binind"]), _p(f["se_k"]), _p(f["rad"]), _p(bin_a),
+                              _p(out["status"]), _p(out["rperi"]), _p(out["W"]), _p(out["rcm"]), _p(out["beta"]))
+    return out

@@ -906,3 +906,96 @@ def test_empty_and_degenerate_inputs():
     c.download()
     assert c.clus.N_MAX == 0 and c.star_r[1] == cm.SF_INFINITY
     c.close()
+
+
+DYN_TOL = 1e-12   # sin / cos / log / pow on the device are CUDA's (<= 2 ulp from glibc's): relative to the pair's velocity / energy scale
+
+
+def _dyn_cluster(d):
+    """cm.dynamics_case on a Cluster: tables of the whole cluster, the records of the local stars with noise in every other byte"""
+    N, nl, first, f = d["N"], d["nl"], d["first"], d["f"]
+    c = Cluster(N, n_star_dim=N + 64, n_bin_dim=d["nb"] + 8)
+    c.load(d["r"], np.zeros(N), np.zeros(N), d["sm"])
+    c.star_phi[:N + 2] = d["pot"]["phi"][:N + 2]
+    rng = np.random.default_rng(3)
+    c.star[1:nl + 1] = rng.integers(0, 256, (nl, c.star.shape[1]), dtype=np.uint8)
+    for k, v in f.items():
+        c.field({"threebb": "threebb_interacted"}.get(k, k))[1:nl + 1] = v
+    if "threebb" not in f:
+        c.field("threebb_interacted")[1:nl + 1] = 0
+    c.bfield("a")[:d["nb"] + 1] = d["bin_a"]
+    c.clus.N_MAX_NEW, c.Start[0], c.End[0] = nl, first, first + nl - 1
+    c.bin_slots_in_use = d["nb"]
+    return c
+
+
+@pytest.mark.parametrize("case,first,nl", [("relax_only", 1, None), ("encounters", 1, None), ("no_relaxation", 1, None), ("threebb_skips", 1, None),
+                                           ("encounters", 5001, 7001), ("large", 1, None)])
+def test_dynamics_apply_pairs_match_oracle(case, first, nl):
+    """SURVEY 8f N3, dynamics_apply's pair loop on the resident arrays (reference cmc_dynamics.c:206-542) against the restatement that is pinned
+    bit for bit against the compiled reference, same three draws per pair: the list of encounter pairs (indices, type) must be the
+    oracle's exactly, Y bit for bit; rperi / W / rcm and the relaxed pairs' new vr, vt, E, J to DYN_TOL (the device's sin / cos / log / pow
+    are not glibc's); the counts of the scattering-angle statistics exactly, their sums to rounding; nothing else in the records changes."""
+    d = cm.dynamics_case(case, first=first, nl=nl)
+    N, nl, cfg = d["N"], d["nl"], d["cfg"]
+    t = ol.tables(d["pot"]["star_r"], d["pot"]["star_m"], d["pot"]["phi"], N, N)
+    dp = ol.dyn_params(**{k: v for k, v in cfg.items() if k in dict(ol.DynParams._fields_)})
+    f0 = {k: v.copy() for k, v in d["f"].items()}
+    want = ol.dynamics_apply_pairs(t, first, d["dt"], dp, d["draws"], f0, d["bin_a"])
+    c = _dyn_cluster(d)
+    c.upload()
+    before = c.star.copy()
+    sw = dict(RELAXATION=cfg["relaxation"], SS_COLLISION=cfg["ss_collision"], BINSINGLE=cfg["binsingle"], BINBIN=cfg["binbin"],
+              TIDAL_CAPTURE=cfg["tidal_capture"], BH_CAPTURE=cfg["bh_capture"], AVEKERNEL=cfg["p"], GAMMA=cfg["gamma"], COLL_FACTOR=cfg["coll_factor"],
+              TC_FACTOR=cfg["tc_factor"], WD_TC=cfg["wd_tc"], units_mstar=cfg["units_mstar"], units_l=cfg["units_l"], units_t=cfg["units_t"],
+              THREEBODYBINARIES=int("threebb" in d["f"]))
+    res = c.dev_dynamics_apply(d["dt"], draws=d["draws"], **sw)
+    c.download()
+    enc = (want["status"] == 1) | (want["status"] == 2)
+    e = res.encounters
+    assert np.array_equal(e["k"], want["pair_k"][enc]) and np.array_equal(e["kp"], want["pair_kp"][enc])
+    assert np.array_equal(e["type"], want["status"][enc])
+    for k in ("rperi", "W", "rcm"):
+        np.testing.assert_allclose(e[k], want[k][enc], rtol=DYN_TOL, atol=0, err_msg=k)
+    cm.assert_bits_equal(c.field("Y")[1:nl + 1], f0["Y"], "Y")
+    vscale = np.sqrt(f0["vr"] ** 2 + f0["vt"] ** 2)
+    for k, scale in (("vr", vscale), ("vt", vscale), ("E", np.abs(f0["E"]) + vscale ** 2), ("J", np.abs(f0["J"]) + 1e-300)):
+        err = np.abs(c.field(k)[1:nl + 1] - f0[k]) / scale
+        assert err.max() <= DYN_TOL, (k, err.max())
+    assert res.Nrel == want["Nrel"] and list(res.Nrelbeta) == list(want["Nrelbeta"])
+    for got, w in ((res.qaverelbeta, want["qave"]), (res.maverelbeta, want["mave"]), (res.raverelbeta, want["rave"])):
+        np.testing.assert_allclose(np.array(got[:]), w, rtol=1e-11)
+    if case in ("encounters", "large"):
+        assert (e["type"] == 1).sum() > 10 and (e["type"] == 2).sum() > 10
+    if cfg["relaxation"]:
+        assert res.Nrel > 0 and np.any(c.field("vr")[1:nl + 1] != d["f"]["vr"])
+    _only_these_fields_changed(before, c, nl, ("vr", "vt", "E", "J", "Y"))
+    c.close()
+
+
+def test_dynamics_apply_philox_mode_is_statistically_the_reference():
+    """production mode (no draw array): Philox draws keyed by (seed, tcount, star).  The relaxation step conserves each pair's momentum and
+    kinetic energy whatever the angles are, and two runs with the same seed are identical while another seed differs."""
+    d = cm.dynamics_case("relax_only")
+    N, nl = d["N"], d["nl"]
+    outs = []
+    for seed in (5, 5, 6):
+        c = _dyn_cluster(d)
+        c.upload()
+        res = c.dev_dynamics_apply(d["dt"], seed=seed)
+        c.download()
+        outs.append((c.field("vr")[1:nl + 1].copy(), c.field("vt")[1:nl + 1].copy(), c.field("Y")[1:nl + 1].copy()))
+        assert res.Nrel == nl // 2 and res.n_encounters == 0
+        c.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert not np.array_equal(outs[0][0], outs[2][0])
+    vr, vt, Y = outs[0]
+    m = d["sm"][:nl]
+    npair = nl // 2
+    ke0 = (m * (d["f"]["vr"] ** 2 + d["f"]["vt"] ** 2))[:2 * npair].reshape(-1, 2).sum(1)
+    ke1 = (m * (vr ** 2 + vt ** 2))[:2 * npair].reshape(-1, 2).sum(1)
+    np.testing.assert_allclose(ke1, ke0, rtol=1e-12)                       # elastic scattering in the pair's centre-of-mass frame
+    pr0 = (m * d["f"]["vr"])[:2 * npair].reshape(-1, 2).sum(1)
+    pr1 = (m * vr)[:2 * npair].reshape(-1, 2).sum(1)
+    np.testing.assert_allclose(pr1, pr0, rtol=0, atol=1e-12 * np.abs(m * np.hypot(d["f"]["vr"], d["f"]["vt"])).max())
+    assert 0.45 < Y[::2][:npair].mean() < 0.55 and Y.min() >= 0.0 and Y.max() < 1.0

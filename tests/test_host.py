@@ -11,6 +11,7 @@ import pytest
 import common as cm
 import oraclelib as ol
 import refharness as rh
+import hostemul as he
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST_EMUL = os.path.join(ROOT, "tests", "host_emul")
@@ -324,3 +325,25 @@ def test_sample_ladder_where_find_root_vr_fires():
     assert np.array_equal(got["kmin"][ok], want["kmin"][ok]) and np.array_equal(got["kmax"][ok], want["kmax"][ok])
     for k in ("rnew", "vrnew", "vtnew"):
         cm.assert_bits_equal(got[k], want[k], k)
+
+
+@pytest.mark.parametrize("case,first,nl", [("relax_only", 1, None), ("encounters", 1, None), ("no_relaxation", 1, None), ("encounters", 5001, 7001)])
+def test_dynamics_pair_core_equals_oracle(case, first, nl):
+    """csrc/dynamics_core.h (the per-pair code of dynamics.cu's kernel) built for the host, where sin / cos / log / pow are glibc's, against
+    the oracle's restatement of dynamics_apply's pair loop: bit for bit, incl. a shard that starts in the middle of the cluster"""
+    d = cm.dynamics_case(case, first=first, nl=nl)
+    N = d["N"]
+    sr, sm, phi = d["pot"]["star_r"], d["pot"]["star_m"], d["pot"]["phi"]
+    t = ol.tables(sr, sm, phi, N, N)
+    dp = ol.dyn_params(**{k: v for k, v in d["cfg"].items() if k in dict(ol.DynParams._fields_)})
+    f0 = {k: v.copy() for k, v in d["f"].items()}
+    want = ol.dynamics_apply_pairs(t, first, d["dt"], dp, d["draws"], f0, d["bin_a"])
+    f1 = {k: v.copy() for k, v in d["f"].items()}
+    got = he.dynamics_pairs(sr, sm, phi, N, N, first, d["dt"], d["cfg"], d["draws"], f1, d["bin_a"])
+    for k in ("vr", "vt", "E", "J", "Y"):
+        cm.assert_bits_equal(f1[k], f0[k], k)
+    assert np.array_equal(got["status"], want["status"])
+    for k in ("rperi", "W", "rcm"):
+        cm.assert_bits_equal(got[k], want[k], k)
+    if case == "encounters":
+        assert (want["status"] == 1).sum() > 10 and (want["status"] == 2).sum() > 10
