@@ -272,7 +272,7 @@ extern "C" int cmcb200_dev_dynamics_apply(cmcb200_ctx *c, const cmcb200_dynamics
 		s = new DynScratch();
 		memset(s, 0, sizeof *s);
 		const long n = c->n_star_dim, n_pairs = n / 2 + 1;
-		s->w.enc_cap = n_pairs / 4 + 1024;
+		s->w.enc_cap = n_pairs; // every pair may be an encounter (40 bytes per pair)
 		CMCB_CUDA_OK(cudaMalloc(&s->w.list, (size_t) n * sizeof(unsigned)));
 		CMCB_CUDA_OK(cudaMalloc(&s->w.blk_cnt, (size_t) (n / DYN_SCAN_BLOCK + 2) * sizeof(unsigned)));
 		CMCB_CUDA_OK(cudaMalloc(&s->w.n_list, sizeof(unsigned)));
