@@ -1,0 +1,213 @@
+// calc_sigma_r's two running window sums (reference src/cmc/cmc_dynamics_helper.c:2821-2975) evaluated in parallel with the reference's
+// own bits.  Shared by sigma.cu and its host build (tests/host_emul/sigma_host.cpp).
+//
+// The reference keeps  y <- fl(fl(y - a_leave) + a_enter)  per star: a chain of 2N separately rounded operations whose value hovers around
+// 2p terms, so it crosses a binade boundary on ~5 % of its operations -- far too often for the event list of exactsum.h / seqscan.cuh, and
+// its rounding drift (up to N 2^-53 relative against a freshly summed window) rules out anything but an exact replay.
+//
+// What makes a replay parallel: a rounding to nearest-even onto the grid u commutes with a translation by a multiple of 2u.  So if along a
+// stretch of operations the binade of every intermediate value is KNOWN (from an approximate value with a rigorous error band that does
+// not straddle a power of two), the stretch's map F: y_in -> y_out satisfies F(y + m P) = F(y) + m P for P = 2 ulp(highest binade visited):
+// F is fixed by its values on the K' = P / ulp(y_in) residues of y_in's mantissa, i.e. by a TABLE indexed with the low log2 K' mantissa
+// bits of y_in.  Going down in binade costs nothing; every binade the stretch climbs above y_in's doubles the table.
+//   segment  S = 8 stars (16 operations), one thread: approximate trajectory from a freshly summed window, classification, and the table
+//            by running the <= 8 candidates through the operations with the hardware's own adds;
+//   tile     256 segments, one CTA: a table of <= 32 entries by walking the candidates through the segment tables;
+//   chain    one thread walks the tile tables in order (one dependent lookup per 2048 stars) and leaves every tile's exact y_in;
+//   finish   each tile walks its segment tables from the exact y_in, each thread replays its 16 operations and stores the outputs.
+// Where the band straddles a power of two ("hard": ~1 operation in 10^8 at N = 10^7) the segment is replayed operation by operation by
+// whoever walks over it, and the tile has no table: the chain walker goes through its segments.  A stretch that climbs more binades than
+// the table sizes allow is replayed the same way.
+//
+// The band: the reference's value differs from the exactly summed window by its accumulated rounding, <= sum over all earlier operations
+// of 2^-53 |y|; D = 2 sum_stars (y~(si-1) + y~(si)) over the approximate values bounds twice that sum, and delta = 2^-52 D another factor
+// two -- valid as long as the true value stays within a factor 2 of the approximate one, which delta <= y~/4 guarantees inductively
+// (otherwise: `broken`, the whole chain is replayed by one thread).
+#pragma once
+#include "fp64_exact.h"
+#include "sigma_core.h"
+
+namespace cmcb {
+
+constexpr int SIG_S = 8;
+constexpr int SIG_THREADS = 256;
+constexpr int SIG_TILE = SIG_S * SIG_THREADS;
+constexpr int SIG_KS_LOG_MAX = 3;
+constexpr int SIG_KT_LOG_MAX = 5;
+constexpr int SIG_KS_MAX = 1 << SIG_KS_LOG_MAX;
+constexpr int SIG_KT_MAX = 1 << SIG_KT_LOG_MAX;
+
+enum { SIG_TABLE = 0, SIG_SEQ = 1, SIG_HARD = 2 };
+
+struct SigSeg {
+	double base;              // candidate 0: the approximate y_in with its low logk mantissa bits cleared
+	double yout[SIG_KS_MAX];
+	int e_in, logk, flag, emax;
+};
+
+struct SigTile {
+	double base;
+	double yout[SIG_KT_MAX];
+	int e_in, logk, flag, pad;
+};
+
+// terms of one chain as the loop sees them: local index k = 1 - p .. n + p at [k + p - 1]
+struct SigTerms {
+	const double *t;
+	long p;
+	CMCB_HD double at(long k) const { return t[k + p - 1]; }
+};
+
+CMCB_HD int sig_expo(double y) { return (int) (dbits(y) >> 52); } // sign included: a negative value never matches a positive one's
+
+// the operations of stars si0 .. si0 + cnt - 1 (si0 >= 2): sub[i] / add[i] = the terms leaving / entering at star si0 + i (0 where the
+// window does not move, src/cmc/cmc_dynamics_helper.c:2923-2931)
+CMCB_HD void sig_segment_terms(const SigmaWindow &w, const SigTerms &T, long si0, int cnt, double *sub, double *add)
+{
+	long prev = w.simin(si0 - 1);
+	for (int i = 0; i < SIG_S; i++) {
+		sub[i] = 0.0;
+		add[i] = 0.0;
+		if (i < cnt) {
+			const long cur = w.simin(si0 + i);
+			if (cur != prev) { sub[i] = T.at(prev); add[i] = T.at(cur + (2 * w.p - 1)); }
+			prev = cur;
+		}
+	}
+}
+
+// the window of star si summed afresh in index order: the approximate value the bands are centred on
+CMCB_HD double sig_fresh_window(const SigmaWindow &w, const SigTerms &T, long si)
+{
+	const long a = w.simin(si);
+	double s = 0.0;
+	for (long k = a; k <= a + 2 * w.p - 1; k++) s = dadd(s, T.at(k));
+	return s;
+}
+
+// the segment's contribution to D (see the header): 2 (y~(si-1) + y~(si)) per star along the approximate trajectory
+CMCB_HD double sig_segment_dsum(const double *sub, const double *add, int cnt, double y)
+{
+	double t = y, ds = 0.0;
+	for (int i = 0; i < cnt; i++) {
+		const double t2 = dadd(dsub(t, sub[i]), add[i]);
+		ds = dadd(ds, dmul(2.0, dadd(t, t2)));
+		t = t2;
+	}
+	return ds;
+}
+
+CMCB_HD double sig_replay(const double *sub, const double *add, int cnt, double y)
+{
+	for (int i = 0; i < cnt; i++) { y = dsub(y, sub[i]); y = dadd(y, add[i]); }
+	return y;
+}
+
+// One segment: classification and table.  y: approximate value entering the segment; dband: 2^-52 D (the drift bound, absolute);
+// *dsum receives the segment's contribution to D; *broken is raised when the band is no longer small against the value.
+CMCB_HD void sig_build_segment(const double *sub, const double *add, int cnt, double y, double dband, long p, SigSeg *o, double *dsum, int *broken)
+{
+	o->e_in = sig_expo(y);
+	o->flag = SIG_TABLE;
+	double t = y, ymax = y, ymin = y, ds = 0.0;
+	for (int i = 0; i < cnt; i++) {
+		const double t1 = dsub(t, sub[i]), t2 = dadd(t1, add[i]);
+		ds = dadd(ds, dmul(2.0, dadd(t, t2)));
+		ymax = dmax(ymax, dmax(t1, t2));
+		ymin = dmin(ymin, dmin(t1, t2));
+		t = t2;
+	}
+	*dsum = ds;
+	// the local trajectory and the fresh sum commit <= 2p + 2S roundings, the candidates sit within 2^KT_LOG_MAX ulps of the approximate value
+	// twice the drift bound: a candidate sits up to one band away from the true value, whose trajectory sits up to one band away from y~
+	const double delta = dadd(dmul(2.0, dband), dmul(dmul((double) (2 * p + 2 * SIG_S + 2 * SIG_KT_MAX + 16), 2.220446049250313e-16 /* 2^-52 */), ymax));
+	if (!(ymin > 0.0) || !dfinite(ymax) || !(delta <= dmul(0.25, ymin))) {
+		o->flag = SIG_HARD;
+		if (broken && !(delta <= dmul(0.25, ymin))) *broken = 1;
+	}
+	int emax = o->e_in;
+	if (o->flag != SIG_HARD) {
+		t = y;
+		if (sig_expo(dsub(t, delta)) != o->e_in || sig_expo(dadd(t, delta)) != o->e_in || o->e_in < 64) o->flag = SIG_HARD;
+		for (int i = 0; i < cnt; i++) {
+			const double t1 = dsub(t, sub[i]), t2 = dadd(t1, add[i]);
+			const int e1 = sig_expo(t1), e2 = sig_expo(t2);
+			if (sig_expo(dsub(t1, delta)) != e1 || sig_expo(dadd(t1, delta)) != e1 || sig_expo(dsub(t2, delta)) != e2 || sig_expo(dadd(t2, delta)) != e2 ||
+			    e1 < 64 || e2 < 64)
+				o->flag = SIG_HARD;
+			emax = e1 > emax ? e1 : emax;
+			emax = e2 > emax ? e2 : emax;
+			t = t2;
+		}
+	}
+	o->emax = emax;
+	o->logk = emax - o->e_in + 1;
+	o->base = y;
+	if (o->flag == SIG_HARD) return;
+	if (o->logk > SIG_KS_LOG_MAX) { o->flag = SIG_SEQ; return; }
+	const uint64_t K = 1ull << o->logk, b0 = dbits(y) & ~(K - 1);
+	o->base = dfrombits(b0);
+	double c[SIG_KS_MAX];
+	for (int r = 0; r < SIG_KS_MAX; r++) c[r] = dfrombits(b0 | (uint64_t) (r & (int) (K - 1)));
+	t = y;
+	int mism = 0;
+	for (int i = 0; i < cnt; i++) {
+		const double t1 = dsub(t, sub[i]), t2 = dadd(t1, add[i]);
+		const int e1 = sig_expo(t1), e2 = sig_expo(t2);
+		for (int r = 0; r < SIG_KS_MAX; r++) {
+			const double c1 = dsub(c[r], sub[i]);
+			c[r] = dadd(c1, add[i]);
+			mism |= (sig_expo(c1) ^ e1) | (sig_expo(c[r]) ^ e2);
+		}
+		t = t2;
+	}
+	if (mism) { o->flag = SIG_HARD; return; } // cannot happen while the band is rigorous; the replay is always right
+	for (int r = 0; r < SIG_KS_MAX; r++) o->yout[r] = c[r];
+}
+
+// the segment applied to the exact (or a candidate) value y
+CMCB_HD double sig_apply_segment(const SigSeg &s, const double *sub, const double *add, int cnt, double y, int *inconsistent)
+{
+	if (s.flag == SIG_TABLE) {
+		if (sig_expo(y) == s.e_in) {
+			const uint64_t idx = dbits(y) & ((1ull << s.logk) - 1);
+			const double yc = dfrombits(dbits(s.base) | idx);
+			return dadd(s.yout[idx], dsub(y, yc));
+		}
+		if (inconsistent) *inconsistent = 1;
+	}
+	return sig_replay(sub, add, cnt, y);
+}
+
+CMCB_HD double sig_apply_tile_table(const SigTile &t, double y, int *inconsistent)
+{
+	if (sig_expo(y) != t.e_in) { if (inconsistent) *inconsistent = 1; }
+	const uint64_t idx = dbits(y) & ((1ull << t.logk) - 1);
+	const double yc = dfrombits(dbits(t.base) | idx);
+	return dadd(t.yout[idx], dsub(y, yc));
+}
+
+// tile header from its segments (the entries are filled by the candidates' walks): HARD when a segment is, or when the tile climbs more
+// binades above its y_in than the table holds
+CMCB_HD void sig_tile_header(const SigSeg *seg, int nseg, SigTile *t)
+{
+	int emax = seg[0].e_in, hard = 0;
+	for (int s = 0; s < nseg; s++) {
+		emax = seg[s].emax > emax ? seg[s].emax : emax;
+		hard |= seg[s].flag == SIG_HARD;
+	}
+	t->e_in = seg[0].e_in;
+	t->logk = emax - seg[0].e_in + 1;
+	t->flag = (hard || t->logk > SIG_KT_LOG_MAX) ? SIG_HARD : SIG_TABLE;
+	t->pad = 0;
+	const uint64_t K = 1ull << (t->logk > SIG_KT_LOG_MAX ? SIG_KT_LOG_MAX : t->logk);
+	// seg[0].base is the approximate y_in with fewer low bits cleared (or none): clear the tile's
+	t->base = dfrombits(dbits(seg[0].base) & ~(K - 1));
+}
+
+CMCB_HD double sig_tile_candidate(const SigTile &t, int r) { return dfrombits(dbits(t.base) | (uint64_t) r); }
+
+// number of tiles of a rank with n local stars: stars 2 .. n in tiles of SIG_TILE
+CMCB_HD long sig_num_tiles(long n) { return n >= 2 ? (n - 1 + SIG_TILE - 1) / SIG_TILE : 0; }
+
+} // namespace cmcb

@@ -1,1 +1,149 @@
-// placeholder
+// TEST-ONLY host build of cmc_cosmic_b200/csrc/sigma_scan.h: the four device passes of sigma.cu run as plain loops over tiles and segments,
+// calling the same per-segment / per-tile code, so that the decomposition can be checked against the oracle without a GPU.
+#include <math.h>
+#include <vector>
+#include "../../cmc_cosmic_b200/csrc/sigma_scan.h"
+
+using namespace cmcb;
+
+namespace {
+
+struct Chain {
+	std::vector<double> term; // [n + 2p]
+	std::vector<double> tileD, dband;
+	std::vector<SigTile> tile;
+	std::vector<double> yin;  // exact value entering each tile
+	std::vector<double> y;    // exact value at every star [n + 1]
+};
+
+void build_segments(const SigmaWindow &w, const SigTerms &T, long tile, double dband, std::vector<SigSeg> &seg, int *nseg, int *broken, double *dsum_out)
+{
+	const long s_first = 2 + tile * SIG_TILE, s_end = s_first + SIG_TILE < w.n + 1 ? s_first + SIG_TILE : w.n + 1;
+	*nseg = 0;
+	double dsum = 0.0;
+	for (long s0 = s_first; s0 < s_end; s0 += SIG_S) {
+		const int cnt = (int) (s0 + SIG_S <= s_end ? SIG_S : s_end - s0);
+		double sub[SIG_S], add[SIG_S], ds;
+		sig_segment_terms(w, T, s0, cnt, sub, add);
+		const double y = sig_fresh_window(w, T, s0 - 1);
+		sig_build_segment(sub, add, cnt, y, dband, w.p, &seg[*nseg], &ds, broken);
+		dsum += ds;
+		(*nseg)++;
+	}
+	if (dsum_out) *dsum_out = dsum;
+}
+
+double walk_segments(const SigmaWindow &w, const SigTerms &T, long tile, const std::vector<SigSeg> &seg, int nseg, double y, double *seg_yin, int *inconsistent)
+{
+	const long s_first = 2 + tile * SIG_TILE, s_end = s_first + SIG_TILE < w.n + 1 ? s_first + SIG_TILE : w.n + 1;
+	for (int s = 0; s < nseg; s++) {
+		const long s0 = s_first + (long) s * SIG_S;
+		const int cnt = (int) (s0 + SIG_S <= s_end ? SIG_S : s_end - s0);
+		if (seg_yin) seg_yin[s] = y;
+		double sub[SIG_S], add[SIG_S];
+		sig_segment_terms(w, T, s0, cnt, sub, add);
+		y = sig_apply_segment(seg[s], sub, add, cnt, y, inconsistent);
+	}
+	return y;
+}
+
+} // namespace
+
+// vr, vt: local stars and ghosts, local index k = 1 - p .. n + p at [k + p - 1].  counters: [0] hard segments, [1] wide (replayed) segments,
+// [2] hard tiles, [3] broken, [4] inconsistent, [5] tiles.  band_scale inflates the drift bound (test hook: forces hard segments).
+extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, const double *star_r, const double *star_m, double madhoc, const double *vr,
+			       const double *vt, int mave, double band_scale, double *out_a, double *out_sigma, long *counters)
+{
+	SigmaWindow w;
+	w.p = p; w.n = n; w.first_global = first_global; w.N_MAX = N_MAX; w.first_rank = first_global == 1;
+	for (int i = 0; i < 6; i++) counters[i] = 0;
+	if (!w.valid()) return -1;
+	Chain ch[2];
+	for (int c = 0; c < 2; c++) ch[c].term.assign(n + 2 * p, 0.0);
+	for (long k = 1 - p; k <= n + p; k++) {
+		const long g = first_global + k - 1;
+		if (g < 1 || g > N_MAX) continue;
+		sigma_terms(star_m[g], madhoc, vr[k + p - 1], vt[k + p - 1], &ch[0].term[k + p - 1], &ch[1].term[k + p - 1]);
+	}
+	const long ntiles = sig_num_tiles(n);
+	counters[5] = ntiles;
+	std::vector<SigSeg> seg(SIG_THREADS);
+	int broken = 0, inconsistent = 0;
+	for (int c = 0; c < 2; c++) {
+		Chain &C = ch[c];
+		SigTerms T{C.term.data(), p};
+		C.tileD.assign(ntiles, 0.0); C.dband.assign(ntiles, 0.0); C.tile.resize(ntiles); C.yin.assign(ntiles + 1, 0.0); C.y.assign(n + 1, 0.0);
+		// pass 1: the tiles' contributions to the drift bound
+		for (long t = 0; t < ntiles; t++) {
+			const long s_first = 2 + t * SIG_TILE, s_end = s_first + SIG_TILE < n + 1 ? s_first + SIG_TILE : n + 1;
+			double d = 0.0;
+			for (long s0 = s_first; s0 < s_end; s0 += SIG_S) {
+				const int cnt = (int) (s0 + SIG_S <= s_end ? SIG_S : s_end - s0);
+				double sub[SIG_S], add[SIG_S];
+				sig_segment_terms(w, T, s0, cnt, sub, add);
+				d += sig_segment_dsum(sub, add, cnt, sig_fresh_window(w, T, s0 - 1));
+			}
+			C.tileD[t] = d;
+		}
+		double D = 4.0 * (double) p * sig_fresh_window(w, T, 1); // the 2p additions that build the first window
+		for (long t = 0; t < ntiles; t++) { D += C.tileD[t]; C.dband[t] = D * 2.220446049250313e-16 * band_scale; }
+		// pass 2: segment tables -> tile tables
+		for (long t = 0; t < ntiles; t++) {
+			int nseg;
+			build_segments(w, T, t, C.dband[t], seg, &nseg, &broken, nullptr);
+			for (int s = 0; s < nseg; s++) { counters[0] += seg[s].flag == SIG_HARD; counters[1] += seg[s].flag == SIG_SEQ; }
+			sig_tile_header(seg.data(), nseg, &C.tile[t]);
+			if (C.tile[t].flag == SIG_TABLE)
+				for (int r = 0; r < (1 << C.tile[t].logk); r++)
+					C.tile[t].yout[r] = walk_segments(w, T, t, seg, nseg, sig_tile_candidate(C.tile[t], r), nullptr, &inconsistent);
+			else counters[2]++;
+		}
+	}
+	counters[3] = broken;
+	for (int c = 0; c < 2; c++) {
+		Chain &C = ch[c];
+		SigTerms T{C.term.data(), p};
+		// pass 3: the chain walker
+		double y = 0.0;
+		for (long j = 0; j < 2 * p; j++) { long k; int sg; w.op(j, &k, &sg); y = dadd(y, T.at(k)); }
+		C.y[1] = y;
+		if (broken) { // one thread replays everything
+			for (long si = 2; si <= n; si++) {
+				const long a = w.simin(si - 1), b = w.simin(si);
+				if (a != b) { y = dsub(y, T.at(a)); y = dadd(y, T.at(b + 2 * p - 1)); }
+				C.y[si] = y;
+			}
+			continue;
+		}
+		for (long t = 0; t < ntiles; t++) {
+			C.yin[t] = y;
+			if (C.tile[t].flag == SIG_TABLE) y = sig_apply_tile_table(C.tile[t], y, &inconsistent);
+			else {
+				int nseg;
+				build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr, nullptr);
+				y = walk_segments(w, T, t, seg, nseg, y, nullptr, &inconsistent);
+			}
+		}
+		// pass 4: every tile from its exact y_in
+		std::vector<double> seg_yin(SIG_THREADS);
+		for (long t = 0; t < ntiles; t++) {
+			int nseg;
+			build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr, nullptr);
+			walk_segments(w, T, t, seg, nseg, C.yin[t], seg_yin.data(), &inconsistent);
+			const long s_first = 2 + t * SIG_TILE, s_end = s_first + SIG_TILE < n + 1 ? s_first + SIG_TILE : n + 1;
+			for (int s = 0; s < nseg; s++) {
+				const long s0 = s_first + (long) s * SIG_S;
+				const int cnt = (int) (s0 + SIG_S <= s_end ? SIG_S : s_end - s0);
+				double sub[SIG_S], add[SIG_S], yy = seg_yin[s];
+				sig_segment_terms(w, T, s0, cnt, sub, add);
+				for (int i = 0; i < cnt; i++) { yy = dsub(yy, sub[i]); yy = dadd(yy, add[i]); C.y[s0 + i] = yy; }
+			}
+		}
+	}
+	counters[4] = inconsistent;
+	for (long si = 1; si <= n; si++) {
+		out_a[si] = mave ? ch[1].y[si] / 2. / p : star_r[first_global + si - 1];
+		out_sigma[si] = sqrt(ch[0].y[si] / ch[1].y[si]);
+	}
+	return 0;
+}

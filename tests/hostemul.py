@@ -43,6 +43,8 @@ def lib():
         L.emul_set_velocities3_second.argtypes = [vp, lg, lg, lg, vp, db, vp, vp, vp, vp]
         L.emul_calc_sigma_r.restype = C.c_int
         L.emul_calc_sigma_r.argtypes = [lg, lg, lg, lg, vp, vp, db, vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        L.emul_sigma_scan.restype = C.c_int
+        L.emul_sigma_scan.argtypes = [lg, lg, lg, lg, vp, vp, db, vp, vp, C.c_int, db, vp, vp, vp]
         L.emul_dynamics_pairs.restype = lg
         L.emul_dynamics_pairs.argtypes = [vp, vp, vp, lg, lg, lg, lg, db] + [vp] * 17
         _lib = L
@@ -142,3 +144,24 @@ def dynamics_pairs(sr, sm, phi, N_MAX, N_STAR, first_global, dt, cfg, draws, f, 
                               _p(f["vt"]), _p(f["E"]), _p(f["J"]), _p(f["Y"]), _p(f["binind"]), _p(f["se_k"]), _p(f["rad"]), _p(bin_a),
                               _p(out["status"]), _p(out["rperi"]), _p(out["W"]), _p(out["rcm"]), _p(out["beta"]))
     return out
+
+
+def sigma_scan(p, star_r, star_m, N_MAX, N_STAR, vr_all, vt_all, first_global=1, n_local=None, mave=False, band_scale=1.0):
+    """calc_sigma_r through the segment / tile tables of csrc/sigma_scan.h, the four passes of sigma.cu as host loops.
+    Returns (r or mean mass, sigma, counters dict); None when the window does not fit the shard."""
+    vr_all, vt_all = np.ascontiguousarray(vr_all, np.float64), np.ascontiguousarray(vt_all, np.float64)
+    lo = first_global - 1
+    n = len(vr_all) - lo if n_local is None else n_local
+    def cut(x):
+        out = np.zeros(n + 2 * p)
+        a, b = lo - p, lo + n + p
+        src = x[max(a, 0):min(b, len(x))]
+        out[max(a, 0) - a:max(a, 0) - a + len(src)] = src
+        return out
+    vr, vt = cut(vr_all), cut(vt_all)
+    a, sg, cnt = np.zeros(n + 1), np.zeros(n + 1), np.zeros(6, np.int64)
+    rc = lib().emul_sigma_scan(p, n, first_global, N_MAX, _p(np.ascontiguousarray(star_r)), _p(np.ascontiguousarray(star_m)), 1.0 / N_STAR, _p(vr), _p(vt),
+                               int(mave), band_scale, _p(a), _p(sg), _p(cnt))
+    if rc != 0:
+        return None
+    return a, sg, dict(zip(("hard_segments", "wide_segments", "hard_tiles", "broken", "inconsistent", "tiles"), cnt.tolist()))

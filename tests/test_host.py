@@ -347,3 +347,38 @@ def test_dynamics_pair_core_equals_oracle(case, first, nl):
         cm.assert_bits_equal(got[k], want[k], k)
     if case == "encounters":
         assert (want["status"] == 1).sum() > 10 and (want["status"] == 2).sum() > 10
+
+
+SIGMA_SCAN_CASES = [
+    # kind, N, masses, p, first, n_local, band_scale
+    ("plummer", 30000, "imf", 20, 1, None, 1.0),
+    ("king", 20000, "equal", 20, 1, None, 1.0),
+    ("plummer", 5000, "imf", 3, 1, None, 1.0),          # BH_AVEKERNEL
+    ("plummer", 200, "imf", 20, 1, None, 1.0),          # less than one tile
+    ("plummer", 60000, "imf", 20, 20001, 20000, 1.0),   # a middle shard: starts from an empty window p stars before its first star
+    ("plummer", 60000, "imf", 20, 40001, 20000, 1.0),   # the last shard: the window stops sliding at the end
+    ("plummer", 60000, "imf", 20, 1, 20000, 1.0),       # the first shard
+    ("plummer", 300000, "imf", 20, 1, None, 1.0),
+    ("plummer", 40000, "imf", 20, 1, None, 3.0e6),      # inflated bands: dozens of hard segments, hard tiles walked segment by segment
+    ("king", 40000, "imf", 20, 1, None, 1.0e12),        # bands wider than the values: `broken`, the whole chain replayed by one thread
+]
+
+
+@pytest.mark.parametrize("kind,N,masses,p,first,nl,band_scale", SIGMA_SCAN_CASES)
+def test_calc_sigma_r_segment_tables_equal_serial_loop(kind, N, masses, p, first, nl, band_scale):
+    """calc_sigma_r as sigma.cu evaluates it (csrc/sigma_scan.h: per-segment tables over the low mantissa bits of the incoming value, tile
+    tables, one serial walk over the tiles, replay) on the host against the oracle's serial loop: both outputs, bit for bit"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + p, masses=masses)
+    sr, smt = cm.make_tables(r, sm)
+    for mave in (False, True):
+        want_a, want_s = ol.calc_sigma_r(p, sr, smt, N, N, vr, vt, first_global=first, n_local=nl, mave=mave)
+        a, sg, cnt = he.sigma_scan(p, sr, smt, N, N, vr, vt, first_global=first, n_local=nl, mave=mave, band_scale=band_scale)
+        cm.assert_bits_equal(a[1:], want_a[1:], "r / mean mass")
+        cm.assert_bits_equal(sg[1:], want_s[1:], "sigma")
+        assert cnt["inconsistent"] == 0
+    if band_scale == 1.0:
+        assert cnt["broken"] == 0 and cnt["hard_segments"] <= 2, cnt
+    elif band_scale < 1e10:
+        assert cnt["broken"] == 0 and cnt["hard_segments"] > 50 and cnt["hard_tiles"] > 10, cnt
+    else:
+        assert cnt["broken"] == 1
