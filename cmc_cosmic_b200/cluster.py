@@ -411,6 +411,26 @@ class Cluster:
         res.encounters = enc
         return res
 
+    def dev_calc_sigma_r(self, p=None, mave=False, ghosts=None, force_sequential=False):
+        """calc_sigma_r (reference src/cmc/cmc_dynamics_helper.c:2821-2975) on the resident arrays, bit for bit.  ghosts (P ranks only):
+        dict prev_vr, prev_vt, next_vr, next_vt of p values each (None on the first / last rank).  Returns (sigma_array.r or the mean mass,
+        sigma_array.sigma), each [n_local + 1] with entry 0 unused, and leaves ``self.sigma_stats``."""
+        p = int(p or self.DYNAMICS["AVEKERNEL"])
+        n = int(self.End[self.myid] - self.Start[self.myid] + 1)
+        prm = _lib.SigmaParams(p, n, int(self.Start[self.myid]), self.clus.N_MAX, self.clus.N_STAR, int(mave), int(force_sequential), None, None, None, None)
+        keep = []
+        for k in ("prev_vr", "prev_vt", "next_vr", "next_vt"):
+            v = (ghosts or {}).get(k)
+            if v is not None:
+                v = np.ascontiguousarray(v, np.float64)
+                assert len(v) == p
+                keep.append(v)
+                setattr(prm, "ghost_" + k, v.ctypes.data)
+        a, sg, st = np.zeros(n + 1), np.zeros(n + 1), np.zeros(6, np.int64)
+        _lib.check(self.L.cmcb200_dev_calc_sigma_r(self.ctx, C.byref(prm), a.ctypes.data, sg.ctypes.data, st.ctypes.data), "dev_calc_sigma_r")
+        self.sigma_stats = dict(zip(("hard_segments", "wide_segments", "hard_tiles", "broken", "rerun", "tiles"), st.tolist()))
+        return a, sg
+
     def dev_qsorts_new(self):
         n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
         _lib.check(self.L.cmcb200_dev_qsorts_new(self.ctx, C.byref(n), max(self.N_b_local, 0), C.byref(nb)), "dev_qsorts_new")

@@ -20,9 +20,11 @@
 // the table sizes allow is replayed the same way.
 //
 // The band: the reference's value differs from the exactly summed window by its accumulated rounding, <= sum over all earlier operations
-// of 2^-53 |y|; D = 2 sum_stars (y~(si-1) + y~(si)) over the approximate values bounds twice that sum, and delta = 2^-52 D another factor
-// two -- valid as long as the true value stays within a factor 2 of the approximate one, which delta <= y~/4 guarantees inductively
-// (otherwise: `broken`, the whole chain is replayed by one thread).
+// of 2^-53 |y|.  Every term sits in at most 2p windows, so the values at the stars so far sum to <= 2p x (the prefix sum of the terms up
+// to the window's end), the values after the subtractions are smaller still, and the 2p additions that build the first window add at most
+// 2p x that prefix: sum |y| <= 6p x prefix.  dband = 2^-52 x 12p x prefix carries a factor 4 on top, which also pays for using the
+// approximate values in the induction (valid while the true value stays within a factor 2 of the approximate one; delta <= y~/4 keeps it
+// there -- otherwise: `broken`, the whole chain is replayed by one thread).
 #pragma once
 #include "fp64_exact.h"
 #include "sigma_core.h"
@@ -33,7 +35,7 @@ constexpr int SIG_S = 8;
 constexpr int SIG_THREADS = 256;
 constexpr int SIG_TILE = SIG_S * SIG_THREADS;
 constexpr int SIG_KS_LOG_MAX = 3;
-constexpr int SIG_KT_LOG_MAX = 5;
+constexpr int SIG_KT_LOG_MAX = 7;
 constexpr int SIG_KS_MAX = 1 << SIG_KS_LOG_MAX;
 constexpr int SIG_KT_MAX = 1 << SIG_KT_LOG_MAX;
 
@@ -45,11 +47,13 @@ struct SigSeg {
 	int e_in, logk, flag, emax;
 };
 
-struct SigTile {
+struct SigTile { // 16-byte multiple: batches are staged with 128-bit copies
 	double base;
 	double yout[SIG_KT_MAX];
 	int e_in, logk, flag, pad;
+	double pad2;
 };
+static_assert(sizeof(SigTile) % 16 == 0, "SigTile is copied in 16-byte words");
 
 // terms of one chain as the loop sees them: local index k = 1 - p .. n + p at [k + p - 1]
 struct SigTerms {
@@ -85,18 +89,6 @@ CMCB_HD double sig_fresh_window(const SigmaWindow &w, const SigTerms &T, long si
 	return s;
 }
 
-// the segment's contribution to D (see the header): 2 (y~(si-1) + y~(si)) per star along the approximate trajectory
-CMCB_HD double sig_segment_dsum(const double *sub, const double *add, int cnt, double y)
-{
-	double t = y, ds = 0.0;
-	for (int i = 0; i < cnt; i++) {
-		const double t2 = dadd(dsub(t, sub[i]), add[i]);
-		ds = dadd(ds, dmul(2.0, dadd(t, t2)));
-		t = t2;
-	}
-	return ds;
-}
-
 CMCB_HD double sig_replay(const double *sub, const double *add, int cnt, double y)
 {
 	for (int i = 0; i < cnt; i++) { y = dsub(y, sub[i]); y = dadd(y, add[i]); }
@@ -104,20 +96,18 @@ CMCB_HD double sig_replay(const double *sub, const double *add, int cnt, double 
 }
 
 // One segment: classification and table.  y: approximate value entering the segment; dband: 2^-52 D (the drift bound, absolute);
-// *dsum receives the segment's contribution to D; *broken is raised when the band is no longer small against the value.
-CMCB_HD void sig_build_segment(const double *sub, const double *add, int cnt, double y, double dband, long p, SigSeg *o, double *dsum, int *broken)
+// *broken is raised when the band is no longer small against the value.
+CMCB_HD void sig_build_segment(const double *sub, const double *add, int cnt, double y, double dband, long p, SigSeg *o, int *broken)
 {
 	o->e_in = sig_expo(y);
 	o->flag = SIG_TABLE;
-	double t = y, ymax = y, ymin = y, ds = 0.0;
+	double t = y, ymax = y, ymin = y;
 	for (int i = 0; i < cnt; i++) {
 		const double t1 = dsub(t, sub[i]), t2 = dadd(t1, add[i]);
-		ds = dadd(ds, dmul(2.0, dadd(t, t2)));
 		ymax = dmax(ymax, dmax(t1, t2));
 		ymin = dmin(ymin, dmin(t1, t2));
 		t = t2;
 	}
-	*dsum = ds;
 	// the local trajectory and the fresh sum commit <= 2p + 2S roundings, the candidates sit within 2^KT_LOG_MAX ulps of the approximate value
 	// twice the drift bound: a candidate sits up to one band away from the true value, whose trajectory sits up to one band away from y~
 	const double delta = dadd(dmul(2.0, dband), dmul(dmul((double) (2 * p + 2 * SIG_S + 2 * SIG_KT_MAX + 16), 2.220446049250313e-16 /* 2^-52 */), ymax));
@@ -206,6 +196,14 @@ CMCB_HD void sig_tile_header(const SigSeg *seg, int nseg, SigTile *t)
 }
 
 CMCB_HD double sig_tile_candidate(const SigTile &t, int r) { return dfrombits(dbits(t.base) | (uint64_t) r); }
+
+// the drift bound of tile t from the inclusive prefix sums of the terms over blocks of SIG_TILE entries (index q = k + p - 1): the tile's
+// last window ends inside block t + 1
+CMCB_HD double sig_dband(const double *block_prefix_incl, long n_blocks, long tile, long p)
+{
+	const long b = tile + 1 < n_blocks ? tile + 1 : n_blocks - 1;
+	return dmul(dmul(2.220446049250313e-16 /* 2^-52 */, (double) (12 * p)), block_prefix_incl[b]);
+}
 
 // number of tiles of a rank with n local stars: stars 2 .. n in tiles of SIG_TILE
 CMCB_HD long sig_num_tiles(long n) { return n >= 2 ? (n - 1 + SIG_TILE - 1) / SIG_TILE : 0; }

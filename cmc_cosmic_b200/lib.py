@@ -38,6 +38,11 @@ class DynamicsParams(C.Structure):
                [("draws", C.c_void_p), ("seed", C.c_ulonglong), ("tcount", C.c_ulonglong)]
 
 
+class SigmaParams(C.Structure):
+    _fields_ = [(k, C.c_long) for k in ("p", "n_local", "first_global", "N_MAX", "N_STAR")] + [("r_0_mave_1", C.c_int), ("force_sequential", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("ghost_prev_vr", "ghost_prev_vt", "ghost_next_vr", "ghost_next_vt")]
+
+
 class DynamicsResult(C.Structure):
     _fields_ = [("n_pairs", C.c_long), ("n_encounters", C.c_long), ("Nrel", C.c_long), ("Nrelbeta", C.c_long * 4),
                 ("qaverelbeta", C.c_double * 4), ("maverelbeta", C.c_double * 4), ("raverelbeta", C.c_double * 4)]
@@ -60,7 +65,7 @@ EXPORTS = [
     "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass", "cmcb200_dev_energy_new_radii",
     "cmcb200_dev_potential", "cmcb200_dev_tidally_strip_select", "cmcb200_dev_compute_energy_totals",
     "cmcb200_shard_step_async", "cmcb200_shard_step_result", "cmcb200_dev_new_orbits_async", "cmcb200_dev_orbit_result", "cmcb200_resident_begin", "cmcb200_resident_begin_sharded", "cmcb200_resident_end", "cmcb200_dev_get", "cmcb200_dev_put", "cmcb200_dev_comp_multi_mass_percent",
-    "cmcb200_dev_dynamics_apply", "cmcb200_dev_dynamics_encounters",
+    "cmcb200_dev_dynamics_apply", "cmcb200_dev_dynamics_encounters", "cmcb200_dev_calc_sigma_r", "cmcb200_dev_sigma_arrays",
 ]
 
 
@@ -132,6 +137,8 @@ def load():
     L.cmcb200_dev_comp_multi_mass_percent.argtypes = [vp, lg, vp, lg, dbl, vp, lg, vp]
     L.cmcb200_dev_dynamics_apply.argtypes = [vp, C.POINTER(DynamicsParams), C.POINTER(DynamicsResult)]
     L.cmcb200_dev_dynamics_encounters.argtypes = [vp, lg, vp, vp, vp, vp, vp, vp, pl]
+    L.cmcb200_dev_calc_sigma_r.argtypes = [vp, C.POINTER(SigmaParams), vp, vp, vp]
+    L.cmcb200_dev_sigma_arrays.argtypes = [vp, vp, vp]
     L.cmcb200_dev_get.argtypes = [vp, vp, lg, vp, lg]
     L.cmcb200_dev_put.argtypes = [vp, vp, lg, vp, lg, vp, lg]
     L.cmcb200_resident_begin_sharded.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg, C.c_ulonglong, lg, lg]

@@ -329,6 +329,29 @@ int cmcb200_dev_dynamics_apply(cmcb200_ctx *ctx, const cmcb200_dynamics_params *
  * 2 with a binary) and what the reference hands to sscollision_do / binint_do (rperi, W, rcm).  More than cap pairs: -3, *count set. */
 int cmcb200_dev_dynamics_encounters(cmcb200_ctx *ctx, long cap, long *k, long *kp, int *type, double *rperi, double *W, double *rcm, long *count);
 
+/* ---- calc_sigma_r (src/cmc/cmc_dynamics_helper.c:2821-2975) on the resident arrays -------------------------------------- */
+/* sigma = sqrt(sum m v^2 / sum m) over the window of 2p stars around every local star, from the reference's two running sums: each star
+ * subtracts the star that left the window and adds the one that entered, every operation rounded on its own, so the values carry the
+ * rounding history of the whole rank -- reproduced BIT FOR BIT (csrc/sigma_scan.h).  sig_r_or_mave / sig_sigma (host, [n_local + 1], entry
+ * 0 untouched; either may be NULL): sigma_array.r / .sigma of dynamics_apply (cmc_dynamics.c:37; r_0_mave_1 == 0) or the mean mass and sigma
+ * of the three-body loop (:94; r_0_mave_1 == 1).  The results also stay on the device (cmcb200_dev_sigma_arrays).
+ * On P ranks every rank starts from an empty window p stars before its first star, like the reference: ghost_prev_* = vr / vt of the last p
+ * stars of the previous rank, ghost_next_* of the first p of the next (host arrays of p doubles; NULL on the first / last rank) -- the
+ * MPI_Send / MPI_Recv pair of :2862-2900 is the caller's.
+ * stats (may be NULL): [0] segments replayed because a band straddled a binade boundary, [1] segments replayed because they climb too many
+ * binades, [2] tiles walked segment by segment, [3] band broken (whole chain replayed by one thread), [4] rerun sequentially, [5] tiles. */
+typedef struct {
+	long p;             /* AVEKERNEL / BH_AVEKERNEL */
+	long n_local;       /* N_LIMIT: mpiEnd - mpiBegin + 1 */
+	long first_global;  /* Start[myid] */
+	long N_MAX, N_STAR;
+	int r_0_mave_1;
+	int force_sequential; /* != 0: one thread replays the loop (diagnostic) */
+	const double *ghost_prev_vr, *ghost_prev_vt, *ghost_next_vr, *ghost_next_vt;
+} cmcb200_sigma_params;
+int cmcb200_dev_calc_sigma_r(cmcb200_ctx *ctx, const cmcb200_sigma_params *p, double *sig_r_or_mave, double *sig_sigma, long stats[6]);
+int cmcb200_dev_sigma_arrays(cmcb200_ctx *ctx, const double **sig_r_or_mave, const double **sig_sigma);
+
 /* ---- radius-sharded operation: one rank per GPU of an NVLink node ---------------------------------------------------------------- */
 /* Replaces sample_sort + load_balance + post_sort_comm (src/cmc/cmc_sort.c:375-791, src/cmc/cmc_utils.c:2259-2288) for procs > 1.
  * The star array is sharded by radius rank exactly like the reference's MPI partition (findLimits), every rank keeps the full

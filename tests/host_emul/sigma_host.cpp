@@ -10,27 +10,24 @@ namespace {
 
 struct Chain {
 	std::vector<double> term; // [n + 2p]
-	std::vector<double> tileD, dband;
+	std::vector<double> dband;
 	std::vector<SigTile> tile;
 	std::vector<double> yin;  // exact value entering each tile
 	std::vector<double> y;    // exact value at every star [n + 1]
 };
 
-void build_segments(const SigmaWindow &w, const SigTerms &T, long tile, double dband, std::vector<SigSeg> &seg, int *nseg, int *broken, double *dsum_out)
+void build_segments(const SigmaWindow &w, const SigTerms &T, long tile, double dband, std::vector<SigSeg> &seg, int *nseg, int *broken)
 {
 	const long s_first = 2 + tile * SIG_TILE, s_end = s_first + SIG_TILE < w.n + 1 ? s_first + SIG_TILE : w.n + 1;
 	*nseg = 0;
-	double dsum = 0.0;
 	for (long s0 = s_first; s0 < s_end; s0 += SIG_S) {
 		const int cnt = (int) (s0 + SIG_S <= s_end ? SIG_S : s_end - s0);
-		double sub[SIG_S], add[SIG_S], ds;
+		double sub[SIG_S], add[SIG_S];
 		sig_segment_terms(w, T, s0, cnt, sub, add);
 		const double y = sig_fresh_window(w, T, s0 - 1);
-		sig_build_segment(sub, add, cnt, y, dband, w.p, &seg[*nseg], &ds, broken);
-		dsum += ds;
+		sig_build_segment(sub, add, cnt, y, dband, w.p, &seg[*nseg], broken);
 		(*nseg)++;
 	}
-	if (dsum_out) *dsum_out = dsum;
 }
 
 double walk_segments(const SigmaWindow &w, const SigTerms &T, long tile, const std::vector<SigSeg> &seg, int nseg, double y, double *seg_yin, int *inconsistent)
@@ -72,25 +69,20 @@ extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, co
 	for (int c = 0; c < 2; c++) {
 		Chain &C = ch[c];
 		SigTerms T{C.term.data(), p};
-		C.tileD.assign(ntiles, 0.0); C.dband.assign(ntiles, 0.0); C.tile.resize(ntiles); C.yin.assign(ntiles + 1, 0.0); C.y.assign(n + 1, 0.0);
-		// pass 1: the tiles' contributions to the drift bound
-		for (long t = 0; t < ntiles; t++) {
-			const long s_first = 2 + t * SIG_TILE, s_end = s_first + SIG_TILE < n + 1 ? s_first + SIG_TILE : n + 1;
-			double d = 0.0;
-			for (long s0 = s_first; s0 < s_end; s0 += SIG_S) {
-				const int cnt = (int) (s0 + SIG_S <= s_end ? SIG_S : s_end - s0);
-				double sub[SIG_S], add[SIG_S];
-				sig_segment_terms(w, T, s0, cnt, sub, add);
-				d += sig_segment_dsum(sub, add, cnt, sig_fresh_window(w, T, s0 - 1));
-			}
-			C.tileD[t] = d;
+		C.dband.assign(ntiles, 0.0); C.tile.resize(ntiles); C.yin.assign(ntiles + 1, 0.0); C.y.assign(n + 1, 0.0);
+		// pass 1: prefix sums of the terms over blocks of SIG_TILE entries -> the tiles' drift bounds
+		const long nq = n + 2 * p, nblk = (nq + SIG_TILE - 1) / SIG_TILE;
+		std::vector<double> pre(nblk);
+		double acc = 0.0;
+		for (long b = 0; b < nblk; b++) {
+			for (long q = b * SIG_TILE; q < nq && q < (b + 1) * SIG_TILE; q++) acc += C.term[q];
+			pre[b] = acc;
 		}
-		double D = 4.0 * (double) p * sig_fresh_window(w, T, 1); // the 2p additions that build the first window
-		for (long t = 0; t < ntiles; t++) { D += C.tileD[t]; C.dband[t] = D * 2.220446049250313e-16 * band_scale; }
+		for (long t = 0; t < ntiles; t++) C.dband[t] = sig_dband(pre.data(), nblk, t, p) * band_scale;
 		// pass 2: segment tables -> tile tables
 		for (long t = 0; t < ntiles; t++) {
 			int nseg;
-			build_segments(w, T, t, C.dband[t], seg, &nseg, &broken, nullptr);
+			build_segments(w, T, t, C.dband[t], seg, &nseg, &broken);
 			for (int s = 0; s < nseg; s++) { counters[0] += seg[s].flag == SIG_HARD; counters[1] += seg[s].flag == SIG_SEQ; }
 			sig_tile_header(seg.data(), nseg, &C.tile[t]);
 			if (C.tile[t].flag == SIG_TABLE)
@@ -120,7 +112,7 @@ extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, co
 			if (C.tile[t].flag == SIG_TABLE) y = sig_apply_tile_table(C.tile[t], y, &inconsistent);
 			else {
 				int nseg;
-				build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr, nullptr);
+				build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr);
 				y = walk_segments(w, T, t, seg, nseg, y, nullptr, &inconsistent);
 			}
 		}
@@ -128,7 +120,7 @@ extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, co
 		std::vector<double> seg_yin(SIG_THREADS);
 		for (long t = 0; t < ntiles; t++) {
 			int nseg;
-			build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr, nullptr);
+			build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr);
 			walk_segments(w, T, t, seg, nseg, C.yin[t], seg_yin.data(), &inconsistent);
 			const long s_first = 2 + t * SIG_TILE, s_end = s_first + SIG_TILE < n + 1 ? s_first + SIG_TILE : n + 1;
 			for (int s = 0; s < nseg; s++) {

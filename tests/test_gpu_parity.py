@@ -999,3 +999,61 @@ def test_dynamics_apply_philox_mode_is_statistically_the_reference():
     pr1 = (m * vr)[:2 * npair].reshape(-1, 2).sum(1)
     np.testing.assert_allclose(pr1, pr0, rtol=0, atol=1e-12 * np.abs(m * np.hypot(d["f"]["vr"], d["f"]["vt"])).max())
     assert 0.45 < Y[::2][:npair].mean() < 0.55 and Y.min() >= 0.0 and Y.max() < 1.0
+
+
+SIGMA_CASES = [
+    # kind, N, masses, p, first, n_local
+    ("plummer", 30000, "imf", 20, 1, None),
+    ("king", 20000, "equal", 20, 1, None),
+    ("plummer", 5000, "imf", 3, 1, None),           # BH_AVEKERNEL
+    ("plummer", 200, "imf", 20, 1, None),           # less than one tile
+    ("plummer", 41, "equal", 20, 1, None),          # hardly more than one window
+    ("plummer", 30, "equal", 20, 1, None),          # the window does not fit: the loop as one thread runs it
+    ("plummer", 60000, "imf", 20, 20001, 20000),    # a middle shard: an empty window p stars before its first star, ghost stars on both sides
+    ("plummer", 60000, "imf", 20, 40001, 20000),    # the last shard
+    ("plummer", 60000, "imf", 20, 1, 20000),        # the first shard
+    ("king", 3000000, "imf", 20, 1, None),
+    ("plummer", 2000000, "equal", 20, 1, None),
+]
+
+
+@pytest.mark.parametrize("kind,N,masses,p,first,nl", SIGMA_CASES)
+def test_calc_sigma_r_bit_exact(kind, N, masses, p, first, nl):
+    """SURVEY 8f N3, calc_sigma_r on the resident arrays (reference cmc_dynamics_helper.c:2821-2975) against the restatement that is pinned
+    against the compiled reference on 1-4 ranks: sigma_array.r / .sigma and the mean-mass variant, bit for bit -- the running window sums
+    carry every rounding of the rank's subtract-then-add updates (csrc/sigma_scan.h), whole clusters and shards with ghost stars; the
+    sequential replay of the same loop as a cross-check; nothing in the records changes."""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + p, masses=masses)
+    sr, smt = cm.make_tables(r, sm)
+    nl = N - first + 1 if nl is None else nl
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    lo = first - 1
+    rng = np.random.default_rng(1)
+    if first > 1 or nl < N:                         # a shard: its records at 1 .. nl
+        c.star[1:nl + 1] = rng.integers(0, 256, (nl, c.star.shape[1]), dtype=np.uint8)
+        c.field("vr")[1:nl + 1], c.field("vt")[1:nl + 1] = vr[lo:lo + nl], vt[lo:lo + nl]
+    c.clus.N_MAX_NEW, c.Start[0], c.End[0] = nl, first, first + nl - 1
+    c.bin_slots_in_use = 0
+    ghosts = {}
+    if first > 1:
+        ghosts.update(prev_vr=vr[lo - p:lo], prev_vt=vt[lo - p:lo])
+    if lo + nl < N:
+        ghosts.update(next_vr=vr[lo + nl:lo + nl + p], next_vt=vt[lo + nl:lo + nl + p])
+    c.upload()
+    before = c.star.copy()
+    for mave in (False, True):
+        want_a, want_s = ol.calc_sigma_r(p, sr, smt, N, N, vr, vt, first_global=first, n_local=nl, mave=mave)
+        a, sg = c.dev_calc_sigma_r(p, mave=mave, ghosts=ghosts)
+        cm.assert_bits_equal(a[1:], want_a[1:], "r / mean mass")
+        cm.assert_bits_equal(sg[1:], want_s[1:], "sigma")
+        st = c.sigma_stats
+        assert st["rerun"] == 0 and st["broken"] == 0 and st["hard_segments"] <= 4, st
+        assert st["hard_tiles"] <= max(2, st["tiles"] // 50), st
+    if N <= 100000:
+        a2, sg2 = c.dev_calc_sigma_r(p, mave=True, ghosts=ghosts, force_sequential=True)
+        cm.assert_bits_equal(a2[1:], want_a[1:], "mean mass, one thread")
+        cm.assert_bits_equal(sg2[1:], want_s[1:], "sigma, one thread")
+    c.download()
+    assert np.array_equal(before, c.star)
+    c.close()
