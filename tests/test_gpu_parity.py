@@ -1024,7 +1024,7 @@ def test_calc_sigma_r_bit_exact(kind, N, masses, p, first, nl):
     carry every rounding of the rank's subtract-then-add updates (csrc/sigma_scan.h), whole clusters and shards with ghost stars; the
     sequential replay of the same loop as a cross-check; nothing in the records changes."""
     r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + p, masses=masses)
-    sr, smt = cm.make_tables(r, sm)
+    sr, smt = cm.make_tables(r, sm, extra=2 * p)    # a window wider than the cluster reads table entries behind the sentinel: zeros, as after start-up
     nl = N - first + 1 if nl is None else nl
     c = Cluster(N, n_star_dim=N + 64)
     c.load(r, vr, vt, sm)
