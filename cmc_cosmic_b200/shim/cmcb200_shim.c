@@ -243,6 +243,7 @@ void __real_tidally_strip_stars(void);
 void __real_ComputeIntermediateEnergy(void);
 void __real_ComputeEnergy(void);
 void __real_comp_mass_percent(void);
+void __real_dynamics_apply(double dt, gsl_rng *rng);
 
 static int win_open = 0;      /* (declared above) the records live on the device; the host copy of star[] / binary[] is stale */
 static int ec1_pending = 0;   /* energy_conservation1's pass has been deferred behind the orbit step (same result: see new_orbits_calculate) */
@@ -289,20 +290,123 @@ static void res_push_star(long j, long k)
 	if (cmcb200_dev_put(ctx, star + j, j, k > 0 ? binary + k : NULL, k, star_m + g, g)) shim_fail("dev_put");
 }
 
-/* src/cmc/cmc_utils.c:2153-2174.  Opens the window.  The pass itself reads vr, vt and the tables and writes vrold, vtold, Uoldrold; the orbit
+/* src/cmc/cmc_utils.c:2153-2174.  Opens the window (unless dynamics_apply did).  The pass itself reads vr, vt and the tables and writes vrold, vtold, Uoldrold; the orbit
  * step that follows reads and writes none of these, so the pass is queued BEHIND it (new_orbits_calculate below) -- the orbit step can then
  * start on the first uploaded chunk instead of waiting for the last one. */
-void SHIM(energy_conservation1)(void)
+static void res_open_window(void)
 {
 	long n_new;
-	if (!res_allowed()) { __real_energy_conservation1(); return; }
 	shim_init();
 	n_new = clus.N_MAX_NEW - (End[myid] - Start[myid] + 1);
 	win_n_bin = N_BIN_DIM_OPT - 1; /* a star may point at any slot (binaries are created in free slots between two sorts) */
 	if (cmcb200_resident_begin(ctx, star + 1, clus.N_MAX_NEW, binary + 1, win_n_bin, star_r, star_m, star_phi, clus.N_MAX + 2 + (n_new > 0 ? n_new : 0), dirty_words))
 		shim_fail("resident_begin");
 	win_open = 1;
+}
+
+void SHIM(energy_conservation1)(void)
+{
+	if (win_open) { ec1_pending = 1; return; } /* dynamics_apply opened the window already */
+	if (!res_allowed()) { __real_energy_conservation1(); return; }
+	res_open_window();
 	ec1_pending = 1;
+}
+
+/* src/cmc/cmc_dynamics.c:17-542.  With nothing between it and energy_conservation1 that reads the records on the host
+ * (STELLAR_EVOLUTION == 0: src/cmc/cmc.c:286-302) the window opens HERE: calc_sigma_r and the loop over neighbouring pairs run on the
+ * resident records behind the upload, and only the pairs whose encounter draw fell below P_enc come back for the reference's own
+ * sscollision_do / binint_do.  The reference's host code that follows the loop (break_wide_binaries) walks every binary and dumps excess
+ * energy on the stars behind it, so the binding is taken for clusters WITHOUT binaries only; everything else runs __real_dynamics_apply. */
+static const double *shim_dyn_draws = NULL;
+SHIM_EXPORT void cmcb200_shim_set_dynamics_draws(const double *draws) { shim_dyn_draws = draws; }
+static cmcb200_dynamics_result last_dynamics;
+SHIM_EXPORT const cmcb200_dynamics_result *cmcb200_shim_last_dynamics(void) { return &last_dynamics; }
+/* flushes what is pending and closes the window (tests; a caller that must read star[] in the middle of a timestep) */
+SHIM_EXPORT void cmcb200_shim_close_window(void)
+{
+	if (!win_open) return;
+	res_flush_ec1();
+	if (cmcb200_resident_end(ctx, star + 1, clus.N_MAX_NEW, binary + 1, win_n_bin, N_BIN_DIM_OPT, NULL, NULL, NULL, 0)) shim_fail("resident_end");
+	win_open = 0;
+}
+
+static int res_dynamics_allowed(void)
+{
+	return res_allowed() && STELLAR_EVOLUTION == 0 && !THREEBODYBINARIES && !TC_POLYTROPE && !(cenma.m > 0.0 && BH_LOSS_CONE) && N_b_local == 0 &&
+	       clus.N_BINARY == 0 && clus.N_MAX_NEW == End[myid] - Start[myid] + 1 && !getenv("CMCB200_NO_DEVICE_DYNAMICS");
+}
+
+void SHIM(dynamics_apply)(double dt, gsl_rng *rng)
+{
+	cmcb200_sigma_params sp;
+	cmcb200_dynamics_params dp;
+	long n = mpiEnd - mpiBegin + 1, ne, i;
+	int j;
+	double relbeta[4] = {PI / 2.0, PI / 4.0, PI / 8.0, PI / 16.0};
+	if (!res_dynamics_allowed()) { __real_dynamics_apply(dt, rng); return; }
+	res_open_window();
+	/* :37 -- sigma_array is read by host code (bh_rand_walk, the binary routines): it comes back */
+	memset(&sp, 0, sizeof sp);
+	sp.p = AVEKERNEL; sp.n_local = n; sp.first_global = Start[myid]; sp.N_MAX = clus.N_MAX; sp.N_STAR = clus.N_STAR; sp.r_0_mave_1 = 0;
+	if (cmcb200_dev_calc_sigma_r(ctx, &sp, sigma_array.r, sigma_array.sigma, NULL)) shim_fail("calc_sigma_r");
+	sigma_array.n = n;
+	if (tcount == 1) { /* :40-46 */
+		pararootfprintf(relaxationfile, "# time");
+		for (j = 0; j < 4; j++) { pararootfprintf(relaxationfile, " thetase>%g:f,q,<M>,<r>", relbeta[j]); }
+		pararootfprintf(relaxationfile, "\n");
+	}
+	DE_bb = 0.0; /* :55-56 */
+	DE_bs = 0.0;
+	rootgprintf("%s(): performing interactions:\n", "dynamics_apply");
+	pararootfprintf(logfile, "%s(): performing interactions:", "dynamics_apply");
+	memset(&dp, 0, sizeof dp);
+	dp.n_local = n; dp.first_global = Start[myid]; dp.N_MAX = clus.N_MAX; dp.N_STAR = clus.N_STAR; dp.dt = dt;
+	dp.relaxation = RELAXATION; dp.ss_collision = SS_COLLISION; dp.binsingle = BINSINGLE; dp.binbin = BINBIN; dp.tidal_capture = TIDAL_CAPTURE;
+	dp.tc_polytrope = TC_POLYTROPE; dp.bh_capture = BH_CAPTURE; dp.bh_loss_cone = BH_LOSS_CONE; dp.avekernel = AVEKERNEL; dp.honor_threebb = 0;
+	dp.cenma_m = cenma.m; dp.gamma = GAMMA; dp.coll_factor = COLL_FACTOR; dp.tc_factor = TC_FACTOR; dp.wd_tc = WD_TC;
+	dp.units_mstar = units.mstar; dp.units_l = units.l; dp.units_t = units.t;
+	dp.draws = shim_dyn_draws; dp.seed = (unsigned long long) IDUM; dp.tcount = (unsigned long long) tcount;
+	if (cmcb200_dev_dynamics_apply(ctx, &dp, &last_dynamics)) shim_fail("dynamics_apply");
+	ne = last_dynamics.n_encounters;
+	if (ne > 0) { /* :444-467: the strong encounters are the reference's own code, pair by pair in the loop's order */
+		long *ek = (long *) malloc(ne * sizeof(long)), *ekp = (long *) malloc(ne * sizeof(long)), cnt = 0;
+		int *et = (int *) malloc(ne * sizeof(int));
+		double *ed = (double *) malloc(3 * ne * sizeof(double));
+		if (cmcb200_dev_dynamics_encounters(ctx, ne, ek, ekp, et, ed, ed + ne, ed + 2 * ne, &cnt)) shim_fail("dynamics_encounters");
+		for (i = 0; i < cnt; i++) {
+			double v[4], vp[4], w[4], W, rcm, vcm[4];
+			long k = ek[i], kp = ekp[i], n_before = clus.N_MAX_NEW, q;
+			if (cmcb200_dev_get(ctx, star + k, k, NULL, 0) || cmcb200_dev_get(ctx, star + kp, kp, NULL, 0)) shim_fail("dev_get");
+			calc_encounter_dyns(k, kp, v, vp, w, &W, &rcm, vcm, rng, 0); /* star[k].Y holds the pair's angle */
+			print_interaction_status("SS");
+			sscollision_do(k, kp, ed[i], w, W, rcm, vcm, rng);
+			res_push_star(k, star[k].binind);
+			res_push_star(kp, star[kp].binind);
+			for (q = n_before + 1; q <= clus.N_MAX_NEW; q++) res_push_star(q, star[q].binind); /* collision products */
+		}
+		free(ek); free(ekp); free(et); free(ed);
+	}
+	{ /* :503-531 */
+		long Nrel = last_dynamics.Nrel;
+		double tmpTimeStart = timeStartSimple();
+		double bd[3][4], bdr[3][4];
+		long bl[5], blr[5];
+		for (j = 0; j < 4; j++) { bd[0][j] = last_dynamics.qaverelbeta[j]; bd[1][j] = last_dynamics.maverelbeta[j]; bd[2][j] = last_dynamics.raverelbeta[j]; bl[j] = last_dynamics.Nrelbeta[j]; }
+		bl[4] = Nrel;
+		MPI_Reduce(bd, bdr, 12, MPI_DOUBLE, MPI_SUM, 0, MPI_COMM_WORLD);
+		MPI_Reduce(bl, blr, 5, MPI_LONG, MPI_SUM, 0, MPI_COMM_WORLD);
+		Nrel = blr[4];
+		timeEndSimple(tmpTimeStart, &t_comm);
+		pararootfprintf(relaxationfile, "%g", TotalTime);
+		for (j = 0; j < 4; j++) {
+			pararootfprintf(relaxationfile, " %g %g %g %g", ((double) blr[j]) / ((double) Nrel), bdr[0][j] / ((double) blr[j]), bdr[1][j] / ((double) blr[j]),
+					bdr[2][j] / ((double) blr[j]));
+		}
+		pararootfprintf(relaxationfile, "\n");
+	}
+	rootgprintf("\n");
+	pararootfprintf(logfile, "\n");
+	/* break_wide_binaries(curr_st) (:541): without binaries it only adds up star[].E_excess, which fewbody alone sets -- nothing to do */
 }
 
 static void res_new_orbits_calculate(void)

@@ -146,3 +146,120 @@ def test_reference_with_resident_shim_equals_reference(kind, N, masses, nb, orbi
             cm.assert_bits_equal(b[f"lagrange{step}"][k], a[f"lagrange{step}"][k], f"step {step}: {k}")
     if orbit_r < 100:
         assert a["n1"] < N and (a["after_orbits1"]["esc_bytes"] > 0 or a["after_strip1"]["esc_bytes"] > 0), "the case must remove or strip stars"
+
+
+def _dyn_setup(R, N, r, vr, vt, sm, seed):
+    R.init(N, n_star_dim=N + 64, n_bin_dim=8, idum=77)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N, N_BINARY=0)
+    rng = np.random.default_rng(seed)
+    R.star_field("se_k", np.int32)[1:N + 1] = rng.choice(np.array([0, 1, 1, 1, 3, 7, 10, 11, 13, 14, 14], np.int32), N)
+    R.star_field("rad")[1:N + 1] = rng.uniform(1e-4, 1e-3, N)
+    R.star_bytes()[1:N + 1, 232:] = rng.integers(0, 256, (N, R.sizeof_star - 232), dtype=np.uint8)     # the cold part of the records travels too
+    R.L.ref_calc_potential_new()
+    R.compute_energy()
+
+
+@pytest.mark.parametrize("kind,N,masses,cfg", [
+    ("plummer", 30001, "imf", dict(relaxation=1)),                                               # examples/PlummerSphere.ini
+    ("king", 24000, "imf", dict(relaxation=1, ss_collision=1, bh_capture=1, tidal_capture=1, tc_factor=3.0, wd_tc=2.5)),
+])
+def test_dynamics_apply_through_the_resident_shim(kind, N, masses, cfg):
+    """dynamics_apply of the compiled reference re-bound to the shim (it opens the window: calc_sigma_r and the pair loop run on the device,
+    the encounter pairs come back for the reference's own sscollision_do -- here the harness's recorder) against the untouched reference on
+    the same state and the same draws: sigma_array bit for bit, the encounter list identical, vr / vt / E / J of the relaxed stars to 1e-12,
+    every other byte of star[] identical, the relaxation file's line equal."""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 5, masses=masses)
+    full = dict(ol.DYN_DEFAULTS)
+    full.update(cfg)
+    dt = 3e-3
+    A = rh.Ref()
+    _dyn_setup(A, N, r, vr, vt, sm, 5)
+    A.L.ref_draw_mode(1)
+    lk, ld, txt = A.dynamics_apply(dt, full)
+    stream = A.draws()
+    A.L.ref_draw_mode(0)
+    A.L.ref_sigma_array.restype = C.c_void_p
+    A.L.ref_sigma_array.argtypes = [C.c_int]
+    sig_a = [A._view(A.L.ref_sigma_array(w), (N + 1) * 8, np.float64).copy() for w in (0, 1)]
+    star_a = A.star_bytes()[:N + 1].copy()
+    fa = {k: A.star_field(k)[1:N + 1].copy() for k in ("vr", "vt", "E", "J", "Y")}
+    A.free()
+    # three draws per pair from the reference's sequential stream (an encounter pair consumed two)
+    enc_first = set(lk[:, 1].tolist())
+    draws, pos = np.zeros(3 * (N // 2)), 0
+    for i in range(N // 2):
+        take = 2 if (2 * i + 1) in enc_first else 3
+        draws[3 * i:3 * i + take] = stream[pos:pos + take]
+        pos += take
+    assert pos == len(stream)
+    B = rh.Ref(REF_B200RES_SO)
+    _dyn_setup(B, N, r, vr, vt, sm, 5)
+    B.L.cmcb200_shim_set_dynamics_draws.argtypes = [C.c_void_p]
+    B.L.cmcb200_shim_set_dynamics_draws(draws.ctypes.data)
+    lk2, ld2, txt2 = B.dynamics_apply(dt, full)
+    B.L.cmcb200_shim_window_open.restype = C.c_int
+    assert B.L.cmcb200_shim_window_open() == 1, "the binding did not take the device path"
+    B.L.ref_sigma_array.restype = C.c_void_p
+    B.L.ref_sigma_array.argtypes = [C.c_int]
+    for w, name in ((0, "sigma_array.r"), (1, "sigma_array.sigma")):
+        cm.assert_bits_equal(B._view(B.L.ref_sigma_array(w), (N + 1) * 8, np.float64)[1:], sig_a[w][1:], name)
+    B.L.cmcb200_shim_close_window()
+    assert np.array_equal(lk2, lk)
+    np.testing.assert_allclose(ld2, ld, rtol=1e-12)
+    cm.assert_bits_equal(B.star_field("Y")[1:N + 1], fa["Y"], "Y")
+    vs = np.sqrt(fa["vr"] ** 2 + fa["vt"] ** 2)
+    for k, scale in (("vr", vs), ("vt", vs), ("E", np.abs(fa["E"]) + vs ** 2), ("J", np.abs(fa["J"]) + 1e-300)):
+        assert (np.abs(B.star_field(k)[1:N + 1] - fa[k]) / scale).max() <= 1e-12, k
+    mask = np.ones(B.sizeof_star, bool)
+    for k in ("vr", "vt", "E", "J"):
+        mask[B.star_offset(k):B.star_offset(k) + 8] = False
+    assert np.array_equal(B.star_bytes()[:N + 1][:, mask], star_a[:, mask])
+    assert txt2.splitlines()[-1].split()[:2] == txt.splitlines()[-1].split()[:2]          # time and the first fraction; the sums differ in the last digit at most
+    np.testing.assert_allclose([float(x) for x in txt2.splitlines()[-1].split()], [float(x) for x in txt.splitlines()[-1].split()], rtol=1e-5, equal_nan=True)
+    if cfg.get("ss_collision"):
+        assert len(lk) > 20
+    B.L.cmcb200_shim_shutdown()
+    B.free()
+
+
+def test_whole_timestep_from_dynamics_apply_in_one_window():
+    """dynamics_apply opens the window and ComputeEnergy closes it: the whole timestep of src/cmc/cmc.c:286-353 on the resident records,
+    through the reference's own function names, with the device's own Philox draws.  Checked through what does not depend on the draws:
+    the stars are a permutation of the input, sorted, the tables are the records', the potential obeys its recurrence, energy is conserved
+    to the scheme's accuracy."""
+    N = 40000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=8, masses="equal")
+    B = rh.Ref(REF_B200RES_SO)
+    _dyn_setup(B, N, r, vr, vt, sm, 6)
+    et = np.zeros(5)
+    B.L.ref_get_etotal.argtypes = [C.c_void_p]
+    B.L.ref_compute_energy()
+    B.L.ref_get_etotal(et.ctypes.data)
+    e0 = et[0]
+    full = dict(ol.DYN_DEFAULTS)
+    for step in range(2):
+        B.dynamics_apply(2e-3, full)
+        B.L.cmcb200_shim_window_open.restype = C.c_int
+        assert B.L.cmcb200_shim_window_open() == 1
+        B.L.ref_energy_conservation1()
+        B.L.ref_new_orbits_calculate()
+        B.L.ref_energy_conservation2()
+        B.tidally_strip_stars(1, 0.11)
+        B.L.ref_compute_intermediate_energy()
+        B.L.ref_qsorts_new()
+        B.L.ref_post_sort_comm()
+        B.L.ref_calc_potential_new()
+        B.L.ref_energy_conservation3()
+        B.L.ref_compute_energy()
+        assert B.L.cmcb200_shim_window_open() == 0
+    n = int(B.scalars()["N_MAX"])
+    assert n == N
+    ids = B.star_field("id", np.int64)[1:n + 1]
+    assert np.array_equal(np.sort(ids), np.arange(1, N + 1))
+    rr = B.star_field("r")[1:n + 1]
+    assert np.all(np.diff(rr) >= 0) and np.array_equal(rr, B.star_r()[1:n + 1])
+    B.L.ref_get_etotal(et.ctypes.data)
+    assert abs(et[0] / e0 - 1) < 2e-3, (et[0], e0)
+    B.L.cmcb200_shim_shutdown()
+    B.free()
