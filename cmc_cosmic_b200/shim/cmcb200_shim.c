@@ -106,6 +106,7 @@ static void shim_init(void)
 }
 
 #define SHIM_EXPORT __attribute__((visibility("default")))
+static void shim_reset_resident(void);
 SHIM_EXPORT void cmcb200_shim_set_draws(const double *draws, const long *draw_off) { shim_draws = draws; shim_draw_off = draw_off; }
 SHIM_EXPORT const cmcb200_orbit_result *cmcb200_shim_last_orbit(void) { return &last_orbit; }
 SHIM_EXPORT void cmcb200_shim_shutdown(void)
@@ -114,6 +115,8 @@ SHIM_EXPORT void cmcb200_shim_shutdown(void)
 	if (ctx && procs > 1) { cmcb200_sync(ctx); MPI_Barrier(MPI_COMM_WORLD); cmcb200_shard_detach(ctx); MPI_Barrier(MPI_COMM_WORLD); } /* nobody unmaps a buffer a peer still uses */
 	if (ctx) cmcb200_destroy(ctx);
 	ctx = NULL; free(status_buf); status_buf = NULL; status_cap = 0;
+	shim_draws = NULL; shim_draw_off = NULL; /* the caller's arrays: not ours to keep beyond a run */
+	shim_reset_resident();
 }
 
 /* src/cmc/cmc_utils.c:2194-2211 */
@@ -636,4 +639,7 @@ void SHIM(ComputeEnergy)(void)
 	if (cmcb200_resident_end(ctx, star + 1, clus.N_MAX_NEW, binary + 1, win_n_bin, N_BIN_DIM_OPT, NULL, NULL, NULL, 0)) shim_fail("resident_end");
 	win_open = 0;
 }
+static void shim_reset_resident(void) { shim_dyn_draws = NULL; win_open = 0; ec1_pending = 0; dirty_words = ~0ull; }
+#else
+static void shim_reset_resident(void) {}
 #endif /* CMCB200_SHIM_RESIDENT */

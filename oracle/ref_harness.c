@@ -317,7 +317,8 @@ EXPORT long ref_dynamics_apply(double dt, const long *flags, const double *par, 
 	if (!mpi_relaxationfile_buf) { mpi_relaxationfile_buf = malloc(STR_BUF_LEN); mpi_relaxationfile_wrbuf = malloc(1 << 16); }
 	mpi_logfile_wrbuf[0] = 0; mpi_logfile_len = 0;
 	mpi_relaxationfile_wrbuf[0] = 0; mpi_relaxationfile_len = 0;
-	if (!sigma_array.r) {
+	{ /* sized for this run's arrays (a test process initialises the library more than once) */
+		free(sigma_array.r); free(sigma_array.sigma);
 		sigma_array.n = 0;
 		sigma_array.r = (double *) calloc(N_STAR_DIM_OPT, sizeof(double));      /* cmc_io.c:2103-2104 */
 		sigma_array.sigma = (double *) calloc(N_STAR_DIM_OPT, sizeof(double));
