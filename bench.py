@@ -405,6 +405,28 @@ def run_cuda(args):
                 timestep_ms = t0.elapsed_time(t1) / 3
             except Exception as exc:            # never lose the bench line over the auxiliary number
                 print(f"bench: auxiliary timestep measurement skipped: {exc}", file=sys.stderr)
+        # ---- auxiliary 2: the WHOLE timestep of src/cmc/cmc.c:286-353 resident -- dynamics_apply (calc_sigma_r + two-body relaxation of every
+        # neighbouring pair) in front of the above.  With it nothing of a PlummerSphere.ini timestep reads the records on the host.
+        timestep_dyn_ms, dyn_stage = None, None
+        if world == 1:
+            try:
+                c.dev_timestep(seed=args.seed, tidally_strip=1, dynamics_dt=1e-3)
+                c.profile(True)
+                c.profile_read(reset=True)
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c.sync()
+                t0.record(stream)
+                for _ in range(3):
+                    c.dev_timestep(seed=args.seed, tidally_strip=1, dynamics_dt=1e-3)
+                t1.record(stream)
+                c.sync()
+                timestep_dyn_ms = t0.elapsed_time(t1) / 3
+                pr = c.profile_read(reset=True)
+                c.profile(False)
+                dyn_stage = {"calc_sigma_r_ms": round(pr["sigma"][0] / 3, 4), "dynamics_apply_pairs_ms": round(pr["dynamics"][0] / 3, 4),
+                             "encounter_pairs": int(c.last_dynamics.n_encounters), "relaxed_pairs": int(c.last_dynamics.Nrel)}
+            except Exception as exc:
+                print(f"bench: auxiliary timestep-with-dynamics measurement skipped: {exc}", file=sys.stderr)
 
         # ---- e2e arm: the same step on HOST arrays through the C ABI of the shim's resident mode, every copy inside the timed region.
         # Per step and rank: cmcb200_resident_begin (tables + this rank's records + binaries up, asynchronous) -> orbit step chunk by chunk
@@ -520,6 +542,8 @@ def run_cuda(args):
         "stage_ms_per_step_max_over_ranks": {k: round(v, 4) for k, v in stage_ms_max.items()},
         "cpu_baseline": cpu,
         "timestep_with_energy_scheme_ms": timestep_ms,
+        "timestep_with_dynamics_ms": timestep_dyn_ms,
+        "dynamics_stage": dyn_stage,
     }
     if world > 1:
         dist.barrier()

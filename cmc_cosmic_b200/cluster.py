@@ -337,13 +337,24 @@ class Cluster:
         p = self.orbit_params()
         _lib.check(self.L.cmcb200_dev_energy_new_radii(self.ctx, C.byref(p)), "dev_energy_new_radii")
 
-    def dev_timestep(self, seed=0, draws=None, draw_off=None, tidally_strip=None, GAMMA=0.11):
+    def dev_timestep(self, seed=0, draws=None, draw_off=None, tidally_strip=None, GAMMA=0.11, dynamics_dt=None, want_sigma=False):
         """One timestep of the reference's main loop around the hot path (src/cmc/cmc.c:302-353, no interacting stars) on the resident arrays:
         energy_conservation1 -> new_orbits_calculate -> energy_conservation2 -> [tidally_strip_stars] -> ComputeIntermediateEnergy ->
         qsorts_new -> calc_potential_new -> energy_conservation3 -> ComputeEnergy.  tidally_strip: None (TIDALLY_STRIP_STARS = 0) or the
         TIDAL_TREATMENT (0 / 1); TidalMassLoss / OldTidalMassLoss are the caller's to maintain across the orbit step
         (reference cmc_utils.c:2197-2210).  Without stripping the passes that read the same data are merged (one lookup for energy_conservation2 +
-        ComputeIntermediateEnergy, the transfer inside the sort's gather); bit-identical to the calls made one by one either way."""
+        ComputeIntermediateEnergy, the transfer inside the sort's gather); bit-identical to the calls made one by one either way.
+        dynamics_dt: a time step Dt puts dynamics_apply (src/cmc/cmc.c:286; calc_sigma_r + the pair loop) in front, so that
+        nothing of the timestep needs the records on the host when no pair is a strong encounter; the encounter pairs are returned in
+        ``self.last_dynamics`` for the caller's host code (cmcb200_dev_get / _put)."""
+        if dynamics_dt is not None:
+            if want_sigma:
+                self.sigma_array = self.dev_calc_sigma_r()
+            else:                                  # sigma_array stays on the device (cmcb200_dev_sigma_arrays): no host reader without encounters
+                prm = _lib.SigmaParams(self.DYNAMICS["AVEKERNEL"], int(self.End[self.myid] - self.Start[self.myid] + 1), int(self.Start[self.myid]),
+                                       self.clus.N_MAX, self.clus.N_STAR, 0, 0, None, None, None, None)
+                _lib.check(self.L.cmcb200_dev_calc_sigma_r(self.ctx, C.byref(prm), None, None, None), "dev_calc_sigma_r")
+            self.last_dynamics = self.dev_dynamics_apply(dynamics_dt, seed=seed)
         self.dev_energy_conservation1()
         res = self.dev_new_orbits(draws, draw_off, seed)
         if tidally_strip is None:

@@ -220,24 +220,23 @@ __global__ void __launch_bounds__(DYN_THREADS) dyn_pair_kernel(DynArgs a)
 }
 
 // totals[0..4] = Nrel, Nrelbeta[0..3]; totals[5 + 4 c + j] = sum c (q, m, r) of threshold j.  Fixed summation order: thread t adds blocks
-// t, t + 256, ... then the threads are added in order.
+// t, t + 256, ... in one pass over the block results, then the threads are added in order.
 __global__ void __launch_bounds__(256) dyn_stats_kernel(DynArgs a, long n_blocks)
 {
-	__shared__ double part[256];
-	for (int q = 0; q < 17; q++) {
-		double s = 0.0;
-		for (long b = threadIdx.x; b < n_blocks; b += 256) {
-			const DynBlockStats &t = a.w.bstats[b];
-			s += q == 0 ? (double) t.Nrel : q < 5 ? (double) t.Nrelbeta[q - 1] : q < 9 ? t.q[q - 5] : q < 13 ? t.m[q - 9] : t.r[q - 13];
-		}
-		part[threadIdx.x] = s;
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			double tot = 0.0;
-			for (int t = 0; t < 256; t++) tot += part[t];
-			a.w.totals[q] = tot;
-		}
-		__syncthreads();
+	__shared__ double part[17][256];
+	double acc[17];
+	for (int q = 0; q < 17; q++) acc[q] = 0.0;
+	for (long b = threadIdx.x; b < n_blocks; b += 256) {
+		const DynBlockStats t = a.w.bstats[b];
+		acc[0] += (double) t.Nrel;
+		for (int j = 0; j < 4; j++) { acc[1 + j] += (double) t.Nrelbeta[j]; acc[5 + j] += t.q[j]; acc[9 + j] += t.m[j]; acc[13 + j] += t.r[j]; }
+	}
+	for (int q = 0; q < 17; q++) part[q][threadIdx.x] = acc[q];
+	__syncthreads();
+	if (threadIdx.x < 17) {
+		double tot = 0.0;
+		for (int t = 0; t < 256; t++) tot += part[threadIdx.x][t];
+		a.w.totals[threadIdx.x] = tot;
 	}
 }
 

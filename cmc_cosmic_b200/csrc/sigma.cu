@@ -4,14 +4,15 @@
 //
 //   sigma_terms_kernel    the two terms of every star of the rank and of its ghost stars (one strided pass over the records), and their
 //                         sums over blocks of 2048 entries; sigma_prefix_kernel turns those into the tiles' drift bounds
-//   sigma_tile_kernel     one CTA per (tile of 2048 stars, chain): the tile's terms staged in shared memory, a segment table per thread,
-//                         the tile table by walking its <= 128 candidates through the segment tables
+//   sigma_tile_kernel     one CTA per (tile of 2048 stars, chain): the tile's terms staged in shared memory, a segment table per thread, a
+//                         table per group of 16 segments (one thread per group and candidate), the tile table by walking its <= 128
+//                         candidates through the 16 group tables
 //   sigma_chain_kernel    one CTA per chain: one thread walks the tile tables in order (batches staged in shared memory) and leaves the
 //                         exact value entering every tile; a tile without a table is rebuilt by the CTA and walked segment by segment
 //   sigma_finish_kernel   one CTA per tile: segment tables again, one walk from the exact value, every thread replays its 16 operations
 //                         for both chains and stores sigma and r / the mean mass
 // Bound: HBM for the streaming part (32-byte sector of each record + 8 B of star_m in, 16 B of terms out and in twice, 16 B of results
-// out = ~100 B/star), the serial walks (256 dependent shared-memory lookups per tile, one per tile in the chain kernel) for the rest.
+// out = ~100 B/star), the serial walks (16 + 16 dependent shared-memory lookups per tile, one per tile in the chain kernel) for the rest.
 #include <string.h>
 #include "ctx.cuh"
 #include "sigma_scan.h"
@@ -81,32 +82,32 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_terms_kernel(SigArgs a)
 	}
 }
 
-// inclusive prefix sums of the block sums, one warp per chain (a few thousand blocks)
+// inclusive prefix sums of the block sums, one warp per chain (a few thousand blocks): every lane sums a contiguous chunk (independent
+// loads), the lanes' sums are scanned by shuffles, every lane writes its chunk's prefixes
 __global__ void sigma_prefix_kernel(SigArgs a)
 {
 	const int c = threadIdx.x >> 5;
 	if (c > 1) return;
-	double carry = 0.0;
-	for (long base = 0; base < a.n_blocks; base += 32) {
-		const long i = base + lane_id();
-		double v = i < a.n_blocks ? a.b.blk[c][i] : 0.0;
-		for (int d = 1; d < 32; d <<= 1) {
-			const double o = __shfl_up_sync(0xffffffffu, v, d);
-			if (lane_id() >= (unsigned) d) v += o;
-		}
-		v += carry;
-		if (i < a.n_blocks) a.b.blk[c][i] = v;
-		carry = __shfl_sync(0xffffffffu, v, 31);
+	const long per = (a.n_blocks + 31) / 32, lo = (long) lane_id() * per, hi = lo + per < a.n_blocks ? lo + per : a.n_blocks;
+	double s = 0.0;
+	for (long i = lo; i < hi; i++) s += a.b.blk[c][i];
+	double inc = s;
+	for (int d = 1; d < 32; d <<= 1) {
+		const double o = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane_id() >= (unsigned) d) inc += o;
 	}
+	double run = inc - s;
+	for (long i = lo; i < hi; i++) { run += a.b.blk[c][i]; a.b.blk[c][i] = run; }
 }
 
 // ---- per-tile machinery shared by the three kernels behind ------------------------------------------------------------------------
 struct alignas(16) TileSmem {
 	double term[SIG_TERM_SMEM_MAX];
 	SigSeg seg[SIG_THREADS];
+	SigGrp grp[SIG_NGRP];
 	SigTile tile;
 	double seg_yin[SIG_THREADS];
-	int nseg;
+	double grp_yin[SIG_NGRP];
 };
 
 // stars [s_first, s_end) of a tile and the local indices its operations touch
@@ -167,10 +168,11 @@ __device__ __forceinline__ void tile_build_segments(const SigArgs &a, const SigT
 	}
 }
 
-// one thread walks the tile's segments from y; seg_yin (may be null) receives the value entering every segment
-__device__ __forceinline__ double tile_walk(const SigArgs &a, const SigTerms &T, const TileRange &t, const TileSmem *sm, double y, double *seg_yin, int *inconsistent)
+// one thread walks segments [s_lo, s_hi) of the tile from y; seg_yin (may be null) receives the value entering every segment
+__device__ __forceinline__ double tile_walk_segments(const SigArgs &a, const SigTerms &T, const TileRange &t, const TileSmem *sm, int s_lo, int s_hi, double y,
+						     double *seg_yin, int *inconsistent)
 {
-	for (int s = 0; s < t.nseg; s++) {
+	for (int s = s_lo; s < s_hi; s++) {
 		if (seg_yin) seg_yin[s] = y;
 		const SigSeg &sg = sm->seg[s];
 		if (sg.flag == SIG_TABLE && sig_expo(y) == sg.e_in) {
@@ -182,6 +184,41 @@ __device__ __forceinline__ double tile_walk(const SigArgs &a, const SigTerms &T,
 			const int cnt = seg_count(t, s);
 			sig_segment_terms(a.w, T, t.s_first + (long) s * SIG_S, cnt, sub, add);
 			y = sig_replay(sub, add, cnt, y);
+		}
+	}
+	return y;
+}
+
+// the group tables of the tile, one thread per (group, candidate); the CTA has synchronised behind tile_build_segments, and is synchronised
+// again when this returns
+__device__ __forceinline__ void tile_build_groups(const SigArgs &a, const SigTerms &T, const TileRange &t, TileSmem *sm)
+{
+	const int g = threadIdx.x / SIG_KG_MAX, r = threadIdx.x % SIG_KG_MAX, ngrp = (t.nseg + SIG_G - 1) / SIG_G;
+	const int s_lo = g * SIG_G, s_hi = s_lo + SIG_G < t.nseg ? s_lo + SIG_G : t.nseg;
+	if (g < ngrp && r == 0) sig_group_header(&sm->seg[s_lo], s_hi - s_lo, &sm->grp[g]);
+	__syncthreads();
+	if (g < ngrp && sm->grp[g].flag == SIG_TABLE && r < (1 << sm->grp[g].logk)) {
+		int inc = 0;
+		sm->grp[g].yout[r] = tile_walk_segments(a, T, t, sm, s_lo, s_hi, sig_group_candidate(sm->grp[g], r), nullptr, &inc);
+		if (inc) atomicExch(&a.b.flags[1], 1);
+	}
+	__syncthreads();
+}
+
+// one thread walks the tile's groups from y: a lookup per group, or the group's segments one by one
+__device__ __forceinline__ double tile_walk_groups(const SigArgs &a, const SigTerms &T, const TileRange &t, const TileSmem *sm, double y, double *grp_yin, int *inconsistent)
+{
+	const int ngrp = (t.nseg + SIG_G - 1) / SIG_G;
+	for (int g = 0; g < ngrp; g++) {
+		if (grp_yin) grp_yin[g] = y;
+		const SigGrp &gr = sm->grp[g];
+		if (gr.flag == SIG_TABLE && sig_expo(y) == gr.e_in) {
+			const uint64_t idx = dbits(y) & ((1ull << gr.logk) - 1);
+			y = dadd(gr.yout[idx], dsub(y, dfrombits(dbits(gr.base) | idx)));
+		} else {
+			if (gr.flag == SIG_TABLE) *inconsistent = 1;
+			const int s_lo = g * SIG_G, s_hi = s_lo + SIG_G < t.nseg ? s_lo + SIG_G : t.nseg;
+			y = tile_walk_segments(a, T, t, sm, s_lo, s_hi, y, nullptr, inconsistent);
 		}
 	}
 	return y;
@@ -199,15 +236,16 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_tile_kernel(SigArgs a)
 	__syncthreads();
 	tile_build_segments(a, T, t, sig_dband(a.b.blk[chain], a.n_blocks, tile, a.w.p), sm, true);
 	__syncthreads();
+	tile_build_groups(a, T, t, sm);
 	if (threadIdx.x == 0) {
-		sig_tile_header(sm->seg, t.nseg, &sm->tile);
+		sig_tile_header_from_groups(sm->grp, (t.nseg + SIG_G - 1) / SIG_G, &sm->tile);
 		if (sm->tile.flag == SIG_HARD) atomicAdd(&a.b.flags[4], 1);
 	}
 	__syncthreads();
 	SigTile *out = &a.b.tile[chain][tile];
 	if (sm->tile.flag == SIG_TABLE && threadIdx.x < (1u << sm->tile.logk)) {
 		int inc = 0;
-		out->yout[threadIdx.x] = tile_walk(a, T, t, sm, sig_tile_candidate(sm->tile, threadIdx.x), nullptr, &inc);
+		out->yout[threadIdx.x] = tile_walk_groups(a, T, t, sm, sig_tile_candidate(sm->tile, threadIdx.x), nullptr, &inc);
 		if (inc) atomicExch(&a.b.flags[1], 1);
 	}
 	if (threadIdx.x == 0) { out->base = sm->tile.base; out->e_in = sm->tile.e_in; out->logk = sm->tile.logk; out->flag = sm->tile.flag; out->pad = 0; }
@@ -262,22 +300,29 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_chain_kernel(SigArgs a)
 		s_pos = 0;
 	}
 	__syncthreads();
-	for (long b0 = 0; b0 < a.n_tiles; b0 += SIG_BATCH) {
+	// the batches of tile tables are double-buffered: while thread 0 walks one, the other threads stage the next
+	auto stage = [&](long b0, SigTile *dst_t, int first_thread, int n_threads) {
 		const long nb = a.n_tiles - b0 < SIG_BATCH ? a.n_tiles - b0 : SIG_BATCH;
-		{ // stage the batch's tables: 16-byte copies
-			const uint4 *src = (const uint4 *) (a.b.tile[chain] + b0);
-			uint4 *dst = (uint4 *) batch;
-			const int n16 = (int) (nb * sizeof(SigTile) / 16);
-			for (int i = threadIdx.x; i < n16; i += SIG_THREADS) dst[i] = src[i];
-		}
-		__syncthreads();
+		if (nb <= 0) return;
+		const uint4 *src = (const uint4 *) (a.b.tile[chain] + b0);
+		uint4 *dst = (uint4 *) dst_t;
+		const int n16 = (int) (nb * sizeof(SigTile) / 16);
+		for (int i = (int) threadIdx.x - first_thread; i < n16; i += n_threads) dst[i] = src[i];
+	};
+	stage(0, batch, 0, SIG_THREADS);
+	__syncthreads();
+	int cur = 0;
+	for (long b0 = 0; b0 < a.n_tiles; b0 += SIG_BATCH, cur ^= 1) {
+		const long nb = a.n_tiles - b0 < SIG_BATCH ? a.n_tiles - b0 : SIG_BATCH;
+		const SigTile *bt = batch + cur * SIG_BATCH;
+		bool first = true;
 		for (;;) {
 			if (threadIdx.x == 0) {
 				double y = s_y;
 				long pos = s_pos;
 				int hard = 0, inc = 0;
 				while (pos < b0 + nb) {
-					const SigTile &tt = batch[pos - b0];
+					const SigTile &tt = bt[pos - b0];
 					if (tt.flag != SIG_TABLE || sig_expo(y) != tt.e_in) { hard = 1; if (tt.flag == SIG_TABLE) inc = 1; break; }
 					a.b.yin[chain][pos] = y;
 					const uint64_t idx = dbits(y) & ((1ull << tt.logk) - 1);
@@ -286,20 +331,22 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_chain_kernel(SigArgs a)
 				}
 				if (inc) atomicExch(&a.b.flags[1], 1);
 				s_y = y; s_pos = pos; s_hard = hard;
-			}
+			} else if (first) stage(b0 + SIG_BATCH, batch + (cur ^ 1) * SIG_BATCH, 1, SIG_THREADS - 1);
+			first = false;
 			__syncthreads();
 			if (!s_hard) break;
-			// a tile without a table: rebuild its segments with the whole CTA, then one thread walks them
+			// a tile without a table: rebuild its segments and groups with the whole CTA, then one thread walks them
 			const long tile = s_pos;
 			const TileRange t = tile_range(a.w, tile);
 			const SigTerms T = tile_stage_terms(a, chain, t, sm->term);
 			__syncthreads();
 			tile_build_segments(a, T, t, sig_dband(a.b.blk[chain], a.n_blocks, tile, a.w.p), sm, false);
 			__syncthreads();
+			tile_build_groups(a, T, t, sm);
 			if (threadIdx.x == 0) {
 				int inc = 0;
 				a.b.yin[chain][tile] = s_y;
-				s_y = tile_walk(a, T, t, sm, s_y, nullptr, &inc);
+				s_y = tile_walk_groups(a, T, t, sm, s_y, nullptr, &inc);
 				s_pos = tile + 1;
 				if (inc) atomicExch(&a.b.flags[1], 1);
 			}
@@ -309,7 +356,7 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_chain_kernel(SigArgs a)
 }
 
 // ---- pass 4: outputs --------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SIG_THREADS) sigma_finish_kernel(SigArgs a)
+__global__ void __launch_bounds__(SIG_THREADS, 3) sigma_finish_kernel(SigArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	TileSmem *sm = (TileSmem *) smem_raw;
@@ -325,9 +372,17 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_finish_kernel(SigArgs a)
 		__syncthreads();
 		tile_build_segments(a, T, t, sig_dband(a.b.blk[chain], a.n_blocks, tile, a.w.p), sm, false);
 		__syncthreads();
+		tile_build_groups(a, T, t, sm);
 		if (threadIdx.x == 0) {
 			int inc = 0;
-			tile_walk(a, T, t, sm, a.b.yin[chain][tile], sm->seg_yin, &inc);
+			tile_walk_groups(a, T, t, sm, a.b.yin[chain][tile], sm->grp_yin, &inc);
+			if (inc) atomicExch(&a.b.flags[1], 1);
+		}
+		__syncthreads();
+		if (threadIdx.x < (t.nseg + SIG_G - 1) / SIG_G) { // one thread per group: the values entering its segments
+			int inc = 0;
+			const int g = threadIdx.x, s_lo = g * SIG_G, s_hi = s_lo + SIG_G < t.nseg ? s_lo + SIG_G : t.nseg;
+			tile_walk_segments(a, T, t, sm, s_lo, s_hi, sm->grp_yin[g], sm->seg_yin, &inc);
 			if (inc) atomicExch(&a.b.flags[1], 1);
 		}
 		__syncthreads();
@@ -408,7 +463,7 @@ extern "C" int cmcb200_dev_calc_sigma_r(cmcb200_ctx *c, const cmcb200_sigma_para
 		CMCB_CUDA_OK(cudaMalloc(&s->b.out_sigma, (size_t) (cap + 1) * sizeof(double)));
 		s->cap_n = cap; s->cap_p = P;
 		c->d_sigma = s;
-		const int smem_tile = (int) sizeof(TileSmem), smem_chain = smem_tile + SIG_BATCH * (int) sizeof(SigTile);
+		const int smem_tile = (int) sizeof(TileSmem), smem_chain = smem_tile + 2 * SIG_BATCH * (int) sizeof(SigTile);
 		CMCB_CUDA_OK(cudaFuncSetAttribute(sigma_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tile));
 		CMCB_CUDA_OK(cudaFuncSetAttribute(sigma_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tile));
 		CMCB_CUDA_OK(cudaFuncSetAttribute(sigma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_chain));
@@ -442,7 +497,7 @@ extern "C" int cmcb200_dev_calc_sigma_r(cmcb200_ctx *c, const cmcb200_sigma_para
 	if (!small) CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	{
 		StageTimer t(c, ST_SIGMA);
-		const int smem_tile = (int) sizeof(TileSmem), smem_chain = smem_tile + SIG_BATCH * (int) sizeof(SigTile);
+		const int smem_tile = (int) sizeof(TileSmem), smem_chain = smem_tile + 2 * SIG_BATCH * (int) sizeof(SigTile);
 		sigma_terms_kernel<<<(unsigned) a.n_blocks, SIG_THREADS, 0, c->stream>>>(a);
 		sigma_prefix_kernel<<<1, 64, 0, c->stream>>>(a);
 		c->launches += 2;

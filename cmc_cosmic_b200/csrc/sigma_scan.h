@@ -12,7 +12,8 @@
 // bits of y_in.  Going down in binade costs nothing; every binade the stretch climbs above y_in's doubles the table.
 //   segment  S = 8 stars (16 operations), one thread: approximate trajectory from a freshly summed window, classification, and the table
 //            by running the <= 8 candidates through the operations with the hardware's own adds;
-//   tile     256 segments, one CTA: a table of <= 32 entries by walking the candidates through the segment tables;
+//   group    16 segments: a table of <= 16 entries by walking the candidates through the segment tables (one thread per candidate);
+//   tile     16 groups, one CTA: a table of <= 128 entries by walking the candidates through the group tables;
 //   chain    one thread walks the tile tables in order (one dependent lookup per 2048 stars) and leaves every tile's exact y_in;
 //   finish   each tile walks its segment tables from the exact y_in, each thread replays its 16 operations and stores the outputs.
 // Where the band straddles a power of two ("hard": ~1 operation in 10^8 at N = 10^7) the segment is replayed operation by operation by
@@ -34,16 +35,29 @@ namespace cmcb {
 constexpr int SIG_S = 8;
 constexpr int SIG_THREADS = 256;
 constexpr int SIG_TILE = SIG_S * SIG_THREADS;
+constexpr int SIG_G = 16;                      // segments per group
+constexpr int SIG_NGRP = SIG_THREADS / SIG_G;  // groups per tile
 constexpr int SIG_KS_LOG_MAX = 3;
+constexpr int SIG_KG_LOG_MAX = 4;
 constexpr int SIG_KT_LOG_MAX = 7;
 constexpr int SIG_KS_MAX = 1 << SIG_KS_LOG_MAX;
 constexpr int SIG_KT_MAX = 1 << SIG_KT_LOG_MAX;
+constexpr int SIG_KG_MAX = 1 << SIG_KG_LOG_MAX;
+static_assert(SIG_NGRP * SIG_KG_MAX <= SIG_THREADS, "one thread per (group, candidate)");
 
 enum { SIG_TABLE = 0, SIG_SEQ = 1, SIG_HARD = 2 };
 
 struct SigSeg {
 	double base;              // candidate 0: the approximate y_in with its low logk mantissa bits cleared
 	double yout[SIG_KS_MAX];
+	int e_in, logk, flag, emax;
+};
+
+// a group of SIG_G consecutive segments: the same kind of table one level up, so that a walk over a tile is SIG_NGRP + SIG_G dependent
+// lookups instead of SIG_THREADS.  SIG_SEQ: the group climbs too many binades for its table -- it is walked segment by segment.
+struct SigGrp {
+	double base;
+	double yout[SIG_KG_MAX];
 	int e_in, logk, flag, emax;
 };
 
@@ -193,6 +207,40 @@ CMCB_HD void sig_tile_header(const SigSeg *seg, int nseg, SigTile *t)
 	const uint64_t K = 1ull << (t->logk > SIG_KT_LOG_MAX ? SIG_KT_LOG_MAX : t->logk);
 	// seg[0].base is the approximate y_in with fewer low bits cleared (or none): clear the tile's
 	t->base = dfrombits(dbits(seg[0].base) & ~(K - 1));
+}
+
+// group header from its segments; the entries are filled by the candidates' walks
+CMCB_HD void sig_group_header(const SigSeg *seg, int nseg, SigGrp *g)
+{
+	int emax = seg[0].e_in, hard = 0;
+	for (int s = 0; s < nseg; s++) {
+		emax = seg[s].emax > emax ? seg[s].emax : emax;
+		hard |= seg[s].flag == SIG_HARD;
+	}
+	g->e_in = seg[0].e_in;
+	g->emax = emax;
+	g->logk = emax - seg[0].e_in + 1;
+	g->flag = hard ? SIG_HARD : (g->logk > SIG_KG_LOG_MAX ? SIG_SEQ : SIG_TABLE);
+	const uint64_t K = 1ull << (g->logk > SIG_KG_LOG_MAX ? SIG_KG_LOG_MAX : g->logk);
+	g->base = dfrombits(dbits(seg[0].base) & ~(K - 1));
+}
+CMCB_HD double sig_group_candidate(const SigGrp &g, int r) { return dfrombits(dbits(g.base) | (uint64_t) r); }
+
+// tile header from its groups
+CMCB_HD void sig_tile_header_from_groups(const SigGrp *grp, int ngrp, SigTile *t)
+{
+	int emax = grp[0].e_in, hard = 0;
+	for (int g = 0; g < ngrp; g++) {
+		emax = grp[g].emax > emax ? grp[g].emax : emax;
+		hard |= grp[g].flag == SIG_HARD;
+	}
+	t->e_in = grp[0].e_in;
+	t->logk = emax - grp[0].e_in + 1;
+	t->flag = (hard || t->logk > SIG_KT_LOG_MAX) ? SIG_HARD : SIG_TABLE;
+	t->pad = 0;
+	t->pad2 = 0.0;
+	const uint64_t K = 1ull << (t->logk > SIG_KT_LOG_MAX ? SIG_KT_LOG_MAX : t->logk);
+	t->base = dfrombits(dbits(grp[0].base) & ~(K - 1));
 }
 
 CMCB_HD double sig_tile_candidate(const SigTile &t, int r) { return dfrombits(dbits(t.base) | (uint64_t) r); }

@@ -30,16 +30,48 @@ void build_segments(const SigmaWindow &w, const SigTerms &T, long tile, double d
 	}
 }
 
-double walk_segments(const SigmaWindow &w, const SigTerms &T, long tile, const std::vector<SigSeg> &seg, int nseg, double y, double *seg_yin, int *inconsistent)
+// segments [s_lo, s_hi) of the tile from y
+double walk_segments(const SigmaWindow &w, const SigTerms &T, long tile, const std::vector<SigSeg> &seg, int s_lo, int s_hi, double y, double *seg_yin, int *inconsistent)
 {
 	const long s_first = 2 + tile * SIG_TILE, s_end = s_first + SIG_TILE < w.n + 1 ? s_first + SIG_TILE : w.n + 1;
-	for (int s = 0; s < nseg; s++) {
+	for (int s = s_lo; s < s_hi; s++) {
 		const long s0 = s_first + (long) s * SIG_S;
 		const int cnt = (int) (s0 + SIG_S <= s_end ? SIG_S : s_end - s0);
 		if (seg_yin) seg_yin[s] = y;
 		double sub[SIG_S], add[SIG_S];
 		sig_segment_terms(w, T, s0, cnt, sub, add);
 		y = sig_apply_segment(seg[s], sub, add, cnt, y, inconsistent);
+	}
+	return y;
+}
+
+// group tables of a tile (after its segments): what the (group, candidate) threads of the device do
+void build_groups(const SigmaWindow &w, const SigTerms &T, long tile, const std::vector<SigSeg> &seg, int nseg, std::vector<SigGrp> &grp, int *ngrp, int *inconsistent)
+{
+	*ngrp = (nseg + SIG_G - 1) / SIG_G;
+	for (int g = 0; g < *ngrp; g++) {
+		const int s_lo = g * SIG_G, s_hi = s_lo + SIG_G < nseg ? s_lo + SIG_G : nseg;
+		sig_group_header(&seg[s_lo], s_hi - s_lo, &grp[g]);
+		if (grp[g].flag == SIG_TABLE)
+			for (int r = 0; r < (1 << grp[g].logk); r++)
+				grp[g].yout[r] = walk_segments(w, T, tile, seg, s_lo, s_hi, sig_group_candidate(grp[g], r), nullptr, inconsistent);
+	}
+}
+
+// the tile's groups from y: a table lookup per group, or its segments one by one
+double walk_groups(const SigmaWindow &w, const SigTerms &T, long tile, const std::vector<SigSeg> &seg, int nseg, const std::vector<SigGrp> &grp, int ngrp, double y,
+		   double *grp_yin, int *inconsistent)
+{
+	for (int g = 0; g < ngrp; g++) {
+		if (grp_yin) grp_yin[g] = y;
+		const int s_lo = g * SIG_G, s_hi = s_lo + SIG_G < nseg ? s_lo + SIG_G : nseg;
+		if (grp[g].flag == SIG_TABLE && sig_expo(y) == grp[g].e_in) {
+			const uint64_t idx = dbits(y) & ((1ull << grp[g].logk) - 1);
+			y = dadd(grp[g].yout[idx], dsub(y, dfrombits(dbits(grp[g].base) | idx)));
+		} else {
+			if (grp[g].flag == SIG_TABLE) *inconsistent = 1;
+			y = walk_segments(w, T, tile, seg, s_lo, s_hi, y, nullptr, inconsistent);
+		}
 	}
 	return y;
 }
@@ -65,6 +97,7 @@ extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, co
 	const long ntiles = sig_num_tiles(n);
 	counters[5] = ntiles;
 	std::vector<SigSeg> seg(SIG_THREADS);
+	std::vector<SigGrp> grp(SIG_NGRP);
 	int broken = 0, inconsistent = 0;
 	for (int c = 0; c < 2; c++) {
 		Chain &C = ch[c];
@@ -84,10 +117,12 @@ extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, co
 			int nseg;
 			build_segments(w, T, t, C.dband[t], seg, &nseg, &broken);
 			for (int s = 0; s < nseg; s++) { counters[0] += seg[s].flag == SIG_HARD; counters[1] += seg[s].flag == SIG_SEQ; }
-			sig_tile_header(seg.data(), nseg, &C.tile[t]);
+			int ngrp;
+			build_groups(w, T, t, seg, nseg, grp, &ngrp, &inconsistent);
+			sig_tile_header_from_groups(grp.data(), ngrp, &C.tile[t]);
 			if (C.tile[t].flag == SIG_TABLE)
 				for (int r = 0; r < (1 << C.tile[t].logk); r++)
-					C.tile[t].yout[r] = walk_segments(w, T, t, seg, nseg, sig_tile_candidate(C.tile[t], r), nullptr, &inconsistent);
+					C.tile[t].yout[r] = walk_groups(w, T, t, seg, nseg, grp, ngrp, sig_tile_candidate(C.tile[t], r), nullptr, &inconsistent);
 			else counters[2]++;
 		}
 	}
@@ -113,7 +148,7 @@ extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, co
 			else {
 				int nseg;
 				build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr);
-				y = walk_segments(w, T, t, seg, nseg, y, nullptr, &inconsistent);
+				y = walk_segments(w, T, t, seg, 0, nseg, y, nullptr, &inconsistent);
 			}
 		}
 		// pass 4: every tile from its exact y_in
@@ -121,7 +156,14 @@ extern "C" int emul_sigma_scan(long p, long n, long first_global, long N_MAX, co
 		for (long t = 0; t < ntiles; t++) {
 			int nseg;
 			build_segments(w, T, t, C.dband[t], seg, &nseg, nullptr);
-			walk_segments(w, T, t, seg, nseg, C.yin[t], seg_yin.data(), &inconsistent);
+			int ngrp;
+			double grp_yin[SIG_NGRP];
+			build_groups(w, T, t, seg, nseg, grp, &ngrp, &inconsistent);
+			walk_groups(w, T, t, seg, nseg, grp, ngrp, C.yin[t], grp_yin, &inconsistent);
+			for (int g = 0; g < ngrp; g++) {
+				const int s_lo = g * SIG_G, s_hi = s_lo + SIG_G < nseg ? s_lo + SIG_G : nseg;
+				walk_segments(w, T, t, seg, s_lo, s_hi, grp_yin[g], seg_yin.data(), &inconsistent);
+			}
 			const long s_first = 2 + t * SIG_TILE, s_end = s_first + SIG_TILE < n + 1 ? s_first + SIG_TILE : n + 1;
 			for (int s = 0; s < nseg; s++) {
 				const long s0 = s_first + (long) s * SIG_S;

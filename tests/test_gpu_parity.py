@@ -1057,3 +1057,66 @@ def test_calc_sigma_r_bit_exact(kind, N, masses, p, first, nl):
     c.download()
     assert np.array_equal(before, c.star)
     c.close()
+
+
+def test_whole_timestep_from_dynamics_apply_resident():
+    """src/cmc/cmc.c:286-353 with nothing on the host: calc_sigma_r -> dynamics_apply's pair loop -> energy_conservation1 -> new_orbits_calculate
+    -> ... -> ComputeEnergy on the resident records.  Checked in two legs, because a relaxed velocity that differs in the last bits (the device's
+    sin / cos) can flip a rejection try of the orbit step: (1) sigma_array bit for bit and the relaxed state to DYN_TOL against the oracle;
+    (2) from the DEVICE's own relaxed state -- the E, J the pair loop stored are what the orbit step reads -- the rest of the timestep bit for
+    bit against the oracle chain."""
+    kind, N, masses, dt = "plummer", 80000, "imf", 2e-3
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 9, masses=masses)
+    pot = cm.oracle_potential(r, sm)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N, 0.0)
+    g = np.arange(1, N + 1)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    c.field("E")[1:N + 1], c.field("J")[1:N + 1] = E, J
+    c.Rtidal = pot["Rtidal"]
+    c.upload()
+    # leg 1
+    a, sg = c.dev_calc_sigma_r()
+    want_a, want_s = ol.calc_sigma_r(20, pot["star_r"], pot["star_m"], N, N, vr, vt)
+    cm.assert_bits_equal(a[1:], want_a[1:], "sigma_array.r")
+    cm.assert_bits_equal(sg[1:], want_s[1:], "sigma_array.sigma")
+    draws = np.random.default_rng(4).random(3 * (N // 2))
+    res = c.dev_dynamics_apply(dt, draws=draws)
+    assert res.n_encounters == 0 and res.Nrel == N // 2
+    f0 = dict(vr=vr.copy(), vt=vt.copy(), E=E.copy(), J=J.copy(), Y=np.zeros(N), binind=np.zeros(N, np.int64), se_k=np.zeros(N, np.int32), rad=np.zeros(N))
+    ol.dynamics_apply_pairs(t, 1, dt, ol.dyn_params(), draws, f0)
+    c.download()
+    vr1, vt1, E1, J1 = (c.field(k)[1:N + 1].copy() for k in ("vr", "vt", "E", "J"))
+    vs = np.sqrt(vr ** 2 + vt ** 2)
+    for k, got, scale in (("vr", vr1, vs), ("vt", vt1, vs), ("E", E1, np.abs(E) + vs ** 2), ("J", J1, np.abs(J) + 1e-300)):
+        assert (np.abs(got - f0[k]) / scale).max() <= DYN_TOL, k
+    # leg 2: the oracle chain from the device's relaxed state
+    o1 = ol.energy_conservation1(t, g, vr1, vt1)
+    want = cm.oracle_orbits(pot["star_r"], pot["star_m"], pot["phi"], N, N, E1, J1, vr1, vt1, pot["Rtidal"], seed=3)
+    Uoldrnew = ol.energy_conservation2(t, g, want["rnew"])
+    order = np.argsort(want["rnew"], kind="stable")
+    n2 = int((want["rnew"] < cm.SF_INFINITY).sum())
+    order = order[:n2]
+    pot2 = cm.oracle_potential(want["rnew"][order], sm[order], N_STAR=N)
+    t2 = ol.tables(pot2["star_r"], pot2["star_m"], pot2["phi"], n2, N, 0.0)
+    f = dict(interacted=np.zeros(n2, np.int64), rOld=r[order], vrold=o1["vrold"][order], vtold=o1["vtold"][order], Uoldrold=o1["Uoldrold"][order],
+             Uoldrnew=Uoldrnew[order], vr=want["vrnew"][order], vt=want["vtnew"][order], vrnew=want["vrnew"][order], vtnew=want["vtnew"][order])
+    io, flags, left0 = ol.set_velocities3_first(t2, np.arange(1, n2 + 1), f)
+    E2, J2 = cm.energies(pot2["phi"][1:n2 + 1], want["rnew"][order], io["vr"], io["vt"])
+    c.dev_timestep(draws=want["draws"], draw_off=want["draw_off"])
+    c.download()
+    assert c.clus.N_MAX == n2
+    cm.assert_bits_equal(c.star_phi[:n2 + 2], pot2["phi"][:n2 + 2], "phi")
+    assert np.array_equal(c.field("id")[1:n2 + 1], order + 1)
+    for k in ol.SV3_IO:
+        cm.assert_bits_equal(c.field(k)[1:n2 + 1], io[k], k)
+    cm.assert_bits_equal(c.field("E")[1:n2 + 1], E2, "E")
+    cm.assert_bits_equal(c.field("J")[1:n2 + 1], J2, "J")
+    # and the production form: one call, Philox draws, nothing read back in between
+    c.dev_timestep(seed=7, tidally_strip=1, dynamics_dt=dt)
+    c.download()
+    n3 = c.clus.N_MAX
+    assert np.all(np.diff(c.field("r")[1:n3 + 1]) >= 0) and len(np.unique(c.field("id")[1:n3 + 1])) == n3
+    c.close()
