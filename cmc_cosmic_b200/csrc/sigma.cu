@@ -300,17 +300,19 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_chain_kernel(SigArgs a)
 		s_pos = 0;
 	}
 	__syncthreads();
-	// the batches of tile tables are double-buffered: while thread 0 walks one, the other threads stage the next
-	auto stage = [&](long b0, SigTile *dst_t, int first_thread, int n_threads) {
+	// the batches of tile tables are double-buffered: the walker asks the TMA unit for the next batch (one bulk copy, completion counted on
+	// an mbarrier) before it walks the current one
+	__shared__ unsigned long long bar[2];
+	unsigned phase[2] = {0, 0};
+	auto stage = [&](long b0, int buf) { // thread 0 only
 		const long nb = a.n_tiles - b0 < SIG_BATCH ? a.n_tiles - b0 : SIG_BATCH;
 		if (nb <= 0) return;
-		const uint4 *src = (const uint4 *) (a.b.tile[chain] + b0);
-		uint4 *dst = (uint4 *) dst_t;
-		const int n16 = (int) (nb * sizeof(SigTile) / 16);
-		for (int i = (int) threadIdx.x - first_thread; i < n16; i += n_threads) dst[i] = src[i];
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the buffer's earlier reads are done before the async proxy overwrites it
+		bulk_copy_g2s(batch + buf * SIG_BATCH, a.b.tile[chain] + b0, (unsigned) (nb * sizeof(SigTile)), &bar[buf]);
 	};
-	stage(0, batch, 0, SIG_THREADS);
+	if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
 	__syncthreads();
+	if (threadIdx.x == 0) stage(0, 0);
 	int cur = 0;
 	for (long b0 = 0; b0 < a.n_tiles; b0 += SIG_BATCH, cur ^= 1) {
 		const long nb = a.n_tiles - b0 < SIG_BATCH ? a.n_tiles - b0 : SIG_BATCH;
@@ -318,20 +320,32 @@ __global__ void __launch_bounds__(SIG_THREADS) sigma_chain_kernel(SigArgs a)
 		bool first = true;
 		for (;;) {
 			if (threadIdx.x == 0) {
+				if (first) {
+					stage(b0 + SIG_BATCH, cur ^ 1);
+					mbar_wait(&bar[cur], phase[cur]);
+					phase[cur] ^= 1;
+				}
 				double y = s_y;
 				long pos = s_pos;
 				int hard = 0, inc = 0;
+				// the header of the next tile is loaded while the current one's entry is on its way: the dependent chain per tile is
+				// index -> one shared-memory load -> two additions
+				int e_in = 0, logk = 0, flag = SIG_HARD;
+				double base = 0.0;
+				if (pos < b0 + nb) { const SigTile &tt = bt[pos - b0]; e_in = tt.e_in; logk = tt.logk; flag = tt.flag; base = tt.base; }
 				while (pos < b0 + nb) {
 					const SigTile &tt = bt[pos - b0];
-					if (tt.flag != SIG_TABLE || sig_expo(y) != tt.e_in) { hard = 1; if (tt.flag == SIG_TABLE) inc = 1; break; }
+					if (flag != SIG_TABLE || sig_expo(y) != e_in) { hard = 1; if (flag == SIG_TABLE) inc = 1; break; }
+					const uint64_t idx = dbits(y) & ((1ull << logk) - 1);
+					const double yo = tt.yout[idx], yc = dfrombits(dbits(base) | idx);
 					a.b.yin[chain][pos] = y;
-					const uint64_t idx = dbits(y) & ((1ull << tt.logk) - 1);
-					y = dadd(tt.yout[idx], dsub(y, dfrombits(dbits(tt.base) | idx)));
 					pos++;
+					if (pos < b0 + nb) { const SigTile &nx = bt[pos - b0]; e_in = nx.e_in; logk = nx.logk; flag = nx.flag; base = nx.base; }
+					y = dadd(yo, dsub(y, yc));
 				}
 				if (inc) atomicExch(&a.b.flags[1], 1);
 				s_y = y; s_pos = pos; s_hard = hard;
-			} else if (first) stage(b0 + SIG_BATCH, batch + (cur ^ 1) * SIG_BATCH, 1, SIG_THREADS - 1);
+			}
 			first = false;
 			__syncthreads();
 			if (!s_hard) break;

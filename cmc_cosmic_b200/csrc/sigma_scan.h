@@ -151,20 +151,37 @@ CMCB_HD void sig_build_segment(const double *sub, const double *add, int cnt, do
 	if (o->logk > SIG_KS_LOG_MAX) { o->flag = SIG_SEQ; return; }
 	const uint64_t K = 1ull << o->logk, b0 = dbits(y) & ~(K - 1);
 	o->base = dfrombits(b0);
+	// the candidates in three batches (0-1, 2-3, 4-7): most segments stay within one binade of y_in and need the first only
 	double c[SIG_KS_MAX];
 	for (int r = 0; r < SIG_KS_MAX; r++) c[r] = dfrombits(b0 | (uint64_t) (r & (int) (K - 1)));
-	t = y;
 	int mism = 0;
+	t = y;
 	for (int i = 0; i < cnt; i++) {
 		const double t1 = dsub(t, sub[i]), t2 = dadd(t1, add[i]);
 		const int e1 = sig_expo(t1), e2 = sig_expo(t2);
-		for (int r = 0; r < SIG_KS_MAX; r++) {
+		for (int r = 0; r < 2; r++) {
 			const double c1 = dsub(c[r], sub[i]);
 			c[r] = dadd(c1, add[i]);
 			mism |= (sig_expo(c1) ^ e1) | (sig_expo(c[r]) ^ e2);
 		}
+		if (K > 2) {
+			for (int r = 2; r < 4; r++) {
+				const double c1 = dsub(c[r], sub[i]);
+				c[r] = dadd(c1, add[i]);
+				mism |= (sig_expo(c1) ^ e1) | (sig_expo(c[r]) ^ e2);
+			}
+		}
+		if (K > 4) {
+			for (int r = 4; r < SIG_KS_MAX; r++) {
+				const double c1 = dsub(c[r], sub[i]);
+				c[r] = dadd(c1, add[i]);
+				mism |= (sig_expo(c1) ^ e1) | (sig_expo(c[r]) ^ e2);
+			}
+		}
 		t = t2;
 	}
+	for (int r = 2; r < SIG_KS_MAX; r++)
+		if ((uint64_t) r >= K) c[r] = c[r & (int) (K - 1)];
 	if (mism) { o->flag = SIG_HARD; return; } // cannot happen while the band is rigorous; the replay is always right
 	for (int r = 0; r < SIG_KS_MAX; r++) o->yout[r] = c[r];
 }
