@@ -240,6 +240,46 @@ class ShardedCluster(Cluster):
         self.Eoops += -E * (1.0 / self.clus.N_STAR)
         return rounds
 
+    def _ghost_velocities(self, p):
+        """what calc_sigma_r exchanges between neighbouring ranks (reference src/cmc/cmc_dynamics_helper.c:2862-2900): vr, vt of the first and
+        last p local stars, read from the resident records, all-gathered (MPI_Send / MPI_Recv pairs in the reference)"""
+        import torch
+        n = int(self.End[self.myid] - self.Start[self.myid] + 1)
+        rec = np.zeros(self.star.shape[1], np.uint8)
+        mine = np.zeros(4 * p)
+        from .layout import STAR_OFFSETS
+        for i in range(p):
+            for half, j in ((0, 1 + i), (2, n - p + 1 + i)):
+                if 1 <= j <= n:
+                    _lib.check(self.L.cmcb200_dev_get(self.ctx, rec.ctypes.data, j, None, 0), "dev_get")
+                    mine[half * p + i] = rec[STAR_OFFSETS["vr"]:STAR_OFFSETS["vr"] + 8].view(np.float64)[0]
+                    mine[(half + 1) * p + i] = rec[STAR_OFFSETS["vt"]:STAR_OFFSETS["vt"] + 8].view(np.float64)[0]
+        with torch.cuda.stream(self._tstream):
+            t = torch.from_numpy(mine).cuda(self.device)
+            parts = [torch.empty_like(t) for _ in range(self.procs)]
+            self.dist.all_gather(parts, t)
+            allv = [x.cpu().numpy() for x in parts]
+        g = {}
+        if self.myid > 0:
+            g["prev_vr"], g["prev_vt"] = allv[self.myid - 1][2 * p:3 * p], allv[self.myid - 1][3 * p:4 * p]
+        if self.myid < self.procs - 1:
+            g["next_vr"], g["next_vt"] = allv[self.myid + 1][0:p], allv[self.myid + 1][p:2 * p]
+        return g
+
+    def dev_calc_sigma_r(self, p=None, mave=False, ghosts=None, force_sequential=False):
+        """calc_sigma_r on P ranks: every rank its own chain from an empty window p stars before its first star, ghost stars from its neighbours"""
+        p = int(p or self.DYNAMICS["AVEKERNEL"])
+        return super().dev_calc_sigma_r(p, mave=mave, ghosts=self._ghost_velocities(p) if ghosts is None else ghosts, force_sequential=force_sequential)
+
+    def dev_dynamics_apply(self, dt, draws=None, seed=0, **switches):
+        """dynamics_apply on P ranks: pairs are formed inside each rank's shard (reference cmc_dynamics.c:216); the scattering-angle statistics
+        are summed over the ranks (MPI_Reduce, :514-515)"""
+        res = super().dev_dynamics_apply(dt, draws=draws, seed=seed, **switches)
+        tot = self._allreduce_sum([res.Nrel] + list(res.Nrelbeta) + list(res.qaverelbeta) + list(res.maverelbeta) + list(res.raverelbeta))
+        res.global_Nrel, res.global_Nrelbeta = int(tot[0]), [int(x) for x in tot[1:5]]
+        res.global_qaverelbeta, res.global_maverelbeta, res.global_raverelbeta = tot[5:9], tot[9:13], tot[13:17]
+        return res
+
     def _allreduce_sum(self, values):
         import torch
         with torch.cuda.stream(self._tstream):

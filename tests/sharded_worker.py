@@ -202,3 +202,55 @@ if __name__ == "__main__":
     # torchrun entry: RANK / WORLD_SIZE / MASTER_PORT from the environment
     run(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("MASTER_PORT", "29511")),
         int(float(sys.argv[1])) if len(sys.argv) > 1 else 200000, int(sys.argv[2]) if len(sys.argv) > 2 else 5000, int(sys.argv[3]) if len(sys.argv) > 3 else 3)
+
+
+def run_dyn(rank, world, port, N):
+    """calc_sigma_r and dynamics_apply's pair loop on `world` GPUs: every rank its own running sums with ghost stars from its neighbours,
+    pairs inside each shard -- against the oracle run as each rank (pinned against the ranks of the compiled reference in
+    tests/ref_multirank_check.py for calc_sigma_r)."""
+    import torch
+    import torch.distributed as dist
+    import common as cm
+    import oraclelib as ol
+    from cmc_cosmic_b200.sharded import ShardedCluster
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=29, masses="imf")
+    pot = cm.oracle_potential(r, sm, N)
+    c = ShardedCluster(N, dist, device=rank)
+    c.load_global(r, vr, vt, sm)
+    c.star_phi[:N + 2] = pot["phi"][:N + 2]
+    c.compute_energy()
+    lo, hi = int(c.Start[rank]), int(c.End[rank])
+    nl = hi - lo + 1
+    c.field("threebb_interacted")[1:nl + 1] = 0
+    c.upload()
+    for mave in (False, True):
+        a, sg = c.dev_calc_sigma_r(20, mave=mave)
+        want_a, want_s = ol.calc_sigma_r(20, pot["star_r"], pot["star_m"], N, N, vr, vt, first_global=lo, n_local=nl, mave=mave)
+        cm.assert_bits_equal(a[1:], want_a[1:], f"rank {rank}: r / mean mass")
+        cm.assert_bits_equal(sg[1:], want_s[1:], f"rank {rank}: sigma")
+    draws = np.random.default_rng(100 + rank).random(3 * (nl // 2))
+    dt = 2e-3
+    res = c.dev_dynamics_apply(dt, draws=draws)
+    c.download()
+    c.sync()
+    t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N)
+    E, J = cm.energies(pot["phi"][1:N + 1], r, vr, vt)
+    f0 = dict(vr=vr[lo - 1:hi].copy(), vt=vt[lo - 1:hi].copy(), E=E[lo - 1:hi].copy(), J=J[lo - 1:hi].copy(), Y=np.zeros(nl), binind=np.zeros(nl, np.int64),
+              se_k=np.zeros(nl, np.int32), rad=np.zeros(nl))
+    want = ol.dynamics_apply_pairs(t, lo, dt, ol.dyn_params(), draws, f0)
+    assert res.Nrel == want["Nrel"] == nl // 2 and res.n_encounters == 0
+    cm.assert_bits_equal(c.field("Y")[1:nl + 1], f0["Y"], "Y")
+    vs = np.sqrt(f0["vr"] ** 2 + f0["vt"] ** 2)
+    for k, scale in (("vr", vs), ("vt", vs), ("E", np.abs(f0["E"]) + vs ** 2), ("J", np.abs(f0["J"]) + 1e-300)):
+        assert (np.abs(c.field(k)[1:nl + 1] - f0[k]) / scale).max() <= 1e-12, (rank, k)
+    S, E_ = c.Start, c.End
+    assert res.global_Nrel == sum(int(E_[q] - S[q] + 1) // 2 for q in range(world))
+    c.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank}/{world}: calc_sigma_r bit-exact, dynamics_apply within 1e-12 of the oracle rank (N={N}, shard {lo}..{hi})", flush=True)

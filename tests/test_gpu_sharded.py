@@ -48,3 +48,15 @@ def test_sharded_tidally_strip_stars():
     import torch.multiprocessing as mp
     import sharded_worker
     mp.spawn(sharded_worker.run_tidal, args=(2, 29561, 100000), nprocs=2, join=True)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world,N", [(2, 120001), (4, 300000)])
+def test_sharded_calc_sigma_r_and_dynamics_apply(world, N):
+    """SURVEY 8f N3 across ranks: calc_sigma_r with ghost stars (reference cmc_dynamics_helper.c:2862-2900) bit for bit per rank, the pair loop
+    inside each shard"""
+    import torch.multiprocessing as mp
+    import sharded_worker
+    if world > _n_gpus():
+        pytest.skip(f"needs {world} GPUs")
+    mp.spawn(sharded_worker.run_dyn, args=(world, 29570 + world, N), nprocs=world, join=True)
