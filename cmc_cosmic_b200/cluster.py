@@ -442,6 +442,15 @@ class Cluster:
         self.sigma_stats = dict(zip(("hard_segments", "wide_segments", "hard_tiles", "broken", "rerun", "tiles"), st.tolist()))
         return a, sg
 
+    def save_restart_file(self, path, rng_state=b"", restart_struct=b"", clus_struct=b"", snapshot_window_counters=()):
+        """save_restart_file (reference src/cmc/cmc_io.c:3829-3884) with the records taken from the device: the three header blocks are the
+        caller's bytes (curr_st, restart_struct_t, clus_struct_t), star[] / binary[] are written whole -- their live part from HBM."""
+        cnt = np.ascontiguousarray(snapshot_window_counters, np.int32)
+        blobs = [np.frombuffer(bytes(b), np.uint8) if len(b) else np.zeros(0, np.uint8) for b in (rng_state, restart_struct, clus_struct)]
+        _lib.check(self.L.cmcb200_restart_write(self.ctx, str(path).encode(), blobs[0].ctypes.data, len(blobs[0]), blobs[1].ctypes.data, len(blobs[1]),
+                                                blobs[2].ctypes.data, len(blobs[2]), self.star.ctypes.data, self.N_STAR_DIM, self.clus.N_MAX_NEW,
+                                                self.binary.ctypes.data, self.N_BIN_DIM, self.N_b_local, cnt.ctypes.data, len(cnt)), "restart_write")
+
     def dev_qsorts_new(self):
         n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
         _lib.check(self.L.cmcb200_dev_qsorts_new(self.ctx, C.byref(n), max(self.N_b_local, 0), C.byref(nb)), "dev_qsorts_new")

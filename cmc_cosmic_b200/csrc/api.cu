@@ -738,6 +738,73 @@ extern "C" int cmcb200_download(cmcb200_ctx *c, void *star1_h, long n_local, voi
 	return 0;
 }
 
+// ---- restart file (reference src/cmc/cmc_io.c:3829-3884) written from the resident arrays ---------------------------------------------
+// save_restart_file() fwrites curr_st, restart_struct, clus, the WHOLE star[] and binary[] arrays (N_STAR_DIM_OPT / N_BIN_DIM_OPT records,
+// :3862-3867) and the snapshot-window counters.  While the records live on the device the host's star[1 .. n] / binary[1 .. nb] are stale:
+// those byte ranges are streamed from HBM through two pinned staging buffers (the copy of chunk i + 1 runs while chunk i is written), the
+// rest -- the three opaque header blocks, star[0], the unused tail of both arrays, the counters -- comes from the caller's memory.
+static int restart_stream(cmcb200_ctx *c, FILE *f, const char *dev, size_t bytes, char *stage[2], size_t chunk, cudaEvent_t ev[2])
+{
+	size_t off = 0;
+	int cur = 0;
+	size_t len[2] = {0, 0};
+	if (bytes == 0) return 0;
+	len[0] = bytes < chunk ? bytes : chunk;
+	CMCB_CUDA_OK(cudaMemcpyAsync(stage[0], dev, len[0], cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaEventRecord(ev[0], c->stream));
+	while (off < bytes) {
+		const size_t next_off = off + len[cur];
+		if (next_off < bytes) {
+			len[cur ^ 1] = bytes - next_off < chunk ? bytes - next_off : chunk;
+			CMCB_CUDA_OK(cudaMemcpyAsync(stage[cur ^ 1], dev + next_off, len[cur ^ 1], cudaMemcpyDeviceToHost, c->stream));
+			CMCB_CUDA_OK(cudaEventRecord(ev[cur ^ 1], c->stream));
+		}
+		CMCB_CUDA_OK(cudaEventSynchronize(ev[cur]));
+		if (fwrite(stage[cur], 1, len[cur], f) != len[cur]) { set_error("restart_write: short write"); return -1; }
+		off = next_off;
+		cur ^= 1;
+	}
+	c->bytes_d2h += (long) bytes;
+	return 0;
+}
+
+extern "C" int cmcb200_restart_write(cmcb200_ctx *c, const char *path, const void *rng_state, long rng_bytes, const void *restart_struct, long restart_bytes,
+				     const void *clus, long clus_bytes, const void *star0, long n_star_dim_opt, long n_resident, const void *binary0,
+				     long n_bin_dim_opt, long n_bin_resident, const int *snapshot_window_counters, long snapshot_window_count)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	if (n_resident + 1 > n_star_dim_opt || n_resident + 1 > c->n_star_dim || n_bin_resident + 1 > n_bin_dim_opt || n_bin_resident + 1 > c->n_bin_dim) {
+		set_error("restart_write: %ld stars / %ld binaries resident do not fit the arrays (%ld / %ld)", n_resident, n_bin_resident, n_star_dim_opt, n_bin_dim_opt);
+		return -1;
+	}
+	FILE *f = fopen(path, "wb");
+	if (!f) { set_error("restart_write: cannot open %s", path); return -1; }
+	const size_t chunk = (size_t) 32 << 20;
+	char *stage[2] = {nullptr, nullptr};
+	cudaEvent_t ev[2];
+	int rc = 0;
+	if (cudaMallocHost(&stage[0], chunk) != cudaSuccess || cudaMallocHost(&stage[1], chunk) != cudaSuccess) { set_error("restart_write: no pinned staging memory"); rc = -1; }
+	cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+	auto put = [&](const void *p, size_t n) { if (!rc && n && fwrite(p, 1, n, f) != n) { set_error("restart_write: short write"); rc = -1; } };
+	put(rng_state, (size_t) rng_bytes);           // :3862
+	put(restart_struct, (size_t) restart_bytes);  // :3863
+	put(clus, (size_t) clus_bytes);               // :3864
+	put(star0, CMCB_SIZEOF_STAR);                 // :3865: star[0], then the resident records, then the unused tail
+	if (!rc) rc = restart_stream(c, f, star1(c), (size_t) n_resident * CMCB_SIZEOF_STAR, stage, chunk, ev);
+	put((const char *) star0 + (size_t) (n_resident + 1) * CMCB_SIZEOF_STAR, (size_t) (n_star_dim_opt - n_resident - 1) * CMCB_SIZEOF_STAR);
+	put(binary0, CMCB_SIZEOF_BINARY);             // :3866
+	if (!rc) rc = restart_stream(c, f, bin1(c), (size_t) n_bin_resident * CMCB_SIZEOF_BINARY, stage, chunk, ev);
+	put((const char *) binary0 + (size_t) (n_bin_resident + 1) * CMCB_SIZEOF_BINARY, (size_t) (n_bin_dim_opt - n_bin_resident - 1) * CMCB_SIZEOF_BINARY);
+	put(snapshot_window_counters, (size_t) snapshot_window_count * sizeof(int)); // :3867
+	if (fclose(f) != 0 && !rc) { set_error("restart_write: close failed"); rc = -1; }
+	cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+	if (stage[0]) cudaFreeHost(stage[0]);
+	if (stage[1]) cudaFreeHost(stage[1]);
+	return rc;
+}
+
 // ---- resident timestep on host arrays: the records cross the host link once each way ---------------------------------------------
 
 // Runs of consecutive dirty 8-byte words of a record (bit w of the mask = word w); returns the number of runs

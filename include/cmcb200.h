@@ -290,6 +290,16 @@ int cmcb200_dev_clusdyn_calculate(cmcb200_ctx *ctx, long N_MAX, long N_STAR, dou
 int cmcb200_dev_comp_multi_mass_percent(cmcb200_ctx *ctx, long N_MAX, const double *mass_bins, long n_bins, double solar_mass_dyn,
 					const double *mass_pc, long count, double *multi_mass_r);
 
+/* ---- restart file (src/cmc/cmc_io.c:3829-3884) written while the records are resident -------------------------------------- */
+/* The file save_restart_file() writes, byte for byte: curr_st (struct rng_t113_state), restart_struct_t, clus_struct_t -- opaque blocks the
+ * caller fills exactly as the reference does (save_global_vars) -- then star[0 .. N_STAR_DIM_OPT) and binary[0 .. N_BIN_DIM_OPT) whole, then
+ * snapshot_window_counters (:3862-3867).  star[1 .. n_resident] and binary[1 .. n_bin_resident] are taken from the DEVICE (streamed through
+ * pinned staging buffers, copy and fwrite overlapped), everything else from the caller's arrays: a checkpoint inside a resident window
+ * needs no refresh of the host's 424-byte records.  load_restart_file() (:3886-3935) reads the file unchanged. */
+int cmcb200_restart_write(cmcb200_ctx *ctx, const char *path, const void *rng_state, long rng_bytes, const void *restart_struct, long restart_bytes,
+			  const void *clus, long clus_bytes, const void *star0, long n_star_dim_opt, long n_resident, const void *binary0,
+			  long n_bin_dim_opt, long n_bin_resident, const int *snapshot_window_counters, long snapshot_window_count);
+
 /* ---- dynamics_apply (src/cmc/cmc_dynamics.c:17-542): the loop over neighbouring pairs on the resident arrays ---------------- */
 /* Everything of the pair loop (:206-500) that is not a strong encounter: per pair (k, kp) = local stars (1,2), (3,4), ... the kinematics of
  * calc_encounter_dyns (src/cmc/cmc_dynamics_helper.c:831-870; star[k].Y = star[kp].Y = the pair's first draw), calc_n_local (:768-786), the

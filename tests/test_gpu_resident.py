@@ -109,3 +109,40 @@ def test_resident_calls_order_themselves_behind_the_upload():
     b.resident_end()
     _same(a, b, "ec1 + sort + potential")
     a.close(); b.close()
+
+
+def test_restart_file_written_from_the_resident_arrays(tmp_path):
+    """save_restart_file (reference src/cmc/cmc_io.c:3829-3884): the file is curr_st | restart_struct | clus | star[N_STAR_DIM_OPT] |
+    binary[N_BIN_DIM_OPT] | snapshot_window_counters (:3862-3867).  Written while the records are resident and the host copy is stale, it
+    must equal, byte for byte, the same layout assembled from the arrays after a download; star[0], the tails and the header blocks are the
+    host's."""
+    N, nb = 150000, 3000          # 64 MB of records: more than one 32 MB staging chunk
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=12, masses="imf")
+    rng = np.random.default_rng(2)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    c = Cluster(N, n_star_dim=N + 300, n_bin_dim=nb + 50)
+    c.load(r, vr, vt, sm, binind=binind)
+    c.binary[1:nb + 1] = rng.integers(0, 256, (nb, c.binary.shape[1]), dtype=np.uint8)
+    c.star[N + 2:] = rng.integers(0, 256, c.star[N + 2:].shape, dtype=np.uint8)          # the unused tails travel too
+    c.binary[nb + 1:] = rng.integers(0, 256, c.binary[nb + 1:].shape, dtype=np.uint8)
+    c.star[0] = rng.integers(0, 256, c.star.shape[1], dtype=np.uint8)
+    c.calc_potential_new()
+    c.compute_energy()
+    c.upload()
+    c.dev_step(seed=3)                          # the device moves on; the host's records are now stale
+    stale = c.star.copy()
+    blobs = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (32, 1208, 56)]
+    counters = np.arange(7, dtype=np.int32)
+    path = tmp_path / "run.restart.1-0.bin"
+    c.save_restart_file(path, *blobs, snapshot_window_counters=counters)
+    got = np.fromfile(path, np.uint8)
+    n_live, nb_live = c.clus.N_MAX_NEW, c.N_b_local
+    tail_star, tail_bin, star0, bin0 = c.star[n_live + 1:].copy(), c.binary[nb_live + 1:].copy(), c.star[0].copy(), c.binary[0].copy()
+    c.download()
+    assert not np.array_equal(stale[1:n_live + 1], c.star[1:n_live + 1])
+    want = np.concatenate([np.frombuffer(b, np.uint8) for b in blobs] + [star0, c.star[1:n_live + 1].reshape(-1), tail_star.reshape(-1), bin0,
+                          c.binary[1:nb_live + 1].reshape(-1), tail_bin.reshape(-1), counters.view(np.uint8)])
+    assert got.size == want.size == 32 + 1208 + 56 + c.N_STAR_DIM * 424 + c.N_BIN_DIM * 464 + 28
+    assert np.array_equal(got, want)
+    c.close()
