@@ -422,6 +422,58 @@ class Cluster:
         res.encounters = enc
         return res
 
+    def dev_simul_relax(self, THETASEMAX=1.0):
+        """simul_relax_new (reference src/cmc/cmc_dynamics_helper.c:2526-2580) on the resident arrays: the relaxation time step, bit for bit"""
+        n, out = int(self.End[self.myid] - self.Start[self.myid] + 1), C.c_double()
+        _lib.check(self.L.cmcb200_dev_simul_relax(self.ctx, n, int(self.Start[self.myid]), self.clus.N_MAX, self.clus.N_STAR, self.DYNAMICS["AVEKERNEL"],
+                                                  THETASEMAX, C.byref(out)), "dev_simul_relax")
+        return out.value
+
+    def calc_timestep(self, THETASEMAX=1.0):
+        """calc_timestep -> GetTimeStep (reference src/cmc/cmc_utils.c:2132-2148, src/cmc/cmc_evolution_thr.c:317-437) for a run whose only
+        physics is two-body relaxation (no collisions, binaries, stellar evolution: every other candidate of GetTimeStep is +inf):
+        Dt = simul_relax_new() on the resident arrays, then calc_timestep's tidal-mass-loss rules; advances TotalTime."""
+        Dt = self._allreduce_min(self.dev_simul_relax(THETASEMAX))
+        if Dt == float("inf"):
+            Dt = 0.001                                                        # cmc_evolution_thr.c:428-430
+        prev = getattr(self, "Prev_Dt", 0.0)
+        lost_old = getattr(self, "TidalMassLoss_old", 0.0) - self.OldTidalMassLoss
+        if lost_old > 0.01:                                                   # cmc_utils.c:2138-2141
+            Dt = prev * 0.8
+        elif Dt > 1.1 * prev and prev > 0 and (self.TidalMassLoss - self.OldTidalMassLoss) > 0.02:
+            Dt = prev * 1.1
+        self.Dt = Dt
+        self.TotalTime = getattr(self, "TotalTime", 0.0) + Dt
+        return Dt
+
+    def _allreduce_min(self, x):
+        return x
+
+    def evolve(self, t_end, max_steps=10**9, seed=0, THETASEMAX=1.0, tidally_strip=0, GAMMA=0.1, mass_pc=None, record_every=1):
+        """The reference's main loop (src/cmc/cmc.c:240-407) for a relaxation-only run (examples/PlummerSphere.ini), every N-sized operation on
+        the resident arrays: calc_timestep (simul_relax_new) -> dynamics_apply (calc_sigma_r, two-body relaxation of every pair) ->
+        energy_conservation1 -> new_orbits_calculate -> energy_conservation2 -> tidally_strip_stars -> ComputeIntermediateEnergy -> qsorts_new
+        -> calc_potential_new -> energy_conservation3 -> comp_mass_percent -> ComputeEnergy.  The 424-byte records never visit the host.
+        Returns the history [(TotalTime, Dt, N_MAX, Lagrange radii)] recorded every `record_every` steps."""
+        hist, steps = [], 0
+        pc = None if mass_pc is None else np.ascontiguousarray(mass_pc, np.float64)
+        while getattr(self, "TotalTime", 0.0) < t_end and steps < max_steps:
+            # cmc.c:245-258: the per-step accumulators
+            self.TidalMassLoss_old, self.TidalMassLoss = self.TidalMassLoss, 0.0
+            Dt = self.calc_timestep(THETASEMAX)
+            self.OldTidalMassLoss = self.TidalMassLoss_old                    # new_orbits_calculate, cmc_utils.c:2197
+            self.dev_timestep(seed=seed, tidally_strip=tidally_strip, GAMMA=GAMMA, dynamics_dt=Dt)
+            self.TidalMassLoss += self.TidalMassLoss_old                      # cmc_utils.c:2210
+            self.Prev_Dt = Dt
+            steps += 1
+            if steps % record_every == 0:
+                lag = None
+                if pc is not None:
+                    self.dev_comp_mass_percent(pc)
+                    lag = self.mass_r.copy()
+                hist.append((self.TotalTime, Dt, self.clus.N_MAX, lag))
+        return hist
+
     def dev_calc_sigma_r(self, p=None, mave=False, ghosts=None, force_sequential=False):
         """calc_sigma_r (reference src/cmc/cmc_dynamics_helper.c:2821-2975) on the resident arrays, bit for bit.  ghosts (P ranks only):
         dict prev_vr, prev_vt, next_vr, next_vt of p values each (None on the first / last rank).  Returns (sigma_array.r or the mean mass,

@@ -240,6 +240,41 @@ __global__ void __launch_bounds__(256) dyn_stats_kernel(DynArgs a, long n_blocks
 	}
 }
 
+// ---- simul_relax_new (reference src/cmc/cmc_dynamics_helper.c:2526-2580): the relaxation time step -----------------------------------------
+// One thread per block of 2p consecutive stars: the three sums freshly added in star order, the local density at the block's centre, dt;
+// the minimum over the blocks through an atomic on the bit pattern (positive doubles order like their bits).  Every operation is an IEEE
+// add / mul / div / sqrt in the reference's order: the result is the reference's double.
+__global__ void __launch_bounds__(128) simul_relax_kernel(const char *star1, const double *r, const double *m, long n_local, long first_global, long N_MAX,
+							    double N_STAR, double madhoc, long p, double thetasemax, unsigned long long *dtmin_bits)
+{
+	const long nblk = n_local - p > 1 + p ? (n_local - p - (1 + p) + 2 * p - 1) / (2 * p) : 0; // si = 1 + p, 1 + 3p, ... while si < n_local - p
+	const long b = (long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nblk) return;
+	const long si = 1 + p + 2 * p * b, simin = si - p, simax = simin + (2 * p - 1);
+	double Mv2ave = 0.0, Mave = 0.0, M2ave = 0.0;
+	for (long k = simin; k <= simax; k++) {
+		const char *rec = star1 + (k - 1) * CMCB_SIZEOF_STAR;
+		const double vr = ldf(rec, CMCB_OFF_VR), vt = ldf(rec, CMCB_OFF_VT);
+		const double tmp = m[first_global + k - 1] * madhoc;
+		Mv2ave += tmp * (dyn_sqr(vr) + dyn_sqr(vt));
+		Mave += tmp;
+		M2ave += dyn_sqr(tmp);
+	}
+	Mv2ave /= (double) (2 * p);
+	Mave /= (double) (2 * p);
+	M2ave /= (double) (2 * p);
+	const double sigma = sqrt(Mv2ave / Mave);
+	const double W = 4.0 * sigma / sqrt(3.0 * DYN_PI);
+	long kmin, kmax;
+	dyn_n_local_range(first_global + si - 1, p, N_MAX, &kmin, &kmax);
+	const double n_local_dens = (2.0 * ((double) p)) * 3.0 / (4.0 * DYN_PI * (dyn_cub(r[kmax]) - dyn_cub(r[kmin])));
+	const double dt = dyn_sqr(2.0 * thetasemax / DYN_PI) * (DYN_PI / 32.0) * dyn_cub(W) / (N_STAR * n_local_dens * (4.0 * M2ave));
+	if (dt < __longlong_as_double((long long) *dtmin_bits)) { // MIN(dtmin, dt): a NaN never replaces the minimum
+		if (dt >= 0.0) atomicMin(dtmin_bits, (unsigned long long) __double_as_longlong(dt));
+		else atomicExch(dtmin_bits, (unsigned long long) __double_as_longlong(dt)); // a negative step: cannot happen with sane inputs; keep it visible
+	}
+}
+
 } // namespace cmcb
 
 struct DynScratch {
@@ -379,5 +414,30 @@ extern "C" int cmcb200_dev_dynamics_encounters(cmcb200_ctx *c, long cap, long *k
 		}
 		k[i] = a0; kp[i] = a1; type[i] = e[i].type; rperi[i] = e[i].rperi; W[i] = e[i].W; rcm[i] = e[i].rcm;
 	}
+	return 0;
+}
+
+// simul_relax_new (src/cmc/cmc_dynamics_helper.c:2526-2580) on the resident arrays: *DTrel = this rank's minimum (+inf without a complete block)
+extern "C" int cmcb200_dev_simul_relax(cmcb200_ctx *c, long n_local, long first_global, long N_MAX, long N_STAR, long avekernel, double thetasemax, double *DTrel)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (join_uploads(c)) return -1;
+	if (avekernel < 1 || n_local + 2 > c->n_star_dim) { set_error("simul_relax: AVEKERNEL %ld, n_local %ld", avekernel, n_local); return -1; }
+	unsigned long long *d = (unsigned long long *) c->d_ostats; // any 8-byte device scalar the orbit step is not using right now
+	double *h = (double *) c->h_pinned;
+	const double inf = __builtin_inf();
+	memcpy(h, &inf, sizeof inf);
+	CMCB_CUDA_OK(cudaMemcpyAsync(d, h, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	const long p = avekernel, nblk = n_local - p > 1 + p ? (n_local - p - (1 + p) + 2 * p - 1) / (2 * p) : 0;
+	if (nblk > 0) {
+		StageTimer t(c, ST_DYNAMICS);
+		simul_relax_kernel<<<(unsigned) ((nblk + 127) / 128), 128, 0, c->stream>>>(star1(c), c->d_r, c->d_m, n_local, first_global, N_MAX, (double) N_STAR,
+											   1.0 / ((double) N_STAR), p, thetasemax, d);
+		c->launches += 1;
+	}
+	CMCB_CUDA_OK(cudaGetLastError());
+	CMCB_CUDA_OK(cudaMemcpyAsync(h + 1, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
+	*DTrel = h[1];
 	return 0;
 }

@@ -339,6 +339,12 @@ int cmcb200_dev_dynamics_apply(cmcb200_ctx *ctx, const cmcb200_dynamics_params *
  * 2 with a binary) and what the reference hands to sscollision_do / binint_do (rperi, W, rcm).  More than cap pairs: -3, *count set. */
 int cmcb200_dev_dynamics_encounters(cmcb200_ctx *ctx, long cap, long *k, long *kp, int *type, double *rperi, double *W, double *rcm, long *count);
 
+/* simul_relax_new (src/cmc/cmc_dynamics_helper.c:2526-2580), the relaxation time step GetTimeStep starts from (src/cmc/cmc_evolution_thr.c:317-331),
+ * on the resident arrays: the minimum over this rank's blocks of 2 AVEKERNEL stars of (2 THETASEMAX / PI)^2 (PI / 32) W^3 / (N_STAR n (4 <m^2>)),
+ * bit for bit (fresh block sums in star order, IEEE sqrt / divisions); +inf when the rank holds no complete block.  The caller takes the
+ * minimum over the ranks (MPI_Allreduce MIN, :2577) and applies calc_timestep's rules (src/cmc/cmc_utils.c:2132-2148). */
+int cmcb200_dev_simul_relax(cmcb200_ctx *ctx, long n_local, long first_global, long N_MAX, long N_STAR, long avekernel, double thetasemax, double *DTrel);
+
 /* ---- calc_sigma_r (src/cmc/cmc_dynamics_helper.c:2821-2975) on the resident arrays -------------------------------------- */
 /* sigma = sqrt(sum m v^2 / sum m) over the window of 2p stars around every local star, from the reference's two running sums: each star
  * subtracts the star that left the window and adds the one that entered, every operation rounded on its own, so the values carry the

@@ -774,6 +774,32 @@ long orc_dynamics_apply_pairs(const orc_tables_t *t, long n_local, long first_gl
 	return npairs;
 }
 
+/* ---- simul_relax_new, src/cmc/cmc_dynamics_helper.c:2526-2580 ------------------------------------------------------------------------------- */
+
+double orc_simul_relax_new(const orc_tables_t *t, long n_local, long first_global, long p, double thetasemax, const double *vr, const double *vt)
+{
+	double dtmin = INFINITY;
+	for (long si = 1 + p; si < n_local - p; si += 2 * p) { /* :2539 */
+		const long simin = si - p, simax = simin + (2 * p - 1);
+		double Mv2ave = 0.0, Mave = 0.0, M2ave = 0.0;
+		for (long k = simin; k <= simax; k++) {
+			const double tmp = t->m[first_global + k - 1] * t->madhoc;
+			Mv2ave += tmp * (orc_sqr(vr[k - 1]) + orc_sqr(vt[k - 1]));
+			Mave += tmp;
+			M2ave += orc_sqr(tmp);
+		}
+		Mv2ave /= (double) (2 * p);
+		Mave /= (double) (2 * p);
+		M2ave /= (double) (2 * p);
+		const double sigma = sqrt(Mv2ave / Mave);
+		const double W = 4.0 * sigma / sqrt(3.0 * ORC_PI);
+		const double n_local_dens = orc_calc_n_local(t->r, first_global + si - 1, p, t->N_MAX);
+		const double dt = orc_sqr(2.0 * thetasemax / ORC_PI) * (ORC_PI / 32.0) * orc_cub(W) / (((double) t->N_STAR) * n_local_dens * (4.0 * M2ave));
+		dtmin = dt < dtmin ? dt : dtmin; /* MIN(dtmin, dt), include/cmc/cmc.h */
+	}
+	return dtmin;
+}
+
 /* ---- tidally_strip_stars, src/cmc/cmc_evolution_thr.c:443-645: the per-star criterion of one pass of its loop ------------------------------ */
 
 long orc_tidally_strip_select(long n_local, int tidal_treatment, double threshold, const double *r_apo, const double *E, double *rnew,

@@ -146,6 +146,12 @@ long orc_dynamics_apply_pairs(const orc_tables_t *t, long n_local, long first_gl
 			      const double *bin_a, const long *threebb, long *pair_k, long *pair_kp, int *pair_status, double *pair_rperi,
 			      double *pair_W, double *pair_rcm, orc_relax_stats_t *stats);
 
+/* simul_relax_new, src/cmc/cmc_dynamics_helper.c:2526-2580: the relaxation time step of GetTimeStep (src/cmc/cmc_evolution_thr.c:317-331) as
+ * ONE rank computes it -- the local stars in consecutive blocks of 2p (the last, incomplete block is left out: si < n_local - p), per block
+ * the freshly summed m v^2, m, m^2, the local density at the block's centre, dt = (2 THETASEMAX / PI)^2 (PI / 32) W^3 / (N_STAR n (4 <m^2>)),
+ * and the minimum over the blocks (+inf when there is no block).  The caller takes the minimum over the ranks (MPI_Allreduce MIN). */
+double orc_simul_relax_new(const orc_tables_t *t, long n_local, long first_global, long p, double thetasemax, const double *vr, const double *vt);
+
 /* tidally_strip_stars, src/cmc/cmc_evolution_thr.c:443-645 (between energy_conservation2 and ComputeIntermediateEnergy, cmc.c:321-322): one
  * pass of its do-while loop over the local stars.  A star still in the cluster (rnew < 1e6) is stripped when r_apo > threshold = Rtidal
  * (TIDAL_TREATMENT 0, :479) or E > threshold = gierszalpha * phi_rtidal (TIDAL_TREATMENT 1, :555): rnew = SF_INFINITY, vrnew = vtnew = 0.

@@ -330,6 +330,9 @@ EXPORT long ref_dynamics_apply(double dt, const long *flags, const double *par, 
 }
 EXPORT const double *ref_sigma_array(int which) { return which ? sigma_array.sigma : sigma_array.r; }
 
+/* simul_relax_new (src/cmc/cmc_dynamics_helper.c:2526-2580) on the harness's cluster state */
+EXPORT double ref_simul_relax_new(long avekernel, double thetasemax) { AVEKERNEL = avekernel; THETASEMAX = thetasemax; return simul_relax_new(); }
+
 /* timing leg for bench.py: one pass of orbit step -> (caller refreshes r) -> sort -> post_sort_comm -> potential.
  * Brackets follow timeStartSimple/timeEndSimple (cmc_utils.c:1681-1707): barrier, wall clock. */
 EXPORT void ref_time_step(double *t_orb, double *t_sort, double *t_comm, double *t_pot)

@@ -179,7 +179,29 @@ def energy_cases(R):
         print(f"energy_{case}: {int((out['out_vr'] != f['vr']).sum())} of {n} velocities corrected, sigma[n/2] = {out['sigma_p20_m0_sigma'][n // 2]:.6f}")
 
 
+def lagrad_run():
+    """plummer_lagrad_run.npz: the Lagrange radii of the reference's OWN example run to core collapse (examples/PlummerSphere.ini; its output
+    docs/sphinx/source/example_output/plummer.lagrad.dat, 4 373 timesteps, 25 mass fractions), averaged over windows of +-0.01 time units
+    around t = 0, 0.05, ..., 1.70 -- what "Lagrangian radii from a full run must statistically agree with the reference run" is checked against."""
+    path = os.path.join(REF, "docs/sphinx/source/example_output/plummer.lagrad.dat")
+    hdr = open(path).readlines()[1]
+    frac = np.array([float(x.split("(")[1].rstrip(")")) for x in hdr.split()[1:]])
+    d = np.loadtxt(path)
+    times = np.arange(0.0, 1.7001, 0.05)
+    rows, count = [], []
+    for t in times:
+        sel = np.abs(d[:, 0] - t) <= 0.01
+        rows.append(d[sel, 1:].mean(axis=0))
+        count.append(int(sel.sum()))
+    np.savez_compressed(os.path.join(HERE, "plummer_lagrad_run.npz"), mass_pc=frac, t=times, r=np.array(rows), rows_averaged=np.array(count),
+                        t_end=d[-1, 0], n_steps=len(d))
+    print("plummer_lagrad_run.npz:", len(times), "times x", len(frac), "fractions; run ends at t =", d[-1, 0], "after", len(d), "steps")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "lagrad":     # the reference's example run (a data file of the reference, no build needed)
+        lagrad_run()
+        return
     assert rh.available(), "build oracle/_ref first (make -C oracle)"
     if len(sys.argv) > 1 and sys.argv[1] == "energy":     # only the energy-scheme / sigma fixtures
         energy_cases(rh.Ref())

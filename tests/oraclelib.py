@@ -81,6 +81,8 @@ def lib():
         L.orc_calc_sigma_r.argtypes = [C.c_long] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
         L.orc_dynamics_apply_pairs.restype = C.c_long
         L.orc_dynamics_apply_pairs.argtypes = [C.POINTER(Tables), C.c_long, C.c_long, C.c_double, C.POINTER(DynParams)] + [C.c_void_p] * 17 + [C.POINTER(RelaxStats)]
+        L.orc_simul_relax_new.restype = C.c_double
+        L.orc_simul_relax_new.argtypes = [C.POINTER(Tables), C.c_long, C.c_long, C.c_long, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_tidally_strip_select.restype = C.c_long
         L.orc_tidally_strip_select.argtypes = [C.c_long, C.c_int, C.c_double] + [C.c_void_p] * 6
         L.orc_compute_energy_totals.argtypes = [C.POINTER(Tables), C.c_long, C.c_long] + [C.c_void_p] * 11
@@ -305,6 +307,12 @@ def dynamics_apply_pairs(t, first_global, dt, dp, draws, f, bin_a=None):
     out["Nrelbeta"] = np.array(st.Nrelbeta[:])
     out["qave"], out["mave"], out["rave"] = np.array(st.qaverelbeta[:]), np.array(st.maverelbeta[:]), np.array(st.raverelbeta[:])
     return out
+
+
+def simul_relax_new(t, first_global, p, thetasemax, vr, vt):
+    """simul_relax_new (reference cmc_dynamics_helper.c:2526-2580) as the rank owning the local stars vr / vt sees it"""
+    vr, vt = np.ascontiguousarray(vr, np.float64), np.ascontiguousarray(vt, np.float64)
+    return lib().orc_simul_relax_new(C.byref(t), len(vr), first_global, p, thetasemax, _p(vr), _p(vt))
 
 
 def tidally_strip_select(tidal_treatment, threshold, f):

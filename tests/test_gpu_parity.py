@@ -1120,3 +1120,71 @@ def test_whole_timestep_from_dynamics_apply_resident():
     n3 = c.clus.N_MAX
     assert np.all(np.diff(c.field("r")[1:n3 + 1]) >= 0) and len(np.unique(c.field("id")[1:n3 + 1])) == n3
     c.close()
+
+
+def test_simul_relax_bit_exact():
+    """simul_relax_new (reference cmc_dynamics_helper.c:2526-2580) on the resident arrays against the restatement pinned against the
+    compiled reference: the same double, whole cluster and a shard"""
+    for kind, N, masses, first, nl in (("plummer", 300000, "imf", 1, None), ("king", 50011, "equal", 1, None), ("plummer", 120000, "imf", 30001, 50001),
+                                       ("plummer", 50, "equal", 1, None)):
+        r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + 2, masses=masses)
+        pot = cm.oracle_potential(r, sm)
+        nl = N - first + 1 if nl is None else nl
+        c = Cluster(N, n_star_dim=N + 64)
+        c.load(r, vr, vt, sm)
+        c.star_phi[:N + 2] = pot["phi"][:N + 2]
+        if first > 1 or nl < N:
+            c.field("vr")[1:nl + 1], c.field("vt")[1:nl + 1] = vr[first - 1:first - 1 + nl], vt[first - 1:first - 1 + nl]
+        c.clus.N_MAX_NEW, c.Start[0], c.End[0] = nl, first, first + nl - 1
+        c.upload()
+        t = ol.tables(pot["star_r"], pot["star_m"], pot["phi"], N, N)
+        for theta in (1.0, 1.4142135623730951):
+            want = ol.simul_relax_new(t, first, 20, theta, vr[first - 1:first - 1 + nl], vt[first - 1:first - 1 + nl])
+            got = c.dev_simul_relax(theta)
+            assert np.float64(got).view(np.uint64) == np.float64(want).view(np.uint64), (kind, N, got, want)
+        c.close()
+
+
+def test_lagrange_radii_of_a_full_run_agree_with_the_reference_run():
+    """"Lagrangian radii from a full run must statistically agree with the reference run" (north star): a Plummer sphere of 10^5 equal-mass
+    stars evolved by two-body relaxation towards core collapse with the configuration of examples/PlummerSphere.ini (CMC_GAMMA 0.1, THETASEMAX 1,
+    AVEKERNEL 20, radial tidal criterion) -- EVERY N-sized operation of the main loop on the resident arrays (Cluster.evolve: calc_timestep,
+    dynamics_apply, the energy scheme, orbits, sort, potential, Lagrange radii), more than a thousand timesteps without the records visiting
+    the host -- against the Lagrange radii of the reference's own example run (docs/.../plummer.lagrad.dat -> tests/golden/plummer_lagrad_run.npz):
+    the inner radii contract and the outer ones expand on the reference's clock.  Tolerances: the sampling noise of the mass fraction in both
+    runs plus the run-to-run scatter of the collapse."""
+    import os
+    ref = np.load(os.path.join(cm.GOLDEN, "plummer_lagrad_run.npz"))
+    fr, t_ref, r_ref = ref["mass_pc"], ref["t"], ref["r"]
+    N = 100000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=77)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, sm)
+    c.calc_potential_new()
+    c.compute_energy()
+    c.upload()
+    before = c.transfer_bytes(reset=True)
+    hist = c.evolve(t_end=1.5, seed=11, THETASEMAX=1.0, tidally_strip=0, GAMMA=0.1, mass_pc=fr, record_every=5)
+    moved = c.transfer_bytes()
+    steps = len(hist) * 5
+    assert 300 < steps < 20000, steps
+    assert moved[0] + moved[1] < 64 * steps * 25 * 8 + (1 << 22), f"the records must stay on the device: {moved} bytes in {steps} steps"
+    th = np.array([h[0] for h in hist])
+    lag = np.array([h[3] for h in hist])
+    sel = [int(np.argmin(np.abs(fr - f))) for f in (0.01, 0.05, 0.1, 0.3, 0.5, 0.7, 0.9)]
+    worst = 0.0
+    for tq in (0.25, 0.5, 0.75, 1.0, 1.25, 1.45):
+        w = np.abs(th - tq) <= 0.015
+        assert w.sum() >= 1, tq
+        mine = lag[w].mean(axis=0)
+        want = r_ref[int(np.argmin(np.abs(t_ref - tq)))]
+        for j in sel:
+            tol = 0.12 if fr[j] <= 0.05 else 0.06
+            dev = abs(mine[j] / want[j] - 1)
+            worst = max(worst, dev)
+            assert dev < tol, f"t = {tq}: r({fr[j]}) = {mine[j]:.4f}, the reference run has {want[j]:.4f}"
+    # the evolution itself, not just the initial model: the 10 % radius has contracted, the 90 % radius expanded, like in the reference run
+    j10, j90 = sel[2], sel[6]
+    assert lag[-1][j10] < 0.75 * lag[0][j10] and lag[-1][j90] > 1.3 * lag[0][j90]
+    print(f"full run: {steps} steps to t = {th[-1]:.3f}, N_MAX {N} -> {hist[-1][2]}, worst Lagrange-radius deviation from the reference run {worst:.3f}")
+    c.close()

@@ -265,6 +265,26 @@ def _g(x):
     return "%g" % x
 
 
+@pytest.mark.parametrize("kind,N,masses,p", [("plummer", 30000, "imf", 20), ("king", 20011, "equal", 20), ("plummer", 5000, "imf", 3), ("plummer", 50, "equal", 20)])
+def test_simul_relax_new(R, kind, N, masses, p):
+    """simul_relax_new, the relaxation time step of GetTimeStep (reference cmc_dynamics_helper.c:2526-2580), compiled reference against the
+    restatement: the same double, bit for bit (fresh block sums, sqrt and divisions only)"""
+    r, vr, vt, sm = cm.cluster_state(kind, N, seed=N + p, masses=masses)
+    R.init(N, n_star_dim=N + 64)
+    R.load_cluster(r, vr, vt, sm)
+    R.set_scalars(N, N)
+    R.L.ref_calc_potential_new()
+    R.L.ref_simul_relax_new.restype = C.c_double
+    R.L.ref_simul_relax_new.argtypes = [C.c_long, C.c_double]
+    t = ol.tables(R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy(), N, N)
+    for theta in (1.0, 1.4142135623730951):
+        want = R.L.ref_simul_relax_new(p, theta)
+        got = ol.simul_relax_new(t, 1, p, theta, vr, vt)
+        assert np.float64(got).view(np.uint64) == np.float64(want).view(np.uint64), (got, want)
+    assert (np.isinf(want) and N < 3 * p) or (0 < want < 1)
+    R.free()
+
+
 @pytest.mark.parametrize("treatment,orbit_r", [(1, 6.0), (0, 6.0), (1, 1.0e6)])
 def test_tidally_strip_stars(R, treatment, orbit_r):
     """tidally_strip_stars (reference cmc_evolution_thr.c:443-645), the step between energy_conservation2 and ComputeIntermediateEnergy when
