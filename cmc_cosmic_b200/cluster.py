@@ -449,12 +449,13 @@ class Cluster:
     def _allreduce_min(self, x):
         return x
 
-    def evolve(self, t_end, max_steps=10**9, seed=0, THETASEMAX=1.0, tidally_strip=0, GAMMA=0.1, mass_pc=None, record_every=1):
+    def evolve(self, t_end, max_steps=10**9, seed=0, THETASEMAX=1.0, tidally_strip=0, GAMMA=0.1, mass_pc=None, record_every=1, min_dt=0.0):
         """The reference's main loop (src/cmc/cmc.c:240-407) for a relaxation-only run (examples/PlummerSphere.ini), every N-sized operation on
         the resident arrays: calc_timestep (simul_relax_new) -> dynamics_apply (calc_sigma_r, two-body relaxation of every pair) ->
         energy_conservation1 -> new_orbits_calculate -> energy_conservation2 -> tidally_strip_stars -> ComputeIntermediateEnergy -> qsorts_new
         -> calc_potential_new -> energy_conservation3 -> comp_mass_percent -> ComputeEnergy.  The 424-byte records never visit the host.
-        Returns the history [(TotalTime, Dt, N_MAX, Lagrange radii)] recorded every `record_every` steps."""
+        Stops at t_end, after max_steps, or when the time step falls below min_dt (the runaway of core collapse, where the reference's
+        STOPATCORECOLLAPSE ends the run).  Returns the history [(TotalTime, Dt, N_MAX, Lagrange radii)] recorded every `record_every` steps."""
         hist, steps = [], 0
         pc = None if mass_pc is None else np.ascontiguousarray(mass_pc, np.float64)
         while getattr(self, "TotalTime", 0.0) < t_end and steps < max_steps:
@@ -466,6 +467,8 @@ class Cluster:
             self.TidalMassLoss += self.TidalMassLoss_old                      # cmc_utils.c:2210
             self.Prev_Dt = Dt
             steps += 1
+            if Dt < min_dt:
+                break
             if steps % record_every == 0:
                 lag = None
                 if pc is not None:

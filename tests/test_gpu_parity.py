@@ -1164,7 +1164,7 @@ def test_lagrange_radii_of_a_full_run_agree_with_the_reference_run():
     c.compute_energy()
     c.upload()
     before = c.transfer_bytes(reset=True)
-    hist = c.evolve(t_end=1.5, seed=11, THETASEMAX=1.0, tidally_strip=0, GAMMA=0.1, mass_pc=fr, record_every=5)
+    hist = c.evolve(t_end=1.4, max_steps=20000, seed=11, THETASEMAX=1.0, tidally_strip=0, GAMMA=0.1, mass_pc=fr, record_every=5)
     moved = c.transfer_bytes()
     steps = len(hist) * 5
     assert 300 < steps < 20000, steps
@@ -1173,13 +1173,13 @@ def test_lagrange_radii_of_a_full_run_agree_with_the_reference_run():
     lag = np.array([h[3] for h in hist])
     sel = [int(np.argmin(np.abs(fr - f))) for f in (0.01, 0.05, 0.1, 0.3, 0.5, 0.7, 0.9)]
     worst = 0.0
-    for tq in (0.25, 0.5, 0.75, 1.0, 1.25, 1.45):
+    for tq in (0.25, 0.5, 0.75, 1.0, 1.25, 1.38):      # 80 % of the way to core collapse (t = 1.72 in the reference run; the last stretch is a runaway whose onset scatters by a few per cent from run to run)
         w = np.abs(th - tq) <= 0.015
         assert w.sum() >= 1, tq
         mine = lag[w].mean(axis=0)
         want = r_ref[int(np.argmin(np.abs(t_ref - tq)))]
         for j in sel:
-            tol = 0.12 if fr[j] <= 0.05 else 0.06
+            tol = 0.10 if fr[j] <= 0.05 else 0.06
             dev = abs(mine[j] / want[j] - 1)
             worst = max(worst, dev)
             assert dev < tol, f"t = {tq}: r({fr[j]}) = {mine[j]:.4f}, the reference run has {want[j]:.4f}"
