@@ -131,7 +131,10 @@ __device__ __forceinline__ void dyn_load_star(const DynArgs &a, long k /* 1-base
 	}
 }
 
-__global__ void __launch_bounds__(DYN_THREADS) dyn_pair_kernel(DynArgs a)
+#ifndef CMCB_DYN_MIN_BLOCKS
+#define CMCB_DYN_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(DYN_THREADS, CMCB_DYN_MIN_BLOCKS) dyn_pair_kernel(DynArgs a)
 {
 	__shared__ DynBlockStats sh[DYN_THREADS / 32];
 	const long i = (long) blockIdx.x * DYN_THREADS + threadIdx.x;

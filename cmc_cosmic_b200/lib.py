@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmcb200.so")
+LIB_PATH = os.environ.get("CMCB200_LIB") or os.path.join(_HERE, "libcmcb200.so")   # CMCB200_LIB: another build of the same library (A/B measurements)
 N_STAGES = 19
 STAGE_NAMES = ["keys_hist", "radix_passes", "record_gather", "binaries", "potential", "orbit_prepare", "transfer", "energy", "h2d", "d2h",
                "orbit_scan", "orbit_tries", "orbit_tables", "shard_keys", "shard_rank", "shard_tables", "lagrange", "dynamics", "sigma"]
