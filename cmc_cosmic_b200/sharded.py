@@ -280,6 +280,14 @@ class ShardedCluster(Cluster):
         res.global_qaverelbeta, res.global_maverelbeta, res.global_raverelbeta = tot[5:9], tot[9:13], tot[13:17]
         return res
 
+    def _allreduce_min(self, x):
+        """MPI_Allreduce(MPI_MIN) of simul_relax_new (reference cmc_dynamics_helper.c:2577)"""
+        import torch
+        with torch.cuda.stream(self._tstream):
+            t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{self.device}")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            return float(t.cpu()[0])
+
     def _allreduce_sum(self, values):
         import torch
         with torch.cuda.stream(self._tstream):

@@ -254,3 +254,51 @@ def run_dyn(rank, world, port, N):
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank}/{world}: calc_sigma_r bit-exact, dynamics_apply within 1e-12 of the oracle rank (N={N}, shard {lo}..{hi})", flush=True)
+
+
+def run_evolve(rank, world, port, N, t_end):
+    """A whole relaxation-driven run (Cluster.evolve: calc_timestep, dynamics_apply, energy scheme, orbits, sort, potential per timestep) on
+    `world` GPUs against the same run on one GPU: the partition's chunks are multiples of 2 AVEKERNEL, so the ranks form the same pairs and
+    blocks, the Philox draws are keyed by global indices -- the sharded run must leave the same records, bit for bit."""
+    import torch
+    import torch.distributed as dist
+    import common as cm
+    from cmc_cosmic_b200.cluster import Cluster
+    from cmc_cosmic_b200.sharded import ShardedCluster
+    from cmc_cosmic_b200.layout import star_field
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=41)
+    pcs = np.array([0.01, 0.1, 0.5, 0.9])
+    c = ShardedCluster(N, dist, device=rank)
+    c.load_global(r, vr, vt, sm)
+    c.calc_potential_new()
+    c.compute_energy()
+    c.upload()
+    hist = c.evolve(t_end=t_end, max_steps=400, seed=13, tidally_strip=None, GAMMA=0.1)
+    c.download()
+    c.sync()
+    lo, hi, nl = int(c.Start[rank]), int(c.End[rank]), c.clus.N_MAX_NEW
+    s = Cluster(N, n_star_dim=N + 64, device=rank)
+    s.load(r, vr, vt, sm)
+    s.calc_potential_new()
+    s.compute_energy()
+    s.upload()
+    hist1 = s.evolve(t_end=t_end, max_steps=400, seed=13, tidally_strip=None, GAMMA=0.1)
+    s.download()
+    assert len(hist) == len(hist1) and len(hist) > 20, (len(hist), len(hist1))
+    assert [h[:3] for h in hist] == [h[:3] for h in hist1], "the time steps of the sharded run differ"
+    assert c.clus.N_MAX == s.clus.N_MAX
+    want, shard = s.star[lo:hi + 1].copy(), c.star[1:nl + 1].copy()
+    bad = np.nonzero((want != shard).any(axis=1))[0]
+    assert bad.size == 0, f"rank {rank}: {bad.size} of {nl} records differ after {len(hist)} timesteps, first local {bad[0]}"
+    for name in ("star_r", "star_m", "star_phi"):
+        assert np.array_equal(getattr(c, name)[:c.clus.N_MAX + 2].view(np.uint64), getattr(s, name)[:c.clus.N_MAX + 2].view(np.uint64)), name
+    c.close()
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank}/{world}: {len(hist)} timesteps to t = {hist[-1][0]:.4f} sharded == single GPU (N={N}, shard {lo}..{hi})", flush=True)

@@ -60,3 +60,12 @@ def test_sharded_calc_sigma_r_and_dynamics_apply(world, N):
     if world > _n_gpus():
         pytest.skip(f"needs {world} GPUs")
     mp.spawn(sharded_worker.run_dyn, args=(world, 29570 + world, N), nprocs=world, join=True)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_sharded_full_run_equals_single_gpu_run():
+    """the reference's main loop for a relaxation-only run (calc_timestep, dynamics_apply, energy scheme, orbits, sharded sort, potential) over
+    dozens of timesteps on 2 GPUs: bit-identical with the same run on one GPU"""
+    import torch.multiprocessing as mp
+    import sharded_worker
+    mp.spawn(sharded_worker.run_evolve, args=(2, 29581, 200000, 0.05), nprocs=2, join=True)
