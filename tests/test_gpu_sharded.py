@@ -68,4 +68,4 @@ def test_sharded_full_run_equals_single_gpu_run():
     dozens of timesteps on 2 GPUs: bit-identical with the same run on one GPU"""
     import torch.multiprocessing as mp
     import sharded_worker
-    mp.spawn(sharded_worker.run_evolve, args=(2, 29581, 200000, 0.05), nprocs=2, join=True)
+    mp.spawn(sharded_worker.run_evolve, args=(2, 29581, 200000, 0.3), nprocs=2, join=True)
