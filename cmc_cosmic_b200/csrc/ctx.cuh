@@ -63,6 +63,7 @@ struct cmcb200_ctx {
 	void *d_multimass; // argument / result block of comp_multi_mass_percent (lagrange.cu), allocated on first use
 	void *d_seqwork2; // exact-scan scratch for chains of 2 n_star_dim elements (ComputeEnergy's potential sum), allocated on first use
 	void *d_dynamics; // scratch of dynamics_apply's pair loop (dynamics.cu), a host struct holding device buffers, allocated on first use
+	unsigned long long *d_dtmin; // result word of simul_relax_new (dynamics.cu), allocated on first use
 	void *d_sigma;    // scratch of calc_sigma_r (sigma.cu), likewise
 	void *d_sv3;      // scratch of set_velocities3 (velocities.cu), allocated on first use for n_star_dim stars
 	int *d_status;

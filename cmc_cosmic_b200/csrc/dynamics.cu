@@ -288,6 +288,7 @@ struct DynScratch {
 
 void dynamics_free(cmcb200_ctx *c)
 {
+	if (c->d_dtmin) { cudaFree(c->d_dtmin); c->d_dtmin = nullptr; }
 	DynScratch *s = (DynScratch *) c->d_dynamics;
 	if (!s) return;
 	cudaFree(s->w.list); cudaFree(s->w.blk_cnt); cudaFree(s->w.n_list); cudaFree(s->w.bstats); cudaFree(s->w.enc); cudaFree(s->w.n_enc); cudaFree(s->w.totals);
@@ -426,7 +427,8 @@ extern "C" int cmcb200_dev_simul_relax(cmcb200_ctx *c, long n_local, long first_
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	if (join_uploads(c)) return -1;
 	if (avekernel < 1 || n_local + 2 > c->n_star_dim) { set_error("simul_relax: AVEKERNEL %ld, n_local %ld", avekernel, n_local); return -1; }
-	unsigned long long *d = (unsigned long long *) c->d_ostats; // any 8-byte device scalar the orbit step is not using right now
+	if (!c->d_dtmin) CMCB_CUDA_OK(cudaMalloc(&c->d_dtmin, sizeof(unsigned long long)));
+	unsigned long long *d = c->d_dtmin;
 	double *h = (double *) c->h_pinned;
 	const double inf = __builtin_inf();
 	memcpy(h, &inf, sizeof inf);

@@ -11,6 +11,10 @@ for W in king_w5_n1e6 king_w7_n2e6_bin plummer_n1e5; do
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_${TAG}_bench.csv python bench.py --steps 2 --warmup 1 --no-parity --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"orbit_prepare_kernel|orbit_try_kernel|sort_gather_records|sort_onesweep_pass|seq_scan_classify|seq_scan_finalize" -c 24 -f -o $OUT/prof_$TAG python tools/perf_orbit.py 1e7 1 > $OUT/ncu_full_$TAG.log 2>&1
+# second half of round 2: the N3 kernels and a whole run
+timeout 300 python tools/perf_sigma.py 1e7 imf > $OUT/perf_sigma_$TAG.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sigma|dyn_|simul_relax" -c 16 --csv --log-file $OUT/ncu_sigma_launches_$TAG.csv python tools/perf_sigma.py 1e7 imf > /dev/null 2>&1
+timeout 200 python tools/full_run.py 1e6 1.40 > $OUT/full_run_${TAG}_n1e6.log 2>&1
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -2 $OUT/smoke_$TAG.log
 python - <<PY
 import json
