@@ -121,10 +121,10 @@ __device__ __forceinline__ TileRange tile_range(const SigmaWindow &w, long tile)
 	t.s_first = 2 + tile * SIG_TILE;
 	t.s_end = t.s_first + SIG_TILE < w.n + 1 ? t.s_first + SIG_TILE : w.n + 1;
 	t.nseg = (int) ((t.s_end - t.s_first + SIG_S - 1) / SIG_S);
-	t.k_lo = t.s_first - 1 - w.p;                        // simin(s_first - 1) >= this
-	if (t.k_lo < 1 - w.p) t.k_lo = 1 - w.p;
-	long k_hi = t.s_end - 1 + w.p - 1;                  // simin(s_end - 1) + 2p - 1 <= this
-	if (k_hi > w.n + w.p) k_hi = w.n + w.p;
+	// simin() never decreases along the stars: the first window of the tile starts at the lowest index its operations touch, the last one ends
+	// at the highest (where the window has stopped sliding at the end of the cluster it lies further back than si - p)
+	t.k_lo = w.simin(t.s_first - 1);
+	long k_hi = w.simin(t.s_end - 1) + (2 * w.p - 1);
 	t.nterm = (int) (k_hi - t.k_lo + 1);
 	return t;
 }

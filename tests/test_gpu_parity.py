@@ -1008,6 +1008,8 @@ SIGMA_CASES = [
     ("plummer", 5000, "imf", 3, 1, None),           # BH_AVEKERNEL
     ("plummer", 200, "imf", 20, 1, None),           # less than one tile
     ("plummer", 41, "equal", 20, 1, None),          # hardly more than one window
+    ("plummer", 6155, "imf", 20, 1, None),          # the last tile (10 stars) lies where the window has stopped sliding: its terms reach back beyond si - p
+    ("plummer", 60000, "imf", 20, 30001, 2048 * 5 + 8),  # the same for a middle shard (the window keeps sliding into the ghost stars)
     ("plummer", 30, "equal", 20, 1, None),          # the window does not fit: the loop as one thread runs it
     ("plummer", 60000, "imf", 20, 20001, 20000),    # a middle shard: an empty window p stars before its first star, ghost stars on both sides
     ("plummer", 60000, "imf", 20, 40001, 20000),    # the last shard
