@@ -104,6 +104,26 @@ class Cluster:
             self.N_b_local = self.clus.N_BINARY = int((np.asarray(binind) > 0).sum())
             self.bin_slots_in_use = int(np.max(binind)) if len(binind) else 0
 
+    @classmethod
+    def from_input_hdf5(cls, path, **kw):
+        """A cluster from one of the reference's initial-condition files (``input.hdf5``, written by COSMIC; reference
+        src/libs/fitslib.c:209-448, src/cmc/cmc_fits.c:100-140): objects 1 .. NOBJ in radius order, star_m = obj_m * N_STAR, binaries in
+        binary[1 .. NBINARY] with the fields the file carries (ids, masses, radii, a, e), RTID as orbit_r."""
+        from . import hdf5_input
+        d = hdf5_input.read_input(path)
+        n, nb = d["NOBJ"], d["NBINARY"]
+        o, b = d["obj"], d["bin"]
+        c = cls(n, n_bin_dim=kw.pop("n_bin_dim", nb + 16), orbit_r=kw.pop("orbit_r", d["RTID"]), **kw)
+        c.load(o["r"][1:n + 1], o["vr"][1:n + 1], o["vt"][1:n + 1], o["m"][1:n + 1] * n, binind=o["binind"][1:n + 1].astype(np.int64),
+               ids=o["id"][1:n + 1].astype(np.int64))
+        for dst, src in (("id1", "id1"), ("id2", "id2")):
+            c.bfield(dst)[1:nb + 1] = b[src][1:nb + 1].astype(np.int64)
+        for dst, src, scale in (("m1", "m1", float(n)), ("m2", "m2", float(n)), ("rad1", "Reff1", 1.0), ("rad2", "Reff2", 1.0), ("a", "a", 1.0), ("e", "e", 1.0)):
+            c.bfield(dst)[1:nb + 1] = b[src][1:nb + 1] * scale
+        c.bfield("inuse")[1:nb + 1] = 1
+        c.input = {k: d[k] for k in ("NOBJ", "NBINARY", "Z", "RVIR", "RTID", "MCLUS")}
+        return c
+
     # ---- the reference's four entry points, host-buffer form ------------------------------------------------------
     def calc_potential_new(self):
         """calc_potential_new -> potential_calculate (reference src/cmc/cmc_utils.c:2006-2012, 675-736)."""

@@ -382,3 +382,41 @@ def test_calc_sigma_r_segment_tables_equal_serial_loop(kind, N, masses, p, first
         assert cnt["broken"] == 0 and cnt["hard_segments"] > 50 and cnt["hard_tiles"] > 10, cnt
     else:
         assert cnt["broken"] == 1
+
+
+CI_INPUT = "/root/reference/ci/input.hdf5"
+
+
+@pytest.mark.skipif(not os.path.exists(CI_INPUT), reason="the reference tree (ci/input.hdf5) is not here")
+def test_input_hdf5_reader_reads_the_reference_ci_input():
+    """cmc_cosmic_b200/hdf5_input.py (the file cmc_read_hdf5_file reads, reference src/libs/fitslib.c:209-448) on the reference's
+    own ci/input.hdf5: the attributes, both tables, and the columns equal to what the committed fixture ci_input.npz was generated from (a raw-
+    byte scan of the same file by tests/golden/make_golden.py -- two independent readers)."""
+    from cmc_cosmic_b200 import hdf5_input
+    d = hdf5_input.read_input(CI_INPUT)
+    assert d["NOBJ"] == 10000 and d["NBINARY"] == 1967 and d["RTID"] == 1.0e6 and d["RVIR"] == 1.0 and abs(d["Z"] - 0.014) < 1e-15
+    o, b = d["obj"], d["bin"]
+    n, nb = d["NOBJ"], d["NBINARY"]
+    g = np.load(os.path.join(cm.GOLDEN, "ci_input.npz"))
+    cm.assert_bits_equal(o["r"][1:n + 1], g["r"], "r")
+    cm.assert_bits_equal(o["vr"][1:n + 1], g["vr"], "vr")
+    cm.assert_bits_equal(o["vt"][1:n + 1], g["vt"], "vt")
+    cm.assert_bits_equal(o["m"][1:n + 1] * n, g["star_m"], "star_m")
+    assert np.array_equal(o["binind"][1:n + 1].astype(np.int64), g["binind"])
+    assert np.array_equal(o["id"][1:n + 1], np.arange(1, n + 1)) and o["r"][0] == np.finfo(float).tiny and o["r"][n + 1] == 1e40
+    assert abs(o["m"].sum() - 1.0) < 1e-12                      # total mass in units of the cluster mass (fitslib convention)
+    assert np.array_equal(np.sort(o["binind"][o["binind"] > 0]), np.arange(1, nb + 1)) and np.array_equal(b["index"][1:nb + 1], np.arange(1, nb + 1))
+    assert np.all(b["a"][1:nb + 1] > 0) and np.all((b["e"][1:nb + 1] >= 0) & (b["e"][1:nb + 1] < 1))
+    k = np.nonzero(o["binind"] > 0)[0]                          # a binary's object carries the sum of the component masses
+    np.testing.assert_allclose(o["m"][k], (b["m1"] + b["m2"])[o["binind"][k].astype(int)], rtol=1e-12)
+
+
+def test_input_hdf5_reader_refuses_what_it_does_not_parse(tmp_path):
+    from cmc_cosmic_b200 import hdf5_input
+    p = tmp_path / "x.hdf5"
+    p.write_bytes(b"not hdf5 at all" * 10)
+    with pytest.raises(hdf5_input.Hdf5FormatError):
+        hdf5_input.read_input(str(p))
+    p.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes([2]) + bytes(200))    # superblock version 2
+    with pytest.raises(hdf5_input.Hdf5FormatError):
+        hdf5_input.read_input(str(p))
