@@ -95,6 +95,10 @@ struct RLadder {
 #ifndef CMCB_SLAD_TOP_ENTRIES
 #define CMCB_SLAD_TOP_ENTRIES 2560
 #endif
+#ifndef CMCB_SLAD_SECANT_STEPS
+#define CMCB_SLAD_SECANT_STEPS 0 /* measured on B200: 8 guided probes make stage A SLOWER (2.97 -> 3.66 ms at N = 1e7; profiles/ab_r02b_secant.log) */
+#endif
+constexpr int SLAD_SECANT_STEPS = CMCB_SLAD_SECANT_STEPS; // 0: plain halving on the coarsest level
 constexpr int SLAD_MIN_SHIFT = 4, SLAD_STEP = 4, SLAD_TOP_ENTRIES = CMCB_SLAD_TOP_ENTRIES; // coarsest level <= 40 KB of (r, Phi) pairs
 struct SLadder {
 	const RPhi *lvl[LADDER_MAX_LEVELS]; // coarsest first
@@ -616,7 +620,7 @@ CMCB_HD int sign_Q_laddered(const OrbitTables &t, const QLadder &L, const LBlock
 // before (sign_Q: FP64 with a rigorous bound, the x87 arithmetic replayed inside it).  Same probe sequence, same signs, same k_min / k_max --
 // with about 3 dependent line fetches instead of 24.  Whatever the proof needs and cannot be established (a bracket end inside the margin:
 // a star at its turning point; an unsorted table) falls back to the plain bisection.
-CMCB_HD int side_Q_margin(const StarConst &s, const RPhi p, double margin, double phi_abs_max)
+CMCB_HD int side_Q_margin(const StarConst &s, const RPhi p, double margin, double phi_abs_max, float *q_approx = nullptr)
 {
 	const double a = dsub(s.E, p.phi);
 	const double r2 = dmul(p.r, p.r);
@@ -624,6 +628,7 @@ CMCB_HD int side_Q_margin(const StarConst &s, const RPhi p, double margin, doubl
 	const double t2 = (p.r >= s.r_j) ? dmul(s.mi, p.r) : dmul(s.c_in, r2);
 	const double S = dsub(dmul(2.0, dsub(t1, t2)), s.JJ);
 	const double Bm = dmul(margin, dadd(dadd(dmul(dadd(s.absE, phi_abs_max), r2), s.JJ), dadd(dabs(t1), dabs(t2))));
+	if (q_approx) *q_approx = (float) S / (float) r2; // Q itself, roughly: only steers the search below, never decides a sign
 	if (S > Bm) return 1;
 	if (S < -Bm) return -1;
 	return 0;
@@ -670,9 +675,10 @@ CMCB_HD kint find_zero_Q_sampled(const OrbitTables &t, const LadderTops &top, co
 	// both bracket ends must carry their sign with the margin: the end where Q > 0 anchors the concavity argument.  Entry 0 (r = ZERO, the
 	// central-mass slot) is never probed by the bisection and lies outside the convex sequence: Q there is -J^2 / ZERO^2.
 	if (kmax - kmin < 2 * (1 << SLAD_MIN_SHIFT)) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
-	if (kmin > 0 && side_Q_margin(s, tbl_rp(t, kmin), L.margin, L.phi_abs_max) != low) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
+	float q_lo = 0.0f, q_hi = 0.0f; // approximate Q at the bracket ends (0: unknown)
+	if (kmin > 0 && side_Q_margin(s, tbl_rp(t, kmin), L.margin, L.phi_abs_max, &q_lo) != low) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
 	if (kmin == 0 && !(increasing && s.JJ > 0.0)) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
-	if (side_Q_margin(s, tbl_rp(t, kmax), L.margin, L.phi_abs_max) != -low) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
+	if (side_Q_margin(s, tbl_rp(t, kmax), L.margin, L.phi_abs_max, &q_hi) != -low) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
 	kint lo = kmin, hi = kmax; // every entry in [kmin, lo] has the sign `low`, every entry in [hi, kmax] the sign -low
 	for (int l = 0; l < L.n_levels; l++) {
 		const int sh = L.shift[l];
@@ -680,14 +686,35 @@ CMCB_HD kint find_zero_Q_sampled(const OrbitTables &t, const LadderTops &top, co
 		kint a = lo >> sh, b = ((hi - 1) >> sh) + 1; // level entries a+1 .. b-1 lie strictly inside (lo, hi)
 		const kint a0 = a, b0 = b;
 		bool undecided = false;
+		// Any entry strictly between a and b may be probed next: the invariant (entries <= a carry `low`, entries >= b carry -low) does not care.
+		// On the coarsest level (thousands of entries, ~12 halvings) the next probe is therefore taken where a secant through the approximate
+		// Q values at the window's ends crosses zero (Illinois variant: an end that stays put has its value halved), falling back to halving
+		// after SLAD_SECANT_STEPS probes or whenever the values do not bracket zero.  Q over the entries is concave (see above): 4-6 probes.
+		float xa = (float) lo / (float) (1 << sh), xb = (float) hi / (float) (1 << sh), qa = q_lo, qb = q_hi;
+		int steps = 0, last = 0;
 		while (b - a > 1) {
-			const kint mid = (a + b) >> 1;
+			kint mid = (a + b) >> 1;
+			if (l == 0 && steps < SLAD_SECANT_STEPS && b - a > 4 && qa * qb < 0.0f) {
+				const float xm = xa + (xb - xa) * (qa / (qa - qb));
+				const kint g = (kint) xm;
+				if (g > a && g < b) mid = g;
+				else if (xm <= (float) a) mid = a + 1;
+				else if (xm >= (float) b) mid = b - 1;
+			}
+			steps++;
 			// the coarsest level sits in shared memory in the kernels (a generic load), the others are read through the read-only path
 			const RPhi smp = (l == 0) ? slad_top_ld(lvl + mid) : slad_ld(lvl + mid);
-			const int sd = side_Q_margin(s, smp, L.margin, L.phi_abs_max);
-			if (sd == low) a = mid;
-			else if (sd == -low) b = mid;
-			else { undecided = true; break; }
+			float qm;
+			const int sd = side_Q_margin(s, smp, L.margin, L.phi_abs_max, &qm);
+			if (sd == low) {
+				a = mid; xa = (float) mid; qa = qm;
+				if (last == 1) qb *= 0.5f;
+				last = 1;
+			} else if (sd == -low) {
+				b = mid; xb = (float) mid; qb = qm;
+				if (last == 2) qa *= 0.5f;
+				last = 2;
+			} else { undecided = true; break; }
 		}
 		if (a > a0) lo = a << sh;
 		if (b < b0) hi = b << sh;
