@@ -95,6 +95,9 @@ struct RLadder {
 #ifndef CMCB_SLAD_TOP_ENTRIES
 #define CMCB_SLAD_TOP_ENTRIES 2560
 #endif
+#ifndef CMCB_SLAD_PAIR
+#define CMCB_SLAD_PAIR 0 /* measured on B200: no faster than the two descents one after the other (2.96 vs 2.98 ms at N = 1e7; profiles/ab_r02b_pair.log) */
+#endif
 #ifndef CMCB_SLAD_SECANT_STEPS
 #define CMCB_SLAD_SECANT_STEPS 0 /* measured on B200: 8 guided probes make stage A SLOWER (2.97 -> 3.66 ms at N = 1e7; profiles/ab_r02b_secant.log) */
 #endif
@@ -735,6 +738,73 @@ CMCB_HD kint find_zero_Q_sampled(const OrbitTables &t, const LadderTops &top, co
 	return kmin;
 }
 
+// Both index bisections of calc_orbit_new (cmc_orbit.c:441, :444) through the sample ladder with their descents run in LOCKSTEP: the two
+// searches are independent (k_min left of the star's own entry, k_max right of it), so their probes on every level are issued together --
+// two independent chains of sample load -> margin test per thread instead of one after the other.  Each search is exactly
+// find_zero_Q_sampled: same proven-sign windows, same replay of the reference's probe sequence, same fall-backs.
+struct SladOne {
+	kint kmin, kmax, lo, hi, a, b, a0, b0;
+	int low;
+	bool increasing, sampled, descending, undecided;
+};
+CMCB_HD void slad_one_init(const OrbitTables &t, const SLadder &L, const StarConst &s, SladOne &q, kint kmin, kint kmax, int *n_exact)
+{
+	q.kmin = kmin; q.kmax = kmax; q.lo = kmin; q.hi = kmax;
+	q.increasing = q_increasing(t, s, kmin, kmax, n_exact);
+	q.low = q.increasing ? -1 : 1;
+	q.sampled = kmax - kmin >= 2 * (1 << SLAD_MIN_SHIFT);
+	if (q.sampled && kmin > 0 && side_Q_margin(s, tbl_rp(t, kmin), L.margin, L.phi_abs_max) != q.low) q.sampled = false;
+	if (q.sampled && kmin == 0 && !(q.increasing && s.JJ > 0.0)) q.sampled = false;
+	if (q.sampled && side_Q_margin(s, tbl_rp(t, kmax), L.margin, L.phi_abs_max) != -q.low) q.sampled = false;
+	q.descending = q.sampled;
+	q.undecided = false;
+	q.a = q.b = q.a0 = q.b0 = 0;
+}
+CMCB_HD kint slad_one_finish(const OrbitTables &t, const StarConst &s, SladOne &q, int *n_exact)
+{
+	if (!q.sampled) return find_zero_Q_plain(t, s, q.kmin, q.kmax, q.increasing, n_exact);
+	kint kmin = q.kmin, kmax = q.kmax;
+	do {
+		kint ktry = (kmin + kmax + 1) / 2;
+		bool up;
+		if (ktry <= q.lo) up = true;
+		else if (ktry >= q.hi) up = false;
+		else {
+			const int sg = sign_Q(t, s, ktry, n_exact);
+			up = q.increasing ? (sg < 0) : (sg > 0);
+		}
+		if (up) kmin = ktry; else kmax = ktry - 1;
+	} while (kmax != kmin);
+	return kmin;
+}
+CMCB_HD void find_zero_Q_sampled_pair(const OrbitTables &t, const LadderTops &top, const StarConst &s, kint ktemp, kint *kmin_out, kint *kmax_out, int *n_exact)
+{
+	const SLadder &L = *top.sdesc;
+	SladOne q1, q2;
+	slad_one_init(t, L, s, q1, 0, ktemp, n_exact);
+	slad_one_init(t, L, s, q2, ktemp, t.N_MAX + 1, n_exact);
+	for (int l = 0; l < L.n_levels && (q1.descending || q2.descending); l++) {
+		const int sh = L.shift[l];
+		const RPhi *lvl = (l == 0) ? top.s : L.lvl[l];
+		q1.a = q1.a0 = q1.lo >> sh; q1.b = q1.b0 = ((q1.hi - 1) >> sh) + 1;
+		q2.a = q2.a0 = q2.lo >> sh; q2.b = q2.b0 = ((q2.hi - 1) >> sh) + 1;
+		for (;;) {
+			const bool act1 = q1.descending && !q1.undecided && q1.b - q1.a > 1, act2 = q2.descending && !q2.undecided && q2.b - q2.a > 1;
+			if (!act1 && !act2) break;
+			const kint m1 = act1 ? (q1.a + q1.b) >> 1 : q1.a0, m2 = act2 ? (q2.a + q2.b) >> 1 : q2.a0; // an idle search re-reads an entry it owns: no branch around the loads
+			const RPhi s1 = (l == 0) ? slad_top_ld(lvl + m1) : slad_ld(lvl + m1);
+			const RPhi s2 = (l == 0) ? slad_top_ld(lvl + m2) : slad_ld(lvl + m2);
+			const int d1 = side_Q_margin(s, s1, L.margin, L.phi_abs_max), d2 = side_Q_margin(s, s2, L.margin, L.phi_abs_max);
+			if (act1) { if (d1 == q1.low) q1.a = m1; else if (d1 == -q1.low) q1.b = m1; else q1.undecided = true; }
+			if (act2) { if (d2 == q2.low) q2.a = m2; else if (d2 == -q2.low) q2.b = m2; else q2.undecided = true; }
+		}
+		if (q1.descending) { if (q1.a > q1.a0) q1.lo = q1.a << sh; if (q1.b < q1.b0) q1.hi = q1.b << sh; if (q1.undecided) q1.descending = false; }
+		if (q2.descending) { if (q2.a > q2.a0) q2.lo = q2.a << sh; if (q2.b < q2.b0) q2.hi = q2.b << sh; if (q2.undecided) q2.descending = false; }
+	}
+	*kmin_out = slad_one_finish(t, s, q1, n_exact);
+	*kmax_out = slad_one_finish(t, s, q2, n_exact);
+}
+
 // find_zero_Q (cmc_nr.c:316-383): the same probe sequence ktry = (kmin+kmax+1)/2
 CMCB_HD kint find_zero_Q(const OrbitTables &t, const LadderTops &top, const StarConst &s, kint kmin, kint kmax, int *n_exact)
 {
@@ -893,8 +963,14 @@ CMCB_HD OrbitRS calc_orbit_new(const OrbitTables &t, const LadderTops &top, cons
 	double rmin = 0, rmax = 0, dQdr_min = 0, dQdr_max = 0;
 	kint kmin = 0, kmax = 0;
 	if (!circular) {
-		kmin = find_zero_Q(t, top, s, 0, ktemp, n_exact);               // :441
-		kmax = find_zero_Q(t, top, s, ktemp, t.N_MAX + 1, n_exact);     // :444
+#if CMCB_SLAD_PAIR
+		if (top.s != nullptr) find_zero_Q_sampled_pair(t, top, s, ktemp, &kmin, &kmax, n_exact); // :441, :444 with their descents in lockstep
+		else
+#endif
+		{
+			kmin = find_zero_Q(t, top, s, 0, ktemp, n_exact);               // :441
+			kmax = find_zero_Q(t, top, s, ktemp, t.N_MAX + 1, n_exact);     // :444
+		}
 		double a, b;
 		const double J = s.J, E = s.E;
 		double JJ2 = dmul(dmul(2.0, J), J);
