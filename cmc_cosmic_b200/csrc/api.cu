@@ -71,7 +71,7 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->n_table_dim = n_table_dim;
 	c->rank = 0; c->nranks = 1; c->r_parity = 0;
 	c->n_bin_dim = n_bin_dim;
-	c->orbit_ladders = 9; // bit 5: the rejection rounds as lookup + try kernels (off: measured slower), bit 4: r-ladder lines read whole (off); bit 3: sample ladder for the index bisections of stage A (find_zero_Q_sampled); bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A), bit 2: FP32 screening copy of the (r, Phi) table for the index bisections
+	c->orbit_ladders = 9; // bit 6 (off; needs a build with CMCB_SLAD_F32_TOP): FP32 copy of the sample ladder's coarsest level (its probes screened in FP32 arithmetic); bit 5: the rejection rounds as lookup + try kernels (off: measured slower), bit 4: r-ladder lines read whole (off); bit 3: sample ladder for the index bisections of stage A (find_zero_Q_sampled); bit 0: r ladder (potential() lookups of the rejection rounds), bit 1: Q ladder (index bisections of stage A), bit 2: FP32 screening copy of the (r, Phi) table for the index bisections
 	c->bytes_h2d = c->bytes_d2h = 0;
 	c->orbit_ctas = 4;
 	c->orbit_max_chunks = 8;
@@ -476,6 +476,7 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 		if (!(c->orbit_ladders & 1)) lb.r = nullptr;
 		lb.r_whole_lines = (c->orbit_ladders & 16) != 0;
 		lb.sampled = (c->orbit_ladders & 8) && !(c->orbit_ladders & 2); // the sample ladder lives in the Q ladder's buffer
+		lb.f32_top = (c->orbit_ladders & 64) != 0;
 		if (!(c->orbit_ladders & 2) && !lb.sampled) lb.q = nullptr;
 		c->launches += orbit_build_tables_device(c->d_r, c->d_phi, c->d_rp, (c->orbit_ladders & 4) ? c->d_rpf : nullptr, p->n_table, p->N_MAX + 1, lb, a, c->stream);
 	}

@@ -100,6 +100,7 @@ __global__ void rlad_build(const double *__restrict__ r, RLadderPlan p)
 // the sample ladder: level blockIdx.y holds the table entries (r, Phi) at k = b << shift
 struct SLadderPlan {
 	RPhi *lvl[LADDER_MAX_LEVELS];
+	RPhiF *topf; // level 0 rounded to FP32 (nullptr: none)
 	int shift[LADDER_MAX_LEVELS];
 	long count[LADDER_MAX_LEVELS];
 };
@@ -107,8 +108,11 @@ __global__ void slad_build(const RPhi *__restrict__ rp, SLadderPlan p)
 {
 	const int l = blockIdx.y;
 	const long stride = (long) gridDim.x * blockDim.x;
-	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < p.count[l]; i += stride)
-		*reinterpret_cast<double2 *>(p.lvl[l] + i) = *reinterpret_cast<const double2 *>(rp + (i << p.shift[l]));
+	for (long i = blockIdx.x * (long) blockDim.x + threadIdx.x; i < p.count[l]; i += stride) {
+		const double2 v = *reinterpret_cast<const double2 *>(rp + (i << p.shift[l]));
+		*reinterpret_cast<double2 *>(p.lvl[l] + i) = v;
+		if (l == 0 && p.topf) *reinterpret_cast<float2 *>(p.topf + i) = make_float2((float) v.x, (float) v.y);
+	}
 }
 
 struct StarIn {
@@ -219,7 +223,10 @@ __global__ void __launch_bounds__(ORBIT_THREADS, CTAS) orbit_prepare_kernel(Orbi
 	const bool slad_on = a.t.slad.n_levels > 0 && *a.lad_unsorted == 0; // (never both: the two ladders share one buffer)
 	top.q = (const LBlock *) stage_top_level(a.t.qlad.blk[0], a.q_top_bytes, lad_on && a.q_top_bytes > 0, orbit_smem, &bar);
 	if (lad_on && a.q_top_bytes == 0) { top.q = a.t.qlad.blk[0]; __syncthreads(); } // coarsest level too large to stage (tuning knobs): read in place
-	top.s = (const RPhi *) stage_top_level(a.t.slad.lvl[0], a.s_top_bytes, slad_on, orbit_smem, &bar);
+	if (CMCB_SLAD_F32_TOP && slad_on && a.s_topf_bytes > 0) { // the FP32 copy of the coarsest level in shared memory; its FP64 entries stay in global memory for the undecided probes
+		top.sf = (const RPhiF *) stage_top_level(a.t.slad.topf, a.s_topf_bytes, true, orbit_smem, &bar);
+		top.s = a.t.slad.lvl[0];
+	} else top.s = (const RPhi *) stage_top_level(a.t.slad.lvl[0], a.s_top_bytes, slad_on, orbit_smem, &bar);
 	if (!lad_on && !slad_on) __syncthreads();
 	top.r = nullptr; // potential() is not called in this stage
 	top.qdesc = &s_qlad;
@@ -629,7 +636,8 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhi
 {
 	a.t.rpf = rpf;
 	a.t.qlad.n_levels = 0; a.t.rlad.n_levels = 0; a.t.rlad.n_top = 0; a.t.slad.n_levels = 0;
-	a.q_top_bytes = a.r_top_bytes = a.s_top_bytes = 0;
+	a.q_top_bytes = a.r_top_bytes = a.s_top_bytes = a.s_topf_bytes = 0;
+	a.t.slad.topf = nullptr;
 	a.lad_unsorted = lb.unsorted;
 	if (n <= 0) return 0;
 	int launches = 0;
@@ -678,6 +686,8 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhi
 		SLadderPlan sp;
 		long off = 0; // in RPhi entries; every level on a 128-byte boundary
 		for (int l = ns - 1; l >= 0; l--) { sp.lvl[l] = (RPhi *) lb.q + off; sp.shift[l] = a.t.slad.shift[l]; sp.count[l] = scnt[l]; off += (scnt[l] + 7) / 8 * 8; }
+		sp.topf = nullptr;
+		if (ns && lb.f32_top && off + (scnt[0] / 2 + 8) <= 2 * lb.q_cap) { sp.topf = (RPhiF *) ((RPhi *) lb.q + off); off += (scnt[0] / 2 + 8) / 8 * 8; }
 		if (ns && off <= 2 * lb.q_cap) {
 			long sb = (scnt[ns - 1] + 255) / 256;
 			if (sb > NUM_SMS_B200 * 8) sb = NUM_SMS_B200 * 8;
@@ -688,6 +698,8 @@ int orbit_build_tables_device(const double *r, const double *phi, RPhi *rp, RPhi
 			a.t.slad.margin = (double) M * 7.105427357601002e-15 /* 2^-47 */ + 9.094947017729282e-13 /* 2^-40 */;
 			a.t.slad.phi_abs_max = 0.0; // filled by the kernels from the innermost entries
 			a.s_top_bytes = (unsigned) (scnt[0] * sizeof(RPhi));
+			a.t.slad.topf = sp.topf;
+			a.s_topf_bytes = sp.topf ? (unsigned) ((scnt[0] + 1) / 2 * 2 * sizeof(RPhiF)) : 0u; // a multiple of 16 bytes for the bulk copy
 		}
 	}
 	a.t.qlad.n_levels = nq;
@@ -748,7 +760,8 @@ int orbit_stage_prepare(const OrbitArgs &a, cudaStream_t s)
 	if (a.n_local <= 0) return 1;
 	long blocks = (a.n_local + ORBIT_THREADS - 1) / ORBIT_THREADS;
 	int ctas = a.prepare_ctas >= 3 && a.prepare_ctas <= 6 ? a.prepare_ctas : ORBIT_CTAS_PER_SM;
-	const unsigned top_bytes = a.q_top_bytes > a.s_top_bytes ? a.q_top_bytes : a.s_top_bytes;
+	const unsigned s_bytes = a.s_topf_bytes ? a.s_topf_bytes : a.s_top_bytes;
+	const unsigned top_bytes = a.q_top_bytes > s_bytes ? a.q_top_bytes : s_bytes;
 	while (ctas > 4 && (long) ctas * (top_bytes + 1024) > 227 * 1024) ctas--; // the staged levels of all resident CTAs must fit
 	if (blocks > (long) NUM_SMS_B200 * ctas) blocks = (long) NUM_SMS_B200 * ctas;
 	if (ctas == 3) orbit_prepare_kernel<3><<<(unsigned) blocks, ORBIT_THREADS, top_bytes, s>>>(a);

@@ -51,6 +51,7 @@ struct OrbitArgs {
 	const int *lad_unsorted; // device flag set by the table builder when star_r is not sorted (or Phi holds a NaN): ladders off
 	int prepare_ctas;  // register-cap variant of orbit_prepare_kernel: 4 (default) or 3 resident CTAs per SM (CMCB200_ORBIT_CTAS)
 	unsigned q_top_bytes, r_top_bytes; // size of the coarsest level of each ladder (what a CTA stages), multiples of 16
+	unsigned s_topf_bytes;             // bytes of the sample ladder's coarsest level rounded to FP32 (t.slad.topf; 0: no FP32 screening)
 	unsigned s_top_bytes;              // the same for the sample ladder (it shares the Q ladder's buffer: one of the two is in use)
 	long *defer_star;  // [ORBIT_DEFER_CAP] local 0-based index of each queued star
 	unsigned *defer_first; // [ORBIT_DEFER_CAP] lowest 256-entry sub-chunk of the table the bound could not prove free of Q > 0 (0xffffffff: none)
@@ -65,6 +66,7 @@ struct LadderBuffers {
 	int *unsorted; // device flag
 	bool r_whole_lines; // the r ladder's lines are read whole (tuning knob: CMCB200_ORBIT_LADDERS bit 4)
 	bool sampled;  // build the sample ladder (in q's memory) instead of the Q ladder
+	bool f32_top;  // with it, an FP32 copy of its coarsest level for FP32 screening of that level's probes (CMCB200_ORBIT_LADDERS bit 6, default on)
 	int q_max_shift, q_max_width_log2, q_factor_log2; // tuning knobs of the Q ladder (CMCB200_QLAD_MAX_SHIFT / _MAX_WIDTH_LOG2 / _FACTOR_LOG2)
 };
 long ladder_q_capacity(long n_table_dim);

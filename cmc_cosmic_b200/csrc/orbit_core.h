@@ -95,6 +95,10 @@ struct RLadder {
 #ifndef CMCB_SLAD_TOP_ENTRIES
 #define CMCB_SLAD_TOP_ENTRIES 2560
 #endif
+#ifndef CMCB_SLAD_F32_TOP
+#define CMCB_SLAD_F32_TOP 0 /* measured on B200: screening the coarsest level's probes in FP32 arithmetic changes nothing (3.10 vs 3.07 ms;
+                              profiles/ab_r02b_f32top.log) and its mere presence costs stage A 0.1 ms: compiled out */
+#endif
 #ifndef CMCB_SLAD_PAIR
 #define CMCB_SLAD_PAIR 0 /* measured on B200: no faster than the two descents one after the other (2.96 vs 2.98 ms at N = 1e7; profiles/ab_r02b_pair.log) */
 #endif
@@ -103,8 +107,10 @@ struct RLadder {
 #endif
 constexpr int SLAD_SECANT_STEPS = CMCB_SLAD_SECANT_STEPS; // 0: plain halving on the coarsest level
 constexpr int SLAD_MIN_SHIFT = 4, SLAD_STEP = 4, SLAD_TOP_ENTRIES = CMCB_SLAD_TOP_ENTRIES; // coarsest level <= 40 KB of (r, Phi) pairs
+struct RPhiF;
 struct SLadder {
 	const RPhi *lvl[LADDER_MAX_LEVELS]; // coarsest first
+	const RPhiF *topf;                  // lvl[0] rounded to FP32 (nullptr: none; set wherever n_levels is): the coarsest level's probes are screened in FP32 arithmetic
 	int shift[LADDER_MAX_LEVELS];
 	int n_levels; // 0: no ladder
 	double margin; // relative margin of a proven sign (see side_Q_margin)
@@ -127,6 +133,7 @@ struct LadderTops {
 	const double *r;
 	const QLadder *qdesc; // the Q ladder's level table: a shared-memory copy in the kernels (dynamic indexing), &t.qlad on the host
 	const RPhi *s;        // coarsest level of the sample ladder (nullptr: plain bisection)
+	const RPhiF *sf = nullptr; // its FP32 copy (shared memory in the kernels; then s points at the global FP64 level, read only by undecided probes)
 	const SLadder *sdesc;
 };
 
@@ -637,6 +644,39 @@ CMCB_HD int side_Q_margin(const StarConst &s, const RPhi p, double margin, doubl
 	return 0;
 }
 
+// The same test in FP32 ARITHMETIC on an FP32 copy of the sample, for the coarsest level: its ~12 probes per bisection are far from the sign
+// change (|Q| is a sizeable fraction of its terms), stage A is bound by the FP64 pipe and by the shared-memory wavefronts of 16-byte entries
+// at unrelated addresses, and an FP32 probe costs a third of either.  Every input is rounded to FP32 once (2^-24 relative), the six
+// operations add as much again, the r >= r_j branch may be taken the other way within 2^-23 of r_j (where both forms of the self term
+// agree to that much): |S32 - S| <= 2^-20 (the sum of the terms' magnitudes), so with the margin raised by 2^-19 a decided FP32 probe
+// implies the decided FP64 probe of the same sign.  0 = undecided here: the caller evaluates side_Q_margin on the FP64 sample.
+struct StarConstF {
+	float E, JJ, mi, c_in, r_j, scaleA, margin;
+};
+CMCB_HD StarConstF star_const_f32(const StarConst &s, double margin, double phi_abs_max)
+{
+	StarConstF f;
+	f.E = (float) s.E; f.JJ = (float) s.JJ; f.mi = (float) s.mi; f.c_in = (float) s.c_in; f.r_j = (float) s.r_j;
+	f.scaleA = (float) dadd(s.absE, phi_abs_max) * 1.000001f;
+	f.margin = (float) margin * 1.000001f + 1.9073486e-6f /* 2^-19 */;
+	return f;
+}
+CMCB_HD int side_Q_margin_f32(const StarConstF &f, float r, float phi)
+{
+	const float a = f.E - phi;
+	const float r2 = r * r;
+	const float t1 = a * r2;
+	const float t2 = (r >= f.r_j) ? f.mi * r : f.c_in * r2;
+	const float S = 2.0f * (t1 - t2) - f.JJ;
+	const float at1 = t1 < 0.0f ? -t1 : t1, at2 = t2 < 0.0f ? -t2 : t2;
+	const float scale = f.scaleA * r2 + f.JJ + at1 + at2;
+	if (!(scale > 1.0e-30f && scale < 1.0e30f && r2 > 1.0e-30f)) return 0; // outside FP32's comfortable range (or NaN): FP64 decides
+	const float B = f.margin * scale;
+	if (S > B) return 1;
+	if (S < -B) return -1;
+	return 0;
+}
+
 CMCB_HD RPhi slad_ld(const RPhi *p)
 {
 #if defined(__CUDA_ARCH__)
@@ -683,6 +723,10 @@ CMCB_HD kint find_zero_Q_sampled(const OrbitTables &t, const LadderTops &top, co
 	if (kmin == 0 && !(increasing && s.JJ > 0.0)) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
 	if (side_Q_margin(s, tbl_rp(t, kmax), L.margin, L.phi_abs_max, &q_hi) != -low) return find_zero_Q_plain(t, s, kmin, kmax, increasing, n_exact);
 	kint lo = kmin, hi = kmax; // every entry in [kmin, lo] has the sign `low`, every entry in [hi, kmax] the sign -low
+#if CMCB_SLAD_F32_TOP
+	StarConstF sf32 = {};
+	if (top.sf) sf32 = star_const_f32(s, L.margin, L.phi_abs_max);
+#endif
 	for (int l = 0; l < L.n_levels; l++) {
 		const int sh = L.shift[l];
 		const RPhi *lvl = (l == 0) ? top.s : L.lvl[l];
@@ -706,9 +750,22 @@ CMCB_HD kint find_zero_Q_sampled(const OrbitTables &t, const LadderTops &top, co
 			}
 			steps++;
 			// the coarsest level sits in shared memory in the kernels (a generic load), the others are read through the read-only path
-			const RPhi smp = (l == 0) ? slad_top_ld(lvl + mid) : slad_ld(lvl + mid);
-			float qm;
-			const int sd = side_Q_margin(s, smp, L.margin, L.phi_abs_max, &qm);
+			float qm = 0.0f;
+			int sd = 0;
+#if CMCB_SLAD_F32_TOP
+			if (l == 0 && top.sf) { // FP32 screening of the coarsest level
+#if defined(__CUDA_ARCH__)
+				const float2 v = *reinterpret_cast<const float2 *>(top.sf + mid);
+				sd = side_Q_margin_f32(sf32, v.x, v.y);
+#else
+				sd = side_Q_margin_f32(sf32, top.sf[mid].r, top.sf[mid].phi);
+#endif
+			}
+#endif
+			if (sd == 0) {
+				const RPhi smp = (l == 0) ? slad_top_ld(lvl + mid) : slad_ld(lvl + mid);
+				sd = side_Q_margin(s, smp, L.margin, L.phi_abs_max, SLAD_SECANT_STEPS ? &qm : nullptr);
+			}
 			if (sd == low) {
 				a = mid; xa = (float) mid; qa = qm;
 				if (last == 1) qb *= 0.5f;
@@ -1122,6 +1179,7 @@ CMCB_HD void orbit_step_star(const OrbitTables &t, kint g_j, bool is_new, double
 	LadderTops top;
 	top.q = t.qlad.n_levels ? t.qlad.blk[0] : nullptr; top.r = t.rlad.n_levels ? t.rlad.lvl[0] : nullptr; top.qdesc = &t.qlad;
 	top.s = t.slad.n_levels ? t.slad.lvl[0] : nullptr; top.sdesc = &t.slad;
+	top.sf = t.slad.n_levels ? t.slad.topf : nullptr;
 	OrbitJob job;
 	orbit_prepare(t, top, s, is_new, rnew_of_new, Rtidal, ktemp_in, allow_defer, out, job);
 	if (out.status == ORBIT_CIRCULAR) { out.vrnew = vr_in; out.vtnew = vt_in; }

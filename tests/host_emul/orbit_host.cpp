@@ -2,6 +2,7 @@
 // suite can check it bit-for-bit against the oracle / the compiled reference without a GPU.
 // TEST-ONLY: the product library never runs this on the host.  Build: g++ -O2 -ffp-contract=off -shared -fPIC.
 #include <algorithm>
+#include <stdlib.h>
 #include <vector>
 #include "../../cmc_cosmic_b200/csrc/orbit_core.h"
 using namespace cmcb;
@@ -78,6 +79,7 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 	if (force_exact == 2) t.qlad.n_levels = 0; // 2: r ladder + FP32 screening of the index bisections, no Q ladder
 	// 3: the device's default configuration -- r ladder + sample ladder (find_zero_Q_sampled), no Q ladder, no screening
 	std::vector<std::vector<RPhi>> slv;
+	std::vector<RPhiF> stopf; // the coarsest sample level rounded to FP32, as slad_build writes it
 	t.slad.n_levels = 0;
 	if (force_exact == 3 && lad.r.n_levels > 0) {
 		t.qlad.n_levels = 0; t.rpf = nullptr;
@@ -89,6 +91,9 @@ extern "C" double emul_get_positions(const double *star_r, const double *star_m,
 			for (long b = 0; b < scnt[l]; b++) slv[l][b] = rp[b << t.slad.shift[l]];
 			t.slad.lvl[l] = slv[l].data();
 		}
+		stopf.resize(ns ? scnt[0] : 0);
+		for (size_t b = 0; b < stopf.size(); b++) { stopf[b].r = (float) slv[0][b].r; stopf[b].phi = (float) slv[0][b].phi; }
+		t.slad.topf = (ns && !getenv("CMCB_EMUL_NO_F32_TOP")) ? stopf.data() : nullptr;
 		t.slad.n_levels = ns;
 		t.slad.margin = (double) (N_MAX + 1) * 7.105427357601002e-15 + 9.094947017729282e-13;
 		t.slad.phi_abs_max = __builtin_fmax(__builtin_fabs(rp[0].phi), __builtin_fabs(rp[1].phi));
