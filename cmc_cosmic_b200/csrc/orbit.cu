@@ -182,14 +182,12 @@ __device__ __forceinline__ void accumulate_stats(OrbitStats *st, int status, dou
 }
 
 // A star whose orbit is known but whose new radius is not drawn yet parks its job -- the envelope F, r_min, r_max and its E, J -- in five
-// compact arrays (OrbitArgs::job); r_peri / r_apo of its record receive r_min / r_max at once (their final values, :919-920).
+// compact arrays (OrbitArgs::job).
 __device__ __forceinline__ void store_prepared(const OrbitArgs &a, long j0, const OrbitOut &o, const OrbitJob &job, double E, double J)
 {
 	if (o.status == ORBIT_PENDING) {
-		char *rec = a.star1 + j0 * CMCB_SIZEOF_STAR;
-		// r_min / r_max are final (:919-920): into the record now.  The job itself goes to the compact arrays the rejection rounds read.
-		st_field(rec, CMCB_OFF_R_PERI, job.rmin);
-		st_field(rec, CMCB_OFF_R_APO, job.rmax);
+		// r_min / r_max (:919-920) reach the record when a try is accepted (store_star, next to X in the same 32-byte sector): storing them here
+		// as well cost stage A a read-modify-write of that sector for every star.  The job goes to the compact arrays the rejection rounds read.
 		a.job[0 * a.job_stride + j0] = job.F;
 		a.job[1 * a.job_stride + j0] = job.rmin;
 		a.job[2 * a.job_stride + j0] = job.rmax;
@@ -532,6 +530,8 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 					if (o.status == ORBIT_OK) {
 						st_field(wrec, CMCB_OFF_RNEW, o.rnew); st_field(wrec, CMCB_OFF_VRNEW, o.vrnew); st_field(wrec, CMCB_OFF_VTNEW, o.vtnew);
 						st_field(wrec, CMCB_OFF_X, o.X);
+						st_field(wrec, CMCB_OFF_R_PERI, o.r_peri); // :919-920, next to X in the same 32-byte sector
+						st_field(wrec, CMCB_OFF_R_APO, o.r_apo);
 					}
 					if (a.status) a.status[j0] = o.status;
 					if (a.n_draws) a.n_draws[j0] = o.n_draws;
