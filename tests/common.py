@@ -209,3 +209,32 @@ def dynamics_case(case, seed=11, first=1, nl=None):
         f["threebb"] = threebb[sl].copy()
     draws = np.random.default_rng(seed + 1).random(3 * (nl // 2))
     return dict(N=N, nb=nb, dt=c["dt"], cfg=cfg, f=f, bin_a=bin_a, r=r, sm=sm, pot=pot, draws=draws, first=first, nl=nl)
+
+
+def adversarial_sigma_inputs(kind, n, rng):
+    """(star_m * N units, vr, vt) built to stress the binade bookkeeping of csrc/sigma_scan.h"""
+    m = np.ones(n)
+    vr, vt = rng.normal(0, 0.5, n), np.abs(rng.normal(0, 0.5, n))
+    if kind == "hover_at_power_of_two":      # window sums that sit ON a binade boundary and wobble across it by a few ulps
+        p = 20
+        m[:] = 1.0
+        v2 = np.full(n, 2.0 ** -10 * n / (2 * p))        # m madhoc v^2 = 2^-10 / 2p: the 2p terms of a window sum to 2^-10 ...
+        v2 *= 1.0 + rng.integers(-3, 4, n) * 2.0 ** -50   # ... give or take a few ulps
+        vr, vt = np.sqrt(v2), np.zeros(n)
+    elif kind == "zeros":                    # stretches of stars at rest: the m v^2 chain drops to exactly 0 and climbs back
+        z = rng.random(n) < 0.3
+        z[1000:1100] = True
+        vr[z], vt[z] = 0.0, 0.0
+    elif kind == "wide_range":               # masses over six decades, a few stars that outweigh their whole window by 10^4
+        m = 10.0 ** rng.uniform(-3, 3, n)
+        m[rng.choice(n, 30, replace=False)] *= 1.0e4
+    elif kind == "steep_trend":              # v^2 falling by 2^-40 across the shard: the value walks down forty binades
+        f = 2.0 ** (-40.0 * np.arange(n) / n)
+        vr, vt = vr * np.sqrt(f), vt * np.sqrt(f)
+    elif kind == "rising_trend":             # ... and up, steeply: every binade above y_in doubles a table
+        f = 2.0 ** (400.0 * np.arange(n) / n)          # 13 binades per tile: more than a tile table holds
+        vr, vt = vr * np.sqrt(f) * 1e-60, vt * np.sqrt(f) * 1e-60
+    elif kind == "spikes":                   # isolated stars a million times faster than their neighbours
+        k = rng.choice(n, 200, replace=False)
+        vr[k] *= 1.0e3
+    return m, vr, vt

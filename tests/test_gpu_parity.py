@@ -1190,3 +1190,25 @@ def test_lagrange_radii_of_a_full_run_agree_with_the_reference_run():
     assert lag[-1][j10] < 0.75 * lag[0][j10] and lag[-1][j90] > 1.3 * lag[0][j90]
     print(f"full run: {steps} steps to t = {th[-1]:.3f}, N_MAX {N} -> {hist[-1][2]}, worst Lagrange-radius deviation from the reference run {worst:.3f}")
     c.close()
+
+
+@pytest.mark.parametrize("kind", ["hover_at_power_of_two", "zeros", "wide_range", "steep_trend", "rising_trend", "spikes"])
+def test_calc_sigma_r_bit_exact_on_adversarial_inputs(kind):
+    """calc_sigma_r on the device where the binade bookkeeping is stressed (tests/common.py: sums hovering on a power of two, chains that reach
+    zero, ten decades of terms, trends over dozens of binades, spikes): the serial loop's bits, through whichever path -- tables, replayed
+    segments, tiles walked group by group, the one-thread replay"""
+    rng = np.random.default_rng(len(kind) * 1000 + 7)
+    N = 60000
+    m, vr, vt = cm.adversarial_sigma_inputs(kind, N, rng)
+    r = np.sort(rng.random(N)) + 0.01
+    sr, smt = cm.make_tables(r, m)
+    c = Cluster(N, n_star_dim=N + 64)
+    c.load(r, vr, vt, m)
+    c.upload()
+    want_a, want_s = ol.calc_sigma_r(20, sr, smt, N, N, vr, vt, mave=True)
+    a, sg = c.dev_calc_sigma_r(20, mave=True)
+    cm.assert_bits_equal(a[1:], want_a[1:], f"{kind}: mean mass")
+    both_nan = np.isnan(sg[1:]) & np.isnan(want_s[1:])
+    cm.assert_bits_equal(np.where(both_nan, 0.0, sg[1:]), np.where(both_nan, 0.0, want_s[1:]), f"{kind}: sigma")
+    assert c.sigma_stats["rerun"] == 0, c.sigma_stats
+    c.close()

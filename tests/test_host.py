@@ -420,3 +420,27 @@ def test_input_hdf5_reader_refuses_what_it_does_not_parse(tmp_path):
     p.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes([2]) + bytes(200))    # superblock version 2
     with pytest.raises(hdf5_input.Hdf5FormatError):
         hdf5_input.read_input(str(p))
+
+
+@pytest.mark.parametrize("kind", ["hover_at_power_of_two", "zeros", "wide_range", "steep_trend", "rising_trend", "spikes"])
+@pytest.mark.parametrize("n,first", [(30011, 1), (9000, 4001)])
+def test_calc_sigma_r_segment_tables_on_adversarial_inputs(kind, n, first):
+    """The replay through segment / group / tile tables must give the serial loop's bits whatever the values do: sums hovering on a power of
+    two, chains that reach exactly zero, terms over ten decades, monotone trends over forty binades, isolated spikes.  What the classification
+    cannot prove is replayed operation by operation -- the counters show that these inputs do reach those paths."""
+    rng = np.random.default_rng(len(kind) * 1000 + n)
+    N = 60000
+    m, vr, vt = cm.adversarial_sigma_inputs(kind, N, rng)
+    r = np.sort(rng.random(N)) + 0.01
+    sr, smt = cm.make_tables(r, m)
+    nl = n
+    want_a, want_s = ol.calc_sigma_r(20, sr, smt, N, N, vr, vt, first_global=first, n_local=nl, mave=True)
+    a, sg, cnt = he.sigma_scan(20, sr, smt, N, N, vr, vt, first_global=first, n_local=nl, mave=True)
+    cm.assert_bits_equal(a[1:], want_a[1:], f"{kind}: mean mass")
+    both_nan = np.isnan(sg[1:]) & np.isnan(want_s[1:])           # 0 / 0 where a whole window is at rest: NaN on both sides
+    cm.assert_bits_equal(np.where(both_nan, 0.0, sg[1:]), np.where(both_nan, 0.0, want_s[1:]), f"{kind}: sigma")
+    assert cnt["inconsistent"] == 0, cnt
+    if kind in ("hover_at_power_of_two",):
+        assert cnt["hard_segments"] > 50, cnt
+    if kind in ("wide_range", "rising_trend", "spikes"):
+        assert cnt["wide_segments"] + cnt["hard_tiles"] + cnt["broken"] > 0, cnt
