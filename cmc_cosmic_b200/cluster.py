@@ -570,11 +570,24 @@ class Cluster:
         self.Etotal = SimpleNamespace(tot=tot, K=K, P=P, Eint=Eint, Eb=Eb)
         return self.Etotal
 
-    def dev_step(self, seed=0, draws=None, draw_off=None, fused=True):
+    def dev_step(self, seed=0, draws=None, draw_off=None, fused=True, one_wait=True):
         """One pass of the hot path on the resident arrays: (E, J from the potential ->) orbit step -> r <- rnew -> sort -> potential.
         fused: the r <- rnew transfer rides on the sort's record gather and E, J are computed inside the orbit step; the unfused form
-        runs them as passes of their own (same results, bit for bit)."""
-        if fused:
+        runs them as passes of their own (same results, bit for bit).  one_wait: the fused form as ONE call that queues everything and waits
+        once (cmcb200_dev_step) instead of three calls with a wait each."""
+        if fused and one_wait and type(self).dev_transfer_and_sort is Cluster.dev_transfer_and_sort:
+            p = self.orbit_params(draws, draw_off, seed, fuse_energy=True)
+            res, out = _lib.OrbitResult(), _lib.StepResult()
+            _lib.check(self.L.cmcb200_dev_step(self.ctx, C.byref(p), max(self.N_b_local, 0), self.cenma.m_new, self.orbit_r, C.byref(res), C.byref(out)), "dev_step")
+            self.last_orbit, self.max_r = res, res.max_r
+            self.clus.N_MAX_NEW = out.n_local
+            self.N_b_local = self.bin_slots_in_use = out.n_bin
+            self.Start[0], self.End[0] = 1, out.n_local
+            self.clus.N_MAX = out.N_MAX
+            self.cenma.m, self.cenma.m_new = out.cenma_m, out.cenma_m_new
+            self.Mtotal, self.Rtidal = out.Mtotal, out.Rtidal
+            self.mpiBegin, self.mpiEnd = 1, self.clus.N_MAX
+        elif fused:
             res = self.dev_new_orbits(draws, draw_off, seed, fuse_energy=True)
             self.dev_transfer_and_sort()
             self.dev_calc_potential_new()

@@ -301,7 +301,9 @@ extern "C" int cmcb200_calc_potential_new(cmcb200_ctx *c, double *star_r, const 
 
 // fuse: the ComputeIntermediateEnergy transfer (r <- rnew ...) happens while the records move; n_old_local / first_global / N_MAX
 // are those of the orbit step that produced rnew
-static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_bin, bool fuse, long n_old_local, long first_global, long N_MAX)
+// sync == false: everything is only queued; the five counters land in the pinned block at `counts_at` and the caller waits and reads them itself
+static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_bin, bool fuse, long n_old_local, long first_global, long N_MAX,
+		       bool sync = true, long counts_at = 0)
 {
 	const long n = *n_local;
 	if (n + 2 > c->n_star_dim) { set_error("qsorts_new: n_local + 2 = %ld exceeds n_star_dim = %ld", n + 2, c->n_star_dim); return -1; }
@@ -345,11 +347,47 @@ static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_
 	c->cur_star ^= 1;
 	c->cur_bin ^= 1;
 	if (fuse) { std::swap(c->d_r, c->d_r_alt); std::swap(c->d_m, c->d_m_alt); c->r_parity ^= 1; }
-	long *h = (long *) c->h_pinned; // n_eq_inf, n_gt_inf, n_total, n_new, n_bin
+	long *h = (long *) ((char *) c->h_pinned + counts_at); // n_eq_inf, n_gt_inf, n_total, n_new, n_bin
 	CMCB_CUDA_OK(cudaMemcpyAsync(h, &c->d_sort->n_eq_inf, 5 * sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+	if (!sync) return 0;
 	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream));
 	*n_local = h[3];
 	*n_bin = h[4];
+	return 0;
+}
+
+// ---- the whole resident step with ONE wait: orbit step -> r <- rnew + sort -> potential rebuild ---------------------------------------
+static int orbit_common(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status, cmcb200_orbit_result *res, bool sync);
+static void orbit_end(cmcb200_ctx *c, const cmcb200_orbit_params *p, int n_chunks, cmcb200_orbit_result *res);
+__global__ void step_table_sentinel(const cmcb::SortState *st, double *star_r, double *star_m)
+{
+	// the entry behind the last star that stayed: potential_calculate finds N_MAX as the first radius that is not < SF_INFINITY (cmc_utils.c:685)
+	star_r[1 + st->n_new] = 1.0e10;
+	star_m[1 + st->n_new] = 0.0;
+}
+extern "C" int cmcb200_dev_step(cmcb200_ctx *c, const cmcb200_orbit_params *p, long n_bin_clear, double cenma_m_new, double orbit_r,
+				cmcb200_orbit_result *orbit, cmcb200_step_result *out)
+{
+	CMCB_CUDA_OK(cudaSetDevice(c->device));
+	if (p->n_local + 2 > c->n_table_dim) { set_error("dev_step: n_local + 2 = %ld exceeds the table capacity %ld", p->n_local + 2, c->n_table_dim); return -1; }
+	if (orbit_common(c, p, false, nullptr, false)) return -1;
+	long n = p->n_local, nb = 0;
+	if (sort_common(c, &n, n_bin_clear, &nb, true, p->n_old_local, p->first_global, p->N_MAX, false, 2048)) return -1;
+	step_table_sentinel<<<1, 1, 0, c->stream>>>(c->d_sort, c->d_r, c->d_m);
+	c->launches += 1;
+	if (potential_enqueue(c, p->n_local, p->N_STAR, p->cenma_m, cenma_m_new, c->stream)) return -1;
+	PotScalars *h = (PotScalars *) c->h_pinned;
+	CMCB_CUDA_OK(cudaMemcpyAsync(h, c->d_pot, sizeof(PotScalars), cudaMemcpyDeviceToHost, c->stream));
+	CMCB_CUDA_OK(cudaStreamSynchronize(c->stream)); // the one wait of the step
+	orbit_end(c, p, c->last_orbit_chunks > 0 ? c->last_orbit_chunks : 1, orbit);
+	const long *cnt = (const long *) ((const char *) c->h_pinned + 2048);
+	out->n_local = cnt[3];
+	out->n_bin = cnt[4];
+	out->N_MAX = h->n_max;
+	out->cenma_m = h->cenma_m;
+	out->cenma_m_new = h->cenma_m_new;
+	out->Mtotal = h->Mtotal;
+	out->Rtidal = orbit_r * pow(h->Mtotal, 1.0 / 3.0); // glibc's pow on the host, like the reference (cmc_utils.c:707)
 	return 0;
 }
 

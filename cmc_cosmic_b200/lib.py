@@ -30,6 +30,11 @@ class MassPcResult(C.Structure):
                [("totals", C.c_double * 4), ("filled", C.c_long)]
 
 
+class StepResult(C.Structure):
+    _fields_ = [("n_local", C.c_long), ("n_bin", C.c_long), ("N_MAX", C.c_long), ("cenma_m", C.c_double), ("cenma_m_new", C.c_double),
+                ("Mtotal", C.c_double), ("Rtidal", C.c_double)]
+
+
 class DynamicsParams(C.Structure):
     _fields_ = [(k, C.c_long) for k in ("n_local", "first_global", "N_MAX", "N_STAR")] + [("dt", C.c_double)] + \
                [(k, C.c_long) for k in ("relaxation", "ss_collision", "binsingle", "binbin", "tidal_capture", "tc_polytrope", "bh_capture",
@@ -65,7 +70,7 @@ EXPORTS = [
     "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass", "cmcb200_dev_energy_new_radii",
     "cmcb200_dev_potential", "cmcb200_dev_tidally_strip_select", "cmcb200_dev_compute_energy_totals",
     "cmcb200_shard_step_async", "cmcb200_shard_step_result", "cmcb200_dev_new_orbits_async", "cmcb200_dev_orbit_result", "cmcb200_resident_begin", "cmcb200_resident_begin_sharded", "cmcb200_resident_end", "cmcb200_dev_get", "cmcb200_dev_put", "cmcb200_dev_comp_multi_mass_percent",
-    "cmcb200_dev_dynamics_apply", "cmcb200_dev_dynamics_encounters", "cmcb200_dev_calc_sigma_r", "cmcb200_dev_sigma_arrays", "cmcb200_restart_write", "cmcb200_dev_simul_relax",
+    "cmcb200_dev_dynamics_apply", "cmcb200_dev_dynamics_encounters", "cmcb200_dev_calc_sigma_r", "cmcb200_dev_sigma_arrays", "cmcb200_restart_write", "cmcb200_dev_simul_relax", "cmcb200_dev_step",
 ]
 
 
@@ -141,6 +146,7 @@ def load():
     L.cmcb200_dev_sigma_arrays.argtypes = [vp, vp, vp]
     L.cmcb200_restart_write.argtypes = [vp, C.c_char_p, vp, lg, vp, lg, vp, lg, vp, lg, lg, vp, lg, lg, vp, lg]
     L.cmcb200_dev_simul_relax.argtypes = [vp, lg, lg, lg, lg, lg, dbl, C.POINTER(dbl)]
+    L.cmcb200_dev_step.argtypes = [vp, C.POINTER(OrbitParams), lg, dbl, dbl, C.POINTER(OrbitResult), C.POINTER(StepResult)]
     L.cmcb200_dev_get.argtypes = [vp, vp, lg, vp, lg]
     L.cmcb200_dev_put.argtypes = [vp, vp, lg, vp, lg, vp, lg]
     L.cmcb200_resident_begin_sharded.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg, C.c_ulonglong, lg, lg]

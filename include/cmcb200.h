@@ -237,6 +237,16 @@ int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, lo
 /* cmcb200_dev_transfer_new_positions + cmcb200_dev_qsorts_new in one pass over the records: the sort key is rnew and the transfer is
  * applied to each 424-byte record while the gather moves it (n_old_local / first_global / N_MAX: those of the orbit step) */
 int cmcb200_dev_transfer_and_sort(cmcb200_ctx *ctx, long *n_local, long n_old_local, long first_global, long N_MAX, long n_bin_clear, long *n_bin);
+/* The three calls above in one: cmcb200_dev_new_orbits -> cmcb200_dev_transfer_and_sort -> cmcb200_dev_calc_potential_new (src/cmc/cmc.c:311-344
+ * without the energy scheme), everything queued on the context's stream and ONE host wait at the end instead of three -- what a resident
+ * timestep costs at N <= 1e5, where the waits and the launch gaps outweigh the kernels.  Bit-identical with the three calls. */
+typedef struct {
+	long n_local, n_bin;  /* after the sort (stars at r = SF_INFINITY trimmed, binaries re-packed) */
+	long N_MAX;           /* and what calc_potential_new leaves */
+	double cenma_m, cenma_m_new, Mtotal, Rtidal;
+} cmcb200_step_result;
+int cmcb200_dev_step(cmcb200_ctx *ctx, const cmcb200_orbit_params *p, long n_bin_clear, double cenma_m_new, double orbit_r,
+		     cmcb200_orbit_result *orbit, cmcb200_step_result *out);
 /* calc_potential_new on the resident tables */
 int cmcb200_dev_calc_potential_new(cmcb200_ctx *ctx, long *N_MAX, long N_STAR, double *cenma_m, double *cenma_m_new, double orbit_r,
 				   double *Mtotal, double *Rtidal);

@@ -1212,3 +1212,33 @@ def test_calc_sigma_r_bit_exact_on_adversarial_inputs(kind):
     cm.assert_bits_equal(np.where(both_nan, 0.0, sg[1:]), np.where(both_nan, 0.0, want_s[1:]), f"{kind}: sigma")
     assert c.sigma_stats["rerun"] == 0, c.sigma_stats
     c.close()
+
+
+def test_one_wait_step_equals_three_calls():
+    """cmcb200_dev_step (orbit step, r <- rnew + sort, potential rebuild queued together, one host wait) against the three calls with a wait each:
+    identical records, binaries, tables and scalars over three steps with binaries and escaping stars"""
+    N, nb = 120000, 4000
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=19, masses="imf")
+    rng = np.random.default_rng(6)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    vr = vr.copy()
+    vr[rng.choice(N, 300, replace=False)] *= 4.0            # a few hundred unbound stars: the sort trims them
+    out = []
+    for one_wait in (True, False):
+        c = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8)
+        c.load(r, vr, vt, sm, binind=binind)
+        c.binary[1:nb + 1] = np.random.default_rng(7).integers(0, 256, (nb, c.binary.shape[1]), dtype=np.uint8)
+        c.calc_potential_new()
+        c.compute_energy()
+        c.upload()
+        for step in range(3):
+            c.dev_step(seed=5, one_wait=one_wait)
+        c.download()
+        out.append((c.clus.N_MAX, c.N_b_local, c.Mtotal, c.Rtidal, c.max_r, c.star[:c.clus.N_MAX + 1].copy(), c.binary[:c.N_b_local + 1].copy(),
+                    c.star_r[:c.clus.N_MAX + 2].copy(), c.star_m[:c.clus.N_MAX + 1].copy(), c.star_phi[:c.clus.N_MAX + 2].copy()))
+        c.close()
+    a, b = out
+    assert a[:5] == b[:5] and a[0] < N, (a[:5], b[:5])
+    for x, y in zip(a[5:], b[5:]):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
