@@ -56,12 +56,14 @@ struct SeqWork {
 
 __device__ __forceinline__ void desc_publish(double2 *d, double value, int state)
 {
-	asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(d), "l"(__double_as_longlong(value)), "l"((long long) state) : "memory");
+	// ONE .b128 access: the PTX memory model guarantees single-copy atomicity for it (a .v2.b64 access is formally two scalar accesses;
+	// both compile to STG.E.128.STRONG.GPU / LDG.E.128.STRONG.GPU)
+	asm volatile("{ .reg .b128 q; mov.b128 q, {%1, %2}; st.relaxed.gpu.global.b128 [%0], q; }" ::"l"(d), "l"(__double_as_longlong(value)), "l"((long long) state) : "memory");
 }
 __device__ __forceinline__ int desc_poll(const double2 *d, double *value)
 {
 	long long v, s;
-	asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(s) : "l"(d) : "memory");
+	asm volatile("{ .reg .b128 q; ld.relaxed.gpu.global.b128 q, [%2]; mov.b128 {%0, %1}, q; }" : "=l"(v), "=l"(s) : "l"(d) : "memory");
 	*value = __longlong_as_double(v);
 	return (int) s;
 }

@@ -15,6 +15,7 @@
 //
 // Bound: HBM.  Algorithmic bytes per star: keys 8 read + 4 written (permutation); records 424 + 424.
 #include "sort.cuh"
+#include <cstdlib>
 
 namespace cmcb {
 
@@ -116,7 +117,24 @@ __global__ void sort_reset(SortState *st, unsigned *tile_hist, long n_words)
 
 constexpr unsigned LB_AGG = 1u << 30, LB_INCL = 2u << 30, LB_MASK = (1u << 30) - 1;
 
-template <bool FIRST, bool LAST>
+// lanes of the warp whose 8-bit digit equals this lane's: one vote per digit bit.  The eight votes of an item depend on nothing but its
+// key, so the votes of a whole batch of items are issued back to back -- unlike MATCH.ANY, whose result each item's shared-memory counter
+// update then waited for (48 % of the pass's stall samples in profiles/ncu_summary_r02b.txt were short-scoreboard waits behind it)
+__device__ __forceinline__ unsigned digit_peers(unsigned d)
+{
+	unsigned m = 0xffffffffu;
+#pragma unroll
+	for (int b = 0; b < 8; b++) {
+		const bool bit = (d >> b) & 1u;
+		const unsigned v = __ballot_sync(0xffffffffu, bit);
+		m &= bit ? v : ~v;
+	}
+	return m;
+}
+
+constexpr int SORT_RANK_BATCH = 8; // items whose peer masks are computed together before their counters are updated in order
+
+template <bool FIRST, bool LAST, bool BALLOT>
 __global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS_PER_SM) sort_onesweep_pass(SortBuffers b, SortState *st, unsigned *tile_hist /*[ntiles][256]*/, long n, int pass)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,16 +179,35 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS_PER_SM) sort_onesweep_
 		}
 		// rank inside the warp's segment, stable: groups of equal digit via match.any, one counter update per group
 		unsigned *cnt = s_cnt + warp * 256;
+		if (BALLOT) {
 #pragma unroll
-		for (int s = 0; s < SORT_ITEMS; s++) {
-			unsigned d = (unsigned) (key[s] >> shift) & 255u;
-			unsigned peers = __match_any_sync(0xffffffffu, d);
-			int leader = __ffs(peers) - 1;
-			unsigned old = 0;
-			if ((int) lane == leader) { old = cnt[d]; cnt[d] = old + __popc(peers); }
-			old = __shfl_sync(0xffffffffu, old, leader);
-			rank[s] = (unsigned short) (old + __popc(peers & lt_mask));
-			__syncwarp();
+			for (int s0 = 0; s0 < SORT_ITEMS; s0 += SORT_RANK_BATCH) {
+				unsigned peers[SORT_RANK_BATCH];
+#pragma unroll
+				for (int t = 0; t < SORT_RANK_BATCH; t++) peers[t] = digit_peers((unsigned) (key[s0 + t] >> shift) & 255u);
+#pragma unroll
+				for (int t = 0; t < SORT_RANK_BATCH; t++) { // in item order: the ranking is stable
+					const unsigned d = (unsigned) (key[s0 + t] >> shift) & 255u;
+					const int leader = __ffs(peers[t]) - 1;
+					unsigned old = 0;
+					if ((int) lane == leader) { old = cnt[d]; cnt[d] = old + __popc(peers[t]); }
+					old = __shfl_sync(0xffffffffu, old, leader);
+					rank[s0 + t] = (unsigned short) (old + __popc(peers[t] & lt_mask));
+					__syncwarp();
+				}
+			}
+		} else {
+#pragma unroll
+			for (int s = 0; s < SORT_ITEMS; s++) {
+				unsigned d = (unsigned) (key[s] >> shift) & 255u;
+				unsigned peers = __match_any_sync(0xffffffffu, d);
+				int leader = __ffs(peers) - 1;
+				unsigned old = 0;
+				if ((int) lane == leader) { old = cnt[d]; cnt[d] = old + __popc(peers); }
+				old = __shfl_sync(0xffffffffu, old, leader);
+				rank[s] = (unsigned short) (old + __popc(peers & lt_mask));
+				__syncwarp();
+			}
 		}
 		__syncthreads();
 		// per digit (threads 0..255, thread d = digit d): turn the per-warp counts into warp offsets, get the tile count
@@ -397,15 +434,22 @@ __global__ void sort_binary_clear(char *bin_out, const SortState *st, long n_cle
 
 // ---- host side ----------------------------------------------------------------------------------------------
 
+static bool g_sort_ballot = true; // ranking by per-bit votes (default) or by MATCH.ANY
+
 size_t sort_smem_bytes() { return SORT_TILE * 8 + SORT_TILE * 4 + SORT_WARPS * 256 * 4 + 256 * 4 * 2; }
 
 int sort_setup()
 {
 	size_t sm = sort_smem_bytes();
 	cudaError_t e;
-	e = cudaFuncSetAttribute(sort_onesweep_pass<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_onesweep_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_onesweep_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+	e = cudaFuncSetAttribute(sort_onesweep_pass<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_onesweep_pass<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_onesweep_pass<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_onesweep_pass<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_onesweep_pass<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_onesweep_pass<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm);
+	const char *k = getenv("CMCB200_SORT_RANK"); // "0": MATCH.ANY ranking (A/B measurement)
+	g_sort_ballot = !(k && atoi(k) == 0);
 	return e == cudaSuccess ? 0 : -1;
 }
 
@@ -442,9 +486,15 @@ int sort_stage_passes(const SortArgs &a, cudaStream_t s)
 	const size_t sm = sort_smem_bytes();
 	for (int p = 0; p < 8; p++) {
 		unsigned *th = a.tile_hist + (long) p * ntiles * 256;
-		if (p == 0) sort_onesweep_pass<true, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
-		else if (p == 7 && !a.keep_keys) sort_onesweep_pass<false, true><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
-		else sort_onesweep_pass<false, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+		if (g_sort_ballot) {
+			if (p == 0) sort_onesweep_pass<true, false, true><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+			else if (p == 7 && !a.keep_keys) sort_onesweep_pass<false, true, true><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+			else sort_onesweep_pass<false, false, true><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+		} else {
+			if (p == 0) sort_onesweep_pass<true, false, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+			else if (p == 7 && !a.keep_keys) sort_onesweep_pass<false, true, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+			else sort_onesweep_pass<false, false, false><<<grid, SORT_THREADS, sm, s>>>(a.buf, a.st, th, n, p);
+		}
 	}
 	return 9;
 }
