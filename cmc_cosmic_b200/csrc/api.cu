@@ -77,6 +77,8 @@ extern "C" int cmcb200_create_sharded(cmcb200_ctx **out, int device, long n_star
 	c->orbit_max_chunks = 8;
 	if (const char *e = getenv("CMCB200_ORBIT_CHUNKS")) c->orbit_max_chunks = atoi(e) < 1 ? 1 : (atoi(e) > ORBIT_MAX_CHUNKS ? ORBIT_MAX_CHUNKS : atoi(e));
 	if (const char *e = getenv("CMCB200_ORBIT_CTAS")) c->orbit_ctas = atoi(e);
+	c->step_emit_keys = true; c->orbit_emit_keys = false;
+	if (const char *e = getenv("CMCB200_STEP_KEYS")) c->step_emit_keys = atoi(e) != 0;
 	if (const char *e = getenv("CMCB200_ORBIT_LADDERS")) c->orbit_ladders = atoi(e); // 0: A/B measurement of the plain bisections
 	CMCB_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	c->own_stream = true;
@@ -302,8 +304,9 @@ extern "C" int cmcb200_calc_potential_new(cmcb200_ctx *c, double *star_r, const 
 // fuse: the ComputeIntermediateEnergy transfer (r <- rnew ...) happens while the records move; n_old_local / first_global / N_MAX
 // are those of the orbit step that produced rnew
 // sync == false: everything is only queued; the five counters land in the pinned block at `counts_at` and the caller waits and reads them itself
+// keys_ready: the orbit step queued in front has written the sort keys of all n records (OrbitArgs::sort_keys)
 static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_bin, bool fuse, long n_old_local, long first_global, long N_MAX,
-		       bool sync = true, long counts_at = 0)
+		       bool sync = true, long counts_at = 0, bool keys_ready = false)
 {
 	const long n = *n_local;
 	if (n + 2 > c->n_star_dim) { set_error("qsorts_new: n_local + 2 = %ld exceeds n_star_dim = %ld", n + 2, c->n_star_dim); return -1; }
@@ -319,6 +322,7 @@ static int sort_common(cmcb200_ctx *c, long *n_local, long n_bin_clear, long *n_
 	a.st = c->d_sort;
 	a.tile_hist = c->d_tile_hist;
 	a.keep_keys = false;
+	a.keys_ready = keys_ready;
 	a.fuse_transfer = fuse;
 	a.old_r = c->d_r; a.old_m = c->d_m;
 	a.n_old_local = n_old_local; a.first_global = first_global; a.N_MAX = N_MAX;
@@ -370,9 +374,14 @@ extern "C" int cmcb200_dev_step(cmcb200_ctx *c, const cmcb200_orbit_params *p, l
 {
 	CMCB_CUDA_OK(cudaSetDevice(c->device));
 	if (p->n_local + 2 > c->n_table_dim) { set_error("dev_step: n_local + 2 = %ld exceeds the table capacity %ld", p->n_local + 2, c->n_table_dim); return -1; }
-	if (orbit_common(c, p, false, nullptr, false)) return -1;
+	// the orbit kernels leave key_from_double(rnew) of every star in the sort's key buffer: the sort skips its strided pass over the records
+	// (0.2 ms of 10.3 at N = 1e7; CMCB200_STEP_KEYS=0 switches it off for A/B measurements)
+	c->orbit_emit_keys = c->step_emit_keys;
+	const int orc = orbit_common(c, p, false, nullptr, false);
+	c->orbit_emit_keys = false;
+	if (orc) return -1;
 	long n = p->n_local, nb = 0;
-	if (sort_common(c, &n, n_bin_clear, &nb, true, p->n_old_local, p->first_global, p->N_MAX, false, 2048)) return -1;
+	if (sort_common(c, &n, n_bin_clear, &nb, true, p->n_old_local, p->first_global, p->N_MAX, false, 2048, c->step_emit_keys)) return -1;
 	step_table_sentinel<<<1, 1, 0, c->stream>>>(c->d_sort, c->d_r, c->d_m);
 	c->launches += 1;
 	if (potential_enqueue(c, p->n_local, p->N_STAR, p->cenma_m, cenma_m_new, c->stream)) return -1;
@@ -484,6 +493,7 @@ int orbit_begin(cmcb200_ctx *c, const cmcb200_orbit_params *p, bool want_status,
 	a.prepare_ctas = c->orbit_ctas;
 	a.defer_first = c->d_defer_first;
 	a.flag = c->d_oflag; a.pend_list[0] = c->d_pend[0]; a.pend_list[1] = c->d_pend[1];
+	a.sort_keys = c->orbit_emit_keys ? (unsigned long long *) c->sbuf.keys_a : nullptr;
 	a.job = c->d_job; a.job_stride = c->n_star_dim;
 	a.split_lookup = (c->orbit_ladders & 32) != 0 && (c->orbit_ladders & 1);
 	a.t.N_MAX = p->N_MAX;
@@ -531,6 +541,7 @@ static int orbit_range(cmcb200_ctx *c, const OrbitArgs &whole, long off, long le
 	a.n_old_local = whole.n_old_local - off; // may be <= 0: every star of the chunk was created this step (get_global_idx, cmc_utils.c:2384-2407)
 	a.first_global = whole.first_global + off;
 	a.flag += off;
+	if (a.sort_keys) a.sort_keys += off;
 	a.job += off;
 	if (a.draw_off) a.draw_off += off;
 	if (a.status) a.status += off;

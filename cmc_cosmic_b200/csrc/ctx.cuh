@@ -80,6 +80,8 @@ struct cmcb200_ctx {
 	double acc_ms[CMCB200_N_STAGES];
 	long acc_n[CMCB200_N_STAGES];
 	long launches; // kernels launched since creation
+	bool step_emit_keys;   // cmcb200_dev_step: the orbit step writes the sort keys (default on; CMCB200_STEP_KEYS=0 for A/B)
+	bool orbit_emit_keys;  // set around the orbit step of cmcb200_dev_step only: every other caller leaves OrbitArgs::sort_keys null
 	int last_orbit_chunks; // chunks of the last orbit step (their statistics wait in the pinned block for cmcb200_dev_orbit_result)
 	long bytes_h2d, bytes_d2h; // bytes the host-buffer entry points moved over PCIe (cmcb200_transfer_bytes)
 	// host-buffer orbit step: copy-in and copy-out streams and per-chunk events of the pipeline (created on first use)

@@ -151,6 +151,7 @@ __device__ __forceinline__ void store_star(const OrbitArgs &a, long j0, const Or
 		st_field(rec, CMCB_OFF_R_PERI, o.r_peri);
 		st_field(rec, CMCB_OFF_R_APO, o.r_apo);
 	}
+	if (a.sort_keys) a.sort_keys[j0] = key_from_double(o.status != ORBIT_NTRY ? o.rnew : ld_field(rec, CMCB_OFF_RNEW)); // what the record now holds
 	if (a.status) a.status[j0] = o.status;
 	if (a.kmin) a.kmin[j0] = o.kmin;
 	if (a.kmax) a.kmax[j0] = o.kmax;
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(ORBIT_TRY_THREADS, 4) orbit_try_kernel(OrbitAr
 						st_field(wrec, CMCB_OFF_R_PERI, o.r_peri); // :919-920, next to X in the same 32-byte sector
 						st_field(wrec, CMCB_OFF_R_APO, o.r_apo);
 					}
+					if (a.sort_keys) a.sort_keys[j0] = key_from_double(o.status == ORBIT_OK ? o.rnew : ld_field(wrec, CMCB_OFF_RNEW));
 					if (a.status) a.status[j0] = o.status;
 					if (a.n_draws) a.n_draws[j0] = o.n_draws;
 					status = o.status; n_draws = o.n_draws; rnew = o.rnew;

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "orbit_core.h"
 #include "star_layout.h"
+#include "sort.cuh"
 
 namespace cmcb {
 
@@ -40,6 +41,8 @@ struct OrbitArgs {
 	long *kmin, *kmax;
 	int *n_draws;
 	OrbitStats *stats;
+	unsigned long long *sort_keys; // [n_local] or null: key_from_double(star[j].rnew) as the step leaves it -- the radix sort that follows (cmcb200_dev_step)
+	                               // then needs no pass over the 424-byte records to collect its keys
 	unsigned char *flag; // [n_local] 1: orbit known, new radius still to be drawn
 	// the pending stars' jobs as five compact arrays (component c of local star j0 at job[c * job_stride + j0]: envelope F, r_min, r_max, E, J) --
 	// stage A writes them coalesced and the rejection rounds read them coalesced instead of five scattered fields of the 424-byte records

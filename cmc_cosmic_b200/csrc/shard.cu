@@ -530,6 +530,7 @@ extern "C" int cmcb200_shard_sort_local(cmcb200_ctx *c, long n_local, long *n_ke
 	a.st = c->d_sort;
 	a.tile_hist = c->d_tile_hist;
 	a.keep_keys = true;
+	a.keys_ready = false;
 	{ StageTimer t(c, ST_KEYS); c->launches += sort_stage_keys(a, c->stream); }
 	{ StageTimer t(c, ST_PASSES); c->launches += sort_stage_passes(a, c->stream); }
 	{
@@ -701,6 +702,7 @@ extern "C" int cmcb200_shard_step_async(cmcb200_ctx *c, long n_local, long n_old
 	a.st = c->d_sort;
 	a.tile_hist = c->d_tile_hist;
 	a.keep_keys = true;
+	a.keys_ready = false;
 	{ StageTimer t(c, ST_KEYS); c->launches += sort_stage_keys(a, c->stream); }
 	{ StageTimer t(c, ST_PASSES); c->launches += sort_stage_passes(a, c->stream); }
 	{

@@ -21,11 +21,6 @@ namespace cmcb {
 
 // ---- keys ---------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint64_t key_from_double(double r)
-{
-	uint64_t b = dbits(r);
-	return (b >> 63) ? ~b : (b | 0x8000000000000000ull); // total order of IEEE doubles as unsigned integers
-}
 __host__ __device__ constexpr uint64_t key_sf_infinity() { return 0x4202A05F20000000ull | 0x8000000000000000ull; } // 1.0e10
 
 __global__ void sort_extract_keys(const char *__restrict__ star, long n, long key_off, uint64_t *__restrict__ keys)
@@ -467,12 +462,12 @@ int sort_stage_keys(const SortArgs &a, cudaStream_t s)
 {
 	const long n = a.n;
 	const long ntiles = (n + SORT_TILE - 1) / SORT_TILE;
-	if (n > 0) sort_extract_keys<<<NUM_SMS_B200 * 4, 256, 0, s>>>(a.star_in, n, a.key_off, a.buf.keys_a);
+	if (n > 0 && !a.keys_ready) sort_extract_keys<<<NUM_SMS_B200 * 4, 256, 0, s>>>(a.star_in, n, a.key_off, a.buf.keys_a);
 	sort_reset<<<NUM_SMS_B200 * 2, 512, 0, s>>>(a.st, a.tile_hist, ntiles * 256 * 8);
 	if (n > 0) sort_histogram<<<NUM_SMS_B200 * 2, 512, 0, s>>>(a.buf.keys_a, n, a.st);
 	sort_scan_hist<<<8, 256, 0, s>>>(a.st, n);
 	sort_plan<<<1, 1, 0, s>>>(a.st, n);
-	return n > 0 ? 5 : 3;
+	return n > 0 ? (a.keys_ready ? 4 : 5) : 3;
 }
 
 // stage 1: the LSD passes (pass 0 generates the indices itself; when it is skipped they come from sort_iota_if_skipped)

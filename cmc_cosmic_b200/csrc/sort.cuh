@@ -12,6 +12,15 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 (key, index) pairs per CTA iteration
 constexpr int SORT_CTAS_PER_SM = 2;
 
+#ifdef __CUDACC__
+// total order of IEEE doubles as unsigned integers: the radix sort's key (also written by the orbit step, OrbitArgs::sort_keys)
+__device__ __forceinline__ uint64_t key_from_double(double r)
+{
+	uint64_t b = (uint64_t) __double_as_longlong(r);
+	return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+#endif
+
 struct SortState { // device-resident bookkeeping of one sort
 	unsigned hist[8][256];    // digit histograms of the 8 LSD passes
 	unsigned base[8][256];    // exclusive scans of them
@@ -46,6 +55,7 @@ struct SortArgs {
 	long n_bin_clear;    // zero bin_out records [n_bin, n_bin_clear)
 	// fused ComputeIntermediateEnergy transfer (reference src/cmc/cmc_utils.c:380-390): the key is rnew, and while a record moves
 	// r <- rnew, vr <- vrnew, vt <- vtnew, m <- star_m[g], rOld <- star_r[g] (g = the record's global index BEFORE the sort)
+	bool keys_ready;     // buf.keys_a already holds the keys of the n records (the orbit step wrote them, cmcb200_dev_step): no extraction pass
 	bool keep_keys;      // materialise the sorted keys too (the sharded sort ranks them against the other ranks' keys)
 	bool fuse_transfer;
 	const double *old_r, *old_m; // the tables the transfer reads (must not alias star_r / star_m, which the gather writes)
