@@ -45,7 +45,7 @@ def measured_peak():
 
 def profile_traffic(kernel):
     """dram bytes per star of a kernel from the committed ncu capture (profiles/traffic_r02.json, else the round-1 file), if there is one"""
-    for name in ("traffic_r02b.json", "traffic_r02.json", "traffic_r01.json"):
+    for name in ("traffic_r02c.json", "traffic_r02b.json", "traffic_r02.json", "traffic_r01.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             try:

@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): sort permutation / integer indices bit-exact; Phi rel. err <= 1e-12; r_min, r_max and the
 new r rel. err <= 1e-10 given the same draws.  The implementation aims higher -- every FP64 output is compared BIT FOR BIT.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -847,6 +849,35 @@ def test_orbit_step_with_stars_created_this_step_bit_exact():
     t = ol.tables(sr, smt, phi, N, N, 0.0)
     cm.assert_bits_equal(c.field("Uoldrnew")[1:N + M + 1], ol.energy_conservation2(t, g_idx, want["rnew"]), "Uoldrnew")
     c.close()
+
+
+def test_step_with_sort_keys_written_by_the_orbit_kernels():
+    """cmcb200_dev_step lets the orbit kernels write the radix sort's keys (key_from_double(rnew)) so that the sort skips its pass over the
+    records; the three-call form extracts them from the records.  Same arrays after three steps, byte for byte, on a cluster with stars
+    created this step (keys of stars placed by FindZero_r) and stars with v_r == 0 from the second step on (queued linear scans); and with the key emission switched off (CMCB200_STEP_KEYS=0, read when the context is created)."""
+    N, M = 90000, 500
+    outs = []
+    for one_wait, env in ((True, None), (False, None), (True, "0")):
+        if env is not None:
+            os.environ["CMCB200_STEP_KEYS"] = env
+        try:
+            c, (sr, smt, phi, E, J, vra, vta, g_idx, is_new, rnew_in), pot = _cluster_with_new_stars(N, M, seed=77)
+        finally:
+            os.environ.pop("CMCB200_STEP_KEYS", None)
+        c.upload()
+        for _ in range(3):
+            res = c.dev_step(seed=11, one_wait=one_wait)
+        c.dev_compute_energy()
+        c.download()
+        n = c.clus.N_MAX
+        outs.append((n, c.star[:n + 1].copy(), c.star_r[:n + 2].copy(), c.star_m[:n + 2].copy(), c.star_phi[:n + 2].copy(), int(res.n_deferred)))
+        c.close()
+    assert outs[0][0] == N + M, "the new stars joined the cluster"
+    for other in outs[1:]:
+        assert outs[0][0] == other[0]
+        assert np.array_equal(outs[0][1], other[1]), "star[]"
+        for x, y, name in zip(outs[0][2:5], other[2:5], ("star_r", "star_m", "star_phi")):
+            cm.assert_bits_equal(x, y, name)
 
 
 def test_pipelined_host_buffer_orbit_step_with_new_stars_in_the_last_chunk():
