@@ -239,7 +239,9 @@ int cmcb200_dev_qsorts_new(cmcb200_ctx *ctx, long *n_local, long n_bin_clear, lo
 int cmcb200_dev_transfer_and_sort(cmcb200_ctx *ctx, long *n_local, long n_old_local, long first_global, long N_MAX, long n_bin_clear, long *n_bin);
 /* The three calls above in one: cmcb200_dev_new_orbits -> cmcb200_dev_transfer_and_sort -> cmcb200_dev_calc_potential_new (src/cmc/cmc.c:311-344
  * without the energy scheme), everything queued on the context's stream and ONE host wait at the end instead of three -- what a resident
- * timestep costs at N <= 1e5, where the waits and the launch gaps outweigh the kernels.  Bit-identical with the three calls. */
+ * timestep costs at N <= 1e5, where the waits and the launch gaps outweigh the kernels.  Because the orbit step and the sort are queued by the
+ * same call, the orbit kernels also leave the sort's keys (rnew as an order-preserving integer) in the sort's key buffer, and the sort
+ * skips its pass over the records that would collect them.  Bit-identical with the three calls. */
 typedef struct {
 	long n_local, n_bin;  /* after the sort (stars at r = SF_INFINITY trimmed, binaries re-packed) */
 	long N_MAX;           /* and what calc_potential_new leaves */
