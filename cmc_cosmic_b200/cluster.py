@@ -526,6 +526,23 @@ class Cluster:
                                                 blobs[2].ctypes.data, len(blobs[2]), self.star.ctypes.data, self.N_STAR_DIM, self.clus.N_MAX_NEW,
                                                 self.binary.ctypes.data, self.N_BIN_DIM, self.N_b_local, cnt.ctypes.data, len(cnt)), "restart_write")
 
+    def dev_snapshot_rows(self, units_m, units_l, sigma=None, avekernel=None, bh_only=False, nan_value=None):
+        """write_snapshot's rows (reference src/cmc/cmc_io.c:3176-3327; the `Snapshot` struct, include/cmc/cmc.h:136-200) built on the device
+        from the resident arrays: a structured array (layout.SNAPSHOT_DTYPE), in star order -- what the reference hands to H5TBmake_table.
+        sigma: sigma_array.sigma ([n_local + 1]) or None for the resident result of dev_calc_sigma_r; nan_value: the caller's `0.0 / 0.0`
+        (default: the x86 default NaN, sign bit set, which is what the compiled reference stores)."""
+        from .layout import SNAPSHOT_DTYPE
+        n = int(self.clus.N_MAX_NEW)
+        nan = np.array([0xFFF8000000000000], np.uint64).view(np.float64)[0] if nan_value is None else nan_value
+        prm = _lib.SnapshotParams(n, int(self.End[self.myid] - self.Start[self.myid] + 1), int(self.Start[self.myid]), self.clus.N_MAX, self.clus.N_STAR,
+                                  units_m, units_l, 1.0 / self.clus.N_STAR, int(avekernel or self.DYNAMICS["AVEKERNEL"]), nan, int(bool(bh_only)))
+        rows = np.zeros(max(n, 1), SNAPSHOT_DTYPE)
+        sg = None if sigma is None else np.ascontiguousarray(sigma, np.float64)
+        assert sg is None or len(sg) >= n + 1
+        got = C.c_long(0)
+        _lib.check(self.L.cmcb200_dev_snapshot_rows(self.ctx, C.byref(prm), None if sg is None else sg.ctypes.data, rows.ctypes.data, len(rows), C.byref(got)), "dev_snapshot_rows")
+        return rows[:got.value]
+
     def dev_qsorts_new(self):
         n, nb = C.c_long(self.clus.N_MAX_NEW), C.c_long(0)
         _lib.check(self.L.cmcb200_dev_qsorts_new(self.ctx, C.byref(n), max(self.N_b_local, 0), C.byref(nb)), "dev_qsorts_new")

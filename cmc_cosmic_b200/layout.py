@@ -30,3 +30,16 @@ def binary_field(buf, name, dtype=None):
     flat = buf.reshape(-1)
     sz = np.dtype(dt).itemsize
     return np.lib.stride_tricks.as_strided(flat[off:off + sz].view(dt), shape=(buf.shape[0],), strides=(BINARY_DTYPE_SIZE,))
+
+
+# Row of the HDF5 snapshot table (reference include/cmc/cmc.h:136-200 `Snapshot`, field names as write_snapshot() gives them to
+# H5TBmake_table, src/cmc/cmc_io.c:2962-2970): 62 fields, 488 bytes (4 bytes of padding behind startype).
+SNAPSHOT_FIELDS = ("id", "m_MSUN", "r", "vr", "vt", "E", "J", "binflag", "m0_MSUN", "m1_MSUN", "id0", "id1", "a_AU", "e", "startype", "luminosity_LSUN",
+                   "radius_RSUN", "bin_startype0", "bin_startype1", "bin_star_lum0_LSUN", "bin_star_lum1_LSUN", "bin_star_radius0_RSUN",
+                   "bin_star_radius1_RSUN", "bin_Eb", "eta", "star_phi", "rad0", "rad1", "tb", "lum0", "lum1", "massc0", "massc1", "radc0", "radc1",
+                   "menv0", "menv1", "renv0", "renv1", "tms0", "tms1", "dmdt0", "dmdt1", "radrol0", "radrol1", "ospin0", "ospin1", "B0", "B1",
+                   "formation0", "formation1", "bacc0", "bacc1", "tacc0", "tacc1", "mass0_0", "mass0_1", "epoch0", "epoch1", "ospin", "B", "formation")
+_SNAP_LONG = {"id", "binflag", "id0", "id1"}
+_SNAP_INT = {"startype", "bin_startype0", "bin_startype1"}
+SNAPSHOT_DTYPE = np.dtype([(n, np.int64 if n in _SNAP_LONG else (np.int32 if n in _SNAP_INT else np.float64)) for n in SNAPSHOT_FIELDS], align=True)
+assert SNAPSHOT_DTYPE.itemsize == 488

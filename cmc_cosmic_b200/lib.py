@@ -48,6 +48,11 @@ class SigmaParams(C.Structure):
                [(k, C.c_void_p) for k in ("ghost_prev_vr", "ghost_prev_vt", "ghost_next_vr", "ghost_next_vt")]
 
 
+class SnapshotParams(C.Structure):
+    _fields_ = [(k, C.c_long) for k in ("n_local", "n_old_local", "first_global", "N_MAX", "N_STAR")] + [(k, C.c_double) for k in ("units_m", "units_l", "madhoc")] + \
+               [("avekernel", C.c_long), ("nan_value", C.c_double), ("bh_only", C.c_int)]
+
+
 class DynamicsResult(C.Structure):
     _fields_ = [("n_pairs", C.c_long), ("n_encounters", C.c_long), ("Nrel", C.c_long), ("Nrelbeta", C.c_long * 4),
                 ("qaverelbeta", C.c_double * 4), ("maverelbeta", C.c_double * 4), ("raverelbeta", C.c_double * 4)]
@@ -70,7 +75,7 @@ EXPORTS = [
     "cmcb200_dev_energy_conservation1", "cmcb200_dev_set_velocities3", "cmcb200_dev_set_velocities3_pass", "cmcb200_dev_energy_new_radii",
     "cmcb200_dev_potential", "cmcb200_dev_tidally_strip_select", "cmcb200_dev_compute_energy_totals",
     "cmcb200_shard_step_async", "cmcb200_shard_step_result", "cmcb200_dev_new_orbits_async", "cmcb200_dev_orbit_result", "cmcb200_resident_begin", "cmcb200_resident_begin_sharded", "cmcb200_resident_end", "cmcb200_dev_get", "cmcb200_dev_put", "cmcb200_dev_comp_multi_mass_percent",
-    "cmcb200_dev_dynamics_apply", "cmcb200_dev_dynamics_encounters", "cmcb200_dev_calc_sigma_r", "cmcb200_dev_sigma_arrays", "cmcb200_restart_write", "cmcb200_dev_simul_relax", "cmcb200_dev_step",
+    "cmcb200_dev_dynamics_apply", "cmcb200_dev_dynamics_encounters", "cmcb200_dev_calc_sigma_r", "cmcb200_dev_sigma_arrays", "cmcb200_restart_write", "cmcb200_dev_simul_relax", "cmcb200_dev_step", "cmcb200_dev_snapshot_rows",
 ]
 
 
@@ -147,6 +152,7 @@ def load():
     L.cmcb200_restart_write.argtypes = [vp, C.c_char_p, vp, lg, vp, lg, vp, lg, vp, lg, lg, vp, lg, lg, vp, lg]
     L.cmcb200_dev_simul_relax.argtypes = [vp, lg, lg, lg, lg, lg, dbl, C.POINTER(dbl)]
     L.cmcb200_dev_step.argtypes = [vp, C.POINTER(OrbitParams), lg, dbl, dbl, C.POINTER(OrbitResult), C.POINTER(StepResult)]
+    L.cmcb200_dev_snapshot_rows.argtypes = [vp, C.POINTER(SnapshotParams), vp, vp, lg, C.POINTER(lg)]
     L.cmcb200_dev_get.argtypes = [vp, vp, lg, vp, lg]
     L.cmcb200_dev_put.argtypes = [vp, vp, lg, vp, lg, vp, lg]
     L.cmcb200_resident_begin_sharded.argtypes = [vp, vp, lg, vp, lg, vp, vp, vp, lg, C.c_ulonglong, lg, lg]

@@ -302,6 +302,27 @@ int cmcb200_dev_clusdyn_calculate(cmcb200_ctx *ctx, long N_MAX, long N_STAR, dou
 int cmcb200_dev_comp_multi_mass_percent(cmcb200_ctx *ctx, long N_MAX, const double *mass_bins, long n_bins, double solar_mass_dyn,
 					const double *mass_pc, long count, double *multi_mass_r);
 
+/* ---- HDF5 snapshot table (src/cmc/cmc_io.c:2960-3345 write_snapshot; include/cmc/cmc.h:136-200 `Snapshot`) ------------------- */
+/* The rows write_snapshot() builds in its loop over the stars (:3176-3327) -- 62 fields, 488 bytes each, the struct the reference hands to
+ * H5TBmake_table / H5TBappend_records (:3333-3343) -- built on the device from the resident star[], binary[], star_r / star_m / star_phi and
+ * written to rows_out, in star order, bit for bit what the reference's loop produces.  The HDF5 calls stay in the reference (the library is
+ * not part of this path): write_snapshot() calls this instead of running its loop.
+ *   sigma      sigma_array.sigma ([n_local + 1], entry 0 unused; read for binaries' eta only), or NULL: the result cmcb200_dev_calc_sigma_r
+ *              left on the device
+ *   nan_value  the caller's `0.0 / 0.0` (:3244-3276 fill 33 fields of a single star with it; its bit pattern is the compiler's)
+ *   bh_only    != 0: only stars with se_k == 14 or a binary component of type 14 (:3170-3171, :3188)
+ * Returns 0, or -3 when the caller's buffer is too small (*n_rows = rows needed, nothing written). */
+typedef struct {
+	long n_local;        /* clus.N_MAX_NEW */
+	long n_old_local, first_global, N_MAX; /* get_global_idx (src/cmc/cmc_utils.c:2384-2407), as in cmcb200_orbit_params */
+	long N_STAR;         /* clus.N_STAR */
+	double units_m, units_l, madhoc; /* units.m, units.l, madhoc */
+	long avekernel;      /* AVEKERNEL (calc_average_mass_sqr, src/cmc/cmc_dynamics_helper.c:2997-3022) */
+	double nan_value;
+	int bh_only;
+} cmcb200_snapshot_params;
+int cmcb200_dev_snapshot_rows(cmcb200_ctx *ctx, const cmcb200_snapshot_params *p, const double *sigma, void *rows_out, long cap_rows, long *n_rows);
+
 /* ---- restart file (src/cmc/cmc_io.c:3829-3884) written while the records are resident -------------------------------------- */
 /* The file save_restart_file() writes, byte for byte: curr_st (struct rng_t113_state), restart_struct_t, clus_struct_t -- opaque blocks the
  * caller fills exactly as the reference does (save_global_vars) -- then star[0 .. N_STAR_DIM_OPT) and binary[0 .. N_BIN_DIM_OPT) whole, then

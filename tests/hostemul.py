@@ -45,6 +45,8 @@ def lib():
         L.emul_calc_sigma_r.argtypes = [lg, lg, lg, lg, vp, vp, db, vp, vp, C.c_int, C.c_int, vp, vp, vp]
         L.emul_sigma_scan.restype = C.c_int
         L.emul_sigma_scan.argtypes = [lg, lg, lg, lg, vp, vp, db, vp, vp, C.c_int, db, vp, vp, vp]
+        L.emul_snapshot_rows.restype = lg
+        L.emul_snapshot_rows.argtypes = [vp] * 6 + [lg] * 5 + [db, db, db, lg, C.c_uint64, C.c_int, vp]
         L.emul_dynamics_pairs.restype = lg
         L.emul_dynamics_pairs.argtypes = [vp, vp, vp, lg, lg, lg, lg, db] + [vp] * 17
         _lib = L
@@ -165,3 +167,17 @@ def sigma_scan(p, star_r, star_m, N_MAX, N_STAR, vr_all, vt_all, first_global=1,
     if rc != 0:
         return None
     return a, sg, dict(zip(("hard_segments", "wide_segments", "hard_tiles", "broken", "inconsistent", "tiles"), cnt.tolist()))
+
+
+def snapshot_rows(star_bytes, binary_bytes, star_r, star_m, star_phi, sigma, n_local, n_old_local, first_global, N_MAX, N_STAR, units_m, units_l,
+                  avekernel, nan_bits, bh_only=False):
+    """write_snapshot's rows through the host build of csrc/snapshot_core.h.  star_bytes / binary_bytes: the (n, 424) / (n, 464) uint8 arrays
+    with record 0 in front; sigma: [n_local + 1] or None.  Returns a structured array (layout.SNAPSHOT_DTYPE)."""
+    from cmc_cosmic_b200 import layout
+    sb, bb = np.ascontiguousarray(star_bytes), np.ascontiguousarray(binary_bytes)
+    rows = np.zeros(max(n_local, 1), layout.SNAPSHOT_DTYPE)
+    sg = None if sigma is None else np.ascontiguousarray(sigma, np.float64)
+    k = lib().emul_snapshot_rows(sb.ctypes.data + layout.STAR_DTYPE_SIZE, bb.ctypes.data, _p(np.ascontiguousarray(star_r)), _p(np.ascontiguousarray(star_m)),
+                                 _p(np.ascontiguousarray(star_phi)), None if sg is None else _p(sg), n_local, n_old_local, first_global, N_MAX, N_STAR,
+                                 units_m, units_l, 1.0 / N_STAR, avekernel, int(nan_bits), int(bh_only), rows.ctypes.data)
+    return rows[:k]

@@ -192,6 +192,30 @@ class Ref:
         self.L.ref_comp_multi_mass_percent(bins.ctypes.data, len(bins), solar_mass_dyn, pc.ctypes.data, len(pc), out.ctypes.data)
         return out
 
+    def write_snapshot(self, units_m, units_l, sigma=None, avekernel=20, bh_only=False):
+        """the reference's write_snapshot (cmc_io.c:2960-3345) on the harness's state with the HDF5 calls re-bound to recorders
+        (oracle/ref_harness.c): the rows it hands to H5TBmake_table as a structured array, plus the table's geometry
+        [(name, offset, H5 type code)]"""
+        from cmc_cosmic_b200 import layout
+        L = self.L
+        L.ref_write_snapshot.restype = C.c_long
+        L.ref_write_snapshot.argtypes = [C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_long, C.c_long]
+        L.ref_snapshot_rows.restype = C.c_void_p
+        L.ref_snapshot_row_size.restype = C.c_long
+        L.ref_snapshot_nfields.restype = C.c_long
+        L.ref_snapshot_field.restype = C.c_long
+        L.ref_snapshot_field.argtypes = [C.c_long, C.c_char_p, C.c_void_p]
+        sg = None if sigma is None else np.ascontiguousarray(sigma[1:], np.float64)
+        n = L.ref_write_snapshot(int(bh_only), units_m, units_l, None if sg is None else sg.ctypes.data, 0 if sg is None else len(sg), avekernel)
+        assert L.ref_snapshot_row_size() == layout.SNAPSHOT_DTYPE.itemsize
+        rows = self._view(L.ref_snapshot_rows(), max(n, 1) * layout.SNAPSHOT_DTYPE.itemsize, layout.SNAPSHOT_DTYPE)[:n].copy()
+        geom = []
+        for i in range(L.ref_snapshot_nfields()):
+            name, typ = C.create_string_buffer(64), C.c_long(0)
+            off = L.ref_snapshot_field(i, name, C.byref(typ))
+            geom.append((name.value.decode(), off, typ.value))
+        return rows, geom
+
     def compute_energy(self):
         """E, J exactly as ComputeEnergy (reference cmc_utils.c:614-615), single rank."""
         n = int(self.scalars()["N_MAX"])

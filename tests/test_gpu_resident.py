@@ -146,3 +146,53 @@ def test_restart_file_written_from_the_resident_arrays(tmp_path):
     assert got.size == want.size == 32 + 1208 + 56 + c.N_STAR_DIM * 424 + c.N_BIN_DIM * 464 + 28
     assert np.array_equal(got, want)
     c.close()
+
+
+@pytest.mark.parametrize("bh_only", [False, True])
+def test_snapshot_rows_from_the_resident_arrays(bh_only):
+    """SURVEY 8f N4, the HDF5 snapshot table: the rows write_snapshot() builds (reference src/cmc/cmc_io.c:3176-3327, the `Snapshot` struct)
+    from the RESIDENT star[], binary[] and tables -- after a step of the resident pipeline, so the host's records are stale -- against the host
+    build of the same core on the downloaded arrays (which tests/test_oracle_vs_ref.py::test_write_snapshot_rows pins against the compiled
+    reference, bit for bit): every field of every row, all stars and bh_only, sigma given by the caller and taken from the resident
+    calc_sigma_r; more rows than one device chunk holds."""
+    import hostemul as he
+    from cmc_cosmic_b200 import layout
+    N, nb = 300000, 20000          # 146 MB of rows: two chunks of 2^18 rows
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=19, masses="imf")
+    rng = np.random.default_rng(4)
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    c = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8)
+    c.star[1:N + 1] = rng.uniform(-50.0, 50.0, (N, c.star.shape[1] // 8)).view(np.uint8).reshape(N, c.star.shape[1])
+    c.binary[1:nb + 1] = rng.uniform(-50.0, 50.0, (nb, c.binary.shape[1] // 8)).view(np.uint8).reshape(nb, c.binary.shape[1])
+    c.field("rnew")[:] = 0.0
+    c.load(r, vr, vt, sm, binind=binind, ids=rng.permutation(np.arange(10, N + 10)))
+    c.field("rad")[1:N + 1] = rng.uniform(1e-9, 1e-7, N)
+    c.field("se_k")[1:N + 1] = rng.integers(0, 16, N)
+    for k, lo, hi in (("m1", 0.1, 5.0), ("m2", 0.1, 5.0), ("a", 1e-6, 1e-3), ("e", 0.0, 0.99), ("rad1", 1e-9, 1e-7), ("rad2", 1e-9, 1e-7)):
+        c.bfield(k)[1:nb + 1] = rng.uniform(lo, hi, nb)
+    kw = np.lib.stride_tricks.as_strided(c.binary.reshape(-1)[84:92].view(np.int32), shape=(c.binary.shape[0], 2), strides=(c.binary.shape[1], 4))   # bse_kw[2]
+    kw[1:nb + 1] = rng.integers(0, 16, (nb, 2))
+    c.calc_potential_new()
+    c.compute_energy()
+    c.upload()
+    c.dev_step(seed=9)                                      # the device moves on: the records are sorted by their new radii
+    n = int(c.clus.N_MAX_NEW)
+    units_m, units_l = 1.989e33 * 4.0e5, 3.0857e18 * 1.7
+    sigma = np.concatenate(([0.0], rng.uniform(0.2, 0.9, n)))
+    got = c.dev_snapshot_rows(units_m, units_l, sigma=sigma, avekernel=20, bh_only=bh_only)
+    _, sg_res = c.dev_calc_sigma_r(20)
+    got_res = c.dev_snapshot_rows(units_m, units_l, sigma=None, avekernel=20, bh_only=bh_only)   # eta from the resident sigma array
+    c.download()
+    nan_bits = 0xFFF8000000000000
+    for rows, sg in ((got, sigma), (got_res, sg_res)):
+        want = he.snapshot_rows(c.star, c.binary, c.star_r[:n + 2].copy(), c.star_m[:n + 2].copy(), c.star_phi[:n + 2].copy(), sg, n, n, 1, c.clus.N_MAX,
+                                c.clus.N_STAR, units_m, units_l, 20, nan_bits, bh_only=bh_only)
+        assert len(rows) == len(want) and (len(rows) == n if not bh_only else 0 < len(rows) < n // 2)
+        for name in layout.SNAPSHOT_FIELDS:
+            if rows[name].dtype == np.float64:
+                cm.assert_bits_equal(rows[name], want[name], name)
+            else:
+                assert np.array_equal(rows[name], want[name]), name
+    assert (got["binflag"] == 1).sum() == (c.field("binind")[1:n + 1] > 0).sum() if not bh_only else True
+    c.close()

@@ -524,3 +524,69 @@ def test_taus113_known_answers(R):
     g1.draws(1 << 20)
     g2.jump(ol.Taus113.JPOLY_2_20)
     assert np.array_equal(g1.z, g2.z)
+
+
+def _snapshot_state(R, N, nb, seed):
+    """a sorted cluster in the compiled reference with random content in every field write_snapshot reads: stellar types (some black holes),
+    luminosities, spins, binaries with BSE blocks"""
+    rng = np.random.default_rng(seed)
+    r, vr, vt, sm = cm.cluster_state("plummer", N, seed=seed, masses="imf")
+    binind = np.zeros(N, np.int64)
+    binind[rng.choice(N, nb, replace=False)] = rng.permutation(np.arange(1, nb + 1))
+    R.init(N, n_star_dim=N + 64, n_bin_dim=nb + 8, idum=7)
+    sb, bb = R.star_bytes(), R.binary_bytes()
+    # finite random doubles everywhere (the se_* / bse_* blocks are copied, not computed with), then the fields with a meaning
+    sb[1:N + 1] = rng.uniform(-50.0, 50.0, (N, R.sizeof_star // 8)).view(np.uint8).reshape(N, R.sizeof_star)
+    bb[1:nb + 1] = rng.uniform(-50.0, 50.0, (nb, R.sizeof_binary // 8)).view(np.uint8).reshape(nb, R.sizeof_binary)
+    bb[0] = 0
+    R.load_cluster(r, vr, vt, sm, binind=binind, ids=rng.permutation(np.arange(10, N + 10)))
+    R.star_field("E")[1:N + 1], R.star_field("J")[1:N + 1] = rng.uniform(-2, 0, N), rng.uniform(0, 1, N)
+    R.star_field("rad")[1:N + 1] = rng.uniform(1e-9, 1e-7, N)
+    layout.star_field(sb, "se_k")[1:N + 1] = rng.integers(0, 16, N)
+    for k, lo, hi in (("m1", 0.1, 5.0), ("m2", 0.1, 5.0), ("a", 1e-6, 1e-3), ("e", 0.0, 0.99), ("rad1", 1e-9, 1e-7), ("rad2", 1e-9, 1e-7)):
+        layout.binary_field(bb, k)[1:nb + 1] = rng.uniform(lo, hi, nb)
+    layout.binary_field(bb, "id1", np.int64)[1:nb + 1] = rng.integers(1, 10 ** 7, nb)
+    layout.binary_field(bb, "id2", np.int64)[1:nb + 1] = rng.integers(1, 10 ** 7, nb)
+    kw = np.lib.stride_tricks.as_strided(bb.reshape(-1)[84:92].view(np.int32), shape=(bb.shape[0], 2), strides=(R.sizeof_binary, 4))   # bse_kw[2]
+    kw[1:nb + 1] = rng.integers(0, 16, (nb, 2))
+    R.set_scalars(N, N, N_BINARY=nb)
+    R.L.ref_calc_potential_new()
+    sigma = np.concatenate(([0.0], rng.uniform(0.2, 0.9, N)))
+    return sigma
+
+
+@pytest.mark.parametrize("bh_only", [False, True])
+def test_write_snapshot_rows(R, bh_only):
+    """SURVEY 8f N4, the HDF5 snapshot table: write_snapshot (cmc_io.c:2960-3345) compiled unmodified with its HDF5 calls re-bound to
+    recorders, against the host build of csrc/snapshot_core.h (what the device kernel runs) on the same arrays -- the table's geometry
+    (62 fields, offsets, H5 types, 488-byte rows) and every field of every row bit for bit: unit conversions, -100 markers, the NaN block of
+    single stars, binaries' BSE blocks, bin_Eb and eta (calc_average_mass_sqr windows at both ends of the cluster); all stars and bh_only"""
+    import hostemul as he
+    N, nb = 6000, 700
+    sigma = _snapshot_state(R, N, nb, seed=123)
+    units_m, units_l = 1.989e33 * 4.0e5, 3.0857e18 * 1.7
+    rows, geom = R.write_snapshot(units_m, units_l, sigma=sigma, avekernel=20, bh_only=bh_only)
+    dt = layout.SNAPSHOT_DTYPE
+    assert [g[0] for g in geom] == list(layout.SNAPSHOT_FIELDS)
+    assert [g[1] for g in geom] == [dt.fields[n][1] for n in layout.SNAPSHOT_FIELDS]
+    assert [g[2] for g in geom] == [{np.dtype(np.float64): 1, np.dtype(np.int64): 2, np.dtype(np.int32): 3}[dt.fields[n][0]] for n in layout.SNAPSHOT_FIELDS]
+    sb, bb = R.star_bytes().copy(), R.binary_bytes().copy()
+    bi = layout.star_field(sb, "binind")[1:N + 1]
+    assert len(rows) == (N if not bh_only else len(rows)) and 0 < len(rows) <= N
+    single = np.flatnonzero(rows["binflag"] == -100)
+    nan_bits = int(rows["rad0"][single[0]].view(np.uint64))
+    assert np.isnan(rows["rad0"][single[0]])
+    got = he.snapshot_rows(sb, bb, R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), R.star_phi()[:N + 2].copy(), sigma, N, N, 1, N, N,
+                           units_m, units_l, 20, nan_bits, bh_only=bh_only)
+    assert len(got) == len(rows)
+    if not bh_only:
+        assert (rows["binflag"] == 1).sum() == nb and np.array_equal(rows["binflag"] == 1, bi > 0)
+    else:
+        assert len(rows) < N // 2
+    for n in layout.SNAPSHOT_FIELDS:
+        a, b = rows[n], got[n]
+        if a.dtype == np.float64:
+            cm.assert_bits_equal(a, b, n)
+        else:
+            assert np.array_equal(a, b), n
+    assert np.isfinite(rows["eta"][rows["binflag"] == 1]).all() and (rows["bin_Eb"][rows["binflag"] == 1] < 0).all()

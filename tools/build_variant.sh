@@ -6,7 +6,7 @@ name=$1; shift
 src=cmc_cosmic_b200/csrc
 out=tools/_build/$name
 mkdir -p $out
-for f in api sort potential orbit shard lagrange velocities dynamics sigma; do
+for f in api sort potential orbit shard lagrange velocities dynamics sigma snapshot; do
 	nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC "$@" -c $src/$f.cu -o $out/$f.o &
 done
 wait
