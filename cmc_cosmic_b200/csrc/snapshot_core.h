@@ -48,7 +48,10 @@ CMCB_HD long snap_global_idx(const SnapArgs &a, long i) { return i > a.n_old_loc
 // the reference's unit constants (include/cmc/cmc.h:66-72)
 constexpr double SNAP_MSUN = 1.989e+33, SNAP_RSUN = 6.9599e10, SNAP_AU = 1.496e+13;
 
-// calc_average_mass_sqr(index, N_LIMIT) (src/cmc/cmc_dynamics_helper.c:2997-3022)
+// calc_average_mass_sqr(index, N_LIMIT) (src/cmc/cmc_dynamics_helper.c:2997-3022).  write_snapshot passes the GLOBAL clus.N_MAX as N_LIMIT for
+// LOCAL indices, so on P > 1 ranks the window of a binary among the last p stars of a shard is not clamped: it runs past the shard's last
+// star and get_global_idx maps the overshoot to the table entries behind N_MAX + 1 -- kept as it is (tests/ref_multirank_check.py compares
+// exactly these stars on 2-4 ranks of the compiled reference)
 CMCB_HD double snap_average_mass_sqr(const SnapArgs &a, long index, long N_LIMIT)
 {
 	const long p = a.avekernel;

@@ -73,6 +73,38 @@ def main(procs, N):
         a, sg = R.calc_sigma_r(20, hi - lo + 1, mave)
         a0, sg0 = ol.calc_sigma_r(20, R.star_r()[:N + 2].copy(), R.star_m()[:N + 2].copy(), N, N, vrs, vts, first_global=lo, n_local=hi - lo + 1, mave=mave)
         ok = ok and np.array_equal(a[1:].view(np.uint64), a0[1:].view(np.uint64)) and np.array_equal(sg[1:].view(np.uint64), sg0[1:].view(np.uint64))
+    # write_snapshot (reference cmc_io.c:2960-3345) with the HDF5 calls recorded: every rank's rows (rank 0 through H5TBmake_table, the others
+    # through H5TBappend_records) against the host build of csrc/snapshot_core.h for its shard -- get_global_idx with Start[myid] > 1, the
+    # calc_average_mass_sqr windows of binaries at both ends of a shard
+    import hostemul as he
+    from cmc_cosmic_b200 import layout
+    nl = hi - lo + 1
+    rng3 = np.random.default_rng(1000 + rank)
+    kb = 12
+    spots = np.unique(np.concatenate(([1, 2, 19, 20, 21, nl - 20, nl - 19, nl - 1, nl], rng3.integers(1, nl + 1, 3))))[:kb]
+    bi = np.zeros(nl, np.int64)
+    bi[spots - 1] = np.arange(1, len(spots) + 1)
+    R.star_field("binind", np.int64)[1:nl + 1] = bi
+    bb = R.binary_bytes()
+    bb[1:len(spots) + 1] = rng3.uniform(0.1, 5.0, (len(spots), R.sizeof_binary // 8)).view(np.uint8).reshape(len(spots), R.sizeof_binary)
+    sb = R.star_bytes()
+    layout.star_field(sb, "se_k")[1:nl + 1] = rng3.integers(0, 16, nl)
+    for k in ("E", "J", "rad"):
+        R.star_field(k)[1:nl + 1] = rng3.uniform(0.01, 1.0, nl)
+    sgm = np.concatenate(([0.0], rng3.uniform(0.2, 0.9, nl)))
+    for bh_only in (False, True):
+        rows, _ = R.write_snapshot(3.0e38, 5.0e18, sigma=sgm, avekernel=20, bh_only=bh_only)
+        nanb = 0xFFF8000000000000
+        # the WHOLE tables: for the last p stars of the last rank calc_average_mass_sqr's window is not clamped (its N_LIMIT is the global
+        # clus.N_MAX, its indices are local) and get_global_idx maps the overshoot to the table entries behind N_MAX + 1
+        mine = he.snapshot_rows(R.star_bytes().copy(), R.binary_bytes().copy(), R.star_r().copy(), R.star_m().copy(), R.star_phi().copy(),
+                                sgm, nl, nl, lo, N, N, 3.0e38, 5.0e18, 20, nanb, bh_only=bh_only)
+        ok = ok and len(rows) == len(mine) and (len(rows) == nl if not bh_only else 0 < len(rows) < nl)
+        for name in layout.SNAPSHOT_FIELDS:
+            a, b = rows[name], mine[name]
+            same = np.array_equal(a.view(np.uint64), b.view(np.uint64)) if a.dtype == np.float64 else np.array_equal(a, b)
+            ok = ok and same
+    R.star_field("binind", np.int64)[1:nl + 1] = 0
     # set_velocities3 (reference cmc_utils.c:254-352): the excess-energy carry runs through every rank's shard and on to the next rank
     # (MPI_Send / MPI_Recv, repeated while the all-reduced leftover is > 0)
     phi = R.star_phi()[:N + 2].copy()
