@@ -39,6 +39,10 @@ extern "C" int cmcb200_dev_snapshot_rows(cmcb200_ctx *c, const cmcb200_snapshot_
 	if (join_uploads(c)) return -1;
 	if (p->n_local + 2 > c->n_star_dim) { set_error("snapshot_rows: n_local + 2 = %ld exceeds n_star_dim = %ld", p->n_local + 2, c->n_star_dim); return -1; }
 	if (p->avekernel < 1) { set_error("snapshot_rows: AVEKERNEL = %ld", p->avekernel); return -1; }
+	{ // the highest table entry a row may read: stars created this step, and on P > 1 ranks the unclamped mass window (snapshot_core.h)
+		const long over = (p->n_local > p->n_old_local ? p->n_local - p->n_old_local : 0) + (p->n_old_local < p->N_MAX ? 2 * p->avekernel : 0);
+		if (1 + p->N_MAX + over >= c->n_table_dim) { set_error("snapshot_rows: table entry %ld beyond the capacity %ld", 1 + p->N_MAX + over, c->n_table_dim); return -1; }
+	}
 	double *d_sigma_tmp = nullptr;
 	long *d_list = nullptr;
 	uint64_t *d_rows = nullptr;
