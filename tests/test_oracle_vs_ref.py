@@ -590,3 +590,36 @@ def test_write_snapshot_rows(R, bh_only):
         else:
             assert np.array_equal(a, b), n
     assert np.isfinite(rows["eta"][rows["binflag"] == 1]).all() and (rows["bin_Eb"][rows["binflag"] == 1] < 0).all()
+
+
+def test_write_snapshot_rows_with_stars_created_this_step(R):
+    """the same with M stars behind the old shard (clus.N_MAX_NEW > End - Start + 1: collision products before the next sort): their table
+    entries sit at N_MAX + 2 .. (get_global_idx, cmc_utils.c:2384-2407), one of them is a binary whose mass window reaches back into the
+    old stars"""
+    import hostemul as he
+    N, nb, M = 3000, 200, 37
+    sigma = _snapshot_state(R, N, nb, seed=321)
+    rng = np.random.default_rng(9)
+    sb, bb = R.star_bytes(), R.binary_bytes()
+    sb[N + 1:N + M + 1] = rng.uniform(-50.0, 50.0, (M, R.sizeof_star // 8)).view(np.uint8).reshape(M, R.sizeof_star)
+    bi = layout.star_field(sb, "binind")
+    bi[N + 1:N + M + 1] = 0
+    donor = int(np.flatnonzero(bi[1:N + 1] > 0)[0]) + 1
+    bi[N + 5], bi[donor] = bi[donor], 0      # a binary among the new stars (it takes over the slot of an old star, which becomes single)
+    layout.star_field(sb, "se_k")[N + 1:N + M + 1] = rng.integers(0, 16, M)
+    layout.star_field(sb, "id")[N + 1:N + M + 1] = 10 ** 6 + np.arange(M)
+    R.star_field("rad")[N + 1:N + M + 1] = rng.uniform(1e-9, 1e-7, M)
+    R.star_r()[N + 2:N + 2 + M], R.star_m()[N + 2:N + 2 + M], R.star_phi()[N + 2:N + 2 + M] = rng.uniform(0.1, 3.0, M), rng.uniform(0.1, 5.0, M), -rng.uniform(0.1, 1.0, M)
+    R.set_scalars(N, N + M, N_BINARY=nb)
+    sigma = np.concatenate((sigma, rng.uniform(0.2, 0.9, M)))
+    rows, _ = R.write_snapshot(7.0e38, 2.0e18, sigma=sigma, avekernel=20)
+    nt = N + 2 + M + 64
+    got = he.snapshot_rows(sb.copy(), bb.copy(), R.star_r()[:nt].copy(), R.star_m()[:nt].copy(), R.star_phi()[:nt].copy(), sigma, N + M, N, 1, N, N,
+                           7.0e38, 2.0e18, 20, 0xFFF8000000000000)
+    assert len(rows) == len(got) == N + M and rows["binflag"][N + 4] == 1 and rows["id"][N + M - 1] == 10 ** 6 + M - 1
+    cm.assert_bits_equal(rows["r"][N:], R.star_r()[N + 2:N + 2 + M].copy(), "r of the new stars")
+    for n in layout.SNAPSHOT_FIELDS:
+        if rows[n].dtype == np.float64:
+            cm.assert_bits_equal(rows[n], got[n], n)
+        else:
+            assert np.array_equal(rows[n], got[n]), n
