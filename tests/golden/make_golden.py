@@ -15,6 +15,7 @@ Cases
                   CLUS_OBJ_DATA table is read straight from the file bytes (no HDF5 library in this image)
   cosmic_plummer_n100 / cosmic_king_n100   the N=100 vectors of COSMIC's own unit tests (tests/data/cmc_*_test.npz)
   lagrange_<case> comp_mass_percent (the Lagrange radii) on the initial state of <case>, `make_golden.py lagrange`
+  snapshot_imf_bin  write_snapshot's rows (the HDF5 calls recorded), `make_golden.py snapshot`
   energy_<case>   energy_conservation1, energy_conservation3 -> set_velocities3 and calc_sigma_r (8f N3) on the initial state
                   of <case> with the scheme's inputs of tests/common.py:sv3_fields, `make_golden.py energy`
 Every case records ONE full pass of the path by the reference:
@@ -198,11 +199,33 @@ def lagrad_run():
     print("plummer_lagrad_run.npz:", len(times), "times x", len(frac), "fractions; run ends at t =", d[-1, 0], "after", len(d), "steps")
 
 
+def snapshot_case(R):
+    """snapshot_imf_bin: the rows write_snapshot() (cmc_io.c:2960-3345, compiled unmodified, HDF5 calls recorded by oracle/ref_harness.c) hands
+    to H5TBmake_table for a 1 000-star cluster with 120 binaries and random content in every field it reads -- all stars and bh_only --
+    with its inputs: star[] / binary[] bytes, the three tables, sigma_array.sigma, the units (`make_golden.py snapshot`)"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_oracle_vs_ref as tv
+    N, nb = 1000, 120
+    sigma = tv._snapshot_state(R, N, nb, seed=2024)
+    units_m, units_l = 1.989e33 * 2.5e5, 3.0857e18 * 2.1
+    rows, geom = R.write_snapshot(units_m, units_l, sigma=sigma, avekernel=20)
+    rows_bh, _ = R.write_snapshot(units_m, units_l, sigma=sigma, avekernel=20, bh_only=True)
+    out = dict(N=N, nb=nb, star=R.star_bytes()[:N + 2].copy(), binary=R.binary_bytes()[:nb + 1].copy(), star_r=R.star_r()[:N + 2].copy(),
+               star_m=R.star_m()[:N + 2].copy(), star_phi=R.star_phi()[:N + 2].copy(), sigma=sigma, units_m=units_m, units_l=units_l, avekernel=20,
+               rows=rows.view(np.uint8).reshape(len(rows), -1), rows_bh=rows_bh.view(np.uint8).reshape(len(rows_bh), -1),
+               field_names=np.array([g[0] for g in geom]), field_offsets=np.array([g[1] for g in geom]), field_types=np.array([g[2] for g in geom]))
+    np.savez_compressed(os.path.join(HERE, "snapshot_imf_bin.npz"), **out)
+    print("snapshot_imf_bin.npz:", len(rows), "rows,", len(rows_bh), "bh_only rows,", (rows["binflag"] == 1).sum(), "binaries")
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "lagrad":     # the reference's example run (a data file of the reference, no build needed)
         lagrad_run()
         return
     assert rh.available(), "build oracle/_ref first (make -C oracle)"
+    if len(sys.argv) > 1 and sys.argv[1] == "snapshot":   # only the snapshot-table fixture
+        snapshot_case(rh.Ref())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "energy":     # only the energy-scheme / sigma fixtures
         energy_cases(rh.Ref())
         return

@@ -16,7 +16,8 @@ import common as cm
 import oraclelib as ol
 
 ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(cm.GOLDEN, "*.npz")))
-CASES = [c for c in ALL if not c.startswith(("lagrange_", "energy_", "plummer_lagrad_run"))]   # the last: the Lagrange radii of the reference's example run
+CASES = [c for c in ALL if not c.startswith(("lagrange_", "energy_", "snapshot_", "plummer_lagrad_run"))]   # the last: the Lagrange radii of the reference's example run
+SNAPSHOT = [c for c in ALL if c.startswith("snapshot_")]
 LAGRANGE = [c for c in ALL if c.startswith("lagrange_")]
 ENERGY = [c for c in ALL if c.startswith("energy_")]
 SF = cm.SF_INFINITY
@@ -270,4 +271,52 @@ def test_cuda_full_step_matches_reference(case):
         assert c.N_b_local == g["N_b_local_after"]
         assert np.array_equal(c.field("binind")[1:n2 + 1], g["sorted_binind"])
         assert np.array_equal(c.binary[1:nb + 1], g["binary_after"])
+    c.close()
+
+
+def _snapshot_rows_equal(got, g, key):
+    from cmc_cosmic_b200 import layout
+    want = np.ascontiguousarray(g[key]).view(layout.SNAPSHOT_DTYPE).reshape(-1)
+    assert list(g["field_names"]) == list(layout.SNAPSHOT_FIELDS)
+    assert list(g["field_offsets"]) == [layout.SNAPSHOT_DTYPE.fields[n][1] for n in layout.SNAPSHOT_FIELDS]
+    assert len(got) == len(want) > 0
+    for n in layout.SNAPSHOT_FIELDS:
+        if want[n].dtype == np.float64:
+            cm.assert_bits_equal(got[n], want[n], f"{key}: {n}")
+        else:
+            assert np.array_equal(got[n], want[n]), (key, n)
+
+
+@pytest.mark.parametrize("case", SNAPSHOT)
+def test_kernel_core_snapshot_rows_match_reference(case):
+    """the rows of the HDF5 snapshot table by the host build of csrc/snapshot_core.h against the rows the compiled reference's
+    write_snapshot handed to H5TBmake_table (fixture: every field of every row, all stars and bh_only), bit for bit"""
+    import hostemul as he
+    g = load(case)
+    assert len(SNAPSHOT) >= 1
+    N = g["N"]
+    nan_bits = int(np.ascontiguousarray(g["rows"]).view(np.uint64).reshape(len(g["rows"]), -1)[np.flatnonzero(g["star"][1:N + 1, 152:160].view(np.int64).reshape(-1) == 0)[0], 25])
+    assert nan_bits == 0xFFF8000000000000
+    for key, bh in (("rows", False), ("rows_bh", True)):
+        got = he.snapshot_rows(g["star"], g["binary"], g["star_r"], g["star_m"], g["star_phi"], g["sigma"], N, N, 1, N, N, g["units_m"], g["units_l"],
+                               g["avekernel"], nan_bits, bh_only=bh)
+        _snapshot_rows_equal(got, g, key)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SNAPSHOT)
+def test_cuda_snapshot_rows_match_reference(case):
+    """the same rows built on the device from the resident arrays (cmcb200_dev_snapshot_rows) against the reference's"""
+    from cmc_cosmic_b200.cluster import Cluster
+    g = load(case)
+    N, nb = g["N"], g["nb"]
+    c = Cluster(N, n_star_dim=N + 64, n_bin_dim=nb + 8)
+    c.star[:N + 2] = g["star"]
+    c.binary[:nb + 1] = g["binary"]
+    c.star_r[:N + 2], c.star_m[:N + 2], c.star_phi[:N + 2] = g["star_r"], g["star_m"], g["star_phi"]
+    c.N_b_local = c.clus.N_BINARY = c.bin_slots_in_use = nb
+    c.upload()
+    for key, bh in (("rows", False), ("rows_bh", True)):
+        got = c.dev_snapshot_rows(g["units_m"], g["units_l"], sigma=g["sigma"], avekernel=g["avekernel"], bh_only=bh)
+        _snapshot_rows_equal(got, g, key)
     c.close()
